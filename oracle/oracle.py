@@ -1,0 +1,176 @@
+"""ctypes front-end of the CPU oracle (oracle/qpad_oracle.c).
+
+TEST INFRASTRUCTURE ONLY.  Importable from tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs; never from qpad_b200/.  PARITY UNPINNED: the reference
+ships no golden vectors; the oracle is pinned by analytic known answers.
+
+Array conventions (numpy, C-contiguous, float64):
+  particles   x (np,2)  p (np,3)  gamma/psi/q (np,)            == Fortran x(2,np), p(3,np)
+  field f1    (P, nr+2, dim)   planes re0, re1, im1, re2, im2…  == Fortran f1(dim,0:nr+1) per plane
+  field f2    (P, nzp+1, nr+2, dim)
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+_ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+
+FK_PSI, FK_EZ, FK_BZ, FK_BT, FK_BPLUS, FK_BMINUS = range(6)
+BND_ZERO, BND_OPEN = 2, 3
+PUSH3_REDUCED, PUSH3_BORIS = 1, 2
+
+
+class Params(C.Structure):
+    _fields_ = [("nr", C.c_int), ("nz", C.c_int), ("max_mode", C.c_int), ("bnd", C.c_int), ("iter_max", C.c_int),
+                ("nstages", C.c_int),
+                ("rmax", C.c_double), ("zmin", C.c_double), ("zmax", C.c_double), ("dt", C.c_double),
+                ("iter_reltol", C.c_double), ("iter_abstol", C.c_double), ("relax_fac", C.c_double),
+                ("ppc1", C.c_int), ("ppc2", C.c_int), ("num_theta", C.c_int), ("sort_freq", C.c_int),
+                ("sp_q", C.c_double), ("sp_m", C.c_double), ("sp_density", C.c_double), ("sp_den_min", C.c_double),
+                ("beam_push_type", C.c_int), ("beam_evol", C.c_int), ("beam_qbm", C.c_double)]
+
+
+def build(fast=False, force=False):
+    target = "liborc_fast.so" if fast else "liborc.so"
+    path = os.path.join(_HERE, target)
+    src = os.path.join(_HERE, "qpad_oracle.c")
+    if force or not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-B", target], stdout=subprocess.DEVNULL)
+    return path
+
+
+_libs = {}
+
+
+def lib(fast=False):
+    if fast in _libs:
+        return _libs[fast]
+    L = C.CDLL(build(fast))
+    i, l, d, vp = C.c_int, C.c_long, C.c_double, C.c_void_p
+    sig = {
+        "orc_qdeposit": (None, [_dp, _dp, l, d, i, i, _dp]),
+        "orc_amjdeposit_robust": (None, [_dp, _dp, _dp, _dp, _dp, l, d, i, i, d, d, _dp, _dp, _dp, _dp, _dp]),
+        "orc_push_u_robust": (None, [_dp, _dp, _dp, l, d, i, i, d, d, _dp, _dp]),
+        "orc_push_x": (None, [_dp, _dp, _dp, l, d]),
+        "orc_update_bound": (l, [_dp, _dp, _dp, _dp, _dp, l, d]),
+        "orc_sort_idx": (None, [_dp, l, d, i, _ip, _ip]),
+        "orc_sort_part2d": (None, [_dp, _dp, _dp, _dp, _dp, l, d, i]),
+        "orc_inject_uniform": (l, [_dp, _dp, _dp, _dp, _dp, i, d, i, i, i, d, d, d]),
+        "orc_build_matrix": (None, [i, i, i, d, i, d, _dp, _dp, _dp]),
+        "orc_tridiag_solve": (None, [_dp, _dp, _dp, _dp, i]),
+        "orc_tridiag_solve_ld": (None, [_dp, _dp, _dp, _dp, i]),
+        "orc_solve_psi": (None, [_dp, _dp, i, i, d, i]),
+        "orc_solve_bt": (None, [_dp, _dp, i, i, d, i]),
+        "orc_solve_bz": (None, [_dp, _dp, i, i, d, i]),
+        "orc_solve_bt_iter": (None, [_dp, _dp, _dp, i, i, d, i, d]),
+        "orc_solve_ez": (None, [_dp, _dp, i, i, d, i]),
+        "orc_solve_et": (None, [_dp, _dp, _dp, i, i, d]),
+        "orc_solve_et_beam": (None, [_dp, _dp, i, i]),
+        "orc_solve_djdxi": (None, [_dp, _dp, _dp, i, i, d]),
+        "orc_smooth_f1": (None, [_dp, i, i, _ip]),
+        "orc_qdeposit3d": (None, [_dp, _dp, l, d, d, i, i, i, i, _dp]),
+        "orc_push3d": (None, [_dp, _dp, l, d, d, i, i, i, i, d, d, i, _dp, _dp]),
+        "orc_update_bound3d": (l, [_dp, _dp, _dp, l, d, d]),
+        "orc_sim_create": (vp, [C.POINTER(Params)]),
+        "orc_sim_destroy": (None, [vp]),
+        "orc_sim_set_beam": (None, [vp, _dp, _dp, _dp, l]),
+        "orc_sim_step3d": (l, [vp, i]),
+        "orc_sim_run_slices": (l, [vp, i]),
+        "orc_sim_nzp": (i, [vp, i]),
+        "orc_sim_plasma_np": (l, [vp, i]),
+        "orc_sim_get_plasma": (None, [vp, i, _dp, _dp, _dp, _dp, _dp]),
+        "orc_sim_beam_np": (l, [vp, i]),
+        "orc_sim_get_beam": (None, [vp, i, _dp, _dp, _dp]),
+        "orc_sim_get_field": (l, [vp, i, C.c_char_p, i, C.c_void_p]),
+        "orc_sim_total_iters": (l, [vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype, fn.argtypes = res, args
+    _libs[fast] = L
+    return L
+
+
+def nplanes(max_mode):
+    return 2 * max_mode + 1
+
+
+def zeros_f1(dim, nr, max_mode):
+    return np.zeros((nplanes(max_mode), nr + 2, dim))
+
+
+def inject_uniform(nr, dr, ppc1, ppc2, num_theta, qm=-1.0, density=1.0, den_min=1e-10):
+    n = nr * ppc1 * ppc2 * num_theta
+    x, p = np.zeros((n, 2)), np.zeros((n, 3))
+    g, psi, q = np.zeros(n), np.zeros(n), np.zeros(n)
+    npp = lib().orc_inject_uniform(x, p, g, psi, q, nr, dr, ppc1, ppc2, num_theta, qm, density, den_min)
+    return x[:npp], p[:npp], g[:npp], psi[:npp], q[:npp]
+
+
+class Sim:
+    """Whole-loop oracle (simulation_class.f03:226-512), optionally as S pipeline stages run in sequence."""
+
+    def __init__(self, fast=False, **kw):
+        self.L = lib(fast)
+        prm = Params()
+        defaults = dict(nr=64, nz=32, max_mode=1, bnd=BND_OPEN, iter_max=1, nstages=1, rmax=5.0, zmin=-5.0, zmax=5.0,
+                        dt=10.0, iter_reltol=1e-3, iter_abstol=1e-3, relax_fac=-1.0, ppc1=2, ppc2=2, num_theta=8,
+                        sort_freq=0, sp_q=-1.0, sp_m=1.0, sp_density=1.0, sp_den_min=1e-10,
+                        beam_push_type=PUSH3_REDUCED, beam_evol=1, beam_qbm=-1.0)
+        defaults.update(kw)
+        for k, v in defaults.items():
+            setattr(prm, k, v)
+        self.prm = prm
+        self.h = self.L.orc_sim_create(C.byref(prm))
+        self.nr, self.nz, self.max_mode, self.nstages = prm.nr, prm.nz, prm.max_mode, max(1, prm.nstages)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.orc_sim_destroy(self.h)
+            self.h = None
+
+    def set_beam(self, x, p, q):
+        x, p, q = (np.ascontiguousarray(a, dtype=np.float64) for a in (x, p, q))
+        self.L.orc_sim_set_beam(self.h, x, p, q, len(q))
+
+    def step3d(self, istep=1):
+        return self.L.orc_sim_step3d(self.h, istep)
+
+    def run_slices(self, n):
+        return self.L.orc_sim_run_slices(self.h, n)
+
+    def nzp(self, stage=0):
+        return self.L.orc_sim_nzp(self.h, stage)
+
+    def plasma(self, stage=0):
+        n = self.L.orc_sim_plasma_np(self.h, stage)
+        x, p = np.zeros((n, 2)), np.zeros((n, 3))
+        g, psi, q = np.zeros(n), np.zeros(n), np.zeros(n)
+        self.L.orc_sim_get_plasma(self.h, stage, x, p, g, psi, q)
+        return x, p, g, psi, q
+
+    def beam(self, stage=0):
+        n = self.L.orc_sim_beam_np(self.h, stage)
+        x, p, q = np.zeros((n, 3)), np.zeros((n, 3)), np.zeros(n)
+        self.L.orc_sim_get_beam(self.h, stage, x, p, q)
+        return x, p, q
+
+    _DIM = dict(psi=1, e=3, b=3, e_spe=3, b_spe=3, e_beam=3, b_beam=3, cu=3, amu=3, acu=2, dcu=2, q_spe=1, q_beam=1,
+                spe_q=1, spe_qn=1)
+
+    def field(self, name, which=1, stage=0):
+        n = self.L.orc_sim_get_field(self.h, stage, name.encode(), which, None)
+        if n < 0:
+            raise KeyError(name)
+        out = np.zeros(n)
+        self.L.orc_sim_get_field(self.h, stage, name.encode(), which, out.ctypes.data_as(C.c_void_p))
+        P, dim = nplanes(self.max_mode), self._DIM[name]
+        if which == 1:
+            return out.reshape(P, self.nr + 2, dim)
+        return out.reshape(P, self.nzp(stage) + 1, self.nr + 2, dim)
+
+    def total_iters(self):
+        return self.L.orc_sim_total_iters(self.h)

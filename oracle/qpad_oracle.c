@@ -1,0 +1,1479 @@
+/*
+ * qpad_oracle.c -- CPU restatement of QPAD's quasi-static slice loop (see qpad_oracle.h).
+ * TEST INFRASTRUCTURE ONLY; PARITY UNPINNED by the reference (no golden vectors exist).
+ * Every routine cites the Fortran it follows, relative to /root/reference/source/.
+ * Build for parity with -O2 -ffp-contract=off (no FMA contraction); see oracle/Makefile.
+ */
+#include "qpad_oracle.h"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <float.h>
+
+#define P_CACHE 1024 /* param.f03:10 p_cache_size */
+
+/* ------------------------------------------------------------------------- */
+/* field indexing                                                            */
+/* ------------------------------------------------------------------------- */
+static inline int nplanes(int max_mode) { return 2 * max_mode + 1; }
+static inline int pl_re(int m) { return m == 0 ? 0 : 2 * m - 1; }
+static inline int pl_im(int m) { return 2 * m; }
+/* f1(c, j) of plane pl ; c is 1-based, j in [0, nr+1] */
+#define F1(f, dim, nr, pl, c, j) ((f)[(((size_t)(pl)) * ((nr) + 2) + (j)) * (dim) + ((c)-1)])
+/* f2(c, j, k) of plane pl ; k in [1, nzp+1] */
+#define F2(f, dim, nr, nzp, pl, c, j, k) \
+    ((f)[((((size_t)(pl)) * ((nzp) + 1) + ((k)-1)) * ((nr) + 2) + (j)) * (dim) + ((c)-1)])
+
+typedef struct { double re, im; } cplx;
+static inline cplx cmul(cplx a, cplx b) { cplx r; r.re = a.re * b.re - a.im * b.im; r.im = a.re * b.im + a.im * b.re; return r; }
+
+/* ------------------------------------------------------------------------- */
+/* species/interp_part2d.f03:28-65 gen_interp_info                            */
+/* ------------------------------------------------------------------------- */
+static void gen_interp_info(const double *x, double dr, long pp, double *w0, double *w1, int *idx, double *pcos, double *psin)
+{
+    double idr = 1.0 / dr;
+    double pos = sqrt(x[2 * pp] * x[2 * pp] + x[2 * pp + 1] * x[2 * pp + 1]);
+    *pcos = x[2 * pp] / pos;
+    *psin = x[2 * pp + 1] / pos;
+    pos = pos * idr;
+    int ip = (int)pos;
+    *idx = ip + 1; /* noff = 0 */
+    pos = pos - ip;
+    *w0 = 1.0 - pos; /* interpolation.f03:10 spline_linear */
+    *w1 = pos;
+}
+
+/* species/interp_part2d.f03:67-109 interp_field (vector, dim 3) */
+static void interp_field3(const double *f, int nr, int max_mode, double w0, double w1, int idx, double pcos, double psin, double fp[3])
+{
+    const int dim = 3;
+    fp[0] = fp[1] = fp[2] = 0.0;
+    cplx phase = {1.0, 0.0}, ph0 = {pcos, psin};
+    const double w[2] = {w0, w1};
+    for (int j = 0; j < 2; j++)
+        for (int c = 1; c <= 3; c++) fp[c - 1] = fp[c - 1] + F1(f, dim, nr, 0, c, idx + j) * w[j];
+    for (int m = 1; m <= max_mode; m++) {
+        phase = cmul(phase, ph0);
+        double phr = 2.0 * phase.re, phi = 2.0 * phase.im;
+        for (int j = 0; j < 2; j++)
+            for (int c = 1; c <= 3; c++)
+                fp[c - 1] = fp[c - 1] + (F1(f, dim, nr, pl_re(m), c, idx + j) * phr - F1(f, dim, nr, pl_im(m), c, idx + j) * phi) * w[j];
+    }
+}
+
+/* ------------------------------------------------------------------------- */
+/* species/part2d_class.f03:231-359 qdeposit_part2d                          */
+/* ------------------------------------------------------------------------- */
+void orc_qdeposit(const double *x, const double *q, long npp, double dr, int nr, int max_mode, double *f)
+{
+    const int dim = 1;
+    double idr = 1.0 / dr;
+    for (long pp = 0; pp < npp; pp++) {
+        double pos = sqrt(x[2 * pp] * x[2 * pp] + x[2 * pp + 1] * x[2 * pp + 1]) * idr;
+        cplx ph0;
+        ph0.re = x[2 * pp] / pos * idr;
+        ph0.im = -x[2 * pp + 1] / pos * idr;
+        int nn = (int)floor(pos);
+        pos = pos - (double)nn;
+        nn = nn + 1;
+        double wt[2] = {1.0 - pos, pos};
+        cplx phase = {1.0 * q[pp], 0.0 * q[pp]};
+        for (int j = 0; j < 2; j++) F1(f, dim, nr, 0, 1, nn + j) += wt[j] * phase.re;
+        for (int m = 1; m <= max_mode; m++) {
+            phase = cmul(phase, ph0);
+            for (int j = 0; j < 2; j++) {
+                F1(f, dim, nr, pl_re(m), 1, nn + j) += wt[j] * phase.re;
+                F1(f, dim, nr, pl_im(m), 1, nn + j) += wt[j] * phase.im;
+            }
+        }
+    }
+    /* noff == 0 branch, :312-333 */
+    F1(f, dim, nr, 0, 1, 0) = 0.0;
+    F1(f, dim, nr, 0, 1, 1) = 8.0 * F1(f, dim, nr, 0, 1, 1);
+    for (int j = 2; j <= nr + 1; j++) {
+        double ir = 1.0 / (double)(j - 1);
+        F1(f, dim, nr, 0, 1, j) = F1(f, dim, nr, 0, 1, j) * ir;
+    }
+    for (int m = 1; m <= max_mode; m++) {
+        int pr = pl_re(m), pi = pl_im(m);
+        F1(f, dim, nr, pr, 1, 0) = 0.0; F1(f, dim, nr, pi, 1, 0) = 0.0;
+        F1(f, dim, nr, pr, 1, 1) = 0.0; F1(f, dim, nr, pi, 1, 1) = 0.0;
+        for (int j = 2; j <= nr + 1; j++) {
+            double ir = 1.0 / (double)(j - 1);
+            F1(f, dim, nr, pr, 1, j) = F1(f, dim, nr, pr, 1, j) * ir;
+            F1(f, dim, nr, pi, 1, j) = F1(f, dim, nr, pi, 1, j) * ir;
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------- */
+/* species/part2d_class.f03:746-1010 amjdeposit_robust_part2d                */
+/* ------------------------------------------------------------------------- */
+void orc_amjdeposit_robust(const double *x, const double *p, const double *q, double *gamma, double *psi, long npp,
+                           double dr, int nr, int max_mode, double qbm, double dt, const double *ef, const double *bf,
+                           double *cu, double *dcu, double *amu)
+{
+    double idt = 1.0 / dt;
+    double qtmh = 0.5 * qbm * dt;
+    for (long pp = 0; pp < npp; pp++) {
+        double w0, w1, pcos, psin, ep[3], bp[3], wp[3], u0[3], u[3], utmp[3];
+        int ix;
+        gen_interp_info(x, dr, pp, &w0, &w1, &ix, &pcos, &psin);
+        interp_field3(ef, nr, max_mode, w0, w1, ix, pcos, psin, ep);
+        interp_field3(bf, nr, max_mode, w0, w1, ix, pcos, psin, bp);
+        /* :816-853 */
+        wp[0] = ep[0] - bp[1];
+        wp[1] = ep[1] + bp[0];
+        wp[2] = ep[2];
+        u0[0] = p[3 * pp] * pcos + p[3 * pp + 1] * psin;
+        u0[1] = p[3 * pp + 1] * pcos - p[3 * pp] * psin;
+        u0[2] = p[3 * pp + 2];
+        double gam = sqrt(1.0 + u0[0] * u0[0] + u0[1] * u0[1] + u0[2] * u0[2]);
+        double qtmh1 = qtmh * gam / (gam - u0[2]);
+        for (int c = 0; c < 3; c++) { ep[c] = ep[c] * qtmh1; utmp[c] = u0[c] + ep[c]; }
+        gam = sqrt(1.0 + utmp[0] * utmp[0] + utmp[1] * utmp[1] + utmp[2] * utmp[2]);
+        double qtmh2 = qtmh / (gam - utmp[2]);
+        for (int c = 0; c < 3; c++) bp[c] = bp[c] * qtmh2;
+        u[0] = utmp[0] + utmp[1] * bp[2] - utmp[2] * bp[1];
+        u[1] = utmp[1] + utmp[2] * bp[0] - utmp[0] * bp[2];
+        u[2] = utmp[2] + utmp[0] * bp[1] - utmp[1] * bp[0];
+        double ostq = 2.0 / (1.0 + bp[0] * bp[0] + bp[1] * bp[1] + bp[2] * bp[2]);
+        for (int c = 0; c < 3; c++) bp[c] = bp[c] * ostq;
+        utmp[0] = utmp[0] + u[1] * bp[2] - u[2] * bp[1];
+        utmp[1] = utmp[1] + u[2] * bp[0] - u[0] * bp[2];
+        utmp[2] = utmp[2] + u[0] * bp[1] - u[1] * bp[0];
+        for (int c = 0; c < 3; c++) u[c] = utmp[c] + ep[c];
+        /* :858-909 */
+        double du[2], u2[3];
+        du[0] = idt * (u[0] - u0[0]);
+        du[1] = idt * (u[1] - u0[1]);
+        for (int c = 0; c < 3; c++) u[c] = 0.5 * (u[c] + u0[c]);
+        gamma[pp] = sqrt(1.0 + u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+        double ipsi = 1.0 / (gamma[pp] - u[2]);
+        psi[pp] = (1.0 - 1.0 / ipsi) / qbm;
+        double dpsi = qbm * (wp[2] - (wp[0] * u[0] + wp[1] * u[1]) * ipsi);
+        du[0] = du[0] + u[0] * dpsi * ipsi;
+        du[1] = du[1] + u[1] * dpsi * ipsi;
+        u2[0] = u[0] * u[0] * ipsi;
+        u2[1] = u[0] * u[1] * ipsi;
+        u2[2] = u[1] * u[1] * ipsi;
+        cplx ph0 = {pcos, -psin};
+        cplx phase = {1.0 * q[pp] * ipsi, 0.0 * q[pp] * ipsi};
+        const double wt[2] = {w0, w1};
+        for (int j = 0; j < 2; j++) {
+            double w = wt[j] * phase.re;
+            for (int c = 1; c <= 3; c++) F1(cu, 3, nr, 0, c, ix + j) += w * u[c - 1];
+            for (int c = 1; c <= 2; c++) F1(dcu, 2, nr, 0, c, ix + j) += w * du[c - 1];
+            for (int c = 1; c <= 3; c++) F1(amu, 3, nr, 0, c, ix + j) += w * u2[c - 1];
+        }
+        for (int m = 1; m <= max_mode; m++) {
+            int pr = pl_re(m), pi = pl_im(m);
+            phase = cmul(phase, ph0);
+            for (int j = 0; j < 2; j++) {
+                double w = wt[j] * phase.re;
+                for (int c = 1; c <= 3; c++) F1(cu, 3, nr, pr, c, ix + j) += w * u[c - 1];
+                for (int c = 1; c <= 2; c++) F1(dcu, 2, nr, pr, c, ix + j) += w * du[c - 1];
+                for (int c = 1; c <= 3; c++) F1(amu, 3, nr, pr, c, ix + j) += w * u2[c - 1];
+                w = wt[j] * phase.im;
+                for (int c = 1; c <= 3; c++) F1(cu, 3, nr, pi, c, ix + j) += w * u[c - 1];
+                for (int c = 1; c <= 2; c++) F1(dcu, 2, nr, pi, c, ix + j) += w * du[c - 1];
+                for (int c = 1; c <= 3; c++) F1(amu, 3, nr, pi, c, ix + j) += w * u2[c - 1];
+            }
+        }
+    }
+    /* axis fix-ups, noff == 0 branch :916-981 */
+    for (int c = 1; c <= 3; c++) { F1(cu, 3, nr, 0, c, 0) = 0.0; F1(amu, 3, nr, 0, c, 0) = 0.0; }
+    for (int c = 1; c <= 2; c++) F1(dcu, 2, nr, 0, c, 0) = 0.0;
+    F1(cu, 3, nr, 0, 1, 1) = 0.0; F1(cu, 3, nr, 0, 2, 1) = 0.0; F1(cu, 3, nr, 0, 3, 1) = 8.0 * F1(cu, 3, nr, 0, 3, 1);
+    F1(dcu, 2, nr, 0, 1, 1) = 0.0; F1(dcu, 2, nr, 0, 2, 1) = 0.0;
+    for (int c = 1; c <= 3; c++) F1(amu, 3, nr, 0, c, 1) = 0.0;
+    for (int m = 1; m <= max_mode; m++) {
+        for (int ri = 0; ri < 2; ri++) {
+            int pl = ri ? pl_im(m) : pl_re(m);
+            for (int c = 1; c <= 3; c++) { F1(cu, 3, nr, pl, c, 0) = 0.0; F1(amu, 3, nr, pl, c, 0) = 0.0; }
+            for (int c = 1; c <= 2; c++) F1(dcu, 2, nr, pl, c, 0) = 0.0;
+            if (m == 1) {
+                F1(cu, 3, nr, pl, 1, 1) = 8.0 * F1(cu, 3, nr, pl, 1, 1);
+                F1(cu, 3, nr, pl, 2, 1) = 8.0 * F1(cu, 3, nr, pl, 2, 1);
+                F1(cu, 3, nr, pl, 3, 1) = 0.0;
+                F1(dcu, 2, nr, pl, 1, 1) = 8.0 * F1(dcu, 2, nr, pl, 1, 1);
+                F1(dcu, 2, nr, pl, 2, 1) = 8.0 * F1(dcu, 2, nr, pl, 2, 1);
+                for (int c = 1; c <= 3; c++) F1(amu, 3, nr, pl, c, 1) = 0.0;
+            } else if (m == 2) {
+                for (int c = 1; c <= 3; c++) F1(cu, 3, nr, pl, c, 1) = 0.0;
+                for (int c = 1; c <= 2; c++) F1(dcu, 2, nr, pl, c, 1) = 0.0;
+                for (int c = 1; c <= 3; c++) F1(amu, 3, nr, pl, c, 1) = 8.0 * F1(amu, 3, nr, pl, c, 1);
+            } else {
+                for (int c = 1; c <= 3; c++) F1(cu, 3, nr, pl, c, 1) = 0.0;
+                for (int c = 1; c <= 2; c++) F1(dcu, 2, nr, pl, c, 1) = 0.0;
+                for (int c = 1; c <= 3; c++) F1(amu, 3, nr, pl, c, 1) = 0.0;
+            }
+        }
+    }
+    int P = nplanes(max_mode);
+    for (int pl = 0; pl < P; pl++)
+        for (int j = 2; j <= nr + 1; j++) {
+            double ir = 1.0 / (double)(j - 1);
+            for (int c = 1; c <= 3; c++) F1(cu, 3, nr, pl, c, j) = F1(cu, 3, nr, pl, c, j) * ir;
+            for (int c = 1; c <= 2; c++) F1(dcu, 2, nr, pl, c, j) = F1(dcu, 2, nr, pl, c, j) * ir;
+            for (int c = 1; c <= 3; c++) F1(amu, 3, nr, pl, c, j) = F1(amu, 3, nr, pl, c, j) * ir;
+        }
+}
+
+/* ------------------------------------------------------------------------- */
+/* species/part2d_class.f03:1879-1965 push_u_robust_part2d                   */
+/* ------------------------------------------------------------------------- */
+void orc_push_u_robust(const double *x, double *p, double *gamma, long npp, double dr, int nr, int max_mode,
+                       double qbm, double dt, const double *ef, const double *bf)
+{
+    double qtmh = qbm * dt * 0.5;
+    for (long pp = 0; pp < npp; pp++) {
+        double w0, w1, pcos, psin, ep[3], bp[3], utmp[3], tmp;
+        int idx;
+        gen_interp_info(x, dr, pp, &w0, &w1, &idx, &pcos, &psin);
+        interp_field3(ef, nr, max_mode, w0, w1, idx, pcos, psin, ep);
+        interp_field3(bf, nr, max_mode, w0, w1, idx, pcos, psin, bp);
+        /* interp_part2d.f03:155 transform_to_cartesian */
+        tmp = ep[0] * pcos - ep[1] * psin; ep[1] = ep[0] * psin + ep[1] * pcos; ep[0] = tmp;
+        tmp = bp[0] * pcos - bp[1] * psin; bp[1] = bp[0] * psin + bp[1] * pcos; bp[0] = tmp;
+        double *pp3 = p + 3 * pp;
+        double gam = sqrt(1.0 + pp3[0] * pp3[0] + pp3[1] * pp3[1] + pp3[2] * pp3[2]);
+        double qtmh1 = qtmh / (gam - pp3[2]);
+        double qtmh2 = qtmh1 * gam;
+        for (int c = 0; c < 3; c++) { ep[c] = ep[c] * qtmh2; bp[c] = bp[c] * qtmh1; }
+        for (int c = 0; c < 3; c++) utmp[c] = pp3[c] + ep[c];
+        pp3[0] = utmp[0] + utmp[1] * bp[2] - utmp[2] * bp[1];
+        pp3[1] = utmp[1] + utmp[2] * bp[0] - utmp[0] * bp[2];
+        pp3[2] = utmp[2] + utmp[0] * bp[1] - utmp[1] * bp[0];
+        double ostq = 2.0 / (1.0 + bp[0] * bp[0] + bp[1] * bp[1] + bp[2] * bp[2]);
+        for (int c = 0; c < 3; c++) bp[c] = bp[c] * ostq;
+        utmp[0] = utmp[0] + pp3[1] * bp[2] - pp3[2] * bp[1];
+        utmp[1] = utmp[1] + pp3[2] * bp[0] - pp3[0] * bp[2];
+        utmp[2] = utmp[2] + pp3[0] * bp[1] - pp3[1] * bp[0];
+        for (int c = 0; c < 3; c++) pp3[c] = utmp[c] + ep[c];
+        gamma[pp] = sqrt(1.0 + pp3[0] * pp3[0] + pp3[1] * pp3[1] + pp3[2] * pp3[2]);
+    }
+}
+
+/* species/part2d_class.f03:2221-2262 push_x_part2d */
+void orc_push_x(double *x, const double *p, const double *gamma, long npp, double dt)
+{
+    for (long pp = 0; pp < npp; pp++) {
+        double dtc = dt / (gamma[pp] - p[3 * pp + 2]);
+        x[2 * pp] = x[2 * pp] + p[3 * pp] * dtc;
+        x[2 * pp + 1] = x[2 * pp + 1] + p[3 * pp + 1] * dtc;
+    }
+}
+
+/* species/part2d_class.f03:2307-2353 update_bound_part2d (0-based restatement of the 1-based loop) */
+long orc_update_bound(double *x, double *p, double *gamma, double *psi, double *q, long npp, double edge)
+{
+    if (npp == 0) return 0;
+    long i = 1;
+    while (i < npp) {
+        double pos = sqrt(x[2 * (i - 1)] * x[2 * (i - 1)] + x[2 * (i - 1) + 1] * x[2 * (i - 1) + 1]);
+        if (pos >= edge) {
+            long l = npp - 1;
+            x[2 * (i - 1)] = x[2 * l]; x[2 * (i - 1) + 1] = x[2 * l + 1];
+            p[3 * (i - 1)] = p[3 * l]; p[3 * (i - 1) + 1] = p[3 * l + 1]; p[3 * (i - 1) + 2] = p[3 * l + 2];
+            gamma[i - 1] = gamma[l]; psi[i - 1] = psi[l]; q[i - 1] = q[l];
+            npp = npp - 1;
+            continue;
+        }
+        i = i + 1;
+    }
+    double pos = sqrt(x[2 * (npp - 1)] * x[2 * (npp - 1)] + x[2 * (npp - 1) + 1] * x[2 * (npp - 1) + 1]);
+    if (pos >= edge) npp = npp - 1;
+    return npp;
+}
+
+/* sort_module.f03:11-42 generate_sort_idx_1d + key rule of part2d_class.f03:2522-2526 */
+void orc_sort_idx(const double *x, long npp, double dr, int nrp, int *ix, int *ip)
+{
+    double idr = 1.0 / dr;
+    int *counter = (int *)calloc((size_t)nrp + 2, sizeof(int));
+    for (long i = 0; i < npp; i++) {
+        double pos = sqrt(x[2 * i] * x[2 * i] + x[2 * i + 1] * x[2 * i + 1]) * idr;
+        ix[i] = (int)floor(pos) + 1;
+    }
+    for (long i = 0; i < npp; i++) counter[ix[i]] += 1;
+    for (int i = 2; i <= nrp; i++) counter[i] += counter[i - 1];
+    for (long i = 0; i < npp; i++) { ip[i] = counter[ix[i]]; counter[ix[i]] -= 1; }
+    free(counter);
+}
+
+/* species/part2d_class.f03:2498-2579 sort_part2d */
+void orc_sort_part2d(double *x, double *p, double *gamma, double *psi, double *q, long npp, double dr, int nrp)
+{
+    int *ix = (int *)malloc(sizeof(int) * (size_t)(npp + 1)), *ip = (int *)malloc(sizeof(int) * (size_t)(npp + 1));
+    double *buf = (double *)malloc(sizeof(double) * (size_t)(npp + 1));
+    orc_sort_idx(x, npp, dr, nrp, ix, ip);
+#define PERMUTE(arr, stride, off)                                          \
+    for (long i = 0; i < npp; i++) buf[i] = arr[(stride)*i + (off)];       \
+    for (long i = 0; i < npp; i++) arr[(stride) * (long)(ip[i] - 1) + (off)] = buf[i];
+    PERMUTE(x, 2, 0) PERMUTE(x, 2, 1) PERMUTE(p, 3, 0) PERMUTE(p, 3, 1) PERMUTE(p, 3, 2)
+    PERMUTE(gamma, 1, 0) PERMUTE(q, 1, 0) PERMUTE(psi, 1, 0)
+#undef PERMUTE
+    free(ix); free(ip); free(buf);
+}
+
+/* species/fdist2d_class.f03:289-357 inject_fdist2d, uniform perp+lon profile (den = 1), uth = 0, ordered theta */
+long orc_inject_uniform(double *x, double *p, double *gamma, double *psi, double *q, int nr, double dr, int ppc1,
+                        int ppc2, int num_theta, double qm, double density, double den_min)
+{
+    const double pi = 4 * atan(1.0); /* param.f03:36 */
+    double dtheta = 2.0 * pi / num_theta;
+    int ppc_tot = ppc1 * ppc2;
+    double den_lon = 1.0, den_perp = 1.0;
+    double coef = copysign(1.0, qm) / ((double)ppc_tot * (double)num_theta);
+    long ipart = 0;
+    for (int j = 1; j <= num_theta; j++)
+        for (int i = 1; i <= nr; i++)
+            for (int i1 = 1; i1 <= ppc1; i1++) {
+                double rn = (i1 - 0.5) / ppc1 + (double)(i - 1);
+                for (int i2 = 1; i2 <= ppc2; i2++) {
+                    double theta = ((i2 - 0.5) / ppc2 + j - 1.0) * dtheta;
+                    double x1 = rn * dr * cos(theta), x2 = rn * dr * sin(theta);
+                    if (den_lon * den_perp * density < den_min) continue;
+                    x[2 * ipart] = x1; x[2 * ipart + 1] = x2;
+                    q[ipart] = rn * den_perp * den_lon * density * coef;
+                    p[3 * ipart] = 0.0; p[3 * ipart + 1] = 0.0; p[3 * ipart + 2] = 0.0;
+                    gamma[ipart] = sqrt(1.0 + 0.0);
+                    psi[ipart] = (1.0 - gamma[ipart] + p[3 * ipart + 2]) / qm;
+                    ipart++;
+                }
+            }
+    return ipart;
+}
+
+/* ------------------------------------------------------------------------- */
+/* fields/field_solver_class.f03:256-561 set_struct_matrix (single r-owner)  */
+/* ------------------------------------------------------------------------- */
+void orc_build_matrix(int kind, int mode, int nr, double dr, int bnd, double relax_fac, double *a, double *b, double *c)
+{
+    double dr2 = dr * dr;
+    int m = mode;
+    double m2 = (double)(m * m);
+    double j = 0.0;
+    for (int i = 1; i < nr; i++) { /* rows 2..nr */
+        j = j + 1.0;
+        a[i] = 1.0 - 0.5 / j;
+        c[i] = 1.0 + 0.5 / j;
+        switch (kind) {
+        case ORC_FK_PSI: case ORC_FK_BT: case ORC_FK_EZ: case ORC_FK_BZ: b[i] = -2.0 - m2 / (j * j); break;
+        case ORC_FK_BPLUS: b[i] = -2.0 - ((double)(m + 1) / j) * ((double)(m + 1) / j) - relax_fac; break;
+        case ORC_FK_BMINUS: b[i] = -2.0 - ((double)(m - 1) / j) * ((double)(m - 1) / j) - relax_fac; break;
+        }
+    }
+    int axis_coupled = 0;
+    double diag0 = -4.0;
+    switch (kind) {
+    case ORC_FK_PSI: case ORC_FK_BT: case ORC_FK_EZ: case ORC_FK_BZ: axis_coupled = (m == 0); break;
+    case ORC_FK_BPLUS: axis_coupled = 0; break;
+    case ORC_FK_BMINUS: axis_coupled = (m == 1); diag0 = -4.0 - relax_fac; break;
+    }
+    if (axis_coupled) { a[0] = 0.0; b[0] = diag0; c[0] = 4.0; }
+    else { a[0] = 0.0; b[0] = 1.0; c[0] = 0.0; a[1] = 0.0; }
+    if (bnd == ORC_BND_ZERO) {
+        c[nr - 1] = 0.0;
+    } else {
+        double jmax = (double)nr;
+        switch (kind) {
+        case ORC_FK_PSI: case ORC_FK_EZ: case ORC_FK_BZ:
+            if (m == 0) c[nr - 1] = 0.0;
+            else { b[nr - 1] = b[nr - 1] + (1.0 - (double)m / jmax) * c[nr - 1]; c[nr - 1] = 0.0; }
+            break;
+        case ORC_FK_BT:
+            if (m == 0) { b[nr - 1] = b[nr - 1] + (1.0 + 1.0 / (jmax * log(jmax * dr))) * c[nr - 1]; c[nr - 1] = 0.0; }
+            else { b[nr - 1] = b[nr - 1] + (1.0 - (double)m / jmax) * c[nr - 1]; c[nr - 1] = 0.0; }
+            break;
+        case ORC_FK_BPLUS: case ORC_FK_BMINUS: /* both use (m+1), :532-540 */
+            b[nr - 1] = b[nr - 1] + (1.0 - (double)(m + 1) / jmax) * c[nr - 1]; c[nr - 1] = 0.0;
+            break;
+        }
+    }
+    for (int i = 0; i < nr; i++) { a[i] = a[i] / dr2; b[i] = b[i] / dr2; c[i] = c[i] / dr2; }
+}
+
+/* direct solve standing in for HYPRE_StructCycRedSolve (field_solver_class.f03:172-177) */
+void orc_tridiag_solve(const double *a, const double *b, const double *c, double *d, int n)
+{
+    double *cp = (double *)malloc(sizeof(double) * (size_t)n);
+    cp[0] = c[0] / b[0];
+    d[0] = d[0] / b[0];
+    for (int i = 1; i < n; i++) {
+        double den = b[i] - a[i] * cp[i - 1];
+        cp[i] = c[i] / den;
+        d[i] = (d[i] - a[i] * d[i - 1]) / den;
+    }
+    for (int i = n - 2; i >= 0; i--) d[i] = d[i] - cp[i] * d[i + 1];
+    free(cp);
+}
+void orc_tridiag_solve_ld(const double *a, const double *b, const double *c, double *d, int n)
+{
+    long double *cp = (long double *)malloc(sizeof(long double) * (size_t)n), *dd = (long double *)malloc(sizeof(long double) * (size_t)n);
+    cp[0] = (long double)c[0] / b[0];
+    dd[0] = (long double)d[0] / b[0];
+    for (int i = 1; i < n; i++) {
+        long double den = (long double)b[i] - (long double)a[i] * cp[i - 1];
+        cp[i] = (long double)c[i] / den;
+        dd[i] = ((long double)d[i] - (long double)a[i] * dd[i - 1]) / den;
+    }
+    for (int i = n - 2; i >= 0; i--) dd[i] = dd[i] - cp[i] * dd[i + 1];
+    for (int i = 0; i < n; i++) d[i] = (double)dd[i];
+    free(cp); free(dd);
+}
+
+static void solve_kind(int kind, int mode, int nr, double dr, int bnd, double relax, double *buf)
+{
+    double *a = (double *)malloc(sizeof(double) * 3 * (size_t)nr), *b = a + nr, *c = b + nr;
+    orc_build_matrix(kind, mode, nr, dr, bnd, relax, a, b, c);
+    orc_tridiag_solve(a, b, c, buf, nr);
+    free(a);
+}
+
+/* cached matrices would be faster; the oracle favours fidelity and brevity over speed here,
+ * but the CPU-baseline timing uses a cached variant (sim_solver below). */
+typedef struct { int nr; double *a, *b, *c, *cp, *iden; } tri_op; /* pre-factored Thomas */
+static void tri_op_init(tri_op *op, int kind, int mode, int nr, double dr, int bnd, double relax)
+{
+    op->nr = nr;
+    op->a = (double *)malloc(sizeof(double) * 5 * (size_t)nr);
+    op->b = op->a + nr; op->c = op->b + nr; op->cp = op->c + nr; op->iden = op->cp + nr;
+    orc_build_matrix(kind, mode, nr, dr, bnd, relax, op->a, op->b, op->c);
+}
+static void tri_op_free(tri_op *op) { free(op->a); op->a = NULL; }
+static void tri_op_solve(const tri_op *op, double *d) { orc_tridiag_solve(op->a, op->b, op->c, d, op->nr); }
+
+/* ------------------------------------------------------------------------- */
+/* fields/field_psi_class.f03:131-254                                        */
+/* ------------------------------------------------------------------------- */
+static void solve_psi_ops(const tri_op *ops, const double *q, double *psi, int nr, int max_mode)
+{
+    double *br = (double *)malloc(sizeof(double) * 2 * (size_t)nr), *bi = br + nr;
+    for (int m = 0; m <= max_mode; m++) {
+        for (int i = 1; i <= nr; i++) br[i - 1] = -1.0 * F1(q, 1, nr, pl_re(m), 1, i);
+        tri_op_solve(&ops[m], br);
+        for (int i = 1; i <= nr; i++) F1(psi, 1, nr, pl_re(m), 1, i) = br[i - 1];
+        if (m > 0) {
+            for (int i = 1; i <= nr; i++) bi[i - 1] = -1.0 * F1(q, 1, nr, pl_im(m), 1, i);
+            tri_op_solve(&ops[m], bi);
+            for (int i = 1; i <= nr; i++) F1(psi, 1, nr, pl_im(m), 1, i) = bi[i - 1];
+            F1(psi, 1, nr, pl_re(m), 1, 1) = 0.0;
+            F1(psi, 1, nr, pl_im(m), 1, 1) = 0.0;
+        }
+    }
+    free(br);
+}
+
+/* fields/field_b_class.f03:305-358 set_source_bt, :545-701 get_solution_bt, :798 solve_field_bt */
+static void solve_bt_ops(const tri_op *ops, const double *qb, double *b, int nr, int max_mode, double dr)
+{
+    double *br = (double *)malloc(sizeof(double) * 2 * (size_t)(nr + 1)), *bi = br + nr + 1; /* 1-based use */
+    double idr = 1.0 / dr, idrh = 0.5 * idr;
+    for (int m = 0; m <= max_mode; m++) {
+        int pr = pl_re(m), pi = pl_im(m);
+        for (int i = 1; i <= nr; i++) br[i] = -1.0 * F1(qb, 1, nr, pr, 1, i);
+        tri_op_solve(&ops[m], br + 1);
+        if (m == 0) {
+            for (int i = 2; i <= nr - 1; i++) {
+                F1(b, 3, nr, pr, 1, i) = 0.0;
+                F1(b, 3, nr, pr, 2, i) = -idrh * (br[i + 1] - br[i - 1]);
+            }
+            F1(b, 3, nr, pr, 1, 1) = 0.0; F1(b, 3, nr, pr, 2, 1) = 0.0;
+            F1(b, 3, nr, pr, 1, nr) = 0.0;
+            F1(b, 3, nr, pr, 2, nr) = -idrh * (3.0 * br[nr] - 4.0 * br[nr - 1] + br[nr - 2]);
+            continue;
+        }
+        for (int i = 1; i <= nr; i++) bi[i] = -1.0 * F1(qb, 1, nr, pi, 1, i);
+        tri_op_solve(&ops[m], bi + 1);
+        for (int i = 2; i <= nr - 1; i++) {
+            double ir = idr / (double)(i - 1);
+            F1(b, 3, nr, pr, 1, i) = -ir * m * bi[i];
+            F1(b, 3, nr, pi, 1, i) = ir * m * br[i];
+            F1(b, 3, nr, pr, 2, i) = -idrh * (br[i + 1] - br[i - 1]);
+            F1(b, 3, nr, pi, 2, i) = -idrh * (bi[i + 1] - bi[i - 1]);
+        }
+        if (m == 1) {
+            F1(b, 3, nr, pr, 1, 1) = -idr * m * bi[2];
+            F1(b, 3, nr, pi, 1, 1) = idr * m * br[2];
+            F1(b, 3, nr, pr, 2, 1) = -idr * br[2];
+            F1(b, 3, nr, pi, 2, 1) = -idr * bi[2];
+        } else {
+            F1(b, 3, nr, pr, 1, 1) = 0.0; F1(b, 3, nr, pi, 1, 1) = 0.0;
+            F1(b, 3, nr, pr, 2, 1) = 0.0; F1(b, 3, nr, pi, 2, 1) = 0.0;
+        }
+        double ir = idr / (double)(nr - 1);
+        F1(b, 3, nr, pr, 1, nr) = -ir * m * bi[nr];
+        F1(b, 3, nr, pi, 1, nr) = ir * m * br[nr];
+        F1(b, 3, nr, pr, 2, nr) = -idrh * (3.0 * br[nr] - 4.0 * br[nr - 1] + br[nr - 2]);
+        F1(b, 3, nr, pi, 2, nr) = -idrh * (3.0 * bi[nr] - 4.0 * bi[nr - 1] + bi[nr - 2]);
+    }
+    free(br);
+}
+
+/* fields/field_b_class.f03:205-303 set_source_bz, :508-543 get_solution_bz, :760 solve_field_bz */
+static void solve_bz_ops(const tri_op *ops, const double *cu, double *b, int nr, int max_mode, double dr)
+{
+    double *br = (double *)calloc(2 * (size_t)(nr + 1), sizeof(double)), *bi = br + nr + 1;
+    double idr = 1.0 / dr, idrh = 0.5 * idr;
+#define JR(c, i) F1(cu, 3, nr, pr, c, i)
+#define JI(c, i) F1(cu, 3, nr, pi, c, i)
+    for (int m = 0; m <= max_mode; m++) {
+        int pr = pl_re(m), pi = pl_im(m);
+        if (m == 0) {
+            for (int i = 2; i <= nr; i++) {
+                double ir = idr / (double)(i - 1);
+                br[i] = -idrh * (JR(2, i + 1) - JR(2, i - 1)) - ir * JR(2, i);
+            }
+            br[1] = -2.0 * idr * JR(2, 2);
+            double ir = idr / (double)(nr - 1);
+            br[nr] = -idrh * (3.0 * JR(2, nr) - 4.0 * JR(2, nr - 1) + JR(2, nr - 2)) - ir * JR(2, nr);
+            tri_op_solve(&ops[m], br + 1);
+            for (int i = 1; i <= nr; i++) F1(b, 3, nr, pr, 3, i) = br[i];
+            continue;
+        }
+        for (int i = 2; i <= nr; i++) {
+            double ir = idr / (double)(i - 1);
+            br[i] = -idrh * (JR(2, i + 1) - JR(2, i - 1)) - ir * JR(2, i) - m * ir * JI(1, i);
+            bi[i] = -idrh * (JI(2, i + 1) - JI(2, i - 1)) - ir * JI(2, i) + m * ir * JR(1, i);
+        }
+        if (m % 2 == 0) {
+            br[1] = -2.0 * idr * JR(2, 2) - m * idr * JI(1, 2);
+            bi[1] = -2.0 * idr * JI(2, 2) + m * idr * JR(1, 2);
+        } else {
+            br[1] = 0.0; bi[1] = 0.0;
+            if (m == 1) {
+                double ir = idr;
+                br[2] = -idr * (JR(2, 3) - JR(2, 2)) - ir * JR(2, 2) - m * ir * JI(1, 2);
+                bi[2] = -idr * (JI(2, 3) - JI(2, 2)) - ir * JI(2, 2) + m * ir * JR(1, 2);
+            }
+        }
+        double ir = idr / (double)(nr - 1);
+        br[nr] = -idrh * (3.0 * JR(2, nr) - 4.0 * JR(2, nr - 1) + JR(2, nr - 2)) - ir * JR(2, nr) - m * ir * JI(1, nr);
+        bi[nr] = -idrh * (3.0 * JI(2, nr) - 4.0 * JI(2, nr - 1) + JI(2, nr - 2)) - ir * JI(2, nr) + m * ir * JR(1, nr);
+        tri_op_solve(&ops[m], br + 1);
+        tri_op_solve(&ops[m], bi + 1);
+        for (int i = 1; i <= nr; i++) { F1(b, 3, nr, pr, 3, i) = br[i]; F1(b, 3, nr, pi, 3, i) = bi[i]; }
+        F1(b, 3, nr, pr, 3, 1) = 0.0; F1(b, 3, nr, pi, 3, 1) = 0.0;
+    }
+    free(br);
+}
+
+/* fields/field_b_class.f03:360-506 set_source_bt_iter, :703-758 get_solution_bt_iter, :836 solve_field_bt_iter */
+static void solve_bt_iter_ops(const tri_op *opp, const tri_op *opm, const double *dcu, const double *cu, double *b,
+                              int nr, int max_mode, double dr, double relax_fac)
+{
+    size_t n1 = (size_t)nr + 1;
+    double *b1r = (double *)calloc(4 * n1, sizeof(double)), *b1i = b1r + n1, *b2r = b1i + n1, *b2i = b2r + n1;
+    double idr = 1.0 / dr, idrh = 0.5 * idr;
+    double relax_idr2 = relax_fac * (idr * idr);
+#define D1R(c, i) F1(dcu, 2, nr, pr, c, i)
+#define D1I(c, i) F1(dcu, 2, nr, pi, c, i)
+#define BR(c, i) F1(b, 3, nr, pr, c, i)
+#define BI(c, i) F1(b, 3, nr, pi, c, i)
+    for (int m = 0; m <= max_mode; m++) {
+        int pr = pl_re(m), pi = pl_im(m);
+        if (m == 0) {
+            for (int i = 2; i <= nr; i++) {
+                b1r[i] = -D1R(2, i) - BR(1, i) * relax_idr2;
+                b2r[i] = D1R(1, i) + idrh * (JR(3, i + 1) - JR(3, i - 1)) - BR(2, i) * relax_idr2;
+            }
+            b1r[1] = 0.0; b2r[1] = 0.0;
+            b2r[2] = D1R(1, 2) + idr * (JR(3, 3) - JR(3, 2)) - BR(2, 2) * relax_idr2;
+            b1r[nr] = -D1R(2, nr) - BR(1, nr) * relax_idr2;
+            b2r[nr] = D1R(1, nr) + idrh * (3.0 * JR(3, nr) - 4.0 * JR(3, nr - 1) + JR(3, nr - 2)) - BR(2, nr) * relax_idr2;
+            tri_op_solve(&opp[m], b1r + 1);
+            tri_op_solve(&opm[m], b2r + 1);
+            for (int i = 1; i <= nr; i++) { BR(1, i) = b1r[i]; BR(2, i) = b2r[i]; }
+            BR(1, 1) = 0.0; BR(2, 1) = 0.0;
+            continue;
+        }
+        double s1_re, s1_im, s2_re, s2_im;
+        for (int i = 2; i <= nr; i++) {
+            double ir = idr / (double)(i - 1);
+            s1_re = -D1R(2, i) + m * JI(3, i) * ir;
+            s1_im = -D1I(2, i) - m * JR(3, i) * ir;
+            s2_re = D1R(1, i) + idrh * (JR(3, i + 1) - JR(3, i - 1));
+            s2_im = D1I(1, i) + idrh * (JI(3, i + 1) - JI(3, i - 1));
+            b1r[i] = s1_re - s2_im - (BR(1, i) - BI(2, i)) * relax_idr2;
+            b1i[i] = s1_im + s2_re - (BI(1, i) + BR(2, i)) * relax_idr2;
+            b2r[i] = s1_re + s2_im - (BR(1, i) + BI(2, i)) * relax_idr2;
+            b2i[i] = s1_im - s2_re - (BI(1, i) - BR(2, i)) * relax_idr2;
+        }
+        if (m == 1) {
+            s1_re = -D1R(2, 1) + idr * m * JI(3, 2);
+            s1_im = -D1I(2, 1) - idr * m * JR(3, 2);
+            s2_re = D1R(1, 1) + idr * JR(3, 2);
+            s2_im = D1I(1, 1) + idr * JI(3, 2);
+        } else if (m % 2 == 0) {
+            s1_re = s1_im = s2_re = s2_im = 0.0;
+        } else { /* :453-458, reference quirk kept as written */
+            s1_re = idr * m * JI(3, 2);
+            s1_im = idr * m * JR(3, 2);
+            s2_re = idr * JR(3, 2);
+            s2_im = idr * JI(3, 2);
+        }
+        b1r[1] = s1_re - s2_im - (BR(1, 1) - BI(2, 1)) * relax_idr2;
+        b1i[1] = s1_im + s2_re - (BI(1, 1) + BR(2, 1)) * relax_idr2;
+        b2r[1] = s1_re + s2_im - (BR(1, 1) + BI(2, 1)) * relax_idr2;
+        b2i[1] = s1_im - s2_re - (BI(1, 1) - BR(2, 1)) * relax_idr2;
+        {
+            double ir = idr / (double)(nr - 1);
+            s1_re = -D1R(2, nr) + m * JI(3, nr) * ir;
+            s1_im = -D1I(2, nr) - m * JR(3, nr) * ir;
+            s2_re = D1R(1, nr) + idrh * (3.0 * JR(3, nr) - 4.0 * JR(3, nr - 1) + JR(3, nr - 2));
+            s2_im = D1I(1, nr) + idrh * (3.0 * JI(3, nr) - 4.0 * JI(3, nr - 1) + JI(3, nr - 2));
+            b1r[nr] = s1_re - s2_im - (BR(1, nr) - BI(2, nr)) * relax_idr2;
+            b1i[nr] = s1_im + s2_re - (BI(1, nr) + BR(2, nr)) * relax_idr2;
+            b2r[nr] = s1_re + s2_im - (BR(1, nr) + BI(2, nr)) * relax_idr2;
+            b2i[nr] = s1_im - s2_re - (BI(1, nr) - BR(2, nr)) * relax_idr2;
+        }
+        tri_op_solve(&opp[m], b1r + 1);
+        tri_op_solve(&opp[m], b1i + 1);
+        tri_op_solve(&opm[m], b2r + 1);
+        tri_op_solve(&opm[m], b2i + 1);
+        for (int i = 1; i <= nr; i++) {
+            BR(1, i) = 0.5 * (b1r[i] + b2r[i]);
+            BI(1, i) = 0.5 * (b1i[i] + b2i[i]);
+            BR(2, i) = 0.5 * (b1i[i] - b2i[i]);
+            BI(2, i) = 0.5 * (-b1r[i] + b2r[i]);
+        }
+        if (m != 1) { BR(1, 1) = 0.0; BI(1, 1) = 0.0; BR(2, 1) = 0.0; BI(2, 1) = 0.0; }
+    }
+    free(b1r);
+}
+
+/* fields/field_e_class.f03:148-263 set_source_ez, :265-296 get_solution_ez, :298 solve_field_ez */
+static void solve_ez_ops(const tri_op *ops, const double *cu, double *e, int nr, int max_mode, double dr)
+{
+    double *br = (double *)calloc(2 * (size_t)(nr + 1), sizeof(double)), *bi = br + nr + 1;
+    double idr = 1.0 / dr, idrh = 0.5 * idr;
+    for (int m = 0; m <= max_mode; m++) {
+        int pr = pl_re(m), pi = pl_im(m);
+        if (m == 0) {
+            for (int i = 1; i <= nr; i++) br[i] = 0.0;
+            double div = 0.0;
+            for (int i = 2; i <= nr - 2; i++) {
+                double ir = idr / (double)(i - 1);
+                br[i] = idrh * (JR(1, i + 1) - JR(1, i - 1)) + ir * JR(1, i);
+                div = div + br[i] * (double)(i - 1);
+            }
+            double ir = idr / (double)(nr - 2);
+            br[nr - 1] = idrh * (JR(1, nr) - JR(1, nr - 2)) + ir * JR(1, nr - 1);
+            ir = idr / (double)(nr - 1);
+            br[nr] = idr * (JR(1, nr) - JR(1, nr - 1)) + ir * JR(1, nr);
+            div = div - idrh * (JR(1, nr - 2) + JR(1, nr - 1)) * ((double)nr - 2.5);
+            br[1] = div;
+            br[1] = -8.0 * br[1];
+            tri_op_solve(&ops[m], br + 1);
+            for (int i = 1; i <= nr; i++) F1(e, 3, nr, pr, 3, i) = br[i];
+            continue;
+        }
+        for (int i = 2; i <= nr; i++) {
+            double ir = idr / (double)(i - 1);
+            br[i] = idrh * (JR(1, i + 1) - JR(1, i - 1)) + ir * JR(1, i) - m * ir * JI(2, i);
+            bi[i] = idrh * (JI(1, i + 1) - JI(1, i - 1)) + ir * JI(1, i) + m * ir * JR(2, i);
+        }
+        if (m % 2 == 0) {
+            br[1] = 2.0 * idr * JR(1, 2) - m * idr * JI(2, 2);
+            bi[1] = 2.0 * idr * JI(1, 2) + m * idr * JR(2, 2);
+        } else {
+            br[1] = 0.0; bi[1] = 0.0;
+            if (m == 1) {
+                double ir = idr;
+                br[2] = idr * (JR(1, 3) - JR(1, 2)) + ir * JR(1, 2) - m * ir * JI(2, 2);
+                bi[2] = idr * (JI(1, 3) - JI(1, 2)) + ir * JI(1, 2) + m * ir * JR(2, 2);
+            }
+        }
+        double ir = idr / (double)(nr - 1);
+        br[nr] = idrh * (3.0 * JR(1, nr) - 4.0 * JR(1, nr - 1) + JR(1, nr - 2)) + ir * JR(1, nr) - m * ir * JI(2, nr);
+        bi[nr] = idrh * (3.0 * JI(1, nr) - 4.0 * JI(1, nr - 1) + JI(1, nr - 2)) + ir * JI(1, nr) + m * ir * JR(2, nr);
+        tri_op_solve(&ops[m], br + 1);
+        tri_op_solve(&ops[m], bi + 1);
+        for (int i = 1; i <= nr; i++) { F1(e, 3, nr, pr, 3, i) = br[i]; F1(e, 3, nr, pi, 3, i) = bi[i]; }
+        F1(e, 3, nr, pr, 3, 1) = 0.0; F1(e, 3, nr, pi, 3, 1) = 0.0;
+    }
+    free(br);
+}
+#undef JR
+#undef JI
+#undef D1R
+#undef D1I
+#undef BR
+#undef BI
+
+/* fields/field_e_class.f03:412-514 solve_field_et */
+void orc_solve_et(const double *b, const double *psi, double *e, int nr, int max_mode, double dr)
+{
+    double idr = 1.0 / dr, idrh = idr * 0.5;
+#define PS(pl, i) F1(psi, 1, nr, pl, 1, i)
+    for (int i = 1; i <= nr; i++) {
+        F1(e, 3, nr, 0, 1, i) = F1(b, 3, nr, 0, 2, i) - idrh * (PS(0, i + 1) - PS(0, i - 1));
+        F1(e, 3, nr, 0, 2, i) = -F1(b, 3, nr, 0, 1, i);
+    }
+    F1(e, 3, nr, 0, 1, 1) = 0.0; F1(e, 3, nr, 0, 2, 1) = 0.0;
+    F1(e, 3, nr, 0, 1, nr) = F1(b, 3, nr, 0, 2, nr) + idrh * (4.0 * PS(0, nr - 1) - PS(0, nr - 2) - 3.0 * PS(0, nr));
+    for (int m = 1; m <= max_mode; m++) {
+        int pr = pl_re(m), pi = pl_im(m);
+        for (int i = 2; i <= nr; i++) {
+            double ir = idr / (double)(i - 1);
+            F1(e, 3, nr, pr, 1, i) = F1(b, 3, nr, pr, 2, i) - idrh * (PS(pr, i + 1) - PS(pr, i - 1));
+            F1(e, 3, nr, pi, 1, i) = F1(b, 3, nr, pi, 2, i) - idrh * (PS(pi, i + 1) - PS(pi, i - 1));
+            F1(e, 3, nr, pr, 2, i) = -F1(b, 3, nr, pr, 1, i) + ir * m * PS(pi, i);
+            F1(e, 3, nr, pi, 2, i) = -F1(b, 3, nr, pi, 1, i) - ir * m * PS(pr, i);
+        }
+        if (m == 1) {
+            F1(e, 3, nr, pr, 1, 1) = F1(b, 3, nr, pr, 2, 1) - idr * PS(pr, 2);
+            F1(e, 3, nr, pi, 1, 1) = F1(b, 3, nr, pi, 2, 1) - idr * PS(pi, 2);
+            F1(e, 3, nr, pr, 2, 1) = -F1(b, 3, nr, pr, 1, 1) + idr * PS(pi, 2);
+            F1(e, 3, nr, pi, 2, 1) = -F1(b, 3, nr, pi, 1, 1) - idr * PS(pr, 2);
+        } else {
+            F1(e, 3, nr, pr, 1, 1) = 0.0; F1(e, 3, nr, pi, 1, 1) = 0.0;
+            F1(e, 3, nr, pr, 2, 1) = 0.0; F1(e, 3, nr, pi, 2, 1) = 0.0;
+        }
+        F1(e, 3, nr, pr, 1, nr) = F1(b, 3, nr, pr, 2, nr) + idrh * (4.0 * PS(pr, nr - 1) - PS(pr, nr - 2) - 3.0 * PS(pr, nr));
+        F1(e, 3, nr, pi, 1, nr) = F1(b, 3, nr, pi, 2, nr) + idrh * (4.0 * PS(pi, nr - 1) - PS(pi, nr - 2) - 3.0 * PS(pi, nr));
+    }
+#undef PS
+}
+
+/* fields/field_e_class.f03:516-563 solve_field_et_beam */
+void orc_solve_et_beam(const double *b, double *e, int nr, int max_mode)
+{
+    int P = nplanes(max_mode);
+    for (int pl = 0; pl < P; pl++)
+        for (int i = 1; i <= nr; i++) {
+            F1(e, 3, nr, pl, 1, i) = F1(b, 3, nr, pl, 2, i);
+            F1(e, 3, nr, pl, 2, i) = -F1(b, 3, nr, pl, 1, i);
+        }
+}
+
+/* fields/field_src_class.f03:273-405 solve_field_djdxi */
+void orc_solve_djdxi(const double *acu, const double *amu, double *dcu, int nr, int max_mode, double dr)
+{
+    double idr = 1.0 / dr, idrh = idr * 0.5;
+#define AC(pl, c, i) F1(acu, 2, nr, pl, c, i)
+#define AM(pl, c, i) F1(amu, 3, nr, pl, c, i)
+#define DC(pl, c, i) F1(dcu, 2, nr, pl, c, i)
+    for (int m = 0; m <= max_mode; m++) {
+        int pr = pl_re(m), pi = pl_im(m);
+        if (m == 0) {
+            for (int i = 2; i <= nr; i++) {
+                double ir = idr / (double)(i - 1);
+                for (int c = 1; c <= 2; c++) DC(pr, c, i) = AC(pr, c, i) - idrh * (AM(pr, c, i + 1) - AM(pr, c, i - 1)) - ir * AM(pr, c, i);
+            }
+            DC(pr, 1, 1) = 0.0; DC(pr, 2, 1) = 0.0;
+            double ir = idr / (double)(nr - 1);
+            for (int c = 1; c <= 2; c++)
+                DC(pr, c, nr) = AC(pr, c, nr) + idrh * (4.0 * AM(pr, c, nr - 1) - AM(pr, c, nr - 2) - 3.0 * AM(pr, c, nr)) - ir * AM(pr, c, nr);
+            continue;
+        }
+        for (int i = 2; i <= nr; i++) {
+            double ir = idr / (double)(i - 1);
+            for (int c = 1; c <= 2; c++) {
+                DC(pr, c, i) = AC(pr, c, i) - idrh * (AM(pr, c, i + 1) - AM(pr, c, i - 1)) - ir * AM(pr, c, i) + m * ir * AM(pi, c + 1, i);
+                DC(pi, c, i) = AC(pi, c, i) - idrh * (AM(pi, c, i + 1) - AM(pi, c, i - 1)) - ir * AM(pi, c, i) - m * ir * AM(pr, c + 1, i);
+            }
+        }
+        if (m == 1) {
+            for (int c = 1; c <= 2; c++) {
+                DC(pr, c, 1) = AC(pr, c, 1) - 2.0 * idr * AM(pr, c, 2) + m * idr * AM(pi, c + 1, 2);
+                DC(pi, c, 1) = AC(pi, c, 1) - 2.0 * idr * AM(pi, c, 2) - m * idr * AM(pr, c + 1, 2);
+            }
+        } else {
+            for (int c = 1; c <= 2; c++) { DC(pr, c, 1) = 0.0; DC(pi, c, 1) = 0.0; }
+            if (m == 2) {
+                double ir = idr;
+                for (int c = 1; c <= 2; c++) {
+                    DC(pr, c, 2) = AC(pr, c, 2) - idr * (AM(pr, c, 3) - AM(pr, c, 2)) - ir * AM(pr, c, 2) + m * ir * AM(pi, c + 1, 2);
+                    DC(pi, c, 2) = AC(pi, c, 2) - idr * (AM(pi, c, 3) - AM(pi, c, 2)) - ir * AM(pi, c, 2) - m * ir * AM(pr, c + 1, 2);
+                }
+            }
+        }
+        double ir = idr / (double)(nr - 1);
+        for (int c = 1; c <= 2; c++) {
+            DC(pr, c, nr) = AC(pr, c, nr) + idrh * (4.0 * AM(pr, c, nr - 1) - AM(pr, c, nr - 2) - 3.0 * AM(pr, c, nr)) - ir * AM(pr, c, nr) + m * ir * AM(pi, c + 1, nr);
+            DC(pi, c, nr) = AC(pi, c, nr) + idrh * (4.0 * AM(pi, c, nr - 1) - AM(pi, c, nr - 2) - 3.0 * AM(pi, c, nr)) - ir * AM(pi, c, nr) - m * ir * AM(pr, c + 1, nr);
+        }
+    }
+#undef AC
+#undef AM
+#undef DC
+}
+
+/* fields/ufield_class.f03:274-339 smooth_f1 (idproc == 0 branch), stencil [1,2,1] */
+void orc_smooth_f1(double *f, int dim, int nr, const int *ax_smooth)
+{
+    double k_m1 = 1.0 / 4.0, k_0 = 2.0 / 4.0, k_p1 = 1.0 / 4.0;
+    double *tmp = (double *)malloc(sizeof(double) * (size_t)dim * (size_t)(nr + 1));
+#define FF(c, j) f[(size_t)(j)*dim + ((c)-1)]
+#define TT(c, j) tmp[(size_t)(j)*dim + ((c)-1)]
+    for (int c = 1; c <= dim; c++) {
+        if (ax_smooth[c - 1]) TT(c, 1) = (k_0 + k_p1) * FF(c, 1) + 8.0 * k_p1 * FF(c, 2);
+        else TT(c, 1) = 0.0;
+        TT(c, 2) = k_0 * FF(c, 2) + 0.125 * k_m1 * FF(c, 1) + 2.0 * k_p1 * FF(c, 3);
+    }
+    for (int j = 3; j <= nr; j++) {
+        int r_idx = j - 1;
+        for (int c = 1; c <= dim; c++)
+            TT(c, j) = k_0 * FF(c, j) + (1.0 - 1.0 / r_idx) * k_m1 * FF(c, j - 1) + (1.0 + 1.0 / r_idx) * k_p1 * FF(c, j + 1);
+    }
+    for (int j = 1; j <= nr; j++)
+        for (int c = 1; c <= dim; c++) FF(c, j) = TT(c, j);
+#undef FF
+#undef TT
+    free(tmp);
+}
+
+/* stand-alone wrappers that build the operators on the fly */
+static tri_op *make_ops(int kind, int nr, int max_mode, double dr, int bnd, double relax)
+{
+    tri_op *ops = (tri_op *)malloc(sizeof(tri_op) * (size_t)(max_mode + 1));
+    for (int m = 0; m <= max_mode; m++) tri_op_init(&ops[m], kind, m, nr, dr, bnd, relax);
+    return ops;
+}
+static void free_ops(tri_op *ops, int max_mode) { for (int m = 0; m <= max_mode; m++) tri_op_free(&ops[m]); free(ops); }
+
+void orc_solve_psi(const double *q, double *psi, int nr, int max_mode, double dr, int bnd)
+{ tri_op *o = make_ops(ORC_FK_PSI, nr, max_mode, dr, bnd, 0.0); solve_psi_ops(o, q, psi, nr, max_mode); free_ops(o, max_mode); }
+void orc_solve_bt(const double *qb, double *b, int nr, int max_mode, double dr, int bnd)
+{ tri_op *o = make_ops(ORC_FK_BT, nr, max_mode, dr, bnd, 0.0); solve_bt_ops(o, qb, b, nr, max_mode, dr); free_ops(o, max_mode); }
+void orc_solve_bz(const double *cu, double *b, int nr, int max_mode, double dr, int bnd)
+{ tri_op *o = make_ops(ORC_FK_BZ, nr, max_mode, dr, bnd, 0.0); solve_bz_ops(o, cu, b, nr, max_mode, dr); free_ops(o, max_mode); }
+void orc_solve_ez(const double *cu, double *e, int nr, int max_mode, double dr, int bnd)
+{ tri_op *o = make_ops(ORC_FK_EZ, nr, max_mode, dr, bnd, 0.0); solve_ez_ops(o, cu, e, nr, max_mode, dr); free_ops(o, max_mode); }
+void orc_solve_bt_iter(const double *dcu, const double *cu, double *b, int nr, int max_mode, double dr, int bnd, double relax_fac)
+{
+    tri_op *op = make_ops(ORC_FK_BPLUS, nr, max_mode, dr, bnd, relax_fac), *om = make_ops(ORC_FK_BMINUS, nr, max_mode, dr, bnd, relax_fac);
+    solve_bt_iter_ops(op, om, dcu, cu, b, nr, max_mode, dr, relax_fac);
+    free_ops(op, max_mode); free_ops(om, max_mode);
+}
+
+/* ------------------------------------------------------------------------- */
+/* beam/part3d_class.f03:221-356 qdeposit_part3d                             */
+/* ------------------------------------------------------------------------- */
+void orc_qdeposit3d(const double *x, const double *q, long npp, double dr, double dz, int nr, int nzp, int noff2,
+                    int max_mode, double *f)
+{
+    double idr = 1.0 / dr, idz = 1.0 / dz;
+    for (long pp = 0; pp < npp; pp++) {
+        double pos_r = sqrt(x[3 * pp] * x[3 * pp] + x[3 * pp + 1] * x[3 * pp + 1]) * idr;
+        double pos_z = x[3 * pp + 2] * idz;
+        cplx ph0;
+        ph0.re = x[3 * pp] / pos_r * idr;
+        ph0.im = -x[3 * pp + 1] / pos_r * idr;
+        int nn = (int)floor(pos_r), mm = (int)floor(pos_z);
+        pos_r = pos_r - (double)nn;
+        pos_z = pos_z - (double)mm;
+        nn = nn + 1;
+        mm = mm - noff2 + 1;
+        double wtr[2] = {1.0 - pos_r, pos_r}, wtz[2] = {1.0 - pos_z, pos_z};
+        cplx phase = {1.0 * q[pp], 0.0 * q[pp]};
+        for (int k = 0; k < 2; k++)
+            for (int j = 0; j < 2; j++) F2(f, 1, nr, nzp, 0, 1, nn + j, mm + k) += wtr[j] * wtz[k] * phase.re;
+        for (int m = 1; m <= max_mode; m++) {
+            phase = cmul(phase, ph0);
+            for (int k = 0; k < 2; k++)
+                for (int j = 0; j < 2; j++) {
+                    F2(f, 1, nr, nzp, pl_re(m), 1, nn + j, mm + k) += wtr[j] * wtz[k] * phase.re;
+                    F2(f, 1, nr, nzp, pl_im(m), 1, nn + j, mm + k) += wtr[j] * wtz[k] * phase.im;
+                }
+        }
+    }
+    for (int k = 1; k <= nzp; k++) {
+        F2(f, 1, nr, nzp, 0, 1, 0, k) = 0.0;
+        F2(f, 1, nr, nzp, 0, 1, 1, k) = 8.0 * F2(f, 1, nr, nzp, 0, 1, 1, k);
+        for (int m = 1; m <= max_mode; m++) {
+            F2(f, 1, nr, nzp, pl_re(m), 1, 0, k) = 0.0; F2(f, 1, nr, nzp, pl_im(m), 1, 0, k) = 0.0;
+            F2(f, 1, nr, nzp, pl_re(m), 1, 1, k) = 0.0; F2(f, 1, nr, nzp, pl_im(m), 1, 1, k) = 0.0;
+        }
+    }
+    int P = nplanes(max_mode);
+    for (int pl = 0; pl < P; pl++)
+        for (int j = 2; j <= nr + 1; j++) {
+            double ir = 1.0 / (double)(j - 1);
+            for (int k = 1; k <= nzp; k++) F2(f, 1, nr, nzp, pl, 1, j, k) = F2(f, 1, nr, nzp, pl, 1, j, k) * ir;
+        }
+}
+
+/* beam/part3d_class.f03:691-790 interp_emf_part3d */
+static void interp_emf3d(const double *ef, const double *bf, const double *x3, double dr, double dz, int nr, int nzp,
+                         int noff2, int max_mode, double ep[3], double bp[3])
+{
+    double idr = 1.0 / dr, idz = 1.0 / dz;
+    double pos_r = sqrt(x3[0] * x3[0] + x3[1] * x3[1]) * idr;
+    double pos_z = x3[2] * idz;
+    double cc = x3[0] / pos_r * idr, ss = x3[1] / pos_r * idr;
+    cplx ph0 = {cc, ss};
+    int nn = (int)pos_r, mm = (int)pos_z;
+    pos_r = pos_r - (double)nn;
+    pos_z = pos_z - (double)mm;
+    nn = nn + 1;
+    mm = mm - noff2 + 1;
+    double wtr[2] = {1.0 - pos_r, pos_r}, wtz[2] = {1.0 - pos_z, pos_z};
+    cplx phase = {1.0, 0.0};
+    for (int c = 0; c < 3; c++) ep[c] = bp[c] = 0.0;
+    for (int k = 0; k < 2; k++)
+        for (int j = 0; j < 2; j++) {
+            double wt = wtr[j] * wtz[k];
+            for (int c = 1; c <= 3; c++) {
+                ep[c - 1] = ep[c - 1] + F2(ef, 3, nr, nzp, 0, c, nn + j, mm + k) * wt;
+                bp[c - 1] = bp[c - 1] + F2(bf, 3, nr, nzp, 0, c, nn + j, mm + k) * wt;
+            }
+        }
+    for (int m = 1; m <= max_mode; m++) {
+        phase = cmul(phase, ph0);
+        double ph_r = 2.0 * phase.re, ph_i = 2.0 * phase.im;
+        for (int k = 0; k < 2; k++)
+            for (int j = 0; j < 2; j++) {
+                double wt = wtr[j] * wtz[k];
+                for (int c = 1; c <= 3; c++) {
+                    ep[c - 1] = ep[c - 1] + (F2(ef, 3, nr, nzp, pl_re(m), c, nn + j, mm + k) * ph_r - F2(ef, 3, nr, nzp, pl_im(m), c, nn + j, mm + k) * ph_i) * wt;
+                    bp[c - 1] = bp[c - 1] + (F2(bf, 3, nr, nzp, pl_re(m), c, nn + j, mm + k) * ph_r - F2(bf, 3, nr, nzp, pl_im(m), c, nn + j, mm + k) * ph_i) * wt;
+                }
+            }
+    }
+    double ph_r = ep[0] * cc - ep[1] * ss, ph_i = ep[0] * ss + ep[1] * cc;
+    ep[0] = ph_r; ep[1] = ph_i;
+    ph_r = bp[0] * cc - bp[1] * ss; ph_i = bp[0] * ss + bp[1] * cc;
+    bp[0] = ph_r; bp[1] = ph_i;
+}
+
+/* beam/part3d_class.f03:477-576 push_reduced_part3d ; :358-475 push_boris_part3d (no spin) */
+void orc_push3d(double *x, double *p, long npp, double dr, double dz, int nr, int nzp, int noff2, int max_mode,
+                double qbm, double dt, int push_type, const double *ef, const double *bf)
+{
+    double qtmh = qbm * dt * 0.5;
+    if (push_type == ORC_PUSH3_BORIS) qtmh = 0.5 * qbm * dt;
+    for (long pp = 0; pp < npp; pp++) {
+        double ep[3], bp[3];
+        double *xp = x + 3 * pp, *pq = p + 3 * pp;
+        interp_emf3d(ef, bf, xp, dr, dz, nr, nzp, noff2, max_mode, ep, bp);
+        if (push_type == ORC_PUSH3_REDUCED) {
+            double wp[3];
+            for (int c = 0; c < 3; c++) { ep[c] = ep[c] * qtmh; bp[c] = bp[c] * qtmh; }
+            wp[0] = ep[0] - bp[1]; wp[1] = ep[1] + bp[0]; wp[2] = ep[2];
+            for (int c = 0; c < 3; c++) pq[c] = pq[c] + wp[c];
+            for (int c = 0; c < 3; c++) pq[c] = pq[c] + wp[c];
+            double dt_gam = dt / sqrt(1.0 + pq[0] * pq[0] + pq[1] * pq[1] + pq[2] * pq[2]);
+            xp[0] = xp[0] + pq[0] * dt_gam;
+            xp[1] = xp[1] + pq[1] * dt_gam;
+            xp[2] = xp[2] - pq[2] * dt_gam + dt;
+        } else {
+            double utmp[3];
+            for (int c = 0; c < 3; c++) { ep[c] = ep[c] * qtmh; utmp[c] = pq[c] + ep[c]; }
+            double u2 = utmp[0] * utmp[0] + utmp[1] * utmp[1] + utmp[2] * utmp[2];
+            double gam = sqrt(1.0 + u2);
+            double gam_qtmh = qtmh / gam;
+            for (int c = 0; c < 3; c++) bp[c] = bp[c] * gam_qtmh;
+            pq[0] = utmp[0] + utmp[1] * bp[2] - utmp[2] * bp[1];
+            pq[1] = utmp[1] + utmp[2] * bp[0] - utmp[0] * bp[2];
+            pq[2] = utmp[2] + utmp[0] * bp[1] - utmp[1] * bp[0];
+            double ostq = 2.0 / (1.0 + bp[0] * bp[0] + bp[1] * bp[1] + bp[2] * bp[2]);
+            for (int c = 0; c < 3; c++) bp[c] = bp[c] * ostq;
+            utmp[0] = utmp[0] + pq[1] * bp[2] - pq[2] * bp[1];
+            utmp[1] = utmp[1] + pq[2] * bp[0] - pq[0] * bp[2];
+            utmp[2] = utmp[2] + pq[0] * bp[1] - pq[1] * bp[0];
+            for (int c = 0; c < 3; c++) pq[c] = utmp[c] + ep[c];
+            gam_qtmh = dt / sqrt(1.0 + pq[0] * pq[0] + pq[1] * pq[1] + pq[2] * pq[2]);
+            xp[0] = xp[0] + pq[0] * gam_qtmh;
+            xp[1] = xp[1] + pq[1] * gam_qtmh;
+            xp[2] = xp[2] - pq[2] * gam_qtmh + dt;
+        }
+    }
+}
+
+/* beam/part3d_class.f03:640-689 update_bound_part3d */
+long orc_update_bound3d(double *x, double *p, double *q, long npp, double edge_r, double edge_z)
+{
+    if (npp == 0) return 0;
+    long i = 1;
+    while (i < npp) {
+        double pos_r = sqrt(x[3 * (i - 1)] * x[3 * (i - 1)] + x[3 * (i - 1) + 1] * x[3 * (i - 1) + 1]);
+        double pos_z = x[3 * (i - 1) + 2];
+        if (pos_r >= edge_r || pos_z >= edge_z) {
+            long l = npp - 1;
+            for (int c = 0; c < 3; c++) { x[3 * (i - 1) + c] = x[3 * l + c]; p[3 * (i - 1) + c] = p[3 * l + c]; }
+            q[i - 1] = q[l];
+            npp = npp - 1;
+            continue;
+        }
+        i = i + 1;
+    }
+    double pos_r = sqrt(x[3 * (npp - 1)] * x[3 * (npp - 1)] + x[3 * (npp - 1) + 1] * x[3 * (npp - 1) + 1]);
+    double pos_z = x[3 * (npp - 1) + 2];
+    if (pos_r >= edge_r || pos_z >= edge_z) npp = npp - 1;
+    return npp;
+}
+
+/* ========================================================================= */
+/* whole simulation: simulation_class.f03:226-512 run_simulation             */
+/* ========================================================================= */
+typedef struct { int dim, nr, nzp, P, has2d; double *f1, *f2; } ofld;
+static void fld_init(ofld *f, int dim, int nr, int nzp, int max_mode, int has2d)
+{
+    f->dim = dim; f->nr = nr; f->nzp = nzp; f->P = nplanes(max_mode); f->has2d = has2d;
+    f->f1 = (double *)calloc((size_t)f->P * (nr + 2) * dim, sizeof(double));
+    f->f2 = has2d ? (double *)calloc((size_t)f->P * (nzp + 1) * (nr + 2) * dim, sizeof(double)) : NULL;
+}
+static void fld_free(ofld *f) { free(f->f1); free(f->f2); }
+static size_t fld_n1(const ofld *f) { return (size_t)f->P * (f->nr + 2) * f->dim; }
+static size_t fld_n2(const ofld *f) { return (size_t)f->P * (f->nzp + 1) * (f->nr + 2) * f->dim; }
+static void fld_zero1(ofld *f) { memset(f->f1, 0, sizeof(double) * fld_n1(f)); }
+static void fld_zero2(ofld *f) { if (f->f2) memset(f->f2, 0, sizeof(double) * fld_n2(f)); }
+/* ufield_class.f03:341-383 copy_slice */
+static void fld_copy_slice(ofld *f, int k, int to2)
+{
+    size_t ns = (size_t)(f->nr + 2) * f->dim;
+    for (int pl = 0; pl < f->P; pl++) {
+        double *s1 = f->f1 + pl * ns, *s2 = f->f2 + ((size_t)pl * (f->nzp + 1) + (k - 1)) * ns;
+        if (to2) memcpy(s2, s1, sizeof(double) * ns); else memcpy(s1, s2, sizeof(double) * ns);
+    }
+}
+/* field_class.f03 add_f1(a, b): b += a */
+static void fld_add1(const ofld *a, ofld *b) { size_t n = fld_n1(a); for (size_t i = 0; i < n; i++) b->f1[i] = b->f1[i] + a->f1[i]; }
+/* add_f1(a1, a2, a3): a3 = a1 + a2 */
+static void fld_add1_3(const ofld *a1, const ofld *a2, ofld *a3) { size_t n = fld_n1(a1); for (size_t i = 0; i < n; i++) a3->f1[i] = a1->f1[i] + a2->f1[i]; }
+/* add_f1(a, b, (/adim/), (/bdim/)) */
+static void fld_add1_dim(const ofld *a, ofld *b, int adim, int bdim)
+{
+    for (int pl = 0; pl < a->P; pl++)
+        for (int j = 0; j <= a->nr + 1; j++) F1(b->f1, b->dim, b->nr, pl, bdim, j) = F1(b->f1, b->dim, b->nr, pl, bdim, j) + F1(a->f1, a->dim, a->nr, pl, adim, j);
+}
+static void fld_dot1(double s, ofld *f) { size_t n = fld_n1(f); for (size_t i = 0; i < n; i++) f->f1[i] = f->f1[i] * s; }
+
+typedef struct {
+    long npmax, npp;
+    double *x, *p, *gamma, *psi, *q;
+} opart2d;
+typedef struct {
+    opart2d part;
+    ofld q, cu, dcu, amu, qn;
+    double qbm;
+} ospecies;
+typedef struct {
+    long npmax, npp;
+    double *x, *p, *q;
+    ofld q3; /* dim-1 volume */
+} obeam;
+
+typedef struct {
+    int nzp, noff2;
+    ofld psi, e_spe, e_beam, e, b_spe, b_beam, b, cu, amu, q_spe, q_beam, dcu, acu;
+    ospecies spe;
+    obeam beam;
+    /* pipeline mailboxes (filled by the upstream / downstream stage) */
+    double *mb_cu, *mb_bspe, *mb_qguard, *mb_e, *mb_b;
+    double *mb_plasma; long mb_plasma_np;
+    double *mb_beam; long mb_beam_np, mb_beam_cap;
+    double *conv_re, *conv_im;
+} ostage;
+
+struct orc_sim {
+    orc_params prm;
+    double dr, dxi, relax;
+    tri_op *op_psi, *op_ez, *op_bz, *op_bt, *op_bp, *op_bm;
+    ostage *st;
+    long total_iters;
+};
+
+static void part2d_alloc(opart2d *pt, long npmax)
+{
+    pt->npmax = npmax; pt->npp = 0;
+    pt->x = (double *)calloc((size_t)npmax * 2, sizeof(double));
+    pt->p = (double *)calloc((size_t)npmax * 3, sizeof(double));
+    pt->gamma = (double *)calloc((size_t)npmax, sizeof(double));
+    pt->psi = (double *)calloc((size_t)npmax, sizeof(double));
+    pt->q = (double *)calloc((size_t)npmax, sizeof(double));
+}
+static void part2d_free(opart2d *pt) { free(pt->x); free(pt->p); free(pt->gamma); free(pt->psi); free(pt->q); }
+static void part2d_reserve(opart2d *pt, long n)
+{
+    if (n <= pt->npmax) return;
+    long nm = (long)(n * 1.5);
+    pt->x = (double *)realloc(pt->x, sizeof(double) * 2 * (size_t)nm);
+    pt->p = (double *)realloc(pt->p, sizeof(double) * 3 * (size_t)nm);
+    pt->gamma = (double *)realloc(pt->gamma, sizeof(double) * (size_t)nm);
+    pt->psi = (double *)realloc(pt->psi, sizeof(double) * (size_t)nm);
+    pt->q = (double *)realloc(pt->q, sizeof(double) * (size_t)nm);
+    pt->npmax = nm;
+}
+
+/* species2d_class.f03:154-184 renew_species2d (and the tail of :73-133 init) */
+static void species_renew(orc_sim *s, ospecies *sp)
+{
+    const orc_params *pr = &s->prm;
+    sp->part.npp = orc_inject_uniform(sp->part.x, sp->part.p, sp->part.gamma, sp->part.psi, sp->part.q, pr->nr, s->dr,
+                                      pr->ppc1, pr->ppc2, pr->num_theta, pr->sp_q, pr->sp_density, pr->sp_den_min);
+    fld_zero1(&sp->q);
+    orc_qdeposit(sp->part.x, sp->part.q, sp->part.npp, s->dr, pr->nr, pr->max_mode, sp->q.f1);
+    memcpy(sp->qn.f1, sp->q.f1, sizeof(double) * fld_n1(&sp->q));
+    fld_dot1(-1.0, &sp->qn);
+}
+
+orc_sim *orc_sim_create(const orc_params *prm)
+{
+    orc_sim *s = (orc_sim *)calloc(1, sizeof(orc_sim));
+    s->prm = *prm;
+    int nr = prm->nr, M = prm->max_mode, S = prm->nstages < 1 ? 1 : prm->nstages;
+    s->prm.nstages = S;
+    s->dr = (prm->rmax - 0.0) / nr;              /* options_class.f03:86 */
+    s->dxi = (prm->zmax - prm->zmin) / prm->nz;  /* options_class.f03:90 */
+    s->relax = prm->relax_fac >= 0.0 ? prm->relax_fac : 1.0e-3 * ((s->dr / 0.02) * (s->dr / 0.02)); /* sim_fields_class.f03:137 */
+    s->op_psi = make_ops(ORC_FK_PSI, nr, M, s->dr, prm->bnd, 0.0);
+    s->op_ez = make_ops(ORC_FK_EZ, nr, M, s->dr, prm->bnd, 0.0);
+    s->op_bz = make_ops(ORC_FK_BZ, nr, M, s->dr, prm->bnd, 0.0);
+    s->op_bt = make_ops(ORC_FK_BT, nr, M, s->dr, prm->bnd, 0.0);
+    s->op_bp = make_ops(ORC_FK_BPLUS, nr, M, s->dr, prm->bnd, s->relax);
+    s->op_bm = make_ops(ORC_FK_BMINUS, nr, M, s->dr, prm->bnd, s->relax);
+    s->st = (ostage *)calloc((size_t)S, sizeof(ostage));
+    int local = prm->nz / S, extra = prm->nz - local * S; /* options_class.f03:103-106 */
+    for (int k = 0; k < S; k++) {
+        ostage *st = &s->st[k];
+        st->noff2 = local * k + (k < extra ? k : extra);
+        st->nzp = local + (k < extra ? 1 : 0);
+        int nzp = st->nzp;
+        fld_init(&st->psi, 1, nr, nzp, M, 1); fld_init(&st->e_spe, 3, nr, nzp, M, 1); fld_init(&st->e_beam, 3, nr, nzp, M, 1);
+        fld_init(&st->e, 3, nr, nzp, M, 1); fld_init(&st->b_spe, 3, nr, nzp, M, 1); fld_init(&st->b_beam, 3, nr, nzp, M, 1);
+        fld_init(&st->b, 3, nr, nzp, M, 1); fld_init(&st->cu, 3, nr, nzp, M, 1); fld_init(&st->amu, 3, nr, nzp, M, 0);
+        fld_init(&st->q_spe, 1, nr, nzp, M, 1); fld_init(&st->q_beam, 1, nr, nzp, M, 1); fld_init(&st->dcu, 2, nr, nzp, M, 0);
+        fld_init(&st->acu, 2, nr, nzp, M, 0);
+        ospecies *sp = &st->spe;
+        sp->qbm = prm->sp_q / prm->sp_m;
+        long npmin = (long)nr * prm->ppc1 * prm->ppc2 * prm->num_theta;
+        part2d_alloc(&sp->part, 2 * npmin); /* fdist2d_class.f03:261-263 */
+        fld_init(&sp->q, 1, nr, nzp, M, 1); fld_init(&sp->cu, 3, nr, nzp, M, 0); fld_init(&sp->dcu, 2, nr, nzp, M, 0);
+        fld_init(&sp->amu, 3, nr, nzp, M, 0); fld_init(&sp->qn, 1, nr, nzp, M, 0);
+        species_renew(s, sp);
+        st->beam.npmax = 0; st->beam.npp = 0; st->beam.x = st->beam.p = st->beam.q = NULL;
+        fld_init(&st->beam.q3, 1, nr, nzp, M, 1);
+        size_t n3 = (size_t)st->cu.P * (nr + 2) * 3, n1 = (size_t)st->cu.P * (nr + 2);
+        st->mb_cu = (double *)calloc(n3, sizeof(double)); st->mb_bspe = (double *)calloc(n3, sizeof(double));
+        st->mb_e = (double *)calloc(n3, sizeof(double)); st->mb_b = (double *)calloc(n3, sizeof(double));
+        st->mb_qguard = (double *)calloc(n1, sizeof(double));
+        st->mb_plasma = NULL; st->mb_plasma_np = 0;
+        st->mb_beam = NULL; st->mb_beam_np = 0; st->mb_beam_cap = 0;
+        st->conv_re = (double *)calloc((size_t)nr + 1, sizeof(double)); st->conv_im = (double *)calloc((size_t)nr + 1, sizeof(double));
+    }
+    return s;
+}
+
+void orc_sim_destroy(orc_sim *s)
+{
+    if (!s) return;
+    int M = s->prm.max_mode;
+    for (int k = 0; k < s->prm.nstages; k++) {
+        ostage *st = &s->st[k];
+        fld_free(&st->psi); fld_free(&st->e_spe); fld_free(&st->e_beam); fld_free(&st->e); fld_free(&st->b_spe);
+        fld_free(&st->b_beam); fld_free(&st->b); fld_free(&st->cu); fld_free(&st->amu); fld_free(&st->q_spe);
+        fld_free(&st->q_beam); fld_free(&st->dcu); fld_free(&st->acu);
+        part2d_free(&st->spe.part);
+        fld_free(&st->spe.q); fld_free(&st->spe.cu); fld_free(&st->spe.dcu); fld_free(&st->spe.amu); fld_free(&st->spe.qn);
+        free(st->beam.x); free(st->beam.p); free(st->beam.q); fld_free(&st->beam.q3);
+        free(st->mb_cu); free(st->mb_bspe); free(st->mb_e); free(st->mb_b); free(st->mb_qguard); free(st->mb_plasma); free(st->mb_beam);
+        free(st->conv_re); free(st->conv_im);
+    }
+    free(s->st);
+    free_ops(s->op_psi, M); free_ops(s->op_ez, M); free_ops(s->op_bz, M); free_ops(s->op_bt, M); free_ops(s->op_bp, M); free_ops(s->op_bm, M);
+    free(s);
+}
+
+static void beam_reserve(obeam *b, long n)
+{
+    if (n <= b->npmax) return;
+    long nm = (long)(n * 1.5) + 16;
+    b->x = (double *)realloc(b->x, sizeof(double) * 3 * (size_t)nm);
+    b->p = (double *)realloc(b->p, sizeof(double) * 3 * (size_t)nm);
+    b->q = (double *)realloc(b->q, sizeof(double) * (size_t)nm);
+    b->npmax = nm;
+}
+
+void orc_sim_set_beam(orc_sim *s, const double *x, const double *p, const double *q, long np)
+{
+    for (int k = 0; k < s->prm.nstages; k++) s->st[k].beam.npp = 0;
+    for (long i = 0; i < np; i++) {
+        /* owner = stage whose slab [noff2, noff2+nzp)*dxi holds xi (part3d_comm.f03 goto_here) */
+        int own = s->prm.nstages - 1;
+        for (int k = 0; k < s->prm.nstages; k++) {
+            double hi = (double)(s->st[k].noff2 + s->st[k].nzp) * s->dxi;
+            if (x[3 * i + 2] < hi) { own = k; break; }
+        }
+        obeam *b = &s->st[own].beam;
+        beam_reserve(b, b->npp + 1);
+        for (int c = 0; c < 3; c++) { b->x[3 * b->npp + c] = x[3 * i + c]; b->p[3 * b->npp + c] = p[3 * i + c]; }
+        b->q[b->npp] = q[i];
+        b->npp++;
+    }
+}
+
+/* simulation_class.f03:522-606 convergence_tester(fld, dim, op) */
+static void conv_record(ostage *st, const ofld *f, int dim, int M)
+{
+    int nr = f->nr;
+    for (int i = 1; i <= nr; i++) { st->conv_re[i] = 0.0; st->conv_im[i] = 0.0; }
+    for (int m = 0; m <= M; m++) {
+        for (int i = 1; i <= nr; i++) st->conv_re[i] = st->conv_re[i] + fabs(F1(f->f1, f->dim, nr, pl_re(m), dim, i));
+        if (m == 0) continue;
+        for (int i = 1; i <= nr; i++) st->conv_im[i] = st->conv_im[i] + fabs(F1(f->f1, f->dim, nr, pl_im(m), dim, i));
+    }
+}
+static void conv_compare(ostage *st, const ofld *f, int dim, int M, double *rel_res, double *abs_res)
+{
+    int nr = f->nr;
+    double mx = 0.0;
+    for (int i = 1; i <= nr; i++) { double v = st->conv_re[i] * st->conv_re[i] + st->conv_im[i] * st->conv_im[i]; if (i == 1 || v > mx) mx = v; }
+    double old_norm = sqrt(mx);
+    for (int m = 0; m <= M; m++) {
+        for (int i = 1; i <= nr; i++) st->conv_re[i] = st->conv_re[i] - fabs(F1(f->f1, f->dim, nr, pl_re(m), dim, i));
+        if (m == 0) continue;
+        for (int i = 1; i <= nr; i++) st->conv_im[i] = st->conv_im[i] - fabs(F1(f->f1, f->dim, nr, pl_im(m), dim, i));
+    }
+    mx = 0.0;
+    for (int i = 1; i <= nr; i++) { double v = st->conv_re[i] * st->conv_re[i] + st->conv_im[i] * st->conv_im[i]; if (i == 1 || v > mx) mx = v; }
+    *abs_res = sqrt(mx);
+    if (old_norm > DBL_EPSILON) *rel_res = *abs_res / old_norm; else *rel_res = DBL_MAX;
+}
+
+/* pack a field slice like field_class.f03:386-404 (dim, nr+2, 2M+1) -- identical to our plane-major f1 layout */
+static void pack_f2_slice(const ofld *f, int k, double *buf)
+{
+    size_t ns = (size_t)(f->nr + 2) * f->dim;
+    for (int pl = 0; pl < f->P; pl++) memcpy(buf + pl * ns, f->f2 + ((size_t)pl * (f->nzp + 1) + (k - 1)) * ns, sizeof(double) * ns);
+}
+static void unpack_f2_slice(ofld *f, int k, const double *buf, int add)
+{
+    size_t ns = (size_t)(f->nr + 2) * f->dim;
+    for (int pl = 0; pl < f->P; pl++) {
+        double *d = f->f2 + ((size_t)pl * (f->nzp + 1) + (k - 1)) * ns;
+        const double *sbuf = buf + pl * ns;
+        if (add) for (size_t i = 0; i < ns; i++) d[i] = d[i] + sbuf[i]; else memcpy(d, sbuf, sizeof(double) * ns);
+    }
+}
+
+/* the 2D loop body, simulation_class.f03:342-469, for slice j of stage k */
+static void slice_step(orc_sim *s, int k, int j)
+{
+    ostage *st = &s->st[k];
+    const orc_params *pr = &s->prm;
+    int nr = pr->nr, M = pr->max_mode;
+    double dr = s->dr, dxi = s->dxi;
+    ospecies *sp = &st->spe;
+    opart2d *pt = &sp->part;
+
+    fld_copy_slice(&st->q_beam, j, 0);                                              /* :344 */
+    solve_bt_ops(s->op_bt, st->q_beam.f1, st->b_beam.f1, nr, M, dr);                /* :345 */
+    fld_zero1(&st->q_spe);                                                          /* :346 */
+    /* species2d_class.f03:186-206 qdp */
+    fld_zero1(&sp->q);
+    orc_qdeposit(pt->x, pt->q, pt->npp, dr, nr, M, sp->q.f1);
+    fld_add1(&sp->q, &st->q_spe);
+    fld_add1(&sp->qn, &st->q_spe);
+    solve_psi_ops(s->op_psi, st->q_spe.f1, st->psi.f1, nr, M);                      /* :356 */
+    solve_bz_ops(s->op_bz, st->cu.f1, st->b_spe.f1, nr, M, dr);                     /* :360 */
+    for (int l = 1; l <= pr->iter_max; l++) {                                       /* :370 */
+        conv_record(st, &st->b_spe, 2, M);                                          /* :373 */
+        fld_add1_3(&st->b_spe, &st->b_beam, &st->b);                                /* :375 */
+        solve_ez_ops(s->op_ez, st->cu.f1, st->e.f1, nr, M, dr);                     /* :376 */
+        orc_solve_et(st->b.f1, st->psi.f1, st->e.f1, nr, M, dr);                    /* :377 */
+        fld_zero1(&st->cu); fld_zero1(&st->acu); fld_zero1(&st->amu);               /* :378-380 */
+        /* species2d_class.f03:233-280 amjdp */
+        fld_zero1(&sp->cu); fld_zero1(&sp->dcu); fld_zero1(&sp->amu);
+        orc_amjdeposit_robust(pt->x, pt->p, pt->q, pt->gamma, pt->psi, pt->npp, dr, nr, M, sp->qbm, dxi, st->e.f1,
+                              st->b.f1, sp->cu.f1, sp->dcu.f1, sp->amu.f1);
+        fld_add1(&sp->cu, &st->cu); fld_add1(&sp->dcu, &st->acu); fld_add1(&sp->amu, &st->amu);
+        orc_solve_djdxi(st->acu.f1, st->amu.f1, st->dcu.f1, nr, M, dr);             /* :390 */
+        solve_bt_iter_ops(s->op_bp, s->op_bm, st->dcu.f1, st->cu.f1, st->b_spe.f1, nr, M, dr, s->relax); /* :391 */
+        solve_bz_ops(s->op_bz, st->cu.f1, st->b_spe.f1, nr, M, dr);                 /* :392 */
+        double rel, ab;
+        conv_compare(st, &st->b_spe, 2, M, &rel, &ab);                              /* :395 */
+        s->total_iters++;
+        if (rel < pr->iter_reltol || ab < pr->iter_abstol) break;                   /* :396 */
+    }
+    fld_add1_dim(&sp->cu, &sp->q, 3, 1); fld_copy_slice(&sp->q, j, 1);              /* :403 cbq */
+    fld_copy_slice(&st->cu, j, 1);                                                  /* :409 */
+    fld_add1_dim(&st->cu, &st->q_spe, 3, 1);                                        /* :410 */
+    fld_copy_slice(&st->q_spe, j, 1);                                               /* :411 */
+    fld_add1_3(&st->b_spe, &st->b_beam, &st->b);                                    /* :413 */
+    orc_solve_et(st->b_spe.f1, st->psi.f1, st->e_spe.f1, nr, M, dr);                /* :414 */
+    solve_ez_ops(s->op_ez, st->cu.f1, st->e.f1, nr, M, dr);                         /* :415 */
+    orc_solve_et(st->b.f1, st->psi.f1, st->e.f1, nr, M, dr);                        /* :416 */
+    fld_dot1(dxi, &st->dcu);                                                        /* :425 */
+    fld_add1_dim(&st->dcu, &st->cu, 1, 1); fld_add1_dim(&st->dcu, &st->cu, 2, 2);   /* :426 */
+    if (j == st->nzp && k + 1 < pr->nstages) {                                      /* :429-434 pipe_send_f1 forward */
+        memcpy(s->st[k + 1].mb_cu, st->cu.f1, sizeof(double) * fld_n1(&st->cu));
+        memcpy(s->st[k + 1].mb_bspe, st->b_spe.f1, sizeof(double) * fld_n1(&st->b_spe));
+    }
+    orc_push_u_robust(pt->x, pt->p, pt->gamma, pt->npp, dr, nr, M, sp->qbm, dxi, st->e.f1, st->b.f1); /* :438 */
+    orc_push_x(pt->x, pt->p, pt->gamma, pt->npp, dxi);                              /* :439, species2d_class.f03:311 */
+    pt->npp = orc_update_bound(pt->x, pt->p, pt->gamma, pt->psi, pt->q, pt->npp, (double)nr * dr);
+    if (pr->sort_freq > 0 && ((st->noff2 + j) % pr->sort_freq) == 0)               /* :440 (commented out upstream) */
+        orc_sort_part2d(pt->x, pt->p, pt->gamma, pt->psi, pt->q, pt->npp, dr, nr);
+    fld_copy_slice(&st->e, j, 1); fld_copy_slice(&st->b, j, 1); fld_copy_slice(&st->psi, j, 1); /* :452-456 */
+    fld_copy_slice(&st->b_spe, j, 1); fld_copy_slice(&st->e_spe, j, 1);
+    if (j == 1 && k > 0) {                                                          /* :460-467 backward, 'inner' */
+        pack_f2_slice(&st->b, 1, s->st[k - 1].mb_b);
+        pack_f2_slice(&st->e, 1, s->st[k - 1].mb_e);
+    }
+}
+
+/* first half of a 3D step for stage k: simulation_class.f03:296-340 */
+static void stage_begin(orc_sim *s, int k)
+{
+    ostage *st = &s->st[k];
+    const orc_params *pr = &s->prm;
+    int nr = pr->nr, M = pr->max_mode;
+    fld_zero1(&st->q_beam); fld_zero2(&st->q_beam);                                 /* :299 q_beam%as(0) */
+    fld_zero1(&st->q_spe); fld_zero2(&st->q_spe);                                   /* :300 */
+    /* beam3d_class.f03:193-221 qdeposit_beam3d */
+    obeam *bm = &st->beam;
+    fld_zero1(&bm->q3); fld_zero2(&bm->q3);
+    if (k > 0) unpack_f2_slice(&bm->q3, 1, st->mb_qguard, 1);                       /* pipe_recv forward inner add */
+    orc_qdeposit3d(bm->x, bm->q, bm->npp, s->dr, s->dxi, nr, st->nzp, st->noff2, M, bm->q3.f2);
+    if (k + 1 < pr->nstages) pack_f2_slice(&bm->q3, st->nzp + 1, s->st[k + 1].mb_qguard); /* pipe_send forward guard */
+    { size_t n = fld_n2(&bm->q3); for (size_t i = 0; i < n; i++) st->q_beam.f2[i] = st->q_beam.f2[i] + bm->q3.f2[i]; } /* add_f2 */
+    /* species precv, part2d_class.f03:2405-2485 */
+    if (k > 0) {
+        opart2d *pt = &st->spe.part;
+        long n = st->mb_plasma_np;
+        part2d_reserve(pt, n);
+        pt->npp = n;
+        for (long i = 0; i < n; i++) {
+            const double *r = st->mb_plasma + 8 * i;
+            pt->x[2 * i] = r[0]; pt->x[2 * i + 1] = r[1];
+            pt->p[3 * i] = r[2]; pt->p[3 * i + 1] = r[3]; pt->p[3 * i + 2] = r[4];
+            pt->gamma[i] = r[5]; pt->psi[i] = r[6]; pt->q[i] = r[7];
+        }
+    }
+    fld_zero1(&st->b); fld_zero1(&st->e); fld_zero1(&st->b_spe); fld_zero1(&st->e_spe); fld_zero1(&st->psi); /* :324-331 */
+    fld_zero1(&st->cu); fld_zero1(&st->acu); fld_zero1(&st->amu);
+    if (k > 0) {                                                                    /* :337-340 pipe_recv_f1 replace */
+        memcpy(st->cu.f1, st->mb_cu, sizeof(double) * fld_n1(&st->cu));
+        memcpy(st->b_spe.f1, st->mb_bspe, sizeof(double) * fld_n1(&st->b_spe));
+    }
+}
+
+/* simulation_class.f03:471-474 psend */
+static void stage_psend(orc_sim *s, int k)
+{
+    if (k + 1 >= s->prm.nstages) return;
+    ostage *st = &s->st[k], *nx = &s->st[k + 1];
+    opart2d *pt = &st->spe.part;
+    nx->mb_plasma = (double *)realloc(nx->mb_plasma, sizeof(double) * 8 * (size_t)(pt->npp + 1));
+    nx->mb_plasma_np = pt->npp;
+    for (long i = 0; i < pt->npp; i++) { /* part2d_class.f03:2377-2390 */
+        double *r = nx->mb_plasma + 8 * i;
+        r[0] = pt->x[2 * i]; r[1] = pt->x[2 * i + 1];
+        r[2] = pt->p[3 * i]; r[3] = pt->p[3 * i + 1]; r[4] = pt->p[3 * i + 2];
+        r[5] = pt->gamma[i]; r[6] = pt->psi[i]; r[7] = pt->q[i];
+    }
+}
+
+/* second half: simulation_class.f03:481-501 */
+static void stage_end(orc_sim *s, int k)
+{
+    ostage *st = &s->st[k];
+    const orc_params *pr = &s->prm;
+    int nr = pr->nr, M = pr->max_mode;
+    if (k + 1 < pr->nstages) {                                                      /* :482-483 backward guard replace */
+        unpack_f2_slice(&st->b, st->nzp + 1, st->mb_b, 0);
+        unpack_f2_slice(&st->e, st->nzp + 1, st->mb_e, 0);
+    }
+    obeam *bm = &st->beam;
+    if (pr->beam_evol) {                                                            /* beam3d_class.f03:223-254 */
+        orc_push3d(bm->x, bm->p, bm->npp, s->dr, s->dxi, nr, st->nzp, st->noff2, M, pr->beam_qbm, pr->dt,
+                   pr->beam_push_type, st->e.f2, st->b.f2);
+        bm->npp = orc_update_bound3d(bm->x, bm->p, bm->q, bm->npp, (double)nr * s->dr, (double)pr->nz * s->dxi);
+        /* move_part3d_comm, part3d_comm.f03:278-314: receive from stage-1, then send forward */
+        if (k > 0 && st->mb_beam_np > 0) {
+            beam_reserve(bm, bm->npp + st->mb_beam_np);
+            for (long i = 0; i < st->mb_beam_np; i++) {
+                const double *r = st->mb_beam + 7 * i;
+                for (int c = 0; c < 3; c++) { bm->x[3 * bm->npp + c] = r[c]; bm->p[3 * bm->npp + c] = r[3 + c]; }
+                bm->q[bm->npp] = r[6];
+                bm->npp++;
+            }
+            st->mb_beam_np = 0;
+        }
+        if (k + 1 < pr->nstages) {
+            ostage *nx = &s->st[k + 1];
+            double zhi = (double)(st->noff2 + st->nzp) * s->dxi;
+            long go = 0, *hole = (long *)malloc(sizeof(long) * (size_t)(bm->npp + 1));
+            for (long i = 0; i < bm->npp; i++) if (bm->x[3 * i + 2] >= zhi) hole[go++] = i;
+            if (go > nx->mb_beam_cap) { nx->mb_beam = (double *)realloc(nx->mb_beam, sizeof(double) * 7 * (size_t)go); nx->mb_beam_cap = go; }
+            nx->mb_beam_np = go;
+            for (long g = 0; g < go; g++) {
+                long i = hole[g];
+                double *r = nx->mb_beam + 7 * g;
+                for (int c = 0; c < 3; c++) { r[c] = bm->x[3 * i + c]; r[3 + c] = bm->p[3 * i + c]; }
+                r[6] = bm->q[i];
+            }
+            long npp = bm->npp; /* fill the holes inversely, part3d_comm.f03:733-745 */
+            for (long g = go - 1; g >= 0; g--) {
+                long h = hole[g], l = npp - 1;
+                for (int c = 0; c < 3; c++) { bm->x[3 * h + c] = bm->x[3 * l + c]; bm->p[3 * h + c] = bm->p[3 * l + c]; }
+                bm->q[h] = bm->q[l];
+                npp--;
+            }
+            bm->npp = npp;
+            free(hole);
+        }
+    }
+    species_renew(s, &st->spe);                                                     /* :498-501 */
+}
+
+long orc_sim_step3d(orc_sim *s, int istep)
+{
+    (void)istep;
+    long updates = 0;
+    for (int k = 0; k < s->prm.nstages; k++) {
+        stage_begin(s, k);
+        for (int j = 1; j <= s->st[k].nzp; j++) { updates += s->st[k].spe.part.npp; slice_step(s, k, j); }
+        stage_psend(s, k);
+    }
+    for (int k = 0; k < s->prm.nstages; k++) stage_end(s, k);
+    return updates;
+}
+
+long orc_sim_run_slices(orc_sim *s, int nslices)
+{
+    long updates = 0;
+    stage_begin(s, 0);
+    for (int j = 1; j <= nslices && j <= s->st[0].nzp; j++) { updates += s->st[0].spe.part.npp; slice_step(s, 0, j); }
+    return updates;
+}
+
+int orc_sim_nzp(const orc_sim *s, int stage) { return s->st[stage].nzp; }
+long orc_sim_plasma_np(const orc_sim *s, int stage) { return s->st[stage].spe.part.npp; }
+void orc_sim_get_plasma(const orc_sim *s, int stage, double *x, double *p, double *gamma, double *psi, double *q)
+{
+    const opart2d *pt = &s->st[stage].spe.part;
+    memcpy(x, pt->x, sizeof(double) * 2 * (size_t)pt->npp); memcpy(p, pt->p, sizeof(double) * 3 * (size_t)pt->npp);
+    memcpy(gamma, pt->gamma, sizeof(double) * (size_t)pt->npp); memcpy(psi, pt->psi, sizeof(double) * (size_t)pt->npp);
+    memcpy(q, pt->q, sizeof(double) * (size_t)pt->npp);
+}
+long orc_sim_beam_np(const orc_sim *s, int stage) { return s->st[stage].beam.npp; }
+void orc_sim_get_beam(const orc_sim *s, int stage, double *x, double *p, double *q)
+{
+    const obeam *b = &s->st[stage].beam;
+    memcpy(x, b->x, sizeof(double) * 3 * (size_t)b->npp); memcpy(p, b->p, sizeof(double) * 3 * (size_t)b->npp);
+    memcpy(q, b->q, sizeof(double) * (size_t)b->npp);
+}
+long orc_sim_get_field(const orc_sim *s, int stage, const char *name, int which, double *out)
+{
+    const ostage *st = &s->st[stage];
+    const ofld *f = NULL;
+    if (!strcmp(name, "psi")) f = &st->psi; else if (!strcmp(name, "e")) f = &st->e; else if (!strcmp(name, "b")) f = &st->b;
+    else if (!strcmp(name, "e_spe")) f = &st->e_spe; else if (!strcmp(name, "b_spe")) f = &st->b_spe;
+    else if (!strcmp(name, "e_beam")) f = &st->e_beam; else if (!strcmp(name, "b_beam")) f = &st->b_beam;
+    else if (!strcmp(name, "cu")) f = &st->cu; else if (!strcmp(name, "amu")) f = &st->amu; else if (!strcmp(name, "acu")) f = &st->acu;
+    else if (!strcmp(name, "dcu")) f = &st->dcu; else if (!strcmp(name, "q_spe")) f = &st->q_spe; else if (!strcmp(name, "q_beam")) f = &st->q_beam;
+    else if (!strcmp(name, "spe_q")) f = &st->spe.q; else if (!strcmp(name, "spe_qn")) f = &st->spe.qn;
+    if (!f) return -1;
+    if (which == 1) { if (out) memcpy(out, f->f1, sizeof(double) * fld_n1(f)); return (long)fld_n1(f); }
+    if (!f->f2) return -1;
+    if (out) memcpy(out, f->f2, sizeof(double) * fld_n2(f));
+    return (long)fld_n2(f);
+}
+long orc_sim_total_iters(const orc_sim *s) { return s->total_iters; }

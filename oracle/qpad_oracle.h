@@ -1,0 +1,112 @@
+/*
+ * qpad_oracle.h -- CPU restatement (fp64, single thread) of QPAD's quasi-static
+ * slice loop.  TEST INFRASTRUCTURE ONLY: nothing under qpad_b200/ may include,
+ * link or call this.  Only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs use it, as the checker / CPU baseline.
+ *
+ * PARITY UNPINNED: the reference (Fortran 2003 + MPI + HYPRE + HDF5) cannot be
+ * built in this image and ships no golden vectors or assertions (SURVEY.md §4,
+ * §8c).  This file is pinned instead against analytic known answers
+ * (tests/test_oracle_*.py) and is a line-by-line restatement of the cited
+ * Fortran.  The tridiagonal systems the reference hands to HYPRE's cyclic
+ * reduction (source/fields/field_solver_class.f03:172-177; HYPRE version not
+ * pinned by the reference, docs recommend 2.11.x) are solved here by the
+ * Thomas algorithm -- a direct solve of the same matrix.
+ *
+ * Layouts follow the reference:
+ *   particles  x(2,np) p(3,np) AoS column-major, gamma/psi/q(np)
+ *   field f1   per plane [0:nr+1][dim]  (Fortran f1(dim,0:nr+1)),
+ *              planes ordered re0, re1, im1, re2, im2, ...
+ *   field f2   per plane [1:nzp+1][0:nr+1][dim]
+ */
+#ifndef QPAD_ORACLE_H
+#define QPAD_ORACLE_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* field-solver kinds, source/param.f03 p_fk_* */
+enum { ORC_FK_PSI = 0, ORC_FK_EZ = 1, ORC_FK_BZ = 2, ORC_FK_BT = 3, ORC_FK_BPLUS = 4, ORC_FK_BMINUS = 5 };
+enum { ORC_BND_ZERO = 2, ORC_BND_OPEN = 3 };
+enum { ORC_PUSH3_REDUCED = 1, ORC_PUSH3_BORIS = 2 };
+
+/* ---- stand-alone routines (one per reference routine) ------------------- */
+/* part2d_class.f03:231 */
+void orc_qdeposit(const double *x, const double *q, long npp, double dr, int nr, int max_mode, double *f1);
+/* part2d_class.f03:746 ; e,b dim 3, cu dim 3, dcu dim 2, amu dim 3 ; writes gamma, psi */
+void orc_amjdeposit_robust(const double *x, const double *p, const double *q, double *gamma, double *psi, long npp,
+                           double dr, int nr, int max_mode, double qbm, double dt, const double *ef, const double *bf,
+                           double *cu, double *dcu, double *amu);
+/* part2d_class.f03:1879 */
+void orc_push_u_robust(const double *x, double *p, double *gamma, long npp, double dr, int nr, int max_mode,
+                       double qbm, double dt, const double *ef, const double *bf);
+/* part2d_class.f03:2221 */
+void orc_push_x(double *x, const double *p, const double *gamma, long npp, double dt);
+/* part2d_class.f03:2307 ; returns new npp */
+long orc_update_bound(double *x, double *p, double *gamma, double *psi, double *q, long npp, double edge);
+/* sort_module.f03:11 + part2d_class.f03:2498 ; ip is 1-based like the reference */
+void orc_sort_idx(const double *x, long npp, double dr, int nrp, int *ix, int *ip);
+void orc_sort_part2d(double *x, double *p, double *gamma, double *psi, double *q, long npp, double dr, int nrp);
+/* fdist2d_class.f03:289 (uniform profile, uth=0, ordered theta); returns npp */
+long orc_inject_uniform(double *x, double *p, double *gamma, double *psi, double *q, int nr, double dr, int ppc1,
+                        int ppc2, int num_theta, double qm, double density, double den_min);
+
+/* field_solver_class.f03:256 ; writes a,b,c (nr each) */
+void orc_build_matrix(int kind, int mode, int nr, double dr, int bnd, double relax_fac, double *a, double *b, double *c);
+void orc_tridiag_solve(const double *a, const double *b, const double *c, double *d, int nr);
+void orc_tridiag_solve_ld(const double *a, const double *b, const double *c, double *d, int nr); /* long double check */
+
+/* field ops; all f1 arrays are full multi-plane fields */
+void orc_solve_psi(const double *q, double *psi, int nr, int max_mode, double dr, int bnd);
+void orc_solve_bt(const double *qb, double *b, int nr, int max_mode, double dr, int bnd);
+void orc_solve_bz(const double *cu, double *b, int nr, int max_mode, double dr, int bnd);
+void orc_solve_bt_iter(const double *dcu, const double *cu, double *b, int nr, int max_mode, double dr, int bnd,
+                       double relax_fac);
+void orc_solve_ez(const double *cu, double *e, int nr, int max_mode, double dr, int bnd);
+void orc_solve_et(const double *b, const double *psi, double *e, int nr, int max_mode, double dr);
+void orc_solve_et_beam(const double *b, double *e, int nr, int max_mode);
+void orc_solve_djdxi(const double *acu, const double *amu, double *dcu, int nr, int max_mode, double dr);
+void orc_smooth_f1(double *f1plane, int dim, int nr, const int *ax_smooth);
+
+/* part3d_class.f03:221/477/358/640 ; x(3,np), p(3,np) ; f2 volumes with nzp+1 slices, noff2 = slab offset */
+void orc_qdeposit3d(const double *x, const double *q, long npp, double dr, double dz, int nr, int nzp, int noff2,
+                    int max_mode, double *f2);
+void orc_push3d(double *x, double *p, long npp, double dr, double dz, int nr, int nzp, int noff2, int max_mode,
+                double qbm, double dt, int push_type, const double *ef2, const double *bf2);
+long orc_update_bound3d(double *x, double *p, double *q, long npp, double edge_r, double edge_z);
+
+/* ---- whole simulation (simulation_class.f03:226-512), optionally as S xi-stages run in sequence ---- */
+typedef struct orc_sim orc_sim;
+typedef struct {
+    int nr, nz, max_mode, bnd, iter_max, nstages;
+    double rmax, zmin, zmax, dt, iter_reltol, iter_abstol, relax_fac; /* relax_fac<0 => default */
+    /* one species (uniform) */
+    int ppc1, ppc2, num_theta, sort_freq;
+    double sp_q, sp_m, sp_density, sp_den_min;
+    /* one beam */
+    int beam_push_type, beam_evol;
+    double beam_qbm;
+} orc_params;
+
+orc_sim *orc_sim_create(const orc_params *prm);
+void orc_sim_destroy(orc_sim *s);
+/* hand the beam particles (global xi measured from zmin) to the stage that owns them */
+void orc_sim_set_beam(orc_sim *s, const double *x, const double *p, const double *q, long np);
+/* run one 3D step (all stages in pipeline order).  Returns total plasma particle-slice updates. */
+long orc_sim_step3d(orc_sim *s, int istep);
+/* run only the first `nslices` slices of stage 0 of a 3D step (parity at slice granularity; no beam push) */
+long orc_sim_run_slices(orc_sim *s, int nslices);
+/* accessors (copy out) */
+int orc_sim_nzp(const orc_sim *s, int stage);
+long orc_sim_plasma_np(const orc_sim *s, int stage);
+void orc_sim_get_plasma(const orc_sim *s, int stage, double *x, double *p, double *gamma, double *psi, double *q);
+long orc_sim_beam_np(const orc_sim *s, int stage);
+void orc_sim_get_beam(const orc_sim *s, int stage, double *x, double *p, double *q);
+/* name in {psi,e,b,e_spe,b_spe,e_beam,b_beam,cu,amu,acu,dcu,q_spe,q_beam}; which=1 -> f1, 2 -> f2 (nzp+1 slices) */
+long orc_sim_get_field(const orc_sim *s, int stage, const char *name, int which, double *out);
+long orc_sim_total_iters(const orc_sim *s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,84 @@
+"""Input-deck helpers that stay on the host (out of the hot path).
+
+* ``load_deck`` reads a QPAD ``qpinput.json`` (``!`` comments allowed, input_class.f03:48-105).
+* ``beam_std`` restates the *lattice* part of ``inject_fdist3d_std`` (beam/fdist3d_std_class.f03:439-613).
+  The reference draws momenta from the compiler's ``random_number`` (math_module.f03:77-102), which is
+  gfortran-version dependent; here the draws come from ``numpy.random.Generator(PCG64(seed))`` -- a documented
+  substitute (SURVEY.md §8c PRNG row).  Both the CUDA path and the oracle consume the same arrays.
+"""
+import json
+import re
+import numpy as np
+
+CONFIGS = {
+    # SURVEY.md §8 config table.  Beam blocks follow input_file/blowout_regime/qpinput_tri-gaussian.json.
+    "C1": dict(nr=250, nz=500, max_mode=1, rmax=5.0, zmin=-5.0, zmax=5.0, dt=10.0, ppc1=2, ppc2=2, num_theta=16,
+               iter_max=10, iter_reltol=1e-3, iter_abstol=1e-3,
+               beam=dict(ppc=(2, 2, 2), num_theta=16, q=-1.0, m=1.0, gamma=20000.0, density=4.0, quiet=True,
+                         center=(0.0, 0.0, -2.5), sigma=(0.25, 0.25, 0.5), range1=(-1.25, 1.25), range2=(-1.25, 1.25),
+                         range3=(-5.0, 0.0), uth=(5.0, 5.0, 0.0), den_min=1e-10)),
+    "C2": dict(nr=1024, nz=2048, max_mode=1, rmax=5.0, zmin=-5.0, zmax=5.0, dt=10.0, ppc1=4, ppc2=4, num_theta=16,
+               iter_max=10, iter_reltol=1e-3, iter_abstol=1e-3,
+               beam=dict(ppc=(2, 2, 2), num_theta=16, q=-1.0, m=1.0, gamma=20000.0, density=4.0, quiet=True,
+                         center=(0.0, 0.0, -2.5), sigma=(0.25, 0.25, 0.5), range1=(-1.25, 1.25), range2=(-1.25, 1.25),
+                         range3=(-5.0, 0.0), uth=(5.0, 5.0, 0.0), den_min=1e-10)),
+    # input_file/hosing/qpinput.json: max_mode 2, two beams, the second off axis (merged into one particle set here)
+    "C3": dict(nr=256, nz=438, max_mode=2, rmax=6.0, zmin=-4.0, zmax=9.7, dt=10.0, ppc1=2, ppc2=2, num_theta=16,
+               iter_max=1, iter_reltol=1e-3, iter_abstol=1e-3,
+               beam=dict(ppc=(2, 2, 2), num_theta=16, q=-1.0, m=1.0, gamma=20000.0, density=5.0, quiet=True,
+                         center=(0.0376, 0.0, 0.0), sigma=(0.2, 0.2, 0.6), range1=(-1.0, 1.0), range2=(-1.0, 1.0),
+                         range3=(-3.0, 3.0), uth=(2.0, 2.0, 0.0), den_min=1e-10)),
+}
+
+
+def load_deck(path):
+    txt = open(path).read()
+    txt = re.sub(r"!.*", "", txt)
+    return json.loads(txt)
+
+
+def beam_std(nr, nz, rmax, zmin, zmax, ppc, num_theta, q, m, gamma, density, center, sigma, range1, range2, range3,
+             uth, den_min=1e-10, quiet=True, seed=10, xi_cells=None, **_):
+    """Tri-Gaussian 'standard' beam in Cartesian geometry.  Returns x(np,3) [x, y, xi - zmin], p(np,3), q(np)."""
+    dr, dz = rmax / nr, (zmax - zmin) / nz
+    dtheta = 2.0 * np.pi / num_theta
+    ppc1, ppc2, ppc3 = ppc
+    coef = np.sign(q / m) / (ppc1 * ppc2 * ppc3 * num_theta)
+    r3 = (range3[0] - zmin, range3[1] - zmin)
+    k0 = max(0, int(np.floor(r3[0] / dz)) - 1)
+    k1 = min(nz, int(np.ceil(r3[1] / dz)) + 1)
+    rmax_beam = np.hypot(max(abs(range1[0]), abs(range1[1])), max(abs(range2[0]), abs(range2[1])))
+    i1max = min(nr, int(np.ceil(rmax_beam / dr)) + 1)
+    # loop order of the reference: k, j, i, i3, i2, i1 (innermost)
+    k = np.arange(k0, k1)
+    j = np.arange(num_theta)
+    i = np.arange(i1max)
+    i3 = (np.arange(ppc3) + 0.5) / ppc3
+    i2 = (np.arange(ppc2) + 0.5) / ppc2
+    i1 = (np.arange(ppc1) + 0.5) / ppc1
+    K, J, I, I3, I2, I1 = np.meshgrid(k, j, i, i3, i2, i1, indexing="ij")
+    zn = (I3 + K).ravel()
+    theta = ((I2 + J) * dtheta).ravel()
+    rn = (I1 + I).ravel()
+    x1 = rn * dr * np.cos(theta)
+    x2 = rn * dr * np.sin(theta)
+    x3 = zn * dz
+    keep = (x1 >= range1[0]) & (x1 <= range1[1]) & (x2 >= range2[0]) & (x2 <= range2[1]) & (x3 >= r3[0]) & (x3 <= r3[1])
+    den = (np.exp(-0.5 * ((x1 - center[0]) / sigma[0]) ** 2) * np.exp(-0.5 * ((x2 - center[1]) / sigma[1]) ** 2)
+           * np.exp(-0.5 * ((x3 - (center[2] - zmin)) / sigma[2]) ** 2)) * density
+    keep &= den >= den_min
+    x1, x2, x3, rn, den = x1[keep], x2[keep], x3[keep], rn[keep], den[keep]
+    n = len(x1)
+    rng = np.random.Generator(np.random.PCG64(seed))
+    g = rng.standard_normal((n, 3))
+    p1, p2 = uth[0] * g[:, 0], uth[1] * g[:, 1]
+    p3 = uth[2] * g[:, 2] + gamma
+    p3 = np.sqrt(p3 ** 2 - p1 ** 2 - p2 ** 2 - 1.0)
+    qq = rn * den * coef
+    x = np.stack([x1, x2, x3], 1)
+    p = np.stack([p1, p2, p3], 1)
+    if quiet:
+        x = np.concatenate([x, x * np.array([-1.0, -1.0, 1.0])])
+        p = np.concatenate([p, p * np.array([-1.0, -1.0, 1.0])])
+        qq = np.concatenate([0.5 * qq, 0.5 * qq])
+    return np.ascontiguousarray(x), np.ascontiguousarray(p), np.ascontiguousarray(qq)
