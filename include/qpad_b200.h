@@ -1,0 +1,212 @@
+/*
+ * qpad_b200.h -- C-ABI of libqpadb200.so: QPAD's quasi-static slice loop on one B200 (sm_100a).
+ *
+ * This is the drop-in boundary of SURVEY.md §8(b): every entry point replaces the body of one
+ * Fortran type-bound procedure of the reference (cited per function, paths relative to
+ * /root/reference/source/), and is what an ISO_C_BINDING shim binds (INTEGRATION.md shows the
+ * `bind(C)` interface block a maintainer adds).  Plain pointers and sizes only; no torch types.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative qpg_status otherwise (the reference never
+ *     returns errors: write_err logs and stops, sysutil_module.f03:165; the shim maps non-zero
+ *     to write_err).  qpg_last_error() gives the message.
+ *   - all arithmetic is fp64 (`real` == fp64 in every reference build config).
+ *   - handles are opaque; memory they refer to lives in HBM and is owned by the library.
+ *   - work is enqueued on the context's CUDA stream; only functions documented "synchronises"
+ *     wait for the device.  One host thread per context.
+ *   - HOST array layouts are the reference's:
+ *        particles  x(2,np) p(3,np) column-major AoS, gamma(np) psi(np) q(np)
+ *        field f1   per plane f1(dim, 0:nr+1); planes ordered re(0), re(1), im(1), re(2), im(2) ...
+ *                   i.e. a C array [P][nr+2][dim], P = 2*max_mode+1  (same as the pipeline wire
+ *                   buffer (dim, nr+2, 2M+1) of fields/field_class.f03:608-634)
+ *        field f2   C array [P][nzp+1][nr+2][dim]
+ *     The DEVICE layout is different (SoA particles; node-interleaved fields).
+ *   - there is no CPU fallback: without a CUDA device every call fails with QPG_ERR_CUDA.
+ */
+#ifndef QPAD_B200_H
+#define QPAD_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    QPG_OK = 0, QPG_ERR_ARG = -1, QPG_ERR_CUDA = -2, QPG_ERR_ALLOC = -3, QPG_ERR_UNSUPPORTED = -4, QPG_ERR_STATE = -5
+} qpg_status;
+
+typedef struct qpg_ctx_s *qpg_ctx;
+typedef struct qpg_field_s *qpg_field;
+typedef struct qpg_part2d_s *qpg_part2d;
+typedef struct qpg_part3d_s *qpg_part3d;
+typedef struct qpg_sim_s *qpg_sim;
+
+/* param.f03 constants mirrored 1:1 */
+enum { QPG_BND_ZERO = 2, QPG_BND_OPEN = 3 };                              /* p_bnd_* */
+enum { QPG_PUSH2_STD = 0, QPG_PUSH2_ROBUST = 1 };                         /* p_push2_* */
+enum { QPG_PUSH3_REDUCED = 1, QPG_PUSH3_BORIS = 2 };                      /* p_push3_* */
+enum { QPG_COPY_1TO2 = 0, QPG_COPY_2TO1 = 1 };                            /* ufield_class.f03 p_copy_* */
+enum { QPG_CONV_RECORD = 0, QPG_CONV_COMPARE = 1 };
+
+const char *qpg_last_error(void);
+int qpg_version(void);
+
+/* ------------------------------------------------------------------------------------------ */
+/* context: grid + solver set.  Replaces options_class.f03 get_* values and the per-(kind,mode)   */
+/* field_solver%new calls of fields/field_{psi,e,b}_class.f03 (HYPRE StructCycRed setup,       */
+/* fields/field_solver_class.f03:58-95, 256-561).                                             */
+/* cuda_stream: a cudaStream_t (0/NULL = library creates its own).  device: CUDA ordinal.      */
+/* relax_fac < 0 selects the reference default 1e-3*(dr/0.02)^2 (sim_fields_class.f03:137).    */
+/* ------------------------------------------------------------------------------------------ */
+int qpg_ctx_create(qpg_ctx *out, int device, void *cuda_stream, int nr, int max_mode, double dr, double dxi,
+                   int field_boundary, double relax_fac);
+int qpg_ctx_destroy(qpg_ctx ctx);
+int qpg_ctx_sync(qpg_ctx ctx);                                   /* synchronises */
+/* named timers with the reference's event names (sysutil_module.f03:298-385 start/stop_tprof):
+ * CUDA-event timing per kernel class.  qpg_tprof_get synchronises. */
+int qpg_tprof_enable(qpg_ctx ctx, int on);
+int qpg_tprof_reset(qpg_ctx ctx);
+int qpg_tprof_get(qpg_ctx ctx, const char *event, double *ms_total, long *ncalls);
+/* number of kernels this context has launched so far */
+long qpg_launch_count(qpg_ctx ctx);
+
+/* ------------------------------------------------------------------------------------------ */
+/* field : fields/field_class.f03:50 `type field` + fields/ufield_class.f03:52 `type ufield`   */
+/* ------------------------------------------------------------------------------------------ */
+int qpg_field_create(qpg_field *out, qpg_ctx ctx, int dim, int nzp, int has_2d);      /* field%new  :190 */
+int qpg_field_destroy(qpg_field f);                                                   /* field%del  :262 */
+int qpg_field_dim(qpg_field f);
+int qpg_field_fill(qpg_field f, double value);                                        /* assign_f1  :917 (`f = value`) */
+int qpg_field_fill_f2(qpg_field f, double value);                                     /* assign_f2  :948 (`f%as(value)`) */
+int qpg_field_copy(qpg_field src, qpg_field dst);                                     /* assign_f1, `dst = src` */
+int qpg_field_copy_slice(qpg_field f, int idx, int dir);                              /* ufield copy_slice :341 (idx 1-based) */
+int qpg_field_add(qpg_field a, qpg_field b);                                          /* add_f1(a,b): b += a  :1053 */
+int qpg_field_add3(qpg_field a1, qpg_field a2, qpg_field a3);                         /* add_f1(a1,a2,a3): a3 = a1+a2 :1035 */
+int qpg_field_add_dim(qpg_field a, qpg_field b, int ndim, const int *adim, const int *bdim); /* add_f1(a,b,adim,bdim) :1011 (1-based comps) */
+int qpg_field_add_f2(qpg_field a, qpg_field b);                                       /* add_f2(a,b): b%f2 += a%f2 */
+int qpg_field_scale(qpg_field f, double s);                                           /* dot_f1(s, f) :1159 */
+int qpg_field_smooth(qpg_field f, int order, int kind);                               /* field_src_class.f03:102/169/243; kind 0 rho,1 jay,2 djdxi */
+int qpg_field_upload_f1(qpg_field f, const double *host);                             /* host [P][nr+2][dim] */
+int qpg_field_download_f1(qpg_field f, double *host);                                 /* synchronises */
+int qpg_field_upload_f2(qpg_field f, const double *host);                             /* host [P][nzp+1][nr+2][dim] */
+int qpg_field_download_f2(qpg_field f, double *host);                                 /* synchronises */
+/* pipeline wire buffers (device pointers, reference wire layout [P][nr+2][dim]):
+ * field_class.f03:560 pipe_send_f1 / :647 pipe_recv_f1 / :312 pipe_send_f2 / :420 pipe_recv_f2.
+ * slice = 0 packs/unpacks f1, slice k>=1 the f2 slice k; add != 0 selects mode 'add'.
+ * The transport itself (NCCL send/recv over NVLink) is done by the caller on these buffers. */
+int qpg_field_pack(qpg_field f, int slice, double *dev_buf);
+int qpg_field_unpack(qpg_field f, int slice, const double *dev_buf, int add);
+long qpg_field_wire_count(qpg_field f);                                               /* doubles per wire buffer */
+/* diagnostics staging: f2(comp, node, 1:nzp) of one plane -> host (nzp doubles); comp 1-based, node 0..nr+1.
+ * The on-axis E_z / psi line-outs of the parity gate; synchronises. */
+int qpg_field_lineout(qpg_field f, int comp, int plane, int node, double *host);
+
+/* ------------------------------------------------------------------------------------------ */
+/* field solves: one call per reference `solve` generic                                       */
+/* ------------------------------------------------------------------------------------------ */
+int qpg_solve_psi(qpg_ctx ctx, qpg_field q, qpg_field psi);                 /* field_psi_class.f03:218 solve_field_psi */
+int qpg_solve_bt(qpg_ctx ctx, qpg_field q_beam, qpg_field b);              /* field_b_class.f03:798 solve_field_bt */
+int qpg_solve_bz(qpg_ctx ctx, qpg_field cu, qpg_field b);                  /* field_b_class.f03:760 solve_field_bz */
+int qpg_solve_bt_iter(qpg_ctx ctx, qpg_field dcu, qpg_field cu, qpg_field b); /* field_b_class.f03:836 solve_field_bt_iter */
+int qpg_solve_ez(qpg_ctx ctx, qpg_field cu, qpg_field e);                  /* field_e_class.f03:298 solve_field_ez */
+int qpg_solve_et(qpg_ctx ctx, qpg_field b, qpg_field psi, qpg_field e);    /* field_e_class.f03:412 solve_field_et */
+int qpg_solve_et_beam(qpg_ctx ctx, qpg_field b, qpg_field e);              /* field_e_class.f03:516 solve_field_et_beam */
+int qpg_solve_djdxi(qpg_ctx ctx, qpg_field acu, qpg_field amu, qpg_field dcu); /* field_src_class.f03:273 solve_field_djdxi */
+/* simulation_class.f03:522 convergence_tester(fld, dim, op, rel_res, abs_res).
+ * op = QPG_CONV_COMPARE synchronises and returns rel/abs. */
+int qpg_bperp_residual(qpg_ctx ctx, qpg_field fld, int dim, int op, double *rel_res, double *abs_res);
+
+/* ------------------------------------------------------------------------------------------ */
+/* part2d : species/part2d_class.f03:24 `type part2d`                                          */
+/* ------------------------------------------------------------------------------------------ */
+int qpg_part2d_create(qpg_part2d *out, qpg_ctx ctx, double qbm, long npmax);                     /* init_part2d :98 */
+int qpg_part2d_destroy(qpg_part2d p);                                                            /* end_part2d :144 */
+int qpg_part2d_upload(qpg_part2d p, const double *x, const double *pm, const double *gamma, const double *psi,
+                      const double *q, long npp);                                                /* host AoS -> device SoA (inject/renew) */
+int qpg_part2d_download(qpg_part2d p, double *x, double *pm, double *gamma, double *psi, double *q, long *npp); /* synchronises; any ptr may be NULL */
+int qpg_part2d_npp(qpg_part2d p, long *npp);                                                     /* synchronises */
+/* renew from the device-resident copy of the lattice made by the first upload (renew_part2d :207: the
+ * uniform/time-independent profiles of the decks re-inject the same particles every 3D step) */
+int qpg_part2d_snapshot(qpg_part2d p);
+int qpg_part2d_renew(qpg_part2d p);
+int qpg_part2d_qdeposit(qpg_part2d p, qpg_field q);                                              /* qdeposit_part2d :231 */
+int qpg_part2d_amjdeposit(qpg_part2d p, int push_type, qpg_field ef, qpg_field bf, qpg_field cu, qpg_field amu,
+                          qpg_field dcu, double dt);                                             /* amjdeposit_robust_part2d :746 */
+int qpg_part2d_push_u(qpg_part2d p, int push_type, qpg_field ef, qpg_field bf, double dt);       /* push_u_robust_part2d :1879 */
+int qpg_part2d_push_x(qpg_part2d p, double dt);                                                  /* push_x_part2d :2221 */
+int qpg_part2d_update_bound(qpg_part2d p);                                                       /* update_bound_part2d :2307 */
+int qpg_part2d_sort(qpg_part2d p);                                                               /* sort_part2d :2498 + sort_module.f03:11 */
+int qpg_part2d_sort_index(qpg_part2d p, int *host_ix, int *host_ip);                             /* generate_sort_idx_1d output (1-based), synchronises */
+/* pipesend_part2d :2355 / piperecv_part2d :2405 : 8 doubles per particle (x1,x2,p1,p2,p3,gamma,psi,q) AoS,
+ * dev_buf[0] additionally carries the count as a double in slot 8*npmax.  wire size = 8*npmax+1 doubles. */
+int qpg_part2d_pack(qpg_part2d p, double *dev_buf);
+int qpg_part2d_unpack(qpg_part2d p, const double *dev_buf);
+long qpg_part2d_wire_count(qpg_part2d p);
+
+/* ------------------------------------------------------------------------------------------ */
+/* part3d : beam/part3d_class.f03:24 `type part3d` (no spin)                                    */
+/* x(3,np) = (x, y, xi - z0) like the reference; noff2/nzp = this stage's xi slab                */
+/* ------------------------------------------------------------------------------------------ */
+int qpg_part3d_create(qpg_part3d *out, qpg_ctx ctx, double qbm, double dt, long npmax, int nz_total, int noff2, int nzp); /* init_part3d :98 */
+int qpg_part3d_destroy(qpg_part3d p);
+int qpg_part3d_upload(qpg_part3d p, const double *x, const double *pm, const double *q, long npp);
+int qpg_part3d_download(qpg_part3d p, double *x, double *pm, double *q, long *npp);              /* synchronises */
+int qpg_part3d_qdeposit(qpg_part3d p, qpg_field q);                                              /* qdeposit_part3d :221 (into q%f2) */
+int qpg_part3d_push(qpg_part3d p, int push_type, qpg_field ef, qpg_field bf);                    /* push_reduced :477 / push_boris :358 */
+int qpg_part3d_update_bound(qpg_part3d p);                                                       /* update_bound_part3d :640 */
+/* forward xi hand-off of beam/part3d_comm.f03:278-314 + pack_particles('pipeline') :685-745:
+ * pack particles with xi >= upper slab edge into dev_buf (7 doubles each, count in slot 7*cap), remove them
+ * ("fill the holes inversely"); unpack appends.  cap = qpg_part3d_wire_cap(). */
+int qpg_part3d_pack_forward(qpg_part3d p, double *dev_buf);
+int qpg_part3d_unpack(qpg_part3d p, const double *dev_buf);
+long qpg_part3d_wire_cap(qpg_part3d p);
+
+/* ------------------------------------------------------------------------------------------ */
+/* fused fast path: the whole `do j = 1, nstep2d` body of simulation_class.f03:342-469 on the  */
+/* device (one species, one beam set), incl. the predictor-corrector loop with a device-side   */
+/* convergence test.  Same arithmetic as the per-routine entry points above.                    */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct {
+    int nr, nz_total, noff2, nzp, max_mode, field_boundary, iter_max, sort_freq;
+    double dr, dxi, dt, iter_reltol, iter_abstol, relax_fac;
+    double sp_qbm;            /* species q/m */
+    long sp_npmax;
+    int beam_push_type, beam_evol;
+    double beam_qbm;
+    long beam_npmax;
+    int use_graph;            /* capture the slice body in a CUDA graph */
+} qpg_sim_params;
+
+int qpg_sim_create(qpg_sim *out, int device, void *cuda_stream, const qpg_sim_params *prm);
+int qpg_sim_destroy(qpg_sim s);
+qpg_ctx qpg_sim_ctx(qpg_sim s);
+/* object access so the host (Fortran shim / tests) can reach the same objects through the per-routine API.
+ * names: psi e b e_spe b_spe e_beam b_beam cu amu acu dcu q_spe q_beam spe_q spe_qn beam_q */
+qpg_field qpg_sim_field(qpg_sim s, const char *name);
+qpg_part2d qpg_sim_species(qpg_sim s);
+qpg_part3d qpg_sim_beam(qpg_sim s);
+/* species2d%new / %renew (species2d_class.f03:73,154): upload lattice, deposit, build qn */
+int qpg_sim_init_species(qpg_sim s, const double *x, const double *pm, const double *gamma, const double *psi,
+                         const double *q, long npp);
+/* beam3d%qdp (beam3d_class.f03:193-221) split around its two pipeline calls:
+ *   qdp_begin : this%q%as(0)                        [caller: unpack upstream guard slice into beam_q slice 1, add]
+ *   qdp_end   : part%qdeposit(this%q)               [caller: pack beam_q slice nzp+1 and send it downstream]      */
+int qpg_sim_beam_qdp_begin(qpg_sim s);
+int qpg_sim_beam_qdp_end(qpg_sim s);
+/* simulation_class.f03:299-331 minus the MPI calls: q_beam = beam_q, q_spe = 0, zero b e b_spe e_spe psi cu acu amu.
+ * [caller, stage > 0: unpack cu and b_spe (slice 0) and the plasma particles received from upstream] */
+int qpg_sim_begin_step(qpg_sim s);
+/* run slices j0..j1 (1-based, inclusive) of this slab: simulation_class.f03:342-469 */
+int qpg_sim_run_slices(qpg_sim s, int j0, int j1);
+/* simulation_class.f03:489-493: beam push + update_bound (E,B guard slice nzp+1 already unpacked by the caller) */
+int qpg_sim_beam_push(qpg_sim s);
+/* simulation_class.f03:498-501 species%renew from the device snapshot of the injected lattice */
+int qpg_sim_renew(qpg_sim s);
+/* counters since creation: particle-slice updates, PC iterations, slices (synchronises) */
+int qpg_sim_stats(qpg_sim s, long *updates, long *pc_iters, long *slices);
+/* switch the slice body between CUDA-graph replay (1) and plain stream launches (0, needed for per-kernel tprof) */
+int qpg_sim_set_graph(qpg_sim s, int use_graph);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,435 @@
+"""ctypes binding of libqpadb200.so (include/qpad_b200.h) -- the same C-ABI a Fortran ISO_C_BINDING shim binds.
+
+Thin object wrappers (Ctx, Field, Part2d, Part3d, Sim) whose method names follow the reference's type-bound
+procedures (species/part2d_class.f03:61-81, fields/field_class.f03, beam/part3d_class.f03:71-84).  numpy arrays use
+the reference's host layouts (see the header).  There is NO CPU fallback: if the shared library is missing, or no
+CUDA device is present, construction raises.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libqpadb200.so")
+
+BND_ZERO, BND_OPEN = 2, 3
+PUSH2_STD, PUSH2_ROBUST = 0, 1
+PUSH3_REDUCED, PUSH3_BORIS = 1, 2
+COPY_1TO2, COPY_2TO1 = 0, 1
+CONV_RECORD, CONV_COMPARE = 0, 1
+
+
+class QpadError(RuntimeError):
+    pass
+
+
+class SimParams(C.Structure):
+    _fields_ = [("nr", C.c_int), ("nz_total", C.c_int), ("noff2", C.c_int), ("nzp", C.c_int), ("max_mode", C.c_int),
+                ("field_boundary", C.c_int), ("iter_max", C.c_int), ("sort_freq", C.c_int),
+                ("dr", C.c_double), ("dxi", C.c_double), ("dt", C.c_double), ("iter_reltol", C.c_double),
+                ("iter_abstol", C.c_double), ("relax_fac", C.c_double),
+                ("sp_qbm", C.c_double), ("sp_npmax", C.c_long),
+                ("beam_push_type", C.c_int), ("beam_evol", C.c_int), ("beam_qbm", C.c_double), ("beam_npmax", C.c_long),
+                ("use_graph", C.c_int)]
+
+
+_lib = None
+_vp, _i, _l, _d = C.c_void_p, C.c_int, C.c_long, C.c_double
+_pd = C.POINTER(C.c_double)
+_pl = C.POINTER(C.c_long)
+_pi = C.POINTER(C.c_int)
+
+# name -> (restype, argtypes); mirrors include/qpad_b200.h one to one
+SIGNATURES = {
+    "qpg_last_error": (C.c_char_p, []),
+    "qpg_version": (_i, []),
+    "qpg_ctx_create": (_i, [C.POINTER(_vp), _i, _vp, _i, _i, _d, _d, _i, _d]),
+    "qpg_ctx_destroy": (_i, [_vp]),
+    "qpg_ctx_sync": (_i, [_vp]),
+    "qpg_tprof_enable": (_i, [_vp, _i]),
+    "qpg_tprof_reset": (_i, [_vp]),
+    "qpg_tprof_get": (_i, [_vp, C.c_char_p, _pd, _pl]),
+    "qpg_launch_count": (_l, [_vp]),
+    "qpg_field_create": (_i, [C.POINTER(_vp), _vp, _i, _i, _i]),
+    "qpg_field_destroy": (_i, [_vp]),
+    "qpg_field_dim": (_i, [_vp]),
+    "qpg_field_fill": (_i, [_vp, _d]),
+    "qpg_field_fill_f2": (_i, [_vp, _d]),
+    "qpg_field_copy": (_i, [_vp, _vp]),
+    "qpg_field_copy_slice": (_i, [_vp, _i, _i]),
+    "qpg_field_add": (_i, [_vp, _vp]),
+    "qpg_field_add3": (_i, [_vp, _vp, _vp]),
+    "qpg_field_add_dim": (_i, [_vp, _vp, _i, _pi, _pi]),
+    "qpg_field_add_f2": (_i, [_vp, _vp]),
+    "qpg_field_scale": (_i, [_vp, _d]),
+    "qpg_field_smooth": (_i, [_vp, _i, _i]),
+    "qpg_field_upload_f1": (_i, [_vp, _vp]),
+    "qpg_field_download_f1": (_i, [_vp, _vp]),
+    "qpg_field_upload_f2": (_i, [_vp, _vp]),
+    "qpg_field_download_f2": (_i, [_vp, _vp]),
+    "qpg_field_pack": (_i, [_vp, _i, _vp]),
+    "qpg_field_unpack": (_i, [_vp, _i, _vp, _i]),
+    "qpg_field_wire_count": (_l, [_vp]),
+    "qpg_field_lineout": (_i, [_vp, _i, _i, _i, _vp]),
+    "qpg_solve_psi": (_i, [_vp, _vp, _vp]),
+    "qpg_solve_bt": (_i, [_vp, _vp, _vp]),
+    "qpg_solve_bz": (_i, [_vp, _vp, _vp]),
+    "qpg_solve_bt_iter": (_i, [_vp, _vp, _vp, _vp]),
+    "qpg_solve_ez": (_i, [_vp, _vp, _vp]),
+    "qpg_solve_et": (_i, [_vp, _vp, _vp, _vp]),
+    "qpg_solve_et_beam": (_i, [_vp, _vp, _vp]),
+    "qpg_solve_djdxi": (_i, [_vp, _vp, _vp, _vp]),
+    "qpg_bperp_residual": (_i, [_vp, _vp, _i, _i, _pd, _pd]),
+    "qpg_part2d_create": (_i, [C.POINTER(_vp), _vp, _d, _l]),
+    "qpg_part2d_destroy": (_i, [_vp]),
+    "qpg_part2d_upload": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _l]),
+    "qpg_part2d_download": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _pl]),
+    "qpg_part2d_npp": (_i, [_vp, _pl]),
+    "qpg_part2d_snapshot": (_i, [_vp]),
+    "qpg_part2d_renew": (_i, [_vp]),
+    "qpg_part2d_qdeposit": (_i, [_vp, _vp]),
+    "qpg_part2d_amjdeposit": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _d]),
+    "qpg_part2d_push_u": (_i, [_vp, _i, _vp, _vp, _d]),
+    "qpg_part2d_push_x": (_i, [_vp, _d]),
+    "qpg_part2d_update_bound": (_i, [_vp]),
+    "qpg_part2d_sort": (_i, [_vp]),
+    "qpg_part2d_sort_index": (_i, [_vp, _vp, _vp]),
+    "qpg_part2d_pack": (_i, [_vp, _vp]),
+    "qpg_part2d_unpack": (_i, [_vp, _vp]),
+    "qpg_part2d_wire_count": (_l, [_vp]),
+    "qpg_part3d_create": (_i, [C.POINTER(_vp), _vp, _d, _d, _l, _i, _i, _i]),
+    "qpg_part3d_destroy": (_i, [_vp]),
+    "qpg_part3d_upload": (_i, [_vp, _vp, _vp, _vp, _l]),
+    "qpg_part3d_download": (_i, [_vp, _vp, _vp, _vp, _pl]),
+    "qpg_part3d_qdeposit": (_i, [_vp, _vp]),
+    "qpg_part3d_push": (_i, [_vp, _i, _vp, _vp]),
+    "qpg_part3d_update_bound": (_i, [_vp]),
+    "qpg_part3d_pack_forward": (_i, [_vp, _vp]),
+    "qpg_part3d_unpack": (_i, [_vp, _vp]),
+    "qpg_part3d_wire_cap": (_l, [_vp]),
+    "qpg_sim_create": (_i, [C.POINTER(_vp), _i, _vp, C.POINTER(SimParams)]),
+    "qpg_sim_destroy": (_i, [_vp]),
+    "qpg_sim_ctx": (_vp, [_vp]),
+    "qpg_sim_field": (_vp, [_vp, C.c_char_p]),
+    "qpg_sim_species": (_vp, [_vp]),
+    "qpg_sim_beam": (_vp, [_vp]),
+    "qpg_sim_init_species": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _l]),
+    "qpg_sim_beam_qdp_begin": (_i, [_vp]),
+    "qpg_sim_beam_qdp_end": (_i, [_vp]),
+    "qpg_sim_begin_step": (_i, [_vp]),
+    "qpg_sim_run_slices": (_i, [_vp, _i, _i]),
+    "qpg_sim_beam_push": (_i, [_vp]),
+    "qpg_sim_renew": (_i, [_vp]),
+    "qpg_sim_stats": (_i, [_vp, _pl, _pl, _pl]),
+    "qpg_sim_set_graph": (_i, [_vp, _i]),
+}
+
+
+def load():
+    """Load libqpadb200.so (no fallback).  Safe without a GPU: only symbols are resolved."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise QpadError(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    _lib = lib
+    return lib
+
+
+def _chk(rc):
+    if rc != 0:
+        raise QpadError(f"libqpadb200 error {rc}: {load().qpg_last_error().decode()}")
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class Ctx:
+    def __init__(self, nr, max_mode, dr, dxi, field_boundary=BND_OPEN, relax_fac=-1.0, device=0, stream=None, handle=None):
+        self.L = load()
+        self.nr, self.max_mode, self.P, self.dr, self.dxi = nr, max_mode, 2 * max_mode + 1, dr, dxi
+        self._own = handle is None
+        if handle is None:
+            h = _vp()
+            _chk(self.L.qpg_ctx_create(C.byref(h), device, stream, nr, max_mode, dr, dxi, field_boundary, relax_fac))
+            handle = h.value
+        self.h = handle
+
+    def close(self):
+        if getattr(self, "h", None) and self._own:
+            self.L.qpg_ctx_destroy(self.h)
+        self.h = None
+
+    __del__ = close
+
+    def sync(self):
+        _chk(self.L.qpg_ctx_sync(self.h))
+
+    def launch_count(self):
+        return self.L.qpg_launch_count(self.h)
+
+    def tprof_enable(self, on=True):
+        _chk(self.L.qpg_tprof_enable(self.h, int(on)))
+
+    def tprof_reset(self):
+        _chk(self.L.qpg_tprof_reset(self.h))
+
+    def tprof_get(self, event):
+        ms, n = _d(), _l()
+        _chk(self.L.qpg_tprof_get(self.h, event.encode(), C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    # field solves, named like the reference generics
+    def solve_psi(self, q, psi): _chk(self.L.qpg_solve_psi(self.h, q.h, psi.h))
+    def solve_bt(self, qb, b): _chk(self.L.qpg_solve_bt(self.h, qb.h, b.h))
+    def solve_bz(self, cu, b): _chk(self.L.qpg_solve_bz(self.h, cu.h, b.h))
+    def solve_bt_iter(self, dcu, cu, b): _chk(self.L.qpg_solve_bt_iter(self.h, dcu.h, cu.h, b.h))
+    def solve_ez(self, cu, e): _chk(self.L.qpg_solve_ez(self.h, cu.h, e.h))
+    def solve_et(self, b, psi, e): _chk(self.L.qpg_solve_et(self.h, b.h, psi.h, e.h))
+    def solve_et_beam(self, b, e): _chk(self.L.qpg_solve_et_beam(self.h, b.h, e.h))
+    def solve_djdxi(self, acu, amu, dcu): _chk(self.L.qpg_solve_djdxi(self.h, acu.h, amu.h, dcu.h))
+
+    def convergence_tester(self, fld, dim, op):
+        rel, ab = _d(), _d()
+        _chk(self.L.qpg_bperp_residual(self.h, fld.h, dim, op, C.byref(rel), C.byref(ab)))
+        return rel.value, ab.value
+
+
+class Field:
+    def __init__(self, ctx, dim, nzp=0, has_2d=False, handle=None):
+        self.ctx, self.L, self.dim, self.nzp, self.has_2d = ctx, ctx.L, dim, nzp, has_2d
+        self._own = handle is None
+        if handle is None:
+            h = _vp()
+            _chk(self.L.qpg_field_create(C.byref(h), ctx.h, dim, nzp, int(has_2d)))
+            handle = h.value
+        self.h = handle
+
+    def close(self):
+        if getattr(self, "h", None) and self._own and self.ctx.h:
+            self.L.qpg_field_destroy(self.h)
+        self.h = None
+
+    __del__ = close
+
+    def fill(self, v=0.0): _chk(self.L.qpg_field_fill(self.h, v))
+    def fill_f2(self, v=0.0): _chk(self.L.qpg_field_fill_f2(self.h, v))
+    def copy_to(self, dst): _chk(self.L.qpg_field_copy(self.h, dst.h))
+    def copy_slice(self, idx, direction): _chk(self.L.qpg_field_copy_slice(self.h, idx, direction))
+    def add_to(self, b): _chk(self.L.qpg_field_add(self.h, b.h))
+    def scale(self, s): _chk(self.L.qpg_field_scale(self.h, s))
+    def smooth(self, order, kind): _chk(self.L.qpg_field_smooth(self.h, order, kind))
+
+    def add_dim_to(self, b, adim, bdim):
+        a1 = (C.c_int * len(adim))(*adim)
+        b1 = (C.c_int * len(bdim))(*bdim)
+        _chk(self.L.qpg_field_add_dim(self.h, b.h, len(adim), a1, b1))
+
+    def add_f2_to(self, b): _chk(self.L.qpg_field_add_f2(self.h, b.h))
+
+    @staticmethod
+    def add3(a1, a2, a3): _chk(a1.L.qpg_field_add3(a1.h, a2.h, a3.h))
+
+    def upload(self, f1):
+        f1 = _f64(f1)
+        assert f1.shape == (self.ctx.P, self.ctx.nr + 2, self.dim), f1.shape
+        _chk(self.L.qpg_field_upload_f1(self.h, _ptr(f1)))
+
+    def download(self):
+        out = np.zeros((self.ctx.P, self.ctx.nr + 2, self.dim))
+        _chk(self.L.qpg_field_download_f1(self.h, _ptr(out)))
+        return out
+
+    def upload_f2(self, f2):
+        f2 = _f64(f2)
+        assert f2.shape == (self.ctx.P, self.nzp + 1, self.ctx.nr + 2, self.dim), f2.shape
+        _chk(self.L.qpg_field_upload_f2(self.h, _ptr(f2)))
+
+    def download_f2(self):
+        out = np.zeros((self.ctx.P, self.nzp + 1, self.ctx.nr + 2, self.dim))
+        _chk(self.L.qpg_field_download_f2(self.h, _ptr(out)))
+        return out
+
+    def lineout(self, comp, plane=0, node=1):
+        out = np.zeros(self.nzp)
+        _chk(self.L.qpg_field_lineout(self.h, comp, plane, node, _ptr(out)))
+        return out
+
+    def wire_count(self): return self.L.qpg_field_wire_count(self.h)
+    def pack(self, slice_idx, dev_ptr): _chk(self.L.qpg_field_pack(self.h, slice_idx, dev_ptr))
+    def unpack(self, slice_idx, dev_ptr, add=False): _chk(self.L.qpg_field_unpack(self.h, slice_idx, dev_ptr, int(add)))
+
+
+class Part2d:
+    def __init__(self, ctx, qbm, npmax, handle=None):
+        self.ctx, self.L, self.qbm, self.npmax = ctx, ctx.L, qbm, npmax
+        self._own = handle is None
+        if handle is None:
+            h = _vp()
+            _chk(self.L.qpg_part2d_create(C.byref(h), ctx.h, qbm, npmax))
+            handle = h.value
+        self.h = handle
+
+    def close(self):
+        if getattr(self, "h", None) and self._own and self.ctx.h:
+            self.L.qpg_part2d_destroy(self.h)
+        self.h = None
+
+    __del__ = close
+
+    def upload(self, x, p, gamma, psi, q):
+        x, p, gamma, psi, q = map(_f64, (x, p, gamma, psi, q))
+        _chk(self.L.qpg_part2d_upload(self.h, _ptr(x), _ptr(p), _ptr(gamma), _ptr(psi), _ptr(q), len(q)))
+
+    def npp(self):
+        n = _l()
+        _chk(self.L.qpg_part2d_npp(self.h, C.byref(n)))
+        return n.value
+
+    def download(self):
+        n = self.npp()
+        x, p = np.zeros((n, 2)), np.zeros((n, 3))
+        g, psi, q = np.zeros(n), np.zeros(n), np.zeros(n)
+        m = _l()
+        _chk(self.L.qpg_part2d_download(self.h, _ptr(x), _ptr(p), _ptr(g), _ptr(psi), _ptr(q), C.byref(m)))
+        assert m.value == n
+        return x, p, g, psi, q
+
+    def snapshot(self): _chk(self.L.qpg_part2d_snapshot(self.h))
+    def renew(self): _chk(self.L.qpg_part2d_renew(self.h))
+    def qdeposit(self, q): _chk(self.L.qpg_part2d_qdeposit(self.h, q.h))
+
+    def amjdeposit_robust(self, ef, bf, cu, amu, dcu, dt):
+        _chk(self.L.qpg_part2d_amjdeposit(self.h, PUSH2_ROBUST, ef.h, bf.h, cu.h, amu.h, dcu.h, dt))
+
+    def push_u_robust(self, ef, bf, dt): _chk(self.L.qpg_part2d_push_u(self.h, PUSH2_ROBUST, ef.h, bf.h, dt))
+    def push_x(self, dt): _chk(self.L.qpg_part2d_push_x(self.h, dt))
+    def update_bound(self): _chk(self.L.qpg_part2d_update_bound(self.h))
+    def sort(self): _chk(self.L.qpg_part2d_sort(self.h))
+
+    def sort_index(self):
+        n = self.npp()
+        ix, ip = np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int32)
+        _chk(self.L.qpg_part2d_sort_index(self.h, _ptr(ix), _ptr(ip)))
+        return ix, ip
+
+    def wire_count(self): return self.L.qpg_part2d_wire_count(self.h)
+    def pack(self, dev_ptr): _chk(self.L.qpg_part2d_pack(self.h, dev_ptr))
+    def unpack(self, dev_ptr): _chk(self.L.qpg_part2d_unpack(self.h, dev_ptr))
+
+
+class Part3d:
+    def __init__(self, ctx, qbm, dt, npmax, nz_total, noff2, nzp, handle=None):
+        self.ctx, self.L = ctx, ctx.L
+        self._own = handle is None
+        if handle is None:
+            h = _vp()
+            _chk(self.L.qpg_part3d_create(C.byref(h), ctx.h, qbm, dt, npmax, nz_total, noff2, nzp))
+            handle = h.value
+        self.h = handle
+
+    def close(self):
+        if getattr(self, "h", None) and self._own and self.ctx.h:
+            self.L.qpg_part3d_destroy(self.h)
+        self.h = None
+
+    __del__ = close
+
+    def upload(self, x, p, q):
+        x, p, q = map(_f64, (x, p, q))
+        _chk(self.L.qpg_part3d_upload(self.h, _ptr(x), _ptr(p), _ptr(q), len(q)))
+
+    def download(self):
+        n = _l()
+        _chk(self.L.qpg_part3d_download(self.h, None, None, None, C.byref(n)))
+        x, p, q = np.zeros((n.value, 3)), np.zeros((n.value, 3)), np.zeros(n.value)
+        if n.value:
+            _chk(self.L.qpg_part3d_download(self.h, _ptr(x), _ptr(p), _ptr(q), C.byref(n)))
+        return x, p, q
+
+    def qdeposit(self, q): _chk(self.L.qpg_part3d_qdeposit(self.h, q.h))
+    def push(self, push_type, ef, bf): _chk(self.L.qpg_part3d_push(self.h, push_type, ef.h, bf.h))
+    def update_bound(self): _chk(self.L.qpg_part3d_update_bound(self.h))
+    def wire_cap(self): return self.L.qpg_part3d_wire_cap(self.h)
+    def pack_forward(self, dev_ptr): _chk(self.L.qpg_part3d_pack_forward(self.h, dev_ptr))
+    def unpack(self, dev_ptr): _chk(self.L.qpg_part3d_unpack(self.h, dev_ptr))
+
+
+class Sim:
+    """Fused slice loop (qpg_sim_*): simulation_class.f03:294-512 for one xi slab on one GPU."""
+
+    FIELD_DIMS = dict(psi=1, e=3, b=3, e_spe=3, b_spe=3, e_beam=3, b_beam=3, cu=3, amu=3, acu=2, dcu=2, q_spe=1, q_beam=1,
+                      spe_q=1, spe_qn=1, spe_cu=3, spe_dcu=2, spe_amu=3, beam_q=1)
+    HAS_2D = {"psi", "e", "b", "e_spe", "b_spe", "e_beam", "b_beam", "cu", "q_spe", "q_beam", "spe_q", "beam_q"}
+
+    def __init__(self, nr, nz, max_mode, rmax, zmin, zmax, dt, sp_qbm=-1.0, sp_npmax=0, beam_qbm=-1.0, beam_npmax=32,
+                 beam_push_type=PUSH3_REDUCED, beam_evol=1, iter_max=1, iter_reltol=1e-3, iter_abstol=1e-3, relax_fac=-1.0,
+                 field_boundary=BND_OPEN, sort_freq=0, use_graph=0, noff2=0, nzp=None, device=0, stream=None):
+        self.L = load()
+        nzp = nz if nzp is None else nzp
+        prm = SimParams(nr=nr, nz_total=nz, noff2=noff2, nzp=nzp, max_mode=max_mode, field_boundary=field_boundary,
+                        iter_max=iter_max, sort_freq=sort_freq, dr=rmax / nr, dxi=(zmax - zmin) / nz, dt=dt,
+                        iter_reltol=iter_reltol, iter_abstol=iter_abstol, relax_fac=relax_fac, sp_qbm=sp_qbm,
+                        sp_npmax=sp_npmax, beam_push_type=beam_push_type, beam_evol=beam_evol, beam_qbm=beam_qbm,
+                        beam_npmax=beam_npmax, use_graph=use_graph)
+        self.prm = prm
+        h = _vp()
+        _chk(self.L.qpg_sim_create(C.byref(h), device, stream, C.byref(prm)))
+        self.h = h.value
+        self.nr, self.nz, self.nzp, self.noff2, self.max_mode = nr, nz, nzp, noff2, max_mode
+        self.ctx = Ctx(nr, max_mode, prm.dr, prm.dxi, handle=self.L.qpg_sim_ctx(self.h))
+        self.species = Part2d(self.ctx, sp_qbm, sp_npmax, handle=self.L.qpg_sim_species(self.h))
+        self.beam = Part3d(self.ctx, beam_qbm, dt, beam_npmax, nz, noff2, nzp, handle=self.L.qpg_sim_beam(self.h))
+        self._fields = {}
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.qpg_sim_destroy(self.h)
+            self.ctx.h = None
+        self.h = None
+
+    __del__ = close
+
+    def field(self, name):
+        if name not in self._fields:
+            fh = self.L.qpg_sim_field(self.h, name.encode())
+            if not fh:
+                raise KeyError(name)
+            self._fields[name] = Field(self.ctx, self.FIELD_DIMS[name], self.nzp, name in self.HAS_2D, handle=fh)
+        return self._fields[name]
+
+    def init_species(self, x, p, gamma, psi, q):
+        x, p, gamma, psi, q = map(_f64, (x, p, gamma, psi, q))
+        _chk(self.L.qpg_sim_init_species(self.h, _ptr(x), _ptr(p), _ptr(gamma), _ptr(psi), _ptr(q), len(q)))
+
+    def beam_qdp_begin(self): _chk(self.L.qpg_sim_beam_qdp_begin(self.h))
+    def beam_qdp_end(self): _chk(self.L.qpg_sim_beam_qdp_end(self.h))
+    def begin_step(self): _chk(self.L.qpg_sim_begin_step(self.h))
+    def run_slices(self, j0, j1): _chk(self.L.qpg_sim_run_slices(self.h, j0, j1))
+    def beam_push(self): _chk(self.L.qpg_sim_beam_push(self.h))
+    def renew(self): _chk(self.L.qpg_sim_renew(self.h))
+    def set_graph(self, on): _chk(self.L.qpg_sim_set_graph(self.h, int(on)))
+
+    def stats(self):
+        u, it, sl = _l(), _l(), _l()
+        _chk(self.L.qpg_sim_stats(self.h, C.byref(u), C.byref(it), C.byref(sl)))
+        return u.value, it.value, sl.value
+
+    def step3d(self):
+        """One 3D step of a single-stage run (simulation_class.f03:294-501 with nodes = [1,1])."""
+        self.beam_qdp_begin()
+        self.beam_qdp_end()
+        self.begin_step()
+        self.run_slices(1, self.nzp)
+        self.beam_push()
+        self.renew()

@@ -1,0 +1,5 @@
+// lib.cu -- unity translation unit of libqpadb200.so (kernels in one module; no relocatable device code needed)
+#include "fields.cu"
+#include "particles.cu"
+#include "beam.cu"
+#include "sim.cu"

@@ -1,0 +1,806 @@
+// particles.cu -- part2d: the per-slice plasma particle kernels (species/part2d_class.f03, interp_part2d.f03).
+//
+// Design:
+//  * SoA fp64 planes, one particle per thread, fully coalesced 8-byte loads/stores.
+//  * gathers read the node-interleaved field images through the read-only path; particles that are close in the
+//    array are close in r (lattice order / counting sort), so a warp reads one or two 72-byte node records.
+//  * deposits never issue one atomic per particle: a warp whose lanes share a radial cell reduce-scatters its
+//    2*8*P (amjdeposit) or 2*P (qdeposit) partial sums with a halving butterfly (47 shuffles for M=1 instead of
+//    240 for a plain per-value butterfly) and then issues ONE fp64 RED per (cell, component) from distinct lanes.
+//    Warps spanning up to 4 cells repeat the butterfly per cell; only scattered warps fall back to per-lane REDs.
+//  * cell index / boundary tests use non-contracted IEEE ops so indices match the reference bit for bit
+//    (pos = sqrt(x1*x1 + x2*x2) * (1/dr), interp_part2d.f03:44-59).
+#include "common.cuh"
+
+#ifndef FULL
+#define FULL 0xffffffffu
+#endif
+#define PT_BLOCK 256
+
+struct PartView {
+    double *x1, *x2, *p1, *p2, *p3, *gamma, *psi, *q;
+    const int *d_npp;
+};
+static PartView view_of(qpg_part2d p) { PartView v{p->x1, p->x2, p->p1, p->p2, p->p3, p->gamma, p->psi, p->q, p->d_npp}; return v; }
+
+struct Interp { double c, s, w0, w1; int idx; };
+
+// species/interp_part2d.f03:28-65 gen_interp_info
+__device__ __forceinline__ Interp interp_info(double x1, double x2, double idr)
+{
+    Interp it;
+    double r = __dsqrt_rn(__dadd_rn(__dmul_rn(x1, x1), __dmul_rn(x2, x2)));
+    it.c = __ddiv_rn(x1, r);
+    it.s = __ddiv_rn(x2, r);
+    double pos = __dmul_rn(r, idr);
+    int ip = (int)pos;
+    it.idx = ip + 1;
+    double f = pos - (double)ip;
+    it.w0 = 1.0 - f;
+    it.w1 = f;
+    return it;
+}
+
+// species/interp_part2d.f03:67-109 interp_field (3-vector) on the node-interleaved image f[(node*P + pl)*3 + c]
+template <int M>
+__device__ __forceinline__ void gather3(const double *__restrict__ f, const Interp &it, double out[3])
+{
+    constexpr int P = 2 * M + 1;
+    const double *n0 = f + (size_t)it.idx * (P * 3);
+    const double *n1 = n0 + P * 3;
+#pragma unroll
+    for (int c = 0; c < 3; c++) out[c] = __ldg(n0 + c) * it.w0;
+#pragma unroll
+    for (int c = 0; c < 3; c++) out[c] = fma(__ldg(n1 + c), it.w1, out[c]);
+    double phr = 1.0, phi = 0.0;
+#pragma unroll
+    for (int m = 1; m <= M; m++) {
+        double t = phr * it.c - phi * it.s;
+        phi = phr * it.s + phi * it.c;
+        phr = t;
+        const double pr2 = 2.0 * phr, pi2 = 2.0 * phi;
+#pragma unroll
+        for (int c = 0; c < 3; c++) out[c] = fma(__ldg(n0 + (2 * m - 1) * 3 + c) * pr2 - __ldg(n0 + (2 * m) * 3 + c) * pi2, it.w0, out[c]);
+#pragma unroll
+        for (int c = 0; c < 3; c++) out[c] = fma(__ldg(n1 + (2 * m - 1) * 3 + c) * pr2 - __ldg(n1 + (2 * m) * 3 + c) * pi2, it.w1, out[c]);
+    }
+}
+
+// ---- warp reduce-scatter ------------------------------------------------------------------
+// Sum N per-lane values over the 32 lanes; afterwards lane L holds the totals of the contiguous index range
+// [base, base+cnt) in v[0..cnt).  Halving butterfly: N/2 + N/4 + ... shuffles instead of 5*N.
+template <int N, int OFF>
+__device__ __forceinline__ void rs_step(double *v, int lane, int &base, int &cnt)
+{
+    constexpr int H = (N + 1) / 2;
+    const bool up = (lane & OFF) != 0;
+#pragma unroll
+    for (int i = 0; i < H; i++) {
+        double a = v[i];
+        double b = (H + i < N) ? v[H + i] : 0.0;
+        double keep = up ? b : a, send = up ? a : b;
+        v[i] = keep + __shfl_xor_sync(FULL, send, OFF);
+    }
+    if (up) { base += H; cnt = cnt - H; if (cnt < 0) cnt = 0; }
+    else if (cnt > H) cnt = H;
+    if constexpr (OFF > 1) rs_step<H, OFF / 2>(v, lane, base, cnt);
+}
+// number of values a lane may hold after 5 halvings
+__host__ __device__ constexpr int final_count(int n) { for (int k = 0; k < 5; k++) n = (n + 1) / 2; return n; }
+
+// deposit the H=NV/2 products X[i] (already multiplied by membership) weighted by w0 / w1 into
+// acc[cell*H + k] (k in [0,H): this cell, [H,2H): next cell)
+template <int H>
+__device__ __forceinline__ void warp_deposit_group(const double *X, double w0, double w1, double *acc_cell, int lane)
+{
+    double v[H];
+    const bool up = (lane & 16) != 0;
+#pragma unroll
+    for (int i = 0; i < H; i++) {
+        double a = w0 * X[i], b = w1 * X[i];
+        double keep = up ? b : a, send = up ? a : b;
+        v[i] = keep + __shfl_xor_sync(FULL, send, 16);
+    }
+    int base = up ? H : 0, cnt = H;
+    rs_step<H, 8>(v, lane, base, cnt);
+    constexpr int NF = final_count(2 * H);
+#pragma unroll
+    for (int k = 0; k < NF; k++)
+        if (k < cnt) atomicAdd(acc_cell + base + k, v[k]);
+}
+
+// common tail of both deposit kernels.  X[H] = per-particle products (phase x value); key = cell or -1
+template <int H>
+__device__ __forceinline__ void warp_deposit(const double *X, double w0, double w1, int key, double *acc, int lane)
+{
+    const unsigned same = __match_any_sync(FULL, key);
+    const bool leader = key >= 0 && (__ffs(same) - 1 == lane);
+    unsigned leaders = __ballot_sync(FULL, leader);
+    const int ng = __popc(leaders);
+    if (ng == 0) return;
+    if (ng <= 4) {
+        while (leaders) {
+            const int l = __ffs(leaders) - 1;
+            leaders &= leaders - 1;
+            const int cell = __shfl_sync(FULL, key, l);
+            const bool mine = key == cell;
+            warp_deposit_group<H>(X, mine ? w0 : 0.0, mine ? w1 : 0.0, acc + (size_t)cell * H, lane);
+        }
+    } else if (key >= 0) {
+        double *a = acc + (size_t)key * H;
+#pragma unroll
+        for (int i = 0; i < H; i++) { atomicAdd(a + i, w0 * X[i]); atomicAdd(a + H + i, w1 * X[i]); }
+    }
+}
+
+// ---- qdeposit: species/part2d_class.f03:231-359 (accumulation part; axis rules live in FOP_QFIX) --------
+template <int M>
+__global__ void __launch_bounds__(PT_BLOCK) k_qdeposit(PartView pv, double *__restrict__ acc1, double idr)
+{
+    constexpr int P = 2 * M + 1;
+    const int npp = *pv.d_npp;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
+    if ((i & ~31) >= npp) return;
+    const bool valid = i < npp;
+    double X[P];
+    double w0 = 0.0, w1 = 0.0;
+    int key = -1;
+    if (valid) {
+        const double x1 = pv.x1[i], x2 = pv.x2[i], q = pv.q[i];
+        double pos = __dmul_rn(__dsqrt_rn(__dadd_rn(__dmul_rn(x1, x1), __dmul_rn(x2, x2))), idr);
+        // phase0 = cmplx(x1, -x2) / pos * idr   (part2d_class.f03:278)
+        const double c0 = x1 / pos * idr, s0 = -x2 / pos * idr;
+        int nn = (int)floor(pos);
+        double f = pos - (double)nn;
+        key = nn + 1;
+        w0 = 1.0 - f; w1 = f;
+        double phr = q, phi = 0.0;
+        X[0] = phr;
+#pragma unroll
+        for (int m = 1; m <= M; m++) {
+            double t = phr * c0 - phi * s0;
+            phi = phr * s0 + phi * c0;
+            phr = t;
+            X[2 * m - 1] = phr;
+            X[2 * m] = phi;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < P; k++) X[k] = 0.0;
+    }
+    warp_deposit<P>(X, w0, w1, key, acc1, lane);
+}
+
+// ---- amjdeposit_robust: species/part2d_class.f03:746-1010 ------------------------------------------------
+template <int M>
+__global__ void __launch_bounds__(PT_BLOCK) k_amjdeposit(PartView pv, const double *__restrict__ ef, const double *__restrict__ bf,
+                                                        double *__restrict__ acc8, double qbm, double dt, double idr,
+                                                        const int *__restrict__ skip_flag)
+{
+    constexpr int P = 2 * M + 1, H = 8 * P;
+    if (skip_flag && *skip_flag) return;
+    const int npp = *pv.d_npp;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
+    if ((i & ~31) >= npp) return;
+    const bool valid = i < npp;
+    double X[H];
+    double w0 = 0.0, w1 = 0.0;
+    int key = -1;
+    if (valid) {
+        const double x1 = pv.x1[i], x2 = pv.x2[i];
+        const double pp1 = pv.p1[i], pp2 = pv.p2[i], pp3 = pv.p3[i], q = pv.q[i];
+        const Interp it = interp_info(x1, x2, idr);
+        double ep[3], bp[3];
+        gather3<M>(ef, it, ep);
+        gather3<M>(bf, it, bp);
+        const double idt = 1.0 / dt, qtmh = 0.5 * qbm * dt;
+        const double wp0 = ep[0] - bp[1], wp1 = ep[1] + bp[0], wp2 = ep[2];
+        const double u00 = pp1 * it.c + pp2 * it.s, u01 = pp2 * it.c - pp1 * it.s, u02 = pp3;
+        double gam = sqrt(1.0 + u00 * u00 + u01 * u01 + u02 * u02);
+        const double qtmh1 = qtmh * gam / (gam - u02);
+        ep[0] *= qtmh1; ep[1] *= qtmh1; ep[2] *= qtmh1;
+        double ut0 = u00 + ep[0], ut1 = u01 + ep[1], ut2 = u02 + ep[2];
+        gam = sqrt(1.0 + ut0 * ut0 + ut1 * ut1 + ut2 * ut2);
+        const double qtmh2 = qtmh / (gam - ut2);
+        bp[0] *= qtmh2; bp[1] *= qtmh2; bp[2] *= qtmh2;
+        double u0 = ut0 + ut1 * bp[2] - ut2 * bp[1];
+        double u1 = ut1 + ut2 * bp[0] - ut0 * bp[2];
+        double u2 = ut2 + ut0 * bp[1] - ut1 * bp[0];
+        const double ostq = 2.0 / (1.0 + bp[0] * bp[0] + bp[1] * bp[1] + bp[2] * bp[2]);
+        bp[0] *= ostq; bp[1] *= ostq; bp[2] *= ostq;
+        ut0 = ut0 + u1 * bp[2] - u2 * bp[1];
+        ut1 = ut1 + u2 * bp[0] - u0 * bp[2];
+        ut2 = ut2 + u0 * bp[1] - u1 * bp[0];
+        u0 = ut0 + ep[0]; u1 = ut1 + ep[1]; u2 = ut2 + ep[2];
+        double du0 = idt * (u0 - u00), du1 = idt * (u1 - u01);
+        u0 = 0.5 * (u0 + u00); u1 = 0.5 * (u1 + u01); u2 = 0.5 * (u2 + u02);
+        const double g = sqrt(1.0 + u0 * u0 + u1 * u1 + u2 * u2);
+        const double ipsi = 1.0 / (g - u2);
+        pv.gamma[i] = g;
+        pv.psi[i] = (1.0 - 1.0 / ipsi) / qbm;
+        const double dpsi = qbm * (wp2 - (wp0 * u0 + wp1 * u1) * ipsi);
+        du0 = du0 + u0 * dpsi * ipsi;
+        du1 = du1 + u1 * dpsi * ipsi;
+        const double vals[8] = {u0, u1, u2, du0, du1, u0 * u0 * ipsi, u0 * u1 * ipsi, u1 * u1 * ipsi};
+        // phase = q*ipsi*(cos - i sin)^m
+        double phr = q * ipsi, phi = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) X[k] = phr * vals[k];
+#pragma unroll
+        for (int m = 1; m <= M; m++) {
+            double t = phr * it.c + phi * it.s;
+            phi = phi * it.c - phr * it.s;
+            phr = t;
+#pragma unroll
+            for (int k = 0; k < 8; k++) { X[(2 * m - 1) * 8 + k] = phr * vals[k]; X[(2 * m) * 8 + k] = phi * vals[k]; }
+        }
+        key = it.idx; w0 = it.w0; w1 = it.w1;
+    } else {
+#pragma unroll
+        for (int k = 0; k < H; k++) X[k] = 0.0;
+    }
+    warp_deposit<H>(X, w0, w1, key, acc8, lane);
+}
+
+// ---- push: push_u_robust :1879-1965, push_x :2221-2262, bound test of update_bound :2323-2348 --------------
+// mode bit0: push_u, bit1: push_x, bit2: flag particles with r >= edge in the bitmap
+template <int M>
+__global__ void __launch_bounds__(PT_BLOCK) k_push(PartView pv, const double *__restrict__ ef, const double *__restrict__ bf, double qbm,
+                                                  double dt, double idr, double edge, int mode, unsigned *__restrict__ outmask,
+                                                  int *__restrict__ d_nout)
+{
+    const int npp = *pv.d_npp;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
+    if ((i & ~31) >= npp) return;
+    const bool valid = i < npp;
+    bool out = false;
+    if (valid) {
+        double x1 = pv.x1[i], x2 = pv.x2[i];
+        double p1 = pv.p1[i], p2 = pv.p2[i], p3 = pv.p3[i], g;
+        if (mode & 1) {
+            const Interp it = interp_info(x1, x2, idr);
+            double ep[3], bp[3];
+            gather3<M>(ef, it, ep);
+            gather3<M>(bf, it, bp);
+            double t = ep[0] * it.c - ep[1] * it.s; ep[1] = ep[0] * it.s + ep[1] * it.c; ep[0] = t;
+            t = bp[0] * it.c - bp[1] * it.s; bp[1] = bp[0] * it.s + bp[1] * it.c; bp[0] = t;
+            const double qtmh = qbm * dt * 0.5;
+            double gam = sqrt(1.0 + p1 * p1 + p2 * p2 + p3 * p3);
+            const double qtmh1 = qtmh / (gam - p3), qtmh2 = qtmh1 * gam;
+            ep[0] *= qtmh2; ep[1] *= qtmh2; ep[2] *= qtmh2;
+            bp[0] *= qtmh1; bp[1] *= qtmh1; bp[2] *= qtmh1;
+            double ut0 = p1 + ep[0], ut1 = p2 + ep[1], ut2 = p3 + ep[2];
+            p1 = ut0 + ut1 * bp[2] - ut2 * bp[1];
+            p2 = ut1 + ut2 * bp[0] - ut0 * bp[2];
+            p3 = ut2 + ut0 * bp[1] - ut1 * bp[0];
+            const double ostq = 2.0 / (1.0 + bp[0] * bp[0] + bp[1] * bp[1] + bp[2] * bp[2]);
+            bp[0] *= ostq; bp[1] *= ostq; bp[2] *= ostq;
+            ut0 = ut0 + p2 * bp[2] - p3 * bp[1];
+            ut1 = ut1 + p3 * bp[0] - p1 * bp[2];
+            ut2 = ut2 + p1 * bp[1] - p2 * bp[0];
+            p1 = ut0 + ep[0]; p2 = ut1 + ep[1]; p3 = ut2 + ep[2];
+            g = sqrt(1.0 + p1 * p1 + p2 * p2 + p3 * p3);
+            pv.p1[i] = p1; pv.p2[i] = p2; pv.p3[i] = p3; pv.gamma[i] = g;
+        } else {
+            g = pv.gamma[i];
+        }
+        if (mode & 2) {
+            const double dtc = dt / (g - p3);
+            x1 = x1 + p1 * dtc;
+            x2 = x2 + p2 * dtc;
+            pv.x1[i] = x1; pv.x2[i] = x2;
+        }
+        if (mode & 4) {
+            const double pos = __dsqrt_rn(__dadd_rn(__dmul_rn(x1, x1), __dmul_rn(x2, x2)));
+            out = pos >= edge;
+        }
+    }
+    if (mode & 4) {
+        const unsigned bal = __ballot_sync(FULL, out);
+        if (lane == 0) {
+            outmask[i >> 5] = bal;
+            if (bal) atomicAdd(d_nout, __popc(bal));
+        }
+    }
+}
+
+// ---- compaction (update_bound_part2d :2307-2353 / pack_particles "fill the holes inversely") ---------------
+// One CTA.  K = n - nout survivors.  Head holes (flagged, index < K) are filled from tail survivors (not flagged,
+// index >= K).  The sequential swap-with-last loop of the reference yields: head holes in ASCENDING order receive
+// tail survivors in DESCENDING order (desc_holes = 0); pack_particles' inverse fill pairs DESCENDING holes with
+// DESCENDING tail survivors (desc_holes = 1).
+__device__ int block_excl_scan_int(int v, int *sm, int *total)
+{
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    int incl = v;
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += t; }
+    __syncthreads();
+    if (lane == 31) sm[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+        int t = lane < nw ? sm[lane] : 0, ti = t;
+        for (int o = 1; o < 32; o <<= 1) { int u = __shfl_up_sync(FULL, ti, o); if (lane >= o) ti += u; }
+        sm[lane] = ti - t;
+        if (lane == 31) sm[32] = ti;
+    }
+    __syncthreads();
+    int res = sm[w] + incl - v;
+    *total = sm[32];
+    __syncthreads();
+    return res;
+}
+
+__global__ void __launch_bounds__(1024, 1) k_compact(double *const *planes, int nplanes, int *d_npp, int *d_nout, unsigned *outmask, int *lists,
+                                                    int desc_holes)
+{
+    __shared__ int sm[40];
+    const int n = *d_npp, nout = *d_nout;
+    if (nout == 0) return;
+    const int K = n - nout, tid = threadIdx.x, nt = blockDim.x;
+    const int nwords = (n + 31) >> 5;
+    int *holes = lists, *surv = lists + nout;
+    // words are split into contiguous per-thread ranges so ranks are ordered
+    const int wpt = (nwords + nt - 1) / nt;
+    const int wbeg = min(tid * wpt, nwords), wend = min(wbeg + wpt, nwords);
+    int ch = 0, cs = 0;
+    for (int w = wbeg; w < wend; w++) {
+        unsigned bits = outmask[w];
+        const int lo = w << 5;
+        unsigned inrange = (lo + 32 <= n) ? FULL : ((1u << (n - lo)) - 1u);
+        bits &= inrange;
+        // head part of the word: indices < K
+        unsigned headmask = (lo + 32 <= K) ? FULL : (lo >= K ? 0u : ((1u << (K - lo)) - 1u));
+        ch += __popc(bits & headmask);
+        cs += __popc(~bits & inrange & ~headmask);
+    }
+    int toth, tots;
+    int oh = block_excl_scan_int(ch, sm, &toth);
+    int os = block_excl_scan_int(cs, sm, &tots);
+    for (int w = wbeg; w < wend; w++) {
+        unsigned bits = outmask[w];
+        const int lo = w << 5;
+        unsigned inrange = (lo + 32 <= n) ? FULL : ((1u << (n - lo)) - 1u);
+        bits &= inrange;
+        unsigned headmask = (lo + 32 <= K) ? FULL : (lo >= K ? 0u : ((1u << (K - lo)) - 1u));
+        unsigned hb = bits & headmask, sb = ~bits & inrange & ~headmask;
+        while (hb) { int b = __ffs(hb) - 1; hb &= hb - 1; holes[oh++] = lo + b; }
+        while (sb) { int b = __ffs(sb) - 1; sb &= sb - 1; surv[os++] = lo + b; }
+        outmask[w] = 0u;
+    }
+    __syncthreads();
+    // toth == tots by construction
+    for (int r = tid; r < toth; r += nt) {
+        const int dst = desc_holes ? holes[toth - 1 - r] : holes[r];
+        const int src = surv[tots - 1 - r];
+        for (int a = 0; a < nplanes; a++) planes[a][dst] = planes[a][src];
+    }
+    if (tid == 0) { *d_npp = K; *d_nout = 0; }
+}
+
+// ---- wire format (part2d_class.f03:2381-2388) ----------------------------------------------------------
+__global__ void k_pack2d(PartView pv, double *__restrict__ buf, long cap)
+{
+    const int npp = *pv.d_npp;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npp; i += gridDim.x * blockDim.x) {
+        double *r = buf + (size_t)8 * i;
+        r[0] = pv.x1[i]; r[1] = pv.x2[i]; r[2] = pv.p1[i]; r[3] = pv.p2[i]; r[4] = pv.p3[i]; r[5] = pv.gamma[i]; r[6] = pv.psi[i]; r[7] = pv.q[i];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) buf[(size_t)8 * cap] = (double)npp;
+}
+__global__ void k_unpack2d(PartView pv, int *d_npp_w, const double *__restrict__ buf, long cap)
+{
+    const int npp = (int)buf[(size_t)8 * cap];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npp; i += gridDim.x * blockDim.x) {
+        const double *r = buf + (size_t)8 * i;
+        pv.x1[i] = r[0]; pv.x2[i] = r[1]; pv.p1[i] = r[2]; pv.p2[i] = r[3]; pv.p3[i] = r[4]; pv.gamma[i] = r[5]; pv.psi[i] = r[6]; pv.q[i] = r[7];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *d_npp_w = npp;
+}
+
+// ---- counting sort (sort_module.f03:11-42 + part2d_class.f03:2498-2579) ---------------------------------
+// Reference: ip(i) = counter(ix(i)); counter(ix(i)) -= 1 in input order, i.e. within a cell the FIRST particle
+// gets the LAST slot (reverse-stable).  new_pos(i) = end(cell) - rank(i), rank = # earlier particles in that cell.
+// Tiles of SORT_TILE particles: (1) per-tile histogram, (2) scan over (cell-major, tile-minor), (3) ranks + scatter.
+#define SORT_TILE 1024
+__global__ void __launch_bounds__(256) k_sort_hist(PartView pv, double idr, int nr, int *__restrict__ keys, int *__restrict__ hist, int ntiles)
+{
+    extern __shared__ int sh[];  // nr+1 counters
+    const int npp = *pv.d_npp, tile = blockIdx.x;
+    for (int k = threadIdx.x; k <= nr; k += blockDim.x) sh[k] = 0;
+    __syncthreads();
+    const int beg = tile * SORT_TILE, end = min(beg + SORT_TILE, npp);
+    for (int i = beg + threadIdx.x; i < end; i += blockDim.x) {
+        const double x1 = pv.x1[i], x2 = pv.x2[i];
+        double pos = __dmul_rn(__dsqrt_rn(__dadd_rn(__dmul_rn(x1, x1), __dmul_rn(x2, x2))), idr);
+        int key = (int)floor(pos) + 1;
+        key = min(max(key, 1), nr);
+        keys[i] = key;
+        atomicAdd(&sh[key], 1);
+    }
+    __syncthreads();
+    for (int k = 1 + threadIdx.x; k <= nr; k += blockDim.x) hist[(size_t)(k - 1) * ntiles + tile] = sh[k];
+}
+// exclusive scan of hist (length n) in place; one CTA
+__global__ void __launch_bounds__(1024, 1) k_sort_scan(int *hist, long n)
+{
+    __shared__ int sm[40];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const long per = (n + nt - 1) / nt;
+    const long beg = min((long)tid * per, n), end = min(beg + per, n);
+    int s = 0;
+    for (long k = beg; k < end; k++) s += hist[k];
+    int tot;
+    int off = block_excl_scan_int(s, sm, &tot);
+    for (long k = beg; k < end; k++) { int v = hist[k]; hist[k] = off; off += v; }
+}
+// ranks inside the tile in input order, then destination = (start of next cell-tile bucket) - 1 - rank
+__global__ void __launch_bounds__(256) k_sort_pos(const int *__restrict__ d_npp, int nr, const int *__restrict__ keys, const int *__restrict__ hist,
+                                                 int ntiles, int *__restrict__ pos)
+{
+    extern __shared__ int sh[];  // running counters per key
+    const int npp = *d_npp, tile = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int k = threadIdx.x; k <= nr; k += blockDim.x) sh[k] = 0;
+    __syncthreads();
+    const int beg = tile * SORT_TILE, end = min(beg + SORT_TILE, npp);
+    // process the tile in order: chunks of blockDim, inside a chunk warp after warp
+    for (int c0 = beg; c0 < end; c0 += blockDim.x) {
+        const int i = c0 + threadIdx.x;
+        const bool valid = i < end;
+        const int key = valid ? keys[i] : -1 - lane;
+        const unsigned same = __match_any_sync(FULL, key);
+        const int before = __popc(same & ((1u << lane) - 1u));  // earlier lanes with my key
+        int rank = 0;
+        for (int ww = 0; ww < nw; ww++) {
+            if (w == ww && valid) {
+                rank = sh[key] + before;
+                if ((same >> lane) == 1u) sh[key] = rank + 1;  // highest lane of the group publishes the new count
+            }
+            __syncthreads();
+        }
+        if (valid) {
+            // bucket (key, tile) spans [hist[key-1][tile], next bucket); the cell's END is the start of cell key+1, but
+            // reverse-stable order over the whole cell means: pos = cell_end - 1 - global_rank, global_rank = (# in
+            // earlier tiles) + rank = (hist[key-1][tile] - cell_start) + rank
+            const int cell_start = hist[(size_t)(key - 1) * ntiles];
+            const int cell_end = (key < nr) ? hist[(size_t)key * ntiles] : npp;
+            const int grank = hist[(size_t)(key - 1) * ntiles + tile] - cell_start + rank;
+            pos[i] = cell_end - 1 - grank;
+        }
+    }
+}
+__global__ void k_sort_scatter(const int *__restrict__ d_npp, const int *__restrict__ pos, const double *__restrict__ src, double *__restrict__ dst,
+                               long npmax)
+{
+    const int npp = *d_npp;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npp) return;
+    const int d = pos[i];
+#pragma unroll
+    for (int a = 0; a < 8; a++) dst[(size_t)a * npmax + d] = src[(size_t)a * npmax + i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// host API
+// ------------------------------------------------------------------------------------------------
+static void set_planes(qpg_part2d p, double *slab)
+{
+    p->slab = slab;
+    p->x1 = slab; p->x2 = slab + p->npmax; p->p1 = slab + 2 * p->npmax; p->p2 = slab + 3 * p->npmax; p->p3 = slab + 4 * p->npmax;
+    p->gamma = slab + 5 * p->npmax; p->psi = slab + 6 * p->npmax; p->q = slab + 7 * p->npmax;
+}
+static double **plane_table(qpg_part2d p) { return (double **)(p->lists + 2 * p->npmax); }  // 64 ints of tail room
+
+extern "C" int qpg_part2d_create(qpg_part2d *out, qpg_ctx ctx, double qbm, long npmax)
+{
+    ARG_TRY(out && ctx, "null arg");
+    ARG_TRY(npmax >= 32 && npmax < (1L << 31) - 64, "npmax out of range");
+    ARG_TRY(qbm != 0.0, "qbm must be non-zero");
+    npmax = (npmax + 31) & ~31L;
+    qpg_part2d p = new qpg_part2d_s();
+    memset(p, 0, sizeof(*p));
+    p->ctx = ctx; p->qbm = qbm; p->npmax = npmax; p->npp_hi = 0;
+    double *slab;
+    CUDA_TRY(cudaMalloc(&slab, sizeof(double) * 8 * npmax));
+    CUDA_TRY(cudaMemsetAsync(slab, 0, sizeof(double) * 8 * npmax, ctx->stream));
+    set_planes(p, slab);
+    CUDA_TRY(cudaMalloc(&p->d_npp, sizeof(int) * 4));
+    CUDA_TRY(cudaMemsetAsync(p->d_npp, 0, sizeof(int) * 4, ctx->stream));
+    p->d_nout = p->d_npp + 1;
+    CUDA_TRY(cudaMalloc(&p->outmask, sizeof(unsigned) * (npmax / 32 + 1)));
+    CUDA_TRY(cudaMemsetAsync(p->outmask, 0, sizeof(unsigned) * (npmax / 32 + 1), ctx->stream));
+    CUDA_TRY(cudaMalloc(&p->lists, sizeof(int) * (2 * npmax + 64)));
+    {
+        double *h[8] = {p->x1, p->x2, p->p1, p->p2, p->p3, p->gamma, p->psi, p->q};
+        CUDA_TRY(cudaMemcpy(plane_table(p), h, sizeof(h), cudaMemcpyHostToDevice));
+    }
+    size_t nacc = (size_t)(ctx->nr + 2) * ctx->P;
+    CUDA_TRY(cudaMalloc(&p->acc1, sizeof(double) * nacc));
+    CUDA_TRY(cudaMemsetAsync(p->acc1, 0, sizeof(double) * nacc, ctx->stream));
+    CUDA_TRY(cudaMalloc(&p->acc8, sizeof(double) * nacc * 8));
+    CUDA_TRY(cudaMemsetAsync(p->acc8, 0, sizeof(double) * nacc * 8, ctx->stream));
+    *out = p;
+    return 0;
+}
+extern "C" int qpg_part2d_destroy(qpg_part2d p)
+{
+    if (!p) return 0;
+    cudaStreamSynchronize(p->ctx->stream);
+    cudaFree(p->slab); cudaFree(p->alt); cudaFree(p->snap); cudaFree(p->d_npp); cudaFree(p->outmask); cudaFree(p->lists);
+    cudaFree(p->acc1); cudaFree(p->acc8); cudaFree(p->sort_keys); cudaFree(p->sort_pos); cudaFree(p->sort_hist);
+    delete p;
+    return 0;
+}
+extern "C" int qpg_part2d_upload(qpg_part2d p, const double *x, const double *pm, const double *gamma, const double *psi, const double *q, long npp)
+{
+    ARG_TRY(p && x && pm && gamma && psi && q, "null arg");
+    ARG_TRY(npp >= 0 && npp <= p->npmax, "npp exceeds npmax");
+    std::vector<double> h((size_t)5 * npp);
+    for (long i = 0; i < npp; i++) {
+        h[i] = x[2 * i]; h[npp + i] = x[2 * i + 1];
+        h[2 * npp + i] = pm[3 * i]; h[3 * npp + i] = pm[3 * i + 1]; h[4 * npp + i] = pm[3 * i + 2];
+    }
+    cudaStream_t st = p->ctx->stream;
+    double *dst[5] = {p->x1, p->x2, p->p1, p->p2, p->p3};
+    for (int a = 0; a < 5; a++) CUDA_TRY(cudaMemcpyAsync(dst[a], h.data() + (size_t)a * npp, sizeof(double) * npp, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(p->gamma, gamma, sizeof(double) * npp, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(p->psi, psi, sizeof(double) * npp, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(p->q, q, sizeof(double) * npp, cudaMemcpyHostToDevice, st));
+    int cnt[2] = {(int)npp, 0};
+    CUDA_TRY(cudaMemcpyAsync(p->d_npp, cnt, sizeof(cnt), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(p->outmask, 0, sizeof(unsigned) * (p->npmax / 32 + 1), st));
+    CUDA_TRY(cudaStreamSynchronize(st));  // h goes out of scope
+    p->npp_hi = npp;
+    return 0;
+}
+extern "C" int qpg_part2d_npp(qpg_part2d p, long *npp)
+{
+    ARG_TRY(p && npp, "null arg");
+    int n = 0;
+    CUDA_TRY(cudaMemcpyAsync(&n, p->d_npp, sizeof(int), cudaMemcpyDeviceToHost, p->ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(p->ctx->stream));
+    *npp = n;
+    p->npp_hi = n;
+    return 0;
+}
+extern "C" int qpg_part2d_download(qpg_part2d p, double *x, double *pm, double *gamma, double *psi, double *q, long *npp_out)
+{
+    ARG_TRY(p, "null arg");
+    long npp;
+    int rc = qpg_part2d_npp(p, &npp);
+    if (rc) return rc;
+    if (npp_out) *npp_out = npp;
+    cudaStream_t st = p->ctx->stream;
+    std::vector<double> h((size_t)5 * npp);
+    if (x || pm) {
+        double *src[5] = {p->x1, p->x2, p->p1, p->p2, p->p3};
+        for (int a = 0; a < 5; a++) CUDA_TRY(cudaMemcpyAsync(h.data() + (size_t)a * npp, src[a], sizeof(double) * npp, cudaMemcpyDeviceToHost, st));
+    }
+    if (gamma) CUDA_TRY(cudaMemcpyAsync(gamma, p->gamma, sizeof(double) * npp, cudaMemcpyDeviceToHost, st));
+    if (psi) CUDA_TRY(cudaMemcpyAsync(psi, p->psi, sizeof(double) * npp, cudaMemcpyDeviceToHost, st));
+    if (q) CUDA_TRY(cudaMemcpyAsync(q, p->q, sizeof(double) * npp, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    for (long i = 0; i < npp; i++) {
+        if (x) { x[2 * i] = h[i]; x[2 * i + 1] = h[npp + i]; }
+        if (pm) { pm[3 * i] = h[2 * npp + i]; pm[3 * i + 1] = h[3 * npp + i]; pm[3 * i + 2] = h[4 * npp + i]; }
+    }
+    return 0;
+}
+extern "C" int qpg_part2d_snapshot(qpg_part2d p)
+{
+    ARG_TRY(p, "null arg");
+    long npp;
+    int rc = qpg_part2d_npp(p, &npp);
+    if (rc) return rc;
+    if (!p->snap) CUDA_TRY(cudaMalloc(&p->snap, sizeof(double) * 8 * p->npmax));
+    CUDA_TRY(cudaMemcpyAsync(p->snap, p->slab, sizeof(double) * 8 * p->npmax, cudaMemcpyDeviceToDevice, p->ctx->stream));
+    p->snap_np = npp;
+    return 0;
+}
+extern "C" int qpg_part2d_renew(qpg_part2d p)
+{
+    ARG_TRY(p, "null arg");
+    if (!p->snap) { qpg_set_error("qpg_part2d_renew: no snapshot taken"); return QPG_ERR_STATE; }
+    cudaStream_t st = p->ctx->stream;
+    CUDA_TRY(cudaMemcpyAsync(p->slab, p->snap, sizeof(double) * 8 * p->npmax, cudaMemcpyDeviceToDevice, st));
+    int cnt[2] = {(int)p->snap_np, 0};
+    CUDA_TRY(cudaMemcpyAsync(p->d_npp, cnt, sizeof(cnt), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(p->outmask, 0, sizeof(unsigned) * (p->npmax / 32 + 1), st));
+    p->npp_hi = p->snap_np;
+    return 0;
+}
+
+#define DISPATCH_M(M, FN, ...)                 \
+    switch (M) {                               \
+    case 0: FN<0>(__VA_ARGS__); break;         \
+    case 1: FN<1>(__VA_ARGS__); break;         \
+    case 2: FN<2>(__VA_ARGS__); break;         \
+    case 3: FN<3>(__VA_ARGS__); break;         \
+    default: FN<4>(__VA_ARGS__); break;        \
+    }
+template <int M> static void l_qdeposit(int grid, cudaStream_t st, PartView pv, double *acc1, double idr)
+{ k_qdeposit<M><<<grid, PT_BLOCK, 0, st>>>(pv, acc1, idr); }
+template <int M> static void l_amjdeposit(int grid, cudaStream_t st, PartView pv, const double *ef, const double *bf, double *acc8, double qbm, double dt, double idr, const int *skip)
+{ k_amjdeposit<M><<<grid, PT_BLOCK, 0, st>>>(pv, ef, bf, acc8, qbm, dt, idr, skip); }
+template <int M> static void l_push(int grid, cudaStream_t st, PartView pv, const double *ef, const double *bf, double qbm, double dt, double idr, double edge, int mode, unsigned *outmask, int *d_nout)
+{ k_push<M><<<grid, PT_BLOCK, 0, st>>>(pv, ef, bf, qbm, dt, idr, edge, mode, outmask, d_nout); }
+
+int part2d_launch_qdeposit(qpg_part2d p)
+{
+    if (p->npp_hi == 0) return 0;
+    qpg_ctx c = p->ctx;
+    const int grid = (int)((p->npp_hi + PT_BLOCK - 1) / PT_BLOCK);
+    PartView pv = view_of(p);
+    TprofScope tp(c, TP_K_QDEP);
+    DISPATCH_M(c->M, l_qdeposit, grid, c->stream, pv, p->acc1, 1.0 / c->dr);
+    count_launch(c);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+int part2d_launch_amjdeposit(qpg_part2d p, qpg_field ef, qpg_field bf, double dt, const int *skip_flag)
+{
+    if (p->npp_hi == 0) return 0;
+    qpg_ctx c = p->ctx;
+    const int grid = (int)((p->npp_hi + PT_BLOCK - 1) / PT_BLOCK);
+    PartView pv = view_of(p);
+    TprofScope tp(c, TP_K_AMJ);
+    DISPATCH_M(c->M, l_amjdeposit, grid, c->stream, pv, ef->f1, bf->f1, p->acc8, p->qbm, dt, 1.0 / c->dr, skip_flag);
+    count_launch(c);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+int part2d_launch_push(qpg_part2d p, qpg_field ef, qpg_field bf, double dt, int mode)
+{
+    if (p->npp_hi == 0) return 0;
+    qpg_ctx c = p->ctx;
+    const int grid = (int)((p->npp_hi + PT_BLOCK - 1) / PT_BLOCK);
+    PartView pv = view_of(p);
+    TprofScope tp(c, TP_K_PUSH);
+    const double edge = (double)c->nr * c->dr;
+    const double *e1 = ef ? ef->f1 : nullptr, *b1 = bf ? bf->f1 : nullptr;
+    DISPATCH_M(c->M, l_push, grid, c->stream, pv, e1, b1, p->qbm, dt, 1.0 / c->dr, edge, mode, p->outmask, p->d_nout);
+    count_launch(c);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+int part2d_launch_compact(qpg_part2d p)
+{
+    qpg_ctx c = p->ctx;
+    double **tbl = plane_table(p);
+    TprofScope tp(c, TP_K_COMPACT);
+    k_compact<<<1, 1024, 0, c->stream>>>(tbl, 8, p->d_npp, p->d_nout, p->outmask, p->lists, 0);
+    count_launch(c);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int part2d_epilogue_q(qpg_part2d p, qpg_field q)
+{
+    FProgBuilder pb(p->ctx);
+    FOp &o = pb.add(FOP_QFIX); o.a = p->acc1; o.b = q->f1; o.da = 1;
+    return pb.launch(TP_DEPOSIT2D);
+}
+
+extern "C" int qpg_part2d_qdeposit(qpg_part2d p, qpg_field q)
+{
+    ARG_TRY(p && q && q->dim == 1 && q->ctx == p->ctx, "bad field handle");
+    int rc = part2d_launch_qdeposit(p);
+    if (rc) return rc;
+    return part2d_epilogue_q(p, q);
+}
+extern "C" int qpg_part2d_amjdeposit(qpg_part2d p, int push_type, qpg_field ef, qpg_field bf, qpg_field cu, qpg_field amu, qpg_field dcu, double dt)
+{
+    ARG_TRY(p && ef && bf && cu && amu && dcu, "null arg");
+    ARG_TRY(ef->dim == 3 && bf->dim == 3 && cu->dim == 3 && amu->dim == 3 && dcu->dim == 2, "field dims must be e3 b3 cu3 amu3 dcu2");
+    if (push_type != QPG_PUSH2_ROBUST) { qpg_set_error("only push_type 'robust' is implemented (std/pgc pushers: SURVEY.md §8f)"); return QPG_ERR_UNSUPPORTED; }
+    int rc = part2d_launch_amjdeposit(p, ef, bf, dt, nullptr);
+    if (rc) return rc;
+    FProgBuilder pb(p->ctx);
+    FOp &o = pb.add(FOP_AMJFIX); o.a = p->acc8; o.b = cu->f1; o.c = dcu->f1; o.d = amu->f1; o.da = 1;
+    return pb.launch(TP_DEPOSIT2D);
+}
+extern "C" int qpg_part2d_push_u(qpg_part2d p, int push_type, qpg_field ef, qpg_field bf, double dt)
+{
+    ARG_TRY(p && ef && bf && ef->dim == 3 && bf->dim == 3, "bad field handles");
+    if (push_type != QPG_PUSH2_ROBUST) { qpg_set_error("only push_type 'robust' is implemented"); return QPG_ERR_UNSUPPORTED; }
+    return part2d_launch_push(p, ef, bf, dt, 1);
+}
+extern "C" int qpg_part2d_push_x(qpg_part2d p, double dt)
+{
+    ARG_TRY(p, "null arg");
+    return part2d_launch_push(p, nullptr, nullptr, dt, 2);
+}
+extern "C" int qpg_part2d_update_bound(qpg_part2d p)
+{
+    ARG_TRY(p, "null arg");
+    int rc = part2d_launch_push(p, nullptr, nullptr, 0.0, 4);
+    if (rc) return rc;
+    return part2d_launch_compact(p);
+}
+
+extern "C" long qpg_part2d_wire_count(qpg_part2d p) { return p ? 8 * p->npmax + 1 : -1; }
+extern "C" int qpg_part2d_pack(qpg_part2d p, double *dev_buf)
+{
+    ARG_TRY(p && dev_buf, "null arg");
+    TprofScope tp(p->ctx, TP_PIPELINE);
+    k_pack2d<<<296, 256, 0, p->ctx->stream>>>(view_of(p), dev_buf, p->npmax);
+    count_launch(p->ctx);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+extern "C" int qpg_part2d_unpack(qpg_part2d p, const double *dev_buf)
+{
+    ARG_TRY(p && dev_buf, "null arg");
+    TprofScope tp(p->ctx, TP_PIPELINE);
+    k_unpack2d<<<296, 256, 0, p->ctx->stream>>>(view_of(p), p->d_npp, dev_buf, p->npmax);
+    count_launch(p->ctx);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemsetAsync(p->d_nout, 0, sizeof(int), p->ctx->stream));
+    p->npp_hi = p->npmax;  // unknown until the next sync; kernels bound themselves by the device count
+    return 0;
+}
+
+static int sort_prepare(qpg_part2d p)
+{
+    qpg_ctx c = p->ctx;
+    long ntiles = (p->npmax + SORT_TILE - 1) / SORT_TILE;
+    if (!p->sort_keys) {
+        CUDA_TRY(cudaMalloc(&p->sort_keys, sizeof(int) * p->npmax));
+        CUDA_TRY(cudaMalloc(&p->sort_pos, sizeof(int) * p->npmax));
+        CUDA_TRY(cudaMalloc(&p->sort_hist, sizeof(int) * ((size_t)c->nr * ntiles + 1)));
+        p->sort_tiles = ntiles;
+    }
+    return 0;
+}
+static int sort_index_device(qpg_part2d p, int *ntiles_out)
+{
+    qpg_ctx c = p->ctx;
+    int rc = sort_prepare(p);
+    if (rc) return rc;
+    int ntiles = (int)((p->npp_hi + SORT_TILE - 1) / SORT_TILE);
+    if (ntiles < 1) ntiles = 1;
+    *ntiles_out = ntiles;
+    PartView pv = view_of(p);
+    size_t sh = sizeof(int) * (c->nr + 1);
+    CUDA_TRY(cudaMemsetAsync(p->sort_hist, 0, sizeof(int) * ((size_t)c->nr * ntiles + 1), c->stream));
+    k_sort_hist<<<ntiles, 256, sh, c->stream>>>(pv, 1.0 / c->dr, c->nr, p->sort_keys, p->sort_hist, ntiles);
+    k_sort_scan<<<1, 1024, 0, c->stream>>>(p->sort_hist, (long)c->nr * ntiles);
+    k_sort_pos<<<ntiles, 256, sh, c->stream>>>(p->d_npp, c->nr, p->sort_keys, p->sort_hist, ntiles, p->sort_pos);
+    count_launch(c, 3);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+extern "C" int qpg_part2d_sort(qpg_part2d p)
+{
+    ARG_TRY(p, "null arg");
+    if (p->npp_hi == 0) return 0;
+    qpg_ctx c = p->ctx;
+    ARG_TRY(sizeof(int) * (c->nr + 1) <= 48 * 1024, "nr too large for the sort histogram");
+    TprofScope tp(c, TP_SORT2D);
+    int ntiles;
+    int rc = sort_index_device(p, &ntiles);
+    if (rc) return rc;
+    if (!p->alt) CUDA_TRY(cudaMalloc(&p->alt, sizeof(double) * 8 * p->npmax));
+    const int grid = (int)((p->npp_hi + 255) / 256);
+    k_sort_scatter<<<grid, 256, 0, c->stream>>>(p->d_npp, p->sort_pos, p->slab, p->alt, p->npmax);
+    count_launch(c);
+    CUDA_TRY(cudaGetLastError());
+    // pointers stay fixed (CUDA-graph friendly): copy the sorted planes back
+    CUDA_TRY(cudaMemcpyAsync(p->slab, p->alt, sizeof(double) * 8 * p->npmax, cudaMemcpyDeviceToDevice, c->stream));
+    return 0;
+}
+extern "C" int qpg_part2d_sort_index(qpg_part2d p, int *host_ix, int *host_ip)
+{
+    ARG_TRY(p && host_ix && host_ip, "null arg");
+    long npp;
+    int rc = qpg_part2d_npp(p, &npp);
+    if (rc) return rc;
+    if (npp == 0) return 0;
+    int ntiles;
+    rc = sort_index_device(p, &ntiles);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(host_ix, p->sort_keys, sizeof(int) * npp, cudaMemcpyDeviceToHost, p->ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(host_ip, p->sort_pos, sizeof(int) * npp, cudaMemcpyDeviceToHost, p->ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(p->ctx->stream));
+    for (long i = 0; i < npp; i++) host_ip[i] += 1;  // 1-based like generate_sort_idx_1d
+    return 0;
+}

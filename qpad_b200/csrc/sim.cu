@@ -1,0 +1,322 @@
+// sim.cu -- fused fast path: the `do j = 1, nstep2d` body of simulation_class.f03:342-469 enqueued without host
+// round trips.  Per slice the device runs
+//     qdeposit -> A -> while(!done){ amjdeposit -> C } -> D -> push(+bound flags) -> compact [-> sort]
+// where A, C, D are single-CTA field programs (fields.cu) and the predictor-corrector loop is a CUDA-graph WHILE
+// node whose condition the C program sets on the device (convergence_tester, simulation_class.f03:522-606).
+// Without graphs (use_graph = 0) the iter_max iterations are enqueued back to back and skip themselves on `done`.
+#include "common.cuh"
+
+int part2d_launch_qdeposit(qpg_part2d p);
+int part2d_launch_amjdeposit(qpg_part2d p, qpg_field ef, qpg_field bf, double dt, const int *skip_flag);
+int part2d_launch_push(qpg_part2d p, qpg_field ef, qpg_field bf, double dt, int mode);
+int part2d_launch_compact(qpg_part2d p);
+
+struct qpg_sim_s {
+    qpg_sim_params prm;
+    qpg_ctx ctx;
+    qpg_field psi, e, b, e_spe, b_spe, e_beam, b_beam, cu, amu, acu, dcu, q_spe, q_beam, spe_q, spe_qn, spe_cu, spe_dcu, spe_amu, beam_q;
+    qpg_part2d spe;
+    qpg_part3d beam;
+    cudaGraph_t graph;
+    cudaGraphExec_t gexec;
+    bool graph_ready;
+    long host_updates, host_iters, host_slices;
+};
+
+// flags: [0] done  [1] PC iterations (since last read)  [2] iteration inside the slice  [3] current slice j
+//        [4] slices executed  ;  counters (long long) live in conv_out[4..] reinterpret: updates
+static void prog_A(qpg_sim s, FProgBuilder &pb)
+{
+    FOp *o;
+    o = &pb.add(FOP_SLICE_2TO1); o->a = s->q_beam->f1; o->b = s->q_beam->f2; o->da = 1; o->i0 = -1;          // :344
+    o = &pb.add(FOP_BT); o->a = s->q_beam->f1; o->b = s->b_beam->f1; o->da = 1;                               // :345
+    o = &pb.add(FOP_ZERO); o->a = s->spe_q->f1; o->da = 1;                                                   // species2d qdp :198
+    o = &pb.add(FOP_QFIX); o->a = s->spe->acc1; o->b = s->spe_q->f1; o->da = 1; o->c = (double *)s->spe->d_npp; o->i1 = 1;
+    o = &pb.add(FOP_ADD3); o->a = s->spe_q->f1; o->b = s->spe_qn->f1; o->c = s->q_spe->f1; o->da = 1;        // q_spe = 0 + q + qn
+    o = &pb.add(FOP_PSI); o->a = s->q_spe->f1; o->b = s->psi->f1; o->da = 1;                                  // :356
+    o = &pb.add(FOP_BZ); o->a = s->cu->f1; o->b = s->b_spe->f1; o->da = 3;                                    // :360
+    o = &pb.add(FOP_PC_BEGIN);
+    o = &pb.add(FOP_CONV_RECORD); o->a = s->b_spe->f1; o->da = 3; o->i0 = 1;                                  // :373
+    o = &pb.add(FOP_ADD3); o->a = s->b_spe->f1; o->b = s->b_beam->f1; o->c = s->b->f1; o->da = 3;             // :375
+    o = &pb.add(FOP_EZ); o->a = s->cu->f1; o->b = s->e->f1; o->da = 3;                                        // :376
+    o = &pb.add(FOP_ET); o->a = s->b->f1; o->b = s->psi->f1; o->c = s->e->f1; o->da = 3;                      // :377
+}
+static void prog_C(qpg_sim s, FProgBuilder &pb)
+{
+    FOp *o;
+    const int F = FOPF_SKIP_IF_DONE;
+    o = &pb.add(FOP_ZERO); o->a = s->spe_cu->f1; o->da = 3; o->flags = F;                                     // species2d amjdp :250-252
+    o = &pb.add(FOP_ZERO); o->a = s->spe_dcu->f1; o->da = 2; o->flags = F;
+    o = &pb.add(FOP_ZERO); o->a = s->spe_amu->f1; o->da = 3; o->flags = F;
+    o = &pb.add(FOP_AMJFIX); o->a = s->spe->acc8; o->b = s->spe_cu->f1; o->c = s->spe_dcu->f1; o->d = s->spe_amu->f1; o->da = 1; o->flags = F;
+    o = &pb.add(FOP_COPY); o->a = s->spe_cu->f1; o->b = s->cu->f1; o->da = 3; o->flags = F;                   // cu = 0 + spe%cu :378,:274
+    o = &pb.add(FOP_COPY); o->a = s->spe_dcu->f1; o->b = s->acu->f1; o->da = 2; o->flags = F;
+    o = &pb.add(FOP_COPY); o->a = s->spe_amu->f1; o->b = s->amu->f1; o->da = 3; o->flags = F;
+    o = &pb.add(FOP_DJDXI); o->a = s->acu->f1; o->b = s->amu->f1; o->c = s->dcu->f1; o->da = 2; o->flags = F;  // :390
+    o = &pb.add(FOP_BTITER); o->a = s->dcu->f1; o->b = s->cu->f1; o->c = s->b_spe->f1; o->da = 2; o->s0 = s->ctx->relax; o->flags = F; // :391
+    o = &pb.add(FOP_BZ); o->a = s->cu->f1; o->b = s->b_spe->f1; o->da = 3; o->flags = F;                      // :392
+    o = &pb.add(FOP_CONV_COMPARE); o->a = s->b_spe->f1; o->da = 3; o->i0 = 1; o->i1 = 1; o->i2 = s->prm.iter_max;
+    o->s0 = s->prm.iter_reltol; o->s1 = s->prm.iter_abstol; o->flags = F;                                     // :395-396
+    o = &pb.add(FOP_CONV_RECORD); o->a = s->b_spe->f1; o->da = 3; o->i0 = 1; o->flags = F;
+    o = &pb.add(FOP_ADD3); o->a = s->b_spe->f1; o->b = s->b_beam->f1; o->c = s->b->f1; o->da = 3; o->flags = F; // :375 / :413
+    o = &pb.add(FOP_EZ); o->a = s->cu->f1; o->b = s->e->f1; o->da = 3; o->flags = F;                          // :376 / :415
+    o = &pb.add(FOP_ET); o->a = s->b->f1; o->b = s->psi->f1; o->c = s->e->f1; o->da = 3; o->flags = F;        // :377 / :416
+}
+static void prog_D(qpg_sim s, FProgBuilder &pb)
+{
+    FOp *o;
+    o = &pb.add(FOP_ADD_DIM); o->a = s->spe_cu->f1; o->b = s->spe_q->f1; o->da = 3; o->db = 1; o->i0 = 2; o->i1 = 0;  // cbq, species2d :396
+    o = &pb.add(FOP_SLICE_1TO2); o->a = s->spe_q->f1; o->b = s->spe_q->f2; o->da = 1; o->i0 = -1;
+    o = &pb.add(FOP_SLICE_1TO2); o->a = s->cu->f1; o->b = s->cu->f2; o->da = 3; o->i0 = -1;                    // :409
+    o = &pb.add(FOP_ADD_DIM); o->a = s->cu->f1; o->b = s->q_spe->f1; o->da = 3; o->db = 1; o->i0 = 2; o->i1 = 0;  // :410
+    o = &pb.add(FOP_SLICE_1TO2); o->a = s->q_spe->f1; o->b = s->q_spe->f2; o->da = 1; o->i0 = -1;              // :411
+    o = &pb.add(FOP_ET); o->a = s->b_spe->f1; o->b = s->psi->f1; o->c = s->e_spe->f1; o->da = 3;               // :414
+    o = &pb.add(FOP_SCALE); o->a = s->dcu->f1; o->da = 2; o->s0 = s->prm.dxi;                                  // :425
+    o = &pb.add(FOP_ADD_DIM); o->a = s->dcu->f1; o->b = s->cu->f1; o->da = 2; o->db = 3; o->i0 = 0; o->i1 = 0;  // :426
+    o = &pb.add(FOP_ADD_DIM); o->a = s->dcu->f1; o->b = s->cu->f1; o->da = 2; o->db = 3; o->i0 = 1; o->i1 = 1;
+    o = &pb.add(FOP_SLICE_1TO2); o->a = s->e->f1; o->b = s->e->f2; o->da = 3; o->i0 = -1;                      // :452-456
+    o = &pb.add(FOP_SLICE_1TO2); o->a = s->b->f1; o->b = s->b->f2; o->da = 3; o->i0 = -1;
+    o = &pb.add(FOP_SLICE_1TO2); o->a = s->psi->f1; o->b = s->psi->f2; o->da = 1; o->i0 = -1;
+    o = &pb.add(FOP_SLICE_1TO2); o->a = s->b_spe->f1; o->b = s->b_spe->f2; o->da = 3; o->i0 = -1;
+    o = &pb.add(FOP_SLICE_1TO2); o->a = s->e_spe->f1; o->b = s->e_spe->f2; o->da = 3; o->i0 = -1;
+    o = &pb.add(FOP_SET_FLAG); o->i0 = 3; o->i1 = -1;  // flags[3] += 1 (next slice), flags[4] += 1
+}
+
+static int enqueue_pc_iteration(qpg_sim s)
+{
+    int rc = part2d_launch_amjdeposit(s->spe, s->e, s->b, s->prm.dxi, s->ctx->flags);
+    if (rc) return rc;
+    FProgBuilder pb(s->ctx);
+    prog_C(s, pb);
+    return pb.launch(TP_FIELD_FUSED);
+}
+static int enqueue_slice_head(qpg_sim s)
+{
+    FProgBuilder pb(s->ctx);
+    prog_A(s, pb);
+    return pb.launch(TP_FIELD_FUSED);
+}
+static int enqueue_slice_tail(qpg_sim s)
+{
+    int rc;
+    { FProgBuilder pb(s->ctx); prog_D(s, pb); rc = pb.launch(TP_FIELD_FUSED); if (rc) return rc; }
+    rc = part2d_launch_push(s->spe, s->e, s->b, s->prm.dxi, 7);  // push_u + push_x + bound flags :438-439
+    if (rc) return rc;
+    rc = part2d_launch_compact(s->spe);                          // update_bound
+    if (rc) return rc;
+    return part2d_launch_qdeposit(s->spe);                       // next slice's qdp (:346-349) on the advanced particles
+}
+
+static int build_graph(qpg_sim s)
+{
+    qpg_ctx c = s->ctx;
+    cudaStream_t st = c->stream;
+    c->capturing = true;
+    int rc = 0;
+    cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+    if (e != cudaSuccess) { c->capturing = false; return qpg_cuda_fail(e, "cudaStreamBeginCapture"); }
+    rc = enqueue_slice_head(s);
+    cudaGraph_t g = nullptr;
+    const cudaGraphNode_t *deps = nullptr;
+    size_t ndeps = 0;
+    cudaStreamCaptureStatus stat;
+    cudaGraphConditionalHandle handle = 0;
+    if (!rc) {
+        e = cudaStreamGetCaptureInfo(st, &stat, nullptr, &g, &deps, &ndeps);
+        if (e != cudaSuccess) rc = qpg_cuda_fail(e, "cudaStreamGetCaptureInfo");
+    }
+    if (!rc) {
+        e = cudaGraphConditionalHandleCreate(&handle, g, 1, cudaGraphCondAssignDefault);
+        if (e != cudaSuccess) rc = qpg_cuda_fail(e, "cudaGraphConditionalHandleCreate");
+    }
+    cudaGraphNode_t cnode;
+    cudaGraphNodeParams cp = {cudaGraphNodeTypeConditional};
+    if (!rc) {
+        cp.type = cudaGraphNodeTypeConditional;
+        cp.conditional.handle = handle;
+        cp.conditional.type = cudaGraphCondTypeWhile;
+        cp.conditional.size = 1;
+        e = cudaGraphAddNode(&cnode, g, deps, ndeps, &cp);
+        if (e != cudaSuccess) rc = qpg_cuda_fail(e, "cudaGraphAddNode(conditional)");
+    }
+    if (!rc) {
+        e = cudaStreamUpdateCaptureDependencies(st, &cnode, 1, cudaStreamSetCaptureDependencies);
+        if (e != cudaSuccess) rc = qpg_cuda_fail(e, "cudaStreamUpdateCaptureDependencies");
+    }
+    if (!rc) {
+        // body of the WHILE node, captured on a second stream into the child graph
+        cudaGraph_t body = cp.conditional.phGraph_out[0];
+        cudaStream_t s2;
+        cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking);
+        e = cudaStreamBeginCaptureToGraph(s2, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal);
+        if (e != cudaSuccess) rc = qpg_cuda_fail(e, "cudaStreamBeginCaptureToGraph");
+        if (!rc) {
+            cudaStream_t keep = c->stream;
+            c->stream = s2;
+            c->cond_handle = (unsigned long long)handle;
+            rc = enqueue_pc_iteration(s);
+            c->cond_handle = 0;
+            c->stream = keep;
+            e = cudaStreamEndCapture(s2, nullptr);
+            if (e != cudaSuccess && !rc) rc = qpg_cuda_fail(e, "cudaStreamEndCapture(body)");
+        }
+        cudaStreamDestroy(s2);
+    }
+    if (!rc) rc = enqueue_slice_tail(s);
+    cudaGraph_t gout = nullptr;
+    e = cudaStreamEndCapture(st, &gout);
+    c->capturing = false;
+    if (e != cudaSuccess && !rc) rc = qpg_cuda_fail(e, "cudaStreamEndCapture");
+    if (rc) { if (gout) cudaGraphDestroy(gout); return rc; }
+    s->graph = gout;
+    e = cudaGraphInstantiate(&s->gexec, s->graph, 0);
+    if (e != cudaSuccess) return qpg_cuda_fail(e, "cudaGraphInstantiate");
+    s->graph_ready = true;
+    return 0;
+}
+
+extern "C" int qpg_sim_create(qpg_sim *out, int device, void *cuda_stream, const qpg_sim_params *prm)
+{
+    ARG_TRY(out && prm, "null arg");
+    ARG_TRY(prm->nzp >= 1 && prm->noff2 >= 0 && prm->noff2 + prm->nzp <= prm->nz_total, "bad xi slab");
+    ARG_TRY(prm->iter_max >= 1, "iter_max must be >= 1");
+    qpg_sim s = new qpg_sim_s();
+    memset(s, 0, sizeof(*s));
+    s->prm = *prm;
+    int rc = qpg_ctx_create(&s->ctx, device, cuda_stream, prm->nr, prm->max_mode, prm->dr, prm->dxi, prm->field_boundary, prm->relax_fac);
+    if (rc) { delete s; return rc; }
+    qpg_ctx c = s->ctx;
+    const int nzp = prm->nzp;
+    struct { qpg_field *f; int dim, has2d; } tbl[] = {
+        {&s->psi, 1, 1}, {&s->e, 3, 1}, {&s->b, 3, 1}, {&s->e_spe, 3, 1}, {&s->b_spe, 3, 1}, {&s->e_beam, 3, 1}, {&s->b_beam, 3, 1},
+        {&s->cu, 3, 1}, {&s->amu, 3, 0}, {&s->acu, 2, 0}, {&s->dcu, 2, 0}, {&s->q_spe, 1, 1}, {&s->q_beam, 1, 1},
+        {&s->spe_q, 1, 1}, {&s->spe_qn, 1, 0}, {&s->spe_cu, 3, 0}, {&s->spe_dcu, 2, 0}, {&s->spe_amu, 3, 0}, {&s->beam_q, 1, 1}};
+    for (auto &t : tbl) { rc = qpg_field_create(t.f, c, t.dim, nzp, t.has2d); if (rc) return rc; }
+    rc = qpg_part2d_create(&s->spe, c, prm->sp_qbm, prm->sp_npmax);
+    if (rc) return rc;
+    rc = qpg_part3d_create(&s->beam, c, prm->beam_qbm, prm->dt, prm->beam_npmax < 32 ? 32 : prm->beam_npmax, prm->nz_total, prm->noff2, nzp);
+    if (rc) return rc;
+    *out = s;
+    return 0;
+}
+extern "C" int qpg_sim_destroy(qpg_sim s)
+{
+    if (!s) return 0;
+    cudaStreamSynchronize(s->ctx->stream);
+    if (s->gexec) cudaGraphExecDestroy(s->gexec);
+    if (s->graph) cudaGraphDestroy(s->graph);
+    qpg_field all[] = {s->psi, s->e, s->b, s->e_spe, s->b_spe, s->e_beam, s->b_beam, s->cu, s->amu, s->acu, s->dcu, s->q_spe, s->q_beam,
+                       s->spe_q, s->spe_qn, s->spe_cu, s->spe_dcu, s->spe_amu, s->beam_q};
+    for (auto f : all) qpg_field_destroy(f);
+    qpg_part2d_destroy(s->spe);
+    qpg_part3d_destroy(s->beam);
+    qpg_ctx_destroy(s->ctx);
+    delete s;
+    return 0;
+}
+extern "C" qpg_ctx qpg_sim_ctx(qpg_sim s) { return s ? s->ctx : nullptr; }
+extern "C" qpg_field qpg_sim_field(qpg_sim s, const char *name)
+{
+    if (!s || !name) return nullptr;
+    struct { const char *n; qpg_field f; } tbl[] = {
+        {"psi", s->psi}, {"e", s->e}, {"b", s->b}, {"e_spe", s->e_spe}, {"b_spe", s->b_spe}, {"e_beam", s->e_beam}, {"b_beam", s->b_beam},
+        {"cu", s->cu}, {"amu", s->amu}, {"acu", s->acu}, {"dcu", s->dcu}, {"q_spe", s->q_spe}, {"q_beam", s->q_beam}, {"spe_q", s->spe_q},
+        {"spe_qn", s->spe_qn}, {"spe_cu", s->spe_cu}, {"spe_dcu", s->spe_dcu}, {"spe_amu", s->spe_amu}, {"beam_q", s->beam_q}};
+    for (auto &t : tbl) if (!strcmp(t.n, name)) return t.f;
+    qpg_set_error("unknown field '%s'", name);
+    return nullptr;
+}
+extern "C" qpg_part2d qpg_sim_species(qpg_sim s) { return s ? s->spe : nullptr; }
+extern "C" qpg_part3d qpg_sim_beam(qpg_sim s) { return s ? s->beam : nullptr; }
+
+// species2d%new (species2d_class.f03:73-133): inject, q = deposit, qn = -q
+extern "C" int qpg_sim_init_species(qpg_sim s, const double *x, const double *pm, const double *gamma, const double *psi, const double *q, long npp)
+{
+    ARG_TRY(s, "null sim");
+    int rc = qpg_part2d_upload(s->spe, x, pm, gamma, psi, q, npp);
+    if (rc) return rc;
+    rc = qpg_part2d_snapshot(s->spe);
+    if (rc) return rc;
+    rc = qpg_field_fill(s->spe_q, 0.0);
+    if (rc) return rc;
+    rc = qpg_part2d_qdeposit(s->spe, s->spe_q);
+    if (rc) return rc;
+    rc = qpg_field_copy(s->spe_q, s->spe_qn);
+    if (rc) return rc;
+    return qpg_field_scale(s->spe_qn, -1.0);
+}
+extern "C" int qpg_sim_beam_qdp_begin(qpg_sim s) { ARG_TRY(s, "null sim"); return qpg_field_fill_f2(s->beam_q, 0.0); }   // beam3d_class.f03:207
+extern "C" int qpg_sim_beam_qdp_end(qpg_sim s) { ARG_TRY(s, "null sim"); return qpg_part3d_qdeposit(s->beam, s->beam_q); } // :210
+// simulation_class.f03:299-331 (everything but the MPI calls)
+extern "C" int qpg_sim_begin_step(qpg_sim s)
+{
+    ARG_TRY(s, "null sim");
+    int rc;
+    if ((rc = qpg_field_fill_f2(s->q_beam, 0.0))) return rc;
+    if ((rc = qpg_field_fill_f2(s->q_spe, 0.0))) return rc;
+    if ((rc = qpg_field_add_f2(s->beam_q, s->q_beam))) return rc;  // beam3d_class.f03:217 add_f2
+    qpg_field z[] = {s->b, s->e, s->b_spe, s->e_spe, s->psi, s->cu, s->acu, s->amu};
+    for (auto f : z) if ((rc = qpg_field_fill(f, 0.0))) return rc;
+    return 0;
+}
+
+extern "C" int qpg_sim_run_slices(qpg_sim s, int j0, int j1)
+{
+    ARG_TRY(s, "null sim");
+    ARG_TRY(j0 >= 1 && j1 <= s->prm.nzp && j0 <= j1, "slice range out of the slab");
+    qpg_ctx c = s->ctx;
+    int rc;
+    {   // slice counter on the device; stand-alone qdeposit for the first slice of the range
+        FProgBuilder pb(c);
+        FOp &o = pb.add(FOP_SET_FLAG); o.i0 = 3; o.i1 = j0;
+        if ((rc = pb.launch(TP_ARITH))) return rc;
+        // acc1 may hold the look-ahead deposit of a previous range / renewed particles: clear and redo
+        CUDA_TRY(cudaMemsetAsync(s->spe->acc1, 0, sizeof(double) * (size_t)(c->nr + 2) * c->P, c->stream));
+        if ((rc = part2d_launch_qdeposit(s->spe))) return rc;
+    }
+    if (s->prm.use_graph && !s->graph_ready) { if ((rc = build_graph(s))) return rc; }
+    for (int j = j0; j <= j1; j++) {
+        if (s->prm.use_graph) {
+            CUDA_TRY(cudaGraphLaunch(s->gexec, c->stream));
+            c->launches += 5 + 2;  // head, tail x4, >= 1 PC iteration (exact count comes from the device iteration counter)
+        } else {
+            if ((rc = enqueue_slice_head(s))) return rc;
+            for (int l = 0; l < s->prm.iter_max; l++) if ((rc = enqueue_pc_iteration(s))) return rc;
+            if ((rc = enqueue_slice_tail(s))) return rc;
+        }
+        if (s->prm.sort_freq > 0 && ((s->prm.noff2 + j) % s->prm.sort_freq) == 0) {
+            if ((rc = qpg_part2d_sort(s->spe))) return rc;
+            CUDA_TRY(cudaMemsetAsync(s->spe->acc1, 0, sizeof(double) * (size_t)(c->nr + 2) * c->P, c->stream));
+            if ((rc = part2d_launch_qdeposit(s->spe))) return rc;
+        }
+    }
+    return 0;
+}
+extern "C" int qpg_sim_beam_push(qpg_sim s)
+{
+    ARG_TRY(s, "null sim");
+    if (!s->prm.beam_evol) return 0;
+    int rc = qpg_part3d_push(s->beam, s->prm.beam_push_type, s->e, s->b);
+    if (rc) return rc;
+    return qpg_part3d_update_bound(s->beam);
+}
+extern "C" int qpg_sim_renew(qpg_sim s)
+{
+    ARG_TRY(s, "null sim");
+    return qpg_part2d_renew(s->spe);  // species2d%renew: same lattice, q and qn unchanged for time-independent profiles
+}
+extern "C" int qpg_sim_stats(qpg_sim s, long *updates, long *pc_iters, long *slices)
+{
+    ARG_TRY(s, "null sim");
+    qpg_ctx c = s->ctx;
+    int fl[8];
+    long long cnt[2];
+    CUDA_TRY(cudaMemcpyAsync(fl, c->flags, sizeof(fl), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(cnt, c->counters, sizeof(cnt), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (updates) *updates = (long)cnt[0];
+    if (pc_iters) *pc_iters = (long)cnt[1];
+    if (slices) *slices = fl[4];
+    return 0;
+}
+extern "C" int qpg_sim_set_graph(qpg_sim s, int use_graph) { ARG_TRY(s, "null sim"); s->prm.use_graph = use_graph != 0; return 0; }

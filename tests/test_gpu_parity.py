@@ -1,0 +1,453 @@
+"""GPU parity: every C-ABI entry point against the CPU oracle on the same seeded inputs.
+
+Gates (BASELINE.json north_star / SURVEY.md §8d): cell indices, sort permutation and compaction order bit-exact;
+per-slice fields <= 1e-10 relative (inf-norm per plane); particle attributes after a push <= 1e-12.
+"""
+import numpy as np
+import pytest
+from util import plane_relerr, smooth_field, perturbed_lattice
+
+pytestmark = pytest.mark.gpu
+
+FIELD_TOL = 1e-10
+CASES = [(64, 0), (64, 1), (250, 1), (96, 2), (1024, 1)]
+
+
+@pytest.fixture(scope="module")
+def mods():
+    from qpad_b200 import capi
+    from oracle import oracle as O
+    capi.load()
+    return capi, O
+
+
+def _ctx(capi, nr, M, rmax=5.0, bnd=3):
+    dr = rmax / nr
+    return capi.Ctx(nr, M, dr, 0.02, bnd), dr
+
+
+def _mk(capi, ctx, dim, arr=None, nzp=0):
+    f = capi.Field(ctx, dim, nzp, nzp > 0)
+    if arr is not None:
+        f.upload(arr)
+    return f
+
+
+def test_field_roundtrip_and_arith(mods):
+    capi, O = mods
+    ctx, dr = _ctx(capi, 50, 2)
+    rng = np.random.default_rng(0)
+    a = rng.standard_normal((5, 52, 3))
+    b = rng.standard_normal((5, 52, 3))
+    fa, fb, fc = _mk(capi, ctx, 3, a), _mk(capi, ctx, 3, b), _mk(capi, ctx, 3)
+    assert np.array_equal(fa.download(), a)
+    capi.Field.add3(fa, fb, fc)
+    assert np.array_equal(fc.download(), a + b)
+    fa.add_to(fb)
+    assert np.array_equal(fb.download(), b + a)
+    fa.scale(0.37)
+    assert np.array_equal(fa.download(), a * 0.37)
+    q = rng.standard_normal((5, 52, 1))
+    fq = _mk(capi, ctx, 1, q)
+    fb.add_dim_to(fq, [3], [1])
+    assert np.array_equal(fq.download()[..., 0], q[..., 0] + (b + a)[..., 2])
+    fq.fill(0.0)
+    assert not fq.download().any()
+    # 2D layout + copy_slice
+    f2 = capi.Field(ctx, 3, 4, True)
+    vol = rng.standard_normal((5, 5, 52, 3))
+    f2.upload_f2(vol)
+    assert np.array_equal(f2.download_f2(), vol)
+    f2.copy_slice(3, capi.COPY_2TO1)
+    assert np.array_equal(f2.download(), vol[:, 2])
+    f2.upload(a)
+    f2.copy_slice(5, capi.COPY_1TO2)
+    assert np.array_equal(f2.download_f2()[:, 4], a)
+
+
+@pytest.mark.parametrize("nr,M", CASES)
+@pytest.mark.parametrize("bnd", [3, 2])
+def test_solves_match_oracle(mods, nr, M, bnd):
+    capi, O = mods
+    if bnd == 2 and nr != 64:
+        pytest.skip("zero boundary covered at nr=64")
+    ctx, dr = _ctx(capi, nr, M, bnd=bnd)
+    L = O.lib()
+    P = 2 * M + 1
+    rng = np.random.default_rng(nr + M)
+    relax = 1.0e-3 * (dr / 0.02) ** 2
+    q = smooth_field(rng, P, nr, 1, dr)
+    cu = smooth_field(rng, P, nr, 3, dr)
+    dcu = smooth_field(rng, P, nr, 2, dr)
+    amu = smooth_field(rng, P, nr, 3, dr)
+    b0 = smooth_field(rng, P, nr, 3, dr)
+    fq, fcu, fdcu, famu = _mk(capi, ctx, 1, q), _mk(capi, ctx, 3, cu), _mk(capi, ctx, 2, dcu), _mk(capi, ctx, 3, amu)
+
+    # psi
+    want = np.zeros_like(q); L.orc_solve_psi(q, want, nr, M, dr, bnd)
+    fpsi = _mk(capi, ctx, 1); ctx.solve_psi(fq, fpsi); got = fpsi.download()
+    assert plane_relerr(got, want) < FIELD_TOL, ("psi", plane_relerr(got, want))
+    psi = want
+    # bt (beam)
+    want = np.zeros((P, nr + 2, 3)); L.orc_solve_bt(q, want, nr, M, dr, bnd)
+    fb = _mk(capi, ctx, 3); ctx.solve_bt(fq, fb); got = fb.download()
+    assert plane_relerr(got, want) < FIELD_TOL, ("bt", plane_relerr(got, want))
+    # bz : writes only component 3, keeps the rest
+    want = b0.copy(); L.orc_solve_bz(cu, want, nr, M, dr, bnd)
+    fb.upload(b0); ctx.solve_bz(fcu, fb); got = fb.download()
+    assert plane_relerr(got, want) < FIELD_TOL, ("bz", plane_relerr(got, want))
+    # ez
+    e0 = smooth_field(rng, P, nr, 3, dr)
+    want = e0.copy(); L.orc_solve_ez(cu, want, nr, M, dr, bnd)
+    fe = _mk(capi, ctx, 3, e0); ctx.solve_ez(fcu, fe); got = fe.download()
+    assert plane_relerr(got, want) < FIELD_TOL, ("ez", plane_relerr(got, want))
+    # bt_iter (uses the previous iterate in b)
+    want = b0.copy(); L.orc_solve_bt_iter(dcu, cu, want, nr, M, dr, bnd, relax)
+    fb.upload(b0); ctx.solve_bt_iter(fdcu, fcu, fb); got = fb.download()
+    assert plane_relerr(got, want) < FIELD_TOL, ("bt_iter", plane_relerr(got, want))
+    # et / et_beam
+    want = e0.copy(); L.orc_solve_et(b0, psi, want, nr, M, dr)
+    fb.upload(b0); fpsi.upload(psi); fe.upload(e0); ctx.solve_et(fb, fpsi, fe); got = fe.download()
+    assert plane_relerr(got, want) < 1e-13, ("et", plane_relerr(got, want))
+    want = e0.copy(); L.orc_solve_et_beam(b0, want, nr, M)
+    fe.upload(e0); ctx.solve_et_beam(fb, fe)
+    assert np.array_equal(fe.download(), want)
+    # djdxi
+    want = np.zeros((P, nr + 2, 2)); L.orc_solve_djdxi(dcu, amu, want, nr, M, dr)
+    fout = _mk(capi, ctx, 2); ctx.solve_djdxi(fdcu, famu, fout); got = fout.download()
+    assert plane_relerr(got, want) < 1e-13, ("djdxi", plane_relerr(got, want))
+
+
+def test_solver_beats_thomas_accuracy(mods):
+    """the scan solver should sit closer to the long-double solution than fp64 Thomas does (m=0, nr=1024)"""
+    capi, O = mods
+    nr, M = 1024, 0
+    ctx, dr = _ctx(capi, nr, M)
+    L = O.lib()
+    r = (np.arange(nr + 2) - 1) * dr
+    q = np.zeros((1, nr + 2, 1)); q[0, :, 0] = -0.5 * np.exp(-((r - 0.4) / 0.05) ** 2)   # test/TEST_field_psi.f03:55-65
+    a, b, c = np.zeros(nr), np.zeros(nr), np.zeros(nr)
+    L.orc_build_matrix(O.FK_PSI, 0, nr, dr, 3, 0.0, a, b, c)
+    ld = -q[0, 1:nr + 1, 0].copy(); L.orc_tridiag_solve_ld(a, b, c, ld, nr)
+    th = -q[0, 1:nr + 1, 0].copy(); L.orc_tridiag_solve(a, b, c, th, nr)
+    fq, fpsi = _mk(capi, ctx, 1, q), _mk(capi, ctx, 1)
+    ctx.solve_psi(fq, fpsi)
+    got = fpsi.download()[0, 1:nr + 1, 0]
+    e_gpu, e_th = np.max(np.abs(got - ld)) / np.max(np.abs(ld)), np.max(np.abs(th - ld)) / np.max(np.abs(ld))
+    assert e_gpu < 1e-13 and e_gpu <= e_th + 1e-15, (e_gpu, e_th)
+
+
+def test_convergence_tester(mods):
+    capi, O = mods
+    nr, M = 80, 2
+    ctx, dr = _ctx(capi, nr, M)
+    rng = np.random.default_rng(4)
+    b1, b2 = smooth_field(rng, 5, nr, 3, dr), smooth_field(rng, 5, nr, 3, dr)
+    f = _mk(capi, ctx, 3, b1)
+    ctx.convergence_tester(f, 2, capi.CONV_RECORD)
+    f.upload(b2)
+    rel, ab = ctx.convergence_tester(f, 2, capi.CONV_COMPARE)
+    sre = lambda b: np.abs(b[[0, 1, 3], 1:nr + 1, 1]).sum(0)
+    sim = lambda b: np.abs(b[[2, 4], 1:nr + 1, 1]).sum(0)
+    old = np.sqrt(np.max(sre(b1) ** 2 + sim(b1) ** 2))
+    want_abs = np.sqrt(np.max((sre(b1) - sre(b2)) ** 2 + (sim(b1) - sim(b2)) ** 2))
+    assert np.isclose(ab, want_abs, rtol=1e-13) and np.isclose(rel, want_abs / old, rtol=1e-13)
+
+
+@pytest.mark.parametrize("nr,M", CASES)
+def test_particle_kernels_match_oracle(mods, nr, M):
+    capi, O = mods
+    ctx, dr = _ctx(capi, nr, M)
+    L = O.lib()
+    P = 2 * M + 1
+    rng = np.random.default_rng(100 + nr + M)
+    ppc, nth = (2, 8) if nr < 1000 else (2, 16)
+    x, p, g, psi, q = perturbed_lattice(O, rng, nr, dr, ppc, ppc, nth)
+    n = len(q)
+    part = capi.Part2d(ctx, -1.0, 2 * n)
+    part.upload(x, p, g, psi, q)
+    gx, gp, gg, gpsi, gq = part.download()
+    assert all(np.array_equal(a, b) for a, b in ((gx, x), (gp, p), (gg, g), (gpsi, psi), (gq, q)))
+
+    # qdeposit
+    want = O.zeros_f1(1, nr, M); L.orc_qdeposit(x, q, n, dr, nr, M, want)
+    fq = _mk(capi, ctx, 1); part.qdeposit(fq); got = fq.download()
+    assert plane_relerr(got, want) < 1e-12, ("qdeposit", plane_relerr(got, want))
+
+    # amjdeposit_robust
+    e, b = smooth_field(rng, P, nr, 3, dr, 0.3), smooth_field(rng, P, nr, 3, dr, 0.3)
+    fe, fb = _mk(capi, ctx, 3, e), _mk(capi, ctx, 3, b)
+    cu, dcu, amu = O.zeros_f1(3, nr, M), O.zeros_f1(2, nr, M), O.zeros_f1(3, nr, M)
+    g_o, psi_o = g.copy(), psi.copy()
+    dt = 0.02
+    L.orc_amjdeposit_robust(x, p, q, g_o, psi_o, n, dr, nr, M, -1.0, dt, e, b, cu, dcu, amu)
+    fcu, fdcu, famu = _mk(capi, ctx, 3), _mk(capi, ctx, 2), _mk(capi, ctx, 3)
+    part.amjdeposit_robust(fe, fb, fcu, famu, fdcu, dt)
+    for name, f, w in (("cu", fcu, cu), ("dcu", fdcu, dcu), ("amu", famu, amu)):
+        err = plane_relerr(f.download(), w)
+        assert err < 1e-11, (name, err)
+    _, _, gg, gpsi, _ = part.download()
+    assert np.max(np.abs(gg - g_o)) < 1e-13 * np.max(np.abs(g_o))
+    assert np.max(np.abs(gpsi - psi_o)) < 1e-12 * max(1.0, np.max(np.abs(psi_o)))
+
+    # push_u_robust + push_x
+    p_o, x_o = p.copy(), x.copy()
+    L.orc_push_u_robust(x_o, p_o, g_o, n, dr, nr, M, -1.0, dt, e, b)
+    part.push_u_robust(fe, fb, dt)
+    _, gp, gg, _, _ = part.download()
+    assert np.max(np.abs(gp - p_o)) < 1e-13 * np.max(np.abs(p_o)) and np.max(np.abs(gg - g_o)) < 1e-13 * np.max(g_o)
+    L.orc_push_x(x_o, p_o, g_o, n, 40 * dt)
+    part.push_x(40 * dt)
+    gx = part.download()[0]
+    assert np.max(np.abs(gx - x_o)) < 1e-13 * np.max(np.abs(x_o))
+
+    # update_bound: exact compaction order on identical inputs (upload the oracle's positions)
+    part.upload(x_o, p_o, g_o, psi_o, q)
+    npp_o = L.orc_update_bound(x_o, p_o, g_o, psi_o, q_o := q.copy(), n, nr * dr)
+    part.update_bound()
+    gx, gp, gg, gpsi, gq = part.download()
+    assert len(gq) == npp_o
+    assert np.array_equal(gx, x_o[:npp_o]) and np.array_equal(gq, q_o[:npp_o]) and np.array_equal(gp, p_o[:npp_o])
+
+
+def test_update_bound_heavy_loss(mods):
+    capi, O = mods
+    nr, M = 64, 1
+    ctx, dr = _ctx(capi, nr, M)
+    rng = np.random.default_rng(9)
+    n = 5000
+    r = rng.uniform(0.1, 7.0, n)            # ~30 % outside r = 5
+    th = rng.uniform(0, 2 * np.pi, n)
+    x = np.ascontiguousarray(np.stack([r * np.cos(th), r * np.sin(th)], 1))
+    p = rng.standard_normal((n, 3)); g = rng.standard_normal(n); psi = rng.standard_normal(n); q = np.arange(n, dtype=float)
+    for tail_out in (False, True):
+        xx = x.copy()
+        if tail_out:
+            xx[-3:] = 9.0
+        part = capi.Part2d(ctx, -1.0, n + 100)
+        part.upload(xx, p, g, psi, q)
+        xo, po, go, pso, qo = xx.copy(), p.copy(), g.copy(), psi.copy(), q.copy()
+        npp = O.lib().orc_update_bound(xo, po, go, pso, qo, n, nr * dr)
+        part.update_bound()
+        gx, gp, gg, gpsi, gq = part.download()
+        assert len(gq) == npp and np.array_equal(gq, qo[:npp]) and np.array_equal(gx, xo[:npp])
+        part.update_bound()                  # idempotent
+        assert np.array_equal(part.download()[4], qo[:npp])
+
+
+@pytest.mark.parametrize("nr,ppc,nth", [(64, 2, 8), (250, 2, 16), (1024, 2, 16)])
+def test_sort_bit_exact(mods, nr, ppc, nth):
+    capi, O = mods
+    ctx, dr = _ctx(capi, nr, 1)
+    rng = np.random.default_rng(nr)
+    x, p, g, psi, q = perturbed_lattice(O, rng, nr, dr, ppc, ppc, nth, jitter=3.0)
+    n = len(q)
+    q = np.arange(n, dtype=float)
+    part = capi.Part2d(ctx, -1.0, n + 64)
+    part.upload(x, p, g, psi, q)
+    ix_o, ip_o = np.zeros(n, np.int32), np.zeros(n, np.int32)
+    O.lib().orc_sort_idx(x, n, dr, nr, ix_o, ip_o)
+    ix, ip = part.sort_index()
+    assert np.array_equal(ix, ix_o), "cell keys differ"
+    assert np.array_equal(ip, ip_o), "sort permutation differs"
+    xo, po, go, pso, qo = x.copy(), p.copy(), g.copy(), psi.copy(), q.copy()
+    O.lib().orc_sort_part2d(xo, po, go, pso, qo, n, dr, nr)
+    part.sort()
+    gx, gp, gg, gpsi, gq = part.download()
+    assert np.array_equal(gq, qo) and np.array_equal(gx, xo) and np.array_equal(gp, po)
+    keys = np.floor(np.hypot(gx[:, 0], gx[:, 1]) / dr)
+    assert np.all(np.diff(keys) >= 0)
+
+
+@pytest.mark.parametrize("M,push", [(1, 1), (2, 2), (0, 1)])
+def test_beam_kernels_match_oracle(mods, M, push):
+    capi, O = mods
+    nr, nz, nzp, noff2 = 64, 40, 16, 8
+    ctx = capi.Ctx(nr, M, 5.0 / nr, 0.25)
+    dr, dz = 5.0 / nr, 0.25
+    L = O.lib()
+    P = 2 * M + 1
+    rng = np.random.default_rng(M * 7 + push)
+    n = 6000
+    x = np.stack([0.6 * rng.standard_normal(n), 0.6 * rng.standard_normal(n), rng.uniform(noff2 * dz, (noff2 + nzp) * dz * 0.999, n)], 1)
+    p = np.stack([rng.standard_normal(n), rng.standard_normal(n), 50.0 + 5 * rng.standard_normal(n)], 1)
+    q = -rng.uniform(0.5, 1.0, n) * 1e-3
+    x, p = np.ascontiguousarray(x), np.ascontiguousarray(p)
+    beam = capi.Part3d(ctx, -1.0, 4.0, n + 64, nz, noff2, nzp)
+    beam.upload(x, p, q)
+    # deposit
+    guard_in = 0.01 * rng.standard_normal((P, nzp + 1, nr + 2, 1))
+    want = guard_in.copy()
+    L.orc_qdeposit3d(x, q, n, dr, dz, nr, nzp, noff2, M, want)
+    fq = capi.Field(ctx, 1, nzp, True)
+    fq.upload_f2(guard_in)
+    beam.qdeposit(fq)
+    got = fq.download_f2()
+    scale = np.max(np.abs(want))
+    assert np.max(np.abs(got - want)) < 1e-12 * scale
+    # push
+    ef = np.stack([smooth_field(rng, P, nr, 3, dr, 0.2) for _ in range(nzp + 1)], 1)
+    bf = np.stack([smooth_field(rng, P, nr, 3, dr, 0.2) for _ in range(nzp + 1)], 1)
+    fe, fb = capi.Field(ctx, 3, nzp, True), capi.Field(ctx, 3, nzp, True)
+    fe.upload_f2(ef); fb.upload_f2(bf)
+    xo, po = x.copy(), p.copy()
+    L.orc_push3d(xo, po, n, dr, dz, nr, nzp, noff2, M, -1.0, 4.0, push, np.ascontiguousarray(ef), np.ascontiguousarray(bf))
+    beam.push(push, fe, fb)
+    gx, gp, gq = beam.download()
+    assert np.max(np.abs(gp - po)) < 1e-13 * np.max(np.abs(po))
+    assert np.max(np.abs(gx - xo)) < 1e-13 * np.max(np.abs(xo))
+    # update_bound: exact order on identical inputs
+    xo[::7, 0] = 9.0
+    xo[5::11, 2] = nz * dz + 0.1
+    beam.upload(xo, po, q)
+    qo = q.copy()
+    npp = L.orc_update_bound3d(xo, po, qo, n, nr * dr, nz * dz)
+    beam.update_bound()
+    gx, gp, gq = beam.download()
+    assert len(gq) == npp and np.array_equal(gq, qo[:npp]) and np.array_equal(gx, xo[:npp])
+
+
+def _deck(O, decks, nr=64, nz=40, M=1, iter_max=3, **kw):
+    cfg = dict(nr=nr, nz=nz, max_mode=M, rmax=5.0, zmin=-5.0, zmax=5.0, dt=10.0, iter_max=iter_max, iter_reltol=1e-3, iter_abstol=1e-3)
+    cfg.update(kw)
+    beam = dict(decks.CONFIGS["C1"]["beam"])
+    if M >= 2:
+        beam["center"] = (0.0376, 0.0, -2.5)      # off-axis like the hosing deck, excites m >= 1
+    bx, bp, bq = decks.beam_std(cfg["nr"], cfg["nz"], cfg["rmax"], cfg["zmin"], cfg["zmax"], **beam)
+    return cfg, (bx, bp, bq)
+
+
+def _gpu_sim(capi, O, cfg, beam, ppc=2, nth=8, use_graph=0, sort_freq=0):
+    x, p, g, psi, q = O.inject_uniform(cfg["nr"], cfg["rmax"] / cfg["nr"], ppc, ppc, nth)
+    sim = capi.Sim(sp_npmax=2 * len(q), beam_npmax=len(beam[2]) + 64, use_graph=use_graph, sort_freq=sort_freq, **cfg)
+    sim.init_species(x, p, g, psi, q)
+    sim.beam.upload(*beam)
+    return sim, len(q)
+
+
+@pytest.mark.parametrize("M,use_graph", [(1, 0), (1, 1), (2, 1), (0, 1)])
+def test_slice_loop_matches_oracle(mods, M, use_graph):
+    capi, O = mods
+    from qpad_b200 import decks
+    cfg, beam = _deck(O, decks, M=M)
+    nsl = 16
+    orc = O.Sim(ppc1=2, ppc2=2, num_theta=8, **cfg)
+    orc.set_beam(*beam)
+    orc.run_slices(nsl)
+    sim, np0 = _gpu_sim(capi, O, cfg, beam, use_graph=use_graph)
+    sim.beam_qdp_begin(); sim.beam_qdp_end(); sim.begin_step()
+    # first slice alone: the "<= 1e-10 after one slice" gate
+    sim.run_slices(1, 1)
+    o1 = O.Sim(ppc1=2, ppc2=2, num_theta=8, **cfg); o1.set_beam(*beam); o1.run_slices(1)
+    for name in ("psi", "e", "b", "cu", "q_spe"):
+        err = plane_relerr(sim.field(name).download(), o1.field(name, 1))
+        assert err < FIELD_TOL, ("slice 1", name, err)
+    sim.run_slices(2, nsl)
+    upd, iters, slices = sim.stats()
+    assert slices == nsl and upd == nsl * np0
+    assert iters == orc.total_iters(), (iters, orc.total_iters())
+    for name in ("psi", "e", "b", "b_spe", "e_spe", "cu", "q_spe"):
+        got = sim.field(name).download_f2()[:, :nsl]
+        want = orc.field(name, 2)[:, :nsl]
+        scale = np.max(np.abs(want))
+        assert scale > 0
+        assert np.max(np.abs(got - want)) < 1e-8 * scale, (name, np.max(np.abs(got - want)) / scale)
+    gx, gp, gg, gpsi, gq = sim.species.download()
+    ox, op, og, opsi, oq = orc.plasma()
+    assert len(gq) == len(oq) and np.array_equal(gq, oq)
+    assert np.max(np.abs(gx - ox)) < 1e-8 and np.max(np.abs(gp - op)) < 1e-8
+
+
+def test_full_3d_step_with_beam_push(mods):
+    capi, O = mods
+    from qpad_b200 import decks
+    cfg, beam = _deck(O, decks, nr=64, nz=32, M=1, iter_max=2)
+    orc = O.Sim(ppc1=2, ppc2=2, num_theta=8, **cfg)
+    orc.set_beam(*beam)
+    sim, np0 = _gpu_sim(capi, O, cfg, beam, use_graph=1)
+    for step in range(2):
+        orc.step3d(step + 1)
+        sim.step3d()
+    for name in ("psi", "e"):
+        got = sim.field(name).download_f2()[:, :-1]
+        want = orc.field(name, 2)[:, :-1]
+        assert np.max(np.abs(got - want)) < 1e-6 * np.max(np.abs(want)), name
+    gx, gp, gq = sim.beam.download()
+    ox, op, oq = orc.beam()
+    assert len(gq) == len(oq) and np.array_equal(gq, oq)
+    assert np.max(np.abs(gx - ox)) < 1e-9 * np.max(np.abs(ox)) and np.max(np.abs(gp - op)) < 1e-9 * np.max(np.abs(op))
+    # beam centroid / emittance (proj_popas/part3d_popas_class.f03:69-110), 1e-6 gate
+    def emit(x, p, q):
+        w = q / q.sum()
+        mx, mp = (w * x[:, 0]).sum(), (w * p[:, 0]).sum()
+        return mx, np.sqrt((w * (x[:, 0] - mx) ** 2).sum() * (w * (p[:, 0] - mp) ** 2).sum() - ((w * (x[:, 0] - mx) * (p[:, 0] - mp)).sum()) ** 2)
+    (cg, eg), (co, eo) = emit(gx, gp, gq), emit(ox, op, oq)
+    assert abs(eg - eo) < 1e-6 * eo and abs(cg - co) < 1e-6 * max(abs(co), 1e-3)
+
+
+def test_sorted_loop_still_matches(mods):
+    """periodic counting sort changes the particle order, not the physics"""
+    capi, O = mods
+    from qpad_b200 import decks
+    cfg, beam = _deck(O, decks, M=1)
+    nsl = 12
+    orc = O.Sim(ppc1=2, ppc2=2, num_theta=8, sort_freq=4, **cfg)
+    orc.set_beam(*beam)
+    orc.run_slices(nsl)
+    sim, np0 = _gpu_sim(capi, O, cfg, beam, use_graph=1, sort_freq=4)
+    sim.beam_qdp_begin(); sim.beam_qdp_end(); sim.begin_step()
+    sim.run_slices(1, nsl)
+    got, want = sim.field("psi").download_f2()[:, :nsl], orc.field("psi", 2)[:, :nsl]
+    assert np.max(np.abs(got - want)) < 1e-8 * np.max(np.abs(want))
+    gq, oq = sim.species.download()[4], orc.plasma()[4]
+    assert np.array_equal(gq, oq)
+
+
+def test_wire_formats(mods):
+    """pipe_send/recv buffers: field slice (dim, nr+2, 2M+1), plasma 8 doubles/particle, beam 7 doubles/particle"""
+    import torch
+    capi, O = mods
+    nr, M = 40, 1
+    ctx, dr = _ctx(capi, nr, M)
+    rng = np.random.default_rng(2)
+    a = rng.standard_normal((3, nr + 2, 3))
+    f = capi.Field(ctx, 3, 3, True); f.upload(a)
+    buf = torch.zeros(f.wire_count(), dtype=torch.float64, device="cuda")
+    f.pack(0, buf.data_ptr()); ctx.sync()
+    assert np.array_equal(buf.cpu().numpy().reshape(3, nr + 2, 3), a)
+    f.unpack(2, buf.data_ptr(), add=False); f.unpack(2, buf.data_ptr(), add=True); ctx.sync()
+    assert np.array_equal(f.download_f2()[:, 1], 2 * a)
+    x, p, g, psi, q = perturbed_lattice(O, rng, nr, dr, 2, 2, 8)
+    n = len(q)
+    pa, pb = capi.Part2d(ctx, -1.0, 2 * n), capi.Part2d(ctx, -1.0, 2 * n)
+    pa.upload(x, p, g, psi, q)
+    wb = torch.zeros(pa.wire_count(), dtype=torch.float64, device="cuda")
+    pa.pack(wb.data_ptr()); ctx.sync()
+    rec = wb.cpu().numpy()
+    assert rec[-1] == n
+    assert np.array_equal(rec[:8 * n].reshape(n, 8), np.column_stack([x, p, g, psi, q]))
+    pb.unpack(wb.data_ptr())
+    assert all(np.array_equal(u, v) for u, v in zip(pb.download(), (x, p, g, psi, q)))
+    # beam forward hand-off
+    nz, nzp = 20, 10
+    c2 = capi.Ctx(nr, M, dr, 0.5)
+    nb = 3000
+    bx = np.ascontiguousarray(np.stack([0.5 * rng.standard_normal(nb), 0.5 * rng.standard_normal(nb), rng.uniform(0, 5.6, nb)], 1))
+    bp = rng.standard_normal((nb, 3)); bq = np.arange(nb, dtype=float)
+    b0 = capi.Part3d(c2, -1.0, 1.0, nb + 64, nz, 0, nzp)
+    b1 = capi.Part3d(c2, -1.0, 1.0, nb + 64, nz, nzp, nzp)
+    b0.upload(bx, bp, bq)
+    hb = torch.zeros(7 * b0.wire_cap() + 1, dtype=torch.float64, device="cuda")
+    b0.pack_forward(hb.data_ptr()); c2.sync()
+    go = np.nonzero(bx[:, 2] >= nzp * 0.5)[0]
+    rec = hb.cpu().numpy()
+    assert rec[-1] == len(go)
+    assert np.array_equal(rec[:7 * len(go)].reshape(-1, 7)[:, 6], bq[go])      # packed in ascending index order
+    keep = b0.download()[2]
+    # "fill the holes inversely" (part3d_comm.f03:733-745)
+    exp = list(bq); npp = nb
+    for h in go[::-1]:
+        exp[h] = exp[npp - 1]; npp -= 1
+    assert np.array_equal(keep, np.array(exp[:npp]))
+    b1.unpack(hb.data_ptr())
+    assert np.array_equal(np.sort(b1.download()[2]), np.sort(bq[go]))

@@ -1,0 +1,161 @@
+"""Pins the CPU oracle (oracle/qpad_oracle.c) against analytic known answers.
+
+The reference ships no golden vectors or assertions; these are the known-answer tests SURVEY.md §8(c)
+prescribes instead.  They run without a GPU.
+"""
+import numpy as np
+import pytest
+from oracle import oracle as O
+
+
+def _psi_error(nr, m, rmax=8.0):
+    dr = rmax / nr
+    r = (np.arange(nr + 2) - 1) * dr
+    P = 2 * m + 1
+    q = np.zeros((P, nr + 2, 1))
+    if m == 0:
+        exact = np.exp(-r * r)
+        src = -(4 * r * r - 4) * np.exp(-r * r)
+    else:
+        exact = r * np.exp(-r * r)
+        src = -(4 * r ** 3 - 8 * r) * np.exp(-r * r)
+    pl = 0 if m == 0 else 1
+    q[pl, :, 0] = src
+    psi = np.zeros_like(q)
+    O.lib().orc_solve_psi(q, psi, nr, m, dr, O.BND_OPEN)
+    return np.max(np.abs(psi[pl, 1:nr + 1, 0] - exact[1:nr + 1]))
+
+
+@pytest.mark.parametrize("m", [0, 1])
+def test_poisson_second_order(m):
+    e1, e2 = _psi_error(128, m), _psi_error(256, m)
+    assert e2 < 2e-3
+    assert 3.3 < e1 / e2 < 4.7, (e1, e2)
+
+
+def test_thomas_matches_long_double():
+    L = O.lib()
+    nr, dr = 250, 0.02
+    rng = np.random.default_rng(1)
+    for kind in range(6):
+        for m in range(3):
+            a, b, c = np.zeros(nr), np.zeros(nr), np.zeros(nr)
+            L.orc_build_matrix(kind, m, nr, dr, O.BND_OPEN, 1e-3, a, b, c)
+            d = rng.standard_normal(nr)
+            x1, x2 = d.copy(), d.copy()
+            L.orc_tridiag_solve(a, b, c, x1, nr)
+            L.orc_tridiag_solve_ld(a, b, c, x2, nr)
+            assert np.max(np.abs(x1 - x2)) <= 1e-11 * np.max(np.abs(x2))
+            # residual of the long-double solution
+            res = b * x2
+            res[1:] += a[1:] * x2[:-1]
+            res[:-1] += c[:-1] * x2[1:]
+            assert np.max(np.abs(res - d)) < 1e-9 * np.max(np.abs(b)) * np.max(np.abs(x2))
+
+
+def test_matrix_rows_match_survey_a6():
+    L = O.lib()
+    nr, dr = 16, 0.1
+    a, b, c = np.zeros(nr), np.zeros(nr), np.zeros(nr)
+    L.orc_build_matrix(O.FK_PSI, 0, nr, dr, O.BND_OPEN, 0.0, a, b, c)
+    assert np.allclose([a[0], b[0], c[0]], np.array([0, -4, 4]) / dr ** 2)
+    j = 3.0
+    assert np.allclose([a[3], b[3], c[3]], np.array([1 - 0.5 / j, -2.0, 1 + 0.5 / j]) / dr ** 2)
+    assert c[-1] == 0.0
+    L.orc_build_matrix(O.FK_BMINUS, 1, nr, dr, O.BND_OPEN, 1e-3, a, b, c)   # k = 0 -> coupled axis with relax
+    assert np.allclose([a[0], b[0], c[0]], np.array([0, -4 - 1e-3, 4]) / dr ** 2)
+    L.orc_build_matrix(O.FK_BPLUS, 1, nr, dr, O.BND_OPEN, 1e-3, a, b, c)    # k = 2 -> decoupled axis
+    assert np.allclose([a[0], b[0], c[0], a[1]], np.array([0, 1, 0, 0]) / dr ** 2)
+    jm = float(nr)
+    exp_diag = (-2.0 - (2.0 / (nr - 1)) ** 2 - 1e-3) + (1 - 2.0 / jm) * (1 + 0.5 / (nr - 1))
+    assert np.isclose(b[-1] * dr ** 2, exp_diag)
+
+
+@pytest.mark.parametrize("max_mode", [0, 1, 2])
+def test_charge_conservation_and_neutrality(max_mode):
+    nr, dr = 48, 0.1
+    x, p, g, psi, q = O.inject_uniform(nr, dr, 2, 2, 8)
+    f = O.zeros_f1(1, nr, max_mode)
+    O.lib().orc_qdeposit(x, q, len(q), dr, nr, max_mode, f)
+    raw = f[0, :, 0].copy()
+    raw[1] /= 8.0
+    raw[2:] *= np.arange(1, nr + 1)
+    assert np.isclose(raw.sum(), q.sum(), rtol=1e-13)
+    # uniform lattice: density -1 away from the axis/edge cells, higher modes vanish
+    dens = f[0, 3:nr - 1, 0] / dr ** 0
+    assert np.allclose(dens, dens[0], rtol=1e-12)
+    if max_mode:
+        assert np.max(np.abs(f[1:])) < 1e-13 * np.max(np.abs(f[0]))
+
+
+def test_boris_rotation_preserves_momentum():
+    nr, dr, M = 32, 0.1, 1
+    rng = np.random.default_rng(3)
+    x, p, g, psi, q = O.inject_uniform(nr, dr, 2, 2, 8)
+    p = rng.standard_normal(p.shape)
+    p0 = p.copy()
+    e = O.zeros_f1(3, nr, M)
+    b = O.zeros_f1(3, nr, M)
+    b[0, :, 2] = 0.7
+    b[0, :, 1] = 0.2
+    O.lib().orc_push_u_robust(x, p, g, len(q), dr, nr, M, -1.0, 0.05, e, b)
+    assert np.allclose((p ** 2).sum(1), (p0 ** 2).sum(1), rtol=1e-13)
+    assert np.allclose(g, np.sqrt(1 + (p ** 2).sum(1)))
+    assert not np.allclose(p, p0)
+
+
+def test_update_bound_order():
+    # particles 1..8 (1-based), 2, 5, 8 out -> sequential swap-with-last gives [1,7,3,4,6]
+    n = 8
+    r = np.full(n, 0.5)
+    r[[1, 4, 7]] = 2.0
+    x = np.stack([r, np.zeros(n)], 1).copy()
+    p = np.zeros((n, 3))
+    tag = np.arange(1, n + 1, dtype=float)
+    g, psi, q = tag.copy(), tag.copy(), tag.copy()
+    npp = O.lib().orc_update_bound(x, p, g, psi, q, n, 1.0)
+    assert npp == 5
+    assert list(q[:npp]) == [1, 7, 3, 4, 6]
+
+
+def test_sort_index_reverse_stable():
+    dr, nrp = 1.0, 4
+    r = np.array([2.5, 0.5, 2.2, 0.7, 3.1])
+    x = np.stack([r, np.zeros_like(r)], 1).copy()
+    ix, ip = np.zeros(5, np.int32), np.zeros(5, np.int32)
+    O.lib().orc_sort_idx(x, 5, dr, nrp, ix, ip)
+    assert list(ix) == [3, 1, 3, 1, 4]
+    assert list(ip) == [4, 2, 3, 1, 5]   # within a cell the first particle takes the last slot
+
+
+def test_neutral_plasma_without_beam_stays_quiet():
+    s = O.Sim(nr=32, nz=8, max_mode=1, iter_max=2, ppc1=2, ppc2=2, num_theta=8)
+    s.step3d()
+    for name in ("psi", "e", "b"):
+        assert np.max(np.abs(s.field(name, 2))) < 1e-12
+
+
+def _beam(cfg, n=4000, seed=5):
+    rng = np.random.default_rng(seed)
+    L = cfg["zmax"] - cfg["zmin"]
+    x = np.stack([0.3 * rng.standard_normal(n), 0.3 * rng.standard_normal(n), rng.uniform(0.15 * L, 0.6 * L, n)], 1)
+    p = np.stack([rng.standard_normal(n), rng.standard_normal(n), 2000.0 + rng.standard_normal(n)], 1)
+    q = np.full(n, -4.0e-4)
+    return x, p, q
+
+
+def test_pipeline_stages_match_single_stage():
+    cfg = dict(nr=48, nz=24, max_mode=1, rmax=4.0, zmin=-3.0, zmax=3.0, dt=5.0, iter_max=3, ppc1=2, ppc2=2, num_theta=8)
+    x, p, q = _beam(cfg)
+    ref = O.Sim(nstages=1, **cfg)
+    ref.set_beam(x, p, q)
+    pip = O.Sim(nstages=3, **cfg)
+    pip.set_beam(x, p, q)
+    for step in (1, 2):
+        u1, u2 = ref.step3d(step), pip.step3d(step)
+        assert u1 == u2
+    full = ref.field("psi", 2)[:, :-1]
+    parts = np.concatenate([pip.field("psi", 2, stage=k)[:, :-1] for k in range(3)], axis=1)
+    assert np.max(np.abs(parts - full)) <= 1e-11 * np.max(np.abs(full))
+    assert sum(len(pip.beam(k)[2]) for k in range(3)) == len(ref.beam(0)[2])
+    assert np.max(np.abs(full)) > 1e-3
