@@ -79,6 +79,7 @@ def lib(fast=False):
         "orc_sim_set_beam": (None, [vp, _dp, _dp, _dp, l]),
         "orc_sim_step3d": (l, [vp, i]),
         "orc_sim_run_slices": (l, [vp, i]),
+        "orc_sim_run_range": (l, [vp, i, i]),
         "orc_sim_nzp": (i, [vp, i]),
         "orc_sim_plasma_np": (l, [vp, i]),
         "orc_sim_get_plasma": (None, [vp, i, _dp, _dp, _dp, _dp, _dp]),
@@ -141,6 +142,9 @@ class Sim:
 
     def run_slices(self, n):
         return self.L.orc_sim_run_slices(self.h, n)
+
+    def run_range(self, j0, j1):
+        return self.L.orc_sim_run_range(self.h, j0, j1)
 
     def nzp(self, stage=0):
         return self.L.orc_sim_nzp(self.h, stage)

@@ -1444,6 +1444,13 @@ long orc_sim_run_slices(orc_sim *s, int nslices)
     return updates;
 }
 
+long orc_sim_run_range(orc_sim *s, int j0, int j1)
+{
+    long updates = 0;
+    for (int j = j0; j <= j1 && j <= s->st[0].nzp; j++) { updates += s->st[0].spe.part.npp; slice_step(s, 0, j); }
+    return updates;
+}
+
 int orc_sim_nzp(const orc_sim *s, int stage) { return s->st[stage].nzp; }
 long orc_sim_plasma_np(const orc_sim *s, int stage) { return s->st[stage].spe.part.npp; }
 void orc_sim_get_plasma(const orc_sim *s, int stage, double *x, double *p, double *gamma, double *psi, double *q)

@@ -96,6 +96,8 @@ void orc_sim_set_beam(orc_sim *s, const double *x, const double *p, const double
 long orc_sim_step3d(orc_sim *s, int istep);
 /* run only the first `nslices` slices of stage 0 of a 3D step (parity at slice granularity; no beam push) */
 long orc_sim_run_slices(orc_sim *s, int nslices);
+/* continue stage 0 with slices j0..j1 (no re-initialisation) */
+long orc_sim_run_range(orc_sim *s, int j0, int j1);
 /* accessors (copy out) */
 int orc_sim_nzp(const orc_sim *s, int stage);
 long orc_sim_plasma_np(const orc_sim *s, int stage);

@@ -242,7 +242,7 @@ extern "C" int qpg_ctx_create(qpg_ctx *out, int device, void *cuda_stream, int n
     CUDA_TRY(cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     int stride = (C == 1) ? 1 : C + 1;
     int per_sys = 2 * 32 * stride * (int)sizeof(double);
-    int want = 2 * c->P * per_sys + 4096;
+    int want = (2 * c->P > 4 ? 2 * c->P : 4) * per_sys + 4096;
     if (want > maxsm) want = (maxsm / 1024) * 1024;
     if (want < 4 * per_sys + 4096) { qpg_set_error("nr=%d needs %d B shared memory per system, device offers %d", nr, per_sys, maxsm); return QPG_ERR_UNSUPPORTED; }
     c->smem_field = want;

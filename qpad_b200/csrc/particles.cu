@@ -342,15 +342,16 @@ __global__ void __launch_bounds__(1024, 1) k_compact(double *const *planes, int 
     // words are split into contiguous per-thread ranges so ranks are ordered
     const int wpt = (nwords + nt - 1) / nt;
     const int wbeg = min(tid * wpt, nwords), wend = min(wbeg + wpt, nwords);
+    // mode 0: holes = flagged indices < K (ascending), surv = unflagged indices >= K (ascending)
+    // mode 1: holes = ALL flagged indices (ascending); sources are found by chasing (see below)
     int ch = 0, cs = 0;
     for (int w = wbeg; w < wend; w++) {
         unsigned bits = outmask[w];
         const int lo = w << 5;
         unsigned inrange = (lo + 32 <= n) ? FULL : ((1u << (n - lo)) - 1u);
         bits &= inrange;
-        // head part of the word: indices < K
         unsigned headmask = (lo + 32 <= K) ? FULL : (lo >= K ? 0u : ((1u << (K - lo)) - 1u));
-        ch += __popc(bits & headmask);
+        ch += __popc(desc_holes ? bits : (bits & headmask));
         cs += __popc(~bits & inrange & ~headmask);
     }
     int toth, tots;
@@ -362,18 +363,36 @@ __global__ void __launch_bounds__(1024, 1) k_compact(double *const *planes, int 
         unsigned inrange = (lo + 32 <= n) ? FULL : ((1u << (n - lo)) - 1u);
         bits &= inrange;
         unsigned headmask = (lo + 32 <= K) ? FULL : (lo >= K ? 0u : ((1u << (K - lo)) - 1u));
-        unsigned hb = bits & headmask, sb = ~bits & inrange & ~headmask;
+        unsigned hb = desc_holes ? bits : (bits & headmask), sb = ~bits & inrange & ~headmask;
         while (hb) { int b = __ffs(hb) - 1; hb &= hb - 1; holes[oh++] = lo + b; }
-        while (sb) { int b = __ffs(sb) - 1; sb &= sb - 1; surv[os++] = lo + b; }
-        outmask[w] = 0u;
+        if (!desc_holes) while (sb) { int b = __ffs(sb) - 1; sb &= sb - 1; surv[os++] = lo + b; }
     }
     __syncthreads();
-    // toth == tots by construction
-    for (int r = tid; r < toth; r += nt) {
-        const int dst = desc_holes ? holes[toth - 1 - r] : holes[r];
-        const int src = surv[tots - 1 - r];
-        for (int a = 0; a < nplanes; a++) planes[a][dst] = planes[a][src];
+    if (!desc_holes) {
+        // sequential swap-with-last (update_bound): ascending head holes <- descending tail survivors
+        for (int r = tid; r < toth; r += nt) {
+            const int dst = holes[r], src = surv[tots - 1 - r];
+            for (int a = 0; a < nplanes; a++) planes[a][dst] = planes[a][src];
+        }
+    } else {
+        // "fill the holes inversely" (part3d_comm.f03:733-745): the t-th largest hole receives the CURRENT content of
+        // position n-t, which may itself be a larger hole filled earlier -> chase until a surviving particle is found.
+        for (int r = tid; r < nout; r += nt) {
+            const int dst = holes[r];
+            if (dst >= K) continue;  // dropped with the tail
+            int pos = n - (nout - r);
+            while (pos != dst && ((outmask[pos >> 5] >> (pos & 31)) & 1u)) {
+                int lo = 0, hi = nout;  // index of pos in holes[]
+                while (lo < hi) { int mid = (lo + hi) >> 1; if (holes[mid] < pos) lo = mid + 1; else hi = mid; }
+                const int np2 = n - (nout - lo);
+                if (np2 == pos) break;
+                pos = np2;
+            }
+            for (int a = 0; a < nplanes; a++) planes[a][dst] = planes[a][pos];
+        }
     }
+    __syncthreads();
+    for (int w = wbeg; w < wend; w++) outmask[w] = 0u;
     if (tid == 0) { *d_npp = K; *d_nout = 0; }
 }
 

@@ -82,3 +82,29 @@ def beam_std(nr, nz, rmax, zmin, zmax, ppc, num_theta, q, m, gamma, density, cen
         p = np.concatenate([p, p * np.array([-1.0, -1.0, 1.0])])
         qq = np.concatenate([0.5 * qq, 0.5 * qq])
     return np.ascontiguousarray(x), np.ascontiguousarray(p), np.ascontiguousarray(qq)
+
+
+def plasma_uniform(nr, rmax, ppc1, ppc2, num_theta, q=-1.0, density=1.0, den_min=1e-10):
+    """Host-side plasma injection for the uniform/uniform profile with uth = 0 and ordered theta: a vectorised
+    restatement of inject_fdist2d (species/fdist2d_class.f03:289-357).  Loop order of the reference: theta sector j,
+    radial cell i, i1, i2 (innermost).  Returns x(np,2), p(np,3), gamma, psi, q in the reference's AoS layout."""
+    dr = rmax / nr
+    if density < den_min:
+        z = np.zeros
+        return z((0, 2)), z((0, 3)), z(0), z(0), z(0)
+    dtheta = 2.0 * np.pi / num_theta
+    j = np.arange(1, num_theta + 1)
+    i = np.arange(1, nr + 1)
+    i1 = (np.arange(1, ppc1 + 1) - 0.5) / ppc1
+    i2 = (np.arange(1, ppc2 + 1) - 0.5) / ppc2
+    J, I, I1, I2 = np.meshgrid(j, i, i1, i2, indexing="ij")
+    rn = (I1 + (I - 1.0)).ravel()
+    theta = ((I2 + J - 1.0) * dtheta).ravel()
+    coef = np.sign(q) / (float(ppc1 * ppc2) * float(num_theta))
+    x = np.stack([rn * dr * np.cos(theta), rn * dr * np.sin(theta)], 1)
+    qq = rn * 1.0 * 1.0 * density * coef
+    n = len(qq)
+    p = np.zeros((n, 3))
+    gamma = np.ones(n)
+    psi = (1.0 - gamma + p[:, 2]) / q
+    return np.ascontiguousarray(x), p, gamma, psi, np.ascontiguousarray(qq)

@@ -1,0 +1,225 @@
+"""Host-side drivers of a 3D step: single stage, and the xi-pipeline over one GPU per stage.
+
+Mirrors the stage logic of simulation_class.f03:294-512 / parallel_module.f03:221-239: `nodes(2)` stages own
+contiguous xi slabs (options_class.f03:103-106), stage s works on 3D step n while stage s+1 works on step n-1.
+The reference's MPI isend/recv pairs become torch.distributed (NCCL over NVLink) p2p transfers of the library's
+wire buffers (qpg_*_pack / qpg_*_unpack); torch is plumbing only (device buffers, streams, process group).
+
+Per 3D step and stage boundary:
+  forward : beam q guard slice (add), plasma particles (8 fp64 each), last-slice cu and b_spe
+  backward: first-slice e and b into the upstream guard slice nzp+1
+  forward : beam particles that crossed the slab edge (7 fp64 each)
+"""
+import numpy as np
+
+from . import capi
+
+
+def slab_partition(nz, nstages):
+    """noff/ndp rule of options_class.f03:103-106 (remainder goes to the first stages)."""
+    local, extra = nz // nstages, nz % nstages
+    out = []
+    for k in range(nstages):
+        out.append((local * k + min(k, extra), local + (1 if k < extra else 0)))
+    return out
+
+
+def split_beam(bx, bp, bq, nz, dxi, nstages):
+    """owner stage of each beam particle: the slab [noff2, noff2+nzp)*dxi that holds xi (part3d_comm.f03 goto_here)"""
+    edges = [noff * dxi for noff, _ in slab_partition(nz, nstages)][1:]
+    owner = np.searchsorted(np.asarray(edges), bx[:, 2], side="right") if nstages > 1 else np.zeros(len(bq), int)
+    return [tuple(np.ascontiguousarray(a[owner == k]) for a in (bx, bp, bq)) for k in range(nstages)]
+
+
+def _make_sim(cfg, npp0, nbeam, stream, device, use_graph, noff2=0, nzp=None, beam_cap=None):
+    cuda_stream = None if stream is None else stream.cuda_stream
+    return capi.Sim(cfg["nr"], cfg["nz"], cfg["max_mode"], cfg["rmax"], cfg["zmin"], cfg["zmax"], cfg["dt"],
+                    sp_qbm=-1.0, sp_npmax=2 * npp0, beam_qbm=-1.0, beam_npmax=beam_cap or (nbeam + 1024),
+                    iter_max=cfg.get("iter_max", 1), iter_reltol=cfg.get("iter_reltol", 1e-3),
+                    iter_abstol=cfg.get("iter_abstol", 1e-3), sort_freq=cfg.get("sort_freq", 0), use_graph=use_graph,
+                    noff2=noff2, nzp=nzp, device=device, stream=cuda_stream)
+
+
+class SingleStage:
+    """nodes = [1, 1]: the whole box on one GPU."""
+
+    def __init__(self, cfg, plasma, beam, stream=None, rank=0, world=1, device=0, use_graph=1):
+        self.cfg, self.plasma = cfg, plasma
+        self.sim = _make_sim(cfg, len(plasma[4]), len(beam[2]), stream, device, use_graph)
+        self.sim.init_species(*plasma)
+        self.sim.beam.upload(*beam)
+
+    def step(self):
+        self.sim.step3d()
+
+    # pieces used by bench.py's roofline leg
+    def prepare_step(self):
+        s = self.sim
+        s.beam_qdp_begin(); s.beam_qdp_end(); s.begin_step()
+
+    def finish_step(self):
+        self.sim.renew()
+
+    def step_e2e(self):
+        """one step through host buffers: the freshly injected plasma goes host -> device (species%renew on the
+        host side, as the Fortran driver does), results come back as on-axis line-outs"""
+        s = self.sim
+        x, p, g, psi, q = self.plasma
+        s.species.upload(x, p, g, psi, q)
+        s.beam_qdp_begin(); s.beam_qdp_end(); s.begin_step()
+        s.run_slices(1, s.nzp)
+        s.beam_push()
+        ez = s.field("e").lineout(3, 0, 1)
+        ps = s.field("psi").lineout(1, 0, 1)
+        st = s.stats()
+        self.last = (ez, ps, st)
+        return 8 * 8 * len(q), 8 * (len(ez) + len(ps)) + 24
+
+    def kernel_microbench(self, peak_gbs, n_big=4 * 1024 * 1024, reps=5):
+        """stream-from-HBM numbers for the three particle kernels: a lattice 16x larger than the L2 can hold
+        (n_big particles x 64 B = 268 MB), fields = the current slice's e and b"""
+        import torch
+        s = self.sim
+        cfg = self.cfg
+        from . import decks
+        nth = max(16, n_big // (cfg["nr"] * cfg["ppc1"] * cfg["ppc2"]))
+        x, p, g, psi, q = decks.plasma_uniform(cfg["nr"], cfg["rmax"], cfg["ppc1"], cfg["ppc2"], nth)
+        n = len(q)
+        rng = np.random.default_rng(0)
+        p = 0.3 * rng.standard_normal(p.shape)
+        g = np.sqrt(1 + (p ** 2).sum(1))
+        part = capi.Part2d(s.ctx, -1.0, n + 64)
+        part.upload(x, p, g, psi, q)
+        e, b = s.field("e"), s.field("b")
+        cu, dcu, amu = capi.Field(s.ctx, 3), capi.Field(s.ctx, 2), capi.Field(s.ctx, 3)
+        fq = capi.Field(s.ctx, 1)
+        res = {}
+        s.ctx.tprof_reset(); s.ctx.tprof_enable(True)
+        for _ in range(reps + 2):
+            part.qdeposit(fq)
+            part.amjdeposit_robust(e, b, cu, amu, dcu, 1e-3)
+            part.push_u_robust(e, b, 1e-3)
+            part.push_x(1e-6)
+        for ev, bpp in (("kernel amjdeposit", 64), ("kernel qdeposit", 24), ("kernel push", None)):
+            ms, nc = s.ctx.tprof_get(ev)
+            res[ev] = (ms, nc)
+        s.ctx.tprof_enable(False)
+        out = {"particles": n, "note": "particle set larger than L2; amjdeposit 64 B, qdeposit 24 B, push_u 72 B + push_x 64 B per particle"}
+        ms, nc = res["kernel amjdeposit"]
+        out["amjdeposit_GBs"] = 64.0 * n / (ms / nc * 1e-3) / 1e9
+        ms, nc = res["kernel qdeposit"]
+        out["qdeposit_GBs"] = 24.0 * n / (ms / nc * 1e-3) / 1e9
+        ms, nc = res["kernel push"]  # push_u and push_x launches alternate: 136 B per pair
+        out["push_u_plus_push_x_GBs"] = 136.0 * n / (2 * ms / nc * 1e-3) / 1e9
+        out["peak"] = peak_gbs
+        out["amjdeposit_frac"] = out["amjdeposit_GBs"] / peak_gbs
+        part.close()
+        return out
+
+    def close(self):
+        self.sim.close()
+
+
+class PipelineStage:
+    """One rank = one xi slab on one GPU; consecutive ranks are consecutive pipeline stages."""
+
+    def __init__(self, cfg, plasma, beam, stream=None, rank=0, world=1, device=0, use_graph=1, dist=None, make_buf=None):
+        import torch
+        import torch.distributed as tdist
+        self.dist = dist or tdist
+        self.rank, self.world, self.cfg, self.plasma = rank, world, cfg, plasma
+        self.noff2, self.nzp = slab_partition(cfg["nz"], world)[rank]
+        dxi = (cfg["zmax"] - cfg["zmin"]) / cfg["nz"]
+        mine = split_beam(*beam, cfg["nz"], dxi, world)[rank]
+        self.sim = _make_sim(cfg, len(plasma[4]), len(mine[2]), stream, device, use_graph, self.noff2, self.nzp, beam_cap=len(beam[2]) + 1024)
+        self.sim.init_species(*plasma)
+        self.sim.beam.upload(*mine)
+        s = self.sim
+        mk = make_buf or (lambda n: torch.zeros(n, dtype=torch.float64, device=torch.device("cuda", device)))
+        self.buf_q = mk(s.field("beam_q").wire_count())
+        self.buf_cu = mk(s.field("cu").wire_count())
+        self.buf_bs = mk(s.field("b_spe").wire_count())
+        self.buf_e = mk(s.field("e").wire_count())
+        self.buf_b = mk(s.field("b").wire_count())
+        self.buf_p = mk(s.species.wire_count())
+        self.buf_beam = mk(7 * s.beam.wire_cap() + 1)
+        # separate in/out buffers wherever a stage both receives and sends the same kind of message
+        self.buf_p_out, self.buf_cu_out, self.buf_bs_out = mk(s.species.wire_count()), mk(s.field("cu").wire_count()), mk(s.field("b_spe").wire_count())
+        self.buf_b_in, self.buf_e_in = mk(s.field("b").wire_count()), mk(s.field("e").wire_count())
+        self.buf_beam_in = mk(7 * s.beam.wire_cap() + 1)
+        self.first, self.last = rank == 0, rank == world - 1
+        self.stream = stream
+        self.torch = torch
+        self.comm = torch.cuda.Stream(device=device) if (stream is not None and make_buf is None) else None
+        self.pending = {}
+
+    # mpi_isend analogue: the transfer runs on the communication stream, the compute stream carries on.  The buffer
+    # is only repacked after _wait(name) (the reference's mpi_wait before every pipe_send, simulation_class.f03:430).
+    def _isend(self, name, t, dst):
+        if self.comm is None:
+            if self.stream is None:
+                self.sim.ctx.sync()
+            self.pending[name] = self.dist.isend(t, dst)
+            return
+        self.comm.wait_stream(self.stream)
+        with self.torch.cuda.stream(self.comm):
+            self.pending[name] = self.dist.isend(t, dst)
+
+    def _wait(self, name):
+        w = self.pending.pop(name, None)
+        if w is not None:
+            w.wait()
+
+    def _recv(self, t, src):
+        self.dist.recv(t, src)
+        if self.comm is None and self.stream is None:
+            pass
+
+    def step(self):
+        s, r = self.sim, self.rank
+        # species%precv, cu / b_spe pipe_recv and the beam q guard slice: everything stage r-1 hands forward arrives
+        # when it has finished its slab (simulation_class.f03:303-340; the guard slice is taken at the same point so
+        # that an upstream stage never waits for a downstream one)
+        s.beam_qdp_begin()                                              # beam3d_class.f03:207
+        if not self.first:
+            self._recv(self.buf_q, r - 1)
+            s.field("beam_q").unpack(1, self.buf_q.data_ptr(), add=True)
+        s.beam_qdp_end()                                                # :210
+        s.begin_step()
+        if not self.first:
+            self._recv(self.buf_p, r - 1)
+            s.species.unpack(self.buf_p.data_ptr())
+            self._recv(self.buf_cu, r - 1)
+            s.field("cu").unpack(0, self.buf_cu.data_ptr())
+            self._recv(self.buf_bs, r - 1)
+            s.field("b_spe").unpack(0, self.buf_bs.data_ptr())
+        # first slice, then the backward hand-off of e and b (:460-467), then the rest of the slab
+        s.run_slices(1, 1)
+        if not self.first:
+            self._wait("b"); s.field("b").pack(1, self.buf_b.data_ptr()); self._isend("b", self.buf_b, r - 1)
+            self._wait("e"); s.field("e").pack(1, self.buf_e.data_ptr()); self._isend("e", self.buf_e, r - 1)
+        if self.nzp > 1:
+            s.run_slices(2, self.nzp)
+        if not self.last:                                               # :210-215, :429-434, :472-474
+            self._wait("q"); s.field("beam_q").pack(self.nzp + 1, self.buf_q.data_ptr()); self._isend("q", self.buf_q, r + 1)
+            self._wait("p"); s.species.pack(self.buf_p_out.data_ptr()); self._isend("p", self.buf_p_out, r + 1)
+            self._wait("cu"); s.field("cu").pack(0, self.buf_cu_out.data_ptr()); self._isend("cu", self.buf_cu_out, r + 1)
+            self._wait("bs"); s.field("b_spe").pack(0, self.buf_bs_out.data_ptr()); self._isend("bs", self.buf_bs_out, r + 1)
+            self._recv(self.buf_b_in, r + 1); s.field("b").unpack(self.nzp + 1, self.buf_b_in.data_ptr())   # :482-483
+            self._recv(self.buf_e_in, r + 1); s.field("e").unpack(self.nzp + 1, self.buf_e_in.data_ptr())
+        # beam push + forward hand-off                                  (:489-493, part3d_comm.f03:278-314)
+        s.beam_push()
+        if not self.first:
+            self._recv(self.buf_beam_in, r - 1)
+            s.beam.unpack(self.buf_beam_in.data_ptr())
+        if not self.last:
+            self._wait("beam"); s.beam.pack_forward(self.buf_beam.data_ptr()); self._isend("beam", self.buf_beam, r + 1)
+        s.renew()                                                       # :498-501
+
+    def drain(self):
+        for k in list(self.pending):
+            self._wait(k)
+
+    def close(self):
+        self.drain()
+        self.sim.close()
