@@ -205,6 +205,8 @@ int qpg_sim_renew(qpg_sim s);
 int qpg_sim_stats(qpg_sim s, long *updates, long *pc_iters, long *slices);
 /* switch the slice body between CUDA-graph replay (1) and plain stream launches (0, needed for per-kernel tprof) */
 int qpg_sim_set_graph(qpg_sim s, int use_graph);
+/* field programs: 1 = thread-block-cluster kernels (default when nr <= 1024 and max_mode <= 2), 0 = generic op-list CTA */
+int qpg_sim_set_fused(qpg_sim s, int on);
 
 #ifdef __cplusplus
 }

@@ -122,6 +122,7 @@ SIGNATURES = {
     "qpg_sim_renew": (_i, [_vp]),
     "qpg_sim_stats": (_i, [_vp, _pl, _pl, _pl]),
     "qpg_sim_set_graph": (_i, [_vp, _i]),
+    "qpg_sim_set_fused": (_i, [_vp, _i]),
 }
 
 
@@ -419,6 +420,7 @@ class Sim:
     def beam_push(self): _chk(self.L.qpg_sim_beam_push(self.h))
     def renew(self): _chk(self.L.qpg_sim_renew(self.h))
     def set_graph(self, on): _chk(self.L.qpg_sim_set_graph(self.h, int(on)))
+    def set_fused(self, on): _chk(self.L.qpg_sim_set_fused(self.h, int(on)))
 
     def stats(self):
         u, it, sl = _l(), _l(), _l()

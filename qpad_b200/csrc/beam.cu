@@ -343,7 +343,7 @@ extern "C" int qpg_part3d_update_bound(qpg_part3d p)
     TprofScope tp(c, TP_PUSH3D);
     const int grid = (int)((p->npp_hi + B3_BLOCK - 1) / B3_BLOCK);
     k_flag3d<<<grid, B3_BLOCK, 0, c->stream>>>(view3(p), (double)c->nr * c->dr, (double)p->nz_total * c->dxi, 0, p->outmask, p->d_nout);
-    k_compact<<<1, 1024, 0, c->stream>>>(plane_table3(p), 7, p->d_npp, p->d_nout, p->outmask, p->lists, 0);
+    k_compact<<<1, 1024, 0, c->stream>>>(plane_table3(p), 7, p->d_npp, p->d_nout, p->outmask, p->lists, 0, nullptr);
     count_launch(c, 2);
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -358,7 +358,7 @@ extern "C" int qpg_part3d_pack_forward(qpg_part3d p, double *dev_buf)
     const int grid = (int)((p->npp_hi + B3_BLOCK - 1) / B3_BLOCK);
     if (grid > 0) k_flag3d<<<grid, B3_BLOCK, 0, c->stream>>>(view3(p), 0.0, (double)(p->noff2 + p->nzp) * c->dxi, 1, p->outmask, p->d_nout);
     k_pack3d<<<1, 1024, 0, c->stream>>>(view3(p), p->d_nout, p->outmask, dev_buf, cap);
-    k_compact<<<1, 1024, 0, c->stream>>>(plane_table3(p), 7, p->d_npp, p->d_nout, p->outmask, p->lists, 1);
+    k_compact<<<1, 1024, 0, c->stream>>>(plane_table3(p), 7, p->d_npp, p->d_nout, p->outmask, p->lists, 1, nullptr);
     count_launch(c, 3);
     CUDA_TRY(cudaGetLastError());
     return 0;

@@ -100,6 +100,7 @@ extern "C" int qpg_tprof_get(qpg_ctx ctx, const char *event, double *ms_total, l
 }
 extern "C" long qpg_launch_count(qpg_ctx ctx) { return ctx ? ctx->launches : -1; }
 
+#define NT_FIELD 1024
 // ------------------------------------------------------------------------------------------------
 // operator construction (fields/field_solver_class.f03:256-561 set_struct_matrix, single r-owner) and its
 // semiseparable factorisation
@@ -156,11 +157,10 @@ static void factor_operator(int kind, int m, int nr, double dr, int bnd, double 
         if (jn < nr - 1) t += c[jn] * w[jn + 1] * u[jn];
         D[jn] = t;
     }
-    int len = 32 * C;
+    int len = NT_FIELD * C;  // C = nodes per thread (IPT); natural node order, zero padded
     for (int i = 0; i < len; i++) hq[i] = hv[i] = hp[i] = hu[i] = 0.0;
     for (int t = off; t < nr; t++) {
-        int lane = t / C, k = t % C;
-        int pos = k * 32 + lane;
+        int pos = t;
         hp[pos] = (double)w[t];
         hq[pos] = (double)(u[t] / D[t]);
         hu[pos] = (double)u[t];
@@ -197,13 +197,14 @@ extern "C" int qpg_ctx_create(qpg_ctx *out, int device, void *cuda_stream, int n
     c->nr = nr; c->M = max_mode; c->P = 2 * max_mode + 1;
     c->dr = dr; c->dxi = dxi; c->bnd = field_boundary;
     c->relax = relax_fac >= 0.0 ? relax_fac : 1.0e-3 * ((dr / 0.02) * (dr / 0.02));
-    int need = (nr + 31) / 32, C = 1, logC = 0;
+    int need = (nr + NT_FIELD - 1) / NT_FIELD, C = 1, logC = 0;  // nodes per thread of the field CTA (1, 2 or 4)
     while (C < need) { C <<= 1; logC++; }
+    if (C > 4) { qpg_set_error("nr=%d exceeds the 4096 radial nodes the field kernel supports", nr); return QPG_ERR_UNSUPPORTED; }
     c->C = C; c->logC = logC;
     c->launches = 0; c->tprof_on = false; c->capturing = false;
     for (int i = 0; i < TP_COUNT; i++) { c->tp_ms[i] = 0; c->tp_calls[i] = 0; }
     // coefficient pool
-    size_t len = (size_t)32 * C, nops = (size_t)FK_NKIND * (max_mode + 1);
+    size_t len = (size_t)NT_FIELD * C, nops = (size_t)FK_NKIND * (max_mode + 1);
     std::vector<double> host(nops * 4 * len);
     CUDA_TRY(cudaMalloc(&c->coef_pool, host.size() * sizeof(double)));
     CtxDev hostdev;
@@ -240,8 +241,7 @@ extern "C" int qpg_ctx_create(qpg_ctx *out, int device, void *cuda_stream, int n
     // field kernel shared memory: as much as the device allows (<= 227 KB)
     int maxsm = 0;
     CUDA_TRY(cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
-    int stride = (C == 1) ? 1 : C + 1;
-    int per_sys = 2 * 32 * stride * (int)sizeof(double);
+    int per_sys = NT_FIELD * C * (int)sizeof(double);
     int want = (2 * c->P > 4 ? 2 * c->P : 4) * per_sys + 4096;
     if (want > maxsm) want = (maxsm / 1024) * 1024;
     if (want < 4 * per_sys + 4096) { qpg_set_error("nr=%d needs %d B shared memory per system, device offers %d", nr, per_sys, maxsm); return QPG_ERR_UNSUPPORTED; }
@@ -308,40 +308,64 @@ __device__ double block_max(double v, double *red)
     return red[32];
 }
 
-// smem index of radial node i (1-based) inside one system's array
-__device__ __forceinline__ int sidx(int i, int logC, int stride) { int t = i - 1; return (t >> logC) * stride + (t & ((1 << logC) - 1)); }
+// smem index of radial node i (1-based) inside one system's array (natural order)
+__device__ __forceinline__ int sidx(int i, int, int) { return i - 1; }
 
-// One warp per system: two scans + combine.  D = right-hand sides, X = solutions (both [nsys][32*stride]).
-__device__ void semisep_solve(const double *D, double *X, int nsys, const OpCoef *const *sysop, int logC)
+// Block-wide forward / reverse scans for NSR systems at once; every thread owns IPT consecutive radial nodes.
+// in : fa[j][s] = q*d, fb[j][s] = v*d of the thread's nodes
+// out: fa[j][s] = sum over nodes <= own (inclusive prefix), fb[j][s] = sum over nodes > own (exclusive suffix)
+template <int IPT, int NSR>
+__device__ __forceinline__ void scan_round(double (&fa)[IPT][NSR], double (&fb)[IPT][NSR], double *sA, double *sB)
 {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    const int C = 1 << logC, stride = (C == 1) ? 1 : C + 1;
-    for (int s = warp; s < nsys; s += nw) {
-        const OpCoef *op = sysop[s];
-        const double *d = D + (size_t)s * 32 * stride + lane * stride;
-        double *x = X + (size_t)s * 32 * stride + lane * stride;
-        const double *qT = op->qT + lane, *vT = op->vT + lane, *pT = op->pT + lane, *uT = op->uT + lane;
-        double SL = 0.0, TL = 0.0;
-        for (int k = 0; k < C; k++) {
-            double dk = d[k];
-            SL = fma(qT[k * 32], dk, SL);
-            TL = fma(vT[k * 32], dk, TL);
-        }
-        // exclusive prefix of SL over lanes, exclusive suffix of TL over lanes
-        double incl = SL;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int s = 0; s < NSR; s++) {
+        double run = 0.0;
+#pragma unroll
+        for (int j = 0; j < IPT; j++) { run += fa[j][s]; fa[j][s] = run; }
+        double incl = run;
+#pragma unroll
         for (int o = 1; o < 32; o <<= 1) { double t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-        double Sprev = __shfl_up_sync(0xffffffffu, incl, 1);
-        if (lane == 0) Sprev = 0.0;
-        double sfx = TL;
-        for (int o = 1; o < 32; o <<= 1) { double t = __shfl_down_sync(0xffffffffu, sfx, o); if (lane + o < 32) sfx += t; }
-        double Tnext = __shfl_down_sync(0xffffffffu, sfx, 1);
-        if (lane == 31) Tnext = 0.0;
-        double t = Tnext;
-        for (int k = C - 1; k >= 0; k--) { x[k] = t; t = fma(vT[k * 32], d[k], t); }
-        double sr = Sprev;
-        for (int k = 0; k < C; k++) { sr = fma(qT[k * 32], d[k], sr); x[k] = pT[k * 32] * sr + uT[k * 32] * x[k]; }
-        if (lane == 0 && op->axis_inv != 0.0) x[0] = d[0] * op->axis_inv;
+        double excl = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane == 0) excl = 0.0;
+        if (lane == 31) sA[s * 32 + warp] = incl;
+#pragma unroll
+        for (int j = 0; j < IPT; j++) fa[j][s] += excl;
+        run = 0.0;
+#pragma unroll
+        for (int j = IPT - 1; j >= 0; j--) { double t = fb[j][s]; fb[j][s] = run; run += t; }
+        incl = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { double t = __shfl_down_sync(0xffffffffu, incl, o); if (lane + o < 32) incl += t; }
+        excl = __shfl_down_sync(0xffffffffu, incl, 1);
+        if (lane == 31) excl = 0.0;
+        if (lane == 0) sB[s * 32 + warp] = incl;
+#pragma unroll
+        for (int j = 0; j < IPT; j++) fb[j][s] += excl;
     }
+    __syncthreads();
+    if (warp < NSR) {            // warp s: exclusive prefix of the 32 warp totals of system s
+        double v = sA[warp * 32 + lane], incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { double t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        double excl = __shfl_up_sync(0xffffffffu, incl, 1);
+        sA[warp * 32 + lane] = lane == 0 ? 0.0 : excl;
+    } else if (warp >= 16 && warp < 16 + NSR) {  // warp 16+s: exclusive suffix
+        const int s = warp - 16;
+        double v = sB[s * 32 + lane], incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { double t = __shfl_down_sync(0xffffffffu, incl, o); if (lane + o < 32) incl += t; }
+        double excl = __shfl_down_sync(0xffffffffu, incl, 1);
+        sB[s * 32 + lane] = lane == 31 ? 0.0 : excl;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int s = 0; s < NSR; s++) {
+        const double oa = sA[s * 32 + warp], ob = sB[s * 32 + warp];
+#pragma unroll
+        for (int j = 0; j < IPT; j++) { fa[j][s] += oa; fb[j][s] += ob; }
+    }
+    __syncthreads();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -457,17 +481,19 @@ __device__ double rhs_bt_iter(const SolveCtx &sc, const double *dcu, const doubl
 // ------------------------------------------------------------------------------------------------
 // the program kernel
 // ------------------------------------------------------------------------------------------------
-__device__ void op_solve(const FProg &pg, const FOp &op, double *smem, double *red, const OpCoef **sysop_s)
+template <int IPT>
+__device__ void op_solve(const FProg &pg, const FOp &op, double *smem, double *red, const OpCoef **sysop_s, double *scanbuf)
 {
-    const int nr = pg.nr, M = pg.M, P = pg.P, logC = pg.logC;
-    const int C = 1 << logC, stride = (C == 1) ? 1 : C + 1;
-    const int per = 32 * stride;
-    SolveCtx sc; sc.nr = nr; sc.M = M; sc.P = P; sc.logC = logC; sc.stride = stride; sc.dr = pg.dr; sc.idr = 1.0 / pg.dr; sc.idrh = 0.5 * sc.idr;
+    constexpr int NSR = IPT == 1 ? 6 : (IPT == 2 ? 3 : 2);  // systems scanned together (register budget)
+    const int nr = pg.nr, M = pg.M, P = pg.P, logC = 0, stride = 1;
+    const int per = NT_FIELD * IPT;
+    SolveCtx sc; sc.nr = nr; sc.M = M; sc.P = P; sc.logC = 0; sc.stride = 1; sc.dr = pg.dr; sc.idr = 1.0 / pg.dr; sc.idrh = 0.5 * sc.idr;
     const int fac = (op.code == FOP_BTITER) ? 2 : 1;  // systems per plane
-    const int maxsys = op.i3;                          // systems that fit in shared memory (host guarantees >= 2*fac)
+    const int maxsys = op.i3;                          // systems whose solutions fit in shared memory
     const double relax_idr2 = op.s0 * (sc.idr * sc.idr);
     const int tid = threadIdx.x, nt = blockDim.x;
-    double *D = smem, *X = smem + (size_t)maxsys * per;
+    double *X = smem;
+    double *sA = scanbuf, *sB = scanbuf + NSR * 32;
     // batches hold whole modes, so the (re, im) planes of a mode and its B+/B- systems are resident together
     int m0 = 0;
     while (m0 <= M) {
@@ -477,7 +503,6 @@ __device__ void op_solve(const FProg &pg, const FOp &op, double *smem, double *r
         const int pl0 = (m0 == 0) ? 0 : 2 * m0 - 1;
         const int ns = fac * npl;
         __syncthreads();
-        for (int k = tid; k < ns * per; k += nt) D[k] = 0.0;  // padding must stay finite
         if (tid < ns) {
             int which = tid / npl, pl = pl0 + tid % npl, m = mode_of(pl), kind;
             switch (op.code) {
@@ -490,31 +515,71 @@ __device__ void op_solve(const FProg &pg, const FOp &op, double *smem, double *r
             sysop_s[tid] = pg.ops + kind * (QPG_MAX_MODE + 1) + m;
         }
         __syncthreads();
-        for (int k = tid; k < ns * nr; k += nt) {
-            int sl = k / nr, i = k % nr + 1, which = sl / npl, pl = pl0 + sl % npl;
-            double v;
-            switch (op.code) {
-            case FOP_PSI: case FOP_BT: v = -1.0 * FX(op.a, 1, i, pl, 0); break;
-            case FOP_BZ: v = rhs_bz(sc, op.a, pl, i); break;
-            case FOP_EZ: v = rhs_ez(sc, op.a, pl, i); break;
-            default: v = rhs_bt_iter(sc, op.a, op.b, op.c, relax_idr2, which, pl, i); break;
+        for (int r0 = 0; r0 < ns; r0 += NSR) {
+            double fa[IPT][NSR], fb[IPT][NSR];
+            // right-hand sides of this thread's nodes
+#pragma unroll
+            for (int ss = 0; ss < NSR; ss++) {
+                const int sl = r0 + ss;
+#pragma unroll
+                for (int j = 0; j < IPT; j++) {
+                    const int i = tid * IPT + j + 1;
+                    double v = 0.0;
+                    if (sl < ns && i <= nr) {
+                        const int which = sl / npl, pl = pl0 + sl % npl;
+                        switch (op.code) {
+                        case FOP_PSI: case FOP_BT: v = -1.0 * FX(op.a, 1, i, pl, 0); break;
+                        case FOP_BZ: v = rhs_bz(sc, op.a, pl, i); break;
+                        case FOP_EZ: v = rhs_ez(sc, op.a, pl, i); break;
+                        default: v = rhs_bt_iter(sc, op.a, op.b, op.c, relax_idr2, which, pl, i); break;
+                        }
+                    }
+                    fa[j][ss] = v;
+                }
             }
-            D[(size_t)sl * per + sidx(i, logC, stride)] = v;
-        }
-        __syncthreads();
-        if (op.code == FOP_EZ && m0 == 0) {
-            // m=0 divergence fix, field_e_class.f03:189-209: row 1 = -8 * ( sum_{i=2}^{nr-2} rhs_i (i-1) - edge term )
-            double part = 0.0;
-            for (int i = 2 + tid; i <= nr - 2; i += nt) part += D[sidx(i, logC, stride)] * (double)(i - 1);
-            double div = block_sum(part, red);
-            if (tid == 0) {
-                const double *cu = op.a;
-                div = div - sc.idrh * (FX(cu, 3, nr - 2, 0, 0) + FX(cu, 3, nr - 1, 0, 0)) * ((double)nr - 2.5);
-                D[sidx(1, logC, stride)] = -8.0 * div;
+            if (op.code == FOP_EZ && m0 == 0 && r0 == 0) {
+                // m=0 divergence fix, field_e_class.f03:189-209: row 1 = -8 * ( sum_{i=2}^{nr-2} rhs_i (i-1) - edge term )
+                double part = 0.0;
+#pragma unroll
+                for (int j = 0; j < IPT; j++) { const int i = tid * IPT + j + 1; if (i >= 2 && i <= nr - 2) part += fa[j][0] * (double)(i - 1); }
+                double div = block_sum(part, red);
+                if (tid == 0) {
+                    const double *cu = op.a;
+                    div = div - sc.idrh * (FX(cu, 3, nr - 2, 0, 0) + FX(cu, 3, nr - 1, 0, 0)) * ((double)nr - 2.5);
+                    fa[0][0] = -8.0 * div;
+                }
             }
-            __syncthreads();
+            double d0[NSR];  // node-1 right-hand sides (decoupled axis rows)
+#pragma unroll
+            for (int ss = 0; ss < NSR; ss++) d0[ss] = fa[0][ss];
+#pragma unroll
+            for (int ss = 0; ss < NSR; ss++) {
+                const int sl = r0 + ss;
+                if (sl < ns) {
+                    const OpCoef *oc = sysop_s[sl];
+#pragma unroll
+                    for (int j = 0; j < IPT; j++) { const int t = tid * IPT + j; const double d = fa[j][ss]; fa[j][ss] = __ldg(oc->qT + t) * d; fb[j][ss] = __ldg(oc->vT + t) * d; }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < IPT; j++) { fa[j][ss] = 0.0; fb[j][ss] = 0.0; }
+                }
+            }
+            scan_round<IPT, NSR>(fa, fb, sA, sB);
+#pragma unroll
+            for (int ss = 0; ss < NSR; ss++) {
+                const int sl = r0 + ss;
+                if (sl < ns) {
+                    const OpCoef *oc = sysop_s[sl];
+#pragma unroll
+                    for (int j = 0; j < IPT; j++) {
+                        const int t = tid * IPT + j;
+                        double x = __ldg(oc->pT + t) * fa[j][ss] + __ldg(oc->uT + t) * fb[j][ss];
+                        if (t == 0 && oc->axis_inv != 0.0) x = d0[ss] * oc->axis_inv;
+                        X[(size_t)sl * per + t] = x;
+                    }
+                }
+            }
         }
-        semisep_solve(D, X, ns, sysop_s, logC);
         __syncthreads();
         if (op.code == FOP_PSI) {
             double *psi = op.b;
@@ -711,6 +776,7 @@ __global__ void __launch_bounds__(NT, 1) k_field_prog(const __grid_constant__ FP
     extern __shared__ double smem_all[];
     __shared__ double red[40];
     __shared__ const OpCoef *sysop_s[64];
+    __shared__ double scanbuf[2 * 6 * 32];
     const int nr = pg.nr, P = pg.P, tid = threadIdx.x, nt = blockDim.x;
     double *smem = smem_all;
     const bool done = pg.flags[0] != 0;
@@ -745,7 +811,11 @@ __global__ void __launch_bounds__(NT, 1) k_field_prog(const __grid_constant__ FP
                 else { double *t = &op.d[(size_t)np * 3 + (c8 - 5)]; *t = axis_fix_amj(j, pl, c8, *t + raw); }
             }
             break;
-        case FOP_PSI: case FOP_BT: case FOP_BZ: case FOP_EZ: case FOP_BTITER: op_solve(pg, op, smem, red, sysop_s); break;
+        case FOP_PSI: case FOP_BT: case FOP_BZ: case FOP_EZ: case FOP_BTITER:
+            if (pg.logC == 0) op_solve<1>(pg, op, smem, red, sysop_s, scanbuf);
+            else if (pg.logC == 1) op_solve<2>(pg, op, smem, red, sysop_s, scanbuf);
+            else op_solve<4>(pg, op, smem, red, sysop_s, scanbuf);
+            break;
         case FOP_ET: op_et(pg, op); break;
         case FOP_ETBEAM:
             for (int k = tid; k < nr * P; k += nt) { int i = k / P + 1, pl = k % P; FX(op.b, 3, i, pl, 0) = FX(op.a, 3, i, pl, 1); FX(op.b, 3, i, pl, 1) = -FX(op.a, 3, i, pl, 0); }
@@ -820,8 +890,7 @@ FOp &FProgBuilder::add(int code)
     FOp &o = prog.op[prog.nops++];
     memset(&o, 0, sizeof(o));
     o.code = code;
-    int C = ctx->C, stride = (C == 1) ? 1 : C + 1;
-    int per_sys = 2 * 32 * stride * (int)sizeof(double);
+    int per_sys = NT_FIELD * ctx->C * (int)sizeof(double);
     int maxsys = (ctx->smem_field - 1024) / per_sys;
     if (maxsys > 2 * ctx->P) maxsys = 2 * ctx->P;
     if (maxsys > 60) maxsys = 60;

@@ -2,4 +2,5 @@
 #include "fields.cu"
 #include "particles.cu"
 #include "beam.cu"
+#include "fused.cu"
 #include "sim.cu"

@@ -331,10 +331,11 @@ __device__ int block_excl_scan_int(int v, int *sm, int *total)
 }
 
 __global__ void __launch_bounds__(1024, 1) k_compact(double *const *planes, int nplanes, int *d_npp, int *d_nout, unsigned *outmask, int *lists,
-                                                    int desc_holes)
+                                                    int desc_holes, int *slice_flags)
 {
     __shared__ int sm[40];
     const int n = *d_npp, nout = *d_nout;
+    if (slice_flags && threadIdx.x == 0) { slice_flags[3] += 1; slice_flags[4] += 1; }  // fused path: slice j is complete
     if (nout == 0) return;
     const int K = n - nout, tid = threadIdx.x, nt = blockDim.x;
     const int nwords = (n + 31) >> 5;
@@ -681,12 +682,12 @@ int part2d_launch_push(qpg_part2d p, qpg_field ef, qpg_field bf, double dt, int 
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
-int part2d_launch_compact(qpg_part2d p)
+int part2d_launch_compact(qpg_part2d p, int *slice_flags)
 {
     qpg_ctx c = p->ctx;
     double **tbl = plane_table(p);
     TprofScope tp(c, TP_K_COMPACT);
-    k_compact<<<1, 1024, 0, c->stream>>>(tbl, 8, p->d_npp, p->d_nout, p->outmask, p->lists, 0);
+    k_compact<<<1, 1024, 0, c->stream>>>(tbl, 8, p->d_npp, p->d_nout, p->outmask, p->lists, 0, slice_flags);
     count_launch(c);
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -733,7 +734,7 @@ extern "C" int qpg_part2d_update_bound(qpg_part2d p)
     ARG_TRY(p, "null arg");
     int rc = part2d_launch_push(p, nullptr, nullptr, 0.0, 4);
     if (rc) return rc;
-    return part2d_launch_compact(p);
+    return part2d_launch_compact(p, nullptr);
 }
 
 extern "C" long qpg_part2d_wire_count(qpg_part2d p) { return p ? 8 * p->npmax + 1 : -1; }

@@ -9,7 +9,7 @@
 int part2d_launch_qdeposit(qpg_part2d p);
 int part2d_launch_amjdeposit(qpg_part2d p, qpg_field ef, qpg_field bf, double dt, const int *skip_flag);
 int part2d_launch_push(qpg_part2d p, qpg_field ef, qpg_field bf, double dt, int mode);
-int part2d_launch_compact(qpg_part2d p);
+int part2d_launch_compact(qpg_part2d p, int *slice_flags);
 
 struct qpg_sim_s {
     qpg_sim_params prm;
@@ -20,6 +20,8 @@ struct qpg_sim_s {
     cudaGraph_t graph;
     cudaGraphExec_t gexec;
     bool graph_ready;
+    bool use_fused;       // cluster kernels of fused.cu instead of the op-list programs
+    double *phi;
     long host_updates, host_iters, host_slices;
 };
 
@@ -82,16 +84,57 @@ static void prog_D(qpg_sim s, FProgBuilder &pb)
     o = &pb.add(FOP_SET_FLAG); o->i0 = 3; o->i1 = -1;  // flags[3] += 1 (next slice), flags[4] += 1
 }
 
+static FusedArgs fused_args(qpg_sim s)
+{
+    FusedArgs a;
+    memset(&a, 0, sizeof(a));
+    qpg_ctx c = s->ctx;
+    a.nr = c->nr; a.iter_max = s->prm.iter_max; a.dr = c->dr; a.dxi = s->prm.dxi; a.relax = c->relax;
+    a.reltol = s->prm.iter_reltol; a.abstol = s->prm.iter_abstol;
+    a.psi = s->psi->f1; a.e = s->e->f1; a.b = s->b->f1; a.e_spe = s->e_spe->f1; a.b_spe = s->b_spe->f1; a.b_beam = s->b_beam->f1;
+    a.cu = s->cu->f1; a.amu = s->amu->f1; a.acu = s->acu->f1; a.dcu = s->dcu->f1; a.q_spe = s->q_spe->f1; a.q_beam = s->q_beam->f1;
+    a.spe_q = s->spe_q->f1; a.spe_qn = s->spe_qn->f1; a.spe_cu = s->spe_cu->f1; a.spe_dcu = s->spe_dcu->f1; a.spe_amu = s->spe_amu->f1;
+    a.q_beam2 = s->q_beam->f2; a.spe_q2 = s->spe_q->f2; a.cu2 = s->cu->f2; a.q_spe2 = s->q_spe->f2; a.e2 = s->e->f2; a.b2 = s->b->f2;
+    a.psi2 = s->psi->f2; a.b_spe2 = s->b_spe->f2; a.e_spe2 = s->e_spe->f2;
+    a.acc1 = s->spe->acc1; a.acc8 = s->spe->acc8; a.phi = s->phi; a.d_npp = s->spe->d_npp;
+    a.ops = qpg_ctx_dev_ops(c); a.conv_old = c->conv_old; a.conv_out = c->conv_out; a.flags = c->flags; a.counters = c->counters;
+    a.cond_handle = c->cond_handle;
+    return a;
+}
+template <int M> static void l_fused(int which, cudaStream_t st, const FusedArgs &a)
+{
+    const int grid = FC;
+    if (which == 0) k_fused_A<M><<<grid, FT, 0, st>>>(a);
+    else if (which == 1) k_fused_C<M><<<grid, FT, 0, st>>>(a);
+    else k_fused_D<M><<<(a.nr + FT - 1) / FT, FT, 0, st>>>(a);
+}
+static int launch_fused(qpg_sim s, int which)
+{
+    qpg_ctx c = s->ctx;
+    FusedArgs a = fused_args(s);
+    TprofScope tp(c, TP_FIELD_FUSED);
+    switch (c->M) {
+    case 0: l_fused<0>(which, c->stream, a); break;
+    case 1: l_fused<1>(which, c->stream, a); break;
+    default: l_fused<2>(which, c->stream, a); break;
+    }
+    count_launch(c);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
 static int enqueue_pc_iteration(qpg_sim s)
 {
     int rc = part2d_launch_amjdeposit(s->spe, s->e, s->b, s->prm.dxi, s->ctx->flags);
     if (rc) return rc;
+    if (s->use_fused) return launch_fused(s, 1);
     FProgBuilder pb(s->ctx);
     prog_C(s, pb);
     return pb.launch(TP_FIELD_FUSED);
 }
 static int enqueue_slice_head(qpg_sim s)
 {
+    if (s->use_fused) return launch_fused(s, 0);
     FProgBuilder pb(s->ctx);
     prog_A(s, pb);
     return pb.launch(TP_FIELD_FUSED);
@@ -99,10 +142,12 @@ static int enqueue_slice_head(qpg_sim s)
 static int enqueue_slice_tail(qpg_sim s)
 {
     int rc;
-    { FProgBuilder pb(s->ctx); prog_D(s, pb); rc = pb.launch(TP_FIELD_FUSED); if (rc) return rc; }
+    if (s->use_fused) rc = launch_fused(s, 2);
+    else { FProgBuilder pb(s->ctx); prog_D(s, pb); rc = pb.launch(TP_FIELD_FUSED); }
+    if (rc) return rc;
     rc = part2d_launch_push(s->spe, s->e, s->b, s->prm.dxi, 7);  // push_u + push_x + bound flags :438-439
     if (rc) return rc;
-    rc = part2d_launch_compact(s->spe);                          // update_bound
+    rc = part2d_launch_compact(s->spe, s->use_fused ? s->ctx->flags : nullptr);  // update_bound (+ slice counter)
     if (rc) return rc;
     return part2d_launch_qdeposit(s->spe);                       // next slice's qdp (:346-349) on the advanced particles
 }
@@ -192,6 +237,9 @@ extern "C" int qpg_sim_create(qpg_sim *out, int device, void *cuda_stream, const
         {&s->cu, 3, 1}, {&s->amu, 3, 0}, {&s->acu, 2, 0}, {&s->dcu, 2, 0}, {&s->q_spe, 1, 1}, {&s->q_beam, 1, 1},
         {&s->spe_q, 1, 1}, {&s->spe_qn, 1, 0}, {&s->spe_cu, 3, 0}, {&s->spe_dcu, 2, 0}, {&s->spe_amu, 3, 0}, {&s->beam_q, 1, 1}};
     for (auto &t : tbl) { rc = qpg_field_create(t.f, c, t.dim, nzp, t.has2d); if (rc) return rc; }
+    s->use_fused = (prm->nr <= FT * FC && prm->max_mode <= 2);
+    CUDA_TRY(cudaMalloc(&s->phi, sizeof(double) * (size_t)(prm->nr + 2) * c->P));
+    CUDA_TRY(cudaMemsetAsync(s->phi, 0, sizeof(double) * (size_t)(prm->nr + 2) * c->P, c->stream));
     rc = qpg_part2d_create(&s->spe, c, prm->sp_qbm, prm->sp_npmax);
     if (rc) return rc;
     rc = qpg_part3d_create(&s->beam, c, prm->beam_qbm, prm->dt, prm->beam_npmax < 32 ? 32 : prm->beam_npmax, prm->nz_total, prm->noff2, nzp);
@@ -208,6 +256,7 @@ extern "C" int qpg_sim_destroy(qpg_sim s)
     qpg_field all[] = {s->psi, s->e, s->b, s->e_spe, s->b_spe, s->e_beam, s->b_beam, s->cu, s->amu, s->acu, s->dcu, s->q_spe, s->q_beam,
                        s->spe_q, s->spe_qn, s->spe_cu, s->spe_dcu, s->spe_amu, s->beam_q};
     for (auto f : all) qpg_field_destroy(f);
+    cudaFree(s->phi);
     qpg_part2d_destroy(s->spe);
     qpg_part3d_destroy(s->beam);
     qpg_ctx_destroy(s->ctx);
@@ -317,6 +366,18 @@ extern "C" int qpg_sim_stats(qpg_sim s, long *updates, long *pc_iters, long *sli
     if (updates) *updates = (long)cnt[0];
     if (pc_iters) *pc_iters = (long)cnt[1];
     if (slices) *slices = fl[4];
+    return 0;
+}
+extern "C" int qpg_sim_set_fused(qpg_sim s, int on)
+{
+    ARG_TRY(s, "null sim");
+    const bool can = s->prm.nr <= FT * FC && s->prm.max_mode <= 2;
+    if (on && !can) { qpg_set_error("fused cluster programs need nr <= %d and max_mode <= 2", FT * FC); return QPG_ERR_UNSUPPORTED; }
+    if ((on != 0) != s->use_fused && s->graph_ready) {   // the captured graph holds the other variant
+        cudaGraphExecDestroy(s->gexec); cudaGraphDestroy(s->graph);
+        s->gexec = nullptr; s->graph = nullptr; s->graph_ready = false;
+    }
+    s->use_fused = on != 0;
     return 0;
 }
 extern "C" int qpg_sim_set_graph(qpg_sim s, int use_graph) { ARG_TRY(s, "null sim"); s->prm.use_graph = use_graph != 0; return 0; }

@@ -317,16 +317,19 @@ def _deck(O, decks, nr=64, nz=40, M=1, iter_max=3, **kw):
     return cfg, (bx, bp, bq)
 
 
-def _gpu_sim(capi, O, cfg, beam, ppc=2, nth=8, use_graph=0, sort_freq=0):
+def _gpu_sim(capi, O, cfg, beam, ppc=2, nth=8, use_graph=0, sort_freq=0, fused=None):
     x, p, g, psi, q = O.inject_uniform(cfg["nr"], cfg["rmax"] / cfg["nr"], ppc, ppc, nth)
     sim = capi.Sim(sp_npmax=2 * len(q), beam_npmax=len(beam[2]) + 64, use_graph=use_graph, sort_freq=sort_freq, **cfg)
+    if fused is not None:
+        sim.set_fused(fused)
     sim.init_species(x, p, g, psi, q)
     sim.beam.upload(*beam)
     return sim, len(q)
 
 
+@pytest.mark.parametrize("fused", [1, 0])
 @pytest.mark.parametrize("M,use_graph", [(1, 0), (1, 1), (2, 1), (0, 1)])
-def test_slice_loop_matches_oracle(mods, M, use_graph):
+def test_slice_loop_matches_oracle(mods, M, use_graph, fused):
     capi, O = mods
     from qpad_b200 import decks
     cfg, beam = _deck(O, decks, M=M)
@@ -334,7 +337,7 @@ def test_slice_loop_matches_oracle(mods, M, use_graph):
     orc = O.Sim(ppc1=2, ppc2=2, num_theta=8, **cfg)
     orc.set_beam(*beam)
     orc_upd = orc.run_slices(nsl)
-    sim, np0 = _gpu_sim(capi, O, cfg, beam, use_graph=use_graph)
+    sim, np0 = _gpu_sim(capi, O, cfg, beam, use_graph=use_graph, fused=fused)
     sim.beam_qdp_begin(); sim.beam_qdp_end(); sim.begin_step()
     sim.run_slices(1, nsl)
     upd, iters, slices = sim.stats()
@@ -352,8 +355,9 @@ def test_slice_loop_matches_oracle(mods, M, use_graph):
     assert np.max(np.abs(gx - ox)) < 1e-8 and np.max(np.abs(gp - op)) < 1e-8
 
 
+@pytest.mark.parametrize("fused", [1, 0])
 @pytest.mark.parametrize("M", [0, 1, 2])
-def test_one_slice_from_identical_state(mods, M):
+def test_one_slice_from_identical_state(mods, M, fused):
     """the north-star gate: <= 1e-10 relative per-slice field error after ONE slice from identical inputs, taken in
     the wake (slice 21 of 40) where every field is O(1)"""
     capi, O = mods
@@ -363,7 +367,7 @@ def test_one_slice_from_identical_state(mods, M):
     orc = O.Sim(ppc1=2, ppc2=2, num_theta=8, **cfg)
     orc.set_beam(*beam)
     orc.run_slices(k)
-    sim, np0 = _gpu_sim(capi, O, cfg, beam, use_graph=1)
+    sim, np0 = _gpu_sim(capi, O, cfg, beam, use_graph=1, fused=fused)
     sim.beam_qdp_begin(); sim.beam_qdp_end(); sim.begin_step()
     sim.species.upload(*orc.plasma())                      # state carried between slices: particles, cu, b_spe
     sim.field("cu").upload(orc.field("cu", 1))
