@@ -183,10 +183,102 @@ __device__ __forceinline__ double green_apply(const OpCoef &oc, int t, double S,
     return x;
 }
 
-// nodes this thread owns in guard-inclusive passes: its own node, plus guard 0 (owner of node 1) / guard nr+1 (owner of nr)
-#define FOR_OWN_NODES(i, nr, n)                                                                   \
-    for (int _pass = 0, n = (i); _pass < 3; _pass++, n = (_pass == 1 ? ((i) == 1 ? 0 : -1) : ((i) == (nr) ? (nr) + 1 : -1))) \
-        if (n >= 0 && n <= (nr) + 1)
+// own-node variant of rhs_bt_iter (field_b_class.f03:360-506): dcu of the node comes from registers
+template <int M>
+__device__ __forceinline__ double rhs_bt_iter_own(const SolveCtx &sc, const double (&dcu)[2 * M + 1][2], const double *cu, const double *b, double relax_idr2,
+                                                  int which, int pl, int i)
+{
+    constexpr int P = 2 * M + 1;
+    const int nr = sc.nr, m = (pl + 1) >> 1;
+    const double idr = sc.idr, idrh = sc.idrh;
+    if (m == 0) {
+        if (i == 1) return 0.0;
+        if (which == 0) return -dcu[0][1] - FX(b, 3, i, 0, 0) * relax_idr2;
+        double dj;
+        if (i == 2) dj = idr * (FX(cu, 3, 3, 0, 2) - FX(cu, 3, 2, 0, 2));
+        else if (i == nr) dj = idrh * (3.0 * FX(cu, 3, nr, 0, 2) - 4.0 * FX(cu, 3, nr - 1, 0, 2) + FX(cu, 3, nr - 2, 0, 2));
+        else dj = idrh * (FX(cu, 3, i + 1, 0, 2) - FX(cu, 3, i - 1, 0, 2));
+        return dcu[0][0] + dj - FX(b, 3, i, 0, 1) * relax_idr2;
+    }
+    const int pr = 2 * m - 1, pi = 2 * m;
+    double s1_re, s1_im, s2_re, s2_im;
+    if (i == 1) {
+        if (m == 1) {
+            s1_re = -dcu[pr][1] + idr * m * FX(cu, 3, 2, pi, 2);
+            s1_im = -dcu[pi][1] - idr * m * FX(cu, 3, 2, pr, 2);
+            s2_re = dcu[pr][0] + idr * FX(cu, 3, 2, pr, 2);
+            s2_im = dcu[pi][0] + idr * FX(cu, 3, 2, pi, 2);
+        } else if ((m & 1) == 0) {
+            s1_re = s1_im = s2_re = s2_im = 0.0;
+        } else {
+            s1_re = idr * m * FX(cu, 3, 2, pi, 2);
+            s1_im = idr * m * FX(cu, 3, 2, pr, 2);
+            s2_re = idr * FX(cu, 3, 2, pr, 2);
+            s2_im = idr * FX(cu, 3, 2, pi, 2);
+        }
+    } else {
+        const double ir = idr / (double)(i - 1);
+        s1_re = -dcu[pr][1] + m * FX(cu, 3, i, pi, 2) * ir;
+        s1_im = -dcu[pi][1] - m * FX(cu, 3, i, pr, 2) * ir;
+        if (i == nr) {
+            s2_re = dcu[pr][0] + idrh * (3.0 * FX(cu, 3, nr, pr, 2) - 4.0 * FX(cu, 3, nr - 1, pr, 2) + FX(cu, 3, nr - 2, pr, 2));
+            s2_im = dcu[pi][0] + idrh * (3.0 * FX(cu, 3, nr, pi, 2) - 4.0 * FX(cu, 3, nr - 1, pi, 2) + FX(cu, 3, nr - 2, pi, 2));
+        } else {
+            s2_re = dcu[pr][0] + idrh * (FX(cu, 3, i + 1, pr, 2) - FX(cu, 3, i - 1, pr, 2));
+            s2_im = dcu[pi][0] + idrh * (FX(cu, 3, i + 1, pi, 2) - FX(cu, 3, i - 1, pi, 2));
+        }
+    }
+    const double brr = FX(b, 3, i, pr, 0), bri = FX(b, 3, i, pi, 0), bpr = FX(b, 3, i, pr, 1), bpi = FX(b, 3, i, pi, 1);
+    const bool im = (pl & 1) == 0;
+    if (which == 0) return im ? (s1_im + s2_re - (bri + bpr) * relax_idr2) : (s1_re - s2_im - (brr - bpi) * relax_idr2);
+    return im ? (s1_im - s2_re - (bri - bpr) * relax_idr2) : (s1_re + s2_im - (brr + bpi) * relax_idr2);
+}
+
+// guard-inclusive node work of program A stage 1 (q_beam slice copy, qdp epilogue) for one node
+template <int M>
+__device__ __forceinline__ void a_stage1_node(const FusedArgs &a, int n, int j, size_t n1, double (&qs)[2 * M + 1], double (&qb)[2 * M + 1])
+{
+    constexpr int P = 2 * M + 1;
+    double raw[P], qn[P];
+#pragma unroll
+    for (int pl = 0; pl < P; pl++) {
+        const size_t k = (size_t)n * P + pl;
+        qb[pl] = a.q_beam2[(size_t)(j - 1) * n1 + k];
+        raw[pl] = a.acc1[k];
+        qn[pl] = a.spe_qn[k];
+    }
+#pragma unroll
+    for (int pl = 0; pl < P; pl++) {
+        const size_t k = (size_t)n * P + pl;
+        const double sq = axis_fix_q(n, pl, raw[pl]);
+        qs[pl] = sq + qn[pl];
+        a.q_beam[k] = qb[pl];       // copy_slice 2to1 :344
+        a.acc1[k] = 0.0;
+        a.spe_q[k] = sq;            // species2d qdp :198-204
+        a.q_spe[k] = qs[pl];
+    }
+}
+// guard-inclusive node work of program C stage 1 (amjdp epilogue, single species)
+template <int M>
+__device__ __forceinline__ void c_stage1_node(const FusedArgs &a, int n)
+{
+    constexpr int P = 2 * M + 1;
+    double v[P][8];
+#pragma unroll
+    for (int pl = 0; pl < P; pl++)
+#pragma unroll
+        for (int c = 0; c < 8; c++) v[pl][c] = a.acc8[((size_t)n * P + pl) * 8 + c];
+#pragma unroll
+    for (int pl = 0; pl < P; pl++) {
+        const size_t np = (size_t)n * P + pl;
+#pragma unroll
+        for (int c = 0; c < 8; c++) { v[pl][c] = axis_fix_amj(n, pl, c, v[pl][c]); a.acc8[np * 8 + c] = 0.0; }
+#pragma unroll
+        for (int c = 0; c < 3; c++) { a.spe_cu[np * 3 + c] = v[pl][c]; a.cu[np * 3 + c] = v[pl][c]; a.spe_amu[np * 3 + c] = v[pl][5 + c]; a.amu[np * 3 + c] = v[pl][5 + c]; }
+#pragma unroll
+        for (int c = 0; c < 2; c++) { a.spe_dcu[np * 2 + c] = v[pl][3 + c]; a.acu[np * 2 + c] = v[pl][3 + c]; }
+    }
+}
 
 // ============================================================================================================
 template <int M>
@@ -206,22 +298,14 @@ __global__ void __cluster_dims__(FC, 1, 1) __launch_bounds__(FT) k_fused_A(const
 #pragma unroll
     for (int s = 0; s < NS; s++) d[s] = 0.0;
     if (valid) {
-        FOR_OWN_NODES(i, nr, n) {
-#pragma unroll
-            for (int pl = 0; pl < P; pl++) {
-                const size_t k = (size_t)n * P + pl;
-                const double qb = a.q_beam2[(size_t)(j - 1) * n1 + k];                   // copy_slice 2to1  :344
-                a.q_beam[k] = qb;
-                const double sq = axis_fix_q(n, pl, a.acc1[k]);                         // species2d qdp  :198-204
-                a.acc1[k] = 0.0;
-                a.spe_q[k] = sq;
-                const double qs = sq + a.spe_qn[k];
-                a.q_spe[k] = qs;
-                if (n == i) { d[pl] = -1.0 * qs; d[P + pl] = -1.0 * qb; }
-            }
-        }
+        double qs[P], qb[P];
 #pragma unroll
         for (int pl = 0; pl < P; pl++) { d[2 * P + pl] = rhs_bz(sc, a.cu, pl, i); d[3 * P + pl] = rhs_ez(sc, a.cu, pl, i); }
+        a_stage1_node<M>(a, i, j, n1, qs, qb);
+#pragma unroll
+        for (int pl = 0; pl < P; pl++) { d[pl] = -1.0 * qs[pl]; d[P + pl] = -1.0 * qb[pl]; }
+        if (i == 1) a_stage1_node<M>(a, 0, j, n1, qs, qb);
+        if (i == nr) a_stage1_node<M>(a, nr + 1, j, n1, qs, qb);
     }
     double red[1] = {0.0};
     if (valid && i >= 2 && i <= nr - 2) red[0] = d[3 * P] * (double)(i - 1);             // field_e_class.f03:189-197
@@ -263,6 +347,7 @@ __global__ void __cluster_dims__(FC, 1, 1) __launch_bounds__(FT) k_fused_A(const
     if (valid) {
         const double idrh = 0.5 * idr;
         double sre = 0.0, sim = 0.0;
+        double ob[P][3], obb[P][2], oe[P][2];
 #pragma unroll
         for (int pl = 0; pl < P; pl++) {
             const int m = (pl + 1) >> 1;
@@ -278,17 +363,19 @@ __global__ void __cluster_dims__(FC, 1, 1) __launch_bounds__(FT) k_fused_A(const
                 if (i == 1) br = (m == 1) ? sg * idr * m * FX(a.phi, 1, 2, po, 0) : 0.0;
                 else br = sg * (idr / (double)(i - 1)) * m * FX(a.phi, 1, i, po, 0);
             }
-            FX(a.b_beam, 3, i, pl, 0) = br;
-            FX(a.b_beam, 3, i, pl, 1) = bphi;
+            obb[pl][0] = br; obb[pl][1] = bphi;
             const double bs_r = FX(a.b_spe, 3, i, pl, 0), bs_p = FX(a.b_spe, 3, i, pl, 1);
             const double v = fabs(bs_p);                                                  // convergence_tester 'record' :548-558
             if (pl > 0 && (pl & 1) == 0) sim += v; else sre += v;
-            const double b_r = bs_r + br, b_p = bs_p + bphi;                              // b = b_spe + b_beam :375
-            const double b_z = x[2 * P + pl] + FX(a.b_beam, 3, i, pl, 2);
-            FX(a.b, 3, i, pl, 0) = b_r; FX(a.b, 3, i, pl, 1) = b_p; FX(a.b, 3, i, pl, 2) = b_z;
-            double er, ephi;
-            et_node<M>(a.psi, nr, idr, pl, i, b_r, b_p, er, ephi);                        // :377
-            FX(a.e, 3, i, pl, 0) = er; FX(a.e, 3, i, pl, 1) = ephi;
+            ob[pl][0] = bs_r + br; ob[pl][1] = bs_p + bphi;                               // b = b_spe + b_beam :375
+            ob[pl][2] = x[2 * P + pl] + FX(a.b_beam, 3, i, pl, 2);
+            et_node<M>(a.psi, nr, idr, pl, i, ob[pl][0], ob[pl][1], oe[pl][0], oe[pl][1]);  // :377
+        }
+#pragma unroll
+        for (int pl = 0; pl < P; pl++) {
+            FX(a.b_beam, 3, i, pl, 0) = obb[pl][0]; FX(a.b_beam, 3, i, pl, 1) = obb[pl][1];
+            FX(a.b, 3, i, pl, 0) = ob[pl][0]; FX(a.b, 3, i, pl, 1) = ob[pl][1]; FX(a.b, 3, i, pl, 2) = ob[pl][2];
+            FX(a.e, 3, i, pl, 0) = oe[pl][0]; FX(a.e, 3, i, pl, 1) = oe[pl][1];
         }
         a.conv_old[i] = sre; a.conv_old[nr + 2 + i] = sim;
     }
@@ -309,19 +396,9 @@ __global__ void __cluster_dims__(FC, 1, 1) __launch_bounds__(FT) k_fused_C(const
     SolveCtx sc; sc.nr = nr; sc.M = M; sc.P = P; sc.logC = 0; sc.stride = 1; sc.dr = a.dr; sc.idr = idr; sc.idrh = 0.5 * idr;
     // stage 1: deposit epilogue (part2d_class.f03:916-981) + species2d amjdp adds (:250-276), single species
     if (valid) {
-        FOR_OWN_NODES(i, nr, n) {
-#pragma unroll
-            for (int pl = 0; pl < P; pl++) {
-                const size_t np = (size_t)n * P + pl;
-                double v[8];
-#pragma unroll
-                for (int c = 0; c < 8; c++) { v[c] = axis_fix_amj(n, pl, c, a.acc8[np * 8 + c]); a.acc8[np * 8 + c] = 0.0; }
-#pragma unroll
-                for (int c = 0; c < 3; c++) { a.spe_cu[np * 3 + c] = v[c]; a.cu[np * 3 + c] = v[c]; a.spe_amu[np * 3 + c] = v[5 + c]; a.amu[np * 3 + c] = v[5 + c]; }
-#pragma unroll
-                for (int c = 0; c < 2; c++) { a.spe_dcu[np * 2 + c] = v[3 + c]; a.acu[np * 2 + c] = v[3 + c]; }
-            }
-        }
+        c_stage1_node<M>(a, i);
+        if (i == 1) c_stage1_node<M>(a, 0);
+        if (i == nr) c_stage1_node<M>(a, nr + 1);
     }
     cluster.sync();
     // stage 2: djdxi (:390), sources of bt_iter (:391), bz (:392), ez (:376 of the next pass / :415)
@@ -330,18 +407,20 @@ __global__ void __cluster_dims__(FC, 1, 1) __launch_bounds__(FT) k_fused_C(const
     for (int s = 0; s < NS; s++) d[s] = 0.0;
     const double relax_idr2 = a.relax * (idr * idr);
     if (valid) {
+        double dcu[P][2];
 #pragma unroll
         for (int pl = 0; pl < P; pl++)
 #pragma unroll
-            for (int c = 0; c < 2; c++) FX(a.dcu, 2, i, pl, c) = djdxi_node<M>(a.acu, a.amu, nr, idr, pl, c, i);
-        // rhs_bt_iter reads dcu of its own node only: written above by this thread
+            for (int c = 0; c < 2; c++) dcu[pl][c] = djdxi_node<M>(a.acu, a.amu, nr, idr, pl, c, i);
 #pragma unroll
         for (int pl = 0; pl < P; pl++) {
-            d[pl] = rhs_bt_iter(sc, a.dcu, a.cu, a.b_spe, relax_idr2, 0, pl, i);
-            d[P + pl] = rhs_bt_iter(sc, a.dcu, a.cu, a.b_spe, relax_idr2, 1, pl, i);
+            d[pl] = rhs_bt_iter_own<M>(sc, dcu, a.cu, a.b_spe, relax_idr2, 0, pl, i);
+            d[P + pl] = rhs_bt_iter_own<M>(sc, dcu, a.cu, a.b_spe, relax_idr2, 1, pl, i);
             d[2 * P + pl] = rhs_bz(sc, a.cu, pl, i);
             d[3 * P + pl] = rhs_ez(sc, a.cu, pl, i);
         }
+#pragma unroll
+        for (int pl = 0; pl < P; pl++) { FX(a.dcu, 2, i, pl, 0) = dcu[pl][0]; FX(a.dcu, 2, i, pl, 1) = dcu[pl][1]; }
     }
     double red[1] = {0.0};
     if (valid && i >= 2 && i <= nr - 2) red[0] = d[3 * P] * (double)(i - 1);
@@ -373,6 +452,7 @@ __global__ void __cluster_dims__(FC, 1, 1) __launch_bounds__(FT) k_fused_C(const
         const double ore = a.conv_old[i], oim = a.conv_old[nr + 2 + i];
         mo = ore * ore + oim * oim;
         double sre = 0.0, sim = 0.0;
+        double obs[P][3], ob[P][3], oe[P][3];
 #pragma unroll
         for (int pl = 0; pl < P; pl++) {
             const int m = (pl + 1) >> 1;
@@ -387,16 +467,17 @@ __global__ void __cluster_dims__(FC, 1, 1) __launch_bounds__(FT) k_fused_C(const
             }
             double bz = x[2 * P + pl], ez = x[3 * P + pl];
             if (pl > 0 && i == 1) { bz = 0.0; ez = 0.0; }
-            FX(a.b_spe, 3, i, pl, 0) = br; FX(a.b_spe, 3, i, pl, 1) = bp; FX(a.b_spe, 3, i, pl, 2) = bz;
-            FX(a.e, 3, i, pl, 2) = ez;
+            obs[pl][0] = br; obs[pl][1] = bp; obs[pl][2] = bz;
+            oe[pl][2] = ez;
             const double v = fabs(bp);
             if (pl > 0 && (pl & 1) == 0) sim += v; else sre += v;
-            const double b_r = br + FX(a.b_beam, 3, i, pl, 0), b_p = bp + FX(a.b_beam, 3, i, pl, 1), b_z = bz + FX(a.b_beam, 3, i, pl, 2);
-            FX(a.b, 3, i, pl, 0) = b_r; FX(a.b, 3, i, pl, 1) = b_p; FX(a.b, 3, i, pl, 2) = b_z;
-            double er, ephi;
-            et_node<M>(a.psi, nr, idr, pl, i, b_r, b_p, er, ephi);
-            FX(a.e, 3, i, pl, 0) = er; FX(a.e, 3, i, pl, 1) = ephi;
+            ob[pl][0] = br + FX(a.b_beam, 3, i, pl, 0); ob[pl][1] = bp + FX(a.b_beam, 3, i, pl, 1); ob[pl][2] = bz + FX(a.b_beam, 3, i, pl, 2);
+            et_node<M>(a.psi, nr, idr, pl, i, ob[pl][0], ob[pl][1], oe[pl][0], oe[pl][1]);
         }
+#pragma unroll
+        for (int pl = 0; pl < P; pl++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) { FX(a.b_spe, 3, i, pl, c) = obs[pl][c]; FX(a.b, 3, i, pl, c) = ob[pl][c]; FX(a.e, 3, i, pl, c) = oe[pl][c]; }
         const double dre = ore - sre, dim = oim - sim;
         mn = dre * dre + dim * dim;
         a.conv_old[i] = sre; a.conv_old[nr + 2 + i] = sim;   // 'record' for the next pass (:373)
@@ -420,45 +501,37 @@ __global__ void __cluster_dims__(FC, 1, 1) __launch_bounds__(FT) k_fused_C(const
 template <int M>
 __global__ void __launch_bounds__(FT) k_fused_D(const __grid_constant__ FusedArgs a)
 {
+    // one thread per (node, plane), guards included; all loads first, then all stores
     constexpr int P = 2 * M + 1;
-    const int nr = a.nr, tid = threadIdx.x, i = blockIdx.x * FT + tid + 1;
-    if (i > nr) return;
+    const int nr = a.nr;
+    const int idx = blockIdx.x * FT + threadIdx.x;
+    if (idx >= (nr + 2) * P) return;
+    const int n = idx / P, pl = idx - n * P;
     const int j = a.flags[3];
-    const size_t n1 = (size_t)(nr + 2) * P;
+    const size_t np = (size_t)idx, n1 = (size_t)(nr + 2) * P, sl = (size_t)(j - 1) * n1 + np;
     const double idr = 1.0 / a.dr;
-    FOR_OWN_NODES(i, nr, n) {
+    double cu[3], dcu[2], bs[3], es[3], e[3], b[3];
 #pragma unroll
-        for (int pl = 0; pl < P; pl++) {
-            const size_t np = (size_t)n * P + pl;
-            double cu[3], dcu[2];
+    for (int c = 0; c < 3; c++) { cu[c] = a.cu[np * 3 + c]; bs[c] = a.b_spe[np * 3 + c]; e[c] = a.e[np * 3 + c]; b[c] = a.b[np * 3 + c]; }
+    es[2] = a.e_spe[np * 3 + 2]; es[0] = a.e_spe[np * 3]; es[1] = a.e_spe[np * 3 + 1];
+    dcu[0] = a.dcu[np * 2]; dcu[1] = a.dcu[np * 2 + 1];
+    const double psi = a.psi[np];
+    const double sq = a.spe_q[np] + a.spe_cu[np * 3 + 2];                                 // cbq, species2d :396
+    const double qs = a.q_spe[np] + cu[2];                                                // :410
+    if (n >= 1 && n <= nr) et_node<M>(a.psi, nr, idr, pl, n, bs[0], bs[1], es[0], es[1]);   // e_spe%solve(b_spe, psi) :414
+    dcu[0] *= a.dxi; dcu[1] *= a.dxi;                                                     // :425
+    a.spe_q[np] = sq; a.spe_q2[sl] = sq;
+    a.q_spe[np] = qs; a.q_spe2[sl] = qs;                                                  // :411
+    a.dcu[np * 2] = dcu[0]; a.dcu[np * 2 + 1] = dcu[1];
+    a.cu[np * 3] = cu[0] + dcu[0]; a.cu[np * 3 + 1] = cu[1] + dcu[1];                     // :426
+    a.psi2[sl] = psi;
 #pragma unroll
-            for (int c = 0; c < 3; c++) cu[c] = a.cu[np * 3 + c];
-            const double sq = a.spe_q[np] + a.spe_cu[np * 3 + 2];                         // cbq, species2d :396
-            a.spe_q[np] = sq;
-            a.spe_q2[(size_t)(j - 1) * n1 + np] = sq;
-#pragma unroll
-            for (int c = 0; c < 3; c++) a.cu2[((size_t)(j - 1) * n1 + np) * 3 + c] = cu[c];  // :409
-            const double qs = a.q_spe[np] + cu[2];                                        // :410
-            a.q_spe[np] = qs;
-            a.q_spe2[(size_t)(j - 1) * n1 + np] = qs;                                      // :411
-#pragma unroll
-            for (int c = 0; c < 2; c++) { dcu[c] = a.dcu[np * 2 + c] * a.dxi; a.dcu[np * 2 + c] = dcu[c]; }  // :425
-            a.cu[np * 3 + 0] = cu[0] + dcu[0];                                           // :426
-            a.cu[np * 3 + 1] = cu[1] + dcu[1];
-            double bs[3], es[3];
-#pragma unroll
-            for (int c = 0; c < 3; c++) { bs[c] = a.b_spe[np * 3 + c]; es[c] = a.e_spe[np * 3 + c]; }
-            if (n >= 1 && n <= nr) et_node<M>(a.psi, nr, idr, pl, n, bs[0], bs[1], es[0], es[1]);  // e_spe%solve(b_spe, psi) :414
-#pragma unroll
-            for (int c = 0; c < 3; c++) {
-                const size_t k3 = np * 3 + c, k2 = ((size_t)(j - 1) * n1 + np) * 3 + c;
-                a.e_spe[k3] = es[c];
-                a.e_spe2[k2] = es[c];                                                     // :452-456
-                a.b_spe2[k2] = bs[c];
-                a.e2[k2] = a.e[k3];
-                a.b2[k2] = a.b[k3];
-            }
-            a.psi2[(size_t)(j - 1) * n1 + np] = a.psi[np];
-        }
+    for (int c = 0; c < 3; c++) {
+        a.cu2[sl * 3 + c] = cu[c];                                                        // :409
+        a.e_spe[np * 3 + c] = es[c];
+        a.e_spe2[sl * 3 + c] = es[c];                                                     // :452-456
+        a.b_spe2[sl * 3 + c] = bs[c];
+        a.e2[sl * 3 + c] = e[c];
+        a.b2[sl * 3 + c] = b[c];
     }
 }

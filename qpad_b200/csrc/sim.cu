@@ -106,7 +106,7 @@ template <int M> static void l_fused(int which, cudaStream_t st, const FusedArgs
     const int grid = FC;
     if (which == 0) k_fused_A<M><<<grid, FT, 0, st>>>(a);
     else if (which == 1) k_fused_C<M><<<grid, FT, 0, st>>>(a);
-    else k_fused_D<M><<<(a.nr + FT - 1) / FT, FT, 0, st>>>(a);
+    else k_fused_D<M><<<((a.nr + 2) * (2 * M + 1) + FT - 1) / FT, FT, 0, st>>>(a);
 }
 static int launch_fused(qpg_sim s, int which)
 {
