@@ -167,11 +167,17 @@ def run_b200(args):
                 dist.barrier()
             torch.cuda.synchronize()
 
+        if args.no_sweep:
+            sim.set_sweep(0)
         for _ in range(args.warmup):
             runner.step()
         sync_all()
         u0, i0, s0 = sim.stats()
         l0 = sim.ctx.launch_count()
+        sweep_on = not args.no_sweep
+        if sweep_on:
+            sim.sweep_profile(reset=True)
+            sim.ctx.tprof_reset(); sim.ctx.tprof_enable(True)      # CUDA events around every sweep-kernel launch
         clk = ClockSampler(local); clk.start()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         sync_all()
@@ -184,7 +190,12 @@ def run_b200(args):
         clocks = clk.stop()
         u1, i1, s1 = sim.stats()
         upd, iters, slices = u1 - u0, i1 - i0, s1 - s0
-        launches = slices * 5 + 2 * iters + args.steps * 12 if sim.prm.use_graph else sim.ctx.launch_count() - l0
+        prof, sweep_ms, sweep_n = None, None, 0
+        if sweep_on:
+            sweep_ms, sweep_n = sim.ctx.tprof_get("kernel sweep")
+            sim.ctx.tprof_enable(False)
+            prof = sim.sweep_profile()
+        launches = sim.ctx.launch_count() - l0 if (sweep_on or not sim.prm.use_graph) else slices * 5 + 2 * iters + args.steps * 12
         t = torch.tensor([ms, float(upd), float(launches), float(iters), float(slices)], dtype=torch.float64, device="cuda")
         if world > 1:
             tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -208,10 +219,37 @@ def run_b200(args):
             e2e = {"value": ue / te, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                    "what": "per step: plasma lattice host->device through qpg_part2d_upload, full 3D step, E_z and psi on-axis line-outs + counters device->host"}
 
-        # ---- roofline leg: per-kernel CUDA-event timing of the same workload (stream launches, no graph) -------
+        # ---- roofline ------------------------------------------------------------------------------------------
         roof = roof_hbm = None
-        kern = {}
-        if rank == 0 and world == 1:
+        if rank == 0 and sweep_on:
+            # dominant kernel = the persistent sweep kernel: CUDA events around each of its launches in the timed region.
+            # algorithmic bytes (fused push): 24 (qdeposit) + 64 per amjdeposit pass + 88 (push_u+push_x) per update
+            peak, peak_src = hbm_peak()
+            u_r, i_r, s_r = (u1 - u0), (i1 - i0), (s1 - s0)
+            nit = i_r / max(s_r, 1)
+            bytes_total = u_r * (112.0 + 64.0 * nit)
+            ach = bytes_total / (sweep_ms * 1e-3) / 1e9
+            nspc = prof["ns_total"] / max(prof["cyc_total"], 1.0)
+            ph = {}
+            for key, cnt, bpp in (("A", prof["slices"], None), ("amj", prof["amj_phases"], 64.0), ("C", prof["amj_phases"], None), ("push", prof["slices"], 112.0)):
+                us = prof["cyc_" + key] * nspc * 1e-3 / max(cnt, 1.0)
+                ph[key] = {"us_per_phase": us, "cta0_work_us": prof["work_" + key] * nspc * 1e-3 / max(cnt, 1.0)}
+                if bpp:
+                    ph[key]["GBs"] = bpp * (u_r / max(s_r, 1)) / (us * 1e-6) / 1e9
+            roof = {"bound": "hbm", "kernel": "k_sweep<%d> (persistent: all slices of a slab in one launch)" % cfg["max_mode"], "achieved": ach, "peak": peak, "unit": "GB/s",
+                    "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                    "bytes_per_update": 112.0 + 64.0 * nit, "updates_per_launch": u_r / max(sweep_n, 1), "avg_launch_ms": sweep_ms / max(sweep_n, 1),
+                    "launches_timed": int(sweep_n), "us_per_slice": sweep_ms * 1e3 / max(s_r, 1),
+                    "phases": {"A||update_bound": ph["A"], "amjdeposit (64 B/particle)": ph["amj"], "C": ph["C"], "push_u+push_x+qdeposit||D (112 B/particle)": ph["push"],
+                               "note": "SM-clock stamps of CTA 0 between grid-barrier releases, scaled by globaltimer; each phase includes its barrier"},
+                    "note": "particle planes (16.8 MB) stay L2-resident between phases at this size; the kernel is bound by fp64 issue + barrier latency, not HBM (DESIGN.md 4)"}
+            if world == 1 and not args.no_micro:
+                runner.prepare_step()
+                sim.run_slices(1, max(1, int(0.55 * cfg["nz"])))   # fields of a slice inside the wake
+                roof_hbm = runner.kernel_microbench(peak)
+                runner.finish_step()
+        elif rank == 0 and world == 1:
+            kern = {}
             peak, peak_src = hbm_peak()
             j0 = max(1, int(0.55 * cfg["nz"]))
             j1 = min(cfg["nz"], j0 + args.roof_slices - 1)
@@ -226,14 +264,11 @@ def run_b200(args):
             sim.ctx.tprof_enable(False)
             sim.set_graph(1)
             ms_amj, n_amj = kern["kernel amjdeposit"]
-            # launches that skipped themselves (converged) are included in n_amj: count the real ones from the iteration counter
-            it_a = sim.stats()[1]
             per = ms_amj / max(n_amj, 1)
-            bytes_amj = 64.0 * n_before
-            ach = bytes_amj / (per * 1e-3) / 1e9
+            ach = 64.0 * n_before / (per * 1e-3) / 1e9
             roof = {"bound": "hbm", "kernel": "k_amjdeposit<1>", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                     "peak_source": peak_src, "bytes_per_particle": 64, "particles_per_launch": int(n_before), "avg_launch_us": per * 1e3,
-                    "note": "in-loop launches (events on the launch stream, slices %d-%d); includes launches that exit early after convergence; particle planes are L2-resident between kernels at this size" % (j0, j1),
+                    "note": "per-slice launch path (--no-sweep): events on the launch stream, slices %d-%d" % (j0, j1),
                     "other_kernels_us": {k: (v[0] / max(v[1], 1)) * 1e3 for k, v in kern.items()}}
             roof_hbm = runner.kernel_microbench(peak)
             runner.finish_step()
@@ -277,6 +312,8 @@ def main():
     ap.add_argument("--ref-slices", type=int, default=24, help="xi slices per CPU sample")
     ap.add_argument("--roof-slices", type=int, default=64)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true", help="per-slice CUDA-graph launches instead of the persistent sweep kernel")
+    ap.add_argument("--no-micro", action="store_true", help="skip the stream-from-HBM kernel microbenchmark")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

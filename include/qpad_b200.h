@@ -207,6 +207,16 @@ int qpg_sim_stats(qpg_sim s, long *updates, long *pc_iters, long *slices);
 int qpg_sim_set_graph(qpg_sim s, int use_graph);
 /* field programs: 1 = thread-block-cluster kernels (default when nr <= 1024 and max_mode <= 2), 0 = generic op-list CTA */
 int qpg_sim_set_fused(qpg_sim s, int on);
+/* slab driver: 1 = ONE persistent cooperative kernel sweeps all slices of a qpg_sim_run_slices call (default when
+ * max_mode <= 2 and nr <= 4096; phases separated by grid barriers, predictor-corrector loop on the device),
+ * 0 = per-slice launches (CUDA graph or plain stream, see qpg_sim_set_graph) */
+int qpg_sim_set_sweep(qpg_sim s, int on);
+/* in-kernel clocks of the sweep kernel since the last reset (synchronises): out12 = SM cycles spent in phase
+ * [0] A||update_bound, [1] amjdeposit, [2] C, [3] push+qdeposit||D; [4] total cycles, [5] total ns (globaltimer),
+ * [6] slices, [7] amjdeposit phases, [8..11] CTA 0's own work cycles in the four phases (the rest of a phase is
+ * barrier latency + waiting for the slowest CTA).  out12 holds 12 doubles.
+ * Fails with QPG_ERR_STATE if the last sweep hit its barrier watchdog. */
+int qpg_sim_sweep_profile(qpg_sim s, double *out12, int reset);
 
 #ifdef __cplusplus
 }

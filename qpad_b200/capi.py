@@ -123,6 +123,8 @@ SIGNATURES = {
     "qpg_sim_stats": (_i, [_vp, _pl, _pl, _pl]),
     "qpg_sim_set_graph": (_i, [_vp, _i]),
     "qpg_sim_set_fused": (_i, [_vp, _i]),
+    "qpg_sim_set_sweep": (_i, [_vp, _i]),
+    "qpg_sim_sweep_profile": (_i, [_vp, _pd, _i]),
 }
 
 
@@ -421,6 +423,15 @@ class Sim:
     def renew(self): _chk(self.L.qpg_sim_renew(self.h))
     def set_graph(self, on): _chk(self.L.qpg_sim_set_graph(self.h, int(on)))
     def set_fused(self, on): _chk(self.L.qpg_sim_set_fused(self.h, int(on)))
+    def set_sweep(self, on): _chk(self.L.qpg_sim_set_sweep(self.h, int(on)))
+
+    def sweep_profile(self, reset=False):
+        """in-kernel phase clocks of the persistent sweep kernel (see qpg_sim_sweep_profile)"""
+        out = (C.c_double * 12)()
+        _chk(self.L.qpg_sim_sweep_profile(self.h, out, int(reset)))
+        keys = ("cyc_A", "cyc_amj", "cyc_C", "cyc_push", "cyc_total", "ns_total", "slices", "amj_phases",
+                "work_A", "work_amj", "work_C", "work_push")
+        return dict(zip(keys, [float(v) for v in out]))
 
     def stats(self):
         u, it, sl = _l(), _l(), _l()

@@ -44,7 +44,7 @@ struct OpCoef {
 enum {
     TP_DEPOSIT2D = 0, TP_PUSH2D, TP_MOVE2D, TP_SORT2D, TP_SOLVE_PSI, TP_SOLVE_BZ, TP_SOLVE_EZ, TP_SOLVE_PBT, TP_SOLVE_BBT,
     TP_SOLVE_PET, TP_SOLVE_BET, TP_SET_SOURCE, TP_ARITH, TP_PIPELINE, TP_DEPOSIT3D, TP_PUSH3D, TP_MOVE3D, TP_FIELD_FUSED,
-    TP_K_QDEP, TP_K_AMJ, TP_K_PUSH, TP_K_COMPACT,
+    TP_K_QDEP, TP_K_AMJ, TP_K_PUSH, TP_K_COMPACT, TP_K_SWEEP,
     TP_COUNT
 };
 extern const char *const qpg_tprof_names[TP_COUNT];

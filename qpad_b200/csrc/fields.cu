@@ -39,7 +39,7 @@ const char *const qpg_tprof_names[TP_COUNT] = {
     "deposit 2D particles", "push 2D particles", "move 2D particles", "sort 2D particles", "solve psi", "solve bz",
     "solve ez", "solve plasma bt", "solve beam bt", "solve plasma et", "solve beam et", "set source", "arithmetics",
     "pipeline", "deposit 3D particles", "push 3D particles", "move 3D particles", "fused field program",
-    "kernel qdeposit", "kernel amjdeposit", "kernel push", "kernel compact"};
+    "kernel qdeposit", "kernel amjdeposit", "kernel push", "kernel compact", "kernel sweep"};
 
 TprofScope::TprofScope(qpg_ctx c, int e) : ctx(c), ev(e), a(nullptr), b(nullptr), on(false)
 {

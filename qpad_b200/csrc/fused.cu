@@ -498,16 +498,13 @@ __global__ void __cluster_dims__(FC, 1, 1) __launch_bounds__(FT) k_fused_C(const
 }
 
 // ============================================================================================================
+// program D for one (node, plane) item, guards included; all loads first, then all stores
 template <int M>
-__global__ void __launch_bounds__(FT) k_fused_D(const __grid_constant__ FusedArgs a)
+__device__ __forceinline__ void fused_D_item(const FusedArgs &a, int idx, int j)
 {
-    // one thread per (node, plane), guards included; all loads first, then all stores
     constexpr int P = 2 * M + 1;
     const int nr = a.nr;
-    const int idx = blockIdx.x * FT + threadIdx.x;
-    if (idx >= (nr + 2) * P) return;
     const int n = idx / P, pl = idx - n * P;
-    const int j = a.flags[3];
     const size_t np = (size_t)idx, n1 = (size_t)(nr + 2) * P, sl = (size_t)(j - 1) * n1 + np;
     const double idr = 1.0 / a.dr;
     double cu[3], dcu[2], bs[3], es[3], e[3], b[3];
@@ -534,4 +531,11 @@ __global__ void __launch_bounds__(FT) k_fused_D(const __grid_constant__ FusedArg
         a.e2[sl * 3 + c] = e[c];
         a.b2[sl * 3 + c] = b[c];
     }
+}
+template <int M>
+__global__ void __launch_bounds__(FT) k_fused_D(const __grid_constant__ FusedArgs a)
+{
+    const int idx = blockIdx.x * FT + threadIdx.x;
+    if (idx >= (a.nr + 2) * (2 * M + 1)) return;
+    fused_D_item<M>(a, idx, a.flags[3]);
 }

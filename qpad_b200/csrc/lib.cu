@@ -3,4 +3,5 @@
 #include "particles.cu"
 #include "beam.cu"
 #include "fused.cu"
+#include "sweep.cu"
 #include "sim.cu"

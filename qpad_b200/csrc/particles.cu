@@ -25,6 +25,11 @@ static PartView view_of(qpg_part2d p) { PartView v{p->x1, p->x2, p->p1, p->p2, p
 
 struct Interp { double c, s, w0, w1; int idx; };
 
+// fire-and-forget reductions.  Written as PTX `red` because ptxas keeps `atomicAdd` as a returning ATOMG (a ~320-cycle
+// round trip per instruction) inside the persistent sweep kernel, where fences / volatile loads are present.
+__device__ __forceinline__ void red_add(double *p, double v) { asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
+__device__ __forceinline__ void red_add(int *p, int v) { asm volatile("red.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
 // species/interp_part2d.f03:28-65 gen_interp_info
 __device__ __forceinline__ Interp interp_info(double x1, double x2, double idr)
 {
@@ -43,15 +48,15 @@ __device__ __forceinline__ Interp interp_info(double x1, double x2, double idr)
 
 // species/interp_part2d.f03:67-109 interp_field (3-vector) on the node-interleaved image f[(node*P + pl)*3 + c]
 template <int M>
-__device__ __forceinline__ void gather3(const double *__restrict__ f, const Interp &it, double out[3])
+__device__ __forceinline__ void gather3(const double *f, const Interp &it, double out[3])
 {
     constexpr int P = 2 * M + 1;
     const double *n0 = f + (size_t)it.idx * (P * 3);
     const double *n1 = n0 + P * 3;
 #pragma unroll
-    for (int c = 0; c < 3; c++) out[c] = __ldg(n0 + c) * it.w0;
+    for (int c = 0; c < 3; c++) out[c] = n0[c] * it.w0;
 #pragma unroll
-    for (int c = 0; c < 3; c++) out[c] = fma(__ldg(n1 + c), it.w1, out[c]);
+    for (int c = 0; c < 3; c++) out[c] = fma(n1[c], it.w1, out[c]);
     double phr = 1.0, phi = 0.0;
 #pragma unroll
     for (int m = 1; m <= M; m++) {
@@ -60,9 +65,9 @@ __device__ __forceinline__ void gather3(const double *__restrict__ f, const Inte
         phr = t;
         const double pr2 = 2.0 * phr, pi2 = 2.0 * phi;
 #pragma unroll
-        for (int c = 0; c < 3; c++) out[c] = fma(__ldg(n0 + (2 * m - 1) * 3 + c) * pr2 - __ldg(n0 + (2 * m) * 3 + c) * pi2, it.w0, out[c]);
+        for (int c = 0; c < 3; c++) out[c] = fma(n0[(2 * m - 1) * 3 + c] * pr2 - n0[(2 * m) * 3 + c] * pi2, it.w0, out[c]);
 #pragma unroll
-        for (int c = 0; c < 3; c++) out[c] = fma(__ldg(n1 + (2 * m - 1) * 3 + c) * pr2 - __ldg(n1 + (2 * m) * 3 + c) * pi2, it.w1, out[c]);
+        for (int c = 0; c < 3; c++) out[c] = fma(n1[(2 * m - 1) * 3 + c] * pr2 - n1[(2 * m) * 3 + c] * pi2, it.w1, out[c]);
     }
 }
 
@@ -106,7 +111,7 @@ __device__ __forceinline__ void warp_deposit_group(const double *X, double w0, d
     constexpr int NF = final_count(2 * H);
 #pragma unroll
     for (int k = 0; k < NF; k++)
-        if (k < cnt) atomicAdd(acc_cell + base + k, v[k]);
+        if (k < cnt) red_add(acc_cell + base + k, v[k]);
 }
 
 // common tail of both deposit kernels.  X[H] = per-particle products (phase x value); key = cell or -1
@@ -129,59 +134,63 @@ __device__ __forceinline__ void warp_deposit(const double *X, double w0, double 
     } else if (key >= 0) {
         double *a = acc + (size_t)key * H;
 #pragma unroll
-        for (int i = 0; i < H; i++) { atomicAdd(a + i, w0 * X[i]); atomicAdd(a + H + i, w1 * X[i]); }
+        for (int i = 0; i < H; i++) { red_add(a + i, w0 * X[i]); red_add(a + H + i, w1 * X[i]); }
     }
 }
 
 // ---- qdeposit: species/part2d_class.f03:231-359 (accumulation part; axis rules live in FOP_QFIX) --------
+// per-particle charge products (part2d_class.f03:277-289): X[pl] = Re/Im(q * phase0^m), key = cell (1-based), weights
 template <int M>
-__global__ void __launch_bounds__(PT_BLOCK) k_qdeposit(PartView pv, double *__restrict__ acc1, double idr)
+__device__ __forceinline__ void qdep_products(double x1, double x2, double q, double idr, double (&X)[2 * M + 1], double &w0, double &w1, int &key)
+{
+    double pos = __dmul_rn(__dsqrt_rn(__dadd_rn(__dmul_rn(x1, x1), __dmul_rn(x2, x2))), idr);
+    // phase0 = cmplx(x1, -x2) / pos * idr   (part2d_class.f03:278)
+    const double c0 = x1 / pos * idr, s0 = -x2 / pos * idr;
+    int nn = (int)floor(pos);
+    double f = pos - (double)nn;
+    key = nn + 1;
+    w0 = 1.0 - f; w1 = f;
+    double phr = q, phi = 0.0;
+    X[0] = phr;
+#pragma unroll
+    for (int m = 1; m <= M; m++) {
+        double t = phr * c0 - phi * s0;
+        phi = phr * s0 + phi * c0;
+        phr = t;
+        X[2 * m - 1] = phr;
+        X[2 * m] = phi;
+    }
+}
+// one warp-tile of qdeposit: particle i (whole warp participates)
+template <int M>
+__device__ __forceinline__ void qdep_body(const PartView &pv, double *acc1, double idr, int npp, int i, int lane)
 {
     constexpr int P = 2 * M + 1;
-    const int npp = *pv.d_npp;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
-    if ((i & ~31) >= npp) return;
-    const bool valid = i < npp;
     double X[P];
     double w0 = 0.0, w1 = 0.0;
     int key = -1;
-    if (valid) {
-        const double x1 = pv.x1[i], x2 = pv.x2[i], q = pv.q[i];
-        double pos = __dmul_rn(__dsqrt_rn(__dadd_rn(__dmul_rn(x1, x1), __dmul_rn(x2, x2))), idr);
-        // phase0 = cmplx(x1, -x2) / pos * idr   (part2d_class.f03:278)
-        const double c0 = x1 / pos * idr, s0 = -x2 / pos * idr;
-        int nn = (int)floor(pos);
-        double f = pos - (double)nn;
-        key = nn + 1;
-        w0 = 1.0 - f; w1 = f;
-        double phr = q, phi = 0.0;
-        X[0] = phr;
-#pragma unroll
-        for (int m = 1; m <= M; m++) {
-            double t = phr * c0 - phi * s0;
-            phi = phr * s0 + phi * c0;
-            phr = t;
-            X[2 * m - 1] = phr;
-            X[2 * m] = phi;
-        }
-    } else {
+    if (i < npp) qdep_products<M>(pv.x1[i], pv.x2[i], pv.q[i], idr, X, w0, w1, key);
+    else {
 #pragma unroll
         for (int k = 0; k < P; k++) X[k] = 0.0;
     }
     warp_deposit<P>(X, w0, w1, key, acc1, lane);
 }
-
-// ---- amjdeposit_robust: species/part2d_class.f03:746-1010 ------------------------------------------------
 template <int M>
-__global__ void __launch_bounds__(PT_BLOCK) k_amjdeposit(PartView pv, const double *__restrict__ ef, const double *__restrict__ bf,
-                                                        double *__restrict__ acc8, double qbm, double dt, double idr,
-                                                        const int *__restrict__ skip_flag)
+__global__ void __launch_bounds__(PT_BLOCK) k_qdeposit(PartView pv, double *__restrict__ acc1, double idr)
 {
-    constexpr int P = 2 * M + 1, H = 8 * P;
-    if (skip_flag && *skip_flag) return;
     const int npp = *pv.d_npp;
     const int i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
     if ((i & ~31) >= npp) return;
+    qdep_body<M>(pv, acc1, idr, npp, i, lane);
+}
+
+// ---- amjdeposit_robust: species/part2d_class.f03:746-1010 ------------------------------------------------
+template <int M>
+__device__ __forceinline__ void amj_body(const PartView &pv, const double *ef, const double *bf, double *acc8, double qbm, double dt, double idr,
+                                         int npp, int i, int lane)
+{
+    constexpr int P = 2 * M + 1, H = 8 * P;
     const bool valid = i < npp;
     double X[H];
     double w0 = 0.0, w1 = 0.0;
@@ -241,19 +250,29 @@ __global__ void __launch_bounds__(PT_BLOCK) k_amjdeposit(PartView pv, const doub
     }
     warp_deposit<H>(X, w0, w1, key, acc8, lane);
 }
-
-// ---- push: push_u_robust :1879-1965, push_x :2221-2262, bound test of update_bound :2323-2348 --------------
-// mode bit0: push_u, bit1: push_x, bit2: flag particles with r >= edge in the bitmap
 template <int M>
-__global__ void __launch_bounds__(PT_BLOCK) k_push(PartView pv, const double *__restrict__ ef, const double *__restrict__ bf, double qbm,
-                                                  double dt, double idr, double edge, int mode, unsigned *__restrict__ outmask,
-                                                  int *__restrict__ d_nout)
+__global__ void __launch_bounds__(PT_BLOCK) k_amjdeposit(PartView pv, const double *__restrict__ ef, const double *__restrict__ bf,
+                                                        double *__restrict__ acc8, double qbm, double dt, double idr,
+                                                        const int *__restrict__ skip_flag)
 {
+    if (skip_flag && *skip_flag) return;
     const int npp = *pv.d_npp;
     const int i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
     if ((i & ~31) >= npp) return;
+    amj_body<M>(pv, ef, bf, acc8, qbm, dt, idr, npp, i, lane);
+}
+
+// ---- push: push_u_robust :1879-1965, push_x :2221-2262, bound test of update_bound :2323-2348 --------------
+// mode bit0: push_u, bit1: push_x, bit2: flag particles with r >= edge in the bitmap
+// acc1 != nullptr: additionally deposit the charge of the advanced, still in-bounds particle (the next slice's qdeposit
+// :346-349 fused into the push; out-of-bounds particles are removed by update_bound before the reference deposits)
+template <int M>
+__device__ __forceinline__ void push_body(const PartView &pv, const double *ef, const double *bf, double qbm, double dt, double idr, double edge,
+                                          int mode, unsigned *outmask, int *d_nout, double *acc1, int npp, int i, int lane)
+{
     const bool valid = i < npp;
     bool out = false;
+    double xn1 = 0.0, xn2 = 0.0, qv = 0.0;
     if (valid) {
         double x1 = pv.x1[i], x2 = pv.x2[i];
         double p1 = pv.p1[i], p2 = pv.p2[i], p3 = pv.p3[i], g;
@@ -290,6 +309,7 @@ __global__ void __launch_bounds__(PT_BLOCK) k_push(PartView pv, const double *__
             x2 = x2 + p2 * dtc;
             pv.x1[i] = x1; pv.x2[i] = x2;
         }
+        xn1 = x1; xn2 = x2;
         if (mode & 4) {
             const double pos = __dsqrt_rn(__dadd_rn(__dmul_rn(x1, x1), __dmul_rn(x2, x2)));
             out = pos >= edge;
@@ -299,9 +319,31 @@ __global__ void __launch_bounds__(PT_BLOCK) k_push(PartView pv, const double *__
         const unsigned bal = __ballot_sync(FULL, out);
         if (lane == 0) {
             outmask[i >> 5] = bal;
-            if (bal) atomicAdd(d_nout, __popc(bal));
+            if (bal) red_add(d_nout, __popc(bal));
         }
     }
+    if (acc1) {
+        constexpr int P = 2 * M + 1;
+        double X[P];
+        double w0 = 0.0, w1 = 0.0;
+        int key = -1;
+        if (valid && !out) { qv = pv.q[i]; qdep_products<M>(xn1, xn2, qv, idr, X, w0, w1, key); }
+        else {
+#pragma unroll
+            for (int k = 0; k < P; k++) X[k] = 0.0;
+        }
+        warp_deposit<P>(X, w0, w1, key, acc1, lane);
+    }
+}
+template <int M>
+__global__ void __launch_bounds__(PT_BLOCK) k_push(PartView pv, const double *__restrict__ ef, const double *__restrict__ bf, double qbm,
+                                                  double dt, double idr, double edge, int mode, unsigned *__restrict__ outmask,
+                                                  int *__restrict__ d_nout)
+{
+    const int npp = *pv.d_npp;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
+    if ((i & ~31) >= npp) return;
+    push_body<M>(pv, ef, bf, qbm, dt, idr, edge, mode, outmask, d_nout, nullptr, npp, i, lane);
 }
 
 // ---- compaction (update_bound_part2d :2307-2353 / pack_particles "fill the holes inversely") ---------------
@@ -330,12 +372,10 @@ __device__ int block_excl_scan_int(int v, int *sm, int *total)
     return res;
 }
 
-__global__ void __launch_bounds__(1024, 1) k_compact(double *const *planes, int nplanes, int *d_npp, int *d_nout, unsigned *outmask, int *lists,
-                                                    int desc_holes, int *slice_flags)
+// all threads of one CTA (any multiple of 32 up to 1024); sm = 40 ints of shared memory
+__device__ void compact_body(double *const *planes, int nplanes, int *d_npp, int *d_nout, unsigned *outmask, int *lists, int desc_holes, int *sm)
 {
-    __shared__ int sm[40];
     const int n = *d_npp, nout = *d_nout;
-    if (slice_flags && threadIdx.x == 0) { slice_flags[3] += 1; slice_flags[4] += 1; }  // fused path: slice j is complete
     if (nout == 0) return;
     const int K = n - nout, tid = threadIdx.x, nt = blockDim.x;
     const int nwords = (n + 31) >> 5;
@@ -395,6 +435,13 @@ __global__ void __launch_bounds__(1024, 1) k_compact(double *const *planes, int 
     __syncthreads();
     for (int w = wbeg; w < wend; w++) outmask[w] = 0u;
     if (tid == 0) { *d_npp = K; *d_nout = 0; }
+}
+__global__ void __launch_bounds__(1024, 1) k_compact(double *const *planes, int nplanes, int *d_npp, int *d_nout, unsigned *outmask, int *lists,
+                                                    int desc_holes, int *slice_flags)
+{
+    __shared__ int sm[40];
+    if (slice_flags && threadIdx.x == 0) { slice_flags[3] += 1; slice_flags[4] += 1; }  // fused path: slice j is complete
+    compact_body(planes, nplanes, d_npp, d_nout, outmask, lists, desc_holes, sm);
 }
 
 // ---- wire format (part2d_class.f03:2381-2388) ----------------------------------------------------------
@@ -509,6 +556,7 @@ static void set_planes(qpg_part2d p, double *slab)
     p->gamma = slab + 5 * p->npmax; p->psi = slab + 6 * p->npmax; p->q = slab + 7 * p->npmax;
 }
 static double **plane_table(qpg_part2d p) { return (double **)(p->lists + 2 * p->npmax); }  // 64 ints of tail room
+static double *const *part2d_plane_table(qpg_part2d p) { return plane_table(p); }
 
 extern "C" int qpg_part2d_create(qpg_part2d *out, qpg_ctx ctx, double qbm, long npmax)
 {

@@ -21,6 +21,11 @@ struct qpg_sim_s {
     cudaGraphExec_t gexec;
     bool graph_ready;
     bool use_fused;       // cluster kernels of fused.cu instead of the op-list programs
+    bool use_sweep;       // persistent cooperative slab-sweep kernel (sweep.cu)
+    int sweep_grid;       // CTAs of the sweep kernel (0 = not yet queried)
+    unsigned *sw_bar;     // grid / team barrier counters + abort flag
+    double *sw_xbuf;      // team exchange records
+    long long *sw_prof;   // in-kernel phase clocks
     double *phi;
     long host_updates, host_iters, host_slices;
 };
@@ -152,6 +157,69 @@ static int enqueue_slice_tail(qpg_sim s)
     return part2d_launch_qdeposit(s->spe);                       // next slice's qdp (:346-349) on the advanced particles
 }
 
+// ---- persistent slab sweep (sweep.cu) ---------------------------------------------------------------------
+static bool sweep_supported(const qpg_sim_params &prm) { return prm.max_mode <= 2 && (prm.nr + ST_N - 1) / ST_N <= SW_MAX_TEAM; }
+template <int M> static cudaError_t sweep_occupancy(int *blocks_per_sm)
+{
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k_sweep<M>, SW_T, 0);
+}
+template <int M> static cudaError_t sweep_launch(int grid, cudaStream_t st, SweepArgs &a)
+{
+    void *args[] = {(void *)&a};
+    return cudaLaunchCooperativeKernel((const void *)k_sweep<M>, dim3(grid), dim3(SW_T), args, 0, st);
+}
+static int sweep_prepare(qpg_sim s)
+{
+    if (s->sweep_grid > 0) return 0;
+    qpg_ctx c = s->ctx;
+    int coop = 0, nsm = 0, per = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device));
+    CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device));
+    if (!coop) { qpg_set_error("device does not support cooperative launches"); return QPG_ERR_UNSUPPORTED; }
+    switch (c->M) {
+    case 0: CUDA_TRY(sweep_occupancy<0>(&per)); break;
+    case 1: CUDA_TRY(sweep_occupancy<1>(&per)); break;
+    default: CUDA_TRY(sweep_occupancy<2>(&per)); break;
+    }
+    const int nteam = (c->nr + ST_N - 1) / ST_N;
+    if (per < 1 || nsm * per <= nteam) { qpg_set_error("sweep kernel: %d CTAs/SM x %d SMs cannot host a field team of %d", per, nsm, nteam); return QPG_ERR_UNSUPPORTED; }
+    CUDA_TRY(cudaMalloc(&s->sw_bar, sizeof(unsigned) * 128));
+    CUDA_TRY(cudaMalloc(&s->sw_xbuf, sizeof(double) * 3 * SW_MAX_TEAM * SW_XK));
+    CUDA_TRY(cudaMemsetAsync(s->sw_xbuf, 0, sizeof(double) * 3 * SW_MAX_TEAM * SW_XK, c->stream));
+    CUDA_TRY(cudaMalloc(&s->sw_prof, sizeof(long long) * 32));
+    CUDA_TRY(cudaMemsetAsync(s->sw_prof, 0, sizeof(long long) * 32, c->stream));
+    s->sweep_grid = nsm;   // one CTA per SM
+    return 0;
+}
+static double *const *part2d_plane_table(qpg_part2d p);
+static int sweep_run(qpg_sim s, int j0, int j1)
+{
+    qpg_ctx c = s->ctx;
+    int rc = sweep_prepare(s);
+    if (rc) return rc;
+    SweepArgs a;
+    memset(&a, 0, sizeof(a));
+    a.f = fused_args(s);
+    qpg_part2d p = s->spe;
+    a.pv = view_of(p);
+    a.planes = part2d_plane_table(p);
+    a.d_npp_w = p->d_npp; a.d_nout = p->d_nout; a.outmask = p->outmask; a.lists = p->lists;
+    a.qbm = p->qbm; a.edge = (double)c->nr * c->dr;
+    a.j0 = j0; a.j1 = j1; a.nteam = (c->nr + ST_N - 1) / ST_N;
+    a.bar = s->sw_bar; a.xbuf = s->sw_xbuf; a.prof = s->sw_prof;
+    CUDA_TRY(cudaMemsetAsync(s->sw_bar, 0, sizeof(unsigned) * 128, c->stream));
+    TprofScope tp(c, TP_K_SWEEP);
+    cudaError_t e;
+    switch (c->M) {
+    case 0: e = sweep_launch<0>(s->sweep_grid, c->stream, a); break;
+    case 1: e = sweep_launch<1>(s->sweep_grid, c->stream, a); break;
+    default: e = sweep_launch<2>(s->sweep_grid, c->stream, a); break;
+    }
+    if (e != cudaSuccess) return qpg_cuda_fail(e, "cudaLaunchCooperativeKernel(k_sweep)");
+    count_launch(c);
+    return 0;
+}
+
 static int build_graph(qpg_sim s)
 {
     qpg_ctx c = s->ctx;
@@ -238,6 +306,7 @@ extern "C" int qpg_sim_create(qpg_sim *out, int device, void *cuda_stream, const
         {&s->spe_q, 1, 1}, {&s->spe_qn, 1, 0}, {&s->spe_cu, 3, 0}, {&s->spe_dcu, 2, 0}, {&s->spe_amu, 3, 0}, {&s->beam_q, 1, 1}};
     for (auto &t : tbl) { rc = qpg_field_create(t.f, c, t.dim, nzp, t.has2d); if (rc) return rc; }
     s->use_fused = (prm->nr <= FT * FC && prm->max_mode <= 2);
+    s->use_sweep = sweep_supported(*prm);
     CUDA_TRY(cudaMalloc(&s->phi, sizeof(double) * (size_t)(prm->nr + 2) * c->P));
     CUDA_TRY(cudaMemsetAsync(s->phi, 0, sizeof(double) * (size_t)(prm->nr + 2) * c->P, c->stream));
     rc = qpg_part2d_create(&s->spe, c, prm->sp_qbm, prm->sp_npmax);
@@ -256,7 +325,7 @@ extern "C" int qpg_sim_destroy(qpg_sim s)
     qpg_field all[] = {s->psi, s->e, s->b, s->e_spe, s->b_spe, s->e_beam, s->b_beam, s->cu, s->amu, s->acu, s->dcu, s->q_spe, s->q_beam,
                        s->spe_q, s->spe_qn, s->spe_cu, s->spe_dcu, s->spe_amu, s->beam_q};
     for (auto f : all) qpg_field_destroy(f);
-    cudaFree(s->phi);
+    cudaFree(s->phi); cudaFree(s->sw_bar); cudaFree(s->sw_xbuf); cudaFree(s->sw_prof);
     qpg_part2d_destroy(s->spe);
     qpg_part3d_destroy(s->beam);
     qpg_ctx_destroy(s->ctx);
@@ -323,6 +392,23 @@ extern "C" int qpg_sim_run_slices(qpg_sim s, int j0, int j1)
         CUDA_TRY(cudaMemsetAsync(s->spe->acc1, 0, sizeof(double) * (size_t)(c->nr + 2) * c->P, c->stream));
         if ((rc = part2d_launch_qdeposit(s->spe))) return rc;
     }
+    if (s->use_sweep) {
+        // one persistent launch per stretch of slices between two sorts
+        int j = j0;
+        while (j <= j1) {
+            int jend = j1;
+            const int sf = s->prm.sort_freq;
+            if (sf > 0) { const int k = sf - ((s->prm.noff2 + j - 1) % sf) - 1; jend = j + k < j1 ? j + k : j1; }
+            if ((rc = sweep_run(s, j, jend))) return rc;
+            if (sf > 0 && ((s->prm.noff2 + jend) % sf) == 0) {
+                if ((rc = qpg_part2d_sort(s->spe))) return rc;
+                CUDA_TRY(cudaMemsetAsync(s->spe->acc1, 0, sizeof(double) * (size_t)(c->nr + 2) * c->P, c->stream));
+                if ((rc = part2d_launch_qdeposit(s->spe))) return rc;
+            }
+            j = jend + 1;
+        }
+        return 0;
+    }
     if (s->prm.use_graph && !s->graph_ready) { if ((rc = build_graph(s))) return rc; }
     for (int j = j0; j <= j1; j++) {
         if (s->prm.use_graph) {
@@ -381,3 +467,32 @@ extern "C" int qpg_sim_set_fused(qpg_sim s, int on)
     return 0;
 }
 extern "C" int qpg_sim_set_graph(qpg_sim s, int use_graph) { ARG_TRY(s, "null sim"); s->prm.use_graph = use_graph != 0; return 0; }
+extern "C" int qpg_sim_set_sweep(qpg_sim s, int on)
+{
+    ARG_TRY(s, "null sim");
+    if (on && !sweep_supported(s->prm)) { qpg_set_error("the persistent sweep kernel needs max_mode <= 2 and nr <= %d", SW_MAX_TEAM * ST_N); return QPG_ERR_UNSUPPORTED; }
+    s->use_sweep = on != 0;
+    return 0;
+}
+extern "C" int qpg_sim_sweep_profile(qpg_sim s, double *out8, int reset)
+{
+    ARG_TRY(s && out8, "null arg");
+    for (int k = 0; k < 12; k++) out8[k] = 0.0;
+    if (!s->sw_prof) return 0;
+    long long h[32];
+    qpg_ctx c = s->ctx;
+    CUDA_TRY(cudaMemcpyAsync(h, s->sw_prof, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    if (reset) CUDA_TRY(cudaMemsetAsync(s->sw_prof, 0, sizeof(h), c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    // the abort flag of the last launch: a watchdog exit must not pass silently
+    unsigned ab = 0;
+    CUDA_TRY(cudaMemcpy(&ab, s->sw_bar + 64, sizeof(ab), cudaMemcpyDeviceToHost));
+    if (ab) { qpg_set_error("sweep kernel aborted: a grid barrier timed out"); return QPG_ERR_STATE; }
+    for (int k = 0; k < 12; k++) out8[k] = (double)h[k];
+    if (getenv("QPG_SWEEP_STAMPS")) {   // development aid: stage stamps inside the field programs (cycles of CTA 0, thread 0)
+        fprintf(stderr, "sweep stamps (cycles/slice):");
+        for (int k = 16; k < 26; k++) fprintf(stderr, " %.0f", (double)h[k] / (h[6] > 0 ? (double)h[6] : 1.0));
+        fprintf(stderr, "\n");
+    }
+    return 0;
+}

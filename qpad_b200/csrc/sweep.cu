@@ -1,0 +1,518 @@
+// sweep.cu -- the slab sweep as ONE persistent cooperative kernel.
+//
+// Why: a slice of the quasi-static loop (simulation_class.f03:342-469) is a strictly sequential chain of small
+// steps (deposit -> field solves -> {deposit -> field solves}* -> push) whose device time at C2 is ~10 us each; as
+// separate kernel launches -- even replayed from a CUDA graph with a device-side WHILE node -- the chain costs
+// ~94 us per slice, one third of it launch / dependency latency.  Here one CTA per SM stays resident for the whole
+// slab; the phases of a slice are separated by a hand-rolled grid barrier (one L2 atomic + one polled line,
+// ~0.5 us) and the predictor-corrector loop is an ordinary loop around a flag every CTA reads after the barrier.
+//
+//   per slice j:   [A on the field team  ||  update_bound compaction on the last CTA]          -- barrier
+//                  { amjdeposit on all CTAs -- barrier -- C on the field team -- barrier }  x n_it
+//                  [push_u + push_x + bound flags + next slice's qdeposit on all CTAs  ||  D items, 1 warp per CTA] -- barrier
+//
+// The field team is the first ceil(nr/128) CTAs, thread <-> radial node (same arithmetic as the cluster kernels of
+// fused.cu); the per-CTA scan totals travel through a small global exchange buffer guarded by a team barrier
+// instead of distributed shared memory, so the kernel needs no cluster co-scheduling and uses every SM for the
+// particle phases.  Every barrier has a watchdog: a CTA that waits longer than ~2 s raises the abort flag, all
+// CTAs leave, and the host reports QPG_ERR_STATE instead of hanging the device.
+#include "common.cuh"
+
+#define SW_T 512           // threads per CTA (16 warps, <= 128 registers per thread)
+#define SW_XK 64           // doubles per CTA in one exchange record
+#define SW_MAX_TEAM 128
+
+struct SweepArgs {
+    FusedArgs f;
+    PartView pv;
+    double *const *planes;
+    int *d_npp_w, *d_nout;
+    unsigned *outmask;
+    int *lists;
+    double qbm, edge;
+    int j0, j1, nteam;
+    unsigned *bar;          // [0] grid arrivals, [32] team arrivals, [64] abort flag (one 128-byte line each)
+    double *xbuf;           // [3][SW_MAX_TEAM][SW_XK] team exchange records: two alternating scan records + the residual maxima
+    long long *prof;        // [0..3] cycles in phase A / amj / C / push, [4] total cycles, [5] total ns, [6] slices, [7] amj phases, [8..11] CTA 0's own work cycles per phase (thread 0's arrival at the barrier)
+};
+
+__device__ __forceinline__ unsigned ld_volatile_u32(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void named_bar(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+// spin until *ctr reaches target (wrap-safe); false on abort / watchdog
+__device__ __forceinline__ bool spin_until(const unsigned *ctr, unsigned target, unsigned *abort_flag)
+{
+    long long t0 = 0;
+    for (unsigned n = 1;; n++) {
+        if ((int)(ld_volatile_u32(ctr) - target) >= 0) return true;
+        if ((n & 63u) == 0) {
+            if (ld_volatile_u32(abort_flag)) return false;
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000LL) { atomicExch(abort_flag, 1u); return false; }
+        }
+    }
+}
+
+// all SW_T threads of every CTA.  Returns false when the sweep must be abandoned.
+__device__ __forceinline__ bool grid_barrier(unsigned *bar, unsigned &epoch, int *sm_i)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        epoch += gridDim.x;
+        __threadfence();
+        atomicAdd(bar, 1u);
+        const bool ok = spin_until(bar, epoch, bar + 64);
+        __threadfence();
+        sm_i[46] = ok ? 1 : 0;
+    }
+    __syncthreads();
+    return sm_i[46] != 0;
+}
+
+// ---- field team: strip decomposition ---------------------------------------------------------------------------
+// Team CTA `rank` owns the ST_N = 32 radial nodes i0 = 32*rank+1 .. i0+31 and ALL its 512 threads work on them:
+//   * source terms / epilogues: one thread per (node, plane, kind) item
+//   * tridiagonal solves: one WARP per system, lane <-> node, so the in-strip scans are pure warp shuffles; the strip
+//     totals of all systems go to the exchange record, and after ONE team barrier every warp folds the other strips'
+//     totals with a masked butterfly
+//   * post-processing: one thread per (node, plane)
+// A thread executes a few hundred instructions per program instead of the ~3000 of the thread-per-node layout, which
+// is what bounds these latency-critical phases (one warp per scheduler cannot hide its own dependency chains).
+#define ST_N 32
+#define ST_H 2             // halo nodes each side of the strip (centred + one-sided 3-point stencils)
+#define ST_W (ST_N + 2 * ST_H)
+
+struct Team {
+    unsigned *ctr, *abort_flag;
+    unsigned epoch;
+    int n, rank, xpar;
+    double *xbuf;
+};
+// all SW_T threads of the team CTAs
+__device__ __forceinline__ void team_barrier(Team &tm)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        tm.epoch += (unsigned)tm.n;
+        __threadfence();
+        atomicAdd(tm.ctr, 1u);
+        spin_until(tm.ctr, tm.epoch, tm.abort_flag);
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+template <int M> struct StripSmem {
+    static constexpr int P = 2 * M + 1, NS = 4 * P;
+    double d[NS][ST_N];            // right-hand sides, then solutions
+    double cu[ST_W * P * 3];       // program C: deposit epilogue values of the strip + halo (node-interleaved like f1)
+    double amu[ST_W * P * 3];
+    double acu[ST_W * P * 2];
+    double dcu[ST_N][P][2];
+    double t[P][ST_N];             // |B_phi| partials of the convergence test
+    double red[2][SW_T / 32];
+};
+
+// warp `s`-th system of a program: strip-local scans, totals -> exchange record.  Returns (inclusive prefix, exclusive
+// suffix) of this lane's node inside the strip.
+__device__ __forceinline__ void strip_scan(const OpCoef &oc, double d, int t, bool valid, int lane, double &fa, double &fb, double *xrec, int slot_a,
+                                           int slot_b)
+{
+    double incl = valid ? __ldg(oc.qT + t) * d : 0.0;
+    double sfx = valid ? __ldg(oc.vT + t) * d : 0.0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double ta = __shfl_up_sync(0xffffffffu, incl, o), tb = __shfl_down_sync(0xffffffffu, sfx, o);
+        if (lane >= o) incl += ta;
+        if (lane + o < 32) sfx += tb;
+    }
+    if (lane == 31) __stcg(xrec + slot_a, incl);
+    if (lane == 0) __stcg(xrec + slot_b, sfx);
+    const double ex = __shfl_down_sync(0xffffffffu, sfx, 1);
+    fa = incl;
+    fb = lane == 31 ? 0.0 : ex;
+}
+// totals of the strips before / after mine (every lane gets both)
+__device__ __forceinline__ void strip_offsets(const double *xb, int nteam, int rank, int lane, int slot_a, int slot_b, double &pa, double &pb)
+{
+    double a = 0.0, b = 0.0;
+    for (int r = lane; r < nteam; r += 32) {
+        if (r < rank) a += __ldcg(xb + (size_t)r * SW_XK + slot_a);
+        if (r > rank) b += __ldcg(xb + (size_t)r * SW_XK + slot_b);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+    pa = a; pb = b;
+}
+__device__ __forceinline__ double strip_total(const double *xb, int nteam, int lane, int slot)
+{
+    double a = 0.0;
+    for (int r = lane; r < nteam; r += 32) a += __ldcg(xb + (size_t)r * SW_XK + slot);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    return a;
+}
+
+// ============================================================================================================
+// program A (simulation_class.f03:344-377): q_beam slice -> bt(beam), qdp epilogue, psi, bz, record, b, ez, et
+template <int M>
+__device__ void sweep_field_A(const FusedArgs &a, int j, Team &tm, StripSmem<M> &sm)
+{
+    constexpr int P = 2 * M + 1, NS = 4 * P, NWARP = SW_T / 32, SPW = (NS + NWARP - 1) / NWARP;
+    static_assert(2 * NS + 1 <= SW_XK, "exchange record too small");
+    const int nr = a.nr, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int i0 = tm.rank * ST_N + 1;
+    const size_t n1 = (size_t)(nr + 2) * P;
+    const double idr = 1.0 / a.dr, idrh = 0.5 * idr;
+    SolveCtx sc; sc.nr = nr; sc.M = M; sc.P = P; sc.logC = 0; sc.stride = 1; sc.dr = a.dr; sc.idr = idr; sc.idrh = idrh;
+    if (tm.rank == 0 && tid == 0) { a.flags[0] = 0; a.flags[2] = 0; }
+    // ---- S1: sources.  threads 0..127: qdp epilogue + beam charge slice (species2d qdp :198-204, copy_slice :344);
+    //          threads 128..511: bz / ez right-hand sides from the predicted current
+    if (tid < 128) {
+        const int nlo = (tm.rank == 0) ? 0 : i0, nhi = (i0 + ST_N - 1 >= nr) ? nr + 1 : i0 + ST_N - 1;
+        for (int it = tid; it < (nhi - nlo + 1) * P; it += 128) {
+            const int n = nlo + it / P, pl = it % P;
+            const size_t k = (size_t)n * P + pl;
+            const double qb = a.q_beam2[(size_t)(j - 1) * n1 + k];
+            const double sq = axis_fix_q(n, pl, a.acc1[k]);
+            const double qs = sq + a.spe_qn[k];
+            a.q_beam[k] = qb; a.acc1[k] = 0.0; a.spe_q[k] = sq; a.q_spe[k] = qs;
+            if (n >= i0 && n <= nr && n < i0 + ST_N) { sm.d[pl][n - i0] = -1.0 * qs; sm.d[P + pl][n - i0] = -1.0 * qb; }
+        }
+    } else {
+        for (int it = tid - 128; it < ST_N * P * 2; it += SW_T - 128) {
+            const int ln = it % ST_N, pl = (it / ST_N) % P, kind = it / (ST_N * P), i = i0 + ln;
+            double v = 0.0;
+            if (i <= nr) v = kind == 0 ? rhs_bz(sc, a.cu, pl, i) : rhs_ez(sc, a.cu, pl, i);
+            sm.d[(2 + kind) * P + pl][ln] = v;
+        }
+    }
+    __syncthreads();
+    // ---- S2: strip scans, one warp per system
+    const int i = i0 + lane, t = i - 1;
+    const bool valid = i <= nr;
+    double *xrec = tm.xbuf + (size_t)tm.xpar * SW_MAX_TEAM * SW_XK + (size_t)tm.rank * SW_XK;
+    double fa[SPW], fb[SPW], dd[SPW];
+#pragma unroll
+    for (int q = 0; q < SPW; q++) {
+        const int s = warp + q * NWARP;
+        if (s < NS) {
+            const int kind = s < P ? FK_PSI : (s < 2 * P ? FK_BT : (s < 3 * P ? FK_BZ : FK_EZ));
+            const OpCoef &oc = a.ops[kind * (QPG_MAX_MODE + 1) + (((s % P) + 1) >> 1)];
+            dd[q] = valid ? sm.d[s][lane] : 0.0;
+            strip_scan(oc, dd[q], t, valid, lane, fa[q], fb[q], xrec, s, NS + s);
+            if (s == 3 * P) {   // E_z m=0 divergence sum, field_e_class.f03:189-197
+                double r = (valid && i >= 2 && i <= nr - 2) ? dd[q] * (double)(i - 1) : 0.0;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+                if (lane == 0) __stcg(xrec + 2 * NS, r);
+            }
+        }
+    }
+    team_barrier(tm);
+    // ---- S3: fold the other strips, apply the Green's-function factors, store
+    const double *xb = tm.xbuf + (size_t)tm.xpar * SW_MAX_TEAM * SW_XK;
+#pragma unroll
+    for (int q = 0; q < SPW; q++) {
+        const int s = warp + q * NWARP;
+        if (s < NS) {
+            const int kind = s < P ? FK_PSI : (s < 2 * P ? FK_BT : (s < 3 * P ? FK_BZ : FK_EZ));
+            const int pl = s % P;
+            const OpCoef &oc = a.ops[kind * (QPG_MAX_MODE + 1) + ((pl + 1) >> 1)];
+            double pa, pb;
+            strip_offsets(xb, tm.n, tm.rank, lane, s, NS + s, pa, pb);
+            double x = 0.0;
+            if (s == 3 * P) {   // row 1 of the E_z m=0 source is -8*(div - edge term) (:199-209); by linearity x += rhs1 * G(:,1)
+                const double tot = strip_total(xb, tm.n, lane, 2 * NS);
+                const double div = tot - idrh * (FX(a.cu, 3, nr - 2, 0, 0) + FX(a.cu, 3, nr - 1, 0, 0)) * ((double)nr - 2.5);
+                if (valid) x = (-8.0 * div) * (__ldg(oc.pT + t) * __ldg(oc.qT));
+            }
+            if (valid) {
+                x += green_apply(oc, t, fa[q] + pa, fb[q] + pb, dd[q]);
+                if (pl > 0 && i == 1 && kind != FK_BT) x = 0.0;
+                sm.d[s][lane] = x;
+                if (kind == FK_PSI) FX(a.psi, 1, i, pl, 0) = x;
+                else if (kind == FK_BT) FX(a.phi, 1, i, pl, 0) = x;
+                else if (kind == FK_BZ) FX(a.b_spe, 3, i, pl, 2) = x;
+                else FX(a.e, 3, i, pl, 2) = x;
+            }
+        }
+    }
+    tm.xpar ^= 1;
+    team_barrier(tm);   // psi / phi of the neighbouring strips
+    // ---- S4: beam B-perp from phi, b = b_spe + b_beam, E-perp, convergence 'record'   (one thread per node, plane)
+    for (int it = tid; it < ST_N * P; it += SW_T) {
+        const int ln = it % ST_N, pl = it / ST_N, ii = i0 + ln, m = (pl + 1) >> 1;
+        if (ii > nr) { sm.t[pl][ln] = 0.0; continue; }
+        // field_b_class.f03:545-701 get_solution_bt
+        double bphi, br = 0.0;
+        if (ii == 1) bphi = (m == 1) ? -idr * FX(a.phi, 1, 2, pl, 0) : 0.0;
+        else if (ii == nr) bphi = -idrh * (3.0 * FX(a.phi, 1, nr, pl, 0) - 4.0 * FX(a.phi, 1, nr - 1, pl, 0) + FX(a.phi, 1, nr - 2, pl, 0));
+        else bphi = -idrh * (FX(a.phi, 1, ii + 1, pl, 0) - FX(a.phi, 1, ii - 1, pl, 0));
+        if (m > 0) {
+            const bool im = (pl & 1) == 0;
+            const int po = im ? pl - 1 : pl + 1;
+            const double sg = im ? 1.0 : -1.0;
+            if (ii == 1) br = (m == 1) ? sg * idr * m * FX(a.phi, 1, 2, po, 0) : 0.0;
+            else br = sg * (idr / (double)(ii - 1)) * m * FX(a.phi, 1, ii, po, 0);
+        }
+        const double bs_r = FX(a.b_spe, 3, ii, pl, 0), bs_p = FX(a.b_spe, 3, ii, pl, 1);
+        sm.t[pl][ln] = fabs(bs_p);                                                        // convergence_tester 'record' :548-558
+        const double b0 = bs_r + br, b1 = bs_p + bphi;                                    // b = b_spe + b_beam :375
+        const double b2 = sm.d[2 * P + pl][ln] + FX(a.b_beam, 3, ii, pl, 2);
+        double er, ephi;
+        et_node<M>(a.psi, nr, idr, pl, ii, b0, b1, er, ephi);                              // :377
+        FX(a.b_beam, 3, ii, pl, 0) = br; FX(a.b_beam, 3, ii, pl, 1) = bphi;
+        FX(a.b, 3, ii, pl, 0) = b0; FX(a.b, 3, ii, pl, 1) = b1; FX(a.b, 3, ii, pl, 2) = b2;
+        FX(a.e, 3, ii, pl, 0) = er; FX(a.e, 3, ii, pl, 1) = ephi;
+    }
+    __syncthreads();
+    if (tid < ST_N && i0 + tid <= nr) {
+        double sre = 0.0, sim = 0.0;
+#pragma unroll
+        for (int pl = 0; pl < P; pl++) { if (pl > 0 && (pl & 1) == 0) sim += sm.t[pl][tid]; else sre += sm.t[pl][tid]; }
+        a.conv_old[i0 + tid] = sre; a.conv_old[nr + 2 + i0 + tid] = sim;
+    }
+}
+
+// program C (:378-396 + :375-377): amjdp epilogue, djdxi, bt_iter, bz, compare, record, b, ez, et.
+// The two per-CTA residual maxima go to the exchange buffer; sweep_conv_decide() combines them after the grid barrier.
+template <int M>
+__device__ void sweep_field_C(const FusedArgs &a, Team &tm, StripSmem<M> &sm)
+{
+    constexpr int P = 2 * M + 1, NS = 4 * P, NWARP = SW_T / 32, SPW = (NS + NWARP - 1) / NWARP;
+    const int nr = a.nr, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int i0 = tm.rank * ST_N + 1;
+    const double idr = 1.0 / a.dr, idrh = 0.5 * idr;
+    SolveCtx sc; sc.nr = nr; sc.M = M; sc.P = P; sc.logC = 0; sc.stride = 1; sc.dr = a.dr; sc.idr = idr; sc.idrh = idrh;
+    // ---- S1: deposit epilogue (part2d_class.f03:916-981) of the strip + halo into shared tiles; the owner also stores
+    //          the species2d amjdp results (:250-276, single species).  acc8 is cleared in S4, after the team barrier,
+    //          because the neighbouring strips read the halo nodes' raw sums here.
+    const int tlo = i0 - ST_H;   // node of tile slot 0
+    const int own_lo = (tm.rank == 0) ? 0 : i0, own_hi = (i0 + ST_N - 1 >= nr) ? nr + 1 : i0 + ST_N - 1;
+    for (int it = tid; it < ST_W * P * 8; it += SW_T) {
+        const int c = it & 7, pl = (it >> 3) % P, sl = (it >> 3) / P, n = tlo + sl;
+        if (n < 0 || n > nr + 1) continue;
+        const size_t np = (size_t)n * P + pl;
+        const double v = axis_fix_amj(n, pl, c, a.acc8[np * 8 + c]);
+        const int tp = sl * P + pl;
+        const bool own = n >= own_lo && n <= own_hi;
+        if (c < 3) { sm.cu[tp * 3 + c] = v; if (own) { a.spe_cu[np * 3 + c] = v; a.cu[np * 3 + c] = v; } }
+        else if (c < 5) { sm.acu[tp * 2 + c - 3] = v; if (own) { a.spe_dcu[np * 2 + c - 3] = v; a.acu[np * 2 + c - 3] = v; } }
+        else { sm.amu[tp * 3 + c - 5] = v; if (own) { a.spe_amu[np * 3 + c - 5] = v; a.amu[np * 3 + c - 5] = v; } }
+    }
+    __syncthreads();
+    // tile pointers addressed with absolute node numbers through FX()
+    const double *cu_t = sm.cu - (ptrdiff_t)tlo * P * 3, *amu_t = sm.amu - (ptrdiff_t)tlo * P * 3, *acu_t = sm.acu - (ptrdiff_t)tlo * P * 2;
+    // ---- S2a: dcu = djdxi(acu, amu) (:390)
+    for (int it = tid; it < ST_N * P * 2; it += SW_T) {
+        const int c = it & 1, pl = (it >> 1) % P, ln = (it >> 1) / P, ii = i0 + ln;
+        double v = 0.0;
+        if (ii <= nr) { v = djdxi_node<M>(acu_t, amu_t, nr, idr, pl, c, ii); FX(a.dcu, 2, ii, pl, c) = v; }
+        sm.dcu[ln][pl][c] = v;
+    }
+    __syncthreads();
+    // ---- S2b: sources of bt_iter (:391), bz (:392), ez (:376 of the next pass / :415)
+    const double relax_idr2 = a.relax * (idr * idr);
+    for (int it = tid; it < ST_N * NS; it += SW_T) {
+        const int ln = it % ST_N, s = it / ST_N, kind = s / P, pl = s % P, ii = i0 + ln;
+        double v = 0.0;
+        if (ii <= nr) {
+            if (kind < 2) {
+                double dcu[P][2];
+#pragma unroll
+                for (int q = 0; q < P; q++) { dcu[q][0] = sm.dcu[ln][q][0]; dcu[q][1] = sm.dcu[ln][q][1]; }
+                v = rhs_bt_iter_own<M>(sc, dcu, cu_t, a.b_spe, relax_idr2, kind, pl, ii);
+            } else v = kind == 2 ? rhs_bz(sc, cu_t, pl, ii) : rhs_ez(sc, cu_t, pl, ii);
+        }
+        sm.d[s][ln] = v;
+    }
+    __syncthreads();
+    // ---- S3: strip scans -> exchange -> solutions
+    const int i = i0 + lane, t = i - 1;
+    const bool valid = i <= nr;
+    double *xrec = tm.xbuf + (size_t)tm.xpar * SW_MAX_TEAM * SW_XK + (size_t)tm.rank * SW_XK;
+    double fa[SPW], fb[SPW], dd[SPW];
+#pragma unroll
+    for (int q = 0; q < SPW; q++) {
+        const int s = warp + q * NWARP;
+        if (s < NS) {
+            const int kind = s < P ? FK_BPLUS : (s < 2 * P ? FK_BMINUS : (s < 3 * P ? FK_BZ : FK_EZ));
+            const OpCoef &oc = a.ops[kind * (QPG_MAX_MODE + 1) + (((s % P) + 1) >> 1)];
+            dd[q] = valid ? sm.d[s][lane] : 0.0;
+            strip_scan(oc, dd[q], t, valid, lane, fa[q], fb[q], xrec, s, NS + s);
+            if (s == 3 * P) {
+                double r = (valid && i >= 2 && i <= nr - 2) ? dd[q] * (double)(i - 1) : 0.0;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+                if (lane == 0) __stcg(xrec + 2 * NS, r);
+            }
+        }
+    }
+    team_barrier(tm);
+    const double *xb = tm.xbuf + (size_t)tm.xpar * SW_MAX_TEAM * SW_XK;
+#pragma unroll
+    for (int q = 0; q < SPW; q++) {
+        const int s = warp + q * NWARP;
+        if (s < NS) {
+            const int kind = s < P ? FK_BPLUS : (s < 2 * P ? FK_BMINUS : (s < 3 * P ? FK_BZ : FK_EZ));
+            const int pl = s % P;
+            const OpCoef &oc = a.ops[kind * (QPG_MAX_MODE + 1) + ((pl + 1) >> 1)];
+            double pa, pb;
+            strip_offsets(xb, tm.n, tm.rank, lane, s, NS + s, pa, pb);
+            double x = 0.0;
+            if (s == 3 * P) {
+                const double tot = strip_total(xb, tm.n, lane, 2 * NS);
+                const double div = tot - idrh * (FX(a.cu, 3, nr - 2, 0, 0) + FX(a.cu, 3, nr - 1, 0, 0)) * ((double)nr - 2.5);
+                if (valid) x = (-8.0 * div) * (__ldg(oc.pT + t) * __ldg(oc.qT));
+            }
+            if (valid) x += green_apply(oc, t, fa[q] + pa, fb[q] + pb, dd[q]);
+            sm.d[s][lane] = x;
+        }
+    }
+    tm.xpar ^= 1;
+    __syncthreads();
+    // ---- S4: get_solution_bt_iter (field_b_class.f03:703-758), bz, ez axis rules; b = b_spe + b_beam; E-perp; compare
+    for (int it = tid; it < ST_N * P; it += SW_T) {
+        const int ln = it % ST_N, pl = it / ST_N, ii = i0 + ln, m = (pl + 1) >> 1;
+        if (ii > nr) { sm.t[pl][ln] = 0.0; continue; }
+        double br, bp;
+        if (m == 0) { br = (ii == 1) ? 0.0 : sm.d[0][ln]; bp = (ii == 1) ? 0.0 : sm.d[P][ln]; }
+        else {
+            const bool im = (pl & 1) == 0;
+            const int po = im ? pl - 1 : pl + 1;
+            br = 0.5 * (sm.d[pl][ln] + sm.d[P + pl][ln]);
+            bp = im ? 0.5 * (-sm.d[po][ln] + sm.d[P + po][ln]) : 0.5 * (sm.d[po][ln] - sm.d[P + po][ln]);
+            if (ii == 1 && m != 1) { br = 0.0; bp = 0.0; }
+        }
+        double bz = sm.d[2 * P + pl][ln], ez = sm.d[3 * P + pl][ln];
+        if (pl > 0 && ii == 1) { bz = 0.0; ez = 0.0; }
+        sm.t[pl][ln] = fabs(bp);
+        const double b0 = br + FX(a.b_beam, 3, ii, pl, 0), b1 = bp + FX(a.b_beam, 3, ii, pl, 1), b2 = bz + FX(a.b_beam, 3, ii, pl, 2);
+        double er, ephi;
+        et_node<M>(a.psi, nr, idr, pl, ii, b0, b1, er, ephi);
+        FX(a.b_spe, 3, ii, pl, 0) = br; FX(a.b_spe, 3, ii, pl, 1) = bp; FX(a.b_spe, 3, ii, pl, 2) = bz;
+        FX(a.b, 3, ii, pl, 0) = b0; FX(a.b, 3, ii, pl, 1) = b1; FX(a.b, 3, ii, pl, 2) = b2;
+        FX(a.e, 3, ii, pl, 0) = er; FX(a.e, 3, ii, pl, 1) = ephi; FX(a.e, 3, ii, pl, 2) = ez;
+    }
+    // clear the raw deposit sums of the strip (+ guards); every strip's halo reads happened before the team barrier
+    for (int it = tid; it < (own_hi - own_lo + 1) * P * 8; it += SW_T) a.acc8[(size_t)own_lo * P * 8 + it] = 0.0;
+    __syncthreads();
+    double mo = 0.0, mn = 0.0;
+    if (tid < ST_N && i0 + tid <= nr) {
+        double sre = 0.0, sim = 0.0;
+#pragma unroll
+        for (int pl = 0; pl < P; pl++) { if (pl > 0 && (pl & 1) == 0) sim += sm.t[pl][tid]; else sre += sm.t[pl][tid]; }
+        const double ore = a.conv_old[i0 + tid], oim = a.conv_old[nr + 2 + i0 + tid];
+        mo = ore * ore + oim * oim;
+        const double dre = ore - sre, dim = oim - sim;
+        mn = dre * dre + dim * dim;
+        a.conv_old[i0 + tid] = sre; a.conv_old[nr + 2 + i0 + tid] = sim;   // 'record' for the next pass (:373)
+    }
+    if (warp == 0) {   // strip maxima -> third exchange slab (read by every CTA after the grid barrier)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { mo = fmax(mo, __shfl_xor_sync(0xffffffffu, mo, o)); mn = fmax(mn, __shfl_xor_sync(0xffffffffu, mn, o)); }
+        if (lane == 0) {
+            double *xm = tm.xbuf + (size_t)2 * SW_MAX_TEAM * SW_XK + (size_t)tm.rank * SW_XK;
+            __stcg(xm, mo); __stcg(xm + 1, mn);
+        }
+    }
+}
+
+// simulation_class.f03:560-599 on the per-CTA maxima published by program C.  Called by one thread per CTA after the
+// grid barrier; every CTA derives the same decision.  `it` = iterations done in this slice including this one.
+__device__ __forceinline__ bool sweep_conv_decide(const SweepArgs &a, int it, bool writer)
+{
+    const double *xb = a.xbuf + (size_t)2 * SW_MAX_TEAM * SW_XK;
+    double mo = 0.0, mn = 0.0;
+    for (int r = 0; r < a.nteam; r++) { mo = fmax(mo, __ldcg(xb + (size_t)r * SW_XK)); mn = fmax(mn, __ldcg(xb + (size_t)r * SW_XK + 1)); }
+    const double old_norm = sqrt(mo), abs_res = sqrt(mn);
+    const double rel = old_norm > 2.220446049250313e-16 ? abs_res / old_norm : 1.7976931348623157e308;
+    const bool fin = rel < a.f.reltol || abs_res < a.f.abstol || it >= a.f.iter_max;
+    if (writer) {
+        a.f.conv_out[0] = rel; a.f.conv_out[1] = abs_res;
+        a.f.counters[1] += 1;
+        a.f.flags[2] = it;
+        if (fin) a.f.flags[0] = 1;
+    }
+    return fin;
+}
+
+// ============================================================================================================
+template <int M>
+__global__ void __launch_bounds__(SW_T, 1) k_sweep(const __grid_constant__ SweepArgs a)
+{
+    constexpr int P = 2 * M + 1;
+    __shared__ StripSmem<M> sm_f;
+    __shared__ int sm_i[48];
+    const int G = gridDim.x, b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const FusedArgs &f = a.f;
+    const double idr = 1.0 / f.dr;
+    unsigned gep = 0;
+    Team tm;
+    tm.ctr = a.bar + 32; tm.abort_flag = a.bar + 64; tm.epoch = 0; tm.n = a.nteam; tm.rank = b; tm.xpar = 0; tm.xbuf = a.xbuf;
+    const bool in_team = b < a.nteam;
+    long long prof[4] = {0, 0, 0, 0}, work[4] = {0, 0, 0, 0}, tprev = 0, tstart = 0, nstart = 0, namj = 0;
+    const bool timer = (b == 0 && tid == 0);
+    if (timer) { tstart = tprev = clock64(); asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(nstart)); }
+    bool ok = true;
+    for (int j = a.j0; j <= a.j1 && ok; j++) {
+        // ---- phase A || compaction -------------------------------------------------------------------------
+        if (in_team) sweep_field_A<M>(f, j, tm, sm_f);
+        else if (b == G - 1) compact_body(a.planes, 8, a.d_npp_w, a.d_nout, a.outmask, a.lists, 0, sm_i);
+        if (timer) work[0] += clock64() - tprev;
+        ok = grid_barrier(a.bar, gep, sm_i);
+        if (timer) { const long long t = clock64(); prof[0] += t - tprev; tprev = t; }
+        if (!ok) break;
+        const int npp = *(volatile const int *)a.pv.d_npp;
+        if (timer) f.counters[0] += (long long)npp;
+        const int ntiles = (npp + 31) >> 5, per = (ntiles + G - 1) / G;
+        const int tile0 = b * per, tile1 = min(tile0 + per, ntiles);
+        // ---- predictor-corrector loop -----------------------------------------------------------------------
+        for (int it = 1; it <= f.iter_max; it++) {
+            for (int tl = tile0 + warp; tl < tile1; tl += SW_T / 32)
+                amj_body<M>(a.pv, f.e, f.b, f.acc8, a.qbm, f.dxi, idr, npp, tl * 32 + lane, lane);
+            if (timer) work[1] += clock64() - tprev;
+            ok = grid_barrier(a.bar, gep, sm_i);
+            if (timer) { const long long t = clock64(); prof[1] += t - tprev; tprev = t; namj++; }
+            if (!ok) break;
+            if (in_team) sweep_field_C<M>(f, tm, sm_f);
+            if (timer) work[2] += clock64() - tprev;
+            ok = grid_barrier(a.bar, gep, sm_i);
+            if (timer) { const long long t = clock64(); prof[2] += t - tprev; tprev = t; }
+            if (!ok) break;
+            if (tid == 0) sm_i[45] = sweep_conv_decide(a, it, b == 0) ? 1 : 0;
+            __syncthreads();
+            if (sm_i[45] != 0) break;
+        }
+        if (!ok) break;
+        // ---- push_u + push_x + bound flags + next slice's qdeposit || D ---------------------------------------
+        if (warp == 0) {
+            const int items = (f.nr + 2) * P, ipc = (items + G - 1) / G;
+            for (int k = b * ipc + lane; k < min((b + 1) * ipc, items); k += 32) fused_D_item<M>(f, k, j);
+        }
+        for (int tl = tile0 + warp; tl < tile1; tl += SW_T / 32)
+            push_body<M>(a.pv, f.e, f.b, a.qbm, f.dxi, idr, a.edge, 7, a.outmask, a.d_nout, f.acc1, npp, tl * 32 + lane, lane);
+        if (timer) work[3] += clock64() - tprev;
+        ok = grid_barrier(a.bar, gep, sm_i);
+        if (timer) { const long long t = clock64(); prof[3] += t - tprev; tprev = t; }
+    }
+    // update_bound of the last slice (the next launch / the host expects compacted particles)
+    if (ok && b == G - 1) compact_body(a.planes, 8, a.d_npp_w, a.d_nout, a.outmask, a.lists, 0, sm_i);
+    if (timer) {
+        long long nend;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(nend));
+        for (int k = 0; k < 4; k++) { a.prof[k] += prof[k]; a.prof[8 + k] += work[k]; }
+        a.prof[4] += clock64() - tstart;
+        a.prof[5] += nend - nstart;
+        a.prof[6] += a.j1 - a.j0 + 1;
+        a.prof[7] += namj;
+        if (ok) { f.flags[3] = a.j1 + 1; f.flags[4] += a.j1 - a.j0 + 1; }
+    }
+}

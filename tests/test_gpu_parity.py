@@ -317,19 +317,27 @@ def _deck(O, decks, nr=64, nz=40, M=1, iter_max=3, **kw):
     return cfg, (bx, bp, bq)
 
 
-def _gpu_sim(capi, O, cfg, beam, ppc=2, nth=8, use_graph=0, sort_freq=0, fused=None):
+# slab drivers: the persistent sweep kernel (default), per-slice CUDA graph with cluster or op-list field programs,
+# plain stream launches
+PATHS = {"sweep": dict(sweep=1), "graph-cluster": dict(sweep=0, use_graph=1, fused=1), "graph-oplist": dict(sweep=0, use_graph=1, fused=0),
+         "stream-cluster": dict(sweep=0, use_graph=0, fused=1)}
+
+
+def _gpu_sim(capi, O, cfg, beam, ppc=2, nth=8, use_graph=0, sort_freq=0, fused=None, sweep=None):
     x, p, g, psi, q = O.inject_uniform(cfg["nr"], cfg["rmax"] / cfg["nr"], ppc, ppc, nth)
     sim = capi.Sim(sp_npmax=2 * len(q), beam_npmax=len(beam[2]) + 64, use_graph=use_graph, sort_freq=sort_freq, **cfg)
     if fused is not None:
         sim.set_fused(fused)
+    if sweep is not None:
+        sim.set_sweep(sweep)
     sim.init_species(x, p, g, psi, q)
     sim.beam.upload(*beam)
     return sim, len(q)
 
 
-@pytest.mark.parametrize("fused", [1, 0])
-@pytest.mark.parametrize("M,use_graph", [(1, 0), (1, 1), (2, 1), (0, 1)])
-def test_slice_loop_matches_oracle(mods, M, use_graph, fused):
+@pytest.mark.parametrize("path", list(PATHS))
+@pytest.mark.parametrize("M", [1, 2, 0])
+def test_slice_loop_matches_oracle(mods, M, path):
     capi, O = mods
     from qpad_b200 import decks
     cfg, beam = _deck(O, decks, M=M)
@@ -337,7 +345,7 @@ def test_slice_loop_matches_oracle(mods, M, use_graph, fused):
     orc = O.Sim(ppc1=2, ppc2=2, num_theta=8, **cfg)
     orc.set_beam(*beam)
     orc_upd = orc.run_slices(nsl)
-    sim, np0 = _gpu_sim(capi, O, cfg, beam, use_graph=use_graph, fused=fused)
+    sim, np0 = _gpu_sim(capi, O, cfg, beam, **PATHS[path])
     sim.beam_qdp_begin(); sim.beam_qdp_end(); sim.begin_step()
     sim.run_slices(1, nsl)
     upd, iters, slices = sim.stats()
@@ -355,9 +363,40 @@ def test_slice_loop_matches_oracle(mods, M, use_graph, fused):
     assert np.max(np.abs(gx - ox)) < 1e-8 and np.max(np.abs(gp - op)) < 1e-8
 
 
-@pytest.mark.parametrize("fused", [1, 0])
+@pytest.mark.parametrize("nr,M,ppc,nth", [(250, 1, 2, 8), (1024, 1, 2, 8), (300, 2, 2, 8), (1024, 0, 1, 8)])
+def test_sweep_kernel_multi_cta_team(mods, nr, M, ppc, nth):
+    """the persistent sweep kernel with a field team of several CTAs (nr > 128): scan totals and residual maxima cross
+    CTAs through the global exchange records; whole-loop parity with the oracle incl. PC iteration counts"""
+    capi, O = mods
+    from qpad_b200 import decks
+    cfg, beam = _deck(O, decks, nr=nr, nz=40, M=M, iter_max=4)
+    nsl = 14
+    orc = O.Sim(ppc1=ppc, ppc2=ppc, num_theta=nth, **cfg)
+    orc.set_beam(*beam)
+    orc_upd = orc.run_slices(nsl)
+    sim, np0 = _gpu_sim(capi, O, cfg, beam, ppc=ppc, nth=nth, sweep=1)
+    sim.beam_qdp_begin(); sim.beam_qdp_end(); sim.begin_step()
+    sim.run_slices(1, 5)          # two launches: the look-ahead deposit and the compaction carry over
+    sim.run_slices(6, nsl)
+    upd, iters, slices = sim.stats()
+    prof = sim.sweep_profile()
+    assert slices == nsl and upd == orc_upd and prof["slices"] == nsl
+    assert iters == orc.total_iters() == prof["amj_phases"], (iters, orc.total_iters(), prof)
+    for name in ("psi", "e", "b", "b_spe", "e_spe", "cu", "q_spe"):
+        got = sim.field(name).download_f2()[:, :nsl]
+        want = orc.field(name, 2)[:, :nsl]
+        scale = np.max(np.abs(want))
+        assert scale > 0
+        assert np.max(np.abs(got - want)) < 1e-8 * scale, (name, np.max(np.abs(got - want)) / scale)
+    gx, gp, gg, gpsi, gq = sim.species.download()
+    ox, op, og, opsi, oq = orc.plasma()
+    assert len(gq) == len(oq) and np.array_equal(gq, oq)
+    assert np.max(np.abs(gx - ox)) < 1e-8 and np.max(np.abs(gp - op)) < 1e-8
+
+
+@pytest.mark.parametrize("path", ["sweep", "graph-cluster", "graph-oplist"])
 @pytest.mark.parametrize("M", [0, 1, 2])
-def test_one_slice_from_identical_state(mods, M, fused):
+def test_one_slice_from_identical_state(mods, M, path):
     """the north-star gate: <= 1e-10 relative per-slice field error after ONE slice from identical inputs, taken in
     the wake (slice 21 of 40) where every field is O(1)"""
     capi, O = mods
@@ -367,7 +406,7 @@ def test_one_slice_from_identical_state(mods, M, fused):
     orc = O.Sim(ppc1=2, ppc2=2, num_theta=8, **cfg)
     orc.set_beam(*beam)
     orc.run_slices(k)
-    sim, np0 = _gpu_sim(capi, O, cfg, beam, use_graph=1, fused=fused)
+    sim, np0 = _gpu_sim(capi, O, cfg, beam, **PATHS[path])
     sim.beam_qdp_begin(); sim.beam_qdp_end(); sim.begin_step()
     sim.species.upload(*orc.plasma())                      # state carried between slices: particles, cu, b_spe
     sim.field("cu").upload(orc.field("cu", 1))
@@ -385,13 +424,14 @@ def test_one_slice_from_identical_state(mods, M, fused):
     assert np.max(np.abs(gx - ox)) < 1e-12 and np.max(np.abs(gp - op)) < 1e-11 * max(1.0, np.max(np.abs(op)))
 
 
-def test_full_3d_step_with_beam_push(mods):
+@pytest.mark.parametrize("path", ["sweep", "graph-cluster"])
+def test_full_3d_step_with_beam_push(mods, path):
     capi, O = mods
     from qpad_b200 import decks
     cfg, beam = _deck(O, decks, nr=64, nz=32, M=1, iter_max=2)
     orc = O.Sim(ppc1=2, ppc2=2, num_theta=8, **cfg)
     orc.set_beam(*beam)
-    sim, np0 = _gpu_sim(capi, O, cfg, beam, use_graph=1)
+    sim, np0 = _gpu_sim(capi, O, cfg, beam, **PATHS[path])
     for step in range(2):
         orc.step3d(step + 1)
         sim.step3d()
@@ -412,7 +452,8 @@ def test_full_3d_step_with_beam_push(mods):
     assert abs(eg - eo) < 1e-6 * eo and abs(cg - co) < 1e-6 * max(abs(co), 1e-3)
 
 
-def test_sorted_loop_still_matches(mods):
+@pytest.mark.parametrize("path", ["sweep", "graph-cluster"])
+def test_sorted_loop_still_matches(mods, path):
     """periodic counting sort changes the particle order, not the physics"""
     capi, O = mods
     from qpad_b200 import decks
@@ -421,7 +462,7 @@ def test_sorted_loop_still_matches(mods):
     orc = O.Sim(ppc1=2, ppc2=2, num_theta=8, sort_freq=4, **cfg)
     orc.set_beam(*beam)
     orc.run_slices(nsl)
-    sim, np0 = _gpu_sim(capi, O, cfg, beam, use_graph=1, sort_freq=4)
+    sim, np0 = _gpu_sim(capi, O, cfg, beam, sort_freq=4, **PATHS[path])
     sim.beam_qdp_begin(); sim.beam_qdp_end(); sim.begin_step()
     sim.run_slices(1, nsl)
     got, want = sim.field("psi").download_f2()[:, :nsl], orc.field("psi", 2)[:, :nsl]
