@@ -211,6 +211,9 @@ int qpg_sim_set_fused(qpg_sim s, int on);
  * max_mode <= 2 and nr <= 4096; phases separated by grid barriers, predictor-corrector loop on the device),
  * 0 = per-slice launches (CUDA graph or plain stream, see qpg_sim_set_graph) */
 int qpg_sim_set_sweep(qpg_sim s, int on);
+/* CTAs of the sweep kernel: n > 0 absolute; n <= 0 = one per SM minus |n| (SMs left free for kernels on other streams,
+ * e.g. the NCCL send/recv kernels of the xi-pipeline, which otherwise could not start until the sweep ends) */
+int qpg_sim_set_sweep_ctas(qpg_sim s, int n);
 /* in-kernel clocks of the sweep kernel since the last reset (synchronises): out12 = SM cycles spent in phase
  * [0] A||update_bound, [1] amjdeposit, [2] C, [3] push+qdeposit||D; [4] total cycles, [5] total ns (globaltimer),
  * [6] slices, [7] amjdeposit phases, [8..11] CTA 0's own work cycles in the four phases (the rest of a phase is

@@ -124,6 +124,7 @@ SIGNATURES = {
     "qpg_sim_set_graph": (_i, [_vp, _i]),
     "qpg_sim_set_fused": (_i, [_vp, _i]),
     "qpg_sim_set_sweep": (_i, [_vp, _i]),
+    "qpg_sim_set_sweep_ctas": (_i, [_vp, _i]),
     "qpg_sim_sweep_profile": (_i, [_vp, _pd, _i]),
 }
 
@@ -424,6 +425,7 @@ class Sim:
     def set_graph(self, on): _chk(self.L.qpg_sim_set_graph(self.h, int(on)))
     def set_fused(self, on): _chk(self.L.qpg_sim_set_fused(self.h, int(on)))
     def set_sweep(self, on): _chk(self.L.qpg_sim_set_sweep(self.h, int(on)))
+    def set_sweep_ctas(self, n): _chk(self.L.qpg_sim_set_sweep_ctas(self.h, int(n)))
 
     def sweep_profile(self, reset=False):
         """in-kernel phase clocks of the persistent sweep kernel (see qpg_sim_sweep_profile)"""

@@ -23,6 +23,7 @@ struct qpg_sim_s {
     bool use_fused;       // cluster kernels of fused.cu instead of the op-list programs
     bool use_sweep;       // persistent cooperative slab-sweep kernel (sweep.cu)
     int sweep_grid;       // CTAs of the sweep kernel (0 = not yet queried)
+    int sweep_ctas_req;   // requested CTA count: > 0 absolute, <= 0 = number of SMs + this (SMs left to other streams)
     unsigned *sw_bar;     // grid / team barrier counters + abort flag
     double *sw_xbuf;      // team exchange records
     long long *sw_prof;   // in-kernel phase clocks
@@ -188,7 +189,10 @@ static int sweep_prepare(qpg_sim s)
     CUDA_TRY(cudaMemsetAsync(s->sw_xbuf, 0, sizeof(double) * 3 * SW_MAX_TEAM * SW_XK, c->stream));
     CUDA_TRY(cudaMalloc(&s->sw_prof, sizeof(long long) * 32));
     CUDA_TRY(cudaMemsetAsync(s->sw_prof, 0, sizeof(long long) * 32, c->stream));
-    s->sweep_grid = nsm;   // one CTA per SM
+    int g = s->sweep_ctas_req > 0 ? s->sweep_ctas_req : nsm * per + s->sweep_ctas_req;   // default: one CTA per SM
+    if (g > nsm * per) g = nsm * per;
+    if (g <= nteam) { qpg_set_error("sweep kernel: %d CTAs cannot host a field team of %d plus the update_bound CTA", g, nteam); return QPG_ERR_ARG; }
+    s->sweep_grid = g;
     return 0;
 }
 static double *const *part2d_plane_table(qpg_part2d p);
@@ -472,6 +476,17 @@ extern "C" int qpg_sim_set_sweep(qpg_sim s, int on)
     ARG_TRY(s, "null sim");
     if (on && !sweep_supported(s->prm)) { qpg_set_error("the persistent sweep kernel needs max_mode <= 2 and nr <= %d", SW_MAX_TEAM * ST_N); return QPG_ERR_UNSUPPORTED; }
     s->use_sweep = on != 0;
+    return 0;
+}
+extern "C" int qpg_sim_set_sweep_ctas(qpg_sim s, int n)
+{
+    ARG_TRY(s, "null sim");
+    s->sweep_ctas_req = n;
+    if (s->sweep_grid > 0) {   // already prepared: re-derive the grid
+        cudaStreamSynchronize(s->ctx->stream);
+        cudaFree(s->sw_bar); cudaFree(s->sw_xbuf); cudaFree(s->sw_prof);
+        s->sw_bar = nullptr; s->sw_xbuf = nullptr; s->sw_prof = nullptr; s->sweep_grid = 0;
+    }
     return 0;
 }
 extern "C" int qpg_sim_sweep_profile(qpg_sim s, double *out8, int reset)

@@ -10,9 +10,20 @@ Per 3D step and stage boundary:
   backward: first-slice e and b into the upstream guard slice nzp+1
   forward : beam particles that crossed the slab edge (7 fp64 each)
 """
+import os
+import sys
+import time
+
 import numpy as np
 
 from . import capi
+
+_TRACE = bool(os.environ.get("QPG_TRACE"))
+
+
+def _trace(rank, msg):
+    if _TRACE:
+        print(f"[{time.time() % 1000:8.3f}] rank {rank}: {msg}", file=sys.stderr, flush=True)
 
 
 def slab_partition(nz, nstages):
@@ -135,6 +146,8 @@ class PipelineStage:
         self.sim.init_species(*plasma)
         self.sim.beam.upload(*mine)
         s = self.sim
+        if world > 1 and make_buf is None:
+            s.set_sweep_ctas(-8)       # leave 8 SMs to the NCCL send/recv kernels that overlap the slab sweep
         mk = make_buf or (lambda n: torch.zeros(n, dtype=torch.float64, device=torch.device("cuda", device)))
         self.buf_q = mk(s.field("beam_q").wire_count())
         self.buf_cu = mk(s.field("cu").wire_count())
@@ -152,6 +165,8 @@ class PipelineStage:
         self.torch = torch
         self.comm = torch.cuda.Stream(device=device) if (stream is not None and make_buf is None) else None
         self.pending = {}
+        self.pending_tail = False
+        self.buf_q_out = mk(s.field("beam_q").wire_count())
 
     # mpi_isend analogue: the transfer runs on the communication stream, the compute stream carries on.  The buffer
     # is only repacked after _wait(name) (the reference's mpi_wait before every pipe_send, simulation_class.f03:430).
@@ -165,6 +180,13 @@ class PipelineStage:
         with self.torch.cuda.stream(self.comm):
             self.pending[name] = self.dist.isend(t, dst)
 
+    def _irecv(self, name, t, src):
+        if self.comm is None:
+            self.pending[name] = self.dist.irecv(t, src)
+            return
+        with self.torch.cuda.stream(self.comm):
+            self.pending[name] = self.dist.irecv(t, src)
+
     def _wait(self, name):
         w = self.pending.pop(name, None)
         if w is not None:
@@ -175,8 +197,13 @@ class PipelineStage:
         if self.comm is None and self.stream is None:
             pass
 
-    def step(self):
+    # A 3D step of one stage = head (everything up to the packed hand-off buffers) + tail (the hand-offs that need the
+    # downstream stage, the beam push and the renewal).  step() = head() + tail(); bench.py primes the pipeline by
+    # letting stage r run (world-1-r) steps ahead and stops every stage between a head and its tail, where no
+    # send is pending -- the reference reaches the same steady state after world-1 steps of fill.
+    def head(self):
         s, r = self.sim, self.rank
+        _trace(r, "head")
         # species%precv, cu / b_spe pipe_recv and the beam q guard slice: everything stage r-1 hands forward arrives
         # when it has finished its slab (simulation_class.f03:303-340; the guard slice is taken at the same point so
         # that an upstream stage never waits for a downstream one)
@@ -198,23 +225,62 @@ class PipelineStage:
         if not self.first:
             self._wait("b"); s.field("b").pack(1, self.buf_b.data_ptr()); self._isend("b", self.buf_b, r - 1)
             self._wait("e"); s.field("e").pack(1, self.buf_e.data_ptr()); self._isend("e", self.buf_e, r - 1)
+            # the beam particles stage r-1 pushes across the slab edge in THIS step arrive while the slab is swept:
+            # post the receive now on the communication stream, consume it in tail() (part3d_comm.f03:278-314)
+            self._irecv("beam_in", self.buf_beam_in, r - 1)
         if self.nzp > 1:
             s.run_slices(2, self.nzp)
         if not self.last:                                               # :210-215, :429-434, :472-474
-            self._wait("q"); s.field("beam_q").pack(self.nzp + 1, self.buf_q.data_ptr()); self._isend("q", self.buf_q, r + 1)
-            self._wait("p"); s.species.pack(self.buf_p_out.data_ptr()); self._isend("p", self.buf_p_out, r + 1)
-            self._wait("cu"); s.field("cu").pack(0, self.buf_cu_out.data_ptr()); self._isend("cu", self.buf_cu_out, r + 1)
-            self._wait("bs"); s.field("b_spe").pack(0, self.buf_bs_out.data_ptr()); self._isend("bs", self.buf_bs_out, r + 1)
+            self._wait("q"); s.field("beam_q").pack(self.nzp + 1, self.buf_q_out.data_ptr())
+            self._wait("p"); s.species.pack(self.buf_p_out.data_ptr())
+            self._wait("cu"); s.field("cu").pack(0, self.buf_cu_out.data_ptr())
+            self._wait("bs"); s.field("b_spe").pack(0, self.buf_bs_out.data_ptr())
+        self.pending_tail = True
+
+    def tail(self):
+        s, r = self.sim, self.rank
+        _trace(r, "tail")
+        if not self.last:
+            self._isend("q", self.buf_q_out, r + 1)
+            self._isend("p", self.buf_p_out, r + 1)
+            self._isend("cu", self.buf_cu_out, r + 1)
+            self._isend("bs", self.buf_bs_out, r + 1)
             self._recv(self.buf_b_in, r + 1); s.field("b").unpack(self.nzp + 1, self.buf_b_in.data_ptr())   # :482-483
             self._recv(self.buf_e_in, r + 1); s.field("e").unpack(self.nzp + 1, self.buf_e_in.data_ptr())
         # beam push + forward hand-off                                  (:489-493, part3d_comm.f03:278-314)
         s.beam_push()
         if not self.first:
-            self._recv(self.buf_beam_in, r - 1)
+            self._wait("beam_in")
             s.beam.unpack(self.buf_beam_in.data_ptr())
         if not self.last:
             self._wait("beam"); s.beam.pack_forward(self.buf_beam.data_ptr()); self._isend("beam", self.buf_beam, r + 1)
         s.renew()                                                       # :498-501
+        self.pending_tail = False
+
+    def step(self):
+        self.head()
+        self.tail()
+
+    def prime(self):
+        """after any number of complete steps: run ahead until this stage has finished the head of its
+        (world-1-rank)-th extra step.  Leaves every stage between a head and its tail (the last one idle)."""
+        for k in range(self.world - 1 - self.rank):
+            if self.pending_tail:
+                self.tail()
+            self.head()
+
+    def step_primed(self):
+        """one steady-state step of a primed stage: the pending tail, then the next head"""
+        if self.pending_tail:
+            self.tail()
+        self.head()
+
+    def unwind(self):
+        """finish every step the first stage has started"""
+        if self.pending_tail:
+            self.tail()
+        for k in range(self.rank):
+            self.step()
 
     def drain(self):
         for k in list(self.pending):
