@@ -134,7 +134,9 @@ class SingleStage:
 class PipelineStage:
     """One rank = one xi slab on one GPU; consecutive ranks are consecutive pipeline stages."""
 
-    def __init__(self, cfg, plasma, beam, stream=None, rank=0, world=1, device=0, use_graph=1, dist=None, make_buf=None):
+    def __init__(self, cfg, plasma, beam, stream=None, rank=0, world=1, device=0, use_graph=1, dist=None, make_buf=None, sim=None):
+        """`sim`, `dist`, `make_buf` are injection points for the host-logic tests (tests/test_pipeline_gloo.py drives the
+        stage protocol over gloo with a recording stand-in for the device object); production code leaves them None."""
         import torch
         import torch.distributed as tdist
         self.dist = dist or tdist
@@ -142,7 +144,7 @@ class PipelineStage:
         self.noff2, self.nzp = slab_partition(cfg["nz"], world)[rank]
         dxi = (cfg["zmax"] - cfg["zmin"]) / cfg["nz"]
         mine = split_beam(*beam, cfg["nz"], dxi, world)[rank]
-        self.sim = _make_sim(cfg, len(plasma[4]), len(mine[2]), stream, device, use_graph, self.noff2, self.nzp, beam_cap=len(beam[2]) + 1024)
+        self.sim = sim if sim is not None else _make_sim(cfg, len(plasma[4]), len(mine[2]), stream, device, use_graph, self.noff2, self.nzp, beam_cap=len(beam[2]) + 1024)
         self.sim.init_species(*plasma)
         self.sim.beam.upload(*mine)
         s = self.sim

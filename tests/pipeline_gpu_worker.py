@@ -1,0 +1,46 @@
+"""torchrun worker of tests/test_gpu_pipeline.py: a 2-stage xi-pipeline on 2 GPUs, results saved per rank."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+from qpad_b200 import decks  # noqa: E402
+from qpad_b200.pipeline import PipelineStage  # noqa: E402
+
+
+def main():
+    out, nsteps = sys.argv[1], int(sys.argv[2])
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl")
+    cfg = dict(nr=64, nz=32, max_mode=1, rmax=5.0, zmin=-5.0, zmax=5.0, dt=10.0, ppc1=2, ppc2=2, num_theta=8, iter_max=2,
+               iter_reltol=1e-3, iter_abstol=1e-3)
+    beam = dict(decks.CONFIGS["C1"]["beam"])
+    bm = decks.beam_std(cfg["nr"], cfg["nz"], cfg["rmax"], cfg["zmin"], cfg["zmax"], **beam)
+    plasma = decks.plasma_uniform(cfg["nr"], cfg["rmax"], cfg["ppc1"], cfg["ppc2"], cfg["num_theta"])
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        st = PipelineStage(cfg, plasma, bm, stream=stream, rank=rank, world=world, device=local)
+        # the steady-state driver of bench.py: complete steps, then prime / primed steps / unwind
+        st.step()
+        st.prime()
+        for _ in range(nsteps - 1):
+            st.step_primed()
+        st.unwind()
+        st.drain()
+        torch.cuda.synchronize()
+        s = st.sim
+        bx, bp, bq = s.beam.download()
+        np.savez(os.path.join(out, f"rank{rank}.npz"), psi=s.field("psi").download_f2(), e=s.field("e").download_f2(), bx=bx, bp=bp, bq=bq,
+                 stats=np.array(s.stats()), noff2=st.noff2, nzp=st.nzp)
+        dist.barrier(device_ids=[local])
+        st.close()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
