@@ -138,6 +138,68 @@ __device__ __forceinline__ void warp_deposit(const double *X, double w0, double 
     }
 }
 
+// ---- segmented warp reduction of the amjdeposit sums on the fp64 tensor pipe -----------------------------------
+// Per particle the 2*P*8 deposited values are an outer product  alpha (x) beta :
+//     alpha[j*P + pl] = w_j * q*ipsi*{Re,Im}(e^{-im phi})     (2P numbers: node weight x mode phase)
+//     beta[k]         = (u_r, u_phi, u_z, du_r, du_phi, u_r u_r, u_r u_phi, u_phi u_phi)/...   (8 numbers)
+// so the sum over the particles of one cell is the small contraction  C[2P x 8] = sum_p alpha_p beta_p^T, which is
+// exactly what mma.sync.m8n8k4.f64 computes: 8 DMMAs contract the 32 particles of a warp (k = 4 particles each) for
+// 8 alpha rows.  alpha/beta go through a per-warp shared-memory tile ([row][lane], row stride DEP_LD = 36 doubles
+// -> conflict-free stores and fragment loads); lanes that do not belong to the cell are masked out of the A
+// fragment, so a warp spanning several cells repeats only the 8 DMMAs + 2 REDs per lane, not a shuffle butterfly
+// (~45 instructions per cell instead of ~620).
+#define DEP_LD 36
+template <int M> struct DepTile { static constexpr int rows = 2 * (2 * M + 1) + 8, doubles = rows * DEP_LD; };
+
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+template <int M>
+__device__ __forceinline__ void warp_deposit_mma(const double (&alpha)[2 * (2 * M + 1)], const double (&beta)[8], int key, double *acc8, double *tile,
+                                                 int lane)
+{
+    constexpr int P = 2 * M + 1, R = 2 * P, NTILE = (R + 7) / 8;
+    __syncwarp();                                   // the previous tile's fragment loads are done
+#pragma unroll
+    for (int r = 0; r < R; r++) tile[r * DEP_LD + lane] = alpha[r];
+#pragma unroll
+    for (int k = 0; k < 8; k++) tile[(R + k) * DEP_LD + lane] = beta[k];
+    __syncwarp();
+    const int row = lane >> 2, kk = lane & 3;
+    double bfr[8];
+#pragma unroll
+    for (int s = 0; s < 8; s++) bfr[s] = tile[(R + row) * DEP_LD + 4 * s + kk];
+    const unsigned same = __match_any_sync(FULL, key);
+    const bool leader = key >= 0 && (__ffs(same) - 1 == lane);
+    unsigned leaders = __ballot_sync(FULL, leader);
+    while (leaders) {
+        const int l = __ffs(leaders) - 1;
+        leaders &= leaders - 1;
+        const int cell = __shfl_sync(FULL, key, l);
+        const unsigned members = __ballot_sync(FULL, key == cell) >> kk;   // bit 4s <-> particle 4s + kk
+#pragma unroll
+        for (int t = 0; t < NTILE; t++) {
+            const int r = t * 8 + row;
+            const bool live = r < R;
+            double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+            for (int s = 0; s < 8; s++) {
+                double a = 0.0;
+                if (live && ((members >> (4 * s)) & 1u)) a = tile[r * DEP_LD + 4 * s + kk];
+                dmma884(c0, c1, a, bfr[s]);
+            }
+            if (live) {
+                const int j = r >= P ? 1 : 0, pl = r - j * P;
+                double *dst = acc8 + ((size_t)(cell + j) * P + pl) * 8 + 2 * kk;
+                red_add(dst, c0);
+                red_add(dst + 1, c1);
+            }
+        }
+    }
+}
+
 // ---- qdeposit: species/part2d_class.f03:231-359 (accumulation part; axis rules live in FOP_QFIX) --------
 // per-particle charge products (part2d_class.f03:277-289): X[pl] = Re/Im(q * phase0^m), key = cell (1-based), weights
 template <int M>
@@ -188,12 +250,11 @@ __global__ void __launch_bounds__(PT_BLOCK) k_qdeposit(PartView pv, double *__re
 // ---- amjdeposit_robust: species/part2d_class.f03:746-1010 ------------------------------------------------
 template <int M>
 __device__ __forceinline__ void amj_body(const PartView &pv, const double *ef, const double *bf, double *acc8, double qbm, double dt, double idr,
-                                         int npp, int i, int lane)
+                                         int npp, int i, int lane, double *tile)
 {
-    constexpr int P = 2 * M + 1, H = 8 * P;
+    constexpr int P = 2 * M + 1;
     const bool valid = i < npp;
-    double X[H];
-    double w0 = 0.0, w1 = 0.0;
+    double alpha[2 * P], beta[8];
     int key = -1;
     if (valid) {
         const double x1 = pv.x1[i], x2 = pv.x2[i];
@@ -230,25 +291,27 @@ __device__ __forceinline__ void amj_body(const PartView &pv, const double *ef, c
         const double dpsi = qbm * (wp2 - (wp0 * u0 + wp1 * u1) * ipsi);
         du0 = du0 + u0 * dpsi * ipsi;
         du1 = du1 + u1 * dpsi * ipsi;
-        const double vals[8] = {u0, u1, u2, du0, du1, u0 * u0 * ipsi, u0 * u1 * ipsi, u1 * u1 * ipsi};
-        // phase = q*ipsi*(cos - i sin)^m
+        beta[0] = u0; beta[1] = u1; beta[2] = u2; beta[3] = du0; beta[4] = du1;
+        beta[5] = u0 * u0 * ipsi; beta[6] = u0 * u1 * ipsi; beta[7] = u1 * u1 * ipsi;
+        // phase = q*ipsi*(cos - i sin)^m ; alpha = node weight x phase
         double phr = q * ipsi, phi = 0.0;
-#pragma unroll
-        for (int k = 0; k < 8; k++) X[k] = phr * vals[k];
+        alpha[0] = it.w0 * phr; alpha[P] = it.w1 * phr;
 #pragma unroll
         for (int m = 1; m <= M; m++) {
             double t = phr * it.c + phi * it.s;
             phi = phi * it.c - phr * it.s;
             phr = t;
-#pragma unroll
-            for (int k = 0; k < 8; k++) { X[(2 * m - 1) * 8 + k] = phr * vals[k]; X[(2 * m) * 8 + k] = phi * vals[k]; }
+            alpha[2 * m - 1] = it.w0 * phr; alpha[2 * m] = it.w0 * phi;
+            alpha[P + 2 * m - 1] = it.w1 * phr; alpha[P + 2 * m] = it.w1 * phi;
         }
-        key = it.idx; w0 = it.w0; w1 = it.w1;
+        key = it.idx;
     } else {
 #pragma unroll
-        for (int k = 0; k < H; k++) X[k] = 0.0;
+        for (int k = 0; k < 2 * P; k++) alpha[k] = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) beta[k] = 0.0;
     }
-    warp_deposit<H>(X, w0, w1, key, acc8, lane);
+    warp_deposit_mma<M>(alpha, beta, key, acc8, tile, lane);
 }
 template <int M>
 __global__ void __launch_bounds__(PT_BLOCK) k_amjdeposit(PartView pv, const double *__restrict__ ef, const double *__restrict__ bf,
@@ -259,7 +322,8 @@ __global__ void __launch_bounds__(PT_BLOCK) k_amjdeposit(PartView pv, const doub
     const int npp = *pv.d_npp;
     const int i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
     if ((i & ~31) >= npp) return;
-    amj_body<M>(pv, ef, bf, acc8, qbm, dt, idr, npp, i, lane);
+    extern __shared__ double dep_tiles[];
+    amj_body<M>(pv, ef, bf, acc8, qbm, dt, idr, npp, i, lane, dep_tiles + (threadIdx.x >> 5) * DepTile<M>::doubles);
 }
 
 // ---- push: push_u_robust :1879-1965, push_x :2221-2262, bound test of update_bound :2323-2348 --------------
@@ -688,7 +752,12 @@ extern "C" int qpg_part2d_renew(qpg_part2d p)
 template <int M> static void l_qdeposit(int grid, cudaStream_t st, PartView pv, double *acc1, double idr)
 { k_qdeposit<M><<<grid, PT_BLOCK, 0, st>>>(pv, acc1, idr); }
 template <int M> static void l_amjdeposit(int grid, cudaStream_t st, PartView pv, const double *ef, const double *bf, double *acc8, double qbm, double dt, double idr, const int *skip)
-{ k_amjdeposit<M><<<grid, PT_BLOCK, 0, st>>>(pv, ef, bf, acc8, qbm, dt, idr, skip); }
+{
+    constexpr size_t smem = sizeof(double) * DepTile<M>::doubles * (PT_BLOCK / 32);
+    static bool attr_set = false;   // > 48 KB of dynamic shared memory needs the opt-in (M >= 3)
+    if (!attr_set) { cudaFuncSetAttribute(k_amjdeposit<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+    k_amjdeposit<M><<<grid, PT_BLOCK, smem, st>>>(pv, ef, bf, acc8, qbm, dt, idr, skip);
+}
 template <int M> static void l_push(int grid, cudaStream_t st, PartView pv, const double *ef, const double *bf, double qbm, double dt, double idr, double edge, int mode, unsigned *outmask, int *d_nout)
 { k_push<M><<<grid, PT_BLOCK, 0, st>>>(pv, ef, bf, qbm, dt, idr, edge, mode, outmask, d_nout); }
 

@@ -160,14 +160,17 @@ static int enqueue_slice_tail(qpg_sim s)
 
 // ---- persistent slab sweep (sweep.cu) ---------------------------------------------------------------------
 static bool sweep_supported(const qpg_sim_params &prm) { return prm.max_mode <= 2 && (prm.nr + ST_N - 1) / ST_N <= SW_MAX_TEAM; }
+template <int M> static constexpr size_t sweep_smem() { return sizeof(double) * DepTile<M>::doubles * (SW_T / 32); }
 template <int M> static cudaError_t sweep_occupancy(int *blocks_per_sm)
 {
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k_sweep<M>, SW_T, 0);
+    cudaError_t e = cudaFuncSetAttribute(k_sweep<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem<M>());
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k_sweep<M>, SW_T, sweep_smem<M>());
 }
 template <int M> static cudaError_t sweep_launch(int grid, cudaStream_t st, SweepArgs &a)
 {
     void *args[] = {(void *)&a};
-    return cudaLaunchCooperativeKernel((const void *)k_sweep<M>, dim3(grid), dim3(SW_T), args, 0, st);
+    return cudaLaunchCooperativeKernel((const void *)k_sweep<M>, dim3(grid), dim3(SW_T), args, sweep_smem<M>(), st);
 }
 static int sweep_prepare(qpg_sim s)
 {

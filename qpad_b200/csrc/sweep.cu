@@ -451,6 +451,7 @@ __global__ void __launch_bounds__(SW_T, 1) k_sweep(const __grid_constant__ Sweep
     constexpr int P = 2 * M + 1;
     __shared__ StripSmem<M> sm_f;
     __shared__ int sm_i[48];
+    extern __shared__ double dep_tiles[];   // per-warp alpha/beta tiles of the DMMA deposit
     const int G = gridDim.x, b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const FusedArgs &f = a.f;
     const double idr = 1.0 / f.dr;
@@ -477,7 +478,7 @@ __global__ void __launch_bounds__(SW_T, 1) k_sweep(const __grid_constant__ Sweep
         // ---- predictor-corrector loop -----------------------------------------------------------------------
         for (int it = 1; it <= f.iter_max; it++) {
             for (int tl = tile0 + warp; tl < tile1; tl += SW_T / 32)
-                amj_body<M>(a.pv, f.e, f.b, f.acc8, a.qbm, f.dxi, idr, npp, tl * 32 + lane, lane);
+                amj_body<M>(a.pv, f.e, f.b, f.acc8, a.qbm, f.dxi, idr, npp, tl * 32 + lane, lane, dep_tiles + warp * DepTile<M>::doubles);
             if (timer) work[1] += clock64() - tprev;
             ok = grid_barrier(a.bar, gep, sm_i);
             if (timer) { const long long t = clock64(); prof[1] += t - tprev; tprev = t; namj++; }
