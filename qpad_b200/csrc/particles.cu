@@ -4,10 +4,10 @@
 //  * SoA fp64 planes, one particle per thread, fully coalesced 8-byte loads/stores.
 //  * gathers read the node-interleaved field images through the read-only path; particles that are close in the
 //    array are close in r (lattice order / counting sort), so a warp reads one or two 72-byte node records.
-//  * deposits never issue one atomic per particle: a warp whose lanes share a radial cell reduce-scatters its
-//    2*8*P (amjdeposit) or 2*P (qdeposit) partial sums with a halving butterfly (47 shuffles for M=1 instead of
-//    240 for a plain per-value butterfly) and then issues ONE fp64 RED per (cell, component) from distinct lanes.
-//    Warps spanning up to 4 cells repeat the butterfly per cell; only scattered warps fall back to per-lane REDs.
+//  * deposits never issue one atomic per particle: the sums over the lanes of a warp that share a radial cell are
+//    small contractions (node weight x mode phase) (x) (momentum moments), done on the fp64 tensor pipe with
+//    mma.sync.m8n8k4 through a per-warp shared-memory tile, then ONE fp64 RED per (cell, plane, component) from
+//    distinct lanes.  Only warps scattered over more than 8 cells fall back to per-lane REDs (charge deposit).
 //  * cell index / boundary tests use non-contracted IEEE ops so indices match the reference bit for bit
 //    (pos = sqrt(x1*x1 + x2*x2) * (1/dr), interp_part2d.f03:44-59).
 #include "common.cuh"
@@ -68,73 +68,6 @@ __device__ __forceinline__ void gather3(const double *f, const Interp &it, doubl
         for (int c = 0; c < 3; c++) out[c] = fma(n0[(2 * m - 1) * 3 + c] * pr2 - n0[(2 * m) * 3 + c] * pi2, it.w0, out[c]);
 #pragma unroll
         for (int c = 0; c < 3; c++) out[c] = fma(n1[(2 * m - 1) * 3 + c] * pr2 - n1[(2 * m) * 3 + c] * pi2, it.w1, out[c]);
-    }
-}
-
-// ---- warp reduce-scatter ------------------------------------------------------------------
-// Sum N per-lane values over the 32 lanes; afterwards lane L holds the totals of the contiguous index range
-// [base, base+cnt) in v[0..cnt).  Halving butterfly: N/2 + N/4 + ... shuffles instead of 5*N.
-template <int N, int OFF>
-__device__ __forceinline__ void rs_step(double *v, int lane, int &base, int &cnt)
-{
-    constexpr int H = (N + 1) / 2;
-    const bool up = (lane & OFF) != 0;
-#pragma unroll
-    for (int i = 0; i < H; i++) {
-        double a = v[i];
-        double b = (H + i < N) ? v[H + i] : 0.0;
-        double keep = up ? b : a, send = up ? a : b;
-        v[i] = keep + __shfl_xor_sync(FULL, send, OFF);
-    }
-    if (up) { base += H; cnt = cnt - H; if (cnt < 0) cnt = 0; }
-    else if (cnt > H) cnt = H;
-    if constexpr (OFF > 1) rs_step<H, OFF / 2>(v, lane, base, cnt);
-}
-// number of values a lane may hold after 5 halvings
-__host__ __device__ constexpr int final_count(int n) { for (int k = 0; k < 5; k++) n = (n + 1) / 2; return n; }
-
-// deposit the H=NV/2 products X[i] (already multiplied by membership) weighted by w0 / w1 into
-// acc[cell*H + k] (k in [0,H): this cell, [H,2H): next cell)
-template <int H>
-__device__ __forceinline__ void warp_deposit_group(const double *X, double w0, double w1, double *acc_cell, int lane)
-{
-    double v[H];
-    const bool up = (lane & 16) != 0;
-#pragma unroll
-    for (int i = 0; i < H; i++) {
-        double a = w0 * X[i], b = w1 * X[i];
-        double keep = up ? b : a, send = up ? a : b;
-        v[i] = keep + __shfl_xor_sync(FULL, send, 16);
-    }
-    int base = up ? H : 0, cnt = H;
-    rs_step<H, 8>(v, lane, base, cnt);
-    constexpr int NF = final_count(2 * H);
-#pragma unroll
-    for (int k = 0; k < NF; k++)
-        if (k < cnt) red_add(acc_cell + base + k, v[k]);
-}
-
-// common tail of both deposit kernels.  X[H] = per-particle products (phase x value); key = cell or -1
-template <int H>
-__device__ __forceinline__ void warp_deposit(const double *X, double w0, double w1, int key, double *acc, int lane)
-{
-    const unsigned same = __match_any_sync(FULL, key);
-    const bool leader = key >= 0 && (__ffs(same) - 1 == lane);
-    unsigned leaders = __ballot_sync(FULL, leader);
-    const int ng = __popc(leaders);
-    if (ng == 0) return;
-    if (ng <= 4) {
-        while (leaders) {
-            const int l = __ffs(leaders) - 1;
-            leaders &= leaders - 1;
-            const int cell = __shfl_sync(FULL, key, l);
-            const bool mine = key == cell;
-            warp_deposit_group<H>(X, mine ? w0 : 0.0, mine ? w1 : 0.0, acc + (size_t)cell * H, lane);
-        }
-    } else if (key >= 0) {
-        double *a = acc + (size_t)key * H;
-#pragma unroll
-        for (int i = 0; i < H; i++) { red_add(a + i, w0 * X[i]); red_add(a + H + i, w1 * X[i]); }
     }
 }
 
@@ -200,6 +133,58 @@ __device__ __forceinline__ void warp_deposit_mma(const double (&alpha)[2 * (2 * 
     }
 }
 
+// Charge deposit (2P sums per cell): all cells of the warp in ONE pass of 8 DMMAs.  A = alpha rows as above, B = the
+// one-hot membership matrix  B[p][g] = (particle p belongs to the g-th distinct cell of the warp), so
+// C[row][g] = sum over the particles of cell g of alpha[row].  Up to 8 cells per warp; more scattered warps fall back
+// to per-lane REDs.
+template <int M>
+__device__ __forceinline__ void warp_deposit_q_mma(const double (&alpha)[2 * (2 * M + 1)], int key, double *acc1, double *tile, int lane)
+{
+    constexpr int P = 2 * M + 1, R = 2 * P, NTILE = (R + 7) / 8;
+    const unsigned same = __match_any_sync(FULL, key);
+    const int myleader = __ffs(same) - 1;
+    const unsigned leaders = __ballot_sync(FULL, key >= 0 && myleader == lane);
+    const int ng = __popc(leaders);
+    if (ng == 0) return;
+    if (ng > 8) {
+        if (key >= 0) {
+            double *a = acc1 + (size_t)key * P;
+#pragma unroll
+            for (int r = 0; r < R; r++) red_add(a + r, alpha[r]);
+        }
+        return;
+    }
+    const int gidx = key >= 0 ? __popc(leaders & ((1u << myleader) - 1u)) : 8;
+    // cell of the c-th group, held by lane c
+    const unsigned lsrc = __fns(leaders, 0, lane + 1);
+    const int kc = __shfl_sync(FULL, key, lsrc & 31);
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < R; r++) tile[r * DEP_LD + lane] = alpha[r];
+    __syncwarp();
+    const int row = lane >> 2, kk = lane & 3;
+    double bfr[8];
+#pragma unroll
+    for (int s = 0; s < 8; s++) bfr[s] = (__shfl_sync(FULL, gidx, 4 * s + kk) == row) ? 1.0 : 0.0;
+    const int cell0 = __shfl_sync(FULL, kc, 2 * kk), cell1 = __shfl_sync(FULL, kc, 2 * kk + 1);
+#pragma unroll
+    for (int t = 0; t < NTILE; t++) {
+        const int r = t * 8 + row;
+        const bool live = r < R;
+        double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+        for (int s = 0; s < 8; s++) {
+            const double a = live ? tile[r * DEP_LD + 4 * s + kk] : 0.0;
+            dmma884(c0, c1, a, bfr[s]);
+        }
+        if (live) {
+            const int j = r >= P ? 1 : 0, pl = r - j * P;
+            if (2 * kk < ng) red_add(acc1 + (size_t)(cell0 + j) * P + pl, c0);
+            if (2 * kk + 1 < ng) red_add(acc1 + (size_t)(cell1 + j) * P + pl, c1);
+        }
+    }
+}
+
 // ---- qdeposit: species/part2d_class.f03:231-359 (accumulation part; axis rules live in FOP_QFIX) --------
 // per-particle charge products (part2d_class.f03:277-289): X[pl] = Re/Im(q * phase0^m), key = cell (1-based), weights
 template <int M>
@@ -225,18 +210,26 @@ __device__ __forceinline__ void qdep_products(double x1, double x2, double q, do
 }
 // one warp-tile of qdeposit: particle i (whole warp participates)
 template <int M>
-__device__ __forceinline__ void qdep_body(const PartView &pv, double *acc1, double idr, int npp, int i, int lane)
+__device__ __forceinline__ void qdep_alpha(double x1, double x2, double q, double idr, double (&alpha)[2 * (2 * M + 1)], int &key)
 {
     constexpr int P = 2 * M + 1;
-    double X[P];
-    double w0 = 0.0, w1 = 0.0;
+    double X[P], w0, w1;
+    qdep_products<M>(x1, x2, q, idr, X, w0, w1, key);
+#pragma unroll
+    for (int k = 0; k < P; k++) { alpha[k] = w0 * X[k]; alpha[P + k] = w1 * X[k]; }
+}
+template <int M>
+__device__ __forceinline__ void qdep_body(const PartView &pv, double *acc1, double idr, int npp, int i, int lane, double *tile)
+{
+    constexpr int P = 2 * M + 1;
+    double alpha[2 * P];
     int key = -1;
-    if (i < npp) qdep_products<M>(pv.x1[i], pv.x2[i], pv.q[i], idr, X, w0, w1, key);
+    if (i < npp) qdep_alpha<M>(pv.x1[i], pv.x2[i], pv.q[i], idr, alpha, key);
     else {
 #pragma unroll
-        for (int k = 0; k < P; k++) X[k] = 0.0;
+        for (int k = 0; k < 2 * P; k++) alpha[k] = 0.0;
     }
-    warp_deposit<P>(X, w0, w1, key, acc1, lane);
+    warp_deposit_q_mma<M>(alpha, key, acc1, tile, lane);
 }
 template <int M>
 __global__ void __launch_bounds__(PT_BLOCK) k_qdeposit(PartView pv, double *__restrict__ acc1, double idr)
@@ -244,7 +237,8 @@ __global__ void __launch_bounds__(PT_BLOCK) k_qdeposit(PartView pv, double *__re
     const int npp = *pv.d_npp;
     const int i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
     if ((i & ~31) >= npp) return;
-    qdep_body<M>(pv, acc1, idr, npp, i, lane);
+    extern __shared__ double dep_tiles[];
+    qdep_body<M>(pv, acc1, idr, npp, i, lane, dep_tiles + (threadIdx.x >> 5) * DepTile<M>::doubles);
 }
 
 // ---- amjdeposit_robust: species/part2d_class.f03:746-1010 ------------------------------------------------
@@ -332,7 +326,7 @@ __global__ void __launch_bounds__(PT_BLOCK) k_amjdeposit(PartView pv, const doub
 // :346-349 fused into the push; out-of-bounds particles are removed by update_bound before the reference deposits)
 template <int M>
 __device__ __forceinline__ void push_body(const PartView &pv, const double *ef, const double *bf, double qbm, double dt, double idr, double edge,
-                                          int mode, unsigned *outmask, int *d_nout, double *acc1, int npp, int i, int lane)
+                                          int mode, unsigned *outmask, int *d_nout, double *acc1, int npp, int i, int lane, double *tile)
 {
     const bool valid = i < npp;
     bool out = false;
@@ -388,15 +382,14 @@ __device__ __forceinline__ void push_body(const PartView &pv, const double *ef, 
     }
     if (acc1) {
         constexpr int P = 2 * M + 1;
-        double X[P];
-        double w0 = 0.0, w1 = 0.0;
+        double alpha[2 * P];
         int key = -1;
-        if (valid && !out) { qv = pv.q[i]; qdep_products<M>(xn1, xn2, qv, idr, X, w0, w1, key); }
+        if (valid && !out) { qv = pv.q[i]; qdep_alpha<M>(xn1, xn2, qv, idr, alpha, key); }
         else {
 #pragma unroll
-            for (int k = 0; k < P; k++) X[k] = 0.0;
+            for (int k = 0; k < 2 * P; k++) alpha[k] = 0.0;
         }
-        warp_deposit<P>(X, w0, w1, key, acc1, lane);
+        warp_deposit_q_mma<M>(alpha, key, acc1, tile, lane);
     }
 }
 template <int M>
@@ -407,7 +400,7 @@ __global__ void __launch_bounds__(PT_BLOCK) k_push(PartView pv, const double *__
     const int npp = *pv.d_npp;
     const int i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
     if ((i & ~31) >= npp) return;
-    push_body<M>(pv, ef, bf, qbm, dt, idr, edge, mode, outmask, d_nout, nullptr, npp, i, lane);
+    push_body<M>(pv, ef, bf, qbm, dt, idr, edge, mode, outmask, d_nout, nullptr, npp, i, lane, nullptr);
 }
 
 // ---- compaction (update_bound_part2d :2307-2353 / pack_particles "fill the holes inversely") ---------------
@@ -750,7 +743,12 @@ extern "C" int qpg_part2d_renew(qpg_part2d p)
     default: FN<4>(__VA_ARGS__); break;        \
     }
 template <int M> static void l_qdeposit(int grid, cudaStream_t st, PartView pv, double *acc1, double idr)
-{ k_qdeposit<M><<<grid, PT_BLOCK, 0, st>>>(pv, acc1, idr); }
+{
+    constexpr size_t smem = sizeof(double) * DepTile<M>::doubles * (PT_BLOCK / 32);
+    static bool attr_set = false;
+    if (!attr_set) { cudaFuncSetAttribute(k_qdeposit<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+    k_qdeposit<M><<<grid, PT_BLOCK, smem, st>>>(pv, acc1, idr);
+}
 template <int M> static void l_amjdeposit(int grid, cudaStream_t st, PartView pv, const double *ef, const double *bf, double *acc8, double qbm, double dt, double idr, const int *skip)
 {
     constexpr size_t smem = sizeof(double) * DepTile<M>::doubles * (PT_BLOCK / 32);

@@ -509,7 +509,7 @@ extern "C" int qpg_sim_sweep_profile(qpg_sim s, double *out8, int reset)
     for (int k = 0; k < 12; k++) out8[k] = (double)h[k];
     if (getenv("QPG_SWEEP_STAMPS")) {   // development aid: stage stamps inside the field programs (cycles of CTA 0, thread 0)
         fprintf(stderr, "sweep stamps (cycles/slice):");
-        for (int k = 16; k < 26; k++) fprintf(stderr, " %.0f", (double)h[k] / (h[6] > 0 ? (double)h[6] : 1.0));
+        for (int k = 16; k < 29; k++) fprintf(stderr, " %.0f", (double)h[k] / (h[6] > 0 ? (double)h[6] : 1.0));
         fprintf(stderr, "\n");
     }
     return 0;

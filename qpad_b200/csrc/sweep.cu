@@ -108,6 +108,7 @@ __device__ __forceinline__ void team_barrier(Team &tm)
     __syncthreads();
 }
 
+#define SW_STAMP(k) do { if (stamp) { const long long _t = clock64(); stamp[k] += _t - tlast; tlast = _t; } } while (0)
 template <int M> struct StripSmem {
     static constexpr int P = 2 * M + 1, NS = 4 * P;
     double d[NS][ST_N];            // right-hand sides, then solutions
@@ -162,8 +163,9 @@ __device__ __forceinline__ double strip_total(const double *xb, int nteam, int l
 // ============================================================================================================
 // program A (simulation_class.f03:344-377): q_beam slice -> bt(beam), qdp epilogue, psi, bz, record, b, ez, et
 template <int M>
-__device__ void sweep_field_A(const FusedArgs &a, int j, Team &tm, StripSmem<M> &sm)
+__device__ void sweep_field_A(const FusedArgs &a, int j, Team &tm, StripSmem<M> &sm, long long *stamp)
 {
+    long long tlast = stamp ? clock64() : 0;
     constexpr int P = 2 * M + 1, NS = 4 * P, NWARP = SW_T / 32, SPW = (NS + NWARP - 1) / NWARP;
     static_assert(2 * NS + 1 <= SW_XK, "exchange record too small");
     const int nr = a.nr, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -194,6 +196,7 @@ __device__ void sweep_field_A(const FusedArgs &a, int j, Team &tm, StripSmem<M> 
         }
     }
     __syncthreads();
+    SW_STAMP(0);
     // ---- S2: strip scans, one warp per system
     const int i = i0 + lane, t = i - 1;
     const bool valid = i <= nr;
@@ -215,7 +218,9 @@ __device__ void sweep_field_A(const FusedArgs &a, int j, Team &tm, StripSmem<M> 
             }
         }
     }
+    SW_STAMP(1);
     team_barrier(tm);
+    SW_STAMP(2);
     // ---- S3: fold the other strips, apply the Green's-function factors, store
     const double *xb = tm.xbuf + (size_t)tm.xpar * SW_MAX_TEAM * SW_XK;
 #pragma unroll
@@ -245,7 +250,9 @@ __device__ void sweep_field_A(const FusedArgs &a, int j, Team &tm, StripSmem<M> 
         }
     }
     tm.xpar ^= 1;
+    SW_STAMP(3);
     team_barrier(tm);   // psi / phi of the neighbouring strips
+    SW_STAMP(4);
     // ---- S4: beam B-perp from phi, b = b_spe + b_beam, E-perp, convergence 'record'   (one thread per node, plane)
     for (int it = tid; it < ST_N * P; it += SW_T) {
         const int ln = it % ST_N, pl = it / ST_N, ii = i0 + ln, m = (pl + 1) >> 1;
@@ -279,13 +286,15 @@ __device__ void sweep_field_A(const FusedArgs &a, int j, Team &tm, StripSmem<M> 
         for (int pl = 0; pl < P; pl++) { if (pl > 0 && (pl & 1) == 0) sim += sm.t[pl][tid]; else sre += sm.t[pl][tid]; }
         a.conv_old[i0 + tid] = sre; a.conv_old[nr + 2 + i0 + tid] = sim;
     }
+    SW_STAMP(5);
 }
 
 // program C (:378-396 + :375-377): amjdp epilogue, djdxi, bt_iter, bz, compare, record, b, ez, et.
 // The two per-CTA residual maxima go to the exchange buffer; sweep_conv_decide() combines them after the grid barrier.
 template <int M>
-__device__ void sweep_field_C(const FusedArgs &a, Team &tm, StripSmem<M> &sm)
+__device__ void sweep_field_C(const FusedArgs &a, Team &tm, StripSmem<M> &sm, long long *stamp)
 {
+    long long tlast = stamp ? clock64() : 0;
     constexpr int P = 2 * M + 1, NS = 4 * P, NWARP = SW_T / 32, SPW = (NS + NWARP - 1) / NWARP;
     const int nr = a.nr, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int i0 = tm.rank * ST_N + 1;
@@ -308,6 +317,7 @@ __device__ void sweep_field_C(const FusedArgs &a, Team &tm, StripSmem<M> &sm)
         else { sm.amu[tp * 3 + c - 5] = v; if (own) { a.spe_amu[np * 3 + c - 5] = v; a.amu[np * 3 + c - 5] = v; } }
     }
     __syncthreads();
+    SW_STAMP(6);
     // tile pointers addressed with absolute node numbers through FX()
     const double *cu_t = sm.cu - (ptrdiff_t)tlo * P * 3, *amu_t = sm.amu - (ptrdiff_t)tlo * P * 3, *acu_t = sm.acu - (ptrdiff_t)tlo * P * 2;
     // ---- S2a: dcu = djdxi(acu, amu) (:390)
@@ -318,6 +328,7 @@ __device__ void sweep_field_C(const FusedArgs &a, Team &tm, StripSmem<M> &sm)
         sm.dcu[ln][pl][c] = v;
     }
     __syncthreads();
+    SW_STAMP(7);
     // ---- S2b: sources of bt_iter (:391), bz (:392), ez (:376 of the next pass / :415)
     const double relax_idr2 = a.relax * (idr * idr);
     for (int it = tid; it < ST_N * NS; it += SW_T) {
@@ -334,6 +345,7 @@ __device__ void sweep_field_C(const FusedArgs &a, Team &tm, StripSmem<M> &sm)
         sm.d[s][ln] = v;
     }
     __syncthreads();
+    SW_STAMP(8);
     // ---- S3: strip scans -> exchange -> solutions
     const int i = i0 + lane, t = i - 1;
     const bool valid = i <= nr;
@@ -355,7 +367,9 @@ __device__ void sweep_field_C(const FusedArgs &a, Team &tm, StripSmem<M> &sm)
             }
         }
     }
+    SW_STAMP(9);
     team_barrier(tm);
+    SW_STAMP(10);
     const double *xb = tm.xbuf + (size_t)tm.xpar * SW_MAX_TEAM * SW_XK;
 #pragma unroll
     for (int q = 0; q < SPW; q++) {
@@ -378,6 +392,7 @@ __device__ void sweep_field_C(const FusedArgs &a, Team &tm, StripSmem<M> &sm)
     }
     tm.xpar ^= 1;
     __syncthreads();
+    SW_STAMP(11);
     // ---- S4: get_solution_bt_iter (field_b_class.f03:703-758), bz, ez axis rules; b = b_spe + b_beam; E-perp; compare
     for (int it = tid; it < ST_N * P; it += SW_T) {
         const int ln = it % ST_N, pl = it / ST_N, ii = i0 + ln, m = (pl + 1) >> 1;
@@ -423,6 +438,7 @@ __device__ void sweep_field_C(const FusedArgs &a, Team &tm, StripSmem<M> &sm)
             __stcg(xm, mo); __stcg(xm + 1, mn);
         }
     }
+    SW_STAMP(12);
 }
 
 // simulation_class.f03:560-599 on the per-CTA maxima published by program C.  Called by one thread per CTA after the
@@ -465,7 +481,7 @@ __global__ void __launch_bounds__(SW_T, 1) k_sweep(const __grid_constant__ Sweep
     bool ok = true;
     for (int j = a.j0; j <= a.j1 && ok; j++) {
         // ---- phase A || compaction -------------------------------------------------------------------------
-        if (in_team) sweep_field_A<M>(f, j, tm, sm_f);
+        if (in_team) sweep_field_A<M>(f, j, tm, sm_f, timer ? a.prof + 16 : nullptr);
         else if (b == G - 1) compact_body(a.planes, 8, a.d_npp_w, a.d_nout, a.outmask, a.lists, 0, sm_i);
         if (timer) work[0] += clock64() - tprev;
         ok = grid_barrier(a.bar, gep, sm_i);
@@ -483,7 +499,7 @@ __global__ void __launch_bounds__(SW_T, 1) k_sweep(const __grid_constant__ Sweep
             ok = grid_barrier(a.bar, gep, sm_i);
             if (timer) { const long long t = clock64(); prof[1] += t - tprev; tprev = t; namj++; }
             if (!ok) break;
-            if (in_team) sweep_field_C<M>(f, tm, sm_f);
+            if (in_team) sweep_field_C<M>(f, tm, sm_f, timer ? a.prof + 16 : nullptr);
             if (timer) work[2] += clock64() - tprev;
             ok = grid_barrier(a.bar, gep, sm_i);
             if (timer) { const long long t = clock64(); prof[2] += t - tprev; tprev = t; }
@@ -499,7 +515,7 @@ __global__ void __launch_bounds__(SW_T, 1) k_sweep(const __grid_constant__ Sweep
             for (int k = b * ipc + lane; k < min((b + 1) * ipc, items); k += 32) fused_D_item<M>(f, k, j);
         }
         for (int tl = tile0 + warp; tl < tile1; tl += SW_T / 32)
-            push_body<M>(a.pv, f.e, f.b, a.qbm, f.dxi, idr, a.edge, 7, a.outmask, a.d_nout, f.acc1, npp, tl * 32 + lane, lane);
+            push_body<M>(a.pv, f.e, f.b, a.qbm, f.dxi, idr, a.edge, 7, a.outmask, a.d_nout, f.acc1, npp, tl * 32 + lane, lane, dep_tiles + warp * DepTile<M>::doubles);
         if (timer) work[3] += clock64() - tprev;
         ok = grid_barrier(a.bar, gep, sm_i);
         if (timer) { const long long t = clock64(); prof[3] += t - tprev; tprev = t; }
