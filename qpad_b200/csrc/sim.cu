@@ -160,7 +160,7 @@ static int enqueue_slice_tail(qpg_sim s)
 
 // ---- persistent slab sweep (sweep.cu) ---------------------------------------------------------------------
 static bool sweep_supported(const qpg_sim_params &prm) { return prm.max_mode <= 2 && (prm.nr + ST_N - 1) / ST_N <= SW_MAX_TEAM; }
-template <int M> static constexpr size_t sweep_smem() { return sizeof(double) * DepTile<M>::doubles * (SW_T / 32); }
+template <int M> static constexpr size_t sweep_smem() { return (sizeof(StripSmem<M>) + 7) / 8 * 8 + sizeof(double) * DepTile<M>::doubles * (SW_T / 32); }
 template <int M> static cudaError_t sweep_occupancy(int *blocks_per_sm)
 {
     cudaError_t e = cudaFuncSetAttribute(k_sweep<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem<M>());

@@ -19,7 +19,7 @@
 #include "common.cuh"
 
 #define SW_T 512           // threads per CTA (16 warps, <= 128 registers per thread)
-#define SW_XK 64           // doubles per CTA in one exchange record
+#define SW_XK 64           // slots of one exchange record; layout [slot][strip] so a warp reads one slot of all strips coalesced
 #define SW_MAX_TEAM 128
 
 struct SweepArgs {
@@ -32,7 +32,7 @@ struct SweepArgs {
     double qbm, edge;
     int j0, j1, nteam;
     unsigned *bar;          // [0] grid arrivals, [32] team arrivals, [64] abort flag (one 128-byte line each)
-    double *xbuf;           // [3][SW_MAX_TEAM][SW_XK] team exchange records: two alternating scan records + the residual maxima
+    double *xbuf;           // [3][SW_XK][SW_MAX_TEAM] team exchange: two alternating scan slabs + the residual maxima
     long long *prof;        // [0..3] cycles in phase A / amj / C / push, [4] total cycles, [5] total ns, [6] slices, [7] amj phases, [8..11] CTA 0's own work cycles per phase (thread 0's arrival at the barrier)
 };
 
@@ -117,75 +117,126 @@ template <int M> struct StripSmem {
     double acu[ST_W * P * 2];
     double dcu[ST_N][P][2];
     double t[P][ST_N];             // |B_phi| partials of the convergence test
-    double red[2][SW_T / 32];
+    // Green's-function factors of this strip's nodes, resident for the whole sweep (the L1 is invalidated by every
+    // barrier fence, so re-reading them from global memory costs an L2 round trip per use): [0 = program A, 1 = C]
+    double fq[2][NS][ST_N], fv[2][NS][ST_N], fp[2][NS][ST_N], fu[2][NS][ST_N];
+    double fax[2][NS];             // axis_inv of the system's operator
+    double ez_q0;                  // q[0] of the E_z m=0 operator (divergence correction)
+    // program A, psi and beam-potential systems (s < 2P): factors of the halo nodes i0-1 and i0+32, the right halo's
+    // source term, and the solutions of strip + halo (so the r-derivatives need no second exchange)
+    double hl_p[2 * P], hl_u[2 * P], hr_q[2 * P], hr_v[2 * P], hr_p[2 * P], hr_u[2 * P], dh[2 * P];
+    double psit[(ST_N + 2) * P], phit[(ST_N + 2) * P];
+    long long stamps[16];          // stage clocks of CTA 0 (kept on chip; flushed to prof[16..] when the kernel ends)
 };
 
-// warp `s`-th system of a program: strip-local scans, totals -> exchange record.  Returns (inclusive prefix, exclusive
-// suffix) of this lane's node inside the strip.
-__device__ __forceinline__ void strip_scan(const OpCoef &oc, double d, int t, bool valid, int lane, double &fa, double &fb, double *xrec, int slot_a,
-                                           int slot_b)
+template <int M> __device__ __forceinline__ int strip_kind(int prog, int s)
 {
-    double incl = valid ? __ldg(oc.qT + t) * d : 0.0;
-    double sfx = valid ? __ldg(oc.vT + t) * d : 0.0;
+    constexpr int P = 2 * M + 1;
+    const int g = s / P;
+    if (prog == 0) return g == 0 ? FK_PSI : (g == 1 ? FK_BT : (g == 2 ? FK_BZ : FK_EZ));
+    return g == 0 ? FK_BPLUS : (g == 1 ? FK_BMINUS : (g == 2 ? FK_BZ : FK_EZ));
+}
+// once per launch: operator factors -> shared memory (all threads of a team CTA)
+template <int M>
+__device__ void strip_load_factors(const FusedArgs &a, int rank, StripSmem<M> &sm)
+{
+    constexpr int P = 2 * M + 1, NS = 4 * P;
+    const int i0 = rank * ST_N + 1, nr = a.nr;
+    for (int it = threadIdx.x; it < 2 * NS * ST_N; it += SW_T) {
+        const int ln = it % ST_N, s = (it / ST_N) % NS, prog = it / (ST_N * NS), t = i0 - 1 + ln;
+        const OpCoef &oc = a.ops[strip_kind<M>(prog, s) * (QPG_MAX_MODE + 1) + (((s % P) + 1) >> 1)];
+        const bool ok = t < nr;
+        sm.fq[prog][s][ln] = ok ? oc.qT[t] : 0.0; sm.fv[prog][s][ln] = ok ? oc.vT[t] : 0.0;
+        sm.fp[prog][s][ln] = ok ? oc.pT[t] : 0.0; sm.fu[prog][s][ln] = ok ? oc.uT[t] : 0.0;
+        if (ln == 0) sm.fax[prog][s] = oc.axis_inv;
+    }
+    for (int s = threadIdx.x; s < 2 * P; s += SW_T) {
+        const OpCoef &oc = a.ops[strip_kind<M>(0, s) * (QPG_MAX_MODE + 1) + (((s % P) + 1) >> 1)];
+        const int tl = i0 - 2, tr = i0 + ST_N - 1;   // 0-based rows of the nodes i0-1 and i0+32
+        sm.hl_p[s] = tl >= 0 ? oc.pT[tl] : 0.0; sm.hl_u[s] = tl >= 0 ? oc.uT[tl] : 0.0;
+        const bool ok = tr < nr;
+        sm.hr_q[s] = ok ? oc.qT[tr] : 0.0; sm.hr_v[s] = ok ? oc.vT[tr] : 0.0; sm.hr_p[s] = ok ? oc.pT[tr] : 0.0; sm.hr_u[s] = ok ? oc.uT[tr] : 0.0;
+    }
+    if (threadIdx.x == 0) sm.ez_q0 = a.ops[FK_EZ * (QPG_MAX_MODE + 1)].qT[0];
+    __syncthreads();
+}
+
+// strip-local scans of one system (one warp): inclusive prefix of q*d and inclusive suffix of v*d; strip totals -> exchange record
+__device__ __forceinline__ void strip_scan(double q, double v, double d, int lane, double &incl, double &sfx, double *xrec, int slot_a, int slot_b)
+{
+    incl = q * d;
+    sfx = v * d;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const double ta = __shfl_up_sync(0xffffffffu, incl, o), tb = __shfl_down_sync(0xffffffffu, sfx, o);
         if (lane >= o) incl += ta;
         if (lane + o < 32) sfx += tb;
     }
-    if (lane == 31) __stcg(xrec + slot_a, incl);
-    if (lane == 0) __stcg(xrec + slot_b, sfx);
-    const double ex = __shfl_down_sync(0xffffffffu, sfx, 1);
-    fa = incl;
-    fb = lane == 31 ? 0.0 : ex;
+    if (lane == 31) __stcg(xrec + (size_t)slot_a * SW_MAX_TEAM, incl);
+    if (lane == 0) __stcg(xrec + (size_t)slot_b * SW_MAX_TEAM, sfx);
 }
-// totals of the strips before / after mine (every lane gets both)
-__device__ __forceinline__ void strip_offsets(const double *xb, int nteam, int rank, int lane, int slot_a, int slot_b, double &pa, double &pb)
+// totals of the strips before / after mine, and (slot_r >= 0) the sum of an all-strip reduction slot; every lane gets all
+__device__ __forceinline__ void strip_fold(const double *xb, int nteam, int rank, int lane, int slot_a, int slot_b, int slot_r, double &pa, double &pb,
+                                           double &tot)
 {
-    double a = 0.0, b = 0.0;
+    double a = 0.0, b = 0.0, c = 0.0;
     for (int r = lane; r < nteam; r += 32) {
-        if (r < rank) a += __ldcg(xb + (size_t)r * SW_XK + slot_a);
-        if (r > rank) b += __ldcg(xb + (size_t)r * SW_XK + slot_b);
+        const double va = __ldcg(xb + (size_t)slot_a * SW_MAX_TEAM + r), vb = __ldcg(xb + (size_t)slot_b * SW_MAX_TEAM + r);
+        const double vc = slot_r >= 0 ? __ldcg(xb + (size_t)slot_r * SW_MAX_TEAM + r) : 0.0;
+        if (r < rank) a += va;
+        if (r > rank) b += vb;
+        c += vc;
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
-    pa = a; pb = b;
-}
-__device__ __forceinline__ double strip_total(const double *xb, int nteam, int lane, int slot)
-{
-    double a = 0.0;
-    for (int r = lane; r < nteam; r += 32) a += __ldcg(xb + (size_t)r * SW_XK + slot);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-    return a;
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o);
+        if (slot_r >= 0) c += __shfl_xor_sync(0xffffffffu, c, o);
+    }
+    pa = a; pb = b; tot = c;
 }
 
 // ============================================================================================================
 // program A (simulation_class.f03:344-377): q_beam slice -> bt(beam), qdp epilogue, psi, bz, record, b, ez, et
+// `halo`: derive psi / phi of the two halo nodes from the exchanged strip totals instead of a second team barrier
 template <int M>
-__device__ void sweep_field_A(const FusedArgs &a, int j, Team &tm, StripSmem<M> &sm, long long *stamp)
+__device__ void sweep_field_A(const FusedArgs &a, int j, Team &tm, StripSmem<M> &sm, bool halo, long long *stamp)
 {
-    long long tlast = stamp ? clock64() : 0;
     constexpr int P = 2 * M + 1, NS = 4 * P, NWARP = SW_T / 32, SPW = (NS + NWARP - 1) / NWARP;
     static_assert(2 * NS + 1 <= SW_XK, "exchange record too small");
+    static_assert(ST_N * P <= SW_T, "one thread per (node, plane) in the post-processing stage");
+    long long tlast = stamp ? clock64() : 0;
     const int nr = a.nr, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int i0 = tm.rank * ST_N + 1;
     const size_t n1 = (size_t)(nr + 2) * P;
     const double idr = 1.0 / a.dr, idrh = 0.5 * idr;
     SolveCtx sc; sc.nr = nr; sc.M = M; sc.P = P; sc.logC = 0; sc.stride = 1; sc.dr = a.dr; sc.idr = idr; sc.idrh = idrh;
     if (tm.rank == 0 && tid == 0) { a.flags[0] = 0; a.flags[2] = 0; }
+    const int nlo = (tm.rank == 0) ? 0 : i0, nhi = (i0 + ST_N - 1 >= nr) ? nr + 1 : i0 + ST_N - 1;   // nodes stored by this strip (+ guards)
+    // inputs of the post-processing stage that do not depend on the solves: fetched now, used after the exchange
+    const int p_ln = tid % ST_N, p_pl = tid / ST_N, p_i = i0 + p_ln;
+    const bool p_on = tid < ST_N * P && p_i <= nr;
+    double p_bsr = 0.0, p_bsp = 0.0, p_bbz = 0.0;
+    if (p_on) { p_bsr = FX(a.b_spe, 3, p_i, p_pl, 0); p_bsp = FX(a.b_spe, 3, p_i, p_pl, 1); p_bbz = FX(a.b_beam, 3, p_i, p_pl, 2); }
     // ---- S1: sources.  threads 0..127: qdp epilogue + beam charge slice (species2d qdp :198-204, copy_slice :344);
     //          threads 128..511: bz / ez right-hand sides from the predicted current
     if (tid < 128) {
-        const int nlo = (tm.rank == 0) ? 0 : i0, nhi = (i0 + ST_N - 1 >= nr) ? nr + 1 : i0 + ST_N - 1;
         for (int it = tid; it < (nhi - nlo + 1) * P; it += 128) {
             const int n = nlo + it / P, pl = it % P;
             const size_t k = (size_t)n * P + pl;
             const double qb = a.q_beam2[(size_t)(j - 1) * n1 + k];
             const double sq = axis_fix_q(n, pl, a.acc1[k]);
             const double qs = sq + a.spe_qn[k];
-            a.q_beam[k] = qb; a.acc1[k] = 0.0; a.spe_q[k] = sq; a.q_spe[k] = qs;
+            a.q_beam[k] = qb; a.spe_q[k] = sq; a.q_spe[k] = qs;
             if (n >= i0 && n <= nr && n < i0 + ST_N) { sm.d[pl][n - i0] = -1.0 * qs; sm.d[P + pl][n - i0] = -1.0 * qb; }
+        }
+        if (tid >= 96 && tid < 96 + 2 * P) {   // right halo node of the psi / phi systems
+            const int s = tid - 96, pl = s % P, ih = i0 + ST_N;
+            double v = 0.0;
+            if (ih <= nr) {
+                const size_t k = (size_t)ih * P + pl;
+                v = s < P ? -1.0 * (axis_fix_q(ih, pl, a.acc1[k]) + a.spe_qn[k]) : -1.0 * a.q_beam2[(size_t)(j - 1) * n1 + k];
+            }
+            sm.dh[s] = v;
         }
     } else {
         for (int it = tid - 128; it < ST_N * P * 2; it += SW_T - 128) {
@@ -195,26 +246,25 @@ __device__ void sweep_field_A(const FusedArgs &a, int j, Team &tm, StripSmem<M> 
             sm.d[(2 + kind) * P + pl][ln] = v;
         }
     }
+    const double cu_e1 = FX(a.cu, 3, nr - 2, 0, 0), cu_e2 = FX(a.cu, 3, nr - 1, 0, 0);   // edge term of the E_z divergence sum
     __syncthreads();
     SW_STAMP(0);
     // ---- S2: strip scans, one warp per system
     const int i = i0 + lane, t = i - 1;
     const bool valid = i <= nr;
-    double *xrec = tm.xbuf + (size_t)tm.xpar * SW_MAX_TEAM * SW_XK + (size_t)tm.rank * SW_XK;
-    double fa[SPW], fb[SPW], dd[SPW];
+    double *xrec = tm.xbuf + (size_t)tm.xpar * SW_MAX_TEAM * SW_XK + tm.rank;   // slot k of this strip: xrec[k * SW_MAX_TEAM]
+    double incl[SPW], sfx[SPW], dd[SPW];
 #pragma unroll
     for (int q = 0; q < SPW; q++) {
         const int s = warp + q * NWARP;
         if (s < NS) {
-            const int kind = s < P ? FK_PSI : (s < 2 * P ? FK_BT : (s < 3 * P ? FK_BZ : FK_EZ));
-            const OpCoef &oc = a.ops[kind * (QPG_MAX_MODE + 1) + (((s % P) + 1) >> 1)];
             dd[q] = valid ? sm.d[s][lane] : 0.0;
-            strip_scan(oc, dd[q], t, valid, lane, fa[q], fb[q], xrec, s, NS + s);
+            strip_scan(sm.fq[0][s][lane], sm.fv[0][s][lane], dd[q], lane, incl[q], sfx[q], xrec, s, NS + s);
             if (s == 3 * P) {   // E_z m=0 divergence sum, field_e_class.f03:189-197
                 double r = (valid && i >= 2 && i <= nr - 2) ? dd[q] * (double)(i - 1) : 0.0;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
-                if (lane == 0) __stcg(xrec + 2 * NS, r);
+                if (lane == 0) __stcg(xrec + (size_t)(2 * NS) * SW_MAX_TEAM, r);
             }
         }
     }
@@ -227,57 +277,70 @@ __device__ void sweep_field_A(const FusedArgs &a, int j, Team &tm, StripSmem<M> 
     for (int q = 0; q < SPW; q++) {
         const int s = warp + q * NWARP;
         if (s < NS) {
-            const int kind = s < P ? FK_PSI : (s < 2 * P ? FK_BT : (s < 3 * P ? FK_BZ : FK_EZ));
-            const int pl = s % P;
-            const OpCoef &oc = a.ops[kind * (QPG_MAX_MODE + 1) + ((pl + 1) >> 1)];
-            double pa, pb;
-            strip_offsets(xb, tm.n, tm.rank, lane, s, NS + s, pa, pb);
-            double x = 0.0;
+            const int kind = strip_kind<M>(0, s), pl = s % P;
+            double pa, pb, tot;
+            strip_fold(xb, tm.n, tm.rank, lane, s, NS + s, s == 3 * P ? 2 * NS : -1, pa, pb, tot);
+            const double fp = sm.fp[0][s][lane], fu = sm.fu[0][s][lane], fax = sm.fax[0][s];
+            const double ex = __shfl_down_sync(0xffffffffu, sfx[q], 1);
+            double x = fp * (incl[q] + pa) + fu * ((lane == 31 ? 0.0 : ex) + pb);
+            if (t == 0 && fax != 0.0) x = dd[q] * fax;
             if (s == 3 * P) {   // row 1 of the E_z m=0 source is -8*(div - edge term) (:199-209); by linearity x += rhs1 * G(:,1)
-                const double tot = strip_total(xb, tm.n, lane, 2 * NS);
-                const double div = tot - idrh * (FX(a.cu, 3, nr - 2, 0, 0) + FX(a.cu, 3, nr - 1, 0, 0)) * ((double)nr - 2.5);
-                if (valid) x = (-8.0 * div) * (__ldg(oc.pT + t) * __ldg(oc.qT));
+                const double div = tot - idrh * (cu_e1 + cu_e2) * ((double)nr - 2.5);
+                x = (-8.0 * div) * (fp * sm.ez_q0) + x;
             }
+            if (pl > 0 && i == 1 && kind != FK_BT) x = 0.0;
             if (valid) {
-                x += green_apply(oc, t, fa[q] + pa, fb[q] + pb, dd[q]);
-                if (pl > 0 && i == 1 && kind != FK_BT) x = 0.0;
                 sm.d[s][lane] = x;
-                if (kind == FK_PSI) FX(a.psi, 1, i, pl, 0) = x;
-                else if (kind == FK_BT) FX(a.phi, 1, i, pl, 0) = x;
+                if (kind == FK_PSI) { FX(a.psi, 1, i, pl, 0) = x; sm.psit[(lane + 1) * P + pl] = x; }
+                else if (kind == FK_BT) { FX(a.phi, 1, i, pl, 0) = x; sm.phit[(lane + 1) * P + pl] = x; }
                 else if (kind == FK_BZ) FX(a.b_spe, 3, i, pl, 2) = x;
                 else FX(a.e, 3, i, pl, 2) = x;
             }
+            if (halo && s < 2 * P) {   // x = p*S + u*T at the nodes i0-1 and i0+32 from the same prefix / suffix sums
+                const double tot_a = __shfl_sync(0xffffffffu, incl[q], 31), tot_b = __shfl_sync(0xffffffffu, sfx[q], 0);
+                double *tile = s < P ? sm.psit : sm.phit;
+                if (lane == 0 && i0 > 1) tile[pl] = sm.hl_p[s] * pa + sm.hl_u[s] * (tot_b + pb);
+                if (lane == 31 && i0 + ST_N <= nr) {
+                    const double dhv = sm.dh[s];
+                    tile[(ST_N + 1) * P + pl] = sm.hr_p[s] * (pa + tot_a + sm.hr_q[s] * dhv) + sm.hr_u[s] * (pb - sm.hr_v[s] * dhv);
+                }
+            }
         }
     }
+    // raw charge sums are consumed (the neighbouring strip read our first node's sum before the barrier)
+    for (int it = tid; it < (nhi - nlo + 1) * P; it += SW_T) a.acc1[(size_t)nlo * P + it] = 0.0;
     tm.xpar ^= 1;
     SW_STAMP(3);
-    team_barrier(tm);   // psi / phi of the neighbouring strips
+    if (halo) __syncthreads();
+    else team_barrier(tm);   // psi / phi of the neighbouring strips through global memory
     SW_STAMP(4);
     // ---- S4: beam B-perp from phi, b = b_spe + b_beam, E-perp, convergence 'record'   (one thread per node, plane)
-    for (int it = tid; it < ST_N * P; it += SW_T) {
-        const int ln = it % ST_N, pl = it / ST_N, ii = i0 + ln, m = (pl + 1) >> 1;
-        if (ii > nr) { sm.t[pl][ln] = 0.0; continue; }
-        // field_b_class.f03:545-701 get_solution_bt
-        double bphi, br = 0.0;
-        if (ii == 1) bphi = (m == 1) ? -idr * FX(a.phi, 1, 2, pl, 0) : 0.0;
-        else if (ii == nr) bphi = -idrh * (3.0 * FX(a.phi, 1, nr, pl, 0) - 4.0 * FX(a.phi, 1, nr - 1, pl, 0) + FX(a.phi, 1, nr - 2, pl, 0));
-        else bphi = -idrh * (FX(a.phi, 1, ii + 1, pl, 0) - FX(a.phi, 1, ii - 1, pl, 0));
-        if (m > 0) {
-            const bool im = (pl & 1) == 0;
-            const int po = im ? pl - 1 : pl + 1;
-            const double sg = im ? 1.0 : -1.0;
-            if (ii == 1) br = (m == 1) ? sg * idr * m * FX(a.phi, 1, 2, po, 0) : 0.0;
-            else br = sg * (idr / (double)(ii - 1)) * m * FX(a.phi, 1, ii, po, 0);
+    const double *psi_s = halo ? sm.psit - (ptrdiff_t)(i0 - 1) * P : a.psi, *phi_s = halo ? sm.phit - (ptrdiff_t)(i0 - 1) * P : a.phi;
+    if (tid < ST_N * P) {
+        const int ln = p_ln, pl = p_pl, ii = p_i, m = (pl + 1) >> 1;
+        if (!p_on) sm.t[pl][ln] = 0.0;
+        else {
+            // field_b_class.f03:545-701 get_solution_bt
+            double bphi, br = 0.0;
+            if (ii == 1) bphi = (m == 1) ? -idr * FX(phi_s, 1, 2, pl, 0) : 0.0;
+            else if (ii == nr) bphi = -idrh * (3.0 * FX(phi_s, 1, nr, pl, 0) - 4.0 * FX(phi_s, 1, nr - 1, pl, 0) + FX(phi_s, 1, nr - 2, pl, 0));
+            else bphi = -idrh * (FX(phi_s, 1, ii + 1, pl, 0) - FX(phi_s, 1, ii - 1, pl, 0));
+            if (m > 0) {
+                const bool im = (pl & 1) == 0;
+                const int po = im ? pl - 1 : pl + 1;
+                const double sg = im ? 1.0 : -1.0;
+                if (ii == 1) br = (m == 1) ? sg * idr * m * FX(phi_s, 1, 2, po, 0) : 0.0;
+                else br = sg * (idr / (double)(ii - 1)) * m * FX(phi_s, 1, ii, po, 0);
+            }
+            sm.t[pl][ln] = fabs(p_bsp);                                                       // convergence_tester 'record' :548-558
+            const double b0 = p_bsr + br, b1 = p_bsp + bphi;                                  // b = b_spe + b_beam :375
+            const double b2 = sm.d[2 * P + pl][ln] + p_bbz;
+            double er, ephi;
+            et_node<M>(psi_s, nr, idr, pl, ii, b0, b1, er, ephi);                              // :377
+            FX(a.b_beam, 3, ii, pl, 0) = br; FX(a.b_beam, 3, ii, pl, 1) = bphi;
+            FX(a.b, 3, ii, pl, 0) = b0; FX(a.b, 3, ii, pl, 1) = b1; FX(a.b, 3, ii, pl, 2) = b2;
+            FX(a.e, 3, ii, pl, 0) = er; FX(a.e, 3, ii, pl, 1) = ephi;
         }
-        const double bs_r = FX(a.b_spe, 3, ii, pl, 0), bs_p = FX(a.b_spe, 3, ii, pl, 1);
-        sm.t[pl][ln] = fabs(bs_p);                                                        // convergence_tester 'record' :548-558
-        const double b0 = bs_r + br, b1 = bs_p + bphi;                                    // b = b_spe + b_beam :375
-        const double b2 = sm.d[2 * P + pl][ln] + FX(a.b_beam, 3, ii, pl, 2);
-        double er, ephi;
-        et_node<M>(a.psi, nr, idr, pl, ii, b0, b1, er, ephi);                              // :377
-        FX(a.b_beam, 3, ii, pl, 0) = br; FX(a.b_beam, 3, ii, pl, 1) = bphi;
-        FX(a.b, 3, ii, pl, 0) = b0; FX(a.b, 3, ii, pl, 1) = b1; FX(a.b, 3, ii, pl, 2) = b2;
-        FX(a.e, 3, ii, pl, 0) = er; FX(a.e, 3, ii, pl, 1) = ephi;
     }
     __syncthreads();
     if (tid < ST_N && i0 + tid <= nr) {
@@ -294,12 +357,21 @@ __device__ void sweep_field_A(const FusedArgs &a, int j, Team &tm, StripSmem<M> 
 template <int M>
 __device__ void sweep_field_C(const FusedArgs &a, Team &tm, StripSmem<M> &sm, long long *stamp)
 {
-    long long tlast = stamp ? clock64() : 0;
     constexpr int P = 2 * M + 1, NS = 4 * P, NWARP = SW_T / 32, SPW = (NS + NWARP - 1) / NWARP;
+    long long tlast = stamp ? clock64() : 0;
     const int nr = a.nr, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int i0 = tm.rank * ST_N + 1;
     const double idr = 1.0 / a.dr, idrh = 0.5 * idr;
     SolveCtx sc; sc.nr = nr; sc.M = M; sc.P = P; sc.logC = 0; sc.stride = 1; sc.dr = a.dr; sc.idr = idr; sc.idrh = idrh;
+    // inputs of the post-processing stage that do not depend on this pass: beam field, psi terms of E-perp, old record
+    const int p_ln = tid % ST_N, p_pl = tid / ST_N, p_i = i0 + p_ln;
+    const bool p_on = tid < ST_N * P && p_i <= nr;
+    double p_bb0 = 0.0, p_bb1 = 0.0, p_bb2 = 0.0, p_er0 = 0.0, p_ephi0 = 0.0, p_ore = 0.0, p_oim = 0.0;
+    if (p_on) {
+        p_bb0 = FX(a.b_beam, 3, p_i, p_pl, 0); p_bb1 = FX(a.b_beam, 3, p_i, p_pl, 1); p_bb2 = FX(a.b_beam, 3, p_i, p_pl, 2);
+        et_node<M>(a.psi, nr, idr, p_pl, p_i, 0.0, 0.0, p_er0, p_ephi0);   // E-perp is affine in B-perp: er = b_phi + er0, ephi = -b_r + ephi0
+    }
+    if (tid < ST_N && i0 + tid <= nr) { p_ore = a.conv_old[i0 + tid]; p_oim = a.conv_old[nr + 2 + i0 + tid]; }
     // ---- S1: deposit epilogue (part2d_class.f03:916-981) of the strip + halo into shared tiles; the owner also stores
     //          the species2d amjdp results (:250-276, single species).  acc8 is cleared in S4, after the team barrier,
     //          because the neighbouring strips read the halo nodes' raw sums here.
@@ -349,21 +421,21 @@ __device__ void sweep_field_C(const FusedArgs &a, Team &tm, StripSmem<M> &sm, lo
     // ---- S3: strip scans -> exchange -> solutions
     const int i = i0 + lane, t = i - 1;
     const bool valid = i <= nr;
-    double *xrec = tm.xbuf + (size_t)tm.xpar * SW_MAX_TEAM * SW_XK + (size_t)tm.rank * SW_XK;
-    double fa[SPW], fb[SPW], dd[SPW];
+    double *xrec = tm.xbuf + (size_t)tm.xpar * SW_MAX_TEAM * SW_XK + tm.rank;   // slot k of this strip: xrec[k * SW_MAX_TEAM]
+    double incl[SPW], sfx[SPW], dd[SPW];
 #pragma unroll
     for (int q = 0; q < SPW; q++) {
         const int s = warp + q * NWARP;
         if (s < NS) {
-            const int kind = s < P ? FK_BPLUS : (s < 2 * P ? FK_BMINUS : (s < 3 * P ? FK_BZ : FK_EZ));
-            const OpCoef &oc = a.ops[kind * (QPG_MAX_MODE + 1) + (((s % P) + 1) >> 1)];
             dd[q] = valid ? sm.d[s][lane] : 0.0;
-            strip_scan(oc, dd[q], t, valid, lane, fa[q], fb[q], xrec, s, NS + s);
+            strip_scan(sm.fq[1][s][lane], sm.fv[1][s][lane], dd[q], lane, incl[q], sfx[q], xrec, s, NS + s);
             if (s == 3 * P) {
                 double r = (valid && i >= 2 && i <= nr - 2) ? dd[q] * (double)(i - 1) : 0.0;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
-                if (lane == 0) __stcg(xrec + 2 * NS, r);
+                // the last strip holds cu(nr-2), cu(nr-1) of this pass: it folds the edge term of the divergence sum in
+                if (tm.rank == tm.n - 1) r -= idrh * (FX(cu_t, 3, nr - 2, 0, 0) + FX(cu_t, 3, nr - 1, 0, 0)) * ((double)nr - 2.5);
+                if (lane == 0) __stcg(xrec + (size_t)(2 * NS) * SW_MAX_TEAM, r);
             }
         }
     }
@@ -375,46 +447,43 @@ __device__ void sweep_field_C(const FusedArgs &a, Team &tm, StripSmem<M> &sm, lo
     for (int q = 0; q < SPW; q++) {
         const int s = warp + q * NWARP;
         if (s < NS) {
-            const int kind = s < P ? FK_BPLUS : (s < 2 * P ? FK_BMINUS : (s < 3 * P ? FK_BZ : FK_EZ));
-            const int pl = s % P;
-            const OpCoef &oc = a.ops[kind * (QPG_MAX_MODE + 1) + ((pl + 1) >> 1)];
-            double pa, pb;
-            strip_offsets(xb, tm.n, tm.rank, lane, s, NS + s, pa, pb);
-            double x = 0.0;
-            if (s == 3 * P) {
-                const double tot = strip_total(xb, tm.n, lane, 2 * NS);
-                const double div = tot - idrh * (FX(a.cu, 3, nr - 2, 0, 0) + FX(a.cu, 3, nr - 1, 0, 0)) * ((double)nr - 2.5);
-                if (valid) x = (-8.0 * div) * (__ldg(oc.pT + t) * __ldg(oc.qT));
-            }
-            if (valid) x += green_apply(oc, t, fa[q] + pa, fb[q] + pb, dd[q]);
-            sm.d[s][lane] = x;
+            double pa, pb, tot;
+            strip_fold(xb, tm.n, tm.rank, lane, s, NS + s, s == 3 * P ? 2 * NS : -1, pa, pb, tot);
+            const double fp = sm.fp[1][s][lane], fu = sm.fu[1][s][lane], fax = sm.fax[1][s];
+            const double ex = __shfl_down_sync(0xffffffffu, sfx[q], 1);
+            double x = fp * (incl[q] + pa) + fu * ((lane == 31 ? 0.0 : ex) + pb);
+            if (t == 0 && fax != 0.0) x = dd[q] * fax;
+            if (s == 3 * P) x = (-8.0 * tot) * (fp * sm.ez_q0) + x;
+            sm.d[s][lane] = valid ? x : 0.0;
         }
     }
     tm.xpar ^= 1;
     __syncthreads();
     SW_STAMP(11);
     // ---- S4: get_solution_bt_iter (field_b_class.f03:703-758), bz, ez axis rules; b = b_spe + b_beam; E-perp; compare
-    for (int it = tid; it < ST_N * P; it += SW_T) {
-        const int ln = it % ST_N, pl = it / ST_N, ii = i0 + ln, m = (pl + 1) >> 1;
-        if (ii > nr) { sm.t[pl][ln] = 0.0; continue; }
-        double br, bp;
-        if (m == 0) { br = (ii == 1) ? 0.0 : sm.d[0][ln]; bp = (ii == 1) ? 0.0 : sm.d[P][ln]; }
+    if (tid < ST_N * P) {
+        const int ln = p_ln, pl = p_pl, ii = p_i, m = (pl + 1) >> 1;
+        if (!p_on) sm.t[pl][ln] = 0.0;
         else {
-            const bool im = (pl & 1) == 0;
-            const int po = im ? pl - 1 : pl + 1;
-            br = 0.5 * (sm.d[pl][ln] + sm.d[P + pl][ln]);
-            bp = im ? 0.5 * (-sm.d[po][ln] + sm.d[P + po][ln]) : 0.5 * (sm.d[po][ln] - sm.d[P + po][ln]);
-            if (ii == 1 && m != 1) { br = 0.0; bp = 0.0; }
+            double br, bp;
+            if (m == 0) { br = (ii == 1) ? 0.0 : sm.d[0][ln]; bp = (ii == 1) ? 0.0 : sm.d[P][ln]; }
+            else {
+                const bool im = (pl & 1) == 0;
+                const int po = im ? pl - 1 : pl + 1;
+                br = 0.5 * (sm.d[pl][ln] + sm.d[P + pl][ln]);
+                bp = im ? 0.5 * (-sm.d[po][ln] + sm.d[P + po][ln]) : 0.5 * (sm.d[po][ln] - sm.d[P + po][ln]);
+                if (ii == 1 && m != 1) { br = 0.0; bp = 0.0; }
+            }
+            double bz = sm.d[2 * P + pl][ln], ez = sm.d[3 * P + pl][ln];
+            if (pl > 0 && ii == 1) { bz = 0.0; ez = 0.0; }
+            sm.t[pl][ln] = fabs(bp);
+            const double b0 = br + p_bb0, b1 = bp + p_bb1, b2 = bz + p_bb2;
+            const bool et_zero = ii == 1 && m != 1;                  // solve_field_et axis rows (field_e_class.f03:450-470)
+            const double er = et_zero ? 0.0 : b1 + p_er0, ephi = et_zero ? 0.0 : -b0 + p_ephi0;
+            FX(a.b_spe, 3, ii, pl, 0) = br; FX(a.b_spe, 3, ii, pl, 1) = bp; FX(a.b_spe, 3, ii, pl, 2) = bz;
+            FX(a.b, 3, ii, pl, 0) = b0; FX(a.b, 3, ii, pl, 1) = b1; FX(a.b, 3, ii, pl, 2) = b2;
+            FX(a.e, 3, ii, pl, 0) = er; FX(a.e, 3, ii, pl, 1) = ephi; FX(a.e, 3, ii, pl, 2) = ez;
         }
-        double bz = sm.d[2 * P + pl][ln], ez = sm.d[3 * P + pl][ln];
-        if (pl > 0 && ii == 1) { bz = 0.0; ez = 0.0; }
-        sm.t[pl][ln] = fabs(bp);
-        const double b0 = br + FX(a.b_beam, 3, ii, pl, 0), b1 = bp + FX(a.b_beam, 3, ii, pl, 1), b2 = bz + FX(a.b_beam, 3, ii, pl, 2);
-        double er, ephi;
-        et_node<M>(a.psi, nr, idr, pl, ii, b0, b1, er, ephi);
-        FX(a.b_spe, 3, ii, pl, 0) = br; FX(a.b_spe, 3, ii, pl, 1) = bp; FX(a.b_spe, 3, ii, pl, 2) = bz;
-        FX(a.b, 3, ii, pl, 0) = b0; FX(a.b, 3, ii, pl, 1) = b1; FX(a.b, 3, ii, pl, 2) = b2;
-        FX(a.e, 3, ii, pl, 0) = er; FX(a.e, 3, ii, pl, 1) = ephi; FX(a.e, 3, ii, pl, 2) = ez;
     }
     // clear the raw deposit sums of the strip (+ guards); every strip's halo reads happened before the team barrier
     for (int it = tid; it < (own_hi - own_lo + 1) * P * 8; it += SW_T) a.acc8[(size_t)own_lo * P * 8 + it] = 0.0;
@@ -424,9 +493,8 @@ __device__ void sweep_field_C(const FusedArgs &a, Team &tm, StripSmem<M> &sm, lo
         double sre = 0.0, sim = 0.0;
 #pragma unroll
         for (int pl = 0; pl < P; pl++) { if (pl > 0 && (pl & 1) == 0) sim += sm.t[pl][tid]; else sre += sm.t[pl][tid]; }
-        const double ore = a.conv_old[i0 + tid], oim = a.conv_old[nr + 2 + i0 + tid];
-        mo = ore * ore + oim * oim;
-        const double dre = ore - sre, dim = oim - sim;
+        mo = p_ore * p_ore + p_oim * p_oim;
+        const double dre = p_ore - sre, dim = p_oim - sim;
         mn = dre * dre + dim * dim;
         a.conv_old[i0 + tid] = sre; a.conv_old[nr + 2 + i0 + tid] = sim;   // 'record' for the next pass (:373)
     }
@@ -434,8 +502,8 @@ __device__ void sweep_field_C(const FusedArgs &a, Team &tm, StripSmem<M> &sm, lo
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { mo = fmax(mo, __shfl_xor_sync(0xffffffffu, mo, o)); mn = fmax(mn, __shfl_xor_sync(0xffffffffu, mn, o)); }
         if (lane == 0) {
-            double *xm = tm.xbuf + (size_t)2 * SW_MAX_TEAM * SW_XK + (size_t)tm.rank * SW_XK;
-            __stcg(xm, mo); __stcg(xm + 1, mn);
+            double *xm = tm.xbuf + (size_t)2 * SW_MAX_TEAM * SW_XK + tm.rank;
+            __stcg(xm, mo); __stcg(xm + SW_MAX_TEAM, mn);
         }
     }
     SW_STAMP(12);
@@ -443,15 +511,17 @@ __device__ void sweep_field_C(const FusedArgs &a, Team &tm, StripSmem<M> &sm, lo
 
 // simulation_class.f03:560-599 on the per-CTA maxima published by program C.  Called by one thread per CTA after the
 // grid barrier; every CTA derives the same decision.  `it` = iterations done in this slice including this one.
-__device__ __forceinline__ bool sweep_conv_decide(const SweepArgs &a, int it, bool writer)
+__device__ __forceinline__ bool sweep_conv_decide(const SweepArgs &a, int it, bool writer, int lane)
 {
     const double *xb = a.xbuf + (size_t)2 * SW_MAX_TEAM * SW_XK;
     double mo = 0.0, mn = 0.0;
-    for (int r = 0; r < a.nteam; r++) { mo = fmax(mo, __ldcg(xb + (size_t)r * SW_XK)); mn = fmax(mn, __ldcg(xb + (size_t)r * SW_XK + 1)); }
+    for (int r = lane; r < a.nteam; r += 32) { mo = fmax(mo, __ldcg(xb + r)); mn = fmax(mn, __ldcg(xb + SW_MAX_TEAM + r)); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { mo = fmax(mo, __shfl_xor_sync(0xffffffffu, mo, o)); mn = fmax(mn, __shfl_xor_sync(0xffffffffu, mn, o)); }
     const double old_norm = sqrt(mo), abs_res = sqrt(mn);
     const double rel = old_norm > 2.220446049250313e-16 ? abs_res / old_norm : 1.7976931348623157e308;
     const bool fin = rel < a.f.reltol || abs_res < a.f.abstol || it >= a.f.iter_max;
-    if (writer) {
+    if (writer && lane == 0) {
         a.f.conv_out[0] = rel; a.f.conv_out[1] = abs_res;
         a.f.counters[1] += 1;
         a.f.flags[2] = it;
@@ -465,9 +535,10 @@ template <int M>
 __global__ void __launch_bounds__(SW_T, 1) k_sweep(const __grid_constant__ SweepArgs a)
 {
     constexpr int P = 2 * M + 1;
-    __shared__ StripSmem<M> sm_f;
     __shared__ int sm_i[48];
-    extern __shared__ double dep_tiles[];   // per-warp alpha/beta tiles of the DMMA deposit
+    extern __shared__ double sm_dyn[];      // [StripSmem<M>][per-warp alpha/beta tiles of the DMMA deposits]
+    StripSmem<M> &sm_f = *reinterpret_cast<StripSmem<M> *>(sm_dyn);
+    double *dep_tiles = sm_dyn + (sizeof(StripSmem<M>) + 7) / 8;
     const int G = gridDim.x, b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const FusedArgs &f = a.f;
     const double idr = 1.0 / f.dr;
@@ -475,13 +546,16 @@ __global__ void __launch_bounds__(SW_T, 1) k_sweep(const __grid_constant__ Sweep
     Team tm;
     tm.ctr = a.bar + 32; tm.abort_flag = a.bar + 64; tm.epoch = 0; tm.n = a.nteam; tm.rank = b; tm.xpar = 0; tm.xbuf = a.xbuf;
     const bool in_team = b < a.nteam;
+    // the halo shortcut of program A needs the one-sided stencil nodes nr-1, nr-2 inside the last strip's tile
+    const bool halo = (a.f.nr - ((a.nteam - 1) * ST_N + 1)) >= 1;
+    if (in_team) strip_load_factors<M>(f, b, sm_f);
     long long prof[4] = {0, 0, 0, 0}, work[4] = {0, 0, 0, 0}, tprev = 0, tstart = 0, nstart = 0, namj = 0;
     const bool timer = (b == 0 && tid == 0);
-    if (timer) { tstart = tprev = clock64(); asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(nstart)); }
+    if (timer) { for (int k = 0; k < 16; k++) sm_f.stamps[k] = 0; tstart = tprev = clock64(); asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(nstart)); }
     bool ok = true;
     for (int j = a.j0; j <= a.j1 && ok; j++) {
         // ---- phase A || compaction -------------------------------------------------------------------------
-        if (in_team) sweep_field_A<M>(f, j, tm, sm_f, timer ? a.prof + 16 : nullptr);
+        if (in_team) sweep_field_A<M>(f, j, tm, sm_f, halo, timer ? sm_f.stamps : nullptr);
         else if (b == G - 1) compact_body(a.planes, 8, a.d_npp_w, a.d_nout, a.outmask, a.lists, 0, sm_i);
         if (timer) work[0] += clock64() - tprev;
         ok = grid_barrier(a.bar, gep, sm_i);
@@ -499,12 +573,12 @@ __global__ void __launch_bounds__(SW_T, 1) k_sweep(const __grid_constant__ Sweep
             ok = grid_barrier(a.bar, gep, sm_i);
             if (timer) { const long long t = clock64(); prof[1] += t - tprev; tprev = t; namj++; }
             if (!ok) break;
-            if (in_team) sweep_field_C<M>(f, tm, sm_f, timer ? a.prof + 16 : nullptr);
+            if (in_team) sweep_field_C<M>(f, tm, sm_f, timer ? sm_f.stamps : nullptr);
             if (timer) work[2] += clock64() - tprev;
             ok = grid_barrier(a.bar, gep, sm_i);
             if (timer) { const long long t = clock64(); prof[2] += t - tprev; tprev = t; }
             if (!ok) break;
-            if (tid == 0) sm_i[45] = sweep_conv_decide(a, it, b == 0) ? 1 : 0;
+            if (warp == 0) { const bool fin = sweep_conv_decide(a, it, b == 0, lane); if (lane == 0) sm_i[45] = fin ? 1 : 0; }   // one warp per CTA, same decision everywhere
             __syncthreads();
             if (sm_i[45] != 0) break;
         }
@@ -526,6 +600,7 @@ __global__ void __launch_bounds__(SW_T, 1) k_sweep(const __grid_constant__ Sweep
         long long nend;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(nend));
         for (int k = 0; k < 4; k++) { a.prof[k] += prof[k]; a.prof[8 + k] += work[k]; }
+        for (int k = 0; k < 16; k++) a.prof[16 + k] += sm_f.stamps[k];
         a.prof[4] += clock64() - tstart;
         a.prof[5] += nend - nstart;
         a.prof[6] += a.j1 - a.j0 + 1;
