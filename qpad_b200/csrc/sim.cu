@@ -26,6 +26,7 @@ struct qpg_sim_s {
     int sweep_ctas_req;   // requested CTA count: > 0 absolute, <= 0 = number of SMs + this (SMs left to other streams)
     unsigned *sw_bar;     // grid / team barrier counters + abort flag
     double *sw_xbuf;      // team exchange records
+    void *sw_xll;         // flagged exchange words of the strip scans
     long long *sw_prof;   // in-kernel phase clocks
     double *phi;
     long host_updates, host_iters, host_slices;
@@ -190,6 +191,7 @@ static int sweep_prepare(qpg_sim s)
     CUDA_TRY(cudaMalloc(&s->sw_bar, sizeof(unsigned) * 128));
     CUDA_TRY(cudaMalloc(&s->sw_xbuf, sizeof(double) * 3 * SW_MAX_TEAM * SW_XK));
     CUDA_TRY(cudaMemsetAsync(s->sw_xbuf, 0, sizeof(double) * 3 * SW_MAX_TEAM * SW_XK, c->stream));
+    CUDA_TRY(cudaMalloc(&s->sw_xll, sizeof(uint4) * 2 * SW_MAX_TEAM * SW_XK));
     CUDA_TRY(cudaMalloc(&s->sw_prof, sizeof(long long) * 32));
     CUDA_TRY(cudaMemsetAsync(s->sw_prof, 0, sizeof(long long) * 32, c->stream));
     int g = s->sweep_ctas_req > 0 ? s->sweep_ctas_req : nsm * per + s->sweep_ctas_req;   // default: one CTA per SM
@@ -213,8 +215,9 @@ static int sweep_run(qpg_sim s, int j0, int j1)
     a.d_npp_w = p->d_npp; a.d_nout = p->d_nout; a.outmask = p->outmask; a.lists = p->lists;
     a.qbm = p->qbm; a.edge = (double)c->nr * c->dr;
     a.j0 = j0; a.j1 = j1; a.nteam = (c->nr + ST_N - 1) / ST_N;
-    a.bar = s->sw_bar; a.xbuf = s->sw_xbuf; a.prof = s->sw_prof;
+    a.bar = s->sw_bar; a.xbuf = s->sw_xbuf; a.xll = (uint4 *)s->sw_xll; a.prof = s->sw_prof;
     CUDA_TRY(cudaMemsetAsync(s->sw_bar, 0, sizeof(unsigned) * 128, c->stream));
+    CUDA_TRY(cudaMemsetAsync(s->sw_xll, 0, sizeof(uint4) * 2 * SW_MAX_TEAM * SW_XK, c->stream));   // sequence numbers restart at 1 every launch
     TprofScope tp(c, TP_K_SWEEP);
     cudaError_t e;
     switch (c->M) {
@@ -332,7 +335,7 @@ extern "C" int qpg_sim_destroy(qpg_sim s)
     qpg_field all[] = {s->psi, s->e, s->b, s->e_spe, s->b_spe, s->e_beam, s->b_beam, s->cu, s->amu, s->acu, s->dcu, s->q_spe, s->q_beam,
                        s->spe_q, s->spe_qn, s->spe_cu, s->spe_dcu, s->spe_amu, s->beam_q};
     for (auto f : all) qpg_field_destroy(f);
-    cudaFree(s->phi); cudaFree(s->sw_bar); cudaFree(s->sw_xbuf); cudaFree(s->sw_prof);
+    cudaFree(s->phi); cudaFree(s->sw_bar); cudaFree(s->sw_xbuf); cudaFree(s->sw_xll); cudaFree(s->sw_prof);
     qpg_part2d_destroy(s->spe);
     qpg_part3d_destroy(s->beam);
     qpg_ctx_destroy(s->ctx);
@@ -487,8 +490,8 @@ extern "C" int qpg_sim_set_sweep_ctas(qpg_sim s, int n)
     s->sweep_ctas_req = n;
     if (s->sweep_grid > 0) {   // already prepared: re-derive the grid
         cudaStreamSynchronize(s->ctx->stream);
-        cudaFree(s->sw_bar); cudaFree(s->sw_xbuf); cudaFree(s->sw_prof);
-        s->sw_bar = nullptr; s->sw_xbuf = nullptr; s->sw_prof = nullptr; s->sweep_grid = 0;
+        cudaFree(s->sw_bar); cudaFree(s->sw_xbuf); cudaFree(s->sw_xll); cudaFree(s->sw_prof);
+        s->sw_bar = nullptr; s->sw_xbuf = nullptr; s->sw_xll = nullptr; s->sw_prof = nullptr; s->sweep_grid = 0;
     }
     return 0;
 }

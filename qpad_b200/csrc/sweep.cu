@@ -32,7 +32,8 @@ struct SweepArgs {
     double qbm, edge;
     int j0, j1, nteam;
     unsigned *bar;          // [0] grid arrivals, [32] team arrivals, [64] abort flag (one 128-byte line each)
-    double *xbuf;           // [3][SW_XK][SW_MAX_TEAM] team exchange: two alternating scan slabs + the residual maxima
+    double *xbuf;           // [3][SW_XK][SW_MAX_TEAM]: slab 2 = residual maxima of program C (read after a grid barrier)
+    uint4 *xll;             // [2][SW_XK][SW_MAX_TEAM] flagged 16-byte exchange words of the strip scans (cleared before each launch)
     long long *prof;        // [0..3] cycles in phase A / amj / C / push, [4] total cycles, [5] total ns, [6] slices, [7] amj phases, [8..11] CTA 0's own work cycles per phase (thread 0's arrival at the barrier)
 };
 
@@ -90,10 +91,27 @@ __device__ __forceinline__ bool grid_barrier(unsigned *bar, unsigned &epoch, int
 
 struct Team {
     unsigned *ctr, *abort_flag;
-    unsigned epoch;
+    unsigned epoch;          // team-barrier arrivals expected so far
+    unsigned xep;            // sequence number of the current strip exchange (flag value of its words)
     int n, rank, xpar;
     double *xbuf;
+    uint4 *xll;
 };
+// Strip totals travel as self-validating 16-byte words {lo32, seq, hi32, seq} (each 8-byte half is written atomically,
+// the protocol NCCL calls LL): a reader polls the word itself, so the exchange needs no barrier and no fence -- its
+// latency is one store + one load through L2 instead of fence + atomic + poll + fence + load.
+__device__ __forceinline__ void ll_store(uint4 *p, double v, unsigned seq)
+{
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"((unsigned)__double2loint(v)), "r"(seq), "r"((unsigned)__double2hiint(v)), "r"(seq)
+                 : "memory");
+}
+__device__ __forceinline__ bool ll_load(const uint4 *p, unsigned seq, double &v)
+{
+    unsigned a, b, c, d;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(p) : "memory");
+    v = __hiloint2double((int)c, (int)a);
+    return b == seq && d == seq;
+}
 // all SW_T threads of the team CTAs
 __device__ __forceinline__ void team_barrier(Team &tm)
 {
@@ -162,7 +180,7 @@ __device__ void strip_load_factors(const FusedArgs &a, int rank, StripSmem<M> &s
 }
 
 // strip-local scans of one system (one warp): inclusive prefix of q*d and inclusive suffix of v*d; strip totals -> exchange record
-__device__ __forceinline__ void strip_scan(double q, double v, double d, int lane, double &incl, double &sfx, double *xrec, int slot_a, int slot_b)
+__device__ __forceinline__ void strip_scan(double q, double v, double d, int lane, double &incl, double &sfx, uint4 *xrec, unsigned seq, int slot_a, int slot_b)
 {
     incl = q * d;
     sfx = v * d;
@@ -172,20 +190,29 @@ __device__ __forceinline__ void strip_scan(double q, double v, double d, int lan
         if (lane >= o) incl += ta;
         if (lane + o < 32) sfx += tb;
     }
-    if (lane == 31) __stcg(xrec + (size_t)slot_a * SW_MAX_TEAM, incl);
-    if (lane == 0) __stcg(xrec + (size_t)slot_b * SW_MAX_TEAM, sfx);
+    if (lane == 31) ll_store(xrec + (size_t)slot_a * SW_MAX_TEAM, incl, seq);
+    if (lane == 0) ll_store(xrec + (size_t)slot_b * SW_MAX_TEAM, sfx, seq);
 }
-// totals of the strips before / after mine, and (slot_r >= 0) the sum of an all-strip reduction slot; every lane gets all
-__device__ __forceinline__ void strip_fold(const double *xb, int nteam, int rank, int lane, int slot_a, int slot_b, int slot_r, double &pa, double &pb,
-                                           double &tot)
+// totals of the strips before / after mine, and (slot_r >= 0) the sum of an all-strip reduction slot; every lane gets
+// all.  Polls the flagged words until every strip has published this exchange.
+__device__ __forceinline__ void strip_fold(const uint4 *xb, unsigned seq, unsigned *abort_flag, int nteam, int rank, int lane, int slot_a, int slot_b,
+                                           int slot_r, double &pa, double &pb, double &tot)
 {
     double a = 0.0, b = 0.0, c = 0.0;
-    for (int r = lane; r < nteam; r += 32) {
-        const double va = __ldcg(xb + (size_t)slot_a * SW_MAX_TEAM + r), vb = __ldcg(xb + (size_t)slot_b * SW_MAX_TEAM + r);
-        const double vc = slot_r >= 0 ? __ldcg(xb + (size_t)slot_r * SW_MAX_TEAM + r) : 0.0;
+    for (int r0 = 0; r0 < nteam; r0 += 32) {
+        const int r = r0 + lane;
+        double va = 0.0, vb = 0.0, vc = 0.0;
+        bool ok = r >= nteam;
+        for (unsigned n = 1; !__all_sync(0xffffffffu, ok); n++) {
+            if (!ok) {
+                ok = ll_load(xb + (size_t)slot_a * SW_MAX_TEAM + r, seq, va) & ll_load(xb + (size_t)slot_b * SW_MAX_TEAM + r, seq, vb);
+                if (slot_r >= 0) ok &= ll_load(xb + (size_t)slot_r * SW_MAX_TEAM + r, seq, vc);
+            }
+            if ((n & 1023u) == 0 && (ld_volatile_u32(abort_flag) || n > (1u << 22))) { atomicExch(abort_flag, 1u); break; }
+        }
         if (r < rank) a += va;
-        if (r > rank) b += vb;
-        c += vc;
+        if (r > rank && r < nteam) b += vb;
+        if (r < nteam) c += vc;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -252,34 +279,34 @@ __device__ void sweep_field_A(const FusedArgs &a, int j, Team &tm, StripSmem<M> 
     // ---- S2: strip scans, one warp per system
     const int i = i0 + lane, t = i - 1;
     const bool valid = i <= nr;
-    double *xrec = tm.xbuf + (size_t)tm.xpar * SW_MAX_TEAM * SW_XK + tm.rank;   // slot k of this strip: xrec[k * SW_MAX_TEAM]
+    tm.xep++;
+    uint4 *xrec = tm.xll + (size_t)tm.xpar * SW_MAX_TEAM * SW_XK + tm.rank;   // slot k of this strip: xrec[k * SW_MAX_TEAM]
     double incl[SPW], sfx[SPW], dd[SPW];
 #pragma unroll
     for (int q = 0; q < SPW; q++) {
         const int s = warp + q * NWARP;
         if (s < NS) {
             dd[q] = valid ? sm.d[s][lane] : 0.0;
-            strip_scan(sm.fq[0][s][lane], sm.fv[0][s][lane], dd[q], lane, incl[q], sfx[q], xrec, s, NS + s);
+            strip_scan(sm.fq[0][s][lane], sm.fv[0][s][lane], dd[q], lane, incl[q], sfx[q], xrec, tm.xep, s, NS + s);
             if (s == 3 * P) {   // E_z m=0 divergence sum, field_e_class.f03:189-197
                 double r = (valid && i >= 2 && i <= nr - 2) ? dd[q] * (double)(i - 1) : 0.0;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
-                if (lane == 0) __stcg(xrec + (size_t)(2 * NS) * SW_MAX_TEAM, r);
+                if (lane == 0) ll_store(xrec + (size_t)(2 * NS) * SW_MAX_TEAM, r, tm.xep);
             }
         }
     }
     SW_STAMP(1);
-    team_barrier(tm);
     SW_STAMP(2);
-    // ---- S3: fold the other strips, apply the Green's-function factors, store
-    const double *xb = tm.xbuf + (size_t)tm.xpar * SW_MAX_TEAM * SW_XK;
+    // ---- S3: fold the other strips (polling their flagged words), apply the Green's-function factors, store
+    const uint4 *xb = tm.xll + (size_t)tm.xpar * SW_MAX_TEAM * SW_XK;
 #pragma unroll
     for (int q = 0; q < SPW; q++) {
         const int s = warp + q * NWARP;
         if (s < NS) {
             const int kind = strip_kind<M>(0, s), pl = s % P;
             double pa, pb, tot;
-            strip_fold(xb, tm.n, tm.rank, lane, s, NS + s, s == 3 * P ? 2 * NS : -1, pa, pb, tot);
+            strip_fold(xb, tm.xep, tm.abort_flag, tm.n, tm.rank, lane, s, NS + s, s == 3 * P ? 2 * NS : -1, pa, pb, tot);
             const double fp = sm.fp[0][s][lane], fu = sm.fu[0][s][lane], fax = sm.fax[0][s];
             const double ex = __shfl_down_sync(0xffffffffu, sfx[q], 1);
             double x = fp * (incl[q] + pa) + fu * ((lane == 31 ? 0.0 : ex) + pb);
@@ -307,13 +334,14 @@ __device__ void sweep_field_A(const FusedArgs &a, int j, Team &tm, StripSmem<M> 
             }
         }
     }
-    // raw charge sums are consumed (the neighbouring strip read our first node's sum before the barrier)
-    for (int it = tid; it < (nhi - nlo + 1) * P; it += SW_T) a.acc1[(size_t)nlo * P + it] = 0.0;
     tm.xpar ^= 1;
     SW_STAMP(3);
     if (halo) __syncthreads();
     else team_barrier(tm);   // psi / phi of the neighbouring strips through global memory
     SW_STAMP(4);
+    // raw charge sums are consumed: the neighbouring strip read our first node's sum in its S1, i.e. before it published
+    // the totals some warp of this CTA has just seen
+    for (int it = tid; it < (nhi - nlo + 1) * P; it += SW_T) a.acc1[(size_t)nlo * P + it] = 0.0;
     // ---- S4: beam B-perp from phi, b = b_spe + b_beam, E-perp, convergence 'record'   (one thread per node, plane)
     const double *psi_s = halo ? sm.psit - (ptrdiff_t)(i0 - 1) * P : a.psi, *phi_s = halo ? sm.phit - (ptrdiff_t)(i0 - 1) * P : a.phi;
     if (tid < ST_N * P) {
@@ -421,34 +449,34 @@ __device__ void sweep_field_C(const FusedArgs &a, Team &tm, StripSmem<M> &sm, lo
     // ---- S3: strip scans -> exchange -> solutions
     const int i = i0 + lane, t = i - 1;
     const bool valid = i <= nr;
-    double *xrec = tm.xbuf + (size_t)tm.xpar * SW_MAX_TEAM * SW_XK + tm.rank;   // slot k of this strip: xrec[k * SW_MAX_TEAM]
+    tm.xep++;
+    uint4 *xrec = tm.xll + (size_t)tm.xpar * SW_MAX_TEAM * SW_XK + tm.rank;   // slot k of this strip: xrec[k * SW_MAX_TEAM]
     double incl[SPW], sfx[SPW], dd[SPW];
 #pragma unroll
     for (int q = 0; q < SPW; q++) {
         const int s = warp + q * NWARP;
         if (s < NS) {
             dd[q] = valid ? sm.d[s][lane] : 0.0;
-            strip_scan(sm.fq[1][s][lane], sm.fv[1][s][lane], dd[q], lane, incl[q], sfx[q], xrec, s, NS + s);
+            strip_scan(sm.fq[1][s][lane], sm.fv[1][s][lane], dd[q], lane, incl[q], sfx[q], xrec, tm.xep, s, NS + s);
             if (s == 3 * P) {
                 double r = (valid && i >= 2 && i <= nr - 2) ? dd[q] * (double)(i - 1) : 0.0;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
                 // the last strip holds cu(nr-2), cu(nr-1) of this pass: it folds the edge term of the divergence sum in
                 if (tm.rank == tm.n - 1) r -= idrh * (FX(cu_t, 3, nr - 2, 0, 0) + FX(cu_t, 3, nr - 1, 0, 0)) * ((double)nr - 2.5);
-                if (lane == 0) __stcg(xrec + (size_t)(2 * NS) * SW_MAX_TEAM, r);
+                if (lane == 0) ll_store(xrec + (size_t)(2 * NS) * SW_MAX_TEAM, r, tm.xep);
             }
         }
     }
     SW_STAMP(9);
-    team_barrier(tm);
     SW_STAMP(10);
-    const double *xb = tm.xbuf + (size_t)tm.xpar * SW_MAX_TEAM * SW_XK;
+    const uint4 *xb = tm.xll + (size_t)tm.xpar * SW_MAX_TEAM * SW_XK;
 #pragma unroll
     for (int q = 0; q < SPW; q++) {
         const int s = warp + q * NWARP;
         if (s < NS) {
             double pa, pb, tot;
-            strip_fold(xb, tm.n, tm.rank, lane, s, NS + s, s == 3 * P ? 2 * NS : -1, pa, pb, tot);
+            strip_fold(xb, tm.xep, tm.abort_flag, tm.n, tm.rank, lane, s, NS + s, s == 3 * P ? 2 * NS : -1, pa, pb, tot);
             const double fp = sm.fp[1][s][lane], fu = sm.fu[1][s][lane], fax = sm.fax[1][s];
             const double ex = __shfl_down_sync(0xffffffffu, sfx[q], 1);
             double x = fp * (incl[q] + pa) + fu * ((lane == 31 ? 0.0 : ex) + pb);
@@ -485,7 +513,7 @@ __device__ void sweep_field_C(const FusedArgs &a, Team &tm, StripSmem<M> &sm, lo
             FX(a.e, 3, ii, pl, 0) = er; FX(a.e, 3, ii, pl, 1) = ephi; FX(a.e, 3, ii, pl, 2) = ez;
         }
     }
-    // clear the raw deposit sums of the strip (+ guards); every strip's halo reads happened before the team barrier
+    // clear the raw deposit sums of the strip (+ guards); every strip read its halo nodes' sums before it published its totals
     for (int it = tid; it < (own_hi - own_lo + 1) * P * 8; it += SW_T) a.acc8[(size_t)own_lo * P * 8 + it] = 0.0;
     __syncthreads();
     double mo = 0.0, mn = 0.0;
@@ -544,7 +572,7 @@ __global__ void __launch_bounds__(SW_T, 1) k_sweep(const __grid_constant__ Sweep
     const double idr = 1.0 / f.dr;
     unsigned gep = 0;
     Team tm;
-    tm.ctr = a.bar + 32; tm.abort_flag = a.bar + 64; tm.epoch = 0; tm.n = a.nteam; tm.rank = b; tm.xpar = 0; tm.xbuf = a.xbuf;
+    tm.ctr = a.bar + 32; tm.abort_flag = a.bar + 64; tm.epoch = 0; tm.xep = 0; tm.n = a.nteam; tm.rank = b; tm.xpar = 0; tm.xbuf = a.xbuf; tm.xll = a.xll;
     const bool in_team = b < a.nteam;
     // the halo shortcut of program A needs the one-sided stencil nodes nr-1, nr-2 inside the last strip's tile
     const bool halo = (a.f.nr - ((a.nteam - 1) * ST_N + 1)) >= 1;
