@@ -137,7 +137,8 @@ __device__ __forceinline__ void warp_deposit_mma(const double (&alpha)[2 * (2 * 
         const int l = __ffs(leaders) - 1;
         leaders &= leaders - 1;
         const int cell = __shfl_sync(FULL, key, l);
-        const unsigned members = __ballot_sync(FULL, key == cell) >> kk;   // bit 4s <-> particle 4s + kk
+        const unsigned memb = __ballot_sync(FULL, key == cell);            // warp-uniform
+        const unsigned members = memb >> kk;                               // bit 4s <-> particle 4s + kk
 #pragma unroll
         for (int t = 0; t < NTILE; t++) {
             const int r = t * 8 + row;
@@ -145,9 +146,11 @@ __device__ __forceinline__ void warp_deposit_mma(const double (&alpha)[2 * (2 * 
             double c0 = 0.0, c1 = 0.0;
 #pragma unroll
             for (int s = 0; s < 8; s++) {
-                double a = 0.0;
-                if (live && ((members >> (4 * s)) & 1u)) a = tile[r * DEP_LD + 4 * s + kk];
-                dmma884(c0, c1, a, bfr[s]);
+                if ((memb >> (4 * s)) & 0xfu) {   // k-steps without a member of this cell contribute nothing: skip (cell-sorted
+                    double a = 0.0;               // tiles then need 8 DMMAs in total, not 8 per cell)
+                    if (live && ((members >> (4 * s)) & 1u)) a = tile[r * DEP_LD + 4 * s + kk];
+                    dmma884(c0, c1, a, bfr[s]);
+                }
             }
             if (live) {
                 const int j = r >= P ? 1 : 0, pl = r - j * P;
