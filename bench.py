@@ -182,6 +182,9 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
+        # the hand-offs are small (<= 17 MB per step): two NCCL channels are plenty and keep the SMs the sweep kernel must
+        # leave free for the communication kernels at 4 (PipelineStage reserves them)
+        os.environ.setdefault("NCCL_MAX_P2P_NCHANNELS", "2")
         dist.init_process_group("nccl")     # lazy init: every stage pair gets its own p2p communicator / stream
     cfg, beam = deck_config(args.config)
     plasma, bm = make_inputs(cfg, beam)

@@ -149,7 +149,9 @@ class PipelineStage:
         self.sim.beam.upload(*mine)
         s = self.sim
         if world > 1 and make_buf is None:
-            s.set_sweep_ctas(-8)       # leave 8 SMs to the NCCL send/recv kernels that overlap the slab sweep
+            # leave a few SMs to the NCCL send/recv kernels that overlap the slab sweep (a cooperative kernel that fills
+            # the GPU would delay the backward e/b hand-off until the slab is done and serialise the pipeline)
+            s.set_sweep_ctas(-int(os.environ.get("QPG_PIPELINE_FREE_SMS", "4")))
         mk = make_buf or (lambda n: torch.zeros(n, dtype=torch.float64, device=torch.device("cuda", device)))
         self.buf_q = mk(s.field("beam_q").wire_count())
         self.buf_cu = mk(s.field("cu").wire_count())
