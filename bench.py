@@ -182,9 +182,10 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
-        # the hand-offs are small (<= 17 MB per step): two NCCL channels are plenty and keep the SMs the sweep kernel must
-        # leave free for the communication kernels at 4 (PipelineStage reserves them)
-        os.environ.setdefault("NCCL_MAX_P2P_NCHANNELS", "2")
+        # the big hand-off (17 MB of plasma particles) happens after the slab sweep, when every SM is free; the messages
+        # that overlap a sweep (first-slice e/b backward, crossing beam particles) are small and use one or two channels,
+        # for which PipelineStage leaves a few SMs free
+        os.environ.setdefault("NCCL_MAX_P2P_NCHANNELS", "8")
         dist.init_process_group("nccl")     # lazy init: every stage pair gets its own p2p communicator / stream
     cfg, beam = deck_config(args.config)
     plasma, bm = make_inputs(cfg, beam)

@@ -136,8 +136,9 @@ int qpg_part2d_push_x(qpg_part2d p, double dt);                                 
 int qpg_part2d_update_bound(qpg_part2d p);                                                       /* update_bound_part2d :2307 */
 int qpg_part2d_sort(qpg_part2d p);                                                               /* sort_part2d :2498 + sort_module.f03:11 */
 int qpg_part2d_sort_index(qpg_part2d p, int *host_ix, int *host_ip);                             /* generate_sort_idx_1d output (1-based), synchronises */
-/* pipesend_part2d :2355 / piperecv_part2d :2405 : 8 doubles per particle (x1,x2,p1,p2,p3,gamma,psi,q) AoS,
- * dev_buf[0] additionally carries the count as a double in slot 8*npmax.  wire size = 8*npmax+1 doubles. */
+/* pipesend_part2d :2355 / piperecv_part2d :2405 : dev_buf[0] = count, then 8 doubles per particle
+ * (x1,x2,p1,p2,p3,gamma,psi,q) AoS.  Capacity = 8*npmax+1 doubles; the transport may move just the live prefix
+ * 1 + 8*n (n >= count, e.g. the injected lattice size: plasma particles only ever leave). */
 int qpg_part2d_pack(qpg_part2d p, double *dev_buf);
 int qpg_part2d_unpack(qpg_part2d p, const double *dev_buf);
 long qpg_part2d_wire_count(qpg_part2d p);
@@ -154,11 +155,15 @@ int qpg_part3d_qdeposit(qpg_part3d p, qpg_field q);                             
 int qpg_part3d_push(qpg_part3d p, int push_type, qpg_field ef, qpg_field bf);                    /* push_reduced :477 / push_boris :358 */
 int qpg_part3d_update_bound(qpg_part3d p);                                                       /* update_bound_part3d :640 */
 /* forward xi hand-off of beam/part3d_comm.f03:278-314 + pack_particles('pipeline') :685-745:
- * pack particles with xi >= upper slab edge into dev_buf (7 doubles each, count in slot 7*cap), remove them
- * ("fill the holes inversely"); unpack appends.  cap = qpg_part3d_wire_cap(). */
+ * pack particles with xi >= upper slab edge into dev_buf (dev_buf[0] = count, then 7 doubles each), remove them
+ * ("fill the holes inversely"); unpack appends.  Buffer size = 1 + 7*cap doubles, cap = qpg_part3d_wire_cap()
+ * (default 0.1*npmax like the reference's nbmax; qpg_part3d_set_wire_cap shrinks the message).  More than cap
+ * crossings in one step raise an overflow flag that qpg_part3d_download reports as QPG_ERR_STATE (the reference
+ * stops with a buffer-overflow error in the same situation). */
 int qpg_part3d_pack_forward(qpg_part3d p, double *dev_buf);
 int qpg_part3d_unpack(qpg_part3d p, const double *dev_buf);
 long qpg_part3d_wire_cap(qpg_part3d p);
+int qpg_part3d_set_wire_cap(qpg_part3d p, long cap);
 
 /* ------------------------------------------------------------------------------------------ */
 /* fused fast path: the whole `do j = 1, nstep2d` body of simulation_class.f03:342-469 on the  */

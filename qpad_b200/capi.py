@@ -107,6 +107,7 @@ SIGNATURES = {
     "qpg_part3d_pack_forward": (_i, [_vp, _vp]),
     "qpg_part3d_unpack": (_i, [_vp, _vp]),
     "qpg_part3d_wire_cap": (_l, [_vp]),
+    "qpg_part3d_set_wire_cap": (_i, [_vp, _l]),
     "qpg_sim_create": (_i, [C.POINTER(_vp), _i, _vp, C.POINTER(SimParams)]),
     "qpg_sim_destroy": (_i, [_vp]),
     "qpg_sim_ctx": (_vp, [_vp]),
@@ -365,6 +366,7 @@ class Part3d:
     def push(self, push_type, ef, bf): _chk(self.L.qpg_part3d_push(self.h, push_type, ef.h, bf.h))
     def update_bound(self): _chk(self.L.qpg_part3d_update_bound(self.h))
     def wire_cap(self): return self.L.qpg_part3d_wire_cap(self.h)
+    def set_wire_cap(self, cap): _chk(self.L.qpg_part3d_set_wire_cap(self.h, int(cap)))
     def pack_forward(self, dev_ptr): _chk(self.L.qpg_part3d_pack_forward(self.h, dev_ptr))
     def unpack(self, dev_ptr): _chk(self.L.qpg_part3d_unpack(self.h, dev_ptr))
 

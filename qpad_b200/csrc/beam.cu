@@ -170,11 +170,12 @@ __global__ void __launch_bounds__(B3_BLOCK) k_flag3d(Part3View pv, double edge_r
 }
 
 // ordered pack of the flagged particles (ascending index like pack_particles :685-745): one CTA
-__global__ void __launch_bounds__(1024, 1) k_pack3d(Part3View pv, const int *d_nout, const unsigned *__restrict__ outmask, double *__restrict__ buf, long cap)
+__global__ void __launch_bounds__(1024, 1) k_pack3d(Part3View pv, const int *d_nout, const unsigned *__restrict__ outmask, double *__restrict__ buf, long cap,
+                                                   int *pv_overflow)
 {
     __shared__ int sm[40];
     const int n = *pv.d_npp, nout = *d_nout, tid = threadIdx.x, nt = blockDim.x;
-    if (tid == 0) buf[(size_t)7 * cap] = (double)(nout > cap ? cap : nout);
+    if (tid == 0) { buf[0] = (double)(nout > cap ? cap : nout); if (nout > cap) pv_overflow[0] = 1; }
     if (nout == 0) return;
     const int nwords = (n + 31) >> 5, wpt = (nwords + nt - 1) / nt;
     const int wbeg = min(tid * wpt, nwords), wend = min(wbeg + wpt, nwords);
@@ -205,7 +206,7 @@ __global__ void __launch_bounds__(1024, 1) k_pack3d(Part3View pv, const int *d_n
             const int b = __ffs(bits) - 1; bits &= bits - 1;
             const int i = lo + b;
             if (off < cap) {
-                double *r = buf + (size_t)7 * off;
+                double *r = buf + 1 + (size_t)7 * off;
                 r[0] = pv.x1[i]; r[1] = pv.x2[i]; r[2] = pv.x3[i]; r[3] = pv.p1[i]; r[4] = pv.p2[i]; r[5] = pv.p3[i]; r[6] = pv.q[i];
             }
             off++;
@@ -214,11 +215,11 @@ __global__ void __launch_bounds__(1024, 1) k_pack3d(Part3View pv, const int *d_n
 }
 __global__ void k_unpack3d(Part3View pv, int *d_npp_w, const double *__restrict__ buf, long cap, long npmax)
 {
-    const int add = (int)buf[(size_t)7 * cap];
+    const int add = (int)min((long)buf[0], cap);
     const int n0 = *pv.d_npp;
     const int room = (int)min((long)add, npmax - n0);
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < room; k += gridDim.x * blockDim.x) {
-        const double *r = buf + (size_t)7 * k;
+        const double *r = buf + 1 + (size_t)7 * k;
         const int i = n0 + k;
         pv.x1[i] = r[0]; pv.x2[i] = r[1]; pv.x3[i] = r[2]; pv.p1[i] = r[3]; pv.p2[i] = r[4]; pv.p3[i] = r[5]; pv.q[i] = r[6];
     }
@@ -226,7 +227,7 @@ __global__ void k_unpack3d(Part3View pv, int *d_npp_w, const double *__restrict_
 }
 __global__ void k_bump_npp(int *d_npp, const double *__restrict__ buf, long cap, long npmax)
 {
-    const int add = (int)buf[(size_t)7 * cap];
+    const int add = (int)min((long)buf[0], cap);
     const int n0 = *d_npp;
     *d_npp = n0 + (int)min((long)add, npmax - n0);
 }
@@ -290,10 +291,12 @@ extern "C" int qpg_part3d_upload(qpg_part3d p, const double *x, const double *pm
 extern "C" int qpg_part3d_download(qpg_part3d p, double *x, double *pm, double *q, long *npp_out)
 {
     ARG_TRY(p, "null arg");
-    int n = 0;
+    int nn[3] = {0, 0, 0};
     cudaStream_t st = p->ctx->stream;
-    CUDA_TRY(cudaMemcpyAsync(&n, p->d_npp, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(nn, p->d_npp, sizeof(nn), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    if (nn[2]) { qpg_set_error("beam hand-off overflow: more than %ld particles crossed the slab edge in one step (qpg_part3d_set_wire_cap)", qpg_part3d_wire_cap(p)); return QPG_ERR_STATE; }
+    const int n = nn[0];
     const long npp = n;
     p->npp_hi = npp;
     if (npp_out) *npp_out = npp;
@@ -348,7 +351,18 @@ extern "C" int qpg_part3d_update_bound(qpg_part3d p)
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
-extern "C" long qpg_part3d_wire_cap(qpg_part3d p) { return p ? (p->npmax / 10 > 1024 ? p->npmax / 10 : 1024) : -1; }  /* nbmax = 0.1 npmax, part3d_class.f03:127 */
+extern "C" long qpg_part3d_wire_cap(qpg_part3d p)
+{
+    if (!p) return -1;
+    if (p->wire_cap > 0) return p->wire_cap;
+    return p->npmax / 10 > 1024 ? p->npmax / 10 : 1024;   /* nbmax = 0.1 npmax, part3d_class.f03:127 */
+}
+extern "C" int qpg_part3d_set_wire_cap(qpg_part3d p, long cap)
+{
+    ARG_TRY(p && cap >= 0 && cap <= p->npmax, "wire cap out of range");
+    p->wire_cap = cap;
+    return 0;
+}
 extern "C" int qpg_part3d_pack_forward(qpg_part3d p, double *dev_buf)
 {
     ARG_TRY(p && dev_buf, "null arg");
@@ -357,7 +371,7 @@ extern "C" int qpg_part3d_pack_forward(qpg_part3d p, double *dev_buf)
     const long cap = qpg_part3d_wire_cap(p);
     const int grid = (int)((p->npp_hi + B3_BLOCK - 1) / B3_BLOCK);
     if (grid > 0) k_flag3d<<<grid, B3_BLOCK, 0, c->stream>>>(view3(p), 0.0, (double)(p->noff2 + p->nzp) * c->dxi, 1, p->outmask, p->d_nout);
-    k_pack3d<<<1, 1024, 0, c->stream>>>(view3(p), p->d_nout, p->outmask, dev_buf, cap);
+    k_pack3d<<<1, 1024, 0, c->stream>>>(view3(p), p->d_nout, p->outmask, dev_buf, cap, p->d_npp + 2);
     k_compact<<<1, 1024, 0, c->stream>>>(plane_table3(p), 7, p->d_npp, p->d_nout, p->outmask, p->lists, 1, nullptr);
     count_launch(c, 3);
     CUDA_TRY(cudaGetLastError());

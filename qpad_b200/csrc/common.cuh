@@ -105,9 +105,10 @@ struct qpg_part3d_s {
     long npmax, npp_hi;
     int nz_total, noff2, nzp;
     double *x1, *x2, *x3, *p1, *p2, *p3, *q, *slab;
-    int *d_npp, *d_nout;
+    int *d_npp, *d_nout;     // d_npp[2] = wire-buffer overflow flag (more particles crossed the slab edge than wire_cap)
     unsigned *outmask;
     int *lists;
+    long wire_cap;           // particles per forward hand-off message (0 = default 0.1 npmax, part3d_class.f03:127)
 };
 
 // ---- launch bookkeeping -------------------------------------------------------------------

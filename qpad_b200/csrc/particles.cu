@@ -536,16 +536,16 @@ __global__ void k_pack2d(PartView pv, double *__restrict__ buf, long cap)
 {
     const int npp = *pv.d_npp;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npp; i += gridDim.x * blockDim.x) {
-        double *r = buf + (size_t)8 * i;
+        double *r = buf + 1 + (size_t)8 * i;
         r[0] = pv.x1[i]; r[1] = pv.x2[i]; r[2] = pv.p1[i]; r[3] = pv.p2[i]; r[4] = pv.p3[i]; r[5] = pv.gamma[i]; r[6] = pv.psi[i]; r[7] = pv.q[i];
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) buf[(size_t)8 * cap] = (double)npp;
+    if (blockIdx.x == 0 && threadIdx.x == 0) buf[0] = (double)npp;   // count first: the transport may send just the live prefix
 }
 __global__ void k_unpack2d(PartView pv, int *d_npp_w, const double *__restrict__ buf, long cap)
 {
-    const int npp = (int)buf[(size_t)8 * cap];
+    const int npp = (int)min((long)buf[0], cap);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npp; i += gridDim.x * blockDim.x) {
-        const double *r = buf + (size_t)8 * i;
+        const double *r = buf + 1 + (size_t)8 * i;
         pv.x1[i] = r[0]; pv.x2[i] = r[1]; pv.p1[i] = r[2]; pv.p2[i] = r[3]; pv.p3[i] = r[4]; pv.gamma[i] = r[5]; pv.psi[i] = r[6]; pv.q[i] = r[7];
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) *d_npp_w = npp;

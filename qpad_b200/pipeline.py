@@ -134,7 +134,8 @@ class SingleStage:
 class PipelineStage:
     """One rank = one xi slab on one GPU; consecutive ranks are consecutive pipeline stages."""
 
-    def __init__(self, cfg, plasma, beam, stream=None, rank=0, world=1, device=0, use_graph=1, dist=None, make_buf=None, sim=None):
+    def __init__(self, cfg, plasma, beam, stream=None, rank=0, world=1, device=0, use_graph=1, dist=None, make_buf=None, sim=None,
+                 beam_wire_cap=None):
         """`sim`, `dist`, `make_buf` are injection points for the host-logic tests (tests/test_pipeline_gloo.py drives the
         stage protocol over gloo with a recording stand-in for the device object); production code leaves them None."""
         import torch
@@ -153,24 +154,28 @@ class PipelineStage:
             # the GPU would delay the backward e/b hand-off until the slab is done and serialise the pipeline)
             s.set_sweep_ctas(-int(os.environ.get("QPG_PIPELINE_FREE_SMS", "4")))
         mk = make_buf or (lambda n: torch.zeros(n, dtype=torch.float64, device=torch.device("cuda", device)))
-        self.buf_q = mk(s.field("beam_q").wire_count())
-        self.buf_cu = mk(s.field("cu").wire_count())
-        self.buf_bs = mk(s.field("b_spe").wire_count())
-        self.buf_e = mk(s.field("e").wire_count())
-        self.buf_b = mk(s.field("b").wire_count())
-        self.buf_p = mk(s.species.wire_count())
-        self.buf_beam = mk(7 * s.beam.wire_cap() + 1)
-        # separate in/out buffers wherever a stage both receives and sends the same kind of message
-        self.buf_p_out, self.buf_cu_out, self.buf_bs_out = mk(s.species.wire_count()), mk(s.field("cu").wire_count()), mk(s.field("b_spe").wire_count())
-        self.buf_b_in, self.buf_e_in = mk(s.field("b").wire_count()), mk(s.field("e").wire_count())
-        self.buf_beam_in = mk(7 * s.beam.wire_cap() + 1)
+        # message sizes: plasma particles only ever leave, so the live prefix of the wire buffer is bounded by the injected
+        # lattice; beam particles crossing a slab edge in one step are few (the reference reserves 0.1 npmax and stops on
+        # overflow, so does this library -- with a smaller default so the hand-off stays off the critical path)
+        self.n_plasma_wire = min(s.species.wire_count(), 1 + 8 * len(plasma[4]))
+        s.beam.set_wire_cap(beam_wire_cap if beam_wire_cap is not None else max(16384, len(beam[2]) // 64))
+        # One message per direction and step: forward [beam-q guard slice | cu | b_spe | plasma particles] (the plasma
+        # record is last so that only its live prefix travels), backward [b | e] of the first slice.  Separate in / out
+        # buffers because a middle stage receives and sends the same kinds of message.
+        nq, ncu, nbs = s.field("beam_q").wire_count(), s.field("cu").wire_count(), s.field("b_spe").wire_count()
+        self.off_fwd = (0, nq, nq + ncu, nq + ncu + nbs)
+        self.n_fwd = nq + ncu + nbs + self.n_plasma_wire
+        self.fwd_in, self.fwd_out = mk(nq + ncu + nbs + s.species.wire_count()), mk(nq + ncu + nbs + s.species.wire_count())
+        nb = s.field("b").wire_count()
+        self.off_back = (0, nb)
+        self.back_in, self.back_out = mk(nb + s.field("e").wire_count()), mk(nb + s.field("e").wire_count())
+        self.buf_beam, self.buf_beam_in = mk(7 * s.beam.wire_cap() + 1), mk(7 * s.beam.wire_cap() + 1)
         self.first, self.last = rank == 0, rank == world - 1
         self.stream = stream
         self.torch = torch
         self.comm = torch.cuda.Stream(device=device) if (stream is not None and make_buf is None) else None
         self.pending = {}
         self.pending_tail = False
-        self.buf_q_out = mk(s.field("beam_q").wire_count())
 
     # mpi_isend analogue: the transfer runs on the communication stream, the compute stream carries on.  The buffer
     # is only repacked after _wait(name) (the reference's mpi_wait before every pipe_send, simulation_class.f03:430).
@@ -212,45 +217,45 @@ class PipelineStage:
         # when it has finished its slab (simulation_class.f03:303-340; the guard slice is taken at the same point so
         # that an upstream stage never waits for a downstream one)
         s.beam_qdp_begin()                                              # beam3d_class.f03:207
+        fin = lambda k: self.fwd_in.data_ptr() + 8 * self.off_fwd[k]
         if not self.first:
-            self._recv(self.buf_q, r - 1)
-            s.field("beam_q").unpack(1, self.buf_q.data_ptr(), add=True)
+            self._recv(self.fwd_in[:self.n_fwd], r - 1)
+            s.field("beam_q").unpack(1, fin(0), add=True)
         s.beam_qdp_end()                                                # :210
         s.begin_step()
         if not self.first:
-            self._recv(self.buf_p, r - 1)
-            s.species.unpack(self.buf_p.data_ptr())
-            self._recv(self.buf_cu, r - 1)
-            s.field("cu").unpack(0, self.buf_cu.data_ptr())
-            self._recv(self.buf_bs, r - 1)
-            s.field("b_spe").unpack(0, self.buf_bs.data_ptr())
+            s.species.unpack(fin(3))
+            s.field("cu").unpack(0, fin(1))
+            s.field("b_spe").unpack(0, fin(2))
         # first slice, then the backward hand-off of e and b (:460-467), then the rest of the slab
         s.run_slices(1, 1)
         if not self.first:
-            self._wait("b"); s.field("b").pack(1, self.buf_b.data_ptr()); self._isend("b", self.buf_b, r - 1)
-            self._wait("e"); s.field("e").pack(1, self.buf_e.data_ptr()); self._isend("e", self.buf_e, r - 1)
+            self._wait("back")
+            s.field("b").pack(1, self.back_out.data_ptr() + 8 * self.off_back[0])
+            s.field("e").pack(1, self.back_out.data_ptr() + 8 * self.off_back[1])
+            self._isend("back", self.back_out, r - 1)
             # the beam particles stage r-1 pushes across the slab edge in THIS step arrive while the slab is swept:
             # post the receive now on the communication stream, consume it in tail() (part3d_comm.f03:278-314)
             self._irecv("beam_in", self.buf_beam_in, r - 1)
         if self.nzp > 1:
             s.run_slices(2, self.nzp)
         if not self.last:                                               # :210-215, :429-434, :472-474
-            self._wait("q"); s.field("beam_q").pack(self.nzp + 1, self.buf_q_out.data_ptr())
-            self._wait("p"); s.species.pack(self.buf_p_out.data_ptr())
-            self._wait("cu"); s.field("cu").pack(0, self.buf_cu_out.data_ptr())
-            self._wait("bs"); s.field("b_spe").pack(0, self.buf_bs_out.data_ptr())
+            fout = lambda k: self.fwd_out.data_ptr() + 8 * self.off_fwd[k]
+            self._wait("fwd")
+            s.field("beam_q").pack(self.nzp + 1, fout(0))
+            s.field("cu").pack(0, fout(1))
+            s.field("b_spe").pack(0, fout(2))
+            s.species.pack(fout(3))
         self.pending_tail = True
 
     def tail(self):
         s, r = self.sim, self.rank
         _trace(r, "tail")
         if not self.last:
-            self._isend("q", self.buf_q_out, r + 1)
-            self._isend("p", self.buf_p_out, r + 1)
-            self._isend("cu", self.buf_cu_out, r + 1)
-            self._isend("bs", self.buf_bs_out, r + 1)
-            self._recv(self.buf_b_in, r + 1); s.field("b").unpack(self.nzp + 1, self.buf_b_in.data_ptr())   # :482-483
-            self._recv(self.buf_e_in, r + 1); s.field("e").unpack(self.nzp + 1, self.buf_e_in.data_ptr())
+            self._isend("fwd", self.fwd_out[:self.n_fwd], r + 1)
+            self._recv(self.back_in, r + 1)                              # :482-483
+            s.field("b").unpack(self.nzp + 1, self.back_in.data_ptr() + 8 * self.off_back[0])
+            s.field("e").unpack(self.nzp + 1, self.back_in.data_ptr() + 8 * self.off_back[1])
         # beam push + forward hand-off                                  (:489-493, part3d_comm.f03:278-314)
         s.beam_push()
         if not self.first:

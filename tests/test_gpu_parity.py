@@ -492,8 +492,8 @@ def test_wire_formats(mods):
     wb = torch.zeros(pa.wire_count(), dtype=torch.float64, device="cuda")
     pa.pack(wb.data_ptr()); ctx.sync()
     rec = wb.cpu().numpy()
-    assert rec[-1] == n
-    assert np.array_equal(rec[:8 * n].reshape(n, 8), np.column_stack([x, p, g, psi, q]))
+    assert rec[0] == n
+    assert np.array_equal(rec[1:1 + 8 * n].reshape(n, 8), np.column_stack([x, p, g, psi, q]))
     pb.unpack(wb.data_ptr())
     assert all(np.array_equal(u, v) for u, v in zip(pb.download(), (x, p, g, psi, q)))
     # beam forward hand-off
@@ -509,8 +509,8 @@ def test_wire_formats(mods):
     b0.pack_forward(hb.data_ptr()); c2.sync()
     go = np.nonzero(bx[:, 2] >= nzp * 0.5)[0]
     rec = hb.cpu().numpy()
-    assert rec[-1] == len(go)
-    assert np.array_equal(rec[:7 * len(go)].reshape(-1, 7)[:, 6], bq[go])      # packed in ascending index order
+    assert rec[0] == len(go)
+    assert np.array_equal(rec[1:1 + 7 * len(go)].reshape(-1, 7)[:, 6], bq[go])      # packed in ascending index order
     keep = b0.download()[2]
     # "fill the holes inversely" (part3d_comm.f03:733-745)
     exp = list(bq); npp = nb

@@ -55,6 +55,9 @@ class _Rec:
     def upload(self, *a):
         pass
 
+    def set_wire_cap(self, cap):
+        pass
+
 
 class FakeSim:
     """records the call order of one stage; step = number of begin_step() calls so far"""
