@@ -182,10 +182,10 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
-        # the big hand-off (17 MB of plasma particles) happens after the slab sweep, when every SM is free; the messages
-        # that overlap a sweep (first-slice e/b backward, crossing beam particles) are small and use one or two channels,
-        # for which PipelineStage leaves a few SMs free
-        os.environ.setdefault("NCCL_MAX_P2P_NCHANNELS", "8")
+        # one NCCL kernel can be resident beside the cooperative sweep kernel (the receive of the crossing beam particles
+        # spins until the upstream stage has pushed its beam): its CTAs (one per channel) must fit in the SMs
+        # PipelineStage leaves free, otherwise the sweep launch waits for the message (measured: 3-4 ms per step)
+        os.environ.setdefault("NCCL_MAX_P2P_NCHANNELS", "4")
         dist.init_process_group("nccl")     # lazy init: every stage pair gets its own p2p communicator / stream
     cfg, beam = deck_config(args.config)
     plasma, bm = make_inputs(cfg, beam)
@@ -340,6 +340,8 @@ def run_b200(args):
             if cpu: line["cpu_baseline"] = cpu
             print(json.dumps(line))
         if world > 1:
+            if os.environ.get("QPG_TRACE_EVENTS"):
+                print(f"rank {rank} step trace (ms): {runner.event_report()}", file=sys.stderr, flush=True)
             runner.unwind()
             sync_all()
         runner.close()

@@ -271,18 +271,27 @@ __global__ void __launch_bounds__(PT_BLOCK) k_qdeposit(PartView pv, double *__re
     qdep_body<M>(pv, acc1, idr, npp, i, lane, dep_tiles + (threadIdx.x >> 5) * DepTile<M>::doubles);
 }
 
+// particle planes of one warp-tile in registers, so a tile loop can fetch the next tile while it works on the current one
+struct PartRegs { double x1, x2, p1, p2, p3, q; };
+__device__ __forceinline__ PartRegs part_load(const PartView &pv, int i, int npp)
+{
+    PartRegs r{1.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    if (i < npp) { r.x1 = pv.x1[i]; r.x2 = pv.x2[i]; r.p1 = pv.p1[i]; r.p2 = pv.p2[i]; r.p3 = pv.p3[i]; r.q = pv.q[i]; }
+    return r;
+}
+
 // ---- amjdeposit_robust: species/part2d_class.f03:746-1010 ------------------------------------------------
 template <int M>
-__device__ __forceinline__ void amj_body(const PartView &pv, const double *ef, const double *bf, double *acc8, double qbm, double dt, double idr,
-                                         int npp, int i, int lane, double *tile)
+__device__ __forceinline__ void amj_core(const PartView &pv, const PartRegs &pr, const double *ef, const double *bf, double *acc8, double qbm, double dt,
+                                         double idr, int npp, int i, int lane, double *tile)
 {
     constexpr int P = 2 * M + 1;
     const bool valid = i < npp;
     double alpha[2 * P], beta[8];
     int key = -1;
     if (valid) {
-        const double x1 = pv.x1[i], x2 = pv.x2[i];
-        const double pp1 = pv.p1[i], pp2 = pv.p2[i], pp3 = pv.p3[i], q = pv.q[i];
+        const double x1 = pr.x1, x2 = pr.x2;
+        const double pp1 = pr.p1, pp2 = pr.p2, pp3 = pr.p3, q = pr.q;
         const Interp it = interp_info(x1, x2, idr);
         double ep[3], bp[3];
         gather3<M>(ef, it, ep);
@@ -338,6 +347,12 @@ __device__ __forceinline__ void amj_body(const PartView &pv, const double *ef, c
     warp_deposit_mma<M>(alpha, beta, key, acc8, tile, lane);
 }
 template <int M>
+__device__ __forceinline__ void amj_body(const PartView &pv, const double *ef, const double *bf, double *acc8, double qbm, double dt, double idr,
+                                         int npp, int i, int lane, double *tile)
+{
+    amj_core<M>(pv, part_load(pv, i, npp), ef, bf, acc8, qbm, dt, idr, npp, i, lane, tile);
+}
+template <int M>
 __global__ void __launch_bounds__(PT_BLOCK) k_amjdeposit(PartView pv, const double *__restrict__ ef, const double *__restrict__ bf,
                                                         double *__restrict__ acc8, double qbm, double dt, double idr,
                                                         const int *__restrict__ skip_flag)
@@ -355,15 +370,15 @@ __global__ void __launch_bounds__(PT_BLOCK) k_amjdeposit(PartView pv, const doub
 // acc1 != nullptr: additionally deposit the charge of the advanced, still in-bounds particle (the next slice's qdeposit
 // :346-349 fused into the push; out-of-bounds particles are removed by update_bound before the reference deposits)
 template <int M>
-__device__ __forceinline__ void push_body(const PartView &pv, const double *ef, const double *bf, double qbm, double dt, double idr, double edge,
-                                          int mode, unsigned *outmask, int *d_nout, double *acc1, int npp, int i, int lane, double *tile)
+__device__ __forceinline__ void push_core(const PartView &pv, const PartRegs &pr, const double *ef, const double *bf, double qbm, double dt, double idr,
+                                          double edge, int mode, unsigned *outmask, int *d_nout, double *acc1, int npp, int i, int lane, double *tile)
 {
     const bool valid = i < npp;
     bool out = false;
     double xn1 = 0.0, xn2 = 0.0, qv = 0.0;
     if (valid) {
-        double x1 = pv.x1[i], x2 = pv.x2[i];
-        double p1 = pv.p1[i], p2 = pv.p2[i], p3 = pv.p3[i], g;
+        double x1 = pr.x1, x2 = pr.x2;
+        double p1 = pr.p1, p2 = pr.p2, p3 = pr.p3, g;
         if (mode & 1) {
             const Interp it = interp_info(x1, x2, idr);
             double ep[3], bp[3];
@@ -414,13 +429,24 @@ __device__ __forceinline__ void push_body(const PartView &pv, const double *ef, 
         constexpr int P = 2 * M + 1;
         double alpha[2 * P];
         int key = -1;
-        if (valid && !out) { qv = pv.q[i]; qdep_alpha<M>(xn1, xn2, qv, idr, alpha, key); }
+        if (valid && !out) { qv = pr.q; qdep_alpha<M>(xn1, xn2, qv, idr, alpha, key); }
         else {
 #pragma unroll
             for (int k = 0; k < 2 * P; k++) alpha[k] = 0.0;
         }
         warp_deposit_q_mma<M>(alpha, key, acc1, tile, lane);
     }
+}
+template <int M>
+__device__ __forceinline__ void push_body(const PartView &pv, const double *ef, const double *bf, double qbm, double dt, double idr, double edge,
+                                          int mode, unsigned *outmask, int *d_nout, double *acc1, int npp, int i, int lane, double *tile)
+{
+    PartRegs pr{1.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    if (i < npp) {   // the position-only modes must not touch momenta they do not need
+        pr.x1 = pv.x1[i]; pr.x2 = pv.x2[i]; pr.p1 = pv.p1[i]; pr.p2 = pv.p2[i]; pr.p3 = pv.p3[i];
+        if (acc1) pr.q = pv.q[i];
+    }
+    push_core<M>(pv, pr, ef, bf, qbm, dt, idr, edge, mode, outmask, d_nout, acc1, npp, i, lane, tile);
 }
 template <int M>
 __global__ void __launch_bounds__(PT_BLOCK) k_push(PartView pv, const double *__restrict__ ef, const double *__restrict__ bf, double qbm,

@@ -595,8 +595,16 @@ __global__ void __launch_bounds__(SW_T, 1) k_sweep(const __grid_constant__ Sweep
         const int tile0 = b * per, tile1 = min(tile0 + per, ntiles);
         // ---- predictor-corrector loop -----------------------------------------------------------------------
         for (int it = 1; it <= f.iter_max; it++) {
-            for (int tl = tile0 + warp; tl < tile1; tl += SW_T / 32)
-                amj_body<M>(a.pv, f.e, f.b, f.acc8, a.qbm, f.dxi, idr, npp, tl * 32 + lane, lane, dep_tiles + warp * DepTile<M>::doubles);
+            {   // the next tile's particle planes are fetched while the current tile is worked on (the tile chain is
+                // latency-bound: one L2 round trip per tile saved)
+                PartRegs cur = part_load(a.pv, (tile0 + warp) * 32 + lane, tile0 + warp < tile1 ? npp : 0);
+                for (int tl = tile0 + warp; tl < tile1; tl += SW_T / 32) {
+                    const int tn = tl + SW_T / 32;
+                    const PartRegs nxt = part_load(a.pv, tn * 32 + lane, tn < tile1 ? npp : 0);
+                    amj_core<M>(a.pv, cur, f.e, f.b, f.acc8, a.qbm, f.dxi, idr, npp, tl * 32 + lane, lane, dep_tiles + warp * DepTile<M>::doubles);
+                    cur = nxt;
+                }
+            }
             if (timer) work[1] += clock64() - tprev;
             ok = grid_barrier(a.bar, gep, sm_i);
             if (timer) { const long long t = clock64(); prof[1] += t - tprev; tprev = t; namj++; }
@@ -616,8 +624,15 @@ __global__ void __launch_bounds__(SW_T, 1) k_sweep(const __grid_constant__ Sweep
             const int items = (f.nr + 2) * P, ipc = (items + G - 1) / G;
             for (int k = b * ipc + lane; k < min((b + 1) * ipc, items); k += 32) fused_D_item<M>(f, k, j);
         }
-        for (int tl = tile0 + warp; tl < tile1; tl += SW_T / 32)
-            push_body<M>(a.pv, f.e, f.b, a.qbm, f.dxi, idr, a.edge, 7, a.outmask, a.d_nout, f.acc1, npp, tl * 32 + lane, lane, dep_tiles + warp * DepTile<M>::doubles);
+        {
+            PartRegs cur = part_load(a.pv, (tile0 + warp) * 32 + lane, tile0 + warp < tile1 ? npp : 0);
+            for (int tl = tile0 + warp; tl < tile1; tl += SW_T / 32) {
+                const int tn = tl + SW_T / 32;
+                const PartRegs nxt = part_load(a.pv, tn * 32 + lane, tn < tile1 ? npp : 0);
+                push_core<M>(a.pv, cur, f.e, f.b, a.qbm, f.dxi, idr, a.edge, 7, a.outmask, a.d_nout, f.acc1, npp, tl * 32 + lane, lane, dep_tiles + warp * DepTile<M>::doubles);
+                cur = nxt;
+            }
+        }
         if (timer) work[3] += clock64() - tprev;
         ok = grid_barrier(a.bar, gep, sm_i);
         if (timer) { const long long t = clock64(); prof[3] += t - tprev; tprev = t; }

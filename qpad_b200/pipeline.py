@@ -176,16 +176,42 @@ class PipelineStage:
         self.comm = torch.cuda.Stream(device=device) if (stream is not None and make_buf is None) else None
         self.pending = {}
         self.pending_tail = False
+        self._ev_on = bool(os.environ.get("QPG_TRACE_EVENTS")) and stream is not None and make_buf is None
+        self._evs = []
+
+    # optional device-time trace of one stage's step (QPG_TRACE_EVENTS=1): CUDA events on the compute stream at the marks
+    def _mark(self, name):
+        if not self._ev_on:
+            return
+        ev = self.torch.cuda.Event(enable_timing=True)
+        ev.record(self.stream)
+        self._evs.append((name, ev))
+
+    def event_report(self):
+        """average device time between consecutive marks over the recorded steps (ms)"""
+        if not self._evs:
+            return {}
+        self.torch.cuda.synchronize()
+        acc, cnt = {}, {}
+        for (n0, e0), (n1, e1) in zip(self._evs[:-1], self._evs[1:]):
+            k = f"{n0}->{n1}"
+            acc[k] = acc.get(k, 0.0) + e0.elapsed_time(e1)
+            cnt[k] = cnt.get(k, 0) + 1
+        out = {k: round(acc[k] / cnt[k], 3) for k in acc}
+        return out
 
     # mpi_isend analogue: the transfer runs on the communication stream, the compute stream carries on.  The buffer
     # is only repacked after _wait(name) (the reference's mpi_wait before every pipe_send, simulation_class.f03:430).
-    def _isend(self, name, t, dst):
+    def _isend(self, name, t, dst, after=None):
         if self.comm is None:
             if self.stream is None:
                 self.sim.ctx.sync()
             self.pending[name] = self.dist.isend(t, dst)
             return
-        self.comm.wait_stream(self.stream)
+        if after is not None:
+            self.comm.wait_event(after)
+        else:
+            self.comm.wait_stream(self.stream)
         with self.torch.cuda.stream(self.comm):
             self.pending[name] = self.dist.isend(t, dst)
 
@@ -216,11 +242,13 @@ class PipelineStage:
         # species%precv, cu / b_spe pipe_recv and the beam q guard slice: everything stage r-1 hands forward arrives
         # when it has finished its slab (simulation_class.f03:303-340; the guard slice is taken at the same point so
         # that an upstream stage never waits for a downstream one)
+        self._mark("head")
         s.beam_qdp_begin()                                              # beam3d_class.f03:207
         fin = lambda k: self.fwd_in.data_ptr() + 8 * self.off_fwd[k]
         if not self.first:
             self._recv(self.fwd_in[:self.n_fwd], r - 1)
             s.field("beam_q").unpack(1, fin(0), add=True)
+        self._mark("recv_fwd")
         s.beam_qdp_end()                                                # :210
         s.begin_step()
         if not self.first:
@@ -228,17 +256,29 @@ class PipelineStage:
             s.field("cu").unpack(0, fin(1))
             s.field("b_spe").unpack(0, fin(2))
         # first slice, then the backward hand-off of e and b (:460-467), then the rest of the slab
+        self._mark("slice1")
         s.run_slices(1, 1)
+        self._mark("slice1_done")
+        ev = None
         if not self.first:
             self._wait("back")
             s.field("b").pack(1, self.back_out.data_ptr() + 8 * self.off_back[0])
             s.field("e").pack(1, self.back_out.data_ptr() + 8 * self.off_back[1])
-            self._isend("back", self.back_out, r - 1)
+            if self.comm is not None:
+                ev = self.torch.cuda.Event()
+                ev.record(self.stream)
+        # The rest of the slab is enqueued BEFORE the NCCL calls: posting a send / receive can block the host for
+        # milliseconds (measured 2.5 ms per step), which must not keep the sweep kernel from starting.  The
+        # communication stream waits for the pack kernels only (event), not for the sweep.
+        self._mark("sweep")
+        if self.nzp > 1:
+            s.run_slices(2, self.nzp)
+        self._mark("sweep_done")
+        if not self.first:
+            self._isend("back", self.back_out, r - 1, after=ev)
             # the beam particles stage r-1 pushes across the slab edge in THIS step arrive while the slab is swept:
             # post the receive now on the communication stream, consume it in tail() (part3d_comm.f03:278-314)
             self._irecv("beam_in", self.buf_beam_in, r - 1)
-        if self.nzp > 1:
-            s.run_slices(2, self.nzp)
         if not self.last:                                               # :210-215, :429-434, :472-474
             fout = lambda k: self.fwd_out.data_ptr() + 8 * self.off_fwd[k]
             self._wait("fwd")
@@ -251,19 +291,23 @@ class PipelineStage:
     def tail(self):
         s, r = self.sim, self.rank
         _trace(r, "tail")
+        self._mark("tail")
         if not self.last:
             self._isend("fwd", self.fwd_out[:self.n_fwd], r + 1)
             self._recv(self.back_in, r + 1)                              # :482-483
             s.field("b").unpack(self.nzp + 1, self.back_in.data_ptr() + 8 * self.off_back[0])
             s.field("e").unpack(self.nzp + 1, self.back_in.data_ptr() + 8 * self.off_back[1])
         # beam push + forward hand-off                                  (:489-493, part3d_comm.f03:278-314)
+        self._mark("beam_push")
         s.beam_push()
         if not self.first:
             self._wait("beam_in")
             s.beam.unpack(self.buf_beam_in.data_ptr())
         if not self.last:
             self._wait("beam"); s.beam.pack_forward(self.buf_beam.data_ptr()); self._isend("beam", self.buf_beam, r + 1)
+        self._mark("renew")
         s.renew()                                                       # :498-501
+        self._mark("step_end")
         self.pending_tail = False
 
     def step(self):

@@ -11,6 +11,8 @@ cfg, beam = bench.deck_config(sys.argv[3] if len(sys.argv) > 3 else "C2")
 plasma, bm = bench.make_inputs(cfg, beam)
 r = SingleStage(cfg, plasma, bm)
 s = r.sim
+if os.environ.get("QPG_SWEEP_CTAS"):
+    s.set_sweep_ctas(int(os.environ["QPG_SWEEP_CTAS"]))
 r.prepare_step()
 if j0 > 1:
     s.run_slices(1, j0 - 1)
