@@ -130,9 +130,12 @@ int qpg_part2d_snapshot(qpg_part2d p);
 int qpg_part2d_renew(qpg_part2d p);
 int qpg_part2d_qdeposit(qpg_part2d p, qpg_field q);                                              /* qdeposit_part2d :231 */
 int qpg_part2d_amjdeposit(qpg_part2d p, int push_type, qpg_field ef, qpg_field bf, qpg_field cu, qpg_field amu,
-                          qpg_field dcu, double dt);                                             /* amjdeposit_robust_part2d :746 */
-int qpg_part2d_push_u(qpg_part2d p, int push_type, qpg_field ef, qpg_field bf, double dt);       /* push_u_robust_part2d :1879 */
+                          qpg_field dcu, double dt);                  /* amjdeposit_robust_part2d :746 / amjdeposit_std_part2d :478 */
+int qpg_part2d_push_u(qpg_part2d p, int push_type, qpg_field ef, qpg_field bf, double dt);       /* push_u_robust_part2d :1879 / push_u_std_part2d :1790 */
 int qpg_part2d_push_x(qpg_part2d p, double dt);                                                  /* push_x_part2d :2221 */
+/* interp_psi_part2d :2264 (std pushers, simulation_class.f03:357-359), including the reference's quirk: `pp` is never
+ * advanced (:2298-2301), so only the first particle of each 1024-particle chunk is written, with the last one's value */
+int qpg_part2d_interp_psi(qpg_part2d p, qpg_field psi);
 int qpg_part2d_update_bound(qpg_part2d p);                                                       /* update_bound_part2d :2307 */
 int qpg_part2d_sort(qpg_part2d p);                                                               /* sort_part2d :2498 + sort_module.f03:11 */
 int qpg_part2d_sort_index(qpg_part2d p, int *host_ix, int *host_ip);                             /* generate_sort_idx_1d output (1-based), synchronises */
@@ -179,6 +182,8 @@ typedef struct {
     double beam_qbm;
     long beam_npmax;
     int use_graph;            /* capture the slice body in a CUDA graph */
+    int sp_push_std;          /* 0 = robust pusher (the decks' choice), 1 = std flavour (amjdeposit_std, push_u_std, interp_psi);
+                                 std runs on the per-slice launch paths, not in the persistent sweep kernel */
 } qpg_sim_params;
 
 int qpg_sim_create(qpg_sim *out, int device, void *cuda_stream, const qpg_sim_params *prm);

@@ -30,7 +30,7 @@ class Params(C.Structure):
                 ("iter_reltol", C.c_double), ("iter_abstol", C.c_double), ("relax_fac", C.c_double),
                 ("ppc1", C.c_int), ("ppc2", C.c_int), ("num_theta", C.c_int), ("sort_freq", C.c_int),
                 ("sp_q", C.c_double), ("sp_m", C.c_double), ("sp_density", C.c_double), ("sp_den_min", C.c_double),
-                ("beam_push_type", C.c_int), ("beam_evol", C.c_int), ("beam_qbm", C.c_double)]
+                ("beam_push_type", C.c_int), ("beam_evol", C.c_int), ("beam_qbm", C.c_double), ("sp_push_type", C.c_int)]
 
 
 def build(fast=False, force=False):
@@ -54,6 +54,9 @@ def lib(fast=False):
         "orc_qdeposit": (None, [_dp, _dp, l, d, i, i, _dp]),
         "orc_amjdeposit_robust": (None, [_dp, _dp, _dp, _dp, _dp, l, d, i, i, d, d, _dp, _dp, _dp, _dp, _dp]),
         "orc_push_u_robust": (None, [_dp, _dp, _dp, l, d, i, i, d, d, _dp, _dp]),
+        "orc_amjdeposit_std": (None, [_dp, _dp, _dp, _dp, _dp, l, d, i, i, d, d, _dp, _dp, _dp, _dp, _dp]),
+        "orc_push_u_std": (None, [_dp, _dp, _dp, _dp, l, d, i, i, d, d, _dp, _dp]),
+        "orc_interp_psi": (None, [_dp, _dp, l, d, i, i, _dp]),
         "orc_push_x": (None, [_dp, _dp, _dp, l, d]),
         "orc_update_bound": (l, [_dp, _dp, _dp, _dp, _dp, l, d]),
         "orc_sort_idx": (None, [_dp, l, d, i, _ip, _ip]),
@@ -120,7 +123,7 @@ class Sim:
         defaults = dict(nr=64, nz=32, max_mode=1, bnd=BND_OPEN, iter_max=1, nstages=1, rmax=5.0, zmin=-5.0, zmax=5.0,
                         dt=10.0, iter_reltol=1e-3, iter_abstol=1e-3, relax_fac=-1.0, ppc1=2, ppc2=2, num_theta=8,
                         sort_freq=0, sp_q=-1.0, sp_m=1.0, sp_density=1.0, sp_den_min=1e-10,
-                        beam_push_type=PUSH3_REDUCED, beam_evol=1, beam_qbm=-1.0)
+                        beam_push_type=PUSH3_REDUCED, beam_evol=1, beam_qbm=-1.0, sp_push_type=1)
         defaults.update(kw)
         for k, v in defaults.items():
             setattr(prm, k, v)

@@ -110,9 +110,11 @@ void orc_qdeposit(const double *x, const double *q, long npp, double dr, int nr,
 /* ------------------------------------------------------------------------- */
 /* species/part2d_class.f03:746-1010 amjdeposit_robust_part2d                */
 /* ------------------------------------------------------------------------- */
-void orc_amjdeposit_robust(const double *x, const double *p, const double *q, double *gamma, double *psi, long npp,
-                           double dr, int nr, int max_mode, double qbm, double dt, const double *ef, const double *bf,
-                           double *cu, double *dcu, double *amu)
+/* push_std != 0: amjdeposit_std_part2d (species/part2d_class.f03:478-744), which differs from the robust flavour only
+ * in the field normalisation (stored psi instead of gamma - u_z, :562-601) and leaves psi untouched */
+static void amjdeposit_impl(const double *x, const double *p, const double *q, double *gamma, double *psi, long npp,
+                            double dr, int nr, int max_mode, double qbm, double dt, const double *ef, const double *bf,
+                            double *cu, double *dcu, double *amu, int push_std)
 {
     double idt = 1.0 / dt;
     double qtmh = 0.5 * qbm * dt;
@@ -130,11 +132,19 @@ void orc_amjdeposit_robust(const double *x, const double *p, const double *q, do
         u0[1] = p[3 * pp + 1] * pcos - p[3 * pp] * psin;
         u0[2] = p[3 * pp + 2];
         double gam = sqrt(1.0 + u0[0] * u0[0] + u0[1] * u0[1] + u0[2] * u0[2]);
-        double qtmh1 = qtmh * gam / (gam - u0[2]);
-        for (int c = 0; c < 3; c++) { ep[c] = ep[c] * qtmh1; utmp[c] = u0[c] + ep[c]; }
-        gam = sqrt(1.0 + utmp[0] * utmp[0] + utmp[1] * utmp[1] + utmp[2] * utmp[2]);
-        double qtmh2 = qtmh / (gam - utmp[2]);
-        for (int c = 0; c < 3; c++) bp[c] = bp[c] * qtmh2;
+        double qtmh1, qtmh2;
+        if (push_std) {                                     /* :562-571 */
+            qtmh2 = qtmh / (1.0 - qbm * psi[pp]);
+            qtmh1 = qtmh2 * gam;
+            for (int c = 0; c < 3; c++) bp[c] = bp[c] * qtmh2;
+            for (int c = 0; c < 3; c++) utmp[c] = u0[c] + ep[c] * qtmh1;
+        } else {
+            qtmh1 = qtmh * gam / (gam - u0[2]);
+            for (int c = 0; c < 3; c++) { ep[c] = ep[c] * qtmh1; utmp[c] = u0[c] + ep[c]; }
+            gam = sqrt(1.0 + utmp[0] * utmp[0] + utmp[1] * utmp[1] + utmp[2] * utmp[2]);
+            qtmh2 = qtmh / (gam - utmp[2]);
+            for (int c = 0; c < 3; c++) bp[c] = bp[c] * qtmh2;
+        }
         u[0] = utmp[0] + utmp[1] * bp[2] - utmp[2] * bp[1];
         u[1] = utmp[1] + utmp[2] * bp[0] - utmp[0] * bp[2];
         u[2] = utmp[2] + utmp[0] * bp[1] - utmp[1] * bp[0];
@@ -143,15 +153,24 @@ void orc_amjdeposit_robust(const double *x, const double *p, const double *q, do
         utmp[0] = utmp[0] + u[1] * bp[2] - u[2] * bp[1];
         utmp[1] = utmp[1] + u[2] * bp[0] - u[0] * bp[2];
         utmp[2] = utmp[2] + u[0] * bp[1] - u[1] * bp[0];
-        for (int c = 0; c < 3; c++) u[c] = utmp[c] + ep[c];
+        if (push_std) {                                     /* :587-590 second half kick with the new gamma */
+            gam = sqrt(1.0 + utmp[0] * utmp[0] + utmp[1] * utmp[1] + utmp[2] * utmp[2]);
+            qtmh1 = qtmh2 * gam;
+            for (int c = 0; c < 3; c++) u[c] = utmp[c] + ep[c] * qtmh1;
+        } else
+            for (int c = 0; c < 3; c++) u[c] = utmp[c] + ep[c];
         /* :858-909 */
         double du[2], u2[3];
         du[0] = idt * (u[0] - u0[0]);
         du[1] = idt * (u[1] - u0[1]);
         for (int c = 0; c < 3; c++) u[c] = 0.5 * (u[c] + u0[c]);
         gamma[pp] = sqrt(1.0 + u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
-        double ipsi = 1.0 / (gamma[pp] - u[2]);
-        psi[pp] = (1.0 - 1.0 / ipsi) / qbm;
+        double ipsi;
+        if (push_std) ipsi = 1.0 / (1.0 - qbm * psi[pp]);   /* :607 */
+        else {
+            ipsi = 1.0 / (gamma[pp] - u[2]);
+            psi[pp] = (1.0 - 1.0 / ipsi) / qbm;
+        }
         double dpsi = qbm * (wp[2] - (wp[0] * u[0] + wp[1] * u[1]) * ipsi);
         du[0] = du[0] + u[0] * dpsi * ipsi;
         du[1] = du[1] + u[1] * dpsi * ipsi;
@@ -221,11 +240,55 @@ void orc_amjdeposit_robust(const double *x, const double *p, const double *q, do
         }
 }
 
+void orc_amjdeposit_robust(const double *x, const double *p, const double *q, double *gamma, double *psi, long npp,
+                           double dr, int nr, int max_mode, double qbm, double dt, const double *ef, const double *bf,
+                           double *cu, double *dcu, double *amu)
+{
+    amjdeposit_impl(x, p, q, gamma, psi, npp, dr, nr, max_mode, qbm, dt, ef, bf, cu, dcu, amu, 0);
+}
+/* species/part2d_class.f03:478-744 amjdeposit_std_part2d */
+void orc_amjdeposit_std(const double *x, const double *p, const double *q, double *gamma, double *psi, long npp,
+                        double dr, int nr, int max_mode, double qbm, double dt, const double *ef, const double *bf,
+                        double *cu, double *dcu, double *amu)
+{
+    amjdeposit_impl(x, p, q, gamma, psi, npp, dr, nr, max_mode, qbm, dt, ef, bf, cu, dcu, amu, 1);
+}
+
+/* species/part2d_class.f03:2264-2305 interp_psi_part2d + interp_part2d.f03:111-153 (scalar interp_field).
+ * Restated WITH the reference's quirk: `pp` is never advanced inside the chunk loop (:2298-2301), so only the first
+ * particle of every p_cache_size = 1024 chunk (param.f03:10) is written, and it receives the value interpolated for
+ * the LAST particle of its chunk. */
+void orc_interp_psi(const double *x, double *psi, long npp, double dr, int nr, int max_mode, const double *psif)
+{
+    const long chunk = 1024;
+    for (long ptrcur = 0; ptrcur < npp; ptrcur += chunk) {
+        long np = ptrcur + chunk > npp ? npp - ptrcur : chunk;
+        double last = 0.0;
+        for (long i = 0; i < np; i++) {
+            double w0, w1, pcos, psin;
+            int idx;
+            gen_interp_info(x, dr, ptrcur + i, &w0, &w1, &idx, &pcos, &psin);
+            double fp = 0.0;
+            cplx phase = {1.0, 0.0}, ph0 = {pcos, psin};
+            const double w[2] = {w0, w1};
+            for (int j = 0; j < 2; j++) fp = fp + F1(psif, 1, nr, 0, 1, idx + j) * w[j];
+            for (int m = 1; m <= max_mode; m++) {
+                phase = cmul(phase, ph0);
+                double phr = 2.0 * phase.re, phi = 2.0 * phase.im;
+                for (int j = 0; j < 2; j++)
+                    fp = fp + (F1(psif, 1, nr, pl_re(m), 1, idx + j) * phr - F1(psif, 1, nr, pl_im(m), 1, idx + j) * phi) * w[j];
+            }
+            last = fp;
+        }
+        psi[ptrcur] = last;
+    }
+}
+
 /* ------------------------------------------------------------------------- */
 /* species/part2d_class.f03:1879-1965 push_u_robust_part2d                   */
 /* ------------------------------------------------------------------------- */
-void orc_push_u_robust(const double *x, double *p, double *gamma, long npp, double dr, int nr, int max_mode,
-                       double qbm, double dt, const double *ef, const double *bf)
+static void push_u_impl(const double *x, double *p, double *gamma, const double *psi, long npp, double dr, int nr, int max_mode,
+                        double qbm, double dt, const double *ef, const double *bf, int push_std)
 {
     double qtmh = qbm * dt * 0.5;
     for (long pp = 0; pp < npp; pp++) {
@@ -238,9 +301,15 @@ void orc_push_u_robust(const double *x, double *p, double *gamma, long npp, doub
         tmp = ep[0] * pcos - ep[1] * psin; ep[1] = ep[0] * psin + ep[1] * pcos; ep[0] = tmp;
         tmp = bp[0] * pcos - bp[1] * psin; bp[1] = bp[0] * psin + bp[1] * pcos; bp[0] = tmp;
         double *pp3 = p + 3 * pp;
-        double gam = sqrt(1.0 + pp3[0] * pp3[0] + pp3[1] * pp3[1] + pp3[2] * pp3[2]);
-        double qtmh1 = qtmh / (gam - pp3[2]);
-        double qtmh2 = qtmh1 * gam;
+        double qtmh1, qtmh2;
+        if (push_std) {                                     /* push_u_std_part2d :1841-1844: stored psi and gamma */
+            qtmh1 = qtmh / (1.0 - qbm * psi[pp]);
+            qtmh2 = qtmh1 * gamma[pp];
+        } else {
+            double gam = sqrt(1.0 + pp3[0] * pp3[0] + pp3[1] * pp3[1] + pp3[2] * pp3[2]);
+            qtmh1 = qtmh / (gam - pp3[2]);
+            qtmh2 = qtmh1 * gam;
+        }
         for (int c = 0; c < 3; c++) { ep[c] = ep[c] * qtmh2; bp[c] = bp[c] * qtmh1; }
         for (int c = 0; c < 3; c++) utmp[c] = pp3[c] + ep[c];
         pp3[0] = utmp[0] + utmp[1] * bp[2] - utmp[2] * bp[1];
@@ -254,6 +323,17 @@ void orc_push_u_robust(const double *x, double *p, double *gamma, long npp, doub
         for (int c = 0; c < 3; c++) pp3[c] = utmp[c] + ep[c];
         gamma[pp] = sqrt(1.0 + pp3[0] * pp3[0] + pp3[1] * pp3[1] + pp3[2] * pp3[2]);
     }
+}
+void orc_push_u_robust(const double *x, double *p, double *gamma, long npp, double dr, int nr, int max_mode,
+                       double qbm, double dt, const double *ef, const double *bf)
+{
+    push_u_impl(x, p, gamma, NULL, npp, dr, nr, max_mode, qbm, dt, ef, bf, 0);
+}
+/* species/part2d_class.f03:1790-1877 push_u_std_part2d */
+void orc_push_u_std(const double *x, double *p, double *gamma, const double *psi, long npp, double dr, int nr, int max_mode,
+                    double qbm, double dt, const double *ef, const double *bf)
+{
+    push_u_impl(x, p, gamma, psi, npp, dr, nr, max_mode, qbm, dt, ef, bf, 1);
 }
 
 /* species/part2d_class.f03:2221-2262 push_x_part2d */
@@ -1271,6 +1351,7 @@ static void slice_step(orc_sim *s, int k, int j)
     fld_add1(&sp->q, &st->q_spe);
     fld_add1(&sp->qn, &st->q_spe);
     solve_psi_ops(s->op_psi, st->q_spe.f1, st->psi.f1, nr, M);                      /* :356 */
+    if (pr->sp_push_type == 0) orc_interp_psi(pt->x, pt->psi, pt->npp, dr, nr, M, st->psi.f1);   /* :357-359 std pushers only */
     solve_bz_ops(s->op_bz, st->cu.f1, st->b_spe.f1, nr, M, dr);                     /* :360 */
     for (int l = 1; l <= pr->iter_max; l++) {                                       /* :370 */
         conv_record(st, &st->b_spe, 2, M);                                          /* :373 */
@@ -1280,7 +1361,7 @@ static void slice_step(orc_sim *s, int k, int j)
         fld_zero1(&st->cu); fld_zero1(&st->acu); fld_zero1(&st->amu);               /* :378-380 */
         /* species2d_class.f03:233-280 amjdp */
         fld_zero1(&sp->cu); fld_zero1(&sp->dcu); fld_zero1(&sp->amu);
-        orc_amjdeposit_robust(pt->x, pt->p, pt->q, pt->gamma, pt->psi, pt->npp, dr, nr, M, sp->qbm, dxi, st->e.f1,
+        (pr->sp_push_type == 0 ? orc_amjdeposit_std : orc_amjdeposit_robust)(pt->x, pt->p, pt->q, pt->gamma, pt->psi, pt->npp, dr, nr, M, sp->qbm, dxi, st->e.f1,
                               st->b.f1, sp->cu.f1, sp->dcu.f1, sp->amu.f1);
         fld_add1(&sp->cu, &st->cu); fld_add1(&sp->dcu, &st->acu); fld_add1(&sp->amu, &st->amu);
         orc_solve_djdxi(st->acu.f1, st->amu.f1, st->dcu.f1, nr, M, dr);             /* :390 */
@@ -1305,7 +1386,8 @@ static void slice_step(orc_sim *s, int k, int j)
         memcpy(s->st[k + 1].mb_cu, st->cu.f1, sizeof(double) * fld_n1(&st->cu));
         memcpy(s->st[k + 1].mb_bspe, st->b_spe.f1, sizeof(double) * fld_n1(&st->b_spe));
     }
-    orc_push_u_robust(pt->x, pt->p, pt->gamma, pt->npp, dr, nr, M, sp->qbm, dxi, st->e.f1, st->b.f1); /* :438 */
+    if (pr->sp_push_type == 0) orc_push_u_std(pt->x, pt->p, pt->gamma, pt->psi, pt->npp, dr, nr, M, sp->qbm, dxi, st->e.f1, st->b.f1);
+    else orc_push_u_robust(pt->x, pt->p, pt->gamma, pt->npp, dr, nr, M, sp->qbm, dxi, st->e.f1, st->b.f1); /* :438 */
     orc_push_x(pt->x, pt->p, pt->gamma, pt->npp, dxi);                              /* :439, species2d_class.f03:311 */
     pt->npp = orc_update_bound(pt->x, pt->p, pt->gamma, pt->psi, pt->q, pt->npp, (double)nr * dr);
     if (pr->sort_freq > 0 && ((st->noff2 + j) % pr->sort_freq) == 0)               /* :440 (commented out upstream) */

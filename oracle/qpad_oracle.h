@@ -42,6 +42,13 @@ void orc_push_u_robust(const double *x, double *p, double *gamma, long npp, doub
                        double qbm, double dt, const double *ef, const double *bf);
 /* part2d_class.f03:2221 */
 void orc_push_x(double *x, const double *p, const double *gamma, long npp, double dt);
+/* std pusher flavour: species/part2d_class.f03:478 amjdeposit_std, :1790 push_u_std, :2264 interp_psi (with its quirk) */
+void orc_amjdeposit_std(const double *x, const double *p, const double *q, double *gamma, double *psi, long npp,
+                        double dr, int nr, int max_mode, double qbm, double dt, const double *ef, const double *bf,
+                        double *cu, double *dcu, double *amu);
+void orc_push_u_std(const double *x, double *p, double *gamma, const double *psi, long npp, double dr, int nr, int max_mode,
+                    double qbm, double dt, const double *ef, const double *bf);
+void orc_interp_psi(const double *x, double *psi, long npp, double dr, int nr, int max_mode, const double *psif);
 /* part2d_class.f03:2307 ; returns new npp */
 long orc_update_bound(double *x, double *p, double *gamma, double *psi, double *q, long npp, double edge);
 /* sort_module.f03:11 + part2d_class.f03:2498 ; ip is 1-based like the reference */
@@ -86,6 +93,7 @@ typedef struct {
     /* one beam */
     int beam_push_type, beam_evol;
     double beam_qbm;
+    int sp_push_type;   /* p_push2_std = 0, p_push2_robust = 1 (param.f03) */
 } orc_params;
 
 orc_sim *orc_sim_create(const orc_params *prm);

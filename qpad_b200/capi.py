@@ -30,7 +30,7 @@ class SimParams(C.Structure):
                 ("iter_abstol", C.c_double), ("relax_fac", C.c_double),
                 ("sp_qbm", C.c_double), ("sp_npmax", C.c_long),
                 ("beam_push_type", C.c_int), ("beam_evol", C.c_int), ("beam_qbm", C.c_double), ("beam_npmax", C.c_long),
-                ("use_graph", C.c_int)]
+                ("use_graph", C.c_int), ("sp_push_std", C.c_int)]
 
 
 _lib = None
@@ -91,6 +91,7 @@ SIGNATURES = {
     "qpg_part2d_amjdeposit": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _d]),
     "qpg_part2d_push_u": (_i, [_vp, _i, _vp, _vp, _d]),
     "qpg_part2d_push_x": (_i, [_vp, _d]),
+    "qpg_part2d_interp_psi": (_i, [_vp, _vp]),
     "qpg_part2d_update_bound": (_i, [_vp]),
     "qpg_part2d_sort": (_i, [_vp]),
     "qpg_part2d_sort_index": (_i, [_vp, _vp, _vp]),
@@ -317,7 +318,12 @@ class Part2d:
     def amjdeposit_robust(self, ef, bf, cu, amu, dcu, dt):
         _chk(self.L.qpg_part2d_amjdeposit(self.h, PUSH2_ROBUST, ef.h, bf.h, cu.h, amu.h, dcu.h, dt))
 
+    def amjdeposit_std(self, ef, bf, cu, amu, dcu, dt):
+        _chk(self.L.qpg_part2d_amjdeposit(self.h, PUSH2_STD, ef.h, bf.h, cu.h, amu.h, dcu.h, dt))
+
     def push_u_robust(self, ef, bf, dt): _chk(self.L.qpg_part2d_push_u(self.h, PUSH2_ROBUST, ef.h, bf.h, dt))
+    def push_u_std(self, ef, bf, dt): _chk(self.L.qpg_part2d_push_u(self.h, PUSH2_STD, ef.h, bf.h, dt))
+    def interp_psi(self, psi): _chk(self.L.qpg_part2d_interp_psi(self.h, psi.h))
     def push_x(self, dt): _chk(self.L.qpg_part2d_push_x(self.h, dt))
     def update_bound(self): _chk(self.L.qpg_part2d_update_bound(self.h))
     def sort(self): _chk(self.L.qpg_part2d_sort(self.h))
@@ -380,14 +386,14 @@ class Sim:
 
     def __init__(self, nr, nz, max_mode, rmax, zmin, zmax, dt, sp_qbm=-1.0, sp_npmax=0, beam_qbm=-1.0, beam_npmax=32,
                  beam_push_type=PUSH3_REDUCED, beam_evol=1, iter_max=1, iter_reltol=1e-3, iter_abstol=1e-3, relax_fac=-1.0,
-                 field_boundary=BND_OPEN, sort_freq=0, use_graph=0, noff2=0, nzp=None, device=0, stream=None):
+                 field_boundary=BND_OPEN, sort_freq=0, use_graph=0, noff2=0, nzp=None, device=0, stream=None, sp_push_std=0):
         self.L = load()
         nzp = nz if nzp is None else nzp
         prm = SimParams(nr=nr, nz_total=nz, noff2=noff2, nzp=nzp, max_mode=max_mode, field_boundary=field_boundary,
                         iter_max=iter_max, sort_freq=sort_freq, dr=rmax / nr, dxi=(zmax - zmin) / nz, dt=dt,
                         iter_reltol=iter_reltol, iter_abstol=iter_abstol, relax_fac=relax_fac, sp_qbm=sp_qbm,
                         sp_npmax=sp_npmax, beam_push_type=beam_push_type, beam_evol=beam_evol, beam_qbm=beam_qbm,
-                        beam_npmax=beam_npmax, use_graph=use_graph)
+                        beam_npmax=beam_npmax, use_graph=use_graph, sp_push_std=sp_push_std)
         self.prm = prm
         h = _vp()
         _chk(self.L.qpg_sim_create(C.byref(h), device, stream, C.byref(prm)))

@@ -281,7 +281,8 @@ __device__ __forceinline__ PartRegs part_load(const PartView &pv, int i, int npp
 }
 
 // ---- amjdeposit_robust: species/part2d_class.f03:746-1010 ------------------------------------------------
-template <int M>
+// STD = amjdeposit_std_part2d (:478-744): field normalisation from the stored psi (:562-601), psi left untouched
+template <int M, bool STD = false>
 __device__ __forceinline__ void amj_core(const PartView &pv, const PartRegs &pr, const double *ef, const double *bf, double *acc8, double qbm, double dt,
                                          double idr, int npp, int i, int lane, double *tile)
 {
@@ -300,12 +301,21 @@ __device__ __forceinline__ void amj_core(const PartView &pv, const PartRegs &pr,
         const double wp0 = ep[0] - bp[1], wp1 = ep[1] + bp[0], wp2 = ep[2];
         const double u00 = pp1 * it.c + pp2 * it.s, u01 = pp2 * it.c - pp1 * it.s, u02 = pp3;
         double gam = fast_sqrt(1.0 + u00 * u00 + u01 * u01 + u02 * u02);
-        const double qtmh1 = qtmh * gam * fast_rcp(gam - u02);
-        ep[0] *= qtmh1; ep[1] *= qtmh1; ep[2] *= qtmh1;
-        double ut0 = u00 + ep[0], ut1 = u01 + ep[1], ut2 = u02 + ep[2];
-        gam = fast_sqrt(1.0 + ut0 * ut0 + ut1 * ut1 + ut2 * ut2);
-        const double qtmh2 = qtmh * fast_rcp(gam - ut2);
-        bp[0] *= qtmh2; bp[1] *= qtmh2; bp[2] *= qtmh2;
+        double ut0, ut1, ut2, std_q2 = 0.0, std_ipsi = 0.0;
+        if constexpr (STD) {
+            std_ipsi = 1.0 / (1.0 - qbm * pv.psi[i]);
+            std_q2 = qtmh * std_ipsi;                               // qtmh2 = qtmh / (1 - qbm psi)
+            const double q1 = std_q2 * gam;
+            bp[0] *= std_q2; bp[1] *= std_q2; bp[2] *= std_q2;
+            ut0 = u00 + ep[0] * q1; ut1 = u01 + ep[1] * q1; ut2 = u02 + ep[2] * q1;
+        } else {
+            const double qtmh1 = qtmh * gam * fast_rcp(gam - u02);
+            ep[0] *= qtmh1; ep[1] *= qtmh1; ep[2] *= qtmh1;
+            ut0 = u00 + ep[0]; ut1 = u01 + ep[1]; ut2 = u02 + ep[2];
+            gam = fast_sqrt(1.0 + ut0 * ut0 + ut1 * ut1 + ut2 * ut2);
+            const double qtmh2 = qtmh * fast_rcp(gam - ut2);
+            bp[0] *= qtmh2; bp[1] *= qtmh2; bp[2] *= qtmh2;
+        }
         double u0 = ut0 + ut1 * bp[2] - ut2 * bp[1];
         double u1 = ut1 + ut2 * bp[0] - ut0 * bp[2];
         double u2 = ut2 + ut0 * bp[1] - ut1 * bp[0];
@@ -314,13 +324,21 @@ __device__ __forceinline__ void amj_core(const PartView &pv, const PartRegs &pr,
         ut0 = ut0 + u1 * bp[2] - u2 * bp[1];
         ut1 = ut1 + u2 * bp[0] - u0 * bp[2];
         ut2 = ut2 + u0 * bp[1] - u1 * bp[0];
-        u0 = ut0 + ep[0]; u1 = ut1 + ep[1]; u2 = ut2 + ep[2];
+        if constexpr (STD) {                                        // second half kick with the new gamma (:587-590)
+            const double q1 = std_q2 * fast_sqrt(1.0 + ut0 * ut0 + ut1 * ut1 + ut2 * ut2);
+            u0 = ut0 + ep[0] * q1; u1 = ut1 + ep[1] * q1; u2 = ut2 + ep[2] * q1;
+        } else { u0 = ut0 + ep[0]; u1 = ut1 + ep[1]; u2 = ut2 + ep[2]; }
         double du0 = idt * (u0 - u00), du1 = idt * (u1 - u01);
         u0 = 0.5 * (u0 + u00); u1 = 0.5 * (u1 + u01); u2 = 0.5 * (u2 + u02);
         const double g = fast_sqrt(1.0 + u0 * u0 + u1 * u1 + u2 * u2);
-        const double gmu = g - u2, ipsi = fast_rcp(gmu);
+        double ipsi;
         pv.gamma[i] = g;
-        pv.psi[i] = (1.0 - gmu) * rqbm;                      // (1 - 1/ipsi)/qbm  :864
+        if constexpr (STD) ipsi = std_ipsi;                         // :607
+        else {
+            const double gmu = g - u2;
+            ipsi = fast_rcp(gmu);
+            pv.psi[i] = (1.0 - gmu) * rqbm;                  // (1 - 1/ipsi)/qbm  :864
+        }
         const double dpsi = qbm * (wp2 - (wp0 * u0 + wp1 * u1) * ipsi);
         du0 = du0 + u0 * dpsi * ipsi;
         du1 = du1 + u1 * dpsi * ipsi;
@@ -346,13 +364,13 @@ __device__ __forceinline__ void amj_core(const PartView &pv, const PartRegs &pr,
     }
     warp_deposit_mma<M>(alpha, beta, key, acc8, tile, lane);
 }
-template <int M>
+template <int M, bool STD = false>
 __device__ __forceinline__ void amj_body(const PartView &pv, const double *ef, const double *bf, double *acc8, double qbm, double dt, double idr,
                                          int npp, int i, int lane, double *tile)
 {
-    amj_core<M>(pv, part_load(pv, i, npp), ef, bf, acc8, qbm, dt, idr, npp, i, lane, tile);
+    amj_core<M, STD>(pv, part_load(pv, i, npp), ef, bf, acc8, qbm, dt, idr, npp, i, lane, tile);
 }
-template <int M>
+template <int M, bool STD = false>
 __global__ void __launch_bounds__(PT_BLOCK) k_amjdeposit(PartView pv, const double *__restrict__ ef, const double *__restrict__ bf,
                                                         double *__restrict__ acc8, double qbm, double dt, double idr,
                                                         const int *__restrict__ skip_flag)
@@ -362,11 +380,11 @@ __global__ void __launch_bounds__(PT_BLOCK) k_amjdeposit(PartView pv, const doub
     const int i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
     if ((i & ~31) >= npp) return;
     extern __shared__ double dep_tiles[];
-    amj_body<M>(pv, ef, bf, acc8, qbm, dt, idr, npp, i, lane, dep_tiles + (threadIdx.x >> 5) * DepTile<M>::doubles);
+    amj_body<M, STD>(pv, ef, bf, acc8, qbm, dt, idr, npp, i, lane, dep_tiles + (threadIdx.x >> 5) * DepTile<M>::doubles);
 }
 
 // ---- push: push_u_robust :1879-1965, push_x :2221-2262, bound test of update_bound :2323-2348 --------------
-// mode bit0: push_u, bit1: push_x, bit2: flag particles with r >= edge in the bitmap
+// mode bit0: push_u, bit1: push_x, bit2: flag particles with r >= edge in the bitmap, bit3: push_u is the std flavour
 // acc1 != nullptr: additionally deposit the charge of the advanced, still in-bounds particle (the next slice's qdeposit
 // :346-349 fused into the push; out-of-bounds particles are removed by update_bound before the reference deposits)
 template <int M>
@@ -387,8 +405,15 @@ __device__ __forceinline__ void push_core(const PartView &pv, const PartRegs &pr
             double t = ep[0] * it.c - ep[1] * it.s; ep[1] = ep[0] * it.s + ep[1] * it.c; ep[0] = t;
             t = bp[0] * it.c - bp[1] * it.s; bp[1] = bp[0] * it.s + bp[1] * it.c; bp[0] = t;
             const double qtmh = qbm * dt * 0.5;
-            double gam = fast_sqrt(1.0 + p1 * p1 + p2 * p2 + p3 * p3);
-            const double qtmh1 = qtmh * fast_rcp(gam - p3), qtmh2 = qtmh1 * gam;
+            double qtmh1, qtmh2;
+            if (mode & 8) {                                         // push_u_std_part2d :1841-1844: stored psi and gamma
+                qtmh1 = qtmh / (1.0 - qbm * pv.psi[i]);
+                qtmh2 = qtmh1 * pv.gamma[i];
+            } else {
+                const double gam = fast_sqrt(1.0 + p1 * p1 + p2 * p2 + p3 * p3);
+                qtmh1 = qtmh * fast_rcp(gam - p3);
+                qtmh2 = qtmh1 * gam;
+            }
             ep[0] *= qtmh2; ep[1] *= qtmh2; ep[2] *= qtmh2;
             bp[0] *= qtmh1; bp[1] *= qtmh1; bp[2] *= qtmh1;
             double ut0 = p1 + ep[0], ut1 = p2 + ep[1], ut2 = p3 + ep[2];
@@ -457,6 +482,35 @@ __global__ void __launch_bounds__(PT_BLOCK) k_push(PartView pv, const double *__
     const int i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
     if ((i & ~31) >= npp) return;
     push_body<M>(pv, ef, bf, qbm, dt, idr, edge, mode, outmask, d_nout, nullptr, npp, i, lane, nullptr);
+}
+
+// ---- interp_psi: species/part2d_class.f03:2264-2305 + interp_part2d.f03:111-153 (std pushers only) ---------------
+// The reference never advances `pp` inside its chunk loop (:2298-2301): of every p_cache_size = 1024 chunk only the
+// FIRST particle's psi is written, with the value interpolated for the LAST particle of the chunk.  Reproduced as is
+// (one thread per chunk).
+template <int M>
+__global__ void k_interp_psi(PartView pv, const double *__restrict__ psif, double idr)
+{
+    constexpr int P = 2 * M + 1;
+    const int npp = *pv.d_npp;
+    const int chunk = blockIdx.x * blockDim.x + threadIdx.x;
+    const long first = (long)chunk * 1024;
+    if (first >= npp) return;
+    const int last = (int)min((long)npp, first + 1024) - 1;
+    const Interp it = interp_info(pv.x1[last], pv.x2[last], idr);
+    const double *n0 = psif + (size_t)it.idx * P, *n1 = n0 + P;
+    double v = n0[0] * it.w0;
+    v = fma(n1[0], it.w1, v);
+    double phr = 1.0, phi = 0.0;
+#pragma unroll
+    for (int m = 1; m <= M; m++) {
+        const double t = phr * it.c - phi * it.s;
+        phi = phr * it.s + phi * it.c;
+        phr = t;
+        v = fma(n0[2 * m - 1] * (2.0 * phr) - n0[2 * m] * (2.0 * phi), it.w0, v);
+        v = fma(n1[2 * m - 1] * (2.0 * phr) - n1[2 * m] * (2.0 * phi), it.w1, v);
+    }
+    pv.psi[first] = v;
 }
 
 // ---- compaction (update_bound_part2d :2307-2353 / pack_particles "fill the holes inversely") ---------------
@@ -805,13 +859,20 @@ template <int M> static void l_qdeposit(int grid, cudaStream_t st, PartView pv, 
     if (!attr_set) { cudaFuncSetAttribute(k_qdeposit<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
     k_qdeposit<M><<<grid, PT_BLOCK, smem, st>>>(pv, acc1, idr);
 }
-template <int M> static void l_amjdeposit(int grid, cudaStream_t st, PartView pv, const double *ef, const double *bf, double *acc8, double qbm, double dt, double idr, const int *skip)
+template <int M> static void l_amjdeposit(int grid, cudaStream_t st, PartView pv, const double *ef, const double *bf, double *acc8, double qbm, double dt, double idr, const int *skip, int std_flavour)
 {
     constexpr size_t smem = sizeof(double) * DepTile<M>::doubles * (PT_BLOCK / 32);
     static bool attr_set = false;   // > 48 KB of dynamic shared memory needs the opt-in (M >= 3)
-    if (!attr_set) { cudaFuncSetAttribute(k_amjdeposit<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
-    k_amjdeposit<M><<<grid, PT_BLOCK, smem, st>>>(pv, ef, bf, acc8, qbm, dt, idr, skip);
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_amjdeposit<M, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_amjdeposit<M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_set = true;
+    }
+    if (std_flavour) k_amjdeposit<M, true><<<grid, PT_BLOCK, smem, st>>>(pv, ef, bf, acc8, qbm, dt, idr, skip);
+    else k_amjdeposit<M, false><<<grid, PT_BLOCK, smem, st>>>(pv, ef, bf, acc8, qbm, dt, idr, skip);
 }
+template <int M> static void l_interp_psi(int grid, cudaStream_t st, PartView pv, const double *psif, double idr)
+{ k_interp_psi<M><<<grid, 128, 0, st>>>(pv, psif, idr); }
 template <int M> static void l_push(int grid, cudaStream_t st, PartView pv, const double *ef, const double *bf, double qbm, double dt, double idr, double edge, int mode, unsigned *outmask, int *d_nout)
 { k_push<M><<<grid, PT_BLOCK, 0, st>>>(pv, ef, bf, qbm, dt, idr, edge, mode, outmask, d_nout); }
 
@@ -827,14 +888,14 @@ int part2d_launch_qdeposit(qpg_part2d p)
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
-int part2d_launch_amjdeposit(qpg_part2d p, qpg_field ef, qpg_field bf, double dt, const int *skip_flag)
+int part2d_launch_amjdeposit(qpg_part2d p, qpg_field ef, qpg_field bf, double dt, const int *skip_flag, int std_flavour)
 {
     if (p->npp_hi == 0) return 0;
     qpg_ctx c = p->ctx;
     const int grid = (int)((p->npp_hi + PT_BLOCK - 1) / PT_BLOCK);
     PartView pv = view_of(p);
     TprofScope tp(c, TP_K_AMJ);
-    DISPATCH_M(c->M, l_amjdeposit, grid, c->stream, pv, ef->f1, bf->f1, p->acc8, p->qbm, dt, 1.0 / c->dr, skip_flag);
+    DISPATCH_M(c->M, l_amjdeposit, grid, c->stream, pv, ef->f1, bf->f1, p->acc8, p->qbm, dt, 1.0 / c->dr, skip_flag, std_flavour);
     count_launch(c);
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -882,8 +943,8 @@ extern "C" int qpg_part2d_amjdeposit(qpg_part2d p, int push_type, qpg_field ef, 
 {
     ARG_TRY(p && ef && bf && cu && amu && dcu, "null arg");
     ARG_TRY(ef->dim == 3 && bf->dim == 3 && cu->dim == 3 && amu->dim == 3 && dcu->dim == 2, "field dims must be e3 b3 cu3 amu3 dcu2");
-    if (push_type != QPG_PUSH2_ROBUST) { qpg_set_error("only push_type 'robust' is implemented (std/pgc pushers: SURVEY.md §8f)"); return QPG_ERR_UNSUPPORTED; }
-    int rc = part2d_launch_amjdeposit(p, ef, bf, dt, nullptr);
+    if (push_type != QPG_PUSH2_ROBUST && push_type != QPG_PUSH2_STD) { qpg_set_error("push_type must be std (0) or robust (1); the pgc flavours need the laser path (SURVEY.md §8f)"); return QPG_ERR_UNSUPPORTED; }
+    int rc = part2d_launch_amjdeposit(p, ef, bf, dt, nullptr, push_type == QPG_PUSH2_STD);
     if (rc) return rc;
     FProgBuilder pb(p->ctx);
     FOp &o = pb.add(FOP_AMJFIX); o.a = p->acc8; o.b = cu->f1; o.c = dcu->f1; o.d = amu->f1; o.da = 1;
@@ -892,8 +953,20 @@ extern "C" int qpg_part2d_amjdeposit(qpg_part2d p, int push_type, qpg_field ef, 
 extern "C" int qpg_part2d_push_u(qpg_part2d p, int push_type, qpg_field ef, qpg_field bf, double dt)
 {
     ARG_TRY(p && ef && bf && ef->dim == 3 && bf->dim == 3, "bad field handles");
-    if (push_type != QPG_PUSH2_ROBUST) { qpg_set_error("only push_type 'robust' is implemented"); return QPG_ERR_UNSUPPORTED; }
-    return part2d_launch_push(p, ef, bf, dt, 1);
+    if (push_type != QPG_PUSH2_ROBUST && push_type != QPG_PUSH2_STD) { qpg_set_error("push_type must be std (0) or robust (1)"); return QPG_ERR_UNSUPPORTED; }
+    return part2d_launch_push(p, ef, bf, dt, push_type == QPG_PUSH2_STD ? 1 | 8 : 1);
+}
+extern "C" int qpg_part2d_interp_psi(qpg_part2d p, qpg_field psi)
+{
+    ARG_TRY(p && psi && psi->dim == 1 && psi->ctx == p->ctx, "bad field handle");
+    if (p->npp_hi == 0) return 0;
+    qpg_ctx c = p->ctx;
+    const int nchunks = (int)((p->npp_hi + 1023) / 1024), grid = (nchunks + 127) / 128;
+    TprofScope tp(c, TP_PUSH2D);
+    DISPATCH_M(c->M, l_interp_psi, grid, c->stream, view_of(p), psi->f1, 1.0 / c->dr);
+    count_launch(c);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
 }
 extern "C" int qpg_part2d_push_x(qpg_part2d p, double dt)
 {

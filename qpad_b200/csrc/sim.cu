@@ -7,7 +7,7 @@
 #include "common.cuh"
 
 int part2d_launch_qdeposit(qpg_part2d p);
-int part2d_launch_amjdeposit(qpg_part2d p, qpg_field ef, qpg_field bf, double dt, const int *skip_flag);
+int part2d_launch_amjdeposit(qpg_part2d p, qpg_field ef, qpg_field bf, double dt, const int *skip_flag, int std_flavour);
 int part2d_launch_push(qpg_part2d p, qpg_field ef, qpg_field bf, double dt, int mode);
 int part2d_launch_compact(qpg_part2d p, int *slice_flags);
 
@@ -132,7 +132,7 @@ static int launch_fused(qpg_sim s, int which)
 
 static int enqueue_pc_iteration(qpg_sim s)
 {
-    int rc = part2d_launch_amjdeposit(s->spe, s->e, s->b, s->prm.dxi, s->ctx->flags);
+    int rc = part2d_launch_amjdeposit(s->spe, s->e, s->b, s->prm.dxi, s->ctx->flags, s->prm.sp_push_std != 0);
     if (rc) return rc;
     if (s->use_fused) return launch_fused(s, 1);
     FProgBuilder pb(s->ctx);
@@ -141,10 +141,14 @@ static int enqueue_pc_iteration(qpg_sim s)
 }
 static int enqueue_slice_head(qpg_sim s)
 {
-    if (s->use_fused) return launch_fused(s, 0);
-    FProgBuilder pb(s->ctx);
-    prog_A(s, pb);
-    return pb.launch(TP_FIELD_FUSED);
+    int rc;
+    if (s->use_fused) rc = launch_fused(s, 0);
+    else { FProgBuilder pb(s->ctx); prog_A(s, pb); rc = pb.launch(TP_FIELD_FUSED); }
+    if (rc) return rc;
+    // simulation_class.f03:357-359: the std pushers read psi at the particle positions (program A has just solved psi;
+    // nothing else in A depends on the particles' psi)
+    if (s->prm.sp_push_std) rc = qpg_part2d_interp_psi(s->spe, s->psi);
+    return rc;
 }
 static int enqueue_slice_tail(qpg_sim s)
 {
@@ -152,7 +156,7 @@ static int enqueue_slice_tail(qpg_sim s)
     if (s->use_fused) rc = launch_fused(s, 2);
     else { FProgBuilder pb(s->ctx); prog_D(s, pb); rc = pb.launch(TP_FIELD_FUSED); }
     if (rc) return rc;
-    rc = part2d_launch_push(s->spe, s->e, s->b, s->prm.dxi, 7);  // push_u + push_x + bound flags :438-439
+    rc = part2d_launch_push(s->spe, s->e, s->b, s->prm.dxi, s->prm.sp_push_std ? 7 | 8 : 7);  // push_u + push_x + bound flags :438-439
     if (rc) return rc;
     rc = part2d_launch_compact(s->spe, s->use_fused ? s->ctx->flags : nullptr);  // update_bound (+ slice counter)
     if (rc) return rc;
@@ -160,7 +164,7 @@ static int enqueue_slice_tail(qpg_sim s)
 }
 
 // ---- persistent slab sweep (sweep.cu) ---------------------------------------------------------------------
-static bool sweep_supported(const qpg_sim_params &prm) { return prm.max_mode <= 2 && (prm.nr + ST_N - 1) / ST_N <= SW_MAX_TEAM; }
+static bool sweep_supported(const qpg_sim_params &prm) { return prm.max_mode <= 2 && (prm.nr + ST_N - 1) / ST_N <= SW_MAX_TEAM && !prm.sp_push_std; }
 template <int M> static constexpr size_t sweep_smem() { return (sizeof(StripSmem<M>) + 7) / 8 * 8 + sizeof(double) * DepTile<M>::doubles * (SW_T / 32); }
 template <int M> static cudaError_t sweep_occupancy(int *blocks_per_sm)
 {
@@ -480,7 +484,7 @@ extern "C" int qpg_sim_set_graph(qpg_sim s, int use_graph) { ARG_TRY(s, "null si
 extern "C" int qpg_sim_set_sweep(qpg_sim s, int on)
 {
     ARG_TRY(s, "null sim");
-    if (on && !sweep_supported(s->prm)) { qpg_set_error("the persistent sweep kernel needs max_mode <= 2 and nr <= %d", SW_MAX_TEAM * ST_N); return QPG_ERR_UNSUPPORTED; }
+    if (on && !sweep_supported(s->prm)) { qpg_set_error("the persistent sweep kernel needs max_mode <= 2, nr <= %d and the robust pusher", SW_MAX_TEAM * ST_N); return QPG_ERR_UNSUPPORTED; }
     s->use_sweep = on != 0;
     return 0;
 }

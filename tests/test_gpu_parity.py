@@ -210,6 +210,81 @@ def test_particle_kernels_match_oracle(mods, nr, M):
     assert np.array_equal(gx, x_o[:npp_o]) and np.array_equal(gq, q_o[:npp_o]) and np.array_equal(gp, p_o[:npp_o])
 
 
+@pytest.mark.parametrize("nr,M", [(64, 1), (96, 2), (250, 0)])
+def test_std_pusher_kernels_match_oracle(mods, nr, M):
+    """amjdeposit_std :478, push_u_std :1790 and interp_psi :2264 (with the reference's chunk quirk) against the oracle"""
+    capi, O = mods
+    ctx, dr = _ctx(capi, nr, M)
+    L = O.lib()
+    P = 2 * M + 1
+    rng = np.random.default_rng(300 + nr + M)
+    x, p, g, psi, q = perturbed_lattice(O, rng, nr, dr, 2, 2, 8)
+    n = len(q)
+    psi = 0.2 * rng.standard_normal(n) - 0.1            # 1 - qbm*psi stays away from 0 for qbm = -1
+    part = capi.Part2d(ctx, -1.0, 2 * n)
+    part.upload(x, p, g, psi, q)
+    # interp_psi: only psi(first of each 1024-chunk) changes, to the value of the chunk's last particle
+    psif = smooth_field(rng, P, nr, 1, dr, 0.3)
+    fpsi = _mk(capi, ctx, 1, psif)
+    psi_o = psi.copy()
+    L.orc_interp_psi(x, psi_o, n, dr, nr, M, psif)
+    part.interp_psi(fpsi)
+    gpsi = part.download()[3]
+    changed = np.nonzero(psi_o != psi)[0]
+    assert len(changed) == (n + 1023) // 1024 and np.array_equal(changed, np.arange(0, n, 1024))
+    assert np.max(np.abs(gpsi - psi_o)) < 1e-13 * max(1.0, np.max(np.abs(psi_o)))
+    assert np.array_equal(np.delete(gpsi, changed), np.delete(psi, changed))
+    # amjdeposit_std: psi untouched, gamma time-centred
+    e, b = smooth_field(rng, P, nr, 3, dr, 0.3), smooth_field(rng, P, nr, 3, dr, 0.3)
+    fe, fb = _mk(capi, ctx, 3, e), _mk(capi, ctx, 3, b)
+    cu, dcu, amu = O.zeros_f1(3, nr, M), O.zeros_f1(2, nr, M), O.zeros_f1(3, nr, M)
+    g_o, psi_in = g.copy(), psi_o.copy()
+    dt = 0.02
+    L.orc_amjdeposit_std(x, p, q, g_o, psi_o, n, dr, nr, M, -1.0, dt, e, b, cu, dcu, amu)
+    assert np.array_equal(psi_o, psi_in)
+    fcu, fdcu, famu = _mk(capi, ctx, 3), _mk(capi, ctx, 2), _mk(capi, ctx, 3)
+    part.amjdeposit_std(fe, fb, fcu, famu, fdcu, dt)
+    for name, f, w in (("cu", fcu, cu), ("dcu", fdcu, dcu), ("amu", famu, amu)):
+        err = plane_relerr(f.download(), w)
+        assert err < 1e-11, (name, err)
+    _, _, gg, gpsi2, _ = part.download()
+    assert np.max(np.abs(gg - g_o)) < 1e-13 * np.max(np.abs(g_o)) and np.array_equal(gpsi2, gpsi)
+    # push_u_std uses the stored psi and gamma
+    p_o = p.copy()
+    L.orc_push_u_std(x, p_o, g_o, psi_o, n, dr, nr, M, -1.0, dt, e, b)
+    part.push_u_std(fe, fb, dt)
+    _, gp, gg, _, _ = part.download()
+    assert np.max(np.abs(gp - p_o)) < 1e-13 * np.max(np.abs(p_o)) and np.max(np.abs(gg - g_o)) < 1e-13 * np.max(g_o)
+
+
+@pytest.mark.parametrize("use_graph", [1, 0])
+def test_std_pusher_slice_loop(mods, use_graph):
+    """the whole slice loop with push_type std (interp_psi after the psi solve, simulation_class.f03:357-359)"""
+    capi, O = mods
+    from qpad_b200 import decks
+    cfg, beam = _deck(O, decks, M=1)
+    nsl = 12
+    orc = O.Sim(ppc1=2, ppc2=2, num_theta=8, sp_push_type=0, **cfg)
+    orc.set_beam(*beam)
+    orc_upd = orc.run_slices(nsl)
+    x, p, g, psi, q = O.inject_uniform(cfg["nr"], cfg["rmax"] / cfg["nr"], 2, 2, 8)
+    sim = capi.Sim(sp_npmax=2 * len(q), beam_npmax=len(beam[2]) + 64, use_graph=use_graph, sp_push_std=1, **cfg)
+    with pytest.raises(capi.QpadError):
+        sim.set_sweep(1)                                   # the persistent kernel implements the robust pusher only
+    sim.init_species(x, p, g, psi, q)
+    sim.beam.upload(*beam)
+    sim.beam_qdp_begin(); sim.beam_qdp_end(); sim.begin_step()
+    sim.run_slices(1, nsl)
+    upd, iters, slices = sim.stats()
+    assert slices == nsl and upd == orc_upd and iters == orc.total_iters()
+    for name in ("psi", "e", "b", "cu"):
+        got, want = sim.field(name).download_f2()[:, :nsl], orc.field(name, 2)[:, :nsl]
+        assert np.max(np.abs(got - want)) < 1e-8 * np.max(np.abs(want)), name
+    gx, gp, gg, gpsi, gq = sim.species.download()
+    ox, op, og, opsi, oq = orc.plasma()
+    assert np.array_equal(gq, oq) and np.max(np.abs(gx - ox)) < 1e-8 and np.max(np.abs(gpsi - opsi)) < 1e-8
+
+
 def test_update_bound_heavy_loss(mods):
     capi, O = mods
     nr, M = 64, 1
@@ -363,10 +438,11 @@ def test_slice_loop_matches_oracle(mods, M, path):
     assert np.max(np.abs(gx - ox)) < 1e-8 and np.max(np.abs(gp - op)) < 1e-8
 
 
-@pytest.mark.parametrize("nr,M,ppc,nth", [(250, 1, 2, 8), (1024, 1, 2, 8), (300, 2, 2, 8), (1024, 0, 1, 8)])
+@pytest.mark.parametrize("nr,M,ppc,nth", [(250, 1, 2, 8), (1024, 1, 2, 8), (300, 2, 2, 8), (1024, 0, 1, 8), (65, 1, 2, 8), (33, 2, 2, 8), (24, 1, 2, 8)])
 def test_sweep_kernel_multi_cta_team(mods, nr, M, ppc, nth):
-    """the persistent sweep kernel with a field team of several CTAs (nr > 128): scan totals and residual maxima cross
-    CTAs through the global exchange records; whole-loop parity with the oracle incl. PC iteration counts"""
+    """the persistent sweep kernel with a field team of several CTAs (one 32-node strip each): scan totals cross CTAs as
+    flagged words, residual maxima through the exchange slab; whole-loop parity with the oracle incl. PC iteration
+    counts.  nr = 65 / 33 end in a one-node strip (no halo shortcut: second team barrier path), nr = 24 is one strip."""
     capi, O = mods
     from qpad_b200 import decks
     cfg, beam = _deck(O, decks, nr=nr, nz=40, M=M, iter_max=4)
