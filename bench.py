@@ -278,8 +278,14 @@ def run_b200(args):
                 ph[key] = {"us_per_phase": us, "cta0_work_us": prof["work_" + key] * nspc * 1e-3 / max(cnt, 1.0)}
                 if bpp:
                     ph[key]["GBs"] = bpp * (u_r / max(s_r, 1)) / (us * 1e-6) / 1e9
+            traffic, traffic_src = None, None
+            tpath = os.path.join(ROOT, "profiles", "r01_sweep_traffic.json")
+            if world == 1 and args.config == "C2" and os.path.exists(tpath):   # ncu capture of this very launch shape (committed)
+                tj = json.load(open(tpath))
+                traffic = float(tj["dram_bytes_read"] + tj["dram_bytes_write"])
+                traffic_src = "profiles/r01_sweep_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum of one 2048-slice launch; the particle planes stay in L2, the DRAM writes are the field-volume slice stores)"
             roof = {"bound": "hbm", "kernel": "k_sweep<%d> (persistent: all slices of a slab in one launch)" % cfg["max_mode"], "achieved": ach, "peak": peak, "unit": "GB/s",
-                    "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                    "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": bytes_total / max(sweep_n, 1), "peak_source": peak_src,
                     "bytes_per_update": 112.0 + 64.0 * nit, "updates_per_launch": u_r / max(sweep_n, 1), "avg_launch_ms": sweep_ms / max(sweep_n, 1),
                     "launches_timed": int(sweep_n), "us_per_slice": sweep_ms * 1e3 / max(s_r, 1),
                     "phases": {"A||update_bound": ph["A"], "amjdeposit (64 B/particle)": ph["amj"], "C": ph["C"], "push_u+push_x+qdeposit||D (112 B/particle)": ph["push"],
