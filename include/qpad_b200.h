@@ -42,7 +42,7 @@ typedef struct qpg_sim_s *qpg_sim;
 
 /* param.f03 constants mirrored 1:1 */
 enum { QPG_BND_ZERO = 2, QPG_BND_OPEN = 3 };                              /* p_bnd_* */
-enum { QPG_PUSH2_STD = 0, QPG_PUSH2_ROBUST = 1 };                         /* p_push2_* */
+enum { QPG_PUSH2_STD = 0, QPG_PUSH2_ROBUST = 1, QPG_PUSH2_STD_PGC = 4, QPG_PUSH2_ROBUST_PGC = 5 };   /* p_push2_* (param.f03:63-64) */
 enum { QPG_PUSH3_REDUCED = 1, QPG_PUSH3_BORIS = 2 };                      /* p_push3_* */
 enum { QPG_COPY_1TO2 = 0, QPG_COPY_2TO1 = 1 };                            /* ufield_class.f03 p_copy_* */
 enum { QPG_CONV_RECORD = 0, QPG_CONV_COMPARE = 1 };
@@ -132,6 +132,15 @@ int qpg_part2d_qdeposit(qpg_part2d p, qpg_field q);                             
 int qpg_part2d_amjdeposit(qpg_part2d p, int push_type, qpg_field ef, qpg_field bf, qpg_field cu, qpg_field amu,
                           qpg_field dcu, double dt);                  /* amjdeposit_robust_part2d :746 / amjdeposit_std_part2d :478 */
 int qpg_part2d_push_u(qpg_part2d p, int push_type, qpg_field ef, qpg_field bf, double dt);       /* push_u_robust_part2d :1879 / push_u_std_part2d :1790 */
+/* ponderomotive-guiding-centre flavours (push_type = QPG_PUSH2_STD_PGC | QPG_PUSH2_ROBUST_PGC).  The laser envelope
+ * arrives as four fields on the same grid: a_r, a_i (dim 1; field_laser get_cfr / get_cfi) and their gradients
+ * (dim 3, cylindrical components; field_laser ar_grad / ai_grad).  amjdeposit_std_pgc_part2d :1012,
+ * amjdeposit_robust_pgc_part2d :1310, push_u_robust_pgc_part2d :1967, push_u_std_pgc_part2d :2094.  The envelope
+ * solver itself (laser/field_laser_class.f03) is not part of this library. */
+int qpg_part2d_amjdeposit_pgc(qpg_part2d p, int push_type, qpg_field ef, qpg_field bf, qpg_field ar, qpg_field ai,
+                              qpg_field ar_grad, qpg_field ai_grad, qpg_field cu, qpg_field amu, qpg_field dcu, double dt);
+int qpg_part2d_push_u_pgc(qpg_part2d p, int push_type, qpg_field ef, qpg_field bf, qpg_field ar, qpg_field ai,
+                          qpg_field ar_grad, qpg_field ai_grad, double dt);
 int qpg_part2d_push_x(qpg_part2d p, double dt);                                                  /* push_x_part2d :2221 */
 /* interp_psi_part2d :2264 (std pushers, simulation_class.f03:357-359), including the reference's quirk: `pp` is never
  * advanced (:2298-2301), so only the first particle of each 1024-particle chunk is written, with the last one's value */

@@ -57,6 +57,8 @@ def lib(fast=False):
         "orc_amjdeposit_std": (None, [_dp, _dp, _dp, _dp, _dp, l, d, i, i, d, d, _dp, _dp, _dp, _dp, _dp]),
         "orc_push_u_std": (None, [_dp, _dp, _dp, _dp, l, d, i, i, d, d, _dp, _dp]),
         "orc_interp_psi": (None, [_dp, _dp, l, d, i, i, _dp]),
+        "orc_amjdeposit_pgc": (None, [_dp, _dp, _dp, _dp, _dp, l, d, i, i, d, d, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, i]),
+        "orc_push_u_pgc": (None, [_dp, _dp, _dp, _dp, l, d, i, i, d, d, _dp, _dp, _dp, _dp, _dp, _dp]),
         "orc_push_x": (None, [_dp, _dp, _dp, l, d]),
         "orc_update_bound": (l, [_dp, _dp, _dp, _dp, _dp, l, d]),
         "orc_sort_idx": (None, [_dp, l, d, i, _ip, _ip]),

@@ -62,6 +62,22 @@ static void interp_field3(const double *f, int nr, int max_mode, double w0, doub
     }
 }
 
+/* species/interp_part2d.f03:111-153 interp_field (scalar, dim 1) */
+static double interp_field1(const double *f, int nr, int max_mode, double w0, double w1, int idx, double pcos, double psin)
+{
+    double fp = 0.0;
+    cplx phase = {1.0, 0.0}, ph0 = {pcos, psin};
+    const double w[2] = {w0, w1};
+    for (int j = 0; j < 2; j++) fp = fp + F1(f, 1, nr, 0, 1, idx + j) * w[j];
+    for (int m = 1; m <= max_mode; m++) {
+        phase = cmul(phase, ph0);
+        double phr = 2.0 * phase.re, phi = 2.0 * phase.im;
+        for (int j = 0; j < 2; j++)
+            fp = fp + (F1(f, 1, nr, pl_re(m), 1, idx + j) * phr - F1(f, 1, nr, pl_im(m), 1, idx + j) * phi) * w[j];
+    }
+    return fp;
+}
+
 /* ------------------------------------------------------------------------- */
 /* species/part2d_class.f03:231-359 qdeposit_part2d                          */
 /* ------------------------------------------------------------------------- */
@@ -112,9 +128,46 @@ void orc_qdeposit(const double *x, const double *q, long npp, double dr, int nr,
 /* ------------------------------------------------------------------------- */
 /* push_std != 0: amjdeposit_std_part2d (species/part2d_class.f03:478-744), which differs from the robust flavour only
  * in the field normalisation (stored psi instead of gamma - u_z, :562-601) and leaves psi untouched */
+/* laser != NULL: the *_pgc flavours (amjdeposit_std_pgc :1012-1308, amjdeposit_robust_pgc :1310-1602): gamma carries
+ * the ponderomotive correction 0.5 qbm^2 |a|^2, E gets the ponderomotive force, and BOTH half kicks re-evaluate
+ * their normalisation.  laser[0..3] = a_r (dim 1), a_i (dim 1), grad a_r (dim 3, cylindrical), grad a_i (dim 3). */
+static void amjdeposit_pgc_one(double *u /*out*/, const double *u0, double *ep, double *bp, double gam_corr, double qtmh, double qbm, double psi_pp,
+                               const double apr, const double api, const double *agr, const double *agi, int push_std)
+{
+    double utmp[3];
+    double gam = sqrt(1.0 + u0[0] * u0[0] + u0[1] * u0[1] + u0[2] * u0[2] + gam_corr);
+    double tmp = 0.5 * qbm / gam;                                            /* :1420-1423 */
+    ep[0] = ep[0] - tmp * (apr * agr[0] + api * agi[0]);
+    ep[1] = ep[1] - tmp * (apr * agr[1] + api * agi[1]);
+    ep[2] = ep[2] + tmp * (apr * agr[2] + api * agi[2]);
+    double qtmh_e, qtmh_b;
+    if (push_std) {                                                          /* :1134-1139 */
+        qtmh_b = qtmh / (1.0 - qbm * psi_pp);
+        qtmh_e = qtmh_b * gam;
+        for (int c = 0; c < 3; c++) utmp[c] = u0[c] + ep[c] * qtmh_e;
+        for (int c = 0; c < 3; c++) bp[c] = bp[c] * qtmh_b;
+    } else {                                                                 /* :1426-1432 */
+        qtmh_e = qtmh * gam / (gam - u0[2]);
+        for (int c = 0; c < 3; c++) utmp[c] = u0[c] + ep[c] * qtmh_e;
+        gam = sqrt(1.0 + utmp[0] * utmp[0] + utmp[1] * utmp[1] + utmp[2] * utmp[2] + gam_corr);
+        qtmh_b = qtmh / (gam - utmp[2]);
+        for (int c = 0; c < 3; c++) bp[c] = bp[c] * qtmh_b;
+    }
+    u[0] = utmp[0] + utmp[1] * bp[2] - utmp[2] * bp[1];
+    u[1] = utmp[1] + utmp[2] * bp[0] - utmp[0] * bp[2];
+    u[2] = utmp[2] + utmp[0] * bp[1] - utmp[1] * bp[0];
+    double ostq = 2.0 / (1.0 + bp[0] * bp[0] + bp[1] * bp[1] + bp[2] * bp[2]);
+    for (int c = 0; c < 3; c++) bp[c] = bp[c] * ostq;
+    utmp[0] = utmp[0] + u[1] * bp[2] - u[2] * bp[1];
+    utmp[1] = utmp[1] + u[2] * bp[0] - u[0] * bp[2];
+    utmp[2] = utmp[2] + u[0] * bp[1] - u[1] * bp[0];
+    gam = sqrt(1.0 + utmp[0] * utmp[0] + utmp[1] * utmp[1] + utmp[2] * utmp[2] + gam_corr);
+    qtmh_e = push_std ? qtmh_b * gam : qtmh * gam / (gam - utmp[2]);         /* :1153-1155 / :1445-1447 */
+    for (int c = 0; c < 3; c++) u[c] = utmp[c] + ep[c] * qtmh_e;
+}
 static void amjdeposit_impl(const double *x, const double *p, const double *q, double *gamma, double *psi, long npp,
                             double dr, int nr, int max_mode, double qbm, double dt, const double *ef, const double *bf,
-                            double *cu, double *dcu, double *amu, int push_std)
+                            double *cu, double *dcu, double *amu, int push_std, const double *const *laser)
 {
     double idt = 1.0 / dt;
     double qtmh = 0.5 * qbm * dt;
@@ -131,6 +184,16 @@ static void amjdeposit_impl(const double *x, const double *p, const double *q, d
         u0[0] = p[3 * pp] * pcos + p[3 * pp + 1] * psin;
         u0[1] = p[3 * pp + 1] * pcos - p[3 * pp] * psin;
         u0[2] = p[3 * pp + 2];
+        double gam_corr = 0.0;
+        if (laser) {
+            double agr[3], agi[3];
+            const double apr = interp_field1(laser[0], nr, max_mode, w0, w1, ix, pcos, psin);
+            const double api = interp_field1(laser[1], nr, max_mode, w0, w1, ix, pcos, psin);
+            interp_field3(laser[2], nr, max_mode, w0, w1, ix, pcos, psin, agr);
+            interp_field3(laser[3], nr, max_mode, w0, w1, ix, pcos, psin, agi);
+            gam_corr = 0.5 * qbm * qbm * (apr * apr + api * api);                /* :1402 */
+            amjdeposit_pgc_one(u, u0, ep, bp, gam_corr, qtmh, qbm, psi[pp], apr, api, agr, agi, push_std);
+        } else {
         double gam = sqrt(1.0 + u0[0] * u0[0] + u0[1] * u0[1] + u0[2] * u0[2]);
         double qtmh1, qtmh2;
         if (push_std) {                                     /* :562-571 */
@@ -159,12 +222,13 @@ static void amjdeposit_impl(const double *x, const double *p, const double *q, d
             for (int c = 0; c < 3; c++) u[c] = utmp[c] + ep[c] * qtmh1;
         } else
             for (int c = 0; c < 3; c++) u[c] = utmp[c] + ep[c];
+        }
         /* :858-909 */
         double du[2], u2[3];
         du[0] = idt * (u[0] - u0[0]);
         du[1] = idt * (u[1] - u0[1]);
         for (int c = 0; c < 3; c++) u[c] = 0.5 * (u[c] + u0[c]);
-        gamma[pp] = sqrt(1.0 + u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+        gamma[pp] = sqrt(1.0 + u[0] * u[0] + u[1] * u[1] + u[2] * u[2] + gam_corr);
         double ipsi;
         if (push_std) ipsi = 1.0 / (1.0 - qbm * psi[pp]);   /* :607 */
         else {
@@ -244,14 +308,24 @@ void orc_amjdeposit_robust(const double *x, const double *p, const double *q, do
                            double dr, int nr, int max_mode, double qbm, double dt, const double *ef, const double *bf,
                            double *cu, double *dcu, double *amu)
 {
-    amjdeposit_impl(x, p, q, gamma, psi, npp, dr, nr, max_mode, qbm, dt, ef, bf, cu, dcu, amu, 0);
+    amjdeposit_impl(x, p, q, gamma, psi, npp, dr, nr, max_mode, qbm, dt, ef, bf, cu, dcu, amu, 0, NULL);
 }
 /* species/part2d_class.f03:478-744 amjdeposit_std_part2d */
 void orc_amjdeposit_std(const double *x, const double *p, const double *q, double *gamma, double *psi, long npp,
                         double dr, int nr, int max_mode, double qbm, double dt, const double *ef, const double *bf,
                         double *cu, double *dcu, double *amu)
 {
-    amjdeposit_impl(x, p, q, gamma, psi, npp, dr, nr, max_mode, qbm, dt, ef, bf, cu, dcu, amu, 1);
+    amjdeposit_impl(x, p, q, gamma, psi, npp, dr, nr, max_mode, qbm, dt, ef, bf, cu, dcu, amu, 1, NULL);
+}
+
+/* species/part2d_class.f03:1012-1308 amjdeposit_std_pgc_part2d (push_std = 1) / :1310-1602 amjdeposit_robust_pgc_part2d */
+void orc_amjdeposit_pgc(const double *x, const double *p, const double *q, double *gamma, double *psi, long npp,
+                        double dr, int nr, int max_mode, double qbm, double dt, const double *ef, const double *bf,
+                        const double *ar, const double *ai, const double *ar_grad, const double *ai_grad,
+                        double *cu, double *dcu, double *amu, int push_std)
+{
+    const double *laser[4] = {ar, ai, ar_grad, ai_grad};
+    amjdeposit_impl(x, p, q, gamma, psi, npp, dr, nr, max_mode, qbm, dt, ef, bf, cu, dcu, amu, push_std, laser);
 }
 
 /* species/part2d_class.f03:2264-2305 interp_psi_part2d + interp_part2d.f03:111-153 (scalar interp_field).
@@ -334,6 +408,53 @@ void orc_push_u_std(const double *x, double *p, double *gamma, const double *psi
                     double qbm, double dt, const double *ef, const double *bf)
 {
     push_u_impl(x, p, gamma, psi, npp, dr, nr, max_mode, qbm, dt, ef, bf, 1);
+}
+
+/* species/part2d_class.f03:1967-2092 push_u_robust_pgc_part2d (:2094-2219 push_u_std_pgc_part2d is the same
+ * arithmetic): stored, already time-centred gamma and psi; ponderomotive force on E; the new gamma includes the
+ * laser amplitude advanced by half a step (:2080-2083) */
+void orc_push_u_pgc(const double *x, double *p, double *gamma, const double *psi, long npp, double dr, int nr, int max_mode,
+                    double qbm, double dt, const double *ef, const double *bf, const double *ar, const double *ai,
+                    const double *ar_grad, const double *ai_grad)
+{
+    double qtmh = qbm * dt * 0.5, qbm2_hf = qbm * qbm * 0.5;
+    for (long pp = 0; pp < npp; pp++) {
+        double w0, w1, pcos, psin, ep[3], bp[3], agr[3], agi[3], utmp[3], tmp;
+        int idx;
+        gen_interp_info(x, dr, pp, &w0, &w1, &idx, &pcos, &psin);
+        interp_field3(ef, nr, max_mode, w0, w1, idx, pcos, psin, ep);
+        interp_field3(bf, nr, max_mode, w0, w1, idx, pcos, psin, bp);
+        const double apr = interp_field1(ar, nr, max_mode, w0, w1, idx, pcos, psin);
+        const double api = interp_field1(ai, nr, max_mode, w0, w1, idx, pcos, psin);
+        interp_field3(ar_grad, nr, max_mode, w0, w1, idx, pcos, psin, agr);
+        interp_field3(ai_grad, nr, max_mode, w0, w1, idx, pcos, psin, agi);
+        tmp = ep[0] * pcos - ep[1] * psin; ep[1] = ep[0] * psin + ep[1] * pcos; ep[0] = tmp;
+        tmp = bp[0] * pcos - bp[1] * psin; bp[1] = bp[0] * psin + bp[1] * pcos; bp[0] = tmp;
+        tmp = agr[0] * pcos - agr[1] * psin; agr[1] = agr[0] * psin + agr[1] * pcos; agr[0] = tmp;
+        tmp = agi[0] * pcos - agi[1] * psin; agi[1] = agi[0] * psin + agi[1] * pcos; agi[0] = tmp;
+        double *pp3 = p + 3 * pp;
+        double gam_corr = qbm2_hf * (apr * apr + api * api);
+        tmp = 0.5 * qbm / gamma[pp];
+        ep[0] = ep[0] - tmp * (apr * agr[0] + api * agi[0]);
+        ep[1] = ep[1] - tmp * (apr * agr[1] + api * agi[1]);
+        ep[2] = ep[2] + tmp * (apr * agr[2] + api * agi[2]);
+        double qtmh_b = qtmh / (1.0 - qbm * psi[pp]);
+        double qtmh_e = qtmh_b * gamma[pp];
+        for (int c = 0; c < 3; c++) { ep[c] = ep[c] * qtmh_e; utmp[c] = pp3[c] + ep[c]; }
+        for (int c = 0; c < 3; c++) bp[c] = bp[c] * qtmh_b;
+        pp3[0] = utmp[0] + utmp[1] * bp[2] - utmp[2] * bp[1];
+        pp3[1] = utmp[1] + utmp[2] * bp[0] - utmp[0] * bp[2];
+        pp3[2] = utmp[2] + utmp[0] * bp[1] - utmp[1] * bp[0];
+        double ostq = 2.0 / (1.0 + bp[0] * bp[0] + bp[1] * bp[1] + bp[2] * bp[2]);
+        for (int c = 0; c < 3; c++) bp[c] = bp[c] * ostq;
+        utmp[0] = utmp[0] + pp3[1] * bp[2] - pp3[2] * bp[1];
+        utmp[1] = utmp[1] + pp3[2] * bp[0] - pp3[0] * bp[2];
+        utmp[2] = utmp[2] + pp3[0] * bp[1] - pp3[1] * bp[0];
+        for (int c = 0; c < 3; c++) pp3[c] = utmp[c] + ep[c];
+        tmp = agr[2] * dt; gam_corr = gam_corr + qbm2_hf * (apr + 0.25 * tmp) * tmp;
+        tmp = agi[2] * dt; gam_corr = gam_corr + qbm2_hf * (api + 0.25 * tmp) * tmp;
+        gamma[pp] = sqrt(1.0 + pp3[0] * pp3[0] + pp3[1] * pp3[1] + pp3[2] * pp3[2] + gam_corr);
+    }
 }
 
 /* species/part2d_class.f03:2221-2262 push_x_part2d */

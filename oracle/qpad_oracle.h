@@ -49,6 +49,14 @@ void orc_amjdeposit_std(const double *x, const double *p, const double *q, doubl
 void orc_push_u_std(const double *x, double *p, double *gamma, const double *psi, long npp, double dr, int nr, int max_mode,
                     double qbm, double dt, const double *ef, const double *bf);
 void orc_interp_psi(const double *x, double *psi, long npp, double dr, int nr, int max_mode, const double *psif);
+/* ponderomotive-guiding-centre flavours: :1012 amjdeposit_std_pgc, :1310 amjdeposit_robust_pgc, :1967/:2094 push_u_*_pgc */
+void orc_amjdeposit_pgc(const double *x, const double *p, const double *q, double *gamma, double *psi, long npp,
+                        double dr, int nr, int max_mode, double qbm, double dt, const double *ef, const double *bf,
+                        const double *ar, const double *ai, const double *ar_grad, const double *ai_grad,
+                        double *cu, double *dcu, double *amu, int push_std);
+void orc_push_u_pgc(const double *x, double *p, double *gamma, const double *psi, long npp, double dr, int nr, int max_mode,
+                    double qbm, double dt, const double *ef, const double *bf, const double *ar, const double *ai,
+                    const double *ar_grad, const double *ai_grad);
 /* part2d_class.f03:2307 ; returns new npp */
 long orc_update_bound(double *x, double *p, double *gamma, double *psi, double *q, long npp, double edge);
 /* sort_module.f03:11 + part2d_class.f03:2498 ; ip is 1-based like the reference */

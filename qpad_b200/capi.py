@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libqpadb200.so")
 
 BND_ZERO, BND_OPEN = 2, 3
-PUSH2_STD, PUSH2_ROBUST = 0, 1
+PUSH2_STD, PUSH2_ROBUST, PUSH2_STD_PGC, PUSH2_ROBUST_PGC = 0, 1, 4, 5
 PUSH3_REDUCED, PUSH3_BORIS = 1, 2
 COPY_1TO2, COPY_2TO1 = 0, 1
 CONV_RECORD, CONV_COMPARE = 0, 1
@@ -90,6 +90,8 @@ SIGNATURES = {
     "qpg_part2d_qdeposit": (_i, [_vp, _vp]),
     "qpg_part2d_amjdeposit": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _d]),
     "qpg_part2d_push_u": (_i, [_vp, _i, _vp, _vp, _d]),
+    "qpg_part2d_amjdeposit_pgc": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _d]),
+    "qpg_part2d_push_u_pgc": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _d]),
     "qpg_part2d_push_x": (_i, [_vp, _d]),
     "qpg_part2d_interp_psi": (_i, [_vp, _vp]),
     "qpg_part2d_update_bound": (_i, [_vp]),
@@ -324,6 +326,13 @@ class Part2d:
     def push_u_robust(self, ef, bf, dt): _chk(self.L.qpg_part2d_push_u(self.h, PUSH2_ROBUST, ef.h, bf.h, dt))
     def push_u_std(self, ef, bf, dt): _chk(self.L.qpg_part2d_push_u(self.h, PUSH2_STD, ef.h, bf.h, dt))
     def interp_psi(self, psi): _chk(self.L.qpg_part2d_interp_psi(self.h, psi.h))
+
+    def amjdeposit_pgc(self, push_type, ef, bf, laser, cu, amu, dcu, dt):
+        """laser = (a_r, a_i, grad a_r, grad a_i) fields"""
+        _chk(self.L.qpg_part2d_amjdeposit_pgc(self.h, push_type, ef.h, bf.h, *(f.h for f in laser), cu.h, amu.h, dcu.h, dt))
+
+    def push_u_pgc(self, push_type, ef, bf, laser, dt):
+        _chk(self.L.qpg_part2d_push_u_pgc(self.h, push_type, ef.h, bf.h, *(f.h for f in laser), dt))
     def push_x(self, dt): _chk(self.L.qpg_part2d_push_x(self.h, dt))
     def update_bound(self): _chk(self.L.qpg_part2d_update_bound(self.h))
     def sort(self): _chk(self.L.qpg_part2d_sort(self.h))

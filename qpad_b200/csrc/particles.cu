@@ -484,6 +484,159 @@ __global__ void __launch_bounds__(PT_BLOCK) k_push(PartView pv, const double *__
     push_body<M>(pv, ef, bf, qbm, dt, idr, edge, mode, outmask, d_nout, nullptr, npp, i, lane, nullptr);
 }
 
+// ---- ponderomotive-guiding-centre flavours (laser envelope a = a_r + i a_i given on the grid) ---------------------
+// amjdeposit_std_pgc :1012-1308 (STD), amjdeposit_robust_pgc :1310-1602, push_u_robust_pgc :1967-2092 (= push_u_std_pgc
+// :2094-2219 arithmetically).  Same gather / deposit machinery as the plain flavours; plain IEEE division and sqrt.
+struct LaserView { const double *ar, *ai, *arg, *aig; };   // a_r, a_i: dim 1; grad a_r, grad a_i: dim 3 (cylindrical)
+
+template <int M>
+__device__ __forceinline__ double gather1(const double *f, const Interp &it)
+{
+    constexpr int P = 2 * M + 1;
+    const double *n0 = f + (size_t)it.idx * P, *n1 = n0 + P;
+    double v = n0[0] * it.w0;
+    v = fma(n1[0], it.w1, v);
+    double phr = 1.0, phi = 0.0;
+#pragma unroll
+    for (int m = 1; m <= M; m++) {
+        const double t = phr * it.c - phi * it.s;
+        phi = phr * it.s + phi * it.c;
+        phr = t;
+        v = fma(n0[2 * m - 1] * (2.0 * phr) - n0[2 * m] * (2.0 * phi), it.w0, v);
+        v = fma(n1[2 * m - 1] * (2.0 * phr) - n1[2 * m] * (2.0 * phi), it.w1, v);
+    }
+    return v;
+}
+
+template <int M, bool STD>
+__global__ void __launch_bounds__(PT_BLOCK) k_amjdeposit_pgc(PartView pv, const double *__restrict__ ef, const double *__restrict__ bf, LaserView lv,
+                                                            double *__restrict__ acc8, double qbm, double dt, double idr)
+{
+    constexpr int P = 2 * M + 1;
+    const int npp = *pv.d_npp;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
+    if ((i & ~31) >= npp) return;
+    extern __shared__ double dep_tiles[];
+    double alpha[2 * P], beta[8];
+    int key = -1;
+    if (i < npp) {
+        const Interp it = interp_info(pv.x1[i], pv.x2[i], idr);
+        double ep[3], bp[3], agr[3], agi[3];
+        gather3<M>(ef, it, ep);
+        gather3<M>(bf, it, bp);
+        const double apr = gather1<M>(lv.ar, it), api = gather1<M>(lv.ai, it);
+        gather3<M>(lv.arg, it, agr);
+        gather3<M>(lv.aig, it, agi);
+        const double idt = 1.0 / dt, qtmh = 0.5 * qbm * dt;
+        const double gam_corr = 0.5 * qbm * qbm * (apr * apr + api * api);                     // :1402
+        const double pp1 = pv.p1[i], pp2 = pv.p2[i];
+        const double u00 = pp1 * it.c + pp2 * it.s, u01 = pp2 * it.c - pp1 * it.s, u02 = pv.p3[i];
+        double gam = sqrt(1.0 + u00 * u00 + u01 * u01 + u02 * u02 + gam_corr);
+        const double wp0 = ep[0] - bp[1], wp1 = ep[1] + bp[0], wp2 = ep[2];
+        const double tmp = 0.5 * qbm / gam;                                                   // ponderomotive force :1420-1423
+        ep[0] -= tmp * (apr * agr[0] + api * agi[0]);
+        ep[1] -= tmp * (apr * agr[1] + api * agi[1]);
+        ep[2] += tmp * (apr * agr[2] + api * agi[2]);
+        double qe, qb, ut0, ut1, ut2;
+        if constexpr (STD) {
+            qb = qtmh / (1.0 - qbm * pv.psi[i]);
+            qe = qb * gam;
+            ut0 = u00 + ep[0] * qe; ut1 = u01 + ep[1] * qe; ut2 = u02 + ep[2] * qe;
+        } else {
+            qe = qtmh * gam / (gam - u02);
+            ut0 = u00 + ep[0] * qe; ut1 = u01 + ep[1] * qe; ut2 = u02 + ep[2] * qe;
+            gam = sqrt(1.0 + ut0 * ut0 + ut1 * ut1 + ut2 * ut2 + gam_corr);
+            qb = qtmh / (gam - ut2);
+        }
+        bp[0] *= qb; bp[1] *= qb; bp[2] *= qb;
+        double u0 = ut0 + ut1 * bp[2] - ut2 * bp[1];
+        double u1 = ut1 + ut2 * bp[0] - ut0 * bp[2];
+        double u2 = ut2 + ut0 * bp[1] - ut1 * bp[0];
+        const double ostq = 2.0 / (1.0 + bp[0] * bp[0] + bp[1] * bp[1] + bp[2] * bp[2]);
+        bp[0] *= ostq; bp[1] *= ostq; bp[2] *= ostq;
+        ut0 = ut0 + u1 * bp[2] - u2 * bp[1];
+        ut1 = ut1 + u2 * bp[0] - u0 * bp[2];
+        ut2 = ut2 + u0 * bp[1] - u1 * bp[0];
+        gam = sqrt(1.0 + ut0 * ut0 + ut1 * ut1 + ut2 * ut2 + gam_corr);
+        qe = STD ? qb * gam : qtmh * gam / (gam - ut2);                                        // second half kick re-normalised
+        u0 = ut0 + ep[0] * qe; u1 = ut1 + ep[1] * qe; u2 = ut2 + ep[2] * qe;
+        double du0 = idt * (u0 - u00), du1 = idt * (u1 - u01);
+        u0 = 0.5 * (u0 + u00); u1 = 0.5 * (u1 + u01); u2 = 0.5 * (u2 + u02);
+        const double g = sqrt(1.0 + u0 * u0 + u1 * u1 + u2 * u2 + gam_corr);
+        pv.gamma[i] = g;
+        double ipsi;
+        if constexpr (STD) ipsi = 1.0 / (1.0 - qbm * pv.psi[i]);
+        else { ipsi = 1.0 / (g - u2); pv.psi[i] = (1.0 - 1.0 / ipsi) / qbm; }
+        const double dpsi = qbm * (wp2 - (wp0 * u0 + wp1 * u1) * ipsi);
+        du0 = du0 + u0 * dpsi * ipsi;
+        du1 = du1 + u1 * dpsi * ipsi;
+        beta[0] = u0; beta[1] = u1; beta[2] = u2; beta[3] = du0; beta[4] = du1;
+        beta[5] = u0 * u0 * ipsi; beta[6] = u0 * u1 * ipsi; beta[7] = u1 * u1 * ipsi;
+        double phr = pv.q[i] * ipsi, phi = 0.0;
+        alpha[0] = it.w0 * phr; alpha[P] = it.w1 * phr;
+#pragma unroll
+        for (int m = 1; m <= M; m++) {
+            const double t = phr * it.c + phi * it.s;
+            phi = phi * it.c - phr * it.s;
+            phr = t;
+            alpha[2 * m - 1] = it.w0 * phr; alpha[2 * m] = it.w0 * phi;
+            alpha[P + 2 * m - 1] = it.w1 * phr; alpha[P + 2 * m] = it.w1 * phi;
+        }
+        key = it.idx;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 2 * P; k++) alpha[k] = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) beta[k] = 0.0;
+    }
+    warp_deposit_mma<M>(alpha, beta, key, acc8, dep_tiles + (threadIdx.x >> 5) * DepTile<M>::doubles, lane);
+}
+
+template <int M>
+__global__ void __launch_bounds__(PT_BLOCK) k_push_u_pgc(PartView pv, const double *__restrict__ ef, const double *__restrict__ bf, LaserView lv, double qbm,
+                                                        double dt, double idr)
+{
+    const int npp = *pv.d_npp;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npp) return;
+    const Interp it = interp_info(pv.x1[i], pv.x2[i], idr);
+    double ep[3], bp[3], agr[3], agi[3];
+    gather3<M>(ef, it, ep);
+    gather3<M>(bf, it, bp);
+    const double apr = gather1<M>(lv.ar, it), api = gather1<M>(lv.ai, it);
+    gather3<M>(lv.arg, it, agr);
+    gather3<M>(lv.aig, it, agi);
+    double t = ep[0] * it.c - ep[1] * it.s; ep[1] = ep[0] * it.s + ep[1] * it.c; ep[0] = t;       // transform_to_cartesian
+    t = bp[0] * it.c - bp[1] * it.s; bp[1] = bp[0] * it.s + bp[1] * it.c; bp[0] = t;
+    t = agr[0] * it.c - agr[1] * it.s; agr[1] = agr[0] * it.s + agr[1] * it.c; agr[0] = t;
+    t = agi[0] * it.c - agi[1] * it.s; agi[1] = agi[0] * it.s + agi[1] * it.c; agi[0] = t;
+    const double qtmh = qbm * dt * 0.5, qbm2_hf = qbm * qbm * 0.5;
+    double p1 = pv.p1[i], p2 = pv.p2[i], p3 = pv.p3[i];
+    const double g0 = pv.gamma[i];
+    double gam_corr = qbm2_hf * (apr * apr + api * api);
+    const double tmp = 0.5 * qbm / g0;
+    ep[0] -= tmp * (apr * agr[0] + api * agi[0]);
+    ep[1] -= tmp * (apr * agr[1] + api * agi[1]);
+    ep[2] += tmp * (apr * agr[2] + api * agi[2]);
+    const double qb = qtmh / (1.0 - qbm * pv.psi[i]), qe = qb * g0;
+    ep[0] *= qe; ep[1] *= qe; ep[2] *= qe;
+    double ut0 = p1 + ep[0], ut1 = p2 + ep[1], ut2 = p3 + ep[2];
+    bp[0] *= qb; bp[1] *= qb; bp[2] *= qb;
+    p1 = ut0 + ut1 * bp[2] - ut2 * bp[1];
+    p2 = ut1 + ut2 * bp[0] - ut0 * bp[2];
+    p3 = ut2 + ut0 * bp[1] - ut1 * bp[0];
+    const double ostq = 2.0 / (1.0 + bp[0] * bp[0] + bp[1] * bp[1] + bp[2] * bp[2]);
+    bp[0] *= ostq; bp[1] *= ostq; bp[2] *= ostq;
+    ut0 = ut0 + p2 * bp[2] - p3 * bp[1];
+    ut1 = ut1 + p3 * bp[0] - p1 * bp[2];
+    ut2 = ut2 + p1 * bp[1] - p2 * bp[0];
+    p1 = ut0 + ep[0]; p2 = ut1 + ep[1]; p3 = ut2 + ep[2];
+    double tt = agr[2] * dt; gam_corr = gam_corr + qbm2_hf * (apr + 0.25 * tt) * tt;                 // :2080-2082
+    tt = agi[2] * dt; gam_corr = gam_corr + qbm2_hf * (api + 0.25 * tt) * tt;
+    pv.p1[i] = p1; pv.p2[i] = p2; pv.p3[i] = p3;
+    pv.gamma[i] = sqrt(1.0 + p1 * p1 + p2 * p2 + p3 * p3 + gam_corr);
+}
+
 // ---- interp_psi: species/part2d_class.f03:2264-2305 + interp_part2d.f03:111-153 (std pushers only) ---------------
 // The reference never advances `pp` inside its chunk loop (:2298-2301): of every p_cache_size = 1024 chunk only the
 // FIRST particle's psi is written, with the value interpolated for the LAST particle of the chunk.  Reproduced as is
@@ -964,6 +1117,67 @@ extern "C" int qpg_part2d_interp_psi(qpg_part2d p, qpg_field psi)
     const int nchunks = (int)((p->npp_hi + 1023) / 1024), grid = (nchunks + 127) / 128;
     TprofScope tp(c, TP_PUSH2D);
     DISPATCH_M(c->M, l_interp_psi, grid, c->stream, view_of(p), psi->f1, 1.0 / c->dr);
+    count_launch(c);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+template <int M> static void l_amj_pgc(int grid, cudaStream_t st, PartView pv, const double *ef, const double *bf, LaserView lv, double *acc8, double qbm, double dt, double idr, int std_flavour)
+{
+    constexpr size_t smem = sizeof(double) * DepTile<M>::doubles * (PT_BLOCK / 32);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_amjdeposit_pgc<M, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_amjdeposit_pgc<M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_set = true;
+    }
+    if (std_flavour) k_amjdeposit_pgc<M, true><<<grid, PT_BLOCK, smem, st>>>(pv, ef, bf, lv, acc8, qbm, dt, idr);
+    else k_amjdeposit_pgc<M, false><<<grid, PT_BLOCK, smem, st>>>(pv, ef, bf, lv, acc8, qbm, dt, idr);
+}
+template <int M> static void l_push_pgc(int grid, cudaStream_t st, PartView pv, const double *ef, const double *bf, LaserView lv, double qbm, double dt, double idr)
+{ k_push_u_pgc<M><<<grid, PT_BLOCK, 0, st>>>(pv, ef, bf, lv, qbm, dt, idr); }
+
+static int laser_view(qpg_part2d p, qpg_field ar, qpg_field ai, qpg_field arg, qpg_field aig, LaserView *lv)
+{
+    ARG_TRY(ar && ai && arg && aig, "null laser field");
+    ARG_TRY(ar->dim == 1 && ai->dim == 1 && arg->dim == 3 && aig->dim == 3, "laser fields must be a_r(1) a_i(1) grad a_r(3) grad a_i(3)");
+    ARG_TRY(ar->ctx == p->ctx && ai->ctx == p->ctx && arg->ctx == p->ctx && aig->ctx == p->ctx, "laser fields belong to another context");
+    lv->ar = ar->f1; lv->ai = ai->f1; lv->arg = arg->f1; lv->aig = aig->f1;
+    return 0;
+}
+extern "C" int qpg_part2d_amjdeposit_pgc(qpg_part2d p, int push_type, qpg_field ef, qpg_field bf, qpg_field ar, qpg_field ai, qpg_field ar_grad,
+                                         qpg_field ai_grad, qpg_field cu, qpg_field amu, qpg_field dcu, double dt)
+{
+    ARG_TRY(p && ef && bf && cu && amu && dcu, "null arg");
+    ARG_TRY(ef->dim == 3 && bf->dim == 3 && cu->dim == 3 && amu->dim == 3 && dcu->dim == 2, "field dims must be e3 b3 cu3 amu3 dcu2");
+    ARG_TRY(push_type == QPG_PUSH2_STD_PGC || push_type == QPG_PUSH2_ROBUST_PGC, "push_type must be std_pgc (4) or robust_pgc (5)");
+    LaserView lv;
+    int rc = laser_view(p, ar, ai, ar_grad, ai_grad, &lv);
+    if (rc) return rc;
+    qpg_ctx c = p->ctx;
+    if (p->npp_hi > 0) {
+        const int grid = (int)((p->npp_hi + PT_BLOCK - 1) / PT_BLOCK);
+        TprofScope tp(c, TP_K_AMJ);
+        DISPATCH_M(c->M, l_amj_pgc, grid, c->stream, view_of(p), ef->f1, bf->f1, lv, p->acc8, p->qbm, dt, 1.0 / c->dr, push_type == QPG_PUSH2_STD_PGC);
+        count_launch(c);
+        CUDA_TRY(cudaGetLastError());
+    }
+    FProgBuilder pb(c);
+    FOp &o = pb.add(FOP_AMJFIX); o.a = p->acc8; o.b = cu->f1; o.c = dcu->f1; o.d = amu->f1; o.da = 1;
+    return pb.launch(TP_DEPOSIT2D);
+}
+extern "C" int qpg_part2d_push_u_pgc(qpg_part2d p, int push_type, qpg_field ef, qpg_field bf, qpg_field ar, qpg_field ai, qpg_field ar_grad,
+                                     qpg_field ai_grad, double dt)
+{
+    ARG_TRY(p && ef && bf && ef->dim == 3 && bf->dim == 3, "bad field handles");
+    ARG_TRY(push_type == QPG_PUSH2_STD_PGC || push_type == QPG_PUSH2_ROBUST_PGC, "push_type must be std_pgc (4) or robust_pgc (5)");
+    LaserView lv;
+    int rc = laser_view(p, ar, ai, ar_grad, ai_grad, &lv);
+    if (rc) return rc;
+    if (p->npp_hi == 0) return 0;
+    qpg_ctx c = p->ctx;
+    const int grid = (int)((p->npp_hi + PT_BLOCK - 1) / PT_BLOCK);
+    TprofScope tp(c, TP_K_PUSH);
+    DISPATCH_M(c->M, l_push_pgc, grid, c->stream, view_of(p), ef->f1, bf->f1, lv, p->qbm, dt, 1.0 / c->dr);
     count_launch(c);
     CUDA_TRY(cudaGetLastError());
     return 0;

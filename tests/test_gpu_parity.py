@@ -257,6 +257,47 @@ def test_std_pusher_kernels_match_oracle(mods, nr, M):
     assert np.max(np.abs(gp - p_o)) < 1e-13 * np.max(np.abs(p_o)) and np.max(np.abs(gg - g_o)) < 1e-13 * np.max(g_o)
 
 
+@pytest.mark.parametrize("nr,M,std", [(64, 0, 0), (64, 1, 0), (96, 2, 0), (64, 1, 1)])
+def test_pgc_pusher_kernels_match_oracle(mods, nr, M, std):
+    """amjdeposit_{robust,std}_pgc :1310/:1012 and push_u_*_pgc :1967/:2094 with a given laser envelope on the grid"""
+    capi, O = mods
+    ctx, dr = _ctx(capi, nr, M)
+    L = O.lib()
+    P = 2 * M + 1
+    rng = np.random.default_rng(500 + nr + M + std)
+    x, p, g, psi, q = perturbed_lattice(O, rng, nr, dr, 2, 2, 8)
+    n = len(q)
+    psi = 0.2 * rng.standard_normal(n) - 0.1
+    part = capi.Part2d(ctx, -1.0, 2 * n)
+    part.upload(x, p, g, psi, q)
+    e, b = smooth_field(rng, P, nr, 3, dr, 0.3), smooth_field(rng, P, nr, 3, dr, 0.3)
+    las = [smooth_field(rng, P, nr, 1, dr, 0.8), smooth_field(rng, P, nr, 1, dr, 0.8), smooth_field(rng, P, nr, 3, dr, 0.5), smooth_field(rng, P, nr, 3, dr, 0.5)]
+    fe, fb = _mk(capi, ctx, 3, e), _mk(capi, ctx, 3, b)
+    fl = [_mk(capi, ctx, a.shape[2], a) for a in las]
+    cu, dcu, amu = O.zeros_f1(3, nr, M), O.zeros_f1(2, nr, M), O.zeros_f1(3, nr, M)
+    g_o, psi_o = g.copy(), psi.copy()
+    dt = 0.02
+    L.orc_amjdeposit_pgc(x, p, q, g_o, psi_o, n, dr, nr, M, -1.0, dt, e, b, *las, cu, dcu, amu, std)
+    fcu, fdcu, famu = _mk(capi, ctx, 3), _mk(capi, ctx, 2), _mk(capi, ctx, 3)
+    ptype = capi.PUSH2_STD_PGC if std else capi.PUSH2_ROBUST_PGC
+    part.amjdeposit_pgc(ptype, fe, fb, fl, fcu, famu, fdcu, dt)
+    for name, f, w in (("cu", fcu, cu), ("dcu", fdcu, dcu), ("amu", famu, amu)):
+        err = plane_relerr(f.download(), w)
+        assert err < 1e-11, (name, err)
+    _, _, gg, gpsi, _ = part.download()
+    assert np.max(np.abs(gg - g_o)) < 1e-13 * np.max(np.abs(g_o))
+    assert np.max(np.abs(gpsi - psi_o)) < 1e-12 * max(1.0, np.max(np.abs(psi_o)))
+    if std:
+        assert np.array_equal(gpsi, psi)
+    p_o = p.copy()
+    L.orc_push_u_pgc(x, p_o, g_o, psi_o, n, dr, nr, M, -1.0, dt, e, b, *las)
+    part.push_u_pgc(ptype, fe, fb, fl, dt)
+    _, gp, gg, _, _ = part.download()
+    assert np.max(np.abs(gp - p_o)) < 1e-13 * np.max(np.abs(p_o)) and np.max(np.abs(gg - g_o)) < 1e-13 * np.max(g_o)
+    with pytest.raises(capi.QpadError):
+        part.push_u_pgc(capi.PUSH2_ROBUST, fe, fb, fl, dt)
+
+
 @pytest.mark.parametrize("use_graph", [1, 0])
 def test_std_pusher_slice_loop(mods, use_graph):
     """the whole slice loop with push_type std (interp_psi after the psi solve, simulation_class.f03:357-359)"""

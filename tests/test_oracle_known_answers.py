@@ -159,3 +159,28 @@ def test_pipeline_stages_match_single_stage():
     assert np.max(np.abs(parts - full)) <= 1e-11 * np.max(np.abs(full))
     assert sum(len(pip.beam(k)[2]) for k in range(3)) == len(ref.beam(0)[2])
     assert np.max(np.abs(full)) > 1e-3
+
+
+def test_std_pgc_without_laser_is_std():
+    """amjdeposit_std_pgc (part2d_class.f03:1012) with a vanishing envelope performs exactly the arithmetic of
+    amjdeposit_std (:478): both half kicks use qtmh/(1 - qbm psi) * gamma.  Pins the pgc restatement to the plain one."""
+    from util import perturbed_lattice, smooth_field
+    L = O.lib()
+    nr, M, dr = 48, 1, 5.0 / 48
+    rng = np.random.default_rng(7)
+    x, p, g, psi, q = perturbed_lattice(O, rng, nr, dr, 2, 2, 8)
+    n = len(q)
+    psi = 0.2 * rng.standard_normal(n) - 0.1
+    e, b = smooth_field(rng, 3, nr, 3, dr, 0.3), smooth_field(rng, 3, nr, 3, dr, 0.3)
+    z1, z3 = O.zeros_f1(1, nr, M), O.zeros_f1(3, nr, M)
+    out = []
+    for fn in ("std", "pgc"):
+        cu, dcu, amu = O.zeros_f1(3, nr, M), O.zeros_f1(2, nr, M), O.zeros_f1(3, nr, M)
+        g1, psi1 = g.copy(), psi.copy()
+        if fn == "std":
+            L.orc_amjdeposit_std(x, p, q, g1, psi1, n, dr, nr, M, -1.0, 0.02, e, b, cu, dcu, amu)
+        else:
+            L.orc_amjdeposit_pgc(x, p, q, g1, psi1, n, dr, nr, M, -1.0, 0.02, e, b, z1, z1, z3, z3, cu, dcu, amu, 1)
+        out.append((cu, dcu, amu, g1, psi1))
+    for a, c in zip(*out):
+        assert np.array_equal(a, c)
