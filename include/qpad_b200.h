@@ -146,6 +146,7 @@ int qpg_part2d_push_x(qpg_part2d p, double dt);                                 
  * advanced (:2298-2301), so only the first particle of each 1024-particle chunk is written, with the last one's value */
 int qpg_part2d_interp_psi(qpg_part2d p, qpg_field psi);
 int qpg_part2d_update_bound(qpg_part2d p);                                                       /* update_bound_part2d :2307 */
+int qpg_part2d_move(qpg_part2d p);   /* move_part2d_comm species/part2d_comm.f03:147: no radial decomposition on one GPU -> no-op */
 int qpg_part2d_sort(qpg_part2d p);                                                               /* sort_part2d :2498 + sort_module.f03:11 */
 int qpg_part2d_sort_index(qpg_part2d p, int *host_ix, int *host_ip);                             /* generate_sort_idx_1d output (1-based), synchronises */
 /* pipesend_part2d :2355 / piperecv_part2d :2405 : dev_buf[0] = count, then 8 doubles per particle

@@ -95,6 +95,7 @@ SIGNATURES = {
     "qpg_part2d_push_x": (_i, [_vp, _d]),
     "qpg_part2d_interp_psi": (_i, [_vp, _vp]),
     "qpg_part2d_update_bound": (_i, [_vp]),
+    "qpg_part2d_move": (_i, [_vp]),
     "qpg_part2d_sort": (_i, [_vp]),
     "qpg_part2d_sort_index": (_i, [_vp, _vp, _vp]),
     "qpg_part2d_pack": (_i, [_vp, _vp]),

@@ -1195,6 +1195,15 @@ extern "C" int qpg_part2d_update_bound(qpg_part2d p)
     return part2d_launch_compact(p, nullptr);
 }
 
+// species/part2d_comm.f03:147 move_part2d_comm: the radial relay between the ranks of one stage.  One GPU owns the whole
+// radial extent (nodes(1) = 1), so after update_bound there is nobody to hand particles to: kept as an entry point so
+// the species2d%push_x call sequence (push_x -> update_bound -> move) maps one to one.
+extern "C" int qpg_part2d_move(qpg_part2d p)
+{
+    ARG_TRY(p, "null arg");
+    return 0;
+}
+
 extern "C" long qpg_part2d_wire_count(qpg_part2d p) { return p ? 8 * p->npmax + 1 : -1; }
 extern "C" int qpg_part2d_pack(qpg_part2d p, double *dev_buf)
 {
