@@ -636,3 +636,58 @@ def test_wire_formats(mods):
     assert np.array_equal(keep, np.array(exp[:npp]))
     b1.unpack(hb.data_ptr())
     assert np.array_equal(np.sort(b1.download()[2]), np.sort(bq[go]))
+
+
+def test_full_size_properties_c2(mods):
+    """BASELINE.json configs[1] sizes (nr = 1024, 262 144 plasma particles per slice), checked through size-independent
+    properties instead of the (slow) oracle: charge conservation of the deposits, sortedness + permutation of the
+    counting sort, exact pack/unpack round trip, update counters and a quiet neutral plasma through the sweep kernel."""
+    import torch
+    capi, O = mods
+    from qpad_b200 import decks
+    cfg = {k: v for k, v in decks.CONFIGS["C2"].items() if k != "beam"}
+    nr, M, dr = cfg["nr"], cfg["max_mode"], cfg["rmax"] / cfg["nr"]
+    x, p, g, psi, q = decks.plasma_uniform(nr, cfg["rmax"], cfg["ppc1"], cfg["ppc2"], cfg["num_theta"])
+    n = len(q)
+    assert n == 262144
+    rng = np.random.default_rng(11)
+    xs = x + 0.3 * dr * rng.standard_normal(x.shape)                      # scrambled: particles change cells
+    ctx, _ = _ctx(capi, nr, M)
+    part = capi.Part2d(ctx, -1.0, 2 * n)
+    part.upload(xs, p, g, psi, q)
+    part.update_bound()                                                   # the scramble pushed a few particles past r_max
+    xs, p, g, psi, q = part.download()
+    n1 = len(q)
+    assert 0 < n - n1 < 2000
+    # (a) charge conservation: sum over nodes of (j-1) * rho_0(j) (the 1/(j-1) of the epilogue undone; node 1 carries a
+    #     factor 8) returns the deposited charge, whatever the particle order
+    fq = _mk(capi, ctx, 1); part.qdeposit(fq); rho = fq.download()[0, :, 0]
+    j = np.arange(nr + 2, dtype=float)
+    tot = np.sum(rho[2:] * (j[2:] - 1.0)) + rho[1] / 8.0
+    assert abs(tot - q.sum()) < 1e-10 * abs(q.sum())
+    # (b) counting sort: keys non-decreasing afterwards, the particle multiset is unchanged
+    key = lambda xx: np.floor(np.hypot(xx[:, 0], xx[:, 1]) / dr).astype(np.int64)
+    part.sort()
+    sx, sp, sg, spsi, sq = part.download()
+    assert np.all(np.diff(np.minimum(key(sx), nr - 1)) >= 0)
+    o0, o1 = np.lexsort((xs[:, 1], xs[:, 0])), np.lexsort((sx[:, 1], sx[:, 0]))
+    assert np.array_equal(xs[o0], sx[o1]) and np.array_equal(q[o0], sq[o1])
+    # (c) pipeline wire record: pack -> unpack into a second particle object is the identity
+    assert len(sq) == n1
+    wb = torch.zeros(part.wire_count(), dtype=torch.float64, device="cuda")
+    part.pack(wb.data_ptr())
+    other = capi.Part2d(ctx, -1.0, 2 * n)
+    other.unpack(wb.data_ptr())
+    assert all(np.array_equal(u, v) for u, v in zip(other.download(), (sx, sp, sg, spsi, sq)))
+    # (d) the sweep kernel at full size: a neutral plasma without beam stays quiet, every particle is updated every slice
+    sim = capi.Sim(sp_npmax=2 * n, beam_npmax=64, use_graph=1, **{k: cfg[k] for k in ("nr", "nz", "max_mode", "rmax", "zmin", "zmax", "dt", "iter_max", "iter_reltol", "iter_abstol")})
+    x, p, g, psi, q = decks.plasma_uniform(nr, cfg["rmax"], cfg["ppc1"], cfg["ppc2"], cfg["num_theta"])
+    sim.init_species(x, p, g, psi, q)
+    sim.beam_qdp_begin(); sim.beam_qdp_end(); sim.begin_step()
+    nsl = 16
+    sim.run_slices(1, nsl)
+    upd, iters, slices = sim.stats()
+    assert upd == nsl * n and slices == nsl and iters == nsl
+    for name in ("psi", "e", "b"):
+        assert np.max(np.abs(sim.field(name).download_f2()[:, :nsl])) < 1e-9, name
+    assert sim.species.npp() == n
