@@ -342,3 +342,163 @@ class PipelineStage:
     def close(self):
         self.drain()
         self.sim.close()
+
+
+class LocalPipeline:
+    """The xi-pipeline on ONE GPU: S stages = S persistent sweep kernels, each on its own stream with 1/S of the SMs.
+
+    Why: a slab sweep is a chain of latency-bound phases (field programs on a 32-CTA team, grid barriers) in which
+    most SMs idle about a third of the time, and its particle phases scale with the SM count only down to a point --
+    measured at C2: 148 CTAs 40 us/slice, 74 CTAs 55 us/slice, 37 CTAs 88 us/slice.  The quasi-static loop already has
+    the concurrency to fill that idle time: the reference's own pipeline over xi slabs (parallel_module.f03:221-239),
+    stage s working on 3D step n-s.  Here the stages are SM partitions of one B200 instead of MPI ranks; hand-offs are
+    pack / unpack through device buffers ordered by CUDA events (no NCCL, no copies through the host).
+
+    One `wave()` = every stage advances by one 3D step (tail of its previous step, then head of the next), i.e. one
+    full deck's worth of slices in steady state; the first S-1 waves fill the pipeline.
+    """
+
+    def __init__(self, cfg, plasma, beam, nstages, device=0, beam_wire_cap=None):
+        import torch
+        self.torch, self.cfg, self.S, self.plasma = torch, cfg, nstages, plasma
+        S = nstages
+        dxi = (cfg["zmax"] - cfg["zmin"]) / cfg["nz"]
+        parts = slab_partition(cfg["nz"], S)
+        beams = split_beam(*beam, cfg["nz"], dxi, S)
+        nsm = torch.cuda.get_device_properties(device).multi_processor_count
+        self.streams = [torch.cuda.Stream(device=device) for _ in range(S)]
+        self.sims = []
+        dev = torch.device("cuda", device)
+        for r in range(S):
+            noff2, nzp = parts[r]
+            sim = _make_sim(cfg, len(plasma[4]), len(beams[r][2]), self.streams[r], device, 1, noff2, nzp, beam_cap=len(beam[2]) + 1024)
+            sim.init_species(*plasma)
+            sim.beam.upload(*beams[r])
+            if S > 1:
+                sim.set_sweep_ctas(nsm // S)
+                sim.beam.set_wire_cap(beam_wire_cap if beam_wire_cap is not None else max(16384, len(beam[2]) // 64))
+            self.sims.append(sim)
+        s0 = self.sims[0]
+        nq, ncu, nbs = s0.field("beam_q").wire_count(), s0.field("cu").wire_count(), s0.field("b_spe").wire_count()
+        self.off_fwd = (0, nq, nq + ncu, nq + ncu + nbs)
+        nb = s0.field("b").wire_count()
+        mk = lambda n: torch.zeros(n, dtype=torch.float64, device=dev)
+        self.fwd = [mk(nq + ncu + nbs + s0.species.wire_count()) for _ in range(S)]      # written by stage r, read by r+1
+        self.back = [mk(nb + s0.field("e").wire_count()) for _ in range(S)]              # written by stage r, read by r-1
+        self.beamb = [mk(7 * s0.beam.wire_cap() + 1) for _ in range(S)]                  # written by stage r, read by r+1
+        self.off_back = (0, nb)
+        self.ev = {}
+        self.w = 0
+
+    # events: recorded on the producer's stream, waited on by the consumer's stream; host order = a valid schedule
+    def _rec(self, name, r):
+        e = self.ev.get((name, r))
+        if e is None:
+            e = self.ev[(name, r)] = self.torch.cuda.Event()
+        e.record(self.streams[self._cur])
+
+    def _wait(self, name, r):
+        e = self.ev.get((name, r))
+        if e is not None:
+            self.streams[self._cur].wait_event(e)
+
+    def _head(self, r, upload=None):
+        s, S = self.sims[r], self.S
+        self._cur = r
+        if upload is not None:
+            s.species.upload(*upload)                                   # the host re-injects the plasma (species%renew)
+        s.beam_qdp_begin()
+        if r > 0:
+            fin = lambda k: self.fwd[r - 1].data_ptr() + 8 * self.off_fwd[k]
+            self._wait("fwd_ready", r - 1)
+            s.field("beam_q").unpack(1, fin(0), add=True)
+        s.beam_qdp_end()
+        s.begin_step()
+        if r > 0:
+            s.species.unpack(fin(3))
+            s.field("cu").unpack(0, fin(1))
+            s.field("b_spe").unpack(0, fin(2))
+            self._rec("fwd_free", r - 1)
+        s.run_slices(1, 1)
+        if r > 0:
+            self._wait("back_free", r)
+            s.field("b").pack(1, self.back[r].data_ptr() + 8 * self.off_back[0])
+            s.field("e").pack(1, self.back[r].data_ptr() + 8 * self.off_back[1])
+            self._rec("back_ready", r)
+        if s.nzp > 1:
+            s.run_slices(2, s.nzp)
+        if r < S - 1:
+            fout = lambda k: self.fwd[r].data_ptr() + 8 * self.off_fwd[k]
+            self._wait("fwd_free", r)
+            s.field("beam_q").pack(s.nzp + 1, fout(0))
+            s.field("cu").pack(0, fout(1))
+            s.field("b_spe").pack(0, fout(2))
+            s.species.pack(fout(3))
+            self._rec("fwd_ready", r)
+
+    def _tail(self, r, renew=True):
+        s, S = self.sims[r], self.S
+        self._cur = r
+        if r < S - 1:
+            self._wait("back_ready", r + 1)
+            s.field("b").unpack(s.nzp + 1, self.back[r + 1].data_ptr() + 8 * self.off_back[0])
+            s.field("e").unpack(s.nzp + 1, self.back[r + 1].data_ptr() + 8 * self.off_back[1])
+            self._rec("back_free", r + 1)
+        s.beam_push()
+        if r > 0:
+            self._wait("beam_ready", r - 1)
+            s.beam.unpack(self.beamb[r - 1].data_ptr())
+            self._rec("beam_free", r - 1)
+        if r < S - 1:
+            self._wait("beam_free", r)
+            s.beam.pack_forward(self.beamb[r].data_ptr())
+            self._rec("beam_ready", r)
+        if renew:
+            s.renew()
+
+    def wave(self, upload=None):
+        """stage r: tail of step w-r-1, then head of step w-r.  Descending r: a stage's tail needs the first slice of
+        the downstream stage's head of the same step, which this order has just enqueued."""
+        w = self.w
+        for r in reversed(range(self.S)):
+            if w - r - 1 >= 0:
+                self._tail(r, renew=not (r == 0 and upload is not None))
+            if w - r >= 0:
+                self._head(r, upload if r == 0 else None)
+        self.w += 1
+
+    def fill(self):
+        while self.w < self.S - 1:
+            self.wave()
+
+    def drain(self):
+        """finish the steps in flight (every stage ends after the same 3D step)"""
+        last = self.w - 1            # newest step stage 0 has started
+        for w in range(self.w, self.w + self.S):
+            for r in reversed(range(self.S)):
+                n_tail, n_head = w - r - 1, w - r
+                if 0 <= n_tail <= last:
+                    self._tail(r)
+                if 0 <= n_head <= last:
+                    self._head(r)
+        self.w += self.S
+        self.sync()
+
+    def sync(self):
+        for st in self.streams:
+            st.synchronize()
+
+    def stats(self):
+        tot = [0, 0, 0]
+        for s in self.sims:
+            for k, v in enumerate(s.stats()):
+                tot[k] += v
+        return tuple(tot)
+
+    def launch_count(self):
+        return sum(s.ctx.launch_count() for s in self.sims)
+
+    def close(self):
+        self.sync()
+        for s in self.sims:
+            s.close()

@@ -691,3 +691,43 @@ def test_full_size_properties_c2(mods):
     for name in ("psi", "e", "b"):
         assert np.max(np.abs(sim.field(name).download_f2()[:, :nsl])) < 1e-9, name
     assert sim.species.npp() == n
+
+
+@pytest.mark.parametrize("S", [2, 3])
+def test_local_pipeline_matches_oracle(mods, S):
+    """the xi-pipeline on ONE GPU (S sweep kernels on S streams, SM-partitioned, event-ordered hand-offs) reproduces the
+    oracle's S-stage run: fields of every slab and the beam of every stage after the same number of 3D steps"""
+    capi, O = mods
+    from qpad_b200 import decks
+    from qpad_b200.pipeline import LocalPipeline
+    cfg = dict(nr=64, nz=32, max_mode=1, rmax=5.0, zmin=-5.0, zmax=5.0, dt=10.0, ppc1=2, ppc2=2, num_theta=8, iter_max=2,
+               iter_reltol=1e-3, iter_abstol=1e-3)
+    beam = dict(decks.CONFIGS["C1"]["beam"])
+    bm = decks.beam_std(cfg["nr"], cfg["nz"], cfg["rmax"], cfg["zmin"], cfg["zmax"], **beam)
+    plasma = decks.plasma_uniform(cfg["nr"], cfg["rmax"], cfg["ppc1"], cfg["ppc2"], cfg["num_theta"])
+    lp = LocalPipeline(cfg, plasma, bm, S)
+    nwaves = 4
+    for _ in range(nwaves):
+        lp.wave()
+    lp.drain()                                   # every stage has now finished 3D steps 0 .. nwaves-1
+    kw = {k: cfg[k] for k in ("nr", "nz", "max_mode", "rmax", "zmin", "zmax", "dt", "iter_max", "iter_reltol", "iter_abstol")}
+    orc = O.Sim(ppc1=2, ppc2=2, num_theta=8, nstages=S, **kw)
+    orc.set_beam(*bm)
+    for k in range(nwaves):
+        orc.step3d(k + 1)
+    upd, iters, slices = lp.stats()
+    assert slices == nwaves * cfg["nz"] and iters == orc.total_iters()
+    nb = 0
+    for r, sim in enumerate(lp.sims):
+        nzp = sim.nzp
+        for name in ("psi", "e", "b"):
+            got, want = sim.field(name).download_f2()[:, :nzp], orc.field(name, 2, stage=r)[:, :nzp]
+            assert np.max(np.abs(got - want)) < 1e-6 * np.max(np.abs(want)), (r, name)
+        gx, gp, gq = sim.beam.download()
+        ox, op, oq = orc.beam(stage=r)
+        assert len(gq) == len(oq) and np.array_equal(gq, oq)
+        if len(oq):
+            assert np.max(np.abs(gx - ox)) < 1e-9 * np.max(np.abs(ox))
+        nb += len(oq)
+    assert nb > 0
+    lp.close()
