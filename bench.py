@@ -356,36 +356,51 @@ def run_b200(args):
 
 
 def run_b200_local(args):
-    """one GPU, the xi-pipeline mapped onto SM partitions (pipeline.LocalPipeline): --stages S sweep kernels run
-    concurrently, stage s on 3D step n-s; a timed step = one wave = every stage sweeps its slab once = one deck's worth of
-    slices, measured in steady state (the pipeline is filled before the timed region, as in the multi-GPU runs)"""
+    """the xi-pipeline mapped onto SM partitions (pipeline.LocalPipeline): --stages S sweep kernels per GPU run
+    concurrently, global stage g on 3D step n-g; with N > 1 GPUs the stages continue across ranks over NCCL.  A timed
+    step = one wave = every stage sweeps its slab once = one deck's worth of slices, measured in steady state (the
+    pipeline is filled before the timed region)."""
     import torch
+    import torch.distributed as dist
     from qpad_b200.pipeline import LocalPipeline
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(0)
+    torch.cuda.set_device(local)
+    if world > 1:
+        # one NCCL kernel can be resident beside the cooperative sweep kernels (e.g. the receive of the crossing beam
+        # particles spins until the upstream stage has pushed its beam): its CTAs (one per channel) must fit in the SMs
+        # LocalPipeline leaves free, otherwise a sweep launch waits for the message
+        os.environ.setdefault("NCCL_MAX_P2P_NCHANNELS", "4")
+        dist.init_process_group("nccl")     # lazy init: every rank pair gets its own p2p communicator / stream
     cfg, beam = deck_config(args.config)
     plasma, bm = make_inputs(cfg, beam)
     npp0 = len(plasma[4])
     S = args.stages
-    lp = LocalPipeline(cfg, plasma, bm, S)
+    lp = LocalPipeline(cfg, plasma, bm, S, device=local, rank=rank, world=world, dist=dist if world > 1 else None)
     main = torch.cuda.current_stream()
 
+    def sync_all():
+        if world > 1:
+            dist.barrier(device_ids=[local])
+        torch.cuda.synchronize()
+
     def join():   # the timing stream waits for everything the stage streams have been given so far
-        for st in lp.streams:
+        for st in lp.streams + ([lp.comm] if lp.comm is not None else []):
             e = torch.cuda.Event(); e.record(st); main.wait_event(e)
 
     lp.fill()
     for _ in range(args.warmup):
         lp.wave()
-    torch.cuda.synchronize()
+    sync_all()
     u0, i0, s0 = lp.stats()
     l0 = lp.launch_count()
     for sim in lp.sims:
         sim.sweep_profile(reset=True); sim.ctx.tprof_reset(); sim.ctx.tprof_enable(True)
-    clk = ClockSampler(0); clk.start()
+    clk = ClockSampler(local); clk.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
+    sync_all()
     ev0.record(main)
     for st in lp.streams:
         st.wait_event(ev0)
@@ -393,7 +408,7 @@ def run_b200_local(args):
         lp.wave()
     join()
     ev1.record(main)
-    torch.cuda.synchronize()
+    sync_all()
     ms = ev0.elapsed_time(ev1)
     clocks = clk.stop()
     u1, i1, s1 = lp.stats()
@@ -406,63 +421,75 @@ def run_b200_local(args):
         sim.ctx.tprof_enable(False)
         profs.append(sim.sweep_profile())
     launches = lp.launch_count() - l0
+    if world > 1:
+        t = torch.tensor([ms, float(upd), float(launches), float(iters), float(slices)], dtype=torch.float64, device="cuda")
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms, upd, launches, iters, slices = tmax[0].item(), tsum[1].item(), tsum[2].item(), tsum[3].item(), tsum[4].item()
     value = upd / (ms * 1e-3)
 
-    # ---- end to end: the plasma lattice goes host -> device every step (stage 0), line-outs of every slab come back ----
-    torch.cuda.synchronize()
-    ue0 = lp.stats()[0]
-    t0 = time.perf_counter()
-    d2h = 0
-    for _ in range(args.steps):
-        lp.wave(upload=plasma)
+    # ---- end to end (N = 1): the plasma lattice goes host -> device every step (stage 0), line-outs of every slab come back
+    e2e = None
+    if world == 1:
+        torch.cuda.synchronize()
+        ue0 = lp.stats()[0]
+        t0 = time.perf_counter()
         d2h = 0
-        for sim in lp.sims:                       # each stage's slab of the E_z and psi on-axis line-outs (the step it has just swept)
-            ez = sim.field("e").lineout(3, 0, 1); ps = sim.field("psi").lineout(1, 0, 1)
-            d2h += 8 * (len(ez) + len(ps))
-        d2h += 24 * S
-        lp.stats()
-    torch.cuda.synchronize()
-    te = time.perf_counter() - t0
-    ue = lp.stats()[0] - ue0
-    e2e = {"value": ue / te, "unit": UNIT, "h2d_bytes_per_step": int(8 * 8 * npp0), "d2h_bytes_per_step": int(d2h),
-           "what": "per step (wave): plasma lattice host->device through qpg_part2d_upload into stage 0, every stage sweeps its slab, E_z and psi on-axis line-outs of every slab + counters device->host"}
+        for _ in range(args.steps):
+            lp.wave(upload=plasma)
+            d2h = 0
+            for sim in lp.sims:                       # each stage's slab of the E_z and psi on-axis line-outs (the step it has just swept)
+                ez = sim.field("e").lineout(3, 0, 1); ps = sim.field("psi").lineout(1, 0, 1)
+                d2h += 8 * (len(ez) + len(ps))
+            d2h += 24 * S
+            lp.stats()
+        torch.cuda.synchronize()
+        te = time.perf_counter() - t0
+        ue = lp.stats()[0] - ue0
+        e2e = {"value": ue / te, "unit": UNIT, "h2d_bytes_per_step": int(8 * 8 * npp0), "d2h_bytes_per_step": int(d2h),
+               "what": "per step (wave): plasma lattice host->device through qpg_part2d_upload into stage 0, every stage sweeps its slab, E_z and psi on-axis line-outs of every slab + counters device->host"}
 
     peak, peak_src = hbm_peak()
     nit = iters / max(slices, 1)
     bytes_total = upd * (112.0 + 64.0 * nit)
-    ach = bytes_total / (ms * 1e-3) / 1e9
+    ach = bytes_total / (ms * 1e-3) / 1e9 / world      # per GPU
     ph = {}
     for key, cntk in (("A", "slices"), ("amj", "amj_phases"), ("C", "amj_phases"), ("push", "slices")):
         us = [p["cyc_" + key] * (p["ns_total"] / max(p["cyc_total"], 1.0)) * 1e-3 / max(p[cntk], 1.0) for p in profs]
         ph[key] = {"us_per_phase_by_stage": [round(u, 2) for u in us]}
-    roof = {"bound": "hbm", "kernel": "k_sweep<%d> x %d concurrent (persistent; each on 1/%d of the SMs, one xi slab each)" % (cfg["max_mode"], S, S),
+    roof = {"bound": "hbm", "kernel": "k_sweep<%d> x %d concurrent per GPU (persistent; each on 1/%d of the SMs, one xi slab each)" % (cfg["max_mode"], S, S),
             "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
-            "bytes_per_update": 112.0 + 64.0 * nit, "algorithmic_bytes_timed": bytes_total, "launches_timed": int(sweep_n),
-            "avg_launch_ms": sweep_ms / max(sweep_n, 1), "us_per_slice_effective": ms * 1e3 / max(slices, 1),
-            "us_per_slice_per_stage": [round(p["ns_total"] * 1e-3 / max(p["slices"], 1.0), 2) for p in profs],
-            "phases": {"A||update_bound": ph["A"], "amjdeposit (64 B/particle)": ph["amj"], "C": ph["C"], "push_u+push_x+qdeposit||D (112 B/particle)": ph["push"]},
-            "note": "achieved = algorithmic bytes of ALL sweep launches in the timed region / its duration (the S kernels overlap: a stage's latency-bound field phases and barriers hide behind the other stages' particle phases); particle planes stay L2-resident"}
-    roof_hbm = None
+            "bytes_per_update": 112.0 + 64.0 * nit, "algorithmic_bytes_timed": bytes_total, "launches_timed_rank0": int(sweep_n),
+            "avg_launch_ms_rank0": sweep_ms / max(sweep_n, 1), "us_per_slice_effective": ms * 1e3 / max(slices, 1),
+            "us_per_slice_per_stage_rank0": [round(p["ns_total"] * 1e-3 / max(p["slices"], 1.0), 2) for p in profs],
+            "phases_rank0": {"A||update_bound": ph["A"], "amjdeposit (64 B/particle)": ph["amj"], "C": ph["C"], "push_u+push_x+qdeposit||D (112 B/particle)": ph["push"]},
+            "note": "achieved = algorithmic bytes of ALL sweep launches in the timed region / its duration, per GPU (the S kernels of a GPU overlap: a stage's latency-bound field phases and barriers hide behind the other stages' particle phases); particle planes stay L2-resident"}
     cpu = None
-    if not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu:
         try:
             upd_c, wall_c, k_c, tmax_c = cpu_parallel(args.config, args.ref_slices)
             cpu = {"value": upd_c / wall_c, "unit": UNIT, "cores": k_c, "kind": "port",
                    "sample": f"{k_c} concurrent stage processes (one per host core, the reference's MPI xi-pipeline in steady state) x the first {args.ref_slices} xi slices of the {args.config} step: {upd_c} updates in {wall_c:.1f} s; oracle restatement, -O3 -march=native"}
         except Exception as exc:
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {exc}"}
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic (lattice plasma per fdist2d rule, PCG64(10) tri-Gaussian beam on a 256x512 lattice)",
-            "config": {"workload": f"{args.config}: nr={cfg['nr']} nz={cfg['nz']} max_mode={cfg['max_mode']} Np/slice={npp0} iter_max={cfg['iter_max']}",
-                       "parallelism": f"one GPU, xi-pipeline over {S} SM partitions: stage s sweeps slab s of 3D step n-s (the reference's pipeline, parallel_module.f03:221-239, with SM partitions for ranks); filled before the timed region, a timed step = every stage sweeps its slab once = {cfg['nz']} slices",
-                       "l2": "step working set (field volumes ~0.9 GB + beam) exceeds the 126 MB L2",
-                       "pc_iters_per_slice": nit},
-            "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roof}
-    if cpu: line["cpu_baseline"] = cpu
-    print(json.dumps(line))
+    if rank == 0:
+        where = "one GPU" if world == 1 else f"{world} GPUs x {S} stages, NCCL send/recv between GPUs"
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic (lattice plasma per fdist2d rule, PCG64(10) tri-Gaussian beam on a 256x512 lattice)",
+                "config": {"workload": f"{args.config}: nr={cfg['nr']} nz={cfg['nz']} max_mode={cfg['max_mode']} Np/slice={npp0} iter_max={cfg['iter_max']}",
+                           "parallelism": f"{where}: xi-pipeline over {world * S} stages, each an SM partition running one persistent sweep kernel; stage g sweeps slab g of 3D step n-g (the reference's pipeline, parallel_module.f03:221-239); filled before the timed region, a timed step = every stage sweeps its slab once = {cfg['nz']} slices",
+                           "l2": "step working set (field volumes ~0.9 GB + beam) exceeds the 126 MB L2",
+                           "pc_iters_per_slice": nit},
+                "clocks": clocks, "gpu_launches": int(launches), "roofline": roof}
+        if e2e: line["e2e"] = e2e
+        if cpu: line["cpu_baseline"] = cpu
+        print(json.dumps(line))
     lp.drain()
+    sync_all()
     lp.close()
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def main():
@@ -477,6 +504,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-sweep", action="store_true", help="per-slice CUDA-graph launches instead of the persistent sweep kernel")
     ap.add_argument("--no-micro", action="store_true", help="skip the stream-from-HBM kernel microbenchmark")
+    ap.add_argument("--legacy-pipeline", action="store_true", help="N>1: one stage per GPU through pipeline.PipelineStage")
     ap.add_argument("--stages", type=int, default=0, help="xi-pipeline stages mapped onto SM partitions of ONE GPU (LocalPipeline); 0 = auto (up to 4), 1 = a single sweep kernel on all SMs")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -485,11 +513,13 @@ def main():
         if args.stages == 0:       # auto: as many stages as the field team (one CTA per 32 radial nodes) and the slab length allow, at most 4
             cfg, _ = deck_config(args.config)
             nteam, stages = (cfg["nr"] + 31) // 32, 1
+            world = int(os.environ.get("WORLD_SIZE", "1"))
             for cand in (2, 3, 4):
-                if 148 // cand > nteam + 1 and cfg["nz"] // cand >= 16 and cfg["max_mode"] <= 2:
+                if (148 - (4 if world > 1 else 0)) // cand > nteam + 1 and cfg["nz"] // (cand * world) >= 64 and cfg["max_mode"] <= 2:
                     stages = cand
             args.stages = stages
-        if int(os.environ.get("WORLD_SIZE", "1")) == 1 and args.stages > 1 and not args.no_sweep:
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        if not args.no_sweep and (args.stages > 1 or (world > 1 and not args.legacy_pipeline)):
             run_b200_local(args)
         else:
             run_b200(args)

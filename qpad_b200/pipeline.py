@@ -345,49 +345,63 @@ class PipelineStage:
 
 
 class LocalPipeline:
-    """The xi-pipeline on ONE GPU: S stages = S persistent sweep kernels, each on its own stream with 1/S of the SMs.
+    """The xi-pipeline over SM partitions: S stages = S persistent sweep kernels per GPU, each on its own stream with 1/S
+    of the SMs; with world > 1 the G = world*S stages continue across GPUs (NCCL between the last stage of rank k and
+    the first stage of rank k+1).
 
     Why: a slab sweep is a chain of latency-bound phases (field programs on a 32-CTA team, grid barriers) in which
     most SMs idle about a third of the time, and its particle phases scale with the SM count only down to a point --
     measured at C2: 148 CTAs 40 us/slice, 74 CTAs 55 us/slice, 37 CTAs 88 us/slice.  The quasi-static loop already has
     the concurrency to fill that idle time: the reference's own pipeline over xi slabs (parallel_module.f03:221-239),
-    stage s working on 3D step n-s.  Here the stages are SM partitions of one B200 instead of MPI ranks; hand-offs are
-    pack / unpack through device buffers ordered by CUDA events (no NCCL, no copies through the host).
+    stage s working on 3D step n-s.  Here the stages are SM partitions of a B200 instead of MPI ranks; hand-offs inside
+    a GPU are pack / unpack through device buffers ordered by CUDA events (no NCCL, no copies through the host).
 
     One `wave()` = every stage advances by one 3D step (tail of its previous step, then head of the next), i.e. one
-    full deck's worth of slices in steady state; the first S-1 waves fill the pipeline.
+    full deck's worth of slices in steady state; the first G-1 waves fill the pipeline.  All NCCL messages of a wave are
+    matched inside the same wave on both ranks, so nothing is pending between waves (barrier + synchronize are safe).
     """
 
-    def __init__(self, cfg, plasma, beam, nstages, device=0, beam_wire_cap=None):
+    def __init__(self, cfg, plasma, beam, nstages, device=0, beam_wire_cap=None, rank=0, world=1, dist=None):
         import torch
         self.torch, self.cfg, self.S, self.plasma = torch, cfg, nstages, plasma
-        S = nstages
+        self.rank, self.world, self.G, self.base = rank, world, world * nstages, rank * nstages
+        self.dist = dist
+        S, G = nstages, self.G
         dxi = (cfg["zmax"] - cfg["zmin"]) / cfg["nz"]
-        parts = slab_partition(cfg["nz"], S)
-        beams = split_beam(*beam, cfg["nz"], dxi, S)
+        parts = slab_partition(cfg["nz"], G)
+        beams = split_beam(*beam, cfg["nz"], dxi, G)
         nsm = torch.cuda.get_device_properties(device).multi_processor_count
+        free = int(os.environ.get("QPG_PIPELINE_FREE_SMS", "4")) if world > 1 else 0   # for the NCCL kernels beside the sweeps
         self.streams = [torch.cuda.Stream(device=device) for _ in range(S)]
+        self.comm = torch.cuda.Stream(device=device) if world > 1 else None
         self.sims = []
         dev = torch.device("cuda", device)
         for r in range(S):
-            noff2, nzp = parts[r]
-            sim = _make_sim(cfg, len(plasma[4]), len(beams[r][2]), self.streams[r], device, 1, noff2, nzp, beam_cap=len(beam[2]) + 1024)
+            noff2, nzp = parts[self.base + r]
+            mine = beams[self.base + r]
+            sim = _make_sim(cfg, len(plasma[4]), len(mine[2]), self.streams[r], device, 1, noff2, nzp, beam_cap=len(beam[2]) + 1024)
             sim.init_species(*plasma)
-            sim.beam.upload(*beams[r])
-            if S > 1:
-                sim.set_sweep_ctas(nsm // S)
+            sim.beam.upload(*mine)
+            if G > 1:
+                if S > 1 or world > 1:
+                    sim.set_sweep_ctas((nsm - free) // S)
                 sim.beam.set_wire_cap(beam_wire_cap if beam_wire_cap is not None else max(16384, len(beam[2]) // 64))
             self.sims.append(sim)
         s0 = self.sims[0]
         nq, ncu, nbs = s0.field("beam_q").wire_count(), s0.field("cu").wire_count(), s0.field("b_spe").wire_count()
         self.off_fwd = (0, nq, nq + ncu, nq + ncu + nbs)
+        self.n_fwd = nq + ncu + nbs + min(s0.species.wire_count(), 1 + 8 * len(plasma[4]))   # live prefix of the plasma record
         nb = s0.field("b").wire_count()
         mk = lambda n: torch.zeros(n, dtype=torch.float64, device=dev)
-        self.fwd = [mk(nq + ncu + nbs + s0.species.wire_count()) for _ in range(S)]      # written by stage r, read by r+1
-        self.back = [mk(nb + s0.field("e").wire_count()) for _ in range(S)]              # written by stage r, read by r-1
-        self.beamb = [mk(7 * s0.beam.wire_cap() + 1) for _ in range(S)]                  # written by stage r, read by r+1
+        nfw, nbk, nbm = nq + ncu + nbs + s0.species.wire_count(), nb + s0.field("e").wire_count(), 7 * s0.beam.wire_cap() + 1
+        self.fwd = [mk(nfw) for _ in range(S)]        # written by stage r, read by the next stage
+        self.back = [mk(nbk) for _ in range(S)]       # written by stage r, read by the previous stage
+        self.beamb = [mk(nbm) for _ in range(S)]      # written by stage r, read by the next stage
+        self.fwd_in = mk(nfw) if rank > 0 else None           # from the last stage of rank-1
+        self.beam_in = mk(nbm) if rank > 0 else None
+        self.back_in = mk(nbk) if rank < world - 1 else None  # from the first stage of rank+1
         self.off_back = (0, nb)
-        self.ev = {}
+        self.ev, self.pending = {}, {}
         self.w = 0
 
     # events: recorded on the producer's stream, waited on by the consumer's stream; host order = a valid schedule
@@ -396,40 +410,75 @@ class LocalPipeline:
         if e is None:
             e = self.ev[(name, r)] = self.torch.cuda.Event()
         e.record(self.streams[self._cur])
+        return e
 
     def _wait(self, name, r):
         e = self.ev.get((name, r))
         if e is not None:
             self.streams[self._cur].wait_event(e)
 
+    # NCCL links to the neighbouring ranks (torch.distributed orders an op after the CURRENT torch stream)
+    def _nccl_wait(self, name, r):
+        w = self.pending.pop(name, None)
+        if w is not None:
+            with self.torch.cuda.stream(self.streams[r]):
+                w.wait()
+
+    def _nccl_isend(self, name, t, dst, after):
+        self.comm.wait_event(after)
+        with self.torch.cuda.stream(self.comm):
+            self.pending[name] = self.dist.isend(t, dst)
+
     def _head(self, r, upload=None):
         s, S = self.sims[r], self.S
         self._cur = r
+        remote_up = r == 0 and self.rank > 0
+        remote_down = r == S - 1 and self.rank < self.world - 1
         if upload is not None:
             s.species.upload(*upload)                                   # the host re-injects the plasma (species%renew)
         s.beam_qdp_begin()
-        if r > 0:
-            fin = lambda k: self.fwd[r - 1].data_ptr() + 8 * self.off_fwd[k]
+        src = None
+        if remote_up:
+            with self.torch.cuda.stream(self.streams[r]):
+                self.dist.recv(self.fwd_in[:self.n_fwd], self.rank - 1)
+            src = self.fwd_in
+        elif r > 0:
             self._wait("fwd_ready", r - 1)
+            src = self.fwd[r - 1]
+        if src is not None:
+            fin = lambda k: src.data_ptr() + 8 * self.off_fwd[k]
             s.field("beam_q").unpack(1, fin(0), add=True)
         s.beam_qdp_end()
         s.begin_step()
-        if r > 0:
+        if src is not None:
             s.species.unpack(fin(3))
             s.field("cu").unpack(0, fin(1))
             s.field("b_spe").unpack(0, fin(2))
-            self._rec("fwd_free", r - 1)
+            if not remote_up:
+                self._rec("fwd_free", r - 1)
         s.run_slices(1, 1)
-        if r > 0:
-            self._wait("back_free", r)
+        ev_back = None
+        if src is not None:
+            if remote_up:
+                self._nccl_wait("back", r)
+            else:
+                self._wait("back_free", r)
             s.field("b").pack(1, self.back[r].data_ptr() + 8 * self.off_back[0])
             s.field("e").pack(1, self.back[r].data_ptr() + 8 * self.off_back[1])
-            self._rec("back_ready", r)
+            ev_back = self._rec("back_ready", r)
         if s.nzp > 1:
             s.run_slices(2, s.nzp)
-        if r < S - 1:
+        if remote_up:
+            # after the sweep is enqueued: posting NCCL operations can block the host for milliseconds
+            self._nccl_isend("back", self.back[r], self.rank - 1, ev_back)
+            with self.torch.cuda.stream(self.comm):
+                self.pending["beam_in"] = self.dist.irecv(self.beam_in, self.rank - 1)
+        if r < S - 1 or remote_down:
             fout = lambda k: self.fwd[r].data_ptr() + 8 * self.off_fwd[k]
-            self._wait("fwd_free", r)
+            if remote_down:
+                self._nccl_wait("fwd", r)
+            else:
+                self._wait("fwd_free", r)
             s.field("beam_q").pack(s.nzp + 1, fout(0))
             s.field("cu").pack(0, fout(1))
             s.field("b_spe").pack(0, fout(2))
@@ -439,17 +488,36 @@ class LocalPipeline:
     def _tail(self, r, renew=True):
         s, S = self.sims[r], self.S
         self._cur = r
-        if r < S - 1:
+        remote_up = r == 0 and self.rank > 0
+        remote_down = r == S - 1 and self.rank < self.world - 1
+        if remote_down:
+            self._nccl_isend("fwd", self.fwd[r][:self.n_fwd], self.rank + 1, self.ev[("fwd_ready", r)])
+            with self.torch.cuda.stream(self.streams[r]):
+                self.dist.recv(self.back_in, self.rank + 1)
+            bsrc = self.back_in
+        elif r < S - 1:
             self._wait("back_ready", r + 1)
-            s.field("b").unpack(s.nzp + 1, self.back[r + 1].data_ptr() + 8 * self.off_back[0])
-            s.field("e").unpack(s.nzp + 1, self.back[r + 1].data_ptr() + 8 * self.off_back[1])
-            self._rec("back_free", r + 1)
+            bsrc = self.back[r + 1]
+        else:
+            bsrc = None
+        if bsrc is not None:
+            s.field("b").unpack(s.nzp + 1, bsrc.data_ptr() + 8 * self.off_back[0])
+            s.field("e").unpack(s.nzp + 1, bsrc.data_ptr() + 8 * self.off_back[1])
+            if not remote_down:
+                self._rec("back_free", r + 1)
         s.beam_push()
-        if r > 0:
+        if remote_up:
+            self._nccl_wait("beam_in", r)
+            s.beam.unpack(self.beam_in.data_ptr())
+        elif r > 0:
             self._wait("beam_ready", r - 1)
             s.beam.unpack(self.beamb[r - 1].data_ptr())
             self._rec("beam_free", r - 1)
-        if r < S - 1:
+        if remote_down:
+            self._nccl_wait("beam", r)
+            s.beam.pack_forward(self.beamb[r].data_ptr())
+            self._nccl_isend("beam", self.beamb[r], self.rank + 1, self._rec("beam_ready", r))
+        elif r < S - 1:
             self._wait("beam_free", r)
             s.beam.pack_forward(self.beamb[r].data_ptr())
             self._rec("beam_ready", r)
@@ -457,36 +525,42 @@ class LocalPipeline:
             s.renew()
 
     def wave(self, upload=None):
-        """stage r: tail of step w-r-1, then head of step w-r.  Descending r: a stage's tail needs the first slice of
-        the downstream stage's head of the same step, which this order has just enqueued."""
+        """global stage g: tail of step w-g-1, then head of step w-g.  Descending order: a stage's tail needs the first
+        slice of the downstream stage's head of the same step, which this order has just enqueued."""
         w = self.w
         for r in reversed(range(self.S)):
-            if w - r - 1 >= 0:
-                self._tail(r, renew=not (r == 0 and upload is not None))
-            if w - r >= 0:
-                self._head(r, upload if r == 0 else None)
+            g = self.base + r
+            if w - g - 1 >= 0:
+                self._tail(r, renew=not (g == 0 and upload is not None))
+            if w - g >= 0:
+                self._head(r, upload if g == 0 else None)
         self.w += 1
 
     def fill(self):
-        while self.w < self.S - 1:
+        while self.w < self.G - 1:
             self.wave()
 
     def drain(self):
         """finish the steps in flight (every stage ends after the same 3D step)"""
-        last = self.w - 1            # newest step stage 0 has started
-        for w in range(self.w, self.w + self.S):
+        last = self.w - 1            # newest step the first stage has started
+        for w in range(self.w, self.w + self.G):
             for r in reversed(range(self.S)):
-                n_tail, n_head = w - r - 1, w - r
+                g = self.base + r
+                n_tail, n_head = w - g - 1, w - g
                 if 0 <= n_tail <= last:
                     self._tail(r)
                 if 0 <= n_head <= last:
                     self._head(r)
-        self.w += self.S
+        self.w += self.G
+        for k in list(self.pending):
+            self.pending.pop(k).wait()
         self.sync()
 
     def sync(self):
         for st in self.streams:
             st.synchronize()
+        if self.comm is not None:
+            self.comm.synchronize()
 
     def stats(self):
         tot = [0, 0, 0]

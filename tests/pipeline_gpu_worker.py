@@ -9,11 +9,12 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 from qpad_b200 import decks  # noqa: E402
-from qpad_b200.pipeline import PipelineStage  # noqa: E402
+from qpad_b200.pipeline import LocalPipeline, PipelineStage  # noqa: E402
 
 
 def main():
     out, nsteps = sys.argv[1], int(sys.argv[2])
+    stages = int(sys.argv[3]) if len(sys.argv) > 3 else 0      # 0: one PipelineStage per rank; S > 0: LocalPipeline with S stages per rank
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl")
@@ -22,6 +23,21 @@ def main():
     beam = dict(decks.CONFIGS["C1"]["beam"])
     bm = decks.beam_std(cfg["nr"], cfg["nz"], cfg["rmax"], cfg["zmin"], cfg["zmax"], **beam)
     plasma = decks.plasma_uniform(cfg["nr"], cfg["rmax"], cfg["ppc1"], cfg["ppc2"], cfg["num_theta"])
+    if stages > 0:
+        lp = LocalPipeline(cfg, plasma, bm, stages, device=local, rank=rank, world=world, dist=dist)
+        lp.fill()
+        for _ in range(nsteps):
+            lp.wave()
+        lp.drain()                                           # every stage has finished 3D steps 0 .. G-2+nsteps
+        torch.cuda.synchronize()
+        for r, s in enumerate(lp.sims):
+            bx, bp, bq = s.beam.download()
+            np.savez(os.path.join(out, f"stage{rank * stages + r}.npz"), psi=s.field("psi").download_f2(), e=s.field("e").download_f2(), bx=bx, bp=bp,
+                     bq=bq, stats=np.array(s.stats()), noff2=s.noff2, nzp=s.nzp)
+        dist.barrier(device_ids=[local])
+        lp.close()
+        dist.destroy_process_group()
+        return
     stream = torch.cuda.Stream()
     with torch.cuda.stream(stream):
         st = PipelineStage(cfg, plasma, bm, stream=stream, rank=rank, world=world, device=local)

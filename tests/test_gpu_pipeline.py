@@ -45,3 +45,40 @@ def test_two_stage_pipeline_matches_oracle(tmp_path):
             assert np.max(np.abs(d["bx"] - ox)) < 1e-9 * np.max(np.abs(ox))
         nb += len(oq)
     assert nb > 0
+
+
+def test_sm_partitioned_pipeline_across_two_gpus(tmp_path):
+    """LocalPipeline with 2 stages per GPU on 2 GPUs (4 global stages: event-ordered hand-offs inside a GPU, NCCL between
+    them) against the oracle's 4-stage run"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from oracle import oracle as O
+    from qpad_b200 import decks
+    nsteps, world, S = 3, 2, 2
+    G = world * S
+    total = G - 1 + nsteps
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", "29534", os.path.join(ROOT, "tests", "pipeline_gpu_worker.py"), str(tmp_path), str(nsteps), str(S)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, NCCL_MAX_P2P_NCHANNELS="4"))
+    assert r.returncode == 0, r.stderr[-3000:]
+    cfg = dict(nr=64, nz=32, max_mode=1, rmax=5.0, zmin=-5.0, zmax=5.0, dt=10.0, iter_max=2, iter_reltol=1e-3, iter_abstol=1e-3)
+    beam = dict(decks.CONFIGS["C1"]["beam"])
+    bm = decks.beam_std(cfg["nr"], cfg["nz"], cfg["rmax"], cfg["zmin"], cfg["zmax"], **beam)
+    orc = O.Sim(ppc1=2, ppc2=2, num_theta=8, nstages=G, **cfg)
+    orc.set_beam(*bm)
+    for k in range(total):
+        orc.step3d(k + 1)
+    nb = 0
+    for g in range(G):
+        d = np.load(tmp_path / f"stage{g}.npz")
+        nzp = int(d["nzp"])
+        for name in ("psi", "e"):
+            got, want = d[name][:, :nzp], orc.field(name, 2, stage=g)[:, :nzp]
+            assert np.max(np.abs(got - want)) < 1e-6 * np.max(np.abs(want)), (g, name)
+        ox, op, oq = orc.beam(stage=g)
+        assert len(d["bq"]) == len(oq) and np.array_equal(d["bq"], oq)
+        if len(oq):
+            assert np.max(np.abs(d["bx"] - ox)) < 1e-9 * np.max(np.abs(ox))
+        nb += len(oq)
+    assert nb > 0
