@@ -404,12 +404,16 @@ def run_b200_local(args):
     ev0.record(main)
     for st in lp.streams:
         st.wait_event(ev0)
+    th0 = time.perf_counter()
     for _ in range(args.steps):
         lp.wave()
+    host_ms_per_wave = 1e3 * (time.perf_counter() - th0) / args.steps      # host time to ENQUEUE a wave (not device time)
     join()
     ev1.record(main)
     sync_all()
     ms = ev0.elapsed_time(ev1)
+    if os.environ.get("QPG_TRACE"):
+        print(f"rank {rank}: host enqueue {host_ms_per_wave:.2f} ms per wave, device {ms / args.steps:.2f} ms per wave", file=sys.stderr, flush=True)
     clocks = clk.stop()
     u1, i1, s1 = lp.stats()
     upd, iters, slices = u1 - u0, i1 - i0, s1 - s0
@@ -460,7 +464,7 @@ def run_b200_local(args):
     roof = {"bound": "hbm", "kernel": "k_sweep<%d> x %d concurrent per GPU (persistent; each on 1/%d of the SMs, one xi slab each)" % (cfg["max_mode"], S, S),
             "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
             "bytes_per_update": 112.0 + 64.0 * nit, "algorithmic_bytes_timed": bytes_total, "launches_timed_rank0": int(sweep_n),
-            "avg_launch_ms_rank0": sweep_ms / max(sweep_n, 1), "us_per_slice_effective": ms * 1e3 / max(slices, 1),
+            "avg_launch_ms_rank0": sweep_ms / max(sweep_n, 1), "us_per_slice_effective": ms * 1e3 / max(slices, 1), "host_enqueue_ms_per_step_rank0": host_ms_per_wave,
             "us_per_slice_per_stage_rank0": [round(p["ns_total"] * 1e-3 / max(p["slices"], 1.0), 2) for p in profs],
             "phases_rank0": {"A||update_bound": ph["A"], "amjdeposit (64 B/particle)": ph["amj"], "C": ph["C"], "push_u+push_x+qdeposit||D (112 B/particle)": ph["push"]},
             "note": "achieved = algorithmic bytes of ALL sweep launches in the timed region / its duration, per GPU (the S kernels of a GPU overlap: a stage's latency-bound field phases and barriers hide behind the other stages' particle phases); particle planes stay L2-resident"}
