@@ -1,21 +1,22 @@
 // sweep.cu -- the slab sweep as ONE persistent cooperative kernel.
 //
 // Why: a slice of the quasi-static loop (simulation_class.f03:342-469) is a strictly sequential chain of small
-// steps (deposit -> field solves -> {deposit -> field solves}* -> push) whose device time at C2 is ~10 us each; as
+// steps (deposit -> field solves -> {deposit -> field solves}* -> push) whose device time at C2 is ~5-12 us each; as
 // separate kernel launches -- even replayed from a CUDA graph with a device-side WHILE node -- the chain costs
-// ~94 us per slice, one third of it launch / dependency latency.  Here one CTA per SM stays resident for the whole
-// slab; the phases of a slice are separated by a hand-rolled grid barrier (one L2 atomic + one polled line,
-// ~0.5 us) and the predictor-corrector loop is an ordinary loop around a flag every CTA reads after the barrier.
+// ~94 us per slice, one third of it launch / dependency latency.  Here one CTA per SM (of the kernel's SM share)
+// stays resident for the whole slab; the phases of a slice are separated by a hand-rolled grid barrier (one L2 RED +
+// one polled line, ~1.3 us) and the predictor-corrector loop is an ordinary loop whose exit every CTA derives from
+// the residual maxima the field team publishes.
 //
 //   per slice j:   [A on the field team  ||  update_bound compaction on the last CTA]          -- barrier
 //                  { amjdeposit on all CTAs -- barrier -- C on the field team -- barrier }  x n_it
 //                  [push_u + push_x + bound flags + next slice's qdeposit on all CTAs  ||  D items, 1 warp per CTA] -- barrier
 //
-// The field team is the first ceil(nr/128) CTAs, thread <-> radial node (same arithmetic as the cluster kernels of
-// fused.cu); the per-CTA scan totals travel through a small global exchange buffer guarded by a team barrier
-// instead of distributed shared memory, so the kernel needs no cluster co-scheduling and uses every SM for the
-// particle phases.  Every barrier has a watchdog: a CTA that waits longer than ~2 s raises the abort flag, all
-// CTAs leave, and the host reports QPG_ERR_STATE instead of hanging the device.
+// The field team is the first ceil(nr/32) CTAs; each owns a strip of 32 radial nodes and works on it with all its
+// threads (see "field team: strip decomposition" below).  Strip totals of the tridiagonal scans cross CTAs as
+// self-validating flagged words, so the programs need no team barrier and no cluster co-scheduling, and several sweep
+// kernels (one per xi slab, pipeline.LocalPipeline) can share a GPU.  Every barrier has a watchdog: a CTA that waits
+// longer than ~2 s raises the abort flag, all CTAs leave, and the host reports QPG_ERR_STATE instead of hanging.
 #include "common.cuh"
 
 #define SW_T 512           // threads per CTA (16 warps, <= 128 registers per thread)
