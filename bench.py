@@ -378,7 +378,7 @@ def run_b200_local(args):
     plasma, bm = make_inputs(cfg, beam)
     npp0 = len(plasma[4])
     S = args.stages
-    lp = LocalPipeline(cfg, plasma, bm, S, device=local, rank=rank, world=world, dist=dist if world > 1 else None)
+    lp = LocalPipeline(cfg, plasma, bm, S, device=local, rank=rank, world=world, dist=dist if world > 1 else None, transport=args.transport)
     main = torch.cuda.current_stream()
 
     def sync_all():
@@ -477,7 +477,9 @@ def run_b200_local(args):
         except Exception as exc:
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {exc}"}
     if rank == 0:
-        where = "one GPU" if world == 1 else f"{world} GPUs x {S} stages, NCCL send/recv between GPUs"
+        how = {"p2p": "hand-offs between GPUs = pack kernels writing into the next GPU's memory over NVLink (CUDA IPC mapping) + flag words awaited by stream memory operations",
+               "nccl": "NCCL send/recv between GPUs"}.get(lp.transport)
+        where = "one GPU" if world == 1 else f"{world} GPUs x {S} stages, {how}"
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic (lattice plasma per fdist2d rule, PCG64(10) tri-Gaussian beam on a 256x512 lattice)",
@@ -509,6 +511,7 @@ def main():
     ap.add_argument("--no-sweep", action="store_true", help="per-slice CUDA-graph launches instead of the persistent sweep kernel")
     ap.add_argument("--no-micro", action="store_true", help="skip the stream-from-HBM kernel microbenchmark")
     ap.add_argument("--legacy-pipeline", action="store_true", help="N>1: one stage per GPU through pipeline.PipelineStage")
+    ap.add_argument("--transport", default=None, choices=["p2p", "nccl"], help="N>1: how the stage hand-offs cross GPUs (default p2p = peer-memory writes + flags, csrc/p2p.cu)")
     ap.add_argument("--stages", type=int, default=0, help="xi-pipeline stages mapped onto SM partitions of ONE GPU (LocalPipeline); 0 = auto (up to 4), 1 = a single sweep kernel on all SMs")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -241,6 +241,25 @@ int qpg_sim_set_sweep_ctas(qpg_sim s, int n);
  * Fails with QPG_ERR_STATE if the last sweep hit its barrier watchdog. */
 int qpg_sim_sweep_profile(qpg_sim s, double *out12, int reset);
 
+/* ------------------------------------------------------------------------------------------ */
+/* peer-memory transport of the xi-pipeline between the GPUs of one box (one process per GPU).
+ * Replaces the mpi_isend / mpi_recv pairs of part2d_class.f03:2355-2450 (pipesend/piperecv), field_class.f03:560-700
+ * (pipe_send/pipe_recv) and part3d_comm.f03:278-314: the producer's qpg_*_pack kernels write the wire record directly
+ * into the consumer GPU's buffer (mapped through a CUDA IPC handle), then raise a flag in the consumer's memory; the
+ * consumer's stream waits for the flag with a stream memory operation.  All calls are asynchronous on `cuda_stream`.
+ *   qpg_wire_alloc/free    : wire buffer or flag block that can be exported (plain cudaMalloc, zero-filled)
+ *   qpg_wire_export/import : 64-byte IPC handle of a buffer / map a peer's buffer into this process
+ *   qpg_stream_signal      : *flag = value after all work enqueued on the stream so far (flag may be peer memory)
+ *   qpg_stream_wait        : the stream's later work starts once (int)(*flag - value) >= 0 (flag in OWN memory)     */
+int qpg_wire_alloc(void **dev_ptr, long bytes);
+int qpg_wire_free(void *dev_ptr);
+int qpg_wire_export(void *dev_ptr, unsigned char *handle64);
+int qpg_wire_import(const unsigned char *handle64, void **dev_ptr);
+int qpg_wire_unmap(void *dev_ptr);
+int qpg_stream_signal(void *cuda_stream, unsigned *flag, unsigned value);
+int qpg_stream_wait(void *cuda_stream, unsigned *flag, unsigned value);
+int qpg_stream_wait_is_memop(void);   /* 1 = cuStreamWaitValue32, 0 = fallback polling kernel */
+
 #ifdef __cplusplus
 }
 #endif

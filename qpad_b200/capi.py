@@ -131,6 +131,14 @@ SIGNATURES = {
     "qpg_sim_set_sweep": (_i, [_vp, _i]),
     "qpg_sim_set_sweep_ctas": (_i, [_vp, _i]),
     "qpg_sim_sweep_profile": (_i, [_vp, _pd, _i]),
+    "qpg_wire_alloc": (_i, [C.POINTER(_vp), _l]),
+    "qpg_wire_free": (_i, [_vp]),
+    "qpg_wire_export": (_i, [_vp, C.c_char_p]),
+    "qpg_wire_import": (_i, [C.c_char_p, C.POINTER(_vp)]),
+    "qpg_wire_unmap": (_i, [_vp]),
+    "qpg_stream_signal": (_i, [_vp, _vp, C.c_uint]),
+    "qpg_stream_wait": (_i, [_vp, _vp, C.c_uint]),
+    "qpg_stream_wait_is_memop": (_i, []),
 }
 
 
@@ -466,3 +474,40 @@ class Sim:
         self.run_slices(1, self.nzp)
         self.beam_push()
         self.renew()
+
+
+class WireBuf:
+    """exportable device buffer (qpg_wire_alloc) or a peer's buffer mapped through its IPC handle (qpg_wire_import)"""
+
+    def __init__(self, nbytes=None, handle=None):
+        self.L = load()
+        p = _vp()
+        self.imported = handle is not None
+        if handle is not None:
+            _chk(self.L.qpg_wire_import(handle, C.byref(p)))
+        else:
+            _chk(self.L.qpg_wire_alloc(C.byref(p), int(nbytes)))
+        self.ptr = p.value
+
+    def data_ptr(self):
+        return self.ptr
+
+    def export(self):
+        buf = C.create_string_buffer(64)
+        _chk(self.L.qpg_wire_export(self.ptr, buf))
+        return buf.raw
+
+    def close(self):
+        if getattr(self, "ptr", None):
+            (self.L.qpg_wire_unmap if self.imported else self.L.qpg_wire_free)(self.ptr)
+        self.ptr = None
+
+    __del__ = close
+
+
+def stream_signal(cuda_stream, flag_ptr, value):
+    _chk(load().qpg_stream_signal(cuda_stream, flag_ptr, value & 0xFFFFFFFF))
+
+
+def stream_wait(cuda_stream, flag_ptr, value):
+    _chk(load().qpg_stream_wait(cuda_stream, flag_ptr, value & 0xFFFFFFFF))

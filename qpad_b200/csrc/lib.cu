@@ -5,3 +5,4 @@
 #include "fused.cu"
 #include "sweep.cu"
 #include "sim.cu"
+#include "p2p.cu"

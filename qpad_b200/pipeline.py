@@ -344,6 +344,49 @@ class PipelineStage:
         self.sim.close()
 
 
+class PeerLinks:
+    """Peer-memory links of one rank to its two neighbours (csrc/p2p.cu): the wire buffers this rank CONSUMES and one
+    block of flag words live in its own memory and are exported through CUDA IPC handles; the neighbours map them and
+    write into them over NVLink.  Flag words (32 bytes apart, one writer each, counting messages):
+
+        ready_fwd, ready_beam, ack_back   written by rank-1      ready_back, ack_fwd, ack_beam   written by rank+1
+    """
+    FLAGS = ("ready_fwd", "ready_beam", "ack_back", "ready_back", "ack_fwd", "ack_beam")
+
+    def __init__(self, dist, rank, world, n_fwd, n_back, n_beam):
+        self.dist, self.rank, self.world = dist, rank, world
+        self.own = {"flags": capi.WireBuf(32 * len(self.FLAGS))}
+        if rank > 0:
+            self.own["fwd_in"] = capi.WireBuf(8 * n_fwd)
+            self.own["beam_in"] = capi.WireBuf(8 * n_beam)
+        if rank < world - 1:
+            self.own["back_in"] = capi.WireBuf(8 * n_back)
+        mine = {k: b.export() for k, b in self.own.items()}
+        every = [None] * world
+        dist.all_gather_object(every, mine)
+        self.up = {k: capi.WireBuf(handle=every[rank - 1][k]) for k in ("flags", "back_in")} if rank > 0 else {}
+        self.down = {k: capi.WireBuf(handle=every[rank + 1][k]) for k in ("flags", "fwd_in", "beam_in")} if rank < world - 1 else {}
+        self.count = {}
+
+    def next(self, link):
+        """number of the next message on a link (both ends count alike: one message per link and 3D step)"""
+        self.count[link] = self.count.get(link, 0) + 1
+        return self.count[link]
+
+    def flag(self, where, name):
+        base = {"own": self.own, "up": self.up, "down": self.down}[where]["flags"].ptr
+        return base + 32 * self.FLAGS.index(name)
+
+    def close(self):
+        self.dist.barrier()          # nobody unmaps or frees while a neighbour may still write
+        for grp in (self.up, self.down):
+            for b in grp.values():
+                b.close()
+        self.dist.barrier()
+        for b in self.own.values():
+            b.close()
+
+
 class LocalPipeline:
     """The xi-pipeline over SM partitions: S stages = S persistent sweep kernels per GPU, each on its own stream with 1/S
     of the SMs; with world > 1 the G = world*S stages continue across GPUs (NCCL between the last stage of rank k and
@@ -359,9 +402,13 @@ class LocalPipeline:
     One `wave()` = every stage advances by one 3D step (tail of its previous step, then head of the next), i.e. one
     full deck's worth of slices in steady state; the first G-1 waves fill the pipeline.  All NCCL messages of a wave are
     matched inside the same wave on both ranks, so nothing is pending between waves (barrier + synchronize are safe).
+
+    transport (world > 1): "p2p" = the pack kernels of the last stage of rank k write straight into the memory of rank
+    k+1 and raise a flag its stream waits on (PeerLinks / csrc/p2p.cu: no library kernel competes with the sweep kernels
+    for SMs, nothing blocks the host); "nccl" = torch.distributed send/recv of local wire buffers.
     """
 
-    def __init__(self, cfg, plasma, beam, nstages, device=0, beam_wire_cap=None, rank=0, world=1, dist=None):
+    def __init__(self, cfg, plasma, beam, nstages, device=0, beam_wire_cap=None, rank=0, world=1, dist=None, transport=None):
         import torch
         self.torch, self.cfg, self.S, self.plasma = torch, cfg, nstages, plasma
         self.rank, self.world, self.G, self.base = rank, world, world * nstages, rank * nstages
@@ -371,9 +418,13 @@ class LocalPipeline:
         parts = slab_partition(cfg["nz"], G)
         beams = split_beam(*beam, cfg["nz"], dxi, G)
         nsm = torch.cuda.get_device_properties(device).multi_processor_count
-        free = int(os.environ.get("QPG_PIPELINE_FREE_SMS", "4")) if world > 1 else 0   # for the NCCL kernels beside the sweeps
+        self.transport = (transport or os.environ.get("QPG_PIPELINE_TRANSPORT", "p2p")) if world > 1 else None
+        if self.transport not in (None, "p2p", "nccl"):
+            raise ValueError(f"unknown pipeline transport {self.transport!r}")
+        self.p2p = self.transport == "p2p"
+        free = int(os.environ.get("QPG_PIPELINE_FREE_SMS", "4")) if self.transport == "nccl" else 0   # for the NCCL kernels beside the sweeps
         self.streams = [torch.cuda.Stream(device=device) for _ in range(S)]
-        self.comm = torch.cuda.Stream(device=device) if world > 1 else None
+        self.comm = torch.cuda.Stream(device=device) if self.transport == "nccl" else None
         self.sims = []
         dev = torch.device("cuda", device)
         for r in range(S):
@@ -397,9 +448,14 @@ class LocalPipeline:
         self.fwd = [mk(nfw) for _ in range(S)]        # written by stage r, read by the next stage
         self.back = [mk(nbk) for _ in range(S)]       # written by stage r, read by the previous stage
         self.beamb = [mk(nbm) for _ in range(S)]      # written by stage r, read by the next stage
-        self.fwd_in = mk(nfw) if rank > 0 else None           # from the last stage of rank-1
-        self.beam_in = mk(nbm) if rank > 0 else None
-        self.back_in = mk(nbk) if rank < world - 1 else None  # from the first stage of rank+1
+        self.links = None
+        if self.p2p:
+            self.links = PeerLinks(dist, rank, world, nfw, nbk, nbm)
+            self.fwd_in, self.beam_in, self.back_in = (self.links.own.get(k) for k in ("fwd_in", "beam_in", "back_in"))
+        else:
+            self.fwd_in = mk(nfw) if rank > 0 else None           # from the last stage of rank-1
+            self.beam_in = mk(nbm) if rank > 0 else None
+            self.back_in = mk(nbk) if rank < world - 1 else None  # from the first stage of rank+1
         self.off_back = (0, nb)
         self.ev, self.pending = {}, {}
         self.w = 0
@@ -429,16 +485,29 @@ class LocalPipeline:
         with self.torch.cuda.stream(self.comm):
             self.pending[name] = self.dist.isend(t, dst)
 
+    # peer-memory links: stream-ordered flag waits / writes on the stage's stream
+    def _pwait(self, r, name, n):
+        if n > 0:
+            capi.stream_wait(self.streams[r].cuda_stream, self.links.flag("own", name), n)
+
+    def _psignal(self, r, where, name, n):
+        capi.stream_signal(self.streams[r].cuda_stream, self.links.flag(where, name), n)
+
     def _head(self, r, upload=None):
         s, S = self.sims[r], self.S
         self._cur = r
         remote_up = r == 0 and self.rank > 0
         remote_down = r == S - 1 and self.rank < self.world - 1
+        p2p_up, p2p_down = remote_up and self.p2p, remote_down and self.p2p
         if upload is not None:
             s.species.upload(*upload)                                   # the host re-injects the plasma (species%renew)
         s.beam_qdp_begin()
         src = None
-        if remote_up:
+        if p2p_up:
+            n_in = self.links.next("fwd_in")
+            self._pwait(r, "ready_fwd", n_in)
+            src = self.fwd_in
+        elif remote_up:
             with self.torch.cuda.stream(self.streams[r]):
                 self.dist.recv(self.fwd_in[:self.n_fwd], self.rank - 1)
             src = self.fwd_in
@@ -454,43 +523,66 @@ class LocalPipeline:
             s.species.unpack(fin(3))
             s.field("cu").unpack(0, fin(1))
             s.field("b_spe").unpack(0, fin(2))
-            if not remote_up:
+            if p2p_up:
+                self._psignal(r, "up", "ack_fwd", n_in)
+            elif not remote_up:
                 self._rec("fwd_free", r - 1)
         s.run_slices(1, 1)
         ev_back = None
         if src is not None:
-            if remote_up:
+            bdst = self.back[r].data_ptr()
+            if p2p_up:
+                n_b = self.links.next("back_out")
+                self._pwait(r, "ack_back", n_b - 1)
+                bdst = self.links.up["back_in"].ptr                     # the upstream GPU's guard-slice buffer
+            elif remote_up:
                 self._nccl_wait("back", r)
             else:
                 self._wait("back_free", r)
-            s.field("b").pack(1, self.back[r].data_ptr() + 8 * self.off_back[0])
-            s.field("e").pack(1, self.back[r].data_ptr() + 8 * self.off_back[1])
-            ev_back = self._rec("back_ready", r)
+            s.field("b").pack(1, bdst + 8 * self.off_back[0])
+            s.field("e").pack(1, bdst + 8 * self.off_back[1])
+            if p2p_up:
+                self._psignal(r, "up", "ready_back", n_b)
+            else:
+                ev_back = self._rec("back_ready", r)
         if s.nzp > 1:
             s.run_slices(2, s.nzp)
-        if remote_up:
+        if remote_up and not self.p2p:
             # after the sweep is enqueued: posting NCCL operations can block the host for milliseconds
             self._nccl_isend("back", self.back[r], self.rank - 1, ev_back)
             with self.torch.cuda.stream(self.comm):
                 self.pending["beam_in"] = self.dist.irecv(self.beam_in, self.rank - 1)
         if r < S - 1 or remote_down:
-            fout = lambda k: self.fwd[r].data_ptr() + 8 * self.off_fwd[k]
-            if remote_down:
+            fdst = self.fwd[r].data_ptr()
+            if p2p_down:
+                n_f = self.links.next("fwd_out")
+                self._pwait(r, "ack_fwd", n_f - 1)
+                fdst = self.links.down["fwd_in"].ptr                    # the downstream GPU's buffer
+            elif remote_down:
                 self._nccl_wait("fwd", r)
             else:
                 self._wait("fwd_free", r)
+            fout = lambda k: fdst + 8 * self.off_fwd[k]
             s.field("beam_q").pack(s.nzp + 1, fout(0))
             s.field("cu").pack(0, fout(1))
             s.field("b_spe").pack(0, fout(2))
             s.species.pack(fout(3))
-            self._rec("fwd_ready", r)
+            if p2p_down:
+                self._psignal(r, "down", "ready_fwd", n_f)
+            else:
+                self._rec("fwd_ready", r)
 
     def _tail(self, r, renew=True):
         s, S = self.sims[r], self.S
         self._cur = r
         remote_up = r == 0 and self.rank > 0
         remote_down = r == S - 1 and self.rank < self.world - 1
-        if remote_down:
+        p2p_up, p2p_down = remote_up and self.p2p, remote_down and self.p2p
+        if p2p_down:
+            n_b = self.links.next("back_in")
+            self._pwait(r, "ready_back", n_b)
+            bsrc = self.back_in
+        elif remote_down:
             self._nccl_isend("fwd", self.fwd[r][:self.n_fwd], self.rank + 1, self.ev[("fwd_ready", r)])
             with self.torch.cuda.stream(self.streams[r]):
                 self.dist.recv(self.back_in, self.rank + 1)
@@ -503,17 +595,29 @@ class LocalPipeline:
         if bsrc is not None:
             s.field("b").unpack(s.nzp + 1, bsrc.data_ptr() + 8 * self.off_back[0])
             s.field("e").unpack(s.nzp + 1, bsrc.data_ptr() + 8 * self.off_back[1])
-            if not remote_down:
+            if p2p_down:
+                self._psignal(r, "down", "ack_back", n_b)
+            elif not remote_down:
                 self._rec("back_free", r + 1)
         s.beam_push()
-        if remote_up:
+        if p2p_up:
+            n_m = self.links.next("beam_in")
+            self._pwait(r, "ready_beam", n_m)
+            s.beam.unpack(self.beam_in.data_ptr())
+            self._psignal(r, "up", "ack_beam", n_m)
+        elif remote_up:
             self._nccl_wait("beam_in", r)
             s.beam.unpack(self.beam_in.data_ptr())
         elif r > 0:
             self._wait("beam_ready", r - 1)
             s.beam.unpack(self.beamb[r - 1].data_ptr())
             self._rec("beam_free", r - 1)
-        if remote_down:
+        if p2p_down:
+            n_m = self.links.next("beam_out")
+            self._pwait(r, "ack_beam", n_m - 1)
+            s.beam.pack_forward(self.links.down["beam_in"].ptr)
+            self._psignal(r, "down", "ready_beam", n_m)
+        elif remote_down:
             self._nccl_wait("beam", r)
             s.beam.pack_forward(self.beamb[r].data_ptr())
             self._nccl_isend("beam", self.beamb[r], self.rank + 1, self._rec("beam_ready", r))
@@ -574,5 +678,7 @@ class LocalPipeline:
 
     def close(self):
         self.sync()
+        if self.links is not None:
+            self.links.close()
         for s in self.sims:
             s.close()

@@ -15,16 +15,21 @@ from qpad_b200.pipeline import LocalPipeline, PipelineStage  # noqa: E402
 def main():
     out, nsteps = sys.argv[1], int(sys.argv[2])
     stages = int(sys.argv[3]) if len(sys.argv) > 3 else 0      # 0: one PipelineStage per rank; S > 0: LocalPipeline with S stages per rank
+    transport = sys.argv[4] if len(sys.argv) > 4 else None     # LocalPipeline transport between ranks: p2p | nccl
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    one_device = bool(os.environ.get("QPG_TEST_ONE_DEVICE"))   # every rank on GPU 0 (peer-memory links through IPC work inside one GPU too)
+    if one_device:
+        local = 0
     torch.cuda.set_device(local)
-    dist.init_process_group("nccl")
+    dist.init_process_group("gloo" if one_device else "nccl")
+    barrier = (lambda: dist.barrier()) if one_device else (lambda: dist.barrier(device_ids=[local]))
     cfg = dict(nr=64, nz=32, max_mode=1, rmax=5.0, zmin=-5.0, zmax=5.0, dt=10.0, ppc1=2, ppc2=2, num_theta=8, iter_max=2,
                iter_reltol=1e-3, iter_abstol=1e-3)
     beam = dict(decks.CONFIGS["C1"]["beam"])
     bm = decks.beam_std(cfg["nr"], cfg["nz"], cfg["rmax"], cfg["zmin"], cfg["zmax"], **beam)
     plasma = decks.plasma_uniform(cfg["nr"], cfg["rmax"], cfg["ppc1"], cfg["ppc2"], cfg["num_theta"])
     if stages > 0:
-        lp = LocalPipeline(cfg, plasma, bm, stages, device=local, rank=rank, world=world, dist=dist)
+        lp = LocalPipeline(cfg, plasma, bm, stages, device=local, rank=rank, world=world, dist=dist, transport=transport)
         lp.fill()
         for _ in range(nsteps):
             lp.wave()
@@ -34,7 +39,7 @@ def main():
             bx, bp, bq = s.beam.download()
             np.savez(os.path.join(out, f"stage{rank * stages + r}.npz"), psi=s.field("psi").download_f2(), e=s.field("e").download_f2(), bx=bx, bp=bp,
                      bq=bq, stats=np.array(s.stats()), noff2=s.noff2, nzp=s.nzp)
-        dist.barrier(device_ids=[local])
+        barrier()
         lp.close()
         dist.destroy_process_group()
         return

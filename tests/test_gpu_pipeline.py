@@ -47,20 +47,18 @@ def test_two_stage_pipeline_matches_oracle(tmp_path):
     assert nb > 0
 
 
-def test_sm_partitioned_pipeline_across_two_gpus(tmp_path):
-    """LocalPipeline with 2 stages per GPU on 2 GPUs (4 global stages: event-ordered hand-offs inside a GPU, NCCL between
-    them) against the oracle's 4-stage run"""
-    import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+def _local_pipeline_vs_oracle(tmp_path, world, S, transport, one_device, port):
     from oracle import oracle as O
     from qpad_b200 import decks
-    nsteps, world, S = 3, 2, 2
+    nsteps = 3
     G = world * S
     total = G - 1 + nsteps
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
-           "--master-port", "29534", os.path.join(ROOT, "tests", "pipeline_gpu_worker.py"), str(tmp_path), str(nsteps), str(S)]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, NCCL_MAX_P2P_NCHANNELS="4"))
+           "--master-port", str(port), os.path.join(ROOT, "tests", "pipeline_gpu_worker.py"), str(tmp_path), str(nsteps), str(S), transport]
+    env = dict(os.environ, NCCL_MAX_P2P_NCHANNELS="4")
+    if one_device:
+        env["QPG_TEST_ONE_DEVICE"] = "1"
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0, r.stderr[-3000:]
     cfg = dict(nr=64, nz=32, max_mode=1, rmax=5.0, zmin=-5.0, zmax=5.0, dt=10.0, iter_max=2, iter_reltol=1e-3, iter_abstol=1e-3)
     beam = dict(decks.CONFIGS["C1"]["beam"])
@@ -82,3 +80,21 @@ def test_sm_partitioned_pipeline_across_two_gpus(tmp_path):
             assert np.max(np.abs(d["bx"] - ox)) < 1e-9 * np.max(np.abs(ox))
         nb += len(oq)
     assert nb > 0
+
+
+@pytest.mark.parametrize("transport", ["p2p", "nccl"])
+def test_sm_partitioned_pipeline_across_two_gpus(tmp_path, transport):
+    """LocalPipeline with 2 stages per GPU on 2 GPUs (4 global stages: event-ordered hand-offs inside a GPU; between the
+    GPUs either peer-memory writes + flags (p2p) or NCCL send/recv) against the oracle's 4-stage run"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    _local_pipeline_vs_oracle(tmp_path, 2, 2, transport, False, 29534)
+
+
+@pytest.mark.parametrize("world,S", [(2, 2), (3, 1)])
+def test_peer_memory_links_between_processes_on_one_gpu(tmp_path, world, S):
+    """the p2p transport (CUDA IPC mapped wire buffers, pack kernels writing into the consumer's memory, flag words
+    awaited by stream memory operations) between rank PROCESSES that share GPU 0 -- the same protocol as across GPUs,
+    testable on a one-GPU box; against the oracle's (world*S)-stage run"""
+    _local_pipeline_vs_oracle(tmp_path, world, S, "p2p", True, 29535 + world)
