@@ -378,7 +378,13 @@ def run_b200_local(args):
     plasma, bm = make_inputs(cfg, beam)
     npp0 = len(plasma[4])
     S = args.stages
-    lp = LocalPipeline(cfg, plasma, bm, S, device=local, rank=rank, world=world, dist=dist if world > 1 else None, transport=args.transport)
+    parts = None
+    if args.balance and world * S > 1:
+        # slabs of equal measured cost instead of equal length (pipeline.balanced_partition): an untimed calibration sweep
+        from qpad_b200.pipeline import probe_partition
+        free = 4 if (world > 1 and (args.transport or os.environ.get("QPG_PIPELINE_TRANSPORT", "p2p")) == "nccl") else 0
+        parts = probe_partition(cfg, plasma, bm, world * S, S, device=local, rank=rank, world=world, dist=dist if world > 1 else None, free_sms=free)
+    lp = LocalPipeline(cfg, plasma, bm, S, device=local, rank=rank, world=world, dist=dist if world > 1 else None, transport=args.transport, partition=parts)
     main = torch.cuda.current_stream()
 
     def sync_all():
@@ -394,6 +400,7 @@ def run_b200_local(args):
     for _ in range(args.warmup):
         lp.wave()
     sync_all()
+    lp.trace_reset()
     u0, i0, s0 = lp.stats()
     l0 = lp.launch_count()
     for sim in lp.sims:
@@ -412,6 +419,10 @@ def run_b200_local(args):
     ev1.record(main)
     sync_all()
     ms = ev0.elapsed_time(ev1)
+    if os.environ.get("QPG_TRACE_EVENTS"):
+        for r_, rep in enumerate(lp.event_report()):
+            print(f"rank {rank} stage {r_} trace (ms): {rep}", file=sys.stderr, flush=True)
+        lp._ev_on = False
     if os.environ.get("QPG_TRACE"):
         print(f"rank {rank}: host enqueue {host_ms_per_wave:.2f} ms per wave, device {ms / args.steps:.2f} ms per wave", file=sys.stderr, flush=True)
     clocks = clk.stop()
@@ -425,6 +436,13 @@ def run_b200_local(args):
         sim.ctx.tprof_enable(False)
         profs.append(sim.sweep_profile())
     launches = lp.launch_count() - l0
+    # device time each stage spent inside its sweep kernel per step (all ranks): the pipeline runs at the pace of the slowest
+    mine = [round(p["ns_total"] * 1e-6 / args.steps, 3) for p in profs]
+    sweep_by_stage = mine
+    if world > 1:
+        every = [None] * world
+        dist.all_gather_object(every, mine)
+        sweep_by_stage = [v for m in every for v in m]
     if world > 1:
         t = torch.tensor([ms, float(upd), float(launches), float(iters), float(slices)], dtype=torch.float64, device="cuda")
         tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -466,6 +484,9 @@ def run_b200_local(args):
             "bytes_per_update": 112.0 + 64.0 * nit, "algorithmic_bytes_timed": bytes_total, "launches_timed_rank0": int(sweep_n),
             "avg_launch_ms_rank0": sweep_ms / max(sweep_n, 1), "us_per_slice_effective": ms * 1e3 / max(slices, 1), "host_enqueue_ms_per_step_rank0": host_ms_per_wave,
             "us_per_slice_per_stage_rank0": [round(p["ns_total"] * 1e-3 / max(p["slices"], 1.0), 2) for p in profs],
+            "sweep_ms_per_step_by_stage": sweep_by_stage,
+            "slab_slices_by_stage": [n for _, n in lp.parts],
+            "slab_partition": "cost-balanced (untimed calibration sweep, pipeline.probe_partition)" if parts is not None else "equal length (options_class.f03:103-106)",
             "phases_rank0": {"A||update_bound": ph["A"], "amjdeposit (64 B/particle)": ph["amj"], "C": ph["C"], "push_u+push_x+qdeposit||D (112 B/particle)": ph["push"]},
             "note": "achieved = algorithmic bytes of ALL sweep launches in the timed region / its duration, per GPU (the S kernels of a GPU overlap: a stage's latency-bound field phases and barriers hide behind the other stages' particle phases); particle planes stay L2-resident"}
     cpu = None
@@ -511,6 +532,7 @@ def main():
     ap.add_argument("--no-sweep", action="store_true", help="per-slice CUDA-graph launches instead of the persistent sweep kernel")
     ap.add_argument("--no-micro", action="store_true", help="skip the stream-from-HBM kernel microbenchmark")
     ap.add_argument("--legacy-pipeline", action="store_true", help="N>1: one stage per GPU through pipeline.PipelineStage")
+    ap.add_argument("--balance", type=int, default=1, help="1 = cost-balanced xi slabs from an untimed calibration sweep (default), 0 = the reference's equal-length slabs")
     ap.add_argument("--transport", default=None, choices=["p2p", "nccl"], help="N>1: how the stage hand-offs cross GPUs (default p2p = peer-memory writes + flags, csrc/p2p.cu)")
     ap.add_argument("--stages", type=int, default=0, help="xi-pipeline stages mapped onto SM partitions of ONE GPU (LocalPipeline); 0 = auto (up to 4), 1 = a single sweep kernel on all SMs")
     args = ap.parse_args()

@@ -240,6 +240,10 @@ int qpg_sim_set_sweep_ctas(qpg_sim s, int n);
  * barrier latency + waiting for the slowest CTA).  out12 holds 12 doubles.
  * Fails with QPG_ERR_STATE if the last sweep hit its barrier watchdog. */
 int qpg_sim_sweep_profile(qpg_sim s, double *out12, int reset);
+/* per-slice record of the sweep kernel's LAST pass over each slice of the slab (synchronises): device time spent in the
+ * slice (ns, %globaltimer) and the predictor-corrector iterations it took (the n_it of simulation_class.f03:379-407).
+ * nzp entries each.  The cost profile along xi that the pipeline's slab partition is balanced with. */
+int qpg_sim_slice_trace(qpg_sim s, double *ns_per_slice, int *iters_per_slice);
 
 /* ------------------------------------------------------------------------------------------ */
 /* peer-memory transport of the xi-pipeline between the GPUs of one box (one process per GPU).

@@ -131,6 +131,7 @@ SIGNATURES = {
     "qpg_sim_set_sweep": (_i, [_vp, _i]),
     "qpg_sim_set_sweep_ctas": (_i, [_vp, _i]),
     "qpg_sim_sweep_profile": (_i, [_vp, _pd, _i]),
+    "qpg_sim_slice_trace": (_i, [_vp, _pd, _pi]),
     "qpg_wire_alloc": (_i, [C.POINTER(_vp), _l]),
     "qpg_wire_free": (_i, [_vp]),
     "qpg_wire_export": (_i, [_vp, C.c_char_p]),
@@ -460,6 +461,12 @@ class Sim:
         keys = ("cyc_A", "cyc_amj", "cyc_C", "cyc_push", "cyc_total", "ns_total", "slices", "amj_phases",
                 "work_A", "work_amj", "work_C", "work_push")
         return dict(zip(keys, [float(v) for v in out]))
+
+    def slice_trace(self):
+        """(ns, PC iterations) of the sweep kernel's last pass over each slice of the slab"""
+        ns, it = np.zeros(self.nzp), np.zeros(self.nzp, dtype=np.int32)
+        _chk(self.L.qpg_sim_slice_trace(self.h, ns.ctypes.data_as(_pd), it.ctypes.data_as(_pi)))
+        return ns, it
 
     def stats(self):
         u, it, sl = _l(), _l(), _l()

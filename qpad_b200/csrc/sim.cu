@@ -28,6 +28,7 @@ struct qpg_sim_s {
     double *sw_xbuf;      // team exchange records
     void *sw_xll;         // flagged exchange words of the strip scans
     long long *sw_prof;   // in-kernel phase clocks
+    long long *sw_trace;  // per-slice time and PC iteration count of the last sweep over each slice [nzp][2]
     double *phi;
     long host_updates, host_iters, host_slices;
 };
@@ -196,6 +197,8 @@ static int sweep_prepare(qpg_sim s)
     CUDA_TRY(cudaMalloc(&s->sw_xbuf, sizeof(double) * 3 * SW_MAX_TEAM * SW_XK));
     CUDA_TRY(cudaMemsetAsync(s->sw_xbuf, 0, sizeof(double) * 3 * SW_MAX_TEAM * SW_XK, c->stream));
     CUDA_TRY(cudaMalloc(&s->sw_xll, sizeof(uint4) * 2 * SW_MAX_TEAM * SW_XK));
+    CUDA_TRY(cudaMalloc(&s->sw_trace, sizeof(long long) * 2 * s->prm.nzp));
+    CUDA_TRY(cudaMemsetAsync(s->sw_trace, 0, sizeof(long long) * 2 * s->prm.nzp, c->stream));
     CUDA_TRY(cudaMalloc(&s->sw_prof, sizeof(long long) * 32));
     CUDA_TRY(cudaMemsetAsync(s->sw_prof, 0, sizeof(long long) * 32, c->stream));
     int g = s->sweep_ctas_req > 0 ? s->sweep_ctas_req : nsm * per + s->sweep_ctas_req;   // default: one CTA per SM
@@ -219,7 +222,7 @@ static int sweep_run(qpg_sim s, int j0, int j1)
     a.d_npp_w = p->d_npp; a.d_nout = p->d_nout; a.outmask = p->outmask; a.lists = p->lists;
     a.qbm = p->qbm; a.edge = (double)c->nr * c->dr;
     a.j0 = j0; a.j1 = j1; a.nteam = (c->nr + ST_N - 1) / ST_N;
-    a.bar = s->sw_bar; a.xbuf = s->sw_xbuf; a.xll = (uint4 *)s->sw_xll; a.prof = s->sw_prof;
+    a.bar = s->sw_bar; a.xbuf = s->sw_xbuf; a.xll = (uint4 *)s->sw_xll; a.prof = s->sw_prof; a.trace = s->sw_trace;
     CUDA_TRY(cudaMemsetAsync(s->sw_bar, 0, sizeof(unsigned) * 128, c->stream));
     CUDA_TRY(cudaMemsetAsync(s->sw_xll, 0, sizeof(uint4) * 2 * SW_MAX_TEAM * SW_XK, c->stream));   // sequence numbers restart at 1 every launch
     TprofScope tp(c, TP_K_SWEEP);
@@ -339,7 +342,7 @@ extern "C" int qpg_sim_destroy(qpg_sim s)
     qpg_field all[] = {s->psi, s->e, s->b, s->e_spe, s->b_spe, s->e_beam, s->b_beam, s->cu, s->amu, s->acu, s->dcu, s->q_spe, s->q_beam,
                        s->spe_q, s->spe_qn, s->spe_cu, s->spe_dcu, s->spe_amu, s->beam_q};
     for (auto f : all) qpg_field_destroy(f);
-    cudaFree(s->phi); cudaFree(s->sw_bar); cudaFree(s->sw_xbuf); cudaFree(s->sw_xll); cudaFree(s->sw_prof);
+    cudaFree(s->phi); cudaFree(s->sw_bar); cudaFree(s->sw_xbuf); cudaFree(s->sw_xll); cudaFree(s->sw_prof); cudaFree(s->sw_trace);
     qpg_part2d_destroy(s->spe);
     qpg_part3d_destroy(s->beam);
     qpg_ctx_destroy(s->ctx);
@@ -494,8 +497,8 @@ extern "C" int qpg_sim_set_sweep_ctas(qpg_sim s, int n)
     s->sweep_ctas_req = n;
     if (s->sweep_grid > 0) {   // already prepared: re-derive the grid
         cudaStreamSynchronize(s->ctx->stream);
-        cudaFree(s->sw_bar); cudaFree(s->sw_xbuf); cudaFree(s->sw_xll); cudaFree(s->sw_prof);
-        s->sw_bar = nullptr; s->sw_xbuf = nullptr; s->sw_xll = nullptr; s->sw_prof = nullptr; s->sweep_grid = 0;
+        cudaFree(s->sw_bar); cudaFree(s->sw_xbuf); cudaFree(s->sw_xll); cudaFree(s->sw_prof); cudaFree(s->sw_trace);
+        s->sw_bar = nullptr; s->sw_xbuf = nullptr; s->sw_xll = nullptr; s->sw_prof = nullptr; s->sw_trace = nullptr; s->sweep_grid = 0;
     }
     return 0;
 }
@@ -519,5 +522,17 @@ extern "C" int qpg_sim_sweep_profile(qpg_sim s, double *out8, int reset)
         for (int k = 16; k < 29; k++) fprintf(stderr, " %.0f", (double)h[k] / (h[6] > 0 ? (double)h[6] : 1.0));
         fprintf(stderr, "\n");
     }
+    return 0;
+}
+extern "C" int qpg_sim_slice_trace(qpg_sim s, double *ns_per_slice, int *iters_per_slice)
+{
+    ARG_TRY(s && ns_per_slice && iters_per_slice, "null arg");
+    const int n = s->prm.nzp;
+    for (int k = 0; k < n; k++) { ns_per_slice[k] = 0.0; iters_per_slice[k] = 0; }
+    if (!s->sw_trace) return 0;
+    std::vector<long long> h(2 * (size_t)n);
+    CUDA_TRY(cudaMemcpyAsync(h.data(), s->sw_trace, sizeof(long long) * 2 * n, cudaMemcpyDeviceToHost, s->ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->ctx->stream));
+    for (int k = 0; k < n; k++) { ns_per_slice[k] = (double)h[2 * k]; iters_per_slice[k] = (int)h[2 * k + 1]; }
     return 0;
 }

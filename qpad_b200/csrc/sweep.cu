@@ -35,6 +35,7 @@ struct SweepArgs {
     unsigned *bar;          // [0] grid arrivals, [32] team arrivals, [64] abort flag (one 128-byte line each)
     double *xbuf;           // [3][SW_XK][SW_MAX_TEAM]: slab 2 = residual maxima of program C (read after a grid barrier)
     uint4 *xll;             // [2][SW_XK][SW_MAX_TEAM] flagged 16-byte exchange words of the strip scans (cleared before each launch)
+    long long *trace;       // per slice of the slab: [2*(j-1)] ns spent in slice j (globaltimer), [2*(j-1)+1] PC iterations it took
     long long *prof;        // [0..3] cycles in phase A / amj / C / push, [4] total cycles, [5] total ns, [6] slices, [7] amj phases, [8..11] CTA 0's own work cycles per phase (thread 0's arrival at the barrier)
 };
 
@@ -582,7 +583,9 @@ __global__ void __launch_bounds__(SW_T, 1) k_sweep(const __grid_constant__ Sweep
     const bool timer = (b == 0 && tid == 0);
     if (timer) { for (int k = 0; k < 16; k++) sm_f.stamps[k] = 0; tstart = tprev = clock64(); asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(nstart)); }
     bool ok = true;
+    long long nprev = nstart;
     for (int j = a.j0; j <= a.j1 && ok; j++) {
+        const long long namj0 = namj;
         // ---- phase A || compaction -------------------------------------------------------------------------
         if (in_team) sweep_field_A<M>(f, j, tm, sm_f, halo, timer ? sm_f.stamps : nullptr);
         else if (b == G - 1) compact_body(a.planes, 8, a.d_npp_w, a.d_nout, a.outmask, a.lists, 0, sm_i);
@@ -636,7 +639,13 @@ __global__ void __launch_bounds__(SW_T, 1) k_sweep(const __grid_constant__ Sweep
         }
         if (timer) work[3] += clock64() - tprev;
         ok = grid_barrier(a.bar, gep, sm_i);
-        if (timer) { const long long t = clock64(); prof[3] += t - tprev; tprev = t; }
+        if (timer) {
+            const long long t = clock64(); prof[3] += t - tprev; tprev = t;
+            long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            a.trace[2 * (j - 1)] = now - nprev; a.trace[2 * (j - 1) + 1] = namj - namj0;
+            nprev = now;
+        }
     }
     // update_bound of the last slice (the next launch / the host expects compacted particles)
     if (ok && b == G - 1) compact_body(a.planes, 8, a.d_npp_w, a.d_nout, a.outmask, a.lists, 0, sm_i);

@@ -35,9 +35,50 @@ def slab_partition(nz, nstages):
     return out
 
 
-def split_beam(bx, bp, bq, nz, dxi, nstages):
+def balanced_partition(cost, nstages, min_len=2):
+    """Contiguous xi slabs of (nearly) equal summed cost instead of equal length: the pipeline advances at the pace of
+    its slowest stage, and the cost of a slice varies along xi (predictor-corrector iterations inside the wake, clustered
+    particles).  `cost[j]` = measured cost of slice j (qpg_sim_slice_trace).  Minimises the largest slab cost (bisection
+    on the bound + greedy fill), every slab at least `min_len` slices.  Returns [(noff, nzp)] like slab_partition."""
+    cost = np.maximum(np.asarray(cost, dtype=np.float64), 1e-30)
+    nz = len(cost)
+    if nstages * min_len > nz:
+        raise ValueError("more stages than slices")
+
+    def fill(bound):
+        cuts, acc, start = [], 0.0, 0
+        for j in range(nz):
+            left = nstages - len(cuts) - 1                       # slabs still to be opened after the current one
+            must_cut = nz - j == left * min_len and j - start >= min_len      # the rest is needed for the remaining slabs
+            if j > start and ((acc + cost[j] > bound and j - start >= min_len and left > 0) or must_cut):
+                cuts.append(j); acc, start = 0.0, j
+            acc += cost[j]
+        return cuts
+
+    def worst(cuts):
+        edges = [0] + cuts + [nz]
+        return max(cost[a:b].sum() for a, b in zip(edges[:-1], edges[1:]))
+
+    lo, hi = cost.sum() / nstages, cost.sum()
+    for _ in range(60):
+        mid = 0.5 * (lo + hi)
+        c = fill(mid)
+        if len(c) == nstages - 1 and worst(c) <= mid * (1 + 1e-12):
+            hi = mid
+        else:
+            lo = mid
+    cuts = fill(hi)
+    while len(cuts) < nstages - 1:                               # (only if the bound was never binding) split the longest slab
+        edges = [0] + cuts + [nz]
+        k = int(np.argmax(np.diff(edges)))
+        cuts = sorted(cuts + [(edges[k] + edges[k + 1]) // 2])
+    edges = [0] + cuts + [nz]
+    return [(a, b - a) for a, b in zip(edges[:-1], edges[1:])]
+
+
+def split_beam(bx, bp, bq, nz, dxi, nstages, parts=None):
     """owner stage of each beam particle: the slab [noff2, noff2+nzp)*dxi that holds xi (part3d_comm.f03 goto_here)"""
-    edges = [noff * dxi for noff, _ in slab_partition(nz, nstages)][1:]
+    edges = [noff * dxi for noff, _ in (parts or slab_partition(nz, nstages))][1:]
     owner = np.searchsorted(np.asarray(edges), bx[:, 2], side="right") if nstages > 1 else np.zeros(len(bq), int)
     return [tuple(np.ascontiguousarray(a[owner == k]) for a in (bx, bp, bq)) for k in range(nstages)]
 
@@ -344,6 +385,40 @@ class PipelineStage:
         self.sim.close()
 
 
+def probe_slice_costs(cfg, plasma, beam, device=0, ctas=0, steps=2):
+    """Cost profile of the deck along xi: one stage sweeps the whole box `steps` times with the CTA count a pipeline
+    stage will have; returns (ns per slice, PC iterations per slice) of the last sweep (qpg_sim_slice_trace)."""
+    sim = _make_sim(cfg, len(plasma[4]), len(beam[2]), None, device, 1)
+    try:
+        if ctas:
+            sim.set_sweep_ctas(ctas)
+        sim.init_species(*plasma)
+        sim.beam.upload(*beam)
+        for _ in range(steps):
+            sim.step3d()
+        return sim.slice_trace()
+    finally:
+        sim.close()
+
+
+def probe_partition(cfg, plasma, beam, nstages_total, stages_per_gpu, device=0, rank=0, world=1, dist=None, free_sms=0):
+    """cost-balanced slab partition for a pipeline of `nstages_total` stages; with several ranks rank 0 measures and
+    everybody uses its answer (the partition must be the same on every rank)"""
+    import torch
+    parts = None
+    if rank == 0:
+        nsm = torch.cuda.get_device_properties(device).multi_processor_count
+        ns, _ = probe_slice_costs(cfg, plasma, beam, device, (nsm - free_sms) // stages_per_gpu if nstages_total > 1 else 0)
+        k = 8                                                     # smooth over a few slices: single-slice timer noise is not load
+        cost = np.convolve(np.pad(ns, (k // 2, k - 1 - k // 2), mode="edge"), np.ones(k) / k, mode="valid")
+        parts = balanced_partition(cost, nstages_total, min_len=min(16, cfg["nz"] // nstages_total))
+    if world > 1:
+        box = [parts]
+        dist.broadcast_object_list(box, src=0)
+        parts = [tuple(p) for p in box[0]]
+    return parts
+
+
 class PeerLinks:
     """Peer-memory links of one rank to its two neighbours (csrc/p2p.cu): the wire buffers this rank CONSUMES and one
     block of flag words live in its own memory and are exported through CUDA IPC handles; the neighbours map them and
@@ -408,15 +483,20 @@ class LocalPipeline:
     for SMs, nothing blocks the host); "nccl" = torch.distributed send/recv of local wire buffers.
     """
 
-    def __init__(self, cfg, plasma, beam, nstages, device=0, beam_wire_cap=None, rank=0, world=1, dist=None, transport=None):
+    def __init__(self, cfg, plasma, beam, nstages, device=0, beam_wire_cap=None, rank=0, world=1, dist=None, transport=None, partition=None):
         import torch
         self.torch, self.cfg, self.S, self.plasma = torch, cfg, nstages, plasma
         self.rank, self.world, self.G, self.base = rank, world, world * nstages, rank * nstages
         self.dist = dist
         S, G = nstages, self.G
         dxi = (cfg["zmax"] - cfg["zmin"]) / cfg["nz"]
-        parts = slab_partition(cfg["nz"], G)
-        beams = split_beam(*beam, cfg["nz"], dxi, G)
+        # xi slabs: the reference's equal-length rule (options_class.f03:103-106) unless a partition is handed in
+        # (balanced_partition / probe_partition: slabs of equal measured cost)
+        parts = [tuple(p) for p in partition] if partition is not None else slab_partition(cfg["nz"], G)
+        if len(parts) != G or parts[0][0] != 0 or sum(n for _, n in parts) != cfg["nz"] or any(a + n != b for (a, n), (b, _) in zip(parts[:-1], parts[1:])):
+            raise ValueError(f"partition {parts} does not tile the {cfg['nz']} slices with {G} contiguous slabs")
+        self.parts = parts
+        beams = split_beam(*beam, cfg["nz"], dxi, G, parts=parts)
         nsm = torch.cuda.get_device_properties(device).multi_processor_count
         self.transport = (transport or os.environ.get("QPG_PIPELINE_TRANSPORT", "p2p")) if world > 1 else None
         if self.transport not in (None, "p2p", "nccl"):
@@ -459,6 +539,8 @@ class LocalPipeline:
         self.off_back = (0, nb)
         self.ev, self.pending = {}, {}
         self.w = 0
+        self._ev_on = bool(os.environ.get("QPG_TRACE_EVENTS"))
+        self._marks = [[] for _ in range(S)]
 
     # events: recorded on the producer's stream, waited on by the consumer's stream; host order = a valid schedule
     def _rec(self, name, r):
@@ -485,6 +567,30 @@ class LocalPipeline:
         with self.torch.cuda.stream(self.comm):
             self.pending[name] = self.dist.isend(t, dst)
 
+    # optional device-time trace (QPG_TRACE_EVENTS=1): CUDA events on the stage's stream at named marks of its wave
+    def _mark(self, r, name):
+        if not self._ev_on:
+            return
+        ev = self.torch.cuda.Event(enable_timing=True)
+        ev.record(self.streams[r])
+        self._marks[r].append((name, ev))
+
+    def event_report(self):
+        """per stage: average device time (ms) between consecutive marks, in order of first appearance"""
+        self.sync()
+        out = []
+        for marks in self._marks:
+            acc, cnt = {}, {}
+            for (n0, e0), (n1, e1) in zip(marks[:-1], marks[1:]):
+                k = f"{n0}>{n1}"
+                acc[k] = acc.get(k, 0.0) + e0.elapsed_time(e1)
+                cnt[k] = cnt.get(k, 0) + 1
+            out.append({k: round(acc[k] / cnt[k], 3) for k in acc})
+        return out
+
+    def trace_reset(self):
+        self._marks = [[] for _ in range(self.S)]
+
     # peer-memory links: stream-ordered flag waits / writes on the stage's stream
     def _pwait(self, r, name, n):
         if n > 0:
@@ -501,8 +607,10 @@ class LocalPipeline:
         p2p_up, p2p_down = remote_up and self.p2p, remote_down and self.p2p
         if upload is not None:
             s.species.upload(*upload)                                   # the host re-injects the plasma (species%renew)
+        self._mark(r, "head")
         s.beam_qdp_begin()
         src = None
+        self._mark(r, "w_fwd")
         if p2p_up:
             n_in = self.links.next("fwd_in")
             self._pwait(r, "ready_fwd", n_in)
@@ -514,10 +622,12 @@ class LocalPipeline:
         elif r > 0:
             self._wait("fwd_ready", r - 1)
             src = self.fwd[r - 1]
+        self._mark(r, "got_fwd")
         if src is not None:
             fin = lambda k: src.data_ptr() + 8 * self.off_fwd[k]
             s.field("beam_q").unpack(1, fin(0), add=True)
         s.beam_qdp_end()
+        self._mark(r, "qdp")
         s.begin_step()
         if src is not None:
             s.species.unpack(fin(3))
@@ -527,7 +637,9 @@ class LocalPipeline:
                 self._psignal(r, "up", "ack_fwd", n_in)
             elif not remote_up:
                 self._rec("fwd_free", r - 1)
+        self._mark(r, "begun")
         s.run_slices(1, 1)
+        self._mark(r, "slice1")
         ev_back = None
         if src is not None:
             bdst = self.back[r].data_ptr()
@@ -545,8 +657,10 @@ class LocalPipeline:
                 self._psignal(r, "up", "ready_back", n_b)
             else:
                 ev_back = self._rec("back_ready", r)
+        self._mark(r, "sweep")
         if s.nzp > 1:
             s.run_slices(2, s.nzp)
+        self._mark(r, "swept")
         if remote_up and not self.p2p:
             # after the sweep is enqueued: posting NCCL operations can block the host for milliseconds
             self._nccl_isend("back", self.back[r], self.rank - 1, ev_back)
@@ -571,6 +685,7 @@ class LocalPipeline:
                 self._psignal(r, "down", "ready_fwd", n_f)
             else:
                 self._rec("fwd_ready", r)
+        self._mark(r, "packed")
 
     def _tail(self, r, renew=True):
         s, S = self.sims[r], self.S
@@ -578,6 +693,7 @@ class LocalPipeline:
         remote_up = r == 0 and self.rank > 0
         remote_down = r == S - 1 and self.rank < self.world - 1
         p2p_up, p2p_down = remote_up and self.p2p, remote_down and self.p2p
+        self._mark(r, "tail")
         if p2p_down:
             n_b = self.links.next("back_in")
             self._pwait(r, "ready_back", n_b)
@@ -592,6 +708,7 @@ class LocalPipeline:
             bsrc = self.back[r + 1]
         else:
             bsrc = None
+        self._mark(r, "got_back")
         if bsrc is not None:
             s.field("b").unpack(s.nzp + 1, bsrc.data_ptr() + 8 * self.off_back[0])
             s.field("e").unpack(s.nzp + 1, bsrc.data_ptr() + 8 * self.off_back[1])
@@ -600,6 +717,7 @@ class LocalPipeline:
             elif not remote_down:
                 self._rec("back_free", r + 1)
         s.beam_push()
+        self._mark(r, "pushed")
         if p2p_up:
             n_m = self.links.next("beam_in")
             self._pwait(r, "ready_beam", n_m)
@@ -625,8 +743,10 @@ class LocalPipeline:
             self._wait("beam_free", r)
             s.beam.pack_forward(self.beamb[r].data_ptr())
             self._rec("beam_ready", r)
+        self._mark(r, "moved")
         if renew:
             s.renew()
+        self._mark(r, "renewed")
 
     def wave(self, upload=None):
         """global stage g: tail of step w-g-1, then head of step w-g.  Descending order: a stage's tail needs the first

@@ -731,3 +731,44 @@ def test_local_pipeline_matches_oracle(mods, S):
         nb += len(oq)
     assert nb > 0
     lp.close()
+
+
+def test_local_pipeline_with_unequal_slabs(mods):
+    """cost-balanced (unequal) xi slabs change nothing but the schedule: a 3-stage pipeline over slabs of 5 / 17 / 10
+    slices reproduces the oracle's single-stage run, and probe_partition returns a valid tiling"""
+    capi, O = mods
+    from qpad_b200 import decks
+    from qpad_b200.pipeline import LocalPipeline, probe_partition
+    cfg = dict(nr=64, nz=32, max_mode=1, rmax=5.0, zmin=-5.0, zmax=5.0, dt=10.0, ppc1=2, ppc2=2, num_theta=8, iter_max=2,
+               iter_reltol=1e-3, iter_abstol=1e-3)
+    beam = dict(decks.CONFIGS["C1"]["beam"])
+    bm = decks.beam_std(cfg["nr"], cfg["nz"], cfg["rmax"], cfg["zmin"], cfg["zmax"], **beam)
+    plasma = decks.plasma_uniform(cfg["nr"], cfg["rmax"], cfg["ppc1"], cfg["ppc2"], cfg["num_theta"])
+    parts = [(0, 5), (5, 17), (22, 10)]
+    lp = LocalPipeline(cfg, plasma, bm, 3, partition=parts)
+    nwaves = 4
+    for _ in range(nwaves):
+        lp.wave()
+    lp.drain()
+    kw = {k: cfg[k] for k in ("nr", "nz", "max_mode", "rmax", "zmin", "zmax", "dt", "iter_max", "iter_reltol", "iter_abstol")}
+    orc = O.Sim(ppc1=2, ppc2=2, num_theta=8, nstages=1, **kw)
+    orc.set_beam(*bm)
+    for k in range(nwaves):
+        orc.step3d(k + 1)
+    upd, iters, slices = lp.stats()
+    assert slices == nwaves * cfg["nz"] and iters == orc.total_iters()
+    got_q = []
+    for (noff, nzp), sim in zip(parts, lp.sims):
+        assert (sim.noff2, sim.nzp) == (noff, nzp)
+        ns, it = sim.slice_trace()
+        assert np.all(ns > 0) and np.all(it >= 1) and np.all(it <= cfg["iter_max"])
+        for name in ("psi", "e", "b"):
+            got, want = sim.field(name).download_f2()[:, :nzp], orc.field(name, 2, stage=0)[:, noff:noff + nzp]
+            assert np.max(np.abs(got - want)) < 1e-6 * np.max(np.abs(want)), (noff, name)
+        got_q.append(sim.beam.download()[2])
+    ox, op, oq = orc.beam(stage=0)
+    assert np.array_equal(np.sort(np.concatenate(got_q)), np.sort(oq)) and len(oq) > 0
+    lp.close()
+    auto = probe_partition(cfg, plasma, bm, 3, 3)
+    assert auto[0][0] == 0 and sum(n for _, n in auto) == cfg["nz"] and all(n >= 2 for _, n in auto)
+    assert all(a + n == b for (a, n), (b, _) in zip(auto[:-1], auto[1:]))
