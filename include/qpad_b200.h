@@ -167,6 +167,9 @@ int qpg_part3d_download(qpg_part3d p, double *x, double *pm, double *q, long *np
 int qpg_part3d_qdeposit(qpg_part3d p, qpg_field q);                                              /* qdeposit_part3d :221 (into q%f2) */
 int qpg_part3d_push(qpg_part3d p, int push_type, qpg_field ef, qpg_field bf);                    /* push_reduced :477 / push_boris :358 */
 int qpg_part3d_update_bound(qpg_part3d p);                                                       /* update_bound_part3d :640 */
+/* qpg_part3d_qdeposit in two halves (see qpg_sim_beam_qdp_raw / _fix) */
+int qpg_part3d_qdeposit_raw(qpg_part3d p, qpg_field q);
+int qpg_part3d_qdeposit_fix(qpg_part3d p, qpg_field q);
 /* forward xi hand-off of beam/part3d_comm.f03:278-314 + pack_particles('pipeline') :685-745:
  * pack particles with xi >= upper slab edge into dev_buf (dev_buf[0] = count, then 7 doubles each), remove them
  * ("fill the holes inversely"); unpack appends.  Buffer size = 1 + 7*cap doubles, cap = qpg_part3d_wire_cap()
@@ -215,6 +218,15 @@ int qpg_sim_beam_qdp_end(qpg_sim s);
 /* simulation_class.f03:299-331 minus the MPI calls: q_beam = beam_q, q_spe = 0, zero b e b_spe e_spe psi cu acu amu.
  * [caller, stage > 0: unpack cu and b_spe (slice 0) and the plasma particles received from upstream] */
 int qpg_sim_begin_step(qpg_sim s);
+/* the same two calls in halves for a pipeline stage that overlaps them with the wait for its upstream neighbour:
+ *   qpg_sim_beam_qdp_raw   : scatter-add of the stage's own beam particles (part3d_class.f03:221-316)
+ *   qpg_sim_beam_qdp_fix   : axis rules and 1/(j-1) (:318-351) -- after the upstream guard slice has been added to slice 1
+ *   qpg_sim_begin_step_zero: the zero fills of simulation_class.f03:299-331   qpg_sim_begin_step_add: q_beam += beam_q
+ * (qpg_sim_beam_qdp_end = raw + fix, qpg_sim_begin_step = zero + add) */
+int qpg_sim_beam_qdp_raw(qpg_sim s);
+int qpg_sim_beam_qdp_fix(qpg_sim s);
+int qpg_sim_begin_step_zero(qpg_sim s);
+int qpg_sim_begin_step_add(qpg_sim s);
 /* run slices j0..j1 (1-based, inclusive) of this slab: simulation_class.f03:342-469 */
 int qpg_sim_run_slices(qpg_sim s, int j0, int j1);
 /* simulation_class.f03:489-493: beam push + update_bound (E,B guard slice nzp+1 already unpacked by the caller) */

@@ -122,6 +122,12 @@ SIGNATURES = {
     "qpg_sim_beam_qdp_begin": (_i, [_vp]),
     "qpg_sim_beam_qdp_end": (_i, [_vp]),
     "qpg_sim_begin_step": (_i, [_vp]),
+    "qpg_sim_beam_qdp_raw": (_i, [_vp]),
+    "qpg_sim_beam_qdp_fix": (_i, [_vp]),
+    "qpg_sim_begin_step_zero": (_i, [_vp]),
+    "qpg_sim_begin_step_add": (_i, [_vp]),
+    "qpg_part3d_qdeposit_raw": (_i, [_vp, _vp]),
+    "qpg_part3d_qdeposit_fix": (_i, [_vp, _vp]),
     "qpg_sim_run_slices": (_i, [_vp, _i, _i]),
     "qpg_sim_beam_push": (_i, [_vp]),
     "qpg_sim_renew": (_i, [_vp]),
@@ -446,6 +452,10 @@ class Sim:
     def beam_qdp_begin(self): _chk(self.L.qpg_sim_beam_qdp_begin(self.h))
     def beam_qdp_end(self): _chk(self.L.qpg_sim_beam_qdp_end(self.h))
     def begin_step(self): _chk(self.L.qpg_sim_begin_step(self.h))
+    def beam_qdp_raw(self): _chk(self.L.qpg_sim_beam_qdp_raw(self.h))
+    def beam_qdp_fix(self): _chk(self.L.qpg_sim_beam_qdp_fix(self.h))
+    def begin_step_zero(self): _chk(self.L.qpg_sim_begin_step_zero(self.h))
+    def begin_step_add(self): _chk(self.L.qpg_sim_begin_step_add(self.h))
     def run_slices(self, j0, j1): _chk(self.L.qpg_sim_run_slices(self.h, j0, j1))
     def beam_push(self): _chk(self.L.qpg_sim_beam_push(self.h))
     def renew(self): _chk(self.L.qpg_sim_renew(self.h))

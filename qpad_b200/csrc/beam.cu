@@ -310,7 +310,10 @@ extern "C" int qpg_part3d_download(qpg_part3d p, double *x, double *pm, double *
         for (int c = 0; c < 3; c++) { if (x) x[3 * i + c] = h[(size_t)c * npp + i]; if (pm) pm[3 * i + c] = h[(size_t)(3 + c) * npp + i]; }
     return 0;
 }
-extern "C" int qpg_part3d_qdeposit(qpg_part3d p, qpg_field q)
+// the deposit in two halves, so that a pipeline stage can scatter its own particles BEFORE the upstream guard slice
+// arrives: raw = the scatter-add of part3d_class.f03:221-316, fix = the axis rules and 1/(j-1) of :318-351 (which must see
+// the upstream stage's guard-slice contribution in slice 1)
+extern "C" int qpg_part3d_qdeposit_raw(qpg_part3d p, qpg_field q)
 {
     ARG_TRY(p && q && q->dim == 1 && q->has2d && q->nzp == p->nzp && q->ctx == p->ctx, "q must be a dim-1 field with this slab's 2D layout");
     qpg_ctx c = p->ctx;
@@ -320,10 +323,23 @@ extern "C" int qpg_part3d_qdeposit(qpg_part3d p, qpg_field q)
         DISPATCH_M(c->M, l_qdep3d, grid, c->stream, view3(p), q->f2, 1.0 / c->dr, 1.0 / c->dxi, c->nr, p->noff2, p->nzp);
         count_launch(c);
     }
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+extern "C" int qpg_part3d_qdeposit_fix(qpg_part3d p, qpg_field q)
+{
+    ARG_TRY(p && q && q->dim == 1 && q->has2d && q->nzp == p->nzp && q->ctx == p->ctx, "q must be a dim-1 field with this slab's 2D layout");
+    qpg_ctx c = p->ctx;
+    TprofScope tp(c, TP_DEPOSIT3D);
     k_qdep3d_fix<<<592, 256, 0, c->stream>>>(q->f2, c->nr, c->P, p->nzp);
     count_launch(c);
     CUDA_TRY(cudaGetLastError());
     return 0;
+}
+extern "C" int qpg_part3d_qdeposit(qpg_part3d p, qpg_field q)
+{
+    int rc = qpg_part3d_qdeposit_raw(p, q);
+    return rc ? rc : qpg_part3d_qdeposit_fix(p, q);
 }
 extern "C" int qpg_part3d_push(qpg_part3d p, int push_type, qpg_field ef, qpg_field bf)
 {

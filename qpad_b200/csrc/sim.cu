@@ -382,17 +382,29 @@ extern "C" int qpg_sim_init_species(qpg_sim s, const double *x, const double *pm
 }
 extern "C" int qpg_sim_beam_qdp_begin(qpg_sim s) { ARG_TRY(s, "null sim"); return qpg_field_fill_f2(s->beam_q, 0.0); }   // beam3d_class.f03:207
 extern "C" int qpg_sim_beam_qdp_end(qpg_sim s) { ARG_TRY(s, "null sim"); return qpg_part3d_qdeposit(s->beam, s->beam_q); } // :210
-// simulation_class.f03:299-331 (everything but the MPI calls)
-extern "C" int qpg_sim_begin_step(qpg_sim s)
+extern "C" int qpg_sim_beam_qdp_raw(qpg_sim s) { ARG_TRY(s, "null sim"); return qpg_part3d_qdeposit_raw(s->beam, s->beam_q); }
+extern "C" int qpg_sim_beam_qdp_fix(qpg_sim s) { ARG_TRY(s, "null sim"); return qpg_part3d_qdeposit_fix(s->beam, s->beam_q); }
+// simulation_class.f03:299-331 (everything but the MPI calls), in two halves: _zero touches nothing a hand-off delivers
+// (a pipeline stage runs it while it waits for the upstream stage), _add folds the finished beam charge into q_beam
+extern "C" int qpg_sim_begin_step_zero(qpg_sim s)
 {
     ARG_TRY(s, "null sim");
     int rc;
     if ((rc = qpg_field_fill_f2(s->q_beam, 0.0))) return rc;
     if ((rc = qpg_field_fill_f2(s->q_spe, 0.0))) return rc;
-    if ((rc = qpg_field_add_f2(s->beam_q, s->q_beam))) return rc;  // beam3d_class.f03:217 add_f2
     qpg_field z[] = {s->b, s->e, s->b_spe, s->e_spe, s->psi, s->cu, s->acu, s->amu};
     for (auto f : z) if ((rc = qpg_field_fill(f, 0.0))) return rc;
     return 0;
+}
+extern "C" int qpg_sim_begin_step_add(qpg_sim s)
+{
+    ARG_TRY(s, "null sim");
+    return qpg_field_add_f2(s->beam_q, s->q_beam);  // beam3d_class.f03:217 add_f2
+}
+extern "C" int qpg_sim_begin_step(qpg_sim s)
+{
+    int rc = qpg_sim_begin_step_zero(s);
+    return rc ? rc : qpg_sim_begin_step_add(s);
 }
 
 extern "C" int qpg_sim_run_slices(qpg_sim s, int j0, int j1)

@@ -387,30 +387,43 @@ class PipelineStage:
 
 def probe_slice_costs(cfg, plasma, beam, device=0, ctas=0, steps=2):
     """Cost profile of the deck along xi: one stage sweeps the whole box `steps` times with the CTA count a pipeline
-    stage will have; returns (ns per slice, PC iterations per slice) of the last sweep (qpg_sim_slice_trace)."""
+    stage will have; returns (ns per slice, PC iterations per slice, ns of beam deposit + push + move per slice) of the
+    last step (qpg_sim_slice_trace; the beam kernels' time is spread over the slices like the beam particles)."""
     sim = _make_sim(cfg, len(plasma[4]), len(beam[2]), None, device, 1)
     try:
         if ctas:
             sim.set_sweep_ctas(ctas)
         sim.init_species(*plasma)
         sim.beam.upload(*beam)
-        for _ in range(steps):
+        for k in range(steps):
+            if k == steps - 1:
+                sim.ctx.tprof_reset(); sim.ctx.tprof_enable(True)
             sim.step3d()
-        return sim.slice_trace()
+        beam_ms = sum(sim.ctx.tprof_get(ev)[0] for ev in ("deposit 3D particles", "push 3D particles", "move 3D particles"))
+        sim.ctx.tprof_enable(False)
+        ns, it = sim.slice_trace()
+        bx = sim.beam.download()[0]
+        dxi = (cfg["zmax"] - cfg["zmin"]) / cfg["nz"]
+        cnt = np.bincount(np.clip((bx[:, 2] / dxi).astype(np.int64), 0, cfg["nz"] - 1), minlength=cfg["nz"]).astype(np.float64)
+        beam_ns = cnt * (beam_ms * 1e6 / max(cnt.sum(), 1.0))
+        return ns, it, beam_ns
     finally:
         sim.close()
 
 
 def probe_partition(cfg, plasma, beam, nstages_total, stages_per_gpu, device=0, rank=0, world=1, dist=None, free_sms=0):
     """cost-balanced slab partition for a pipeline of `nstages_total` stages; with several ranks rank 0 measures and
-    everybody uses its answer (the partition must be the same on every rank)"""
+    everybody uses its answer (the partition must be the same on every rank).  Cost of a slice = its sweep time with a
+    stage's CTA count + its share of the beam deposit / push (measured on the whole GPU, a stage has 1/stages_per_gpu of
+    it while its neighbours sweep)."""
     import torch
     parts = None
     if rank == 0:
         nsm = torch.cuda.get_device_properties(device).multi_processor_count
-        ns, _ = probe_slice_costs(cfg, plasma, beam, device, (nsm - free_sms) // stages_per_gpu if nstages_total > 1 else 0)
+        ns, _, beam_ns = probe_slice_costs(cfg, plasma, beam, device, (nsm - free_sms) // stages_per_gpu if nstages_total > 1 else 0)
         k = 8                                                     # smooth over a few slices: single-slice timer noise is not load
         cost = np.convolve(np.pad(ns, (k // 2, k - 1 - k // 2), mode="edge"), np.ones(k) / k, mode="valid")
+        cost = cost + float(os.environ.get("QPG_BALANCE_BEAM_WEIGHT", stages_per_gpu)) * beam_ns
         parts = balanced_partition(cost, nstages_total, min_len=min(16, cfg["nz"] // nstages_total))
     if world > 1:
         box = [parts]
@@ -608,7 +621,10 @@ class LocalPipeline:
         if upload is not None:
             s.species.upload(*upload)                                   # the host re-injects the plasma (species%renew)
         self._mark(r, "head")
+        # everything that does not need the upstream hand-off first: the stage does it while it waits
         s.beam_qdp_begin()
+        s.beam_qdp_raw()
+        s.begin_step_zero()
         src = None
         self._mark(r, "w_fwd")
         if p2p_up:
@@ -626,9 +642,9 @@ class LocalPipeline:
         if src is not None:
             fin = lambda k: src.data_ptr() + 8 * self.off_fwd[k]
             s.field("beam_q").unpack(1, fin(0), add=True)
-        s.beam_qdp_end()
+        s.beam_qdp_fix()
         self._mark(r, "qdp")
-        s.begin_step()
+        s.begin_step_add()
         if src is not None:
             s.species.unpack(fin(3))
             s.field("cu").unpack(0, fin(1))
@@ -694,6 +710,8 @@ class LocalPipeline:
         remote_down = r == S - 1 and self.rank < self.world - 1
         p2p_up, p2p_down = remote_up and self.p2p, remote_down and self.p2p
         self._mark(r, "tail")
+        if renew:
+            s.renew()                                                   # needs nothing from the neighbours: before the wait
         if p2p_down:
             n_b = self.links.next("back_in")
             self._pwait(r, "ready_back", n_b)
@@ -744,9 +762,6 @@ class LocalPipeline:
             s.beam.pack_forward(self.beamb[r].data_ptr())
             self._rec("beam_ready", r)
         self._mark(r, "moved")
-        if renew:
-            s.renew()
-        self._mark(r, "renewed")
 
     def wave(self, upload=None):
         """global stage g: tail of step w-g-1, then head of step w-g.  Descending order: a stage's tail needs the first

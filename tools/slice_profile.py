@@ -12,9 +12,10 @@ name = sys.argv[1] if len(sys.argv) > 1 else "C2"
 ctas = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 cfg, beam = deck_config(name)
 plasma, bm = make_inputs(cfg, beam)
-ns, it = probe_slice_costs(cfg, plasma, bm, 0, ctas)
+ns, it, beam_ns = probe_slice_costs(cfg, plasma, bm, 0, ctas)
+print(f'beam deposit+push+move: {beam_ns.sum() * 1e-6:.3f} ms on the whole GPU')
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-np.savez(os.path.join(ROOT, "gpurun_out", f"slice_profile_{name}_{ctas}.npz"), ns=ns, it=it)
+np.savez(os.path.join(ROOT, "gpurun_out", f"slice_profile_{name}_{ctas}.npz"), ns=ns, it=it, beam_ns=beam_ns)
 blk = max(1, len(ns) // 32)
 print(f"{name} ctas={ctas}: total {ns.sum() * 1e-6:.2f} ms, mean {ns.mean() * 1e-3:.1f} us/slice, iterations/slice {it.mean():.3f}")
 print("us/slice by 1/32 of the box:", [round(float(ns[k:k + blk].mean()) * 1e-3, 1) for k in range(0, len(ns), blk)])
