@@ -404,7 +404,7 @@ def run_b200_local(args):
     u0, i0, s0 = lp.stats()
     l0 = lp.launch_count()
     for sim in lp.sims:
-        sim.sweep_profile(reset=True); sim.ctx.tprof_reset(); sim.ctx.tprof_enable(True)
+        sim.sweep_profile(reset=True)      # in-kernel clocks only: no event pairs around the library calls of the timed region
     clk = ClockSampler(local); clk.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
@@ -432,11 +432,10 @@ def run_b200_local(args):
     sweep_ms = sweep_n = 0
     profs = []
     for sim in lp.sims:
-        m_, n_ = sim.ctx.tprof_get("kernel sweep")
-        sweep_ms += m_; sweep_n += n_
-        sim.ctx.tprof_enable(False)
         profs.append(sim.sweep_profile())
     launches = lp.launch_count() - l0
+    sweep_ms = sum(p["ns_total"] for p in profs) * 1e-6           # %globaltimer inside the kernels
+    sweep_n = args.steps * (S + (1 if (lp.transport == "nccl" and rank > 0) else 0))   # one launch per slab (NCCL transport: first slice of a rank's first stage separately)
     # device time each stage spent inside its sweep kernel per step (all ranks): the pipeline runs at the pace of the slowest
     mine = [round(p["ns_total"] * 1e-6 / args.steps, 3) for p in profs]
     sweep_by_stage = mine
@@ -523,7 +522,7 @@ def run_b200_local(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="C2")

@@ -229,6 +229,12 @@ int qpg_sim_begin_step_zero(qpg_sim s);
 int qpg_sim_begin_step_add(qpg_sim s);
 /* run slices j0..j1 (1-based, inclusive) of this slab: simulation_class.f03:342-469 */
 int qpg_sim_run_slices(qpg_sim s, int j0, int j1);
+/* backward hand-off of the xi-pipeline (simulation_class.f03:460-467) without leaving the sweep: the next
+ * qpg_sim_run_slices call that starts at slice 1 writes b and e of that slice in wire layout ([P][nr+2][3] each) into
+ * wire_b / wire_e -- device pointers, possibly the upstream GPU's memory mapped with qpg_wire_import -- as soon as the
+ * slice is complete, then sets *flag = seq (system-scope release).  The consumer orders its stream behind it with
+ * qpg_stream_wait(flag, seq).  One-shot: applies to one first slice. */
+int qpg_sim_set_back_handoff(qpg_sim s, double *wire_b, double *wire_e, unsigned *flag, unsigned seq);
 /* simulation_class.f03:489-493: beam push + update_bound (E,B guard slice nzp+1 already unpacked by the caller) */
 int qpg_sim_beam_push(qpg_sim s);
 /* simulation_class.f03:498-501 species%renew from the device snapshot of the injected lattice */

@@ -122,6 +122,7 @@ SIGNATURES = {
     "qpg_sim_beam_qdp_begin": (_i, [_vp]),
     "qpg_sim_beam_qdp_end": (_i, [_vp]),
     "qpg_sim_begin_step": (_i, [_vp]),
+    "qpg_sim_set_back_handoff": (_i, [_vp, _vp, _vp, _vp, C.c_uint]),
     "qpg_sim_beam_qdp_raw": (_i, [_vp]),
     "qpg_sim_beam_qdp_fix": (_i, [_vp]),
     "qpg_sim_begin_step_zero": (_i, [_vp]),
@@ -452,6 +453,9 @@ class Sim:
     def beam_qdp_begin(self): _chk(self.L.qpg_sim_beam_qdp_begin(self.h))
     def beam_qdp_end(self): _chk(self.L.qpg_sim_beam_qdp_end(self.h))
     def begin_step(self): _chk(self.L.qpg_sim_begin_step(self.h))
+    def set_back_handoff(self, wire_b, wire_e, flag, seq):
+        _chk(self.L.qpg_sim_set_back_handoff(self.h, wire_b, wire_e, flag, seq & 0xFFFFFFFF))
+
     def beam_qdp_raw(self): _chk(self.L.qpg_sim_beam_qdp_raw(self.h))
     def beam_qdp_fix(self): _chk(self.L.qpg_sim_beam_qdp_fix(self.h))
     def begin_step_zero(self): _chk(self.L.qpg_sim_begin_step_zero(self.h))

@@ -28,6 +28,7 @@ struct qpg_sim_s {
     double *sw_xbuf;      // team exchange records
     void *sw_xll;         // flagged exchange words of the strip scans
     long long *sw_prof;   // in-kernel phase clocks
+    double *back_b, *back_e; unsigned *back_flag; unsigned back_seq;   // one-shot backward hand-off of the next first slice (qpg_sim_set_back_handoff)
     long long *sw_trace;  // per-slice time and PC iteration count of the last sweep over each slice [nzp][2]
     double *phi;
     long host_updates, host_iters, host_slices;
@@ -222,6 +223,10 @@ static int sweep_run(qpg_sim s, int j0, int j1)
     a.d_npp_w = p->d_npp; a.d_nout = p->d_nout; a.outmask = p->outmask; a.lists = p->lists;
     a.qbm = p->qbm; a.edge = (double)c->nr * c->dr;
     a.j0 = j0; a.j1 = j1; a.nteam = (c->nr + ST_N - 1) / ST_N;
+    if (j0 == 1 && s->back_flag) {   // the launch that sweeps the slab's first slice publishes it (one-shot)
+        a.back_b = s->back_b; a.back_e = s->back_e; a.back_flag = s->back_flag; a.back_seq = s->back_seq;
+        s->back_flag = nullptr;
+    }
     a.bar = s->sw_bar; a.xbuf = s->sw_xbuf; a.xll = (uint4 *)s->sw_xll; a.prof = s->sw_prof; a.trace = s->sw_trace;
     CUDA_TRY(cudaMemsetAsync(s->sw_bar, 0, sizeof(unsigned) * 128, c->stream));
     CUDA_TRY(cudaMemsetAsync(s->sw_xll, 0, sizeof(uint4) * 2 * SW_MAX_TEAM * SW_XK, c->stream));   // sequence numbers restart at 1 every launch
@@ -448,12 +453,24 @@ extern "C" int qpg_sim_run_slices(qpg_sim s, int j0, int j1)
             for (int l = 0; l < s->prm.iter_max; l++) if ((rc = enqueue_pc_iteration(s))) return rc;
             if ((rc = enqueue_slice_tail(s))) return rc;
         }
+        if (j == 1 && s->back_flag) {   // per-slice launch paths: pack kernels + flag write after the first slice
+            if ((rc = qpg_field_pack(s->b, 1, s->back_b))) return rc;
+            if ((rc = qpg_field_pack(s->e, 1, s->back_e))) return rc;
+            if ((rc = qpg_stream_signal(c->stream, s->back_flag, s->back_seq))) return rc;
+            s->back_flag = nullptr;
+        }
         if (s->prm.sort_freq > 0 && ((s->prm.noff2 + j) % s->prm.sort_freq) == 0) {
             if ((rc = qpg_part2d_sort(s->spe))) return rc;
             CUDA_TRY(cudaMemsetAsync(s->spe->acc1, 0, sizeof(double) * (size_t)(c->nr + 2) * c->P, c->stream));
             if ((rc = part2d_launch_qdeposit(s->spe))) return rc;
         }
     }
+    return 0;
+}
+extern "C" int qpg_sim_set_back_handoff(qpg_sim s, double *wire_b, double *wire_e, unsigned *flag, unsigned seq)
+{
+    ARG_TRY(s && wire_b && wire_e && flag, "null arg");
+    s->back_b = wire_b; s->back_e = wire_e; s->back_flag = flag; s->back_seq = seq;
     return 0;
 }
 extern "C" int qpg_sim_beam_push(qpg_sim s)

@@ -35,6 +35,9 @@ struct SweepArgs {
     unsigned *bar;          // [0] grid arrivals, [32] team arrivals, [64] abort flag (one 128-byte line each)
     double *xbuf;           // [3][SW_XK][SW_MAX_TEAM]: slab 2 = residual maxima of program C (read after a grid barrier)
     uint4 *xll;             // [2][SW_XK][SW_MAX_TEAM] flagged 16-byte exchange words of the strip scans (cleared before each launch)
+    double *back_b, *back_e; // wire buffers [P][nr+2][3] (possibly in the upstream GPU's memory) that receive b and e of the slab's FIRST slice
+    unsigned *back_flag;    // ... and the flag word raised once they are complete (null: no backward hand-off from this launch)
+    unsigned back_seq;
     long long *trace;       // per slice of the slab: [2*(j-1)] ns spent in slice j (globaltimer), [2*(j-1)+1] PC iterations it took
     long long *prof;        // [0..3] cycles in phase A / amj / C / push, [4] total cycles, [5] total ns, [6] slices, [7] amj phases, [8..11] CTA 0's own work cycles per phase (thread 0's arrival at the barrier)
 };
@@ -561,6 +564,27 @@ __device__ __forceinline__ bool sweep_conv_decide(const SweepArgs &a, int it, bo
 }
 
 // ============================================================================================================
+// Backward hand-off of the xi-pipeline from inside the sweep (simulation_class.f03:460-467: e and b of the slab's first slice
+// go to the upstream stage, which needs them as guard slice nzp+1 for its beam push).  One CTA that idles during phase A
+// copies the two slice images into the wire layout [P][nr+2][3] -- the destination may be mapped peer memory -- and raises
+// the flag the consumer's stream waits for (csrc/p2p.cu).  The upstream stage gets its guard slice one slice into the
+// sweep instead of after a separate first-slice launch + pack kernels.
+template <int M>
+__device__ void sweep_publish_back(const SweepArgs &a)
+{
+    constexpr int P = 2 * M + 1;
+    const int n = (a.f.nr + 2) * P * 3;
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+        const int c = k % 3, r = k / 3, j = r % (a.f.nr + 2), pl = r / (a.f.nr + 2);
+        const size_t src = ((size_t)j * P + pl) * 3 + c;       // slice 1 = the first image of the f2 volume
+        a.back_b[k] = __ldcg(a.f.b2 + src);
+        a.back_e[k] = __ldcg(a.f.e2 + src);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.back_flag), "r"(a.back_seq) : "memory");
+}
+
 template <int M>
 __global__ void __launch_bounds__(SW_T, 1) k_sweep(const __grid_constant__ SweepArgs a)
 {
@@ -646,6 +670,7 @@ __global__ void __launch_bounds__(SW_T, 1) k_sweep(const __grid_constant__ Sweep
             a.trace[2 * (j - 1)] = now - nprev; a.trace[2 * (j - 1) + 1] = namj - namj0;
             nprev = now;
         }
+        if (ok && j == 1 && a.back_flag && b == min(a.nteam, G - 1)) sweep_publish_back<M>(a);
     }
     // update_bound of the last slice (the next launch / the host expects compacted particles)
     if (ok && b == G - 1) compact_body(a.planes, 8, a.d_npp_w, a.d_nout, a.outmask, a.lists, 0, sm_i);

@@ -554,6 +554,9 @@ class LocalPipeline:
         self.w = 0
         self._ev_on = bool(os.environ.get("QPG_TRACE_EVENTS"))
         self._marks = [[] for _ in range(S)]
+        self.lflags = capi.WireBuf(32 * S)            # [r]: number of the last back message stage r's sweep kernel has published
+        self.nback_out, self.nback_in = [0] * S, [0] * S
+        self._zeroed = [False] * S
 
     # events: recorded on the producer's stream, waited on by the consumer's stream; host order = a valid schedule
     def _rec(self, name, r):
@@ -622,9 +625,11 @@ class LocalPipeline:
             s.species.upload(*upload)                                   # the host re-injects the plasma (species%renew)
         self._mark(r, "head")
         # everything that does not need the upstream hand-off first: the stage does it while it waits
-        s.beam_qdp_begin()
+        if not self._zeroed[r]:
+            s.beam_qdp_begin()
+            s.begin_step_zero()
+        self._zeroed[r] = False
         s.beam_qdp_raw()
-        s.begin_step_zero()
         src = None
         self._mark(r, "w_fwd")
         if p2p_up:
@@ -654,28 +659,33 @@ class LocalPipeline:
             elif not remote_up:
                 self._rec("fwd_free", r - 1)
         self._mark(r, "begun")
-        s.run_slices(1, 1)
-        self._mark(r, "slice1")
         ev_back = None
-        if src is not None:
-            bdst = self.back[r].data_ptr()
+        if src is not None and not (remote_up and not self.p2p):
+            # b and e of the first slice go back to the upstream stage FROM INSIDE the sweep kernel (it writes the wire
+            # buffer, possibly in the upstream GPU's memory, and raises the flag the upstream stream waits on): one launch
+            # per slab, the guard slice leaves one slice into the sweep
             if p2p_up:
                 n_b = self.links.next("back_out")
                 self._pwait(r, "ack_back", n_b - 1)
-                bdst = self.links.up["back_in"].ptr                     # the upstream GPU's guard-slice buffer
-            elif remote_up:
-                self._nccl_wait("back", r)
+                bdst, flag = self.links.up["back_in"].ptr, self.links.flag("up", "ready_back")
             else:
+                self.nback_out[r] += 1
+                n_b = self.nback_out[r]
                 self._wait("back_free", r)
-            s.field("b").pack(1, bdst + 8 * self.off_back[0])
-            s.field("e").pack(1, bdst + 8 * self.off_back[1])
-            if p2p_up:
-                self._psignal(r, "up", "ready_back", n_b)
-            else:
-                ev_back = self._rec("back_ready", r)
-        self._mark(r, "sweep")
-        if s.nzp > 1:
-            s.run_slices(2, s.nzp)
+                bdst, flag = self.back[r].data_ptr(), self.lflags.ptr + 32 * r
+            s.set_back_handoff(bdst + 8 * self.off_back[0], bdst + 8 * self.off_back[1], flag, n_b)
+            s.run_slices(1, s.nzp)
+        elif src is not None:
+            # NCCL transport: separate first-slice launch, pack kernels, isend
+            s.run_slices(1, 1)
+            self._nccl_wait("back", r)
+            s.field("b").pack(1, self.back[r].data_ptr() + 8 * self.off_back[0])
+            s.field("e").pack(1, self.back[r].data_ptr() + 8 * self.off_back[1])
+            ev_back = self._rec("back_ready", r)
+            if s.nzp > 1:
+                s.run_slices(2, s.nzp)
+        else:
+            s.run_slices(1, s.nzp)
         self._mark(r, "swept")
         if remote_up and not self.p2p:
             # after the sweep is enqueued: posting NCCL operations can block the host for milliseconds
@@ -712,6 +722,9 @@ class LocalPipeline:
         self._mark(r, "tail")
         if renew:
             s.renew()                                                   # needs nothing from the neighbours: before the wait
+        s.beam_qdp_begin()                                              # the next step's zero fills too (the beam push reads
+        s.begin_step_zero()                                             # the e / b VOLUMES, the fills clear slice images)
+        self._zeroed[r] = True
         if p2p_down:
             n_b = self.links.next("back_in")
             self._pwait(r, "ready_back", n_b)
@@ -722,7 +735,8 @@ class LocalPipeline:
                 self.dist.recv(self.back_in, self.rank + 1)
             bsrc = self.back_in
         elif r < S - 1:
-            self._wait("back_ready", r + 1)
+            self.nback_in[r] += 1
+            capi.stream_wait(self.streams[r].cuda_stream, self.lflags.ptr + 32 * (r + 1), self.nback_in[r])   # raised by stage r+1's sweep kernel
             bsrc = self.back[r + 1]
         else:
             bsrc = None
@@ -815,5 +829,6 @@ class LocalPipeline:
         self.sync()
         if self.links is not None:
             self.links.close()
+        self.lflags.close()
         for s in self.sims:
             s.close()
