@@ -489,6 +489,13 @@ def run_b200_local(args):
             "slab_partition": "cost-balanced (untimed calibration sweep, pipeline.probe_partition)" if parts is not None else "equal length (options_class.f03:103-106)",
             "phases_rank0": {"A||update_bound": ph["A"], "amjdeposit (64 B/particle)": ph["amj"], "C": ph["C"], "push_u+push_x+qdeposit||D (112 B/particle)": ph["push"]},
             "note": "achieved = algorithmic bytes of ALL sweep launches in the timed region / its duration, per GPU (the S kernels of a GPU overlap: a stage's latency-bound field phases and barriers hide behind the other stages' particle phases); particle planes stay L2-resident"}
+    roof_hbm = None
+    if world == 1 and not args.no_micro:
+        # the push and deposit kernels individually, streaming from HBM (north star: >= 60 % of the HBM roofline): fields of
+        # the slab that holds the wake (the stage's current slice images)
+        from qpad_b200.pipeline import kernel_microbench
+        lp.sync()
+        roof_hbm = kernel_microbench(lp.sims[min(1, S - 1)], cfg, peak)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         try:
@@ -510,6 +517,7 @@ def run_b200_local(args):
                            "pc_iters_per_slice": nit},
                 "clocks": clocks, "gpu_launches": int(launches), "roofline": roof}
         if e2e: line["e2e"] = e2e
+        if roof_hbm: line["roofline_hbm_stream"] = roof_hbm
         if cpu: line["cpu_baseline"] = cpu
         print(json.dumps(line))
     lp.drain()

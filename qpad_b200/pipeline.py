@@ -92,6 +92,46 @@ def _make_sim(cfg, npp0, nbeam, stream, device, use_graph, noff2=0, nzp=None, be
                     noff2=noff2, nzp=nzp, device=device, stream=cuda_stream)
 
 
+def kernel_microbench(sim, cfg, peak_gbs, n_big=4 * 1024 * 1024, reps=5):
+    """stream-from-HBM numbers for the three particle kernels: a lattice 16x larger than the L2 can hold
+    (n_big particles x 64 B = 268 MB), fields = the current slice's e and b of `sim`"""
+    from . import decks
+    s = sim
+    nth = max(16, n_big // (cfg["nr"] * cfg["ppc1"] * cfg["ppc2"]))
+    x, p, g, psi, q = decks.plasma_uniform(cfg["nr"], cfg["rmax"], cfg["ppc1"], cfg["ppc2"], nth)
+    n = len(q)
+    rng = np.random.default_rng(0)
+    p = 0.3 * rng.standard_normal(p.shape)
+    g = np.sqrt(1 + (p ** 2).sum(1))
+    part = capi.Part2d(s.ctx, -1.0, n + 64)
+    part.upload(x, p, g, psi, q)
+    e, b = s.field("e"), s.field("b")
+    cu, dcu, amu = capi.Field(s.ctx, 3), capi.Field(s.ctx, 2), capi.Field(s.ctx, 3)
+    fq = capi.Field(s.ctx, 1)
+    res = {}
+    s.ctx.tprof_reset(); s.ctx.tprof_enable(True)
+    for _ in range(reps + 2):
+        part.qdeposit(fq)
+        part.amjdeposit_robust(e, b, cu, amu, dcu, 1e-3)
+        part.push_u_robust(e, b, 1e-3)
+        part.push_x(1e-6)
+    for ev in ("kernel amjdeposit", "kernel qdeposit", "kernel push"):
+        res[ev] = s.ctx.tprof_get(ev)
+    s.ctx.tprof_enable(False)
+    out = {"particles": n, "note": "stand-alone particle kernels on a particle set larger than L2 (CUDA events per launch); algorithmic bytes: amjdeposit 64 B, qdeposit 24 B, push_u 72 B + push_x 64 B per particle"}
+    ms, nc = res["kernel amjdeposit"]
+    out["amjdeposit_GBs"] = 64.0 * n / (ms / nc * 1e-3) / 1e9
+    ms, nc = res["kernel qdeposit"]
+    out["qdeposit_GBs"] = 24.0 * n / (ms / nc * 1e-3) / 1e9
+    ms, nc = res["kernel push"]  # push_u and push_x launches alternate: 136 B per pair
+    out["push_u_plus_push_x_GBs"] = 136.0 * n / (2 * ms / nc * 1e-3) / 1e9
+    out["peak"] = peak_gbs
+    for k in ("amjdeposit", "qdeposit", "push_u_plus_push_x"):
+        out[k + "_frac"] = out[k + "_GBs"] / peak_gbs
+    part.close()
+    return out
+
+
 class SingleStage:
     """nodes = [1, 1]: the whole box on one GPU."""
 
@@ -128,45 +168,7 @@ class SingleStage:
         return 8 * 8 * len(q), 8 * (len(ez) + len(ps)) + 24
 
     def kernel_microbench(self, peak_gbs, n_big=4 * 1024 * 1024, reps=5):
-        """stream-from-HBM numbers for the three particle kernels: a lattice 16x larger than the L2 can hold
-        (n_big particles x 64 B = 268 MB), fields = the current slice's e and b"""
-        import torch
-        s = self.sim
-        cfg = self.cfg
-        from . import decks
-        nth = max(16, n_big // (cfg["nr"] * cfg["ppc1"] * cfg["ppc2"]))
-        x, p, g, psi, q = decks.plasma_uniform(cfg["nr"], cfg["rmax"], cfg["ppc1"], cfg["ppc2"], nth)
-        n = len(q)
-        rng = np.random.default_rng(0)
-        p = 0.3 * rng.standard_normal(p.shape)
-        g = np.sqrt(1 + (p ** 2).sum(1))
-        part = capi.Part2d(s.ctx, -1.0, n + 64)
-        part.upload(x, p, g, psi, q)
-        e, b = s.field("e"), s.field("b")
-        cu, dcu, amu = capi.Field(s.ctx, 3), capi.Field(s.ctx, 2), capi.Field(s.ctx, 3)
-        fq = capi.Field(s.ctx, 1)
-        res = {}
-        s.ctx.tprof_reset(); s.ctx.tprof_enable(True)
-        for _ in range(reps + 2):
-            part.qdeposit(fq)
-            part.amjdeposit_robust(e, b, cu, amu, dcu, 1e-3)
-            part.push_u_robust(e, b, 1e-3)
-            part.push_x(1e-6)
-        for ev, bpp in (("kernel amjdeposit", 64), ("kernel qdeposit", 24), ("kernel push", None)):
-            ms, nc = s.ctx.tprof_get(ev)
-            res[ev] = (ms, nc)
-        s.ctx.tprof_enable(False)
-        out = {"particles": n, "note": "particle set larger than L2; amjdeposit 64 B, qdeposit 24 B, push_u 72 B + push_x 64 B per particle"}
-        ms, nc = res["kernel amjdeposit"]
-        out["amjdeposit_GBs"] = 64.0 * n / (ms / nc * 1e-3) / 1e9
-        ms, nc = res["kernel qdeposit"]
-        out["qdeposit_GBs"] = 24.0 * n / (ms / nc * 1e-3) / 1e9
-        ms, nc = res["kernel push"]  # push_u and push_x launches alternate: 136 B per pair
-        out["push_u_plus_push_x_GBs"] = 136.0 * n / (2 * ms / nc * 1e-3) / 1e9
-        out["peak"] = peak_gbs
-        out["amjdeposit_frac"] = out["amjdeposit_GBs"] / peak_gbs
-        part.close()
-        return out
+        return kernel_microbench(self.sim, self.cfg, peak_gbs, n_big, reps)
 
     def close(self):
         self.sim.close()
