@@ -36,8 +36,8 @@ class Params(C.Structure):
 def build(fast=False, force=False):
     target = "liborc_fast.so" if fast else "liborc.so"
     path = os.path.join(_HERE, target)
-    src = os.path.join(_HERE, "qpad_oracle.c")
-    if force or not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(src):
+    newest = max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("qpad_oracle.c", "qpad_oracle_laser.c", "qpad_oracle.h"))
+    if force or not os.path.exists(path) or os.path.getmtime(path) < newest:
         subprocess.check_call(["make", "-C", _HERE, "-B", target], stdout=subprocess.DEVNULL)
     return path
 
@@ -92,6 +92,16 @@ def lib(fast=False):
         "orc_sim_get_beam": (None, [vp, i, _dp, _dp, _dp]),
         "orc_sim_get_field": (l, [vp, i, C.c_char_p, i, C.c_void_p]),
         "orc_sim_total_iters": (l, [vp]),
+        "orc_laser_volume_size": (l, [i, i, i]),
+        "orc_deposit_ax_corr": (d, [i]),
+        "orc_deposit_chi": (None, [_dp, _dp, _dp, l, d, i, i, d, d, _dp]),
+        "orc_laser_gaussian_point": (None, [d, d, d, d, d, d, C.POINTER(d), C.POINTER(d)]),
+        "orc_laser_launch_gaussian": (None, [d, d, d, d, d, d, d, d, d, d, d, i, i, i, _dp, _dp]),
+        "orc_laser_build_matrix": (None, [i, i, d, d, d, d, _dp]),
+        "orc_penta_solve": (None, [_dp, _dp, i]),
+        "orc_laser_set_rhs": (None, [_dp, _dp, _dp, i, i, i, d, d, d, d, _dp, _dp]),
+        "orc_laser_solve": (None, [_dp, _dp, _dp, _dp, _dp, i, i, i, d, d, d, d, i]),
+        "orc_laser_set_grad": (None, [_dp, _dp, i, i, i, i, d, d, _dp, _dp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -183,3 +193,40 @@ class Sim:
 
     def total_iters(self):
         return self.L.orc_sim_total_iters(self.h)
+
+
+class Laser:
+    """One laser envelope on one stage owning the whole box (laser/field_laser_class.f03): volumes a_r, a_i of shape
+    (P, nz+3, nr+2) with xi slice j at index j+1 (two lower guard slices), advanced by set_rhs + solve per 3D step
+    (sim_lasers_class.f03:197-222 advance)."""
+
+    def __init__(self, nr, nz, max_mode, rmax, zmin, zmax, ds, k0, iteration=1):
+        self.L = lib()
+        self.nr, self.nz, self.max_mode, self.k0, self.ds, self.iter = nr, nz, max_mode, k0, ds, iteration
+        self.dr, self.dz, self.z0 = rmax / nr, (zmax - zmin) / nz, zmin
+        shape = (nplanes(max_mode), nz + 3, nr + 2)
+        self.ar, self.ai = np.zeros(shape), np.zeros(shape)
+        self.sr, self.si = np.zeros(shape), np.zeros(shape)
+
+    def launch_gaussian(self, a0, w0, focal_distance=0.0, lon_center=0.0, t_rise=1.0, t_flat=0.0, t_fall=1.0):
+        self.L.orc_laser_launch_gaussian(self.k0, a0, w0, focal_distance, lon_center, t_rise, t_flat, t_fall, self.z0, self.dz, self.dr,
+                                         self.nr, self.nz, self.max_mode, self.ar, self.ai)
+
+    def advance(self, chi=None):
+        """chi: (P, nz+1, nr+2, 1) susceptibility volume (None = vacuum)"""
+        if chi is None:
+            chi = np.zeros((nplanes(self.max_mode), self.nz + 1, self.nr + 2, 1))
+        chi = np.ascontiguousarray(chi, dtype=np.float64)
+        a = (self.nr, self.nz, self.max_mode, self.k0, self.ds, self.dr, self.dz)
+        self.L.orc_laser_set_rhs(self.ar, self.ai, chi, *a, self.sr, self.si)
+        self.L.orc_laser_solve(self.ar, self.ai, self.sr, self.si, chi, *a, self.iter)
+
+    def set_grad(self, j):
+        g = zeros_f1(3, self.nr, self.max_mode), zeros_f1(3, self.nr, self.max_mode)
+        self.L.orc_laser_set_grad(self.ar, self.ai, j, self.nr, self.nz, self.max_mode, self.dr, self.dz, g[0], g[1])
+        return g
+
+    def gaussian_point(self, r, z, w0, f_dist):
+        a, b = C.c_double(), C.c_double()
+        self.L.orc_laser_gaussian_point(r, z, self.k0, self.k0, w0, f_dist, C.byref(a), C.byref(b))
+        return a.value, b.value

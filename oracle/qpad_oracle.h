@@ -124,6 +124,28 @@ void orc_sim_get_beam(const orc_sim *s, int stage, double *x, double *p, double 
 long orc_sim_get_field(const orc_sim *s, int stage, const char *name, int which, double *out);
 long orc_sim_total_iters(const orc_sim *s);
 
+/* ---- laser envelope (ponderomotive guiding centre) field path, qpad_oracle_laser.c ---------------------------------
+ * laser volumes v[plane][slice j = -1..nz+1 at index j+1][node 0..nr+1]; chi = dim-1 f2 volume; gradients = dim-3 f1 fields */
+long orc_laser_volume_size(int nr, int nz, int max_mode);
+/* species/part2d_class.f03:2581 ; :361 (chi = dim-1 multi-plane f1, accumulated into) */
+double orc_deposit_ax_corr(int ppc_r);
+void orc_deposit_chi(const double *x, const double *q, const double *psi, long npp, double dr, int nr, int max_mode, double qbm,
+                     double ax_corr, double *chi);
+/* laser/profile_laser_lib.f03:56 ; laser/profile_laser_class.f03:318 (gaussian x sin2) */
+void orc_laser_gaussian_point(double r, double z, double k, double k0, double w0, double f_dist, double *ar, double *ai);
+void orc_laser_launch_gaussian(double k0, double a0, double w0, double f_dist, double lon_center, double t_rise, double t_flat, double t_fall,
+                               double z0, double dz, double dr, int nr, int nz, int max_mode, double *ar, double *ai);
+/* laser/field_laser_class.f03:269 (A = [2nr][5] rows a,b,c,d,e) ; direct pentadiagonal solve (rhs -> x in place) */
+void orc_laser_build_matrix(int m, int nr, double k0, double ds, double dr, double dz, double *A);
+void orc_penta_solve(const double *A, double *x, int n);
+/* laser/field_laser_class.f03:393 set_rhs, :752 solve, :637 set_grad */
+void orc_laser_set_rhs(const double *ar, const double *ai, const double *chi, int nr, int nz, int max_mode, double k0, double ds, double dr,
+                       double dz, double *sr, double *si);
+void orc_laser_solve(double *ar, double *ai, const double *sr, const double *si, const double *chi, int nr, int nz, int max_mode,
+                     double k0, double ds, double dr, double dz, int iter);
+void orc_laser_set_grad(const double *ar, const double *ai, int slice, int nr, int nz, int max_mode, double dr, double dz, double *ar_grad,
+                        double *ai_grad);
+
 #ifdef __cplusplus
 }
 #endif
