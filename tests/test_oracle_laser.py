@@ -124,8 +124,8 @@ def test_set_grad_is_second_order_and_keeps_the_axis_quirk():
     j = 40
     gr, gi = las.set_grad(j)
     xj = (j - 1) * las.dz
-    assert np.max(np.abs(gr[0, 2:nr, 0] - np.sin(0.7 * xj) * (-2 * r[2:nr] * f[2:nr]))) < 2e-3          # d/dr
-    assert np.max(np.abs(gr[0, 1:nr + 1, 2] - 0.7 * np.cos(0.7 * xj) * f[1:nr + 1])) < 2e-3           # d/dxi (3-point backward)
+    assert np.max(np.abs(gr[0, 2:nr, 0] - np.sin(0.7 * xj) * (-2 * r[2:nr] * f[2:nr]))) < 4e-3          # d/dr (central difference, dr = 1/16)
+    assert np.max(np.abs(gr[0, 1:nr + 1, 2] - 0.7 * np.cos(0.7 * xj) * f[1:nr + 1])) < 4e-3           # d/dxi (3-point backward)
     assert np.allclose(gr[1, 2:nr + 1, 1], -1.0 / r[2:nr + 1] * las.ar[2, j + 1, 2:nr + 1])             # -(m/r) Im
     assert np.allclose(gr[2, 2:nr + 1, 1], 1.0 / r[2:nr + 1] * las.ar[1, j + 1, 2:nr + 1])
     # the reference writes the m = 1 axis rule with the loop variable after the loop (field_laser_class.f03:708-717):
