@@ -30,7 +30,8 @@ class Params(C.Structure):
                 ("iter_reltol", C.c_double), ("iter_abstol", C.c_double), ("relax_fac", C.c_double),
                 ("ppc1", C.c_int), ("ppc2", C.c_int), ("num_theta", C.c_int), ("sort_freq", C.c_int),
                 ("sp_q", C.c_double), ("sp_m", C.c_double), ("sp_density", C.c_double), ("sp_den_min", C.c_double),
-                ("beam_push_type", C.c_int), ("beam_evol", C.c_int), ("beam_qbm", C.c_double), ("sp_push_type", C.c_int)]
+                ("beam_push_type", C.c_int), ("beam_evol", C.c_int), ("beam_qbm", C.c_double), ("sp_push_type", C.c_int),
+                ("laser_on", C.c_int), ("laser_iter", C.c_int), ("laser_k0", C.c_double)]
 
 
 def build(fast=False, force=False):
@@ -92,6 +93,8 @@ def lib(fast=False):
         "orc_sim_get_beam": (None, [vp, i, _dp, _dp, _dp]),
         "orc_sim_get_field": (l, [vp, i, C.c_char_p, i, C.c_void_p]),
         "orc_sim_total_iters": (l, [vp]),
+        "orc_sim_set_laser": (None, [vp, _dp, _dp]),
+        "orc_sim_get_laser": (None, [vp, _dp, _dp, _dp]),
         "orc_laser_volume_size": (l, [i, i, i]),
         "orc_deposit_ax_corr": (d, [i]),
         "orc_deposit_chi": (None, [_dp, _dp, _dp, l, d, i, i, d, d, _dp]),
@@ -135,7 +138,7 @@ class Sim:
         defaults = dict(nr=64, nz=32, max_mode=1, bnd=BND_OPEN, iter_max=1, nstages=1, rmax=5.0, zmin=-5.0, zmax=5.0,
                         dt=10.0, iter_reltol=1e-3, iter_abstol=1e-3, relax_fac=-1.0, ppc1=2, ppc2=2, num_theta=8,
                         sort_freq=0, sp_q=-1.0, sp_m=1.0, sp_density=1.0, sp_den_min=1e-10,
-                        beam_push_type=PUSH3_REDUCED, beam_evol=1, beam_qbm=-1.0, sp_push_type=1)
+                        beam_push_type=PUSH3_REDUCED, beam_evol=1, beam_qbm=-1.0, sp_push_type=1, laser_on=0, laser_iter=1, laser_k0=10.0)
         defaults.update(kw)
         for k, v in defaults.items():
             setattr(prm, k, v)
@@ -193,6 +196,16 @@ class Sim:
 
     def total_iters(self):
         return self.L.orc_sim_total_iters(self.h)
+
+    def set_laser(self, ar, ai):
+        """envelope volumes of shape (P, nz+3, nr+2), xi slice j at index j+1 (see Laser)"""
+        self.L.orc_sim_set_laser(self.h, np.ascontiguousarray(ar, dtype=np.float64), np.ascontiguousarray(ai, dtype=np.float64))
+
+    def laser(self):
+        shape = (nplanes(self.max_mode), self.nz + 3, self.nr + 2)
+        ar, ai, chi = np.zeros(shape), np.zeros(shape), np.zeros((nplanes(self.max_mode), self.nz + 1, self.nr + 2))
+        self.L.orc_sim_get_laser(self.h, ar, ai, chi)
+        return ar, ai, chi
 
 
 class Laser:

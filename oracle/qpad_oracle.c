@@ -1278,6 +1278,10 @@ struct orc_sim {
     tri_op *op_psi, *op_ez, *op_bz, *op_bt, *op_bp, *op_bm;
     ostage *st;
     long total_iters;
+    /* one laser (sim_lasers_class.f03): envelope volumes, rhs volumes, the slice images the pgc pushers gather from
+     * (laser_all: a_r, a_i dim 1; their gradients dim 3) and the susceptibility chi (f1 + volume) */
+    double *las_ar, *las_ai, *las_sr, *las_si, *las_ar1, *las_ai1, *las_arg, *las_aig;
+    ofld chi;
 };
 
 static void part2d_alloc(opart2d *pt, long npmax)
@@ -1314,6 +1318,7 @@ static void species_renew(orc_sim *s, ospecies *sp)
     fld_dot1(-1.0, &sp->qn);
 }
 
+static void laser_alloc(orc_sim *s);
 orc_sim *orc_sim_create(const orc_params *prm)
 {
     orc_sim *s = (orc_sim *)calloc(1, sizeof(orc_sim));
@@ -1358,6 +1363,8 @@ orc_sim *orc_sim_create(const orc_params *prm)
         st->mb_beam = NULL; st->mb_beam_np = 0; st->mb_beam_cap = 0;
         st->conv_re = (double *)calloc((size_t)nr + 1, sizeof(double)); st->conv_im = (double *)calloc((size_t)nr + 1, sizeof(double));
     }
+    /* the pgc pushers gather from the laser slice images even when the envelope is zero; one laser, one stage */
+    if (s->prm.laser_on || s->prm.sp_push_type == 4 || s->prm.sp_push_type == 5) { s->prm.laser_on = 1; laser_alloc(s); }
     return s;
 }
 
@@ -1377,6 +1384,10 @@ void orc_sim_destroy(orc_sim *s)
         free(st->conv_re); free(st->conv_im);
     }
     free(s->st);
+    if (s->las_ar) {
+        free(s->las_ar); free(s->las_ai); free(s->las_sr); free(s->las_si); free(s->las_ar1); free(s->las_ai1); free(s->las_arg); free(s->las_aig);
+        fld_free(&s->chi);
+    }
     free_ops(s->op_psi, M); free_ops(s->op_ez, M); free_ops(s->op_bz, M); free_ops(s->op_bt, M); free_ops(s->op_bp, M); free_ops(s->op_bm, M);
     free(s);
 }
@@ -1453,6 +1464,7 @@ static void unpack_f2_slice(ofld *f, int k, const double *buf, int add)
     }
 }
 
+static void laser_slice(orc_sim *s, int j);
 /* the 2D loop body, simulation_class.f03:342-469, for slice j of stage k */
 static void slice_step(orc_sim *s, int k, int j)
 {
@@ -1472,8 +1484,10 @@ static void slice_step(orc_sim *s, int k, int j)
     fld_add1(&sp->q, &st->q_spe);
     fld_add1(&sp->qn, &st->q_spe);
     solve_psi_ops(s->op_psi, st->q_spe.f1, st->psi.f1, nr, M);                      /* :356 */
-    if (pr->sp_push_type == 0) orc_interp_psi(pt->x, pt->psi, pt->npp, dr, nr, M, st->psi.f1);   /* :357-359 std pushers only */
+    const int pgc = pr->sp_push_type == 4 || pr->sp_push_type == 5, pstd = pr->sp_push_type == 0 || pr->sp_push_type == 4;
+    if (pstd) orc_interp_psi(pt->x, pt->psi, pt->npp, dr, nr, M, st->psi.f1);       /* :357-359 std pushers only (species2d_class.f03:447) */
     solve_bz_ops(s->op_bz, st->cu.f1, st->b_spe.f1, nr, M, dr);                     /* :360 */
+    if (pr->laser_on) laser_slice(s, j);                                            /* :361-366 */
     for (int l = 1; l <= pr->iter_max; l++) {                                       /* :370 */
         conv_record(st, &st->b_spe, 2, M);                                          /* :373 */
         fld_add1_3(&st->b_spe, &st->b_beam, &st->b);                                /* :375 */
@@ -1482,7 +1496,9 @@ static void slice_step(orc_sim *s, int k, int j)
         fld_zero1(&st->cu); fld_zero1(&st->acu); fld_zero1(&st->amu);               /* :378-380 */
         /* species2d_class.f03:233-280 amjdp */
         fld_zero1(&sp->cu); fld_zero1(&sp->dcu); fld_zero1(&sp->amu);
-        (pr->sp_push_type == 0 ? orc_amjdeposit_std : orc_amjdeposit_robust)(pt->x, pt->p, pt->q, pt->gamma, pt->psi, pt->npp, dr, nr, M, sp->qbm, dxi, st->e.f1,
+        if (pgc) orc_amjdeposit_pgc(pt->x, pt->p, pt->q, pt->gamma, pt->psi, pt->npp, dr, nr, M, sp->qbm, dxi, st->e.f1, st->b.f1, s->las_ar1, s->las_ai1,
+                                    s->las_arg, s->las_aig, sp->cu.f1, sp->dcu.f1, sp->amu.f1, pstd);
+        else (pstd ? orc_amjdeposit_std : orc_amjdeposit_robust)(pt->x, pt->p, pt->q, pt->gamma, pt->psi, pt->npp, dr, nr, M, sp->qbm, dxi, st->e.f1,
                               st->b.f1, sp->cu.f1, sp->dcu.f1, sp->amu.f1);
         fld_add1(&sp->cu, &st->cu); fld_add1(&sp->dcu, &st->acu); fld_add1(&sp->amu, &st->amu);
         orc_solve_djdxi(st->acu.f1, st->amu.f1, st->dcu.f1, nr, M, dr);             /* :390 */
@@ -1492,6 +1508,11 @@ static void slice_step(orc_sim *s, int k, int j)
         conv_compare(st, &st->b_spe, 2, M, &rel, &ab);                              /* :395 */
         s->total_iters++;
         if (rel < pr->iter_reltol || ab < pr->iter_abstol) break;                   /* :396 */
+    }
+    if (pr->laser_on) {                                                             /* :401 lasers%deposit_chi (sim_lasers_class.f03:175-195) */
+        fld_zero1(&s->chi);
+        orc_deposit_chi(pt->x, pt->q, pt->psi, pt->npp, dr, nr, M, sp->qbm, orc_deposit_ax_corr(pr->ppc1), s->chi.f1);
+        fld_copy_slice(&s->chi, j, 1);
     }
     fld_add1_dim(&sp->cu, &sp->q, 3, 1); fld_copy_slice(&sp->q, j, 1);              /* :403 cbq */
     fld_copy_slice(&st->cu, j, 1);                                                  /* :409 */
@@ -1507,7 +1528,8 @@ static void slice_step(orc_sim *s, int k, int j)
         memcpy(s->st[k + 1].mb_cu, st->cu.f1, sizeof(double) * fld_n1(&st->cu));
         memcpy(s->st[k + 1].mb_bspe, st->b_spe.f1, sizeof(double) * fld_n1(&st->b_spe));
     }
-    if (pr->sp_push_type == 0) orc_push_u_std(pt->x, pt->p, pt->gamma, pt->psi, pt->npp, dr, nr, M, sp->qbm, dxi, st->e.f1, st->b.f1);
+    if (pgc) orc_push_u_pgc(pt->x, pt->p, pt->gamma, pt->psi, pt->npp, dr, nr, M, sp->qbm, dxi, st->e.f1, st->b.f1, s->las_ar1, s->las_ai1, s->las_arg, s->las_aig);
+    else if (pr->sp_push_type == 0) orc_push_u_std(pt->x, pt->p, pt->gamma, pt->psi, pt->npp, dr, nr, M, sp->qbm, dxi, st->e.f1, st->b.f1);
     else orc_push_u_robust(pt->x, pt->p, pt->gamma, pt->npp, dr, nr, M, sp->qbm, dxi, st->e.f1, st->b.f1); /* :438 */
     orc_push_x(pt->x, pt->p, pt->gamma, pt->npp, dxi);                              /* :439, species2d_class.f03:311 */
     pt->npp = orc_update_bound(pt->x, pt->p, pt->gamma, pt->psi, pt->q, pt->npp, (double)nr * dr);
@@ -1626,6 +1648,51 @@ static void stage_end(orc_sim *s, int k)
     species_renew(s, &st->spe);                                                     /* :498-501 */
 }
 
+static void laser_alloc(orc_sim *s)
+{
+    const int nr = s->prm.nr, nz = s->prm.nz, M = s->prm.max_mode;
+    const size_t nv = (size_t)orc_laser_volume_size(nr, nz, M), n1 = (size_t)(2 * M + 1) * (nr + 2);
+    s->las_ar = (double *)calloc(nv, sizeof(double)); s->las_ai = (double *)calloc(nv, sizeof(double));
+    s->las_sr = (double *)calloc(nv, sizeof(double)); s->las_si = (double *)calloc(nv, sizeof(double));
+    s->las_ar1 = (double *)calloc(n1, sizeof(double)); s->las_ai1 = (double *)calloc(n1, sizeof(double));
+    s->las_arg = (double *)calloc(3 * n1, sizeof(double)); s->las_aig = (double *)calloc(3 * n1, sizeof(double));
+    fld_init(&s->chi, 1, nr, nz, M, 1);
+}
+void orc_sim_set_laser(orc_sim *s, const double *ar, const double *ai)
+{
+    if (!s->las_ar) laser_alloc(s);
+    const size_t nv = (size_t)orc_laser_volume_size(s->prm.nr, s->prm.nz, s->prm.max_mode);
+    memcpy(s->las_ar, ar, sizeof(double) * nv);
+    memcpy(s->las_ai, ai, sizeof(double) * nv);
+}
+void orc_sim_get_laser(const orc_sim *s, double *ar, double *ai, double *chi)
+{
+    const size_t nv = (size_t)orc_laser_volume_size(s->prm.nr, s->prm.nz, s->prm.max_mode);
+    if (ar) memcpy(ar, s->las_ar, sizeof(double) * nv);
+    if (ai) memcpy(ai, s->las_ai, sizeof(double) * nv);
+    if (chi) memcpy(chi, s->chi.f2, sizeof(double) * fld_n2(&s->chi));
+}
+/* simulation_class.f03:361-366: laser_all = 0; copy_slice(j, 2to1); set_grad(j); gather -- one laser, so laser_all is a copy */
+static void laser_slice(orc_sim *s, int j)
+{
+    const int nr = s->prm.nr, nz = s->prm.nz, P = 2 * s->prm.max_mode + 1;
+    for (int pl = 0; pl < P; pl++)
+        for (int i = 0; i <= nr + 1; i++) {
+            const size_t src = ((size_t)pl * (nz + 3) + (size_t)(j + 1)) * (nr + 2) + i;
+            s->las_ar1[(size_t)pl * (nr + 2) + i] = s->las_ar[src];
+            s->las_ai1[(size_t)pl * (nr + 2) + i] = s->las_ai[src];
+        }
+    orc_laser_set_grad(s->las_ar, s->las_ai, j, nr, nz, s->prm.max_mode, s->dr, s->dxi, s->las_arg, s->las_aig);
+}
+/* sim_lasers_class.f03:197-222 advance (one stage: the pipe_recv / pipe_send of the lower guard slices are no-ops) */
+static void laser_advance(orc_sim *s)
+{
+    const orc_params *pr = &s->prm;
+    orc_laser_set_rhs(s->las_ar, s->las_ai, s->chi.f2, pr->nr, pr->nz, pr->max_mode, pr->laser_k0, pr->dt, s->dr, s->dxi, s->las_sr, s->las_si);
+    orc_laser_solve(s->las_ar, s->las_ai, s->las_sr, s->las_si, s->chi.f2, pr->nr, pr->nz, pr->max_mode, pr->laser_k0, pr->dt, s->dr, s->dxi,
+                    pr->laser_iter < 1 ? 1 : pr->laser_iter);
+}
+
 long orc_sim_step3d(orc_sim *s, int istep)
 {
     (void)istep;
@@ -1635,6 +1702,7 @@ long orc_sim_step3d(orc_sim *s, int istep)
         for (int j = 1; j <= s->st[k].nzp; j++) { updates += s->st[k].spe.part.npp; slice_step(s, k, j); }
         stage_psend(s, k);
     }
+    if (s->prm.laser_on) laser_advance(s);                                          /* simulation_class.f03:486 */
     for (int k = 0; k < s->prm.nstages; k++) stage_end(s, k);
     return updates;
 }

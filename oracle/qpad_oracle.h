@@ -101,7 +101,10 @@ typedef struct {
     /* one beam */
     int beam_push_type, beam_evol;
     double beam_qbm;
-    int sp_push_type;   /* p_push2_std = 0, p_push2_robust = 1 (param.f03) */
+    int sp_push_type;   /* p_push2_std = 0, p_push2_robust = 1, p_push2_std_pgc = 4, p_push2_robust_pgc = 5 (param.f03:63-64) */
+    /* one laser envelope (nlasers = 1; single stage only): the envelope is handed in with orc_sim_set_laser */
+    int laser_on, laser_iter;
+    double laser_k0;
 } orc_params;
 
 orc_sim *orc_sim_create(const orc_params *prm);
@@ -123,6 +126,10 @@ void orc_sim_get_beam(const orc_sim *s, int stage, double *x, double *p, double 
 /* name in {psi,e,b,e_spe,b_spe,e_beam,b_beam,cu,amu,acu,dcu,q_spe,q_beam}; which=1 -> f1, 2 -> f2 (nzp+1 slices) */
 long orc_sim_get_field(const orc_sim *s, int stage, const char *name, int which, double *out);
 long orc_sim_total_iters(const orc_sim *s);
+/* laser envelope volumes a_r, a_i (layout of orc_laser_volume_size) of the single stage: copy in / copy out; chi = the
+ * susceptibility volume deposited during the last 3D step, (P, nz+1, nr+2) */
+void orc_sim_set_laser(orc_sim *s, const double *ar, const double *ai);
+void orc_sim_get_laser(const orc_sim *s, double *ar, double *ai, double *chi);
 
 /* ---- laser envelope (ponderomotive guiding centre) field path, qpad_oracle_laser.c ---------------------------------
  * laser volumes v[plane][slice j = -1..nz+1 at index j+1][node 0..nr+1]; chi = dim-1 f2 volume; gradients = dim-3 f1 fields */

@@ -132,3 +132,32 @@ def test_set_grad_is_second_order_and_keeps_the_axis_quirk():
     # it lands on the guard node nr+1, node 1 keeps 0
     assert gr[1, 1, 0] == 0.0 and gr[1, nr + 1, 0] == 2.0 * (0.5 / las.dr) * las.ar[1, j + 1, 2]
     assert np.all(gi == 0.0)
+
+
+def test_linear_laser_wakefield_matches_theory():
+    """The coupled path (robust_pgc deposit + push, psi solve, chi deposit, envelope advance) in the linear regime:
+    behind a weak (a0 = 0.05), wide (w0 = 8) pulse the on-axis wake potential obeys  psi'' + psi = |a|^2 / 4
+    (linear polarisation, k_p = 1), i.e. psi(xi) = 1/4 int_{-inf}^{xi} sin(xi - xi') |a(xi')|^2 dxi'."""
+    nr, nz, rmax, zmin, zmax, a0, w0 = 256, 256, 24.0, -3.0, 9.0, 0.05, 8.0
+    sim = O.Sim(nr=nr, nz=nz, max_mode=0, rmax=rmax, zmin=zmin, zmax=zmax, dt=2.0, ppc1=2, ppc2=2, num_theta=4, iter_max=5,
+                iter_reltol=1e-4, iter_abstol=1e-9, sp_push_type=5, laser_on=1, laser_iter=1, laser_k0=20.0, beam_evol=0)
+    las = O.Laser(nr, nz, 0, rmax, zmin, zmax, 2.0, 20.0, 1)
+    las.launch_gaussian(a0, w0, 0.0, 0.0, 1.5, 0.0, 1.5)
+    sim.set_laser(las.ar, las.ai)
+    sim.set_beam(np.zeros((0, 3)), np.zeros((0, 3)), np.zeros(0))
+    sim.step3d(1)
+    psi = sim.field("psi", 2)[0, :nz, 1, 0]
+    dz = (zmax - zmin) / nz
+    xi = np.arange(nz) * dz + zmin
+    a2 = las.ar[0, 2:nz + 2, 1] ** 2 + las.ai[0, 2:nz + 2, 1] ** 2
+    G = np.array([np.sum(np.sin(xi[j] - xi[:j + 1]) * a2[:j + 1]) * dz for j in range(nz)])
+    assert abs(np.dot(psi, G) / np.dot(G, G) - 0.25) < 2.5e-3
+    assert np.max(np.abs(psi - 0.25 * G)) < 0.02 * np.max(np.abs(0.25 * G))
+    # E_z = d psi / d xi behind the pulse
+    ez = sim.field("e", 2)[0, :nz, 1, 2]
+    dpsi = np.gradient(psi, dz)
+    assert np.max(np.abs(ez[8:-8] - dpsi[8:-8])) < 0.03 * np.max(np.abs(ez))
+    # the susceptibility of the barely perturbed plasma is -n/(1 + psi) ~ -1, and the envelope has been advanced
+    ar, ai, chi = sim.laser()
+    assert np.max(np.abs(chi[0, 8:nz, 2:nr // 2] + 1.0)) < 5e-3
+    assert 0 < np.max(np.abs(ar - las.ar)) < 0.05 * a0
