@@ -39,6 +39,7 @@ typedef struct qpg_field_s *qpg_field;
 typedef struct qpg_part2d_s *qpg_part2d;
 typedef struct qpg_part3d_s *qpg_part3d;
 typedef struct qpg_sim_s *qpg_sim;
+typedef struct qpg_laser_s *qpg_laser;
 
 /* param.f03 constants mirrored 1:1 */
 enum { QPG_BND_ZERO = 2, QPG_BND_OPEN = 3 };                              /* p_bnd_* */
@@ -197,6 +198,12 @@ typedef struct {
     int use_graph;            /* capture the slice body in a CUDA graph */
     int sp_push_std;          /* 0 = robust pusher (the decks' choice), 1 = std flavour (amjdeposit_std, push_u_std, interp_psi);
                                  std runs on the per-slice launch paths, not in the persistent sweep kernel */
+    int sp_push_pgc;          /* 1 = ponderomotive-guiding-centre flavour of the chosen pusher (param.f03 p_push2_std_pgc / p_push2_robust_pgc):
+                                 the sim owns ONE laser envelope (qpg_sim_laser) and runs simulation_class.f03:361-366 / :401 per slice;
+                                 single stage (noff2 = 0, nzp = nz_total), per-slice launch path */
+    int laser_iter;           /* laser.iteration: fixed-point passes of the envelope solve per slice (>= 1) */
+    double laser_k0;          /* laser.k0 */
+    int sp_ppc_r;             /* species ppc(1): the on-axis correction of the susceptibility deposit (part2d_class.f03:2581) */
 } qpg_sim_params;
 
 int qpg_sim_create(qpg_sim *out, int device, void *cuda_stream, const qpg_sim_params *prm);
@@ -237,6 +244,9 @@ int qpg_sim_run_slices(qpg_sim s, int j0, int j1);
 int qpg_sim_set_back_handoff(qpg_sim s, double *wire_b, double *wire_e, unsigned *flag, unsigned seq);
 /* simulation_class.f03:489-493: beam push + update_bound (E,B guard slice nzp+1 already unpacked by the caller) */
 int qpg_sim_beam_push(qpg_sim s);
+/* the sim's laser envelope (NULL unless sp_push_pgc) and simulation_class.f03:486 lasers%advance (after the slab) */
+qpg_laser qpg_sim_laser(qpg_sim s);
+int qpg_sim_laser_advance(qpg_sim s);
 /* simulation_class.f03:498-501 species%renew from the device snapshot of the injected lattice */
 int qpg_sim_renew(qpg_sim s);
 /* counters since creation: particle-slice updates, PC iterations, slices (synchronises) */
@@ -281,6 +291,27 @@ int qpg_wire_unmap(void *dev_ptr);
 int qpg_stream_signal(void *cuda_stream, unsigned *flag, unsigned value);
 int qpg_stream_wait(void *cuda_stream, unsigned *flag, unsigned value);
 int qpg_stream_wait_is_memop(void);   /* 1 = cuStreamWaitValue32, 0 = fallback polling kernel */
+
+/* ------------------------------------------------------------------------------------------ */
+/* laser envelope (ponderomotive guiding centre), laser/field_laser_class.f03 + sim_lasers_class.f03; one xi stage.
+ * Envelope volumes a_r, a_i on the host: C arrays [P][nz+3][nr+2], xi slice j (1-based) at index j+1 -- two lower guard
+ * slices for the 3-point backward xi difference (gc_num(1,2) = 2), one upper; radial guards at 0 and nr+1.
+ *   qpg_laser_create      : init_field_laser :104 + init_solver :269 (nr <= 1024)
+ *   qpg_laser_upload      : the launched profile (profile_laser%launch :318 stays on the host) ; qpg_laser_download for diagnostics
+ *   qpg_laser_slice(j)    : copy_slice(j, 2to1) + set_grad(j) :637 + gather :929 -> the four slice images qpg_laser_field(0..3)
+ *                           that qpg_part2d_amjdeposit_pgc / qpg_part2d_push_u_pgc take (a_r, a_i dim 1; grad a_r, grad a_i dim 3)
+ *   qpg_laser_deposit_chi : part2d%deposit_chi :361 of one species into chi (qpg_laser_field(4)), slice j of its volume
+ *                           (sim_lasers_class.f03:175-195; j = 0: slice image only); ax_corr = 12 ppc_r^2 / (1 + 2 ppc_r^2)
+ *   qpg_laser_advance     : set_rhs :393 + solve :752 with the chi volume (sim_lasers_class.f03:197-222)                    */
+int qpg_laser_create(qpg_laser *out, qpg_ctx ctx, int nz, double k0, double ds, int iter);
+int qpg_laser_destroy(qpg_laser l);
+long qpg_laser_volume_size(qpg_laser l);
+int qpg_laser_upload(qpg_laser l, const double *ar, const double *ai);
+int qpg_laser_download(qpg_laser l, double *ar, double *ai);
+qpg_field qpg_laser_field(qpg_laser l, int which);
+int qpg_laser_slice(qpg_laser l, int j);
+int qpg_laser_deposit_chi(qpg_laser l, qpg_part2d p, int j, double ax_corr);
+int qpg_laser_advance(qpg_laser l);
 
 #ifdef __cplusplus
 }

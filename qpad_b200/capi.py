@@ -30,7 +30,8 @@ class SimParams(C.Structure):
                 ("iter_abstol", C.c_double), ("relax_fac", C.c_double),
                 ("sp_qbm", C.c_double), ("sp_npmax", C.c_long),
                 ("beam_push_type", C.c_int), ("beam_evol", C.c_int), ("beam_qbm", C.c_double), ("beam_npmax", C.c_long),
-                ("use_graph", C.c_int), ("sp_push_std", C.c_int)]
+                ("use_graph", C.c_int), ("sp_push_std", C.c_int), ("sp_push_pgc", C.c_int), ("laser_iter", C.c_int),
+                ("laser_k0", C.c_double), ("sp_ppc_r", C.c_int)]
 
 
 _lib = None
@@ -138,6 +139,17 @@ SIGNATURES = {
     "qpg_sim_set_sweep": (_i, [_vp, _i]),
     "qpg_sim_set_sweep_ctas": (_i, [_vp, _i]),
     "qpg_sim_sweep_profile": (_i, [_vp, _pd, _i]),
+    "qpg_sim_laser": (_vp, [_vp]),
+    "qpg_sim_laser_advance": (_i, [_vp]),
+    "qpg_laser_create": (_i, [C.POINTER(_vp), _vp, _i, _d, _d, _i]),
+    "qpg_laser_destroy": (_i, [_vp]),
+    "qpg_laser_volume_size": (_l, [_vp]),
+    "qpg_laser_upload": (_i, [_vp, _vp, _vp]),
+    "qpg_laser_download": (_i, [_vp, _vp, _vp]),
+    "qpg_laser_field": (_vp, [_vp, _i]),
+    "qpg_laser_slice": (_i, [_vp, _i]),
+    "qpg_laser_deposit_chi": (_i, [_vp, _vp, _i, _d]),
+    "qpg_laser_advance": (_i, [_vp]),
     "qpg_sim_slice_trace": (_i, [_vp, _pd, _pi]),
     "qpg_wire_alloc": (_i, [C.POINTER(_vp), _l]),
     "qpg_wire_free": (_i, [_vp]),
@@ -403,6 +415,47 @@ class Part3d:
     def unpack(self, dev_ptr): _chk(self.L.qpg_part3d_unpack(self.h, dev_ptr))
 
 
+class Laser:
+    """field_laser (laser/field_laser_class.f03) on one xi stage: envelope volumes of shape (P, nz+3, nr+2), xi slice j at
+    index j+1; method names follow the type-bound procedures (set_grad + gather = slice, solve = advance)."""
+
+    def __init__(self, ctx, nz, k0, ds, iteration=1, handle=None):
+        self.ctx, self.L, self.nz = ctx, ctx.L, nz
+        self._own = handle is None
+        if handle is None:
+            h = _vp()
+            _chk(self.L.qpg_laser_create(C.byref(h), ctx.h, nz, k0, ds, iteration))
+            handle = h.value
+        self.h = handle
+        self.shape = (ctx.P, nz + 3, ctx.nr + 2)
+
+    def close(self):
+        if getattr(self, "h", None) and self._own and self.ctx.h:
+            self.L.qpg_laser_destroy(self.h)
+        self.h = None
+
+    __del__ = close
+
+    def upload(self, ar, ai):
+        ar, ai = _f64(ar), _f64(ai)
+        assert ar.shape == self.shape and ai.shape == self.shape, (ar.shape, self.shape)
+        _chk(self.L.qpg_laser_upload(self.h, _ptr(ar), _ptr(ai)))
+
+    def download(self):
+        ar, ai = np.zeros(self.shape), np.zeros(self.shape)
+        _chk(self.L.qpg_laser_download(self.h, _ptr(ar), _ptr(ai)))
+        return ar, ai
+
+    def field(self, which):
+        """0 a_r, 1 a_i, 2 grad a_r, 3 grad a_i (slice images of `slice`), 4 chi"""
+        dim = (1, 1, 3, 3, 1)[which]
+        return Field(self.ctx, dim, self.nz if which == 4 else 0, which == 4, handle=self.L.qpg_laser_field(self.h, which))
+
+    def slice(self, j): _chk(self.L.qpg_laser_slice(self.h, j))
+    def deposit_chi(self, part, j, ax_corr): _chk(self.L.qpg_laser_deposit_chi(self.h, part.h, j, ax_corr))
+    def advance(self): _chk(self.L.qpg_laser_advance(self.h))
+
+
 class Sim:
     """Fused slice loop (qpg_sim_*): simulation_class.f03:294-512 for one xi slab on one GPU."""
 
@@ -412,14 +465,16 @@ class Sim:
 
     def __init__(self, nr, nz, max_mode, rmax, zmin, zmax, dt, sp_qbm=-1.0, sp_npmax=0, beam_qbm=-1.0, beam_npmax=32,
                  beam_push_type=PUSH3_REDUCED, beam_evol=1, iter_max=1, iter_reltol=1e-3, iter_abstol=1e-3, relax_fac=-1.0,
-                 field_boundary=BND_OPEN, sort_freq=0, use_graph=0, noff2=0, nzp=None, device=0, stream=None, sp_push_std=0):
+                 field_boundary=BND_OPEN, sort_freq=0, use_graph=0, noff2=0, nzp=None, device=0, stream=None, sp_push_std=0,
+                 sp_push_pgc=0, laser_iter=1, laser_k0=10.0, sp_ppc_r=1):
         self.L = load()
         nzp = nz if nzp is None else nzp
         prm = SimParams(nr=nr, nz_total=nz, noff2=noff2, nzp=nzp, max_mode=max_mode, field_boundary=field_boundary,
                         iter_max=iter_max, sort_freq=sort_freq, dr=rmax / nr, dxi=(zmax - zmin) / nz, dt=dt,
                         iter_reltol=iter_reltol, iter_abstol=iter_abstol, relax_fac=relax_fac, sp_qbm=sp_qbm,
                         sp_npmax=sp_npmax, beam_push_type=beam_push_type, beam_evol=beam_evol, beam_qbm=beam_qbm,
-                        beam_npmax=beam_npmax, use_graph=use_graph, sp_push_std=sp_push_std)
+                        beam_npmax=beam_npmax, use_graph=use_graph, sp_push_std=sp_push_std, sp_push_pgc=sp_push_pgc,
+                        laser_iter=laser_iter, laser_k0=laser_k0, sp_ppc_r=sp_ppc_r)
         self.prm = prm
         h = _vp()
         _chk(self.L.qpg_sim_create(C.byref(h), device, stream, C.byref(prm)))
@@ -429,6 +484,10 @@ class Sim:
         self.species = Part2d(self.ctx, sp_qbm, sp_npmax, handle=self.L.qpg_sim_species(self.h))
         self.beam = Part3d(self.ctx, beam_qbm, dt, beam_npmax, nz, noff2, nzp, handle=self.L.qpg_sim_beam(self.h))
         self._fields = {}
+        lh = self.L.qpg_sim_laser(self.h)
+        self.laser = Laser(self.ctx, nzp, laser_k0, dt, laser_iter, handle=lh) if lh else None
+
+    def laser_advance(self): _chk(self.L.qpg_sim_laser_advance(self.h))
 
     def close(self):
         if getattr(self, "h", None):
@@ -493,6 +552,7 @@ class Sim:
         self.beam_qdp_end()
         self.begin_step()
         self.run_slices(1, self.nzp)
+        self.laser_advance()
         self.beam_push()
         self.renew()
 

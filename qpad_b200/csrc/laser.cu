@@ -1,0 +1,404 @@
+// laser.cu -- the laser-envelope (ponderomotive guiding centre) field path, SURVEY.md §8(f) rank 1.
+//
+//   laser/field_laser_class.f03:269-391  init_solver          -> laser_rows + pcr_factor (host, long double)
+//   laser/field_laser_class.f03:393-635  set_rhs_field_laser   -> k_laser_set_rhs
+//   laser/field_laser_class.f03:637-750  set_grad + copy_slice + gather (simulation_class.f03:361-366) -> k_laser_slice
+//   laser/field_laser_class.f03:752-927  solve_field_laser     -> k_laser_solve (ONE persistent CTA sweeps all xi slices)
+//   species/part2d_class.f03:361-476     deposit_chi_part2d    -> k_deposit_chi + k_chi_fix
+//   sim_lasers_class.f03:175-222         deposit_chi / advance -> qpg_laser_deposit_chi / qpg_laser_advance
+//
+// The envelope a = a_r + i a_i obeys (i k0 + d/dxi) da/ds = lap_perp(a)/2 + chi a / 4 ...; per xi slice and azimuthal plane
+// the reference solves a 2nr x 2nr pentadiagonal system (unknowns a_r, a_i interleaved) with a parallel cyclic reduction
+// whose coefficients are generated once (pcr-fortran/fpcr_penta_class.f03:270).  Here the same system is written as a
+// BLOCK-tridiagonal one (2x2 blocks coupling the (a_r, a_i) pairs of neighbouring radial nodes) and reduced by parallel
+// cyclic reduction over the nodes: the operator never changes, so the elimination matrices of every level are
+// pre-computed on the host in long double and a solve only transforms the right-hand side -- ceil(log2 nr) levels of
+// two 2x2 mat-vecs per node, one thread per node, the vectors in shared memory.  The xi recurrence (slice j needs the
+// NEW slices j-1, j-2) is inherently sequential: one persistent CTA walks the slices, so a 3D step costs one launch.
+//
+// Device layout of the envelope volumes (a_r, a_i, s_r, s_i): v[plane][slice j = -1..nz+1 at index j+1][node 0..nr+1]
+// (node contiguous: one thread per node reads/writes coalesced).  Host layout of upload / download is the same.
+#include "common.cuh"
+
+struct qpg_laser_s {
+    qpg_ctx ctx;
+    int nz, iter, nsteps, nthreads;
+    double k0, ds, dz;
+    size_t nvol;
+    double *ar, *ai, *sr, *si;
+    qpg_field f_ar, f_ai, f_gr, f_gi, chi;
+    double *chi_acc;     // raw susceptibility sums [(nr+2)][P]
+    double *pcr;         // [M+1][nsteps][8][nr] elimination matrices (alpha 2x2 | gamma 2x2, row-major), then [M+1][4][nr] inverse diagonal blocks
+};
+
+#define LVI(pl, i, j) ((((size_t)(pl)) * (nz + 3) + (size_t)((j) + 1)) * (nr + 2) + (i))
+
+// ---- host: operator rows and their cyclic-reduction factors ------------------------------------------------------
+typedef long double ld;
+struct M2 { ld a, b, c, d; };   // [[a, b], [c, d]]
+static M2 m2mul(const M2 &x, const M2 &y) { return {x.a * y.a + x.b * y.c, x.a * y.b + x.b * y.d, x.c * y.a + x.d * y.c, x.c * y.b + x.d * y.d}; }
+static M2 m2add(const M2 &x, const M2 &y) { return {x.a + y.a, x.b + y.b, x.c + y.c, x.d + y.d}; }
+static M2 m2neg(const M2 &x) { return {-x.a, -x.b, -x.c, -x.d}; }
+static M2 m2inv(const M2 &x) { const ld det = x.a * x.d - x.b * x.c; return {x.d / det, -x.b / det, -x.c / det, x.a / det}; }
+
+// block rows of mode m (field_laser_class.f03:269-391): A couples to node i-1, B is the diagonal block, C couples to node i+1
+static void laser_rows(int m, int nr, double k0, double ds, double dr, double dz, std::vector<M2> &A, std::vector<M2> &B, std::vector<M2> &C)
+{
+    const ld q = 0.25L * ds, h = 1.5L * dr * dr / dz, kap = (ld)k0 * dr * dr, m2 = (ld)m * m;
+    A.assign(nr, {0, 0, 0, 0}); B.assign(nr, {0, 0, 0, 0}); C.assign(nr, {0, 0, 0, 0});
+    for (int i = 0; i < nr; i++) {          // node i+1, radius i*dr
+        if (i == 0) {
+            if (m == 0) { B[i] = {ds + h, -kap, kap, ds + h}; C[i] = {-(ld)ds, 0, 0, -(ld)ds}; }   // :318-340
+            else B[i] = {1, 0, 0, 1};                                                               // decoupled, :325-331
+            continue;
+        }
+        const ld j = i, lo = -q * (1.0L - 0.5L / j), hi = -q * (1.0L + 0.5L / j), c = q * (2.0L + m2 / (j * j)) + h;
+        A[i] = {lo, 0, 0, lo};
+        B[i] = {c, -kap, kap, c};
+        if (i < nr - 1) C[i] = {hi, 0, 0, hi};   // outer rows: e = 0 (:356-373)
+    }
+}
+static void pcr_factor(int m, int nr, int nsteps, double k0, double ds, double dr, double dz, double *lvl /*[nsteps][8][nr]*/, double *binv /*[4][nr]*/)
+{
+    std::vector<M2> A, B, C;
+    laser_rows(m, nr, k0, ds, dr, dz, A, B, C);
+    for (int s = 0; s < nsteps; s++) {
+        const int hstep = 1 << s;
+        std::vector<M2> A2(nr), B2(nr), C2(nr);
+        for (int i = 0; i < nr; i++) {
+            M2 al = {0, 0, 0, 0}, ga = {0, 0, 0, 0};
+            B2[i] = B[i]; A2[i] = {0, 0, 0, 0}; C2[i] = {0, 0, 0, 0};
+            if (i - hstep >= 0) { al = m2neg(m2mul(A[i], m2inv(B[i - hstep]))); A2[i] = m2mul(al, A[i - hstep]); B2[i] = m2add(B2[i], m2mul(al, C[i - hstep])); }
+            if (i + hstep < nr) { ga = m2neg(m2mul(C[i], m2inv(B[i + hstep]))); C2[i] = m2mul(ga, C[i + hstep]); B2[i] = m2add(B2[i], m2mul(ga, A[i + hstep])); }
+            double *o = lvl + (size_t)s * 8 * nr + i;
+            o[0 * nr] = (double)al.a; o[1 * nr] = (double)al.b; o[2 * nr] = (double)al.c; o[3 * nr] = (double)al.d;
+            o[4 * nr] = (double)ga.a; o[5 * nr] = (double)ga.b; o[6 * nr] = (double)ga.c; o[7 * nr] = (double)ga.d;
+        }
+        A.swap(A2); B.swap(B2); C.swap(C2);
+    }
+    for (int i = 0; i < nr; i++) {
+        const M2 bi = m2inv(B[i]);
+        binv[0 * nr + i] = (double)bi.a; binv[1 * nr + i] = (double)bi.b; binv[2 * nr + i] = (double)bi.c; binv[3 * nr + i] = (double)bi.d;
+    }
+}
+
+// ---- device ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int lz_re(int m) { return m == 0 ? 0 : 2 * m - 1; }
+__device__ __forceinline__ int lz_im(int m) { return 2 * m; }
+
+// plasma-susceptibility couplings of one node (field_laser_class.f03:563-631 = :787-852): t += ds/4 dr^2 (chi * a)_m
+__device__ __forceinline__ void chi_coupling(const double *ar, const double *ai, const double *chi, int M, double w, double *tr, double *ti)
+{
+    for (int m = 0; m <= M; m++) {
+        double rr = 0.0, ri = 0.0, ir = 0.0, ii = 0.0;   // (t_r re, t_r im, t_i re, t_i im) of mode m
+        for (int k = m - M; k <= M; k++) {
+            const int ak = k < 0 ? -k : k, amk = m - k < 0 ? k - m : m - k;
+            rr += w * chi[lz_re(ak)] * ar[lz_re(amk)];
+            ir += w * chi[lz_re(ak)] * ai[lz_re(amk)];
+            if (k == 0 || k == m) continue;
+            const double sg = (k >= 0 && k <= m) ? 1.0 : -1.0;
+            rr -= w * sg * chi[lz_im(ak)] * ar[lz_im(amk)];
+            ir -= w * sg * chi[lz_im(ak)] * ai[lz_im(amk)];
+        }
+        tr[lz_re(m)] = rr; ti[lz_re(m)] = ir;
+        if (m == 0) continue;
+        for (int k = m - M; k <= M; k++) {
+            const int ak = k < 0 ? -k : k, amk = m - k < 0 ? k - m : m - k;
+            if (k != 0) {
+                const double sg = k < 0 ? -1.0 : 1.0;
+                ri += w * sg * chi[lz_im(ak)] * ar[lz_re(amk)];
+                ii += w * sg * chi[lz_im(ak)] * ai[lz_re(amk)];
+            }
+            if (k != m) {
+                const double sg = k > m ? -1.0 : 1.0;
+                ri += w * sg * chi[lz_re(ak)] * ar[lz_im(amk)];
+                ii += w * sg * chi[lz_re(ak)] * ai[lz_im(amk)];
+            }
+        }
+        tr[lz_im(m)] = ri; ti[lz_im(m)] = ii;
+    }
+}
+
+// explicit half from the OLD envelope, one thread per (node 1..nr, slice 1..nz)
+__global__ void k_laser_set_rhs(const double *__restrict__ ar, const double *__restrict__ ai, const double *__restrict__ chi2, double *__restrict__ sr,
+                                double *__restrict__ si, int nr, int nz, int M, double k0, double ds, double dr, double dz)
+{
+    const int P = 2 * M + 1;
+    const long n = (long)nr * nz;
+    const double dr2_idzh = 0.5 * dr * dr / dz, kappa = k0 * dr * dr, ds_qtr = 0.25 * ds, w = ds_qtr * dr * dr;
+    for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < n; t += (long)gridDim.x * blockDim.x) {
+        const int i = (int)(t % nr) + 1, j = (int)(t / nr) + 1;
+        double a_r[2 * QPG_MAX_MODE + 1], a_i[2 * QPG_MAX_MODE + 1], ch[2 * QPG_MAX_MODE + 1], tr[2 * QPG_MAX_MODE + 1], ti[2 * QPG_MAX_MODE + 1];
+        for (int pl = 0; pl < P; pl++) {
+            a_r[pl] = ar[LVI(pl, i, j)]; a_i[pl] = ai[LVI(pl, i, j)];
+            ch[pl] = chi2[(size_t)(j - 1) * (nr + 2) * P + (size_t)i * P + pl];
+        }
+        chi_coupling(a_r, a_i, ch, M, w, tr, ti);
+        for (int pl = 0; pl < P; pl++) {
+            const int m = (pl + 1) / 2;
+            double beta_m, beta_p, alpha, vr, vi;
+            if (i == 1 && m > 0) { vr = 0.0; vi = 0.0; }                                       // :507-512
+            else {
+                if (i == 1) { beta_m = 0.0; beta_p = ds; alpha = -ds; }                        // :439-444
+                else {
+                    const double ik = 1.0 / (double)(i - 1);
+                    beta_m = ds_qtr * (1.0 - 0.5 * ik);
+                    beta_p = i == nr ? 0.0 : ds_qtr * (1.0 + 0.5 * ik);
+                    alpha = -ds_qtr * (2.0 + (double)(m * m) * ik * ik);
+                }
+                vr = dr2_idzh * (3.0 * a_r[pl] - 4.0 * ar[LVI(pl, i, j - 1)] + ar[LVI(pl, i, j - 2)]) - kappa * a_i[pl]
+                     + beta_m * ar[LVI(pl, i - 1, j)] + alpha * a_r[pl] + beta_p * ar[LVI(pl, i + 1, j)];
+                vi = dr2_idzh * (3.0 * a_i[pl] - 4.0 * ai[LVI(pl, i, j - 1)] + ai[LVI(pl, i, j - 2)]) + kappa * a_r[pl]
+                     + beta_m * ai[LVI(pl, i - 1, j)] + alpha * a_i[pl] + beta_p * ai[LVI(pl, i + 1, j)];
+            }
+            sr[LVI(pl, i, j)] = vr + tr[pl];
+            si[LVI(pl, i, j)] = vi + ti[pl];
+        }
+    }
+}
+
+// implicit half: ONE CTA, thread t <-> node t+1; slices in order, `iter` fixed-point passes over the chi coupling per slice
+__global__ void __launch_bounds__(1024, 1) k_laser_solve(double *__restrict__ ar, double *__restrict__ ai, const double *__restrict__ sr, const double *__restrict__ si,
+                                                        const double *__restrict__ chi2, const double *__restrict__ pcr, int nr, int nz, int M, int iter,
+                                                        int nsteps, double ds, double dr, double dz)
+{
+    extern __shared__ double laser_sh[];   // [2 buffers][2 components][nthreads]
+    const int P = 2 * M + 1, t = threadIdx.x, nt = blockDim.x, i = t + 1;
+    const bool live = t < nr;
+    const double dr2_idzh = 0.5 * dr * dr / dz, w = 0.25 * ds * dr * dr;
+    const double *binv_all = pcr + (size_t)(M + 1) * nsteps * 8 * nr;
+    int cur = 0;   // the two exchange buffers alternate over ALL levels of all solves: a buffer is rewritten only after the barrier of the level in between
+    for (int j = 1; j <= nz; j++)
+        for (int l = 0; l < iter; l++) {
+            double a_r[2 * QPG_MAX_MODE + 1], a_i[2 * QPG_MAX_MODE + 1], ch[2 * QPG_MAX_MODE + 1], tr[2 * QPG_MAX_MODE + 1], ti[2 * QPG_MAX_MODE + 1];
+            if (live) {
+                for (int pl = 0; pl < P; pl++) {
+                    a_r[pl] = ar[LVI(pl, i, j)]; a_i[pl] = ai[LVI(pl, i, j)];
+                    ch[pl] = chi2[(size_t)(j - 1) * (nr + 2) * P + (size_t)i * P + pl];
+                }
+                chi_coupling(a_r, a_i, ch, M, w, tr, ti);
+            }
+            for (int pl = 0; pl < P; pl++) {
+                const int m = (pl + 1) / 2;
+                double d0 = 0.0, d1 = 0.0;
+                if (live) {
+                    d0 = sr[LVI(pl, i, j)] + tr[pl] + dr2_idzh * (4.0 * ar[LVI(pl, i, j - 1)] - ar[LVI(pl, i, j - 2)]);
+                    d1 = si[LVI(pl, i, j)] + ti[pl] + dr2_idzh * (4.0 * ai[LVI(pl, i, j - 1)] - ai[LVI(pl, i, j - 2)]);
+                }
+                const double *lv = pcr + (size_t)m * nsteps * 8 * nr;
+                for (int s = 0; s < nsteps; s++) {
+                    double *buf = laser_sh + (size_t)cur * 2 * nt;
+                    buf[t] = d0; buf[nt + t] = d1;
+                    __syncthreads();
+                    if (live) {
+                        const int hs = 1 << s;
+                        const double *c = lv + (size_t)s * 8 * nr + t;
+                        if (t - hs >= 0) {
+                            const double x0 = buf[t - hs], x1 = buf[nt + t - hs];
+                            d0 += c[0] * x0 + c[(size_t)nr] * x1;
+                            d1 += c[2 * (size_t)nr] * x0 + c[3 * (size_t)nr] * x1;
+                        }
+                        if (t + hs < nr) {
+                            const double x0 = buf[t + hs], x1 = buf[nt + t + hs];
+                            d0 += c[4 * (size_t)nr] * x0 + c[5 * (size_t)nr] * x1;
+                            d1 += c[6 * (size_t)nr] * x0 + c[7 * (size_t)nr] * x1;
+                        }
+                    }
+                    cur ^= 1;   // the next level writes the other buffer: no second barrier needed
+                }
+                if (live) {
+                    const double *bi = binv_all + (size_t)m * 4 * nr + t;
+                    double xr = bi[0] * d0 + bi[(size_t)nr] * d1, xi = bi[2 * (size_t)nr] * d0 + bi[3 * (size_t)nr] * d1;
+                    if (m > 0 && i == 1) { xr = 0.0; xi = 0.0; }      // :913-918 (the decoupled axis rows give 0 anyway)
+                    ar[LVI(pl, i, j)] = xr; ai[LVI(pl, i, j)] = xi;
+                }
+            }
+            __syncthreads();   // slice j (and this pass) complete before anyone reads it as j-1 / in the next pass
+        }
+}
+
+// copy_slice(j, 2to1) + set_grad(j) + gather into the four slice images the pgc pushers read; one thread per (node, plane)
+__global__ void k_laser_slice(const double *__restrict__ ar, const double *__restrict__ ai, int nr, int nz, int M, int j, double dr, double dz,
+                              double *__restrict__ f_ar, double *__restrict__ f_ai, double *__restrict__ f_gr, double *__restrict__ f_gi)
+{
+    const int P = 2 * M + 1, n = (nr + 2) * P;
+    const double idrh = 0.5 / dr, idzh = 0.5 / dz;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const int i = k / P, pl = k % P, m = (pl + 1) / 2;
+        const bool is_im = m > 0 && pl == 2 * m;
+        const int other = m == 0 ? pl : (is_im ? pl - 1 : pl + 1);   // the partner plane (re <-> im) of the same mode
+        f_ar[k] = ar[LVI(pl, i, j)];
+        f_ai[k] = ai[LVI(pl, i, j)];
+        double *gr = f_gr + (size_t)k * 3, *gi = f_gi + (size_t)k * 3;
+        if (i >= 1 && i <= nr) {
+            gr[2] = idzh * (3.0 * ar[LVI(pl, i, j)] - 4.0 * ar[LVI(pl, i, j - 1)] + ar[LVI(pl, i, j - 2)]);
+            gi[2] = idzh * (3.0 * ai[LVI(pl, i, j)] - 4.0 * ai[LVI(pl, i, j - 1)] + ai[LVI(pl, i, j - 2)]);
+        }
+        if (i >= 2 && i <= nr) {
+            gr[0] = idrh * (ar[LVI(pl, i + 1, j)] - ar[LVI(pl, i - 1, j)]);
+            gi[0] = idrh * (ai[LVI(pl, i + 1, j)] - ai[LVI(pl, i - 1, j)]);
+            if (m == 0) { gr[1] = 0.0; gi[1] = 0.0; }
+            else {
+                const double ir = 1.0 / ((double)(i - 1) * dr), sg = is_im ? 1.0 : -1.0;   // re: -(m/r) Im ; im: +(m/r) Re
+                gr[1] = sg * ir * m * ar[LVI(other, i, j)];
+                gi[1] = sg * ir * m * ai[LVI(other, i, j)];
+            }
+        }
+        if (m == 0 && i == 1) { gr[0] = 0.0; gr[1] = 0.0; gi[0] = 0.0; gi[1] = 0.0; }
+        // reference quirk (field_laser_class.f03:708-730): the m > 0 axis rules are written with the loop variable AFTER the
+        // `do i = 2, nrp` loop, i.e. into node nrp+1; node 1 keeps components 1, 2 (zero since creation)
+        if (m > 0 && i == nr + 1) {
+            if (m % 2 == 1) {
+                const double g1r = 2.0 * idrh * ar[LVI(pl, 2, j)], g1i = 2.0 * idrh * ai[LVI(pl, 2, j)];
+                const double o1r = 2.0 * idrh * ar[LVI(other, 2, j)], o1i = 2.0 * idrh * ai[LVI(other, 2, j)];
+                gr[0] = g1r; gi[0] = g1i;
+                gr[1] = is_im ? m * o1r : -m * o1r;      // re: -m * grad_im(1) ; im: m * grad_re(1)
+                gi[1] = is_im ? m * o1i : -m * o1i;
+            } else { gr[0] = 0.0; gr[1] = 0.0; gi[0] = 0.0; gi[1] = 0.0; }
+        }
+    }
+}
+
+// species/part2d_class.f03:361-430: raw sums of -qbm q / (1 - qbm psi) e^{-im phi}, linear weights
+template <int M>
+__global__ void k_deposit_chi(PartView pv, double *__restrict__ acc, double idr, double qbm)
+{
+    constexpr int P = 2 * M + 1;
+    const int npp = *pv.d_npp;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < npp; p += gridDim.x * blockDim.x) {
+        const double x1 = pv.x1[p], x2 = pv.x2[p];
+        double pos = __dmul_rn(__dsqrt_rn(__dadd_rn(__dmul_rn(x1, x1), __dmul_rn(x2, x2))), idr);
+        const double c0 = x1 / pos * idr, s0 = -x2 / pos * idr;
+        const int nn = (int)floor(pos);
+        const double f = pos - (double)nn, w0 = 1.0 - f, w1 = f;
+        double phr = -1.0 * qbm * pv.q[p] / (1.0 - qbm * pv.psi[p]), phi = 0.0;
+        double *a0 = acc + (size_t)(nn + 1) * P, *a1 = a0 + P;
+        atomicAdd(a0, w0 * phr); atomicAdd(a1, w1 * phr);
+#pragma unroll
+        for (int m = 1; m <= M; m++) {
+            const double t = phr * c0 - phi * s0;
+            phi = phr * s0 + phi * c0;
+            phr = t;
+            atomicAdd(a0 + 2 * m - 1, w0 * phr); atomicAdd(a1 + 2 * m - 1, w1 * phr);
+            atomicAdd(a0 + 2 * m, w0 * phi); atomicAdd(a1 + 2 * m, w1 * phi);
+        }
+    }
+}
+// :432-452 axis rules (get_deposit_ax_corr instead of the charge deposit's 8) and 1/(j-1); chi = fix(raw), raw cleared;
+// the slice image also goes into the chi volume (sim_lasers_class.f03:191 copy_slice 1to2)
+__global__ void k_chi_fix(double *__restrict__ acc, double *__restrict__ chi1, double *__restrict__ chi2_slice, int nr, int P, double ax_corr)
+{
+    const int n = (nr + 2) * P;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const int j = k / P, pl = k % P;
+        double v = acc[k];
+        acc[k] = 0.0;
+        if (j == 0) v = 0.0;
+        else if (j == 1) v = pl == 0 ? v * ax_corr : 0.0;
+        else v = v * (1.0 / (double)(j - 1));
+        chi1[k] = v;
+        if (chi2_slice) chi2_slice[k] = v;
+    }
+}
+template <int M> static void l_deposit_chi(int grid, cudaStream_t st, PartView pv, double *acc, double idr, double qbm) { k_deposit_chi<M><<<grid, 256, 0, st>>>(pv, acc, idr, qbm); }
+
+// ---- C-ABI -------------------------------------------------------------------------------------------------------
+extern "C" int qpg_laser_create(qpg_laser *out, qpg_ctx ctx, int nz, double k0, double ds, int iter)
+{
+    ARG_TRY(out && ctx && nz >= 1 && iter >= 1, "bad arg");
+    if (ctx->nr > 1024) { qpg_set_error("the envelope solver keeps one thread per radial node in one CTA: nr <= 1024"); return QPG_ERR_UNSUPPORTED; }
+    qpg_laser l = new qpg_laser_s();
+    memset(l, 0, sizeof(*l));
+    l->ctx = ctx; l->nz = nz; l->iter = iter; l->k0 = k0; l->ds = ds; l->dz = ctx->dxi;
+    const int nr = ctx->nr, P = ctx->P, M = ctx->M;
+    l->nvol = (size_t)P * (nz + 3) * (nr + 2);
+    double **vol[4] = {&l->ar, &l->ai, &l->sr, &l->si};
+    for (auto v : vol) { CUDA_TRY(cudaMalloc(v, sizeof(double) * l->nvol)); CUDA_TRY(cudaMemsetAsync(*v, 0, sizeof(double) * l->nvol, ctx->stream)); }
+    int rc;
+    if ((rc = qpg_field_create(&l->f_ar, ctx, 1, 0, 0)) || (rc = qpg_field_create(&l->f_ai, ctx, 1, 0, 0)) || (rc = qpg_field_create(&l->f_gr, ctx, 3, 0, 0)) ||
+        (rc = qpg_field_create(&l->f_gi, ctx, 3, 0, 0)) || (rc = qpg_field_create(&l->chi, ctx, 1, nz, 1))) return rc;
+    CUDA_TRY(cudaMalloc(&l->chi_acc, sizeof(double) * (size_t)(nr + 2) * P));
+    CUDA_TRY(cudaMemsetAsync(l->chi_acc, 0, sizeof(double) * (size_t)(nr + 2) * P, ctx->stream));
+    l->nsteps = 0;
+    while ((1 << l->nsteps) < nr) l->nsteps++;
+    l->nthreads = (nr + 31) / 32 * 32;
+    const size_t nlv = (size_t)(M + 1) * l->nsteps * 8 * nr, nbi = (size_t)(M + 1) * 4 * nr;
+    std::vector<double> h(nlv + nbi);
+    for (int m = 0; m <= M; m++) pcr_factor(m, nr, l->nsteps, k0, ds, ctx->dr, l->dz, h.data() + (size_t)m * l->nsteps * 8 * nr, h.data() + nlv + (size_t)m * 4 * nr);
+    CUDA_TRY(cudaMalloc(&l->pcr, sizeof(double) * (nlv + nbi)));
+    CUDA_TRY(cudaMemcpy(l->pcr, h.data(), sizeof(double) * (nlv + nbi), cudaMemcpyHostToDevice));
+    *out = l;
+    return 0;
+}
+extern "C" int qpg_laser_destroy(qpg_laser l)
+{
+    if (!l) return 0;
+    cudaStreamSynchronize(l->ctx->stream);
+    cudaFree(l->ar); cudaFree(l->ai); cudaFree(l->sr); cudaFree(l->si); cudaFree(l->chi_acc); cudaFree(l->pcr);
+    qpg_field_destroy(l->f_ar); qpg_field_destroy(l->f_ai); qpg_field_destroy(l->f_gr); qpg_field_destroy(l->f_gi); qpg_field_destroy(l->chi);
+    delete l;
+    return 0;
+}
+extern "C" long qpg_laser_volume_size(qpg_laser l) { return l ? (long)l->nvol : -1; }
+extern "C" int qpg_laser_upload(qpg_laser l, const double *ar, const double *ai)
+{
+    ARG_TRY(l && ar && ai, "null arg");
+    CUDA_TRY(cudaMemcpyAsync(l->ar, ar, sizeof(double) * l->nvol, cudaMemcpyHostToDevice, l->ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(l->ai, ai, sizeof(double) * l->nvol, cudaMemcpyHostToDevice, l->ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(l->ctx->stream));
+    return 0;
+}
+extern "C" int qpg_laser_download(qpg_laser l, double *ar, double *ai)
+{
+    ARG_TRY(l && ar && ai, "null arg");
+    CUDA_TRY(cudaMemcpyAsync(ar, l->ar, sizeof(double) * l->nvol, cudaMemcpyDeviceToHost, l->ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(ai, l->ai, sizeof(double) * l->nvol, cudaMemcpyDeviceToHost, l->ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(l->ctx->stream));
+    return 0;
+}
+// which: 0 a_r, 1 a_i (dim 1), 2 grad a_r, 3 grad a_i (dim 3) -- the slice images of qpg_laser_slice; 4 chi (dim 1, with volume)
+extern "C" qpg_field qpg_laser_field(qpg_laser l, int which)
+{
+    if (!l) return nullptr;
+    switch (which) { case 0: return l->f_ar; case 1: return l->f_ai; case 2: return l->f_gr; case 3: return l->f_gi; case 4: return l->chi; }
+    qpg_set_error("qpg_laser_field: which must be 0..4");
+    return nullptr;
+}
+extern "C" int qpg_laser_slice(qpg_laser l, int j)
+{
+    ARG_TRY(l && j >= 1 && j <= l->nz, "slice out of range");
+    qpg_ctx c = l->ctx;
+    const int n = (c->nr + 2) * c->P;
+    k_laser_slice<<<(n + 255) / 256, 256, 0, c->stream>>>(l->ar, l->ai, c->nr, l->nz, c->M, j, c->dr, l->dz, l->f_ar->f1, l->f_ai->f1, l->f_gr->f1, l->f_gi->f1);
+    count_launch(c);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+extern "C" int qpg_laser_deposit_chi(qpg_laser l, qpg_part2d p, int j, double ax_corr)
+{
+    ARG_TRY(l && p && p->ctx == l->ctx && j >= 0 && j <= l->nz, "bad arg");
+    qpg_ctx c = l->ctx;
+    if (p->npp_hi > 0) {
+        const int grid = (int)((p->npp_hi + 255) / 256);
+        DISPATCH_M(c->M, l_deposit_chi, grid, c->stream, view_of(p), l->chi_acc, 1.0 / c->dr, p->qbm);
+        count_launch(c);
+    }
+    const int n = (c->nr + 2) * c->P;
+    k_chi_fix<<<(n + 255) / 256, 256, 0, c->stream>>>(l->chi_acc, l->chi->f1, j >= 1 ? l->chi->f2 + (size_t)(j - 1) * l->chi->n1 : nullptr, c->nr, c->P, ax_corr);
+    count_launch(c);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+extern "C" int qpg_laser_advance(qpg_laser l)
+{
+    ARG_TRY(l, "null arg");
+    qpg_ctx c = l->ctx;
+    const int nr = c->nr, nz = l->nz;
+    const long n = (long)nr * nz;
+    k_laser_set_rhs<<<(int)((n + 255) / 256), 256, 0, c->stream>>>(l->ar, l->ai, l->chi->f2, l->sr, l->si, nr, nz, c->M, l->k0, l->ds, c->dr, l->dz);
+    const size_t smem = sizeof(double) * 4 * l->nthreads;
+    k_laser_solve<<<1, l->nthreads, smem, c->stream>>>(l->ar, l->ai, l->sr, l->si, l->chi->f2, l->pcr, nr, nz, c->M, l->iter, l->nsteps, l->ds, c->dr, l->dz);
+    count_launch(c, 2);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}

@@ -2,6 +2,7 @@
 #include "fields.cu"
 #include "particles.cu"
 #include "beam.cu"
+#include "laser.cu"
 #include "fused.cu"
 #include "sweep.cu"
 #include "sim.cu"

@@ -510,9 +510,10 @@ __device__ __forceinline__ double gather1(const double *f, const Interp &it)
 
 template <int M, bool STD>
 __global__ void __launch_bounds__(PT_BLOCK) k_amjdeposit_pgc(PartView pv, const double *__restrict__ ef, const double *__restrict__ bf, LaserView lv,
-                                                            double *__restrict__ acc8, double qbm, double dt, double idr)
+                                                            double *__restrict__ acc8, double qbm, double dt, double idr, const int *__restrict__ skip)
 {
     constexpr int P = 2 * M + 1;
+    if (skip && *skip) return;   // predictor-corrector loop already converged (per-slice launch path of the sim)
     const int npp = *pv.d_npp;
     const int i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
     if ((i & ~31) >= npp) return;
@@ -1121,7 +1122,7 @@ extern "C" int qpg_part2d_interp_psi(qpg_part2d p, qpg_field psi)
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
-template <int M> static void l_amj_pgc(int grid, cudaStream_t st, PartView pv, const double *ef, const double *bf, LaserView lv, double *acc8, double qbm, double dt, double idr, int std_flavour)
+template <int M> static void l_amj_pgc(int grid, cudaStream_t st, PartView pv, const double *ef, const double *bf, LaserView lv, double *acc8, double qbm, double dt, double idr, int std_flavour, const int *skip = nullptr)
 {
     constexpr size_t smem = sizeof(double) * DepTile<M>::doubles * (PT_BLOCK / 32);
     static bool attr_set = false;
@@ -1130,8 +1131,8 @@ template <int M> static void l_amj_pgc(int grid, cudaStream_t st, PartView pv, c
         cudaFuncSetAttribute(k_amjdeposit_pgc<M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_set = true;
     }
-    if (std_flavour) k_amjdeposit_pgc<M, true><<<grid, PT_BLOCK, smem, st>>>(pv, ef, bf, lv, acc8, qbm, dt, idr);
-    else k_amjdeposit_pgc<M, false><<<grid, PT_BLOCK, smem, st>>>(pv, ef, bf, lv, acc8, qbm, dt, idr);
+    if (std_flavour) k_amjdeposit_pgc<M, true><<<grid, PT_BLOCK, smem, st>>>(pv, ef, bf, lv, acc8, qbm, dt, idr, skip);
+    else k_amjdeposit_pgc<M, false><<<grid, PT_BLOCK, smem, st>>>(pv, ef, bf, lv, acc8, qbm, dt, idr, skip);
 }
 template <int M> static void l_push_pgc(int grid, cudaStream_t st, PartView pv, const double *ef, const double *bf, LaserView lv, double qbm, double dt, double idr)
 { k_push_u_pgc<M><<<grid, PT_BLOCK, 0, st>>>(pv, ef, bf, lv, qbm, dt, idr); }
@@ -1142,6 +1143,21 @@ static int laser_view(qpg_part2d p, qpg_field ar, qpg_field ai, qpg_field arg, q
     ARG_TRY(ar->dim == 1 && ai->dim == 1 && arg->dim == 3 && aig->dim == 3, "laser fields must be a_r(1) a_i(1) grad a_r(3) grad a_i(3)");
     ARG_TRY(ar->ctx == p->ctx && ai->ctx == p->ctx && arg->ctx == p->ctx && aig->ctx == p->ctx, "laser fields belong to another context");
     lv->ar = ar->f1; lv->ai = ai->f1; lv->arg = arg->f1; lv->aig = aig->f1;
+    return 0;
+}
+// raw variants for the sim's per-slice path: sums stay in acc8 for program C, the push is push_u only
+int part2d_launch_amjdeposit_pgc(qpg_part2d p, qpg_field ef, qpg_field bf, qpg_field ar, qpg_field ai, qpg_field arg, qpg_field aig, double dt, const int *skip_flag, int std_flavour)
+{
+    if (p->npp_hi == 0) return 0;
+    LaserView lv;
+    int rc = laser_view(p, ar, ai, arg, aig, &lv);
+    if (rc) return rc;
+    qpg_ctx c = p->ctx;
+    const int grid = (int)((p->npp_hi + PT_BLOCK - 1) / PT_BLOCK);
+    TprofScope tp(c, TP_K_AMJ);
+    DISPATCH_M(c->M, l_amj_pgc, grid, c->stream, view_of(p), ef->f1, bf->f1, lv, p->acc8, p->qbm, dt, 1.0 / c->dr, std_flavour, skip_flag);
+    count_launch(c);
+    CUDA_TRY(cudaGetLastError());
     return 0;
 }
 extern "C" int qpg_part2d_amjdeposit_pgc(qpg_part2d p, int push_type, qpg_field ef, qpg_field bf, qpg_field ar, qpg_field ai, qpg_field ar_grad,

@@ -10,6 +10,7 @@ int part2d_launch_qdeposit(qpg_part2d p);
 int part2d_launch_amjdeposit(qpg_part2d p, qpg_field ef, qpg_field bf, double dt, const int *skip_flag, int std_flavour);
 int part2d_launch_push(qpg_part2d p, qpg_field ef, qpg_field bf, double dt, int mode);
 int part2d_launch_compact(qpg_part2d p, int *slice_flags);
+int part2d_launch_amjdeposit_pgc(qpg_part2d p, qpg_field ef, qpg_field bf, qpg_field ar, qpg_field ai, qpg_field arg, qpg_field aig, double dt, const int *skip_flag, int std_flavour);
 
 struct qpg_sim_s {
     qpg_sim_params prm;
@@ -17,6 +18,8 @@ struct qpg_sim_s {
     qpg_field psi, e, b, e_spe, b_spe, e_beam, b_beam, cu, amu, acu, dcu, q_spe, q_beam, spe_q, spe_qn, spe_cu, spe_dcu, spe_amu, beam_q;
     qpg_part2d spe;
     qpg_part3d beam;
+    qpg_laser laser;      // sp_push_pgc: the one laser envelope of the run
+    int cur_j;            // slice being enqueued (per-slice launch path)
     cudaGraph_t graph;
     cudaGraphExec_t gexec;
     bool graph_ready;
@@ -134,7 +137,12 @@ static int launch_fused(qpg_sim s, int which)
 
 static int enqueue_pc_iteration(qpg_sim s)
 {
-    int rc = part2d_launch_amjdeposit(s->spe, s->e, s->b, s->prm.dxi, s->ctx->flags, s->prm.sp_push_std != 0);
+    int rc;
+    if (s->prm.sp_push_pgc) {    // species2d_class.f03:256-259 amjdeposit_{std,robust}_pgc with laser_all's slice images
+        qpg_laser l = s->laser;
+        rc = part2d_launch_amjdeposit_pgc(s->spe, s->e, s->b, qpg_laser_field(l, 0), qpg_laser_field(l, 1), qpg_laser_field(l, 2), qpg_laser_field(l, 3),
+                                          s->prm.dxi, s->ctx->flags, s->prm.sp_push_std != 0);
+    } else rc = part2d_launch_amjdeposit(s->spe, s->e, s->b, s->prm.dxi, s->ctx->flags, s->prm.sp_push_std != 0);
     if (rc) return rc;
     if (s->use_fused) return launch_fused(s, 1);
     FProgBuilder pb(s->ctx);
@@ -150,15 +158,25 @@ static int enqueue_slice_head(qpg_sim s)
     // simulation_class.f03:357-359: the std pushers read psi at the particle positions (program A has just solved psi;
     // nothing else in A depends on the particles' psi)
     if (s->prm.sp_push_std) rc = qpg_part2d_interp_psi(s->spe, s->psi);
+    if (!rc && s->prm.sp_push_pgc) rc = qpg_laser_slice(s->laser, s->cur_j);    // simulation_class.f03:361-366
     return rc;
 }
 static int enqueue_slice_tail(qpg_sim s)
 {
     int rc;
+    if (s->prm.sp_push_pgc) {   // simulation_class.f03:401 lasers%deposit_chi (psi of the particles is the converged iteration's)
+        const int ppc = s->prm.sp_ppc_r > 0 ? s->prm.sp_ppc_r : 1;
+        if ((rc = qpg_laser_deposit_chi(s->laser, s->spe, s->cur_j, (12.0 * ppc * ppc) / (1.0 + 2.0 * ppc * ppc)))) return rc;
+    }
     if (s->use_fused) rc = launch_fused(s, 2);
     else { FProgBuilder pb(s->ctx); prog_D(s, pb); rc = pb.launch(TP_FIELD_FUSED); }
     if (rc) return rc;
-    rc = part2d_launch_push(s->spe, s->e, s->b, s->prm.dxi, s->prm.sp_push_std ? 7 | 8 : 7);  // push_u + push_x + bound flags :438-439
+    if (s->prm.sp_push_pgc) {   // push_u_{std,robust}_pgc (:438), then push_x + bound flags (:439)
+        qpg_laser l = s->laser;
+        rc = qpg_part2d_push_u_pgc(s->spe, s->prm.sp_push_std ? QPG_PUSH2_STD_PGC : QPG_PUSH2_ROBUST_PGC, s->e, s->b, qpg_laser_field(l, 0), qpg_laser_field(l, 1),
+                                   qpg_laser_field(l, 2), qpg_laser_field(l, 3), s->prm.dxi);
+        if (!rc) rc = part2d_launch_push(s->spe, s->e, s->b, s->prm.dxi, 6);
+    } else rc = part2d_launch_push(s->spe, s->e, s->b, s->prm.dxi, s->prm.sp_push_std ? 7 | 8 : 7);  // push_u + push_x + bound flags :438-439
     if (rc) return rc;
     rc = part2d_launch_compact(s->spe, s->use_fused ? s->ctx->flags : nullptr);  // update_bound (+ slice counter)
     if (rc) return rc;
@@ -166,7 +184,7 @@ static int enqueue_slice_tail(qpg_sim s)
 }
 
 // ---- persistent slab sweep (sweep.cu) ---------------------------------------------------------------------
-static bool sweep_supported(const qpg_sim_params &prm) { return prm.max_mode <= 2 && (prm.nr + ST_N - 1) / ST_N <= SW_MAX_TEAM && !prm.sp_push_std; }
+static bool sweep_supported(const qpg_sim_params &prm) { return prm.max_mode <= 2 && (prm.nr + ST_N - 1) / ST_N <= SW_MAX_TEAM && !prm.sp_push_std && !prm.sp_push_pgc; }
 template <int M> static constexpr size_t sweep_smem() { return (sizeof(StripSmem<M>) + 7) / 8 * 8 + sizeof(double) * DepTile<M>::doubles * (SW_T / 32); }
 template <int M> static cudaError_t sweep_occupancy(int *blocks_per_sm)
 {
@@ -335,6 +353,12 @@ extern "C" int qpg_sim_create(qpg_sim *out, int device, void *cuda_stream, const
     if (rc) return rc;
     rc = qpg_part3d_create(&s->beam, c, prm->beam_qbm, prm->dt, prm->beam_npmax < 32 ? 32 : prm->beam_npmax, prm->nz_total, prm->noff2, nzp);
     if (rc) return rc;
+    if (prm->sp_push_pgc) {
+        if (prm->noff2 != 0 || nzp != prm->nz_total) { qpg_set_error("the laser path runs on one xi stage (noff2 = 0, nzp = nz_total)"); return QPG_ERR_UNSUPPORTED; }
+        rc = qpg_laser_create(&s->laser, c, nzp, prm->laser_k0, prm->dt, prm->laser_iter < 1 ? 1 : prm->laser_iter);
+        if (rc) return rc;
+        s->prm.use_graph = 0;   // the slice index is a host-side argument of the laser kernels
+    }
     *out = s;
     return 0;
 }
@@ -348,6 +372,7 @@ extern "C" int qpg_sim_destroy(qpg_sim s)
                        s->spe_q, s->spe_qn, s->spe_cu, s->spe_dcu, s->spe_amu, s->beam_q};
     for (auto f : all) qpg_field_destroy(f);
     cudaFree(s->phi); cudaFree(s->sw_bar); cudaFree(s->sw_xbuf); cudaFree(s->sw_xll); cudaFree(s->sw_prof); cudaFree(s->sw_trace);
+    qpg_laser_destroy(s->laser);
     qpg_part2d_destroy(s->spe);
     qpg_part3d_destroy(s->beam);
     qpg_ctx_destroy(s->ctx);
@@ -445,6 +470,7 @@ extern "C" int qpg_sim_run_slices(qpg_sim s, int j0, int j1)
     }
     if (s->prm.use_graph && !s->graph_ready) { if ((rc = build_graph(s))) return rc; }
     for (int j = j0; j <= j1; j++) {
+        s->cur_j = j;
         if (s->prm.use_graph) {
             CUDA_TRY(cudaGraphLaunch(s->gexec, c->stream));
             c->launches += 5 + 2;  // head, tail x4, >= 1 PC iteration (exact count comes from the device iteration counter)
@@ -512,7 +538,14 @@ extern "C" int qpg_sim_set_fused(qpg_sim s, int on)
     s->use_fused = on != 0;
     return 0;
 }
-extern "C" int qpg_sim_set_graph(qpg_sim s, int use_graph) { ARG_TRY(s, "null sim"); s->prm.use_graph = use_graph != 0; return 0; }
+extern "C" int qpg_sim_set_graph(qpg_sim s, int use_graph) { ARG_TRY(s, "null sim"); s->prm.use_graph = use_graph != 0 && !s->prm.sp_push_pgc; return 0; }
+extern "C" qpg_laser qpg_sim_laser(qpg_sim s) { return s ? s->laser : nullptr; }
+extern "C" int qpg_sim_laser_advance(qpg_sim s)
+{
+    ARG_TRY(s, "null sim");
+    if (!s->laser) return 0;
+    return qpg_laser_advance(s->laser);
+}
 extern "C" int qpg_sim_set_sweep(qpg_sim s, int on)
 {
     ARG_TRY(s, "null sim");
