@@ -28,6 +28,11 @@ CONFIGS = {
                beam=dict(ppc=(2, 2, 2), num_theta=16, q=-1.0, m=1.0, gamma=20000.0, density=5.0, quiet=True,
                          center=(0.0376, 0.0, 0.0), sigma=(0.2, 0.2, 0.6), range1=(-1.0, 1.0), range2=(-1.0, 1.0),
                          range3=(-3.0, 3.0), uth=(2.0, 2.0, 0.0), den_min=1e-10)),
+    # input_file/lwfa/qpinput.json: no beam, one laser (gaussian x sin2), robust_pgc plasma, max_mode 0, time 10.1 / dt 2 = 5 steps
+    "C4": dict(nr=512, nz=512, max_mode=0, rmax=15.0, zmin=-3.0, zmax=12.0, dt=2.0, ppc1=8, ppc2=2, num_theta=8,
+               iter_max=10, iter_reltol=1e-2, iter_abstol=1e-3, nstep3d=5,
+               laser=dict(k0=20.0, a0=2.0, w0=2.828427, focal_distance=0.0, lon_center=0.0, t_rise=2.0, t_flat=0.0, t_fall=2.0,
+                          iteration=3)),
 }
 
 
@@ -108,3 +113,36 @@ def plasma_uniform(nr, rmax, ppc1, ppc2, num_theta, q=-1.0, density=1.0, den_min
     gamma = np.ones(n)
     psi = (1.0 - gamma + p[:, 2]) / q
     return np.ascontiguousarray(x), p, gamma, psi, np.ascontiguousarray(qq)
+
+
+def laser_gaussian(nr, nz, rmax, zmin, zmax, k0, a0, w0, focal_distance=0.0, lon_center=0.0, t_rise=1.0, t_flat=0.0,
+                   t_fall=1.0, max_mode=0, **_):
+    """Host-side launch of a laser pulse with a Gaussian transverse and sin^2 longitudinal profile at t = 0: a vectorised
+    restatement of profile_laser%launch (laser/profile_laser_class.f03:318-378) with get_prof_perp_gaussian
+    (laser/profile_laser_lib.f03:56-96) and get_prof_lon_sin2 (:472-502), no chirp.  Stays on the host like the input
+    deck; the result is uploaded with qpg_laser_upload.  Returns a_r, a_i of shape (P, nz+3, nr+2): xi slice j (1-based)
+    at index j+1 (two lower guard slices, zero: nothing is ahead of the box), radial guards zero."""
+    dr, dz = rmax / nr, (zmax - zmin) / nz
+    P = 2 * max_mode + 1
+    ar, ai = np.zeros((P, nz + 3, nr + 2)), np.zeros((P, nz + 3, nr + 2))
+    z = (np.arange(1, nz + 1) - 1.0) * dz + zmin - lon_center          # "z" is xi = t - z
+    pih = 1.570796326794897
+    fs, fe = -0.5 * t_flat, 0.5 * t_flat
+    env = np.zeros(nz)
+    rise = (z >= fs - t_rise) & (z < fs)
+    env[rise] = np.cos((z[rise] - fs) / t_rise * pih) ** 2
+    env[(z >= fs) & (z < fe)] = 1.0
+    fall = (z >= fe) & (z < fe + t_fall)
+    env[fall] = np.cos((z[fall] - fe) / t_fall * pih) ** 2
+    r = (np.arange(1, nr + 1) - 1.0) * dr
+    zs = -1.0 * (z + focal_distance)
+    zr = 0.5 * k0 * w0 * w0
+    curv = zs / (zs * zs + zr * zr)
+    w = w0 * np.sqrt(1.0 + zs * zs / (zr * zr))
+    gouy = np.arctan2(zs, zr)
+    r2 = (r * r)[None, :]
+    phase = 0.5 * k0 * r2 * curv[:, None] - gouy[:, None]
+    amp = (w0 / w)[:, None] * np.exp(-r2 / (w * w)[:, None])
+    ar[0, 2:nz + 2, 1:nr + 1] = (env * a0)[:, None] * amp * np.cos(phase)
+    ai[0, 2:nz + 2, 1:nr + 1] = -(env * a0)[:, None] * amp * np.sin(phase)
+    return ar, ai

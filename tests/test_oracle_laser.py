@@ -161,3 +161,17 @@ def test_linear_laser_wakefield_matches_theory():
     ar, ai, chi = sim.laser()
     assert np.max(np.abs(chi[0, 8:nz, 2:nr // 2] + 1.0)) < 5e-3
     assert 0 < np.max(np.abs(ar - las.ar)) < 0.05 * a0
+
+
+def test_host_side_laser_launch_matches_oracle():
+    """qpad_b200.decks.laser_gaussian (the host-side profile launch the GPU path uploads) against the oracle's restatement of
+    profile_laser%launch, at the lwfa deck's parameters"""
+    from qpad_b200 import decks
+    cfg = dict(decks.CONFIGS["C4"])
+    las = cfg.pop("laser")
+    nr, nz = 128, 96
+    ar, ai = decks.laser_gaussian(nr, nz, cfg["rmax"], cfg["zmin"], cfg["zmax"], **las)
+    o = O.Laser(nr, nz, 0, cfg["rmax"], cfg["zmin"], cfg["zmax"], cfg["dt"], las["k0"], las["iteration"])
+    o.launch_gaussian(las["a0"], las["w0"], las["focal_distance"], las["lon_center"], las["t_rise"], las["t_flat"], las["t_fall"])
+    assert np.max(np.abs(o.ar)) > 1.9
+    assert np.max(np.abs(ar - o.ar)) < 1e-14 and np.max(np.abs(ai - o.ai)) < 1e-14
