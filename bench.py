@@ -31,7 +31,7 @@ UNIT = "updates/s"
 def deck_config(name):
     from qpad_b200 import decks
     cfg = dict(decks.CONFIGS[name])
-    beam = dict(cfg.pop("beam"))
+    beam = dict(cfg.pop("beam")) if "beam" in cfg else None
     return cfg, beam
 
 
@@ -40,6 +40,8 @@ def make_inputs(cfg, beam, beam_lattice=(256, 512)):
     The beam lattice is capped at 256 x 512 cells (the C1-class lattice) so the particle count stays ~4e6."""
     from qpad_b200 import decks
     pl = decks.plasma_uniform(cfg["nr"], cfg["rmax"], cfg["ppc1"], cfg["ppc2"], cfg["num_theta"])
+    if beam is None:                      # laser-driven deck (C4): no beam particles
+        return pl, (np.zeros((0, 3)), np.zeros((0, 3)), np.zeros(0))
     bnr, bnz = min(cfg["nr"], beam_lattice[0]), min(cfg["nz"], beam_lattice[1])
     bm = decks.beam_std(bnr, bnz, cfg["rmax"], cfg["zmin"], cfg["zmax"], **beam)
     return pl, bm
@@ -100,7 +102,13 @@ def hbm_peak():
 def cpu_sample(cfg, plasma, beam_arrays, nslices, fast=True, nstages=1):
     from oracle import oracle as O
     kw = {k: cfg[k] for k in ("nr", "nz", "max_mode", "rmax", "zmin", "zmax", "dt", "iter_max", "iter_reltol", "iter_abstol", "ppc1", "ppc2", "num_theta")}
+    las = cfg.get("laser")
+    if las:                               # C4: robust_pgc plasma + one laser envelope (launched on the host, decks.laser_gaussian)
+        from qpad_b200 import decks
+        kw.update(sp_push_type=5, laser_on=1, laser_iter=las["iteration"], laser_k0=las["k0"], beam_evol=0)
     sim = O.Sim(fast=fast, nstages=nstages, **kw)
+    if las:
+        sim.set_laser(*decks.laser_gaussian(cfg["nr"], cfg["nz"], cfg["rmax"], cfg["zmin"], cfg["zmax"], **las))
     sim.set_beam(*beam_arrays)
     t0 = time.perf_counter()
     upd = sim.run_slices(nslices)
@@ -355,6 +363,90 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def run_c4(args):
+    """config 4 (input_file/lwfa): laser-driven wake, robust_pgc plasma, envelope advanced every 3D step -- one xi stage on one
+    GPU through the per-slice launch path (the laser hooks are not in the persistent sweep kernel yet).  A step = one 3D
+    step = nz slices + the envelope advance."""
+    import torch
+    from qpad_b200 import capi, decks
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference for the CPU arm)")
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        raise SystemExit("bench.py --config C4: the laser path runs on one xi stage (one GPU)")
+    cfg, _ = deck_config("C4")
+    las = cfg["laser"]
+    plasma, _bm = make_inputs(cfg, None)
+    x, p, g, psi, q = plasma
+    npp0 = len(q)
+    stream = torch.cuda.Stream()
+    simkw = {k: cfg[k] for k in ("nr", "nz", "max_mode", "rmax", "zmin", "zmax", "dt", "iter_max", "iter_reltol", "iter_abstol")}
+    sim = capi.Sim(sp_npmax=2 * npp0, beam_npmax=64, beam_evol=0, sp_push_pgc=1, laser_iter=las["iteration"], laser_k0=las["k0"], sp_ppc_r=cfg["ppc1"],
+                   use_graph=0 if args.no_graph else 1, stream=stream.cuda_stream, **simkw)
+    sim.init_species(x, p, g, psi, q)
+    a_r, a_i = decks.laser_gaussian(cfg["nr"], cfg["nz"], cfg["rmax"], cfg["zmin"], cfg["zmax"], **las)
+    sim.laser.upload(a_r, a_i)
+    for _ in range(args.warmup):
+        sim.step3d()
+    torch.cuda.synchronize()
+    u0, i0, s0 = sim.stats()
+    l0 = sim.ctx.launch_count()
+    clk = ClockSampler(0); clk.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        sim.step3d()
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    clocks = clk.stop()
+    u1, i1, s1 = sim.stats()
+    upd, iters, slices = u1 - u0, i1 - i0, s1 - s0
+    launches = sim.ctx.launch_count() - l0 if args.no_graph else slices * 9 + 2 * iters + 2 * args.steps   # graph replay: head 2, tail 7, 2 per PC iteration
+    # end to end: plasma lattice host -> device every step, wake + envelope line-outs device -> host
+    t0 = time.perf_counter()
+    ue0 = sim.stats()[0]
+    d2h = 0
+    for _ in range(args.steps):
+        sim.species.upload(x, p, g, psi, q)
+        sim.beam_qdp_begin(); sim.beam_qdp_end(); sim.begin_step()
+        sim.run_slices(1, sim.nzp)
+        sim.laser_advance()
+        ez = sim.field("e").lineout(3, 0, 1); ps = sim.field("psi").lineout(1, 0, 1)
+        d2h = 8 * (len(ez) + len(ps)) + 24
+        sim.stats()
+    torch.cuda.synchronize()
+    te = time.perf_counter() - t0
+    e2e = {"value": (sim.stats()[0] - ue0) / te, "unit": UNIT, "h2d_bytes_per_step": int(64 * npp0), "d2h_bytes_per_step": int(d2h),
+           "what": "per step: plasma lattice host->device (qpg_part2d_upload), nz slices + envelope advance, E_z and psi on-axis line-outs + counters device->host"}
+    peak, peak_src = hbm_peak()
+    nit = iters / max(slices, 1)
+    # algorithmic bytes per update: qdeposit 24 + amjdeposit_pgc 72 per pass (reads psi too) + push_u_pgc 80 + push_x 64 + deposit_chi 32
+    bpu = 24.0 + 72.0 * nit + 80.0 + 64.0 + 32.0
+    ach = upd * bpu / (ms * 1e-3) / 1e9
+    roof = {"bound": "hbm", "kernel": "per-slice launch path: k_amjdeposit_pgc / k_push_u_pgc / k_push / k_qdeposit / k_deposit_chi + field programs (65 536 particles per slice: the latency of the ~12 dependent kernels of a slice bounds it, not the particle bytes)",
+            "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src, "bytes_per_update": bpu,
+            "us_per_slice": ms * 1e3 / max(slices, 1)}
+    cpu = None
+    if not args.no_cpu:
+        try:
+            upd_c, wall_c, k_c, _t = cpu_parallel("C4", args.ref_slices)
+            cpu = {"value": upd_c / wall_c, "unit": UNIT, "cores": k_c, "kind": "port",
+                   "sample": f"{k_c} concurrent stage processes (one per host core) x the first {args.ref_slices} xi slices of the C4 step (the slices that hold the pulse): {upd_c} updates in {wall_c:.1f} s; oracle restatement, -O3 -march=native"}
+        except Exception as exc:
+            cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {exc}"}
+    line = {"metric": METRIC, "value": upd / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic (lattice plasma per fdist2d rule, Gaussian x sin^2 laser pulse of the lwfa deck)",
+            "config": {"workload": f"C4: nr={cfg['nr']} nz={cfg['nz']} max_mode=0 Np/slice={npp0} robust_pgc, laser a0={las['a0']} k0={las['k0']} iteration {las['iteration']}",
+                       "parallelism": ("single stage, slice body " + ("as plain stream launches" if args.no_graph else "replayed from a CUDA graph (device-side WHILE node for the predictor-corrector loop)") + " + one persistent envelope-solve CTA per step"), "l2": "field volumes + envelope volumes ~60 MB, particle planes 4 MB: L2 resident",
+                       "pc_iters_per_slice": nit},
+            "clocks": clocks, "gpu_launches": int(launches), "roofline": roof, "e2e": e2e}
+    if cpu: line["cpu_baseline"] = cpu
+    print(json.dumps(line))
+    sim.close()
+
+
 def run_b200_local(args):
     """the xi-pipeline mapped onto SM partitions (pipeline.LocalPipeline): --stages S sweep kernels per GPU run
     concurrently, global stage g on 3D step n-g; with N > 1 GPUs the stages continue across ranks over NCCL.  A timed
@@ -537,6 +629,7 @@ def main():
     ap.add_argument("--ref-slices", type=int, default=48, help="xi slices per CPU sample and core")
     ap.add_argument("--roof-slices", type=int, default=64)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="C4: plain stream launches instead of CUDA-graph replay of the slice body")
     ap.add_argument("--no-sweep", action="store_true", help="per-slice CUDA-graph launches instead of the persistent sweep kernel")
     ap.add_argument("--no-micro", action="store_true", help="skip the stream-from-HBM kernel microbenchmark")
     ap.add_argument("--legacy-pipeline", action="store_true", help="N>1: one stage per GPU through pipeline.PipelineStage")
@@ -546,6 +639,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.config == "C4":
+        run_c4(args)
     else:
         if args.stages == 0:       # auto: as many stages as the field team (one CTA per 32 radial nodes) and the slab length allow, at most 4
             cfg, _ = deck_config(args.config)

@@ -200,7 +200,7 @@ typedef struct {
                                  std runs on the per-slice launch paths, not in the persistent sweep kernel */
     int sp_push_pgc;          /* 1 = ponderomotive-guiding-centre flavour of the chosen pusher (param.f03 p_push2_std_pgc / p_push2_robust_pgc):
                                  the sim owns ONE laser envelope (qpg_sim_laser) and runs simulation_class.f03:361-366 / :401 per slice;
-                                 single stage (noff2 = 0, nzp = nz_total), per-slice launch path */
+                                 single stage (noff2 = 0, nzp = nz_total), per-slice launch paths (CUDA graph or plain stream) */
     int laser_iter;           /* laser.iteration: fixed-point passes of the envelope solve per slice (>= 1) */
     double laser_k0;          /* laser.k0 */
     int sp_ppc_r;             /* species ppc(1): the on-axis correction of the susceptibility deposit (part2d_class.f03:2581) */
@@ -299,7 +299,8 @@ int qpg_stream_wait_is_memop(void);   /* 1 = cuStreamWaitValue32, 0 = fallback p
  *   qpg_laser_create      : init_field_laser :104 + init_solver :269 (nr <= 1024)
  *   qpg_laser_upload      : the launched profile (profile_laser%launch :318 stays on the host) ; qpg_laser_download for diagnostics
  *   qpg_laser_slice(j)    : copy_slice(j, 2to1) + set_grad(j) :637 + gather :929 -> the four slice images qpg_laser_field(0..3)
- *                           that qpg_part2d_amjdeposit_pgc / qpg_part2d_push_u_pgc take (a_r, a_i dim 1; grad a_r, grad a_i dim 3)
+ *                           that qpg_part2d_amjdeposit_pgc / qpg_part2d_push_u_pgc take (a_r, a_i dim 1; grad a_r, grad a_i dim 3);
+ *                           j = -1 (here and in deposit_chi): the slice counter a qpg_sim keeps on the device (CUDA-graph replay)
  *   qpg_laser_deposit_chi : part2d%deposit_chi :361 of one species into chi (qpg_laser_field(4)), slice j of its volume
  *                           (sim_lasers_class.f03:175-195; j = 0: slice image only); ax_corr = 12 ppc_r^2 / (1 + 2 ppc_r^2)
  *   qpg_laser_advance     : set_rhs :393 + solve :752 with the chi volume (sim_lasers_class.f03:197-222)                    */

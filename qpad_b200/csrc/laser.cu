@@ -218,9 +218,11 @@ __global__ void __launch_bounds__(1024, 1) k_laser_solve(double *__restrict__ ar
 }
 
 // copy_slice(j, 2to1) + set_grad(j) + gather into the four slice images the pgc pushers read; one thread per (node, plane)
-__global__ void k_laser_slice(const double *__restrict__ ar, const double *__restrict__ ai, int nr, int nz, int M, int j, double dr, double dz,
-                              double *__restrict__ f_ar, double *__restrict__ f_ai, double *__restrict__ f_gr, double *__restrict__ f_gi)
+__global__ void k_laser_slice(const double *__restrict__ ar, const double *__restrict__ ai, int nr, int nz, int M, int j, const int *__restrict__ jflag, double dr,
+                              double dz, double *__restrict__ f_ar, double *__restrict__ f_ai, double *__restrict__ f_gr, double *__restrict__ f_gi)
 {
+    if (jflag) j = jflag[3];   // the sim's device-side slice counter (CUDA-graph replay has no host-side j)
+    if (j < 1 || j > nz) return;
     const int P = 2 * M + 1, n = (nr + 2) * P;
     const double idrh = 0.5 / dr, idzh = 0.5 / dz;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
@@ -286,9 +288,12 @@ __global__ void k_deposit_chi(PartView pv, double *__restrict__ acc, double idr,
 }
 // :432-452 axis rules (get_deposit_ax_corr instead of the charge deposit's 8) and 1/(j-1); chi = fix(raw), raw cleared;
 // the slice image also goes into the chi volume (sim_lasers_class.f03:191 copy_slice 1to2)
-__global__ void k_chi_fix(double *__restrict__ acc, double *__restrict__ chi1, double *__restrict__ chi2_slice, int nr, int P, double ax_corr)
+__global__ void k_chi_fix(double *__restrict__ acc, double *__restrict__ chi1, double *__restrict__ chi2, int nz, int j, const int *__restrict__ jflag, int nr, int P,
+                          double ax_corr)
 {
     const int n = (nr + 2) * P;
+    if (jflag) j = jflag[3];
+    double *chi2_slice = (j >= 1 && j <= nz) ? chi2 + (size_t)(j - 1) * n : nullptr;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         const int j = k / P, pl = k % P;
         double v = acc[k];
@@ -366,17 +371,18 @@ extern "C" qpg_field qpg_laser_field(qpg_laser l, int which)
 }
 extern "C" int qpg_laser_slice(qpg_laser l, int j)
 {
-    ARG_TRY(l && j >= 1 && j <= l->nz, "slice out of range");
+    ARG_TRY(l && (j == -1 || (j >= 1 && j <= l->nz)), "slice out of range");
     qpg_ctx c = l->ctx;
     const int n = (c->nr + 2) * c->P;
-    k_laser_slice<<<(n + 255) / 256, 256, 0, c->stream>>>(l->ar, l->ai, c->nr, l->nz, c->M, j, c->dr, l->dz, l->f_ar->f1, l->f_ai->f1, l->f_gr->f1, l->f_gi->f1);
+    k_laser_slice<<<(n + 255) / 256, 256, 0, c->stream>>>(l->ar, l->ai, c->nr, l->nz, c->M, j, j == -1 ? c->flags : nullptr, c->dr, l->dz, l->f_ar->f1, l->f_ai->f1,
+                                                          l->f_gr->f1, l->f_gi->f1);
     count_launch(c);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
 extern "C" int qpg_laser_deposit_chi(qpg_laser l, qpg_part2d p, int j, double ax_corr)
 {
-    ARG_TRY(l && p && p->ctx == l->ctx && j >= 0 && j <= l->nz, "bad arg");
+    ARG_TRY(l && p && p->ctx == l->ctx && j >= -1 && j <= l->nz, "bad arg");
     qpg_ctx c = l->ctx;
     if (p->npp_hi > 0) {
         const int grid = (int)((p->npp_hi + 255) / 256);
@@ -384,7 +390,7 @@ extern "C" int qpg_laser_deposit_chi(qpg_laser l, qpg_part2d p, int j, double ax
         count_launch(c);
     }
     const int n = (c->nr + 2) * c->P;
-    k_chi_fix<<<(n + 255) / 256, 256, 0, c->stream>>>(l->chi_acc, l->chi->f1, j >= 1 ? l->chi->f2 + (size_t)(j - 1) * l->chi->n1 : nullptr, c->nr, c->P, ax_corr);
+    k_chi_fix<<<(n + 255) / 256, 256, 0, c->stream>>>(l->chi_acc, l->chi->f1, l->chi->f2, l->nz, j, j == -1 ? c->flags : nullptr, c->nr, c->P, ax_corr);
     count_launch(c);
     CUDA_TRY(cudaGetLastError());
     return 0;

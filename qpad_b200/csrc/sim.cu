@@ -158,7 +158,7 @@ static int enqueue_slice_head(qpg_sim s)
     // simulation_class.f03:357-359: the std pushers read psi at the particle positions (program A has just solved psi;
     // nothing else in A depends on the particles' psi)
     if (s->prm.sp_push_std) rc = qpg_part2d_interp_psi(s->spe, s->psi);
-    if (!rc && s->prm.sp_push_pgc) rc = qpg_laser_slice(s->laser, s->cur_j);    // simulation_class.f03:361-366
+    if (!rc && s->prm.sp_push_pgc) rc = qpg_laser_slice(s->laser, -1);    // simulation_class.f03:361-366, slice j = the device-side counter
     return rc;
 }
 static int enqueue_slice_tail(qpg_sim s)
@@ -166,7 +166,7 @@ static int enqueue_slice_tail(qpg_sim s)
     int rc;
     if (s->prm.sp_push_pgc) {   // simulation_class.f03:401 lasers%deposit_chi (psi of the particles is the converged iteration's)
         const int ppc = s->prm.sp_ppc_r > 0 ? s->prm.sp_ppc_r : 1;
-        if ((rc = qpg_laser_deposit_chi(s->laser, s->spe, s->cur_j, (12.0 * ppc * ppc) / (1.0 + 2.0 * ppc * ppc)))) return rc;
+        if ((rc = qpg_laser_deposit_chi(s->laser, s->spe, -1, (12.0 * ppc * ppc) / (1.0 + 2.0 * ppc * ppc)))) return rc;
     }
     if (s->use_fused) rc = launch_fused(s, 2);
     else { FProgBuilder pb(s->ctx); prog_D(s, pb); rc = pb.launch(TP_FIELD_FUSED); }
@@ -357,7 +357,6 @@ extern "C" int qpg_sim_create(qpg_sim *out, int device, void *cuda_stream, const
         if (prm->noff2 != 0 || nzp != prm->nz_total) { qpg_set_error("the laser path runs on one xi stage (noff2 = 0, nzp = nz_total)"); return QPG_ERR_UNSUPPORTED; }
         rc = qpg_laser_create(&s->laser, c, nzp, prm->laser_k0, prm->dt, prm->laser_iter < 1 ? 1 : prm->laser_iter);
         if (rc) return rc;
-        s->prm.use_graph = 0;   // the slice index is a host-side argument of the laser kernels
     }
     *out = s;
     return 0;
@@ -538,7 +537,7 @@ extern "C" int qpg_sim_set_fused(qpg_sim s, int on)
     s->use_fused = on != 0;
     return 0;
 }
-extern "C" int qpg_sim_set_graph(qpg_sim s, int use_graph) { ARG_TRY(s, "null sim"); s->prm.use_graph = use_graph != 0 && !s->prm.sp_push_pgc; return 0; }
+extern "C" int qpg_sim_set_graph(qpg_sim s, int use_graph) { ARG_TRY(s, "null sim"); s->prm.use_graph = use_graph != 0; return 0; }
 extern "C" qpg_laser qpg_sim_laser(qpg_sim s) { return s ? s->laser : nullptr; }
 extern "C" int qpg_sim_laser_advance(qpg_sim s)
 {
