@@ -31,13 +31,15 @@ class Params(C.Structure):
                 ("ppc1", C.c_int), ("ppc2", C.c_int), ("num_theta", C.c_int), ("sort_freq", C.c_int),
                 ("sp_q", C.c_double), ("sp_m", C.c_double), ("sp_density", C.c_double), ("sp_den_min", C.c_double),
                 ("beam_push_type", C.c_int), ("beam_evol", C.c_int), ("beam_qbm", C.c_double), ("sp_push_type", C.c_int),
-                ("laser_on", C.c_int), ("laser_iter", C.c_int), ("laser_k0", C.c_double)]
+                ("laser_on", C.c_int), ("laser_iter", C.c_int), ("laser_k0", C.c_double),
+                ("neut_on", C.c_int), ("neut_elem", C.c_int), ("neut_ion_max", C.c_int), ("neut_ppc1", C.c_int), ("neut_ppc2", C.c_int),
+                ("neut_num_theta", C.c_int), ("neut_q", C.c_double), ("neut_m", C.c_double), ("neut_density", C.c_double), ("n0", C.c_double)]
 
 
 def build(fast=False, force=False):
     target = "liborc_fast.so" if fast else "liborc.so"
     path = os.path.join(_HERE, target)
-    newest = max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("qpad_oracle.c", "qpad_oracle_laser.c", "qpad_oracle.h"))
+    newest = max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("qpad_oracle.c", "qpad_oracle_laser.c", "qpad_oracle_neutral.c", "qpad_oracle.h"))
     if force or not os.path.exists(path) or os.path.getmtime(path) < newest:
         subprocess.check_call(["make", "-C", _HERE, "-B", target], stdout=subprocess.DEVNULL)
     return path
@@ -93,6 +95,15 @@ def lib(fast=False):
         "orc_sim_get_beam": (None, [vp, i, _dp, _dp, _dp]),
         "orc_sim_get_field": (l, [vp, i, C.c_char_p, i, C.c_void_p]),
         "orc_sim_total_iters": (l, [vp]),
+        "orc_adk_params": (i, [i, i, _dp]),
+        "orc_plasma_frequency": (d, [d]),
+        "orc_neutral_reset": (None, [_dp, i, i, i]),
+        "orc_neutral_ionize": (None, [_dp, _dp, _dp, d, d, i, i, i, i, i, i]),
+        "orc_neutral_add_particles": (l, [_dp, _dp, i, i, i, i, i, d, d, d, d, _dp, _dp, _dp, _dp, _dp, C.POINTER(l), _dp, _dp]),
+        "orc_neutral_ion_deposit": (None, [_dp, _dp, l, d, i, i, _dp, _dp]),
+        "orc_sim_neutral_np": (l, [vp, i]),
+        "orc_sim_get_neutral": (None, [vp, i, _dp, _dp, _dp, _dp, _dp]),
+        "orc_sim_get_levels": (None, [vp, i, _dp]),
         "orc_sim_set_laser": (None, [vp, _dp, _dp]),
         "orc_sim_get_laser": (None, [vp, _dp, _dp, _dp]),
         "orc_laser_volume_size": (l, [i, i, i]),
@@ -138,7 +149,9 @@ class Sim:
         defaults = dict(nr=64, nz=32, max_mode=1, bnd=BND_OPEN, iter_max=1, nstages=1, rmax=5.0, zmin=-5.0, zmax=5.0,
                         dt=10.0, iter_reltol=1e-3, iter_abstol=1e-3, relax_fac=-1.0, ppc1=2, ppc2=2, num_theta=8,
                         sort_freq=0, sp_q=-1.0, sp_m=1.0, sp_density=1.0, sp_den_min=1e-10,
-                        beam_push_type=PUSH3_REDUCED, beam_evol=1, beam_qbm=-1.0, sp_push_type=1, laser_on=0, laser_iter=1, laser_k0=10.0)
+                        beam_push_type=PUSH3_REDUCED, beam_evol=1, beam_qbm=-1.0, sp_push_type=1, laser_on=0, laser_iter=1, laser_k0=10.0,
+                        neut_on=0, neut_elem=3, neut_ion_max=1, neut_ppc1=2, neut_ppc2=2, neut_num_theta=8, neut_q=-1.0, neut_m=1.0, neut_density=1.0,
+                        n0=1.0e17)
         defaults.update(kw)
         for k, v in defaults.items():
             setattr(prm, k, v)
@@ -196,6 +209,21 @@ class Sim:
 
     def total_iters(self):
         return self.L.orc_sim_total_iters(self.h)
+
+    def neutral(self, stage=0):
+        """electrons created by field ionisation so far (plasma-particle layout)"""
+        n = self.L.orc_sim_neutral_np(self.h, stage)
+        x, p = np.zeros((n, 2)), np.zeros((n, 3))
+        g, psi, q = np.zeros(n), np.zeros(n), np.zeros(n)
+        if n:
+            self.L.orc_sim_get_neutral(self.h, stage, x, p, g, psi, q)
+        return x, p, g, psi, q
+
+    def levels(self, multi_max, stage=0):
+        """(multi_max + 2, n_theta, nr): charge states 1..multi_max, neutral residue, total discrete ion level"""
+        lev = np.zeros((multi_max + 2, self.prm.neut_num_theta, self.nr))
+        self.L.orc_sim_get_levels(self.h, stage, lev)
+        return lev
 
     def set_laser(self, ar, ai):
         """envelope volumes of shape (P, nz+3, nr+2), xi slice j at index j+1 (see Laser)"""

@@ -1260,10 +1260,22 @@ typedef struct {
     ofld q3; /* dim-1 volume */
 } obeam;
 
+/* neutral_class.f03:320-345 type neutral: created electrons, their deposit fields, the ionisation levels per (cell, sector),
+ * the position buffer of the ions created in the last update and the accumulated ion charge */
+typedef struct {
+    opart2d part;
+    ofld q, cu, dcu, amu, rho_ion;
+    double *lev, *ion_old, *xa, *qa, adk[60];
+    long nadd;
+    int multi_max;
+    double qbm, wp;
+} oneutral;
+
 typedef struct {
     int nzp, noff2;
     ofld psi, e_spe, e_beam, e, b_spe, b_beam, b, cu, amu, q_spe, q_beam, dcu, acu;
     ospecies spe;
+    oneutral neut;
     obeam beam;
     /* pipeline mailboxes (filled by the upstream / downstream stage) */
     double *mb_cu, *mb_bspe, *mb_qguard, *mb_e, *mb_b;
@@ -1353,6 +1365,22 @@ orc_sim *orc_sim_create(const orc_params *prm)
         fld_init(&sp->q, 1, nr, nzp, M, 1); fld_init(&sp->cu, 3, nr, nzp, M, 0); fld_init(&sp->dcu, 2, nr, nzp, M, 0);
         fld_init(&sp->amu, 3, nr, nzp, M, 0); fld_init(&sp->qn, 1, nr, nzp, M, 0);
         species_renew(s, sp);
+        if (prm->neut_on) {                        /* neutral_class.f03:408-574 init_neutral (single stage) */
+            oneutral *ne = &st->neut;
+            const int nth = prm->neut_num_theta;
+            ne->qbm = prm->neut_q / prm->neut_m;
+            ne->wp = orc_plasma_frequency(prm->n0);
+            ne->multi_max = orc_adk_params(prm->neut_elem, prm->neut_ion_max < 20 ? prm->neut_ion_max : 20, ne->adk);
+            const long cap = (long)nr * nth * prm->neut_ppc1 * prm->neut_ppc2 + 64;
+            part2d_alloc(&ne->part, cap);
+            fld_init(&ne->q, 1, nr, nzp, M, 1); fld_init(&ne->cu, 3, nr, nzp, M, 0); fld_init(&ne->dcu, 2, nr, nzp, M, 0);
+            fld_init(&ne->amu, 3, nr, nzp, M, 0); fld_init(&ne->rho_ion, 1, nr, nzp, M, 1);
+            ne->lev = (double *)calloc((size_t)(ne->multi_max + 2) * nth * nr, sizeof(double));
+            ne->ion_old = (double *)calloc((size_t)nth * nr, sizeof(double));
+            ne->xa = (double *)calloc(2 * (size_t)cap, sizeof(double)); ne->qa = (double *)calloc((size_t)cap, sizeof(double));
+            ne->nadd = 0;
+            orc_neutral_reset(ne->lev, nr, nth, ne->multi_max);
+        }
         st->beam.npmax = 0; st->beam.npp = 0; st->beam.x = st->beam.p = st->beam.q = NULL;
         fld_init(&st->beam.q3, 1, nr, nzp, M, 1);
         size_t n3 = (size_t)st->cu.P * (nr + 2) * 3, n1 = (size_t)st->cu.P * (nr + 2);
@@ -1378,6 +1406,11 @@ void orc_sim_destroy(orc_sim *s)
         fld_free(&st->b_beam); fld_free(&st->b); fld_free(&st->cu); fld_free(&st->amu); fld_free(&st->q_spe);
         fld_free(&st->q_beam); fld_free(&st->dcu); fld_free(&st->acu);
         part2d_free(&st->spe.part);
+        if (s->prm.neut_on) {
+            oneutral *ne = &st->neut;
+            part2d_free(&ne->part); fld_free(&ne->q); fld_free(&ne->cu); fld_free(&ne->dcu); fld_free(&ne->amu); fld_free(&ne->rho_ion);
+            free(ne->lev); free(ne->ion_old); free(ne->xa); free(ne->qa);
+        }
         fld_free(&st->spe.q); fld_free(&st->spe.cu); fld_free(&st->spe.dcu); fld_free(&st->spe.amu); fld_free(&st->spe.qn);
         free(st->beam.x); free(st->beam.p); free(st->beam.q); fld_free(&st->beam.q3);
         free(st->mb_cu); free(st->mb_bspe); free(st->mb_e); free(st->mb_b); free(st->mb_qguard); free(st->mb_plasma); free(st->mb_beam);
@@ -1483,6 +1516,14 @@ static void slice_step(orc_sim *s, int k, int j)
     orc_qdeposit(pt->x, pt->q, pt->npp, dr, nr, M, sp->q.f1);
     fld_add1(&sp->q, &st->q_spe);
     fld_add1(&sp->qn, &st->q_spe);
+    oneutral *ne = pr->neut_on ? &st->neut : NULL;
+    if (ne) {                                                                       /* :351-354 neut%qdp, neut%ion_deposit */
+        fld_zero1(&ne->q);
+        if (ne->part.npp > 0) orc_qdeposit(ne->part.x, ne->part.q, ne->part.npp, dr, nr, M, ne->q.f1);
+        fld_add1(&ne->q, &st->q_spe);
+        orc_neutral_ion_deposit(ne->xa, ne->qa, ne->nadd, dr, nr, M, ne->rho_ion.f1, st->q_spe.f1);
+        ne->nadd = 0;
+    }
     solve_psi_ops(s->op_psi, st->q_spe.f1, st->psi.f1, nr, M);                      /* :356 */
     const int pgc = pr->sp_push_type == 4 || pr->sp_push_type == 5, pstd = pr->sp_push_type == 0 || pr->sp_push_type == 4;
     if (pstd) orc_interp_psi(pt->x, pt->psi, pt->npp, dr, nr, M, st->psi.f1);       /* :357-359 std pushers only (species2d_class.f03:447) */
@@ -1501,6 +1542,13 @@ static void slice_step(orc_sim *s, int k, int j)
         else (pstd ? orc_amjdeposit_std : orc_amjdeposit_robust)(pt->x, pt->p, pt->q, pt->gamma, pt->psi, pt->npp, dr, nr, M, sp->qbm, dxi, st->e.f1,
                               st->b.f1, sp->cu.f1, sp->dcu.f1, sp->amu.f1);
         fld_add1(&sp->cu, &st->cu); fld_add1(&sp->dcu, &st->acu); fld_add1(&sp->amu, &st->amu);
+        if (ne) {                                                                   /* :386-388 neut%amjdp (neutral_class.f03:932-973) */
+            fld_zero1(&ne->cu); fld_zero1(&ne->dcu); fld_zero1(&ne->amu);
+            if (ne->part.npp > 0)
+                orc_amjdeposit_robust(ne->part.x, ne->part.p, ne->part.q, ne->part.gamma, ne->part.psi, ne->part.npp, dr, nr, M, ne->qbm, dxi, st->e.f1,
+                                      st->b.f1, ne->cu.f1, ne->dcu.f1, ne->amu.f1);
+            fld_add1(&ne->cu, &st->cu); fld_add1(&ne->dcu, &st->acu); fld_add1(&ne->amu, &st->amu);
+        }
         orc_solve_djdxi(st->acu.f1, st->amu.f1, st->dcu.f1, nr, M, dr);             /* :390 */
         solve_bt_iter_ops(s->op_bp, s->op_bm, st->dcu.f1, st->cu.f1, st->b_spe.f1, nr, M, dr, s->relax); /* :391 */
         solve_bz_ops(s->op_bz, st->cu.f1, st->b_spe.f1, nr, M, dr);                 /* :392 */
@@ -1515,6 +1563,7 @@ static void slice_step(orc_sim *s, int k, int j)
         fld_copy_slice(&s->chi, j, 1);
     }
     fld_add1_dim(&sp->cu, &sp->q, 3, 1); fld_copy_slice(&sp->q, j, 1);              /* :403 cbq */
+    if (ne) { fld_add1_dim(&ne->cu, &ne->q, 3, 1); fld_copy_slice(&ne->q, j, 1); fld_copy_slice(&ne->rho_ion, j, 1); }   /* :406 cbq_neutral */
     fld_copy_slice(&st->cu, j, 1);                                                  /* :409 */
     fld_add1_dim(&st->cu, &st->q_spe, 3, 1);                                        /* :410 */
     fld_copy_slice(&st->q_spe, j, 1);                                               /* :411 */
@@ -1535,6 +1584,18 @@ static void slice_step(orc_sim *s, int k, int j)
     pt->npp = orc_update_bound(pt->x, pt->p, pt->gamma, pt->psi, pt->q, pt->npp, (double)nr * dr);
     if (pr->sort_freq > 0 && ((st->noff2 + j) % pr->sort_freq) == 0)               /* :440 (commented out upstream) */
         orc_sort_part2d(pt->x, pt->p, pt->gamma, pt->psi, pt->q, pt->npp, dr, nr);
+    if (ne) {                                                                       /* :444-450 ionize, create electrons, advance them */
+        const int nth = pr->neut_num_theta, mm = ne->multi_max;
+        memcpy(ne->ion_old, ne->lev + (size_t)(mm + 1) * nth * nr, sizeof(double) * (size_t)nth * nr);       /* neutral_class.f03:591 */
+        orc_neutral_ionize(ne->lev, ne->adk, st->e.f1, ne->wp, dxi, pr->neut_ppc1, pr->neut_ppc2, nr, nth, M, mm);
+        ne->nadd = orc_neutral_add_particles(ne->lev, ne->ion_old, nr, nth, mm, pr->neut_ppc1, pr->neut_ppc2, dr, ne->qbm, pr->neut_density, 1e-10,
+                                             ne->part.x, ne->part.p, ne->part.gamma, ne->part.psi, ne->part.q, &ne->part.npp, ne->xa, ne->qa);
+        if (ne->part.npp > 0) {
+            orc_push_u_robust(ne->part.x, ne->part.p, ne->part.gamma, ne->part.npp, dr, nr, M, ne->qbm, dxi, st->e.f1, st->b.f1);
+            orc_push_x(ne->part.x, ne->part.p, ne->part.gamma, ne->part.npp, dxi);
+            ne->part.npp = orc_update_bound(ne->part.x, ne->part.p, ne->part.gamma, ne->part.psi, ne->part.q, ne->part.npp, (double)nr * dr);
+        }
+    }
     fld_copy_slice(&st->e, j, 1); fld_copy_slice(&st->b, j, 1); fld_copy_slice(&st->psi, j, 1); /* :452-456 */
     fld_copy_slice(&st->b_spe, j, 1); fld_copy_slice(&st->e_spe, j, 1);
     if (j == 1 && k > 0) {                                                          /* :460-467 backward, 'inner' */
@@ -1646,6 +1707,12 @@ static void stage_end(orc_sim *s, int k)
         }
     }
     species_renew(s, &st->spe);                                                     /* :498-501 */
+    if (pr->neut_on) {                                                              /* :504-510 neut%renew (neutral_class.f03:839-878) */
+        oneutral *ne = &st->neut;
+        ne->part.npp = 0; ne->nadd = 0;
+        fld_zero1(&ne->q); fld_zero1(&ne->cu); fld_zero1(&ne->rho_ion);
+        orc_neutral_reset(ne->lev, nr, pr->neut_num_theta, ne->multi_max);
+    }
 }
 
 static void laser_alloc(orc_sim *s)
@@ -1755,3 +1822,16 @@ long orc_sim_get_field(const orc_sim *s, int stage, const char *name, int which,
     return (long)fld_n2(f);
 }
 long orc_sim_total_iters(const orc_sim *s) { return s->total_iters; }
+long orc_sim_neutral_np(const orc_sim *s, int stage) { return s->prm.neut_on ? s->st[stage].neut.part.npp : 0; }
+void orc_sim_get_neutral(const orc_sim *s, int stage, double *x, double *p, double *gamma, double *psi, double *q)
+{
+    const opart2d *pt = &s->st[stage].neut.part;
+    memcpy(x, pt->x, sizeof(double) * 2 * (size_t)pt->npp); memcpy(p, pt->p, sizeof(double) * 3 * (size_t)pt->npp);
+    memcpy(gamma, pt->gamma, sizeof(double) * (size_t)pt->npp); memcpy(psi, pt->psi, sizeof(double) * (size_t)pt->npp);
+    memcpy(q, pt->q, sizeof(double) * (size_t)pt->npp);
+}
+void orc_sim_get_levels(const orc_sim *s, int stage, double *lev)
+{
+    const oneutral *ne = &s->st[stage].neut;
+    memcpy(lev, ne->lev, sizeof(double) * (size_t)(ne->multi_max + 2) * s->prm.neut_num_theta * s->prm.nr);
+}

@@ -105,6 +105,10 @@ typedef struct {
     /* one laser envelope (nlasers = 1; single stage only): the envelope is handed in with orc_sim_set_laser */
     int laser_on, laser_iter;
     double laser_k0;
+    /* one field-ionisation neutral species (nneutrals = 1; single stage only; uniform profile, robust pusher):
+     * element = atomic number (1 H, 2 He, 3 Li), ion_max = deepest charge state followed, n0 = plasma density in cm^-3 */
+    int neut_on, neut_elem, neut_ion_max, neut_ppc1, neut_ppc2, neut_num_theta;
+    double neut_q, neut_m, neut_density, n0;
 } orc_params;
 
 orc_sim *orc_sim_create(const orc_params *prm);
@@ -130,6 +134,23 @@ long orc_sim_total_iters(const orc_sim *s);
  * susceptibility volume deposited during the last 3D step, (P, nz+1, nr+2) */
 void orc_sim_set_laser(orc_sim *s, const double *ar, const double *ai);
 void orc_sim_get_laser(const orc_sim *s, double *ar, double *ai, double *chi);
+
+/* ---- field-ionisation neutral species, qpad_oracle_neutral.c (species/neutral_class.f03) -----------------------------
+ * level array lev[(i * n_theta + k) * nr + j]: i < multi_max charge states 1..multi_max, i = multi_max neutral residue,
+ * i = multi_max + 1 total discrete ion level */
+int orc_adk_params(int element, int max_e, double *out);
+double orc_plasma_frequency(double n0);
+void orc_neutral_reset(double *lev, int nr, int n_theta, int multi_max);
+void orc_neutral_ionize(double *lev, const double *adk, const double *ef, double wp, double dt, int ppc1, int ppc2, int nr, int n_theta,
+                        int max_mode, int multi_max);
+long orc_neutral_add_particles(const double *lev, const double *ion_old, int nr, int n_theta, int multi_max, int ppc1, int ppc2, double dr,
+                               double qm, double density, double den_min, double *x, double *p, double *gamma, double *psi, double *q, long *npp,
+                               double *xa, double *qa);
+void orc_neutral_ion_deposit(const double *xa, const double *qa, long nadd, double dr, int nr, int max_mode, double *rho_ion, double *q_tot);
+/* whole-loop accessors of the neutral species of a stage: electrons created so far (plasma-particle layout), level array */
+long orc_sim_neutral_np(const orc_sim *s, int stage);
+void orc_sim_get_neutral(const orc_sim *s, int stage, double *x, double *p, double *gamma, double *psi, double *q);
+void orc_sim_get_levels(const orc_sim *s, int stage, double *lev);
 
 /* ---- laser envelope (ponderomotive guiding centre) field path, qpad_oracle_laser.c ---------------------------------
  * laser volumes v[plane][slice j = -1..nz+1 at index j+1][node 0..nr+1]; chi = dim-1 f2 volume; gradients = dim-3 f1 fields */
