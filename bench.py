@@ -581,6 +581,18 @@ def run_b200_local(args):
             "slab_partition": "cost-balanced (untimed calibration sweep, pipeline.probe_partition)" if parts is not None else "equal length (options_class.f03:103-106)",
             "phases_rank0": {"A||update_bound": ph["A"], "amjdeposit (64 B/particle)": ph["amj"], "C": ph["C"], "push_u+push_x+qdeposit||D (112 B/particle)": ph["push"]},
             "note": "achieved = algorithmic bytes of ALL sweep launches in the timed region / its duration, per GPU (the S kernels of a GPU overlap: a stage's latency-bound field phases and barriers hide behind the other stages' particle phases); particle planes stay L2-resident"}
+    # the other roofline of this path: fp64 issue.  SASS of this build (cuobjdump, max_mode 1): amjdeposit 252 fp64 instructions per
+    # thread + 8 DMMA per warp (= 64 DFMA-equivalents), push 206, qdeposit 45 + 8 DMMA -> per warp of 32 particles 316 per
+    # amjdeposit pass and 315 for push + qdeposit; B200 issues 2 fp64 warp-instructions per clock and SM (37 TFLOP/s measured)
+    try:
+        if cfg["max_mode"] == 1:
+            wi = 316.0 * nit + 315.0
+            mhz = clocks.get("sm_max_mhz") or 1965.0
+            bound = 148 * mhz * 1e6 * 64.0 / wi
+            roof["fp64_pipe"] = {"fp64_warp_instr_per_32_updates": wi, "bound_updates_per_s_per_gpu": bound, "achieved_frac": value / world / bound,
+                                 "note": "arithmetic intensity ~10 flop/B against a machine balance of 5.6 flop/B: the fp64 pipe, not HBM, is the nearer roof"}
+    except Exception:   # an explanatory extra must never cost the bench line
+        pass
     roof_hbm = None
     if world == 1 and not args.no_micro:
         # the push and deposit kernels individually, streaming from HBM (north star: >= 60 % of the HBM roofline): fields of
