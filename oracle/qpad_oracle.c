@@ -1271,11 +1271,20 @@ typedef struct {
     double qbm, wp;
 } oneutral;
 
+/* one laser on one stage (laser/field_laser_class.f03 + sim_lasers_class.f03): envelope and rhs volumes of the slab with their
+ * own lower guard slices (the upstream stage's last two slices as of the stage's last advance), the slice images the pgc
+ * pushers gather from (laser_all: a_r, a_i dim 1; gradients dim 3) and the susceptibility chi (f1 + volume) */
+typedef struct {
+    double *ar, *ai, *sr, *si, *ar1, *ai1, *arg, *aig;
+    ofld chi;
+} olaser;
+
 typedef struct {
     int nzp, noff2;
     ofld psi, e_spe, e_beam, e, b_spe, b_beam, b, cu, amu, q_spe, q_beam, dcu, acu;
     ospecies spe;
     oneutral neut;
+    olaser las;
     obeam beam;
     /* pipeline mailboxes (filled by the upstream / downstream stage) */
     double *mb_cu, *mb_bspe, *mb_qguard, *mb_e, *mb_b;
@@ -1290,10 +1299,7 @@ struct orc_sim {
     tri_op *op_psi, *op_ez, *op_bz, *op_bt, *op_bp, *op_bm;
     ostage *st;
     long total_iters;
-    /* one laser (sim_lasers_class.f03): envelope volumes, rhs volumes, the slice images the pgc pushers gather from
-     * (laser_all: a_r, a_i dim 1; their gradients dim 3) and the susceptibility chi (f1 + volume) */
-    double *las_ar, *las_ai, *las_sr, *las_si, *las_ar1, *las_ai1, *las_arg, *las_aig;
-    ofld chi;
+    int las_alloc;   /* the stages' olaser are allocated */
 };
 
 static void part2d_alloc(opart2d *pt, long npmax)
@@ -1416,11 +1422,13 @@ void orc_sim_destroy(orc_sim *s)
         free(st->mb_cu); free(st->mb_bspe); free(st->mb_e); free(st->mb_b); free(st->mb_qguard); free(st->mb_plasma); free(st->mb_beam);
         free(st->conv_re); free(st->conv_im);
     }
+    if (s->las_alloc)
+        for (int k = 0; k < s->prm.nstages; k++) {
+            olaser *l = &s->st[k].las;
+            free(l->ar); free(l->ai); free(l->sr); free(l->si); free(l->ar1); free(l->ai1); free(l->arg); free(l->aig);
+            fld_free(&l->chi);
+        }
     free(s->st);
-    if (s->las_ar) {
-        free(s->las_ar); free(s->las_ai); free(s->las_sr); free(s->las_si); free(s->las_ar1); free(s->las_ai1); free(s->las_arg); free(s->las_aig);
-        fld_free(&s->chi);
-    }
     free_ops(s->op_psi, M); free_ops(s->op_ez, M); free_ops(s->op_bz, M); free_ops(s->op_bt, M); free_ops(s->op_bp, M); free_ops(s->op_bm, M);
     free(s);
 }
@@ -1497,7 +1505,7 @@ static void unpack_f2_slice(ofld *f, int k, const double *buf, int add)
     }
 }
 
-static void laser_slice(orc_sim *s, int j);
+static void laser_slice(orc_sim *s, int k, int j);
 /* the 2D loop body, simulation_class.f03:342-469, for slice j of stage k */
 static void slice_step(orc_sim *s, int k, int j)
 {
@@ -1528,7 +1536,8 @@ static void slice_step(orc_sim *s, int k, int j)
     const int pgc = pr->sp_push_type == 4 || pr->sp_push_type == 5, pstd = pr->sp_push_type == 0 || pr->sp_push_type == 4;
     if (pstd) orc_interp_psi(pt->x, pt->psi, pt->npp, dr, nr, M, st->psi.f1);       /* :357-359 std pushers only (species2d_class.f03:447) */
     solve_bz_ops(s->op_bz, st->cu.f1, st->b_spe.f1, nr, M, dr);                     /* :360 */
-    if (pr->laser_on) laser_slice(s, j);                                            /* :361-366 */
+    if (pr->laser_on) laser_slice(s, k, j);                                         /* :361-366 */
+    olaser *las = &st->las;
     for (int l = 1; l <= pr->iter_max; l++) {                                       /* :370 */
         conv_record(st, &st->b_spe, 2, M);                                          /* :373 */
         fld_add1_3(&st->b_spe, &st->b_beam, &st->b);                                /* :375 */
@@ -1537,8 +1546,8 @@ static void slice_step(orc_sim *s, int k, int j)
         fld_zero1(&st->cu); fld_zero1(&st->acu); fld_zero1(&st->amu);               /* :378-380 */
         /* species2d_class.f03:233-280 amjdp */
         fld_zero1(&sp->cu); fld_zero1(&sp->dcu); fld_zero1(&sp->amu);
-        if (pgc) orc_amjdeposit_pgc(pt->x, pt->p, pt->q, pt->gamma, pt->psi, pt->npp, dr, nr, M, sp->qbm, dxi, st->e.f1, st->b.f1, s->las_ar1, s->las_ai1,
-                                    s->las_arg, s->las_aig, sp->cu.f1, sp->dcu.f1, sp->amu.f1, pstd);
+        if (pgc) orc_amjdeposit_pgc(pt->x, pt->p, pt->q, pt->gamma, pt->psi, pt->npp, dr, nr, M, sp->qbm, dxi, st->e.f1, st->b.f1, las->ar1, las->ai1,
+                                    las->arg, las->aig, sp->cu.f1, sp->dcu.f1, sp->amu.f1, pstd);
         else (pstd ? orc_amjdeposit_std : orc_amjdeposit_robust)(pt->x, pt->p, pt->q, pt->gamma, pt->psi, pt->npp, dr, nr, M, sp->qbm, dxi, st->e.f1,
                               st->b.f1, sp->cu.f1, sp->dcu.f1, sp->amu.f1);
         fld_add1(&sp->cu, &st->cu); fld_add1(&sp->dcu, &st->acu); fld_add1(&sp->amu, &st->amu);
@@ -1558,9 +1567,9 @@ static void slice_step(orc_sim *s, int k, int j)
         if (rel < pr->iter_reltol || ab < pr->iter_abstol) break;                   /* :396 */
     }
     if (pr->laser_on) {                                                             /* :401 lasers%deposit_chi (sim_lasers_class.f03:175-195) */
-        fld_zero1(&s->chi);
-        orc_deposit_chi(pt->x, pt->q, pt->psi, pt->npp, dr, nr, M, sp->qbm, orc_deposit_ax_corr(pr->ppc1), s->chi.f1);
-        fld_copy_slice(&s->chi, j, 1);
+        fld_zero1(&las->chi);
+        orc_deposit_chi(pt->x, pt->q, pt->psi, pt->npp, dr, nr, M, sp->qbm, orc_deposit_ax_corr(pr->ppc1), las->chi.f1);
+        fld_copy_slice(&las->chi, j, 1);
     }
     fld_add1_dim(&sp->cu, &sp->q, 3, 1); fld_copy_slice(&sp->q, j, 1);              /* :403 cbq */
     if (ne) { fld_add1_dim(&ne->cu, &ne->q, 3, 1); fld_copy_slice(&ne->q, j, 1); fld_copy_slice(&ne->rho_ion, j, 1); }   /* :406 cbq_neutral */
@@ -1577,7 +1586,7 @@ static void slice_step(orc_sim *s, int k, int j)
         memcpy(s->st[k + 1].mb_cu, st->cu.f1, sizeof(double) * fld_n1(&st->cu));
         memcpy(s->st[k + 1].mb_bspe, st->b_spe.f1, sizeof(double) * fld_n1(&st->b_spe));
     }
-    if (pgc) orc_push_u_pgc(pt->x, pt->p, pt->gamma, pt->psi, pt->npp, dr, nr, M, sp->qbm, dxi, st->e.f1, st->b.f1, s->las_ar1, s->las_ai1, s->las_arg, s->las_aig);
+    if (pgc) orc_push_u_pgc(pt->x, pt->p, pt->gamma, pt->psi, pt->npp, dr, nr, M, sp->qbm, dxi, st->e.f1, st->b.f1, las->ar1, las->ai1, las->arg, las->aig);
     else if (pr->sp_push_type == 0) orc_push_u_std(pt->x, pt->p, pt->gamma, pt->psi, pt->npp, dr, nr, M, sp->qbm, dxi, st->e.f1, st->b.f1);
     else orc_push_u_robust(pt->x, pt->p, pt->gamma, pt->npp, dr, nr, M, sp->qbm, dxi, st->e.f1, st->b.f1); /* :438 */
     orc_push_x(pt->x, pt->p, pt->gamma, pt->npp, dxi);                              /* :439, species2d_class.f03:311 */
@@ -1717,47 +1726,90 @@ static void stage_end(orc_sim *s, int k)
 
 static void laser_alloc(orc_sim *s)
 {
-    const int nr = s->prm.nr, nz = s->prm.nz, M = s->prm.max_mode;
-    const size_t nv = (size_t)orc_laser_volume_size(nr, nz, M), n1 = (size_t)(2 * M + 1) * (nr + 2);
-    s->las_ar = (double *)calloc(nv, sizeof(double)); s->las_ai = (double *)calloc(nv, sizeof(double));
-    s->las_sr = (double *)calloc(nv, sizeof(double)); s->las_si = (double *)calloc(nv, sizeof(double));
-    s->las_ar1 = (double *)calloc(n1, sizeof(double)); s->las_ai1 = (double *)calloc(n1, sizeof(double));
-    s->las_arg = (double *)calloc(3 * n1, sizeof(double)); s->las_aig = (double *)calloc(3 * n1, sizeof(double));
-    fld_init(&s->chi, 1, nr, nz, M, 1);
+    const int nr = s->prm.nr, M = s->prm.max_mode;
+    for (int k = 0; k < s->prm.nstages; k++) {
+        olaser *l = &s->st[k].las;
+        const int nzp = s->st[k].nzp;
+        const size_t nv = (size_t)orc_laser_volume_size(nr, nzp, M), n1 = (size_t)(2 * M + 1) * (nr + 2);
+        l->ar = (double *)calloc(nv, sizeof(double)); l->ai = (double *)calloc(nv, sizeof(double));
+        l->sr = (double *)calloc(nv, sizeof(double)); l->si = (double *)calloc(nv, sizeof(double));
+        l->ar1 = (double *)calloc(n1, sizeof(double)); l->ai1 = (double *)calloc(n1, sizeof(double));
+        l->arg = (double *)calloc(3 * n1, sizeof(double)); l->aig = (double *)calloc(3 * n1, sizeof(double));
+        fld_init(&l->chi, 1, nr, nzp, M, 1);
+    }
+    s->las_alloc = 1;
 }
+#define GV(v, nzz, pl, i, j) ((v)[(((size_t)(pl)) * ((nzz) + 3) + (size_t)((j) + 1)) * (nr + 2) + (i)])
+/* the launched envelope of the WHOLE box (layout of orc_laser_volume_size(nr, nz)) goes to the stages: each takes its slab and,
+ * as guard slices, its neighbours' edge slices (init_field_laser :163-169: pipe_send / pipe_recv of the guards, both directions) */
 void orc_sim_set_laser(orc_sim *s, const double *ar, const double *ai)
 {
-    if (!s->las_ar) laser_alloc(s);
-    const size_t nv = (size_t)orc_laser_volume_size(s->prm.nr, s->prm.nz, s->prm.max_mode);
-    memcpy(s->las_ar, ar, sizeof(double) * nv);
-    memcpy(s->las_ai, ai, sizeof(double) * nv);
+    if (!s->las_alloc) laser_alloc(s);
+    const int nr = s->prm.nr, nz = s->prm.nz, P = 2 * s->prm.max_mode + 1;
+    for (int k = 0; k < s->prm.nstages; k++) {
+        olaser *l = &s->st[k].las;
+        const int nzp = s->st[k].nzp, off = s->st[k].noff2;
+        for (int pl = 0; pl < P; pl++)
+            for (int j = -1; j <= nzp + 1; j++)
+                for (int i = 0; i <= nr + 1; i++) {
+                    GV(l->ar, nzp, pl, i, j) = GV(ar, nz, pl, i, off + j);
+                    GV(l->ai, nzp, pl, i, j) = GV(ai, nz, pl, i, off + j);
+                }
+    }
 }
+/* gather: slices 1..nzp of every stage (+ the first stage's lower and the last stage's upper guards) back into whole-box volumes;
+ * chi (P, nz+1, nr+2): slices of the last 3D step */
 void orc_sim_get_laser(const orc_sim *s, double *ar, double *ai, double *chi)
 {
-    const size_t nv = (size_t)orc_laser_volume_size(s->prm.nr, s->prm.nz, s->prm.max_mode);
-    if (ar) memcpy(ar, s->las_ar, sizeof(double) * nv);
-    if (ai) memcpy(ai, s->las_ai, sizeof(double) * nv);
-    if (chi) memcpy(chi, s->chi.f2, sizeof(double) * fld_n2(&s->chi));
+    const int nr = s->prm.nr, nz = s->prm.nz, P = 2 * s->prm.max_mode + 1, S = s->prm.nstages;
+    for (int k = 0; k < S; k++) {
+        const olaser *l = &s->st[k].las;
+        const int nzp = s->st[k].nzp, off = s->st[k].noff2;
+        for (int pl = 0; pl < P; pl++)
+            for (int j = (k == 0 ? -1 : 1); j <= (k == S - 1 ? nzp + 1 : nzp); j++)
+                for (int i = 0; i <= nr + 1; i++) {
+                    if (ar) GV(ar, nz, pl, i, off + j) = GV(l->ar, nzp, pl, i, j);
+                    if (ai) GV(ai, nz, pl, i, off + j) = GV(l->ai, nzp, pl, i, j);
+                }
+        if (chi)
+            for (int pl = 0; pl < P; pl++)
+                for (int j = 1; j <= (k == S - 1 ? nzp + 1 : nzp); j++)
+                    memcpy(chi + ((size_t)pl * (nz + 1) + (size_t)(off + j - 1)) * (nr + 2), l->chi.f2 + ((size_t)pl * (nzp + 1) + (size_t)(j - 1)) * (nr + 2),
+                           sizeof(double) * (nr + 2));
+    }
 }
 /* simulation_class.f03:361-366: laser_all = 0; copy_slice(j, 2to1); set_grad(j); gather -- one laser, so laser_all is a copy */
-static void laser_slice(orc_sim *s, int j)
+static void laser_slice(orc_sim *s, int k, int j)
 {
-    const int nr = s->prm.nr, nz = s->prm.nz, P = 2 * s->prm.max_mode + 1;
+    olaser *l = &s->st[k].las;
+    const int nr = s->prm.nr, nzp = s->st[k].nzp, P = 2 * s->prm.max_mode + 1;
     for (int pl = 0; pl < P; pl++)
         for (int i = 0; i <= nr + 1; i++) {
-            const size_t src = ((size_t)pl * (nz + 3) + (size_t)(j + 1)) * (nr + 2) + i;
-            s->las_ar1[(size_t)pl * (nr + 2) + i] = s->las_ar[src];
-            s->las_ai1[(size_t)pl * (nr + 2) + i] = s->las_ai[src];
+            l->ar1[(size_t)pl * (nr + 2) + i] = GV(l->ar, nzp, pl, i, j);
+            l->ai1[(size_t)pl * (nr + 2) + i] = GV(l->ai, nzp, pl, i, j);
         }
-    orc_laser_set_grad(s->las_ar, s->las_ai, j, nr, nz, s->prm.max_mode, s->dr, s->dxi, s->las_arg, s->las_aig);
+    orc_laser_set_grad(l->ar, l->ai, j, nr, nzp, s->prm.max_mode, s->dr, s->dxi, l->arg, l->aig);
 }
-/* sim_lasers_class.f03:197-222 advance (one stage: the pipe_recv / pipe_send of the lower guard slices are no-ops) */
-static void laser_advance(orc_sim *s)
+/* sim_lasers_class.f03:197-222 advance of stage k: set_rhs with the old envelope (guards = the upstream stage's previous
+ * hand-off), pipe_recv 'forward' 'guard' (the upstream stage's NEW last two slices -- it has advanced already), solve;
+ * the pipe_send of the own last slices is the read the next stage does here */
+static void laser_advance(orc_sim *s, int k)
 {
     const orc_params *pr = &s->prm;
-    orc_laser_set_rhs(s->las_ar, s->las_ai, s->chi.f2, pr->nr, pr->nz, pr->max_mode, pr->laser_k0, pr->dt, s->dr, s->dxi, s->las_sr, s->las_si);
-    orc_laser_solve(s->las_ar, s->las_ai, s->las_sr, s->las_si, s->chi.f2, pr->nr, pr->nz, pr->max_mode, pr->laser_k0, pr->dt, s->dr, s->dxi,
-                    pr->laser_iter < 1 ? 1 : pr->laser_iter);
+    olaser *l = &s->st[k].las;
+    const int nr = pr->nr, nzp = s->st[k].nzp, P = 2 * pr->max_mode + 1;
+    orc_laser_set_rhs(l->ar, l->ai, l->chi.f2, nr, nzp, pr->max_mode, pr->laser_k0, pr->dt, s->dr, s->dxi, l->sr, l->si);
+    if (k > 0) {
+        const olaser *u = &s->st[k - 1].las;
+        const int nzu = s->st[k - 1].nzp;
+        for (int pl = 0; pl < P; pl++)
+            for (int g = 0; g < 2; g++)                       /* guard slice 0 <- upstream nzp, guard slice -1 <- upstream nzp-1 */
+                for (int i = 0; i <= nr + 1; i++) {
+                    GV(l->ar, nzp, pl, i, -g) = GV(u->ar, nzu, pl, i, nzu - g);
+                    GV(l->ai, nzp, pl, i, -g) = GV(u->ai, nzu, pl, i, nzu - g);
+                }
+    }
+    orc_laser_solve(l->ar, l->ai, l->sr, l->si, l->chi.f2, nr, nzp, pr->max_mode, pr->laser_k0, pr->dt, s->dr, s->dxi, pr->laser_iter < 1 ? 1 : pr->laser_iter);
 }
 
 long orc_sim_step3d(orc_sim *s, int istep)
@@ -1768,8 +1820,8 @@ long orc_sim_step3d(orc_sim *s, int istep)
         stage_begin(s, k);
         for (int j = 1; j <= s->st[k].nzp; j++) { updates += s->st[k].spe.part.npp; slice_step(s, k, j); }
         stage_psend(s, k);
+        if (s->prm.laser_on) laser_advance(s, k);                                   /* simulation_class.f03:486 */
     }
-    if (s->prm.laser_on) laser_advance(s);                                          /* simulation_class.f03:486 */
     for (int k = 0; k < s->prm.nstages; k++) stage_end(s, k);
     return updates;
 }

@@ -175,3 +175,30 @@ def test_host_side_laser_launch_matches_oracle():
     o.launch_gaussian(las["a0"], las["w0"], las["focal_distance"], las["lon_center"], las["t_rise"], las["t_flat"], las["t_fall"])
     assert np.max(np.abs(o.ar)) > 1.9
     assert np.max(np.abs(ar - o.ar)) < 1e-14 and np.max(np.abs(ai - o.ai)) < 1e-14
+
+
+def test_laser_pipeline_stages_match_single_stage():
+    """the envelope across xi stages (sim_lasers%advance: each stage receives the upstream stage's NEW last two slices as its
+    lower guard slices before it solves, while its slice loop still sees the OLD ones) reproduces the single-stage run: the
+    lwfa deck's nodes = [1, 4] in small"""
+    from qpad_b200 import decks
+    cfg = dict(nr=64, nz=48, max_mode=0, rmax=10.0, zmin=-3.0, zmax=5.0, dt=2.0, iter_max=4, iter_reltol=1e-3, iter_abstol=1e-6,
+               ppc1=2, ppc2=2, num_theta=4, sp_push_type=5, laser_on=1, laser_iter=2, laser_k0=20.0, beam_evol=0)
+    ar, ai = decks.laser_gaussian(cfg["nr"], cfg["nz"], cfg["rmax"], cfg["zmin"], cfg["zmax"], k0=20.0, a0=1.0, w0=2.0, t_rise=1.5, t_fall=1.5)
+    sims = [O.Sim(nstages=S, **cfg) for S in (1, 4)]
+    for s in sims:
+        s.set_laser(ar, ai)
+        s.set_beam(np.zeros((0, 3)), np.zeros((0, 3)), np.zeros(0))
+        assert np.array_equal(s.laser()[0], ar) and np.array_equal(s.laser()[1], ai)      # scatter / gather round trip
+        for step in (1, 2, 3):
+            s.step3d(step)
+    ref, pip = sims
+    a1, b1, c1 = ref.laser()
+    a4, b4, c4 = pip.laser()
+    assert np.max(np.abs(a1 - ar)) > 1e-3                                                   # the pulse has evolved
+    assert np.max(np.abs(a4 - a1)) <= 1e-12 * np.max(np.abs(a1)) and np.max(np.abs(b4 - b1)) <= 1e-12 * np.max(np.abs(b1))
+    assert np.max(np.abs(c4[:, :-1] - c1[:, :-1])) <= 1e-11 * np.max(np.abs(c1))
+    for name in ("psi", "e"):
+        full = ref.field(name, 2)[:, :-1]
+        parts = np.concatenate([pip.field(name, 2, stage=k)[:, :-1] for k in range(4)], axis=1)
+        assert np.max(np.abs(full)) > 1e-3 and np.max(np.abs(parts - full)) <= 1e-11 * np.max(np.abs(full)), name
