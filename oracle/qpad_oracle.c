@@ -1641,6 +1641,19 @@ static void stage_begin(orc_sim *s, int k)
             pt->gamma[i] = r[5]; pt->psi[i] = r[6]; pt->q[i] = r[7];
         }
     }
+    if (pr->neut_on && k > 0) {      /* neut%precv (neutral_class.f03:1065-1101): created electrons, the ions' position buffer, rho_ion, levels */
+        const oneutral *u = &s->st[k - 1].neut;
+        oneutral *ne = &st->neut;
+        const size_t np_ = (size_t)u->part.npp, nl = (size_t)(u->multi_max + 2) * pr->neut_num_theta * nr;
+        ne->part.npp = u->part.npp;
+        memcpy(ne->part.x, u->part.x, sizeof(double) * 2 * np_); memcpy(ne->part.p, u->part.p, sizeof(double) * 3 * np_);
+        memcpy(ne->part.gamma, u->part.gamma, sizeof(double) * np_); memcpy(ne->part.psi, u->part.psi, sizeof(double) * np_);
+        memcpy(ne->part.q, u->part.q, sizeof(double) * np_);
+        ne->nadd = u->nadd;
+        memcpy(ne->xa, u->xa, sizeof(double) * 2 * (size_t)u->nadd); memcpy(ne->qa, u->qa, sizeof(double) * (size_t)u->nadd);
+        memcpy(ne->rho_ion.f1, u->rho_ion.f1, sizeof(double) * fld_n1(&u->rho_ion));
+        memcpy(ne->lev, u->lev, sizeof(double) * nl);
+    }
     fld_zero1(&st->b); fld_zero1(&st->e); fld_zero1(&st->b_spe); fld_zero1(&st->e_spe); fld_zero1(&st->psi); /* :324-331 */
     fld_zero1(&st->cu); fld_zero1(&st->acu); fld_zero1(&st->amu);
     if (k > 0) {                                                                    /* :337-340 pipe_recv_f1 replace */
@@ -1818,7 +1831,7 @@ long orc_sim_step3d(orc_sim *s, int istep)
     long updates = 0;
     for (int k = 0; k < s->prm.nstages; k++) {
         stage_begin(s, k);
-        for (int j = 1; j <= s->st[k].nzp; j++) { updates += s->st[k].spe.part.npp; slice_step(s, k, j); }
+        for (int j = 1; j <= s->st[k].nzp; j++) { updates += s->st[k].spe.part.npp + (s->prm.neut_on ? s->st[k].neut.part.npp : 0); slice_step(s, k, j); }
         stage_psend(s, k);
         if (s->prm.laser_on) laser_advance(s, k);                                   /* simulation_class.f03:486 */
     }
@@ -1830,14 +1843,14 @@ long orc_sim_run_slices(orc_sim *s, int nslices)
 {
     long updates = 0;
     stage_begin(s, 0);
-    for (int j = 1; j <= nslices && j <= s->st[0].nzp; j++) { updates += s->st[0].spe.part.npp; slice_step(s, 0, j); }
+    for (int j = 1; j <= nslices && j <= s->st[0].nzp; j++) { updates += s->st[0].spe.part.npp + (s->prm.neut_on ? s->st[0].neut.part.npp : 0); slice_step(s, 0, j); }
     return updates;
 }
 
 long orc_sim_run_range(orc_sim *s, int j0, int j1)
 {
     long updates = 0;
-    for (int j = j0; j <= j1 && j <= s->st[0].nzp; j++) { updates += s->st[0].spe.part.npp; slice_step(s, 0, j); }
+    for (int j = j0; j <= j1 && j <= s->st[0].nzp; j++) { updates += s->st[0].spe.part.npp + (s->prm.neut_on ? s->st[0].neut.part.npp : 0); slice_step(s, 0, j); }
     return updates;
 }
 

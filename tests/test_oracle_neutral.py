@@ -147,3 +147,25 @@ def test_beam_ionises_lithium_gas_and_drives_a_wake():
     assert fpsi.max() > 0.1 and fpsi.min() > -1e-12 and fez.max() > 0.05 and fez.min() < -0.02
     r = np.hypot(x[:, 0], x[:, 1])
     assert 1.0 < r.max() < 6.0
+
+
+def test_neutral_pipeline_stages_match_single_stage():
+    """the neutral species across xi stages (psend / precv, neutral_class.f03:1025-1101: created electrons, the ions' position
+    buffer, rho_ion and the ionisation levels travel forward) reproduces the single-stage run -- the ionization deck's nodes = [1, 2]"""
+    from qpad_b200 import decks
+    cfg = dict(nr=64, nz=48, max_mode=1, rmax=5.0, zmin=0.0, zmax=6.0, dt=10.0, iter_max=3, ppc1=2, ppc2=2, num_theta=8, sp_density=0.0,
+               neut_on=1, neut_elem=3, neut_ion_max=2, neut_ppc1=2, neut_ppc2=2, neut_num_theta=8, n0=1.0e17)
+    beam = dict(decks.CONFIGS["C1"]["beam"])
+    beam.update(center=(0.0, 0.0, 2.0), range3=(0.0, 4.0))
+    bm = decks.beam_std(cfg["nr"], cfg["nz"], cfg["rmax"], cfg["zmin"], cfg["zmax"], **beam)
+    ref, pip = O.Sim(nstages=1, **cfg), O.Sim(nstages=3, **cfg)
+    for s in (ref, pip):
+        s.set_beam(*bm)
+    # the state just before the renewal: run the slices of a step through the public stepping, compare the stored volumes
+    u1, u2 = ref.step3d(1), pip.step3d(1)
+    assert u1 == u2 > 1000                                     # particle-slice updates of the released electrons
+    for name in ("psi", "e", "b"):
+        full = ref.field(name, 2)[:, :-1]
+        parts = np.concatenate([pip.field(name, 2, stage=k)[:, :-1] for k in range(3)], axis=1)
+        assert np.max(np.abs(full)) > 1e-2 and np.max(np.abs(parts - full)) <= 1e-11 * np.max(np.abs(full)), name
+    assert ref.total_iters() == pip.total_iters()
