@@ -31,7 +31,9 @@ UNIT = "updates/s"
 def deck_config(name):
     from qpad_b200 import decks
     cfg = dict(decks.CONFIGS[name])
-    beam = dict(cfg.pop("beam")) if "beam" in cfg else None
+    beam = cfg.pop("beam", None)            # one beam block, a list of them (C3), or none (C4)
+    beam = [dict(b) for b in beam] if isinstance(beam, (list, tuple)) else (dict(beam) if beam is not None else None)
+    cfg.pop("nstep3d", None)
     return cfg, beam
 
 
@@ -43,7 +45,9 @@ def make_inputs(cfg, beam, beam_lattice=(256, 512)):
     if beam is None:                      # laser-driven deck (C4): no beam particles
         return pl, (np.zeros((0, 3)), np.zeros((0, 3)), np.zeros(0))
     bnr, bnz = min(cfg["nr"], beam_lattice[0]), min(cfg["nz"], beam_lattice[1])
-    bm = decks.beam_std(bnr, bnz, cfg["rmax"], cfg["zmin"], cfg["zmax"], **beam)
+    blocks = beam if isinstance(beam, list) else [beam]
+    parts = [decks.beam_std(bnr, bnz, cfg["rmax"], cfg["zmin"], cfg["zmax"], **dict(b, seed=10 + k)) for k, b in enumerate(blocks)]
+    bm = tuple(np.concatenate([p[a] for p in parts]) for a in range(3))      # beams of equal q/m share one particle set
     return pl, bm
 
 

@@ -22,17 +22,28 @@ CONFIGS = {
                beam=dict(ppc=(2, 2, 2), num_theta=16, q=-1.0, m=1.0, gamma=20000.0, density=4.0, quiet=True,
                          center=(0.0, 0.0, -2.5), sigma=(0.25, 0.25, 0.5), range1=(-1.25, 1.25), range2=(-1.25, 1.25),
                          range3=(-5.0, 0.0), uth=(5.0, 5.0, 0.0), den_min=1e-10)),
-    # input_file/hosing/qpinput.json: max_mode 2, two beams, the second off axis (merged into one particle set here)
-    "C3": dict(nr=256, nz=438, max_mode=2, rmax=6.0, zmin=-4.0, zmax=9.7, dt=10.0, ppc1=2, ppc2=2, num_theta=16,
-               iter_max=1, iter_reltol=1e-3, iter_abstol=1e-3,
-               beam=dict(ppc=(2, 2, 2), num_theta=16, q=-1.0, m=1.0, gamma=20000.0, density=5.0, quiet=True,
-                         center=(0.0376, 0.0, 0.0), sigma=(0.2, 0.2, 0.6), range1=(-1.0, 1.0), range2=(-1.0, 1.0),
-                         range3=(-3.0, 3.0), uth=(2.0, 2.0, 0.0), den_min=1e-10)),
+    # input_file/hosing/qpinput.json: max_mode 2, a drive beam on the axis and a witness beam 0.0376 off it (both q/m = -1:
+    # one particle set here), nodes [1, 4], time 20.1 / dt 10 = 2 steps
+    "C3": dict(nr=256, nz=438, max_mode=2, rmax=9.395847, zmin=0.0, zmax=9.6, dt=10.0, ppc1=2, ppc2=2, num_theta=16,
+               iter_max=10, iter_reltol=1e-3, iter_abstol=1e-3, nstep3d=2,
+               beam=[dict(ppc=(1, 1, 1), num_theta=16, q=-1.0, m=1.0, gamma=20000.0, density=93.4633, quiet=True,
+                          center=(0.0, 0.0, 3.0067), sigma=(0.1371, 0.1371, 0.4798), range1=(-0.6854, 0.6854), range2=(-0.6854, 0.6854),
+                          range3=(0.6077, 5.4056), uth=(13.7083, 13.7083, 0.0), den_min=1e-10),
+                     dict(ppc=(1, 1, 1), num_theta=16, q=-1.0, m=1.0, gamma=20000.0, density=56.078, quiet=True,
+                          center=(0.0376, 0.0, 8.6442), sigma=(0.1371, 0.1371, 0.2399), range1=(-0.6854, 0.6854), range2=(-0.6854, 0.6854),
+                          range3=(7.4447, 9.8437), uth=(13.7083, 13.7083, 0.0), den_min=1e-10)]),
     # input_file/lwfa/qpinput.json: no beam, one laser (gaussian x sin2), robust_pgc plasma, max_mode 0, time 10.1 / dt 2 = 5 steps
     "C4": dict(nr=512, nz=512, max_mode=0, rmax=15.0, zmin=-3.0, zmax=12.0, dt=2.0, ppc1=8, ppc2=2, num_theta=8,
                iter_max=10, iter_reltol=1e-2, iter_abstol=1e-3, nstep3d=5,
                laser=dict(k0=20.0, a0=2.0, w0=2.828427, focal_distance=0.0, lon_center=0.0, t_rise=2.0, t_flat=0.0, t_fall=2.0,
                           iteration=3)),
+    # input_file/ionization/qpinput.json: nspecies 0, one lithium neutral (ADK, ion_max 3), one beam, nodes [1, 2]; oracle only so far
+    "C5": dict(nr=500, nz=1000, max_mode=1, rmax=5.0, zmin=0.0, zmax=10.0, dt=10.0, ppc1=8, ppc2=8, num_theta=32,
+               iter_max=10, iter_reltol=1e-3, iter_abstol=1e-3, nstep3d=1, n0=1.0e17,
+               neutral=dict(element=3, ion_max=3, q=-1.0, m=1.0, density=1.0),
+               beam=dict(ppc=(1, 1, 1), num_theta=16, q=-1.0, m=1.0, gamma=20000.0, density=4.0, quiet=True,
+                         center=(0.0, 0.0, 2.5), sigma=(0.25, 0.25, 0.5), range1=(-1.25, 1.25), range2=(-1.25, 1.25),
+                         range3=(0.0, 5.0), uth=(5.0, 5.0, 0.0), den_min=1e-10)),
 }
 
 
