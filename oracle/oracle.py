@@ -33,7 +33,8 @@ class Params(C.Structure):
                 ("beam_push_type", C.c_int), ("beam_evol", C.c_int), ("beam_qbm", C.c_double), ("sp_push_type", C.c_int),
                 ("laser_on", C.c_int), ("laser_iter", C.c_int), ("laser_k0", C.c_double),
                 ("neut_on", C.c_int), ("neut_elem", C.c_int), ("neut_ion_max", C.c_int), ("neut_ppc1", C.c_int), ("neut_ppc2", C.c_int),
-                ("neut_num_theta", C.c_int), ("neut_q", C.c_double), ("neut_m", C.c_double), ("neut_density", C.c_double), ("n0", C.c_double)]
+                ("neut_num_theta", C.c_int), ("neut_q", C.c_double), ("neut_m", C.c_double), ("neut_density", C.c_double), ("n0", C.c_double),
+                ("subcyc_on", C.c_int), ("subcyc_exp_fac_max", C.c_double), ("subcyc_exp_fac_clamped", C.c_double), ("subcyc_dt_min", C.c_double)]
 
 
 def build(fast=False, force=False):
@@ -95,6 +96,10 @@ def lib(fast=False):
         "orc_sim_get_beam": (None, [vp, i, _dp, _dp, _dp]),
         "orc_sim_get_field": (l, [vp, i, C.c_char_p, i, C.c_void_p]),
         "orc_sim_total_iters": (l, [vp]),
+        "orc_sim_total_subcycles": (l, [vp]),
+        "orc_exp_fac_max": (d, [_dp, _dp, l]),
+        "orc_clamp_exp_fac": (None, [_dp, _dp, l, d]),
+        "orc_subcyc_step": (None, [d, d, d, d, C.POINTER(d), C.POINTER(i)]),
         "orc_adk_params": (i, [i, i, _dp]),
         "orc_plasma_frequency": (d, [d]),
         "orc_neutral_reset": (None, [_dp, i, i, i]),
@@ -151,7 +156,7 @@ class Sim:
                         sort_freq=0, sp_q=-1.0, sp_m=1.0, sp_density=1.0, sp_den_min=1e-10,
                         beam_push_type=PUSH3_REDUCED, beam_evol=1, beam_qbm=-1.0, sp_push_type=1, laser_on=0, laser_iter=1, laser_k0=10.0,
                         neut_on=0, neut_elem=3, neut_ion_max=1, neut_ppc1=2, neut_ppc2=2, neut_num_theta=8, neut_q=-1.0, neut_m=1.0, neut_density=1.0,
-                        n0=1.0e17)
+                        n0=1.0e17, subcyc_on=0, subcyc_exp_fac_max=1.5, subcyc_exp_fac_clamped=10.0, subcyc_dt_min=1e-3)
         defaults.update(kw)
         for k, v in defaults.items():
             setattr(prm, k, v)
@@ -209,6 +214,9 @@ class Sim:
 
     def total_iters(self):
         return self.L.orc_sim_total_iters(self.h)
+
+    def total_subcycles(self):
+        return self.L.orc_sim_total_subcycles(self.h)
 
     def neutral(self, stage=0):
         """electrons created by field ionisation so far (plasma-particle layout)"""

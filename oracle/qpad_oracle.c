@@ -1298,7 +1298,7 @@ struct orc_sim {
     double dr, dxi, relax;
     tri_op *op_psi, *op_ez, *op_bz, *op_bt, *op_bp, *op_bm;
     ostage *st;
-    long total_iters;
+    long total_iters, total_subcycles;
     int las_alloc;   /* the stages' olaser are allocated */
 };
 
@@ -1613,6 +1613,156 @@ static void slice_step(orc_sim *s, int k, int j)
     }
 }
 
+/* proj_subcyc/part2d_subcyc_class.f03:28-46 get_exp_fac_max: max gamma / (gamma - p_z) over the particles (1 if there are none) */
+double orc_exp_fac_max(const double *p, const double *gamma, long npp)
+{
+    if (npp <= 0) return 1.0;
+    double m = gamma[0] / (gamma[0] - p[2]);
+    for (long i = 1; i < npp; i++) { const double f = gamma[i] / (gamma[i] - p[3 * i + 2]); if (f > m) m = f; }
+    return m;
+}
+/* proj_subcyc/part2d_subcyc_class.f03:48-66 clamp_exp_fac: particles whose expansion factor exceeds the clamp are slowed down
+ * along their momentum direction until gamma / (gamma - p_z) equals it */
+void orc_clamp_exp_fac(double *p, double *gamma, long npp, double exp_fac_clamped)
+{
+    for (long i = 0; i < npp; i++) {
+        const double exp_fac = gamma[i] / (gamma[i] - p[3 * i + 2]);
+        if (exp_fac > exp_fac_clamped) {
+            double scale_fac = (exp_fac_clamped - 1.0) * (exp_fac_clamped - 1.0);
+            scale_fac = scale_fac / (exp_fac_clamped * exp_fac_clamped * p[3 * i + 2] * p[3 * i + 2] - scale_fac * (gamma[i] * gamma[i] - 1.0));
+            scale_fac = sqrt(scale_fac);
+            p[3 * i] = p[3 * i] * scale_fac; p[3 * i + 1] = p[3 * i + 1] * scale_fac; p[3 * i + 2] = p[3 * i + 2] * scale_fac;
+            gamma[i] = sqrt(1.0 + p[3 * i] * p[3 * i] + p[3 * i + 1] * p[3 * i + 1] + p[3 * i + 2] * p[3 * i + 2]);
+        }
+    }
+}
+/* proj_subcyc/simulation_subcyc_class.f03:431-451 */
+void orc_subcyc_step(double exp_fac, double exp_fac_max, double dt, double dt_min, double *dt_subcyc, int *n_subcyc)
+{
+    if (exp_fac > exp_fac_max) {
+        *n_subcyc = (int)ceil(exp_fac / exp_fac_max);
+        *dt_subcyc = dt / *n_subcyc;
+        if (*dt_subcyc < dt_min) { *n_subcyc = (int)floor(dt / dt_min); *dt_subcyc = dt / *n_subcyc; }
+    } else { *n_subcyc = 1; *dt_subcyc = dt; }
+}
+
+/* the 2D loop body of the sub-cycling variant, proj_subcyc/simulation_subcyc_class.f03:216-376: the whole deposit / solve /
+ * predictor-corrector / push sequence of a slice is repeated n_subcyc times with dxi / n_subcyc when the largest expansion
+ * factor gamma / (gamma - p_z) of the plasma exceeds `expansion_fac_max`; pushed particles are clamped to `expansion_fac_clamped` */
+static void slice_step_subcyc(orc_sim *s, int k, int j)
+{
+    ostage *st = &s->st[k];
+    const orc_params *pr = &s->prm;
+    int nr = pr->nr, M = pr->max_mode;
+    double dr = s->dr, dxi = s->dxi;
+    ospecies *sp = &st->spe;
+    opart2d *pt = &sp->part;
+    oneutral *ne = pr->neut_on ? &st->neut : NULL;
+    olaser *las = &st->las;
+    const int pgc = pr->sp_push_type == 4 || pr->sp_push_type == 5, pstd = pr->sp_push_type == 0 || pr->sp_push_type == 4;
+
+    fld_copy_slice(&st->q_beam, j, 0);                                              /* :218 */
+    solve_bt_ops(s->op_bt, st->q_beam.f1, st->b_beam.f1, nr, M, dr);                /* :219 */
+    if (pr->laser_on) laser_slice(s, k, j);                                         /* :221-226 */
+    double exp_fac_max = 1.0, dxi_sub;                                              /* :229-236 sim_plasma_subcyc%get_exp_fac_max */
+    int n_sub;
+    { const double f = orc_exp_fac_max(pt->p, pt->gamma, pt->npp); if (f > exp_fac_max) exp_fac_max = f; }
+    if (ne) { const double f = orc_exp_fac_max(ne->part.p, ne->part.gamma, ne->part.npp); if (f > exp_fac_max) exp_fac_max = f; }
+    orc_subcyc_step(exp_fac_max, pr->subcyc_exp_fac_max, dxi, pr->subcyc_dt_min, &dxi_sub, &n_sub);
+    s->total_subcycles += n_sub;
+    for (int isub = 1; isub <= n_sub; isub++) {                                     /* :239-325 */
+        fld_zero1(&st->q_spe);
+        fld_zero1(&sp->q);
+        orc_qdeposit(pt->x, pt->q, pt->npp, dr, nr, M, sp->q.f1);
+        fld_add1(&sp->q, &st->q_spe);
+        fld_add1(&sp->qn, &st->q_spe);
+        if (ne) {
+            fld_zero1(&ne->q);
+            if (ne->part.npp > 0) orc_qdeposit(ne->part.x, ne->part.q, ne->part.npp, dr, nr, M, ne->q.f1);
+            fld_add1(&ne->q, &st->q_spe);
+            orc_neutral_ion_deposit(ne->xa, ne->qa, ne->nadd, dr, nr, M, ne->rho_ion.f1, st->q_spe.f1);
+            ne->nadd = 0;
+        }
+        solve_psi_ops(s->op_psi, st->q_spe.f1, st->psi.f1, nr, M);
+        if (pstd) orc_interp_psi(pt->x, pt->psi, pt->npp, dr, nr, M, st->psi.f1);
+        solve_bz_ops(s->op_bz, st->cu.f1, st->b_spe.f1, nr, M, dr);
+        for (int l = 1; l <= pr->iter_max; l++) {
+            conv_record(st, &st->b_spe, 2, M);
+            fld_add1_3(&st->b_spe, &st->b_beam, &st->b);
+            solve_ez_ops(s->op_ez, st->cu.f1, st->e.f1, nr, M, dr);
+            orc_solve_et(st->b.f1, st->psi.f1, st->e.f1, nr, M, dr);
+            fld_zero1(&st->cu); fld_zero1(&st->acu); fld_zero1(&st->amu);
+            fld_zero1(&sp->cu); fld_zero1(&sp->dcu); fld_zero1(&sp->amu);
+            if (pgc) orc_amjdeposit_pgc(pt->x, pt->p, pt->q, pt->gamma, pt->psi, pt->npp, dr, nr, M, sp->qbm, dxi_sub, st->e.f1, st->b.f1, las->ar1, las->ai1,
+                                        las->arg, las->aig, sp->cu.f1, sp->dcu.f1, sp->amu.f1, pstd);
+            else (pstd ? orc_amjdeposit_std : orc_amjdeposit_robust)(pt->x, pt->p, pt->q, pt->gamma, pt->psi, pt->npp, dr, nr, M, sp->qbm, dxi_sub, st->e.f1,
+                                  st->b.f1, sp->cu.f1, sp->dcu.f1, sp->amu.f1);
+            fld_add1(&sp->cu, &st->cu); fld_add1(&sp->dcu, &st->acu); fld_add1(&sp->amu, &st->amu);
+            if (ne) {
+                fld_zero1(&ne->cu); fld_zero1(&ne->dcu); fld_zero1(&ne->amu);
+                if (ne->part.npp > 0)
+                    orc_amjdeposit_robust(ne->part.x, ne->part.p, ne->part.q, ne->part.gamma, ne->part.psi, ne->part.npp, dr, nr, M, ne->qbm, dxi_sub, st->e.f1,
+                                          st->b.f1, ne->cu.f1, ne->dcu.f1, ne->amu.f1);
+                fld_add1(&ne->cu, &st->cu); fld_add1(&ne->dcu, &st->acu); fld_add1(&ne->amu, &st->amu);
+            }
+            orc_solve_djdxi(st->acu.f1, st->amu.f1, st->dcu.f1, nr, M, dr);
+            solve_bt_iter_ops(s->op_bp, s->op_bm, st->dcu.f1, st->cu.f1, st->b_spe.f1, nr, M, dr, s->relax);
+            solve_bz_ops(s->op_bz, st->cu.f1, st->b_spe.f1, nr, M, dr);
+            double rel, ab;
+            conv_compare(st, &st->b_spe, 2, M, &rel, &ab);
+            s->total_iters++;
+            if (rel < pr->iter_reltol || ab < pr->iter_abstol) break;
+        }
+        fld_add1_3(&st->b_spe, &st->b_beam, &st->b);                                /* :292-295 */
+        orc_solve_et(st->b_spe.f1, st->psi.f1, st->e_spe.f1, nr, M, dr);
+        solve_ez_ops(s->op_ez, st->cu.f1, st->e.f1, nr, M, dr);
+        orc_solve_et(st->b.f1, st->psi.f1, st->e.f1, nr, M, dr);
+        /* :298-309 push_u, clamp, push_x of the species */
+        if (pgc) orc_push_u_pgc(pt->x, pt->p, pt->gamma, pt->psi, pt->npp, dr, nr, M, sp->qbm, dxi_sub, st->e.f1, st->b.f1, las->ar1, las->ai1, las->arg, las->aig);
+        else if (pr->sp_push_type == 0) orc_push_u_std(pt->x, pt->p, pt->gamma, pt->psi, pt->npp, dr, nr, M, sp->qbm, dxi_sub, st->e.f1, st->b.f1);
+        else orc_push_u_robust(pt->x, pt->p, pt->gamma, pt->npp, dr, nr, M, sp->qbm, dxi_sub, st->e.f1, st->b.f1);
+        orc_clamp_exp_fac(pt->p, pt->gamma, pt->npp, pr->subcyc_exp_fac_clamped);
+        orc_push_x(pt->x, pt->p, pt->gamma, pt->npp, dxi_sub);
+        pt->npp = orc_update_bound(pt->x, pt->p, pt->gamma, pt->psi, pt->q, pt->npp, (double)nr * dr);
+        if (ne) {                                                                   /* :312-323 */
+            const int nth = pr->neut_num_theta, mm = ne->multi_max;
+            memcpy(ne->ion_old, ne->lev + (size_t)(mm + 1) * nth * nr, sizeof(double) * (size_t)nth * nr);
+            orc_neutral_ionize(ne->lev, ne->adk, st->e.f1, ne->wp, dxi, pr->neut_ppc1, pr->neut_ppc2, nr, nth, M, mm);   /* neutral%dt stays dxi (:424) */
+            ne->nadd = orc_neutral_add_particles(ne->lev, ne->ion_old, nr, nth, mm, pr->neut_ppc1, pr->neut_ppc2, dr, ne->qbm, pr->neut_density, 1e-10,
+                                                 ne->part.x, ne->part.p, ne->part.gamma, ne->part.psi, ne->part.q, &ne->part.npp, ne->xa, ne->qa);
+            if (ne->part.npp > 0) {
+                orc_push_u_robust(ne->part.x, ne->part.p, ne->part.gamma, ne->part.npp, dr, nr, M, ne->qbm, dxi_sub, st->e.f1, st->b.f1);
+                orc_clamp_exp_fac(ne->part.p, ne->part.gamma, ne->part.npp, pr->subcyc_exp_fac_clamped);
+                orc_push_x(ne->part.x, ne->part.p, ne->part.gamma, ne->part.npp, dxi_sub);
+                ne->part.npp = orc_update_bound(ne->part.x, ne->part.p, ne->part.gamma, ne->part.psi, ne->part.q, ne->part.npp, (double)nr * dr);
+            }
+        }
+    }
+    if (pr->laser_on) {                                                             /* :328 deposit chi */
+        fld_zero1(&las->chi);
+        orc_deposit_chi(pt->x, pt->q, pt->psi, pt->npp, dr, nr, M, sp->qbm, orc_deposit_ax_corr(pr->ppc1), las->chi.f1);
+        fld_copy_slice(&las->chi, j, 1);
+    }
+    fld_add1_dim(&sp->cu, &sp->q, 3, 1); fld_copy_slice(&sp->q, j, 1);              /* :330-332 cbq */
+    if (ne) { fld_add1_dim(&ne->cu, &ne->q, 3, 1); fld_copy_slice(&ne->q, j, 1); fld_copy_slice(&ne->rho_ion, j, 1); }
+    fld_copy_slice(&st->cu, j, 1);                                                  /* :336 */
+    fld_add1_dim(&st->cu, &st->q_spe, 3, 1);
+    fld_copy_slice(&st->q_spe, j, 1);
+    fld_dot1(dxi, &st->dcu);                                                        /* :347-348 (the full dxi) */
+    fld_add1_dim(&st->dcu, &st->cu, 1, 1); fld_add1_dim(&st->dcu, &st->cu, 2, 2);
+    if (j == st->nzp && k + 1 < pr->nstages) {                                      /* :351-356 */
+        memcpy(s->st[k + 1].mb_cu, st->cu.f1, sizeof(double) * fld_n1(&st->cu));
+        memcpy(s->st[k + 1].mb_bspe, st->b_spe.f1, sizeof(double) * fld_n1(&st->b_spe));
+    }
+    fld_copy_slice(&st->e, j, 1); fld_copy_slice(&st->b, j, 1); fld_copy_slice(&st->psi, j, 1); /* :358-362 */
+    fld_copy_slice(&st->b_spe, j, 1); fld_copy_slice(&st->e_spe, j, 1);
+    if (j == 1 && k > 0) {                                                          /* :366-373 */
+        pack_f2_slice(&st->b, 1, s->st[k - 1].mb_b);
+        pack_f2_slice(&st->e, 1, s->st[k - 1].mb_e);
+    }
+}
+
+
 /* first half of a 3D step for stage k: simulation_class.f03:296-340 */
 static void stage_begin(orc_sim *s, int k)
 {
@@ -1831,7 +1981,7 @@ long orc_sim_step3d(orc_sim *s, int istep)
     long updates = 0;
     for (int k = 0; k < s->prm.nstages; k++) {
         stage_begin(s, k);
-        for (int j = 1; j <= s->st[k].nzp; j++) { updates += s->st[k].spe.part.npp + (s->prm.neut_on ? s->st[k].neut.part.npp : 0); slice_step(s, k, j); }
+        for (int j = 1; j <= s->st[k].nzp; j++) { updates += s->st[k].spe.part.npp + (s->prm.neut_on ? s->st[k].neut.part.npp : 0); (s->prm.subcyc_on ? slice_step_subcyc : slice_step)(s, k, j); }
         stage_psend(s, k);
         if (s->prm.laser_on) laser_advance(s, k);                                   /* simulation_class.f03:486 */
     }
@@ -1843,14 +1993,14 @@ long orc_sim_run_slices(orc_sim *s, int nslices)
 {
     long updates = 0;
     stage_begin(s, 0);
-    for (int j = 1; j <= nslices && j <= s->st[0].nzp; j++) { updates += s->st[0].spe.part.npp + (s->prm.neut_on ? s->st[0].neut.part.npp : 0); slice_step(s, 0, j); }
+    for (int j = 1; j <= nslices && j <= s->st[0].nzp; j++) { updates += s->st[0].spe.part.npp + (s->prm.neut_on ? s->st[0].neut.part.npp : 0); (s->prm.subcyc_on ? slice_step_subcyc : slice_step)(s, 0, j); }
     return updates;
 }
 
 long orc_sim_run_range(orc_sim *s, int j0, int j1)
 {
     long updates = 0;
-    for (int j = j0; j <= j1 && j <= s->st[0].nzp; j++) { updates += s->st[0].spe.part.npp + (s->prm.neut_on ? s->st[0].neut.part.npp : 0); slice_step(s, 0, j); }
+    for (int j = j0; j <= j1 && j <= s->st[0].nzp; j++) { updates += s->st[0].spe.part.npp + (s->prm.neut_on ? s->st[0].neut.part.npp : 0); (s->prm.subcyc_on ? slice_step_subcyc : slice_step)(s, 0, j); }
     return updates;
 }
 
@@ -1887,6 +2037,7 @@ long orc_sim_get_field(const orc_sim *s, int stage, const char *name, int which,
     return (long)fld_n2(f);
 }
 long orc_sim_total_iters(const orc_sim *s) { return s->total_iters; }
+long orc_sim_total_subcycles(const orc_sim *s) { return s->total_subcycles; }
 long orc_sim_neutral_np(const orc_sim *s, int stage) { return s->prm.neut_on ? s->st[stage].neut.part.npp : 0; }
 void orc_sim_get_neutral(const orc_sim *s, int stage, double *x, double *p, double *gamma, double *psi, double *q)
 {

@@ -109,6 +109,9 @@ typedef struct {
      * element = atomic number (1 H, 2 He, 3 Li), ion_max = deepest charge state followed, n0 = plasma density in cm^-3 */
     int neut_on, neut_elem, neut_ion_max, neut_ppc1, neut_ppc2, neut_num_theta;
     double neut_q, neut_m, neut_density, n0;
+    /* "subcycling" algorithm (proj_subcyc/simulation_subcyc_class.f03): simulation.expansion_fac_max / expansion_fac_clamped / dt_2d_min */
+    int subcyc_on;
+    double subcyc_exp_fac_max, subcyc_exp_fac_clamped, subcyc_dt_min;
 } orc_params;
 
 orc_sim *orc_sim_create(const orc_params *prm);
@@ -130,6 +133,11 @@ void orc_sim_get_beam(const orc_sim *s, int stage, double *x, double *p, double 
 /* name in {psi,e,b,e_spe,b_spe,e_beam,b_beam,cu,amu,acu,dcu,q_spe,q_beam}; which=1 -> f1, 2 -> f2 (nzp+1 slices) */
 long orc_sim_get_field(const orc_sim *s, int stage, const char *name, int which, double *out);
 long orc_sim_total_iters(const orc_sim *s);
+long orc_sim_total_subcycles(const orc_sim *s);   /* sub-steps taken so far (= slices when nothing was sub-cycled) */
+/* proj_subcyc/part2d_subcyc_class.f03:28 / :48 ; simulation_subcyc_class.f03:431 */
+double orc_exp_fac_max(const double *p, const double *gamma, long npp);
+void orc_clamp_exp_fac(double *p, double *gamma, long npp, double exp_fac_clamped);
+void orc_subcyc_step(double exp_fac, double exp_fac_max, double dt, double dt_min, double *dt_subcyc, int *n_subcyc);
 /* laser envelope volumes a_r, a_i (layout of orc_laser_volume_size) of the single stage: copy in / copy out; chi = the
  * susceptibility volume deposited during the last 3D step, (P, nz+1, nr+2) */
 void orc_sim_set_laser(orc_sim *s, const double *ar, const double *ai);
