@@ -18,7 +18,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
 _ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
 
-FK_PSI, FK_EZ, FK_BZ, FK_BT, FK_BPLUS, FK_BMINUS = range(6)
+FK_PSI, FK_EZ, FK_BZ, FK_BT, FK_BPLUS, FK_BMINUS, FK_VPOTZ, FK_VPOTP, FK_VPOTM = range(9)
 BND_ZERO, BND_OPEN = 2, 3
 PUSH3_REDUCED, PUSH3_BORIS = 1, 2
 
@@ -80,6 +80,8 @@ def lib(fast=False):
         "orc_solve_et_beam": (None, [_dp, _dp, i, i]),
         "orc_solve_djdxi": (None, [_dp, _dp, _dp, i, i, d]),
         "orc_smooth_f1": (None, [_dp, i, i, _ip]),
+        "orc_solve_vpotz": (None, [_dp, _dp, i, i, d, i]),
+        "orc_solve_vpott": (None, [_dp, _dp, i, i, d, i]),
         "orc_qdeposit3d": (None, [_dp, _dp, l, d, d, i, i, i, i, _dp]),
         "orc_push3d": (None, [_dp, _dp, l, d, d, i, i, i, i, d, d, i, _dp, _dp]),
         "orc_update_bound3d": (l, [_dp, _dp, _dp, l, d, d]),

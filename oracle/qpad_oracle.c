@@ -562,7 +562,9 @@ void orc_build_matrix(int kind, int mode, int nr, double dr, int bnd, double rel
         a[i] = 1.0 - 0.5 / j;
         c[i] = 1.0 + 0.5 / j;
         switch (kind) {
-        case ORC_FK_PSI: case ORC_FK_BT: case ORC_FK_EZ: case ORC_FK_BZ: b[i] = -2.0 - m2 / (j * j); break;
+        case ORC_FK_PSI: case ORC_FK_BT: case ORC_FK_EZ: case ORC_FK_BZ: case ORC_FK_VPOTZ: b[i] = -2.0 - m2 / (j * j); break;
+        case ORC_FK_VPOTP: b[i] = -2.0 - ((double)(m + 1) / j) * ((double)(m + 1) / j); break;   /* :418-427 */
+        case ORC_FK_VPOTM: b[i] = -2.0 - ((double)(m - 1) / j) * ((double)(m - 1) / j); break;   /* :447-456 */
         case ORC_FK_BPLUS: b[i] = -2.0 - ((double)(m + 1) / j) * ((double)(m + 1) / j) - relax_fac; break;
         case ORC_FK_BMINUS: b[i] = -2.0 - ((double)(m - 1) / j) * ((double)(m - 1) / j) - relax_fac; break;
         }
@@ -570,7 +572,9 @@ void orc_build_matrix(int kind, int mode, int nr, double dr, int bnd, double rel
     int axis_coupled = 0;
     double diag0 = -4.0;
     switch (kind) {
-    case ORC_FK_PSI: case ORC_FK_BT: case ORC_FK_EZ: case ORC_FK_BZ: axis_coupled = (m == 0); break;
+    case ORC_FK_PSI: case ORC_FK_BT: case ORC_FK_EZ: case ORC_FK_BZ: case ORC_FK_VPOTZ: axis_coupled = (m == 0); break;
+    case ORC_FK_VPOTP: axis_coupled = 0; break;                                                   /* :430-439 */
+    case ORC_FK_VPOTM: axis_coupled = (m == 1); break;                                            /* :459-472 */
     case ORC_FK_BPLUS: axis_coupled = 0; break;
     case ORC_FK_BMINUS: axis_coupled = (m == 1); diag0 = -4.0 - relax_fac; break;
     }
@@ -581,7 +585,7 @@ void orc_build_matrix(int kind, int mode, int nr, double dr, int bnd, double rel
     } else {
         double jmax = (double)nr;
         switch (kind) {
-        case ORC_FK_PSI: case ORC_FK_EZ: case ORC_FK_BZ:
+        case ORC_FK_PSI: case ORC_FK_EZ: case ORC_FK_BZ: case ORC_FK_VPOTZ:
             if (m == 0) c[nr - 1] = 0.0;
             else { b[nr - 1] = b[nr - 1] + (1.0 - (double)m / jmax) * c[nr - 1]; c[nr - 1] = 0.0; }
             break;
@@ -589,7 +593,7 @@ void orc_build_matrix(int kind, int mode, int nr, double dr, int bnd, double rel
             if (m == 0) { b[nr - 1] = b[nr - 1] + (1.0 + 1.0 / (jmax * log(jmax * dr))) * c[nr - 1]; c[nr - 1] = 0.0; }
             else { b[nr - 1] = b[nr - 1] + (1.0 - (double)m / jmax) * c[nr - 1]; c[nr - 1] = 0.0; }
             break;
-        case ORC_FK_BPLUS: case ORC_FK_BMINUS: /* both use (m+1), :532-540 */
+        case ORC_FK_BPLUS: case ORC_FK_BMINUS: case ORC_FK_VPOTP: case ORC_FK_VPOTM: /* all use (m+1), :532-540 */
             b[nr - 1] = b[nr - 1] + (1.0 - (double)(m + 1) / jmax) * c[nr - 1]; c[nr - 1] = 0.0;
             break;
         }
@@ -1002,6 +1006,61 @@ void orc_solve_djdxi(const double *acu, const double *amu, double *dcu, int nr, 
 #undef AC
 #undef AM
 #undef DC
+}
+
+/* fields/field_vpot_class.f03:354-390 solve_field_vpotz: lap_m A_z = -J_z per mode (source :159-205, solution :260-295: A_z of the
+ * m > 0 modes vanishes on the axis).  vpot is a dim-3 multi-plane f1 (component 3 = A_z). */
+void orc_solve_vpotz(const double *cu, double *vpot, int nr, int max_mode, double dr, int bnd)
+{
+    double *a = (double *)malloc(sizeof(double) * 4 * (size_t)nr), *b = a + nr, *c = b + nr, *d = c + nr;
+    for (int m = 0; m <= max_mode; m++) {
+        orc_build_matrix(ORC_FK_VPOTZ, m, nr, dr, bnd, 0.0, a, b, c);
+        const int npl = m == 0 ? 1 : 2;
+        for (int h = 0; h < npl; h++) {
+            const int pl = h == 0 ? pl_re(m) : pl_im(m);
+            for (int i = 1; i <= nr; i++) d[i - 1] = -1.0 * F1(cu, 3, nr, pl, 3, i);
+            orc_tridiag_solve(a, b, c, d, nr);
+            for (int i = 1; i <= nr; i++) F1(vpot, 3, nr, pl, 3, i) = d[i - 1];
+            if (m > 0) F1(vpot, 3, nr, pl, 3, 1) = 0.0;
+        }
+    }
+    free(a);
+}
+/* fields/field_vpot_class.f03:392-431 solve_field_vpott: A_+ = A_r + i A_phi obeys lap_{m+1}, A_- = A_r - i A_phi obeys lap_{m-1}
+ * (sources :207-258, recombination and axis rules :297-352); components 1, 2 = A_r, A_phi */
+void orc_solve_vpott(const double *cu, double *vpot, int nr, int max_mode, double dr, int bnd)
+{
+    double *a = (double *)malloc(sizeof(double) * 10 * (size_t)nr), *b = a + nr, *c = b + nr;
+    double *ap = c + nr, *bp = ap + nr, *cp = bp + nr, *b1r = cp + nr, *b1i = b1r + nr, *b2r = b1i + nr, *b2i = b2r + nr;
+    for (int m = 0; m <= max_mode; m++) {
+        const int pr = pl_re(m), pi = pl_im(m);
+        orc_build_matrix(ORC_FK_VPOTP, m, nr, dr, bnd, 0.0, ap, bp, cp);
+        orc_build_matrix(ORC_FK_VPOTM, m, nr, dr, bnd, 0.0, a, b, c);
+        if (m == 0) {
+            for (int i = 1; i <= nr; i++) { b1r[i - 1] = -F1(cu, 3, nr, 0, 1, i); b2r[i - 1] = -F1(cu, 3, nr, 0, 2, i); }
+            orc_tridiag_solve(ap, bp, cp, b1r, nr);
+            orc_tridiag_solve(a, b, c, b2r, nr);
+            for (int i = 1; i <= nr; i++) { F1(vpot, 3, nr, 0, 1, i) = b1r[i - 1]; F1(vpot, 3, nr, 0, 2, i) = b2r[i - 1]; }
+            F1(vpot, 3, nr, 0, 1, 1) = 0.0; F1(vpot, 3, nr, 0, 2, 1) = 0.0;
+            continue;
+        }
+        for (int i = 1; i <= nr; i++) {
+            b1r[i - 1] = -F1(cu, 3, nr, pr, 1, i) + F1(cu, 3, nr, pi, 2, i);
+            b1i[i - 1] = -F1(cu, 3, nr, pi, 1, i) - F1(cu, 3, nr, pr, 2, i);
+            b2r[i - 1] = -F1(cu, 3, nr, pr, 1, i) - F1(cu, 3, nr, pi, 2, i);
+            b2i[i - 1] = -F1(cu, 3, nr, pi, 1, i) + F1(cu, 3, nr, pr, 2, i);
+        }
+        orc_tridiag_solve(ap, bp, cp, b1r, nr); orc_tridiag_solve(ap, bp, cp, b1i, nr);
+        orc_tridiag_solve(a, b, c, b2r, nr); orc_tridiag_solve(a, b, c, b2i, nr);
+        for (int i = 1; i <= nr; i++) {
+            F1(vpot, 3, nr, pr, 1, i) = 0.5 * (b1r[i - 1] + b2r[i - 1]);
+            F1(vpot, 3, nr, pi, 1, i) = 0.5 * (b1i[i - 1] + b2i[i - 1]);
+            F1(vpot, 3, nr, pr, 2, i) = 0.5 * (b1i[i - 1] - b2i[i - 1]);
+            F1(vpot, 3, nr, pi, 2, i) = 0.5 * (-b1r[i - 1] + b2r[i - 1]);
+        }
+        if (m != 1) { F1(vpot, 3, nr, pr, 1, 1) = 0.0; F1(vpot, 3, nr, pi, 1, 1) = 0.0; F1(vpot, 3, nr, pr, 2, 1) = 0.0; F1(vpot, 3, nr, pi, 2, 1) = 0.0; }
+    }
+    free(a);
 }
 
 /* fields/ufield_class.f03:274-339 smooth_f1 (idproc == 0 branch), stencil [1,2,1] */

@@ -26,7 +26,7 @@ extern "C" {
 #endif
 
 /* field-solver kinds, source/param.f03 p_fk_* */
-enum { ORC_FK_PSI = 0, ORC_FK_EZ = 1, ORC_FK_BZ = 2, ORC_FK_BT = 3, ORC_FK_BPLUS = 4, ORC_FK_BMINUS = 5 };
+enum { ORC_FK_PSI = 0, ORC_FK_EZ = 1, ORC_FK_BZ = 2, ORC_FK_BT = 3, ORC_FK_BPLUS = 4, ORC_FK_BMINUS = 5, ORC_FK_VPOTZ = 6, ORC_FK_VPOTP = 7, ORC_FK_VPOTM = 8 };
 enum { ORC_BND_ZERO = 2, ORC_BND_OPEN = 3 };
 enum { ORC_PUSH3_REDUCED = 1, ORC_PUSH3_BORIS = 2 };
 
@@ -82,6 +82,9 @@ void orc_solve_et(const double *b, const double *psi, double *e, int nr, int max
 void orc_solve_et_beam(const double *b, double *e, int nr, int max_mode);
 void orc_solve_djdxi(const double *acu, const double *amu, double *dcu, int nr, int max_mode, double dr);
 void orc_smooth_f1(double *f1plane, int dim, int nr, const int *ax_smooth);
+/* vector-potential diagnostics, fields/field_vpot_class.f03:354 / :392 (vpot: dim-3 field A_r, A_phi, A_z) */
+void orc_solve_vpotz(const double *cu, double *vpot, int nr, int max_mode, double dr, int bnd);
+void orc_solve_vpott(const double *cu, double *vpot, int nr, int max_mode, double dr, int bnd);
 
 /* part3d_class.f03:221/477/358/640 ; x(3,np), p(3,np) ; f2 volumes with nzp+1 slices, noff2 = slab offset */
 void orc_qdeposit3d(const double *x, const double *q, long npp, double dr, double dz, int nr, int nzp, int noff2,

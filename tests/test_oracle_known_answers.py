@@ -184,3 +184,46 @@ def test_std_pgc_without_laser_is_std():
         out.append((cu, dcu, amu, g1, psi1))
     for a, c in zip(*out):
         assert np.array_equal(a, c)
+
+
+def test_vector_potential_diagnostics():
+    """field_vpot_class.f03: A_z solves the same operator as psi with the source -J_z; A_r +- i A_phi solve the m+-1 operators.
+    Known answers: (i) A_z from J_z = the psi solve from q = J_z, bit for bit; (ii) m = 0: A_r and A_phi are the k = 1 Poisson
+    solutions of J_r and J_phi, checked on r exp(-r^2) at second order; (iii) m = 1 recombination: a source that only drives
+    A_+ (J_r = i J_phi) leaves A_- = 0, i.e. A_phi = -i A_r."""
+    L = O.lib()
+    nr, dr = 256, 8.0 / 256
+    r = (np.arange(nr + 2) - 1) * dr
+    for M in (0, 1, 2):
+        rng = np.random.default_rng(M)
+        cu = rng.standard_normal((2 * M + 1, nr + 2, 3)) * np.exp(-r * r)[None, :, None]
+        q = np.ascontiguousarray(cu[:, :, 2:3])
+        psi, vp = np.zeros_like(q), np.zeros_like(cu)
+        L.orc_solve_psi(q, psi, nr, M, dr, O.BND_OPEN)
+        L.orc_solve_vpotz(cu, vp, nr, M, dr, O.BND_OPEN)
+        assert np.array_equal(vp[:, 1:nr + 1, 2], psi[:, 1:nr + 1, 0]) and not vp[..., :2].any()
+
+    def err(n):
+        d = 8.0 / n
+        rr = (np.arange(n + 2) - 1) * d
+        cu = np.zeros((1, n + 2, 3))
+        src = -(4 * rr ** 3 - 8 * rr) * np.exp(-rr * rr)            # -lap_1 (r exp(-r^2))
+        cu[0, :, 0], cu[0, :, 1] = src, 0.5 * src
+        vp = np.zeros_like(cu)
+        L.orc_solve_vpott(cu, vp, n, 0, d, O.BND_OPEN)
+        exact = rr * np.exp(-rr * rr)
+        return max(np.max(np.abs(vp[0, 1:n + 1, 0] - exact[1:n + 1])), np.max(np.abs(vp[0, 1:n + 1, 1] - 0.5 * exact[1:n + 1])))
+    e1, e2 = err(128), err(256)
+    assert e2 < 2e-3 and 3.3 < e1 / e2 < 4.7, (e1, e2)
+    # m = 1, J_r = f, J_phi = -i f (complex amplitudes): buf2 = -(J_r - i J_phi)... only A_+ is driven
+    f = r ** 2 * np.exp(-r * r)
+    cu = np.zeros((3, nr + 2, 3))
+    cu[1, :, 0] = f            # Re J_r
+    cu[2, :, 1] = -f           # Im J_phi = -f  ->  J_phi = -i f
+    vp = np.zeros_like(cu)
+    L.orc_solve_vpott(cu, vp, nr, 1, dr, O.BND_OPEN)
+    ar = vp[1, :, 0] + 1j * vp[2, :, 0]
+    aphi = vp[1, :, 1] + 1j * vp[2, :, 1]
+    assert np.max(np.abs(ar)) > 1e-3
+    plus, minus = ar + 1j * aphi, ar - 1j * aphi
+    assert min(np.max(np.abs(plus[2:nr])), np.max(np.abs(minus[2:nr]))) < 1e-13 * max(np.max(np.abs(plus)), np.max(np.abs(minus)))
