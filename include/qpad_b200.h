@@ -40,6 +40,7 @@ typedef struct qpg_part2d_s *qpg_part2d;
 typedef struct qpg_part3d_s *qpg_part3d;
 typedef struct qpg_sim_s *qpg_sim;
 typedef struct qpg_laser_s *qpg_laser;
+typedef struct qpg_neutral_s *qpg_neutral;
 
 /* param.f03 constants mirrored 1:1 */
 enum { QPG_BND_ZERO = 2, QPG_BND_OPEN = 3 };                              /* p_bnd_* */
@@ -313,6 +314,26 @@ qpg_field qpg_laser_field(qpg_laser l, int which);
 int qpg_laser_slice(qpg_laser l, int j);
 int qpg_laser_deposit_chi(qpg_laser l, qpg_part2d p, int j, double ax_corr);
 int qpg_laser_advance(qpg_laser l);
+
+/* ------------------------------------------------------------------------------------------ */
+/* field-ionisation (ADK) neutral species, species/neutral_class.f03 -- NOT YET VALIDATED ON A GPU (written at the end of
+ * round 1 against oracle/qpad_oracle_neutral.c; tests/test_gpu_neutral.py, enabled with QPG_TEST_NEUTRAL=1).
+ * A neutral owns the ionisation levels per (radial cell, theta sector); the released electrons and the ions' position
+ * buffer are two ordinary qpg_part2d sets (`part`, `part_add` of the reference) that go through the part2d entry points:
+ *   neut%qdp(q)         = qpg_part2d_qdeposit(electrons, q)                     (:880)
+ *   neut%ion_deposit(q) = qpg_part2d_qdeposit(ions, rho_ion_add) + field adds   (:904)
+ *   neut%amjdp / push_u / push_x = the part2d calls on `electrons`              (:932-1016)
+ *   neut%update(e, ..)  = qpg_neutral_update(n, e, electrons, ions)             (:576: ionize :600 + add_particles :755)
+ *   neut%renew          = qpg_neutral_reset(n) + qpg_part2d_clear(electrons) + qpg_part2d_clear(ions)   (:839)
+ * element = atomic number (1 H, 2 He, 3 Li), n0 = plasma density [cm^-3] (omega_p of sim_plasma_class.f03:84), dt_xi = dxi. */
+int qpg_neutral_create(qpg_neutral *out, qpg_ctx ctx, int element, int ion_max, int ppc1, int ppc2, int num_theta, double q, double m,
+                       double density, double n0, double dt_xi);
+int qpg_neutral_destroy(qpg_neutral n);
+int qpg_neutral_reset(qpg_neutral n);
+int qpg_neutral_multi_max(qpg_neutral n);
+int qpg_neutral_update(qpg_neutral n, qpg_field e, qpg_part2d electrons, qpg_part2d ions);
+int qpg_neutral_levels(qpg_neutral n, double *host);      /* [(multi_max + 2)][num_theta][nr], synchronises */
+int qpg_part2d_clear(qpg_part2d p);                        /* npp = 0 on the device */
 
 #ifdef __cplusplus
 }

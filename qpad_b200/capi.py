@@ -150,6 +150,13 @@ SIGNATURES = {
     "qpg_laser_slice": (_i, [_vp, _i]),
     "qpg_laser_deposit_chi": (_i, [_vp, _vp, _i, _d]),
     "qpg_laser_advance": (_i, [_vp]),
+    "qpg_neutral_create": (_i, [C.POINTER(_vp), _vp, _i, _i, _i, _i, _i, _d, _d, _d, _d, _d]),
+    "qpg_neutral_destroy": (_i, [_vp]),
+    "qpg_neutral_reset": (_i, [_vp]),
+    "qpg_neutral_multi_max": (_i, [_vp]),
+    "qpg_neutral_update": (_i, [_vp, _vp, _vp, _vp]),
+    "qpg_neutral_levels": (_i, [_vp, _vp]),
+    "qpg_part2d_clear": (_i, [_vp]),
     "qpg_sim_slice_trace": (_i, [_vp, _pd, _pi]),
     "qpg_wire_alloc": (_i, [C.POINTER(_vp), _l]),
     "qpg_wire_free": (_i, [_vp]),
@@ -372,6 +379,7 @@ class Part2d:
         _chk(self.L.qpg_part2d_sort_index(self.h, _ptr(ix), _ptr(ip)))
         return ix, ip
 
+    def clear(self): _chk(self.L.qpg_part2d_clear(self.h))
     def wire_count(self): return self.L.qpg_part2d_wire_count(self.h)
     def pack(self, dev_ptr): _chk(self.L.qpg_part2d_pack(self.h, dev_ptr))
     def unpack(self, dev_ptr): _chk(self.L.qpg_part2d_unpack(self.h, dev_ptr))
@@ -413,6 +421,41 @@ class Part3d:
     def set_wire_cap(self, cap): _chk(self.L.qpg_part3d_set_wire_cap(self.h, int(cap)))
     def pack_forward(self, dev_ptr): _chk(self.L.qpg_part3d_pack_forward(self.h, dev_ptr))
     def unpack(self, dev_ptr): _chk(self.L.qpg_part3d_unpack(self.h, dev_ptr))
+
+
+class Neutral:
+    """neutral (species/neutral_class.f03): ionisation levels per (radial cell, theta sector) + the two particle sets the
+    reference calls `part` (released electrons) and `part_add` (positions of the ions created by the last update).
+    NOT YET VALIDATED ON A GPU (see include/qpad_b200.h)."""
+
+    def __init__(self, ctx, element, ion_max, ppc, num_theta, q=-1.0, m=1.0, density=1.0, n0=1.0e17, dt_xi=None):
+        self.ctx, self.L, self.num_theta = ctx, ctx.L, num_theta
+        h = _vp()
+        _chk(self.L.qpg_neutral_create(C.byref(h), ctx.h, element, ion_max, ppc[0], ppc[1], num_theta, q, m, density, n0, ctx.dxi if dt_xi is None else dt_xi))
+        self.h = h.value
+        self.multi_max = self.L.qpg_neutral_multi_max(self.h)
+        cap = ctx.nr * num_theta * ppc[0] * ppc[1] + 64
+        self.part = Part2d(ctx, q / m, cap)
+        self.part_add = Part2d(ctx, q / m, cap)
+
+    def close(self):
+        if getattr(self, "h", None) and self.ctx.h:
+            self.part.close(); self.part_add.close()
+            self.L.qpg_neutral_destroy(self.h)
+        self.h = None
+
+    __del__ = close
+
+    def update(self, e): _chk(self.L.qpg_neutral_update(self.h, e.h, self.part.h, self.part_add.h))
+
+    def renew(self):
+        _chk(self.L.qpg_neutral_reset(self.h))
+        self.part.clear(); self.part_add.clear()
+
+    def levels(self):
+        out = np.zeros((self.multi_max + 2, self.num_theta, self.ctx.nr))
+        _chk(self.L.qpg_neutral_levels(self.h, _ptr(out)))
+        return out
 
 
 class Laser:
