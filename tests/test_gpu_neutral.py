@@ -77,7 +77,7 @@ def test_ionization_loop_matches_oracle(mods):
     assert st.iters == orc.total_iters()
     lev = orc.levels(1)
     assert np.max(np.abs(st.neut.levels() - lev)) < 1e-10
-    assert st.neut.part.npp() == len(orc.neutral()[4]) > 400
+    assert st.neut.part.npp() == len(orc.neutral()[4]) > 100
     for name, f in (("psi", st.psi), ("e", st.e), ("b", st.b)):
         got, want = f.download_f2()[:, :nsl], orc.field(name, 2)[:, :nsl]
         assert np.max(np.abs(want)) > 1e-2 and np.max(np.abs(got - want)) < 1e-8 * np.max(np.abs(want)), name
