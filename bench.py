@@ -597,6 +597,14 @@ def run_b200_local(args):
                                  "note": "arithmetic intensity ~10 flop/B against a machine balance of 5.6 flop/B: the fp64 pipe, not HBM, is the nearer roof"}
     except Exception:   # an explanatory extra must never cost the bench line
         pass
+    try:   # DRAM traffic: measured with ncu --set full on ONE sweep launch over the whole deck (profiles/r01_sweep_traffic.json); this launch shape
+        # (S kernels of ~nz/S slices) has not been captured separately, so `traffic` stays null and the capture is quoted as a reference
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_sweep_traffic.json")))
+        roof["traffic_reference"] = {"dram_bytes_per_2048_slice_launch": float(tj["dram_bytes_read"] + tj["dram_bytes_write"]),
+                                     "algorithmic_bytes_same_launch": 5.37e8 * (112.0 + 64.0 * 1.09),
+                                     "source": "profiles/r01_sweep_traffic.json: one k_sweep<1> launch on 148 SMs, 2048 slices; DRAM traffic = the field-volume slice stores, the particle planes stay in L2"}
+    except Exception:
+        pass
     roof_hbm = None
     if world == 1 and not args.no_micro:
         # the push and deposit kernels individually, streaming from HBM (north star: >= 60 % of the HBM roofline): fields of
