@@ -1,0 +1,23 @@
+"""Device code checked on the CPU: the shuffle-free kernels of qpad_b200/csrc (neutral.cu, subcyc.cu, vpot.cu, diag.cu) are
+compiled for the host through tests/emu (CTA threads = fibers, exact __syncthreads) and compared with the oracle through the
+same case bodies the GPU tests use (tests/kernel_cases.py).  This is a check of the kernels' LOGIC (indexing, ordering, the
+scan, the host entry points) -- it is not the parity gate: that is `pytest -m gpu` on the B200 through libqpadb200.so."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+import kernel_cases as K
+from emu import emu
+
+
+def test_launch_rewrite():
+    from emu.build import transform
+    src = "k_a<<<(n + 127) / 128, 128, 0, c->stream>>>(x, f(y, z));\nDISPATCH(k_b<2><<<dim3(3, 2), 64>>>(p));"
+    assert transform(src) == "emu::launch((n + 127) / 128, 128, [&] { k_a(x, f(y, z)); });\nDISPATCH(emu::launch(dim3(3, 2), 64, [&] { k_b<2>(p); }));"
+
+
+@pytest.mark.parametrize("elem,mm,M", [(1, 1, 0), (3, 3, 1), (2, 2, 2)])
+def test_neutral_update_emulated(elem, mm, M):
+    n0 = emu.lib().emu_launches()
+    K.neutral_update(emu, O, elem, mm, M)
+    assert emu.lib().emu_launches() - n0 >= 6 * 4
