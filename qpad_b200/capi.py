@@ -157,6 +157,18 @@ SIGNATURES = {
     "qpg_neutral_update": (_i, [_vp, _vp, _vp, _vp]),
     "qpg_neutral_levels": (_i, [_vp, _vp]),
     "qpg_part2d_clear": (_i, [_vp]),
+    "qpg_part2d_exp_fac_max": (_i, [_vp, _pd]),
+    "qpg_part2d_clamp_exp_fac": (_i, [_vp, _d]),
+    "qpg_subcyc_step": (_i, [_d, _d, _d, _d, _pd, _pi]),
+    "qpg_solve_vpotz": (_i, [_vp, _vp, _vp]),
+    "qpg_solve_vpott": (_i, [_vp, _vp, _vp]),
+    "qpg_vpot_release": (_i, [_vp]),
+    "qpg_stage_create": (_i, [C.POINTER(_vp), _vp, _l]),
+    "qpg_stage_destroy": (_i, [_vp]),
+    "qpg_stage_field": (_i, [_vp, _vp, _pl]),
+    "qpg_stage_part2d": (_i, [_vp, _vp, _i, _pl]),
+    "qpg_stage_part3d": (_i, [_vp, _vp, _i, _d, _pl]),
+    "qpg_stage_wait": (_i, [_vp, C.POINTER(_pd), _pl]),
     "qpg_sim_slice_trace": (_i, [_vp, _pd, _pi]),
     "qpg_wire_alloc": (_i, [C.POINTER(_vp), _l]),
     "qpg_wire_free": (_i, [_vp]),
@@ -211,6 +223,7 @@ class Ctx:
 
     def close(self):
         if getattr(self, "h", None) and self._own:
+            self.L.qpg_vpot_release(self.h)
             self.L.qpg_ctx_destroy(self.h)
         self.h = None
 
@@ -242,6 +255,8 @@ class Ctx:
     def solve_et(self, b, psi, e): _chk(self.L.qpg_solve_et(self.h, b.h, psi.h, e.h))
     def solve_et_beam(self, b, e): _chk(self.L.qpg_solve_et_beam(self.h, b.h, e.h))
     def solve_djdxi(self, acu, amu, dcu): _chk(self.L.qpg_solve_djdxi(self.h, acu.h, amu.h, dcu.h))
+    def solve_vpotz(self, cu, vpot): _chk(self.L.qpg_solve_vpotz(self.h, cu.h, vpot.h))     # field_vpot%solve_vpotz
+    def solve_vpott(self, cu, vpot): _chk(self.L.qpg_solve_vpott(self.h, cu.h, vpot.h))     # field_vpot%solve_vpott
 
     def convergence_tester(self, fld, dim, op):
         rel, ab = _d(), _d()
@@ -380,6 +395,14 @@ class Part2d:
         return ix, ip
 
     def clear(self): _chk(self.L.qpg_part2d_clear(self.h))
+
+    def exp_fac_max(self):
+        """part2d_subcyc%get_exp_fac_max (proj_subcyc/part2d_subcyc_class.f03:28); synchronises"""
+        v = _d()
+        _chk(self.L.qpg_part2d_exp_fac_max(self.h, C.byref(v)))
+        return v.value
+
+    def clamp_exp_fac(self, exp_fac_clamped): _chk(self.L.qpg_part2d_clamp_exp_fac(self.h, exp_fac_clamped))
     def wire_count(self): return self.L.qpg_part2d_wire_count(self.h)
     def pack(self, dev_ptr): _chk(self.L.qpg_part2d_pack(self.h, dev_ptr))
     def unpack(self, dev_ptr): _chk(self.L.qpg_part2d_unpack(self.h, dev_ptr))
@@ -421,6 +444,57 @@ class Part3d:
     def set_wire_cap(self, cap): _chk(self.L.qpg_part3d_set_wire_cap(self.h, int(cap)))
     def pack_forward(self, dev_ptr): _chk(self.L.qpg_part3d_pack_forward(self.h, dev_ptr))
     def unpack(self, dev_ptr): _chk(self.L.qpg_part3d_unpack(self.h, dev_ptr))
+
+
+def subcyc_step(exp_fac, exp_fac_max, dt, dt_min, L=None):
+    """simulation_subcyc_class.f03:431-451 -> (dt_subcyc, n_subcyc)"""
+    dts, n = _d(), _i()
+    _chk((L or load()).qpg_subcyc_step(exp_fac, exp_fac_max, dt, dt_min, C.byref(dts), C.byref(n)))
+    return dts.value, n.value
+
+
+class Stage:
+    """Diagnostics staging (csrc/diag.cu): device re-layout + asynchronous copy into a pinned host buffer.  `field`, `part2d`,
+    `part3d` enqueue; `wait` blocks and returns the datasets in the layouts the HDF5 writer takes (hdf5io_class.f03:591, :1027,
+    :1220)."""
+
+    def __init__(self, ctx, capacity_doubles):
+        self.ctx, self.L = ctx, ctx.L
+        h = _vp()
+        _chk(self.L.qpg_stage_create(C.byref(h), ctx.h, capacity_doubles))
+        self.h, self._shape = h.value, None
+
+    def close(self):
+        if getattr(self, "h", None) and self.ctx.h:
+            self.L.qpg_stage_destroy(self.h)
+        self.h = None
+
+    __del__ = close
+
+    def field(self, f):
+        _chk(self.L.qpg_stage_field(self.h, f.h, None))
+        self._shape = ("field", (self.ctx.P, f.dim, f.nzp, self.ctx.nr))
+
+    def part2d(self, p, dspl):
+        st = _l()
+        _chk(self.L.qpg_stage_part2d(self.h, p.h, dspl, C.byref(st)))
+        self._shape = ("part", (6, st.value))
+
+    def part3d(self, p, dspl, z0=0.0):
+        st = _l()
+        _chk(self.L.qpg_stage_part3d(self.h, p.h, dspl, z0, C.byref(st)))
+        self._shape = ("part", (7, st.value))
+
+    def wait(self):
+        """field: array [plane][comp][slice][node]; particles: array [dataset][tnpp]"""
+        host, n = _pd(), _l()
+        _chk(self.L.qpg_stage_wait(self.h, C.byref(host), C.byref(n)))
+        a = np.ctypeslib.as_array(host, shape=(n.value,)).copy()
+        kind, shape = self._shape
+        if kind == "field":
+            return a.reshape(shape)
+        tnpp = int(a[0])
+        return a[1:].reshape(shape)[:, :tnpp]
 
 
 class Neutral:

@@ -52,7 +52,9 @@ class Ctx:
         self.h = h.value
 
     def launch_count(self): return self.L.emu_ctx_launches(self.h)
-    def close(self): pass
+    def solve_vpotz(self, cu, vpot): _chk(self.L.qpg_solve_vpotz(self.h, cu.h, vpot.h))
+    def solve_vpott(self, cu, vpot): _chk(self.L.qpg_solve_vpott(self.h, cu.h, vpot.h))
+    def close(self): self.L.qpg_vpot_release(self.h)
 
 
 class Field:
@@ -105,6 +107,13 @@ class Part2d:
     def clear(self): _chk(self.L.qpg_part2d_clear(self.h))
     def close(self): pass
 
+    def exp_fac_max(self):
+        v = _d()
+        _chk(self.L.qpg_part2d_exp_fac_max(self.h, C.byref(v)))
+        return v.value
+
+    def clamp_exp_fac(self, exp_fac_clamped): _chk(self.L.qpg_part2d_clamp_exp_fac(self.h, exp_fac_clamped))
+
 
 class Part3d:
     def __init__(self, ctx, qbm, dt, npmax):
@@ -116,6 +125,14 @@ class Part3d:
     def upload(self, x, p, q):
         a = [np.ascontiguousarray(v, dtype=np.float64) for v in (x, p, q)]
         _chk(self.L.emu_part3d_upload(self.h, *[_ptr(v) for v in a], len(a[2])))
+
+
+def subcyc_step(exp_fac, exp_fac_max, dt, dt_min):
+    return capi.subcyc_step(exp_fac, exp_fac_max, dt, dt_min, L=lib())
+
+
+class Stage(capi.Stage):
+    """capi.Stage over the emulated library (same code: only ctx.L differs)"""
 
 
 class Neutral:

@@ -51,3 +51,114 @@ def neutral_update(api, O, elem, mm, M):
     lev0 = np.zeros_like(lev); L.orc_neutral_reset(lev0, nr, nth, mm)
     assert np.array_equal(ne.levels(), lev0)
     ne.close()
+
+
+def subcyc_particles(api, O):
+    """part2d_subcyc%get_exp_fac_max / clamp_exp_fac (proj_subcyc/part2d_subcyc_class.f03:28-66) and the sub-step rule
+    (simulation_subcyc_class.f03:431-451): bit-exact against the oracle"""
+    L = O.lib()
+    ctx = api.Ctx(64, 1, 0.1, 0.02)
+    rng = np.random.default_rng(7)
+    n = 5003
+    p = rng.normal(size=(n, 3)) * np.array([0.5, 0.5, 3.0])
+    p[::17, 2] = np.abs(p[::17, 2]) * 40.0 + 5.0                    # a few strongly forward-moving particles: large gamma / (gamma - p_z)
+    g = np.sqrt(1.0 + np.sum(p * p, axis=1))
+    x = rng.random((n, 2)); psi = rng.random(n); q = -rng.random(n)
+    pt = api.Part2d(ctx, -1.0, n + 100)
+    assert pt.exp_fac_max() == 1.0                                   # no particles (:43)
+    pt.upload(x, p, g, psi, q)
+    want = L.orc_exp_fac_max(np.ascontiguousarray(p), g, n)
+    got = pt.exp_fac_max()
+    assert got == want and want > 20.0
+    for clamp in (50.0, 4.0, 1.5):
+        po, go = p.copy(), g.copy()
+        L.orc_clamp_exp_fac(po, go, n, clamp)
+        pt.upload(x, p, g, psi, q)
+        pt.clamp_exp_fac(clamp)
+        gx, gp, gg, gpsi, gq = pt.download()
+        assert np.array_equal(gp, po) and np.array_equal(gg, go), clamp
+        assert np.array_equal(gx, x) and np.array_equal(gq, q)
+        assert np.any(po != p)
+        assert pt.exp_fac_max() == L.orc_exp_fac_max(po, go, n) <= clamp * (1 + 1e-12)
+    for ef, efm, dt, dtmin in ((1.0, 2.0, 0.02, 0.001), (7.3, 2.0, 0.02, 0.001), (900.0, 2.0, 0.02, 0.001), (2.0, 2.0, 0.02, 0.001), (4.0000001, 2.0, 0.02, 0.0)):
+        dts, ns = C.c_double(), C.c_int()
+        L.orc_subcyc_step(ef, efm, dt, dtmin, C.byref(dts), C.byref(ns))
+        assert api.subcyc_step(ef, efm, dt, dtmin) == (dts.value, ns.value)
+    pt.close(); ctx.close()
+
+
+def vpot(api, O, M, bnd, nr=96, exact=False):
+    """field_vpot%solve_vpotz / solve_vpott (fields/field_vpot_class.f03:354, :392) on a random current"""
+    L = O.lib()
+    dr = 0.05
+    ctx = api.Ctx(nr, M, dr, 0.02, field_boundary=bnd)
+    rng = np.random.default_rng(100 + M)
+    r = (np.arange(nr + 2) - 1) * dr
+    cu = rng.normal(size=(2 * M + 1, nr + 2, 3)) * np.exp(-((r - 1.5) / 0.8) ** 2)[None, :, None]
+    fcu, fv = api.Field(ctx, 3), api.Field(ctx, 3)
+    fcu.upload(cu)
+    marker = rng.normal(size=cu.shape)                               # what a solve must leave alone: the other components and the guards
+    fv.upload(marker)
+    want = marker.copy()
+    L.orc_solve_vpotz(cu, want, nr, M, dr, bnd)
+    ctx.solve_vpotz(fcu, fv)
+    got = fv.download()
+    assert np.max(np.abs(want[:, 1:nr + 1, 2])) > 1e-3
+    assert np.max(np.abs(got - want)) <= (0.0 if exact else 1e-13 * np.max(np.abs(want)))
+    L.orc_solve_vpott(cu, want, nr, M, dr, bnd)
+    ctx.solve_vpott(fcu, fv)
+    got = fv.download()
+    assert np.max(np.abs(want[:, 1:nr + 1, :2])) > 1e-3
+    assert np.max(np.abs(got - want)) <= (0.0 if exact else 1e-13 * np.max(np.abs(want)))
+    assert np.array_equal(got[:, 0], marker[:, 0]) and np.array_equal(got[:, nr + 1], marker[:, nr + 1])
+    ctx.close()
+
+
+def stage(api, O):
+    """diagnostics staging (csrc/diag.cu): datasets in the layouts of hdf5io_class.f03 pwfield_pipe :591 (f2(dim, 1:nr, 1:nzp) per
+    plane), pwpart_2d_r :1027 and pwpart_3d_pipe :1220 (tnpp = int(npp / dspl), every dspl-th particle, x3 + z0)"""
+    nr, nzp, M = 40, 9, 1
+    ctx = api.Ctx(nr, M, 0.1, 0.02)
+    rng = np.random.default_rng(3)
+    st = api.Stage(ctx, 3 * 3 * nzp * nr + 8 * 2000)
+    for dim in (1, 3):
+        f = api.Field(ctx, dim, nzp, True)
+        vol = rng.normal(size=(2 * M + 1, nzp + 1, nr + 2, dim))
+        f.upload_f2(vol)
+        st.field(f)
+        with pytest_raises_state(api):
+            st.field(f)                                              # one transfer in flight per stage
+        got = st.wait()
+        assert got.shape == (2 * M + 1, dim, nzp, nr)
+        assert np.array_equal(got, np.transpose(vol[:, :nzp, 1:nr + 1, :], (0, 3, 1, 2)))
+    n = 1003
+    x, p = rng.random((n, 2)), rng.normal(size=(n, 3))
+    g, psi, q = rng.random(n) + 1, rng.random(n), -rng.random(n)
+    pt = api.Part2d(ctx, -1.0, 1500)
+    pt.upload(x, p, g, psi, q)
+    for dspl in (1, 7, 2000):
+        st.part2d(pt, dspl)
+        got = st.wait()
+        t = n // dspl
+        sel = np.arange(t) * dspl
+        assert got.shape == (6, t)
+        assert np.array_equal(got, np.stack([x[sel, 0], x[sel, 1], p[sel, 0], p[sel, 1], p[sel, 2], q[sel]]))
+    x3, p3 = rng.random((n, 3)), rng.normal(size=(n, 3))
+    bm = api.Part3d(ctx, -1.0, 10.0, 1500) if api.__name__.endswith("emu") else api.Part3d(ctx, -1.0, 10.0, 1500, nzp, 0, nzp)
+    bm.upload(x3, p3, q)
+    st.part3d(bm, 5, z0=-3.25)
+    got = st.wait()
+    sel = np.arange(n // 5) * 5
+    assert np.array_equal(got, np.stack([x3[sel, 0], x3[sel, 1], x3[sel, 2] + (-3.25), p3[sel, 0], p3[sel, 1], p3[sel, 2], q[sel]]))
+    st.close(); ctx.close()
+
+
+class pytest_raises_state:
+    """the call inside must fail with the library's QPG_ERR_STATE (-5)"""
+
+    def __init__(self, api): pass
+    def __enter__(self): return self
+
+    def __exit__(self, et, ev, tb):
+        assert et is not None and "-5" in str(ev), "expected QPG_ERR_STATE"
+        return True

@@ -21,3 +21,20 @@ def test_neutral_update_emulated(elem, mm, M):
     n0 = emu.lib().emu_launches()
     K.neutral_update(emu, O, elem, mm, M)
     assert emu.lib().emu_launches() - n0 >= 6 * 4
+
+
+def test_subcyc_particles_emulated():
+    K.subcyc_particles(emu, O)
+
+
+@pytest.mark.parametrize("M,bnd", [(0, O.BND_OPEN), (1, O.BND_OPEN), (2, O.BND_OPEN), (2, O.BND_ZERO)])
+def test_vpot_emulated(M, bnd):
+    K.vpot(emu, O, M, bnd, exact=True)
+
+
+def test_vpot_nr1024_emulated():
+    K.vpot(emu, O, 1, O.BND_OPEN, nr=1024, exact=True)
+
+
+def test_stage_emulated():
+    K.stage(emu, O)

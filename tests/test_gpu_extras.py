@@ -1,0 +1,45 @@
+"""GPU parity of the device code written after round 1's GPU minutes were spent -- csrc/subcyc.cu, csrc/vpot.cu, csrc/diag.cu --
+against the oracle, through the C-ABI.  The case bodies are shared with tests/test_emu_kernels.py, where the same device sources
+(compiled for the host) already pass; these tests are opt-in (QPG_TEST_EXTRAS=1) until their first run on a B200 so that an
+unvalidated path cannot mask the state of the validated ones."""
+import os
+
+import pytest
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not os.environ.get("QPG_TEST_EXTRAS"), reason="awaits its first GPU run (set QPG_TEST_EXTRAS=1)")]
+
+
+@pytest.fixture(scope="module")
+def mods():
+    from qpad_b200 import capi
+    from oracle import oracle as O
+    import kernel_cases as K
+    capi.load()
+    return capi, O, K
+
+
+def test_subcyc_particles(mods):
+    capi, O, K = mods
+    K.subcyc_particles(capi, O)
+
+
+@pytest.mark.parametrize("M,bnd", [(0, 3), (1, 3), (2, 3), (2, 2)])
+def test_vpot(mods, M, bnd):
+    capi, O, K = mods
+    K.vpot(capi, O, M, bnd)
+
+
+def test_vpot_nr1024(mods):
+    capi, O, K = mods
+    K.vpot(capi, O, 1, 3, nr=1024)
+
+
+def test_stage(mods):
+    capi, O, K = mods
+    K.stage(capi, O)
+
+
+def test_subcyc_loop_matches_oracle(mods):
+    """the sub-cycled slice loop through the per-routine C-ABI (qpad_b200.subcyc.SubcycStage) against the oracle's"""
+    capi, O, K = mods
+    K.subcyc_loop(capi, O)
