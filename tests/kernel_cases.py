@@ -162,3 +162,23 @@ class pytest_raises_state:
     def __exit__(self, et, ev, tb):
         assert et is not None and "-5" in str(ev), "expected QPG_ERR_STATE"
         return True
+
+
+def subcyc_loop(api, O):
+    """qpad_b200.subcyc.SubcycStage on the GPU against the oracle's sub-cycling loop (the call sequence itself is pinned on the CPU
+    by tests/test_subcyc_host_loop.py)"""
+    from qpad_b200 import decks, subcyc
+    cfg = dict(nr=64, nz=32, max_mode=1, rmax=5.0, zmin=-5.0, zmax=5.0, dt=10.0, iter_max=3, iter_reltol=1e-3, iter_abstol=1e-3)
+    bm = decks.beam_std(cfg["nr"], cfg["nz"], cfg["rmax"], cfg["zmin"], cfg["zmax"], **dict(decks.CONFIGS["C1"]["beam"]))
+    nsl = 24
+    for efm, clamp, dtmin in ((1.1, 50.0, 1e-3), (1.05, 1.6, 1e-3)):
+        orc = O.Sim(ppc1=2, ppc2=2, num_theta=8, subcyc_on=1, subcyc_exp_fac_max=efm, subcyc_exp_fac_clamped=clamp, subcyc_dt_min=dtmin, **cfg)
+        orc.set_beam(*bm)
+        orc.run_slices(nsl)
+        st = subcyc.SubcycStage(dict(cfg, exp_fac_max=efm, exp_fac_clamped=clamp, dt_min=dtmin), O.inject_uniform(cfg["nr"], cfg["rmax"] / cfg["nr"], 2, 2, 8), bm)
+        st.step3d(nslices=nsl)
+        assert st.subcycles == orc.total_subcycles() > nsl and st.iters == orc.total_iters()
+        for name, f in (("psi", st.psi), ("e", st.e), ("b", st.b)):
+            got, want = f.download_f2()[:, :nsl], orc.field(name, 2)[:, :nsl]
+            assert np.max(np.abs(want)) > 1e-3 and np.max(np.abs(got - want)) < 1e-8 * np.max(np.abs(want)), name
+        st.close()
