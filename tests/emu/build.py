@@ -1,6 +1,10 @@
-"""TEST INFRASTRUCTURE ONLY: builds tests/emu/_build/libqpademu.so -- the shuffle-free kernels of qpad_b200/csrc compiled for the
-HOST through tests/emu/cuda_runtime.h (fibers for CTA threads).  The only source transformation is the launch syntax:
-`kernel<<<grid, block, smem, stream>>>(args)` becomes `emu::launch(grid, block, [&] { kernel(args); })`."""
+"""TEST INFRASTRUCTURE ONLY: builds tests/emu/_build/libqpademu.so -- the per-routine part of qpad_b200/csrc (everything except the
+persistent sweep kernel, the CUDA-graph simulation object, the laser and the peer-memory transport) compiled for the HOST through
+tests/emu/cuda_runtime.h (fibers for CTA threads, exact barriers and warp collectives).  The product sources are not touched;
+the textual transformations applied to the copies under _build/ are:
+  * `kernel<<<grid, block, smem, stream>>>(args)`  ->  `emu::launch(grid, block, smem, [&] { kernel(args); })`
+  * `extern __shared__ T name[];`                  ->  `T *name = (T *)emu::dyn_smem;`
+  * the five inline-PTX statements of particles.cu ->  their C++ meaning (PTX table below; each must match exactly once)"""
 import os
 import re
 import subprocess
@@ -9,7 +13,17 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "qpad_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
-SOURCES = ["neutral.cu", "subcyc.cu", "vpot.cu", "diag.cu"]      # device code that has no warp-level primitives / PTX
+SOURCES = ["fields.cu", "particles.cu", "beam.cu", "neutral.cu", "subcyc.cu", "vpot.cu", "diag.cu"]
+PTX = {
+    "particles.cu": [
+        ('asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(y));', "r = 1.0 / y;"),
+        ('asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));', "y = 1.0 / std::sqrt(x);"),
+        ('asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");', "*p += v;"),
+        ('asm volatile("red.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");', "*p += v;"),
+        ('asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));',
+         "emu_dmma_m8n8k4(c0, c1, a, b);"),
+    ],
+}
 LIB = os.path.join(OUT, "libqpademu.so")
 
 
@@ -51,9 +65,19 @@ def transform(text):
         cfg = _split_top(text[m.end():cfg_end])
         a0 = text.index("(", cfg_end)
         a1 = _match(text, a0, "(", ")")
-        out += text[pos:m.start()] + f"emu::launch({cfg[0]}, {cfg[1]}, [&] {{ {m.group(1)}{text[a0:a1]}; }})"
+        smem = cfg[2] if len(cfg) > 2 else "0"
+        out += text[pos:m.start()] + f"emu::launch({cfg[0]}, {cfg[1]}, {smem}, [&] {{ {m.group(1)}{text[a0:a1]}; }})"
         pos = a1
-    return out + text[pos:]
+    out += text[pos:]
+    return re.sub(r"extern\s+__shared__\s+(\w+)\s+(\w+)\[\];", r"\1 *\2 = (\1 *)emu::dyn_smem;", out)
+
+
+def transform_file(name, text):
+    for ptx, cpp in PTX.get(name, []):
+        assert text.count(ptx) == 1, (name, ptx)
+        text = text.replace(ptx, cpp)
+    assert not re.search(r"\basm\b", re.sub(r"//.*", "", text)), f"{name}: unhandled inline assembly"
+    return transform(text)
 
 
 def build(force=False):
@@ -65,7 +89,7 @@ def build(force=False):
         return LIB
     for s in srcs:
         with open(s) as f:
-            t = transform(f.read())
+            t = transform_file(os.path.basename(s), f.read())
         with open(os.path.join(OUT, os.path.basename(s) + ".cpp"), "w") as f:
             f.write(t)
     defs = [f"-DEMU_HAVE_{os.path.basename(s).split('.')[0].upper()}" for s in srcs]

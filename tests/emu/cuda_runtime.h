@@ -1,8 +1,10 @@
 // tests/emu/cuda_runtime.h -- TEST INFRASTRUCTURE ONLY.  A host stand-in for the CUDA runtime + the CUDA C++ language extensions,
-// just large enough to compile the *simple* kernels of qpad_b200/csrc (no warp shuffles, no inline PTX, no cooperative launch)
-// with g++ and run them on the CPU: the threads of a CTA are ucontext fibers on ONE OS thread (a __syncthreads() is a yield to the
-// round-robin scheduler, so barriers are exact and runs are deterministic), CTAs run one after the other, "device memory" is host
-// memory and streams are no-ops.  It exists so that device code written when no GPU time is left (neutral.cu, subcyc.cu, vpot.cu,
+// large enough to compile the per-routine kernels of qpad_b200/csrc (no cooperative launch, no CUDA graphs, no peer memory; the few
+// inline-PTX statements have a QPG_EMU branch) with g++ and run them on the CPU: the threads of a CTA are fibers on ONE OS thread;
+// __syncthreads() and the warp collectives (__shfl_*_sync, __ballot_sync, __match_any_sync, __syncwarp, the emulated DMMA) are
+// yields to a scheduler that releases a barrier / a warp collective only when every participant has arrived, so synchronisation is
+// exact, a missing participant is reported as a deadlock, and runs are deterministic.  CTAs run one after the other, "device
+// memory" is host memory and streams are no-ops.  It exists so that device code written when no GPU time is left (neutral.cu, subcyc.cu, vpot.cu,
 // diag.cu) can be checked against the oracle before its first run on a B200.  It is found before the real <cuda_runtime.h>
 // because tests/emu is the first -I directory of the emulation build (tests/emu/build.py); nothing in the product uses it.
 #pragma once
@@ -13,7 +15,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
-#include <ucontext.h>
+#include <cstdio>
 #include <vector>
 
 #define QPG_EMU 1
@@ -55,6 +57,31 @@ inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = nullptr) { return
 inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return cudaSuccess; }
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+inline cudaError_t cudaMemset(void *p, int v, size_t n) { memset(p, v, n); return cudaSuccess; }
+inline cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = nullptr; return cudaSuccess; }
+inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t, cudaEvent_t) { *ms = 0.0f; return cudaSuccess; }
+inline cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
+enum cudaDeviceAttr { cudaDevAttrMultiProcessorCount, cudaDevAttrMaxSharedMemoryPerBlockOptin, cudaDevAttrCooperativeLaunch };
+inline cudaError_t cudaDeviceGetAttribute(int *v, cudaDeviceAttr a, int) { *v = a == cudaDevAttrMultiProcessorCount ? 148 : (a == cudaDevAttrMaxSharedMemoryPerBlockOptin ? 232448 : 0); return cudaSuccess; }
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize };
+template <class F> inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
+typedef unsigned long long cudaGraphConditionalHandle;
+inline void cudaGraphSetConditional(cudaGraphConditionalHandle, unsigned) {}
+template <class T> inline T __ldg(const T *p) { return *p; }
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline int __ffs(int v) { return __builtin_ffs(v); }
+inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
+// position of the offset-th set bit of mask counting upwards from bit `base` (offset >= 1), 0xffffffff if there is none
+inline unsigned __fns(unsigned mask, unsigned base, int offset)
+{
+    if (offset == 0) return ((mask >> base) & 1u) ? base : 0xffffffffu;
+    if (offset > 0) { for (unsigned k = base; k < 32; k++) if (((mask >> k) & 1u) && --offset == 0) return k; return 0xffffffffu; }
+    for (int k = (int)base; k >= 0; k--) if (((mask >> k) & 1u) && ++offset == 0) return (unsigned)k;
+    return 0xffffffffu;
+}
+inline int __double2hiint(double a) { unsigned long long r; memcpy(&r, &a, 8); return (int)(r >> 32); }
+inline int __double2loint(double a) { unsigned long long r; memcpy(&r, &a, 8); return (int)(r & 0xffffffffu); }
+inline double __hiloint2double(int hi, int lo) { unsigned long long r = ((unsigned long long)(unsigned)hi << 32) | (unsigned)lo; double a; memcpy(&a, &r, 8); return a; }
 inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 inline const char *cudaGetErrorString(cudaError_t) { return "emulated"; }
 
@@ -75,46 +102,188 @@ template <class T> inline T atomicMax(T *p, T v) { T o = *p; if (v > o) *p = v; 
 template <class T> inline T atomicMin(T *p, T v) { T o = *p; if (v < o) *p = v; return o; }
 
 namespace emu {
-struct Fiber { ucontext_t ctx; bool done; };
-inline ucontext_t g_sched;
+// ---- fibers: a minimal x86-64 context switch (no signal-mask system call, unlike swapcontext) ----------------------------------
+#if !defined(__x86_64__)
+#error "tests/emu needs x86-64 (the fiber switch is written in assembly)"
+#endif
+extern "C" void emu_switch(void **save_sp, void *load_sp);
+asm(R"(
+.text
+.globl emu_switch
+.type emu_switch,@function
+emu_switch:
+    pushq %rbp
+    pushq %rbx
+    pushq %r12
+    pushq %r13
+    pushq %r14
+    pushq %r15
+    movq %rsp, (%rdi)
+    movq %rsi, %rsp
+    popq %r15
+    popq %r14
+    popq %r13
+    popq %r12
+    popq %rbx
+    popq %rbp
+    ret
+.size emu_switch,.-emu_switch
+)");
+enum { ST_RUN = 0, ST_BARRIER, ST_WARP, ST_DONE };
+struct Fiber { void *sp; int state; unsigned mask; unsigned seq; };
+inline void *g_sched_sp = nullptr;
 inline Fiber *g_cur = nullptr;
 inline std::function<void()> *g_body = nullptr;
-inline long g_launches = 0, g_barriers = 0;
-inline void tramp() { (*g_body)(); g_cur->done = true; swapcontext(&g_cur->ctx, &g_sched); }
-inline void sync_threads() { g_barriers++; swapcontext(&g_cur->ctx, &g_sched); }
-template <class F> void launch(dim3 g, dim3 b, F f)
+inline long g_launches = 0, g_barriers = 0, g_collectives = 0;
+inline unsigned g_tid = 0;                                   // flattened thread index of the running fiber
+inline unsigned long long (*g_slots)[2][32] = nullptr;       // [warp][parity][lane] exchange words of the warp collectives
+inline unsigned char *dyn_smem = nullptr;                    // `extern __shared__` storage of the running CTA
+inline void yield_to_scheduler() { emu_switch(&g_cur->sp, g_sched_sp); }
+inline void tramp()
+{
+    (*g_body)();
+    g_cur->state = ST_DONE;
+    yield_to_scheduler();
+    abort();
+}
+inline void sync_threads() { g_barriers++; g_cur->state = ST_BARRIER; yield_to_scheduler(); }
+// every lane named in `mask` publishes one 64-bit word; returns once all of them have, with the 32 words of the warp in out[]
+inline void warp_exchange(unsigned mask, unsigned long long v, unsigned long long out[32])
+{
+    Fiber *f = g_cur;
+    const unsigned tid = g_tid, w = tid >> 5, lane = tid & 31, par = f->seq & 1;
+    g_collectives++;
+    g_slots[w][par][lane] = v;
+    f->mask = mask; f->state = ST_WARP;
+    yield_to_scheduler();
+    memcpy(out, g_slots[w][par], sizeof(unsigned long long) * 32);
+    f->seq++;
+}
+template <class F> void launch(dim3 g, dim3 b, size_t smem, F f)
 {
     std::function<void()> body = f;
     g_body = &body; g_launches++;
     gridDim = g; blockDim = b;
-    const unsigned nt = b.x * b.y * b.z;
+    const unsigned nt = b.x * b.y * b.z, nw = (nt + 31) / 32;
     const size_t stack = 256 * 1024;
     static std::vector<char> stacks;
-    if (stacks.size() < stack * nt) stacks.resize(stack * nt);
+    if (stacks.size() < stack * nt + 64) stacks.resize(stack * nt + 64);
     std::vector<Fiber> fib(nt);
+    std::vector<unsigned long long> slots((size_t)nw * 64);
+    g_slots = (unsigned long long(*)[2][32])slots.data();
+    std::vector<unsigned char> dyn(smem + 64);
+    dyn_smem = (unsigned char *)(((uintptr_t)dyn.data() + 63) & ~(uintptr_t)63);
     for (unsigned bz = 0; bz < g.z; bz++) for (unsigned by = 0; by < g.y; by++) for (unsigned bx = 0; bx < g.x; bx++) {
         blockIdx = uint3{bx, by, bz};
         for (unsigned t = 0; t < nt; t++) {
-            getcontext(&fib[t].ctx);
-            fib[t].ctx.uc_stack.ss_sp = stacks.data() + stack * t; fib[t].ctx.uc_stack.ss_size = stack; fib[t].ctx.uc_link = &g_sched;
-            fib[t].done = false;
-            makecontext(&fib[t].ctx, (void (*)())tramp, 0);
+            uintptr_t top = ((uintptr_t)stacks.data() + stack * (t + 1)) & ~(uintptr_t)15;
+            void **sp = (void **)(top - 8);          // after the `ret` into tramp: rsp % 16 == 8, as at any function entry
+            *--sp = (void *)tramp;
+            for (int r = 0; r < 6; r++) *--sp = nullptr;
+            fib[t] = Fiber{(void *)sp, ST_RUN, 0u, 0u};
         }
         unsigned live = nt;
-        while (live) {                                    // one round = one barrier phase of the CTA
-            unsigned finished = 0;
+        while (live) {
+            bool ran = false;
             for (unsigned t = 0; t < nt; t++) {
-                if (fib[t].done) continue;
+                if (fib[t].state != ST_RUN) continue;
                 threadIdx = uint3{t % b.x, (t / b.x) % b.y, t / (b.x * b.y)};
-                g_cur = &fib[t];
-                swapcontext(&g_sched, &fib[t].ctx);
-                if (fib[t].done) finished++;
+                g_tid = t; g_cur = &fib[t];
+                emu_switch(&g_sched_sp, fib[t].sp);
+                ran = true;
+                if (fib[t].state == ST_DONE) live--;
             }
-            // CUDA requires every thread of a CTA to reach the same barriers: a round in which some threads ended and others
-            // are still waiting at a barrier is legal only if those others end without another barrier -- not checked here
-            live -= finished;
+            bool released = false;
+            for (unsigned w = 0; w < nw; w++) {          // warp collectives: all lanes named in a waiting lane's mask must wait with that mask
+                const unsigned base = w * 32, nl = std::min(32u, nt - base);
+                for (unsigned l = 0; l < nl; l++) {
+                    if (fib[base + l].state != ST_WARP) continue;
+                    const unsigned m = fib[base + l].mask & (nl == 32 ? 0xffffffffu : ((1u << nl) - 1u));
+                    bool all = true;
+                    for (unsigned k = 0; k < nl && all; k++) if ((m >> k) & 1u) all = fib[base + k].state == ST_WARP && fib[base + k].mask == fib[base + l].mask;
+                    if (all) { for (unsigned k = 0; k < nl; k++) if ((m >> k) & 1u) fib[base + k].state = ST_RUN; released = true; }
+                }
+            }
+            if (!released && live) {                    // CTA barrier: every live thread waits at it
+                unsigned at = 0;
+                for (unsigned t = 0; t < nt; t++) at += fib[t].state == ST_BARRIER;
+                if (at == live) { for (unsigned t = 0; t < nt; t++) if (fib[t].state == ST_BARRIER) fib[t].state = ST_RUN; released = true; }
+            }
+            if (live && !ran && !released) {
+                unsigned nb = 0, nwp = 0;
+                for (unsigned t = 0; t < nt; t++) { nb += fib[t].state == ST_BARRIER; nwp += fib[t].state == ST_WARP; }
+                fprintf(stderr, "emu: DEADLOCK in CTA (%u,%u,%u): %u threads live, %u at __syncthreads, %u in a warp collective\n", bx, by, bz, live, nb, nwp);
+                abort();
+            }
         }
     }
 }
+template <class F> void launch(dim3 g, dim3 b, F f) { launch(g, b, 0, f); }
 }  // namespace emu
 #define __syncthreads() emu::sync_threads()
+
+// ---- warp collectives on top of emu::warp_exchange ------------------------------------------------------------------------------
+namespace emu {
+template <class T> inline unsigned long long to_bits(T v) { unsigned long long r = 0; static_assert(sizeof(T) <= 8, "warp word"); memcpy(&r, &v, sizeof(T)); return r; }
+template <class T> inline T from_bits(unsigned long long r) { T v; memcpy(&v, &r, sizeof(T)); return v; }
+template <class T> inline T shfl_from(unsigned mask, T v, int src, bool valid)
+{
+    unsigned long long all[32];
+    warp_exchange(mask, to_bits(v), all);
+    return (valid && ((mask >> src) & 1u)) ? from_bits<T>(all[src]) : v;
+}
+}  // namespace emu
+template <class T> inline T __shfl_sync(unsigned mask, T v, int src, int width = 32)
+{
+    const int lane = emu::g_tid & 31, seg = lane & ~(width - 1);
+    return emu::shfl_from(mask, v, seg | (src & (width - 1)), true);
+}
+template <class T> inline T __shfl_up_sync(unsigned mask, T v, unsigned delta, int width = 32)
+{
+    const int lane = emu::g_tid & 31, seg = lane & ~(width - 1), src = lane - (int)delta;
+    return emu::shfl_from(mask, v, src < seg ? lane : src, src >= seg);
+}
+template <class T> inline T __shfl_down_sync(unsigned mask, T v, unsigned delta, int width = 32)
+{
+    const int lane = emu::g_tid & 31, seg = lane & ~(width - 1), src = lane + (int)delta;
+    return emu::shfl_from(mask, v, src >= seg + width ? lane : src, src < seg + width);
+}
+template <class T> inline T __shfl_xor_sync(unsigned mask, T v, int lm, int width = 32)
+{
+    const int lane = emu::g_tid & 31, src = lane ^ lm;
+    return emu::shfl_from(mask, v, src, (src & ~(width - 1)) == (lane & ~(width - 1)));
+}
+inline unsigned __ballot_sync(unsigned mask, int pred)
+{
+    unsigned long long all[32];
+    emu::warp_exchange(mask, pred ? 1ull : 0ull, all);
+    unsigned r = 0;
+    for (int k = 0; k < 32; k++) if (((mask >> k) & 1u) && all[k]) r |= 1u << k;
+    return r;
+}
+inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0; }
+inline int __all_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) == mask; }
+template <class T> inline unsigned __match_any_sync(unsigned mask, T v)
+{
+    unsigned long long all[32];
+    const unsigned long long mine = emu::to_bits(v);
+    emu::warp_exchange(mask, mine, all);
+    unsigned r = 0;
+    for (int k = 0; k < 32; k++) if (((mask >> k) & 1u) && all[k] == mine) r |= 1u << k;
+    return r;
+}
+inline void __syncwarp(unsigned mask = 0xffffffffu) { unsigned long long all[32]; emu::warp_exchange(mask, 0ull, all); }
+// mma.sync.aligned.m8n8k4.row.col.f64: D[8x8] += A[8x4] B[4x8]; lane holds a = A[lane / 4][lane % 4], b = B[lane % 4][lane / 4],
+// c0, c1 = C[lane / 4][2 (lane % 4) + {0, 1}]
+inline void emu_dmma_m8n8k4(double &c0, double &c1, double a, double b)
+{
+    unsigned long long A[32], B[32];
+    emu::warp_exchange(0xffffffffu, emu::to_bits(a), A);
+    emu::warp_exchange(0xffffffffu, emu::to_bits(b), B);
+    const int lane = emu::g_tid & 31, row = lane >> 2, col = (lane & 3) * 2;
+    for (int k = 0; k < 4; k++) {
+        const double av = emu::from_bits<double>(A[row * 4 + k]);
+        c0 = std::fma(av, emu::from_bits<double>(B[col * 4 + k]), c0);
+        c1 = std::fma(av, emu::from_bits<double>(B[(col + 1) * 4 + k]), c1);
+    }
+}

@@ -13,28 +13,34 @@ from emu import emu
 def test_launch_rewrite():
     from emu.build import transform
     src = "k_a<<<(n + 127) / 128, 128, 0, c->stream>>>(x, f(y, z));\nDISPATCH(k_b<2><<<dim3(3, 2), 64>>>(p));"
-    assert transform(src) == "emu::launch((n + 127) / 128, 128, [&] { k_a(x, f(y, z)); });\nDISPATCH(emu::launch(dim3(3, 2), 64, [&] { k_b<2>(p); }));"
+    assert transform(src) == "emu::launch((n + 127) / 128, 128, 0, [&] { k_a(x, f(y, z)); });\nDISPATCH(emu::launch(dim3(3, 2), 64, 0, [&] { k_b<2>(p); }));"
+
+
+@pytest.fixture()
+def api():
+    with emu.patched() as capi:
+        yield capi
 
 
 @pytest.mark.parametrize("elem,mm,M", [(1, 1, 0), (3, 3, 1), (2, 2, 2)])
-def test_neutral_update_emulated(elem, mm, M):
+def test_neutral_update_emulated(api, elem, mm, M):
     n0 = emu.lib().emu_launches()
-    K.neutral_update(emu, O, elem, mm, M)
+    K.neutral_update(api, O, elem, mm, M)
     assert emu.lib().emu_launches() - n0 >= 6 * 4
 
 
-def test_subcyc_particles_emulated():
-    K.subcyc_particles(emu, O)
+def test_subcyc_particles_emulated(api):
+    K.subcyc_particles(api, O)
 
 
 @pytest.mark.parametrize("M,bnd", [(0, O.BND_OPEN), (1, O.BND_OPEN), (2, O.BND_OPEN), (2, O.BND_ZERO)])
-def test_vpot_emulated(M, bnd):
-    K.vpot(emu, O, M, bnd, exact=True)
+def test_vpot_emulated(api, M, bnd):
+    K.vpot(api, O, M, bnd, exact=True)
 
 
-def test_vpot_nr1024_emulated():
-    K.vpot(emu, O, 1, O.BND_OPEN, nr=1024, exact=True)
+def test_vpot_nr1024_emulated(api):
+    K.vpot(api, O, 1, O.BND_OPEN, nr=1024, exact=True)
 
 
-def test_stage_emulated():
-    K.stage(emu, O)
+def test_stage_emulated(api):
+    K.stage(api, O)

@@ -1,0 +1,63 @@
+"""The per-routine C-ABI of libqpadb200.so checked on the CPU: the SAME test bodies as the GPU parity tests (tests/test_gpu_parity.py,
+tests/kernel_cases.py) run against the host emulation of the device sources (tests/emu: fields.cu, particles.cu, beam.cu, neutral.cu,
+subcyc.cu, vpot.cu, diag.cu compiled for the host; CTA threads are fibers, barriers and warp collectives -- shuffles, ballots,
+match_any, the m8n8k4 DMMA -- are exact).  What this covers: indexing, ordering, reductions, scans, the field-program interpreter,
+the axis rules, the host entry points -- i.e. the LOGIC of the kernels, incl. code that has not yet had GPU time (neutral species,
+sub-cycling, vpot, staging).  What it does not cover: anything about the hardware (memory model, occupancy, launch limits, the
+MUFU-seeded reciprocal's last bits), the persistent sweep kernel, CUDA graphs and the peer-memory transport.  The parity gate
+proper remains `pytest -m gpu` on a B200."""
+import pytest
+
+from oracle import oracle as O
+from emu import emu
+import kernel_cases as K
+import test_gpu_parity as G
+
+
+@pytest.fixture()
+def mods():
+    with emu.patched() as capi:
+        yield capi, O
+
+
+def test_field_roundtrip_and_arith(mods): G.test_field_roundtrip_and_arith(mods)
+
+
+@pytest.mark.parametrize("nr,M,bnd", [(64, 0, 3), (64, 1, 3), (250, 1, 2), (96, 2, 3), (1024, 1, 3)])
+def test_solves_match_oracle(mods, nr, M, bnd): G.test_solves_match_oracle(mods, nr, M, bnd)
+
+
+def test_convergence_tester(mods): G.test_convergence_tester(mods)
+
+
+@pytest.mark.parametrize("nr,M", [(64, 0), (64, 1), (96, 2)])
+def test_particle_kernels_match_oracle(mods, nr, M): G.test_particle_kernels_match_oracle(mods, nr, M)
+
+
+@pytest.mark.parametrize("nr,M", [(64, 1), (96, 2)])
+def test_std_pusher_kernels_match_oracle(mods, nr, M): G.test_std_pusher_kernels_match_oracle(mods, nr, M)
+
+
+@pytest.mark.parametrize("nr,M,std", [(64, 0, 0), (64, 1, 0), (64, 1, 1)])
+def test_pgc_pusher_kernels_match_oracle(mods, nr, M, std): G.test_pgc_pusher_kernels_match_oracle(mods, nr, M, std)
+
+
+def test_update_bound_heavy_loss(mods): G.test_update_bound_heavy_loss(mods)
+
+
+@pytest.mark.parametrize("nr,ppc,nth", [(64, 2, 8), (250, 2, 16)])
+def test_sort_bit_exact(mods, nr, ppc, nth): G.test_sort_bit_exact(mods, nr, ppc, nth)
+
+
+@pytest.mark.parametrize("M,push", [(1, 1), (2, 2), (0, 1)])
+def test_beam_kernels_match_oracle(mods, M, push): G.test_beam_kernels_match_oracle(mods, M, push)
+
+
+def test_ionization_loop_matches_oracle(mods):
+    """the ionisation deck (config 5 in small) through qpad_b200.ionization.IonizationStage: neutral.cu + every per-routine kernel"""
+    K.ionization_loop(mods[0], O, nsl=32)
+
+
+def test_subcyc_loop_matches_oracle(mods):
+    """the sub-cycled slice loop through qpad_b200.subcyc.SubcycStage"""
+    K.subcyc_loop(mods[0], O)

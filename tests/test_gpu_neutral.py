@@ -28,25 +28,8 @@ def test_neutral_update_matches_oracle(mods, elem, mm, M):
 
 
 def test_ionization_loop_matches_oracle(mods):
-    """config 5 in small through the per-routine C-ABI (qpad_b200.ionization.IonizationStage) against the oracle's loop"""
+    """config 5 in small through the per-routine C-ABI (qpad_b200.ionization.IonizationStage) against the oracle's loop (body shared
+    with tests/test_emu_parity.py)"""
     capi, O = mods
-    from qpad_b200 import decks
-    from qpad_b200.ionization import IonizationStage
-    cfg = dict(nr=96, nz=64, max_mode=1, rmax=6.0, zmin=0.0, zmax=8.0, dt=10.0, iter_max=3, iter_reltol=1e-3, iter_abstol=1e-3, n0=1.0e17)
-    beam = dict(decks.CONFIGS["C5"]["beam"])
-    bm = decks.beam_std(cfg["nr"], cfg["nz"], cfg["rmax"], cfg["zmin"], cfg["zmax"], **beam)
-    orc = O.Sim(sp_density=0.0, neut_on=1, neut_elem=3, neut_ion_max=1, neut_ppc1=2, neut_ppc2=2, neut_num_theta=8, ppc1=2, ppc2=2, num_theta=8,
-                **{k: v for k, v in cfg.items()})
-    orc.set_beam(*bm)
-    nsl = 48
-    orc.run_slices(nsl)
-    st = IonizationStage(cfg, dict(element=3, ion_max=1, ppc=(2, 2), num_theta=8), bm)
-    st.step3d(nslices=nsl, beam_push=False)
-    assert st.iters == orc.total_iters()
-    lev = orc.levels(1)
-    assert np.max(np.abs(st.neut.levels() - lev)) < 1e-10
-    assert st.neut.part.npp() == len(orc.neutral()[4]) > 100
-    for name, f in (("psi", st.psi), ("e", st.e), ("b", st.b)):
-        got, want = f.download_f2()[:, :nsl], orc.field(name, 2)[:, :nsl]
-        assert np.max(np.abs(want)) > 1e-2 and np.max(np.abs(got - want)) < 1e-8 * np.max(np.abs(want)), name
-    st.close()
+    import kernel_cases as K
+    K.ionization_loop(capi, O)
