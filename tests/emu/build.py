@@ -1,5 +1,5 @@
 """TEST INFRASTRUCTURE ONLY: builds tests/emu/_build/libqpademu.so -- the per-routine part of qpad_b200/csrc (everything except the
-persistent sweep kernel, the CUDA-graph simulation object, the laser and the peer-memory transport) compiled for the HOST through
+persistent sweep kernel, the cluster kernels, the CUDA-graph simulation object and the peer-memory transport) compiled for the HOST through
 tests/emu/cuda_runtime.h (fibers for CTA threads, exact barriers and warp collectives).  The product sources are not touched;
 the textual transformations applied to the copies under _build/ are:
   * `kernel<<<grid, block, smem, stream>>>(args)`  ->  `emu::launch(grid, block, smem, [&] { kernel(args); })`
@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "qpad_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
-SOURCES = ["fields.cu", "particles.cu", "beam.cu", "neutral.cu", "subcyc.cu", "vpot.cu", "diag.cu"]
+SOURCES = ["fields.cu", "particles.cu", "beam.cu", "laser.cu", "neutral.cu", "subcyc.cu", "vpot.cu", "diag.cu"]
 PTX = {
     "particles.cu": [
         ('asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(y));', "r = 1.0 / y;"),

@@ -1,5 +1,5 @@
 """The per-routine C-ABI of libqpadb200.so checked on the CPU: the SAME test bodies as the GPU parity tests (tests/test_gpu_parity.py,
-tests/kernel_cases.py) run against the host emulation of the device sources (tests/emu: fields.cu, particles.cu, beam.cu, neutral.cu,
+tests/kernel_cases.py) run against the host emulation of the device sources (tests/emu: fields.cu, particles.cu, beam.cu, laser.cu, neutral.cu,
 subcyc.cu, vpot.cu, diag.cu compiled for the host; CTA threads are fibers, barriers and warp collectives -- shuffles, ballots,
 match_any, the m8n8k4 DMMA -- are exact).  What this covers: indexing, ordering, reductions, scans, the field-program interpreter,
 the axis rules, the host entry points -- i.e. the LOGIC of the kernels, incl. code that has not yet had GPU time (neutral species,
@@ -12,6 +12,7 @@ from oracle import oracle as O
 from emu import emu
 import kernel_cases as K
 import test_gpu_parity as G
+import test_gpu_laser as GL
 
 
 @pytest.fixture()
@@ -51,6 +52,18 @@ def test_sort_bit_exact(mods, nr, ppc, nth): G.test_sort_bit_exact(mods, nr, ppc
 
 @pytest.mark.parametrize("M,push", [(1, 1), (2, 2), (0, 1)])
 def test_beam_kernels_match_oracle(mods, M, push): G.test_beam_kernels_match_oracle(mods, M, push)
+
+
+@pytest.mark.parametrize("nr,nz,M", [(64, 12, 0), (50, 9, 2)])
+def test_laser_slice_images_match_oracle(mods, nr, nz, M): GL.test_laser_slice_images_match_oracle(mods, nr, nz, M)
+
+
+@pytest.mark.parametrize("nr,M", [(64, 0), (96, 2)])
+def test_deposit_chi_matches_oracle(mods, nr, M): GL.test_deposit_chi_matches_oracle(mods, nr, M)
+
+
+@pytest.mark.parametrize("nr,nz,M,iters", [(100, 24, 1, 2), (64, 16, 2, 1), (33, 8, 1, 1)])
+def test_envelope_advance_matches_oracle(mods, nr, nz, M, iters): GL.test_envelope_advance_matches_oracle(mods, nr, nz, M, iters)
 
 
 def test_ionization_loop_matches_oracle(mods):
