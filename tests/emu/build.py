@@ -13,7 +13,20 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "qpad_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
-SOURCES = ["fields.cu", "particles.cu", "beam.cu", "laser.cu", "neutral.cu", "subcyc.cu", "vpot.cu", "diag.cu"]
+COMPILE_ONLY = ["fused.cu", "sweep.cu"]        # needed to link sim.cu; their kernels need live clusters / a live grid and are not run
+SOURCES = ["fields.cu", "particles.cu", "beam.cu", "laser.cu", "fused.cu", "sweep.cu", "sim.cu", "neutral.cu", "subcyc.cu", "vpot.cu", "diag.cu"]
+# the emulation runs only the plain per-slice launches of qpg_sim: CUDA-graph replay, the cluster programs and the sweep kernel
+# are switched off (a request for graphs is ignored -- same launches, replayed or not; the other two refuse to be switched on)
+PATCH = {
+    "sim.cu": [
+        ("s->prm = *prm;", "s->prm = *prm; s->prm.use_graph = 0;"),
+        ("s->prm.use_graph = use_graph != 0;", "(void)use_graph;"),
+        ("s->use_fused = (prm->nr <= FT * FC && prm->max_mode <= 2);", "s->use_fused = false;"),
+        ("s->use_sweep = sweep_supported(*prm);", "s->use_sweep = false;"),
+        ("const bool can = s->prm.nr <= FT * FC && s->prm.max_mode <= 2;", "const bool can = false;"),
+        ("if (on && !sweep_supported(s->prm))", "if (on)"),
+    ],
+}
 PTX = {
     "particles.cu": [
         ('asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(y));', "r = 1.0 / y;"),
@@ -72,8 +85,20 @@ def transform(text):
     return re.sub(r"extern\s+__shared__\s+(\w+)\s+(\w+)\[\];", r"\1 *\2 = (\1 *)emu::dyn_smem;", out)
 
 
+def strip_ptx(text):
+    """compile-only files: every inline-PTX statement becomes a call that aborts if it is ever reached"""
+    out, pos = "", 0
+    for m in re.finditer(r"\basm\s+volatile\s*\(", text):
+        end = _match(text, m.end() - 1, "(", ")")
+        out += text[pos:m.start()] + "emu_unsupported_ptx()"
+        pos = end
+    return out + text[pos:]
+
+
 def transform_file(name, text):
-    for ptx, cpp in PTX.get(name, []):
+    if name in COMPILE_ONLY:
+        text = strip_ptx(text)
+    for ptx, cpp in PTX.get(name, []) + PATCH.get(name, []):
         assert text.count(ptx) == 1, (name, ptx)
         text = text.replace(ptx, cpp)
     assert not re.search(r"\basm\b", re.sub(r"//.*", "", text)), f"{name}: unhandled inline assembly"

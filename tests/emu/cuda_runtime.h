@@ -65,8 +65,43 @@ enum cudaDeviceAttr { cudaDevAttrMultiProcessorCount, cudaDevAttrMaxSharedMemory
 inline cudaError_t cudaDeviceGetAttribute(int *v, cudaDeviceAttr a, int) { *v = a == cudaDevAttrMultiProcessorCount ? 148 : (a == cudaDevAttrMaxSharedMemoryPerBlockOptin ? 232448 : 0); return cudaSuccess; }
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize };
 template <class F> inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
+// ---- compile-only stubs: CUDA graphs, cooperative launch, occupancy (sim.cu links; these paths fail loudly in emulation) ----------
+enum { cudaErrorNotSupported = 801 };
+typedef struct emu_graph_s *cudaGraph_t;
+typedef struct emu_graphexec_s *cudaGraphExec_t;
+typedef struct emu_graphnode_s *cudaGraphNode_t;
+enum cudaStreamCaptureMode { cudaStreamCaptureModeThreadLocal };
+enum cudaStreamCaptureStatus { cudaStreamCaptureStatusNone };
+enum cudaGraphNodeType { cudaGraphNodeTypeConditional };
+enum cudaGraphConditionalNodeType { cudaGraphCondTypeWhile };
+enum { cudaGraphCondAssignDefault = 1, cudaStreamSetCaptureDependencies = 1 };
 typedef unsigned long long cudaGraphConditionalHandle;
+struct cudaConditionalNodeParams { cudaGraphConditionalHandle handle; cudaGraphConditionalNodeType type; unsigned size; cudaGraph_t *phGraph_out; };
+struct cudaGraphNodeParams { cudaGraphNodeType type; cudaConditionalNodeParams conditional; };
+inline cudaError_t cudaStreamBeginCapture(cudaStream_t, cudaStreamCaptureMode) { return cudaErrorNotSupported; }
+inline cudaError_t cudaStreamGetCaptureInfo(cudaStream_t, cudaStreamCaptureStatus *, unsigned long long *, cudaGraph_t *, const cudaGraphNode_t **, size_t *) { return cudaErrorNotSupported; }
+inline cudaError_t cudaGraphConditionalHandleCreate(cudaGraphConditionalHandle *, cudaGraph_t, unsigned, unsigned) { return cudaErrorNotSupported; }
+inline cudaError_t cudaGraphAddNode(cudaGraphNode_t *, cudaGraph_t, const cudaGraphNode_t *, size_t, cudaGraphNodeParams *) { return cudaErrorNotSupported; }
+inline cudaError_t cudaStreamUpdateCaptureDependencies(cudaStream_t, cudaGraphNode_t *, size_t, unsigned) { return cudaErrorNotSupported; }
+inline cudaError_t cudaStreamBeginCaptureToGraph(cudaStream_t, cudaGraph_t, const cudaGraphNode_t *, const void *, size_t, cudaStreamCaptureMode) { return cudaErrorNotSupported; }
+inline cudaError_t cudaStreamEndCapture(cudaStream_t, cudaGraph_t *) { return cudaErrorNotSupported; }
+inline cudaError_t cudaGraphInstantiate(cudaGraphExec_t *, cudaGraph_t, unsigned long long) { return cudaErrorNotSupported; }
+inline cudaError_t cudaGraphLaunch(cudaGraphExec_t, cudaStream_t) { return cudaErrorNotSupported; }
+inline cudaError_t cudaGraphDestroy(cudaGraph_t) { return cudaSuccess; }
+inline cudaError_t cudaGraphExecDestroy(cudaGraphExec_t) { return cudaSuccess; }
+inline cudaError_t cudaLaunchCooperativeKernel(const void *, dim3, dim3, void **, size_t, cudaStream_t) { return cudaErrorNotSupported; }
+template <class F> inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *n, F, int, size_t) { *n = 1; return cudaSuccess; }
 inline void cudaGraphSetConditional(cudaGraphConditionalHandle, unsigned) {}
+template <class T> inline T __ldcg(const T *p) { return *p; }
+template <class T> inline void __stcg(T *p, T v) { *p = v; }
+#define __cluster_dims__(...)
+struct uint4 { unsigned x, y, z, w; };
+inline long long clock64() { return 0; }
+inline void __threadfence() {}
+inline void __threadfence_system() {}
+inline void __nanosleep(unsigned) {}
+template <class T> inline T atomicExch(T *p, T v) { T o = *p; *p = v; return o; }
+inline void emu_unsupported_ptx() { fprintf(stderr, "emu: this inline-PTX statement is compile-only in the emulation\n"); abort(); }
 template <class T> inline T __ldg(const T *p) { return *p; }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __ffs(int v) { return __builtin_ffs(v); }

@@ -1,18 +1,24 @@
 // TEST INFRASTRUCTURE ONLY (see cuda_runtime.h in this directory): the translation unit of the host-emulation library = the
-// unity build of qpad_b200/csrc/lib.cu without sweep.cu, sim.cu, fused.cu and p2p.cu (cooperative launch, CUDA graphs,
-// peer memory).  The included files are the launch-rewritten copies that tests/emu/build.py writes to _build/; the extern "C"
+// unity build of qpad_b200/csrc/lib.cu without p2p.cu (peer memory).  fused.cu (thread-block clusters) and sweep.cu (cooperative
+// persistent kernel) are compiled so that sim.cu links, but cannot run here: of the slice-loop paths of qpg_sim only the plain
+// per-slice launches (use_graph = 0, qpg_sim_set_fused(s, 0), qpg_sim_set_sweep(s, 0)) are emulated; the others fail loudly.  The included files are the launch-rewritten copies that tests/emu/build.py writes to _build/; the extern "C"
 // entry points are therefore the very code that runs on the GPU, with "device memory" on the host heap.
 #include <cuda_runtime.h>
 #include "fields.cu.cpp"
 #include "particles.cu.cpp"
 #include "beam.cu.cpp"
 #include "laser.cu.cpp"
+#include "fused.cu.cpp"
+#include "sweep.cu.cpp"
+#include "sim.cu.cpp"
 #include "neutral.cu.cpp"
 #include "subcyc.cu.cpp"
 #include "vpot.cu.cpp"
 #include "diag.cu.cpp"
 
 extern "C" {
+// p2p.cu is not part of the emulation
+int qpg_stream_signal(void *, unsigned *, unsigned) { qpg_set_error("qpg_stream_signal: peer-memory transport is not emulated"); return QPG_ERR_UNSUPPORTED; }
 long emu_launches(void) { return emu::g_launches; }
 long emu_barriers(void) { return emu::g_barriers; }
 long emu_collectives(void) { return emu::g_collectives; }

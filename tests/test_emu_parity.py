@@ -13,6 +13,9 @@ from emu import emu
 import kernel_cases as K
 import test_gpu_parity as G
 import test_gpu_laser as GL
+import test_golden as TG
+
+G.PATHS["stream-oplist"] = dict(sweep=0, use_graph=0, fused=0)      # the slab driver the emulation can run: plain per-slice launches
 
 
 @pytest.fixture()
@@ -74,3 +77,32 @@ def test_ionization_loop_matches_oracle(mods):
 def test_subcyc_loop_matches_oracle(mods):
     """the sub-cycled slice loop through qpad_b200.subcyc.SubcycStage"""
     K.subcyc_loop(mods[0], O)
+
+
+# ---- qpg_sim (csrc/sim.cu) on its plain per-slice launch path: the field programs A / C / D as op lists, the particle kernels with
+# the device-side skip flags of the predictor-corrector loop, compaction, look-ahead deposit, beam deposit / push, sorting -------------
+@pytest.mark.parametrize("M", [1, 2])
+def test_slice_loop_matches_oracle(mods, M): G.test_slice_loop_matches_oracle(mods, M, "stream-oplist")
+
+
+def test_one_slice_from_identical_state(mods): G.test_one_slice_from_identical_state(mods, 1, "stream-oplist")
+
+
+def test_full_3d_step_with_beam_push(mods): G.test_full_3d_step_with_beam_push(mods, "stream-oplist")
+
+
+def test_sorted_loop_still_matches(mods): G.test_sorted_loop_still_matches(mods, "stream-oplist")
+
+
+def test_std_pusher_slice_loop(mods): G.test_std_pusher_slice_loop(mods, 0)
+
+
+def test_golden_blowout_fixture(mods):
+    """the committed fixture (tests/golden/blowout_small.npz): 1e-10 per-slice fields, 1e-6 line-outs and beam moments"""
+    TG.test_cuda_blowout_matches_fixture()
+
+
+def test_golden_lwfa_fixture(mods):
+    """laser envelope + ponderomotive pushers + qpg_sim over two 3D steps against tests/golden/lwfa_small.npz (~70 s: the envelope
+    solve is one persistent CTA with 2 log2(nr) barriers per slice)"""
+    TG.test_cuda_lwfa_matches_fixture()
