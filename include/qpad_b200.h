@@ -335,6 +335,13 @@ int qpg_neutral_multi_max(qpg_neutral n);
 int qpg_neutral_update(qpg_neutral n, qpg_field e, qpg_part2d electrons, qpg_part2d ions);
 int qpg_neutral_levels(qpg_neutral n, double *host);      /* [(multi_max + 2)][num_theta][nr], synchronises */
 int qpg_part2d_clear(qpg_part2d p);                        /* npp = 0 on the device */
+/* The neutral species inside the fast path: after this call qpg_sim_run_slices runs the hooks of simulation_class.f03:351-354
+ * (neut%qdp, neut%ion_deposit), :386-388 (neut%amjdp), :404-407 (neut%cbq) and :444-450 (neut%update, push_u, push_x) per slice and
+ * qpg_sim_renew the neutral's renewal (:504-510), on the per-slice launch paths (CUDA-graph replay or plain stream; the persistent
+ * sweep kernel and the cluster programs are switched off).  `electrons` / `ions` are created on qpg_sim_ctx(sim) with npmax >=
+ * nr * num_theta * ppc1 * ppc2.  Extra fields of qpg_sim_field: "neut_q" (the electrons' charge volume), "rho_ion".
+ * Passes against the oracle's ionisation loop in host emulation; NOT YET RUN ON A GPU (tests/test_gpu_neutral.py). */
+int qpg_sim_attach_neutral(qpg_sim sim, qpg_neutral n, qpg_part2d electrons, qpg_part2d ions);
 
 /* ------------------------------------------------------------------------------------------ */
 /* The three groups below were written after round 1's GPU minutes were spent: they pass the oracle comparison on the CPU

@@ -157,6 +157,7 @@ SIGNATURES = {
     "qpg_neutral_update": (_i, [_vp, _vp, _vp, _vp]),
     "qpg_neutral_levels": (_i, [_vp, _vp]),
     "qpg_part2d_clear": (_i, [_vp]),
+    "qpg_sim_attach_neutral": (_i, [_vp, _vp, _vp, _vp]),
     "qpg_part2d_exp_fac_max": (_i, [_vp, _pd]),
     "qpg_part2d_clamp_exp_fac": (_i, [_vp, _d]),
     "qpg_subcyc_step": (_i, [_d, _d, _d, _d, _pd, _pi]),
@@ -577,8 +578,8 @@ class Sim:
     """Fused slice loop (qpg_sim_*): simulation_class.f03:294-512 for one xi slab on one GPU."""
 
     FIELD_DIMS = dict(psi=1, e=3, b=3, e_spe=3, b_spe=3, e_beam=3, b_beam=3, cu=3, amu=3, acu=2, dcu=2, q_spe=1, q_beam=1,
-                      spe_q=1, spe_qn=1, spe_cu=3, spe_dcu=2, spe_amu=3, beam_q=1)
-    HAS_2D = {"psi", "e", "b", "e_spe", "b_spe", "e_beam", "b_beam", "cu", "q_spe", "q_beam", "spe_q", "beam_q"}
+                      spe_q=1, spe_qn=1, spe_cu=3, spe_dcu=2, spe_amu=3, beam_q=1, neut_q=1, rho_ion=1)
+    HAS_2D = {"psi", "e", "b", "e_spe", "b_spe", "e_beam", "b_beam", "cu", "q_spe", "q_beam", "spe_q", "beam_q", "neut_q", "rho_ion"}
 
     def __init__(self, nr, nz, max_mode, rmax, zmin, zmax, dt, sp_qbm=-1.0, sp_npmax=0, beam_qbm=-1.0, beam_npmax=32,
                  beam_push_type=PUSH3_REDUCED, beam_evol=1, iter_max=1, iter_reltol=1e-3, iter_abstol=1e-3, relax_fac=-1.0,
@@ -606,8 +607,18 @@ class Sim:
 
     def laser_advance(self): _chk(self.L.qpg_sim_laser_advance(self.h))
 
+    def attach_neutral(self, element, ion_max, ppc, num_theta, q=-1.0, m=1.0, density=1.0, n0=1.0e17):
+        """a field-ionisation neutral species inside the slice loop (qpg_sim_attach_neutral): per-slice launch paths only"""
+        self.neutral = Neutral(self.ctx, element, ion_max, ppc, num_theta, q, m, density, n0, self.ctx.dxi)
+        _chk(self.L.qpg_sim_attach_neutral(self.h, self.neutral.h, self.neutral.part.h, self.neutral.part_add.h))
+        return self.neutral
+
     def close(self):
         if getattr(self, "h", None):
+            if getattr(self, "neutral", None):
+                self.ctx.sync()
+                self.neutral.close()
+                self.neutral = None
             self.L.qpg_sim_destroy(self.h)
             self.ctx.h = None
         self.h = None

@@ -35,6 +35,11 @@ struct qpg_sim_s {
     long long *sw_trace;  // per-slice time and PC iteration count of the last sweep over each slice [nzp][2]
     double *phi;
     long host_updates, host_iters, host_slices;
+    // field-ionisation neutral species attached with qpg_sim_attach_neutral (not owned): its released electrons and the position
+    // buffer of the ions are two more particle sets of the per-slice launch paths (simulation_class.f03:351-354, :386-388, :444-450)
+    qpg_neutral neut;
+    qpg_part2d neut_e, neut_i;
+    qpg_field neut_q, neut_cu, neut_dcu, neut_amu, rho_ion, rho_ion_add;
 };
 
 // flags: [0] done  [1] PC iterations (since last read)  [2] iteration inside the slice  [3] current slice j
@@ -47,6 +52,15 @@ static void prog_A(qpg_sim s, FProgBuilder &pb)
     o = &pb.add(FOP_ZERO); o->a = s->spe_q->f1; o->da = 1;                                                   // species2d qdp :198
     o = &pb.add(FOP_QFIX); o->a = s->spe->acc1; o->b = s->spe_q->f1; o->da = 1; o->c = (double *)s->spe->d_npp; o->i1 = 1;
     o = &pb.add(FOP_ADD3); o->a = s->spe_q->f1; o->b = s->spe_qn->f1; o->c = s->q_spe->f1; o->da = 1;        // q_spe = 0 + q + qn
+    if (s->neut) {
+        o = &pb.add(FOP_ZERO); o->a = s->neut_q->f1; o->da = 1;                                              // neut%qdp, neutral_class.f03:880
+        o = &pb.add(FOP_QFIX); o->a = s->neut_e->acc1; o->b = s->neut_q->f1; o->da = 1; o->c = (double *)s->neut_e->d_npp; o->i1 = 1;
+        o = &pb.add(FOP_ADD); o->a = s->neut_q->f1; o->b = s->q_spe->f1; o->da = 1;
+        o = &pb.add(FOP_ZERO); o->a = s->rho_ion_add->f1; o->da = 1;                                         // neut%ion_deposit :904-930
+        o = &pb.add(FOP_QFIX); o->a = s->neut_i->acc1; o->b = s->rho_ion_add->f1; o->da = 1; o->i1 = 0;
+        o = &pb.add(FOP_ADD); o->a = s->rho_ion_add->f1; o->b = s->rho_ion->f1; o->da = 1;
+        o = &pb.add(FOP_ADD); o->a = s->rho_ion->f1; o->b = s->q_spe->f1; o->da = 1;
+    }
     o = &pb.add(FOP_PSI); o->a = s->q_spe->f1; o->b = s->psi->f1; o->da = 1;                                  // :356
     o = &pb.add(FOP_BZ); o->a = s->cu->f1; o->b = s->b_spe->f1; o->da = 3;                                    // :360
     o = &pb.add(FOP_PC_BEGIN);
@@ -66,6 +80,15 @@ static void prog_C(qpg_sim s, FProgBuilder &pb)
     o = &pb.add(FOP_COPY); o->a = s->spe_cu->f1; o->b = s->cu->f1; o->da = 3; o->flags = F;                   // cu = 0 + spe%cu :378,:274
     o = &pb.add(FOP_COPY); o->a = s->spe_dcu->f1; o->b = s->acu->f1; o->da = 2; o->flags = F;
     o = &pb.add(FOP_COPY); o->a = s->spe_amu->f1; o->b = s->amu->f1; o->da = 3; o->flags = F;
+    if (s->neut) {                                                                                           // neut%amjdp :932, simulation_class.f03:386-388
+        o = &pb.add(FOP_ZERO); o->a = s->neut_cu->f1; o->da = 3; o->flags = F;
+        o = &pb.add(FOP_ZERO); o->a = s->neut_dcu->f1; o->da = 2; o->flags = F;
+        o = &pb.add(FOP_ZERO); o->a = s->neut_amu->f1; o->da = 3; o->flags = F;
+        o = &pb.add(FOP_AMJFIX); o->a = s->neut_e->acc8; o->b = s->neut_cu->f1; o->c = s->neut_dcu->f1; o->d = s->neut_amu->f1; o->da = 1; o->flags = F;
+        o = &pb.add(FOP_ADD); o->a = s->neut_cu->f1; o->b = s->cu->f1; o->da = 3; o->flags = F;
+        o = &pb.add(FOP_ADD); o->a = s->neut_dcu->f1; o->b = s->acu->f1; o->da = 2; o->flags = F;
+        o = &pb.add(FOP_ADD); o->a = s->neut_amu->f1; o->b = s->amu->f1; o->da = 3; o->flags = F;
+    }
     o = &pb.add(FOP_DJDXI); o->a = s->acu->f1; o->b = s->amu->f1; o->c = s->dcu->f1; o->da = 2; o->flags = F;  // :390
     o = &pb.add(FOP_BTITER); o->a = s->dcu->f1; o->b = s->cu->f1; o->c = s->b_spe->f1; o->da = 2; o->s0 = s->ctx->relax; o->flags = F; // :391
     o = &pb.add(FOP_BZ); o->a = s->cu->f1; o->b = s->b_spe->f1; o->da = 3; o->flags = F;                      // :392
@@ -81,6 +104,11 @@ static void prog_D(qpg_sim s, FProgBuilder &pb)
     FOp *o;
     o = &pb.add(FOP_ADD_DIM); o->a = s->spe_cu->f1; o->b = s->spe_q->f1; o->da = 3; o->db = 1; o->i0 = 2; o->i1 = 0;  // cbq, species2d :396
     o = &pb.add(FOP_SLICE_1TO2); o->a = s->spe_q->f1; o->b = s->spe_q->f2; o->da = 1; o->i0 = -1;
+    if (s->neut) {                                                                                             // neut%cbq :404-407
+        o = &pb.add(FOP_ADD_DIM); o->a = s->neut_cu->f1; o->b = s->neut_q->f1; o->da = 3; o->db = 1; o->i0 = 2; o->i1 = 0;
+        o = &pb.add(FOP_SLICE_1TO2); o->a = s->neut_q->f1; o->b = s->neut_q->f2; o->da = 1; o->i0 = -1;
+        o = &pb.add(FOP_SLICE_1TO2); o->a = s->rho_ion->f1; o->b = s->rho_ion->f2; o->da = 1; o->i0 = -1;
+    }
     o = &pb.add(FOP_SLICE_1TO2); o->a = s->cu->f1; o->b = s->cu->f2; o->da = 3; o->i0 = -1;                    // :409
     o = &pb.add(FOP_ADD_DIM); o->a = s->cu->f1; o->b = s->q_spe->f1; o->da = 3; o->db = 1; o->i0 = 2; o->i1 = 0;  // :410
     o = &pb.add(FOP_SLICE_1TO2); o->a = s->q_spe->f1; o->b = s->q_spe->f2; o->da = 1; o->i0 = -1;              // :411
@@ -144,6 +172,7 @@ static int enqueue_pc_iteration(qpg_sim s)
                                           s->prm.dxi, s->ctx->flags, s->prm.sp_push_std != 0);
     } else rc = part2d_launch_amjdeposit(s->spe, s->e, s->b, s->prm.dxi, s->ctx->flags, s->prm.sp_push_std != 0);
     if (rc) return rc;
+    if (s->neut && (rc = part2d_launch_amjdeposit(s->neut_e, s->e, s->b, s->prm.dxi, s->ctx->flags, 0))) return rc;   // robust pusher (:958)
     if (s->use_fused) return launch_fused(s, 1);
     FProgBuilder pb(s->ctx);
     prog_C(s, pb);
@@ -180,7 +209,17 @@ static int enqueue_slice_tail(qpg_sim s)
     if (rc) return rc;
     rc = part2d_launch_compact(s->spe, s->use_fused ? s->ctx->flags : nullptr);  // update_bound (+ slice counter)
     if (rc) return rc;
-    return part2d_launch_qdeposit(s->spe);                       // next slice's qdp (:346-349) on the advanced particles
+    if ((rc = part2d_launch_qdeposit(s->spe))) return rc;        // next slice's qdp (:346-349) on the advanced particles
+    if (s->neut) {
+        // simulation_class.f03:444-450: ionise with this slice's E and create the released electrons (they are pushed in the same
+        // slice), push the neutral's electrons; then the look-ahead deposits of the next slice's neut%qdp and neut%ion_deposit
+        if ((rc = qpg_neutral_update(s->neut, s->e, s->neut_e, s->neut_i))) return rc;
+        if ((rc = part2d_launch_push(s->neut_e, s->e, s->b, s->prm.dxi, 7))) return rc;
+        if ((rc = part2d_launch_compact(s->neut_e, nullptr))) return rc;
+        if ((rc = part2d_launch_qdeposit(s->neut_e))) return rc;
+        if ((rc = part2d_launch_qdeposit(s->neut_i))) return rc;
+    }
+    return 0;
 }
 
 // ---- persistent slab sweep (sweep.cu) ---------------------------------------------------------------------
@@ -370,6 +409,7 @@ extern "C" int qpg_sim_destroy(qpg_sim s)
     qpg_field all[] = {s->psi, s->e, s->b, s->e_spe, s->b_spe, s->e_beam, s->b_beam, s->cu, s->amu, s->acu, s->dcu, s->q_spe, s->q_beam,
                        s->spe_q, s->spe_qn, s->spe_cu, s->spe_dcu, s->spe_amu, s->beam_q};
     for (auto f : all) qpg_field_destroy(f);
+    for (auto f : {s->neut_q, s->neut_cu, s->neut_dcu, s->neut_amu, s->rho_ion, s->rho_ion_add}) if (f) qpg_field_destroy(f);
     cudaFree(s->phi); cudaFree(s->sw_bar); cudaFree(s->sw_xbuf); cudaFree(s->sw_xll); cudaFree(s->sw_prof); cudaFree(s->sw_trace);
     qpg_laser_destroy(s->laser);
     qpg_part2d_destroy(s->spe);
@@ -385,8 +425,9 @@ extern "C" qpg_field qpg_sim_field(qpg_sim s, const char *name)
     struct { const char *n; qpg_field f; } tbl[] = {
         {"psi", s->psi}, {"e", s->e}, {"b", s->b}, {"e_spe", s->e_spe}, {"b_spe", s->b_spe}, {"e_beam", s->e_beam}, {"b_beam", s->b_beam},
         {"cu", s->cu}, {"amu", s->amu}, {"acu", s->acu}, {"dcu", s->dcu}, {"q_spe", s->q_spe}, {"q_beam", s->q_beam}, {"spe_q", s->spe_q},
-        {"spe_qn", s->spe_qn}, {"spe_cu", s->spe_cu}, {"spe_dcu", s->spe_dcu}, {"spe_amu", s->spe_amu}, {"beam_q", s->beam_q}};
-    for (auto &t : tbl) if (!strcmp(t.n, name)) return t.f;
+        {"spe_qn", s->spe_qn}, {"spe_cu", s->spe_cu}, {"spe_dcu", s->spe_dcu}, {"spe_amu", s->spe_amu}, {"beam_q", s->beam_q},
+        {"neut_q", s->neut_q}, {"rho_ion", s->rho_ion}};
+    for (auto &t : tbl) if (t.f && !strcmp(t.n, name)) return t.f;
     qpg_set_error("unknown field '%s'", name);
     return nullptr;
 }
@@ -449,6 +490,12 @@ extern "C" int qpg_sim_run_slices(qpg_sim s, int j0, int j1)
         // acc1 may hold the look-ahead deposit of a previous range / renewed particles: clear and redo
         CUDA_TRY(cudaMemsetAsync(s->spe->acc1, 0, sizeof(double) * (size_t)(c->nr + 2) * c->P, c->stream));
         if ((rc = part2d_launch_qdeposit(s->spe))) return rc;
+        if (s->neut) {
+            for (qpg_part2d p : {s->neut_e, s->neut_i}) {
+                CUDA_TRY(cudaMemsetAsync(p->acc1, 0, sizeof(double) * (size_t)(c->nr + 2) * c->P, c->stream));
+                if ((rc = part2d_launch_qdeposit(p))) return rc;
+            }
+        }
     }
     if (s->use_sweep) {
         // one persistent launch per stretch of slices between two sorts
@@ -506,10 +553,44 @@ extern "C" int qpg_sim_beam_push(qpg_sim s)
     if (rc) return rc;
     return qpg_part3d_update_bound(s->beam);
 }
+// neut%renew (neutral_class.f03:839-878) + the zeroing of its fields; the particle sets keep npp_hi = npmax so that launches
+// captured in a CUDA graph are sized for any number of released electrons (the kernels bound themselves by the device count)
+static int neutral_renew(qpg_sim s)
+{
+    int rc;
+    if ((rc = qpg_neutral_reset(s->neut))) return rc;
+    for (qpg_part2d p : {s->neut_e, s->neut_i}) {
+        if ((rc = qpg_part2d_clear(p))) return rc;
+        p->npp_hi = p->npmax;
+        CUDA_TRY(cudaMemsetAsync(p->acc1, 0, sizeof(double) * (size_t)(s->ctx->nr + 2) * s->ctx->P, s->ctx->stream));
+    }
+    for (qpg_field f : {s->rho_ion, s->neut_q, s->neut_cu}) if ((rc = qpg_field_fill(f, 0.0))) return rc;
+    return 0;
+}
+// Attaches a neutral species (qpg_neutral_create) and its two particle sets to the slice loop of this sim.  Runs on the per-slice
+// launch paths (CUDA-graph replay or plain stream): the persistent sweep kernel and the cluster programs are switched off.
+// Call before the first qpg_sim_run_slices; the handles stay owned by the caller and must outlive the sim's use of them.
+extern "C" int qpg_sim_attach_neutral(qpg_sim s, qpg_neutral n, qpg_part2d electrons, qpg_part2d ions)
+{
+    ARG_TRY(s && n && electrons && ions && electrons != ions, "null / identical handles");
+    ARG_TRY(electrons->ctx == s->ctx && ions->ctx == s->ctx, "the particle sets must be created on qpg_sim_ctx(sim)");
+    ARG_TRY(!s->neut, "a neutral species is already attached");
+    ARG_TRY(!s->prm.sp_push_std && !s->prm.sp_push_pgc, "neutral species: robust pusher only");
+    qpg_ctx c = s->ctx;
+    int rc;
+    struct { qpg_field *f; int dim, has2d; } tbl[] = {{&s->neut_q, 1, 1}, {&s->neut_cu, 3, 0}, {&s->neut_dcu, 2, 0}, {&s->neut_amu, 3, 0}, {&s->rho_ion, 1, 1}, {&s->rho_ion_add, 1, 0}};
+    for (auto &t : tbl) if ((rc = qpg_field_create(t.f, c, t.dim, s->prm.nzp, t.has2d))) return rc;
+    if (s->graph_ready) { cudaGraphExecDestroy(s->gexec); cudaGraphDestroy(s->graph); s->gexec = nullptr; s->graph = nullptr; s->graph_ready = false; }
+    s->use_sweep = false; s->use_fused = false;
+    s->neut = n; s->neut_e = electrons; s->neut_i = ions;
+    return neutral_renew(s);
+}
 extern "C" int qpg_sim_renew(qpg_sim s)
 {
     ARG_TRY(s, "null sim");
-    return qpg_part2d_renew(s->spe);  // species2d%renew: same lattice, q and qn unchanged for time-independent profiles
+    int rc = qpg_part2d_renew(s->spe);  // species2d%renew: same lattice, q and qn unchanged for time-independent profiles
+    if (rc || !s->neut) return rc;
+    return neutral_renew(s);
 }
 extern "C" int qpg_sim_stats(qpg_sim s, long *updates, long *pc_iters, long *slices)
 {
@@ -529,6 +610,7 @@ extern "C" int qpg_sim_set_fused(qpg_sim s, int on)
 {
     ARG_TRY(s, "null sim");
     const bool can = s->prm.nr <= FT * FC && s->prm.max_mode <= 2;
+    if (on && s->neut) { qpg_set_error("a neutral species runs on the op-list programs only"); return QPG_ERR_UNSUPPORTED; }
     if (on && !can) { qpg_set_error("fused cluster programs need nr <= %d and max_mode <= 2", FT * FC); return QPG_ERR_UNSUPPORTED; }
     if ((on != 0) != s->use_fused && s->graph_ready) {   // the captured graph holds the other variant
         cudaGraphExecDestroy(s->gexec); cudaGraphDestroy(s->graph);
@@ -548,6 +630,7 @@ extern "C" int qpg_sim_laser_advance(qpg_sim s)
 extern "C" int qpg_sim_set_sweep(qpg_sim s, int on)
 {
     ARG_TRY(s, "null sim");
+    if (on && s->neut) { qpg_set_error("a neutral species runs on the per-slice launch paths only"); return QPG_ERR_UNSUPPORTED; }
     if (on && !sweep_supported(s->prm)) { qpg_set_error("the persistent sweep kernel needs max_mode <= 2, nr <= %d and the robust pusher", SW_MAX_TEAM * ST_N); return QPG_ERR_UNSUPPORTED; }
     s->use_sweep = on != 0;
     return 0;

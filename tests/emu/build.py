@@ -24,7 +24,7 @@ PATCH = {
         ("s->use_fused = (prm->nr <= FT * FC && prm->max_mode <= 2);", "s->use_fused = false;"),
         ("s->use_sweep = sweep_supported(*prm);", "s->use_sweep = false;"),
         ("const bool can = s->prm.nr <= FT * FC && s->prm.max_mode <= 2;", "const bool can = false;"),
-        ("if (on && !sweep_supported(s->prm))", "if (on)"),
+        ("if (on && !sweep_supported(s->prm)) {", "if (on) {"),
     ],
 }
 PTX = {

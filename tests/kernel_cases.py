@@ -205,3 +205,65 @@ def ionization_loop(api, O, nsl=48):
         got, want = f.download_f2()[:, :nsl], orc.field(name, 2)[:, :nsl]
         assert np.max(np.abs(want)) > 1e-2 and np.max(np.abs(got - want)) < 1e-8 * np.max(np.abs(want)), name
     st.close()
+
+
+def sim_neutral_loop(api, O, use_graph=0, nsl=40, ion_max=1, with_plasma=False):
+    """the neutral species inside qpg_sim (qpg_sim_attach_neutral; per-slice launch paths) against the oracle's ionisation loop:
+    levels, number / order of the released electrons, fields, and the sim's update and iteration counters"""
+    from qpad_b200 import decks
+    cfg = dict(nr=96, nz=64, max_mode=1, rmax=6.0, zmin=0.0, zmax=8.0, dt=10.0, iter_max=3, iter_reltol=1e-3, iter_abstol=1e-3)
+    bm = decks.beam_std(cfg["nr"], cfg["nz"], cfg["rmax"], cfg["zmin"], cfg["zmax"], **dict(decks.CONFIGS["C5"]["beam"]))
+    orc = O.Sim(sp_density=1.0 if with_plasma else 0.0, neut_on=1, neut_elem=3, neut_ion_max=ion_max, neut_ppc1=2, neut_ppc2=2, neut_num_theta=8,
+                ppc1=2, ppc2=2, num_theta=8, n0=1.0e17, **cfg)
+    orc.set_beam(*bm)
+    upd = orc.run_slices(nsl)
+    lattice = O.inject_uniform(cfg["nr"], cfg["rmax"] / cfg["nr"], 2, 2, 8)
+    if not with_plasma:
+        lattice = tuple(a[:0] for a in lattice)                       # input_file/ionization: nspecies 0
+    sim = api.Sim(sp_npmax=2 * max(len(lattice[4]), 32), beam_npmax=len(bm[2]) + 64, use_graph=use_graph, **cfg)
+    sim.init_species(*lattice)
+    ne = sim.attach_neutral(3, ion_max, (2, 2), 8, n0=1.0e17)
+    sim.beam.upload(*bm)
+    sim.beam_qdp_begin(); sim.beam_qdp_end(); sim.begin_step()
+    sim.run_slices(1, nsl // 2)
+    sim.run_slices(nsl // 2 + 1, nsl)                                 # a second range: the look-ahead deposits are redone
+    u, it, sl = sim.stats()
+    assert sl == nsl and it == orc.total_iters() and u == upd > 1000, (u, upd, it, orc.total_iters())
+    assert np.max(np.abs(ne.levels() - orc.levels(ion_max))) < 1e-10
+    ox, op, og, opsi, oq = orc.neutral()
+    gx, gp, gg, gpsi, gq = ne.part.download()
+    assert len(gq) == len(oq) > 100 and np.max(np.abs(gq - oq)) < 1e-12 and np.max(np.abs(gx - ox)) < 1e-7 and np.max(np.abs(gp - op)) < 1e-7
+    for name in ("psi", "e", "b", "cu", "q_spe"):
+        got, want = sim.field(name).download_f2()[:, :nsl], orc.field(name, 2)[:, :nsl]
+        assert np.max(np.abs(want)) > 1e-2 and np.max(np.abs(got - want)) < 1e-8 * np.max(np.abs(want)), name
+    sim.close()
+
+
+def sim_neutral_full_step(api, O, use_graph=0):
+    """a complete 3D step with the neutral attached (beam push, renewal of the neutral: levels reset, electrons and ions cleared,
+    rho_ion zeroed), then the first slices of the next step, against the oracle"""
+    from qpad_b200 import decks
+    cfg = dict(nr=64, nz=32, max_mode=1, rmax=6.0, zmin=0.0, zmax=8.0, dt=10.0, iter_max=3, iter_reltol=1e-3, iter_abstol=1e-3)
+    bm = decks.beam_std(cfg["nr"], cfg["nz"], cfg["rmax"], cfg["zmin"], cfg["zmax"], **dict(decks.CONFIGS["C5"]["beam"]))
+    orc = O.Sim(sp_density=0.0, neut_on=1, neut_elem=3, neut_ion_max=1, neut_ppc1=2, neut_ppc2=2, neut_num_theta=8, ppc1=2, ppc2=2, num_theta=8, n0=1.0e17, **cfg)
+    orc.set_beam(*bm)
+    orc.step3d(1)
+    orc.run_slices(12)
+    empty = tuple(a[:0] for a in O.inject_uniform(cfg["nr"], cfg["rmax"] / cfg["nr"], 2, 2, 8))
+    sim = api.Sim(sp_npmax=64, beam_npmax=len(bm[2]) + 64, use_graph=use_graph, **cfg)
+    sim.init_species(*empty)
+    ne = sim.attach_neutral(3, 1, (2, 2), 8, n0=1.0e17)
+    sim.beam.upload(*bm)
+    sim.step3d()
+    assert ne.part.npp() == 0 and ne.part_add.npp() == 0
+    sim.beam_qdp_begin(); sim.beam_qdp_end(); sim.begin_step()
+    sim.run_slices(1, 12)
+    assert np.max(np.abs(ne.levels() - orc.levels(1))) < 1e-10 and ne.part.npp() == len(orc.neutral()[4]) > 20
+    for name in ("psi", "e", "rho_ion"):
+        got = sim.field(name).download_f2()[:, :12]
+        want = orc.field(name, 2)[:, :12] if name != "rho_ion" else None
+        if want is not None:
+            assert np.max(np.abs(got - want)) < 1e-8 * np.max(np.abs(want)), name
+        else:
+            assert np.max(np.abs(got)) > 0          # the ions' charge of this step only (zeroed by the renewal)
+    sim.close()

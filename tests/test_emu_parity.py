@@ -106,3 +106,17 @@ def test_golden_lwfa_fixture(mods):
     """laser envelope + ponderomotive pushers + qpg_sim over two 3D steps against tests/golden/lwfa_small.npz (~70 s: the envelope
     solve is one persistent CTA with 2 log2(nr) barriers per slice)"""
     TG.test_cuda_lwfa_matches_fixture()
+
+
+# ---- the neutral species inside qpg_sim (qpg_sim_attach_neutral) ------------------------------------------------------------------
+def test_sim_neutral_loop_matches_oracle(mods):
+    """input_file/ionization in small (nspecies 0, Li, one beam) through the fast-path object"""
+    K.sim_neutral_loop(mods[0], O)
+
+
+def test_sim_neutral_loop_two_levels_with_plasma(mods):
+    K.sim_neutral_loop(mods[0], O, ion_max=2, with_plasma=True, nsl=32)
+
+
+def test_sim_neutral_full_step(mods):
+    K.sim_neutral_full_step(mods[0], O)

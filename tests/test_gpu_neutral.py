@@ -33,3 +33,19 @@ def test_ionization_loop_matches_oracle(mods):
     capi, O = mods
     import kernel_cases as K
     K.ionization_loop(capi, O)
+
+
+@pytest.mark.parametrize("use_graph", [0, 1])
+def test_sim_neutral_loop_matches_oracle(mods, use_graph):
+    """the neutral species inside qpg_sim (qpg_sim_attach_neutral), plain launches and CUDA-graph replay"""
+    capi, O = mods
+    import kernel_cases as K
+    K.sim_neutral_loop(capi, O, use_graph=use_graph)
+    K.sim_neutral_loop(capi, O, use_graph=use_graph, ion_max=2, with_plasma=True, nsl=32)
+
+
+@pytest.mark.parametrize("use_graph", [0, 1])
+def test_sim_neutral_full_step(mods, use_graph):
+    capi, O = mods
+    import kernel_cases as K
+    K.sim_neutral_full_step(capi, O, use_graph=use_graph)
