@@ -37,18 +37,38 @@ def deck_config(name):
     return cfg, beam
 
 
-def make_inputs(cfg, beam, beam_lattice=(256, 512)):
+LEGACY_BEAM = bool(int(os.environ.get("QPAD_BENCH_LEGACY_BEAM", "0")))
+
+
+def make_inputs(cfg, beam, beam_lattice=(256, 512), xi_cells=None):
     """Synthetic inputs of the deck's shape: lattice plasma (deterministic) + tri-Gaussian beam (PCG64 seed 10).
-    The beam lattice is capped at 256 x 512 cells (the C1-class lattice) so the particle count stays ~4e6."""
+    The reference initialises a beam on the simulation grid (ppc per cell); at C2 that would be ~7e7 particles, so on grids finer
+    than the C1-class 256 x 512 lattice the beam is thinned to ONE particle per radial cell width and per slice -- radial lattice of
+    nr / ppc_r cells (particle spacing = dr), the grid's own xi cells with one layer each -- and the charge of a particle is scaled
+    by (nr / lattice cells)^2 (its weight is r / dr_lattice and the radial spacing grows with the lattice cell, both linear), so that
+    the DEPOSITED beam density is the deck's in every node of every slice.  C2: 1.8e7 beam particles.
+    xi_cells = (k0, k1): only the beam of those xi cells (the CPU arm's bounded sample).
+    [Until the end of round 1 the lattice was capped at 256 x 512 WITHOUT the charge scaling: at C2 the beam density was 64x
+    below the deck's on average and present in every 4th slice only -- a weakly driven wake (1.1 predictor-corrector iterations
+    per slice instead of ~4).  QPAD_BENCH_LEGACY_BEAM=1 reproduces those inputs.]"""
     from qpad_b200 import decks
     pl = decks.plasma_uniform(cfg["nr"], cfg["rmax"], cfg["ppc1"], cfg["ppc2"], cfg["num_theta"])
     if beam is None:                      # laser-driven deck (C4): no beam particles
         return pl, (np.zeros((0, 3)), np.zeros((0, 3)), np.zeros(0))
-    bnr, bnz = min(cfg["nr"], beam_lattice[0]), min(cfg["nz"], beam_lattice[1])
     blocks = beam if isinstance(beam, list) else [beam]
-    parts = [decks.beam_std(bnr, bnz, cfg["rmax"], cfg["zmin"], cfg["zmax"], **dict(b, seed=10 + k)) for k, b in enumerate(blocks)]
+    if LEGACY_BEAM:
+        bnr, bnz, qscale = min(cfg["nr"], beam_lattice[0]), min(cfg["nz"], beam_lattice[1]), 1.0
+    else:
+        ppc_r = max(int(b["ppc"][0]) for b in blocks)
+        bnr = cfg["nr"] if cfg["nr"] <= beam_lattice[0] else max(beam_lattice[0], -(-cfg["nr"] // ppc_r))
+        bnz, qscale = cfg["nz"], (cfg["nr"] / bnr) ** 2
+        if cfg["nz"] > beam_lattice[1]:   # keep the particle count: one layer per slice instead of ppc3 layers per (coarser) lattice cell
+            blocks = [dict(b, ppc=(b["ppc"][0], b["ppc"][1], 1)) for b in blocks]
+    if xi_cells is not None:
+        xi_cells = (xi_cells[0] * bnz // cfg["nz"], -(-xi_cells[1] * bnz // cfg["nz"]))
+    parts = [decks.beam_std(bnr, bnz, cfg["rmax"], cfg["zmin"], cfg["zmax"], **dict(b, seed=10 + k, xi_cells=xi_cells)) for k, b in enumerate(blocks)]
     bm = tuple(np.concatenate([p[a] for p in parts]) for a in range(3))      # beams of equal q/m share one particle set
-    return pl, bm
+    return pl, (bm[0], bm[1], bm[2] * qscale)
 
 
 class ClockSampler:
@@ -110,6 +130,10 @@ def cpu_sample(cfg, plasma, beam_arrays, nslices, fast=True, nstages=1):
     if las:                               # C4: robust_pgc plasma + one laser envelope (launched on the host, decks.laser_gaussian)
         from qpad_b200 import decks
         kw.update(sp_push_type=5, laser_on=1, laser_iter=las["iteration"], laser_k0=las["k0"], beam_evol=0)
+    neu = cfg.get("neutral")
+    if neu:                               # C5: nspecies 0, one ADK neutral species (input_file/ionization)
+        kw.update(sp_density=0.0, neut_on=1, neut_elem=neu["element"], neut_ion_max=neu["ion_max"], neut_ppc1=cfg["ppc1"], neut_ppc2=cfg["ppc2"],
+                  neut_num_theta=cfg["num_theta"], neut_density=neu.get("density", 1.0), n0=cfg.get("n0", 1.0e17))
     sim = O.Sim(fast=fast, nstages=nstages, **kw)
     if las:
         sim.set_laser(*decks.laser_gaussian(cfg["nr"], cfg["nz"], cfg["rmax"], cfg["zmin"], cfg["zmax"], **las))
@@ -134,7 +158,7 @@ def _cpu_worker(args):
     bounded sample"""
     name, nslices = args
     cfg, beam = deck_config(name)
-    plasma, bm = make_inputs(cfg, beam)
+    plasma, bm = make_inputs(cfg, beam, xi_cells=(0, nslices + 2))      # the beam charge the sampled slices see
     cpu_sample(cfg, plasma, bm, 2)                      # warm-up (page in, caches)
     if _cpu_barrier is not None:
         _cpu_barrier.wait()                             # all stages start their timed sample together
@@ -643,6 +667,89 @@ def run_b200_local(args):
         dist.destroy_process_group()
 
 
+def run_c5(args):
+    """config 5 (input_file/ionization): nspecies 0, one lithium neutral species ionised by the beam (ADK), electrons created on the
+    device -- one xi stage on one GPU, the neutral attached to qpg_sim (qpg_sim_attach_neutral: per-slice launch path, CUDA-graph
+    replay of the slice body).  A step = one 3D step = nz slices + beam push + renewal; the particle count of a slice grows from 0
+    inside the step, so `value` counts the updates the device counters report (released electrons only)."""
+    import torch
+    from qpad_b200 import capi, decks
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference for the CPU arm)")
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        raise SystemExit("bench.py --config C5: the neutral species runs on one xi stage (one GPU)")
+    cfg, beam = deck_config("C5")
+    neu = cfg["neutral"]
+    _pl, bm = make_inputs(cfg, beam)
+    stream = torch.cuda.Stream()
+    simkw = {k: cfg[k] for k in ("nr", "nz", "max_mode", "rmax", "zmin", "zmax", "dt", "iter_max", "iter_reltol", "iter_abstol")}
+    sim = capi.Sim(sp_npmax=64, beam_npmax=len(bm[2]) + 1024, use_graph=0 if args.no_graph else 1, stream=stream.cuda_stream, **simkw)
+    empty = (np.zeros((0, 2)), np.zeros((0, 3)), np.zeros(0), np.zeros(0), np.zeros(0))
+    sim.init_species(*empty)
+    ne = sim.attach_neutral(neu["element"], neu["ion_max"], (cfg["ppc1"], cfg["ppc2"]), cfg["num_theta"], neu.get("q", -1.0), neu.get("m", 1.0),
+                            neu.get("density", 1.0), cfg.get("n0", 1.0e17))
+    sim.beam.upload(*bm)
+    for _ in range(args.warmup):
+        sim.step3d()
+    torch.cuda.synchronize()
+    u0, i0, s0 = sim.stats()
+    l0 = sim.ctx.launch_count()
+    clk = ClockSampler(0); clk.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        sim.step3d()
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    clocks = clk.stop()
+    u1, i1, s1 = sim.stats()
+    upd, iters, slices = u1 - u0, i1 - i0, s1 - s0
+    # graph replay: head 1, PC iteration 3 (two amjdeposits + program C), tail 12 (program D, push, compact, qdeposit, neutral update 4, push, compact, 2 qdeposits)
+    launches = sim.ctx.launch_count() - l0 if args.no_graph else slices * 13 + 3 * iters + 8 * args.steps
+    t0 = time.perf_counter()
+    ue0 = sim.stats()[0]
+    d2h = 0
+    for _ in range(args.steps):
+        sim.beam.upload(*bm)
+        sim.beam_qdp_begin(); sim.beam_qdp_end(); sim.begin_step()
+        sim.run_slices(1, sim.nzp)
+        ez = sim.field("e").lineout(3, 0, 1); ps = sim.field("psi").lineout(1, 0, 1)
+        d2h = 8 * (len(ez) + len(ps)) + 24
+        sim.stats()
+        sim.beam_push(); sim.renew()
+    torch.cuda.synchronize()
+    te = time.perf_counter() - t0
+    e2e = {"value": (sim.stats()[0] - ue0) / te, "unit": UNIT, "h2d_bytes_per_step": int(56 * len(bm[2])), "d2h_bytes_per_step": int(d2h),
+           "what": "per step: beam particles host->device (qpg_part3d_upload), nz slices with ionisation, E_z and psi on-axis line-outs + counters device->host, beam push, renewal"}
+    peak, peak_src = hbm_peak()
+    nit = iters / max(slices, 1)
+    bpu = 112.0 + 64.0 * nit
+    ach = upd * bpu / (ms * 1e-3) / 1e9
+    roof = {"bound": "hbm", "kernel": "per-slice launch path: k_amjdeposit / k_push / k_qdeposit on the released electrons + k_neutral_ionize / _scan / _add + field programs (the electron count of a slice grows from 0 to its final value inside the step: the ~16 dependent launches of a slice bound it, not the particle bytes)",
+            "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src, "bytes_per_update": bpu,
+            "us_per_slice": ms * 1e3 / max(slices, 1)}
+    cpu = None
+    if not args.no_cpu:
+        try:
+            upd_c, wall_c, k_c, _t = cpu_parallel("C5", args.ref_slices)
+            cpu = {"value": upd_c / wall_c, "unit": UNIT, "cores": k_c, "kind": "port",
+                   "sample": f"{k_c} concurrent stage processes (one per host core) x the first {args.ref_slices} xi slices of the C5 step: {upd_c} updates in {wall_c:.1f} s; oracle restatement, -O3 -march=native"}
+        except Exception as exc:
+            cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {exc}"}
+    line = {"metric": METRIC, "value": upd / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic (no pre-ionised plasma, lithium neutral gas, bi-Gaussian beam of the ionization deck with a fixed-seed NumPy generator)",
+            "config": {"workload": f"C5: nr={cfg['nr']} nz={cfg['nz']} max_mode={cfg['max_mode']} neutral Li ion_max={neu['ion_max']} ppc {cfg['ppc1']}x{cfg['ppc2']} num_theta {cfg['num_theta']}, updates/step={upd // max(args.steps, 1)}",
+                       "parallelism": "single stage, slice body " + ("as plain stream launches" if args.no_graph else "replayed from a CUDA graph (device-side WHILE node for the predictor-corrector loop)"),
+                       "l2": "field volumes ~100 MB + up to 65 MB of electron planes: larger than L2 late in the step", "pc_iters_per_slice": nit},
+            "clocks": clocks, "gpu_launches": int(launches), "roofline": roof, "e2e": e2e}
+    if cpu: line["cpu_baseline"] = cpu
+    print(json.dumps(line))
+    sim.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -661,10 +768,14 @@ def main():
     ap.add_argument("--transport", default=None, choices=["p2p", "nccl"], help="N>1: how the stage hand-offs cross GPUs (default p2p = peer-memory writes + flags, csrc/p2p.cu)")
     ap.add_argument("--stages", type=int, default=0, help="xi-pipeline stages mapped onto SM partitions of ONE GPU (LocalPipeline); 0 = auto (up to 4), 1 = a single sweep kernel on all SMs")
     args = ap.parse_args()
+    if args.config == "C5" and args.ref_slices == 48:
+        args.ref_slices = 300          # ionisation starts where the beam field reaches a few GV/m: the first 48 slices release no electrons
     if args.impl == "reference":
         run_reference(args)
     elif args.config == "C4":
         run_c4(args)
+    elif args.config == "C5":
+        run_c5(args)
     else:
         if args.stages == 0:       # auto: as many stages as the field team (one CTA per 32 radial nodes) and the slab length allow, at most 4
             cfg, _ = deck_config(args.config)

@@ -63,6 +63,10 @@ def beam_std(nr, nz, rmax, zmin, zmax, ppc, num_theta, q, m, gamma, density, cen
     r3 = (range3[0] - zmin, range3[1] - zmin)
     k0 = max(0, int(np.floor(r3[0] / dz)) - 1)
     k1 = min(nz, int(np.ceil(r3[1] / dz)) + 1)
+    if xi_cells is not None:            # only the beam particles of lattice cells xi_cells[0] <= k < xi_cells[1] (a bounded sample of the step)
+        k0, k1 = max(k0, int(xi_cells[0])), min(k1, int(xi_cells[1]))
+        if k1 <= k0:
+            return np.zeros((0, 3)), np.zeros((0, 3)), np.zeros(0)
     rmax_beam = np.hypot(max(abs(range1[0]), abs(range1[1])), max(abs(range2[0]), abs(range2[1])))
     i1max = min(nr, int(np.ceil(rmax_beam / dr)) + 1)
     # loop order of the reference: k, j, i, i3, i2, i1 (innermost)
