@@ -145,6 +145,7 @@ def cpu_sample(cfg, plasma, beam_arrays, nslices, fast=True, nstages=1):
 
 
 _cpu_barrier = None
+LAST_CPU_NIT = None
 
 
 def _cpu_init(barrier):
@@ -163,8 +164,8 @@ def _cpu_worker(args):
     if _cpu_barrier is not None:
         _cpu_barrier.wait()                             # all stages start their timed sample together
     t0 = time.time()
-    upd, dt, _ = cpu_sample(cfg, plasma, bm, nslices)
-    return upd, dt, t0, time.time()
+    upd, dt, iters = cpu_sample(cfg, plasma, bm, nslices)
+    return upd, dt, t0, time.time(), iters / max(nslices, 1)
 
 
 def cpu_parallel(name, nslices, ncores=None):
@@ -176,8 +177,10 @@ def cpu_parallel(name, nslices, ncores=None):
     ctx = mp.get_context("spawn")
     with ctx.Pool(k, initializer=_cpu_init, initargs=(ctx.Barrier(k),)) as pool:
         res = pool.map(_cpu_worker, [(name, nslices)] * k, chunksize=1)
+    global LAST_CPU_NIT
     upd = sum(r[0] for r in res)
     wall = max(r[3] for r in res) - min(r[2] for r in res)
+    LAST_CPU_NIT = float(np.mean([r[4] for r in res]))   # predictor-corrector iterations per slice of the sample (the GPU arm's whole step takes more inside the beam)
     return upd, wall, k, max(r[1] for r in res)
 
 
@@ -200,7 +203,8 @@ def run_reference(args):
             "data": "synthetic (lattice plasma, PCG64(10) tri-Gaussian beam)",
             "config": {"workload": f"{args.config}: nr={cfg['nr']} nz={cfg['nz']} max_mode={cfg['max_mode']} Np/slice={len(plasma[4])}", "parallelism": f"cpu: {k} stage processes (one per host core)"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": k, "kind": "port",
-                             "sample": f"per timed step: {k} concurrent stage processes x the first {nsl} xi slices of the {args.config} 3D step (oracle restatement of the reference algorithm, -O3 -march=native; the Fortran reference is MPI-pipelined with one single-threaded rank per core and cannot be built here)"},
+                             "sample": f"per timed step: {k} concurrent stage processes x the first {nsl} xi slices of the {args.config} 3D step ({LAST_CPU_NIT:.2f} predictor-corrector iterations per slice in this sample; oracle restatement of the reference algorithm, -O3 -march=native; the Fortran reference is MPI-pipelined with one single-threaded rank per core and cannot be built here)",
+                             "pc_iters_per_slice": LAST_CPU_NIT},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line))
 
@@ -363,7 +367,7 @@ def run_b200(args):
             try:
                 upd_c, wall_c, k_c, tmax_c = cpu_parallel(args.config, args.ref_slices)
                 cpu = {"value": upd_c / wall_c, "unit": UNIT, "cores": k_c, "kind": "port",
-                       "sample": f"{k_c} concurrent stage processes (one per host core, the reference's MPI xi-pipeline in steady state) x the first {args.ref_slices} xi slices of the {args.config} step: {upd_c} updates in {wall_c:.1f} s; oracle restatement, -O3 -march=native"}
+                       "sample": f"{k_c} concurrent stage processes (one per host core, the reference's MPI xi-pipeline in steady state) x the first {args.ref_slices} xi slices of the {args.config} step ({LAST_CPU_NIT:.2f} predictor-corrector iterations per slice in this sample): {upd_c} updates in {wall_c:.1f} s; oracle restatement, -O3 -march=native"}
             except Exception as exc:  # the GPU result must not be lost to a CPU-side problem
                 cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {exc}"}
 
@@ -641,7 +645,7 @@ def run_b200_local(args):
         try:
             upd_c, wall_c, k_c, tmax_c = cpu_parallel(args.config, args.ref_slices)
             cpu = {"value": upd_c / wall_c, "unit": UNIT, "cores": k_c, "kind": "port",
-                   "sample": f"{k_c} concurrent stage processes (one per host core, the reference's MPI xi-pipeline in steady state) x the first {args.ref_slices} xi slices of the {args.config} step: {upd_c} updates in {wall_c:.1f} s; oracle restatement, -O3 -march=native"}
+                   "sample": f"{k_c} concurrent stage processes (one per host core, the reference's MPI xi-pipeline in steady state) x the first {args.ref_slices} xi slices of the {args.config} step ({LAST_CPU_NIT:.2f} predictor-corrector iterations per slice in this sample): {upd_c} updates in {wall_c:.1f} s; oracle restatement, -O3 -march=native"}
         except Exception as exc:
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {exc}"}
     if rank == 0:
