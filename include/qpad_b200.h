@@ -342,6 +342,13 @@ int qpg_part2d_clear(qpg_part2d p);                        /* npp = 0 on the dev
  * nr * num_theta * ppc1 * ppc2.  Extra fields of qpg_sim_field: "neut_q" (the electrons' charge volume), "rho_ion".
  * Passes against the oracle's ionisation loop in host emulation; NOT YET RUN ON A GPU (tests/test_gpu_neutral.py). */
 int qpg_sim_attach_neutral(qpg_sim sim, qpg_neutral n, qpg_part2d electrons, qpg_part2d ions);
+/* The sub-cycling variant inside the fast path (proj_subcyc/simulation_subcyc_class.f03:216-376; input-deck keys
+ * expansion_fac_max, expansion_fac_clamped, dt_min of simulation_subcyc): per slice the largest expansion factor of the plasma (and
+ * of an attached neutral's electrons) chooses n_subcyc, the slice body is repeated with dxi / n_subcyc, pushed particles are
+ * clamped.  Plain per-slice launches with one host synchronisation per slice (the reference's allreduce); no graph, no sweep kernel.
+ * qpg_sim_subcycles = sub-steps taken so far.  Passes against the oracle in host emulation; NOT YET RUN ON A GPU. */
+int qpg_sim_set_subcyc(qpg_sim sim, int on, double exp_fac_max, double exp_fac_clamped, double dt_min);
+long qpg_sim_subcycles(qpg_sim sim);
 
 /* ------------------------------------------------------------------------------------------ */
 /* The three groups below were written after round 1's GPU minutes were spent: they pass the oracle comparison on the CPU

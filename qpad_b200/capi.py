@@ -158,6 +158,8 @@ SIGNATURES = {
     "qpg_neutral_levels": (_i, [_vp, _vp]),
     "qpg_part2d_clear": (_i, [_vp]),
     "qpg_sim_attach_neutral": (_i, [_vp, _vp, _vp, _vp]),
+    "qpg_sim_set_subcyc": (_i, [_vp, _i, _d, _d, _d]),
+    "qpg_sim_subcycles": (_l, [_vp]),
     "qpg_part2d_exp_fac_max": (_i, [_vp, _pd]),
     "qpg_part2d_clamp_exp_fac": (_i, [_vp, _d]),
     "qpg_subcyc_step": (_i, [_d, _d, _d, _d, _pd, _pi]),
@@ -606,6 +608,12 @@ class Sim:
         self.laser = Laser(self.ctx, nzp, laser_k0, dt, laser_iter, handle=lh) if lh else None
 
     def laser_advance(self): _chk(self.L.qpg_sim_laser_advance(self.h))
+
+    def set_subcyc(self, exp_fac_max, exp_fac_clamped, dt_min, on=True):
+        """the sub-cycling variant of the slice loop (proj_subcyc): plain per-slice launches, one host synchronisation per slice"""
+        _chk(self.L.qpg_sim_set_subcyc(self.h, int(on), exp_fac_max, exp_fac_clamped, dt_min))
+
+    def subcycles(self): return self.L.qpg_sim_subcycles(self.h)
 
     def attach_neutral(self, element, ion_max, ppc, num_theta, q=-1.0, m=1.0, density=1.0, n0=1.0e17):
         """a field-ionisation neutral species inside the slice loop (qpg_sim_attach_neutral): per-slice launch paths only"""

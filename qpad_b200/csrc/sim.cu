@@ -37,6 +37,11 @@ struct qpg_sim_s {
     long host_updates, host_iters, host_slices;
     // field-ionisation neutral species attached with qpg_sim_attach_neutral (not owned): its released electrons and the position
     // buffer of the ions are two more particle sets of the per-slice launch paths (simulation_class.f03:351-354, :386-388, :444-450)
+    // sub-cycling variant (qpg_sim_set_subcyc; proj_subcyc/simulation_subcyc_class.f03:216-376): plain per-slice launches only
+    bool subcyc;
+    double sc_exp_fac_max, sc_exp_fac_clamped, sc_dt_min;
+    double cur_dt;        // xi step of the deposits / pushes being enqueued (dxi, or dxi / n_subcyc)
+    long host_subcycles;
     qpg_neutral neut;
     qpg_part2d neut_e, neut_i;
     qpg_field neut_q, neut_cu, neut_dcu, neut_amu, rho_ion, rho_ion_add;
@@ -44,17 +49,17 @@ struct qpg_sim_s {
 
 // flags: [0] done  [1] PC iterations (since last read)  [2] iteration inside the slice  [3] current slice j
 //        [4] slices executed  ;  counters (long long) live in conv_out[4..] reinterpret: updates
-static void prog_A(qpg_sim s, FProgBuilder &pb)
+static void prog_A(qpg_sim s, FProgBuilder &pb, int count_updates = 1)
 {
     FOp *o;
     o = &pb.add(FOP_SLICE_2TO1); o->a = s->q_beam->f1; o->b = s->q_beam->f2; o->da = 1; o->i0 = -1;          // :344
     o = &pb.add(FOP_BT); o->a = s->q_beam->f1; o->b = s->b_beam->f1; o->da = 1;                               // :345
     o = &pb.add(FOP_ZERO); o->a = s->spe_q->f1; o->da = 1;                                                   // species2d qdp :198
-    o = &pb.add(FOP_QFIX); o->a = s->spe->acc1; o->b = s->spe_q->f1; o->da = 1; o->c = (double *)s->spe->d_npp; o->i1 = 1;
+    o = &pb.add(FOP_QFIX); o->a = s->spe->acc1; o->b = s->spe_q->f1; o->da = 1; o->c = (double *)s->spe->d_npp; o->i1 = count_updates;
     o = &pb.add(FOP_ADD3); o->a = s->spe_q->f1; o->b = s->spe_qn->f1; o->c = s->q_spe->f1; o->da = 1;        // q_spe = 0 + q + qn
     if (s->neut) {
         o = &pb.add(FOP_ZERO); o->a = s->neut_q->f1; o->da = 1;                                              // neut%qdp, neutral_class.f03:880
-        o = &pb.add(FOP_QFIX); o->a = s->neut_e->acc1; o->b = s->neut_q->f1; o->da = 1; o->c = (double *)s->neut_e->d_npp; o->i1 = 1;
+        o = &pb.add(FOP_QFIX); o->a = s->neut_e->acc1; o->b = s->neut_q->f1; o->da = 1; o->c = (double *)s->neut_e->d_npp; o->i1 = count_updates;
         o = &pb.add(FOP_ADD); o->a = s->neut_q->f1; o->b = s->q_spe->f1; o->da = 1;
         o = &pb.add(FOP_ZERO); o->a = s->rho_ion_add->f1; o->da = 1;                                         // neut%ion_deposit :904-930
         o = &pb.add(FOP_QFIX); o->a = s->neut_i->acc1; o->b = s->rho_ion_add->f1; o->da = 1; o->i1 = 0;
@@ -169,10 +174,10 @@ static int enqueue_pc_iteration(qpg_sim s)
     if (s->prm.sp_push_pgc) {    // species2d_class.f03:256-259 amjdeposit_{std,robust}_pgc with laser_all's slice images
         qpg_laser l = s->laser;
         rc = part2d_launch_amjdeposit_pgc(s->spe, s->e, s->b, qpg_laser_field(l, 0), qpg_laser_field(l, 1), qpg_laser_field(l, 2), qpg_laser_field(l, 3),
-                                          s->prm.dxi, s->ctx->flags, s->prm.sp_push_std != 0);
-    } else rc = part2d_launch_amjdeposit(s->spe, s->e, s->b, s->prm.dxi, s->ctx->flags, s->prm.sp_push_std != 0);
+                                          s->cur_dt, s->ctx->flags, s->prm.sp_push_std != 0);
+    } else rc = part2d_launch_amjdeposit(s->spe, s->e, s->b, s->cur_dt, s->ctx->flags, s->prm.sp_push_std != 0);
     if (rc) return rc;
-    if (s->neut && (rc = part2d_launch_amjdeposit(s->neut_e, s->e, s->b, s->prm.dxi, s->ctx->flags, 0))) return rc;   // robust pusher (:958)
+    if (s->neut && (rc = part2d_launch_amjdeposit(s->neut_e, s->e, s->b, s->cur_dt, s->ctx->flags, 0))) return rc;   // robust pusher (:958)
     if (s->use_fused) return launch_fused(s, 1);
     FProgBuilder pb(s->ctx);
     prog_C(s, pb);
@@ -220,6 +225,46 @@ static int enqueue_slice_tail(qpg_sim s)
         if ((rc = part2d_launch_qdeposit(s->neut_i))) return rc;
     }
     return 0;
+}
+
+// ---- sub-cycling variant of the slice body (proj_subcyc/simulation_subcyc_class.f03:216-376) -------------------------------
+// The largest expansion factor gamma / (gamma - p_z) of the plasma decides the number of sub-steps (:229-236, :431-451: one host
+// synchronisation per slice, as the reference's mpi_allreduce); the deposit / solve / predictor-corrector / push sequence is
+// repeated with dxi / n_subcyc, pushed particles are clamped (:298-309), the slice is stored once (:330-362, the full dxi).
+int qpg_part2d_exp_fac_max(qpg_part2d p, double *exp_fac_max);
+int qpg_part2d_clamp_exp_fac(qpg_part2d p, double exp_fac_clamped);
+int qpg_subcyc_step(double exp_fac, double exp_fac_max, double dt, double dt_min, double *dt_subcyc, int *n_subcyc);
+static int enqueue_slice_subcyc(qpg_sim s)
+{
+    int rc, n_sub = 1;
+    double fac = 1.0, f, dt_sub = s->prm.dxi;
+    if ((rc = qpg_part2d_exp_fac_max(s->spe, &f))) return rc;
+    if (f > fac) fac = f;
+    if (s->neut) { if ((rc = qpg_part2d_exp_fac_max(s->neut_e, &f))) return rc; if (f > fac) fac = f; }
+    if ((rc = qpg_subcyc_step(fac, s->sc_exp_fac_max, s->prm.dxi, s->sc_dt_min, &dt_sub, &n_sub))) return rc;
+    s->host_subcycles += n_sub;
+    s->cur_dt = dt_sub;
+    for (int isub = 0; isub < n_sub && !rc; isub++) {
+        { FProgBuilder pb(s->ctx); prog_A(s, pb, isub == 0); if ((rc = pb.launch(TP_FIELD_FUSED))) break; }
+        for (int l = 0; l < s->prm.iter_max; l++) if ((rc = enqueue_pc_iteration(s))) break;
+        if (rc) break;
+        qpg_part2d sets[2] = {s->spe, s->neut ? s->neut_e : nullptr};
+        for (qpg_part2d p : sets) {
+            if (!p) continue;
+            if (p == s->neut_e && (rc = qpg_neutral_update(s->neut, s->e, s->neut_e, s->neut_i))) break;   // :312-317, inside every sub-step
+            if ((rc = part2d_launch_push(p, s->e, s->b, dt_sub, 1))) break;                                    // push_u
+            if ((rc = qpg_part2d_clamp_exp_fac(p, s->sc_exp_fac_clamped))) break;
+            if ((rc = part2d_launch_push(p, s->e, s->b, dt_sub, 6))) break;                                    // push_x + bound flags
+            if ((rc = part2d_launch_compact(p, nullptr))) break;
+            if ((rc = part2d_launch_qdeposit(p))) break;                                                       // the next sub-step's / slice's qdp
+        }
+        if (!rc && s->neut) rc = part2d_launch_qdeposit(s->neut_i);
+    }
+    s->cur_dt = s->prm.dxi;
+    if (rc) return rc;
+    FProgBuilder pb(s->ctx);
+    prog_D(s, pb);
+    return pb.launch(TP_FIELD_FUSED);
 }
 
 // ---- persistent slab sweep (sweep.cu) ---------------------------------------------------------------------
@@ -384,6 +429,7 @@ extern "C" int qpg_sim_create(qpg_sim *out, int device, void *cuda_stream, const
         {&s->cu, 3, 1}, {&s->amu, 3, 0}, {&s->acu, 2, 0}, {&s->dcu, 2, 0}, {&s->q_spe, 1, 1}, {&s->q_beam, 1, 1},
         {&s->spe_q, 1, 1}, {&s->spe_qn, 1, 0}, {&s->spe_cu, 3, 0}, {&s->spe_dcu, 2, 0}, {&s->spe_amu, 3, 0}, {&s->beam_q, 1, 1}};
     for (auto &t : tbl) { rc = qpg_field_create(t.f, c, t.dim, nzp, t.has2d); if (rc) return rc; }
+    s->cur_dt = prm->dxi;
     s->use_fused = (prm->nr <= FT * FC && prm->max_mode <= 2);
     s->use_sweep = sweep_supported(*prm);
     CUDA_TRY(cudaMalloc(&s->phi, sizeof(double) * (size_t)(prm->nr + 2) * c->P));
@@ -520,6 +566,8 @@ extern "C" int qpg_sim_run_slices(qpg_sim s, int j0, int j1)
         if (s->prm.use_graph) {
             CUDA_TRY(cudaGraphLaunch(s->gexec, c->stream));
             c->launches += 5 + 2;  // head, tail x4, >= 1 PC iteration (exact count comes from the device iteration counter)
+        } else if (s->subcyc) {
+            if ((rc = enqueue_slice_subcyc(s))) return rc;
         } else {
             if ((rc = enqueue_slice_head(s))) return rc;
             for (int l = 0; l < s->prm.iter_max; l++) if ((rc = enqueue_pc_iteration(s))) return rc;
@@ -585,6 +633,19 @@ extern "C" int qpg_sim_attach_neutral(qpg_sim s, qpg_neutral n, qpg_part2d elect
     s->neut = n; s->neut_e = electrons; s->neut_i = ions;
     return neutral_renew(s);
 }
+// Switches the sub-cycling variant of the slice loop on (off): plain per-slice launches with one host synchronisation per slice.
+extern "C" int qpg_sim_set_subcyc(qpg_sim s, int on, double exp_fac_max, double exp_fac_clamped, double dt_min)
+{
+    ARG_TRY(s, "null sim");
+    if (!on) { s->subcyc = false; return 0; }
+    ARG_TRY(exp_fac_max > 1.0 && exp_fac_clamped > 1.0 && dt_min >= 0.0, "expansion factors must exceed 1");
+    ARG_TRY(!s->prm.sp_push_std && !s->prm.sp_push_pgc, "sub-cycling: robust pusher only");
+    if (s->graph_ready) { cudaGraphExecDestroy(s->gexec); cudaGraphDestroy(s->graph); s->gexec = nullptr; s->graph = nullptr; s->graph_ready = false; }
+    s->subcyc = true; s->sc_exp_fac_max = exp_fac_max; s->sc_exp_fac_clamped = exp_fac_clamped; s->sc_dt_min = dt_min;
+    s->use_sweep = false; s->use_fused = false; s->prm.use_graph = 0;
+    return 0;
+}
+extern "C" long qpg_sim_subcycles(qpg_sim s) { return s ? s->host_subcycles : -1; }
 extern "C" int qpg_sim_renew(qpg_sim s)
 {
     ARG_TRY(s, "null sim");
@@ -610,7 +671,7 @@ extern "C" int qpg_sim_set_fused(qpg_sim s, int on)
 {
     ARG_TRY(s, "null sim");
     const bool can = s->prm.nr <= FT * FC && s->prm.max_mode <= 2;
-    if (on && s->neut) { qpg_set_error("a neutral species runs on the op-list programs only"); return QPG_ERR_UNSUPPORTED; }
+    if (on && (s->neut || s->subcyc)) { qpg_set_error("a neutral species / sub-cycling runs on the op-list programs only"); return QPG_ERR_UNSUPPORTED; }
     if (on && !can) { qpg_set_error("fused cluster programs need nr <= %d and max_mode <= 2", FT * FC); return QPG_ERR_UNSUPPORTED; }
     if ((on != 0) != s->use_fused && s->graph_ready) {   // the captured graph holds the other variant
         cudaGraphExecDestroy(s->gexec); cudaGraphDestroy(s->graph);
@@ -619,7 +680,7 @@ extern "C" int qpg_sim_set_fused(qpg_sim s, int on)
     s->use_fused = on != 0;
     return 0;
 }
-extern "C" int qpg_sim_set_graph(qpg_sim s, int use_graph) { ARG_TRY(s, "null sim"); s->prm.use_graph = use_graph != 0; return 0; }
+extern "C" int qpg_sim_set_graph(qpg_sim s, int use_graph) { ARG_TRY(s, "null sim"); ARG_TRY(!(use_graph && s->subcyc), "sub-cycling needs the plain launch path"); s->prm.use_graph = use_graph != 0; return 0; }
 extern "C" qpg_laser qpg_sim_laser(qpg_sim s) { return s ? s->laser : nullptr; }
 extern "C" int qpg_sim_laser_advance(qpg_sim s)
 {
@@ -630,7 +691,7 @@ extern "C" int qpg_sim_laser_advance(qpg_sim s)
 extern "C" int qpg_sim_set_sweep(qpg_sim s, int on)
 {
     ARG_TRY(s, "null sim");
-    if (on && s->neut) { qpg_set_error("a neutral species runs on the per-slice launch paths only"); return QPG_ERR_UNSUPPORTED; }
+    if (on && (s->neut || s->subcyc)) { qpg_set_error("a neutral species / sub-cycling runs on the per-slice launch paths only"); return QPG_ERR_UNSUPPORTED; }
     if (on && !sweep_supported(s->prm)) { qpg_set_error("the persistent sweep kernel needs max_mode <= 2, nr <= %d and the robust pusher", SW_MAX_TEAM * ST_N); return QPG_ERR_UNSUPPORTED; }
     s->use_sweep = on != 0;
     return 0;

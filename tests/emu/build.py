@@ -20,7 +20,7 @@ SOURCES = ["fields.cu", "particles.cu", "beam.cu", "laser.cu", "fused.cu", "swee
 PATCH = {
     "sim.cu": [
         ("s->prm = *prm;", "s->prm = *prm; s->prm.use_graph = 0;"),
-        ("s->prm.use_graph = use_graph != 0;", "(void)use_graph;"),
+        ("s->prm.use_graph = use_graph != 0; return 0; }", "(void)use_graph; return 0; }"),
         ("s->use_fused = (prm->nr <= FT * FC && prm->max_mode <= 2);", "s->use_fused = false;"),
         ("s->use_sweep = sweep_supported(*prm);", "s->use_sweep = false;"),
         ("const bool can = s->prm.nr <= FT * FC && s->prm.max_mode <= 2;", "const bool can = false;"),

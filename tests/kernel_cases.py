@@ -267,3 +267,43 @@ def sim_neutral_full_step(api, O, use_graph=0):
         else:
             assert np.max(np.abs(got)) > 0          # the ions' charge of this step only (zeroed by the renewal)
     sim.close()
+
+
+def sim_subcyc_loop(api, O, with_neutral=False):
+    """the sub-cycling variant inside qpg_sim (qpg_sim_set_subcyc) against the oracle's sub-cycled loop: number of sub-steps,
+    iterations, update counter, fields, particle momenta (clamped)"""
+    from qpad_b200 import decks
+    if with_neutral:
+        cfg = dict(nr=96, nz=64, max_mode=1, rmax=6.0, zmin=0.0, zmax=8.0, dt=10.0, iter_max=3, iter_reltol=1e-3, iter_abstol=1e-3)
+        bm = decks.beam_std(cfg["nr"], cfg["nz"], cfg["rmax"], cfg["zmin"], cfg["zmax"], **dict(decks.CONFIGS["C5"]["beam"]))
+        okw = dict(sp_density=0.0, neut_on=1, neut_elem=3, neut_ion_max=1, neut_ppc1=2, neut_ppc2=2, neut_num_theta=8, n0=1.0e17)
+        nsl, cases = 48, ((1.002, 1.01, 1e-4),)
+    else:
+        cfg = dict(nr=64, nz=32, max_mode=1, rmax=5.0, zmin=-5.0, zmax=5.0, dt=10.0, iter_max=3, iter_reltol=1e-3, iter_abstol=1e-3)
+        bm = decks.beam_std(cfg["nr"], cfg["nz"], cfg["rmax"], cfg["zmin"], cfg["zmax"], **dict(decks.CONFIGS["C1"]["beam"]))
+        okw = {}
+        nsl, cases = 24, ((1.1, 50.0, 1e-3), (1.05, 1.6, 1e-3))
+    for efm, clamp, dtmin in cases:
+        orc = O.Sim(ppc1=2, ppc2=2, num_theta=8, subcyc_on=1, subcyc_exp_fac_max=efm, subcyc_exp_fac_clamped=clamp, subcyc_dt_min=dtmin, **okw, **cfg)
+        orc.set_beam(*bm)
+        upd = orc.run_slices(nsl)
+        lattice = O.inject_uniform(cfg["nr"], cfg["rmax"] / cfg["nr"], 2, 2, 8)
+        if with_neutral:
+            lattice = tuple(a[:0] for a in lattice)
+        sim = api.Sim(sp_npmax=2 * max(len(lattice[4]), 32), beam_npmax=len(bm[2]) + 64, **cfg)
+        sim.init_species(*lattice)
+        ne = sim.attach_neutral(3, 1, (2, 2), 8, n0=1.0e17) if with_neutral else None
+        sim.set_subcyc(efm, clamp, dtmin)
+        sim.beam.upload(*bm)
+        sim.beam_qdp_begin(); sim.beam_qdp_end(); sim.begin_step()
+        sim.run_slices(1, nsl)
+        u, it, sl = sim.stats()
+        assert sim.subcycles() == orc.total_subcycles() > nsl, (sim.subcycles(), orc.total_subcycles())
+        assert sl == nsl and it == orc.total_iters() and u == upd, (u, upd, it, orc.total_iters())
+        for name in ("psi", "e", "b", "cu"):
+            got, want = sim.field(name).download_f2()[:, :nsl], orc.field(name, 2)[:, :nsl]
+            assert np.max(np.abs(want)) > 1e-3 and np.max(np.abs(got - want)) < 1e-8 * np.max(np.abs(want)), name
+        ox, op, og, opsi, oq = orc.neutral() if with_neutral else orc.plasma()
+        gx, gp, gg, gpsi, gq = (ne.part if with_neutral else sim.species).download()
+        assert len(gq) == len(oq) > 50 and np.max(np.abs(gp - op)) < 1e-7 and np.max(np.abs(gx - ox)) < 1e-7
+        sim.close()

@@ -120,3 +120,13 @@ def test_sim_neutral_loop_two_levels_with_plasma(mods):
 
 def test_sim_neutral_full_step(mods):
     K.sim_neutral_full_step(mods[0], O)
+
+
+# ---- the sub-cycling variant inside qpg_sim (qpg_sim_set_subcyc) ------------------------------------------------------------------
+def test_sim_subcyc_loop_matches_oracle(mods):
+    K.sim_subcyc_loop(mods[0], O)
+
+
+def test_sim_subcyc_with_neutral_matches_oracle(mods):
+    """both at once: the released electrons are sub-cycled and clamped too, the ionisation runs in every sub-step (:312-323)"""
+    K.sim_subcyc_loop(mods[0], O, with_neutral=True)

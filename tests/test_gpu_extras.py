@@ -43,3 +43,10 @@ def test_subcyc_loop_matches_oracle(mods):
     """the sub-cycled slice loop through the per-routine C-ABI (qpad_b200.subcyc.SubcycStage) against the oracle's"""
     capi, O, K = mods
     K.subcyc_loop(capi, O)
+
+
+@pytest.mark.parametrize("with_neutral", [False, True])
+def test_sim_subcyc_loop_matches_oracle(mods, with_neutral):
+    """the sub-cycling variant inside qpg_sim (qpg_sim_set_subcyc), without and with an attached neutral species"""
+    capi, O, K = mods
+    K.sim_subcyc_loop(capi, O, with_neutral=with_neutral)
