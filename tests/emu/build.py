@@ -106,6 +106,12 @@ def transform_file(name, text):
 
 
 def build(force=False):
+    """QPAD_EMU_ASAN=1: the AddressSanitizer build (run python with LD_PRELOAD=$(gcc -print-file-name=libasan.so) and
+    ASAN_OPTIONS=detect_leaks=0:detect_stack_use_after_return=0): every access of a kernel to 'device' memory (the host heap) is
+    bounds-checked -- a memcheck of the device sources without a GPU."""
+    global LIB
+    asan = bool(int(os.environ.get("QPAD_EMU_ASAN", "0")))
+    LIB = os.path.join(OUT, "libqpademu_asan.so" if asan else "libqpademu.so")
     os.makedirs(OUT, exist_ok=True)
     srcs = [os.path.join(CSRC, f) for f in SOURCES if os.path.exists(os.path.join(CSRC, f))]
     deps = srcs + [os.path.join(HERE, f) for f in ("cuda_runtime.h", "emu_lib.cpp", "build.py")] + [os.path.join(CSRC, "common.cuh"),
@@ -118,7 +124,8 @@ def build(force=False):
         with open(os.path.join(OUT, os.path.basename(s) + ".cpp"), "w") as f:
             f.write(t)
     defs = [f"-DEMU_HAVE_{os.path.basename(s).split('.')[0].upper()}" for s in srcs]
-    subprocess.check_call(["g++", "-std=c++17", "-O1", "-g", "-ffp-contract=off", "-fPIC", "-shared", "-I", HERE, "-I", OUT, "-I", CSRC] + defs +
+    san = ["-fsanitize=address", "-fno-omit-frame-pointer"] if asan else []
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-g", "-ffp-contract=off", "-fPIC", "-shared"] + san + ["-I", HERE, "-I", OUT, "-I", CSRC] + defs +
                           [os.path.join(HERE, "emu_lib.cpp"), "-o", LIB])
     return LIB
 
