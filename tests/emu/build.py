@@ -13,10 +13,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "qpad_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
-COMPILE_ONLY = ["fused.cu", "sweep.cu"]        # needed to link sim.cu; their kernels need live clusters / a live grid and are not run
+COMPILE_ONLY = ["fused.cu"]        # needed to link sim.cu; its kernels need live thread-block clusters and are not run
 SOURCES = ["fields.cu", "particles.cu", "beam.cu", "laser.cu", "fused.cu", "sweep.cu", "sim.cu", "neutral.cu", "subcyc.cu", "vpot.cu", "diag.cu"]
-# the emulation runs only the plain per-slice launches of qpg_sim: CUDA-graph replay, the cluster programs and the sweep kernel
-# are switched off (a request for graphs is ignored -- same launches, replayed or not; the other two refuse to be switched on)
+# by default the emulation runs the plain per-slice launches of qpg_sim: a request for CUDA graphs is ignored (same launches,
+# replayed or not), the cluster programs refuse to be switched on, the persistent sweep kernel is off unless qpg_sim_set_sweep(s, 1)
 PATCH = {
     "sim.cu": [
         ("s->prm = *prm;", "s->prm = *prm; s->prm.use_graph = 0;"),
@@ -24,10 +24,28 @@ PATCH = {
         ("s->use_fused = (prm->nr <= FT * FC && prm->max_mode <= 2);", "s->use_fused = false;"),
         ("s->use_sweep = sweep_supported(*prm);", "s->use_sweep = false;"),
         ("const bool can = s->prm.nr <= FT * FC && s->prm.max_mode <= 2;", "const bool can = false;"),
-        ("if (on && !sweep_supported(s->prm)) {", "if (on) {"),
+        # the persistent sweep kernel runs as a cooperative launch of the emulation: all CTAs alive at once (emu::launch_coop)
+        ("void *args[] = {(void *)&a};\n    return cudaLaunchCooperativeKernel((const void *)k_sweep<M>, dim3(grid), dim3(SW_T), args, sweep_smem<M>(), st);",
+         "emu::launch_coop(dim3(grid), dim3(SW_T), sweep_smem<M>(), [&] { k_sweep<M>(a); });\n    return cudaSuccess;"),
+    ],
+    "sweep.cu": [
+        ("__shared__ int sm_i[48];", "int *sm_i = (int *)emu::cta_static(48 * sizeof(int), 1);"),     # per CTA: the CTAs of this kernel are alive together
     ],
 }
 PTX = {
+    # sweep.cu: the loads that poll for another CTA (grid / team barrier counters, flagged exchange words) yield to the scheduler
+    "sweep.cu": [
+        ('asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");', "v = *(const volatile unsigned *)p; emu::poll_yield();"),
+        ('asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");', "(void)id; (void)nthreads; emu_unsupported_ptx();"),
+        ('asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"((unsigned)__double2loint(v)), "r"(seq), "r"((unsigned)__double2hiint(v)), "r"(seq)\n                 : "memory");',
+         "*p = uint4{(unsigned)__double2loint(v), seq, (unsigned)__double2hiint(v), seq};"),
+        ('asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(p) : "memory");',
+         "{ const uint4 w = *p; a = w.x; b = w.y; c = w.z; d = w.w; } emu::poll_yield();"),
+        ('asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.back_flag), "r"(a.back_seq) : "memory");', "*a.back_flag = a.back_seq;"),
+        ('asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(nstart));', "nstart = 0;"),
+        ('asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));', "now = 0;"),
+        ('asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(nend));', "nend = 0;"),
+    ],
     "particles.cu": [
         ('asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(y));', "r = 1.0 / y;"),
         ('asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));', "y = 1.0 / std::sqrt(x);"),

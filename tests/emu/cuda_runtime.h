@@ -16,6 +16,8 @@
 #include <cstring>
 #include <functional>
 #include <cstdio>
+#include <map>
+#include <sys/mman.h>
 #include <vector>
 
 #define QPG_EMU 1
@@ -62,7 +64,8 @@ inline cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = nullptr; return cudaSu
 inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t, cudaEvent_t) { *ms = 0.0f; return cudaSuccess; }
 inline cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
 enum cudaDeviceAttr { cudaDevAttrMultiProcessorCount, cudaDevAttrMaxSharedMemoryPerBlockOptin, cudaDevAttrCooperativeLaunch };
-inline cudaError_t cudaDeviceGetAttribute(int *v, cudaDeviceAttr a, int) { *v = a == cudaDevAttrMultiProcessorCount ? 148 : (a == cudaDevAttrMaxSharedMemoryPerBlockOptin ? 232448 : 0); return cudaSuccess; }
+// the emulated device: 12 SMs by default (a cooperative launch keeps 512 fibers per CTA alive), 227 KB of shared memory, cooperative launch
+inline cudaError_t cudaDeviceGetAttribute(int *v, cudaDeviceAttr a, int) { *v = a == cudaDevAttrMultiProcessorCount ? (getenv("QPAD_EMU_SMS") ? atoi(getenv("QPAD_EMU_SMS")) : 12) : (a == cudaDevAttrMaxSharedMemoryPerBlockOptin ? 232448 : 1); return cudaSuccess; }
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize };
 template <class F> inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
 // ---- compile-only stubs: CUDA graphs, cooperative launch, occupancy (sim.cu links; these paths fail loudly in emulation) ----------
@@ -169,7 +172,7 @@ struct Fiber { void *sp; int state; unsigned mask; unsigned seq; };
 inline void *g_sched_sp = nullptr;
 inline Fiber *g_cur = nullptr;
 inline std::function<void()> *g_body = nullptr;
-inline long g_launches = 0, g_barriers = 0, g_collectives = 0;
+inline long g_launches = 0, g_barriers = 0, g_collectives = 0, g_coop_launches = 0, g_polls = 0;
 inline unsigned g_tid = 0;                                   // flattened thread index of the running fiber
 inline unsigned long long (*g_slots)[2][32] = nullptr;       // [warp][parity][lane] exchange words of the warp collectives
 inline unsigned char *dyn_smem = nullptr;                    // `extern __shared__` storage of the running CTA
@@ -194,65 +197,105 @@ inline void warp_exchange(unsigned mask, unsigned long long v, unsigned long lon
     memcpy(out, g_slots[w][par], sizeof(unsigned long long) * 32);
     f->seq++;
 }
-template <class F> void launch(dim3 g, dim3 b, size_t smem, F f)
+// per-CTA storage of a static __shared__ variable of a kernel whose CTAs run concurrently (launch_coop); `id` names the variable
+inline std::vector<std::map<int, std::vector<unsigned char>>> *g_statics = nullptr;
+inline unsigned g_cta = 0;
+inline void *cta_static(size_t bytes, int id)
+{
+    auto &v = (*g_statics)[g_cta][id];
+    if (v.size() < bytes) v.assign(bytes, 0);
+    return v.data();
+}
+// a polling loop (a load that waits for another CTA) hands the processor on but stays runnable
+inline void poll_yield() { g_polls++; g_cur->state = ST_RUN; yield_to_scheduler(); }
+inline char *fiber_stacks(size_t bytes)
+{
+    static char *base = nullptr;
+    static size_t cap = 0;
+    if (bytes > cap) {
+        if (base) munmap(base, cap);
+        base = (char *)mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+        if (base == MAP_FAILED) { perror("emu: mmap of the fiber stacks"); abort(); }
+        cap = bytes;
+    }
+    return base;
+}
+// concurrent = false: CTAs run one after the other (an ordinary launch).  concurrent = true: the fibers of ALL CTAs are alive at
+// once and scheduled round-robin -- a cooperative launch whose CTAs synchronise through global memory (their polling loads call
+// poll_yield()).
+template <class F> void launch_impl(dim3 g, dim3 b, size_t smem, F f, bool concurrent)
 {
     std::function<void()> body = f;
     g_body = &body; g_launches++;
     gridDim = g; blockDim = b;
-    const unsigned nt = b.x * b.y * b.z, nw = (nt + 31) / 32;
-    const size_t stack = 256 * 1024;
-    static std::vector<char> stacks;
-    if (stacks.size() < stack * nt + 64) stacks.resize(stack * nt + 64);
-    std::vector<Fiber> fib(nt);
-    std::vector<unsigned long long> slots((size_t)nw * 64);
+    const unsigned nt = b.x * b.y * b.z, nw = (nt + 31) / 32, ncta = g.x * g.y * g.z, group = concurrent ? ncta : 1;
+    const size_t stack = concurrent ? 96 * 1024 : 256 * 1024;
+    char *stacks = fiber_stacks(stack * nt * group + 64);
+    std::vector<Fiber> fib((size_t)nt * group);
+    std::vector<unsigned long long> slots((size_t)nw * group * 64);
     g_slots = (unsigned long long(*)[2][32])slots.data();
-    std::vector<unsigned char> dyn(smem + 64);
-    dyn_smem = (unsigned char *)(((uintptr_t)dyn.data() + 63) & ~(uintptr_t)63);
-    for (unsigned bz = 0; bz < g.z; bz++) for (unsigned by = 0; by < g.y; by++) for (unsigned bx = 0; bx < g.x; bx++) {
-        blockIdx = uint3{bx, by, bz};
-        for (unsigned t = 0; t < nt; t++) {
-            uintptr_t top = ((uintptr_t)stacks.data() + stack * (t + 1)) & ~(uintptr_t)15;
+    const size_t dyn_each = (smem + 127) & ~(size_t)63;
+    std::vector<unsigned char> dyn(dyn_each * group + 64);
+    unsigned char *dyn0 = (unsigned char *)(((uintptr_t)dyn.data() + 63) & ~(uintptr_t)63);
+    std::vector<std::map<int, std::vector<unsigned char>>> statics(group);
+    g_statics = &statics;
+    for (unsigned first = 0; first < ncta; first += group) {
+        for (auto &m : statics) m.clear();
+        for (size_t t = 0; t < fib.size(); t++) {
+            uintptr_t top = ((uintptr_t)stacks + stack * (t + 1)) & ~(uintptr_t)15;
             void **sp = (void **)(top - 8);          // after the `ret` into tramp: rsp % 16 == 8, as at any function entry
             *--sp = (void *)tramp;
             for (int r = 0; r < 6; r++) *--sp = nullptr;
             fib[t] = Fiber{(void *)sp, ST_RUN, 0u, 0u};
         }
-        unsigned live = nt;
+        std::vector<unsigned> live_cta(group, nt);
+        size_t live = fib.size();
         while (live) {
-            bool ran = false;
-            for (unsigned t = 0; t < nt; t++) {
-                if (fib[t].state != ST_RUN) continue;
-                threadIdx = uint3{t % b.x, (t / b.x) % b.y, t / (b.x * b.y)};
-                g_tid = t; g_cur = &fib[t];
-                emu_switch(&g_sched_sp, fib[t].sp);
-                ran = true;
-                if (fib[t].state == ST_DONE) live--;
-            }
-            bool released = false;
-            for (unsigned w = 0; w < nw; w++) {          // warp collectives: all lanes named in a waiting lane's mask must wait with that mask
-                const unsigned base = w * 32, nl = std::min(32u, nt - base);
-                for (unsigned l = 0; l < nl; l++) {
-                    if (fib[base + l].state != ST_WARP) continue;
-                    const unsigned m = fib[base + l].mask & (nl == 32 ? 0xffffffffu : ((1u << nl) - 1u));
-                    bool all = true;
-                    for (unsigned k = 0; k < nl && all; k++) if ((m >> k) & 1u) all = fib[base + k].state == ST_WARP && fib[base + k].mask == fib[base + l].mask;
-                    if (all) { for (unsigned k = 0; k < nl; k++) if ((m >> k) & 1u) fib[base + k].state = ST_RUN; released = true; }
+            bool ran = false, released = false;
+            for (unsigned c = 0; c < group; c++) {
+                if (!live_cta[c]) continue;
+                const unsigned lin = first + c;
+                Fiber *fc = &fib[(size_t)c * nt];
+                for (unsigned t = 0; t < nt; t++) {
+                    if (fc[t].state != ST_RUN) continue;
+                    blockIdx = uint3{lin % g.x, (lin / g.x) % g.y, lin / (g.x * g.y)};
+                    threadIdx = uint3{t % b.x, (t / b.x) % b.y, t / (b.x * b.y)};
+                    g_tid = t; g_cta = c; g_cur = &fc[t]; dyn_smem = dyn0 + dyn_each * c;
+                    g_slots = (unsigned long long(*)[2][32])slots.data() + (size_t)c * nw;
+                    emu_switch(&g_sched_sp, fc[t].sp);
+                    ran = true;
+                    if (fc[t].state == ST_DONE) { live--; live_cta[c]--; }
                 }
-            }
-            if (!released && live) {                    // CTA barrier: every live thread waits at it
-                unsigned at = 0;
-                for (unsigned t = 0; t < nt; t++) at += fib[t].state == ST_BARRIER;
-                if (at == live) { for (unsigned t = 0; t < nt; t++) if (fib[t].state == ST_BARRIER) fib[t].state = ST_RUN; released = true; }
+                bool rel_c = false;
+                for (unsigned w = 0; w < nw; w++) {      // warp collectives: all lanes named in a waiting lane's mask must wait with that mask
+                    const unsigned base = w * 32, nl = std::min(32u, nt - base);
+                    for (unsigned l = 0; l < nl; l++) {
+                        if (fc[base + l].state != ST_WARP) continue;
+                        const unsigned m = fc[base + l].mask & (nl == 32 ? 0xffffffffu : ((1u << nl) - 1u));
+                        bool all = true;
+                        for (unsigned k = 0; k < nl && all; k++) if ((m >> k) & 1u) all = fc[base + k].state == ST_WARP && fc[base + k].mask == fc[base + l].mask;
+                        if (all) { for (unsigned k = 0; k < nl; k++) if ((m >> k) & 1u) fc[base + k].state = ST_RUN; rel_c = true; }
+                    }
+                }
+                if (!rel_c && live_cta[c]) {              // CTA barrier: every live thread of the CTA waits at it
+                    unsigned at = 0;
+                    for (unsigned t = 0; t < nt; t++) at += fc[t].state == ST_BARRIER;
+                    if (at == live_cta[c]) { for (unsigned t = 0; t < nt; t++) if (fc[t].state == ST_BARRIER) fc[t].state = ST_RUN; rel_c = true; }
+                }
+                released |= rel_c;
             }
             if (live && !ran && !released) {
-                unsigned nb = 0, nwp = 0;
-                for (unsigned t = 0; t < nt; t++) { nb += fib[t].state == ST_BARRIER; nwp += fib[t].state == ST_WARP; }
-                fprintf(stderr, "emu: DEADLOCK in CTA (%u,%u,%u): %u threads live, %u at __syncthreads, %u in a warp collective\n", bx, by, bz, live, nb, nwp);
+                size_t nb = 0, nwp = 0;
+                for (auto &x : fib) { nb += x.state == ST_BARRIER; nwp += x.state == ST_WARP; }
+                fprintf(stderr, "emu: DEADLOCK (CTAs %u..%u of %u): %zu threads live, %zu at __syncthreads, %zu in a warp collective\n", first, first + group - 1, ncta, live, nb, nwp);
                 abort();
             }
         }
     }
+    g_statics = nullptr;
 }
+template <class F> void launch(dim3 g, dim3 b, size_t smem, F f) { launch_impl(g, b, smem, f, false); }
+template <class F> void launch_coop(dim3 g, dim3 b, size_t smem, F f) { g_coop_launches++; launch_impl(g, b, smem, f, true); }
 template <class F> void launch(dim3 g, dim3 b, F f) { launch(g, b, 0, f); }
 }  // namespace emu
 #define __syncthreads() emu::sync_threads()

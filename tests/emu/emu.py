@@ -9,7 +9,8 @@ from qpad_b200 import capi
 from . import build as _build
 
 _lib = None
-_EMU_SIGS = {"emu_launches": (C.c_long, []), "emu_barriers": (C.c_long, []), "emu_collectives": (C.c_long, [])}
+_EMU_SIGS = {"emu_launches": (C.c_long, []), "emu_barriers": (C.c_long, []), "emu_collectives": (C.c_long, []), "emu_coop_launches": (C.c_long, []),
+             "emu_polls": (C.c_long, [])}
 
 
 def lib():

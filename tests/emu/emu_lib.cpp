@@ -1,7 +1,9 @@
 // TEST INFRASTRUCTURE ONLY (see cuda_runtime.h in this directory): the translation unit of the host-emulation library = the
-// unity build of qpad_b200/csrc/lib.cu without p2p.cu (peer memory).  fused.cu (thread-block clusters) and sweep.cu (cooperative
-// persistent kernel) are compiled so that sim.cu links, but cannot run here: of the slice-loop paths of qpg_sim only the plain
-// per-slice launches (use_graph = 0, qpg_sim_set_fused(s, 0), qpg_sim_set_sweep(s, 0)) are emulated; the others fail loudly.  The included files are the launch-rewritten copies that tests/emu/build.py writes to _build/; the extern "C"
+// unity build of qpad_b200/csrc/lib.cu without p2p.cu (peer memory).  fused.cu (thread-block clusters) is compiled so that sim.cu links
+// but cannot run here.  Of the slab drivers of qpg_sim the emulation runs the plain per-slice launches (the default here; a request
+// for CUDA-graph replay is ignored) and, after qpg_sim_set_sweep(s, 1), the persistent cooperative sweep kernel of sweep.cu: all
+// its CTAs are alive at once (emu::launch_coop) and meet at its hand-rolled grid / team barriers and flagged exchange words
+// through "global memory", their polling loads yielding to the scheduler.  The included files are the launch-rewritten copies that tests/emu/build.py writes to _build/; the extern "C"
 // entry points are therefore the very code that runs on the GPU, with "device memory" on the host heap.
 #include <cuda_runtime.h>
 #include "fields.cu.cpp"
@@ -22,4 +24,6 @@ int qpg_stream_signal(void *, unsigned *, unsigned) { qpg_set_error("qpg_stream_
 long emu_launches(void) { return emu::g_launches; }
 long emu_barriers(void) { return emu::g_barriers; }
 long emu_collectives(void) { return emu::g_collectives; }
+long emu_coop_launches(void) { return emu::g_coop_launches; }
+long emu_polls(void) { return emu::g_polls; }
 }

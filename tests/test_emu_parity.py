@@ -130,3 +130,26 @@ def test_sim_subcyc_loop_matches_oracle(mods):
 def test_sim_subcyc_with_neutral_matches_oracle(mods):
     """both at once: the released electrons are sub-cycled and clamped too, the ionisation runs in every sub-step (:312-323)"""
     K.sim_subcyc_loop(mods[0], O, with_neutral=True)
+
+
+# ---- the persistent cooperative sweep kernel (csrc/sweep.cu), the default slab driver on the GPU: all CTAs alive at once, meeting at
+# its hand-rolled grid / team barriers and flagged 16-byte exchange words; field team of 1 .. 8 CTAs here (nr = 1024 = 32 CTAs passes
+# too with QPAD_EMU_SMS=40, 25 s) -----------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M", [0, 1, 2])
+def test_sweep_slice_loop_matches_oracle(mods, M):
+    c0 = emu.lib().emu_coop_launches()
+    G.test_slice_loop_matches_oracle(mods, M, "sweep")
+    assert emu.lib().emu_coop_launches() > c0 and emu.lib().emu_polls() > 0
+
+
+def test_sweep_one_slice_from_identical_state(mods): G.test_one_slice_from_identical_state(mods, 1, "sweep")
+
+
+def test_sweep_full_3d_step_with_beam_push(mods): G.test_full_3d_step_with_beam_push(mods, "sweep")
+
+
+def test_sweep_sorted_loop(mods): G.test_sorted_loop_still_matches(mods, "sweep")
+
+
+@pytest.mark.parametrize("nr,M,ppc,nth", [(250, 1, 2, 8), (65, 1, 2, 8), (33, 2, 2, 8), (24, 1, 2, 8)])
+def test_sweep_kernel_multi_cta_team(mods, nr, M, ppc, nth): G.test_sweep_kernel_multi_cta_team(mods, nr, M, ppc, nth)
