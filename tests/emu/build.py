@@ -129,7 +129,9 @@ def build(force=False):
     bounds-checked -- a memcheck of the device sources without a GPU."""
     global LIB
     asan = bool(int(os.environ.get("QPAD_EMU_ASAN", "0")))
-    LIB = os.path.join(OUT, "libqpademu_asan.so" if asan else "libqpademu.so")
+    extra = os.environ.get("QPAD_EMU_DEFS", "").split()          # e.g. -DQPG_GATHER_FOLDED: an experimental variant of the device sources
+    tag = ("_asan" if asan else "") + "".join("_" + re.sub(r"\W", "", d) for d in extra)
+    LIB = os.path.join(OUT, f"libqpademu{tag}.so")
     os.makedirs(OUT, exist_ok=True)
     srcs = [os.path.join(CSRC, f) for f in SOURCES if os.path.exists(os.path.join(CSRC, f))]
     deps = srcs + [os.path.join(HERE, f) for f in ("cuda_runtime.h", "emu_lib.cpp", "build.py")] + [os.path.join(CSRC, "common.cuh"),
@@ -143,7 +145,7 @@ def build(force=False):
             f.write(t)
     defs = [f"-DEMU_HAVE_{os.path.basename(s).split('.')[0].upper()}" for s in srcs]
     san = ["-fsanitize=address", "-fno-omit-frame-pointer"] if asan else []
-    subprocess.check_call(["g++", "-std=c++17", "-O1", "-g", "-ffp-contract=off", "-fPIC", "-shared"] + san + ["-I", HERE, "-I", OUT, "-I", CSRC] + defs +
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-g", "-ffp-contract=off", "-fPIC", "-shared"] + san + ["-I", HERE, "-I", OUT, "-I", CSRC] + defs + extra +
                           [os.path.join(HERE, "emu_lib.cpp"), "-o", LIB])
     return LIB
 
