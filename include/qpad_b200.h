@@ -385,6 +385,10 @@ int qpg_stage_part2d(qpg_stage s, qpg_part2d p, int dspl, long *stride);
 int qpg_stage_part3d(qpg_stage s, qpg_part3d p, int dspl, double z0, long *stride);
 int qpg_stage_wait(qpg_stage s, const double **host, long *count);   /* blocks the host until the copy has landed */
 
+/* Accuracy probe (not part of the reference's interface): the MUFU-seeded reciprocal and square root of the momentum arithmetic
+ * evaluated on the device for n host values; tests/test_gpu_extras.py::test_fastmath_accuracy bounds their error in ulp. */
+int qpg_debug_fastmath(qpg_ctx ctx, long n, const double *host_x, double *host_rcp, double *host_sqrt);
+
 #ifdef __cplusplus
 }
 #endif

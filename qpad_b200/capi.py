@@ -157,6 +157,7 @@ SIGNATURES = {
     "qpg_neutral_update": (_i, [_vp, _vp, _vp, _vp]),
     "qpg_neutral_levels": (_i, [_vp, _vp]),
     "qpg_part2d_clear": (_i, [_vp]),
+    "qpg_debug_fastmath": (_i, [_vp, _l, _vp, _vp, _vp]),
     "qpg_sim_attach_neutral": (_i, [_vp, _vp, _vp, _vp]),
     "qpg_sim_set_subcyc": (_i, [_vp, _i, _d, _d, _d]),
     "qpg_sim_subcycles": (_l, [_vp]),
@@ -258,6 +259,12 @@ class Ctx:
     def solve_et(self, b, psi, e): _chk(self.L.qpg_solve_et(self.h, b.h, psi.h, e.h))
     def solve_et_beam(self, b, e): _chk(self.L.qpg_solve_et_beam(self.h, b.h, e.h))
     def solve_djdxi(self, acu, amu, dcu): _chk(self.L.qpg_solve_djdxi(self.h, acu.h, amu.h, dcu.h))
+    def debug_fastmath(self, x):
+        """(fast_rcp(x), fast_sqrt(x)) of the momentum arithmetic evaluated on the device"""
+        x = _f64(x); r, q = np.zeros_like(x), np.zeros_like(x)
+        _chk(self.L.qpg_debug_fastmath(self.h, x.size, _ptr(x), _ptr(r), _ptr(q)))
+        return r, q
+
     def solve_vpotz(self, cu, vpot): _chk(self.L.qpg_solve_vpotz(self.h, cu.h, vpot.h))     # field_vpot%solve_vpotz
     def solve_vpott(self, cu, vpot): _chk(self.L.qpg_solve_vpott(self.h, cu.h, vpot.h))     # field_vpot%solve_vpott
 

@@ -34,9 +34,16 @@ __device__ __forceinline__ double fast_rcp(double y)
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(y));
     double e = fma(-y, r, 1.0);
+#ifdef QPG_FASTMATH_SHORT
+    // EXPERIMENT (off by default): one cubic step r (1 + e + e^2) instead of two quadratic ones -- seed error eps ->
+    // eps^3 (2^-60 or better for a 2^-20 seed) in 3 instead of 4 dependent FMAs.  qpg_debug_fastmath measures the ulp error on the GPU.
+    e = fma(e, e, e);
+    return fma(r, e, r);
+#else
     r = fma(r, e, r);
     e = fma(-y, r, 1.0);
     return fma(r, e, r);
+#endif
 }
 __device__ __forceinline__ double fast_sqrt(double x)
 {
@@ -45,9 +52,33 @@ __device__ __forceinline__ double fast_sqrt(double x)
     double g = x * y, h = 0.5 * y;
     double r = fma(-g, h, 0.5);
     g = fma(g, r, g); h = fma(h, r, h);
+#ifndef QPG_FASTMATH_SHORT      // the experiment drops this second coupled step: eps -> 1.5 eps^2 (first step) -> ~eps^4 (the final Heron correction)
     r = fma(-g, h, 0.5);
     g = fma(g, r, g); h = fma(h, r, h);
+#endif
     return fma(fma(-g, g, x), h, g);
+}
+
+// accuracy probe of the two routines above on the device (tests/test_gpu_extras.py::test_fastmath_accuracy): out_rcp[i] =
+// fast_rcp(x[i]), out_sqrt[i] = fast_sqrt(x[i])
+__global__ void k_debug_fastmath(const double *__restrict__ x, double *__restrict__ out_rcp, double *__restrict__ out_sqrt, long n)
+{
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) { out_rcp[i] = fast_rcp(x[i]); out_sqrt[i] = fast_sqrt(x[i]); }
+}
+extern "C" int qpg_debug_fastmath(qpg_ctx ctx, long n, const double *host_x, double *host_rcp, double *host_sqrt)
+{
+    ARG_TRY(ctx && n > 0 && host_x && host_rcp && host_sqrt, "bad arg");
+    double *d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, sizeof(double) * 3 * n));
+    CUDA_TRY(cudaMemcpyAsync(d, host_x, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+    k_debug_fastmath<<<148, 256, 0, ctx->stream>>>(d, d + n, d + 2 * n, n);
+    count_launch(ctx);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(host_rcp, d + n, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(host_sqrt, d + 2 * n, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(cudaFree(d));
+    return 0;
 }
 
 // fire-and-forget reductions.  Written as PTX `red` because ptxas keeps `atomicAdd` as a returning ATOMG (a ~320-cycle

@@ -307,3 +307,19 @@ def sim_subcyc_loop(api, O, with_neutral=False):
         gx, gp, gg, gpsi, gq = (ne.part if with_neutral else sim.species).download()
         assert len(gq) == len(oq) > 50 and np.max(np.abs(gp - op)) < 1e-7 and np.max(np.abs(gx - ox)) < 1e-7
         sim.close()
+
+
+def fastmath_accuracy(api, max_ulp=2.0):
+    """the MUFU-seeded reciprocal / square root of the momentum arithmetic (particles.cu fast_rcp / fast_sqrt) against IEEE over the
+    range of their arguments (gamma-like, 1e-3 .. 1e6): error in units of the last place"""
+    ctx = api.Ctx(32, 1, 0.1, 0.02)
+    rng = np.random.default_rng(5)
+    x = np.concatenate([10.0 ** rng.uniform(-3, 6, 200000), 1.0 + rng.random(100000) * 1e-3, np.array([1.0, 2.0, 4.0, 0.5, 3.0, 1e-3, 1e6])])
+    r, q = ctx.debug_fastmath(x)
+    want_r = (np.longdouble(1.0) / x.astype(np.longdouble))
+    want_q = np.sqrt(x.astype(np.longdouble))
+    ulp_r = np.abs((r.astype(np.longdouble) - want_r) / np.spacing(np.asarray(want_r, dtype=np.float64)).astype(np.longdouble))
+    ulp_q = np.abs((q.astype(np.longdouble) - want_q) / np.spacing(np.asarray(want_q, dtype=np.float64)).astype(np.longdouble))
+    assert float(ulp_r.max()) <= max_ulp and float(ulp_q.max()) <= max_ulp, (float(ulp_r.max()), float(ulp_q.max()))
+    ctx.close()
+    return float(ulp_r.max()), float(ulp_q.max())

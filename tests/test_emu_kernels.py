@@ -44,3 +44,9 @@ def test_vpot_nr1024_emulated(api):
 
 def test_stage_emulated(api):
     K.stage(api, O)
+
+
+def test_fastmath_probe_emulated(api):
+    """plumbing of qpg_debug_fastmath only: in the emulation the MUFU seeds are exact IEEE values, the GPU test measures the real thing"""
+    ur, uq = K.fastmath_accuracy(api, max_ulp=1.0)
+    assert ur <= 1.0 and uq <= 1.0

@@ -50,3 +50,10 @@ def test_sim_subcyc_loop_matches_oracle(mods, with_neutral):
     """the sub-cycling variant inside qpg_sim (qpg_sim_set_subcyc), without and with an attached neutral species"""
     capi, O, K = mods
     K.sim_subcyc_loop(capi, O, with_neutral=with_neutral)
+
+
+def test_fastmath_accuracy(mods):
+    """fast_rcp / fast_sqrt (MUFU seed + Newton steps) stay within 2 ulp of IEEE on the device -- also the gate for the shorter
+    variants of the QPG_FASTMATH_SHORT experiment (build with QPG_NVCC_EXTRA=-DQPG_FASTMATH_SHORT)"""
+    capi, O, K = mods
+    print("max ulp error (rcp, sqrt):", K.fastmath_accuracy(capi))
