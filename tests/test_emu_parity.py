@@ -69,6 +69,11 @@ def test_deposit_chi_matches_oracle(mods, nr, M): GL.test_deposit_chi_matches_or
 def test_envelope_advance_matches_oracle(mods, nr, nz, M, iters): GL.test_envelope_advance_matches_oracle(mods, nr, nz, M, iters)
 
 
+def test_wire_formats(mods):
+    """the hand-off records of the xi pipeline (pipe_send / recv of a field slice, pipesend_part2d, the beam's forward hand-off)"""
+    G.test_wire_formats(mods)
+
+
 def test_ionization_loop_matches_oracle(mods):
     """the ionisation deck (config 5 in small) through qpad_b200.ionization.IonizationStage: neutral.cu + every per-routine kernel"""
     K.ionization_loop(mods[0], O, nsl=32)
@@ -153,3 +158,10 @@ def test_sweep_sorted_loop(mods): G.test_sorted_loop_still_matches(mods, "sweep"
 
 @pytest.mark.parametrize("nr,M,ppc,nth", [(250, 1, 2, 8), (65, 1, 2, 8), (33, 2, 2, 8), (24, 1, 2, 8)])
 def test_sweep_kernel_multi_cta_team(mods, nr, M, ppc, nth): G.test_sweep_kernel_multi_cta_team(mods, nr, M, ppc, nth)
+
+
+def test_graft_entry_smoke_body(mods, capsys):
+    """__graft_entry__.smoke() -- what the driver runs on cuda:0 before the bench -- with the library replaced by the emulation"""
+    import __graft_entry__ as ge
+    ge.smoke()
+    assert "psi rel err vs oracle" in capsys.readouterr().out

@@ -588,30 +588,46 @@ def test_sorted_loop_still_matches(mods, path):
     assert np.array_equal(gq, oq)
 
 
+class _DevBuf:
+    """a zeroed fp64 wire buffer in device memory: torch on the GPU; in the host emulation (tests/test_emu_parity.py) device memory
+    is the host heap, so a numpy array serves"""
+
+    def __init__(self, capi, n):
+        self.emu = hasattr(capi.load(), "emu_launches")
+        if self.emu:
+            self.a = np.zeros(n)
+            self.ptr = self.a.ctypes.data
+        else:
+            import torch
+            self.a = torch.zeros(n, dtype=torch.float64, device="cuda")
+            self.ptr = self.a.data_ptr()
+
+    def numpy(self): return self.a.copy() if self.emu else self.a.cpu().numpy()
+
+
 def test_wire_formats(mods):
     """pipe_send/recv buffers: field slice (dim, nr+2, 2M+1), plasma 8 doubles/particle, beam 7 doubles/particle"""
-    import torch
     capi, O = mods
     nr, M = 40, 1
     ctx, dr = _ctx(capi, nr, M)
     rng = np.random.default_rng(2)
     a = rng.standard_normal((3, nr + 2, 3))
     f = capi.Field(ctx, 3, 3, True); f.upload(a)
-    buf = torch.zeros(f.wire_count(), dtype=torch.float64, device="cuda")
-    f.pack(0, buf.data_ptr()); ctx.sync()
-    assert np.array_equal(buf.cpu().numpy().reshape(3, nr + 2, 3), a)
-    f.unpack(2, buf.data_ptr(), add=False); f.unpack(2, buf.data_ptr(), add=True); ctx.sync()
+    buf = _DevBuf(capi, f.wire_count())
+    f.pack(0, buf.ptr); ctx.sync()
+    assert np.array_equal(buf.numpy().reshape(3, nr + 2, 3), a)
+    f.unpack(2, buf.ptr, add=False); f.unpack(2, buf.ptr, add=True); ctx.sync()
     assert np.array_equal(f.download_f2()[:, 1], 2 * a)
     x, p, g, psi, q = perturbed_lattice(O, rng, nr, dr, 2, 2, 8)
     n = len(q)
     pa, pb = capi.Part2d(ctx, -1.0, 2 * n), capi.Part2d(ctx, -1.0, 2 * n)
     pa.upload(x, p, g, psi, q)
-    wb = torch.zeros(pa.wire_count(), dtype=torch.float64, device="cuda")
-    pa.pack(wb.data_ptr()); ctx.sync()
-    rec = wb.cpu().numpy()
+    wb = _DevBuf(capi, pa.wire_count())
+    pa.pack(wb.ptr); ctx.sync()
+    rec = wb.numpy()
     assert rec[0] == n
     assert np.array_equal(rec[1:1 + 8 * n].reshape(n, 8), np.column_stack([x, p, g, psi, q]))
-    pb.unpack(wb.data_ptr())
+    pb.unpack(wb.ptr)
     assert all(np.array_equal(u, v) for u, v in zip(pb.download(), (x, p, g, psi, q)))
     # beam forward hand-off
     nz, nzp = 20, 10
@@ -622,10 +638,10 @@ def test_wire_formats(mods):
     b0 = capi.Part3d(c2, -1.0, 1.0, nb + 64, nz, 0, nzp)
     b1 = capi.Part3d(c2, -1.0, 1.0, nb + 64, nz, nzp, nzp)
     b0.upload(bx, bp, bq)
-    hb = torch.zeros(7 * b0.wire_cap() + 1, dtype=torch.float64, device="cuda")
-    b0.pack_forward(hb.data_ptr()); c2.sync()
+    hb = _DevBuf(capi, 7 * b0.wire_cap() + 1)
+    b0.pack_forward(hb.ptr); c2.sync()
     go = np.nonzero(bx[:, 2] >= nzp * 0.5)[0]
-    rec = hb.cpu().numpy()
+    rec = hb.numpy()
     assert rec[0] == len(go)
     assert np.array_equal(rec[1:1 + 7 * len(go)].reshape(-1, 7)[:, 6], bq[go])      # packed in ascending index order
     keep = b0.download()[2]
@@ -634,7 +650,7 @@ def test_wire_formats(mods):
     for h in go[::-1]:
         exp[h] = exp[npp - 1]; npp -= 1
     assert np.array_equal(keep, np.array(exp[:npp]))
-    b1.unpack(hb.data_ptr())
+    b1.unpack(hb.ptr)
     assert np.array_equal(np.sort(b1.download()[2]), np.sort(bq[go]))
 
 
