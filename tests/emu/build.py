@@ -22,7 +22,7 @@ PATCH = {
         ("s->prm = *prm;", "s->prm = *prm; s->prm.use_graph = 0;"),
         ("s->prm.use_graph = use_graph != 0; return 0; }", "(void)use_graph; return 0; }"),
         ("s->use_fused = (prm->nr <= FT * FC && prm->max_mode <= 2);", "s->use_fused = false;"),
-        ("s->use_sweep = sweep_supported(*prm);", "s->use_sweep = false;"),
+        ("s->use_sweep = sweep_supported(*prm);", "s->use_sweep = getenv(\"QPAD_EMU_SWEEP\") ? sweep_supported(*prm) : false;"),
         ("const bool can = s->prm.nr <= FT * FC && s->prm.max_mode <= 2;", "const bool can = false;"),
         # the persistent sweep kernel runs as a cooperative launch of the emulation: all CTAs alive at once (emu::launch_coop)
         ("void *args[] = {(void *)&a};\n    return cudaLaunchCooperativeKernel((const void *)k_sweep<M>, dim3(grid), dim3(SW_T), args, sweep_smem<M>(), st);",
@@ -42,9 +42,9 @@ PTX = {
         ('asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(p) : "memory");',
          "{ const uint4 w = *p; a = w.x; b = w.y; c = w.z; d = w.w; } emu::poll_yield();"),
         ('asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.back_flag), "r"(a.back_seq) : "memory");', "*a.back_flag = a.back_seq;"),
-        ('asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(nstart));', "nstart = 0;"),
-        ('asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));', "now = 0;"),
-        ('asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(nend));', "nend = 0;"),
+        ('asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(nstart));', "nstart = clock64();"),
+        ('asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));', "now = clock64();"),
+        ('asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(nend));', "nend = clock64();"),
     ],
     "particles.cu": [
         ('asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(y));', "r = 1.0 / y;"),

@@ -99,7 +99,8 @@ template <class T> inline T __ldcg(const T *p) { return *p; }
 template <class T> inline void __stcg(T *p, T v) { *p = v; }
 #define __cluster_dims__(...)
 struct uint4 { unsigned x, y, z, w; };
-inline long long clock64() { return 0; }
+inline long long g_emu_clock = 0;
+inline long long clock64() { return ++g_emu_clock; }          // a counter, not a clock: monotonic, one tick per reading
 inline void __threadfence() {}
 inline void __threadfence_system() {}
 inline void __nanosleep(unsigned) {}

@@ -19,8 +19,22 @@
 #include "diag.cu.cpp"
 
 extern "C" {
-// p2p.cu is not part of the emulation
-int qpg_stream_signal(void *, unsigned *, unsigned) { qpg_set_error("qpg_stream_signal: peer-memory transport is not emulated"); return QPG_ERR_UNSUPPORTED; }
+// p2p.cu (CUDA IPC, stream memory operations) is not part of the emulation; the wire buffers and flags of ONE process are plain
+// host memory here, and because every enqueued operation has already run when the call returns, a stream-ordered wait for a flag
+// either finds it raised or would wait forever (reported as an error)
+int qpg_wire_alloc(void **dev_ptr, long bytes) { *dev_ptr = calloc((size_t)(bytes > 0 ? bytes : 1), 1); return *dev_ptr ? 0 : QPG_ERR_ALLOC; }
+int qpg_wire_free(void *dev_ptr) { free(dev_ptr); return 0; }
+int qpg_wire_export(void *, unsigned char *) { qpg_set_error("qpg_wire_export: CUDA IPC is not emulated"); return QPG_ERR_UNSUPPORTED; }
+int qpg_wire_import(const unsigned char *, void **) { qpg_set_error("qpg_wire_import: CUDA IPC is not emulated"); return QPG_ERR_UNSUPPORTED; }
+int qpg_wire_unmap(void *) { return 0; }
+int qpg_stream_wait_is_memop(void) { return 0; }
+int qpg_stream_signal(void *, unsigned *flag, unsigned value) { *flag = value; return 0; }
+int qpg_stream_wait(void *, unsigned *flag, unsigned value)
+{
+    if ((int)(*flag - value) >= 0) return 0;
+    qpg_set_error("qpg_stream_wait: flag %u < %u and its producer has not been enqueued -- on a GPU this stream would wait forever", *flag, value);
+    return QPG_ERR_STATE;
+}
 long emu_launches(void) { return emu::g_launches; }
 long emu_barriers(void) { return emu::g_barriers; }
 long emu_collectives(void) { return emu::g_collectives; }

@@ -1,0 +1,52 @@
+"""TEST INFRASTRUCTURE ONLY: the handful of torch names qpad_b200.pipeline.LocalPipeline touches (streams, events, device buffers),
+for running it against the host emulation of the library: operations execute when they are enqueued, so streams and events are
+bookkeeping only and a "device" tensor is a numpy array.  Installed as sys.modules["torch"] for the duration of a test."""
+import contextlib
+import types
+
+import numpy as np
+
+float64 = np.float64
+
+
+class _Tensor:
+    def __init__(self, a): self.a = a
+    def data_ptr(self): return self.a.ctypes.data
+    def cpu(self): return self
+    def numpy(self): return self.a.copy()
+    def zero_(self): self.a[:] = 0; return self
+    def __getitem__(self, k): return _Tensor(self.a[k])
+    def __len__(self): return len(self.a)
+
+
+def zeros(n, dtype=float64, device=None): return _Tensor(np.zeros(n, dtype=dtype))
+def empty(n, dtype=float64, device=None): return zeros(n, dtype, device)
+def device(kind, index=0): return (kind, index)
+
+
+class _Stream:
+    _next = 1
+
+    def __init__(self, device=None):
+        _Stream._next += 1
+        self.cuda_stream = _Stream._next
+
+    def wait_event(self, ev): assert ev.recorded, "wait on an event that was never recorded"
+    def synchronize(self): pass
+
+
+class _Event:
+    def __init__(self, enable_timing=False): self.recorded = False
+    def record(self, stream=None): self.recorded = True
+    def synchronize(self): pass
+    def elapsed_time(self, other): return 0.0
+
+
+@contextlib.contextmanager
+def _stream_ctx(s):
+    yield
+
+
+cuda = types.SimpleNamespace(Stream=_Stream, Event=_Event, stream=_stream_ctx, synchronize=lambda *a: None, is_available=lambda: True,
+                             set_device=lambda d: None, current_stream=lambda *a: _Stream(),
+                             get_device_properties=lambda d: types.SimpleNamespace(multi_processor_count=12, name="emulated"))

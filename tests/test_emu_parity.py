@@ -165,3 +165,27 @@ def test_graft_entry_smoke_body(mods, capsys):
     import __graft_entry__ as ge
     ge.smoke()
     assert "psi rel err vs oracle" in capsys.readouterr().out
+
+
+# ---- pipeline.LocalPipeline, the default driver of bench.py: S persistent sweep kernels on S streams of one GPU, event-ordered hand-offs,
+# the backward e / b hand-off published from inside the downstream sweep kernel.  torch is replaced by tests/emu/faketorch.py (streams
+# and events are bookkeeping: every operation has run when its enqueue returns, and the host's issue order is a valid schedule -- a
+# stream-ordered flag wait whose producer was not enqueued first is reported as an error) --------------------------------------------
+@pytest.fixture()
+def pipeline_mods(mods, monkeypatch):
+    import sys
+    from emu import faketorch
+    monkeypatch.setitem(sys.modules, "torch", faketorch)
+    monkeypatch.setenv("QPAD_EMU_SWEEP", "1")          # qpg_sim defaults to the sweep kernel, as on the GPU
+    return mods
+
+
+@pytest.mark.parametrize("S", [2, 3])
+def test_local_pipeline_matches_oracle(pipeline_mods, S):
+    c0 = emu.lib().emu_coop_launches()
+    G.test_local_pipeline_matches_oracle(pipeline_mods, S)
+    assert emu.lib().emu_coop_launches() - c0 >= 4 * S
+
+
+def test_local_pipeline_with_unequal_slabs(pipeline_mods):
+    G.test_local_pipeline_with_unequal_slabs(pipeline_mods)
