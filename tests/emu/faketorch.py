@@ -2,6 +2,7 @@
 for running it against the host emulation of the library: operations execute when they are enqueued, so streams and events are
 bookkeeping only and a "device" tensor is a numpy array.  Installed as sys.modules["torch"] for the duration of a test."""
 import contextlib
+import os
 import types
 
 import numpy as np
@@ -49,4 +50,4 @@ def _stream_ctx(s):
 
 cuda = types.SimpleNamespace(Stream=_Stream, Event=_Event, stream=_stream_ctx, synchronize=lambda *a: None, is_available=lambda: True,
                              set_device=lambda d: None, current_stream=lambda *a: _Stream(),
-                             get_device_properties=lambda d: types.SimpleNamespace(multi_processor_count=12, name="emulated"))
+                             get_device_properties=lambda d: types.SimpleNamespace(multi_processor_count=int(os.environ.get("QPAD_EMU_SMS", "12")), name="emulated"))
