@@ -189,3 +189,38 @@ def test_local_pipeline_matches_oracle(pipeline_mods, S):
 
 def test_local_pipeline_with_unequal_slabs(pipeline_mods):
     G.test_local_pipeline_with_unequal_slabs(pipeline_mods)
+
+
+def test_local_pipeline_e2e_wave_with_upload(pipeline_mods):
+    """the end-to-end leg of bench.py: every wave re-uploads the plasma lattice into the first stage (instead of the on-device renewal)
+    and reads the slabs' line-outs and the counters back -- same physics as the resident run, i.e. the oracle's S-stage run"""
+    import numpy as np
+    capi, _ = pipeline_mods
+    from qpad_b200 import decks
+    from qpad_b200.pipeline import LocalPipeline
+    S = 2
+    cfg = dict(nr=64, nz=32, max_mode=1, rmax=5.0, zmin=-5.0, zmax=5.0, dt=10.0, ppc1=2, ppc2=2, num_theta=8, iter_max=2, iter_reltol=1e-3, iter_abstol=1e-3)
+    bm = decks.beam_std(cfg["nr"], cfg["nz"], cfg["rmax"], cfg["zmin"], cfg["zmax"], **dict(decks.CONFIGS["C1"]["beam"]))
+    plasma = decks.plasma_uniform(cfg["nr"], cfg["rmax"], cfg["ppc1"], cfg["ppc2"], cfg["num_theta"])
+    lp = LocalPipeline(cfg, plasma, bm, S)
+    lp.fill()
+    nwaves = 3
+    for _ in range(nwaves):
+        lp.wave(upload=plasma)
+        for sim in lp.sims:
+            assert np.all(np.isfinite(sim.field("e").lineout(3, 0, 1))) and np.all(np.isfinite(sim.field("psi").lineout(1, 0, 1)))
+        lp.stats()
+    lp.drain()
+    upd, iters, slices = lp.stats()
+    nsteps = slices // cfg["nz"]
+    kw = {k: cfg[k] for k in ("nr", "nz", "max_mode", "rmax", "zmin", "zmax", "dt", "iter_max", "iter_reltol", "iter_abstol")}
+    orc = O.Sim(ppc1=2, ppc2=2, num_theta=8, nstages=S, **kw)
+    orc.set_beam(*bm)
+    for k in range(nsteps):
+        orc.step3d(k + 1)
+    assert nsteps >= nwaves and iters == orc.total_iters() and upd == nsteps * cfg["nz"] * len(plasma[4])
+    for r, sim in enumerate(lp.sims):
+        for name in ("psi", "e"):
+            got, want = sim.field(name).download_f2()[:, :sim.nzp], orc.field(name, 2, stage=r)[:, :sim.nzp]
+            assert np.max(np.abs(got - want)) < 1e-6 * np.max(np.abs(want)), (r, name)
+    lp.close()
