@@ -882,9 +882,13 @@ __global__ void __launch_bounds__(256) k_sort_pos(const int *__restrict__ d_npp,
         const int before = __popc(same & ((1u << lane) - 1u));  // earlier lanes with my key
         int rank = 0;
         for (int ww = 0; ww < nw; ww++) {
-            if (w == ww && valid) {
-                rank = sh[key] + before;
-                if ((same >> lane) == 1u) sh[key] = rank + 1;  // highest lane of the group publishes the new count
+            if (w == ww) {                      // the whole warp: every lane of a key group reads the count BEFORE its highest lane updates it
+                const int cur = valid ? sh[key] : 0;
+                __syncwarp();
+                if (valid) {
+                    rank = cur + before;
+                    if ((same >> lane) == 1u) sh[key] = rank + 1;  // highest lane of the group publishes the new count
+                }
             }
             __syncthreads();
         }

@@ -17,6 +17,7 @@
 #include <functional>
 #include <cstdio>
 #include <map>
+#include <numeric>
 #include <sys/mman.h>
 #include <vector>
 
@@ -201,6 +202,9 @@ inline void warp_exchange(unsigned mask, unsigned long long v, unsigned long lon
 // per-CTA storage of a static __shared__ variable of a kernel whose CTAs run concurrently (launch_coop); `id` names the variable
 inline std::vector<std::map<int, std::vector<unsigned char>>> *g_statics = nullptr;
 inline unsigned g_cta = 0;
+inline int g_order = getenv("QPAD_EMU_ORDER") ? atoi(getenv("QPAD_EMU_ORDER")) : 0;
+inline unsigned g_ord_rot = 0, g_ord_stride = 1;
+inline unsigned long long g_ord_state = 0x9E3779B97F4A7C15ull + (unsigned long long)g_order;
 inline void *cta_static(size_t bytes, int id)
 {
     auto &v = (*g_statics)[g_cta][id];
@@ -253,11 +257,23 @@ template <class F> void launch_impl(dim3 g, dim3 b, size_t smem, F f, bool concu
         size_t live = fib.size();
         while (live) {
             bool ran = false, released = false;
+            if (g_order >= 2) {                       // a stride coprime to nt and a rotation, new every round
+                g_ord_state = g_ord_state * 6364136223846793005ull + 1442695040888963407ull;
+                g_ord_rot = (unsigned)((g_ord_state >> 33) % nt);
+                g_ord_stride = 1 + 2 * (unsigned)((g_ord_state >> 13) % 64);
+                while (std::gcd(g_ord_stride, nt) != 1) g_ord_stride += 2;
+            }
             for (unsigned c = 0; c < group; c++) {
                 if (!live_cta[c]) continue;
                 const unsigned lin = first + c;
                 Fiber *fc = &fib[(size_t)c * nt];
-                for (unsigned t = 0; t < nt; t++) {
+                for (unsigned tt = 0; tt < nt; tt++) {
+                    // QPAD_EMU_ORDER: the order in which the runnable threads of a CTA get the processor between two synchronisation
+                    // points -- 0 ascending (default), 1 descending, >= 2 a pseudo-random rotation + stride per round (seed).  Correctly
+                    // synchronised code gives the same results under every order: a cheap racecheck for missing barriers.
+                    unsigned t = tt;
+                    if (g_order == 1) t = nt - 1 - tt;
+                    else if (g_order >= 2) t = (unsigned)(((unsigned long long)tt * g_ord_stride + g_ord_rot) % nt);
                     if (fc[t].state != ST_RUN) continue;
                     blockIdx = uint3{lin % g.x, (lin / g.x) % g.y, lin / (g.x * g.y)};
                     threadIdx = uint3{t % b.x, (t / b.x) % b.y, t / (b.x * b.y)};
