@@ -40,7 +40,7 @@ class _Event:
     def __init__(self, enable_timing=False): self.recorded = False
     def record(self, stream=None): self.recorded = True
     def synchronize(self): pass
-    def elapsed_time(self, other): return 0.0
+    def elapsed_time(self, other): return 1.0          # not a clock: a non-zero constant so that rates can be formed
 
 
 @contextlib.contextmanager
@@ -51,3 +51,16 @@ def _stream_ctx(s):
 cuda = types.SimpleNamespace(Stream=_Stream, Event=_Event, stream=_stream_ctx, synchronize=lambda *a: None, is_available=lambda: True,
                              set_device=lambda d: None, current_stream=lambda *a: _Stream(),
                              get_device_properties=lambda d: types.SimpleNamespace(multi_processor_count=int(os.environ.get("QPAD_EMU_SMS", "12")), name="emulated"))
+
+distributed = types.ModuleType("torch.distributed")          # world = 1 only: imported by bench.py, never called
+
+
+def install(monkeypatch=None):
+    """put this module in the place of torch (and torch.distributed) in sys.modules"""
+    import sys
+    me = sys.modules[__name__]
+    for name, mod in (("torch", me), ("torch.distributed", distributed)):
+        if monkeypatch is not None:
+            monkeypatch.setitem(sys.modules, name, mod)
+        else:
+            sys.modules[name] = mod

@@ -1,0 +1,56 @@
+"""bench.py's B200 arms executed end to end on the CPU: the library is the host emulation (tests/emu), torch its stand-in
+(tests/emu/faketorch.py), the decks shrunk.  Time is not emulated, so every rate in the printed line is meaningless -- what is
+checked is that the functions the driver runs (`run_b200_local`: probe_partition -> LocalPipeline with 4 sweep-kernel stages -> fill ->
+timed waves -> end-to-end waves; `run_c5`: the neutral inside qpg_sim) execute without error on the current inputs (incl. the
+thinned, charge-scaled beam of make_inputs) and emit the JSON contract of the task."""
+import contextlib
+import io
+import json
+import types
+
+import pytest
+
+from emu import emu, faketorch
+
+KEYS = ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config",
+        "clocks", "gpu_launches", "roofline", "e2e")
+
+
+@pytest.fixture()
+def bench_mod(monkeypatch):
+    faketorch.install(monkeypatch)
+    monkeypatch.setenv("QPAD_EMU_SWEEP", "1")
+    monkeypatch.setenv("QPAD_EMU_SMS", "16")
+    import bench
+    with emu.patched():
+        yield bench
+
+
+def _run(fn, args):
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        fn(args)
+    return json.loads(buf.getvalue().strip().splitlines()[-1])
+
+
+def test_default_bench_function_runs(bench_mod, monkeypatch):
+    from qpad_b200 import decks
+    monkeypatch.setitem(decks.CONFIGS, "C2", dict(decks.CONFIGS["C2"], nr=64, nz=128, ppc1=2, ppc2=2, num_theta=8, iter_max=3))
+    args = types.SimpleNamespace(gpus=1, steps=2, warmup=1, config="C2", balance=1, transport=None, stages=4, no_cpu=True, no_micro=True, roof_slices=16,
+                                 ref_slices=8, no_sweep=False, no_graph=False, legacy_pipeline=False, impl="b200")
+    c0 = emu.lib().emu_coop_launches()
+    line = _run(bench_mod.run_b200_local, args)
+    assert all(k in line for k in KEYS), [k for k in KEYS if k not in line]
+    assert line["n_gpus"] == 1 and line["steps"] == 2 and line["dtype"] == "f64" and line["gpu_launches"] > 0
+    assert {"bound", "achieved", "peak", "frac", "traffic"} <= set(line["roofline"]) and {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(line["e2e"])
+    assert line["e2e"]["h2d_bytes_per_step"] == 64 * 2048 and line["config"]["pc_iters_per_slice"] > 1.2      # a driven wake, not the quiet plasma
+    assert emu.lib().emu_coop_launches() - c0 >= 4 * 3                                                        # the sweep kernels of the 4 stages ran
+
+
+def test_c5_bench_function_runs(bench_mod, monkeypatch):
+    from qpad_b200 import decks
+    monkeypatch.setitem(decks.CONFIGS, "C5", dict(decks.CONFIGS["C5"], nr=64, nz=48, ppc1=2, ppc2=2, num_theta=8, iter_max=3, rmax=6.0, zmax=8.0))
+    args = types.SimpleNamespace(steps=1, warmup=1, no_graph=False, no_cpu=True, ref_slices=8)
+    line = _run(bench_mod.run_c5, args)
+    assert all(k in line for k in KEYS), [k for k in KEYS if k not in line]
+    assert line["value"] > 0 and "neutral Li" in line["config"]["workload"] and line["e2e"]["h2d_bytes_per_step"] > 0
