@@ -21,6 +21,7 @@ class _Tensor:
 
 
 def zeros(n, dtype=float64, device=None): return _Tensor(np.zeros(n, dtype=dtype))
+def tensor(values, dtype=float64, device=None): return _Tensor(np.asarray(values, dtype=dtype))
 def empty(n, dtype=float64, device=None): return zeros(n, dtype, device)
 def device(kind, index=0): return (kind, index)
 

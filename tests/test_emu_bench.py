@@ -54,3 +54,14 @@ def test_c5_bench_function_runs(bench_mod, monkeypatch):
     line = _run(bench_mod.run_c5, args)
     assert all(k in line for k in KEYS), [k for k in KEYS if k not in line]
     assert line["value"] > 0 and "neutral Li" in line["config"]["workload"] and line["e2e"]["h2d_bytes_per_step"] > 0
+
+
+def test_single_stage_bench_function_runs(bench_mod, monkeypatch):
+    """`bench.py --stages 1` (run_b200): one sweep kernel on all SMs, the command the ncu captures are taken from"""
+    from qpad_b200 import decks
+    monkeypatch.setitem(decks.CONFIGS, "C2", dict(decks.CONFIGS["C2"], nr=64, nz=64, ppc1=2, ppc2=2, num_theta=8, iter_max=3))
+    args = types.SimpleNamespace(gpus=1, steps=1, warmup=1, config="C2", balance=1, transport=None, stages=1, no_cpu=True, no_micro=True, roof_slices=16,
+                                 ref_slices=8, no_sweep=False, no_graph=False, legacy_pipeline=False, impl="b200")
+    line = _run(bench_mod.run_b200, args)
+    assert all(k in line for k in KEYS), [k for k in KEYS if k not in line]
+    assert line["gpu_launches"] > 0 and line["roofline"]["bound"] == "hbm"
