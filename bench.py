@@ -26,6 +26,12 @@ import numpy as np  # noqa: E402
 
 METRIC = "plasma particle-slice updates/s"
 UNIT = "updates/s"
+DATA = "synthetic (lattice plasma per fdist2d rule; PCG64(10) tri-Gaussian beam thinned to one particle per radial cell width and slice, charge-scaled to deposit the deck's density)"
+
+
+def workload_string(name, cfg, npp0):
+    """identical in the B200 arm and the reference arm (the driver compares them)"""
+    return f"{name}: nr={cfg['nr']} nz={cfg['nz']} max_mode={cfg['max_mode']} Np/slice={npp0} iter_max={cfg['iter_max']}"
 
 
 def deck_config(name):
@@ -146,6 +152,7 @@ def cpu_sample(cfg, plasma, beam_arrays, nslices, fast=True, nstages=1):
 
 _cpu_barrier = None
 LAST_CPU_NIT = None
+LAST_CPU_INFO = {}
 
 
 def _cpu_init(barrier):
@@ -154,34 +161,92 @@ def _cpu_init(barrier):
 
 
 def _cpu_worker(args):
-    """one host core = one pipeline stage of the reference's `mpirun -np k` run in steady state: every stage sweeps
-    slices of its own 3D step at the same time (parallel_module.f03:221-239); here every worker sweeps the same
-    bounded sample"""
-    name, nslices = args
+    """one host core = one stage of the reference's `mpirun -np k` xi-pipeline in steady state (parallel_module.f03:221-239): stage i
+    owns slab i of the deck (equal-length slabs, options_class.f03:103-106) and all stages sweep their slabs AT THE SAME TIME, each
+    on its own 3D step.  A stage's slab needs the plasma state the upstream stages hand down; here every worker produces it itself
+    in an UNTIMED preparation sweep over the slices ahead of its slab (the quasi-static recurrence has no shortcut), snapshots it,
+    and then times `reps` sweeps of its slab from that state -- together the k timed slabs are exactly one 3D step of the deck,
+    with the deck's own predictor-corrector iteration counts."""
+    name, j0, n, reps, nwarm = args
     cfg, beam = deck_config(name)
-    plasma, bm = make_inputs(cfg, beam, xi_cells=(0, nslices + 2))      # the beam charge the sampled slices see
-    cpu_sample(cfg, plasma, bm, 2)                      # warm-up (page in, caches)
-    if _cpu_barrier is not None:
-        _cpu_barrier.wait()                             # all stages start their timed sample together
-    t0 = time.time()
-    upd, dt, iters = cpu_sample(cfg, plasma, bm, nslices)
-    return upd, dt, t0, time.time(), iters / max(nslices, 1)
+    plasma, bm = make_inputs(cfg, beam, xi_cells=(0, j0 + n + 2))       # the beam charge the slices up to the slab's end see
+    from oracle import oracle as O
+    kw = {k: cfg[k] for k in ("nr", "nz", "max_mode", "rmax", "zmin", "zmax", "dt", "iter_max", "iter_reltol", "iter_abstol", "ppc1", "ppc2", "num_theta")}
+    las = cfg.get("laser")
+    if las:
+        from qpad_b200 import decks
+        kw.update(sp_push_type=5, laser_on=1, laser_iter=las["iteration"], laser_k0=las["k0"], beam_evol=0)
+    neu = cfg.get("neutral")
+    if neu:
+        kw.update(sp_density=0.0, neut_on=1, neut_elem=neu["element"], neut_ion_max=neu["ion_max"], neut_ppc1=cfg["ppc1"], neut_ppc2=cfg["ppc2"],
+                  neut_num_theta=cfg["num_theta"], neut_density=neu.get("density", 1.0), n0=cfg.get("n0", 1.0e17))
+    sim = O.Sim(fast=True, **kw)
+    if las:
+        sim.set_laser(*decks.laser_gaussian(cfg["nr"], cfg["nz"], cfg["rmax"], cfg["zmin"], cfg["zmax"], **las))
+    sim.set_beam(*bm)
+    tp = time.time()
+    sim.run_slices(j0)                                   # untimed: the state at the slab's first slice (stage_begin + slices 1..j0)
+    can_snap = not (las or neu)
+    if can_snap:
+        sim.snapshot()
+    prep = time.time() - tp
+    out = []
+    for r in range(nwarm + reps):
+        if r > 0:
+            if not can_snap:
+                break
+            sim.restore()
+        if _cpu_barrier is not None:
+            _cpu_barrier.wait()                          # all stages start their slab together, every repetition
+        i0 = sim.total_iters()
+        t0 = time.time()
+        upd = sim.run_range(j0 + 1, j0 + n)
+        t1 = time.time()
+        if r >= nwarm or not can_snap:
+            out.append((upd, t0, t1, sim.total_iters() - i0))
+    return out, prep, n
 
 
-def cpu_parallel(name, nslices, ncores=None):
-    """all host cores: k independent stage processes, aggregate updates / wall time of the slowest overlap window"""
+def cpu_parallel(name, nslices=None, ncores=None, reps=1, nwarm=0):
+    """All host cores as the k stages of the reference's xi-pipeline in steady state over ONE 3D step of the deck (see _cpu_worker).
+    Returns (updates of the timed steps, wall seconds = sum over steps of the slowest stage's slab time, cores, per-step list).
+    `nslices` caps the slab length (a bounded sample for very large k * slab products); None = the whole deck."""
     import multiprocessing as mp
     from oracle import oracle as O
+    from qpad_b200.pipeline import slab_partition
     O.build(fast=True, force=True)                      # -O3 -march=native of THIS box, once, before the workers start
-    k = ncores or os.cpu_count() or 1
+    cfg, _ = deck_config(name)
+    k = min(ncores or os.cpu_count() or 1, cfg["nz"] // 2)
+    parts = slab_partition(cfg["nz"], k)
+    if nslices:
+        parts = [(a, min(n, nslices)) for a, n in parts]
+    if cfg.get("laser") or cfg.get("neutral"):
+        reps, nwarm = 1, 0
     ctx = mp.get_context("spawn")
     with ctx.Pool(k, initializer=_cpu_init, initargs=(ctx.Barrier(k),)) as pool:
-        res = pool.map(_cpu_worker, [(name, nslices)] * k, chunksize=1)
-    global LAST_CPU_NIT
-    upd = sum(r[0] for r in res)
-    wall = max(r[3] for r in res) - min(r[2] for r in res)
-    LAST_CPU_NIT = float(np.mean([r[4] for r in res]))   # predictor-corrector iterations per slice of the sample (the GPU arm's whole step takes more inside the beam)
-    return upd, wall, k, max(r[1] for r in res)
+        res = pool.map(_cpu_worker, [(name, a, n, reps, nwarm) for a, n in parts], chunksize=1)
+    global LAST_CPU_NIT, LAST_CPU_INFO
+    steps = []
+    for r in range(len(res[0][0])):
+        upd = sum(w[0][r][0] for w in res)
+        wall = max(w[0][r][2] for w in res) - min(w[0][r][1] for w in res)
+        steps.append((upd, wall))
+    iters = sum(w[0][0][3] for w in res)
+    nsl = sum(w[2] for w in res)
+    LAST_CPU_NIT = iters / max(nsl, 1)
+    slab_s = [w[0][-1][2] - w[0][-1][1] for w in res]
+    LAST_CPU_INFO = {"slices_timed_per_step": nsl, "stages": k, "prep_s_max": max(w[1] for w in res), "slab_s_min": min(slab_s), "slab_s_max": max(slab_s)}
+    return sum(u for u, _ in steps), sum(t for _, t in steps), k, steps
+
+
+def cpu_sample_text(name, k):
+    i = LAST_CPU_INFO
+    return (f"the reference's xi-pipeline in steady state on {k} host cores: {k} concurrent single-threaded stage processes, stage i sweeps slab i of the "
+            f"{name} deck (equal-length slabs, options_class.f03:103-106) -- together {i['slices_timed_per_step']} slices = "
+            f"{'one whole 3D step' if i['slices_timed_per_step'] >= deck_config(name)[0]['nz'] else 'a bounded sample of the 3D step'} per timed step, "
+            f"{LAST_CPU_NIT:.3f} predictor-corrector iterations per slice; a step costs the slowest slab ({i['slab_s_max']:.1f} s, fastest {i['slab_s_min']:.1f} s); "
+            f"each stage first produced the plasma state at its slab's first slice in an untimed sweep (up to {i['prep_s_max']:.0f} s); "
+            "oracle restatement of the reference algorithm (-O3 -march=native; the Fortran/MPI/HYPRE reference cannot be built here)")
 
 
 def run_reference(args):
@@ -189,22 +254,16 @@ def run_reference(args):
     if rank != 0:
         return
     cfg, beam = deck_config(args.config)
-    plasma, bm = make_inputs(cfg, beam)
-    nsl = args.ref_slices
-    vals = []
-    for it in range(args.warmup + args.steps):
-        upd, wall, k, tmax = cpu_parallel(args.config, 2 if it < args.warmup else nsl)
-        if it >= args.warmup:
-            vals.append((upd, wall))
-    upd = sum(u for u, _ in vals); dt = sum(t for _, t in vals)
+    plasma, bm = make_inputs(cfg, beam) if args.config not in ("C4", "C5") else (make_inputs(cfg, None)[0], None)
+    upd, dt, k, steps = cpu_parallel(args.config, args.ref_slices or None, reps=args.steps, nwarm=min(args.warmup, 1))
+    nst = len(steps)
     value = upd / dt
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic (lattice plasma, PCG64(10) tri-Gaussian beam)",
-            "config": {"workload": f"{args.config}: nr={cfg['nr']} nz={cfg['nz']} max_mode={cfg['max_mode']} Np/slice={len(plasma[4])}", "parallelism": f"cpu: {k} stage processes (one per host core)"},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": k, "kind": "port",
-                             "sample": f"per timed step: {k} concurrent stage processes x the first {nsl} xi slices of the {args.config} 3D step ({LAST_CPU_NIT:.2f} predictor-corrector iterations per slice in this sample; oracle restatement of the reference algorithm, -O3 -march=native; the Fortran reference is MPI-pipelined with one single-threaded rank per core and cannot be built here)",
-                             "pc_iters_per_slice": LAST_CPU_NIT},
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": nst, "warmup": min(args.warmup, 1),
+            "ms_per_step": 1e3 * dt / nst, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": DATA,
+            "config": {"workload": workload_string(args.config, cfg, len(plasma[4])), "parallelism": f"cpu: {k} stage processes (one per host core)",
+                       "pc_iters_per_slice": LAST_CPU_NIT},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": k, "kind": "port", "sample": cpu_sample_text(args.config, k), "pc_iters_per_slice": LAST_CPU_NIT},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line))
 
@@ -365,17 +424,16 @@ def run_b200(args):
         cpu = None
         if rank == 0 and world == 1 and not args.no_cpu:
             try:
-                upd_c, wall_c, k_c, tmax_c = cpu_parallel(args.config, args.ref_slices)
-                cpu = {"value": upd_c / wall_c, "unit": UNIT, "cores": k_c, "kind": "port",
-                       "sample": f"{k_c} concurrent stage processes (one per host core, the reference's MPI xi-pipeline in steady state) x the first {args.ref_slices} xi slices of the {args.config} step ({LAST_CPU_NIT:.2f} predictor-corrector iterations per slice in this sample): {upd_c} updates in {wall_c:.1f} s; oracle restatement, -O3 -march=native"}
+                upd_c, wall_c, k_c, _steps = cpu_parallel(args.config, args.ref_slices or None)
+                cpu = {"value": upd_c / wall_c, "unit": UNIT, "cores": k_c, "kind": "port", "sample": cpu_sample_text(args.config, k_c), "pc_iters_per_slice": LAST_CPU_NIT}
             except Exception as exc:  # the GPU result must not be lost to a CPU-side problem
                 cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {exc}"}
 
         if rank == 0:
             line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                     "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-                    "data": "synthetic (lattice plasma per fdist2d rule, PCG64(10) tri-Gaussian beam on a 256x512 lattice)",
-                    "config": {"workload": f"{args.config}: nr={cfg['nr']} nz={cfg['nz']} max_mode={cfg['max_mode']} Np/slice={npp0} iter_max={cfg['iter_max']}",
+                    "data": DATA,
+                    "config": {"workload": workload_string(args.config, cfg, npp0),
                                "parallelism": "single" if world == 1 else f"xi-pipeline x{world}: one xi slab per GPU, NCCL send/recv hand-offs; pipeline filled before the timed region (stage r runs {world}-1-r steps ahead), every stage then times {args.steps} steady-state steps",
                                "l2": "step working set (field volumes ~0.9 GB + beam) exceeds the 126 MB L2",
                                "pc_iters_per_slice": iters / max(slices, 1)},
@@ -393,6 +451,83 @@ def run_b200(args):
         runner.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+
+def beam_sums(x, p, q):
+    """additive moments of a beam particle set (so that shards on several ranks can be summed)"""
+    v = [q.sum()]
+    for k in (0, 1):
+        v += [np.sum(q * x[:, k]), np.sum(q * p[:, k]), np.sum(q * x[:, k] ** 2), np.sum(q * p[:, k] ** 2), np.sum(q * x[:, k] * p[:, k])]
+    v.append(np.sum(q * p[:, 2]))
+    return np.array(v, dtype=np.float64)
+
+
+def beam_moments_from_sums(v):
+    out = {}
+    for k, ax in enumerate("xy"):
+        sx, sp, sxx, spp, sxp = (v[1 + 5 * k + i] / v[0] for i in range(5))
+        vxx, vpp, vxp = sxx - sx * sx, spp - sp * sp, sxp - sx * sp
+        out[ax] = (sx, np.sqrt(max(vxx, 0.0)), np.sqrt(max(vxx * vpp - vxp * vxp, 0.0)))
+    out["pz"] = v[11] / v[0]
+    return out
+
+
+def parity_check(cfg, plasma, bm, lp, nsteps, device, rank, world, dist, tol=1e-6):
+    """Correctness of the pipelined run carried by the bench line: after lp.drain() every stage holds the fields of 3D step
+    `nsteps` - 1 on its slab; the same `nsteps` steps are re-run on ONE stage (a single sweep kernel over the whole box, the
+    path the full-size oracle parity tests validate: tests/test_gpu_fullsize.py) and the E_z / psi on-axis line-outs of every slab
+    and the beam centroid / rms size / emittance are compared (north star: <= 1e-6 relative).  Every rank checks its own slabs."""
+    import torch
+    from qpad_b200.pipeline import _make_sim
+    st = torch.cuda.Stream(device=device)
+    sim = _make_sim(cfg, len(plasma[4]), len(bm[2]), st, device, 1)
+    sim.init_species(*plasma)
+    sim.beam.upload(*bm)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    for k in range(nsteps):
+        if k == nsteps - 1:
+            ev[0].record(st)
+        sim.step3d()
+    ev[1].record(st)
+    st.synchronize()
+    single_ms = ev[0].elapsed_time(ev[1])
+    ez1, ps1 = sim.field("e").lineout(3, 0, 1), sim.field("psi").lineout(1, 0, 1)
+    upd1, it1, sl1 = sim.stats()
+    err_ez = err_ps = 0.0
+    for (off, n), s in zip(lp.parts[lp.base:lp.base + lp.S], lp.sims):
+        ez, ps = s.field("e").lineout(3, 0, 1), s.field("psi").lineout(1, 0, 1)
+        err_ez = max(err_ez, float(np.max(np.abs(ez[:n] - ez1[off:off + n]))))
+        err_ps = max(err_ps, float(np.max(np.abs(ps[:n] - ps1[off:off + n]))))
+    err_ez /= float(np.max(np.abs(ez1))); err_ps /= float(np.max(np.abs(ps1)))
+    sums = np.zeros(12)
+    nb = 0
+    for s in lp.sims:
+        bx, bp, bq = s.beam.download()
+        nb += len(bq)
+        if len(bq):
+            sums += beam_sums(bx, bp, bq)
+    t = torch.tensor(list(sums) + [float(nb)], dtype=torch.float64, device="cuda")
+    e = torch.tensor([err_ez, err_ps], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        dist.all_reduce(e, op=dist.ReduceOp.MAX)
+    sums, nb = t[:12].cpu().numpy(), int(t[12].item())
+    err_ez, err_ps = float(e[0].item()), float(e[1].item())
+    bx, bp, bq = sim.beam.download()
+    m1, mp_ = beam_moments_from_sums(beam_sums(bx, bp, bq)), beam_moments_from_sums(sums)
+    sim.close()
+    berr = 0.0
+    for ax in "xy":
+        c1, s1, e1 = m1[ax]; c2, s2, e2 = mp_[ax]
+        berr = max(berr, abs(c1 - c2) / s1, abs(s1 - s2) / s1, abs(e1 - e2) / e1)
+    berr = max(berr, abs(m1["pz"] - mp_["pz"]) / abs(m1["pz"]))
+    ok = bool(err_ez < tol and err_ps < tol and berr < tol and nb == len(bq))
+    return {"ok": ok, "tol": tol, "steps_compared": nsteps, "ez_lineout_rel_err": err_ez, "psi_lineout_rel_err": err_ps,
+            "beam_centroid_size_emittance_rel_err": berr, "beam_particles": nb, "beam_particles_single_stage": int(len(bq)),
+            "against": "the same 3D steps on ONE stage (one sweep kernel over the whole box) on this GPU; that path is checked against the CPU oracle at full size in tests/test_gpu_fullsize.py"}, \
+        {"single_step_ms": single_ms, "what": "latency of ONE 3D step on one GPU without the SM-partitioned pipeline (--stages 1: one sweep kernel on all SMs + beam deposit / push)",
+         "updates_per_s": upd1 / max(nsteps, 1) / (single_ms * 1e-3)}
 
 
 def run_c4(args):
@@ -462,9 +597,8 @@ def run_c4(args):
     cpu = None
     if not args.no_cpu:
         try:
-            upd_c, wall_c, k_c, _t = cpu_parallel("C4", args.ref_slices)
-            cpu = {"value": upd_c / wall_c, "unit": UNIT, "cores": k_c, "kind": "port",
-                   "sample": f"{k_c} concurrent stage processes (one per host core) x the first {args.ref_slices} xi slices of the C4 step (the slices that hold the pulse): {upd_c} updates in {wall_c:.1f} s; oracle restatement, -O3 -march=native"}
+            upd_c, wall_c, k_c, _t = cpu_parallel("C4", args.ref_slices or None)
+            cpu = {"value": upd_c / wall_c, "unit": UNIT, "cores": k_c, "kind": "port", "sample": cpu_sample_text("C4", k_c), "pc_iters_per_slice": LAST_CPU_NIT}
         except Exception as exc:
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {exc}"}
     line = {"metric": METRIC, "value": upd / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
@@ -640,12 +774,39 @@ def run_b200_local(args):
         from qpad_b200.pipeline import kernel_microbench
         lp.sync()
         roof_hbm = kernel_microbench(lp.sims[min(1, S - 1)], cfg, peak)
+    # ---- correctness of THIS run + what a user gets outside the steady state --------------------------------------------
+    nsteps_done = lp.w                 # after the drain every stage has finished 3D steps 0 .. lp.w - 1
+    lp.drain()
+    sync_all()
+    parity = single = None
+    if args.check:
+        parity, single = parity_check(cfg, plasma, bm, lp, nsteps_done, local, rank, world, dist if world > 1 else None)
+    fill_incl = None
+    if args.fill_steps:
+        fill_incl = {"what": "updates/s of a run of K 3D steps INCLUDING pipeline fill and drain (K + stages - 1 waves), host wall clock around wave() x K + drain(), max over ranks",
+                     "stages": lp.G}
+        for K in args.fill_steps:
+            lp.restart()
+            sync_all()
+            u_a = lp.stats()[0]
+            t_a = time.perf_counter()
+            for _ in range(K):
+                lp.wave()
+            lp.drain()
+            sync_all()
+            dt_f = time.perf_counter() - t_a
+            u_f = lp.stats()[0] - u_a
+            tt = torch.tensor([dt_f, float(u_f)], dtype=torch.float64, device="cuda")
+            if world > 1:
+                tm = tt.clone(); dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+                ts = tt.clone(); dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+                dt_f, u_f = tm[0].item(), ts[1].item()
+            fill_incl[f"K={K}"] = {"updates_per_s": u_f / dt_f, "seconds": dt_f, "model_K_over_K_plus_S_minus_1": K / (K + lp.G - 1.0)}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         try:
-            upd_c, wall_c, k_c, tmax_c = cpu_parallel(args.config, args.ref_slices)
-            cpu = {"value": upd_c / wall_c, "unit": UNIT, "cores": k_c, "kind": "port",
-                   "sample": f"{k_c} concurrent stage processes (one per host core, the reference's MPI xi-pipeline in steady state) x the first {args.ref_slices} xi slices of the {args.config} step ({LAST_CPU_NIT:.2f} predictor-corrector iterations per slice in this sample): {upd_c} updates in {wall_c:.1f} s; oracle restatement, -O3 -march=native"}
+            upd_c, wall_c, k_c, _steps = cpu_parallel(args.config, args.ref_slices or None)
+            cpu = {"value": upd_c / wall_c, "unit": UNIT, "cores": k_c, "kind": "port", "sample": cpu_sample_text(args.config, k_c), "pc_iters_per_slice": LAST_CPU_NIT}
         except Exception as exc:
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {exc}"}
     if rank == 0:
@@ -654,8 +815,8 @@ def run_b200_local(args):
         where = "one GPU" if world == 1 else f"{world} GPUs x {S} stages, {how}"
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-                "data": "synthetic (lattice plasma per fdist2d rule, PCG64(10) tri-Gaussian beam on a 256x512 lattice)",
-                "config": {"workload": f"{args.config}: nr={cfg['nr']} nz={cfg['nz']} max_mode={cfg['max_mode']} Np/slice={npp0} iter_max={cfg['iter_max']}",
+                "data": DATA,
+                "config": {"workload": workload_string(args.config, cfg, npp0),
                            "parallelism": f"{where}: xi-pipeline over {world * S} stages, each an SM partition running one persistent sweep kernel; stage g sweeps slab g of 3D step n-g (the reference's pipeline, parallel_module.f03:221-239); filled before the timed region, a timed step = every stage sweeps its slab once = {cfg['nz']} slices",
                            "l2": "step working set (field volumes ~0.9 GB + beam) exceeds the 126 MB L2",
                            "pc_iters_per_slice": nit},
@@ -663,9 +824,10 @@ def run_b200_local(args):
         if e2e: line["e2e"] = e2e
         if roof_hbm: line["roofline_hbm_stream"] = roof_hbm
         if cpu: line["cpu_baseline"] = cpu
+        if parity: line["parity_check"] = parity
+        if single: line["single_step"] = single
+        if fill_incl: line["fill_inclusive"] = fill_incl
         print(json.dumps(line))
-    lp.drain()
-    sync_all()
     lp.close()
     if world > 1:
         dist.destroy_process_group()
@@ -737,9 +899,8 @@ def run_c5(args):
     cpu = None
     if not args.no_cpu:
         try:
-            upd_c, wall_c, k_c, _t = cpu_parallel("C5", args.ref_slices)
-            cpu = {"value": upd_c / wall_c, "unit": UNIT, "cores": k_c, "kind": "port",
-                   "sample": f"{k_c} concurrent stage processes (one per host core) x the first {args.ref_slices} xi slices of the C5 step: {upd_c} updates in {wall_c:.1f} s; oracle restatement, -O3 -march=native"}
+            upd_c, wall_c, k_c, _t = cpu_parallel("C5", args.ref_slices or None)
+            cpu = {"value": upd_c / wall_c, "unit": UNIT, "cores": k_c, "kind": "port", "sample": cpu_sample_text("C5", k_c), "pc_iters_per_slice": LAST_CPU_NIT}
         except Exception as exc:
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {exc}"}
     line = {"metric": METRIC, "value": upd / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
@@ -761,9 +922,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="C2")
-    ap.add_argument("--ref-slices", type=int, default=48, help="xi slices per CPU sample and core")
+    ap.add_argument("--ref-slices", type=int, default=0, help="CPU arm: cap of the slab length each host core times (0 = the whole deck: k cores x their equal-length slabs = one 3D step)")
     ap.add_argument("--roof-slices", type=int, default=64)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--check", type=int, default=1, help="1 (default): after the timed region compare the pipelined run's E_z / psi line-outs and beam moments with a one-stage run of the same 3D steps (parity_check in the JSON line)")
+    ap.add_argument("--fill-steps", type=int, nargs="*", default=[28, 128], help="report updates/s of runs of K 3D steps including pipeline fill and drain (fill_inclusive); empty = skip")
     ap.add_argument("--no-graph", action="store_true", help="C4: plain stream launches instead of CUDA-graph replay of the slice body")
     ap.add_argument("--no-sweep", action="store_true", help="per-slice CUDA-graph launches instead of the persistent sweep kernel")
     ap.add_argument("--no-micro", action="store_true", help="skip the stream-from-HBM kernel microbenchmark")
@@ -772,8 +935,6 @@ def main():
     ap.add_argument("--transport", default=None, choices=["p2p", "nccl"], help="N>1: how the stage hand-offs cross GPUs (default p2p = peer-memory writes + flags, csrc/p2p.cu)")
     ap.add_argument("--stages", type=int, default=0, help="xi-pipeline stages mapped onto SM partitions of ONE GPU (LocalPipeline); 0 = auto (up to 4), 1 = a single sweep kernel on all SMs")
     args = ap.parse_args()
-    if args.config == "C5" and args.ref_slices == 48:
-        args.ref_slices = 300          # ionisation starts where the beam field reaches a few GV/m: the first 48 slices release no electrons
     if args.impl == "reference":
         run_reference(args)
     elif args.config == "C4":

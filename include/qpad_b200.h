@@ -274,6 +274,10 @@ int qpg_sim_sweep_profile(qpg_sim s, double *out12, int reset);
  * slice (ns, %globaltimer) and the predictor-corrector iterations it took (the n_it of simulation_class.f03:379-407).
  * nzp entries each.  The cost profile along xi that the pipeline's slab partition is balanced with. */
 int qpg_sim_slice_trace(qpg_sim s, double *ns_per_slice, int *iters_per_slice);
+/* test hook: raises the sweep kernel's (sticky) watchdog word as a timed-out barrier would.  The next qpg_sim_run_slices leaves at
+ * once, still releases a pending backward hand-off flag (qpg_sim_set_back_handoff) so that the upstream stage does not hang, and
+ * qpg_sim_stats / qpg_ctx_sync / qpg_sim_sweep_profile return QPG_ERR_STATE from then on. */
+int qpg_sim_debug_abort(qpg_sim s);
 
 /* ------------------------------------------------------------------------------------------ */
 /* peer-memory transport of the xi-pipeline between the GPUs of one box (one process per GPU).

@@ -98,6 +98,9 @@ def lib(fast=False):
         "orc_sim_get_beam": (None, [vp, i, _dp, _dp, _dp]),
         "orc_sim_get_field": (l, [vp, i, C.c_char_p, i, C.c_void_p]),
         "orc_sim_total_iters": (l, [vp]),
+        "orc_sim_snapshot": (None, [vp]),
+        "orc_sim_restore": (None, [vp]),
+        "orc_sim_get_slice_iters": (None, [vp, i, _ip]),
         "orc_sim_total_subcycles": (l, [vp]),
         "orc_exp_fac_max": (d, [_dp, _dp, l]),
         "orc_clamp_exp_fac": (None, [_dp, _dp, l, d]),
@@ -216,6 +219,18 @@ class Sim:
 
     def total_iters(self):
         return self.L.orc_sim_total_iters(self.h)
+
+    def snapshot(self):
+        self.L.orc_sim_snapshot(self.h)
+
+    def restore(self):
+        self.L.orc_sim_restore(self.h)
+
+    def slice_iters(self, stage=0):
+        """predictor-corrector iterations of each slice of the stage's last sweep"""
+        out = np.zeros(self.nzp(stage), dtype=np.int32)
+        self.L.orc_sim_get_slice_iters(self.h, stage, out)
+        return out
 
     def total_subcycles(self):
         return self.L.orc_sim_total_subcycles(self.h)

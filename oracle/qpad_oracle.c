@@ -1350,6 +1350,7 @@ typedef struct {
     double *mb_plasma; long mb_plasma_np;
     double *mb_beam; long mb_beam_np, mb_beam_cap;
     double *conv_re, *conv_im;
+    int *slice_iters;   /* predictor-corrector iterations of each slice in the stage's last sweep (test bookkeeping, not in the reference) */
 } ostage;
 
 struct orc_sim {
@@ -1455,6 +1456,7 @@ orc_sim *orc_sim_create(const orc_params *prm)
         st->mb_plasma = NULL; st->mb_plasma_np = 0;
         st->mb_beam = NULL; st->mb_beam_np = 0; st->mb_beam_cap = 0;
         st->conv_re = (double *)calloc((size_t)nr + 1, sizeof(double)); st->conv_im = (double *)calloc((size_t)nr + 1, sizeof(double));
+        st->slice_iters = (int *)calloc((size_t)st->nzp + 1, sizeof(int));
     }
     /* the pgc pushers gather from the laser slice images even when the envelope is zero; one laser, one stage */
     if (s->prm.laser_on || s->prm.sp_push_type == 4 || s->prm.sp_push_type == 5) { s->prm.laser_on = 1; laser_alloc(s); }
@@ -1479,7 +1481,7 @@ void orc_sim_destroy(orc_sim *s)
         fld_free(&st->spe.q); fld_free(&st->spe.cu); fld_free(&st->spe.dcu); fld_free(&st->spe.amu); fld_free(&st->spe.qn);
         free(st->beam.x); free(st->beam.p); free(st->beam.q); fld_free(&st->beam.q3);
         free(st->mb_cu); free(st->mb_bspe); free(st->mb_e); free(st->mb_b); free(st->mb_qguard); free(st->mb_plasma); free(st->mb_beam);
-        free(st->conv_re); free(st->conv_im);
+        free(st->conv_re); free(st->conv_im); free(st->slice_iters);
     }
     if (s->las_alloc)
         for (int k = 0; k < s->prm.nstages; k++) {
@@ -1569,6 +1571,7 @@ static void laser_slice(orc_sim *s, int k, int j);
 static void slice_step(orc_sim *s, int k, int j)
 {
     ostage *st = &s->st[k];
+    st->slice_iters[j - 1] = 0;
     const orc_params *pr = &s->prm;
     int nr = pr->nr, M = pr->max_mode;
     double dr = s->dr, dxi = s->dxi;
@@ -1622,7 +1625,7 @@ static void slice_step(orc_sim *s, int k, int j)
         solve_bz_ops(s->op_bz, st->cu.f1, st->b_spe.f1, nr, M, dr);                 /* :392 */
         double rel, ab;
         conv_compare(st, &st->b_spe, 2, M, &rel, &ab);                              /* :395 */
-        s->total_iters++;
+        s->total_iters++; st->slice_iters[j - 1]++;
         if (rel < pr->iter_reltol || ab < pr->iter_abstol) break;                   /* :396 */
     }
     if (pr->laser_on) {                                                             /* :401 lasers%deposit_chi (sim_lasers_class.f03:175-195) */
@@ -1711,6 +1714,7 @@ void orc_subcyc_step(double exp_fac, double exp_fac_max, double dt, double dt_mi
 static void slice_step_subcyc(orc_sim *s, int k, int j)
 {
     ostage *st = &s->st[k];
+    st->slice_iters[j - 1] = 0;
     const orc_params *pr = &s->prm;
     int nr = pr->nr, M = pr->max_mode;
     double dr = s->dr, dxi = s->dxi;
@@ -1769,7 +1773,7 @@ static void slice_step_subcyc(orc_sim *s, int k, int j)
             solve_bz_ops(s->op_bz, st->cu.f1, st->b_spe.f1, nr, M, dr);
             double rel, ab;
             conv_compare(st, &st->b_spe, 2, M, &rel, &ab);
-            s->total_iters++;
+            s->total_iters++; st->slice_iters[j - 1]++;
             if (rel < pr->iter_reltol || ab < pr->iter_abstol) break;
         }
         fld_add1_3(&st->b_spe, &st->b_beam, &st->b);                                /* :292-295 */
@@ -2063,6 +2067,42 @@ long orc_sim_run_range(orc_sim *s, int j0, int j1)
     return updates;
 }
 
+/* ---- bench.py's CPU arm only (not in the reference): save / restore the SLICE state of stage 0 -- plasma particles and the f1
+ * images the slice loop carries from one slice to the next -- so that a worker can time the same xi slab repeatedly after one
+ * untimed sweep up to the slab's first slice.  The f2 volumes are not saved: a slab sweep only rewrites its own slices. */
+typedef struct { long npp; double *x, *p, *gamma, *psi, *q, *f1[20], *conv_re, *conv_im; } osnap;
+static osnap g_snap;
+static ofld *snap_field(ostage *st, int i)
+{
+    ofld *t[] = {&st->psi, &st->e_spe, &st->e_beam, &st->e, &st->b_spe, &st->b_beam, &st->b, &st->cu, &st->amu, &st->q_spe, &st->q_beam, &st->dcu,
+                 &st->acu, &st->spe.q, &st->spe.cu, &st->spe.dcu, &st->spe.amu, &st->spe.qn};
+    return i < (int)(sizeof(t) / sizeof(t[0])) ? t[i] : NULL;
+}
+static void snap_copy(double **dst, const double *src, size_t n) { *dst = (double *)realloc(*dst, sizeof(double) * (n ? n : 1)); memcpy(*dst, src, sizeof(double) * n); }
+void orc_sim_snapshot(orc_sim *s)
+{
+    ostage *st = &s->st[0];
+    const opart2d *pt = &st->spe.part;
+    const size_t n = (size_t)pt->npp;
+    g_snap.npp = pt->npp;
+    snap_copy(&g_snap.x, pt->x, 2 * n); snap_copy(&g_snap.p, pt->p, 3 * n); snap_copy(&g_snap.gamma, pt->gamma, n);
+    snap_copy(&g_snap.psi, pt->psi, n); snap_copy(&g_snap.q, pt->q, n);
+    for (int i = 0; snap_field(st, i); i++) snap_copy(&g_snap.f1[i], snap_field(st, i)->f1, fld_n1(snap_field(st, i)));
+    snap_copy(&g_snap.conv_re, st->conv_re, (size_t)s->prm.nr + 1); snap_copy(&g_snap.conv_im, st->conv_im, (size_t)s->prm.nr + 1);
+}
+void orc_sim_restore(orc_sim *s)
+{
+    ostage *st = &s->st[0];
+    opart2d *pt = &st->spe.part;
+    const size_t n = (size_t)g_snap.npp;
+    part2d_reserve(pt, g_snap.npp);
+    pt->npp = g_snap.npp;
+    memcpy(pt->x, g_snap.x, sizeof(double) * 2 * n); memcpy(pt->p, g_snap.p, sizeof(double) * 3 * n); memcpy(pt->gamma, g_snap.gamma, sizeof(double) * n);
+    memcpy(pt->psi, g_snap.psi, sizeof(double) * n); memcpy(pt->q, g_snap.q, sizeof(double) * n);
+    for (int i = 0; snap_field(st, i); i++) memcpy(snap_field(st, i)->f1, g_snap.f1[i], sizeof(double) * fld_n1(snap_field(st, i)));
+    memcpy(st->conv_re, g_snap.conv_re, sizeof(double) * ((size_t)s->prm.nr + 1)); memcpy(st->conv_im, g_snap.conv_im, sizeof(double) * ((size_t)s->prm.nr + 1));
+}
+
 int orc_sim_nzp(const orc_sim *s, int stage) { return s->st[stage].nzp; }
 long orc_sim_plasma_np(const orc_sim *s, int stage) { return s->st[stage].spe.part.npp; }
 void orc_sim_get_plasma(const orc_sim *s, int stage, double *x, double *p, double *gamma, double *psi, double *q)
@@ -2096,6 +2136,7 @@ long orc_sim_get_field(const orc_sim *s, int stage, const char *name, int which,
     return (long)fld_n2(f);
 }
 long orc_sim_total_iters(const orc_sim *s) { return s->total_iters; }
+void orc_sim_get_slice_iters(const orc_sim *s, int stage, int *out) { for (int j = 0; j < s->st[stage].nzp; j++) out[j] = s->st[stage].slice_iters[j]; }
 long orc_sim_total_subcycles(const orc_sim *s) { return s->total_subcycles; }
 long orc_sim_neutral_np(const orc_sim *s, int stage) { return s->prm.neut_on ? s->st[stage].neut.part.npp : 0; }
 void orc_sim_get_neutral(const orc_sim *s, int stage, double *x, double *p, double *gamma, double *psi, double *q)

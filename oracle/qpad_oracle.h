@@ -135,7 +135,11 @@ long orc_sim_beam_np(const orc_sim *s, int stage);
 void orc_sim_get_beam(const orc_sim *s, int stage, double *x, double *p, double *q);
 /* name in {psi,e,b,e_spe,b_spe,e_beam,b_beam,cu,amu,acu,dcu,q_spe,q_beam}; which=1 -> f1, 2 -> f2 (nzp+1 slices) */
 long orc_sim_get_field(const orc_sim *s, int stage, const char *name, int which, double *out);
+/* bench.py's CPU arm: save / restore the slice state of stage 0 (one snapshot per process) */
+void orc_sim_snapshot(orc_sim *s);
+void orc_sim_restore(orc_sim *s);
 long orc_sim_total_iters(const orc_sim *s);
+void orc_sim_get_slice_iters(const orc_sim *s, int stage, int *out);   /* PC iterations of each slice of the stage's last sweep (nzp ints) */
 long orc_sim_total_subcycles(const orc_sim *s);   /* sub-steps taken so far (= slices when nothing was sub-cycled) */
 /* proj_subcyc/part2d_subcyc_class.f03:28 / :48 ; simulation_subcyc_class.f03:431 */
 double orc_exp_fac_max(const double *p, const double *gamma, long npp);

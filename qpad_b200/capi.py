@@ -174,6 +174,7 @@ SIGNATURES = {
     "qpg_stage_part3d": (_i, [_vp, _vp, _i, _d, _pl]),
     "qpg_stage_wait": (_i, [_vp, C.POINTER(_pd), _pl]),
     "qpg_sim_slice_trace": (_i, [_vp, _pd, _pi]),
+    "qpg_sim_debug_abort": (_i, [_vp]),
     "qpg_wire_alloc": (_i, [C.POINTER(_vp), _l]),
     "qpg_wire_free": (_i, [_vp]),
     "qpg_wire_export": (_i, [_vp, C.c_char_p]),
@@ -396,6 +397,7 @@ class Part2d:
         _chk(self.L.qpg_part2d_push_u_pgc(self.h, push_type, ef.h, bf.h, *(f.h for f in laser), dt))
     def push_x(self, dt): _chk(self.L.qpg_part2d_push_x(self.h, dt))
     def update_bound(self): _chk(self.L.qpg_part2d_update_bound(self.h))
+    def move(self): _chk(self.L.qpg_part2d_move(self.h))                 # move_part2d_comm (species/part2d_comm.f03:147)
     def sort(self): _chk(self.L.qpg_part2d_sort(self.h))
 
     def sort_index(self):
@@ -683,6 +685,10 @@ class Sim:
         ns, it = np.zeros(self.nzp), np.zeros(self.nzp, dtype=np.int32)
         _chk(self.L.qpg_sim_slice_trace(self.h, ns.ctypes.data_as(_pd), it.ctypes.data_as(_pi)))
         return ns, it
+
+    def debug_abort(self):
+        """test hook: raise the sweep kernel's sticky watchdog word (qpg_sim_debug_abort)"""
+        _chk(self.L.qpg_sim_debug_abort(self.h))
 
     def stats(self):
         u, it, sl = _l(), _l(), _l()

@@ -264,7 +264,15 @@ extern "C" int qpg_ctx_destroy(qpg_ctx c)
     delete c;
     return 0;
 }
-extern "C" int qpg_ctx_sync(qpg_ctx c) { ARG_TRY(c, "null ctx"); CUDA_TRY(cudaStreamSynchronize(c->stream)); return 0; }
+extern "C" int qpg_ctx_sync(qpg_ctx c)
+{
+    ARG_TRY(c, "null ctx");
+    int ab = 0;   // flags[6]: latched by a sweep kernel that left through its watchdog (sweep.cu)
+    CUDA_TRY(cudaMemcpyAsync(&ab, c->flags + 6, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (ab) { qpg_set_error("sweep kernel aborted (a grid barrier or strip exchange timed out): results on this context are invalid"); return QPG_ERR_STATE; }
+    return 0;
+}
 
 // ------------------------------------------------------------------------------------------------
 // device helpers

@@ -297,6 +297,7 @@ static int sweep_prepare(qpg_sim s)
     const int nteam = (c->nr + ST_N - 1) / ST_N;
     if (per < 1 || nsm * per <= nteam) { qpg_set_error("sweep kernel: %d CTAs/SM x %d SMs cannot host a field team of %d", per, nsm, nteam); return QPG_ERR_UNSUPPORTED; }
     CUDA_TRY(cudaMalloc(&s->sw_bar, sizeof(unsigned) * 128));
+    CUDA_TRY(cudaMemsetAsync(s->sw_bar, 0, sizeof(unsigned) * 128, c->stream));   // incl. the sticky abort word [64], never cleared again
     CUDA_TRY(cudaMalloc(&s->sw_xbuf, sizeof(double) * 3 * SW_MAX_TEAM * SW_XK));
     CUDA_TRY(cudaMemsetAsync(s->sw_xbuf, 0, sizeof(double) * 3 * SW_MAX_TEAM * SW_XK, c->stream));
     CUDA_TRY(cudaMalloc(&s->sw_xll, sizeof(uint4) * 2 * SW_MAX_TEAM * SW_XK));
@@ -330,7 +331,7 @@ static int sweep_run(qpg_sim s, int j0, int j1)
         s->back_flag = nullptr;
     }
     a.bar = s->sw_bar; a.xbuf = s->sw_xbuf; a.xll = (uint4 *)s->sw_xll; a.prof = s->sw_prof; a.trace = s->sw_trace;
-    CUDA_TRY(cudaMemsetAsync(s->sw_bar, 0, sizeof(unsigned) * 128, c->stream));
+    CUDA_TRY(cudaMemsetAsync(s->sw_bar, 0, sizeof(unsigned) * 64, c->stream));    // barrier counters only: the abort word [64] is sticky
     CUDA_TRY(cudaMemsetAsync(s->sw_xll, 0, sizeof(uint4) * 2 * SW_MAX_TEAM * SW_XK, c->stream));   // sequence numbers restart at 1 every launch
     TprofScope tp(c, TP_K_SWEEP);
     cudaError_t e;
@@ -665,6 +666,7 @@ extern "C" int qpg_sim_stats(qpg_sim s, long *updates, long *pc_iters, long *sli
     if (updates) *updates = (long)cnt[0];
     if (pc_iters) *pc_iters = (long)cnt[1];
     if (slices) *slices = fl[4];
+    if (fl[6]) { qpg_set_error("sweep kernel aborted (a grid barrier or strip exchange timed out): fields and particles of this sim are invalid"); return QPG_ERR_STATE; }
     return 0;
 }
 extern "C" int qpg_sim_set_fused(qpg_sim s, int on)
@@ -719,7 +721,8 @@ extern "C" int qpg_sim_sweep_profile(qpg_sim s, double *out8, int reset)
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     // the abort flag of the last launch: a watchdog exit must not pass silently
     unsigned ab = 0;
-    CUDA_TRY(cudaMemcpy(&ab, s->sw_bar + 64, sizeof(ab), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpyAsync(&ab, s->sw_bar + 64, sizeof(ab), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
     if (ab) { qpg_set_error("sweep kernel aborted: a grid barrier timed out"); return QPG_ERR_STATE; }
     for (int k = 0; k < 12; k++) out8[k] = (double)h[k];
     if (getenv("QPG_SWEEP_STAMPS")) {   // development aid: stage stamps inside the field programs (cycles of CTA 0, thread 0)
@@ -727,6 +730,17 @@ extern "C" int qpg_sim_sweep_profile(qpg_sim s, double *out8, int reset)
         for (int k = 16; k < 29; k++) fprintf(stderr, " %.0f", (double)h[k] / (h[6] > 0 ? (double)h[6] : 1.0));
         fprintf(stderr, "\n");
     }
+    return 0;
+}
+extern "C" int qpg_sim_debug_abort(qpg_sim s)
+{
+    ARG_TRY(s, "null sim");
+    if (!s->use_sweep) { qpg_set_error("the watchdog belongs to the persistent sweep kernel"); return QPG_ERR_UNSUPPORTED; }
+    int rc = sweep_prepare(s);
+    if (rc) return rc;
+    const unsigned one = 1;
+    CUDA_TRY(cudaMemcpyAsync(s->sw_bar + 64, &one, sizeof(one), cudaMemcpyHostToDevice, s->ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->ctx->stream));
     return 0;
 }
 extern "C" int qpg_sim_slice_trace(qpg_sim s, double *ns_per_slice, int *iters_per_slice)

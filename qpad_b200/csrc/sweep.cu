@@ -48,6 +48,7 @@ __device__ __forceinline__ unsigned ld_volatile_u32(const unsigned *p)
     asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ void named_bar(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 // spin until *ctr reaches target (wrap-safe); false on abort / watchdog
@@ -582,7 +583,7 @@ __device__ void sweep_publish_back(const SweepArgs &a)
     }
     __threadfence_system();
     __syncthreads();
-    if (threadIdx.x == 0) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.back_flag), "r"(a.back_seq) : "memory");
+    if (threadIdx.x == 0) st_release_sys(a.back_flag, a.back_seq);
 }
 
 template <int M>
@@ -606,7 +607,9 @@ __global__ void __launch_bounds__(SW_T, 1) k_sweep(const __grid_constant__ Sweep
     long long prof[4] = {0, 0, 0, 0}, work[4] = {0, 0, 0, 0}, tprev = 0, tstart = 0, nstart = 0, namj = 0;
     const bool timer = (b == 0 && tid == 0);
     if (timer) { for (int k = 0; k < 16; k++) sm_f.stamps[k] = 0; tstart = tprev = clock64(); asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(nstart)); }
-    bool ok = true;
+    // the abort word is sticky (the host never clears it between launches): a sweep that follows an aborted one leaves at once,
+    // and the host reports QPG_ERR_STATE at its next synchronisation point (ctx->flags[6], qpg_sim_stats / qpg_ctx_sync)
+    bool ok = ld_volatile_u32(a.bar + 64) == 0;
     long long nprev = nstart;
     for (int j = a.j0; j <= a.j1 && ok; j++) {
         const long long namj0 = namj;
@@ -671,6 +674,12 @@ __global__ void __launch_bounds__(SW_T, 1) k_sweep(const __grid_constant__ Sweep
             nprev = now;
         }
         if (ok && j == 1 && a.back_flag && b == min(a.nteam, G - 1)) sweep_publish_back<M>(a);
+    }
+    if (!ok && tid == 0) {
+        f.flags[6] = 1;   // latched for the host: this sim's state is not to be trusted any more
+        // the upstream stage waits for this launch's backward hand-off with a stream memory operation: release it (poisoned
+        // data, the error surfaces on the host) instead of leaving its stream hanging
+        if (a.back_flag && b == min(a.nteam, G - 1)) st_release_sys(a.back_flag, a.back_seq);
     }
     // update_bound of the last slice (the next launch / the host expects compacted particles)
     if (ok && b == G - 1) compact_body(a.planes, 8, a.d_npp_w, a.d_nout, a.outmask, a.lists, 0, sm_i);

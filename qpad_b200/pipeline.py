@@ -811,6 +811,13 @@ class LocalPipeline:
             self.pending.pop(k).wait()
         self.sync()
 
+    def restart(self):
+        """after drain(): start a new run of the pipeline (fill again) on the state the stages hold -- every stage has finished the
+        same 3D step, nothing is in flight; the message counters of the links keep counting"""
+        if self.pending:
+            raise RuntimeError("restart() needs a drained pipeline")
+        self.w = 0
+
     def sync(self):
         for st in self.streams:
             st.synchronize()

@@ -41,7 +41,7 @@ PTX = {
          "*p = uint4{(unsigned)__double2loint(v), seq, (unsigned)__double2hiint(v), seq};"),
         ('asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(p) : "memory");',
          "{ const uint4 w = *p; a = w.x; b = w.y; c = w.z; d = w.w; } emu::poll_yield();"),
-        ('asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.back_flag), "r"(a.back_seq) : "memory");', "*a.back_flag = a.back_seq;"),
+        ('asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");', "*p = v;"),
         ('asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(nstart));', "nstart = clock64();"),
         ('asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));', "now = clock64();"),
         ('asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(nend));', "nend = clock64();"),

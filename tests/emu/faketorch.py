@@ -16,6 +16,8 @@ class _Tensor:
     def cpu(self): return self
     def numpy(self): return self.a.copy()
     def zero_(self): self.a[:] = 0; return self
+    def item(self): return self.a.item()
+    def clone(self): return _Tensor(self.a.copy())
     def __getitem__(self, k): return _Tensor(self.a[k])
     def __len__(self): return len(self.a)
 

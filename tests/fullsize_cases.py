@@ -1,0 +1,81 @@
+"""Oracle legs of the full-size parity tests (tests/test_gpu_fullsize.py): BASELINE.json's decks at their own sizes.
+
+Each case builds the deck inputs exactly as bench.py does (bench.deck_config + bench.make_inputs), runs the CPU oracle
+(oracle/qpad_oracle.c, strict IEEE build) for the stated number of 3D steps / slices and returns what the GPU leg is compared
+with.  The cases are independent, so the test module runs them in worker processes side by side (spawn context; this module
+must stay importable without a GPU)."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+KEYS = ("nr", "nz", "max_mode", "rmax", "zmin", "zmax", "dt", "iter_max", "iter_reltol", "iter_abstol")
+
+
+def deck(case):
+    """(cfg, plasma arrays, beam arrays, nsteps, nslices) of a case.
+    C1  input_file/blowout_regime/qpinput_tri-gaussian.json as shipped (250 x 500, max_mode 1): one whole 3D step incl. beam push
+    C3  input_file/hosing/qpinput.json (256 x 438, max_mode 2, drive + off-axis witness beam): its two 3D steps
+    C2w the C2 grid (nr 1024, 262 144 plasma particles per slice) at C2's own d(xi) = 10/2048: a 288-slice window through the
+        peak of the beam (slice 192 of the window)
+    C2c the C2 radial grid and particle load over the WHOLE 10 c/wp box at 4x coarser d(xi) (512 slices): the full wake incl. the
+        sheath crossing behind the bubble, where the predictor-corrector loop takes several iterations"""
+    import bench
+    name = {"C1": "C1", "C3": "C3", "C2w": "C2", "C2c": "C2"}[case]
+    cfg, beam = bench.deck_config(name)
+    nsteps, nslices = 1, None
+    if case == "C3":
+        nsteps = 2
+    elif case == "C2w":
+        dxi = (cfg["zmax"] - cfg["zmin"]) / cfg["nz"]
+        z0 = -2.5 - 192 * dxi
+        cfg.update(nz=288, zmin=z0, zmax=z0 + 288 * dxi)
+        nsteps, nslices = 0, 288
+    elif case == "C2c":
+        cfg.update(nz=512)
+        nsteps, nslices = 0, 512
+    plasma, bm = bench.make_inputs(cfg, beam)
+    return cfg, plasma, bm, nsteps, nslices
+
+
+def beam_moments(x, p, q):
+    """charge-weighted centroid, rms size and normalised rms emittance of the two transverse planes"""
+    w = q / q.sum()
+    out = {}
+    for k, ax in enumerate("xy"):
+        xc, pc = np.sum(w * x[:, k]), np.sum(w * p[:, k])
+        dx, dp = x[:, k] - xc, p[:, k] - pc
+        sxx, spp, sxp = np.sum(w * dx * dx), np.sum(w * dp * dp), np.sum(w * dx * dp)
+        out[ax] = (xc, np.sqrt(sxx), np.sqrt(max(sxx * spp - sxp * sxp, 0.0)))
+    out["pz"] = np.sum(w * p[:, 2])
+    return out
+
+
+def run_oracle(case):
+    from oracle import oracle as O
+    cfg, plasma, bm, nsteps, nslices = deck(case)
+    kw = {k: cfg[k] for k in KEYS + ("ppc1", "ppc2", "num_theta")}
+    sim = O.Sim(**kw)
+    sim.set_beam(*bm)
+    res = {"case": case, "iters_by_step": []}
+    if nsteps:
+        for k in range(nsteps):
+            i0 = sim.total_iters()
+            sim.step3d(k + 1)
+            res["iters_by_step"].append(sim.total_iters() - i0)
+        nsl = cfg["nz"]
+    else:
+        res["updates"] = sim.run_slices(nslices)
+        nsl = nslices
+    res["slice_iters"] = sim.slice_iters()
+    res["total_iters"] = sim.total_iters()
+    for name in ("psi", "e", "b"):
+        res[name] = sim.field(name, 2)[:, :nsl].copy()
+    res["beam"] = sim.beam()
+    if not nsteps:
+        res["plasma"] = sim.plasma()
+    return res

@@ -323,3 +323,56 @@ def fastmath_accuracy(api, max_ulp=2.0):
     assert float(ulp_r.max()) <= max_ulp and float(ulp_q.max()) <= max_ulp, (float(ulp_r.max()), float(ulp_q.max()))
     ctx.close()
     return float(ulp_r.max()), float(ulp_q.max())
+
+
+def field_smooth(api, O, M, dim, kind, order, nr=64):
+    """field_rho / field_jay / field_djdxi %smooth (fields/field_src_class.f03:102-271) = `order` passes of smooth_f1
+    (fields/ufield_class.f03:274-339, stencil [1,2,1]) per mode plane with the per-component on-axis policy of the three source
+    classes.  Bit-exact against the oracle's smooth_f1 except for the contraction of a multiply-add (<= 2 ulp per pass)."""
+    L = O.lib()
+    P = 2 * M + 1
+    ctx = api.Ctx(nr, M, 0.07, 0.02)
+    rng = np.random.default_rng(100 * kind + 10 * M + dim)
+    f = rng.normal(size=(P, nr + 2, dim))
+    fld = api.Field(ctx, dim); fld.upload(f)
+    fld.smooth(order, kind)
+    got = fld.download()
+    want = f.copy()
+    for _ in range(order):
+        for pl in range(P):
+            m = (pl + 1) // 2
+            if kind == 0:
+                ax = [m == 0]
+            elif kind == 1:
+                ax = [False, False, True] if m == 0 else ([True, True, False] if m == 1 else [False, False, False])
+            else:
+                ax = [m == 1, m == 1]
+            plane = np.ascontiguousarray(want[pl])
+            L.orc_smooth_f1(plane, dim, nr, np.asarray(ax, dtype=np.int32))
+            want[pl] = plane
+    scale = _mx(want)
+    assert _mx(got[:, 1:nr + 1] - want[:, 1:nr + 1]) <= 4e-16 * order * scale
+    assert np.array_equal(got[:, 0], f[:, 0]) and np.array_equal(got[:, nr + 1], f[:, nr + 1])      # guard cells untouched (copy_gc_f1 on one radial rank)
+    if order == 0:
+        assert np.array_equal(got, f)
+
+
+def part2d_move(api, O):
+    """move_part2d_comm (species/part2d_comm.f03:147) on a single radial partition: update_bound has already removed what left the
+    box, nothing crosses a radial processor boundary -- the particle set must come back bit for bit, in order, count unchanged."""
+    ctx = api.Ctx(64, 1, 0.1, 0.02)
+    rng = np.random.default_rng(3)
+    n = 4099
+    x = rng.uniform(-4.0, 4.0, size=(n, 2)); p = rng.normal(size=(n, 3))
+    g = np.sqrt(1.0 + np.sum(p * p, axis=1)); psi = rng.random(n); q = -rng.random(n)
+    pt = api.Part2d(ctx, -1.0, n + 64)
+    pt.move()
+    assert pt.npp() == 0                                   # empty set
+    pt.upload(x, p, g, psi, q)
+    pt.update_bound()
+    before = pt.download()
+    pt.move()
+    after = pt.download()
+    assert pt.npp() == len(before[4]) <= n
+    for a, b in zip(before, after):
+        assert np.array_equal(a, b)

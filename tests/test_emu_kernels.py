@@ -50,3 +50,12 @@ def test_fastmath_probe_emulated(api):
     """plumbing of qpg_debug_fastmath only: in the emulation the MUFU seeds are exact IEEE values, the GPU test measures the real thing"""
     ur, uq = K.fastmath_accuracy(api, max_ulp=1.0)
     assert ur <= 1.0 and uq <= 1.0
+
+
+@pytest.mark.parametrize("M,dim,kind,order", [(0, 1, 0, 1), (2, 3, 1, 2), (2, 2, 2, 2), (1, 2, 2, 0)])
+def test_field_smooth_emulated(api, M, dim, kind, order):
+    K.field_smooth(api, O, M, dim, kind, order)
+
+
+def test_part2d_move_emulated(api):
+    K.part2d_move(api, O)

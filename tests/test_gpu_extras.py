@@ -1,12 +1,8 @@
-"""GPU parity of the device code written after round 1's GPU minutes were spent -- csrc/subcyc.cu, csrc/vpot.cu, csrc/diag.cu --
-against the oracle, through the C-ABI.  The case bodies are shared with tests/test_emu_kernels.py, where the same device sources
-(compiled for the host) already pass; these tests are opt-in (QPG_TEST_EXTRAS=1) until their first run on a B200 so that an
-unvalidated path cannot mask the state of the validated ones."""
-import os
-
+"""GPU parity of csrc/subcyc.cu, csrc/vpot.cu, csrc/diag.cu, smooth_f1 and move_part2d_comm against the oracle, through the C-ABI.
+The case bodies are shared with tests/test_emu_kernels.py (the same device sources compiled for the host)."""
 import pytest
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not os.environ.get("QPG_TEST_EXTRAS"), reason="awaits its first GPU run (set QPG_TEST_EXTRAS=1)")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture(scope="module")
@@ -57,3 +53,50 @@ def test_fastmath_accuracy(mods):
     variants of the QPG_FASTMATH_SHORT experiment (build with QPG_NVCC_EXTRA=-DQPG_FASTMATH_SHORT)"""
     capi, O, K = mods
     print("max ulp error (rcp, sqrt):", K.fastmath_accuracy(capi))
+
+
+@pytest.mark.parametrize("M,dim,kind,order", [(0, 1, 0, 1), (1, 1, 0, 2), (2, 3, 1, 1), (1, 3, 1, 3), (2, 2, 2, 2), (1, 2, 2, 0)])
+def test_field_smooth(mods, M, dim, kind, order):
+    """field_rho / field_jay / field_djdxi %smooth (fields/field_src_class.f03:102-271, ufield_class.f03:274-339)"""
+    capi, O, K = mods
+    K.field_smooth(capi, O, M, dim, kind, order)
+
+
+def test_field_smooth_nr1024(mods):
+    capi, O, K = mods
+    K.field_smooth(capi, O, 1, 3, 1, 2, nr=1024)
+
+
+def test_part2d_move(mods):
+    """move_part2d_comm (species/part2d_comm.f03:147) on one radial partition"""
+    capi, O, K = mods
+    K.part2d_move(capi, O)
+
+
+def test_sweep_watchdog_is_reported(mods):
+    """a sweep kernel that leaves through its watchdog must not pass silently: the abort word is sticky, the next launch leaves at
+    once, qpg_sim_stats / qpg_ctx_sync return QPG_ERR_STATE, and a pending backward hand-off flag is still raised (the upstream
+    stage's stream must not hang)"""
+    capi, O, K = mods
+    import numpy as np
+    cfg = dict(nr=64, nz=8, max_mode=1, rmax=5.0, zmin=-1.0, zmax=1.0, dt=10.0, iter_max=2)
+    x, p, g, psi, q = O.inject_uniform(cfg["nr"], cfg["rmax"] / cfg["nr"], 2, 2, 8)
+    sim = capi.Sim(sp_npmax=2 * len(q), beam_npmax=64, use_graph=0, **cfg)
+    sim.init_species(x, p, g, psi, q)
+    sim.beam_qdp_begin(); sim.beam_qdp_end(); sim.begin_step()
+    sim.run_slices(1, 2)
+    assert sim.stats()[2] == 2
+    import torch
+    nb = sim.field("b").wire_count()
+    wb = torch.zeros(2 * nb + 8, dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    sim.debug_abort()
+    sim.set_back_handoff(wb.data_ptr(), wb.data_ptr() + 8 * nb, wb.data_ptr() + 16 * nb, 7)
+    sim.begin_step()
+    sim.run_slices(1, 2)
+    with pytest.raises(capi.QpadError, match="aborted"):
+        sim.stats()
+    with pytest.raises(capi.QpadError, match="aborted"):
+        sim.ctx.sync()
+    assert int(wb[2 * nb:].view(torch.int32)[0].item()) == 7     # the flag was raised although the sweep did no work
+    sim.close()

@@ -1,13 +1,10 @@
 """GPU parity of the field-ionisation neutral species (csrc/neutral.cu, qpad_b200/ionization.py) against the oracle
-(oracle/qpad_oracle_neutral.c).  The device code was written at the end of round 1 after the round's GPU minutes were
-spent: until it has had a first run on a GPU these tests are opt-in (QPG_TEST_NEUTRAL=1) so that an unvalidated path cannot
-mask the state of the validated ones."""
-import os
-
+(oracle/qpad_oracle_neutral.c), through the C-ABI.  First run on a B200 at the start of round 2 (all green); the case bodies are
+shared with the host-emulation tests (tests/test_emu_kernels.py, tests/test_emu_parity.py)."""
 import numpy as np
 import pytest
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not os.environ.get("QPG_TEST_NEUTRAL"), reason="neutral path awaits its first GPU run (set QPG_TEST_NEUTRAL=1)")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture(scope="module")
