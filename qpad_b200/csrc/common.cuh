@@ -71,6 +71,7 @@ struct qpg_ctx_s {
     std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> tp_pending;
     std::vector<cudaEvent_t> ev_pool;
     int smem_field;        // dynamic smem bytes for the field kernel
+    double *scratch; size_t scratch_n;   // lazily allocated global temporary (smooth_f1 of images that do not fit the shared-memory scratch)
     bool capturing;        // inside stream capture: no event timing
 };
 

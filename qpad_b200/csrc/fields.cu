@@ -257,7 +257,7 @@ extern "C" int qpg_ctx_destroy(qpg_ctx c)
     cudaStreamSynchronize(c->stream);
     for (auto &pe : c->tp_pending) { cudaEventDestroy(pe.second.first); cudaEventDestroy(pe.second.second); }
     for (auto ev : c->ev_pool) cudaEventDestroy(ev);
-    cudaFree(c->coef_pool); cudaFree(c->conv_old); cudaFree(c->conv_out); cudaFree(c->flags); cudaFree(c->counters);
+    cudaFree(c->scratch); cudaFree(c->coef_pool); cudaFree(c->conv_old); cudaFree(c->conv_out); cudaFree(c->flags); cudaFree(c->counters);
     auto it = g_devops.find(c);
     if (it != g_devops.end()) { cudaFree(it->second); g_devops.erase(it); }
     if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -766,7 +766,7 @@ __device__ void op_smooth(const FProg &pg, const FOp &op, double *smem)
     double *f = op.a;
     const double km1 = 0.25, k0 = 0.5, kp1 = 0.25;
     const int n = P * dim;
-    // process in radial chunks that fit the scratch (smem holds (nr)*n doubles when it fits; else chunked with halo)
+    if (op.b) smem = op.b;     // image larger than the shared-memory scratch: a global temporary (qpg_field_smooth)
     for (int k = threadIdx.x; k < nr * n; k += blockDim.x) {
         int j = k / n + 1, r = k % n, pl = r / dim, c = r % dim, m = mode_of(pl);
         double v;
@@ -1029,10 +1029,21 @@ extern "C" int qpg_field_scale(qpg_field f, double s)
 extern "C" int qpg_field_smooth(qpg_field f, int order, int kind)
 {
     ARG_TRY(f && order >= 0 && kind >= 0 && kind <= 2, "bad arguments");
-    ARG_TRY((size_t)f->ctx->nr * f->ctx->P * f->dim * sizeof(double) <= (size_t)f->ctx->smem_field, "field too large for the smoothing scratch");
+    qpg_ctx c = f->ctx;
+    const size_t need = (size_t)c->nr * c->P * f->dim;
+    double *tmp = nullptr;
+    if (need * sizeof(double) > (size_t)c->smem_field) {
+        if (c->scratch_n < need) {
+            CUDA_TRY(cudaStreamSynchronize(c->stream));
+            cudaFree(c->scratch); c->scratch = nullptr; c->scratch_n = 0;
+            CUDA_TRY(cudaMalloc(&c->scratch, sizeof(double) * need));
+            c->scratch_n = need;
+        }
+        tmp = c->scratch;
+    }
     for (int k = 0; k < order; k++) {
         ONE_OP_PROLOGUE(f->ctx);
-        FOp &o = pb.add(FOP_SMOOTH); o.a = f->f1; o.da = f->dim; o.i0 = kind;
+        FOp &o = pb.add(FOP_SMOOTH); o.a = f->f1; o.da = f->dim; o.i0 = kind; o.b = tmp;
         int rc = pb.launch(TP_ARITH);
         if (rc) return rc;
     }

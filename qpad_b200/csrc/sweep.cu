@@ -19,7 +19,9 @@
 // longer than ~2 s raises the abort flag, all CTAs leave, and the host reports QPG_ERR_STATE instead of hanging.
 #include "common.cuh"
 
+#ifndef SW_T
 #define SW_T 512           // threads per CTA (16 warps, <= 128 registers per thread)
+#endif
 #define SW_XK 64           // slots of one exchange record; layout [slot][strip] so a warp reads one slot of all strips coalesced
 #define SW_MAX_TEAM 128
 
