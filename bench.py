@@ -637,12 +637,26 @@ def run_b200_local(args):
     npp0 = len(plasma[4])
     S = args.stages
     parts = None
+    balance_log = []
+    mk = lambda pt: LocalPipeline(cfg, plasma, bm, S, device=local, rank=rank, world=world, dist=dist if world > 1 else None, transport=args.transport, partition=pt)
     if args.balance and world * S > 1:
-        # slabs of equal measured cost instead of equal length (pipeline.balanced_partition): an untimed calibration sweep
-        from qpad_b200.pipeline import probe_partition
+        # slabs of equal measured cost instead of equal length (pipeline.balanced_partition).  Open loop first: an untimed calibration
+        # sweep of one stage alone (probe_partition); then closed loop: the running pipeline measures its own stages side by side and the
+        # slabs are re-cut until the stages' sweep times agree within 3 % (measured_partition; at most --rebalance rounds, all untimed)
+        from qpad_b200.pipeline import probe_partition, measured_partition
         free = 4 if (world > 1 and (args.transport or os.environ.get("QPG_PIPELINE_TRANSPORT", "p2p")) == "nccl") else 0
-        parts = probe_partition(cfg, plasma, bm, world * S, S, device=local, rank=rank, world=world, dist=dist if world > 1 else None, free_sms=free)
-    lp = LocalPipeline(cfg, plasma, bm, S, device=local, rank=rank, world=world, dist=dist if world > 1 else None, transport=args.transport, partition=parts)
+        parts, beam_ns = probe_partition(cfg, plasma, bm, world * S, S, device=local, rank=rank, world=world, dist=dist if world > 1 else None, free_sms=free, with_beam_cost=True)
+        lp = mk(parts)
+        for rnd in range(args.rebalance):
+            new_parts, stage_ms, spread = measured_partition(lp, cfg, beam_ns)
+            balance_log.append({"round": rnd, "spread": round(spread, 4), "sweep_ms_by_stage": [round(v, 3) for v in stage_ms]})
+            if new_parts is None or [tuple(p) for p in new_parts] == [tuple(p) for p in parts]:
+                break
+            lp.drain(); lp.close()
+            parts = new_parts
+            lp = mk(parts)
+    else:
+        lp = mk(parts)
     main = torch.cuda.current_stream()
 
     def sync_all():
@@ -744,7 +758,9 @@ def run_b200_local(args):
             "us_per_slice_per_stage_rank0": [round(p["ns_total"] * 1e-3 / max(p["slices"], 1.0), 2) for p in profs],
             "sweep_ms_per_step_by_stage": sweep_by_stage,
             "slab_slices_by_stage": [n for _, n in lp.parts],
-            "slab_partition": "cost-balanced (untimed calibration sweep, pipeline.probe_partition)" if parts is not None else "equal length (options_class.f03:103-106)",
+            "slab_partition": "cost-balanced: untimed calibration sweep (pipeline.probe_partition) + closed loop on the running pipeline (pipeline.measured_partition)" if parts is not None else "equal length (options_class.f03:103-106)",
+            "slab_balance_rounds": balance_log,
+            "stage_time_spread": (max(sweep_by_stage) / (sum(sweep_by_stage) / len(sweep_by_stage)) - 1.0) if sweep_by_stage else None,
             "phases_rank0": {"A||update_bound": ph["A"], "amjdeposit (64 B/particle)": ph["amj"], "C": ph["C"], "push_u+push_x+qdeposit||D (112 B/particle)": ph["push"]},
             "note": "achieved = algorithmic bytes of ALL sweep launches in the timed region / its duration, per GPU (the S kernels of a GPU overlap: a stage's latency-bound field phases and barriers hide behind the other stages' particle phases); particle planes stay L2-resident"}
     # the other roofline of this path: fp64 issue.  SASS of this build (cuobjdump, max_mode 1): amjdeposit 252 fp64 instructions per
@@ -931,6 +947,7 @@ def main():
     ap.add_argument("--no-sweep", action="store_true", help="per-slice CUDA-graph launches instead of the persistent sweep kernel")
     ap.add_argument("--no-micro", action="store_true", help="skip the stream-from-HBM kernel microbenchmark")
     ap.add_argument("--legacy-pipeline", action="store_true", help="N>1: one stage per GPU through pipeline.PipelineStage")
+    ap.add_argument("--rebalance", type=int, default=3, help="closed-loop rounds of the slab balancing (pipeline.measured_partition); 0 = open-loop calibration only")
     ap.add_argument("--balance", type=int, default=1, help="1 = cost-balanced xi slabs from an untimed calibration sweep (default), 0 = the reference's equal-length slabs")
     ap.add_argument("--transport", default=None, choices=["p2p", "nccl"], help="N>1: how the stage hand-offs cross GPUs (default p2p = peer-memory writes + flags, csrc/p2p.cu)")
     ap.add_argument("--stages", type=int, default=0, help="xi-pipeline stages mapped onto SM partitions of ONE GPU (LocalPipeline); 0 = auto (up to 4), 1 = a single sweep kernel on all SMs")

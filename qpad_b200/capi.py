@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libqpadb200.so")
+# QPG_LIB: an alternative build of the SAME library (A/B experiments of compile-time options, tools/ab_bench.py); never a fallback
+LIB_PATH = os.environ.get("QPG_LIB") or os.path.join(_HERE, "libqpadb200.so")
 
 BND_ZERO, BND_OPEN = 2, 3
 PUSH2_STD, PUSH2_ROBUST, PUSH2_STD_PGC, PUSH2_ROBUST_PGC = 0, 1, 4, 5

@@ -15,6 +15,13 @@
 #ifndef FULL
 #define FULL 0xffffffffu
 #endif
+// Defaults since round 2 (A/B on a B200, profiles/r02_ab_variants.txt: -3.3 % step time; measured max error of the short Newton
+// chains on the device: 0.51 ulp reciprocal, 0.50 ulp square root -- tests/test_gpu_extras.py::test_fastmath_accuracy, gate 2 ulp).
+// -DQPG_LEGACY_MATH restores round 1's longer sequences.
+#ifndef QPG_LEGACY_MATH
+#define QPG_GATHER_FOLDED 1
+#define QPG_FASTMATH_SHORT 1
+#endif
 #define PT_BLOCK 256
 
 struct PartView {
@@ -35,7 +42,7 @@ __device__ __forceinline__ double fast_rcp(double y)
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(y));
     double e = fma(-y, r, 1.0);
 #ifdef QPG_FASTMATH_SHORT
-    // EXPERIMENT (off by default): one cubic step r (1 + e + e^2) instead of two quadratic ones -- seed error eps ->
+    // one cubic step r (1 + e + e^2) instead of two quadratic ones -- seed error eps ->
     // eps^3 (2^-60 or better for a 2^-20 seed) in 3 instead of 4 dependent FMAs.  qpg_debug_fastmath measures the ulp error on the GPU.
     e = fma(e, e, e);
     return fma(r, e, r);
@@ -52,7 +59,7 @@ __device__ __forceinline__ double fast_sqrt(double x)
     double g = x * y, h = 0.5 * y;
     double r = fma(-g, h, 0.5);
     g = fma(g, r, g); h = fma(h, r, h);
-#ifndef QPG_FASTMATH_SHORT      // the experiment drops this second coupled step: eps -> 1.5 eps^2 (first step) -> ~eps^4 (the final Heron correction)
+#ifndef QPG_FASTMATH_SHORT      // the short variant drops this second coupled step: eps -> 1.5 eps^2 (first step) -> ~eps^4 (the final Heron correction)
     r = fma(-g, h, 0.5);
     g = fma(g, r, g); h = fma(h, r, h);
 #endif
@@ -83,7 +90,11 @@ extern "C" int qpg_debug_fastmath(qpg_ctx ctx, long n, const double *host_x, dou
 
 // fire-and-forget reductions.  Written as PTX `red` because ptxas keeps `atomicAdd` as a returning ATOMG (a ~320-cycle
 // round trip per instruction) inside the persistent sweep kernel, where fences / volatile loads are present.
+#ifdef QPG_EXP_NO_RED   // bottleneck experiment only (results are wrong): deposits never reach memory
+__device__ __forceinline__ void red_add(double *p, double v) { if (v == 1.2345e-300) *p = v; }
+#else
 __device__ __forceinline__ void red_add(double *p, double v) { asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
+#endif
 __device__ __forceinline__ void red_add(int *p, int v) { asm volatile("red.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
 // species/interp_part2d.f03:28-65 gen_interp_info
@@ -108,7 +119,11 @@ template <int M>
 __device__ __forceinline__ void gather3(const double *f, const Interp &it, double out[3])
 {
     constexpr int P = 2 * M + 1;
+#ifdef QPG_EXP_FIXED_NODE   // bottleneck experiment only: every particle gathers from node 1 (one address per warp, always an L1 hit)
+    const double *n0 = f + (size_t)(it.idx > 100000 ? it.idx : 1) * (P * 3);
+#else
     const double *n0 = f + (size_t)it.idx * (P * 3);
+#endif
     const double *n1 = n0 + P * 3;
 #pragma unroll
     for (int c = 0; c < 3; c++) out[c] = n0[c] * it.w0;
@@ -122,7 +137,7 @@ __device__ __forceinline__ void gather3(const double *f, const Interp &it, doubl
         phr = t;
         const double pr2 = 2.0 * phr, pi2 = 2.0 * phi;
 #ifdef QPG_GATHER_FOLDED
-        // EXPERIMENT (off by default, -DQPG_GATHER_FOLDED): node weight x mode phase once per particle -- the four
+        // node weight x mode phase once per particle -- the four
         // products are common to every gather of the particle (the compiler shares them between the e and b gathers) -- then two
         // FMAs per (node, component, mode) instead of a multiply and two FMAs: -8 fp64 instructions per particle at M = 1 in
         // amjdeposit and in push (tools/sass_mix.py).  Same sums in a different association (~1e-16 relative).
@@ -163,6 +178,9 @@ __device__ __forceinline__ void warp_deposit_mma(const double (&alpha)[2 * (2 * 
                                                  int lane)
 {
     constexpr int P = 2 * M + 1, R = 2 * P, NTILE = (R + 7) / 8;
+#ifdef QPG_EXP_NO_DEPOSIT   // bottleneck experiment only
+    { double sacc = 0.0; for (int r = 0; r < R; r++) sacc += alpha[r]; for (int k = 0; k < 8; k++) sacc += beta[k]; if (sacc == 1.2345e-300) acc8[0] = sacc; return; }
+#endif
     __syncwarp();                                   // the previous tile's fragment loads are done
 #pragma unroll
     for (int r = 0; r < R; r++) tile[r * DEP_LD + lane] = alpha[r];
@@ -1060,9 +1078,12 @@ template <int M> static void l_qdeposit(int grid, cudaStream_t st, PartView pv, 
     if (!attr_set) { cudaFuncSetAttribute(k_qdeposit<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
     k_qdeposit<M><<<grid, PT_BLOCK, smem, st>>>(pv, acc1, idr);
 }
+// development aid (tools/occupancy_probe.py): QPG_DEV_EXTRA_SMEM=<bytes> pads the dynamic shared memory of the amjdeposit launches to
+// cap the resident blocks per SM
+static size_t dev_extra_smem() { static long v = -1; if (v < 0) { const char *e = getenv("QPG_DEV_EXTRA_SMEM"); v = e ? atol(e) : 0; } return (size_t)v; }
 template <int M> static void l_amjdeposit(int grid, cudaStream_t st, PartView pv, const double *ef, const double *bf, double *acc8, double qbm, double dt, double idr, const int *skip, int std_flavour)
 {
-    constexpr size_t smem = sizeof(double) * DepTile<M>::doubles * (PT_BLOCK / 32);
+    const size_t smem = sizeof(double) * DepTile<M>::doubles * (PT_BLOCK / 32) + dev_extra_smem();
     static bool attr_set = false;   // > 48 KB of dynamic shared memory needs the opt-in (M >= 3)
     if (!attr_set) {
         cudaFuncSetAttribute(k_amjdeposit<M, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

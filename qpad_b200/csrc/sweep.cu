@@ -234,6 +234,9 @@ __device__ __forceinline__ void strip_fold(const uint4 *xb, unsigned seq, unsign
 // program A (simulation_class.f03:344-377): q_beam slice -> bt(beam), qdp epilogue, psi, bz, record, b, ez, et
 // `halo`: derive psi / phi of the two halo nodes from the exchanged strip totals instead of a second team barrier
 template <int M>
+#ifdef QPG_SWEEP_NOINLINE
+__noinline__
+#endif
 __device__ void sweep_field_A(const FusedArgs &a, int j, Team &tm, StripSmem<M> &sm, bool halo, long long *stamp)
 {
     constexpr int P = 2 * M + 1, NS = 4 * P, NWARP = SW_T / 32, SPW = (NS + NWARP - 1) / NWARP;
@@ -391,6 +394,9 @@ __device__ void sweep_field_A(const FusedArgs &a, int j, Team &tm, StripSmem<M> 
 // program C (:378-396 + :375-377): amjdp epilogue, djdxi, bt_iter, bz, compare, record, b, ez, et.
 // The two per-CTA residual maxima go to the exchange buffer; sweep_conv_decide() combines them after the grid barrier.
 template <int M>
+#ifdef QPG_SWEEP_NOINLINE
+__noinline__
+#endif
 __device__ void sweep_field_C(const FusedArgs &a, Team &tm, StripSmem<M> &sm, long long *stamp)
 {
     constexpr int P = 2 * M + 1, NS = 4 * P, NWARP = SW_T / 32, SPW = (NS + NWARP - 1) / NWARP;
@@ -588,6 +594,59 @@ __device__ void sweep_publish_back(const SweepArgs &a)
     if (threadIdx.x == 0) st_release_sys(a.back_flag, a.back_seq);
 }
 
+// ---- particle phases of a slice: the warps of a CTA take the CTA's tiles (32 particles) round-robin ---------------------------
+// QPG_SWEEP_NOINLINE: the phases are separate functions (own register allocation: the particle arithmetic fits 64 registers on its
+// own, tools/ab_bench.py); QPG_SWEEP_PREFETCH: the next tile's particle planes are fetched while the current tile is worked on
+// (one L2 round trip per tile saved at the price of 12 registers)
+#ifdef QPG_SWEEP_NOINLINE
+#define SW_PHASE_FN __device__ __noinline__
+#else
+#define SW_PHASE_FN __device__ __forceinline__
+#endif
+#ifndef QPG_SWEEP_PREFETCH
+#define QPG_SWEEP_PREFETCH 1
+#endif
+template <int M>
+SW_PHASE_FN void sweep_amj_phase(const SweepArgs &a, int npp, int tile0, int tile1, double *dep_tiles)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const FusedArgs &f = a.f;
+    const double idr = 1.0 / f.dr;
+    double *tile = dep_tiles + warp * DepTile<M>::doubles;
+#if QPG_SWEEP_PREFETCH
+    PartRegs cur = part_load(a.pv, (tile0 + warp) * 32 + lane, tile0 + warp < tile1 ? npp : 0);
+    for (int tl = tile0 + warp; tl < tile1; tl += SW_T / 32) {
+        const int tn = tl + SW_T / 32;
+        const PartRegs nxt = part_load(a.pv, tn * 32 + lane, tn < tile1 ? npp : 0);
+        amj_core<M>(a.pv, cur, f.e, f.b, f.acc8, a.qbm, f.dxi, idr, npp, tl * 32 + lane, lane, tile);
+        cur = nxt;
+    }
+#else
+    for (int tl = tile0 + warp; tl < tile1; tl += SW_T / 32)
+        amj_core<M>(a.pv, part_load(a.pv, tl * 32 + lane, npp), f.e, f.b, f.acc8, a.qbm, f.dxi, idr, npp, tl * 32 + lane, lane, tile);
+#endif
+}
+template <int M>
+SW_PHASE_FN void sweep_push_phase(const SweepArgs &a, int npp, int tile0, int tile1, double *dep_tiles)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const FusedArgs &f = a.f;
+    const double idr = 1.0 / f.dr;
+    double *tile = dep_tiles + warp * DepTile<M>::doubles;
+#if QPG_SWEEP_PREFETCH
+    PartRegs cur = part_load(a.pv, (tile0 + warp) * 32 + lane, tile0 + warp < tile1 ? npp : 0);
+    for (int tl = tile0 + warp; tl < tile1; tl += SW_T / 32) {
+        const int tn = tl + SW_T / 32;
+        const PartRegs nxt = part_load(a.pv, tn * 32 + lane, tn < tile1 ? npp : 0);
+        push_core<M>(a.pv, cur, f.e, f.b, a.qbm, f.dxi, idr, a.edge, 7, a.outmask, a.d_nout, f.acc1, npp, tl * 32 + lane, lane, tile);
+        cur = nxt;
+    }
+#else
+    for (int tl = tile0 + warp; tl < tile1; tl += SW_T / 32)
+        push_core<M>(a.pv, part_load(a.pv, tl * 32 + lane, npp), f.e, f.b, a.qbm, f.dxi, idr, a.edge, 7, a.outmask, a.d_nout, f.acc1, npp, tl * 32 + lane, lane, tile);
+#endif
+}
+
 template <int M>
 __global__ void __launch_bounds__(SW_T, 1) k_sweep(const __grid_constant__ SweepArgs a)
 {
@@ -628,16 +687,7 @@ __global__ void __launch_bounds__(SW_T, 1) k_sweep(const __grid_constant__ Sweep
         const int tile0 = b * per, tile1 = min(tile0 + per, ntiles);
         // ---- predictor-corrector loop -----------------------------------------------------------------------
         for (int it = 1; it <= f.iter_max; it++) {
-            {   // the next tile's particle planes are fetched while the current tile is worked on (the tile chain is
-                // latency-bound: one L2 round trip per tile saved)
-                PartRegs cur = part_load(a.pv, (tile0 + warp) * 32 + lane, tile0 + warp < tile1 ? npp : 0);
-                for (int tl = tile0 + warp; tl < tile1; tl += SW_T / 32) {
-                    const int tn = tl + SW_T / 32;
-                    const PartRegs nxt = part_load(a.pv, tn * 32 + lane, tn < tile1 ? npp : 0);
-                    amj_core<M>(a.pv, cur, f.e, f.b, f.acc8, a.qbm, f.dxi, idr, npp, tl * 32 + lane, lane, dep_tiles + warp * DepTile<M>::doubles);
-                    cur = nxt;
-                }
-            }
+            sweep_amj_phase<M>(a, npp, tile0, tile1, dep_tiles);
             if (timer) work[1] += clock64() - tprev;
             ok = grid_barrier(a.bar, gep, sm_i);
             if (timer) { const long long t = clock64(); prof[1] += t - tprev; tprev = t; namj++; }
@@ -657,15 +707,7 @@ __global__ void __launch_bounds__(SW_T, 1) k_sweep(const __grid_constant__ Sweep
             const int items = (f.nr + 2) * P, ipc = (items + G - 1) / G;
             for (int k = b * ipc + lane; k < min((b + 1) * ipc, items); k += 32) fused_D_item<M>(f, k, j);
         }
-        {
-            PartRegs cur = part_load(a.pv, (tile0 + warp) * 32 + lane, tile0 + warp < tile1 ? npp : 0);
-            for (int tl = tile0 + warp; tl < tile1; tl += SW_T / 32) {
-                const int tn = tl + SW_T / 32;
-                const PartRegs nxt = part_load(a.pv, tn * 32 + lane, tn < tile1 ? npp : 0);
-                push_core<M>(a.pv, cur, f.e, f.b, a.qbm, f.dxi, idr, a.edge, 7, a.outmask, a.d_nout, f.acc1, npp, tl * 32 + lane, lane, dep_tiles + warp * DepTile<M>::doubles);
-                cur = nxt;
-            }
-        }
+        sweep_push_phase<M>(a, npp, tile0, tile1, dep_tiles);
         if (timer) work[3] += clock64() - tprev;
         ok = grid_barrier(a.bar, gep, sm_i);
         if (timer) {

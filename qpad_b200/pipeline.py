@@ -413,25 +413,52 @@ def probe_slice_costs(cfg, plasma, beam, device=0, ctas=0, steps=2):
         sim.close()
 
 
-def probe_partition(cfg, plasma, beam, nstages_total, stages_per_gpu, device=0, rank=0, world=1, dist=None, free_sms=0):
+def _slab_cost(ns, beam_ns, stages_per_gpu):
+    k = 8                                                     # smooth over a few slices: single-slice timer noise is not load
+    cost = np.convolve(np.pad(ns, (k // 2, k - 1 - k // 2), mode="edge"), np.ones(k) / k, mode="valid")
+    return cost + float(os.environ.get("QPG_BALANCE_BEAM_WEIGHT", stages_per_gpu)) * beam_ns
+
+
+def measured_partition(lp, cfg, beam_ns, nwaves=2, tol=0.03):
+    """Closed loop of the slab balancing: the RUNNING pipeline is the probe.  Fills it, runs `nwaves` more waves, reads every stage's
+    per-slice device times (qpg_sim_slice_trace: taken inside the sweep kernels while all stages of the GPU run side by side, which the
+    open-loop probe_partition cannot see) and cuts slabs of equal cost from that profile.  Returns (partition or None if the measured
+    spread of the stages' sweep times is already below `tol`, per-stage ms of the last wave, spread).  Same answer on every rank."""
+    lp.fill()
+    for _ in range(nwaves):
+        lp.wave()
+    lp.sync()
+    mine = [sim.slice_trace()[0] for sim in lp.sims]
+    every = [mine]
+    if lp.world > 1:
+        every = [None] * lp.world
+        lp.dist.all_gather_object(every, mine)
+    traces = [t for m in every for t in m]
+    ns = np.concatenate(traces)
+    stage_ms = [float(t.sum()) * 1e-6 for t in traces]
+    spread = max(stage_ms) / (sum(stage_ms) / len(stage_ms)) - 1.0
+    if spread < tol or len(ns) != cfg["nz"]:
+        return None, stage_ms, spread
+    cost = _slab_cost(ns, beam_ns if beam_ns is not None else np.zeros(len(ns)), lp.S)
+    return balanced_partition(cost, lp.G, min_len=min(16, cfg["nz"] // lp.G)), stage_ms, spread
+
+
+def probe_partition(cfg, plasma, beam, nstages_total, stages_per_gpu, device=0, rank=0, world=1, dist=None, free_sms=0, with_beam_cost=False):
     """cost-balanced slab partition for a pipeline of `nstages_total` stages; with several ranks rank 0 measures and
     everybody uses its answer (the partition must be the same on every rank).  Cost of a slice = its sweep time with a
     stage's CTA count + its share of the beam deposit / push (measured on the whole GPU, a stage has 1/stages_per_gpu of
     it while its neighbours sweep)."""
     import torch
-    parts = None
+    parts = beam_ns = None
     if rank == 0:
         nsm = torch.cuda.get_device_properties(device).multi_processor_count
         ns, _, beam_ns = probe_slice_costs(cfg, plasma, beam, device, (nsm - free_sms) // stages_per_gpu if nstages_total > 1 else 0)
-        k = 8                                                     # smooth over a few slices: single-slice timer noise is not load
-        cost = np.convolve(np.pad(ns, (k // 2, k - 1 - k // 2), mode="edge"), np.ones(k) / k, mode="valid")
-        cost = cost + float(os.environ.get("QPG_BALANCE_BEAM_WEIGHT", stages_per_gpu)) * beam_ns
-        parts = balanced_partition(cost, nstages_total, min_len=min(16, cfg["nz"] // nstages_total))
+        parts = balanced_partition(_slab_cost(ns, beam_ns, stages_per_gpu), nstages_total, min_len=min(16, cfg["nz"] // nstages_total))
     if world > 1:
-        box = [parts]
+        box = [parts, beam_ns]
         dist.broadcast_object_list(box, src=0)
-        parts = [tuple(p) for p in box[0]]
-    return parts
+        parts, beam_ns = [tuple(p) for p in box[0]], box[1]
+    return (parts, beam_ns) if with_beam_cost else parts
 
 
 class PeerLinks:
