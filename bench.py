@@ -648,13 +648,15 @@ def run_b200_local(args):
         parts, beam_ns = probe_partition(cfg, plasma, bm, world * S, S, device=local, rank=rank, world=world, dist=dist if world > 1 else None, free_sms=free, with_beam_cost=True)
         lp = mk(parts)
         for rnd in range(args.rebalance):
-            new_parts, stage_ms, spread = measured_partition(lp, cfg, beam_ns)
-            balance_log.append({"round": rnd, "spread": round(spread, 4), "sweep_ms_by_stage": [round(v, 3) for v in stage_ms]})
-            if new_parts is None or [tuple(p) for p in new_parts] == [tuple(p) for p in parts]:
-                break
+            # measured over the same 3D step numbers the timed region will see (the wake deepens as the beam focuses: a slab's cost drifts)
+            new_parts, stage_ms, spread = measured_partition(lp, cfg, beam_ns, nwaves=args.steps, nwarm=args.warmup)
+            balance_log.append({"round": rnd, "spread": round(spread, 4), "busy_ms_by_stage": [round(v, 3) for v in stage_ms], "slab_slices": [n for _, n in parts]})
+            done = new_parts is None or [tuple(p) for p in new_parts] == [tuple(p) for p in parts]
             lp.drain(); lp.close()
-            parts = new_parts
-            lp = mk(parts)
+            parts = parts if done else new_parts
+            lp = mk(parts)             # a fresh pipeline either way: the timed region then sees the 3D steps the partition was measured on
+            if done:
+                break
     else:
         lp = mk(parts)
     main = torch.cuda.current_stream()

@@ -419,28 +419,52 @@ def _slab_cost(ns, beam_ns, stages_per_gpu):
     return cost + float(os.environ.get("QPG_BALANCE_BEAM_WEIGHT", stages_per_gpu)) * beam_ns
 
 
-def measured_partition(lp, cfg, beam_ns, nwaves=2, tol=0.03):
-    """Closed loop of the slab balancing: the RUNNING pipeline is the probe.  Fills it, runs `nwaves` more waves, reads every stage's
-    per-slice device times (qpg_sim_slice_trace: taken inside the sweep kernels while all stages of the GPU run side by side, which the
-    open-loop probe_partition cannot see) and cuts slabs of equal cost from that profile.  Returns (partition or None if the measured
-    spread of the stages' sweep times is already below `tol`, per-stage ms of the last wave, spread).  Same answer on every rank."""
+def measured_partition(lp, cfg, beam_ns=None, nwaves=4, tol=0.03, nwarm=1):
+    """Closed loop of the slab balancing: the RUNNING pipeline is the probe.  Fills it, runs `nwaves` waves with CUDA-event marks on
+    every stage's stream, and takes (a) each stage's busy time per wave = everything between its marks except the two blocking waits
+    for the neighbours' messages -- sweep kernel, beam deposit / push (which run on the stage's own SM share once its sweep kernel has
+    left), hand-off kernels, fills -- and (b) the per-slice device times inside the sweep kernels (qpg_sim_slice_trace, the shape of
+    the cost along xi), both measured while all stages of the GPU run side by side, which the open-loop probe_partition cannot see.
+    Cost of slice j of stage g = its trace share of the stage's sweep time + an equal share of the stage's non-sweep time; slabs of
+    equal cost are cut from that profile.  Returns (partition or None if the spread max/mean - 1 of the busy times is already below
+    `tol`, per-stage busy ms, spread).  The same answer on every rank.
+    The cost of a slab drifts with the 3D step (the beam focuses and the wake deepens over the first betatron quarter period), so the
+    caller measures over the step numbers it cares about: `nwarm` waves after the fill are skipped, `nwaves` are measured."""
     lp.fill()
-    for _ in range(nwaves):
+    for _ in range(max(nwarm, 1)):
         lp.wave()
     lp.sync()
-    mine = [sim.slice_trace()[0] for sim in lp.sims]
+    on = lp._ev_on
+    lp._ev_on = True
+    lp.trace_reset()
+    for sim in lp.sims:
+        sim.sweep_profile(reset=True)
+    for _ in range(nwaves):
+        lp.wave()
+    reps = lp.event_report()
+    lp._ev_on = on
+    lp.trace_reset()
+    mine = []
+    for sim, rep in zip(lp.sims, reps):
+        busy = sum(v for k, v in rep.items() if k not in ("w_fwd>got_fwd", "tail>got_back"))        # ms per wave
+        sweep = sim.sweep_profile()["ns_total"] * 1e-6 / nwaves
+        mine.append((sim.slice_trace()[0], busy, sweep))
     every = [mine]
     if lp.world > 1:
         every = [None] * lp.world
         lp.dist.all_gather_object(every, mine)
-    traces = [t for m in every for t in m]
-    ns = np.concatenate(traces)
-    stage_ms = [float(t.sum()) * 1e-6 for t in traces]
-    spread = max(stage_ms) / (sum(stage_ms) / len(stage_ms)) - 1.0
-    if spread < tol or len(ns) != cfg["nz"]:
-        return None, stage_ms, spread
-    cost = _slab_cost(ns, beam_ns if beam_ns is not None else np.zeros(len(ns)), lp.S)
-    return balanced_partition(cost, lp.G, min_len=min(16, cfg["nz"] // lp.G)), stage_ms, spread
+    stages = [t for m in every for t in m]
+    busy_ms = [b for _, b, _ in stages]
+    spread = max(busy_ms) / (sum(busy_ms) / len(busy_ms)) - 1.0
+    if spread < tol or sum(len(t) for t, _, _ in stages) != cfg["nz"]:
+        return None, busy_ms, spread
+    cost = []
+    for tr, busy, sweep in stages:
+        k = min(8, len(tr))
+        sm = np.convolve(np.pad(tr, (k // 2, k - 1 - k // 2), mode="edge"), np.ones(k) / k, mode="valid")
+        sweep = min(sweep, busy)
+        cost.append(sm * (sweep / max(sm.sum() * 1e-6, 1e-12)) * 1e-6 + max(busy - sweep, 0.0) / len(tr))
+    return balanced_partition(np.concatenate(cost), lp.G, min_len=min(16, cfg["nz"] // lp.G)), busy_ms, spread
 
 
 def probe_partition(cfg, plasma, beam, nstages_total, stages_per_gpu, device=0, rank=0, world=1, dist=None, free_sms=0, with_beam_cost=False):
