@@ -512,8 +512,7 @@ class Stage:
 
 class Neutral:
     """neutral (species/neutral_class.f03): ionisation levels per (radial cell, theta sector) + the two particle sets the
-    reference calls `part` (released electrons) and `part_add` (positions of the ions created by the last update).
-    NOT YET VALIDATED ON A GPU (see include/qpad_b200.h)."""
+    reference calls `part` (released electrons) and `part_add` (positions of the ions created by the last update)."""
 
     def __init__(self, ctx, element, ion_max, ppc, num_theta, q=-1.0, m=1.0, density=1.0, n0=1.0e17, dt_xi=None):
         self.ctx, self.L, self.num_theta = ctx, ctx.L, num_theta
@@ -521,8 +520,8 @@ class Neutral:
         _chk(self.L.qpg_neutral_create(C.byref(h), ctx.h, element, ion_max, ppc[0], ppc[1], num_theta, q, m, density, n0, ctx.dxi if dt_xi is None else dt_xi))
         self.h = h.value
         self.multi_max = self.L.qpg_neutral_multi_max(self.h)
-        cap = ctx.nr * num_theta * ppc[0] * ppc[1] + 64
-        self.part = Part2d(ctx, q / m, cap)
+        cap = ctx.nr * num_theta * ppc[0] * ppc[1] + 64          # one update releases at most ppc electrons per (cell, sector)
+        self.part = Part2d(ctx, q / m, cap * max(1, self.multi_max))   # ... and a step at most multi_max times that (an overflow is reported)
         self.part_add = Part2d(ctx, q / m, cap)
 
     def close(self):

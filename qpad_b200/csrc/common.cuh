@@ -61,7 +61,7 @@ struct qpg_ctx_s {
     double *coef_pool;     // device pool backing all OpCoef arrays
     double *conv_old;      // [2][nr+2] record of sum|B| (re, im)
     double *conv_out;      // [0]=rel [1]=abs (device)
-    int *flags;            // device ints: [0] done [2] iteration in slice [3] current slice j [4] slices executed
+    int *flags;            // device ints: [0] done [2] iteration in slice [3] current slice j [4] slices executed [6] sweep kernel aborted (sticky) [7] neutral particle set overflow (sticky)
     long long *counters;   // device: [0] particle-slice updates [1] PC iterations
     unsigned long long cond_handle;  // CUDA-graph WHILE handle while capturing the PC-loop body (else 0)
     long launches;
@@ -159,3 +159,5 @@ OpCoef *qpg_ctx_dev_ops(qpg_ctx ctx);
 
 // helpers used across translation units
 int part2d_epilogue_q(qpg_part2d p, qpg_field q);
+long qpg_neutral_max_new_per_update(qpg_neutral ne);   // neutral.cu
+int qpg_ctx_check_latches(qpg_ctx c, const int *host_flags);   // fields.cu: flags[6] sweep watchdog, flags[7] neutral overflow

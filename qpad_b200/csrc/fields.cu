@@ -264,14 +264,20 @@ extern "C" int qpg_ctx_destroy(qpg_ctx c)
     delete c;
     return 0;
 }
+int qpg_ctx_check_latches(qpg_ctx c, const int *fl)
+{
+    (void)c;
+    if (fl[6]) { qpg_set_error("sweep kernel aborted (a grid barrier or strip exchange timed out): results on this context are invalid"); return QPG_ERR_STATE; }
+    if (fl[7]) { qpg_set_error("neutral species: released electrons did not fit the particle set (npmax too small): charge was lost"); return QPG_ERR_STATE; }
+    return 0;
+}
 extern "C" int qpg_ctx_sync(qpg_ctx c)
 {
     ARG_TRY(c, "null ctx");
-    int ab = 0;   // flags[6]: latched by a sweep kernel that left through its watchdog (sweep.cu)
-    CUDA_TRY(cudaMemcpyAsync(&ab, c->flags + 6, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    int fl[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // sticky error latches written by kernels: see qpg_ctx_check_latches
+    CUDA_TRY(cudaMemcpyAsync(fl, c->flags, sizeof(fl), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
-    if (ab) { qpg_set_error("sweep kernel aborted (a grid barrier or strip exchange timed out): results on this context are invalid"); return QPG_ERR_STATE; }
-    return 0;
+    return qpg_ctx_check_latches(c, fl);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -129,12 +129,17 @@ __global__ void k_neutral_add(const int *__restrict__ cnt, const int *__restrict
         }
     }
 }
-__global__ void k_neutral_counts(int *npp_e, int *npp_i, const int *d_nadd, long cap_e, long cap_i)
+// flags[7] of the context is latched when released electrons (or ion positions) did not fit the particle sets: the host reports
+// QPG_ERR_STATE at its next synchronisation point instead of silently losing charge (beam.cu does the same for its wire buffer)
+__global__ void k_neutral_counts(int *npp_e, int *npp_i, const int *d_nadd, long cap_e, long cap_i, int *ctx_flags)
 {
     const int add = *d_nadd;
+    if ((long)*npp_e + add > cap_e || (long)add > cap_i) ctx_flags[7] = 1;
     *npp_e = (int)min((long)*npp_e + add, cap_e);
     *npp_i = (int)min((long)add, cap_i);
 }
+// most electrons one update can release: every (cell, sector) ionises all its ppc particles at once
+long qpg_neutral_max_new_per_update(qpg_neutral ne) { return ne ? (long)ne->ppc1 * ne->ppc2 * ne->ctx->nr * ne->n_theta : 0; }
 
 extern "C" int qpg_neutral_create(qpg_neutral *out, qpg_ctx ctx, int element, int ion_max, int ppc1, int ppc2, int num_theta, double q, double m, double density,
                                   double n0, double dt_xi)
@@ -202,7 +207,7 @@ extern "C" int qpg_neutral_update(qpg_neutral ne, qpg_field e, qpg_part2d electr
     const double coef = (double)ne->multi_max * (ne->qm < 0 ? -1.0 : 1.0) / ((double)(ne->ppc1 * ne->ppc2) * (double)ne->n_theta);
     k_neutral_add<<<(nc + 127) / 128, 128, 0, c->stream>>>(ne->cnt, ne->off, view_of(electrons), view_of(ions), electrons->npmax, ions->npmax, c->dr, ne->density, ne->den_min,
                                                          coef, c->nr, ne->n_theta);
-    k_neutral_counts<<<1, 1, 0, c->stream>>>(electrons->d_npp, ions->d_npp, ne->d_nadd, electrons->npmax, ions->npmax);
+    k_neutral_counts<<<1, 1, 0, c->stream>>>(electrons->d_npp, ions->d_npp, ne->d_nadd, electrons->npmax, ions->npmax, c->flags);
     count_launch(c, 4);
     CUDA_TRY(cudaGetLastError());
     electrons->npp_hi = electrons->npmax;     // unknown until the next sync; the kernels bound themselves by the device count

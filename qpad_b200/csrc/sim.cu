@@ -296,18 +296,22 @@ static int sweep_prepare(qpg_sim s)
     }
     const int nteam = (c->nr + ST_N - 1) / ST_N;
     if (per < 1 || nsm * per <= nteam) { qpg_set_error("sweep kernel: %d CTAs/SM x %d SMs cannot host a field team of %d", per, nsm, nteam); return QPG_ERR_UNSUPPORTED; }
-    CUDA_TRY(cudaMalloc(&s->sw_bar, sizeof(unsigned) * 128));
-    CUDA_TRY(cudaMemsetAsync(s->sw_bar, 0, sizeof(unsigned) * 128, c->stream));   // incl. the sticky abort word [64], never cleared again
-    CUDA_TRY(cudaMalloc(&s->sw_xbuf, sizeof(double) * 3 * SW_MAX_TEAM * SW_XK));
-    CUDA_TRY(cudaMemsetAsync(s->sw_xbuf, 0, sizeof(double) * 3 * SW_MAX_TEAM * SW_XK, c->stream));
-    CUDA_TRY(cudaMalloc(&s->sw_xll, sizeof(uint4) * 2 * SW_MAX_TEAM * SW_XK));
-    CUDA_TRY(cudaMalloc(&s->sw_trace, sizeof(long long) * 2 * s->prm.nzp));
-    CUDA_TRY(cudaMemsetAsync(s->sw_trace, 0, sizeof(long long) * 2 * s->prm.nzp, c->stream));
-    CUDA_TRY(cudaMalloc(&s->sw_prof, sizeof(long long) * 32));
-    CUDA_TRY(cudaMemsetAsync(s->sw_prof, 0, sizeof(long long) * 32, c->stream));
     int g = s->sweep_ctas_req > 0 ? s->sweep_ctas_req : nsm * per + s->sweep_ctas_req;   // default: one CTA per SM
     if (g > nsm * per) g = nsm * per;
     if (g <= nteam) { qpg_set_error("sweep kernel: %d CTAs cannot host a field team of %d plus the update_bound CTA", g, nteam); return QPG_ERR_ARG; }
+    // every check has passed: allocate (all or nothing, so that a failed attempt leaks nothing and can be repeated)
+    cudaError_t e = cudaSuccess;
+    auto alloc = [&](void **p, size_t bytes) { if (e == cudaSuccess) { e = cudaMalloc(p, bytes); if (e == cudaSuccess) e = cudaMemsetAsync(*p, 0, bytes, c->stream); } };
+    alloc((void **)&s->sw_bar, sizeof(unsigned) * 128);                              // incl. the sticky abort word [64], never cleared again
+    alloc((void **)&s->sw_xbuf, sizeof(double) * 3 * SW_MAX_TEAM * SW_XK);
+    alloc((void **)&s->sw_xll, sizeof(uint4) * 2 * SW_MAX_TEAM * SW_XK);
+    alloc((void **)&s->sw_trace, sizeof(long long) * 2 * s->prm.nzp);
+    alloc((void **)&s->sw_prof, sizeof(long long) * 32);
+    if (e != cudaSuccess) {
+        cudaFree(s->sw_bar); cudaFree(s->sw_xbuf); cudaFree(s->sw_xll); cudaFree(s->sw_trace); cudaFree(s->sw_prof);
+        s->sw_bar = nullptr; s->sw_xbuf = nullptr; s->sw_xll = nullptr; s->sw_trace = nullptr; s->sw_prof = nullptr;
+        return qpg_cuda_fail(e, "sweep_prepare: cudaMalloc");
+    }
     s->sweep_grid = g;
     return 0;
 }
@@ -625,6 +629,10 @@ extern "C" int qpg_sim_attach_neutral(qpg_sim s, qpg_neutral n, qpg_part2d elect
     ARG_TRY(electrons->ctx == s->ctx && ions->ctx == s->ctx, "the particle sets must be created on qpg_sim_ctx(sim)");
     ARG_TRY(!s->neut, "a neutral species is already attached");
     ARG_TRY(!s->prm.sp_push_std && !s->prm.sp_push_pgc, "neutral species: robust pusher only");
+    // one update can release ppc1 * ppc2 electrons in every (cell, sector): the ion buffer must hold that, the electron set at least that
+    // (it accumulates over the slices of a step; an overflow later on latches QPG_ERR_STATE, neutral.cu k_neutral_counts)
+    ARG_TRY(ions->npmax >= qpg_neutral_max_new_per_update(n) && electrons->npmax >= qpg_neutral_max_new_per_update(n),
+            "particle sets too small: need npmax >= ppc1 * ppc2 * nr * num_theta");
     qpg_ctx c = s->ctx;
     int rc;
     struct { qpg_field *f; int dim, has2d; } tbl[] = {{&s->neut_q, 1, 1}, {&s->neut_cu, 3, 0}, {&s->neut_dcu, 2, 0}, {&s->neut_amu, 3, 0}, {&s->rho_ion, 1, 1}, {&s->rho_ion_add, 1, 0}};
@@ -666,8 +674,7 @@ extern "C" int qpg_sim_stats(qpg_sim s, long *updates, long *pc_iters, long *sli
     if (updates) *updates = (long)cnt[0];
     if (pc_iters) *pc_iters = (long)cnt[1];
     if (slices) *slices = fl[4];
-    if (fl[6]) { qpg_set_error("sweep kernel aborted (a grid barrier or strip exchange timed out): fields and particles of this sim are invalid"); return QPG_ERR_STATE; }
-    return 0;
+    return qpg_ctx_check_latches(c, fl);
 }
 extern "C" int qpg_sim_set_fused(qpg_sim s, int on)
 {

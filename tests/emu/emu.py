@@ -16,6 +16,10 @@ _EMU_SIGS = {"emu_launches": (C.c_long, []), "emu_barriers": (C.c_long, []), "em
 def lib():
     global _lib
     if _lib is None:
+        import platform
+        if platform.machine() not in ("x86_64", "AMD64"):      # the fiber switch of tests/emu/cuda_runtime.h is x86-64 assembly
+            import pytest
+            pytest.skip("tests/emu (host emulation of the device sources) needs an x86-64 host")
         L = C.CDLL(_build.build())
         for name, (res, args) in list(_EMU_SIGS.items()) + list(capi.SIGNATURES.items()):
             if hasattr(L, name):

@@ -376,3 +376,25 @@ def part2d_move(api, O):
     assert pt.npp() == len(before[4]) <= n
     for a, b in zip(before, after):
         assert np.array_equal(a, b)
+
+
+def neutral_overflow(api, O):
+    """released electrons that do not fit the particle set must not vanish silently: the device latches the overflow and the next
+    host synchronisation returns QPG_ERR_STATE (neutral.cu k_neutral_counts; the beam's wire buffer does the same)"""
+    import pytest
+    nr, nth = 48, 8
+    ctx = api.Ctx(nr, 0, 0.1, 0.02)
+    e = np.zeros((1, nr + 2, 3)); e[0, :, 0] = 400.0 / (O.lib().orc_plasma_frequency(1.0e17) * 1.708e-12)      # ionises everything at once
+    fe = api.Field(ctx, 3); fe.upload(e)
+    ne = api.Neutral(ctx, 1, 1, (2, 2), nth, n0=1.0e17, dt_xi=0.02)
+    ne.update(fe)
+    ctx.sync()                                              # fits: no error
+    assert ne.part.npp() == nr * nth * 4
+    ne.renew()
+    ne.part.close()
+    ne.part = api.Part2d(ctx, -1.0, 200)                    # far too small
+    ne.update(fe)
+    with pytest.raises(api.QpadError, match="did not fit"):
+        ctx.sync()
+    assert 200 <= ne.part.npp() <= 256 < nr * nth * 4       # clamped to the (alignment-rounded) capacity, and reported
+    ne.close()

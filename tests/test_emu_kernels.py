@@ -59,3 +59,7 @@ def test_field_smooth_emulated(api, M, dim, kind, order):
 
 def test_part2d_move_emulated(api):
     K.part2d_move(api, O)
+
+
+def test_neutral_overflow_emulated(api):
+    K.neutral_overflow(api, O)

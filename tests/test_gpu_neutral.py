@@ -46,3 +46,9 @@ def test_sim_neutral_full_step(mods, use_graph):
     capi, O = mods
     import kernel_cases as K
     K.sim_neutral_full_step(capi, O, use_graph=use_graph)
+
+
+def test_neutral_overflow_is_reported(mods):
+    capi, O = mods
+    import kernel_cases as K
+    K.neutral_overflow(capi, O)
