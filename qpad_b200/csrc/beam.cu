@@ -16,45 +16,65 @@ struct Part3View {
 static Part3View view3(qpg_part3d p) { Part3View v{p->x1, p->x2, p->x3, p->p1, p->p2, p->p3, p->q, p->d_npp}; return v; }
 static double **plane_table3(qpg_part3d p) { return (double **)(p->lists + 2 * p->npmax); }
 
-// beam/part3d_class.f03:221-356 qdeposit_part3d (accumulation); f2 image layout [slice][node][P] (dim 1)
+// beam/part3d_class.f03:221-356 qdeposit_part3d (accumulation); f2 image layout [slice][node][P] (dim 1).
+// Beam particles are created slice by slice, sector by sector, cell by cell (fdist3d_std_class.f03:439-613), so the lanes of a warp
+// share a few (slice, cell) pairs: the 4 P sums a particle contributes to its four nodes are reduced over the warp with the one-hot
+// DMMA reduction of the plasma charge deposit (particles.cu warp_deposit_q_mma, key = flattened node index of the f2 volume) -- one
+// RED per (node, plane) and warp instead of one atomic per lane: the scatter was atomic-throughput bound (12 atomics per particle
+// onto ~50 radial cells).  Launched as a grid-stride loop over warp tiles: the host only knows an upper bound of the live count.
+#define B3_MAX_GRID (148 * 8)
+static inline int b3_grid(long n) { const long g = (n + B3_BLOCK - 1) / B3_BLOCK; return (int)(g < B3_MAX_GRID ? g : B3_MAX_GRID); }
 template <int M>
 __global__ void __launch_bounds__(B3_BLOCK) k_qdeposit3d(Part3View pv, double *__restrict__ f2, double idr, double idz, int nr, int noff2, int nzp)
 {
     constexpr int P = 2 * M + 1;
-    const int npp = *pv.d_npp;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= npp) return;
-    const double x1 = pv.x1[i], x2 = pv.x2[i], x3 = pv.x3[i], q = pv.q[i];
-    double pos_r = __dmul_rn(__dsqrt_rn(__dadd_rn(__dmul_rn(x1, x1), __dmul_rn(x2, x2))), idr);
-    double pos_z = __dmul_rn(x3, idz);
-    const double c0 = x1 / pos_r * idr, s0 = -x2 / pos_r * idr;
-    int nn = (int)floor(pos_r), mm = (int)floor(pos_z);
-    const double fr = pos_r - (double)nn, fz = pos_z - (double)mm;
-    nn = nn + 1;
-    mm = mm - noff2 + 1;
-    if (mm < 1 || mm > nzp || nn < 1 || nn > nr) return;  // not ours (hand-off pending) -- never deposit out of bounds
-    const size_t n1 = (size_t)(nr + 2) * P;
-    const double wr[2] = {1.0 - fr, fr}, wz[2] = {1.0 - fz, fz};
-    double ph[P];
-    double phr = q, phi = 0.0;
-    ph[0] = phr;
+    extern __shared__ double dep_tiles[];
+    const int npp = *pv.d_npp, lane = threadIdx.x & 31;
+    double *tile = dep_tiles + (threadIdx.x >> 5) * DepTile<M>::doubles;
+    for (long base = (long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < npp; base += (long)gridDim.x * blockDim.x) {   // warp-uniform
+        const long i = base + lane;
+        bool ok = i < npp;
+        double ph[P], wr[2] = {0.0, 0.0}, wz[2] = {0.0, 0.0};
+        int nn = 0, mm = 0;
 #pragma unroll
-    for (int m = 1; m <= M; m++) {
-        double t = phr * c0 - phi * s0;
-        phi = phr * s0 + phi * c0;
-        phr = t;
-        ph[2 * m - 1] = phr;
-        ph[2 * m] = phi;
-    }
+        for (int pl = 0; pl < P; pl++) ph[pl] = 0.0;
+        if (ok) {
+            const double x1 = pv.x1[i], x2 = pv.x2[i], x3 = pv.x3[i], q = pv.q[i];
+            double pos_r = __dmul_rn(__dsqrt_rn(__dadd_rn(__dmul_rn(x1, x1), __dmul_rn(x2, x2))), idr);
+            double pos_z = __dmul_rn(x3, idz);
+            const double c0 = x1 / pos_r * idr, s0 = -x2 / pos_r * idr;
+            nn = (int)floor(pos_r); mm = (int)floor(pos_z);
+            const double fr = pos_r - (double)nn, fz = pos_z - (double)mm;
+            nn = nn + 1;
+            mm = mm - noff2 + 1;
+            ok = !(mm < 1 || mm > nzp || nn < 1 || nn > nr);  // not ours (hand-off pending) -- never deposit out of bounds
+            wr[0] = 1.0 - fr; wr[1] = fr; wz[0] = 1.0 - fz; wz[1] = fz;
+            double phr = q, phi = 0.0;
+            ph[0] = phr;
 #pragma unroll
-    for (int k = 0; k < 2; k++)
-#pragma unroll
-        for (int j = 0; j < 2; j++) {
-            double *dst = f2 + (size_t)(mm + k - 1) * n1 + (size_t)(nn + j) * P;
-            const double w = wr[j] * wz[k];
-#pragma unroll
-            for (int pl = 0; pl < P; pl++) atomicAdd(dst + pl, w * ph[pl]);
+            for (int m = 1; m <= M; m++) {
+                double t = phr * c0 - phi * s0;
+                phi = phr * s0 + phi * c0;
+                phr = t;
+                ph[2 * m - 1] = phr;
+                ph[2 * m] = phi;
+            }
         }
+#pragma unroll
+        for (int k = 0; k < 2; k++) {   // slice mm + k - 1: nodes nn, nn + 1 are the pair (key, key + 1) of the flattened volume
+            double alpha[2 * P];
+#pragma unroll
+            for (int j = 0; j < 2; j++)
+#pragma unroll
+                for (int pl = 0; pl < P; pl++) alpha[j * P + pl] = ok ? (wr[j] * wz[k]) * ph[pl] : 0.0;
+            const int key = ok ? (mm + k - 1) * (nr + 2) + nn : -1;
+#ifdef QPG_BEAM_DEPOSIT_PLAIN   // A/B aid: one RED per lane and value instead of the warp reduction
+            if (ok) for (int r = 0; r < 2 * P; r++) red_add(f2 + (size_t)key * P + r, alpha[r]);
+#else
+            warp_deposit_q_mma<M>(alpha, key, f2, tile, lane);
+#endif
+        }
+    }
 }
 // axis rules + 1/(j-1) for slices 1..nzp, part3d_class.f03:318-351
 __global__ void k_qdep3d_fix(double *__restrict__ f2, int nr, int P, int nzp)
@@ -78,8 +98,7 @@ __global__ void __launch_bounds__(B3_BLOCK) k_push3d(Part3View pv, const double 
 {
     constexpr int P = 2 * M + 1;
     const int npp = *pv.d_npp;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= npp) return;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < npp; i += (long)gridDim.x * blockDim.x) {   // the host knows an upper bound only
     double x1 = pv.x1[i], x2 = pv.x2[i], x3 = pv.x3[i];
     double p1 = pv.p1[i], p2 = pv.p2[i], p3 = pv.p3[i];
     double pos_r = __dmul_rn(__dsqrt_rn(__dadd_rn(__dmul_rn(x1, x1), __dmul_rn(x2, x2))), idr);
@@ -89,7 +108,7 @@ __global__ void __launch_bounds__(B3_BLOCK) k_push3d(Part3View pv, const double 
     const double fr = pos_r - (double)nn, fz = pos_z - (double)mm;
     nn = nn + 1;
     mm = mm - noff2 + 1;
-    if (mm < 1 || mm > nzp || nn < 1 || nn > nr) return;
+    if (mm < 1 || mm > nzp || nn < 1 || nn > nr) continue;
     const size_t n1 = (size_t)(nr + 2) * P * 3;
     const double wr[2] = {1.0 - fr, fr}, wz[2] = {1.0 - fz, fz};
     double ep[3] = {0, 0, 0}, bp[3] = {0, 0, 0};
@@ -149,24 +168,26 @@ __global__ void __launch_bounds__(B3_BLOCK) k_push3d(Part3View pv, const double 
     x3 = x3 - p3 * dt_gam + dt;
     pv.x1[i] = x1; pv.x2[i] = x2; pv.x3[i] = x3;
     pv.p1[i] = p1; pv.p2[i] = p2; pv.p3[i] = p3;
+    }
 }
 
 // flag kernel: kind 0 -> out of the box (r >= edge_r or xi >= edge_z); kind 1 -> xi >= zhi (forward hand-off)
 __global__ void __launch_bounds__(B3_BLOCK) k_flag3d(Part3View pv, double edge_r, double edge_z, int kind, unsigned *__restrict__ outmask, int *__restrict__ d_nout)
 {
-    const int npp = *pv.d_npp;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
-    if ((i & ~31) >= npp) return;
-    bool out = false;
-    if (i < npp) {
-        const double x1 = pv.x1[i], x2 = pv.x2[i], x3 = pv.x3[i];
-        if (kind == 0) {
-            const double pos = __dsqrt_rn(__dadd_rn(__dmul_rn(x1, x1), __dmul_rn(x2, x2)));
-            out = (pos >= edge_r) || (x3 >= edge_z);
-        } else out = x3 >= edge_z;
+    const int npp = *pv.d_npp, lane = threadIdx.x & 31;
+    for (long base = (long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < npp; base += (long)gridDim.x * blockDim.x) {   // warp-uniform
+        const long i = base + lane;
+        bool out = false;
+        if (i < npp) {
+            const double x1 = pv.x1[i], x2 = pv.x2[i], x3 = pv.x3[i];
+            if (kind == 0) {
+                const double pos = __dsqrt_rn(__dadd_rn(__dmul_rn(x1, x1), __dmul_rn(x2, x2)));
+                out = (pos >= edge_r) || (x3 >= edge_z);
+            } else out = x3 >= edge_z;
+        }
+        const unsigned bal = __ballot_sync(FULL, out);
+        if (lane == 0) { outmask[i >> 5] = bal; if (bal) atomicAdd(d_nout, __popc(bal)); }
     }
-    const unsigned bal = __ballot_sync(FULL, out);
-    if (lane == 0) { outmask[i >> 5] = bal; if (bal) atomicAdd(d_nout, __popc(bal)); }
 }
 
 // ordered pack of the flagged particles (ascending index like pack_particles :685-745): one CTA
@@ -233,7 +254,12 @@ __global__ void k_bump_npp(int *d_npp, const double *__restrict__ buf, long cap,
 }
 
 template <int M> static void l_qdep3d(int grid, cudaStream_t st, Part3View pv, double *f2, double idr, double idz, int nr, int noff2, int nzp)
-{ k_qdeposit3d<M><<<grid, B3_BLOCK, 0, st>>>(pv, f2, idr, idz, nr, noff2, nzp); }
+{
+    constexpr size_t smem = sizeof(double) * DepTile<M>::doubles * (B3_BLOCK / 32);
+    static bool attr_set = false;   // > 48 KB of dynamic shared memory needs the opt-in (M >= 3)
+    if (!attr_set) { cudaFuncSetAttribute(k_qdeposit3d<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+    k_qdeposit3d<M><<<grid, B3_BLOCK, smem, st>>>(pv, f2, idr, idz, nr, noff2, nzp);
+}
 template <int M> static void l_push3d(int grid, cudaStream_t st, Part3View pv, const double *e, const double *b, double idr, double idz, int nr, int noff2, int nzp, double qbm, double dt, int pt)
 { k_push3d<M><<<grid, B3_BLOCK, 0, st>>>(pv, e, b, idr, idz, nr, noff2, nzp, qbm, dt, pt); }
 
@@ -319,7 +345,7 @@ extern "C" int qpg_part3d_qdeposit_raw(qpg_part3d p, qpg_field q)
     qpg_ctx c = p->ctx;
     TprofScope tp(c, TP_DEPOSIT3D);
     if (p->npp_hi > 0) {
-        const int grid = (int)((p->npp_hi + B3_BLOCK - 1) / B3_BLOCK);
+        const int grid = b3_grid(p->npp_hi);
         DISPATCH_M(c->M, l_qdep3d, grid, c->stream, view3(p), q->f2, 1.0 / c->dr, 1.0 / c->dxi, c->nr, p->noff2, p->nzp);
         count_launch(c);
     }
@@ -348,7 +374,7 @@ extern "C" int qpg_part3d_push(qpg_part3d p, int push_type, qpg_field ef, qpg_fi
     if (p->npp_hi == 0) return 0;
     qpg_ctx c = p->ctx;
     TprofScope tp(c, TP_PUSH3D);
-    const int grid = (int)((p->npp_hi + B3_BLOCK - 1) / B3_BLOCK);
+    const int grid = b3_grid(p->npp_hi);
     DISPATCH_M(c->M, l_push3d, grid, c->stream, view3(p), ef->f2, bf->f2, 1.0 / c->dr, 1.0 / c->dxi, c->nr, p->noff2, p->nzp, p->qbm, p->dt, push_type);
     count_launch(c);
     CUDA_TRY(cudaGetLastError());
@@ -360,7 +386,7 @@ extern "C" int qpg_part3d_update_bound(qpg_part3d p)
     if (p->npp_hi == 0) return 0;
     qpg_ctx c = p->ctx;
     TprofScope tp(c, TP_PUSH3D);
-    const int grid = (int)((p->npp_hi + B3_BLOCK - 1) / B3_BLOCK);
+    const int grid = b3_grid(p->npp_hi);
     k_flag3d<<<grid, B3_BLOCK, 0, c->stream>>>(view3(p), (double)c->nr * c->dr, (double)p->nz_total * c->dxi, 0, p->outmask, p->d_nout);
     k_compact<<<1, 1024, 0, c->stream>>>(plane_table3(p), 7, p->d_npp, p->d_nout, p->outmask, p->lists, 0, nullptr);
     count_launch(c, 2);
@@ -385,7 +411,7 @@ extern "C" int qpg_part3d_pack_forward(qpg_part3d p, double *dev_buf)
     qpg_ctx c = p->ctx;
     TprofScope tp(c, TP_MOVE3D);
     const long cap = qpg_part3d_wire_cap(p);
-    const int grid = (int)((p->npp_hi + B3_BLOCK - 1) / B3_BLOCK);
+    const int grid = b3_grid(p->npp_hi);
     if (grid > 0) k_flag3d<<<grid, B3_BLOCK, 0, c->stream>>>(view3(p), 0.0, (double)(p->noff2 + p->nzp) * c->dxi, 1, p->outmask, p->d_nout);
     k_pack3d<<<1, 1024, 0, c->stream>>>(view3(p), p->d_nout, p->outmask, dev_buf, cap, p->d_npp + 2);
     k_compact<<<1, 1024, 0, c->stream>>>(plane_table3(p), 7, p->d_npp, p->d_nout, p->outmask, p->lists, 1, nullptr);

@@ -666,11 +666,13 @@ extern "C" int qpg_sim_stats(qpg_sim s, long *updates, long *pc_iters, long *sli
 {
     ARG_TRY(s, "null sim");
     qpg_ctx c = s->ctx;
-    int fl[8];
+    int fl[8], nbeam = 0;
     long long cnt[2];
     CUDA_TRY(cudaMemcpyAsync(fl, c->flags, sizeof(fl), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaMemcpyAsync(cnt, c->counters, sizeof(cnt), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(&nbeam, s->beam->d_npp, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
+    s->beam->npp_hi = nbeam;   // the host's upper bound of the beam count grows with every hand-off (qpg_part3d_unpack): resynchronise it here
     if (updates) *updates = (long)cnt[0];
     if (pc_iters) *pc_iters = (long)cnt[1];
     if (slices) *slices = fl[4];

@@ -630,7 +630,11 @@ template <int M>
 SW_PHASE_FN void sweep_push_phase(const SweepArgs &a, int npp, int tile0, int tile1, double *dep_tiles)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#ifdef QPG_EXP_NO_PUSH_QDEP   // bottleneck experiment only (results are wrong): the push phase without the fused charge deposit
+    FusedArgs f = a.f; f.acc1 = nullptr;
+#else
     const FusedArgs &f = a.f;
+#endif
     const double idr = 1.0 / f.dr;
     double *tile = dep_tiles + warp * DepTile<M>::doubles;
 #if QPG_SWEEP_PREFETCH
@@ -657,7 +661,6 @@ __global__ void __launch_bounds__(SW_T, 1) k_sweep(const __grid_constant__ Sweep
     double *dep_tiles = sm_dyn + (sizeof(StripSmem<M>) + 7) / 8;
     const int G = gridDim.x, b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const FusedArgs &f = a.f;
-    const double idr = 1.0 / f.dr;
     unsigned gep = 0;
     Team tm;
     tm.ctr = a.bar + 32; tm.abort_flag = a.bar + 64; tm.epoch = 0; tm.xep = 0; tm.n = a.nteam; tm.rank = b; tm.xpar = 0; tm.xbuf = a.xbuf; tm.xll = a.xll;
