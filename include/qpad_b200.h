@@ -296,6 +296,12 @@ int qpg_wire_import(const unsigned char *handle64, void **dev_ptr);
 int qpg_wire_unmap(void *dev_ptr);
 int qpg_stream_signal(void *cuda_stream, unsigned *flag, unsigned value);
 int qpg_stream_wait(void *cuda_stream, unsigned *flag, unsigned value);
+/* like qpg_stream_wait, but the stream waits only if the int at dev_count is non-zero when the wait is reached (a polling kernel of one
+ * thread): the backward e / b hand-off of the xi-pipeline (simulation_class.f03:460-467, :482-483) matters only to a stage that holds
+ * beam particles -- dev_count = qpg_part3d_count_ptr(beam) */
+int qpg_stream_wait_unless_empty(void *cuda_stream, const int *dev_count, unsigned *flag, unsigned value);
+/* device address of the live particle count of a beam particle set (an int the kernels of this library keep up to date) */
+const int *qpg_part3d_count_ptr(qpg_part3d p);
 int qpg_stream_wait_is_memop(void);   /* 1 = cuStreamWaitValue32, 0 = fallback polling kernel */
 
 /* ------------------------------------------------------------------------------------------ */

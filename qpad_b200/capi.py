@@ -183,6 +183,8 @@ SIGNATURES = {
     "qpg_wire_unmap": (_i, [_vp]),
     "qpg_stream_signal": (_i, [_vp, _vp, C.c_uint]),
     "qpg_stream_wait": (_i, [_vp, _vp, C.c_uint]),
+    "qpg_stream_wait_unless_empty": (_i, [_vp, _vp, _vp, C.c_uint]),
+    "qpg_part3d_count_ptr": (_vp, [_vp]),
     "qpg_stream_wait_is_memop": (_i, []),
 }
 
@@ -453,6 +455,7 @@ class Part3d:
     def qdeposit(self, q): _chk(self.L.qpg_part3d_qdeposit(self.h, q.h))
     def push(self, push_type, ef, bf): _chk(self.L.qpg_part3d_push(self.h, push_type, ef.h, bf.h))
     def update_bound(self): _chk(self.L.qpg_part3d_update_bound(self.h))
+    def count_ptr(self): return self.L.qpg_part3d_count_ptr(self.h)          # device address of the live particle count
     def wire_cap(self): return self.L.qpg_part3d_wire_cap(self.h)
     def set_wire_cap(self, cap): _chk(self.L.qpg_part3d_set_wire_cap(self.h, int(cap)))
     def pack_forward(self, dev_ptr): _chk(self.L.qpg_part3d_pack_forward(self.h, dev_ptr))
@@ -741,3 +744,8 @@ def stream_signal(cuda_stream, flag_ptr, value):
 
 def stream_wait(cuda_stream, flag_ptr, value):
     _chk(load().qpg_stream_wait(cuda_stream, flag_ptr, value & 0xFFFFFFFF))
+
+
+def stream_wait_unless_empty(cuda_stream, count_ptr, flag_ptr, value):
+    """wait for the flag only if the device int at count_ptr is non-zero (qpg_stream_wait_unless_empty)"""
+    _chk(load().qpg_stream_wait_unless_empty(cuda_stream, count_ptr, flag_ptr, value & 0xFFFFFFFF))

@@ -393,6 +393,7 @@ extern "C" int qpg_part3d_update_bound(qpg_part3d p)
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
+extern "C" const int *qpg_part3d_count_ptr(qpg_part3d p) { return p ? p->d_npp : nullptr; }
 extern "C" long qpg_part3d_wire_cap(qpg_part3d p)
 {
     if (!p) return -1;

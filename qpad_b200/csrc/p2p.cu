@@ -34,6 +34,24 @@ __global__ void k_p2p_spin(const unsigned *flag, unsigned value)
     } while (true);
 }
 
+// conditional wait: the stream blocks on the flag only if *count != 0 when the kernel runs.  Used for hand-offs whose payload matters
+// only to a stage that holds beam particles (the backward e / b guard slice feeds the beam push alone): a stage without beam
+// particles does not wait for its downstream neighbour, so the start-up skew of the pipeline (each stage waits for the first slice
+// of the next one) accumulates over the beam-carrying stages only.  One polling thread on an SM the stage's own sweep kernel has
+// just left; a producer that never signals trips the trap after ~20 s instead of hanging the GPU.
+__global__ void k_p2p_spin_unless_empty(const int *count, const unsigned *flag, unsigned value)
+{
+    if (*count == 0) return;
+    const long long t0 = clock64();
+    unsigned v;
+    do {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if ((int)(v - value) >= 0) break;
+        __nanosleep(200);
+        if (clock64() - t0 > 40000000000LL) __trap();
+    } while (true);
+}
+
 typedef CUresult (*fn_wait32_t)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
 static fn_wait32_t p2p_wait_entry()
 {
@@ -102,6 +120,13 @@ extern "C" int qpg_stream_wait(void *cuda_stream, unsigned *flag, unsigned value
         return QPG_ERR_CUDA;
     }
     k_p2p_spin<<<1, 1, 0, (cudaStream_t)cuda_stream>>>(flag, value);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+extern "C" int qpg_stream_wait_unless_empty(void *cuda_stream, const int *dev_count, unsigned *flag, unsigned value)
+{
+    ARG_TRY(flag && dev_count, "null arg");
+    k_p2p_spin_unless_empty<<<1, 1, 0, (cudaStream_t)cuda_stream>>>(dev_count, flag, value);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

@@ -778,9 +778,13 @@ class LocalPipeline:
         s.beam_qdp_begin()                                              # the next step's zero fills too (the beam push reads
         s.begin_step_zero()                                             # the e / b VOLUMES, the fills clear slice images)
         self._zeroed[r] = True
+        # The backward message (e, b of the downstream stage's first slice) feeds the beam push only: a stage without beam particles
+        # does not wait for it (qpg_stream_wait_unless_empty looks at the device-side particle count when the stream gets there), so
+        # the skew "every stage starts after the first slice of the next one" builds up over the beam-carrying stages only.  The
+        # unpack below then copies a possibly stale record into the guard slice nobody reads; the message counters stay in step.
         if p2p_down:
             n_b = self.links.next("back_in")
-            self._pwait(r, "ready_back", n_b)
+            capi.stream_wait_unless_empty(self.streams[r].cuda_stream, s.beam.count_ptr(), self.links.flag("own", "ready_back"), n_b)
             bsrc = self.back_in
         elif remote_down:
             self._nccl_isend("fwd", self.fwd[r][:self.n_fwd], self.rank + 1, self.ev[("fwd_ready", r)])
@@ -789,7 +793,7 @@ class LocalPipeline:
             bsrc = self.back_in
         elif r < S - 1:
             self.nback_in[r] += 1
-            capi.stream_wait(self.streams[r].cuda_stream, self.lflags.ptr + 32 * (r + 1), self.nback_in[r])   # raised by stage r+1's sweep kernel
+            capi.stream_wait_unless_empty(self.streams[r].cuda_stream, s.beam.count_ptr(), self.lflags.ptr + 32 * (r + 1), self.nback_in[r])   # raised by stage r+1's sweep kernel
             bsrc = self.back[r + 1]
         else:
             bsrc = None

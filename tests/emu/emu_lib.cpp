@@ -35,6 +35,11 @@ int qpg_stream_wait(void *, unsigned *flag, unsigned value)
     qpg_set_error("qpg_stream_wait: flag %u < %u and its producer has not been enqueued -- on a GPU this stream would wait forever", *flag, value);
     return QPG_ERR_STATE;
 }
+int qpg_stream_wait_unless_empty(void *st, const int *dev_count, unsigned *flag, unsigned value)
+{
+    if (*dev_count == 0) return 0;
+    return qpg_stream_wait(st, flag, value);
+}
 long emu_launches(void) { return emu::g_launches; }
 long emu_barriers(void) { return emu::g_barriers; }
 long emu_collectives(void) { return emu::g_collectives; }

@@ -100,3 +100,33 @@ def test_sweep_watchdog_is_reported(mods):
         sim.ctx.sync()
     assert int(wb[2 * nb:].view(torch.int32)[0].item()) == 7     # the flag was raised although the sweep did no work
     sim.close()
+
+
+def test_conditional_stream_wait(mods):
+    """qpg_stream_wait_unless_empty: the backward hand-off of the xi-pipeline is awaited only by a stage that holds beam particles"""
+    import time
+    import torch
+    capi, O, K = mods
+    flag = torch.zeros(8, dtype=torch.int32, device="cuda")
+    cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    st, st2 = torch.cuda.Stream(), torch.cuda.Stream()
+    capi.stream_wait_unless_empty(st.cuda_stream, cnt.data_ptr(), flag.data_ptr(), 5)     # count 0: must not block although the flag is 0
+    st.synchronize()
+    cnt.fill_(3); flag[0] = 7
+    torch.cuda.synchronize()
+    capi.stream_wait_unless_empty(st.cuda_stream, cnt.data_ptr(), flag.data_ptr(), 5)     # count > 0, flag already past the value
+    st.synchronize()
+    flag.zero_()
+    torch.cuda.synchronize()
+    # count > 0, flag not there yet: blocks until another stream raises it.  As everywhere in the pipeline the PRODUCER is enqueued first
+    # (a polling kernel may only depend on work that is already in some hardware queue: streams can share one)
+    with torch.cuda.stream(st2):                            # ~0.1 s of work on st2, then the signal
+        torch.cuda._sleep(200_000_000)
+    capi.stream_signal(st2.cuda_stream, flag.data_ptr(), 2)
+    capi.stream_wait_unless_empty(st.cuda_stream, cnt.data_ptr(), flag.data_ptr(), 2)
+    ev = torch.cuda.Event(); ev.record(st)
+    time.sleep(0.02)
+    assert not ev.query()
+    st.synchronize()
+    assert ev.query() and int(flag[0].item()) == 2

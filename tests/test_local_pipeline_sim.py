@@ -169,6 +169,7 @@ class FakeBeam:
         self.sim, self.cap = sim, 128
 
     def upload(self, *a): pass
+    def count_ptr(self): return 0
     def set_wire_cap(self, c): self.cap = int(c)
     def wire_cap(self): return self.cap
 
@@ -241,6 +242,11 @@ class FakeCapi:
 
     @staticmethod
     def stream_wait(cuda_stream, flag, value):
+        stream_of(cuda_stream).push("wait_flag", flag=flag, value=value)
+
+    @staticmethod
+    def stream_wait_unless_empty(cuda_stream, count_ptr, flag, value):
+        # the stand-in's stages all hold beam particles: the conditional wait of the backward hand-off is a wait
         stream_of(cuda_stream).push("wait_flag", flag=flag, value=value)
 
     @staticmethod
@@ -384,6 +390,7 @@ def test_the_checker_catches_a_missing_wait(fake_device, monkeypatch):
     cfg, plasma, beam = _inputs(32)
     FakeSim.G_OF = {noff: g for g, (noff, _) in enumerate(pipeline.slab_partition(32, 2))}
     monkeypatch.setattr(FakeCapi, "stream_wait", staticmethod(lambda cuda_stream, flag, value: None))
+    monkeypatch.setattr(FakeCapi, "stream_wait_unless_empty", staticmethod(lambda cuda_stream, count_ptr, flag, value: None))
     out = {}
     _run_rank(cfg, plasma, beam, 2, 0, 1, None, None, 4, False, out)
     assert not isinstance(out[0], Exception), out[0]
