@@ -777,12 +777,14 @@ def run_b200_local(args):
                                  "note": "arithmetic intensity ~10 flop/B against a machine balance of 5.6 flop/B: the fp64 pipe, not HBM, is the nearer roof"}
     except Exception:   # an explanatory extra must never cost the bench line
         pass
-    try:   # DRAM traffic: measured with ncu --set full on ONE sweep launch over the whole deck (profiles/r01_sweep_traffic.json); this launch shape
-        # (S kernels of ~nz/S slices) has not been captured separately, so `traffic` stays null and the capture is quoted as a reference
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_sweep_traffic.json")))
-        roof["traffic_reference"] = {"dram_bytes_per_2048_slice_launch": float(tj["dram_bytes_read"] + tj["dram_bytes_write"]),
-                                     "algorithmic_bytes_same_launch": 5.37e8 * (112.0 + 64.0 * 1.09),
-                                     "source": "profiles/r01_sweep_traffic.json: one k_sweep<1> launch on 148 SMs, 2048 slices; DRAM traffic = the field-volume slice stores, the particle planes stay in L2"}
+    try:   # DRAM traffic: ncu --set full of ONE sweep launch in this very launch shape (37 CTAs = one SM partition), per slice, x the slices of a launch
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r02_sweep_traffic.json")))
+        if args.config == "C2":
+            per_launch = slices / max(sweep_n * world, 1)
+            roof["traffic"] = float(tj["dram_bytes_per_slice"]) * per_launch
+            roof["traffic_source"] = (f"{tj['source']}: {tj['dram_bytes_per_slice'] / 1e3:.0f} KB of DRAM traffic per slice x {per_launch:.0f} slices per launch; algorithmic particle bytes "
+                                      f"per slice {npp0 * (112.0 + 64.0 * nit) / 1e6:.1f} MB: the particle planes stay in L2, DRAM sees the field-volume slice stores")
+            roof["algorithmic_bytes_per_launch"] = bytes_total / max(sweep_n * world, 1)
     except Exception:
         pass
     roof_hbm = None
