@@ -967,8 +967,10 @@ def main():
             cfg, _ = deck_config(args.config)
             nteam, stages = (cfg["nr"] + 31) // 32, 1
             world = int(os.environ.get("WORLD_SIZE", "1"))
-            for cand in (2, 3, 4):
-                if (148 - (4 if world > 1 else 0)) // cand > nteam + 1 and cfg["nz"] // (cand * world) >= 64 and cfg["max_mode"] <= 2:
+            # (measured on one B200: C2 -- team of 32 CTAs -- 4 stages; C1 / C3 -- team of 8 -- 8 stages: 2.0e9 / 1.07e9 updates/s against
+            # 1.4e9 / 7.1e8 with 4: the smaller the deck, the more of a slice is barrier and field-program latency that other stages can fill)
+            for cand in (2, 3, 4, 5, 6, 7, 8):
+                if 148 // cand > nteam + 1 and cfg["nz"] // (cand * world) >= 48 and cfg["max_mode"] <= 2:
                     stages = cand
             args.stages = stages
         world = int(os.environ.get("WORLD_SIZE", "1"))

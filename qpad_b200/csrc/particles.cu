@@ -343,14 +343,16 @@ __device__ __forceinline__ PartRegs part_load(const PartView &pv, int i, int npp
 
 // ---- amjdeposit_robust: species/part2d_class.f03:746-1010 ------------------------------------------------
 // STD = amjdeposit_std_part2d (:478-744): field normalisation from the stored psi (:562-601), psi left untouched
+// the per-particle arithmetic of amjdeposit: gathers, the implicit Boris step, gamma / psi stores -> the factors alpha (x) beta of the
+// particle's 2P x 8 contributions and its cell (key = -1: no particle).  Free of warp-level synchronisation, so that a caller can
+// interleave the arithmetic of two independent tiles (the chains of one particle are long and serial: sweep.cu QPG_SWEEP_ILP2)
 template <int M, bool STD = false>
-__device__ __forceinline__ void amj_core(const PartView &pv, const PartRegs &pr, const double *ef, const double *bf, double *acc8, double qbm, double dt,
-                                         double idr, int npp, int i, int lane, double *tile)
+__device__ __forceinline__ void amj_math(const PartView &pv, const PartRegs &pr, const double *ef, const double *bf, double qbm, double dt, double idr, int npp, int i,
+                                         double (&alpha)[2 * (2 * M + 1)], double (&beta)[8], int &key)
 {
     constexpr int P = 2 * M + 1;
     const bool valid = i < npp;
-    double alpha[2 * P], beta[8];
-    int key = -1;
+    key = -1;
     if (valid) {
         const double x1 = pr.x1, x2 = pr.x2;
         const double pp1 = pr.p1, pp2 = pr.p2, pp3 = pr.p3, q = pr.q;
@@ -423,6 +425,15 @@ __device__ __forceinline__ void amj_core(const PartView &pv, const PartRegs &pr,
 #pragma unroll
         for (int k = 0; k < 8; k++) beta[k] = 0.0;
     }
+}
+template <int M, bool STD = false>
+__device__ __forceinline__ void amj_core(const PartView &pv, const PartRegs &pr, const double *ef, const double *bf, double *acc8, double qbm, double dt,
+                                         double idr, int npp, int i, int lane, double *tile)
+{
+    constexpr int P = 2 * M + 1;
+    double alpha[2 * P], beta[8];
+    int key;
+    amj_math<M, STD>(pv, pr, ef, bf, qbm, dt, idr, npp, i, alpha, beta, key);
     warp_deposit_mma<M>(alpha, beta, key, acc8, tile, lane);
 }
 template <int M, bool STD = false>
@@ -448,13 +459,15 @@ __global__ void __launch_bounds__(PT_BLOCK) k_amjdeposit(PartView pv, const doub
 // mode bit0: push_u, bit1: push_x, bit2: flag particles with r >= edge in the bitmap, bit3: push_u is the std flavour
 // acc1 != nullptr: additionally deposit the charge of the advanced, still in-bounds particle (the next slice's qdeposit
 // :346-349 fused into the push; out-of-bounds particles are removed by update_bound before the reference deposits)
+// the per-particle arithmetic of the push (no warp-level synchronisation: two tiles can be interleaved, sweep.cu QPG_SWEEP_ILP2);
+// returns the advanced position and the out-of-bounds flag
 template <int M>
-__device__ __forceinline__ void push_core(const PartView &pv, const PartRegs &pr, const double *ef, const double *bf, double qbm, double dt, double idr,
-                                          double edge, int mode, unsigned *outmask, int *d_nout, double *acc1, int npp, int i, int lane, double *tile)
+__device__ __forceinline__ void push_math(const PartView &pv, const PartRegs &pr, const double *ef, const double *bf, double qbm, double dt, double idr,
+                                          double edge, int mode, int npp, int i, double &xn1, double &xn2, bool &out)
 {
     const bool valid = i < npp;
-    bool out = false;
-    double xn1 = 0.0, xn2 = 0.0, qv = 0.0;
+    out = false;
+    xn1 = 0.0; xn2 = 0.0;
     if (valid) {
         double x1 = pr.x1, x2 = pr.x2;
         double p1 = pr.p1, p2 = pr.p2, p3 = pr.p3, g;
@@ -504,6 +517,14 @@ __device__ __forceinline__ void push_core(const PartView &pv, const PartRegs &pr
             out = pos >= edge;
         }
     }
+}
+// the warp-level part of the push: bound-flag bitmap and the fused charge deposit of the advanced, in-bounds particle
+template <int M>
+__device__ __forceinline__ void push_finish(const PartRegs &pr, double xn1, double xn2, bool out, double idr, int mode, unsigned *outmask, int *d_nout, double *acc1,
+                                            int npp, int i, int lane, double *tile)
+{
+    const bool valid = i < npp;
+    double qv = 0.0;
     if (mode & 4) {
         const unsigned bal = __ballot_sync(FULL, out);
         if (lane == 0) {
@@ -522,6 +543,15 @@ __device__ __forceinline__ void push_core(const PartView &pv, const PartRegs &pr
         }
         warp_deposit_q_mma<M>(alpha, key, acc1, tile, lane);
     }
+}
+template <int M>
+__device__ __forceinline__ void push_core(const PartView &pv, const PartRegs &pr, const double *ef, const double *bf, double qbm, double dt, double idr,
+                                          double edge, int mode, unsigned *outmask, int *d_nout, double *acc1, int npp, int i, int lane, double *tile)
+{
+    double xn1, xn2;
+    bool out;
+    push_math<M>(pv, pr, ef, bf, qbm, dt, idr, edge, mode, npp, i, xn1, xn2, out);
+    push_finish<M>(pr, xn1, xn2, out, idr, mode, outmask, d_nout, acc1, npp, i, lane, tile);
 }
 template <int M>
 __device__ __forceinline__ void push_body(const PartView &pv, const double *ef, const double *bf, double qbm, double dt, double idr, double edge,

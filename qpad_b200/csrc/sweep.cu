@@ -603,6 +603,10 @@ __device__ void sweep_publish_back(const SweepArgs &a)
 #else
 #define SW_PHASE_FN __device__ __forceinline__
 #endif
+#ifdef QPG_SWEEP_ILP2
+#undef QPG_SWEEP_PREFETCH
+#define QPG_SWEEP_PREFETCH 0
+#endif
 #ifndef QPG_SWEEP_PREFETCH
 #define QPG_SWEEP_PREFETCH 1
 #endif
@@ -620,6 +624,20 @@ SW_PHASE_FN void sweep_amj_phase(const SweepArgs &a, int npp, int tile0, int til
         const PartRegs nxt = part_load(a.pv, tn * 32 + lane, tn < tile1 ? npp : 0);
         amj_core<M>(a.pv, cur, f.e, f.b, f.acc8, a.qbm, f.dxi, idr, npp, tl * 32 + lane, lane, tile);
         cur = nxt;
+    }
+#elif defined(QPG_SWEEP_ILP2)
+    // two tiles per warp and pass: the arithmetic of tile A and tile B is independent, the scheduler interleaves the two dependency chains
+    // (a particle's chain is long and serial and only 4 warps share a scheduler); the reductions follow one after the other
+    constexpr int P = 2 * M + 1;
+    for (int tl = tile0 + 2 * warp; tl < tile1; tl += 2 * (SW_T / 32)) {
+        const int ia = tl * 32 + lane, ib = ia + 32, nb = tl + 1 < tile1 ? npp : 0;
+        const PartRegs pa = part_load(a.pv, ia, npp), pb = part_load(a.pv, ib, nb);
+        double al_a[2 * P], be_a[8], al_b[2 * P], be_b[8];
+        int key_a, key_b;
+        amj_math<M>(a.pv, pa, f.e, f.b, a.qbm, f.dxi, idr, npp, ia, al_a, be_a, key_a);
+        amj_math<M>(a.pv, pb, f.e, f.b, a.qbm, f.dxi, idr, nb, ib, al_b, be_b, key_b);
+        warp_deposit_mma<M>(al_a, be_a, key_a, f.acc8, tile, lane);
+        if (tl + 1 < tile1) warp_deposit_mma<M>(al_b, be_b, key_b, f.acc8, tile, lane);
     }
 #else
     for (int tl = tile0 + warp; tl < tile1; tl += SW_T / 32)
@@ -644,6 +662,17 @@ SW_PHASE_FN void sweep_push_phase(const SweepArgs &a, int npp, int tile0, int ti
         const PartRegs nxt = part_load(a.pv, tn * 32 + lane, tn < tile1 ? npp : 0);
         push_core<M>(a.pv, cur, f.e, f.b, a.qbm, f.dxi, idr, a.edge, 7, a.outmask, a.d_nout, f.acc1, npp, tl * 32 + lane, lane, tile);
         cur = nxt;
+    }
+#elif defined(QPG_SWEEP_ILP2)
+    for (int tl = tile0 + 2 * warp; tl < tile1; tl += 2 * (SW_T / 32)) {   // two tiles per warp and pass, see sweep_amj_phase
+        const int ia = tl * 32 + lane, ib = ia + 32, nb = tl + 1 < tile1 ? npp : 0;
+        const PartRegs pa = part_load(a.pv, ia, npp), pb = part_load(a.pv, ib, nb);
+        double xa1, xa2, xb1, xb2;
+        bool oa, ob;
+        push_math<M>(a.pv, pa, f.e, f.b, a.qbm, f.dxi, idr, a.edge, 7, npp, ia, xa1, xa2, oa);
+        push_math<M>(a.pv, pb, f.e, f.b, a.qbm, f.dxi, idr, a.edge, 7, nb, ib, xb1, xb2, ob);
+        push_finish<M>(pa, xa1, xa2, oa, idr, 7, a.outmask, a.d_nout, f.acc1, npp, ia, lane, tile);
+        if (tl + 1 < tile1) push_finish<M>(pb, xb1, xb2, ob, idr, 7, a.outmask, a.d_nout, f.acc1, nb, ib, lane, tile);
     }
 #else
     for (int tl = tile0 + warp; tl < tile1; tl += SW_T / 32)
