@@ -549,6 +549,8 @@ def run_c4(args):
     simkw = {k: cfg[k] for k in ("nr", "nz", "max_mode", "rmax", "zmin", "zmax", "dt", "iter_max", "iter_reltol", "iter_abstol")}
     sim = capi.Sim(sp_npmax=2 * npp0, beam_npmax=64, beam_evol=0, sp_push_pgc=1, laser_iter=las["iteration"], laser_k0=las["k0"], sp_ppc_r=cfg["ppc1"],
                    use_graph=0 if args.no_graph else 1, stream=stream.cuda_stream, **simkw)
+    sweep_on = not args.no_sweep
+    sim.set_sweep(1 if sweep_on else 0)      # default: the laser hooks inside the persistent sweep kernel (k_sweep<M, PGC = true>)
     sim.init_species(x, p, g, psi, q)
     a_r, a_i = decks.laser_gaussian(cfg["nr"], cfg["nz"], cfg["rmax"], cfg["zmin"], cfg["zmax"], **las)
     sim.laser.upload(a_r, a_i)
@@ -569,7 +571,7 @@ def run_c4(args):
     clocks = clk.stop()
     u1, i1, s1 = sim.stats()
     upd, iters, slices = u1 - u0, i1 - i0, s1 - s0
-    launches = sim.ctx.launch_count() - l0 if args.no_graph else slices * 9 + 2 * iters + 2 * args.steps   # graph replay: head 2, tail 7, 2 per PC iteration
+    launches = sim.ctx.launch_count() - l0 if (args.no_graph or sweep_on) else slices * 9 + 2 * iters + 2 * args.steps   # graph replay: head 2, tail 7, 2 per PC iteration
     # end to end: plasma lattice host -> device every step, wake + envelope line-outs device -> host
     t0 = time.perf_counter()
     ue0 = sim.stats()[0]
@@ -591,7 +593,8 @@ def run_c4(args):
     # algorithmic bytes per update: qdeposit 24 + amjdeposit_pgc 72 per pass (reads psi too) + push_u_pgc 80 + push_x 64 + deposit_chi 32
     bpu = 24.0 + 72.0 * nit + 80.0 + 64.0 + 32.0
     ach = upd * bpu / (ms * 1e-3) / 1e9
-    roof = {"bound": "hbm", "kernel": "per-slice launch path: k_amjdeposit_pgc / k_push_u_pgc / k_push / k_qdeposit / k_deposit_chi + field programs (65 536 particles per slice: the latency of the ~12 dependent kernels of a slice bounds it, not the particle bytes)",
+    roof = {"bound": "hbm", "kernel": ("k_sweep<0, PGC> (persistent: all slices of the step in one launch; laser slice images, pgc pushers and the susceptibility deposit inside it) + one persistent envelope-solve CTA per step; 65 536 particles per slice: barrier and field-program latency bound it, not the particle bytes"
+                                       if sweep_on else "per-slice launch path: k_amjdeposit_pgc / k_push_u_pgc / k_push / k_qdeposit / k_deposit_chi + field programs (65 536 particles per slice: the latency of the ~12 dependent kernels of a slice bounds it, not the particle bytes)"),
             "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src, "bytes_per_update": bpu,
             "us_per_slice": ms * 1e3 / max(slices, 1)}
     cpu = None
@@ -605,7 +608,8 @@ def run_c4(args):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic (lattice plasma per fdist2d rule, Gaussian x sin^2 laser pulse of the lwfa deck)",
             "config": {"workload": f"C4: nr={cfg['nr']} nz={cfg['nz']} max_mode=0 Np/slice={npp0} robust_pgc, laser a0={las['a0']} k0={las['k0']} iteration {las['iteration']}",
-                       "parallelism": ("single stage, slice body " + ("as plain stream launches" if args.no_graph else "replayed from a CUDA graph (device-side WHILE node for the predictor-corrector loop)") + " + one persistent envelope-solve CTA per step"), "l2": "field volumes + envelope volumes ~60 MB, particle planes 4 MB: L2 resident",
+                       "parallelism": ("single stage: one persistent sweep kernel per 3D step + one persistent envelope-solve CTA" if sweep_on else
+                                       "single stage, slice body " + ("as plain stream launches" if args.no_graph else "replayed from a CUDA graph (device-side WHILE node for the predictor-corrector loop)") + " + one persistent envelope-solve CTA per step"), "l2": "field volumes + envelope volumes ~60 MB, particle planes 4 MB: L2 resident",
                        "pc_iters_per_slice": nit},
             "clocks": clocks, "gpu_launches": int(launches), "roofline": roof, "e2e": e2e}
     if cpu: line["cpu_baseline"] = cpu

@@ -29,6 +29,9 @@ struct qpg_laser_s {
     qpg_field f_ar, f_ai, f_gr, f_gi, chi;
     double *chi_acc;     // raw susceptibility sums [(nr+2)][P]
     double *pcr;         // [M+1][nsteps][8][nr] elimination matrices (alpha 2x2 | gamma 2x2, row-major), then [M+1][4][nr] inverse diagonal blocks
+    double *pcrc;        // the same as complex numbers (every block of this operator is [[x, -y], [y, x]]): [M+1][nsteps][4][nr] (alpha x, y | gamma x, y), then
+                         // [M+1][2][nr] inverse diagonal (x, y); null if the structure check failed (then the general kernel runs)
+    size_t pcrc_n;
 };
 
 #define LVI(pl, i, j) ((((size_t)(pl)) * (nz + 3) + (size_t)((j) + 1)) * (nr + 2) + (i))
@@ -217,6 +220,99 @@ __global__ void __launch_bounds__(1024, 1) k_laser_solve(double *__restrict__ ar
         }
 }
 
+// The same solve with the elimination matrices as COMPLEX numbers (the 2x2 blocks of this operator all have the form [[x, -y], [y, x]]:
+// a_r + i a_i is multiplied by x + i y) and resident in shared memory when they fit (nr = 512, one mode: 147 KB): the general kernel
+// above re-read 8 doubles per node and level from L2 on every level of every pass (the 295 KB of one mode do not stay in L1) and spent
+// ~1350 cycles per level on that latency -- 18.7 us per slice, 9.6 ms per 3D step of config 4 with the other 147 SMs idle.  Per slice the
+// pass-invariant inputs are loaded once, a(j-1) and a(j-2) stay in registers from the previous slices, the iterate stays in registers
+// between the fixed-point passes.
+template <int MM>
+__global__ void __launch_bounds__(1024, 1) k_laser_solve_c(double *__restrict__ ar, double *__restrict__ ai, const double *__restrict__ sr, const double *__restrict__ si,
+                                                          const double *__restrict__ chi2, const double *__restrict__ pcrc, int nr, int nz, int iter, int nsteps,
+                                                          double ds, double dr, double dz, int coef_in_smem)
+{
+    constexpr int M = MM, P = 2 * M + 1;
+    extern __shared__ double laser_sh[];   // [2 buffers][2 components][nthreads] exchange, then (optionally) the coefficients
+    const int t = threadIdx.x, nt = blockDim.x, i = t + 1;
+    const bool live = t < nr;
+    const double dr2_idzh = 0.5 * dr * dr / dz, w = 0.25 * ds * dr * dr;
+    const size_t nlv = (size_t)(M + 1) * nsteps * 4 * nr, nbi = (size_t)(M + 1) * 2 * nr;
+    const double *coef = pcrc;
+    if (coef_in_smem) {
+        double *dst = laser_sh + 4 * (size_t)nt;
+        for (size_t k = t; k < nlv + nbi; k += nt) dst[k] = pcrc[k];
+        coef = dst;
+        __syncthreads();
+    }
+    const double *binv_all = coef + nlv;
+    double am1r[P], am1i[P], am2r[P], am2i[P];      // the new a(j-1), a(j-2) of this thread's node
+#pragma unroll
+    for (int pl = 0; pl < P; pl++) {
+        am1r[pl] = live ? ar[LVI(pl, i, 0)] : 0.0; am1i[pl] = live ? ai[LVI(pl, i, 0)] : 0.0;
+        am2r[pl] = live ? ar[LVI(pl, i, -1)] : 0.0; am2i[pl] = live ? ai[LVI(pl, i, -1)] : 0.0;
+    }
+    int cur = 0;
+    for (int j = 1; j <= nz; j++) {
+        double a_r[P], a_i[P], ch[P], s_r[P], s_i[P];
+#pragma unroll
+        for (int pl = 0; pl < P; pl++) {
+            a_r[pl] = live ? ar[LVI(pl, i, j)] : 0.0; a_i[pl] = live ? ai[LVI(pl, i, j)] : 0.0;       // old envelope = first guess
+            ch[pl] = live ? chi2[(size_t)(j - 1) * (nr + 2) * P + (size_t)i * P + pl] : 0.0;
+            s_r[pl] = live ? sr[LVI(pl, i, j)] + dr2_idzh * (4.0 * am1r[pl] - am2r[pl]) : 0.0;
+            s_i[pl] = live ? si[LVI(pl, i, j)] + dr2_idzh * (4.0 * am1i[pl] - am2i[pl]) : 0.0;
+        }
+        for (int l = 0; l < iter; l++) {
+            double tr[P], ti[P];
+            chi_coupling(a_r, a_i, ch, M, w, tr, ti);
+#pragma unroll
+            for (int pl = 0; pl < P; pl++) {
+                const int m = (pl + 1) / 2;
+                double d0 = s_r[pl] + tr[pl], d1 = s_i[pl] + ti[pl];
+                const double *lv = coef + (size_t)m * nsteps * 4 * nr;
+                for (int s = 0; s < nsteps; s++) {
+                    double *buf = laser_sh + (size_t)cur * 2 * nt;
+                    buf[t] = d0; buf[nt + t] = d1;
+                    __syncthreads();
+                    if (live) {
+                        const int hs = 1 << s;
+                        const double *c = lv + (size_t)s * 4 * nr + t;
+                        if (t - hs >= 0) {
+                            const double x0 = buf[t - hs], x1 = buf[nt + t - hs], cx = c[0], cy = c[(size_t)nr];
+                            d0 += cx * x0 - cy * x1;
+                            d1 += cy * x0 + cx * x1;
+                        }
+                        if (t + hs < nr) {
+                            const double x0 = buf[t + hs], x1 = buf[nt + t + hs], cx = c[2 * (size_t)nr], cy = c[3 * (size_t)nr];
+                            d0 += cx * x0 - cy * x1;
+                            d1 += cy * x0 + cx * x1;
+                        }
+                    }
+                    cur ^= 1;
+                }
+                if (live) {
+                    const double *bi = binv_all + (size_t)m * 2 * nr + t;
+                    const double bx = bi[0], by = bi[(size_t)nr];
+                    double xr = bx * d0 - by * d1, xi = by * d0 + bx * d1;
+                    if (m > 0 && i == 1) { xr = 0.0; xi = 0.0; }
+                    a_r[pl] = xr; a_i[pl] = xi;
+                }
+            }
+        }
+#pragma unroll
+        for (int pl = 0; pl < P; pl++) {
+            if (live) { ar[LVI(pl, i, j)] = a_r[pl]; ai[LVI(pl, i, j)] = a_i[pl]; }
+            am2r[pl] = am1r[pl]; am2i[pl] = am1i[pl]; am1r[pl] = a_r[pl]; am1i[pl] = a_i[pl];
+        }
+    }
+}
+template <int MM> static void l_laser_solve_c(int nthreads, size_t smem, cudaStream_t st, double *ar, double *ai, const double *sr, const double *si, const double *chi2,
+                                              const double *pcrc, int nr, int nz, int iter, int nsteps, double ds, double dr, double dz, int in_smem)
+{
+    static size_t attr = 0;
+    if (smem > attr) { cudaFuncSetAttribute(k_laser_solve_c<MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = smem; }
+    k_laser_solve_c<MM><<<1, nthreads, smem, st>>>(ar, ai, sr, si, chi2, pcrc, nr, nz, iter, nsteps, ds, dr, dz, in_smem);
+}
+
 // copy_slice(j, 2to1) + set_grad(j) + gather into the four slice images the pgc pushers read; one thread per (node, plane)
 __global__ void k_laser_slice(const double *__restrict__ ar, const double *__restrict__ ai, int nr, int nz, int M, int j, const int *__restrict__ jflag, double dr,
                               double dz, double *__restrict__ f_ar, double *__restrict__ f_ai, double *__restrict__ f_gr, double *__restrict__ f_gi)
@@ -332,6 +428,35 @@ extern "C" int qpg_laser_create(qpg_laser *out, qpg_ctx ctx, int nz, double k0, 
     for (int m = 0; m <= M; m++) pcr_factor(m, nr, l->nsteps, k0, ds, ctx->dr, l->dz, h.data() + (size_t)m * l->nsteps * 8 * nr, h.data() + nlv + (size_t)m * 4 * nr);
     CUDA_TRY(cudaMalloc(&l->pcr, sizeof(double) * (nlv + nbi)));
     CUDA_TRY(cudaMemcpy(l->pcr, h.data(), sizeof(double) * (nlv + nbi), cudaMemcpyHostToDevice));
+    {   // the complex form of the same factors (k_laser_solve_c): valid iff every block is [[x, -y], [y, x]]
+        const size_t nlc = (size_t)(M + 1) * l->nsteps * 4 * nr, nbc = (size_t)(M + 1) * 2 * nr;
+        std::vector<double> hc(nlc + nbc);
+        bool ok = true;
+        double scale = 0.0;
+        for (double v : h) scale = fabs(v) > scale ? fabs(v) : scale;
+        for (int m = 0; m <= M && ok; m++) {
+            for (int sstep = 0; sstep < l->nsteps && ok; sstep++)
+                for (int half = 0; half < 2; half++)
+                    for (int i = 0; i < nr; i++) {
+                        const double *o = h.data() + (size_t)m * l->nsteps * 8 * nr + (size_t)sstep * 8 * nr + (size_t)half * 4 * nr + i;
+                        const double a = o[0], b = o[(size_t)nr], cc = o[2 * (size_t)nr], d = o[3 * (size_t)nr];
+                        if (fabs(a - d) > 1e-13 * scale || fabs(b + cc) > 1e-13 * scale) ok = false;
+                        double *q = hc.data() + (size_t)m * l->nsteps * 4 * nr + (size_t)sstep * 4 * nr + (size_t)half * 2 * nr + i;
+                        q[0] = a; q[(size_t)nr] = cc;
+                    }
+            for (int i = 0; i < nr; i++) {
+                const double *o = h.data() + nlv + (size_t)m * 4 * nr + i;
+                if (fabs(o[0] - o[3 * (size_t)nr]) > 1e-13 * scale || fabs(o[(size_t)nr] + o[2 * (size_t)nr]) > 1e-13 * scale) ok = false;
+                double *q = hc.data() + nlc + (size_t)m * 2 * nr + i;
+                q[0] = o[0]; q[(size_t)nr] = o[2 * (size_t)nr];
+            }
+        }
+        if (ok && M <= 2) {
+            CUDA_TRY(cudaMalloc(&l->pcrc, sizeof(double) * (nlc + nbc)));
+            CUDA_TRY(cudaMemcpy(l->pcrc, hc.data(), sizeof(double) * (nlc + nbc), cudaMemcpyHostToDevice));
+            l->pcrc_n = nlc + nbc;
+        }
+    }
     *out = l;
     return 0;
 }
@@ -339,7 +464,7 @@ extern "C" int qpg_laser_destroy(qpg_laser l)
 {
     if (!l) return 0;
     cudaStreamSynchronize(l->ctx->stream);
-    cudaFree(l->ar); cudaFree(l->ai); cudaFree(l->sr); cudaFree(l->si); cudaFree(l->chi_acc); cudaFree(l->pcr);
+    cudaFree(l->ar); cudaFree(l->ai); cudaFree(l->sr); cudaFree(l->si); cudaFree(l->chi_acc); cudaFree(l->pcr); cudaFree(l->pcrc);
     qpg_field_destroy(l->f_ar); qpg_field_destroy(l->f_ai); qpg_field_destroy(l->f_gr); qpg_field_destroy(l->f_gi); qpg_field_destroy(l->chi);
     delete l;
     return 0;
@@ -403,7 +528,17 @@ extern "C" int qpg_laser_advance(qpg_laser l)
     const long n = (long)nr * nz;
     k_laser_set_rhs<<<(int)((n + 255) / 256), 256, 0, c->stream>>>(l->ar, l->ai, l->chi->f2, l->sr, l->si, nr, nz, c->M, l->k0, l->ds, c->dr, l->dz);
     const size_t smem = sizeof(double) * 4 * l->nthreads;
-    k_laser_solve<<<1, l->nthreads, smem, c->stream>>>(l->ar, l->ai, l->sr, l->si, l->chi->f2, l->pcr, nr, nz, c->M, l->iter, l->nsteps, l->ds, c->dr, l->dz);
+    if (l->pcrc && !getenv("QPG_LASER_GENERAL_SOLVE")) {
+        const size_t with_coef = smem + sizeof(double) * l->pcrc_n;
+        const int in_smem = with_coef <= 220 * 1024;
+        const size_t sm = in_smem ? with_coef : smem;
+        switch (c->M) {
+        case 0: l_laser_solve_c<0>(l->nthreads, sm, c->stream, l->ar, l->ai, l->sr, l->si, l->chi->f2, l->pcrc, nr, nz, l->iter, l->nsteps, l->ds, c->dr, l->dz, in_smem); break;
+        case 1: l_laser_solve_c<1>(l->nthreads, sm, c->stream, l->ar, l->ai, l->sr, l->si, l->chi->f2, l->pcrc, nr, nz, l->iter, l->nsteps, l->ds, c->dr, l->dz, in_smem); break;
+        default: l_laser_solve_c<2>(l->nthreads, sm, c->stream, l->ar, l->ai, l->sr, l->si, l->chi->f2, l->pcrc, nr, nz, l->iter, l->nsteps, l->ds, c->dr, l->dz, in_smem); break;
+        }
+    } else
+        k_laser_solve<<<1, l->nthreads, smem, c->stream>>>(l->ar, l->ai, l->sr, l->si, l->chi->f2, l->pcr, nr, nz, c->M, l->iter, l->nsteps, l->ds, c->dr, l->dz);
     count_launch(c, 2);
     CUDA_TRY(cudaGetLastError());
     return 0;

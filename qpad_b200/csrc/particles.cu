@@ -599,18 +599,14 @@ __device__ __forceinline__ double gather1(const double *f, const Interp &it)
     return v;
 }
 
+// per-particle arithmetic of amjdeposit_{std,robust}_pgc (no warp-level synchronisation; shared by the stand-alone kernel and the
+// persistent sweep kernel)
 template <int M, bool STD>
-__global__ void __launch_bounds__(PT_BLOCK) k_amjdeposit_pgc(PartView pv, const double *__restrict__ ef, const double *__restrict__ bf, LaserView lv,
-                                                            double *__restrict__ acc8, double qbm, double dt, double idr, const int *__restrict__ skip)
+__device__ __forceinline__ void amj_math_pgc(const PartView &pv, const double *ef, const double *bf, const LaserView &lv, double qbm, double dt, double idr, int npp, int i,
+                                             double (&alpha)[2 * (2 * M + 1)], double (&beta)[8], int &key)
 {
     constexpr int P = 2 * M + 1;
-    if (skip && *skip) return;   // predictor-corrector loop already converged (per-slice launch path of the sim)
-    const int npp = *pv.d_npp;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
-    if ((i & ~31) >= npp) return;
-    extern __shared__ double dep_tiles[];
-    double alpha[2 * P], beta[8];
-    int key = -1;
+    key = -1;
     if (i < npp) {
         const Interp it = interp_info(pv.x1[i], pv.x2[i], idr);
         double ep[3], bp[3], agr[3], agi[3];
@@ -623,42 +619,42 @@ __global__ void __launch_bounds__(PT_BLOCK) k_amjdeposit_pgc(PartView pv, const 
         const double gam_corr = 0.5 * qbm * qbm * (apr * apr + api * api);                     // :1402
         const double pp1 = pv.p1[i], pp2 = pv.p2[i];
         const double u00 = pp1 * it.c + pp2 * it.s, u01 = pp2 * it.c - pp1 * it.s, u02 = pv.p3[i];
-        double gam = sqrt(1.0 + u00 * u00 + u01 * u01 + u02 * u02 + gam_corr);
+        double gam = fast_sqrt(1.0 + u00 * u00 + u01 * u01 + u02 * u02 + gam_corr);
         const double wp0 = ep[0] - bp[1], wp1 = ep[1] + bp[0], wp2 = ep[2];
-        const double tmp = 0.5 * qbm / gam;                                                   // ponderomotive force :1420-1423
+        const double tmp = 0.5 * qbm * fast_rcp(gam);                                                   // ponderomotive force :1420-1423
         ep[0] -= tmp * (apr * agr[0] + api * agi[0]);
         ep[1] -= tmp * (apr * agr[1] + api * agi[1]);
         ep[2] += tmp * (apr * agr[2] + api * agi[2]);
         double qe, qb, ut0, ut1, ut2;
         if constexpr (STD) {
-            qb = qtmh / (1.0 - qbm * pv.psi[i]);
+            qb = qtmh * fast_rcp(1.0 - qbm * pv.psi[i]);
             qe = qb * gam;
             ut0 = u00 + ep[0] * qe; ut1 = u01 + ep[1] * qe; ut2 = u02 + ep[2] * qe;
         } else {
-            qe = qtmh * gam / (gam - u02);
+            qe = qtmh * gam * fast_rcp(gam - u02);
             ut0 = u00 + ep[0] * qe; ut1 = u01 + ep[1] * qe; ut2 = u02 + ep[2] * qe;
-            gam = sqrt(1.0 + ut0 * ut0 + ut1 * ut1 + ut2 * ut2 + gam_corr);
-            qb = qtmh / (gam - ut2);
+            gam = fast_sqrt(1.0 + ut0 * ut0 + ut1 * ut1 + ut2 * ut2 + gam_corr);
+            qb = qtmh * fast_rcp(gam - ut2);
         }
         bp[0] *= qb; bp[1] *= qb; bp[2] *= qb;
         double u0 = ut0 + ut1 * bp[2] - ut2 * bp[1];
         double u1 = ut1 + ut2 * bp[0] - ut0 * bp[2];
         double u2 = ut2 + ut0 * bp[1] - ut1 * bp[0];
-        const double ostq = 2.0 / (1.0 + bp[0] * bp[0] + bp[1] * bp[1] + bp[2] * bp[2]);
+        const double ostq = 2.0 * fast_rcp(1.0 + bp[0] * bp[0] + bp[1] * bp[1] + bp[2] * bp[2]);
         bp[0] *= ostq; bp[1] *= ostq; bp[2] *= ostq;
         ut0 = ut0 + u1 * bp[2] - u2 * bp[1];
         ut1 = ut1 + u2 * bp[0] - u0 * bp[2];
         ut2 = ut2 + u0 * bp[1] - u1 * bp[0];
-        gam = sqrt(1.0 + ut0 * ut0 + ut1 * ut1 + ut2 * ut2 + gam_corr);
-        qe = STD ? qb * gam : qtmh * gam / (gam - ut2);                                        // second half kick re-normalised
+        gam = fast_sqrt(1.0 + ut0 * ut0 + ut1 * ut1 + ut2 * ut2 + gam_corr);
+        qe = STD ? qb * gam : qtmh * gam * fast_rcp(gam - ut2);                                        // second half kick re-normalised
         u0 = ut0 + ep[0] * qe; u1 = ut1 + ep[1] * qe; u2 = ut2 + ep[2] * qe;
         double du0 = idt * (u0 - u00), du1 = idt * (u1 - u01);
         u0 = 0.5 * (u0 + u00); u1 = 0.5 * (u1 + u01); u2 = 0.5 * (u2 + u02);
-        const double g = sqrt(1.0 + u0 * u0 + u1 * u1 + u2 * u2 + gam_corr);
+        const double g = fast_sqrt(1.0 + u0 * u0 + u1 * u1 + u2 * u2 + gam_corr);
         pv.gamma[i] = g;
         double ipsi;
-        if constexpr (STD) ipsi = 1.0 / (1.0 - qbm * pv.psi[i]);
-        else { ipsi = 1.0 / (g - u2); pv.psi[i] = (1.0 - 1.0 / ipsi) / qbm; }
+        if constexpr (STD) ipsi = fast_rcp(1.0 - qbm * pv.psi[i]);
+        else { const double gmu = g - u2; ipsi = fast_rcp(gmu); pv.psi[i] = (1.0 - gmu) * (1.0 / qbm); }
         const double dpsi = qbm * (wp2 - (wp0 * u0 + wp1 * u1) * ipsi);
         du0 = du0 + u0 * dpsi * ipsi;
         du1 = du1 + u1 * dpsi * ipsi;
@@ -681,16 +677,27 @@ __global__ void __launch_bounds__(PT_BLOCK) k_amjdeposit_pgc(PartView pv, const 
 #pragma unroll
         for (int k = 0; k < 8; k++) beta[k] = 0.0;
     }
+}
+template <int M, bool STD>
+__global__ void __launch_bounds__(PT_BLOCK) k_amjdeposit_pgc(PartView pv, const double *__restrict__ ef, const double *__restrict__ bf, LaserView lv,
+                                                            double *__restrict__ acc8, double qbm, double dt, double idr, const int *__restrict__ skip)
+{
+    constexpr int P = 2 * M + 1;
+    if (skip && *skip) return;   // predictor-corrector loop already converged (per-slice launch path of the sim)
+    const int npp = *pv.d_npp;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
+    if ((i & ~31) >= npp) return;
+    extern __shared__ double dep_tiles[];
+    double alpha[2 * P], beta[8];
+    int key;
+    amj_math_pgc<M, STD>(pv, ef, bf, lv, qbm, dt, idr, npp, i, alpha, beta, key);
     warp_deposit_mma<M>(alpha, beta, key, acc8, dep_tiles + (threadIdx.x >> 5) * DepTile<M>::doubles, lane);
 }
 
+// per-particle arithmetic of push_u_{std,robust}_pgc :1967-2219 (shared by the stand-alone kernel and the persistent sweep kernel)
 template <int M>
-__global__ void __launch_bounds__(PT_BLOCK) k_push_u_pgc(PartView pv, const double *__restrict__ ef, const double *__restrict__ bf, LaserView lv, double qbm,
-                                                        double dt, double idr)
+__device__ __forceinline__ void push_u_pgc_math(const PartView &pv, const double *ef, const double *bf, const LaserView &lv, double qbm, double dt, double idr, int i)
 {
-    const int npp = *pv.d_npp;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= npp) return;
     const Interp it = interp_info(pv.x1[i], pv.x2[i], idr);
     double ep[3], bp[3], agr[3], agi[3];
     gather3<M>(ef, it, ep);
@@ -706,18 +713,18 @@ __global__ void __launch_bounds__(PT_BLOCK) k_push_u_pgc(PartView pv, const doub
     double p1 = pv.p1[i], p2 = pv.p2[i], p3 = pv.p3[i];
     const double g0 = pv.gamma[i];
     double gam_corr = qbm2_hf * (apr * apr + api * api);
-    const double tmp = 0.5 * qbm / g0;
+    const double tmp = 0.5 * qbm * fast_rcp(g0);
     ep[0] -= tmp * (apr * agr[0] + api * agi[0]);
     ep[1] -= tmp * (apr * agr[1] + api * agi[1]);
     ep[2] += tmp * (apr * agr[2] + api * agi[2]);
-    const double qb = qtmh / (1.0 - qbm * pv.psi[i]), qe = qb * g0;
+    const double qb = qtmh * fast_rcp(1.0 - qbm * pv.psi[i]), qe = qb * g0;
     ep[0] *= qe; ep[1] *= qe; ep[2] *= qe;
     double ut0 = p1 + ep[0], ut1 = p2 + ep[1], ut2 = p3 + ep[2];
     bp[0] *= qb; bp[1] *= qb; bp[2] *= qb;
     p1 = ut0 + ut1 * bp[2] - ut2 * bp[1];
     p2 = ut1 + ut2 * bp[0] - ut0 * bp[2];
     p3 = ut2 + ut0 * bp[1] - ut1 * bp[0];
-    const double ostq = 2.0 / (1.0 + bp[0] * bp[0] + bp[1] * bp[1] + bp[2] * bp[2]);
+    const double ostq = 2.0 * fast_rcp(1.0 + bp[0] * bp[0] + bp[1] * bp[1] + bp[2] * bp[2]);
     bp[0] *= ostq; bp[1] *= ostq; bp[2] *= ostq;
     ut0 = ut0 + p2 * bp[2] - p3 * bp[1];
     ut1 = ut1 + p3 * bp[0] - p1 * bp[2];
@@ -726,7 +733,16 @@ __global__ void __launch_bounds__(PT_BLOCK) k_push_u_pgc(PartView pv, const doub
     double tt = agr[2] * dt; gam_corr = gam_corr + qbm2_hf * (apr + 0.25 * tt) * tt;                 // :2080-2082
     tt = agi[2] * dt; gam_corr = gam_corr + qbm2_hf * (api + 0.25 * tt) * tt;
     pv.p1[i] = p1; pv.p2[i] = p2; pv.p3[i] = p3;
-    pv.gamma[i] = sqrt(1.0 + p1 * p1 + p2 * p2 + p3 * p3 + gam_corr);
+    pv.gamma[i] = fast_sqrt(1.0 + p1 * p1 + p2 * p2 + p3 * p3 + gam_corr);
+}
+template <int M>
+__global__ void __launch_bounds__(PT_BLOCK) k_push_u_pgc(PartView pv, const double *__restrict__ ef, const double *__restrict__ bf, LaserView lv, double qbm,
+                                                        double dt, double idr)
+{
+    const int npp = *pv.d_npp;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npp) return;
+    push_u_pgc_math<M>(pv, ef, bf, lv, qbm, dt, idr, i);
 }
 
 // ---- interp_psi: species/part2d_class.f03:2264-2305 + interp_part2d.f03:111-153 (std pushers only) ---------------

@@ -268,18 +268,19 @@ static int enqueue_slice_subcyc(qpg_sim s)
 }
 
 // ---- persistent slab sweep (sweep.cu) ---------------------------------------------------------------------
-static bool sweep_supported(const qpg_sim_params &prm) { return prm.max_mode <= 2 && (prm.nr + ST_N - 1) / ST_N <= SW_MAX_TEAM && !prm.sp_push_std && !prm.sp_push_pgc; }
+// robust pusher, with or without the ponderomotive-guiding-centre terms of a laser envelope (robust_pgc)
+static bool sweep_supported(const qpg_sim_params &prm) { return prm.max_mode <= 2 && (prm.nr + ST_N - 1) / ST_N <= SW_MAX_TEAM && !prm.sp_push_std; }
 template <int M> static constexpr size_t sweep_smem() { return (sizeof(StripSmem<M>) + 7) / 8 * 8 + sizeof(double) * DepTile<M>::doubles * (SW_T / 32); }
-template <int M> static cudaError_t sweep_occupancy(int *blocks_per_sm)
+template <int M, bool PGC> static cudaError_t sweep_occupancy(int *blocks_per_sm)
 {
-    cudaError_t e = cudaFuncSetAttribute(k_sweep<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem<M>());
+    cudaError_t e = cudaFuncSetAttribute(k_sweep<M, PGC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem<M>());
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k_sweep<M>, SW_T, sweep_smem<M>());
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k_sweep<M, PGC>, SW_T, sweep_smem<M>());
 }
-template <int M> static cudaError_t sweep_launch(int grid, cudaStream_t st, SweepArgs &a)
+template <int M, bool PGC> static cudaError_t sweep_launch(int grid, cudaStream_t st, SweepArgs &a)
 {
     void *args[] = {(void *)&a};
-    return cudaLaunchCooperativeKernel((const void *)k_sweep<M>, dim3(grid), dim3(SW_T), args, sweep_smem<M>(), st);
+    return cudaLaunchCooperativeKernel((const void *)k_sweep<M, PGC>, dim3(grid), dim3(SW_T), args, sweep_smem<M>(), st);
 }
 static int sweep_prepare(qpg_sim s)
 {
@@ -289,10 +290,11 @@ static int sweep_prepare(qpg_sim s)
     CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device));
     CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device));
     if (!coop) { qpg_set_error("device does not support cooperative launches"); return QPG_ERR_UNSUPPORTED; }
+    const bool pgc = s->prm.sp_push_pgc != 0;
     switch (c->M) {
-    case 0: CUDA_TRY(sweep_occupancy<0>(&per)); break;
-    case 1: CUDA_TRY(sweep_occupancy<1>(&per)); break;
-    default: CUDA_TRY(sweep_occupancy<2>(&per)); break;
+    case 0: CUDA_TRY(pgc ? (sweep_occupancy<0, true>(&per)) : (sweep_occupancy<0, false>(&per))); break;
+    case 1: CUDA_TRY(pgc ? (sweep_occupancy<1, true>(&per)) : (sweep_occupancy<1, false>(&per))); break;
+    default: CUDA_TRY(pgc ? (sweep_occupancy<2, true>(&per)) : (sweep_occupancy<2, false>(&per))); break;
     }
     const int nteam = (c->nr + ST_N - 1) / ST_N;
     if (per < 1 || nsm * per <= nteam) { qpg_set_error("sweep kernel: %d CTAs/SM x %d SMs cannot host a field team of %d", per, nsm, nteam); return QPG_ERR_UNSUPPORTED; }
@@ -339,10 +341,20 @@ static int sweep_run(qpg_sim s, int j0, int j1)
     CUDA_TRY(cudaMemsetAsync(s->sw_xll, 0, sizeof(uint4) * 2 * SW_MAX_TEAM * SW_XK, c->stream));   // sequence numbers restart at 1 every launch
     TprofScope tp(c, TP_K_SWEEP);
     cudaError_t e;
+    const bool pgc = s->prm.sp_push_pgc != 0;
+    if (pgc) {   // the laser hooks of the slice loop run inside the kernel: slice images, pgc pushers, susceptibility deposit
+        qpg_laser l = s->laser;
+        a.lv = LaserView{l->f_ar->f1, l->f_ai->f1, l->f_gr->f1, l->f_gi->f1};
+        a.las_far = l->f_ar->f1; a.las_fai = l->f_ai->f1; a.las_fgr = l->f_gr->f1; a.las_fgi = l->f_gi->f1;
+        a.las_ar = l->ar; a.las_ai = l->ai; a.las_nz = l->nz; a.las_dz = l->dz;
+        a.chi_acc = l->chi_acc; a.chi1 = l->chi->f1; a.chi2 = l->chi->f2;
+        const int ppc = s->prm.sp_ppc_r > 0 ? s->prm.sp_ppc_r : 1;
+        a.chi_ax = (12.0 * ppc * ppc) / (1.0 + 2.0 * ppc * ppc);
+    }
     switch (c->M) {
-    case 0: e = sweep_launch<0>(s->sweep_grid, c->stream, a); break;
-    case 1: e = sweep_launch<1>(s->sweep_grid, c->stream, a); break;
-    default: e = sweep_launch<2>(s->sweep_grid, c->stream, a); break;
+    case 0: e = pgc ? sweep_launch<0, true>(s->sweep_grid, c->stream, a) : sweep_launch<0, false>(s->sweep_grid, c->stream, a); break;
+    case 1: e = pgc ? sweep_launch<1, true>(s->sweep_grid, c->stream, a) : sweep_launch<1, false>(s->sweep_grid, c->stream, a); break;
+    default: e = pgc ? sweep_launch<2, true>(s->sweep_grid, c->stream, a) : sweep_launch<2, false>(s->sweep_grid, c->stream, a); break;
     }
     if (e != cudaSuccess) return qpg_cuda_fail(e, "cudaLaunchCooperativeKernel(k_sweep)");
     count_launch(c);

@@ -40,6 +40,13 @@ struct SweepArgs {
     double *back_b, *back_e; // wire buffers [P][nr+2][3] (possibly in the upstream GPU's memory) that receive b and e of the slab's FIRST slice
     unsigned *back_flag;    // ... and the flag word raised once they are complete (null: no backward hand-off from this launch)
     unsigned back_seq;
+    // ponderomotive-guiding-centre path (PGC = true): the laser envelope of the run (laser.cu)
+    LaserView lv;           // slice images a_r, a_i (dim 1) and their gradients (dim 3) the pgc pushers gather from
+    double *las_far, *las_fai, *las_fgr, *las_fgi;   // ... the same images, writable: refreshed for every slice in phase A
+    const double *las_ar, *las_ai;                   // envelope volumes [plane][slice -1..nz+1][node]
+    double *chi_acc, *chi1, *chi2;                   // raw susceptibility sums, slice image, volume
+    double las_dz, chi_ax;
+    int las_nz;
     long long *trace;       // per slice of the slab: [2*(j-1)] ns spent in slice j (globaltimer), [2*(j-1)+1] PC iterations it took
     long long *prof;        // [0..3] cycles in phase A / amj / C / push, [4] total cycles, [5] total ns, [6] slices, [7] amj phases, [8..11] CTA 0's own work cycles per phase (thread 0's arrival at the barrier)
 };
@@ -680,7 +687,126 @@ SW_PHASE_FN void sweep_push_phase(const SweepArgs &a, int npp, int tile0, int ti
 #endif
 }
 
+// ---- laser hooks of the slice loop inside the sweep (simulation_class.f03:361-366, :401): one helper CTA --------------------------
+// set_grad + copy_slice + gather of slice j (laser/field_laser_class.f03:637-750; the stand-alone version is k_laser_slice of laser.cu)
+__device__ void sweep_laser_slice(const SweepArgs &a, int M, int j)
+{
+    const int nr = a.f.nr, nz = a.las_nz, P = 2 * M + 1, n = (nr + 2) * P;
+    if (j < 1 || j > nz) return;
+    const double *ar = a.las_ar, *ai = a.las_ai;
+    const double idrh = 0.5 / a.f.dr, idzh = 0.5 / a.las_dz, dr = a.f.dr;
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+        const int i = k / P, pl = k % P, m = (pl + 1) / 2;
+        const bool is_im = m > 0 && pl == 2 * m;
+        const int other = m == 0 ? pl : (is_im ? pl - 1 : pl + 1);
+        a.las_far[k] = __ldcg(ar + LVI(pl, i, j));
+        a.las_fai[k] = __ldcg(ai + LVI(pl, i, j));
+        double *gr = a.las_fgr + (size_t)k * 3, *gi = a.las_fgi + (size_t)k * 3;
+        if (i >= 1 && i <= nr) {
+            gr[2] = idzh * (3.0 * __ldcg(ar + LVI(pl, i, j)) - 4.0 * __ldcg(ar + LVI(pl, i, j - 1)) + __ldcg(ar + LVI(pl, i, j - 2)));
+            gi[2] = idzh * (3.0 * __ldcg(ai + LVI(pl, i, j)) - 4.0 * __ldcg(ai + LVI(pl, i, j - 1)) + __ldcg(ai + LVI(pl, i, j - 2)));
+        }
+        if (i >= 2 && i <= nr) {
+            gr[0] = idrh * (__ldcg(ar + LVI(pl, i + 1, j)) - __ldcg(ar + LVI(pl, i - 1, j)));
+            gi[0] = idrh * (__ldcg(ai + LVI(pl, i + 1, j)) - __ldcg(ai + LVI(pl, i - 1, j)));
+            if (m == 0) { gr[1] = 0.0; gi[1] = 0.0; }
+            else {
+                const double ir = 1.0 / ((double)(i - 1) * dr), sg = is_im ? 1.0 : -1.0;
+                gr[1] = sg * ir * m * __ldcg(ar + LVI(other, i, j));
+                gi[1] = sg * ir * m * __ldcg(ai + LVI(other, i, j));
+            }
+        }
+        if (m == 0 && i == 1) { gr[0] = 0.0; gr[1] = 0.0; gi[0] = 0.0; gi[1] = 0.0; }
+        if (m > 0 && i == nr + 1) {   // the reference's quirk, see k_laser_slice
+            if (m % 2 == 1) {
+                const double g1r = 2.0 * idrh * __ldcg(ar + LVI(pl, 2, j)), g1i = 2.0 * idrh * __ldcg(ai + LVI(pl, 2, j));
+                const double o1r = 2.0 * idrh * __ldcg(ar + LVI(other, 2, j)), o1i = 2.0 * idrh * __ldcg(ai + LVI(other, 2, j));
+                gr[0] = g1r; gi[0] = g1i;
+                gr[1] = is_im ? m * o1r : -m * o1r;
+                gi[1] = is_im ? m * o1i : -m * o1i;
+            } else { gr[0] = 0.0; gr[1] = 0.0; gi[0] = 0.0; gi[1] = 0.0; }
+        }
+    }
+}
+// axis rules + 1/(j-1) of the susceptibility deposited during slice j's push phase, stored as slice j of the chi volume (k_chi_fix)
+__device__ void sweep_chi_fix(const SweepArgs &a, int M, int j)
+{
+    const int nr = a.f.nr, P = 2 * M + 1, n = (nr + 2) * P;
+    double *chi2_slice = (j >= 1 && j <= a.las_nz) ? a.chi2 + (size_t)(j - 1) * n : nullptr;
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+        const int jj = k / P, pl = k % P;
+        double v = __ldcg(a.chi_acc + k);
+        a.chi_acc[k] = 0.0;
+        if (jj == 0) v = 0.0;
+        else if (jj == 1) v = pl == 0 ? v * a.chi_ax : 0.0;
+        else v = v * (1.0 / (double)(jj - 1));
+        a.chi1[k] = v;
+        if (chi2_slice) chi2_slice[k] = v;
+    }
+}
+// pgc particle phases (robust_pgc pusher; one tile per warp and pass)
 template <int M>
+SW_PHASE_FN void sweep_amj_phase_pgc(const SweepArgs &a, int npp, int tile0, int tile1, double *dep_tiles)
+{
+    constexpr int P = 2 * M + 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const FusedArgs &f = a.f;
+    const double idr = 1.0 / f.dr;
+    double *tile = dep_tiles + warp * DepTile<M>::doubles;
+    for (int tl = tile0 + warp; tl < tile1; tl += SW_T / 32) {
+        double alpha[2 * P], beta[8];
+        int key;
+        amj_math_pgc<M, false>(a.pv, f.e, f.b, a.lv, a.qbm, f.dxi, idr, npp, tl * 32 + lane, alpha, beta, key);
+        warp_deposit_mma<M>(alpha, beta, key, f.acc8, tile, lane);
+    }
+}
+template <int M>
+SW_PHASE_FN void sweep_push_phase_pgc(const SweepArgs &a, int npp, int tile0, int tile1, double *dep_tiles)
+{
+    constexpr int P = 2 * M + 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const FusedArgs &f = a.f;
+    const double idr = 1.0 / f.dr;
+    double *tile = dep_tiles + warp * DepTile<M>::doubles;
+    for (int tl = tile0 + warp; tl < tile1; tl += SW_T / 32) {
+        const int i = tl * 32 + lane;
+        const bool valid = i < npp;
+        // lasers%deposit_chi (simulation_class.f03:401, part2d_class.f03:361-430) with the converged psi, at the position before the push
+        double alpha[2 * P];
+        int key = -1;
+        if (valid) {
+            const double x1 = a.pv.x1[i], x2 = a.pv.x2[i];
+            const double pos = __dmul_rn(__dsqrt_rn(__dadd_rn(__dmul_rn(x1, x1), __dmul_rn(x2, x2))), idr);
+            const double rpos = fast_rcp(pos) * idr;
+            const double c0 = x1 * rpos, s0 = -x2 * rpos;
+            const int nn = (int)floor(pos);
+            const double fr = pos - (double)nn, w0 = 1.0 - fr, w1 = fr;
+            double phr = -1.0 * a.qbm * a.pv.q[i] * fast_rcp(1.0 - a.qbm * a.pv.psi[i]), phi = 0.0;
+            alpha[0] = w0 * phr; alpha[P] = w1 * phr;
+#pragma unroll
+            for (int m = 1; m <= M; m++) {
+                const double t = phr * c0 - phi * s0;
+                phi = phr * s0 + phi * c0;
+                phr = t;
+                alpha[2 * m - 1] = w0 * phr; alpha[P + 2 * m - 1] = w1 * phr;
+                alpha[2 * m] = w0 * phi; alpha[P + 2 * m] = w1 * phi;
+            }
+            key = nn + 1;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 2 * P; k++) alpha[k] = 0.0;
+        }
+        warp_deposit_q_mma<M>(alpha, key, a.chi_acc, tile, lane);
+        if (valid) push_u_pgc_math<M>(a.pv, f.e, f.b, a.lv, a.qbm, f.dxi, idr, i);          // push_u_robust_pgc :1967 (stores p, gamma)
+        const PartRegs pr = part_load(a.pv, i, npp);                                       // the advanced momenta
+        double xn1, xn2;
+        bool out;
+        push_math<M>(a.pv, pr, f.e, f.b, a.qbm, f.dxi, idr, a.edge, 6, npp, i, xn1, xn2, out);   // push_x + bound test
+        push_finish<M>(pr, xn1, xn2, out, idr, 6, a.outmask, a.d_nout, f.acc1, npp, i, lane, tile);
+    }
+}
+
+template <int M, bool PGC = false>
 __global__ void __launch_bounds__(SW_T, 1) k_sweep(const __grid_constant__ SweepArgs a)
 {
     constexpr int P = 2 * M + 1;
@@ -694,6 +820,7 @@ __global__ void __launch_bounds__(SW_T, 1) k_sweep(const __grid_constant__ Sweep
     Team tm;
     tm.ctr = a.bar + 32; tm.abort_flag = a.bar + 64; tm.epoch = 0; tm.xep = 0; tm.n = a.nteam; tm.rank = b; tm.xpar = 0; tm.xbuf = a.xbuf; tm.xll = a.xll;
     const bool in_team = b < a.nteam;
+    const int las_cta = G - 2 >= a.nteam ? G - 2 : G - 1;   // PGC: the CTA that prepares the laser slice images (an idle one if there is one)
     // the halo shortcut of program A needs the one-sided stencil nodes nr-1, nr-2 inside the last strip's tile
     const bool halo = (a.f.nr - ((a.nteam - 1) * ST_N + 1)) >= 1;
     if (in_team) strip_load_factors<M>(f, b, sm_f);
@@ -709,6 +836,10 @@ __global__ void __launch_bounds__(SW_T, 1) k_sweep(const __grid_constant__ Sweep
         // ---- phase A || compaction -------------------------------------------------------------------------
         if (in_team) sweep_field_A<M>(f, j, tm, sm_f, halo, timer ? sm_f.stamps : nullptr);
         else if (b == G - 1) compact_body(a.planes, 8, a.d_npp_w, a.d_nout, a.outmask, a.lists, 0, sm_i);
+        if (PGC && b == las_cta) {   // the helper CTA: chi of the previous slice -> volume, laser slice images of this slice
+            if (j > a.j0) sweep_chi_fix(a, M, j - 1);
+            sweep_laser_slice(a, M, j);
+        }
         if (timer) work[0] += clock64() - tprev;
         ok = grid_barrier(a.bar, gep, sm_i);
         if (timer) { const long long t = clock64(); prof[0] += t - tprev; tprev = t; }
@@ -719,7 +850,8 @@ __global__ void __launch_bounds__(SW_T, 1) k_sweep(const __grid_constant__ Sweep
         const int tile0 = b * per, tile1 = min(tile0 + per, ntiles);
         // ---- predictor-corrector loop -----------------------------------------------------------------------
         for (int it = 1; it <= f.iter_max; it++) {
-            sweep_amj_phase<M>(a, npp, tile0, tile1, dep_tiles);
+            if (PGC) sweep_amj_phase_pgc<M>(a, npp, tile0, tile1, dep_tiles);
+            else sweep_amj_phase<M>(a, npp, tile0, tile1, dep_tiles);
             if (timer) work[1] += clock64() - tprev;
             ok = grid_barrier(a.bar, gep, sm_i);
             if (timer) { const long long t = clock64(); prof[1] += t - tprev; tprev = t; namj++; }
@@ -739,7 +871,8 @@ __global__ void __launch_bounds__(SW_T, 1) k_sweep(const __grid_constant__ Sweep
             const int items = (f.nr + 2) * P, ipc = (items + G - 1) / G;
             for (int k = b * ipc + lane; k < min((b + 1) * ipc, items); k += 32) fused_D_item<M>(f, k, j);
         }
-        sweep_push_phase<M>(a, npp, tile0, tile1, dep_tiles);
+        if (PGC) sweep_push_phase_pgc<M>(a, npp, tile0, tile1, dep_tiles);
+        else sweep_push_phase<M>(a, npp, tile0, tile1, dep_tiles);
         if (timer) work[3] += clock64() - tprev;
         ok = grid_barrier(a.bar, gep, sm_i);
         if (timer) {
@@ -757,6 +890,7 @@ __global__ void __launch_bounds__(SW_T, 1) k_sweep(const __grid_constant__ Sweep
         // data, the error surfaces on the host) instead of leaving its stream hanging
         if (a.back_flag && b == min(a.nteam, G - 1)) st_release_sys(a.back_flag, a.back_seq);
     }
+    if (PGC && ok && b == las_cta) sweep_chi_fix(a, M, a.j1);   // the last slice's susceptibility (the deposits are behind the slice's final barrier)
     // update_bound of the last slice (the next launch / the host expects compacted particles)
     if (ok && b == G - 1) compact_body(a.planes, 8, a.d_npp_w, a.d_nout, a.outmask, a.lists, 0, sm_i);
     if (timer) {

@@ -25,8 +25,8 @@ PATCH = {
         ("s->use_sweep = sweep_supported(*prm);", "s->use_sweep = getenv(\"QPAD_EMU_SWEEP\") ? sweep_supported(*prm) : false;"),
         ("const bool can = s->prm.nr <= FT * FC && s->prm.max_mode <= 2;", "const bool can = false;"),
         # the persistent sweep kernel runs as a cooperative launch of the emulation: all CTAs alive at once (emu::launch_coop)
-        ("void *args[] = {(void *)&a};\n    return cudaLaunchCooperativeKernel((const void *)k_sweep<M>, dim3(grid), dim3(SW_T), args, sweep_smem<M>(), st);",
-         "emu::launch_coop(dim3(grid), dim3(SW_T), sweep_smem<M>(), [&] { k_sweep<M>(a); });\n    return cudaSuccess;"),
+        ("void *args[] = {(void *)&a};\n    return cudaLaunchCooperativeKernel((const void *)k_sweep<M, PGC>, dim3(grid), dim3(SW_T), args, sweep_smem<M>(), st);",
+         "emu::launch_coop(dim3(grid), dim3(SW_T), sweep_smem<M>(), [&] { k_sweep<M, PGC>(a); });\n    return cudaSuccess;"),
     ],
     "sweep.cu": [
         ("__shared__ int sm_i[48];", "int *sm_i = (int *)emu::cta_static(48 * sizeof(int), 1);"),     # per CTA: the CTAs of this kernel are alive together

@@ -156,6 +156,12 @@ def test_sweep_full_3d_step_with_beam_push(mods): G.test_full_3d_step_with_beam_
 def test_sweep_sorted_loop(mods): G.test_sorted_loop_still_matches(mods, "sweep")
 
 
+def test_sweep_lwfa_slice_loop(mods):
+    """config 4 in small with the laser hooks INSIDE the sweep kernel (k_sweep<M, PGC = true>: slice images by a helper CTA, pgc pushers,
+    susceptibility deposit fused into the push phase), two 3D steps with the envelope advance in between"""
+    GL.test_lwfa_slice_loop_matches_oracle(mods, 0, 1)
+
+
 @pytest.mark.parametrize("nr,M,ppc,nth", [(250, 1, 2, 8), (65, 1, 2, 8), (33, 2, 2, 8), (24, 1, 2, 8)])
 def test_sweep_kernel_multi_cta_team(mods, nr, M, ppc, nth): G.test_sweep_kernel_multi_cta_team(mods, nr, M, ppc, nth)
 

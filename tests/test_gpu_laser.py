@@ -116,8 +116,8 @@ def test_envelope_advance_matches_oracle(mods, nr, nz, M, iters):
     assert scale > 0.1
 
 
-@pytest.mark.parametrize("use_graph", [0, 1])
-def test_lwfa_slice_loop_matches_oracle(mods, use_graph):
+@pytest.mark.parametrize("use_graph,sweep", [(0, 0), (1, 0), (0, 1)])
+def test_lwfa_slice_loop_matches_oracle(mods, use_graph, sweep):
     """config 4 in small: robust_pgc plasma driven by a Gaussian laser pulse, envelope advanced with the deposited
     susceptibility, two 3D steps (simulation_class.f03:294-512 with nlasers = 1, nbeams = 0)"""
     capi, O = mods
@@ -132,6 +132,7 @@ def test_lwfa_slice_loop_matches_oracle(mods, use_graph):
     x, p, g, psi, q = O.inject_uniform(nr, cfg["rmax"] / nr, ppc1, ppc2, nth)
     sim = capi.Sim(sp_npmax=2 * len(q), beam_npmax=64, sp_push_pgc=1, laser_iter=iters, laser_k0=k0, sp_ppc_r=ppc1, beam_evol=0, use_graph=use_graph, **cfg)
     assert sim.laser is not None
+    sim.set_sweep(sweep)       # 1: the laser hooks inside the persistent sweep kernel (k_sweep<M, PGC = true>); 0: per-slice launches
     sim.init_species(x, p, g, psi, q)
     sim.laser.upload(olas.ar, olas.ai)
     for step in range(2):
