@@ -32,6 +32,12 @@ struct qpg_laser_s {
     double *pcrc;        // the same as complex numbers (every block of this operator is [[x, -y], [y, x]]): [M+1][nsteps][4][nr] (alpha x, y | gamma x, y), then
                          // [M+1][2][nr] inverse diagonal (x, y); null if the structure check failed (then the general kernel runs)
     size_t pcrc_n;
+    // overlapped advance (qpg_laser_advance_overlapped): the solve runs on a side stream and publishes the number of finished slices
+    cudaStream_t side;           // created lazily
+    cudaEvent_t ev_main, ev_done;
+    unsigned *progress;          // device word: (advances launched - 1) * nz + slices finished by the running solve
+    unsigned adv_count;          // overlapped advances launched so far
+    bool pending;                // an overlapped advance may still be running: join before anybody else touches the envelope
 };
 
 #define LVI(pl, i, j) ((((size_t)(pl)) * (nz + 3) + (size_t)((j) + 1)) * (nr + 2) + (i))
@@ -229,7 +235,7 @@ __global__ void __launch_bounds__(1024, 1) k_laser_solve(double *__restrict__ ar
 template <int MM>
 __global__ void __launch_bounds__(1024, 1) k_laser_solve_c(double *__restrict__ ar, double *__restrict__ ai, const double *__restrict__ sr, const double *__restrict__ si,
                                                           const double *__restrict__ chi2, const double *__restrict__ pcrc, int nr, int nz, int iter, int nsteps,
-                                                          double ds, double dr, double dz, int coef_in_smem)
+                                                          double ds, double dr, double dz, int coef_in_smem, unsigned *progress, unsigned progress_base)
 {
     constexpr int M = MM, P = 2 * M + 1;
     extern __shared__ double laser_sh[];   // [2 buffers][2 components][nthreads] exchange, then (optionally) the coefficients
@@ -303,14 +309,19 @@ __global__ void __launch_bounds__(1024, 1) k_laser_solve_c(double *__restrict__ 
             if (live) { ar[LVI(pl, i, j)] = a_r[pl]; ai[LVI(pl, i, j)] = a_i[pl]; }
             am2r[pl] = am1r[pl]; am2i[pl] = am1i[pl]; am1r[pl] = a_r[pl]; am1i[pl] = a_i[pl];
         }
+        if (progress) {   // slice j is final: a sweep kernel of the NEXT 3D step that runs beside this solve may read it (sweep.cu sweep_laser_wait)
+            __syncthreads();
+            if (t == 0) { __threadfence(); asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(progress), "r"(progress_base + (unsigned)j) : "memory"); }
+        }
     }
 }
 template <int MM> static void l_laser_solve_c(int nthreads, size_t smem, cudaStream_t st, double *ar, double *ai, const double *sr, const double *si, const double *chi2,
-                                              const double *pcrc, int nr, int nz, int iter, int nsteps, double ds, double dr, double dz, int in_smem)
+                                              const double *pcrc, int nr, int nz, int iter, int nsteps, double ds, double dr, double dz, int in_smem, unsigned *progress,
+                                              unsigned progress_base)
 {
     static size_t attr = 0;
     if (smem > attr) { cudaFuncSetAttribute(k_laser_solve_c<MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = smem; }
-    k_laser_solve_c<MM><<<1, nthreads, smem, st>>>(ar, ai, sr, si, chi2, pcrc, nr, nz, iter, nsteps, ds, dr, dz, in_smem);
+    k_laser_solve_c<MM><<<1, nthreads, smem, st>>>(ar, ai, sr, si, chi2, pcrc, nr, nz, iter, nsteps, ds, dr, dz, in_smem, progress, progress_base);
 }
 
 // copy_slice(j, 2to1) + set_grad(j) + gather into the four slice images the pgc pushers read; one thread per (node, plane)
@@ -465,14 +476,22 @@ extern "C" int qpg_laser_destroy(qpg_laser l)
     if (!l) return 0;
     cudaStreamSynchronize(l->ctx->stream);
     cudaFree(l->ar); cudaFree(l->ai); cudaFree(l->sr); cudaFree(l->si); cudaFree(l->chi_acc); cudaFree(l->pcr); cudaFree(l->pcrc);
+    if (l->progress) { cudaStreamSynchronize(l->side); cudaStreamDestroy(l->side); cudaEventDestroy(l->ev_main); cudaEventDestroy(l->ev_done); cudaFree(l->progress); }
     qpg_field_destroy(l->f_ar); qpg_field_destroy(l->f_ai); qpg_field_destroy(l->f_gr); qpg_field_destroy(l->f_gi); qpg_field_destroy(l->chi);
     delete l;
     return 0;
 }
 extern "C" long qpg_laser_volume_size(qpg_laser l) { return l ? (long)l->nvol : -1; }
+// an overlapped advance may still be running on the side stream: everything else that touches the envelope orders itself behind it
+static int laser_join(qpg_laser l)
+{
+    if (l && l->pending) { CUDA_TRY(cudaStreamWaitEvent(l->ctx->stream, l->ev_done, 0)); l->pending = false; }
+    return 0;
+}
 extern "C" int qpg_laser_upload(qpg_laser l, const double *ar, const double *ai)
 {
     ARG_TRY(l && ar && ai, "null arg");
+    { int rc = laser_join(l); if (rc) return rc; }
     CUDA_TRY(cudaMemcpyAsync(l->ar, ar, sizeof(double) * l->nvol, cudaMemcpyHostToDevice, l->ctx->stream));
     CUDA_TRY(cudaMemcpyAsync(l->ai, ai, sizeof(double) * l->nvol, cudaMemcpyHostToDevice, l->ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(l->ctx->stream));
@@ -481,6 +500,7 @@ extern "C" int qpg_laser_upload(qpg_laser l, const double *ar, const double *ai)
 extern "C" int qpg_laser_download(qpg_laser l, double *ar, double *ai)
 {
     ARG_TRY(l && ar && ai, "null arg");
+    { int rc = laser_join(l); if (rc) return rc; }
     CUDA_TRY(cudaMemcpyAsync(ar, l->ar, sizeof(double) * l->nvol, cudaMemcpyDeviceToHost, l->ctx->stream));
     CUDA_TRY(cudaMemcpyAsync(ai, l->ai, sizeof(double) * l->nvol, cudaMemcpyDeviceToHost, l->ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(l->ctx->stream));
@@ -497,6 +517,7 @@ extern "C" qpg_field qpg_laser_field(qpg_laser l, int which)
 extern "C" int qpg_laser_slice(qpg_laser l, int j)
 {
     ARG_TRY(l && (j == -1 || (j >= 1 && j <= l->nz)), "slice out of range");
+    { int rc = laser_join(l); if (rc) return rc; }
     qpg_ctx c = l->ctx;
     const int n = (c->nr + 2) * c->P;
     k_laser_slice<<<(n + 255) / 256, 256, 0, c->stream>>>(l->ar, l->ai, c->nr, l->nz, c->M, j, j == -1 ? c->flags : nullptr, c->dr, l->dz, l->f_ar->f1, l->f_ai->f1,
@@ -508,6 +529,7 @@ extern "C" int qpg_laser_slice(qpg_laser l, int j)
 extern "C" int qpg_laser_deposit_chi(qpg_laser l, qpg_part2d p, int j, double ax_corr)
 {
     ARG_TRY(l && p && p->ctx == l->ctx && j >= -1 && j <= l->nz, "bad arg");
+    { int rc = laser_join(l); if (rc) return rc; }
     qpg_ctx c = l->ctx;
     if (p->npp_hi > 0) {
         const int grid = (int)((p->npp_hi + 255) / 256);
@@ -520,26 +542,63 @@ extern "C" int qpg_laser_deposit_chi(qpg_laser l, qpg_part2d p, int j, double ax
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
-extern "C" int qpg_laser_advance(qpg_laser l)
+static int laser_launch_advance(qpg_laser l, cudaStream_t st, unsigned *progress, unsigned base)
 {
-    ARG_TRY(l, "null arg");
     qpg_ctx c = l->ctx;
     const int nr = c->nr, nz = l->nz;
     const long n = (long)nr * nz;
-    k_laser_set_rhs<<<(int)((n + 255) / 256), 256, 0, c->stream>>>(l->ar, l->ai, l->chi->f2, l->sr, l->si, nr, nz, c->M, l->k0, l->ds, c->dr, l->dz);
+    k_laser_set_rhs<<<(int)((n + 255) / 256), 256, 0, st>>>(l->ar, l->ai, l->chi->f2, l->sr, l->si, nr, nz, c->M, l->k0, l->ds, c->dr, l->dz);
     const size_t smem = sizeof(double) * 4 * l->nthreads;
     if (l->pcrc && !getenv("QPG_LASER_GENERAL_SOLVE")) {
         const size_t with_coef = smem + sizeof(double) * l->pcrc_n;
         const int in_smem = with_coef <= 220 * 1024;
         const size_t sm = in_smem ? with_coef : smem;
         switch (c->M) {
-        case 0: l_laser_solve_c<0>(l->nthreads, sm, c->stream, l->ar, l->ai, l->sr, l->si, l->chi->f2, l->pcrc, nr, nz, l->iter, l->nsteps, l->ds, c->dr, l->dz, in_smem); break;
-        case 1: l_laser_solve_c<1>(l->nthreads, sm, c->stream, l->ar, l->ai, l->sr, l->si, l->chi->f2, l->pcrc, nr, nz, l->iter, l->nsteps, l->ds, c->dr, l->dz, in_smem); break;
-        default: l_laser_solve_c<2>(l->nthreads, sm, c->stream, l->ar, l->ai, l->sr, l->si, l->chi->f2, l->pcrc, nr, nz, l->iter, l->nsteps, l->ds, c->dr, l->dz, in_smem); break;
+        case 0: l_laser_solve_c<0>(l->nthreads, sm, st, l->ar, l->ai, l->sr, l->si, l->chi->f2, l->pcrc, nr, nz, l->iter, l->nsteps, l->ds, c->dr, l->dz, in_smem, progress, base); break;
+        case 1: l_laser_solve_c<1>(l->nthreads, sm, st, l->ar, l->ai, l->sr, l->si, l->chi->f2, l->pcrc, nr, nz, l->iter, l->nsteps, l->ds, c->dr, l->dz, in_smem, progress, base); break;
+        default: l_laser_solve_c<2>(l->nthreads, sm, st, l->ar, l->ai, l->sr, l->si, l->chi->f2, l->pcrc, nr, nz, l->iter, l->nsteps, l->ds, c->dr, l->dz, in_smem, progress, base); break;
         }
-    } else
-        k_laser_solve<<<1, l->nthreads, smem, c->stream>>>(l->ar, l->ai, l->sr, l->si, l->chi->f2, l->pcr, nr, nz, c->M, l->iter, l->nsteps, l->ds, c->dr, l->dz);
+    } else {
+        if (progress) { qpg_set_error("the overlapped advance needs the complex-factor solve"); return QPG_ERR_UNSUPPORTED; }
+        k_laser_solve<<<1, l->nthreads, smem, st>>>(l->ar, l->ai, l->sr, l->si, l->chi->f2, l->pcr, nr, nz, c->M, l->iter, l->nsteps, l->ds, c->dr, l->dz);
+    }
     count_launch(c, 2);
     CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+extern "C" int qpg_laser_advance(qpg_laser l)
+{
+    ARG_TRY(l, "null arg");
+    int rc = laser_join(l);
+    if (rc) return rc;
+    return laser_launch_advance(l, l->ctx->stream, nullptr, 0);
+}
+// The advance on a SIDE stream, overlapped with what follows on the context's stream: a sweep kernel of the next 3D step (sweep.cu) may run
+// beside the solve and follows its progress word slice by slice (slice j of the new envelope is needed by slice j of the next sweep; the
+// solve takes ~8 us per slice, the sweep ~27).  Everything else that touches the envelope joins first (laser_join).  Returns the progress
+// word and the value it will hold once slice 0 ... i.e. the caller waits for  *progress - base >= j  (wrap-safe).
+int qpg_laser_advance_overlapped(qpg_laser l, unsigned **progress, unsigned *base)
+{
+    ARG_TRY(l && progress && base, "null arg");
+    if (!l->pcrc || getenv("QPG_LASER_GENERAL_SOLVE")) return QPG_ERR_UNSUPPORTED;
+    int rc = laser_join(l);      // at most one overlapped advance in flight
+    if (rc) return rc;
+    qpg_ctx c = l->ctx;
+    if (!l->progress) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&l->side, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&l->ev_main, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&l->ev_done, cudaEventDisableTiming));
+        CUDA_TRY(cudaMalloc(&l->progress, 128));
+        CUDA_TRY(cudaMemsetAsync(l->progress, 0, 128, c->stream));
+    }
+    CUDA_TRY(cudaEventRecord(l->ev_main, c->stream));            // behind the sweep that deposited chi
+    CUDA_TRY(cudaStreamWaitEvent(l->side, l->ev_main, 0));
+    *base = l->adv_count * (unsigned)l->nz;
+    l->adv_count++;
+    rc = laser_launch_advance(l, l->side, l->progress, *base);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(l->ev_done, l->side));
+    l->pending = true;
+    *progress = l->progress;
     return 0;
 }

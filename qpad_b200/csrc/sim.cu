@@ -19,6 +19,7 @@ struct qpg_sim_s {
     qpg_part2d spe;
     qpg_part3d beam;
     qpg_laser laser;      // sp_push_pgc: the one laser envelope of the run
+    unsigned *las_progress; unsigned las_base; bool las_overlap;   // overlapped envelope advance (qpg_sim_laser_advance): progress word of the running solve
     int cur_j;            // slice being enqueued (per-slice launch path)
     cudaGraph_t graph;
     cudaGraphExec_t gexec;
@@ -298,6 +299,8 @@ static int sweep_prepare(qpg_sim s)
     }
     const int nteam = (c->nr + ST_N - 1) / ST_N;
     if (per < 1 || nsm * per <= nteam) { qpg_set_error("sweep kernel: %d CTAs/SM x %d SMs cannot host a field team of %d", per, nsm, nteam); return QPG_ERR_UNSUPPORTED; }
+    s->las_overlap = s->prm.sp_push_pgc && s->sweep_ctas_req == 0 && !getenv("QPG_LASER_NO_OVERLAP");
+    if (s->las_overlap) s->sweep_ctas_req = -1;   // the envelope solve of the previous step (one CTA) runs beside the sweep: leave it an SM
     int g = s->sweep_ctas_req > 0 ? s->sweep_ctas_req : nsm * per + s->sweep_ctas_req;   // default: one CTA per SM
     if (g > nsm * per) g = nsm * per;
     if (g <= nteam) { qpg_set_error("sweep kernel: %d CTAs cannot host a field team of %d plus the update_bound CTA", g, nteam); return QPG_ERR_ARG; }
@@ -350,6 +353,10 @@ static int sweep_run(qpg_sim s, int j0, int j1)
         a.chi_acc = l->chi_acc; a.chi1 = l->chi->f1; a.chi2 = l->chi->f2;
         const int ppc = s->prm.sp_ppc_r > 0 ? s->prm.sp_ppc_r : 1;
         a.chi_ax = (12.0 * ppc * ppc) / (1.0 + 2.0 * ppc * ppc);
+        if (j0 == 1) { a.las_progress = s->las_progress; a.las_base = s->las_base; }   // the step's first launch may overlap the previous step's advance ...
+        else if (s->las_progress) {                                                     // ... any later one simply waits for it
+            a.las_progress = s->las_progress; a.las_base = s->las_base;
+        }
     }
     switch (c->M) {
     case 0: e = pgc ? sweep_launch<0, true>(s->sweep_grid, c->stream, a) : sweep_launch<0, false>(s->sweep_grid, c->stream, a); break;
@@ -705,10 +712,18 @@ extern "C" int qpg_sim_set_fused(qpg_sim s, int on)
 }
 extern "C" int qpg_sim_set_graph(qpg_sim s, int use_graph) { ARG_TRY(s, "null sim"); ARG_TRY(!(use_graph && s->subcyc), "sub-cycling needs the plain launch path"); s->prm.use_graph = use_graph != 0; return 0; }
 extern "C" qpg_laser qpg_sim_laser(qpg_sim s) { return s ? s->laser : nullptr; }
+int qpg_laser_advance_overlapped(qpg_laser l, unsigned **progress, unsigned *base);   // laser.cu
 extern "C" int qpg_sim_laser_advance(qpg_sim s)
 {
     ARG_TRY(s, "null sim");
     if (!s->laser) return 0;
+    s->las_progress = nullptr;
+    if (s->use_sweep && s->sweep_grid > 0 && s->las_overlap) {
+        // the next sweep kernel runs beside the solve (it leaves one SM free, sweep_prepare) and follows its progress slice by slice
+        int rc = qpg_laser_advance_overlapped(s->laser, &s->las_progress, &s->las_base);
+        if (rc != QPG_ERR_UNSUPPORTED) return rc;
+        s->las_progress = nullptr;
+    }
     return qpg_laser_advance(s->laser);
 }
 extern "C" int qpg_sim_set_sweep(qpg_sim s, int on)

@@ -47,6 +47,8 @@ struct SweepArgs {
     double *chi_acc, *chi1, *chi2;                   // raw susceptibility sums, slice image, volume
     double las_dz, chi_ax;
     int las_nz;
+    const unsigned *las_progress;   // != null: an envelope advance runs beside this sweep (laser.cu); slice j may be read once *las_progress - las_base >= j
+    unsigned las_base;
     long long *trace;       // per slice of the slab: [2*(j-1)] ns spent in slice j (globaltimer), [2*(j-1)+1] PC iterations it took
     long long *prof;        // [0..3] cycles in phase A / amj / C / push, [4] total cycles, [5] total ns, [6] slices, [7] amj phases, [8..11] CTA 0's own work cycles per phase (thread 0's arrival at the barrier)
 };
@@ -837,6 +839,23 @@ __global__ void __launch_bounds__(SW_T, 1) k_sweep(const __grid_constant__ Sweep
         if (in_team) sweep_field_A<M>(f, j, tm, sm_f, halo, timer ? sm_f.stamps : nullptr);
         else if (b == G - 1) compact_body(a.planes, 8, a.d_npp_w, a.d_nout, a.outmask, a.lists, 0, sm_i);
         if (PGC && b == las_cta) {   // the helper CTA: chi of the previous slice -> volume, laser slice images of this slice
+            if (a.las_progress) {    // the envelope advance of the previous step may still be running on another SM: follow its progress
+                if (tid == 0) {
+                    long long t0 = 0;
+                    for (unsigned n = 1;; n++) {
+                        unsigned v;
+                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.las_progress) : "memory");
+                        if ((int)(v - a.las_base) >= min(j, a.las_nz)) break;
+                        if ((n & 63u) == 0) {
+                            if (ld_volatile_u32(a.bar + 64)) break;
+                            const long long now = clock64();
+                            if (t0 == 0) t0 = now;
+                            else if (now - t0 > 4000000000LL) { atomicExch(a.bar + 64, 1u); break; }
+                        }
+                    }
+                }
+                __syncthreads();
+            }
             if (j > a.j0) sweep_chi_fix(a, M, j - 1);
             sweep_laser_slice(a, M, j);
         }

@@ -42,9 +42,13 @@ PTX = {
         ('asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(p) : "memory");',
          "{ const uint4 w = *p; a = w.x; b = w.y; c = w.z; d = w.w; } emu::poll_yield();"),
         ('asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");', "*p = v;"),
+        ('asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.las_progress) : "memory");', "v = *(const volatile unsigned *)a.las_progress; emu::poll_yield();"),
         ('asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(nstart));', "nstart = clock64();"),
         ('asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));', "now = clock64();"),
         ('asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(nend));', "nend = clock64();"),
+    ],
+    "laser.cu": [
+        ('asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(progress), "r"(progress_base + (unsigned)j) : "memory");', "*progress = progress_base + (unsigned)j;"),
     ],
     "particles.cu": [
         ('asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(y));', "r = 1.0 / y;"),
