@@ -699,7 +699,7 @@ def run_b200_local(args):
     ms = ev0.elapsed_time(ev1)
     if os.environ.get("QPG_TRACE_EVENTS"):
         for r_, rep in enumerate(lp.event_report()):
-            waits = sum(v for k, v in rep.items() if k in ("w_fwd>got_fwd", "tail>got_back"))
+            waits = sum(v for k, v in rep.items() if k in ("w_fwd>got_fwd", "pre>got_back"))
             print(f"rank {rank} stage {r_} trace (ms): busy {sum(rep.values()) - waits:.2f} waits {waits:.2f} {rep}", file=sys.stderr, flush=True)
         lp._ev_on = False
     if os.environ.get("QPG_TRACE"):

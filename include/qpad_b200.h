@@ -169,6 +169,14 @@ int qpg_part3d_upload(qpg_part3d p, const double *x, const double *pm, const dou
 int qpg_part3d_download(qpg_part3d p, double *x, double *pm, double *q, long *npp);              /* synchronises */
 int qpg_part3d_qdeposit(qpg_part3d p, qpg_field q);                                              /* qdeposit_part3d :221 (into q%f2) */
 int qpg_part3d_push(qpg_part3d p, int push_type, qpg_field ef, qpg_field bf);                    /* push_reduced :477 / push_boris :358 */
+/* push_* in two passes for a stage of the xi-pipeline (part3d_class.f03:358-576 per particle, unchanged): `interior` advances the particles
+ * whose field gather does not touch the guard slice nzp + 1 -- it does not need the downstream stage's first-slice e / b
+ * (simulation_class.f03:482-483) -- `edge` the others.  interior, then edge == qpg_part3d_push */
+int qpg_part3d_push_interior(qpg_part3d p, int push_type, qpg_field ef, qpg_field bf);
+int qpg_part3d_push_edge(qpg_part3d p, int push_type, qpg_field ef, qpg_field bf);
+/* qdeposit_part3d :221-316 (the scatter) restricted to: part 1 = the particles advanced by qpg_part3d_push_interior, 2 = the others (call
+ * before update_bound), 3 = the particles appended by the last qpg_part3d_unpack (call before qpg_part3d_pack_forward) */
+int qpg_part3d_qdeposit_part(qpg_part3d p, qpg_field q, int part);
 int qpg_part3d_update_bound(qpg_part3d p);                                                       /* update_bound_part3d :640 */
 /* qpg_part3d_qdeposit in two halves (see qpg_sim_beam_qdp_raw / _fix) */
 int qpg_part3d_qdeposit_raw(qpg_part3d p, qpg_field q);
@@ -246,6 +254,14 @@ int qpg_sim_run_slices(qpg_sim s, int j0, int j1);
 int qpg_sim_set_back_handoff(qpg_sim s, double *wire_b, double *wire_e, unsigned *flag, unsigned seq);
 /* simulation_class.f03:489-493: beam push + update_bound (E,B guard slice nzp+1 already unpacked by the caller) */
 int qpg_sim_beam_push(qpg_sim s);
+/* qpg_sim_beam_push in two halves for a stage of the xi-pipeline, with the NEXT step's raw beam deposit riding on them (the beam charge
+ * volume must have been zeroed: qpg_sim_beam_qdp_begin): _interior advances and deposits the particles that do not gather from the guard
+ * slice (needs nothing from the downstream stage); _edge advances and deposits the rest, then update_bound.  Particles that arrive from the
+ * upstream stage afterwards (qpg_part3d_unpack) are deposited with qpg_sim_beam_qdp_part(s, 3) before qpg_part3d_pack_forward; the
+ * deposit is completed by qpg_sim_beam_qdp_fix as usual (no qpg_sim_beam_qdp_raw in that step). */
+int qpg_sim_beam_push_interior(qpg_sim s);
+int qpg_sim_beam_push_edge(qpg_sim s);
+int qpg_sim_beam_qdp_part(qpg_sim s, int part);
 /* the sim's laser envelope (NULL unless sp_push_pgc) and simulation_class.f03:486 lasers%advance (after the slab) */
 qpg_laser qpg_sim_laser(qpg_sim s);
 int qpg_sim_laser_advance(qpg_sim s);

@@ -110,6 +110,12 @@ SIGNATURES = {
     "qpg_part3d_qdeposit": (_i, [_vp, _vp]),
     "qpg_part3d_push": (_i, [_vp, _i, _vp, _vp]),
     "qpg_part3d_update_bound": (_i, [_vp]),
+    "qpg_part3d_push_interior": (_i, [_vp, _i, _vp, _vp]),
+    "qpg_part3d_push_edge": (_i, [_vp, _i, _vp, _vp]),
+    "qpg_sim_beam_push_interior": (_i, [_vp]),
+    "qpg_sim_beam_push_edge": (_i, [_vp]),
+    "qpg_sim_beam_qdp_part": (_i, [_vp, _i]),
+    "qpg_part3d_qdeposit_part": (_i, [_vp, _vp, _i]),
     "qpg_part3d_pack_forward": (_i, [_vp, _vp]),
     "qpg_part3d_unpack": (_i, [_vp, _vp]),
     "qpg_part3d_wire_cap": (_l, [_vp]),
@@ -454,6 +460,8 @@ class Part3d:
 
     def qdeposit(self, q): _chk(self.L.qpg_part3d_qdeposit(self.h, q.h))
     def push(self, push_type, ef, bf): _chk(self.L.qpg_part3d_push(self.h, push_type, ef.h, bf.h))
+    def push_interior(self, push_type, ef, bf): _chk(self.L.qpg_part3d_push_interior(self.h, push_type, ef.h, bf.h))
+    def push_edge(self, push_type, ef, bf): _chk(self.L.qpg_part3d_push_edge(self.h, push_type, ef.h, bf.h))
     def update_bound(self): _chk(self.L.qpg_part3d_update_bound(self.h))
     def count_ptr(self): return self.L.qpg_part3d_count_ptr(self.h)          # device address of the live particle count
     def wire_cap(self): return self.L.qpg_part3d_wire_cap(self.h)
@@ -669,6 +677,9 @@ class Sim:
     def begin_step_add(self): _chk(self.L.qpg_sim_begin_step_add(self.h))
     def run_slices(self, j0, j1): _chk(self.L.qpg_sim_run_slices(self.h, j0, j1))
     def beam_push(self): _chk(self.L.qpg_sim_beam_push(self.h))
+    def beam_push_interior(self): _chk(self.L.qpg_sim_beam_push_interior(self.h))   # the half of the push that needs nothing from the downstream stage
+    def beam_push_edge(self): _chk(self.L.qpg_sim_beam_push_edge(self.h))           # the other half + update_bound
+    def beam_qdp_part(self, part): _chk(self.L.qpg_sim_beam_qdp_part(self.h, part))  # 3: the particles the upstream stage has just handed over
     def renew(self): _chk(self.L.qpg_sim_renew(self.h))
     def set_graph(self, on): _chk(self.L.qpg_sim_set_graph(self.h, int(on)))
     def set_fused(self, on): _chk(self.L.qpg_sim_set_fused(self.h, int(on)))

@@ -25,15 +25,24 @@ static double **plane_table3(qpg_part3d p) { return (double **)(p->lists + 2 * p
 #define B3_MAX_GRID (148 * 8)
 static inline int b3_grid(long n) { const long g = (n + B3_BLOCK - 1) / B3_BLOCK; return (int)(g < B3_MAX_GRID ? g : B3_MAX_GRID); }
 template <int M>
-__global__ void __launch_bounds__(B3_BLOCK) k_qdeposit3d(Part3View pv, double *__restrict__ f2, double idr, double idz, int nr, int noff2, int nzp)
+__global__ void __launch_bounds__(B3_BLOCK) k_qdeposit3d(Part3View pv, double *__restrict__ f2, double idr, double idz, int nr, int noff2, int nzp, int mode,
+                                                        const unsigned *__restrict__ pushed)
 {
+    // mode 0: every particle.  The split deposit of a pipeline stage (qpg_part3d_qdeposit_part): 1 = the particles the interior pass of the
+    // split push has advanced (bit set in `pushed`), 2 = the others, 3 = the particles appended since the last hand-off (index >= d_npp[3])
     constexpr int P = 2 * M + 1;
     extern __shared__ double dep_tiles[];
     const int npp = *pv.d_npp, lane = threadIdx.x & 31;
+    const int first = mode == 3 ? pv.d_npp[3] : 0;
     double *tile = dep_tiles + (threadIdx.x >> 5) * DepTile<M>::doubles;
     for (long base = (long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < npp; base += (long)gridDim.x * blockDim.x) {   // warp-uniform
         const long i = base + lane;
-        bool ok = i < npp;
+        bool ok = i < npp && i >= first;
+        if (mode == 1 || mode == 2) {
+            const unsigned w = pushed[base >> 5];
+            if ((mode == 1 && w == 0u) || (mode == 2 && w == 0xffffffffu)) continue;      // warp-uniform: nothing to do in this tile
+            ok = ok && (((w >> lane) & 1u) == (mode == 1 ? 1u : 0u));
+        } else if (base + 32 <= first) continue;
         double ph[P], wr[2] = {0.0, 0.0}, wz[2] = {0.0, 0.0};
         int nn = 0, mm = 0;
 #pragma unroll
@@ -94,13 +103,19 @@ __global__ void k_qdep3d_fix(double *__restrict__ f2, int nr, int P, int nzp)
 // r >= edge_r or xi >= edge_z (update_bound_part3d :640-689) when flag != 0
 template <int M>
 __global__ void __launch_bounds__(B3_BLOCK) k_push3d(Part3View pv, const double *__restrict__ ef2, const double *__restrict__ bf2, double idr, double idz,
-                                                    int nr, int noff2, int nzp, double qbm, double dt, int push_type)
+                                                    int nr, int noff2, int nzp, double qbm, double dt, int push_type, int pass, unsigned *__restrict__ pushed)
 {
+    // pass 0: every particle of the slab.  The xi-pipeline splits the push (pipeline.LocalPipeline._tail): pass 1 = the particles whose
+    // gather does not touch the guard slice nzp + 1 (slice index < nzp) -- it runs BEFORE the downstream stage's first-slice e / b has
+    // arrived -- and records them in the bitmap `pushed`; pass 2 = the rest (the last slice of the slab), after the message.
     constexpr int P = 2 * M + 1;
-    const int npp = *pv.d_npp;
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < npp; i += (long)gridDim.x * blockDim.x) {   // the host knows an upper bound only
-    double x1 = pv.x1[i], x2 = pv.x2[i], x3 = pv.x3[i];
-    double p1 = pv.p1[i], p2 = pv.p2[i], p3 = pv.p3[i];
+    const int npp = *pv.d_npp, lane = threadIdx.x & 31;
+    for (long base = (long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < npp; base += (long)gridDim.x * blockDim.x) {   // warp-uniform; the host knows an upper bound only
+    const long i = base + lane;
+    const bool live = i < npp;
+    if (pass == 2 && pushed[base >> 5] == 0xffffffffu) continue;      // warp-uniform: the interior pass has advanced the whole tile
+    double x1 = 1.0, x2 = 0.0, x3 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
+    if (live) { x1 = pv.x1[i]; x2 = pv.x2[i]; x3 = pv.x3[i]; p1 = pv.p1[i]; p2 = pv.p2[i]; p3 = pv.p3[i]; }
     double pos_r = __dmul_rn(__dsqrt_rn(__dadd_rn(__dmul_rn(x1, x1), __dmul_rn(x2, x2))), idr);
     double pos_z = __dmul_rn(x3, idz);
     const double cc = x1 / pos_r * idr, ss = x2 / pos_r * idr;
@@ -108,7 +123,13 @@ __global__ void __launch_bounds__(B3_BLOCK) k_push3d(Part3View pv, const double 
     const double fr = pos_r - (double)nn, fz = pos_z - (double)mm;
     nn = nn + 1;
     mm = mm - noff2 + 1;
-    if (mm < 1 || mm > nzp || nn < 1 || nn > nr) continue;
+    bool go = live && !(mm < 1 || mm > nzp || nn < 1 || nn > nr);
+    if (pass == 1) {
+        go = go && mm < nzp;
+        const unsigned bal = __ballot_sync(FULL, go);
+        if (lane == 0) pushed[base >> 5] = bal;
+    } else if (pass == 2) go = go && !((pushed[base >> 5] >> lane) & 1u);
+    if (!go) continue;
     const size_t n1 = (size_t)(nr + 2) * P * 3;
     const double wr[2] = {1.0 - fr, fr}, wz[2] = {1.0 - fz, fz};
     double ep[3] = {0, 0, 0}, bp[3] = {0, 0, 0};
@@ -250,18 +271,20 @@ __global__ void k_bump_npp(int *d_npp, const double *__restrict__ buf, long cap,
 {
     const int add = (int)min((long)buf[0], cap);
     const int n0 = *d_npp;
+    d_npp[3] = n0;                                   // first index of the appended particles (qpg_part3d_qdeposit_part, part 3)
     *d_npp = n0 + (int)min((long)add, npmax - n0);
 }
 
-template <int M> static void l_qdep3d(int grid, cudaStream_t st, Part3View pv, double *f2, double idr, double idz, int nr, int noff2, int nzp)
+template <int M> static void l_qdep3d(int grid, cudaStream_t st, Part3View pv, double *f2, double idr, double idz, int nr, int noff2, int nzp, int mode, const unsigned *pushed)
 {
     constexpr size_t smem = sizeof(double) * DepTile<M>::doubles * (B3_BLOCK / 32);
     static bool attr_set = false;   // > 48 KB of dynamic shared memory needs the opt-in (M >= 3)
     if (!attr_set) { cudaFuncSetAttribute(k_qdeposit3d<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
-    k_qdeposit3d<M><<<grid, B3_BLOCK, smem, st>>>(pv, f2, idr, idz, nr, noff2, nzp);
+    k_qdeposit3d<M><<<grid, B3_BLOCK, smem, st>>>(pv, f2, idr, idz, nr, noff2, nzp, mode, pushed);
 }
-template <int M> static void l_push3d(int grid, cudaStream_t st, Part3View pv, const double *e, const double *b, double idr, double idz, int nr, int noff2, int nzp, double qbm, double dt, int pt)
-{ k_push3d<M><<<grid, B3_BLOCK, 0, st>>>(pv, e, b, idr, idz, nr, noff2, nzp, qbm, dt, pt); }
+template <int M> static void l_push3d(int grid, cudaStream_t st, Part3View pv, const double *e, const double *b, double idr, double idz, int nr, int noff2, int nzp, double qbm, double dt, int pt,
+                                      int pass, unsigned *pushed)
+{ k_push3d<M><<<grid, B3_BLOCK, 0, st>>>(pv, e, b, idr, idz, nr, noff2, nzp, qbm, dt, pt, pass, pushed); }
 
 extern "C" int qpg_part3d_create(qpg_part3d *out, qpg_ctx ctx, double qbm, double dt, long npmax, int nz_total, int noff2, int nzp)
 {
@@ -282,6 +305,8 @@ extern "C" int qpg_part3d_create(qpg_part3d *out, qpg_ctx ctx, double qbm, doubl
     p->d_nout = p->d_npp + 1;
     CUDA_TRY(cudaMalloc(&p->outmask, sizeof(unsigned) * (npmax / 32 + 1)));
     CUDA_TRY(cudaMemsetAsync(p->outmask, 0, sizeof(unsigned) * (npmax / 32 + 1), ctx->stream));
+    CUDA_TRY(cudaMalloc(&p->pushed, sizeof(unsigned) * (npmax / 32 + 1)));
+    CUDA_TRY(cudaMemsetAsync(p->pushed, 0, sizeof(unsigned) * (npmax / 32 + 1), ctx->stream));
     CUDA_TRY(cudaMalloc(&p->lists, sizeof(int) * (2 * npmax + 64)));
     double *h[7] = {p->x1, p->x2, p->x3, p->p1, p->p2, p->p3, p->q};
     CUDA_TRY(cudaMemcpy(plane_table3(p), h, sizeof(h), cudaMemcpyHostToDevice));
@@ -292,7 +317,7 @@ extern "C" int qpg_part3d_destroy(qpg_part3d p)
 {
     if (!p) return 0;
     cudaStreamSynchronize(p->ctx->stream);
-    cudaFree(p->slab); cudaFree(p->d_npp); cudaFree(p->outmask); cudaFree(p->lists);
+    cudaFree(p->slab); cudaFree(p->d_npp); cudaFree(p->outmask); cudaFree(p->pushed); cudaFree(p->lists);
     delete p;
     return 0;
 }
@@ -346,7 +371,24 @@ extern "C" int qpg_part3d_qdeposit_raw(qpg_part3d p, qpg_field q)
     TprofScope tp(c, TP_DEPOSIT3D);
     if (p->npp_hi > 0) {
         const int grid = b3_grid(p->npp_hi);
-        DISPATCH_M(c->M, l_qdep3d, grid, c->stream, view3(p), q->f2, 1.0 / c->dr, 1.0 / c->dxi, c->nr, p->noff2, p->nzp);
+        DISPATCH_M(c->M, l_qdep3d, grid, c->stream, view3(p), q->f2, 1.0 / c->dr, 1.0 / c->dxi, c->nr, p->noff2, p->nzp, 0, p->pushed);
+        count_launch(c);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+/* the raw deposit in three parts for a stage of the xi-pipeline, so that only a sliver of it stays behind the backward hand-off:
+ * part 1 = the particles advanced by qpg_part3d_push_interior, 2 = the others (after qpg_part3d_push_edge, BEFORE update_bound: the bitmap is
+ * indexed by the pre-compaction order), 3 = the particles appended by the last qpg_part3d_unpack (before qpg_part3d_pack_forward compacts).
+ * Particles that have left the slab or the box deposit nothing, exactly as in the full deposit after update_bound / the hand-off. */
+extern "C" int qpg_part3d_qdeposit_part(qpg_part3d p, qpg_field q, int part)
+{
+    ARG_TRY(p && q && q->dim == 1 && q->has2d && q->nzp == p->nzp && q->ctx == p->ctx && part >= 1 && part <= 3, "bad arg");
+    qpg_ctx c = p->ctx;
+    TprofScope tp(c, TP_DEPOSIT3D);
+    if (p->npp_hi > 0) {
+        const int grid = b3_grid(p->npp_hi);
+        DISPATCH_M(c->M, l_qdep3d, grid, c->stream, view3(p), q->f2, 1.0 / c->dr, 1.0 / c->dxi, c->nr, p->noff2, p->nzp, part, p->pushed);
         count_launch(c);
     }
     CUDA_TRY(cudaGetLastError());
@@ -367,7 +409,7 @@ extern "C" int qpg_part3d_qdeposit(qpg_part3d p, qpg_field q)
     int rc = qpg_part3d_qdeposit_raw(p, q);
     return rc ? rc : qpg_part3d_qdeposit_fix(p, q);
 }
-extern "C" int qpg_part3d_push(qpg_part3d p, int push_type, qpg_field ef, qpg_field bf)
+static int part3d_push_pass(qpg_part3d p, int push_type, qpg_field ef, qpg_field bf, int pass)
 {
     ARG_TRY(p && ef && bf && ef->dim == 3 && bf->dim == 3 && ef->has2d && bf->has2d && ef->nzp == p->nzp && bf->nzp == p->nzp, "e, b must be dim-3 fields with this slab's 2D layout");
     ARG_TRY(push_type == QPG_PUSH3_REDUCED || push_type == QPG_PUSH3_BORIS, "Invalid pusher type! Only \"reduced\" and \"boris\" are supported currently.");
@@ -375,11 +417,16 @@ extern "C" int qpg_part3d_push(qpg_part3d p, int push_type, qpg_field ef, qpg_fi
     qpg_ctx c = p->ctx;
     TprofScope tp(c, TP_PUSH3D);
     const int grid = b3_grid(p->npp_hi);
-    DISPATCH_M(c->M, l_push3d, grid, c->stream, view3(p), ef->f2, bf->f2, 1.0 / c->dr, 1.0 / c->dxi, c->nr, p->noff2, p->nzp, p->qbm, p->dt, push_type);
+    DISPATCH_M(c->M, l_push3d, grid, c->stream, view3(p), ef->f2, bf->f2, 1.0 / c->dr, 1.0 / c->dxi, c->nr, p->noff2, p->nzp, p->qbm, p->dt, push_type, pass, p->pushed);
     count_launch(c);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
+extern "C" int qpg_part3d_push(qpg_part3d p, int push_type, qpg_field ef, qpg_field bf) { return part3d_push_pass(p, push_type, ef, bf, 0); }
+/* the push in two passes for a pipeline stage: `interior` = the particles that do not gather from the guard slice nzp + 1 (may run before
+ * the downstream stage's first-slice e / b has arrived), `edge` = the others; interior must precede edge, together they are qpg_part3d_push */
+extern "C" int qpg_part3d_push_interior(qpg_part3d p, int push_type, qpg_field ef, qpg_field bf) { return part3d_push_pass(p, push_type, ef, bf, 1); }
+extern "C" int qpg_part3d_push_edge(qpg_part3d p, int push_type, qpg_field ef, qpg_field bf) { return part3d_push_pass(p, push_type, ef, bf, 2); }
 extern "C" int qpg_part3d_update_bound(qpg_part3d p)
 {
     ARG_TRY(p, "null arg");

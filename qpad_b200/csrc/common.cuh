@@ -108,6 +108,7 @@ struct qpg_part3d_s {
     double *x1, *x2, *x3, *p1, *p2, *p3, *q, *slab;
     int *d_npp, *d_nout;     // d_npp[2] = wire-buffer overflow flag (more particles crossed the slab edge than wire_cap)
     unsigned *outmask;
+    unsigned *pushed;        // bitmap of the particles the interior pass of the split push has advanced (qpg_part3d_push_interior / _edge)
     int *lists;
     long wire_cap;           // particles per forward hand-off message (0 = default 0.1 npmax, part3d_class.f03:127)
 };

@@ -19,6 +19,7 @@ struct qpg_sim_s {
     qpg_part2d spe;
     qpg_part3d beam;
     qpg_laser laser;      // sp_push_pgc: the one laser envelope of the run
+    bool split_deposit;   // the pipeline's split beam push is in use: the raw beam deposit rides on it (qpg_sim_beam_push_interior / _edge, qpg_sim_beam_qdp_part)
     unsigned *las_progress; unsigned las_base; bool las_overlap;   // overlapped envelope advance (qpg_sim_laser_advance): progress word of the running solve
     int cur_j;            // slice being enqueued (per-slice launch path)
     cudaGraph_t graph;
@@ -524,6 +525,9 @@ extern "C" int qpg_sim_beam_qdp_begin(qpg_sim s) { ARG_TRY(s, "null sim"); retur
 extern "C" int qpg_sim_beam_qdp_end(qpg_sim s) { ARG_TRY(s, "null sim"); return qpg_part3d_qdeposit(s->beam, s->beam_q); } // :210
 extern "C" int qpg_sim_beam_qdp_raw(qpg_sim s) { ARG_TRY(s, "null sim"); return qpg_part3d_qdeposit_raw(s->beam, s->beam_q); }
 extern "C" int qpg_sim_beam_qdp_fix(qpg_sim s) { ARG_TRY(s, "null sim"); return qpg_part3d_qdeposit_fix(s->beam, s->beam_q); }
+// the raw deposit of a pipeline stage in three parts (qpg_part3d_qdeposit_part): 1 behind qpg_sim_beam_push_interior, 2 behind the push of the
+// rest, 3 behind the arrival of the upstream stage's particles
+extern "C" int qpg_sim_beam_qdp_part(qpg_sim s, int part) { ARG_TRY(s, "null sim"); return qpg_part3d_qdeposit_part(s->beam, s->beam_q, part); }
 // simulation_class.f03:299-331 (everything but the MPI calls), in two halves: _zero touches nothing a hand-off delivers
 // (a pipeline stage runs it while it waits for the upstream stage), _add folds the finished beam charge into q_beam
 extern "C" int qpg_sim_begin_step_zero(qpg_sim s)
@@ -623,6 +627,28 @@ extern "C" int qpg_sim_beam_push(qpg_sim s)
     if (!s->prm.beam_evol) return 0;
     int rc = qpg_part3d_push(s->beam, s->prm.beam_push_type, s->e, s->b);
     if (rc) return rc;
+    return qpg_part3d_update_bound(s->beam);
+}
+// the beam push of a pipeline stage in two halves (qpg_part3d_push_interior / _edge): `interior` needs nothing from the downstream stage
+extern "C" int qpg_sim_beam_push_interior(qpg_sim s)
+{
+    ARG_TRY(s, "null sim");
+    if (!s->prm.beam_evol) {       // a frozen beam: nothing moves, the whole deposit can be done here
+        s->split_deposit = false;
+        return qpg_part3d_qdeposit_raw(s->beam, s->beam_q);
+    }
+    int rc = qpg_part3d_push_interior(s->beam, s->prm.beam_push_type, s->e, s->b);
+    if (rc) return rc;
+    s->split_deposit = true;       // the next step's beam charge is deposited in parts as the particles are advanced (the volume was zeroed before)
+    return qpg_part3d_qdeposit_part(s->beam, s->beam_q, 1);
+}
+extern "C" int qpg_sim_beam_push_edge(qpg_sim s)
+{
+    ARG_TRY(s, "null sim");
+    if (!s->prm.beam_evol) return 0;
+    int rc = qpg_part3d_push_edge(s->beam, s->prm.beam_push_type, s->e, s->b);
+    if (rc) return rc;
+    if (s->split_deposit && (rc = qpg_part3d_qdeposit_part(s->beam, s->beam_q, 2))) return rc;   // before update_bound: the bitmap follows the pre-compaction order
     return qpg_part3d_update_bound(s->beam);
 }
 // neut%renew (neutral_class.f03:839-878) + the zeroing of its fields; the particle sets keep npp_hi = npmax so that launches

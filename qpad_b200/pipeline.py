@@ -446,7 +446,7 @@ def measured_partition(lp, cfg, beam_ns=None, nwaves=4, tol=0.03, nwarm=1):
     lp.trace_reset()
     mine = []
     for sim, rep in zip(lp.sims, reps):
-        busy = sum(v for k, v in rep.items() if k not in ("w_fwd>got_fwd", "tail>got_back"))        # ms per wave
+        busy = sum(v for k, v in rep.items() if k not in ("w_fwd>got_fwd", "pre>got_back"))        # ms per wave
         sweep = sim.sweep_profile()["ns_total"] * 1e-6 / nwaves
         mine.append((sim.slice_trace()[0], busy, sweep))
     every = [mine]
@@ -610,6 +610,7 @@ class LocalPipeline:
         self.lflags = capi.WireBuf(32 * S)            # [r]: number of the last back message stage r's sweep kernel has published
         self.nback_out, self.nback_in = [0] * S, [0] * S
         self._zeroed = [False] * S
+        self._deposited = [False] * S                 # the stage's tail has already scattered the next step's beam charge (split push / deposit)
 
     # events: recorded on the producer's stream, waited on by the consumer's stream; host order = a valid schedule
     def _rec(self, name, r):
@@ -682,7 +683,9 @@ class LocalPipeline:
             s.beam_qdp_begin()
             s.begin_step_zero()
         self._zeroed[r] = False
-        s.beam_qdp_raw()
+        if not self._deposited[r]:                                      # (the first step of a stage: no tail has run before)
+            s.beam_qdp_raw()
+        self._deposited[r] = False
         src = None
         self._mark(r, "w_fwd")
         if p2p_up:
@@ -778,6 +781,10 @@ class LocalPipeline:
         s.beam_qdp_begin()                                              # the next step's zero fills too (the beam push reads
         s.begin_step_zero()                                             # the e / b VOLUMES, the fills clear slice images)
         self._zeroed[r] = True
+        # the beam particles whose gather does not touch the guard slice nzp + 1 (all but those in the slab's last slice) are pushed
+        # NOW, before the wait for the downstream stage's first slice: only the rest of the push stays on the backward link
+        s.beam_push_interior()
+        self._mark(r, "pre")                                            # tail>pre is work, pre>got_back the wait for the downstream stage
         # The backward message (e, b of the downstream stage's first slice) feeds the beam push only: a stage without beam particles
         # does not wait for it (qpg_stream_wait_unless_empty looks at the device-side particle count when the stream gets there), so
         # the skew "every stage starts after the first slice of the next one" builds up over the beam-carrying stages only.  The
@@ -805,7 +812,7 @@ class LocalPipeline:
                 self._psignal(r, "down", "ack_back", n_b)
             elif not remote_down:
                 self._rec("back_free", r + 1)
-        s.beam_push()
+        s.beam_push_edge()
         self._mark(r, "pushed")
         if p2p_up:
             n_m = self.links.next("beam_in")
@@ -819,6 +826,9 @@ class LocalPipeline:
             self._wait("beam_ready", r - 1)
             s.beam.unpack(self.beamb[r - 1].data_ptr())
             self._rec("beam_free", r - 1)
+        if self.base + r > 0:
+            s.beam_qdp_part(3)                                          # the arrivals' charge (before pack_forward compacts the set)
+        self._deposited[r] = True                                       # the next head does not scatter the beam charge again
         if p2p_down:
             n_m = self.links.next("beam_out")
             self._pwait(r, "ack_beam", n_m - 1)

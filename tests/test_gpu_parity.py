@@ -412,6 +412,18 @@ def test_beam_kernels_match_oracle(mods, M, push):
     gx, gp, gq = beam.download()
     assert np.max(np.abs(gp - po)) < 1e-13 * np.max(np.abs(po))
     assert np.max(np.abs(gx - xo)) < 1e-13 * np.max(np.abs(xo))
+    # the split push of a pipeline stage: interior (no guard slice needed) + edge == push, bit for bit; the interior pass must not have
+    # touched a particle of the slab's last slice (the guard slice may not have arrived yet) and must have moved the others
+    beam2 = capi.Part3d(ctx, -1.0, 4.0, n + 64, nz, noff2, nzp)
+    beam2.upload(x, p, q)
+    beam2.push_interior(push, fe, fb)
+    hx, hp, _ = beam2.download()
+    last = np.floor(x[:, 2] / dz).astype(int) - noff2 + 1 == nzp
+    assert last.sum() > 100 and np.array_equal(hx[last], x[last]) and np.array_equal(hp[last], p[last])
+    assert np.array_equal(hx[~last], gx[~last]) and np.array_equal(hp[~last], gp[~last])
+    beam2.push_edge(push, fe, fb)
+    hx, hp, _ = beam2.download()
+    assert np.array_equal(hx, gx) and np.array_equal(hp, gp)
     # update_bound: exact order on identical inputs
     xo[::7, 0] = 9.0
     xo[5::11, 2] = nz * dz + 0.1

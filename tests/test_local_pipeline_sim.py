@@ -211,6 +211,9 @@ class FakeSim:
     def begin_step_zero(self): self.kernel(lambda sid, vc: None)
     def begin_step_add(self): self.kernel(lambda sid, vc: None)
     def beam_push(self): self.log.append(("push", self.cur - 1)); self.kernel(lambda sid, vc: None)
+    def beam_push_interior(self): self.kernel(lambda sid, vc: None)
+    def beam_qdp_part(self, part): self.kernel(lambda sid, vc: None)
+    def beam_push_edge(self): self.log.append(("push", self.cur - 1)); self.kernel(lambda sid, vc: None)
     def renew(self): self.kernel(lambda sid, vc: None)
     def stats(self): return (0, 0, 0)
     def close(self): pass
