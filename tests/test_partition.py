@@ -66,3 +66,54 @@ def test_split_beam_follows_the_partition():
     same = split_beam(bx, bp, bq, nz, dxi, 4)
     for (noff, n), (x, _, _) in zip(slab_partition(nz, 4), same):
         assert np.all(x[:, 2] >= noff * dxi) and np.all(x[:, 2] < (noff + n) * dxi)
+
+
+class _StubSim:
+    def __init__(self, trace, sweep_ms):
+        self.trace, self.sweep_ms = np.asarray(trace, dtype=float), sweep_ms
+
+    def sweep_profile(self, reset=False):
+        return {"ns_total": self.sweep_ms * 1e6 * 4}          # measured_partition divides by its nwaves (4 below)
+
+    def slice_trace(self):
+        return self.trace, np.ones(len(self.trace), dtype=np.int32)
+
+
+class _StubPipeline:
+    """the surface of LocalPipeline that pipeline.measured_partition uses"""
+
+    def __init__(self, parts, ns_per_slice, other_ms):
+        self.parts, self.G, self.S, self.world, self.dist = parts, len(parts), len(parts), 1, None
+        self.sims = [_StubSim(ns_per_slice[a:a + n], ns_per_slice[a:a + n].sum() * 1e-6) for a, n in parts]
+        self.other_ms, self._ev_on, self.waves = other_ms, False, 0
+
+    def fill(self): pass
+    def wave(self): self.waves += 1
+    def sync(self): pass
+    def trace_reset(self): pass
+
+    def event_report(self):
+        return [{"begun>swept": s.sweep_ms, "tail>pre": o, "pre>got_back": 3.3, "w_fwd>got_fwd": 1.1} for s, o in zip(self.sims, self.other_ms)]
+
+
+def test_closed_loop_partition_equalises_busy_time():
+    """pipeline.measured_partition: slabs are re-cut from what the running pipeline measures -- per-stage busy time (waits excluded) and
+    the per-slice cost profile -- until the busy times agree; the non-sweep work of a stage (beam kernels) counts"""
+    from qpad_b200.pipeline import measured_partition
+    nz = 2048
+    ns = np.full(nz, 90e3)                       # 90 us per slice ...
+    ns[1100:1500] = 125e3                        # ... 125 us inside the wake
+    cfg = {"nz": nz}
+    parts = slab_partition(nz, 4)
+    other = [4.0, 4.0, 0.1, 0.1]                 # ms of beam work per wave in the stages that hold the beam
+    for rnd in range(4):
+        lp = _StubPipeline(parts, ns, other)
+        new, busy, spread = measured_partition(lp, cfg, nwaves=4, nwarm=1)
+        assert lp.waves == 5 and len(busy) == 4
+        assert all(abs(b - (s.sweep_ms + o)) < 1e-9 for b, s, o in zip(busy, lp.sims, other))       # the two waits are not busy time
+        if new is None:
+            break
+        assert _tiles(new, nz)
+        parts = new
+    assert new is None and spread < 0.03 and rnd <= 2
+    assert parts != slab_partition(nz, 4) and parts[2][1] < parts[3][1]      # the stage that holds the wake got a shorter slab than the quiet tail
