@@ -104,11 +104,11 @@ def test_sweep_watchdog_is_reported(mods):
 
 def test_conditional_stream_wait(mods):
     """qpg_stream_wait_unless_empty: the backward hand-off of the xi-pipeline is awaited only by a stage that holds beam particles"""
-    import time
     import torch
     capi, O, K = mods
     flag = torch.zeros(8, dtype=torch.int32, device="cuda")
     cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+    out = torch.zeros(1, dtype=torch.int32, device="cuda")
     torch.cuda.synchronize()
     st, st2 = torch.cuda.Stream(), torch.cuda.Stream()
     capi.stream_wait_unless_empty(st.cuda_stream, cnt.data_ptr(), flag.data_ptr(), 5)     # count 0: must not block although the flag is 0
@@ -125,8 +125,7 @@ def test_conditional_stream_wait(mods):
         torch.cuda._sleep(200_000_000)
     capi.stream_signal(st2.cuda_stream, flag.data_ptr(), 2)
     capi.stream_wait_unless_empty(st.cuda_stream, cnt.data_ptr(), flag.data_ptr(), 2)
-    ev = torch.cuda.Event(); ev.record(st)
-    time.sleep(0.02)
-    assert not ev.query()
+    with torch.cuda.stream(st):
+        out.copy_(flag[:1])                                 # ordered behind the wait: must see the raised flag, not the 0 of ~0.1 s earlier
     st.synchronize()
-    assert ev.query() and int(flag[0].item()) == 2
+    assert int(out.item()) == 2 and int(flag[0].item()) == 2
