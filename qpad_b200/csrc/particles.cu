@@ -101,8 +101,15 @@ __device__ __forceinline__ void red_add(int *p, int v) { asm volatile("red.globa
 __device__ __forceinline__ Interp interp_info(double x1, double x2, double idr)
 {
     Interp it;
+#ifdef QPG_EXP_CHEAP_INTERP   // bottleneck experiment only (results are wrong in the last bits -> different cells now and then): what would the particle
+    // phases gain if cos / sin / r/dr came from stored planes instead of an IEEE square root + reciprocal per pass?
+    double rinv;
+    { const double r2 = fma(x1, x1, x2 * x2); asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(rinv) : "d"(r2)); }
+    double r = (x1 * x1 + x2 * x2) * rinv;
+#else
     double r = __dsqrt_rn(__dadd_rn(__dmul_rn(x1, x1), __dmul_rn(x2, x2)));
     const double rinv = fast_rcp(r);
+#endif
     it.c = x1 * rinv;
     it.s = x2 * rinv;
     double pos = __dmul_rn(r, idr);
