@@ -617,6 +617,151 @@ def run_c4(args):
     sim.close()
 
 
+def run_c4_pipeline(args):
+    """config 4 on the xi-pipeline (the deck is `nodes [1,4]`; sim_lasers_class.f03:197-222): --stages S sweep kernels per GPU on SM
+    partitions, every stage with its slab of the envelope, advanced after its sweep from the upstream stage's new last two slices
+    (capi.Laser.set_handoff; one SM per stage is left to the envelope solves, which run beside the next sweeps).  A timed step = one wave =
+    every stage sweeps and advances its slab once, in steady state; after the timed region the pipeline is drained and the SAME number of
+    3D steps is re-run on one stage: envelope and wake line-outs must agree (parity_check)."""
+    import torch
+    import torch.distributed as dist
+    from qpad_b200 import capi, decks
+    from qpad_b200.pipeline import LocalPipeline
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl")
+    cfg, _ = deck_config("C4")
+    las = cfg["laser"]
+    plasma, _bm = make_inputs(cfg, None)
+    npp0 = len(plasma[4])
+    empty = (np.zeros((0, 3)), np.zeros((0, 3)), np.zeros(0))
+    a_r, a_i = decks.laser_gaussian(cfg["nr"], cfg["nz"], cfg["rmax"], cfg["zmin"], cfg["zmax"], **las)
+    S = args.stages
+    lp = LocalPipeline(cfg, plasma, empty, S, device=local, rank=rank, world=world, dist=dist if world > 1 else None, transport="p2p" if world > 1 else None, laser=(a_r, a_i))
+    main = torch.cuda.current_stream()
+
+    def sync_all():
+        lp.sync()
+        if world > 1:
+            dist.barrier(device_ids=[local])
+        torch.cuda.synchronize()
+
+    lp.fill()
+    for _ in range(args.warmup):
+        lp.wave()
+    sync_all()
+    u0, i0, s0 = lp.stats()
+    l0 = lp.launch_count()
+    clk = ClockSampler(local); clk.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    ev0.record(main)
+    for st in lp.streams:
+        st.wait_event(ev0)
+    for _ in range(args.steps):
+        lp.wave()
+    for st in lp.streams:     # the envelope advances on the side streams are not waited for: a stage's advance of step n overlaps its sweep of n+1
+        e = torch.cuda.Event(); e.record(st); main.wait_event(e)
+    ev1.record(main)
+    sync_all()
+    ms = ev0.elapsed_time(ev1)
+    clocks = clk.stop()
+    u1, i1, s1 = lp.stats()
+    upd, iters, slices = u1 - u0, i1 - i0, s1 - s0
+    launches = lp.launch_count() - l0
+    if world > 1:
+        t = torch.tensor([ms, float(upd), float(launches), float(iters), float(slices)], dtype=torch.float64, device="cuda")
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms, upd, launches, iters, slices = tmax[0].item(), tsum[1].item(), tsum[2].item(), tsum[3].item(), tsum[4].item()
+    # end to end (N = 1): plasma lattice host -> device into stage 0 every wave, line-outs of every slab + counters back
+    e2e = None
+    if world == 1:
+        ue0 = lp.stats()[0]
+        t0 = time.perf_counter()
+        d2h = 0
+        for _ in range(args.steps):
+            lp.wave(upload=plasma)
+            d2h = 24 * S
+            for sim in lp.sims:
+                ez = sim.field("e").lineout(3, 0, 1); ps = sim.field("psi").lineout(1, 0, 1)
+                d2h += 8 * (len(ez) + len(ps))
+            lp.stats()
+        sync_all()
+        te = time.perf_counter() - t0
+        e2e = {"value": (lp.stats()[0] - ue0) / te, "unit": UNIT, "h2d_bytes_per_step": int(64 * npp0), "d2h_bytes_per_step": int(d2h),
+               "what": "per step (wave): plasma lattice host->device (qpg_part2d_upload) into stage 0, every stage sweeps + advances its slab, E_z and psi on-axis line-outs of every slab + counters device->host"}
+    # parity of the pipelined run: the same number of 3D steps on one stage
+    check = None
+    if args.check:
+        lp.drain()
+        nsteps = lp.sims[0].stats()[2] // lp.sims[0].nzp
+        simkw = {k: cfg[k] for k in ("nr", "nz", "max_mode", "rmax", "zmin", "zmax", "dt", "iter_max", "iter_reltol", "iter_abstol")}
+        st1 = torch.cuda.Stream(device=local)
+        one = capi.Sim(sp_npmax=2 * npp0, beam_npmax=64, beam_evol=0, sp_push_pgc=1, laser_iter=las["iteration"], laser_k0=las["k0"], sp_ppc_r=cfg["ppc1"], use_graph=1,
+                       device=local, stream=st1.cuda_stream, **simkw)
+        one.init_species(*plasma)
+        one.laser.upload(a_r, a_i)
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        for k in range(nsteps):
+            if k == nsteps - 1:
+                evs[0].record(st1)
+            one.step3d()
+        evs[1].record(st1)
+        st1.synchronize()
+        r1, i1_ = one.laser.download()
+        ez1, ps1 = one.field("e").lineout(3, 0, 1), one.field("psi").lineout(1, 0, 1)
+        err = {"ez": 0.0, "psi": 0.0, "a": 0.0}
+        for (off, n), sim in zip(lp.parts[lp.base:lp.base + S], lp.sims):
+            gr, gi = sim.laser.download()
+            err["a"] = max(err["a"], float(np.max(np.abs(gr[:, 2:2 + n] - r1[:, off + 2:off + 2 + n]))), float(np.max(np.abs(gi[:, 2:2 + n] - i1_[:, off + 2:off + 2 + n]))))
+            ez, ps = sim.field("e").lineout(3, 0, 1), sim.field("psi").lineout(1, 0, 1)
+            err["ez"] = max(err["ez"], float(np.max(np.abs(ez[:n] - ez1[off:off + n]))))
+            err["psi"] = max(err["psi"], float(np.max(np.abs(ps[:n] - ps1[off:off + n]))))
+        err["a"] /= float(max(np.max(np.abs(r1)), np.max(np.abs(i1_)))); err["ez"] /= float(np.max(np.abs(ez1))); err["psi"] /= float(np.max(np.abs(ps1)))
+        if world > 1:
+            e = torch.tensor([err["a"], err["ez"], err["psi"]], dtype=torch.float64, device="cuda")
+            dist.all_reduce(e, op=dist.ReduceOp.MAX)
+            err["a"], err["ez"], err["psi"] = (float(v) for v in e.tolist())
+        moved = float(np.max(np.abs(r1 - a_r)) / np.max(np.abs(a_r)))
+        check = {"ok": bool(max(err.values()) < 1e-6 and moved > 1e-3), "tol": 1e-6, "steps_compared": int(nsteps), "envelope_rel_err": err["a"], "ez_lineout_rel_err": err["ez"],
+                 "psi_lineout_rel_err": err["psi"], "envelope_change_since_launch": moved, "single_step_ms": evs[0].elapsed_time(evs[1]),
+                 "against": "one xi stage (a single k_sweep<0, PGC> over the whole box + one envelope solve per step: the path tests/test_gpu_laser.py holds against the oracle)"}
+        one.close()
+    peak, peak_src = hbm_peak()
+    nit = iters / max(slices, 1)
+    bpu = 24.0 + 72.0 * nit + 80.0 + 64.0 + 32.0
+    ach = upd * bpu / (ms * 1e-3) / 1e9 / world
+    roof = {"bound": "hbm", "kernel": f"k_sweep<0, PGC> x {S} concurrent per GPU (persistent, one xi slab each on {(148 - S) // S} SMs; laser slice images, pgc pushers and the susceptibility deposit inside) "
+                                       f"+ {S} envelope-solve CTAs on SMs of their own; 65 536 particles per slice: barrier and field-program latency bound a stage, the other stages fill it",
+            "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src, "bytes_per_update": bpu,
+            "us_per_slice_effective": ms * 1e3 / max(slices, 1), "slab_slices_by_stage": [n for _, n in lp.parts]}
+    if rank == 0:
+        line = {"metric": METRIC, "value": upd / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic (lattice plasma per fdist2d rule, Gaussian x sin^2 laser pulse of the lwfa deck)",
+                "config": {"workload": f"C4: nr={cfg['nr']} nz={cfg['nz']} max_mode=0 Np/slice={npp0} robust_pgc, laser a0={las['a0']} k0={las['k0']} iteration {las['iteration']}",
+                           "parallelism": f"xi-pipeline: {S} stages per GPU on SM partitions x {world} GPU(s), envelope slabs with guard hand-off, steady state (filled before the timed region)",
+                           "l2": "field volumes + envelope volumes ~60 MB, particle planes 4 MB: L2 resident", "pc_iters_per_slice": nit},
+                "clocks": clocks, "gpu_launches": int(launches), "roofline": roof}
+        if e2e: line["e2e"] = e2e
+        if check: line["parity_check"] = check
+        if not args.no_cpu:
+            try:
+                upd_c, wall_c, k_c, _t = cpu_parallel("C4", args.ref_slices or None)
+                line["cpu_baseline"] = {"value": upd_c / wall_c, "unit": UNIT, "cores": k_c, "kind": "port", "sample": cpu_sample_text("C4", k_c), "pc_iters_per_slice": LAST_CPU_NIT}
+            except Exception as exc:
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {exc}"}
+        print(json.dumps(line))
+    lp.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_b200_local(args):
     """the xi-pipeline mapped onto SM partitions (pipeline.LocalPipeline): --stages S sweep kernels per GPU run
     concurrently, global stage g on 3D step n-g; with N > 1 GPUs the stages continue across ranks over NCCL.  A timed
@@ -963,7 +1108,9 @@ def main():
     if args.impl == "reference":
         run_reference(args)
     elif args.config == "C4":
-        run_c4(args)
+        if args.stages == 0:
+            args.stages = 4 if not (args.no_sweep or args.no_graph) else 1      # the deck's own `nodes [1,4]`
+        (run_c4_pipeline if args.stages > 1 else run_c4)(args)
     elif args.config == "C5":
         run_c5(args)
     else:

@@ -265,6 +265,9 @@ int qpg_sim_beam_qdp_part(qpg_sim s, int part);
 /* the sim's laser envelope (NULL unless sp_push_pgc) and simulation_class.f03:486 lasers%advance (after the slab) */
 qpg_laser qpg_sim_laser(qpg_sim s);
 int qpg_sim_laser_advance(qpg_sim s);
+/* on = the envelope solve of a 3D step may run beside the sweep kernel of the next one also when the caller chose the sweep grid
+ * (qpg_sim_set_sweep_ctas n > 0): the caller vouches that an SM stays free for the solve's CTA (it cannot share one with a sweep CTA) */
+int qpg_sim_set_laser_overlap(qpg_sim s, int on);
 /* simulation_class.f03:498-501 species%renew from the device snapshot of the injected lattice */
 int qpg_sim_renew(qpg_sim s);
 /* counters since creation: particle-slice updates, PC iterations, slices (synchronises) */
@@ -321,7 +324,7 @@ const int *qpg_part3d_count_ptr(qpg_part3d p);
 int qpg_stream_wait_is_memop(void);   /* 1 = cuStreamWaitValue32, 0 = fallback polling kernel */
 
 /* ------------------------------------------------------------------------------------------ */
-/* laser envelope (ponderomotive guiding centre), laser/field_laser_class.f03 + sim_lasers_class.f03; one xi stage.
+/* laser envelope (ponderomotive guiding centre), laser/field_laser_class.f03 + sim_lasers_class.f03; one xi stage (nz = the slab).
  * Envelope volumes a_r, a_i on the host: C arrays [P][nz+3][nr+2], xi slice j (1-based) at index j+1 -- two lower guard
  * slices for the 3-point backward xi difference (gc_num(1,2) = 2), one upper; radial guards at 0 and nr+1.
  *   qpg_laser_create      : init_field_laser :104 + init_solver :269 (nr <= 1024)
@@ -341,6 +344,15 @@ qpg_field qpg_laser_field(qpg_laser l, int which);
 int qpg_laser_slice(qpg_laser l, int j);
 int qpg_laser_deposit_chi(qpg_laser l, qpg_part2d p, int j, double ax_corr);
 int qpg_laser_advance(qpg_laser l);
+/* The envelope on a xi-pipeline (sim_lasers_class.f03:216-218 pipe_recv / pipe_send 'forward' tag 'guard'; init_field_laser :163-169): the
+ * slab's lower guard slices 0, -1 are the upstream stage's last two slices.  With a hand-off set, every qpg_laser_advance (n-th call = message
+ * n on both links) runs  set_rhs (old guards) -> wait *in_ready >= n, copy guard_in into the guards, *in_ack = n -> solve -> wait *out_ack >=
+ * n-1, write the own new slices nz, nz-1 to guard_out, *out_ready = n  on the stream of the advance.  guard_in / in_ready / out_ack live in
+ * THIS GPU's memory, guard_out / out_ready / in_ack may be peer memory (qpg_wire_map); a record has qpg_laser_guard_size doubles.  NULL
+ * triples switch a link off (first / last stage).  The caller enqueues the upstream stage's advance of a 3D step before the downstream one's. */
+int qpg_laser_sync(qpg_laser l);   /* host waits for everything enqueued for this envelope, an overlapped advance on its side stream included */
+long qpg_laser_guard_size(qpg_laser l);
+int qpg_laser_set_handoff(qpg_laser l, const double *guard_in, unsigned *in_ready, unsigned *in_ack, double *guard_out, unsigned *out_ready, unsigned *out_ack);
 
 /* ------------------------------------------------------------------------------------------ */
 /* field-ionisation (ADK) neutral species, species/neutral_class.f03 -- NOT YET VALIDATED ON A GPU (written at the end of

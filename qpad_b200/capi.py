@@ -157,6 +157,10 @@ SIGNATURES = {
     "qpg_laser_slice": (_i, [_vp, _i]),
     "qpg_laser_deposit_chi": (_i, [_vp, _vp, _i, _d]),
     "qpg_laser_advance": (_i, [_vp]),
+    "qpg_laser_sync": (_i, [_vp]),
+    "qpg_laser_guard_size": (_l, [_vp]),
+    "qpg_laser_set_handoff": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "qpg_sim_set_laser_overlap": (_i, [_vp, _i]),
     "qpg_neutral_create": (_i, [C.POINTER(_vp), _vp, _i, _i, _i, _i, _i, _d, _d, _d, _d, _d]),
     "qpg_neutral_destroy": (_i, [_vp]),
     "qpg_neutral_reset": (_i, [_vp]),
@@ -594,6 +598,18 @@ class Laser:
     def slice(self, j): _chk(self.L.qpg_laser_slice(self.h, j))
     def deposit_chi(self, part, j, ax_corr): _chk(self.L.qpg_laser_deposit_chi(self.h, part.h, j, ax_corr))
     def advance(self): _chk(self.L.qpg_laser_advance(self.h))
+    def sync(self): _chk(self.L.qpg_laser_sync(self.h))
+    def guard_size(self): return int(self.L.qpg_laser_guard_size(self.h))
+
+    def set_handoff(self, guard_in=None, in_ready=None, in_ack=None, guard_out=None, out_ready=None, out_ack=None):
+        """the stage's two envelope links of a xi-pipeline (device addresses; None = no link on that side), see include/qpad_b200.h"""
+        _chk(self.L.qpg_laser_set_handoff(self.h, guard_in, in_ready, in_ack, guard_out, out_ready, out_ack))
+
+    def upload_slab(self, ar, ai, noff2):
+        """the stage's part of WHOLE-BOX envelope volumes (P, nz_total+3, nr+2): its slices and, as guards, the neighbours' edge slices
+        (init_field_laser :163-169)"""
+        sl = slice(noff2, noff2 + self.nz + 3)
+        self.upload(np.ascontiguousarray(ar[:, sl]), np.ascontiguousarray(ai[:, sl]))
 
 
 class Sim:
@@ -628,6 +644,7 @@ class Sim:
         self.laser = Laser(self.ctx, nzp, laser_k0, dt, laser_iter, handle=lh) if lh else None
 
     def laser_advance(self): _chk(self.L.qpg_sim_laser_advance(self.h))
+    def set_laser_overlap(self, on): _chk(self.L.qpg_sim_set_laser_overlap(self.h, int(on)))
 
     def set_subcyc(self, exp_fac_max, exp_fac_clamped, dt_min, on=True):
         """the sub-cycling variant of the slice loop (proj_subcyc): plain per-slice launches, one host synchronisation per slice"""

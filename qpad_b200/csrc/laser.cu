@@ -38,6 +38,10 @@ struct qpg_laser_s {
     unsigned *progress;          // device word: (advances launched - 1) * nz + slices finished by the running solve
     unsigned adv_count;          // overlapped advances launched so far
     bool pending;                // an overlapped advance may still be running: join before anybody else touches the envelope
+    // xi-pipeline hand-off of the envelope (qpg_laser_set_handoff): wire buffers and message counters of the two links of this stage
+    const double *g_in; unsigned *g_in_ready, *g_in_ack;
+    double *g_out; unsigned *g_out_ready, *g_out_ack;
+    unsigned g_seq;              // advances done with a hand-off = number of the last message on either link
 };
 
 #define LVI(pl, i, j) ((((size_t)(pl)) * (nz + 3) + (size_t)((j) + 1)) * (nr + 2) + (i))
@@ -488,6 +492,13 @@ static int laser_join(qpg_laser l)
     if (l && l->pending) { CUDA_TRY(cudaStreamWaitEvent(l->ctx->stream, l->ev_done, 0)); l->pending = false; }
     return 0;
 }
+extern "C" int qpg_laser_sync(qpg_laser l)
+{
+    ARG_TRY(l, "null arg");
+    { int rc = laser_join(l); if (rc) return rc; }
+    CUDA_TRY(cudaStreamSynchronize(l->ctx->stream));
+    return 0;
+}
 extern "C" int qpg_laser_upload(qpg_laser l, const double *ar, const double *ai)
 {
     ARG_TRY(l && ar && ai, "null arg");
@@ -542,12 +553,56 @@ extern "C" int qpg_laser_deposit_chi(qpg_laser l, qpg_part2d p, int j, double ax
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
+// The envelope on a xi-pipeline (sim_lasers_class.f03:197-222, field_laser_class.f03:163-169): a stage's slab has the two lower guard slices
+// 0 and -1 = the last two slices of the upstream stage.  The explicit half of an advance (set_rhs) reads them OLD; then the upstream stage's
+// NEW last two slices arrive (pipe_recv 'forward' 'guard': the upstream stage advanced its slab of this 3D step before) and the implicit half
+// marches from them.  Wire record: [a_r | a_i][plane][g = 0: slice nz -> guard 0, g = 1: slice nz-1 -> guard -1][node 0..nr+1].
+// Message n of a link belongs to the n-th advance of both of its ends; flag words count messages (ready: producer -> consumer, written after
+// the record; ack: consumer -> producer, written after the record was copied out, so that one wire buffer per link is enough).
+__global__ void k_laser_guard_unpack(double *__restrict__ ar, double *__restrict__ ai, const double *__restrict__ src, int nr, int nz, int P)
+{
+    const int n = 4 * P * (nr + 2);
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+        const int i = t % (nr + 2), g = (t / (nr + 2)) & 1, pl = (t / (2 * (nr + 2))) % P, im = t / (2 * P * (nr + 2));
+        (im ? ai : ar)[LVI(pl, i, -g)] = src[t];
+    }
+}
+__global__ void k_laser_guard_pack(const double *__restrict__ ar, const double *__restrict__ ai, double *__restrict__ dst, int nr, int nz, int P)
+{
+    const int n = 4 * P * (nr + 2);
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+        const int i = t % (nr + 2), g = (t / (nr + 2)) & 1, pl = (t / (2 * (nr + 2))) % P, im = t / (2 * P * (nr + 2));
+        dst[t] = (im ? ai : ar)[LVI(pl, i, nz - g)];
+    }
+}
+extern "C" long qpg_laser_guard_size(qpg_laser l) { return l ? 4L * l->ctx->P * (l->ctx->nr + 2) : -1; }
+extern "C" int qpg_laser_set_handoff(qpg_laser l, const double *guard_in, unsigned *in_ready, unsigned *in_ack, double *guard_out, unsigned *out_ready, unsigned *out_ack)
+{
+    ARG_TRY(l, "null arg");
+    ARG_TRY((guard_in == nullptr) == (in_ready == nullptr) && (guard_in == nullptr) == (in_ack == nullptr), "upstream link: buffer, ready and ack words go together");
+    ARG_TRY((guard_out == nullptr) == (out_ready == nullptr) && (guard_out == nullptr) == (out_ack == nullptr), "downstream link: buffer, ready and ack words go together");
+    ARG_TRY(l->nz >= 2 || !guard_out, "a stage that hands its last two slices on needs a slab of at least two");
+    { int rc = laser_join(l); if (rc) return rc; }
+    l->g_in = guard_in; l->g_in_ready = in_ready; l->g_in_ack = in_ack;
+    l->g_out = guard_out; l->g_out_ready = out_ready; l->g_out_ack = out_ack;
+    l->g_seq = 0;
+    return 0;
+}
 static int laser_launch_advance(qpg_laser l, cudaStream_t st, unsigned *progress, unsigned base)
 {
     qpg_ctx c = l->ctx;
     const int nr = c->nr, nz = l->nz;
     const long n = (long)nr * nz;
+    const unsigned seq = (l->g_in || l->g_out) ? ++l->g_seq : 0;
+    const int ng = 4 * c->P * (nr + 2);
     k_laser_set_rhs<<<(int)((n + 255) / 256), 256, 0, st>>>(l->ar, l->ai, l->chi->f2, l->sr, l->si, nr, nz, c->M, l->k0, l->ds, c->dr, l->dz);
+    if (l->g_in) {   // the upstream stage's NEW last two slices replace the guards between the explicit and the implicit half
+        int rc = qpg_stream_wait((void *)st, l->g_in_ready, seq);
+        if (rc) return rc;
+        k_laser_guard_unpack<<<(ng + 255) / 256, 256, 0, st>>>(l->ar, l->ai, l->g_in, nr, nz, c->P);
+        count_launch(c);
+        if ((rc = qpg_stream_signal((void *)st, l->g_in_ack, seq))) return rc;
+    }
     const size_t smem = sizeof(double) * 4 * l->nthreads;
     if (l->pcrc && !getenv("QPG_LASER_GENERAL_SOLVE")) {
         const size_t with_coef = smem + sizeof(double) * l->pcrc_n;
@@ -564,6 +619,14 @@ static int laser_launch_advance(qpg_laser l, cudaStream_t st, unsigned *progress
     }
     count_launch(c, 2);
     CUDA_TRY(cudaGetLastError());
+    if (l->g_out) {   // pipe_send of the own NEW last two slices, into the downstream stage's wire buffer once it has consumed the previous record
+        int rc = seq > 1 ? qpg_stream_wait((void *)st, l->g_out_ack, seq - 1) : 0;
+        if (rc) return rc;
+        k_laser_guard_pack<<<(ng + 255) / 256, 256, 0, st>>>(l->ar, l->ai, l->g_out, nr, nz, c->P);
+        count_launch(c);
+        CUDA_TRY(cudaGetLastError());
+        if ((rc = qpg_stream_signal((void *)st, l->g_out_ready, seq))) return rc;
+    }
     return 0;
 }
 extern "C" int qpg_laser_advance(qpg_laser l)

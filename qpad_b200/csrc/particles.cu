@@ -52,10 +52,15 @@ __device__ __forceinline__ double fast_rcp(double y)
     return fma(r, e, r);
 #endif
 }
-__device__ __forceinline__ double fast_sqrt(double x)
+__device__ __forceinline__ double rsqrt_seed(double x)
 {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    return y;
+}
+__device__ __forceinline__ double fast_sqrt(double x)
+{
+    double y = rsqrt_seed(x);
     double g = x * y, h = 0.5 * y;
     double r = fma(-g, h, 0.5);
     g = fma(g, r, g); h = fma(h, r, h);
@@ -103,8 +108,7 @@ __device__ __forceinline__ Interp interp_info(double x1, double x2, double idr)
     Interp it;
 #ifdef QPG_EXP_CHEAP_INTERP   // bottleneck experiment only (results are wrong in the last bits -> different cells now and then): what would the particle
     // phases gain if cos / sin / r/dr came from stored planes instead of an IEEE square root + reciprocal per pass?
-    double rinv;
-    { const double r2 = fma(x1, x1, x2 * x2); asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(rinv) : "d"(r2)); }
+    const double rinv = rsqrt_seed(fma(x1, x1, x2 * x2));
     double r = (x1 * x1 + x2 * x2) * rinv;
 #else
     double r = __dsqrt_rn(__dadd_rn(__dmul_rn(x1, x1), __dmul_rn(x2, x2)));

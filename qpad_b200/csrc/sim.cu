@@ -20,7 +20,7 @@ struct qpg_sim_s {
     qpg_part3d beam;
     qpg_laser laser;      // sp_push_pgc: the one laser envelope of the run
     bool split_deposit;   // the pipeline's split beam push is in use: the raw beam deposit rides on it (qpg_sim_beam_push_interior / _edge, qpg_sim_beam_qdp_part)
-    unsigned *las_progress; unsigned las_base; bool las_overlap;   // overlapped envelope advance (qpg_sim_laser_advance): progress word of the running solve
+    unsigned *las_progress; unsigned las_base; bool las_overlap, las_overlap_req;   // overlapped envelope advance (qpg_sim_laser_advance): progress word of the running solve
     int cur_j;            // slice being enqueued (per-slice launch path)
     cudaGraph_t graph;
     cudaGraphExec_t gexec;
@@ -300,8 +300,10 @@ static int sweep_prepare(qpg_sim s)
     }
     const int nteam = (c->nr + ST_N - 1) / ST_N;
     if (per < 1 || nsm * per <= nteam) { qpg_set_error("sweep kernel: %d CTAs/SM x %d SMs cannot host a field team of %d", per, nsm, nteam); return QPG_ERR_UNSUPPORTED; }
-    s->las_overlap = s->prm.sp_push_pgc && s->sweep_ctas_req == 0 && !getenv("QPG_LASER_NO_OVERLAP");
-    if (s->las_overlap) s->sweep_ctas_req = -1;   // the envelope solve of the previous step (one CTA) runs beside the sweep: leave it an SM
+    // the envelope solve of the previous step (one CTA that needs an SM of its own) runs beside the sweep: with the default grid one SM is left
+    // to it; with a grid chosen by the caller (SM partitions of a pipeline) only if the caller vouches for the free SM (qpg_sim_set_laser_overlap)
+    s->las_overlap = s->prm.sp_push_pgc && (s->sweep_ctas_req <= 0 || s->las_overlap_req) && !getenv("QPG_LASER_NO_OVERLAP");
+    if (s->las_overlap && s->sweep_ctas_req == 0) s->sweep_ctas_req = -1;
     int g = s->sweep_ctas_req > 0 ? s->sweep_ctas_req : nsm * per + s->sweep_ctas_req;   // default: one CTA per SM
     if (g > nsm * per) g = nsm * per;
     if (g <= nteam) { qpg_set_error("sweep kernel: %d CTAs cannot host a field team of %d plus the update_bound CTA", g, nteam); return QPG_ERR_ARG; }
@@ -464,7 +466,7 @@ extern "C" int qpg_sim_create(qpg_sim *out, int device, void *cuda_stream, const
     rc = qpg_part3d_create(&s->beam, c, prm->beam_qbm, prm->dt, prm->beam_npmax < 32 ? 32 : prm->beam_npmax, prm->nz_total, prm->noff2, nzp);
     if (rc) return rc;
     if (prm->sp_push_pgc) {
-        if (prm->noff2 != 0 || nzp != prm->nz_total) { qpg_set_error("the laser path runs on one xi stage (noff2 = 0, nzp = nz_total)"); return QPG_ERR_UNSUPPORTED; }
+        // a slab of a xi-pipeline holds the envelope of its own slices + guards; the stages exchange them through qpg_laser_set_handoff
         rc = qpg_laser_create(&s->laser, c, nzp, prm->laser_k0, prm->dt, prm->laser_iter < 1 ? 1 : prm->laser_iter);
         if (rc) return rc;
     }
@@ -751,6 +753,13 @@ extern "C" int qpg_sim_laser_advance(qpg_sim s)
         s->las_progress = nullptr;
     }
     return qpg_laser_advance(s->laser);
+}
+extern "C" int qpg_sim_set_laser_overlap(qpg_sim s, int on)
+{
+    ARG_TRY(s, "null sim");
+    s->las_overlap_req = on != 0;
+    if (s->sweep_grid > 0) return qpg_sim_set_sweep_ctas(s, s->sweep_ctas_req);   // re-derive
+    return 0;
 }
 extern "C" int qpg_sim_set_sweep(qpg_sim s, int on)
 {

@@ -85,11 +85,13 @@ def split_beam(bx, bp, bq, nz, dxi, nstages, parts=None):
 
 def _make_sim(cfg, npp0, nbeam, stream, device, use_graph, noff2=0, nzp=None, beam_cap=None):
     cuda_stream = None if stream is None else stream.cuda_stream
+    las = cfg.get("laser")
+    pgc = {} if not las else dict(sp_push_pgc=1, laser_iter=las["iteration"], laser_k0=las["k0"], sp_ppc_r=cfg["ppc1"], beam_evol=0 if nbeam == 0 else 1)
     return capi.Sim(cfg["nr"], cfg["nz"], cfg["max_mode"], cfg["rmax"], cfg["zmin"], cfg["zmax"], cfg["dt"],
                     sp_qbm=-1.0, sp_npmax=2 * npp0, beam_qbm=-1.0, beam_npmax=beam_cap or (nbeam + 1024),
                     iter_max=cfg.get("iter_max", 1), iter_reltol=cfg.get("iter_reltol", 1e-3),
                     iter_abstol=cfg.get("iter_abstol", 1e-3), sort_freq=cfg.get("sort_freq", 0), use_graph=use_graph,
-                    noff2=noff2, nzp=nzp, device=device, stream=cuda_stream)
+                    noff2=noff2, nzp=nzp, device=device, stream=cuda_stream, **pgc)
 
 
 def kernel_microbench(sim, cfg, peak_gbs, n_big=4 * 1024 * 1024, reps=5):
@@ -490,23 +492,26 @@ class PeerLinks:
     block of flag words live in its own memory and are exported through CUDA IPC handles; the neighbours map them and
     write into them over NVLink.  Flag words (32 bytes apart, one writer each, counting messages):
 
-        ready_fwd, ready_beam, ack_back   written by rank-1      ready_back, ack_fwd, ack_beam   written by rank+1
+        ready_fwd, ready_beam, ack_back, ready_las   written by rank-1      ready_back, ack_fwd, ack_beam, ack_las   written by rank+1
+    (the *_las pair and the las_in buffer: the laser envelope's guard slices, capi.Laser.set_handoff)
     """
-    FLAGS = ("ready_fwd", "ready_beam", "ack_back", "ready_back", "ack_fwd", "ack_beam")
+    FLAGS = ("ready_fwd", "ready_beam", "ack_back", "ready_back", "ack_fwd", "ack_beam", "ready_las", "ack_las")
 
-    def __init__(self, dist, rank, world, n_fwd, n_back, n_beam):
+    def __init__(self, dist, rank, world, n_fwd, n_back, n_beam, n_las=0):
         self.dist, self.rank, self.world = dist, rank, world
         self.own = {"flags": capi.WireBuf(32 * len(self.FLAGS))}
         if rank > 0:
             self.own["fwd_in"] = capi.WireBuf(8 * n_fwd)
             self.own["beam_in"] = capi.WireBuf(8 * n_beam)
+            if n_las:
+                self.own["las_in"] = capi.WireBuf(8 * n_las)
         if rank < world - 1:
             self.own["back_in"] = capi.WireBuf(8 * n_back)
         mine = {k: b.export() for k, b in self.own.items()}
         every = [None] * world
         dist.all_gather_object(every, mine)
         self.up = {k: capi.WireBuf(handle=every[rank - 1][k]) for k in ("flags", "back_in")} if rank > 0 else {}
-        self.down = {k: capi.WireBuf(handle=every[rank + 1][k]) for k in ("flags", "fwd_in", "beam_in")} if rank < world - 1 else {}
+        self.down = {k: capi.WireBuf(handle=every[rank + 1][k]) for k in ("flags", "fwd_in", "beam_in") + (("las_in",) if n_las else ())} if rank < world - 1 else {}
         self.count = {}
 
     def next(self, link):
@@ -549,7 +554,9 @@ class LocalPipeline:
     for SMs, nothing blocks the host); "nccl" = torch.distributed send/recv of local wire buffers.
     """
 
-    def __init__(self, cfg, plasma, beam, nstages, device=0, beam_wire_cap=None, rank=0, world=1, dist=None, transport=None, partition=None):
+    def __init__(self, cfg, plasma, beam, nstages, device=0, beam_wire_cap=None, rank=0, world=1, dist=None, transport=None, partition=None, laser=None):
+        """laser = (a_r, a_i): the launched envelope of the whole box (capi.Laser layout) for a cfg with a "laser" block (robust_pgc plasma): every
+        stage holds its slab of the envelope and advances it after its sweep, the new last two slices travel to the next stage's guards"""
         import torch
         self.torch, self.cfg, self.S, self.plasma = torch, cfg, nstages, plasma
         self.rank, self.world, self.G, self.base = rank, world, world * nstages, rank * nstages
@@ -569,6 +576,13 @@ class LocalPipeline:
             raise ValueError(f"unknown pipeline transport {self.transport!r}")
         self.p2p = self.transport == "p2p"
         free = int(os.environ.get("QPG_PIPELINE_FREE_SMS", "4")) if self.transport == "nccl" else 0   # for the NCCL kernels beside the sweeps
+        self.pgc = bool(cfg.get("laser"))
+        if self.pgc:
+            if laser is None:
+                raise ValueError("a cfg with a laser block needs the launched envelope (laser=(a_r, a_i))")
+            if self.transport == "nccl":
+                raise ValueError("the envelope hand-off between GPUs uses the peer-memory transport (p2p)")
+            free += S                                 # one SM per stage for its envelope solve (one CTA that cannot share an SM with a sweep CTA)
         self.streams = [torch.cuda.Stream(device=device) for _ in range(S)]
         self.comm = torch.cuda.Stream(device=device) if self.transport == "nccl" else None
         self.sims = []
@@ -579,10 +593,14 @@ class LocalPipeline:
             sim = _make_sim(cfg, len(plasma[4]), len(mine[2]), self.streams[r], device, 1, noff2, nzp, beam_cap=len(beam[2]) + 1024)
             sim.init_species(*plasma)
             sim.beam.upload(*mine)
+            if self.pgc:
+                sim.laser.upload_slab(laser[0], laser[1], noff2)
             if G > 1:
                 if S > 1 or world > 1:
                     sim.set_sweep_ctas((nsm - free) // S)
-                sim.beam.set_wire_cap(beam_wire_cap if beam_wire_cap is not None else max(16384, len(beam[2]) // 64))
+                    if self.pgc:
+                        sim.set_laser_overlap(1)      # the SMs counted in `free` above
+                sim.beam.set_wire_cap(beam_wire_cap if beam_wire_cap is not None else min(len(beam[2]) + 1024, max(16384, len(beam[2]) // 64)))
             self.sims.append(sim)
         s0 = self.sims[0]
         nq, ncu, nbs = s0.field("beam_q").wire_count(), s0.field("cu").wire_count(), s0.field("b_spe").wire_count()
@@ -595,8 +613,9 @@ class LocalPipeline:
         self.back = [mk(nbk) for _ in range(S)]       # written by stage r, read by the previous stage
         self.beamb = [mk(nbm) for _ in range(S)]      # written by stage r, read by the next stage
         self.links = None
+        n_las = s0.laser.guard_size() if self.pgc else 0
         if self.p2p:
-            self.links = PeerLinks(dist, rank, world, nfw, nbk, nbm)
+            self.links = PeerLinks(dist, rank, world, nfw, nbk, nbm, n_las)
             self.fwd_in, self.beam_in, self.back_in = (self.links.own.get(k) for k in ("fwd_in", "beam_in", "back_in"))
         else:
             self.fwd_in = mk(nfw) if rank > 0 else None           # from the last stage of rank-1
@@ -611,6 +630,23 @@ class LocalPipeline:
         self.nback_out, self.nback_in = [0] * S, [0] * S
         self._zeroed = [False] * S
         self._deposited = [False] * S                 # the stage's tail has already scattered the next step's beam charge (split push / deposit)
+        if self.pgc:
+            # envelope links (sim_lasers_class.f03:216-218): stage r's advance waits for the new last two slices of stage r-1; buffer and ready
+            # word at the consumer, ack word at the producer; flag words [r] = ready of the link INTO stage r, [S + r] = ack of the link OUT of r
+            self.lasbuf = [mk(n_las) if r > 0 else None for r in range(S)]
+            self.lasflags = capi.WireBuf(32 * 2 * S)
+            fl = lambda k: self.lasflags.ptr + 32 * k
+            for r, sim in enumerate(self.sims):
+                link_in = link_out = (None, None, None)
+                if r > 0:
+                    link_in = (self.lasbuf[r].data_ptr(), fl(r), fl(S + r - 1))
+                elif rank > 0:
+                    link_in = (self.links.own["las_in"].ptr, self.links.flag("own", "ready_las"), self.links.flag("up", "ack_las"))
+                if r < S - 1:
+                    link_out = (self.lasbuf[r + 1].data_ptr(), fl(r + 1), fl(S + r))
+                elif rank < world - 1:
+                    link_out = (self.links.down["las_in"].ptr, self.links.flag("down", "ready_las"), self.links.flag("own", "ack_las"))
+                sim.laser.set_handoff(*link_in, *link_out)
 
     # events: recorded on the producer's stream, waited on by the consumer's stream; host order = a valid schedule
     def _rec(self, name, r):
@@ -768,6 +804,9 @@ class LocalPipeline:
             else:
                 self._rec("fwd_ready", r)
         self._mark(r, "packed")
+        if self.pgc:
+            s.laser_advance()                                           # simulation_class.f03:486 (+ the envelope hand-off, capi.Laser.set_handoff)
+            self._mark(r, "advanced")
 
     def _tail(self, r, renew=True):
         s, S = self.sims[r], self.S
@@ -884,6 +923,9 @@ class LocalPipeline:
         self.w = 0
 
     def sync(self):
+        if self.pgc:
+            for s in self.sims:
+                s.laser.sync()                        # overlapped envelope advances run on side streams
         for st in self.streams:
             st.synchronize()
         if self.comm is not None:
@@ -906,3 +948,5 @@ class LocalPipeline:
         self.lflags.close()
         for s in self.sims:
             s.close()
+        if self.pgc:
+            self.lasflags.close()

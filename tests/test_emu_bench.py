@@ -69,3 +69,17 @@ def test_single_stage_bench_function_runs(bench_mod, monkeypatch):
     line = _run(bench_mod.run_b200, args)
     assert all(k in line for k in KEYS), [k for k in KEYS if k not in line]
     assert line["gpu_launches"] > 0 and line["roofline"]["bound"] == "hbm"
+
+
+def test_c4_pipeline_bench_function_runs(bench_mod, monkeypatch):
+    """`bench.py --config C4` (run_c4_pipeline): the laser-wakefield deck on the xi-pipeline, envelope slabs with guard hand-off; the line carries
+    the comparison of the pipelined envelope and wake with a one-stage run of the same 3D steps"""
+    from qpad_b200 import decks
+    monkeypatch.setitem(decks.CONFIGS, "C4", dict(decks.CONFIGS["C4"], nr=64, nz=48, ppc1=2, ppc2=2, num_theta=8, iter_max=3))
+    args = types.SimpleNamespace(gpus=1, steps=2, warmup=1, config="C4", stages=2, no_cpu=True, ref_slices=8, no_sweep=False, no_graph=False, impl="b200", check=1)
+    c0 = emu.lib().emu_coop_launches()
+    line = _run(bench_mod.run_c4_pipeline, args)
+    assert all(k in line for k in KEYS), [k for k in KEYS if k not in line]
+    assert line["gpu_launches"] > 0 and emu.lib().emu_coop_launches() - c0 >= 2 * 3 and "2 stages per GPU" in line["config"]["parallelism"]
+    pc = line["parity_check"]
+    assert pc["ok"] and pc["envelope_rel_err"] < 1e-6 and pc["envelope_change_since_launch"] > 1e-3, pc

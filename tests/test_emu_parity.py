@@ -193,6 +193,13 @@ def test_local_pipeline_matches_oracle(pipeline_mods, S):
     assert emu.lib().emu_coop_launches() - c0 >= 4 * S
 
 
+@pytest.mark.parametrize("S", [2, 3])
+def test_lwfa_local_pipeline(pipeline_mods, S):
+    """the envelope across xi stages: slabs of the envelope per stage, guard hand-off between the explicit and the implicit half of the advance
+    (the GPU test's deck at half the resolution)"""
+    GL.test_lwfa_local_pipeline_matches_oracle(pipeline_mods, S, nr=64, nz=48, nsteps=3)
+
+
 def test_local_pipeline_with_unequal_slabs(pipeline_mods):
     G.test_local_pipeline_with_unequal_slabs(pipeline_mods)
 

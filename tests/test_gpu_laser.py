@@ -149,3 +149,55 @@ def test_lwfa_slice_loop_matches_oracle(mods, use_graph, sweep):
         assert max(np.max(np.abs(gar - oar)), np.max(np.abs(gai - oai))) < 1e-9 * np.max(np.abs(oar)), step
     upd, iters_done, slices = sim.stats()
     assert slices == 2 * nz and iters_done == orc.total_iters()
+
+
+@pytest.mark.parametrize("S", [2, 3])
+def test_lwfa_local_pipeline_matches_oracle(mods, S, nr=128, nz=96, nsteps=4):
+    """the envelope on the xi-pipeline (sim_lasers_class.f03:197-222, the C4 deck is `nodes [1,4]`): S stages on one GPU, each with its slab
+    of the envelope; a stage advances its slab after its sweep from the NEW last two slices of the upstream stage (guard hand-off through
+    flag-ordered wire buffers, capi.Laser.set_handoff).  Four 3D steps against the oracle's S-stage run -- which equals its one-stage run."""
+    capi, O = mods
+    from qpad_b200.pipeline import LocalPipeline
+    k0, iters = 20.0, 3
+    cfg = dict(nr=nr, nz=nz, max_mode=0, rmax=12.0, zmin=-3.0, zmax=6.0, dt=2.0, iter_max=6, iter_reltol=1e-3, iter_abstol=1e-6, ppc1=4, ppc2=2, num_theta=8,
+               laser=dict(k0=k0, iteration=iters))
+    keys = ("nr", "nz", "max_mode", "rmax", "zmin", "zmax", "dt", "iter_max", "iter_reltol", "iter_abstol")
+    olas = O.Laser(nr, nz, 0, cfg["rmax"], cfg["zmin"], cfg["zmax"], cfg["dt"], k0, iters)
+    olas.launch_gaussian(1.2, 2.5, 0.0, 0.0, 1.5, 0.0, 1.5)
+    plasma = O.inject_uniform(nr, cfg["rmax"] / nr, 4, 2, 8)
+    empty = (np.zeros((0, 3)), np.zeros((0, 3)), np.zeros(0))
+    orcs = []
+    for nst in (S, 1):
+        orc = O.Sim(ppc1=4, ppc2=2, num_theta=8, sp_push_type=5, laser_on=1, laser_iter=iters, laser_k0=k0, beam_evol=0, nstages=nst, **{k: cfg[k] for k in keys})
+        orc.set_laser(olas.ar, olas.ai)
+        orc.set_beam(*empty)
+        orcs.append(orc)
+    parts = [(0, 5 * nz // 12), (5 * nz // 12, nz - 5 * nz // 12)] if S == 2 else None      # unequal slabs too
+    lp = LocalPipeline(cfg, plasma, empty, S, partition=parts, laser=(olas.ar.copy(), olas.ai.copy()))
+    for _ in range(nsteps):
+        lp.wave()
+    lp.drain()
+    for orc in orcs:
+        for k in range(nsteps):
+            orc.step3d(k + 1)
+    oar, oai, ochi = orcs[0].laser()
+    o1r, o1i, _ = orcs[1].laser()
+    assert max(np.max(np.abs(oar - o1r)), np.max(np.abs(oai - o1i))) < 1e-12 * np.max(np.abs(o1r))      # the pipelined envelope IS the one-stage one
+    assert np.max(np.abs(oar - olas.ar)) > 1e-3 * np.max(np.abs(oar))                                    # and it has moved
+    upd, iters_done, slices = lp.stats()
+    assert slices == nsteps * nz and iters_done == orcs[0].total_iters()
+    for r, sim in enumerate(lp.sims):
+        off, nzp = sim.noff2, sim.nzp
+        gar, gai = sim.laser.download()
+        want_r, want_i = oar[:, off + 2:off + 2 + nzp], oai[:, off + 2:off + 2 + nzp]
+        assert max(np.max(np.abs(gar[:, 2:2 + nzp] - want_r)), np.max(np.abs(gai[:, 2:2 + nzp] - want_i))) < 1e-9 * np.max(np.abs(oar)), r
+        if r > 0:       # the lower guards hold the upstream stage's new last two slices
+            assert np.max(np.abs(gar[:, 0:2] - oar[:, off:off + 2])) < 1e-9 * np.max(np.abs(oar)), r
+        gchi = sim.laser.field(4).download_f2()[..., 0]
+        assert np.max(np.abs(gchi[:, :nzp] - ochi[:, off:off + nzp])) < 1e-9 * np.max(np.abs(ochi)), r
+        for name in ("psi", "e", "b"):
+            whole = orcs[1].field(name, 2)[:, :nz]                          # the one-stage oracle: any partition must reproduce it
+            got, want = sim.field(name).download_f2()[:, :nzp], whole[:, off:off + nzp]
+            assert np.max(np.abs(whole)) > 1e-3
+            assert np.max(np.abs(got - want)) < 1e-7 * np.max(np.abs(whole)), (r, name)
+    lp.close()
