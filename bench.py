@@ -641,7 +641,22 @@ def run_c4_pipeline(args):
     empty = (np.zeros((0, 3)), np.zeros((0, 3)), np.zeros(0))
     a_r, a_i = decks.laser_gaussian(cfg["nr"], cfg["nz"], cfg["rmax"], cfg["zmin"], cfg["zmax"], **las)
     S = args.stages
-    lp = LocalPipeline(cfg, plasma, empty, S, device=local, rank=rank, world=world, dist=dist if world > 1 else None, transport="p2p" if world > 1 else None, laser=(a_r, a_i))
+    mk = lambda pt: LocalPipeline(cfg, plasma, empty, S, device=local, rank=rank, world=world, dist=dist if world > 1 else None, transport="p2p" if world > 1 else None,
+                                  partition=pt, laser=(a_r, a_i))
+    parts, balance_log = None, []
+    if getattr(args, "balance", 0):
+        # slabs of equal measured cost (the pulse and the bubble behind it take more predictor-corrector passes than the quiet plasma ahead):
+        # closed loop on the running pipeline over the 3D step numbers the timed region will see (pipeline.measured_partition), all untimed
+        from qpad_b200.pipeline import measured_partition
+        for rnd in range(max(getattr(args, "rebalance", 0), 0)):
+            lp = mk(parts)
+            new_parts, stage_ms, spread = measured_partition(lp, cfg, None, nwaves=args.steps, nwarm=args.warmup)
+            balance_log.append({"round": rnd, "spread": round(spread, 4), "busy_ms_by_stage": [round(v, 3) for v in stage_ms], "slab_slices": [n for _, n in lp.parts]})
+            lp.drain(); lp.close()
+            if new_parts is None or [tuple(q) for q in new_parts] == [tuple(q) for q in lp.parts]:
+                break
+            parts = new_parts
+    lp = mk(parts)
     main = torch.cuda.current_stream()
 
     def sync_all():
@@ -654,8 +669,11 @@ def run_c4_pipeline(args):
     for _ in range(args.warmup):
         lp.wave()
     sync_all()
+    lp.trace_reset()
     u0, i0, s0 = lp.stats()
     l0 = lp.launch_count()
+    for sim in lp.sims:
+        sim.sweep_profile(reset=True)
     clk = ClockSampler(local); clk.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
@@ -670,9 +688,18 @@ def run_c4_pipeline(args):
     sync_all()
     ms = ev0.elapsed_time(ev1)
     clocks = clk.stop()
+    if os.environ.get("QPG_TRACE_EVENTS"):
+        for r_, rep in enumerate(lp.event_report()):
+            waits = sum(v for k, v in rep.items() if k in ("w_fwd>got_fwd", "pre>got_back"))
+            print(f"rank {rank} stage {r_} trace (ms): busy {sum(rep.values()) - waits:.2f} waits {waits:.2f} {rep}", file=sys.stderr, flush=True)
+        lp._ev_on = False
     u1, i1, s1 = lp.stats()
     upd, iters, slices = u1 - u0, i1 - i0, s1 - s0
     launches = lp.launch_count() - l0
+    profs = [sim.sweep_profile() for sim in lp.sims]
+    ph = {}
+    for key, cntk in (("A", "slices"), ("amj", "amj_phases"), ("C", "amj_phases"), ("push", "slices")):
+        ph[key] = [round(p["cyc_" + key] * (p["ns_total"] / max(p["cyc_total"], 1.0)) * 1e-3 / max(p[cntk], 1.0), 2) for p in profs]
     if world > 1:
         t = torch.tensor([ms, float(upd), float(launches), float(iters), float(slices)], dtype=torch.float64, device="cuda")
         tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -739,7 +766,9 @@ def run_c4_pipeline(args):
     roof = {"bound": "hbm", "kernel": f"k_sweep<0, PGC> x {S} concurrent per GPU (persistent, one xi slab each on {(148 - S) // S} SMs; laser slice images, pgc pushers and the susceptibility deposit inside) "
                                        f"+ {S} envelope-solve CTAs on SMs of their own; 65 536 particles per slice: barrier and field-program latency bound a stage, the other stages fill it",
             "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src, "bytes_per_update": bpu,
-            "us_per_slice_effective": ms * 1e3 / max(slices, 1), "slab_slices_by_stage": [n for _, n in lp.parts]}
+            "us_per_slice_effective": ms * 1e3 / max(slices, 1), "slab_slices_by_stage": [n for _, n in lp.parts], "slab_balance_rounds": balance_log,
+            "sweep_ms_per_step_by_stage_rank0": [round(p["ns_total"] * 1e-6 / args.steps, 3) for p in profs],
+            "us_per_phase_by_stage_rank0": {"A (laser slice images beside it)": ph["A"], "amjdeposit_pgc per pass": ph["amj"], "C per pass": ph["C"], "push_u_pgc+push_x+qdeposit+chi || D": ph["push"]}}
     if rank == 0:
         line = {"metric": METRIC, "value": upd / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
@@ -760,6 +789,134 @@ def run_c4_pipeline(args):
     lp.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_c5_pipeline(args):
+    """config 5 on the xi-pipeline (the deck is `nodes [1,2]`): --stages S slabs on one GPU, every stage with the neutral species attached to
+    its sim (per-slice launch path, CUDA-graph replay) on its own stream -- a C5 slice is a chain of ~16 small dependent kernels that leaves
+    the GPU almost empty, so S slabs in flight overlap nearly perfectly; the neutral's state (released electrons, ion buffer, rho_ion,
+    levels) travels forward with the plasma hand-off (neutral_class.f03:1025-1101).  A timed step = one wave = every stage runs its slab
+    once, in steady state; afterwards the pipeline is drained and the same number of 3D steps re-run on one stage (parity_check)."""
+    import torch
+    from qpad_b200 import capi
+    from qpad_b200.pipeline import LocalPipeline
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference for the CPU arm)")
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        raise SystemExit("bench.py --config C5: the neutral species' hand-off runs between the stages of one GPU")
+    cfg, beam = deck_config("C5")
+    neu = cfg["neutral"]
+    _pl, bm = make_inputs(cfg, beam)
+    empty = (np.zeros((0, 2)), np.zeros((0, 3)), np.zeros(0), np.zeros(0), np.zeros(0))
+    S = args.stages
+    lp = LocalPipeline(cfg, empty, bm, S)
+    main = torch.cuda.current_stream()
+    lp.fill()
+    for _ in range(args.warmup):
+        lp.wave()
+    lp.sync(); torch.cuda.synchronize()
+    u0, i0, s0 = lp.stats()
+    l0 = lp.launch_count()
+    clk = ClockSampler(0); clk.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record(main)
+    for st in lp.streams:
+        st.wait_event(ev0)
+    th0 = time.perf_counter()
+    for _ in range(args.steps):
+        lp.wave()
+    host_ms = 1e3 * (time.perf_counter() - th0) / args.steps
+    for st in lp.streams:
+        e = torch.cuda.Event(); e.record(st); main.wait_event(e)
+    ev1.record(main)
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    clocks = clk.stop()
+    u1, i1, s1 = lp.stats()
+    upd, iters, slices = u1 - u0, i1 - i0, s1 - s0
+    launches = slices * 13 + 3 * iters + 30 * S * args.steps if not args.no_graph else lp.launch_count() - l0    # graph replay: head 1, 3 per PC iteration, tail 12; ~30 hand-off / beam launches per stage and wave
+    # end to end: beam particles of stage 0's slab host -> device every wave, line-outs of every slab + counters back
+    ue0 = lp.stats()[0]
+    t0 = time.perf_counter()
+    d2h = 0
+    for _ in range(args.steps):
+        lp.wave()
+        d2h = 24 * S
+        for sim in lp.sims:
+            ez = sim.field("e").lineout(3, 0, 1); ps = sim.field("psi").lineout(1, 0, 1)
+            d2h += 8 * (len(ez) + len(ps))
+        lp.stats()
+    lp.sync(); torch.cuda.synchronize()
+    te = time.perf_counter() - t0
+    e2e = {"value": (lp.stats()[0] - ue0) / te, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(d2h),
+           "what": "per step (wave): every stage runs its slab with ionisation, E_z and psi on-axis line-outs of every slab + counters device->host each wave (the neutral deck has no "
+                   "per-step host input: the gas is renewed on the device, the beam lives on the device between its hand-offs)"}
+    check = None
+    if args.check:
+        lp.drain()
+        nsteps = lp.sims[0].stats()[2] // lp.sims[0].nzp
+        simkw = {k: cfg[k] for k in ("nr", "nz", "max_mode", "rmax", "zmin", "zmax", "dt", "iter_max", "iter_reltol", "iter_abstol")}
+        st1 = torch.cuda.Stream()
+        one = capi.Sim(sp_npmax=64, beam_npmax=len(bm[2]) + 1024, use_graph=1, stream=st1.cuda_stream, **simkw)
+        one.init_species(*empty)
+        one.attach_neutral(neu["element"], neu["ion_max"], (cfg["ppc1"], cfg["ppc2"]), cfg["num_theta"], neu.get("q", -1.0), neu.get("m", 1.0), neu.get("density", 1.0), cfg.get("n0", 1.0e17))
+        one.beam.upload(*bm)
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        for k in range(nsteps):
+            if k == nsteps - 1:
+                evs[0].record(st1)
+            one.step3d()
+        evs[1].record(st1)
+        st1.synchronize()
+        ez1, ps1 = one.field("e").lineout(3, 0, 1), one.field("psi").lineout(1, 0, 1)
+        err_ez = err_ps = 0.0
+        sums, nb = np.zeros(12), 0
+        for (off, n), sim in zip(lp.parts, lp.sims):
+            ez, ps = sim.field("e").lineout(3, 0, 1), sim.field("psi").lineout(1, 0, 1)
+            err_ez = max(err_ez, float(np.max(np.abs(ez[:n] - ez1[off:off + n]))))
+            err_ps = max(err_ps, float(np.max(np.abs(ps[:n] - ps1[off:off + n]))))
+            bx, bp, bq = sim.beam.download()
+            nb += len(bq)
+            if len(bq):
+                sums += beam_sums(bx, bp, bq)
+        err_ez /= float(np.max(np.abs(ez1))); err_ps /= float(np.max(np.abs(ps1)))
+        bx, bp, bq = one.beam.download()
+        m1, m2 = beam_moments_from_sums(beam_sums(bx, bp, bq)), beam_moments_from_sums(sums)
+        berr = 0.0
+        for ax in "xy":
+            c1, s1_, e1 = m1[ax]; c2, s2_, e2 = m2[ax]
+            berr = max(berr, abs(c1 - c2) / s1_, abs(s1_ - s2_) / s1_, abs(e1 - e2) / e1)
+        upd_one, upd_pipe = one.stats()[0], lp.stats()[0]
+        check = {"ok": bool(err_ez < 1e-6 and err_ps < 1e-6 and berr < 1e-6 and nb == len(bq)), "tol": 1e-6, "steps_compared": int(nsteps), "ez_lineout_rel_err": err_ez,
+                 "psi_lineout_rel_err": err_ps, "beam_moments_rel_err": berr, "beam_particles": nb, "beam_particles_single_stage": int(len(bq)),
+                 "updates_per_step_single_stage": upd_one / nsteps, "single_step_ms": evs[0].elapsed_time(evs[1]),
+                 "against": "one xi stage with the neutral attached (qpg_sim_attach_neutral, CUDA-graph replay: the path tests/test_gpu_neutral.py holds against the oracle)"}
+        one.close()
+    peak, peak_src = hbm_peak()
+    nit = iters / max(slices, 1)
+    bpu = 112.0 + 64.0 * nit
+    ach = upd * bpu / (ms * 1e-3) / 1e9
+    roof = {"bound": "hbm", "kernel": f"per-slice launch path x {S} concurrent slabs (k_amjdeposit / k_push / k_qdeposit on the released electrons + k_neutral_ionize / _scan / _add + field programs; "
+                                       "the ~16 dependent launches of a slice bound one slab, the slabs overlap)",
+            "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src, "bytes_per_update": bpu,
+            "us_per_slice_effective": ms * 1e3 / max(slices, 1), "slab_slices_by_stage": [n for _, n in lp.parts], "host_enqueue_ms_per_step": host_ms}
+    line = {"metric": METRIC, "value": upd / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic (tri-Gaussian beam per the ionization deck, lithium gas ionised on the device)",
+            "config": {"workload": f"C5: nr={cfg['nr']} nz={cfg['nz']} max_mode={cfg['max_mode']} neutral Li ion_max={neu['ion_max']} ppc {cfg['ppc1']}x{cfg['ppc2']} num_theta {cfg['num_theta']}, updates/step={upd / args.steps:.0f}",
+                       "parallelism": f"xi-pipeline: {S} stages on one GPU as concurrent streams (slice body replayed from a CUDA graph), neutral state in the forward hand-off, steady state",
+                       "l2": "field volumes ~100 MB + electron planes: larger than L2 late in the step", "pc_iters_per_slice": nit},
+            "clocks": clocks, "gpu_launches": int(launches), "roofline": roof, "e2e": e2e}
+    if check: line["parity_check"] = check
+    if not args.no_cpu:
+        try:
+            upd_c, wall_c, k_c, _t = cpu_parallel("C5", args.ref_slices or None)
+            line["cpu_baseline"] = {"value": upd_c / wall_c, "unit": UNIT, "cores": k_c, "kind": "port", "sample": cpu_sample_text("C5", k_c), "pc_iters_per_slice": LAST_CPU_NIT}
+        except Exception as exc:
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {exc}"}
+    print(json.dumps(line))
+    lp.close()
 
 
 def run_b200_local(args):
@@ -1112,7 +1269,9 @@ def main():
             args.stages = 4 if not (args.no_sweep or args.no_graph) else 1      # the deck's own `nodes [1,4]`
         (run_c4_pipeline if args.stages > 1 else run_c4)(args)
     elif args.config == "C5":
-        run_c5(args)
+        if args.stages == 0:
+            args.stages = 1 if args.no_graph else 4
+        (run_c5_pipeline if args.stages > 1 else run_c5)(args)
     else:
         if args.stages == 0:       # auto: as many stages as the field team (one CTA per 32 radial nodes) and the slab length allow, at most 4
             cfg, _ = deck_config(args.config)

@@ -378,20 +378,26 @@ int qpg_part2d_clear(qpg_part2d p);                        /* npp = 0 on the dev
  * qpg_sim_renew the neutral's renewal (:504-510), on the per-slice launch paths (CUDA-graph replay or plain stream; the persistent
  * sweep kernel and the cluster programs are switched off).  `electrons` / `ions` are created on qpg_sim_ctx(sim) with npmax >=
  * nr * num_theta * ppc1 * ppc2.  Extra fields of qpg_sim_field: "neut_q" (the electrons' charge volume), "rho_ion".
- * Passes against the oracle's ionisation loop in host emulation; NOT YET RUN ON A GPU (tests/test_gpu_neutral.py). */
+ * Parity with the oracle's ionisation loop on the GPU and in host emulation (tests/test_gpu_neutral.py, tests/test_emu_parity.py). */
 int qpg_sim_attach_neutral(qpg_sim sim, qpg_neutral n, qpg_part2d electrons, qpg_part2d ions);
+/* neut%psend / precv (neutral_class.f03:1025-1101) for a sim that is one slab of a xi-pipeline: after the slab's last slice the released
+ * electrons, the ions' position buffer, the rho_ion image and the ionisation levels go to the next stage in one wire record of
+ * qpg_sim_neutral_wire_count doubles (device buffer, possibly peer memory); the next stage unpacks it after its qpg_sim_renew and before
+ * its first slice.  Stream-ordered like qpg_part2d_pack / _unpack. */
+long qpg_sim_neutral_wire_count(qpg_sim sim);
+int qpg_sim_neutral_pack(qpg_sim sim, double *dev_buf);
+int qpg_sim_neutral_unpack(qpg_sim sim, const double *dev_buf);
 /* The sub-cycling variant inside the fast path (proj_subcyc/simulation_subcyc_class.f03:216-376; input-deck keys
  * expansion_fac_max, expansion_fac_clamped, dt_min of simulation_subcyc): per slice the largest expansion factor of the plasma (and
  * of an attached neutral's electrons) chooses n_subcyc, the slice body is repeated with dxi / n_subcyc, pushed particles are
  * clamped.  Plain per-slice launches with one host synchronisation per slice (the reference's allreduce); no graph, no sweep kernel.
- * qpg_sim_subcycles = sub-steps taken so far.  Passes against the oracle in host emulation; NOT YET RUN ON A GPU. */
+ * qpg_sim_subcycles = sub-steps taken so far.  Parity with the oracle on the GPU and in host emulation (tests/test_gpu_extras.py). */
 int qpg_sim_set_subcyc(qpg_sim sim, int on, double exp_fac_max, double exp_fac_clamped, double dt_min);
 long qpg_sim_subcycles(qpg_sim sim);
 
 /* ------------------------------------------------------------------------------------------ */
-/* The three groups below were written after round 1's GPU minutes were spent: they pass the oracle comparison on the CPU
- * through the host emulation of tests/emu (tests/test_emu_kernels.py) and await their first run on a GPU
- * (tests/test_gpu_extras.py, enabled with QPG_TEST_EXTRAS=1).
+/* The three groups below are held against the oracle on the GPU by tests/test_gpu_extras.py and on the CPU
+ * through the host emulation of tests/emu (tests/test_emu_kernels.py).
  *
  * Sub-cycling / clamp variant of the slice loop (proj_subcyc/):
  *   part2d_subcyc%get_exp_fac_max (part2d_subcyc_class.f03:28)  = qpg_part2d_exp_fac_max : max gamma / (gamma - p_z), 1 if empty;

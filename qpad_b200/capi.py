@@ -163,6 +163,9 @@ SIGNATURES = {
     "qpg_sim_set_laser_overlap": (_i, [_vp, _i]),
     "qpg_neutral_create": (_i, [C.POINTER(_vp), _vp, _i, _i, _i, _i, _i, _d, _d, _d, _d, _d]),
     "qpg_neutral_destroy": (_i, [_vp]),
+    "qpg_sim_neutral_wire_count": (_l, [_vp]),
+    "qpg_sim_neutral_pack": (_i, [_vp, _vp]),
+    "qpg_sim_neutral_unpack": (_i, [_vp, _vp]),
     "qpg_neutral_reset": (_i, [_vp]),
     "qpg_neutral_multi_max": (_i, [_vp]),
     "qpg_neutral_update": (_i, [_vp, _vp, _vp, _vp]),
@@ -657,6 +660,10 @@ class Sim:
         self.neutral = Neutral(self.ctx, element, ion_max, ppc, num_theta, q, m, density, n0, self.ctx.dxi)
         _chk(self.L.qpg_sim_attach_neutral(self.h, self.neutral.h, self.neutral.part.h, self.neutral.part_add.h))
         return self.neutral
+
+    def neutral_wire_count(self): return int(self.L.qpg_sim_neutral_wire_count(self.h))
+    def neutral_pack(self, ptr): _chk(self.L.qpg_sim_neutral_pack(self.h, ptr))
+    def neutral_unpack(self, ptr): _chk(self.L.qpg_sim_neutral_unpack(self.h, ptr))
 
     def close(self):
         if getattr(self, "h", None):

@@ -17,9 +17,8 @@
 //   part2d  : [0] = tnpp, then 6 datasets x1 x2 p1 p2 p3 q of `stride` entries each, the first tnpp valid
 //   part3d  : [0] = tnpp, then 7 datasets x1 x2 x3+z0 p1 p2 p3 q          (stride = int(npp_hi / dspl) is returned to the caller)
 //
-// STATUS: written at the end of round 1 when no GPU time was left; the kernels pass their checks on the CPU through the host
-// emulation of tests/emu (streams and events are no-ops there: the OVERLAP is untested); has NOT run on a GPU yet
-// (tests/test_gpu_extras.py, QPG_TEST_EXTRAS=1).  Nothing on the validated paths depends on this file.
+// STATUS: the re-layout kernels and the copy / event protocol pass on the GPU (tests/test_gpu_extras.py, run by default since round 2)
+// and, kernels only, in the host emulation of tests/emu (streams and events are no-ops there).
 #include "common.cuh"
 
 struct qpg_stage_s {

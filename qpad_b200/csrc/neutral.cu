@@ -7,9 +7,9 @@
 //   :839-878  renew            -> qpg_neutral_reset
 //   :880-930  qdeposit / ion_deposit, :932-1016 amjdeposit / push_u / push_x reuse the part2d kernels on the two particle sets.
 //
-// STATUS: written against oracle/qpad_oracle_neutral.c at the end of round 1 when no GPU time was left -- it compiles for
-// sm_100a but HAS NOT RUN ON A GPU YET; its parity tests (tests/test_gpu_neutral.py) are switched on with QPG_TEST_NEUTRAL=1.
-// Nothing on the validated paths (sweep kernel, pipeline, laser) depends on this file.
+// STATUS: parity with oracle/qpad_oracle_neutral.c on the GPU (tests/test_gpu_neutral.py: levels and released electrons bit-exact in
+// order and count, the ionisation slice loop of config 5 to 1e-7) and in the host emulation; the neutral's state also travels
+// along the xi-pipeline (qpg_sim_neutral_pack / _unpack below, neut%psend / precv :1018-1101).
 //
 // Level array on the device: lev[(i * n_theta + k) * nr + j], i = 0..multi_max-1 charge states 1..multi_max, i = multi_max
 // neutral residue, i = multi_max + 1 total discrete ion level (the layout of the oracle).
@@ -228,5 +228,46 @@ extern "C" int qpg_part2d_clear(qpg_part2d p)
     ARG_TRY(p, "null arg");
     CUDA_TRY(cudaMemsetAsync(p->d_npp, 0, 2 * sizeof(int), p->ctx->stream));
     p->npp_hi = 0;
+    return 0;
+}
+
+// ---- the neutral on a xi-pipeline: neut%psend / precv (neutral_class.f03:1025-1101) ----------------------------------------------
+// What travels to the next stage after a slab: the released electrons (`part`), the ions' position buffer of the last update (`part_add`),
+// the ion density image rho_ion (pipe_send 'forward' / pipe_recv 'replace') and the level array multi_ion.  One wire record at fixed
+// offsets: [electrons: qpg_part2d_wire_count][ions: qpg_part2d_wire_count][rho_ion f1: (nr+2) P][levels: (multi_max+2) num_theta nr];
+// the particle records copy their live prefix only.  The look-ahead deposits of the slab's first slice are redone by qpg_sim_run_slices.
+extern "C" long qpg_sim_neutral_wire_count(qpg_sim s)
+{
+    if (!s || !s->neut) return -1;
+    return qpg_part2d_wire_count(s->neut_e) + qpg_part2d_wire_count(s->neut_i) + (long)s->rho_ion->n1 + (long)(s->neut->multi_max + 2) * s->neut->n_theta * s->ctx->nr;
+}
+extern "C" int qpg_sim_neutral_pack(qpg_sim s, double *dev_buf)
+{
+    ARG_TRY(s && s->neut && dev_buf, "no neutral attached / null buffer");
+    int rc;
+    double *b = dev_buf;
+    if ((rc = qpg_part2d_pack(s->neut_e, b))) return rc;
+    b += qpg_part2d_wire_count(s->neut_e);
+    if ((rc = qpg_part2d_pack(s->neut_i, b))) return rc;
+    b += qpg_part2d_wire_count(s->neut_i);
+    cudaStream_t st = s->ctx->stream;
+    CUDA_TRY(cudaMemcpyAsync(b, s->rho_ion->f1, sizeof(double) * s->rho_ion->n1, cudaMemcpyDeviceToDevice, st));
+    b += s->rho_ion->n1;
+    CUDA_TRY(cudaMemcpyAsync(b, s->neut->lev, sizeof(double) * (size_t)(s->neut->multi_max + 2) * s->neut->n_theta * s->ctx->nr, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+extern "C" int qpg_sim_neutral_unpack(qpg_sim s, const double *dev_buf)
+{
+    ARG_TRY(s && s->neut && dev_buf, "no neutral attached / null buffer");
+    int rc;
+    const double *b = dev_buf;
+    if ((rc = qpg_part2d_unpack(s->neut_e, b))) return rc;
+    b += qpg_part2d_wire_count(s->neut_e);
+    if ((rc = qpg_part2d_unpack(s->neut_i, b))) return rc;
+    b += qpg_part2d_wire_count(s->neut_i);
+    cudaStream_t st = s->ctx->stream;
+    CUDA_TRY(cudaMemcpyAsync(s->rho_ion->f1, b, sizeof(double) * s->rho_ion->n1, cudaMemcpyDeviceToDevice, st));
+    b += s->rho_ion->n1;
+    CUDA_TRY(cudaMemcpyAsync(s->neut->lev, b, sizeof(double) * (size_t)(s->neut->multi_max + 2) * s->neut->n_theta * s->ctx->nr, cudaMemcpyDeviceToDevice, st));
     return 0;
 }

@@ -336,11 +336,12 @@ __device__ __forceinline__ void qdep_body(const PartView &pv, double *acc1, doub
 template <int M>
 __global__ void __launch_bounds__(PT_BLOCK) k_qdeposit(PartView pv, double *__restrict__ acc1, double idr)
 {
-    const int npp = *pv.d_npp;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
-    if ((i & ~31) >= npp) return;
+    const int npp = *pv.d_npp, lane = threadIdx.x & 31;
     extern __shared__ double dep_tiles[];
-    qdep_body<M>(pv, acc1, idr, npp, i, lane, dep_tiles + (threadIdx.x >> 5) * DepTile<M>::doubles);
+    // grid-stride over the tiles: the grid is capped (pt_grid) so that a set whose live count only the device knows (npp_hi = capacity:
+    // a neutral's electrons, a set just unpacked) does not pay for thousands of empty blocks; an exactly sized grid runs the loop once
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; (i & ~31) < npp; i += gridDim.x * blockDim.x)
+        qdep_body<M>(pv, acc1, idr, npp, i, lane, dep_tiles + (threadIdx.x >> 5) * DepTile<M>::doubles);
 }
 
 // particle planes of one warp-tile in registers, so a tile loop can fetch the next tile while it works on the current one
@@ -459,11 +460,10 @@ __global__ void __launch_bounds__(PT_BLOCK) k_amjdeposit(PartView pv, const doub
                                                         const int *__restrict__ skip_flag)
 {
     if (skip_flag && *skip_flag) return;
-    const int npp = *pv.d_npp;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
-    if ((i & ~31) >= npp) return;
+    const int npp = *pv.d_npp, lane = threadIdx.x & 31;
     extern __shared__ double dep_tiles[];
-    amj_body<M, STD>(pv, ef, bf, acc8, qbm, dt, idr, npp, i, lane, dep_tiles + (threadIdx.x >> 5) * DepTile<M>::doubles);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; (i & ~31) < npp; i += gridDim.x * blockDim.x)      // see k_qdeposit
+        amj_body<M, STD>(pv, ef, bf, acc8, qbm, dt, idr, npp, i, lane, dep_tiles + (threadIdx.x >> 5) * DepTile<M>::doubles);
 }
 
 // ---- push: push_u_robust :1879-1965, push_x :2221-2262, bound test of update_bound :2323-2348 --------------
@@ -580,10 +580,9 @@ __global__ void __launch_bounds__(PT_BLOCK) k_push(PartView pv, const double *__
                                                   double dt, double idr, double edge, int mode, unsigned *__restrict__ outmask,
                                                   int *__restrict__ d_nout)
 {
-    const int npp = *pv.d_npp;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
-    if ((i & ~31) >= npp) return;
-    push_body<M>(pv, ef, bf, qbm, dt, idr, edge, mode, outmask, d_nout, nullptr, npp, i, lane, nullptr);
+    const int npp = *pv.d_npp, lane = threadIdx.x & 31;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; (i & ~31) < npp; i += gridDim.x * blockDim.x)      // see k_qdeposit
+        push_body<M>(pv, ef, bf, qbm, dt, idr, edge, mode, outmask, d_nout, nullptr, npp, i, lane, nullptr);
 }
 
 // ---- ponderomotive-guiding-centre flavours (laser envelope a = a_r + i a_i given on the grid) ---------------------
@@ -1155,11 +1154,14 @@ template <int M> static void l_interp_psi(int grid, cudaStream_t st, PartView pv
 template <int M> static void l_push(int grid, cudaStream_t st, PartView pv, const double *ef, const double *bf, double qbm, double dt, double idr, double edge, int mode, unsigned *outmask, int *d_nout)
 { k_push<M><<<grid, PT_BLOCK, 0, st>>>(pv, ef, bf, qbm, dt, idr, edge, mode, outmask, d_nout); }
 
+// grid of the tile kernels above: one block per PT_BLOCK particles of the host's upper bound, at most PT_GRID_CAP (the kernels stride)
+#define PT_GRID_CAP (148 * 8)
+static inline int pt_grid(long npp_hi) { const long g = (npp_hi + PT_BLOCK - 1) / PT_BLOCK; return (int)(g < PT_GRID_CAP ? g : PT_GRID_CAP); }
 int part2d_launch_qdeposit(qpg_part2d p)
 {
     if (p->npp_hi == 0) return 0;
     qpg_ctx c = p->ctx;
-    const int grid = (int)((p->npp_hi + PT_BLOCK - 1) / PT_BLOCK);
+    const int grid = pt_grid(p->npp_hi);
     PartView pv = view_of(p);
     TprofScope tp(c, TP_K_QDEP);
     DISPATCH_M(c->M, l_qdeposit, grid, c->stream, pv, p->acc1, 1.0 / c->dr);
@@ -1171,7 +1173,7 @@ int part2d_launch_amjdeposit(qpg_part2d p, qpg_field ef, qpg_field bf, double dt
 {
     if (p->npp_hi == 0) return 0;
     qpg_ctx c = p->ctx;
-    const int grid = (int)((p->npp_hi + PT_BLOCK - 1) / PT_BLOCK);
+    const int grid = pt_grid(p->npp_hi);
     PartView pv = view_of(p);
     TprofScope tp(c, TP_K_AMJ);
     DISPATCH_M(c->M, l_amjdeposit, grid, c->stream, pv, ef->f1, bf->f1, p->acc8, p->qbm, dt, 1.0 / c->dr, skip_flag, std_flavour);
@@ -1183,7 +1185,7 @@ int part2d_launch_push(qpg_part2d p, qpg_field ef, qpg_field bf, double dt, int 
 {
     if (p->npp_hi == 0) return 0;
     qpg_ctx c = p->ctx;
-    const int grid = (int)((p->npp_hi + PT_BLOCK - 1) / PT_BLOCK);
+    const int grid = pt_grid(p->npp_hi);
     PartView pv = view_of(p);
     TprofScope tp(c, TP_K_PUSH);
     const double edge = (double)c->nr * c->dr;

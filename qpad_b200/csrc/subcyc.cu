@@ -9,10 +9,9 @@
 // times with dxi / n_subcyc: every other routine it calls already exists (qpg_part2d_qdeposit / amjdeposit / push_u / push_x
 // take dt as an argument); the host loop is qpad_b200/subcyc.py.
 //
-// STATUS: written at the end of round 1 when no GPU time was left.  Both kernels pass the oracle comparison on the CPU through
-// the host emulation of tests/emu (bit-exact: the expansion factor is one IEEE division, the clamp uses non-contracted IEEE
-// operations in the reference's order); they have NOT run on a GPU yet (tests/test_gpu_extras.py, QPG_TEST_EXTRAS=1).
-// Nothing on the validated paths depends on this file.
+// STATUS: both kernels are bit-exact against the oracle on the GPU (tests/test_gpu_extras.py, run by default since round 2) and in
+// the host emulation of tests/emu: the expansion factor is one IEEE division, the clamp uses non-contracted IEEE operations in
+// the reference's order.
 #include "common.cuh"
 
 // bit pattern order == numeric order for positive doubles (the expansion factor is > 0 because gamma > p_z)

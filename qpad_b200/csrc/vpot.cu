@@ -13,8 +13,7 @@
 // IEEE operations in the order of the oracle's Thomas solve, so the result is bit-identical to oracle/qpad_oracle.c
 // (orc_solve_vpotz / orc_solve_vpott); HYPRE's cyclic reduction of the reference agrees to O(cond * eps) like every other solve.
 //
-// STATUS: written at the end of round 1 when no GPU time was left; passes the oracle comparison on the CPU through the host
-// emulation of tests/emu; has NOT run on a GPU yet (tests/test_gpu_extras.py, QPG_TEST_EXTRAS=1).
+// STATUS: parity with the oracle on the GPU (tests/test_gpu_extras.py, run by default since round 2) and in the host emulation of tests/emu.
 #include "common.cuh"
 #include <cmath>
 

@@ -88,7 +88,7 @@ def _make_sim(cfg, npp0, nbeam, stream, device, use_graph, noff2=0, nzp=None, be
     las = cfg.get("laser")
     pgc = {} if not las else dict(sp_push_pgc=1, laser_iter=las["iteration"], laser_k0=las["k0"], sp_ppc_r=cfg["ppc1"], beam_evol=0 if nbeam == 0 else 1)
     return capi.Sim(cfg["nr"], cfg["nz"], cfg["max_mode"], cfg["rmax"], cfg["zmin"], cfg["zmax"], cfg["dt"],
-                    sp_qbm=-1.0, sp_npmax=2 * npp0, beam_qbm=-1.0, beam_npmax=beam_cap or (nbeam + 1024),
+                    sp_qbm=-1.0, sp_npmax=max(2 * npp0, 64), beam_qbm=-1.0, beam_npmax=beam_cap or (nbeam + 1024),
                     iter_max=cfg.get("iter_max", 1), iter_reltol=cfg.get("iter_reltol", 1e-3),
                     iter_abstol=cfg.get("iter_abstol", 1e-3), sort_freq=cfg.get("sort_freq", 0), use_graph=use_graph,
                     noff2=noff2, nzp=nzp, device=device, stream=cuda_stream, **pgc)
@@ -556,7 +556,10 @@ class LocalPipeline:
 
     def __init__(self, cfg, plasma, beam, nstages, device=0, beam_wire_cap=None, rank=0, world=1, dist=None, transport=None, partition=None, laser=None):
         """laser = (a_r, a_i): the launched envelope of the whole box (capi.Laser layout) for a cfg with a "laser" block (robust_pgc plasma): every
-        stage holds its slab of the envelope and advances it after its sweep, the new last two slices travel to the next stage's guards"""
+        stage holds its slab of the envelope and advances it after its sweep, the new last two slices travel to the next stage's guards.
+        A cfg with a "neutral" block (field ionisation, decks.CONFIGS["C5"]): every stage attaches the neutral species to its sim (per-slice
+        launch path instead of the sweep kernel: the stages overlap as concurrent streams of small kernels) and the neutral's state --
+        released electrons, ion buffer, rho_ion, levels -- travels forward with the plasma hand-off (neutral_class.f03:1025-1101)."""
         import torch
         self.torch, self.cfg, self.S, self.plasma = torch, cfg, nstages, plasma
         self.rank, self.world, self.G, self.base = rank, world, world * nstages, rank * nstages
@@ -583,6 +586,9 @@ class LocalPipeline:
             if self.transport == "nccl":
                 raise ValueError("the envelope hand-off between GPUs uses the peer-memory transport (p2p)")
             free += S                                 # one SM per stage for its envelope solve (one CTA that cannot share an SM with a sweep CTA)
+        self.neu = cfg.get("neutral")
+        if self.neu and world > 1:
+            raise ValueError("the neutral species' hand-off is implemented between the stages of one GPU")
         self.streams = [torch.cuda.Stream(device=device) for _ in range(S)]
         self.comm = torch.cuda.Stream(device=device) if self.transport == "nccl" else None
         self.sims = []
@@ -595,6 +601,10 @@ class LocalPipeline:
             sim.beam.upload(*mine)
             if self.pgc:
                 sim.laser.upload_slab(laser[0], laser[1], noff2)
+            if self.neu:
+                nu = self.neu
+                sim.attach_neutral(nu["element"], nu["ion_max"], (cfg["ppc1"], cfg["ppc2"]), cfg["num_theta"], nu.get("q", -1.0), nu.get("m", 1.0), nu.get("density", 1.0),
+                                   cfg.get("n0", 1.0e17))
             if G > 1:
                 if S > 1 or world > 1:
                     sim.set_sweep_ctas((nsm - free) // S)
@@ -612,6 +622,7 @@ class LocalPipeline:
         self.fwd = [mk(nfw) for _ in range(S)]        # written by stage r, read by the next stage
         self.back = [mk(nbk) for _ in range(S)]       # written by stage r, read by the previous stage
         self.beamb = [mk(nbm) for _ in range(S)]      # written by stage r, read by the next stage
+        self.neub = [mk(s0.neutral_wire_count()) if r < S - 1 else None for r in range(S)] if self.neu else None   # neut%psend record of stage r
         self.links = None
         n_las = s0.laser.guard_size() if self.pgc else 0
         if self.p2p:
@@ -746,6 +757,8 @@ class LocalPipeline:
             s.species.unpack(fin(3))
             s.field("cu").unpack(0, fin(1))
             s.field("b_spe").unpack(0, fin(2))
+            if self.neu:
+                s.neutral_unpack(self.neub[r - 1].data_ptr())           # neut%precv (after the renewal of the stage's tail)
             if p2p_up:
                 self._psignal(r, "up", "ack_fwd", n_in)
             elif not remote_up:
@@ -799,6 +812,8 @@ class LocalPipeline:
             s.field("cu").pack(0, fout(1))
             s.field("b_spe").pack(0, fout(2))
             s.species.pack(fout(3))
+            if self.neu:
+                s.neutral_pack(self.neub[r].data_ptr())                 # neut%psend
             if p2p_down:
                 self._psignal(r, "down", "ready_fwd", n_f)
             else:
@@ -950,3 +965,4 @@ class LocalPipeline:
             s.close()
         if self.pgc:
             self.lasflags.close()
+

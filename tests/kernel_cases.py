@@ -269,6 +269,42 @@ def sim_neutral_full_step(api, O, use_graph=0):
     sim.close()
 
 
+def neutral_local_pipeline(api, O, S, nwaves=3):
+    """config 5 in small on the xi-pipeline (the deck is `nodes [1,2]`): S stages on one GPU, every stage with the neutral attached to its
+    sim; the released electrons, the ions' buffer, rho_ion and the ionisation levels travel forward with the plasma hand-off (neut%psend /
+    precv, neutral_class.f03:1025-1101).  `nwaves` 3D steps against the oracle's S-stage run: the wake of a downstream slab is driven by
+    electrons released upstream, so its fields agree only if the neutral's state arrived."""
+    from qpad_b200 import decks
+    from qpad_b200.pipeline import LocalPipeline
+    cfg = dict(nr=64, nz=36, max_mode=1, rmax=6.0, zmin=0.0, zmax=8.0, dt=10.0, iter_max=3, iter_reltol=1e-3, iter_abstol=1e-3, ppc1=2, ppc2=2, num_theta=8, n0=1.0e17,
+               neutral=dict(element=3, ion_max=2))
+    keys = ("nr", "nz", "max_mode", "rmax", "zmin", "zmax", "dt", "iter_max", "iter_reltol", "iter_abstol")
+    bm = decks.beam_std(cfg["nr"], cfg["nz"], cfg["rmax"], cfg["zmin"], cfg["zmax"], **dict(decks.CONFIGS["C5"]["beam"]))
+    orc = O.Sim(sp_density=0.0, neut_on=1, neut_elem=3, neut_ion_max=2, neut_ppc1=2, neut_ppc2=2, neut_num_theta=8, ppc1=2, ppc2=2, num_theta=8, n0=1.0e17, nstages=S,
+                **{k: cfg[k] for k in keys})
+    orc.set_beam(*bm)
+    upd_o = sum(orc.step3d(k + 1) for k in range(nwaves))
+    empty = tuple(a[:0] for a in O.inject_uniform(cfg["nr"], cfg["rmax"] / cfg["nr"], 2, 2, 8))
+    lp = LocalPipeline(cfg, empty, bm, S)
+    for _ in range(nwaves):
+        lp.wave()
+    lp.drain()
+    upd, iters, slices = lp.stats()
+    assert slices == nwaves * cfg["nz"] and iters == orc.total_iters() and upd == upd_o > 100, (upd, upd_o, iters, orc.total_iters())
+    for r, sim in enumerate(lp.sims):
+        nzp = sim.nzp
+        for name in ("psi", "e", "b"):
+            got, want = sim.field(name).download_f2()[:, :nzp], orc.field(name, 2, stage=r)[:, :nzp]
+            assert np.max(np.abs(want)) > 1e-6, (r, name)
+            assert np.max(np.abs(got - want)) < 1e-7 * np.max(np.abs(orc.field(name, 2, stage=0))) + 1e-7 * np.max(np.abs(want)), (r, name)
+        gx, gp, gq = sim.beam.download()
+        ox, op, oq = orc.beam(stage=r)
+        assert len(gq) == len(oq) and np.array_equal(gq, oq)
+        # the renewal at the end of the last step has emptied the neutral on both sides
+        assert sim.neutral.part.npp() == 0 and len(orc.neutral(stage=r)[4]) == 0
+    lp.close()
+
+
 def sim_subcyc_loop(api, O, with_neutral=False):
     """the sub-cycling variant inside qpg_sim (qpg_sim_set_subcyc) against the oracle's sub-cycled loop: number of sub-steps,
     iterations, update counter, fields, particle momenta (clamped)"""

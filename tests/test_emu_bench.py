@@ -76,10 +76,22 @@ def test_c4_pipeline_bench_function_runs(bench_mod, monkeypatch):
     the comparison of the pipelined envelope and wake with a one-stage run of the same 3D steps"""
     from qpad_b200 import decks
     monkeypatch.setitem(decks.CONFIGS, "C4", dict(decks.CONFIGS["C4"], nr=64, nz=48, ppc1=2, ppc2=2, num_theta=8, iter_max=3))
-    args = types.SimpleNamespace(gpus=1, steps=2, warmup=1, config="C4", stages=2, no_cpu=True, ref_slices=8, no_sweep=False, no_graph=False, impl="b200", check=1)
+    args = types.SimpleNamespace(gpus=1, steps=2, warmup=1, config="C4", stages=2, no_cpu=True, ref_slices=8, no_sweep=False, no_graph=False, impl="b200", check=1, balance=1, rebalance=1)
     c0 = emu.lib().emu_coop_launches()
     line = _run(bench_mod.run_c4_pipeline, args)
     assert all(k in line for k in KEYS), [k for k in KEYS if k not in line]
     assert line["gpu_launches"] > 0 and emu.lib().emu_coop_launches() - c0 >= 2 * 3 and "2 stages per GPU" in line["config"]["parallelism"]
     pc = line["parity_check"]
     assert pc["ok"] and pc["envelope_rel_err"] < 1e-6 and pc["envelope_change_since_launch"] > 1e-3, pc
+
+
+def test_c5_pipeline_bench_function_runs(bench_mod, monkeypatch):
+    """`bench.py --config C5` (run_c5_pipeline): the ionisation deck on the xi-pipeline, the neutral's state in the forward hand-off"""
+    from qpad_b200 import decks
+    monkeypatch.setitem(decks.CONFIGS, "C5", dict(decks.CONFIGS["C5"], nr=64, nz=48, ppc1=2, ppc2=2, num_theta=8, iter_max=3, rmax=6.0, zmax=8.0))
+    args = types.SimpleNamespace(steps=1, warmup=1, no_graph=False, no_cpu=True, ref_slices=8, stages=2, check=1)
+    line = _run(bench_mod.run_c5_pipeline, args)
+    assert all(k in line for k in KEYS), [k for k in KEYS if k not in line]
+    assert line["value"] > 0 and "neutral Li" in line["config"]["workload"] and "2 stages" in line["config"]["parallelism"]
+    pc = line["parity_check"]
+    assert pc["ok"] and pc["beam_particles"] == pc["beam_particles_single_stage"] > 0, pc

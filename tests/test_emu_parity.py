@@ -200,6 +200,11 @@ def test_lwfa_local_pipeline(pipeline_mods, S):
     GL.test_lwfa_local_pipeline_matches_oracle(pipeline_mods, S, nr=64, nz=48, nsteps=3)
 
 
+def test_neutral_local_pipeline(pipeline_mods):
+    """the neutral species across xi stages (released electrons, ion buffer, rho_ion, levels in the forward hand-off)"""
+    K.neutral_local_pipeline(pipeline_mods[0], pipeline_mods[1], 2)
+
+
 def test_local_pipeline_with_unequal_slabs(pipeline_mods):
     G.test_local_pipeline_with_unequal_slabs(pipeline_mods)
 

@@ -52,3 +52,11 @@ def test_neutral_overflow_is_reported(mods):
     capi, O = mods
     import kernel_cases as K
     K.neutral_overflow(capi, O)
+
+
+@pytest.mark.parametrize("S", [2, 3])
+def test_neutral_local_pipeline_matches_oracle(mods, S):
+    """the neutral's state in the xi hand-offs (neutral_class.f03:1025-1101): S pipeline stages on one GPU against the oracle's S-stage run"""
+    capi, O = mods
+    import kernel_cases as K
+    K.neutral_local_pipeline(capi, O, S)
