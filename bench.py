@@ -1266,7 +1266,7 @@ def main():
         run_reference(args)
     elif args.config == "C4":
         if args.stages == 0:
-            args.stages = 4 if not (args.no_sweep or args.no_graph) else 1      # the deck's own `nodes [1,4]`
+XX
         (run_c4_pipeline if args.stages > 1 else run_c4)(args)
     elif args.config == "C5":
         if args.stages == 0:

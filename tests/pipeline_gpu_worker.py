@@ -28,8 +28,17 @@ def main():
     beam = dict(decks.CONFIGS["C1"]["beam"])
     bm = decks.beam_std(cfg["nr"], cfg["nz"], cfg["rmax"], cfg["zmin"], cfg["zmax"], **beam)
     plasma = decks.plasma_uniform(cfg["nr"], cfg["rmax"], cfg["ppc1"], cfg["ppc2"], cfg["num_theta"])
+    lwfa = len(sys.argv) > 5 and sys.argv[5] == "lwfa"          # laser-driven deck: the envelope slabs and their guard hand-off cross the ranks too
+    laser = None
+    if lwfa:
+        z = np.load(os.path.join(out, "lwfa_inputs.npz"))
+        cfg = dict(nr=int(z["nr"]), nz=int(z["nz"]), max_mode=0, rmax=12.0, zmin=-3.0, zmax=6.0, dt=2.0, iter_max=6, iter_reltol=1e-3, iter_abstol=1e-6, ppc1=4, ppc2=2,
+                   num_theta=8, laser=dict(k0=20.0, iteration=3))
+        plasma = tuple(z[k] for k in ("x", "p", "g", "psi", "q"))
+        bm = (np.zeros((0, 3)), np.zeros((0, 3)), np.zeros(0))
+        laser = (z["ar"], z["ai"])
     if stages > 0:
-        lp = LocalPipeline(cfg, plasma, bm, stages, device=local, rank=rank, world=world, dist=dist, transport=transport)
+        lp = LocalPipeline(cfg, plasma, bm, stages, device=local, rank=rank, world=world, dist=dist, transport=transport, laser=laser)
         lp.fill()
         for _ in range(nsteps):
             lp.wave()
@@ -37,8 +46,11 @@ def main():
         torch.cuda.synchronize()
         for r, s in enumerate(lp.sims):
             bx, bp, bq = s.beam.download()
+            extra = {}
+            if lwfa:
+                extra["ar"], extra["ai"] = s.laser.download()
             np.savez(os.path.join(out, f"stage{rank * stages + r}.npz"), psi=s.field("psi").download_f2(), e=s.field("e").download_f2(), bx=bx, bp=bp,
-                     bq=bq, stats=np.array(s.stats()), noff2=s.noff2, nzp=s.nzp)
+                     bq=bq, stats=np.array(s.stats()), noff2=s.noff2, nzp=s.nzp, **extra)
         barrier()
         lp.close()
         dist.destroy_process_group()

@@ -98,3 +98,41 @@ def test_peer_memory_links_between_processes_on_one_gpu(tmp_path, world, S):
     awaited by stream memory operations) between rank PROCESSES that share GPU 0 -- the same protocol as across GPUs,
     testable on a one-GPU box; against the oracle's (world*S)-stage run"""
     _local_pipeline_vs_oracle(tmp_path, world, S, "p2p", True, 29535 + world)
+
+
+@pytest.mark.parametrize("world,S", [(2, 1), (2, 2)])
+def test_lwfa_envelope_handoff_between_processes(tmp_path, world, S):
+    """the laser envelope's guard hand-off over the peer-memory links (capi.Laser.set_handoff with the wire buffer and the ready / ack words in
+    the neighbour PROCESS's memory, CUDA IPC): rank processes sharing GPU 0, S stages each, against the oracle's one-stage run"""
+    from oracle import oracle as O
+    nr, nz, k0, iters, nsteps = 128, 96, 20.0, 3, 3
+    G = world * S
+    total = G - 1 + nsteps
+    cfg = dict(nr=nr, nz=nz, max_mode=0, rmax=12.0, zmin=-3.0, zmax=6.0, dt=2.0, iter_max=6, iter_reltol=1e-3, iter_abstol=1e-6)
+    olas = O.Laser(nr, nz, 0, cfg["rmax"], cfg["zmin"], cfg["zmax"], cfg["dt"], k0, iters)
+    olas.launch_gaussian(1.2, 2.5, 0.0, 0.0, 1.5, 0.0, 1.5)
+    x, p, g, psi, q = O.inject_uniform(nr, cfg["rmax"] / nr, 4, 2, 8)
+    np.savez(tmp_path / "lwfa_inputs.npz", nr=nr, nz=nz, ar=olas.ar, ai=olas.ai, x=x, p=p, g=g, psi=psi, q=q)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(29560 + S), os.path.join(ROOT, "tests", "pipeline_gpu_worker.py"), str(tmp_path), str(nsteps), str(S), "p2p", "lwfa"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, QPG_TEST_ONE_DEVICE="1"))
+    assert r.returncode == 0, r.stderr[-3000:]
+    orc = O.Sim(ppc1=4, ppc2=2, num_theta=8, sp_push_type=5, laser_on=1, laser_iter=iters, laser_k0=k0, beam_evol=0, **cfg)
+    orc.set_laser(olas.ar, olas.ai)
+    orc.set_beam(np.zeros((0, 3)), np.zeros((0, 3)), np.zeros(0))
+    for k in range(total):
+        orc.step3d(k + 1)
+    oar, oai, _ = orc.laser()
+    assert np.max(np.abs(oar - olas.ar)) > 1e-3 * np.max(np.abs(oar))
+    covered = 0
+    for gidx in range(G):
+        d = np.load(tmp_path / f"stage{gidx}.npz")
+        off, nzp = int(d["noff2"]), int(d["nzp"])
+        covered += nzp
+        assert int(d["stats"][2]) == total * nzp
+        err = max(np.max(np.abs(d["ar"][:, 2:2 + nzp] - oar[:, off + 2:off + 2 + nzp])), np.max(np.abs(d["ai"][:, 2:2 + nzp] - oai[:, off + 2:off + 2 + nzp])))
+        assert err < 1e-9 * np.max(np.abs(oar)), (gidx, err)
+        for name in ("psi", "e"):
+            whole = orc.field(name, 2)[:, :nz]
+            assert np.max(np.abs(d[name][:, :nzp] - whole[:, off:off + nzp])) < 1e-7 * np.max(np.abs(whole)), (gidx, name)
+    assert covered == nz
