@@ -333,15 +333,22 @@ __device__ __forceinline__ void qdep_body(const PartView &pv, double *acc1, doub
     }
     warp_deposit_q_mma<M>(alpha, key, acc1, tile, lane);
 }
-template <int M>
+// STRIDE: grid-stride over the tiles under a capped grid (pt_grid) for a set whose live count only the device knows (npp_hi = capacity: a
+// neutral's electrons, a set just unpacked), which would otherwise pay for thousands of empty blocks.  A separate instantiation: the loop
+// costs registers (amjdeposit 64 -> 72, qdeposit 32 -> 48: one resident block less per SM), which the exactly sized launches must not pay.
+template <int M, bool STRIDE = false>
 __global__ void __launch_bounds__(PT_BLOCK) k_qdeposit(PartView pv, double *__restrict__ acc1, double idr)
 {
     const int npp = *pv.d_npp, lane = threadIdx.x & 31;
     extern __shared__ double dep_tiles[];
-    // grid-stride over the tiles: the grid is capped (pt_grid) so that a set whose live count only the device knows (npp_hi = capacity:
-    // a neutral's electrons, a set just unpacked) does not pay for thousands of empty blocks; an exactly sized grid runs the loop once
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; (i & ~31) < npp; i += gridDim.x * blockDim.x)
+    if constexpr (STRIDE) {
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; (i & ~31) < npp; i += gridDim.x * blockDim.x)
+            qdep_body<M>(pv, acc1, idr, npp, i, lane, dep_tiles + (threadIdx.x >> 5) * DepTile<M>::doubles);
+    } else {
+        const int i = blockIdx.x * blockDim.x + threadIdx.x;
+        if ((i & ~31) >= npp) return;
         qdep_body<M>(pv, acc1, idr, npp, i, lane, dep_tiles + (threadIdx.x >> 5) * DepTile<M>::doubles);
+    }
 }
 
 // particle planes of one warp-tile in registers, so a tile loop can fetch the next tile while it works on the current one
@@ -454,7 +461,7 @@ __device__ __forceinline__ void amj_body(const PartView &pv, const double *ef, c
 {
     amj_core<M, STD>(pv, part_load(pv, i, npp), ef, bf, acc8, qbm, dt, idr, npp, i, lane, tile);
 }
-template <int M, bool STD = false>
+template <int M, bool STD = false, bool STRIDE = false>
 __global__ void __launch_bounds__(PT_BLOCK) k_amjdeposit(PartView pv, const double *__restrict__ ef, const double *__restrict__ bf,
                                                         double *__restrict__ acc8, double qbm, double dt, double idr,
                                                         const int *__restrict__ skip_flag)
@@ -462,8 +469,14 @@ __global__ void __launch_bounds__(PT_BLOCK) k_amjdeposit(PartView pv, const doub
     if (skip_flag && *skip_flag) return;
     const int npp = *pv.d_npp, lane = threadIdx.x & 31;
     extern __shared__ double dep_tiles[];
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; (i & ~31) < npp; i += gridDim.x * blockDim.x)      // see k_qdeposit
+    if constexpr (STRIDE) {      // see k_qdeposit
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; (i & ~31) < npp; i += gridDim.x * blockDim.x)
+            amj_body<M, STD>(pv, ef, bf, acc8, qbm, dt, idr, npp, i, lane, dep_tiles + (threadIdx.x >> 5) * DepTile<M>::doubles);
+    } else {
+        const int i = blockIdx.x * blockDim.x + threadIdx.x;
+        if ((i & ~31) >= npp) return;
         amj_body<M, STD>(pv, ef, bf, acc8, qbm, dt, idr, npp, i, lane, dep_tiles + (threadIdx.x >> 5) * DepTile<M>::doubles);
+    }
 }
 
 // ---- push: push_u_robust :1879-1965, push_x :2221-2262, bound test of update_bound :2323-2348 --------------
@@ -575,14 +588,20 @@ __device__ __forceinline__ void push_body(const PartView &pv, const double *ef, 
     }
     push_core<M>(pv, pr, ef, bf, qbm, dt, idr, edge, mode, outmask, d_nout, acc1, npp, i, lane, tile);
 }
-template <int M>
+template <int M, bool STRIDE = false>
 __global__ void __launch_bounds__(PT_BLOCK) k_push(PartView pv, const double *__restrict__ ef, const double *__restrict__ bf, double qbm,
                                                   double dt, double idr, double edge, int mode, unsigned *__restrict__ outmask,
                                                   int *__restrict__ d_nout)
 {
     const int npp = *pv.d_npp, lane = threadIdx.x & 31;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; (i & ~31) < npp; i += gridDim.x * blockDim.x)      // see k_qdeposit
+    if constexpr (STRIDE) {      // see k_qdeposit
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; (i & ~31) < npp; i += gridDim.x * blockDim.x)
+            push_body<M>(pv, ef, bf, qbm, dt, idr, edge, mode, outmask, d_nout, nullptr, npp, i, lane, nullptr);
+    } else {
+        const int i = blockIdx.x * blockDim.x + threadIdx.x;
+        if ((i & ~31) >= npp) return;
         push_body<M>(pv, ef, bf, qbm, dt, idr, edge, mode, outmask, d_nout, nullptr, npp, i, lane, nullptr);
+    }
 }
 
 // ---- ponderomotive-guiding-centre flavours (laser envelope a = a_r + i a_i given on the grid) ---------------------
@@ -1131,8 +1150,13 @@ template <int M> static void l_qdeposit(int grid, cudaStream_t st, PartView pv, 
 {
     constexpr size_t smem = sizeof(double) * DepTile<M>::doubles * (PT_BLOCK / 32);
     static bool attr_set = false;
-    if (!attr_set) { cudaFuncSetAttribute(k_qdeposit<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
-    k_qdeposit<M><<<grid, PT_BLOCK, smem, st>>>(pv, acc1, idr);
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_qdeposit<M, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_qdeposit<M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_set = true;
+    }
+    if (grid < 0) k_qdeposit<M, true><<<-grid, PT_BLOCK, smem, st>>>(pv, acc1, idr);      // pt_grid: a negative grid = the capped, striding launch
+    else k_qdeposit<M, false><<<grid, PT_BLOCK, smem, st>>>(pv, acc1, idr);
 }
 // development aid (tools/occupancy_probe.py): QPG_DEV_EXTRA_SMEM=<bytes> pads the dynamic shared memory of the amjdeposit launches to
 // cap the resident blocks per SM
@@ -1142,17 +1166,25 @@ template <int M> static void l_amjdeposit(int grid, cudaStream_t st, PartView pv
     const size_t smem = sizeof(double) * DepTile<M>::doubles * (PT_BLOCK / 32) + dev_extra_smem();
     static bool attr_set = false;   // > 48 KB of dynamic shared memory needs the opt-in (M >= 3)
     if (!attr_set) {
-        cudaFuncSetAttribute(k_amjdeposit<M, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(k_amjdeposit<M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_amjdeposit<M, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_amjdeposit<M, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_amjdeposit<M, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_amjdeposit<M, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_set = true;
     }
-    if (std_flavour) k_amjdeposit<M, true><<<grid, PT_BLOCK, smem, st>>>(pv, ef, bf, acc8, qbm, dt, idr, skip);
-    else k_amjdeposit<M, false><<<grid, PT_BLOCK, smem, st>>>(pv, ef, bf, acc8, qbm, dt, idr, skip);
+    if (grid < 0) {
+        if (std_flavour) k_amjdeposit<M, true, true><<<-grid, PT_BLOCK, smem, st>>>(pv, ef, bf, acc8, qbm, dt, idr, skip);
+        else k_amjdeposit<M, false, true><<<-grid, PT_BLOCK, smem, st>>>(pv, ef, bf, acc8, qbm, dt, idr, skip);
+    } else if (std_flavour) k_amjdeposit<M, true, false><<<grid, PT_BLOCK, smem, st>>>(pv, ef, bf, acc8, qbm, dt, idr, skip);
+    else k_amjdeposit<M, false, false><<<grid, PT_BLOCK, smem, st>>>(pv, ef, bf, acc8, qbm, dt, idr, skip);
 }
 template <int M> static void l_interp_psi(int grid, cudaStream_t st, PartView pv, const double *psif, double idr)
 { k_interp_psi<M><<<grid, 128, 0, st>>>(pv, psif, idr); }
 template <int M> static void l_push(int grid, cudaStream_t st, PartView pv, const double *ef, const double *bf, double qbm, double dt, double idr, double edge, int mode, unsigned *outmask, int *d_nout)
-{ k_push<M><<<grid, PT_BLOCK, 0, st>>>(pv, ef, bf, qbm, dt, idr, edge, mode, outmask, d_nout); }
+{
+    if (grid < 0) k_push<M, true><<<-grid, PT_BLOCK, 0, st>>>(pv, ef, bf, qbm, dt, idr, edge, mode, outmask, d_nout);
+    else k_push<M, false><<<grid, PT_BLOCK, 0, st>>>(pv, ef, bf, qbm, dt, idr, edge, mode, outmask, d_nout);
+}
 
 // grid of the tile kernels above: one block per PT_BLOCK particles of the host's upper bound npp_hi.  When that bound is the capacity itself --
 // the state "live count known to the device only" after a hand-off or a neutral's update -- the grid is capped at PT_GRID_CAP blocks and the
@@ -1163,7 +1195,7 @@ template <int M> static void l_push(int grid, cudaStream_t st, PartView pv, cons
 static inline int pt_grid(qpg_part2d p)
 {
     const long g = (p->npp_hi + PT_BLOCK - 1) / PT_BLOCK;
-    return (int)((p->npp_hi >= p->npmax && g > PT_GRID_CAP) ? PT_GRID_CAP : g);
+    return (int)((p->npp_hi >= p->npmax && g > PT_GRID_CAP) ? -PT_GRID_CAP : g);      // negative: the launchers pick the striding instantiation
 }
 int part2d_launch_qdeposit(qpg_part2d p)
 {
