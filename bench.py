@@ -680,8 +680,10 @@ def run_c4_pipeline(args):
     ev0.record(main)
     for st in lp.streams:
         st.wait_event(ev0)
+    th0 = time.perf_counter()
     for _ in range(args.steps):
         lp.wave()
+    host_ms = 1e3 * (time.perf_counter() - th0) / args.steps      # host time to ENQUEUE a wave
     for st in lp.streams:     # the envelope advances on the side streams are not waited for: a stage's advance of step n overlaps its sweep of n+1
         e = torch.cuda.Event(); e.record(st); main.wait_event(e)
     ev1.record(main)
@@ -766,7 +768,7 @@ def run_c4_pipeline(args):
     roof = {"bound": "hbm", "kernel": f"k_sweep<0, PGC> x {S} concurrent per GPU (persistent, one xi slab each on {(148 - S) // S} SMs; laser slice images, pgc pushers and the susceptibility deposit inside) "
                                        f"+ {S} envelope-solve CTAs on SMs of their own; 65 536 particles per slice: barrier and field-program latency bound a stage, the other stages fill it",
             "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src, "bytes_per_update": bpu,
-            "us_per_slice_effective": ms * 1e3 / max(slices, 1), "slab_slices_by_stage": [n for _, n in lp.parts], "slab_balance_rounds": balance_log,
+            "us_per_slice_effective": ms * 1e3 / max(slices, 1), "slab_slices_by_stage": [n for _, n in lp.parts], "slab_balance_rounds": balance_log, "host_enqueue_ms_per_step_rank0": host_ms,
             "sweep_ms_per_step_by_stage_rank0": [round(p["ns_total"] * 1e-6 / args.steps, 3) for p in profs],
             "us_per_phase_by_stage_rank0": {"A (laser slice images beside it)": ph["A"], "amjdeposit_pgc per pass": ph["amj"], "C per pass": ph["C"], "push_u_pgc+push_x+qdeposit+chi || D": ph["push"]}}
     if rank == 0:
