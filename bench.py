@@ -805,7 +805,7 @@ def run_c5_pipeline(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference for the CPU arm)")
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:
-        raise SystemExit("bench.py --config C5: the neutral species' hand-off runs between the stages of one GPU")
+        raise SystemExit("bench.py --config C5 runs on one GPU (the neutral's hand-off crosses GPUs too -- LocalPipeline with the p2p transport -- but this bench function does not drive it)")
     cfg, beam = deck_config("C5")
     neu = cfg["neutral"]
     _pl, bm = make_inputs(cfg, beam)

@@ -497,7 +497,7 @@ class PeerLinks:
     """
     FLAGS = ("ready_fwd", "ready_beam", "ack_back", "ready_back", "ack_fwd", "ack_beam", "ready_las", "ack_las")
 
-    def __init__(self, dist, rank, world, n_fwd, n_back, n_beam, n_las=0):
+    def __init__(self, dist, rank, world, n_fwd, n_back, n_beam, n_las=0, n_neu=0):
         self.dist, self.rank, self.world = dist, rank, world
         self.own = {"flags": capi.WireBuf(32 * len(self.FLAGS))}
         if rank > 0:
@@ -505,13 +505,15 @@ class PeerLinks:
             self.own["beam_in"] = capi.WireBuf(8 * n_beam)
             if n_las:
                 self.own["las_in"] = capi.WireBuf(8 * n_las)
+            if n_neu:
+                self.own["neu_in"] = capi.WireBuf(8 * n_neu)          # the neutral's record travels with the forward message (same ready / ack words)
         if rank < world - 1:
             self.own["back_in"] = capi.WireBuf(8 * n_back)
         mine = {k: b.export() for k, b in self.own.items()}
         every = [None] * world
         dist.all_gather_object(every, mine)
         self.up = {k: capi.WireBuf(handle=every[rank - 1][k]) for k in ("flags", "back_in")} if rank > 0 else {}
-        self.down = {k: capi.WireBuf(handle=every[rank + 1][k]) for k in ("flags", "fwd_in", "beam_in") + (("las_in",) if n_las else ())} if rank < world - 1 else {}
+        self.down = {k: capi.WireBuf(handle=every[rank + 1][k]) for k in ("flags", "fwd_in", "beam_in") + (("las_in",) if n_las else ()) + (("neu_in",) if n_neu else ())} if rank < world - 1 else {}
         self.count = {}
 
     def next(self, link):
@@ -587,8 +589,8 @@ class LocalPipeline:
                 raise ValueError("the envelope hand-off between GPUs uses the peer-memory transport (p2p)")
             free += S                                 # one SM per stage for its envelope solve (one CTA that cannot share an SM with a sweep CTA)
         self.neu = cfg.get("neutral")
-        if self.neu and world > 1:
-            raise ValueError("the neutral species' hand-off is implemented between the stages of one GPU")
+        if self.neu and self.transport == "nccl":
+            raise ValueError("the neutral species' hand-off between GPUs uses the peer-memory transport (p2p)")
         self.streams = [torch.cuda.Stream(device=device) for _ in range(S)]
         self.comm = torch.cuda.Stream(device=device) if self.transport == "nccl" else None
         self.sims = []
@@ -626,7 +628,7 @@ class LocalPipeline:
         self.links = None
         n_las = s0.laser.guard_size() if self.pgc else 0
         if self.p2p:
-            self.links = PeerLinks(dist, rank, world, nfw, nbk, nbm, n_las)
+            self.links = PeerLinks(dist, rank, world, nfw, nbk, nbm, n_las, s0.neutral_wire_count() if self.neu else 0)
             self.fwd_in, self.beam_in, self.back_in = (self.links.own.get(k) for k in ("fwd_in", "beam_in", "back_in"))
         else:
             self.fwd_in = mk(nfw) if rank > 0 else None           # from the last stage of rank-1
@@ -757,8 +759,8 @@ class LocalPipeline:
             s.species.unpack(fin(3))
             s.field("cu").unpack(0, fin(1))
             s.field("b_spe").unpack(0, fin(2))
-            if self.neu:
-                s.neutral_unpack(self.neub[r - 1].data_ptr())           # neut%precv (after the renewal of the stage's tail)
+            if self.neu:                                                # neut%precv (after the renewal of the stage's tail)
+                s.neutral_unpack(self.links.own["neu_in"].ptr if p2p_up else self.neub[r - 1].data_ptr())
             if p2p_up:
                 self._psignal(r, "up", "ack_fwd", n_in)
             elif not remote_up:
@@ -812,8 +814,8 @@ class LocalPipeline:
             s.field("cu").pack(0, fout(1))
             s.field("b_spe").pack(0, fout(2))
             s.species.pack(fout(3))
-            if self.neu:
-                s.neutral_pack(self.neub[r].data_ptr())                 # neut%psend
+            if self.neu:                                                # neut%psend
+                s.neutral_pack(self.links.down["neu_in"].ptr if p2p_down else self.neub[r].data_ptr())
             if p2p_down:
                 self._psignal(r, "down", "ready_fwd", n_f)
             else:

@@ -37,6 +37,11 @@ def main():
         plasma = tuple(z[k] for k in ("x", "p", "g", "psi", "q"))
         bm = (np.zeros((0, 3)), np.zeros((0, 3)), np.zeros(0))
         laser = (z["ar"], z["ai"])
+    if len(sys.argv) > 5 and sys.argv[5] == "neutral":           # ionisation deck: the neutral's record crosses the ranks with the forward message
+        cfg = dict(nr=64, nz=36, max_mode=1, rmax=6.0, zmin=0.0, zmax=8.0, dt=10.0, iter_max=3, iter_reltol=1e-3, iter_abstol=1e-3, ppc1=2, ppc2=2, num_theta=8, n0=1.0e17,
+                   neutral=dict(element=3, ion_max=2))
+        bm = decks.beam_std(cfg["nr"], cfg["nz"], cfg["rmax"], cfg["zmin"], cfg["zmax"], **dict(decks.CONFIGS["C5"]["beam"]))
+        plasma = (np.zeros((0, 2)), np.zeros((0, 3)), np.zeros(0), np.zeros(0), np.zeros(0))
     if stages > 0:
         lp = LocalPipeline(cfg, plasma, bm, stages, device=local, rank=rank, world=world, dist=dist, transport=transport, laser=laser)
         lp.fill()

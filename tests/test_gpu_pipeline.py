@@ -136,3 +136,37 @@ def test_lwfa_envelope_handoff_between_processes(tmp_path, world, S):
             whole = orc.field(name, 2)[:, :nz]
             assert np.max(np.abs(d[name][:, :nzp] - whole[:, off:off + nzp])) < 1e-7 * np.max(np.abs(whole)), (gidx, name)
     assert covered == nz
+
+
+@pytest.mark.parametrize("world,S", [(2, 1), (2, 2)])
+def test_neutral_handoff_between_processes(tmp_path, world, S):
+    """neut%psend / precv (neutral_class.f03:1025-1101) over the peer-memory links: the record of the released electrons, the ion buffer, rho_ion
+    and the levels is written into the next rank PROCESS's memory (CUDA IPC) ahead of the forward message's ready word; ranks share GPU 0,
+    S stages each, against the oracle's (world*S)-stage run of the ionisation deck in small"""
+    from oracle import oracle as O
+    from qpad_b200 import decks
+    nsteps = 2
+    G = world * S
+    total = G - 1 + nsteps
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(29570 + S), os.path.join(ROOT, "tests", "pipeline_gpu_worker.py"), str(tmp_path), str(nsteps), str(S), "p2p", "neutral"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, QPG_TEST_ONE_DEVICE="1"))
+    assert r.returncode == 0, r.stderr[-3000:]
+    cfg = dict(nr=64, nz=36, max_mode=1, rmax=6.0, zmin=0.0, zmax=8.0, dt=10.0, iter_max=3, iter_reltol=1e-3, iter_abstol=1e-3)
+    bm = decks.beam_std(cfg["nr"], cfg["nz"], cfg["rmax"], cfg["zmin"], cfg["zmax"], **dict(decks.CONFIGS["C5"]["beam"]))
+    orc = O.Sim(sp_density=0.0, neut_on=1, neut_elem=3, neut_ion_max=2, neut_ppc1=2, neut_ppc2=2, neut_num_theta=8, ppc1=2, ppc2=2, num_theta=8, n0=1.0e17, nstages=G, **cfg)
+    orc.set_beam(*bm)
+    upd_o = sum(orc.step3d(k + 1) for k in range(total))
+    upd = 0
+    for g in range(G):
+        d = np.load(tmp_path / f"stage{g}.npz")
+        nzp = int(d["nzp"])
+        upd += int(d["stats"][0])
+        for name in ("psi", "e"):
+            got, want = d[name][:, :nzp], orc.field(name, 2, stage=g)[:, :nzp]
+            if g == G - 1:
+                assert np.max(np.abs(want)) > 1e-6                      # the wake of the electrons released upstream
+            assert np.max(np.abs(got - want)) < 1e-7 * np.max(np.abs(orc.field(name, 2, stage=G - 1))) + 1e-7 * np.max(np.abs(want)), (g, name)
+        ox, op, oq = orc.beam(stage=g)
+        assert len(d["bq"]) == len(oq) and np.array_equal(d["bq"], oq)
+    assert upd == upd_o > 100      # every electron released upstream was pushed downstream
