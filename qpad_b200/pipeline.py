@@ -643,6 +643,9 @@ class LocalPipeline:
         self.nback_out, self.nback_in = [0] * S, [0] * S
         self._zeroed = [False] * S
         self._deposited = [False] * S                 # the stage's tail has already scattered the next step's beam charge (split push / deposit)
+        # split beam push / deposit around the wait for the downstream stage: shortens the beam link of a multi-GPU
+        # pipeline; QPG_PIPELINE_SPLIT_BEAM=0 pushes and deposits in one piece behind the message (A/B)
+        self.split = bool(int(os.environ.get("QPG_PIPELINE_SPLIT_BEAM", "1")))
         if self.pgc:
             # envelope links (sim_lasers_class.f03:216-218): stage r's advance waits for the new last two slices of stage r-1; buffer and ready
             # word at the consumer, ack word at the producer; flag words [r] = ready of the link INTO stage r, [S + r] = ack of the link OUT of r
@@ -839,7 +842,8 @@ class LocalPipeline:
         self._zeroed[r] = True
         # the beam particles whose gather does not touch the guard slice nzp + 1 (all but those in the slab's last slice) are pushed
         # NOW, before the wait for the downstream stage's first slice: only the rest of the push stays on the backward link
-        s.beam_push_interior()
+        if self.split:
+            s.beam_push_interior()
         self._mark(r, "pre")                                            # tail>pre is work, pre>got_back the wait for the downstream stage
         # The backward message (e, b of the downstream stage's first slice) feeds the beam push only: a stage without beam particles
         # does not wait for it (qpg_stream_wait_unless_empty looks at the device-side particle count when the stream gets there), so
@@ -868,7 +872,10 @@ class LocalPipeline:
                 self._psignal(r, "down", "ack_back", n_b)
             elif not remote_down:
                 self._rec("back_free", r + 1)
-        s.beam_push_edge()
+        if self.split:
+            s.beam_push_edge()
+        else:
+            s.beam_push()
         self._mark(r, "pushed")
         if p2p_up:
             n_m = self.links.next("beam_in")
@@ -882,9 +889,10 @@ class LocalPipeline:
             self._wait("beam_ready", r - 1)
             s.beam.unpack(self.beamb[r - 1].data_ptr())
             self._rec("beam_free", r - 1)
-        if self.base + r > 0:
-            s.beam_qdp_part(3)                                          # the arrivals' charge (before pack_forward compacts the set)
-        self._deposited[r] = True                                       # the next head does not scatter the beam charge again
+        if self.split:
+            if self.base + r > 0:
+                s.beam_qdp_part(3)                                      # the arrivals' charge (before pack_forward compacts the set)
+            self._deposited[r] = True                                   # the next head does not scatter the beam charge again
         if p2p_down:
             n_m = self.links.next("beam_out")
             self._pwait(r, "ack_beam", n_m - 1)
