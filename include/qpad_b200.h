@@ -191,6 +191,16 @@ int qpg_part3d_pack_forward(qpg_part3d p, double *dev_buf);
 int qpg_part3d_unpack(qpg_part3d p, const double *dev_buf);
 long qpg_part3d_wire_cap(qpg_part3d p);
 int qpg_part3d_set_wire_cap(qpg_part3d p, long cap);
+/* Beam with spin (part3d%has_spin, init_part3d :117-135 with `amm` = anomalous magnetic moment; array s(3, npmax) :53-57): after
+ * qpg_part3d_enable_spin every qpg_part3d_push also advances the spin vectors (push_spin_part3d :578-638, called from push_boris :425-427
+ * BEFORE the new momentum is stored and from push_reduced :550-557 after it), qpg_part3d_update_bound moves them with the particles
+ * (:668-670) and the hand-off record has 10 instead of 7 reals (part3d_comm.f03:683-694): the buffer of qpg_part3d_pack_forward / _unpack
+ * holds qpg_part3d_wire_count doubles.  upload_spin / download_spin: s[npp][3] in the particle order of qpg_part3d_upload / _download. */
+int qpg_part3d_enable_spin(qpg_part3d p, double amm);
+int qpg_part3d_has_spin(qpg_part3d p);
+int qpg_part3d_upload_spin(qpg_part3d p, const double *s, long npp);
+int qpg_part3d_download_spin(qpg_part3d p, double *s, long *npp_out);
+long qpg_part3d_wire_count(qpg_part3d p);
 
 /* ------------------------------------------------------------------------------------------ */
 /* fused fast path: the whole `do j = 1, nstep2d` body of simulation_class.f03:342-469 on the  */

@@ -85,6 +85,8 @@ def lib(fast=False):
         "orc_qdeposit3d": (None, [_dp, _dp, l, d, d, i, i, i, i, _dp]),
         "orc_push3d": (None, [_dp, _dp, l, d, d, i, i, i, i, d, d, i, _dp, _dp]),
         "orc_update_bound3d": (l, [_dp, _dp, _dp, l, d, d]),
+        "orc_push3d_spin": (None, [_dp, _dp, _dp, d, l, d, d, i, i, i, i, d, d, i, _dp, _dp]),
+        "orc_update_bound3d_spin": (l, [_dp, _dp, _dp, _dp, l, d, d]),
         "orc_sim_create": (vp, [C.POINTER(Params)]),
         "orc_sim_destroy": (None, [vp]),
         "orc_sim_set_beam": (None, [vp, _dp, _dp, _dp, l]),

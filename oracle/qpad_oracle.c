@@ -1202,21 +1202,56 @@ static void interp_emf3d(const double *ef, const double *bf, const double *x3, d
 }
 
 /* beam/part3d_class.f03:477-576 push_reduced_part3d ; :358-475 push_boris_part3d (no spin) */
-void orc_push3d(double *x, double *p, long npp, double dr, double dz, int nr, int nzp, int noff2, int max_mode,
-                double qbm, double dt, int push_type, const double *ef, const double *bf)
+/* beam/part3d_class.f03:578-638 push_spin_part3d (T-BMT precession of the spin vector; a = anomalous magnetic moment): ep, bp as the
+ * callers hand them over (ep = E q dt/2m, bp = B q dt/(2m gamma)), p_old = momentum before the push, p_now = this%p AT THE TIME OF THE CALL --
+ * the Boris pusher calls it before it stores the new momentum (:425-427), so there the "time-centred velocity" is p_old / gamma; the
+ * reduced pusher calls it after both half advances (:551-556) */
+static void push_spin3d(double *sp, const double *ep, const double *bp, const double *p_old, const double *p_now, double gam, double a)
+{
+    double vtemp[3], omega[3], stemp[3];
+    for (int c = 0; c < 3; c++) vtemp[c] = 0.5 * (p_old[c] + p_now[c]) / gam;
+    double coef = a + 1.0 / gam;
+    for (int c = 0; c < 3; c++) omega[c] = coef * bp[c] * gam;
+    coef = -1.0 * (a + 1.0 / (1.0 + gam));
+    omega[0] = omega[0] + coef * (vtemp[1] * ep[2] - vtemp[2] * ep[1]);
+    omega[1] = omega[1] + coef * (vtemp[2] * ep[0] - vtemp[0] * ep[2]);
+    omega[2] = omega[2] + coef * (vtemp[0] * ep[1] - vtemp[1] * ep[0]);
+    const double vdotb = vtemp[0] * bp[0] + vtemp[1] * bp[1] + vtemp[2] * bp[2];
+    coef = -1.0 * (a * (gam * gam) / (1.0 + gam) * vdotb);
+    for (int c = 0; c < 3; c++) omega[c] = omega[c] + coef * vtemp[c];
+    stemp[0] = sp[0] + (sp[1] * omega[2] - sp[2] * omega[1]);
+    stemp[1] = sp[1] + (sp[2] * omega[0] - sp[0] * omega[2]);
+    stemp[2] = sp[2] + (sp[0] * omega[1] - sp[1] * omega[0]);
+    coef = 2.0 / (1.0 + omega[0] * omega[0] + omega[1] * omega[1] + omega[2] * omega[2]);
+    const double n0 = sp[0] + coef * (stemp[1] * omega[2] - stemp[2] * omega[1]);
+    const double n1 = sp[1] + coef * (stemp[2] * omega[0] - stemp[0] * omega[2]);
+    const double n2 = sp[2] + coef * (stemp[0] * omega[1] - stemp[1] * omega[0]);
+    sp[0] = n0; sp[1] = n1; sp[2] = n2;
+}
+
+/* beam/part3d_class.f03:358-475 push_boris, :477-576 push_reduced; spin != NULL: has_spin (init_part3d :117-121) with amm */
+void orc_push3d_spin(double *x, double *p, double *spin, double amm, long npp, double dr, double dz, int nr, int nzp, int noff2, int max_mode,
+                     double qbm, double dt, int push_type, const double *ef, const double *bf)
 {
     double qtmh = qbm * dt * 0.5;
     if (push_type == ORC_PUSH3_BORIS) qtmh = 0.5 * qbm * dt;
     for (long pp = 0; pp < npp; pp++) {
-        double ep[3], bp[3];
+        double ep[3], bp[3], p_old[3];
         double *xp = x + 3 * pp, *pq = p + 3 * pp;
         interp_emf3d(ef, bf, xp, dr, dz, nr, nzp, noff2, max_mode, ep, bp);
+        for (int c = 0; c < 3; c++) p_old[c] = pq[c];
         if (push_type == ORC_PUSH3_REDUCED) {
             double wp[3];
             for (int c = 0; c < 3; c++) { ep[c] = ep[c] * qtmh; bp[c] = bp[c] * qtmh; }
             wp[0] = ep[0] - bp[1]; wp[1] = ep[1] + bp[0]; wp[2] = ep[2];
             for (int c = 0; c < 3; c++) pq[c] = pq[c] + wp[c];
+            const double gam = sqrt(1.0 + pq[0] * pq[0] + pq[1] * pq[1] + pq[2] * pq[2]);   /* :536 */
             for (int c = 0; c < 3; c++) pq[c] = pq[c] + wp[c];
+            if (spin) {                                                                     /* :550-557 */
+                const double igam = 1.0 / gam;
+                for (int c = 0; c < 3; c++) bp[c] = bp[c] * igam;
+                push_spin3d(spin + 3 * pp, ep, bp, p_old, pq, gam, amm);
+            }
             double dt_gam = dt / sqrt(1.0 + pq[0] * pq[0] + pq[1] * pq[1] + pq[2] * pq[2]);
             xp[0] = xp[0] + pq[0] * dt_gam;
             xp[1] = xp[1] + pq[1] * dt_gam;
@@ -1228,6 +1263,7 @@ void orc_push3d(double *x, double *p, long npp, double dr, double dz, int nr, in
             double gam = sqrt(1.0 + u2);
             double gam_qtmh = qtmh / gam;
             for (int c = 0; c < 3; c++) bp[c] = bp[c] * gam_qtmh;
+            if (spin) push_spin3d(spin + 3 * pp, ep, bp, p_old, pq, gam, amm);              /* :425-427: this%p is still the old momentum */
             pq[0] = utmp[0] + utmp[1] * bp[2] - utmp[2] * bp[1];
             pq[1] = utmp[1] + utmp[2] * bp[0] - utmp[0] * bp[2];
             pq[2] = utmp[2] + utmp[0] * bp[1] - utmp[1] * bp[0];
@@ -1244,9 +1280,14 @@ void orc_push3d(double *x, double *p, long npp, double dr, double dz, int nr, in
         }
     }
 }
+void orc_push3d(double *x, double *p, long npp, double dr, double dz, int nr, int nzp, int noff2, int max_mode,
+                double qbm, double dt, int push_type, const double *ef, const double *bf)
+{
+    orc_push3d_spin(x, p, NULL, 0.0, npp, dr, dz, nr, nzp, noff2, max_mode, qbm, dt, push_type, ef, bf);
+}
 
 /* beam/part3d_class.f03:640-689 update_bound_part3d */
-long orc_update_bound3d(double *x, double *p, double *q, long npp, double edge_r, double edge_z)
+long orc_update_bound3d_spin(double *x, double *p, double *q, double *spin, long npp, double edge_r, double edge_z)
 {
     if (npp == 0) return 0;
     long i = 1;
@@ -1256,6 +1297,7 @@ long orc_update_bound3d(double *x, double *p, double *q, long npp, double edge_r
         if (pos_r >= edge_r || pos_z >= edge_z) {
             long l = npp - 1;
             for (int c = 0; c < 3; c++) { x[3 * (i - 1) + c] = x[3 * l + c]; p[3 * (i - 1) + c] = p[3 * l + c]; }
+            if (spin) for (int c = 0; c < 3; c++) spin[3 * (i - 1) + c] = spin[3 * l + c];   /* :668-670 */
             q[i - 1] = q[l];
             npp = npp - 1;
             continue;
@@ -1266,6 +1308,10 @@ long orc_update_bound3d(double *x, double *p, double *q, long npp, double edge_r
     double pos_z = x[3 * (npp - 1) + 2];
     if (pos_r >= edge_r || pos_z >= edge_z) npp = npp - 1;
     return npp;
+}
+long orc_update_bound3d(double *x, double *p, double *q, long npp, double edge_r, double edge_z)
+{
+    return orc_update_bound3d_spin(x, p, q, NULL, npp, edge_r, edge_z);
 }
 
 /* ========================================================================= */

@@ -92,6 +92,10 @@ void orc_qdeposit3d(const double *x, const double *q, long npp, double dr, doubl
 void orc_push3d(double *x, double *p, long npp, double dr, double dz, int nr, int nzp, int noff2, int max_mode,
                 double qbm, double dt, int push_type, const double *ef2, const double *bf2);
 long orc_update_bound3d(double *x, double *p, double *q, long npp, double edge_r, double edge_z);
+/* the same two with the spin vectors of a beam with has_spin (part3d_class.f03:53-63, :578-638 push_spin, :668-670); spin = NULL: none */
+void orc_push3d_spin(double *x, double *p, double *spin, double amm, long npp, double dr, double dz, int nr, int nzp, int noff2, int max_mode,
+                     double qbm, double dt, int push_type, const double *ef, const double *bf);
+long orc_update_bound3d_spin(double *x, double *p, double *q, double *spin, long npp, double edge_r, double edge_z);
 
 /* ---- whole simulation (simulation_class.f03:226-512), optionally as S xi-stages run in sequence ---- */
 typedef struct orc_sim orc_sim;

@@ -120,6 +120,11 @@ SIGNATURES = {
     "qpg_part3d_unpack": (_i, [_vp, _vp]),
     "qpg_part3d_wire_cap": (_l, [_vp]),
     "qpg_part3d_set_wire_cap": (_i, [_vp, _l]),
+    "qpg_part3d_enable_spin": (_i, [_vp, _d]),
+    "qpg_part3d_has_spin": (_i, [_vp]),
+    "qpg_part3d_upload_spin": (_i, [_vp, _vp, _l]),
+    "qpg_part3d_download_spin": (_i, [_vp, _vp, C.POINTER(_l)]),
+    "qpg_part3d_wire_count": (_l, [_vp]),
     "qpg_sim_create": (_i, [C.POINTER(_vp), _i, _vp, C.POINTER(SimParams)]),
     "qpg_sim_destroy": (_i, [_vp]),
     "qpg_sim_ctx": (_vp, [_vp]),
@@ -465,6 +470,25 @@ class Part3d:
             _chk(self.L.qpg_part3d_download(self.h, _ptr(x), _ptr(p), _ptr(q), C.byref(n)))
         return x, p, q
 
+    def enable_spin(self, amm):
+        """part3d%has_spin with the anomalous magnetic moment `amm` (init_part3d :117-135)"""
+        _chk(self.L.qpg_part3d_enable_spin(self.h, float(amm)))
+
+    def has_spin(self): return bool(self.L.qpg_part3d_has_spin(self.h))
+
+    def upload_spin(self, s):
+        s = _f64(s)
+        _chk(self.L.qpg_part3d_upload_spin(self.h, _ptr(s), len(s)))
+
+    def download_spin(self):
+        n = _l()
+        _chk(self.L.qpg_part3d_download_spin(self.h, None, C.byref(n)))
+        s = np.zeros((n.value, 3))
+        if n.value:
+            _chk(self.L.qpg_part3d_download_spin(self.h, _ptr(s), C.byref(n)))
+        return s
+
+    def wire_count(self): return int(self.L.qpg_part3d_wire_count(self.h))     # doubles of a hand-off message (7 or 10 reals per particle + the count)
     def qdeposit(self, q): _chk(self.L.qpg_part3d_qdeposit(self.h, q.h))
     def push(self, push_type, ef, bf): _chk(self.L.qpg_part3d_push(self.h, push_type, ef.h, bf.h))
     def push_interior(self, push_type, ef, bf): _chk(self.L.qpg_part3d_push_interior(self.h, push_type, ef.h, bf.h))

@@ -12,8 +12,31 @@
 struct Part3View {
     double *x1, *x2, *x3, *p1, *p2, *p3, *q;
     const int *d_npp;
+    double *s1, *s2, *s3;   // spin planes (null: no spin)
+    double amm;
 };
-static Part3View view3(qpg_part3d p) { Part3View v{p->x1, p->x2, p->x3, p->p1, p->p2, p->p3, p->q, p->d_npp}; return v; }
+static Part3View view3(qpg_part3d p) { Part3View v{p->x1, p->x2, p->x3, p->p1, p->p2, p->p3, p->q, p->d_npp, p->s1, p->s2, p->s3, p->amm}; return v; }
+static inline int nplanes3(qpg_part3d p) { return p->s1 ? 10 : 7; }   // planes the compaction moves = reals of a wire record (part3d_comm.f03:683-694)
+
+// beam/part3d_class.f03:578-638 push_spin_part3d: T-BMT precession of the spin vector s by the rotation vector omega (Boris-like rotation:
+// |s| is conserved); ep = E q dt / 2m, bp = B q dt / (2 m gamma), v = the "time-centred velocity" (p_old + p_now) / (2 gamma) with p_now =
+// this%p at the time of the call (see k_push3d)
+__device__ __forceinline__ void push_spin3(double &s0, double &s1, double &s2, const double *ep, const double *bp, const double *v, double gam, double a)
+{
+    double coef = a + 1.0 / gam;
+    double o0 = coef * bp[0] * gam, o1 = coef * bp[1] * gam, o2 = coef * bp[2] * gam;
+    coef = -1.0 * (a + 1.0 / (1.0 + gam));
+    o0 = o0 + coef * (v[1] * ep[2] - v[2] * ep[1]);
+    o1 = o1 + coef * (v[2] * ep[0] - v[0] * ep[2]);
+    o2 = o2 + coef * (v[0] * ep[1] - v[1] * ep[0]);
+    const double vdotb = v[0] * bp[0] + v[1] * bp[1] + v[2] * bp[2];
+    coef = -1.0 * (a * (gam * gam) / (1.0 + gam) * vdotb);
+    o0 = o0 + coef * v[0]; o1 = o1 + coef * v[1]; o2 = o2 + coef * v[2];
+    const double t0 = s0 + (s1 * o2 - s2 * o1), t1 = s1 + (s2 * o0 - s0 * o2), t2 = s2 + (s0 * o1 - s1 * o0);
+    coef = 2.0 / (1.0 + o0 * o0 + o1 * o1 + o2 * o2);
+    const double n0 = s0 + coef * (t1 * o2 - t2 * o1), n1 = s1 + coef * (t2 * o0 - t0 * o2), n2 = s2 + coef * (t0 * o1 - t1 * o0);
+    s0 = n0; s1 = n1; s2 = n2;
+}
 static double **plane_table3(qpg_part3d p) { return (double **)(p->lists + 2 * p->npmax); }
 
 // beam/part3d_class.f03:221-356 qdeposit_part3d (accumulation); f2 image layout [slice][node][P] (dim 1).
@@ -164,8 +187,18 @@ __global__ void __launch_bounds__(B3_BLOCK) k_push3d(Part3View pv, const double 
 #pragma unroll
         for (int c = 0; c < 3; c++) { ep[c] *= qtmh; bp[c] *= qtmh; }
         const double w0 = ep[0] - bp[1], w1 = ep[1] + bp[0], w2 = ep[2];
+        const double po[3] = {p1, p2, p3};
         p1 = p1 + w0; p2 = p2 + w1; p3 = p3 + w2;
+        const double gam = sqrt(1.0 + p1 * p1 + p2 * p2 + p3 * p3);            // :536, of the half-advanced momentum
         p1 = p1 + w0; p2 = p2 + w1; p3 = p3 + w2;
+        if (pv.s1) {                                                            // :550-557: after both half advances
+            const double igam = 1.0 / gam;
+            bp[0] *= igam; bp[1] *= igam; bp[2] *= igam;
+            const double v[3] = {0.5 * (po[0] + p1) / gam, 0.5 * (po[1] + p2) / gam, 0.5 * (po[2] + p3) / gam};
+            double s0 = pv.s1[i], s1 = pv.s2[i], s2 = pv.s3[i];
+            push_spin3(s0, s1, s2, ep, bp, v, gam, pv.amm);
+            pv.s1[i] = s0; pv.s2[i] = s1; pv.s3[i] = s2;
+        }
     } else {
 #pragma unroll
         for (int c = 0; c < 3; c++) ep[c] *= qtmh;
@@ -173,6 +206,12 @@ __global__ void __launch_bounds__(B3_BLOCK) k_push3d(Part3View pv, const double 
         const double gam = sqrt(1.0 + (ut0 * ut0 + ut1 * ut1 + ut2 * ut2));
         const double gq = qtmh / gam;
         bp[0] *= gq; bp[1] *= gq; bp[2] *= gq;
+        if (pv.s1) {                                                            // :425-427: this%p still holds the OLD momentum, so v = p_old / gamma
+            const double v[3] = {0.5 * (p1 + p1) / gam, 0.5 * (p2 + p2) / gam, 0.5 * (p3 + p3) / gam};
+            double s0 = pv.s1[i], s1 = pv.s2[i], s2 = pv.s3[i];
+            push_spin3(s0, s1, s2, ep, bp, v, gam, pv.amm);
+            pv.s1[i] = s0; pv.s2[i] = s1; pv.s3[i] = s2;
+        }
         p1 = ut0 + ut1 * bp[2] - ut2 * bp[1];
         p2 = ut1 + ut2 * bp[0] - ut0 * bp[2];
         p3 = ut2 + ut0 * bp[1] - ut1 * bp[0];
@@ -215,6 +254,7 @@ __global__ void __launch_bounds__(B3_BLOCK) k_flag3d(Part3View pv, double edge_r
 __global__ void __launch_bounds__(1024, 1) k_pack3d(Part3View pv, const int *d_nout, const unsigned *__restrict__ outmask, double *__restrict__ buf, long cap,
                                                    int *pv_overflow)
 {
+    const int nrec = pv.s1 ? 10 : 7;     // reals of a wire record: x, p, q (+ s)
     __shared__ int sm[40];
     const int n = *pv.d_npp, nout = *d_nout, tid = threadIdx.x, nt = blockDim.x;
     if (tid == 0) { buf[0] = (double)(nout > cap ? cap : nout); if (nout > cap) pv_overflow[0] = 1; }
@@ -248,8 +288,9 @@ __global__ void __launch_bounds__(1024, 1) k_pack3d(Part3View pv, const int *d_n
             const int b = __ffs(bits) - 1; bits &= bits - 1;
             const int i = lo + b;
             if (off < cap) {
-                double *r = buf + 1 + (size_t)7 * off;
+                double *r = buf + 1 + (size_t)nrec * off;
                 r[0] = pv.x1[i]; r[1] = pv.x2[i]; r[2] = pv.x3[i]; r[3] = pv.p1[i]; r[4] = pv.p2[i]; r[5] = pv.p3[i]; r[6] = pv.q[i];
+                if (pv.s1) { r[7] = pv.s1[i]; r[8] = pv.s2[i]; r[9] = pv.s3[i]; }
             }
             off++;
         }
@@ -261,9 +302,10 @@ __global__ void k_unpack3d(Part3View pv, int *d_npp_w, const double *__restrict_
     const int n0 = *pv.d_npp;
     const int room = (int)min((long)add, npmax - n0);
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < room; k += gridDim.x * blockDim.x) {
-        const double *r = buf + 1 + (size_t)7 * k;
+        const double *r = buf + 1 + (size_t)(pv.s1 ? 10 : 7) * k;
         const int i = n0 + k;
         pv.x1[i] = r[0]; pv.x2[i] = r[1]; pv.x3[i] = r[2]; pv.p1[i] = r[3]; pv.p2[i] = r[4]; pv.p3[i] = r[5]; pv.q[i] = r[6];
+        if (pv.s1) { pv.s1[i] = r[7]; pv.s2[i] = r[8]; pv.s3[i] = r[9]; }
     }
     // the count is bumped by a follow-up single-thread kernel so every block sees the old n0
 }
@@ -317,10 +359,58 @@ extern "C" int qpg_part3d_destroy(qpg_part3d p)
 {
     if (!p) return 0;
     cudaStreamSynchronize(p->ctx->stream);
-    cudaFree(p->slab); cudaFree(p->d_npp); cudaFree(p->outmask); cudaFree(p->pushed); cudaFree(p->lists);
+    cudaFree(p->slab); cudaFree(p->d_npp); cudaFree(p->outmask); cudaFree(p->pushed); cudaFree(p->lists); cudaFree(p->s1);
     delete p;
     return 0;
 }
+// has_spin (init_part3d :117-135 with `amm` present): three more planes that follow the particles through the push (push_spin :578), the
+// removal of particles (update_bound :668-670) and the hand-off to the next stage (10-real wire record, part3d_comm.f03:683-694)
+extern "C" int qpg_part3d_enable_spin(qpg_part3d p, double amm)
+{
+    ARG_TRY(p, "null arg");
+    if (!p->s1) {
+        CUDA_TRY(cudaMalloc(&p->s1, sizeof(double) * 3 * p->npmax));
+        CUDA_TRY(cudaMemsetAsync(p->s1, 0, sizeof(double) * 3 * p->npmax, p->ctx->stream));
+        p->s2 = p->s1 + p->npmax; p->s3 = p->s1 + 2 * p->npmax;
+        double *h[10] = {p->x1, p->x2, p->x3, p->p1, p->p2, p->p3, p->q, p->s1, p->s2, p->s3};
+        CUDA_TRY(cudaMemcpy(plane_table3(p), h, sizeof(h), cudaMemcpyHostToDevice));
+    }
+    p->amm = amm;
+    return 0;
+}
+extern "C" int qpg_part3d_has_spin(qpg_part3d p) { return p && p->s1 ? 1 : 0; }
+// s[npp][3] for the particles of the last qpg_part3d_upload (same order) / of the current set
+extern "C" int qpg_part3d_upload_spin(qpg_part3d p, const double *s, long npp)
+{
+    ARG_TRY(p && p->s1 && (npp == 0 || s), "no spin planes (qpg_part3d_enable_spin) / null arg");
+    ARG_TRY(npp >= 0 && npp <= p->npmax, "npp exceeds npmax");
+    std::vector<double> h((size_t)3 * npp);
+    for (long i = 0; i < npp; i++)
+        for (int c = 0; c < 3; c++) h[(size_t)c * npp + i] = s[3 * i + c];
+    double *dst[3] = {p->s1, p->s2, p->s3};
+    for (int a = 0; a < 3 && npp; a++) CUDA_TRY(cudaMemcpyAsync(dst[a], h.data() + (size_t)a * npp, sizeof(double) * npp, cudaMemcpyHostToDevice, p->ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(p->ctx->stream));
+    return 0;
+}
+extern "C" int qpg_part3d_download_spin(qpg_part3d p, double *s, long *npp_out)
+{
+    ARG_TRY(p && p->s1, "no spin planes (qpg_part3d_enable_spin)");
+    int n = 0;
+    cudaStream_t st = p->ctx->stream;
+    CUDA_TRY(cudaMemcpyAsync(&n, p->d_npp, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (npp_out) *npp_out = n;
+    if (!s || !n) return 0;
+    std::vector<double> h((size_t)3 * n);
+    double *src[3] = {p->s1, p->s2, p->s3};
+    for (int a = 0; a < 3; a++) CUDA_TRY(cudaMemcpyAsync(h.data() + (size_t)a * n, src[a], sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    for (long i = 0; i < n; i++)
+        for (int c = 0; c < 3; c++) s[3 * i + c] = h[(size_t)c * n + i];
+    return 0;
+}
+// doubles of a forward hand-off message: the count + wire_cap records of 7 (10 with spin) reals
+extern "C" long qpg_part3d_wire_count(qpg_part3d p) { return p ? 1 + (long)nplanes3(p) * qpg_part3d_wire_cap(p) : -1; }
 extern "C" int qpg_part3d_upload(qpg_part3d p, const double *x, const double *pm, const double *q, long npp)
 {
     ARG_TRY(p && (npp == 0 || (x && pm && q)), "null arg");
@@ -435,7 +525,7 @@ extern "C" int qpg_part3d_update_bound(qpg_part3d p)
     TprofScope tp(c, TP_PUSH3D);
     const int grid = b3_grid(p->npp_hi);
     k_flag3d<<<grid, B3_BLOCK, 0, c->stream>>>(view3(p), (double)c->nr * c->dr, (double)p->nz_total * c->dxi, 0, p->outmask, p->d_nout);
-    k_compact<<<1, 1024, 0, c->stream>>>(plane_table3(p), 7, p->d_npp, p->d_nout, p->outmask, p->lists, 0, nullptr);
+    k_compact<<<1, 1024, 0, c->stream>>>(plane_table3(p), nplanes3(p), p->d_npp, p->d_nout, p->outmask, p->lists, 0, nullptr);
     count_launch(c, 2);
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -462,7 +552,7 @@ extern "C" int qpg_part3d_pack_forward(qpg_part3d p, double *dev_buf)
     const int grid = b3_grid(p->npp_hi);
     if (grid > 0) k_flag3d<<<grid, B3_BLOCK, 0, c->stream>>>(view3(p), 0.0, (double)(p->noff2 + p->nzp) * c->dxi, 1, p->outmask, p->d_nout);
     k_pack3d<<<1, 1024, 0, c->stream>>>(view3(p), p->d_nout, p->outmask, dev_buf, cap, p->d_npp + 2);
-    k_compact<<<1, 1024, 0, c->stream>>>(plane_table3(p), 7, p->d_npp, p->d_nout, p->outmask, p->lists, 1, nullptr);
+    k_compact<<<1, 1024, 0, c->stream>>>(plane_table3(p), nplanes3(p), p->d_npp, p->d_nout, p->outmask, p->lists, 1, nullptr);
     count_launch(c, 3);
     CUDA_TRY(cudaGetLastError());
     return 0;

@@ -111,6 +111,8 @@ struct qpg_part3d_s {
     unsigned *pushed;        // bitmap of the particles the interior pass of the split push has advanced (qpg_part3d_push_interior / _edge)
     int *lists;
     long wire_cap;           // particles per forward hand-off message (0 = default 0.1 npmax, part3d_class.f03:127)
+    double *s1, *s2, *s3;    // spin vector planes, null unless qpg_part3d_enable_spin (has_spin, part3d_class.f03:53-63)
+    double amm;              // anomalous magnetic moment of the spin push
 };
 
 // ---- launch bookkeeping -------------------------------------------------------------------

@@ -76,11 +76,13 @@ def balanced_partition(cost, nstages, min_len=2):
     return [(a, b - a) for a, b in zip(edges[:-1], edges[1:])]
 
 
-def split_beam(bx, bp, bq, nz, dxi, nstages, parts=None):
-    """owner stage of each beam particle: the slab [noff2, noff2+nzp)*dxi that holds xi (part3d_comm.f03 goto_here)"""
+def split_beam(bx, bp, bq, nz, dxi, nstages, parts=None, spin=None):
+    """owner stage of each beam particle: the slab [noff2, noff2+nzp)*dxi that holds xi (part3d_comm.f03 goto_here); with `spin` (s[np][3])
+    every stage's tuple gets its particles' spin vectors as a fourth array"""
     edges = [noff * dxi for noff, _ in (parts or slab_partition(nz, nstages))][1:]
     owner = np.searchsorted(np.asarray(edges), bx[:, 2], side="right") if nstages > 1 else np.zeros(len(bq), int)
-    return [tuple(np.ascontiguousarray(a[owner == k]) for a in (bx, bp, bq)) for k in range(nstages)]
+    arrays = (bx, bp, bq) + ((spin,) if spin is not None else ())
+    return [tuple(np.ascontiguousarray(a[owner == k]) for a in arrays) for k in range(nstages)]
 
 
 def _make_sim(cfg, npp0, nbeam, stream, device, use_graph, noff2=0, nzp=None, beam_cap=None):
@@ -214,7 +216,7 @@ class PipelineStage:
         nb = s.field("b").wire_count()
         self.off_back = (0, nb)
         self.back_in, self.back_out = mk(nb + s.field("e").wire_count()), mk(nb + s.field("e").wire_count())
-        self.buf_beam, self.buf_beam_in = mk(7 * s.beam.wire_cap() + 1), mk(7 * s.beam.wire_cap() + 1)
+        self.buf_beam, self.buf_beam_in = mk(s.beam.wire_count()), mk(s.beam.wire_count())
         self.first, self.last = rank == 0, rank == world - 1
         self.stream = stream
         self.torch = torch
@@ -556,12 +558,14 @@ class LocalPipeline:
     for SMs, nothing blocks the host); "nccl" = torch.distributed send/recv of local wire buffers.
     """
 
-    def __init__(self, cfg, plasma, beam, nstages, device=0, beam_wire_cap=None, rank=0, world=1, dist=None, transport=None, partition=None, laser=None):
+    def __init__(self, cfg, plasma, beam, nstages, device=0, beam_wire_cap=None, rank=0, world=1, dist=None, transport=None, partition=None, laser=None,
+                 beam_spin=None):
         """laser = (a_r, a_i): the launched envelope of the whole box (capi.Laser layout) for a cfg with a "laser" block (robust_pgc plasma): every
         stage holds its slab of the envelope and advances it after its sweep, the new last two slices travel to the next stage's guards.
         A cfg with a "neutral" block (field ionisation, decks.CONFIGS["C5"]): every stage attaches the neutral species to its sim (per-slice
         launch path instead of the sweep kernel: the stages overlap as concurrent streams of small kernels) and the neutral's state --
-        released electrons, ion buffer, rho_ion, levels -- travels forward with the plasma hand-off (neutral_class.f03:1025-1101)."""
+        released electrons, ion buffer, rho_ion, levels -- travels forward with the plasma hand-off (neutral_class.f03:1025-1101).
+        beam_spin = (s[np][3], amm): the beam carries spin vectors (part3d%has_spin): pushed with the particles, 10-real hand-off records."""
         import torch
         self.torch, self.cfg, self.S, self.plasma = torch, cfg, nstages, plasma
         self.rank, self.world, self.G, self.base = rank, world, world * nstages, rank * nstages
@@ -574,7 +578,7 @@ class LocalPipeline:
         if len(parts) != G or parts[0][0] != 0 or sum(n for _, n in parts) != cfg["nz"] or any(a + n != b for (a, n), (b, _) in zip(parts[:-1], parts[1:])):
             raise ValueError(f"partition {parts} does not tile the {cfg['nz']} slices with {G} contiguous slabs")
         self.parts = parts
-        beams = split_beam(*beam, cfg["nz"], dxi, G, parts=parts)
+        beams = split_beam(*beam, cfg["nz"], dxi, G, parts=parts, spin=beam_spin[0] if beam_spin is not None else None)
         nsm = torch.cuda.get_device_properties(device).multi_processor_count
         self.transport = (transport or os.environ.get("QPG_PIPELINE_TRANSPORT", "p2p")) if world > 1 else None
         if self.transport not in (None, "p2p", "nccl"):
@@ -600,7 +604,11 @@ class LocalPipeline:
             mine = beams[self.base + r]
             sim = _make_sim(cfg, len(plasma[4]), len(mine[2]), self.streams[r], device, 1, noff2, nzp, beam_cap=len(beam[2]) + 1024)
             sim.init_species(*plasma)
-            sim.beam.upload(*mine)
+            if beam_spin is not None:
+                sim.beam.enable_spin(beam_spin[1])
+            sim.beam.upload(*mine[:3])
+            if beam_spin is not None:
+                sim.beam.upload_spin(mine[3])
             if self.pgc:
                 sim.laser.upload_slab(laser[0], laser[1], noff2)
             if self.neu:
@@ -620,7 +628,7 @@ class LocalPipeline:
         self.n_fwd = nq + ncu + nbs + min(s0.species.wire_count(), 1 + 8 * len(plasma[4]))   # live prefix of the plasma record
         nb = s0.field("b").wire_count()
         mk = lambda n: torch.zeros(n, dtype=torch.float64, device=dev)
-        nfw, nbk, nbm = nq + ncu + nbs + s0.species.wire_count(), nb + s0.field("e").wire_count(), 7 * s0.beam.wire_cap() + 1
+        nfw, nbk, nbm = nq + ncu + nbs + s0.species.wire_count(), nb + s0.field("e").wire_count(), s0.beam.wire_count()
         self.fwd = [mk(nfw) for _ in range(S)]        # written by stage r, read by the next stage
         self.back = [mk(nbk) for _ in range(S)]       # written by stage r, read by the previous stage
         self.beamb = [mk(nbm) for _ in range(S)]      # written by stage r, read by the next stage

@@ -305,6 +305,47 @@ def neutral_local_pipeline(api, O, S, nwaves=3):
     lp.close()
 
 
+def beam_spin_pipeline(api, S=2, nwaves=3):
+    """a beam with spin on the xi-pipeline: the spin vectors are pushed in every stage (split push included), follow their particles through
+    update_bound and cross the stage boundary in the 10-real hand-off record -- the pipelined run must reproduce the one-stage run of the same
+    3D steps particle by particle (particles are tagged through their charge; the one-stage spin push is held against the oracle in
+    tests/test_gpu_parity.py::test_beam_spin_push_matches_oracle)"""
+    from qpad_b200 import decks
+    from qpad_b200.pipeline import LocalPipeline
+    cfg = dict(nr=64, nz=32, max_mode=1, rmax=5.0, zmin=-5.0, zmax=5.0, dt=10.0, ppc1=2, ppc2=2, num_theta=8, iter_max=2, iter_reltol=1e-3, iter_abstol=1e-3)
+    beam = dict(decks.CONFIGS["C1"]["beam"], gamma=40.0)               # a slow beam: particles slip backwards in xi and cross the slab edges
+    bx, bp, bq = decks.beam_std(cfg["nr"], cfg["nz"], cfg["rmax"], cfg["zmin"], cfg["zmax"], **beam)
+    n = len(bq)
+    bq = bq * (1.0 + 1e-9 * np.arange(n))                              # unique tags
+    rng = np.random.default_rng(5)
+    spin = rng.standard_normal((n, 3)); spin /= np.linalg.norm(spin, axis=1)[:, None]
+    amm = 0.00115965
+    plasma = decks.plasma_uniform(cfg["nr"], cfg["rmax"], cfg["ppc1"], cfg["ppc2"], cfg["num_theta"])
+    keys = ("nr", "nz", "max_mode", "rmax", "zmin", "zmax", "dt", "iter_max", "iter_reltol", "iter_abstol")
+    one = api.Sim(sp_npmax=2 * len(plasma[4]), beam_npmax=n + 1024, **{k: cfg[k] for k in keys})
+    one.init_species(*plasma)
+    one.beam.enable_spin(amm)
+    one.beam.upload(bx, bp, bq); one.beam.upload_spin(spin)
+    for _ in range(nwaves):
+        one.step3d()
+    ox, op, oq = one.beam.download()
+    os_ = one.beam.download_spin()
+    lp = LocalPipeline(cfg, plasma, (bx, bp, bq), S, beam_spin=(spin, amm))
+    for _ in range(nwaves):
+        lp.wave()
+    lp.drain()
+    parts = [(sim.beam.download(), sim.beam.download_spin()) for sim in lp.sims]
+    gx = np.concatenate([b[0][0] for b in parts]); gq = np.concatenate([b[0][2] for b in parts]); gs = np.concatenate([b[1] for b in parts])
+    crossed = sum(len(b[0][2]) for b in parts[1:]) - int(np.sum(bx[:, 2] >= lp.parts[1][0] * (cfg["zmax"] - cfg["zmin"]) / cfg["nz"]))
+    assert len(gq) == len(oq) and crossed > 0, (len(gq), len(oq), crossed)          # particles did cross a stage boundary
+    io, ig = np.argsort(oq), np.argsort(gq)
+    assert np.array_equal(oq[io], gq[ig])
+    assert np.max(np.abs(gx[ig] - ox[io])) < 1e-9 * np.max(np.abs(ox))
+    assert np.max(np.abs(gs[ig] - os_[io])) < 1e-9 and np.max(np.abs(os_[io] - spin[np.argsort(bq)][np.isin(np.sort(bq), oq)])) > 1e-6
+    assert np.max(np.abs(np.linalg.norm(gs, axis=1) - 1.0)) < 1e-11
+    lp.close(); one.close()
+
+
 def sim_subcyc_loop(api, O, with_neutral=False):
     """the sub-cycling variant inside qpg_sim (qpg_sim_set_subcyc) against the oracle's sub-cycled loop: number of sub-steps,
     iterations, update counter, fields, particle momenta (clamped)"""

@@ -35,7 +35,7 @@ def _run(fn, args):
 
 def test_default_bench_function_runs(bench_mod, monkeypatch):
     from qpad_b200 import decks
-    monkeypatch.setitem(decks.CONFIGS, "C2", dict(decks.CONFIGS["C2"], nr=64, nz=128, ppc1=2, ppc2=2, num_theta=8, iter_max=3))
+    monkeypatch.setitem(decks.CONFIGS, "C2", dict(decks.CONFIGS["C2"], nr=64, nz=64, ppc1=2, ppc2=2, num_theta=8, iter_max=3))
     args = types.SimpleNamespace(gpus=1, steps=2, warmup=1, config="C2", balance=1, transport=None, stages=4, no_cpu=True, no_micro=True, roof_slices=16,
                                  ref_slices=8, no_sweep=False, no_graph=False, legacy_pipeline=False, impl="b200", check=1, fill_steps=[3], rebalance=1)
     c0 = emu.lib().emu_coop_launches()

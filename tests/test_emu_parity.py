@@ -57,6 +57,10 @@ def test_sort_bit_exact(mods, nr, ppc, nth): G.test_sort_bit_exact(mods, nr, ppc
 def test_beam_kernels_match_oracle(mods, M, push): G.test_beam_kernels_match_oracle(mods, M, push)
 
 
+@pytest.mark.parametrize("M,push", [(1, 1), (2, 2)])
+def test_beam_spin_push_matches_oracle(mods, M, push): G.test_beam_spin_push_matches_oracle(mods, M, push)
+
+
 @pytest.mark.parametrize("nr,nz,M", [(64, 12, 0), (50, 9, 2)])
 def test_laser_slice_images_match_oracle(mods, nr, nz, M): GL.test_laser_slice_images_match_oracle(mods, nr, nz, M)
 
@@ -159,7 +163,7 @@ def test_sweep_sorted_loop(mods): G.test_sorted_loop_still_matches(mods, "sweep"
 def test_sweep_lwfa_slice_loop(mods):
     """config 4 in small with the laser hooks INSIDE the sweep kernel (k_sweep<M, PGC = true>: slice images by a helper CTA, pgc pushers,
     susceptibility deposit fused into the push phase), two 3D steps with the envelope advance in between"""
-    GL.test_lwfa_slice_loop_matches_oracle(mods, 0, 1)
+    GL.test_lwfa_slice_loop_matches_oracle(mods, 0, 1, nr=64, nz=64)
 
 
 @pytest.mark.parametrize("nr,M,ppc,nth", [(250, 1, 2, 8), (65, 1, 2, 8), (33, 2, 2, 8), (24, 1, 2, 8)])
@@ -198,6 +202,10 @@ def test_lwfa_local_pipeline(pipeline_mods, S):
     """the envelope across xi stages: slabs of the envelope per stage, guard hand-off between the explicit and the implicit half of the advance
     (the GPU test's deck at half the resolution)"""
     GL.test_lwfa_local_pipeline_matches_oracle(pipeline_mods, S, nr=64, nz=48, nsteps=3)
+
+
+def test_beam_spin_on_the_pipeline(pipeline_mods):
+    K.beam_spin_pipeline(pipeline_mods[0])
 
 
 def test_neutral_local_pipeline(pipeline_mods):

@@ -117,11 +117,10 @@ def test_envelope_advance_matches_oracle(mods, nr, nz, M, iters):
 
 
 @pytest.mark.parametrize("use_graph,sweep", [(0, 0), (1, 0), (0, 1)])
-def test_lwfa_slice_loop_matches_oracle(mods, use_graph, sweep):
+def test_lwfa_slice_loop_matches_oracle(mods, use_graph, sweep, nr=128, nz=96):
     """config 4 in small: robust_pgc plasma driven by a Gaussian laser pulse, envelope advanced with the deposited
     susceptibility, two 3D steps (simulation_class.f03:294-512 with nlasers = 1, nbeams = 0)"""
     capi, O = mods
-    nr, nz = 128, 96
     cfg = dict(nr=nr, nz=nz, max_mode=0, rmax=12.0, zmin=-3.0, zmax=6.0, dt=2.0, iter_max=6, iter_reltol=1e-3, iter_abstol=1e-6)
     ppc1, ppc2, nth, k0, iters = 4, 2, 8, 20.0, 3
     orc = O.Sim(ppc1=ppc1, ppc2=ppc2, num_theta=nth, sp_push_type=5, laser_on=1, laser_iter=iters, laser_k0=k0, beam_evol=0, **cfg)

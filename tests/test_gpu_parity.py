@@ -435,6 +435,95 @@ def test_beam_kernels_match_oracle(mods, M, push):
     assert len(gq) == npp and np.array_equal(gq, qo[:npp]) and np.array_equal(gx, xo[:npp])
 
 
+@pytest.mark.parametrize("M,push", [(1, 1), (2, 2)])
+def test_beam_spin_push_matches_oracle(mods, M, push):
+    """a beam with spin (part3d%has_spin, amm): push_spin_part3d :578-638 inside both pushers (the Boris pusher calls it before it stores the
+    new momentum, the reduced one after), the spin vectors following their particles through update_bound (:668-670), the split push of a
+    pipeline stage and the 10-real hand-off record (part3d_comm.f03:683-694)"""
+    capi, O = mods
+    nr, nz, nzp, noff2 = 64, 40, 16, 8
+    dr, dz = 5.0 / nr, 0.25
+    ctx = capi.Ctx(nr, M, dr, dz)
+    L = O.lib()
+    P = 2 * M + 1
+    rng = np.random.default_rng(100 + M * 7 + push)
+    n, amm = 5000, 0.00115965
+    x = np.ascontiguousarray(np.stack([0.6 * rng.standard_normal(n), 0.6 * rng.standard_normal(n), rng.uniform(noff2 * dz, (noff2 + nzp) * dz * 0.999, n)], 1))
+    p = np.ascontiguousarray(np.stack([rng.standard_normal(n), rng.standard_normal(n), 50.0 + 5 * rng.standard_normal(n)], 1))
+    q = -rng.uniform(0.5, 1.0, n) * 1e-3
+    s = rng.standard_normal((n, 3))
+    s /= np.linalg.norm(s, axis=1)[:, None]
+    ef = np.ascontiguousarray(np.stack([smooth_field(rng, P, nr, 3, dr, 0.2) for _ in range(nzp + 1)], 1))
+    bf = np.ascontiguousarray(np.stack([smooth_field(rng, P, nr, 3, dr, 0.2) for _ in range(nzp + 1)], 1))
+    fe, fb = capi.Field(ctx, 3, nzp, True), capi.Field(ctx, 3, nzp, True)
+    fe.upload_f2(ef); fb.upload_f2(bf)
+    beam = capi.Part3d(ctx, -1.0, 4.0, n + 64, nz, noff2, nzp)
+    assert not beam.has_spin() and beam.wire_count() == 7 * beam.wire_cap() + 1
+    beam.enable_spin(amm)
+    assert beam.has_spin() and beam.wire_count() == 10 * beam.wire_cap() + 1
+    beam.upload(x, p, q); beam.upload_spin(s)
+    assert np.array_equal(beam.download_spin(), s)
+    xo, po, so = x.copy(), p.copy(), s.copy()
+    L.orc_push3d_spin(xo, po, so, amm, n, dr, dz, nr, nzp, noff2, M, -1.0, 4.0, push, ef, bf)
+    assert np.max(np.abs(so - s)) > 1e-3                                           # the spins have precessed
+    assert np.max(np.abs(np.linalg.norm(so, axis=1) - 1.0)) < 1e-12                # a rotation
+    beam.push(push, fe, fb)
+    gx, gp, gq = beam.download()
+    gs = beam.download_spin()
+    assert np.max(np.abs(gp - po)) < 1e-13 * np.max(np.abs(po)) and np.max(np.abs(gx - xo)) < 1e-13 * np.max(np.abs(xo))
+    assert np.max(np.abs(gs - so)) < 1e-12
+    # the momenta and positions do not depend on the spin: same as the spin-less oracle push
+    x2, p2 = x.copy(), p.copy()
+    L.orc_push3d(x2, p2, n, dr, dz, nr, nzp, noff2, M, -1.0, 4.0, push, ef, bf)
+    assert np.array_equal(x2, xo) and np.array_equal(p2, po)
+    # split push of a pipeline stage: interior + edge == one pass, bit for bit, spins included
+    beam2 = capi.Part3d(ctx, -1.0, 4.0, n + 64, nz, noff2, nzp)
+    beam2.enable_spin(amm)
+    beam2.upload(x, p, q); beam2.upload_spin(s)
+    beam2.push_interior(push, fe, fb)
+    last = np.floor(x[:, 2] / dz).astype(int) - noff2 + 1 == nzp
+    hs = beam2.download_spin()
+    assert last.sum() > 100 and np.array_equal(hs[last], s[last]) and np.array_equal(hs[~last], gs[~last])
+    beam2.push_edge(push, fe, fb)
+    assert np.array_equal(beam2.download_spin(), gs) and np.array_equal(beam2.download()[0], gx)
+    # update_bound: the spin vectors move with their particles (exact order on identical inputs)
+    xo[::7, 0] = 9.0
+    xo[5::11, 2] = nz * dz + 0.1
+    beam.upload(xo, po, q); beam.upload_spin(so)
+    qo = q.copy()
+    npp = L.orc_update_bound3d_spin(xo, po, qo, so, n, nr * dr, nz * dz)
+    beam.update_bound()
+    gx, gp, gq = beam.download()
+    assert len(gq) == npp < n and np.array_equal(gq, qo[:npp]) and np.array_equal(gx, xo[:npp]) and np.array_equal(beam.download_spin(), so[:npp])
+    # forward hand-off: 10 reals per particle, the receiving set appends particles and spins together
+    c2 = capi.Ctx(nr, M, dr, 0.5)
+    nb = 2000
+    bx = np.ascontiguousarray(np.stack([0.5 * rng.standard_normal(nb), 0.5 * rng.standard_normal(nb), rng.uniform(0, 5.6, nb)], 1))
+    bp = rng.standard_normal((nb, 3)); bq = np.arange(nb, dtype=float)
+    bs = rng.standard_normal((nb, 3))
+    b0 = capi.Part3d(c2, -1.0, 1.0, nb + 64, 20, 0, 10)
+    b1 = capi.Part3d(c2, -1.0, 1.0, nb + 64, 20, 10, 10)
+    b0.enable_spin(amm); b1.enable_spin(amm)
+    b0.upload(bx, bp, bq); b0.upload_spin(bs)
+    hb = _DevBuf(capi, b0.wire_count())
+    b0.pack_forward(hb.ptr); c2.sync()
+    go = np.nonzero(bx[:, 2] >= 10 * 0.5)[0]
+    rec = hb.numpy()
+    assert rec[0] == len(go) > 100
+    recs = rec[1:1 + 10 * len(go)].reshape(-1, 10)
+    assert np.array_equal(recs[:, 6], bq[go]) and np.array_equal(recs[:, 7:10], bs[go]) and np.array_equal(recs[:, 0:3], bx[go])
+    kept_q, kept_s = b0.download()[2], b0.download_spin()
+    assert np.array_equal(kept_s, bs[kept_q.astype(int)])                            # still aligned after the holes were filled
+    b1.unpack(hb.ptr)
+    got_q, got_s = b1.download()[2], b1.download_spin()
+    assert np.array_equal(got_q, bq[go]) and np.array_equal(got_s, bs[go])
+
+
+def test_beam_spin_on_the_pipeline(mods):
+    import kernel_cases as K
+    K.beam_spin_pipeline(mods[0])
+
+
 def _deck(O, decks, nr=64, nz=40, M=1, iter_max=3, **kw):
     cfg = dict(nr=nr, nz=nz, max_mode=M, rmax=5.0, zmin=-5.0, zmax=5.0, dt=10.0, iter_max=iter_max, iter_reltol=1e-3, iter_abstol=1e-3)
     cfg.update(kw)

@@ -172,6 +172,7 @@ class FakeBeam:
     def count_ptr(self): return 0
     def set_wire_cap(self, c): self.cap = int(c)
     def wire_cap(self): return self.cap
+    def wire_count(self): return 7 * self.cap + 1
 
     def pack_forward(self, ptr):
         s = self.sim
