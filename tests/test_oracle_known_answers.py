@@ -261,3 +261,24 @@ def test_linear_beam_driven_wake_matches_green_function():
     assert abs(amp - 1.0) < 2e-3, amp                       # sign included: the bunch's own electrons are decelerated
     assert np.max(np.abs(ez - an)) < 1e-2 * np.max(np.abs(an))
     assert abs(np.max(ez) / (nb0 * R0 * np.sqrt(2 * np.pi) * sz * np.exp(-sz * sz / 2)) - 1.0) < 2e-3   # the textbook amplitude behind the bunch
+
+
+@pytest.mark.parametrize("push", [1, 2])
+def test_spin_precession_in_uniform_b(push):
+    """pin of orc_push3d_spin (part3d_class.f03:578-638): a particle at rest in a uniform B_z, E = 0 -- the T-BMT rotation vector is
+    omega = (a + 1) B q dt / 2m, the update is the Boris-like rotation by the angle 2 atan|omega| about z, |s| is conserved, the momentum
+    and position are those of the spin-less push; both pushers (they call push_spin at different points) agree for p = 0"""
+    L = O.lib()
+    nr, nz, a, bz, qbm, dt = 16, 8, 0.00115965, 0.3, -1.0, 0.5
+    ef = np.zeros((1, nz + 1, nr + 2, 3)); bf = np.zeros((1, nz + 1, nr + 2, 3)); bf[..., 2] = bz
+    x = np.array([[0.37, 0.21, 0.45]]); p = np.zeros((1, 3)); s = np.array([[0.6, 0.0, 0.8]])
+    xs, ps, ss = x.copy(), p.copy(), s.copy()
+    L.orc_push3d_spin(xs, ps, ss, a, 1, 0.1, 0.1, nr, nz, 0, 0, qbm, dt, push, ef, bf)
+    omega = (a + 1.0) * bz * qbm * dt * 0.5
+    ang = 2.0 * np.arctan(omega)                     # rotation of s about z by -ang (s' = s + s x omega ...)
+    want = np.array([0.6 * np.cos(ang), -0.6 * np.sin(ang), 0.8])
+    assert np.max(np.abs(ss[0] - want)) < 1e-14, (ss, want)
+    assert abs(np.linalg.norm(ss) - 1.0) < 1e-15
+    x2, p2 = x.copy(), p.copy()
+    L.orc_push3d(x2, p2, 1, 0.1, 0.1, nr, nz, 0, 0, qbm, dt, push, ef, bf)
+    assert np.array_equal(x2, xs) and np.array_equal(p2, ps)
