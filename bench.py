@@ -824,28 +824,39 @@ def run_c5_pipeline(args):
     levels) travels forward with the plasma hand-off (neutral_class.f03:1025-1101).  A timed step = one wave = every stage runs its slab
     once, in steady state; afterwards the pipeline is drained and the same number of 3D steps re-run on one stage (parity_check)."""
     import torch
+    import torch.distributed as dist
     from qpad_b200 import capi
     from qpad_b200.pipeline import LocalPipeline
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference for the CPU arm)")
-    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
-        raise SystemExit("bench.py --config C5 runs on one GPU (the neutral's hand-off crosses GPUs too -- LocalPipeline with the p2p transport -- but this bench function does not drive it)")
+    torch.cuda.set_device(local)
+    if world > 1:          # the stages continue across GPUs: the neutral's record travels over peer memory with the forward message
+        dist.init_process_group("nccl")
     cfg, beam = deck_config("C5")
     neu = cfg["neutral"]
     _pl, bm = make_inputs(cfg, beam)
     empty = (np.zeros((0, 2)), np.zeros((0, 3)), np.zeros(0), np.zeros(0), np.zeros(0))
     S = args.stages
-    lp = LocalPipeline(cfg, empty, bm, S)
+    lp = LocalPipeline(cfg, empty, bm, S, device=local, rank=rank, world=world, dist=dist if world > 1 else None, transport="p2p" if world > 1 else None)
     main = torch.cuda.current_stream()
+
+    def sync_all():
+        lp.sync()
+        if world > 1:
+            dist.barrier(device_ids=[local])
+        torch.cuda.synchronize()
+
     lp.fill()
     for _ in range(args.warmup):
         lp.wave()
-    lp.sync(); torch.cuda.synchronize()
+    sync_all()
     u0, i0, s0 = lp.stats()
     l0 = lp.launch_count()
-    clk = ClockSampler(0); clk.start()
+    clk = ClockSampler(local); clk.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
+    sync_all()
     ev0.record(main)
     for st in lp.streams:
         st.wait_event(ev0)
@@ -856,19 +867,24 @@ def run_c5_pipeline(args):
     for st in lp.streams:
         e = torch.cuda.Event(); e.record(st); main.wait_event(e)
     ev1.record(main)
-    torch.cuda.synchronize()
+    sync_all()
     ms = ev0.elapsed_time(ev1)
     clocks = clk.stop()
     u1, i1, s1 = lp.stats()
     upd, iters, slices = u1 - u0, i1 - i0, s1 - s0
+    if world > 1:
+        t = torch.tensor([ms, float(upd), float(iters), float(slices)], dtype=torch.float64, device="cuda")
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms, upd, iters, slices = tmax[0].item(), tsum[1].item(), tsum[2].item(), tsum[3].item()
     launches = slices * 13 + 3 * iters + 30 * S * args.steps if not args.no_graph else lp.launch_count() - l0    # graph replay: head 1, 3 per PC iteration, tail 12; ~30 hand-off / beam launches per stage and wave
     check = None
     if args.check:
         lp.drain()
         nsteps = lp.sims[0].stats()[2] // lp.sims[0].nzp
         simkw = {k: cfg[k] for k in ("nr", "nz", "max_mode", "rmax", "zmin", "zmax", "dt", "iter_max", "iter_reltol", "iter_abstol")}
-        st1 = torch.cuda.Stream()
-        one = capi.Sim(sp_npmax=64, beam_npmax=len(bm[2]) + 1024, use_graph=1, stream=st1.cuda_stream, **simkw)
+        st1 = torch.cuda.Stream(device=local)
+        one = capi.Sim(sp_npmax=64, beam_npmax=len(bm[2]) + 1024, use_graph=1, device=local, stream=st1.cuda_stream, **simkw)
         one.init_species(*empty)
         one.attach_neutral(neu["element"], neu["ion_max"], (cfg["ppc1"], cfg["ppc2"]), cfg["num_theta"], neu.get("q", -1.0), neu.get("m", 1.0), neu.get("density", 1.0), cfg.get("n0", 1.0e17))
         one.beam.upload(*bm)
@@ -882,7 +898,7 @@ def run_c5_pipeline(args):
         ez1, ps1 = one.field("e").lineout(3, 0, 1), one.field("psi").lineout(1, 0, 1)
         err_ez = err_ps = 0.0
         sums, nb = np.zeros(12), 0
-        for (off, n), sim in zip(lp.parts, lp.sims):
+        for (off, n), sim in zip(lp.parts[lp.base:lp.base + S], lp.sims):
             ez, ps = sim.field("e").lineout(3, 0, 1), sim.field("psi").lineout(1, 0, 1)
             err_ez = max(err_ez, float(np.max(np.abs(ez[:n] - ez1[off:off + n]))))
             err_ps = max(err_ps, float(np.max(np.abs(ps[:n] - ps1[off:off + n]))))
@@ -891,13 +907,18 @@ def run_c5_pipeline(args):
             if len(bq):
                 sums += beam_sums(bx, bp, bq)
         err_ez /= float(np.max(np.abs(ez1))); err_ps /= float(np.max(np.abs(ps1)))
+        if world > 1:
+            tt = torch.tensor(list(sums) + [float(nb)], dtype=torch.float64, device="cuda"); dist.all_reduce(tt, op=dist.ReduceOp.SUM)
+            ee = torch.tensor([err_ez, err_ps], dtype=torch.float64, device="cuda"); dist.all_reduce(ee, op=dist.ReduceOp.MAX)
+            sums, nb = tt[:12].cpu().numpy(), int(tt[12].item())
+            err_ez, err_ps = float(ee[0].item()), float(ee[1].item())
         bx, bp, bq = one.beam.download()
         m1, m2 = beam_moments_from_sums(beam_sums(bx, bp, bq)), beam_moments_from_sums(sums)
         berr = 0.0
         for ax in "xy":
             c1, s1_, e1 = m1[ax]; c2, s2_, e2 = m2[ax]
             berr = max(berr, abs(c1 - c2) / s1_, abs(s1_ - s2_) / s1_, abs(e1 - e2) / e1)
-        upd_one, upd_pipe = one.stats()[0], lp.stats()[0]
+        upd_one = one.stats()[0]
         check = {"ok": bool(err_ez < 1e-6 and err_ps < 1e-6 and berr < 1e-6 and nb == len(bq)), "tol": 1e-6, "steps_compared": int(nsteps), "ez_lineout_rel_err": err_ez,
                  "psi_lineout_rel_err": err_ps, "beam_moments_rel_err": berr, "beam_particles": nb, "beam_particles_single_stage": int(len(bq)),
                  "updates_per_step_single_stage": upd_one / nsteps, "single_step_ms": evs[0].elapsed_time(evs[1]),
@@ -910,8 +931,8 @@ def run_c5_pipeline(args):
         lp.fill()
     from qpad_b200.pipeline import split_beam
     dxi = (cfg["zmax"] - cfg["zmin"]) / cfg["nz"]
-    b0 = split_beam(*bm, cfg["nz"], dxi, S, parts=lp.parts)[0]
-    lp.sync(); torch.cuda.synchronize()
+    b0 = split_beam(*bm, cfg["nz"], dxi, lp.G, parts=lp.parts)[lp.base]           # the beam of this rank's first slab
+    sync_all()
     ue0 = lp.stats()[0]
     t0 = time.perf_counter()
     d2h = 0
@@ -923,9 +944,12 @@ def run_c5_pipeline(args):
             ez = sim.field("e").lineout(3, 0, 1); ps = sim.field("psi").lineout(1, 0, 1)
             d2h += 8 * (len(ez) + len(ps))
         lp.stats()
-    lp.sync(); torch.cuda.synchronize()
+    sync_all()
     te = time.perf_counter() - t0
-    e2e = {"value": (lp.stats()[0] - ue0) / te, "unit": UNIT, "h2d_bytes_per_step": int(56 * len(b0[2])), "d2h_bytes_per_step": int(d2h),
+    ue = float(lp.stats()[0] - ue0)
+    if world > 1:
+        tt = torch.tensor([ue], dtype=torch.float64, device="cuda"); dist.all_reduce(tt, op=dist.ReduceOp.SUM); ue = tt[0].item()
+    e2e = {"value": ue / te, "unit": UNIT, "h2d_bytes_per_step": int(56 * len(b0[2])), "d2h_bytes_per_step": int(d2h),
            "what": "per step (wave): beam particles of the first slab host->device (qpg_part3d_upload), every stage runs its slab with ionisation, E_z and psi on-axis line-outs of every "
                    "slab + counters device->host"}
     peak, peak_src = hbm_peak()
@@ -936,14 +960,18 @@ def run_c5_pipeline(args):
                                        "the ~16 dependent launches of a slice bound one slab, the slabs overlap)",
             "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src, "bytes_per_update": bpu,
             "us_per_slice_effective": ms * 1e3 / max(slices, 1), "slab_slices_by_stage": [n for _, n in lp.parts], "host_enqueue_ms_per_step": host_ms}
-    line = {"metric": METRIC, "value": upd / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+    line = {"metric": METRIC, "value": upd / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic (tri-Gaussian beam per the ionization deck, lithium gas ionised on the device)",
             "config": {"workload": f"C5: nr={cfg['nr']} nz={cfg['nz']} max_mode={cfg['max_mode']} neutral Li ion_max={neu['ion_max']} ppc {cfg['ppc1']}x{cfg['ppc2']} num_theta {cfg['num_theta']}, updates/step={upd / args.steps:.0f}",
-                       "parallelism": f"xi-pipeline: {S} stages on one GPU as concurrent streams (slice body replayed from a CUDA graph), neutral state in the forward hand-off, steady state",
+                       "parallelism": f"xi-pipeline: {S} stages per GPU x {world} GPU(s) as concurrent streams (slice body replayed from a CUDA graph), neutral state in the forward hand-off, steady state",
                        "l2": "field volumes ~100 MB + electron planes: larger than L2 late in the step", "pc_iters_per_slice": nit},
             "clocks": clocks, "gpu_launches": int(launches), "roofline": roof, "e2e": e2e}
     if check: line["parity_check"] = check
+    if rank != 0:
+        lp.close()
+        dist.destroy_process_group()
+        return
     if not args.no_cpu:
         try:
             upd_c, wall_c, k_c, _t = cpu_parallel("C5", args.ref_slices or None)
@@ -952,6 +980,8 @@ def run_c5_pipeline(args):
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {exc}"}
     print(json.dumps(line))
     lp.close()
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def run_b200_local(args):

@@ -92,6 +92,6 @@ def test_c5_pipeline_bench_function_runs(bench_mod, monkeypatch):
     args = types.SimpleNamespace(steps=1, warmup=1, no_graph=False, no_cpu=True, ref_slices=8, stages=2, check=1)
     line = _run(bench_mod.run_c5_pipeline, args)
     assert all(k in line for k in KEYS), [k for k in KEYS if k not in line]
-    assert line["value"] > 0 and "neutral Li" in line["config"]["workload"] and "2 stages" in line["config"]["parallelism"]
+    assert line["value"] > 0 and "neutral Li" in line["config"]["workload"] and "2 stages per GPU" in line["config"]["parallelism"]
     pc = line["parity_check"]
     assert pc["ok"] and pc["beam_particles"] == pc["beam_particles_single_stage"] > 0, pc
