@@ -1335,7 +1335,7 @@ def main():
         (run_c4_pipeline if args.stages > 1 else run_c4)(args)
     elif args.config == "C5":
         if args.stages == 0:
-            args.stages = 1 if args.no_graph else 4
+            args.stages = 1 if args.no_graph else 8       # measured on one B200: 1 stage 1.5e8, 4 stages 3.6e8, 8 stages (unrolled slice graph) 4.5e8
         (run_c5_pipeline if args.stages > 1 else run_c5)(args)
     else:
         if args.stages == 0:       # auto: as many stages as the field team (one CTA per 32 radial nodes) and the slab length allow, at most 4

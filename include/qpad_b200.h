@@ -275,6 +275,11 @@ int qpg_sim_beam_qdp_part(qpg_sim s, int part);
 /* the sim's laser envelope (NULL unless sp_push_pgc) and simulation_class.f03:486 lasers%advance (after the slab) */
 qpg_laser qpg_sim_laser(qpg_sim s);
 int qpg_sim_laser_advance(qpg_sim s);
+/* CUDA-graph replay of the slice body (use_graph): on = capture all iter_max predictor-corrector iterations (the ones behind the converged
+ * one skip themselves on the device) instead of a WHILE node around one.  Launching a graph with a conditional node costs ~100 us of host
+ * time against ~4 us for a plain one: worth it when many short slabs are enqueued from one host thread (a pipeline of >= 6 stages on the
+ * per-slice launch path), not for one slab (each skipped iteration costs two near-empty kernels on the device). */
+int qpg_sim_set_graph_unroll(qpg_sim s, int on);
 /* on = the envelope solve of a 3D step may run beside the sweep kernel of the next one also when the caller chose the sweep grid
  * (qpg_sim_set_sweep_ctas n > 0): the caller vouches that an SM stays free for the solve's CTA (it cannot share one with a sweep CTA) */
 int qpg_sim_set_laser_overlap(qpg_sim s, int on);

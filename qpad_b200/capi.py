@@ -166,6 +166,7 @@ SIGNATURES = {
     "qpg_laser_guard_size": (_l, [_vp]),
     "qpg_laser_set_handoff": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "qpg_sim_set_laser_overlap": (_i, [_vp, _i]),
+    "qpg_sim_set_graph_unroll": (_i, [_vp, _i]),
     "qpg_neutral_create": (_i, [C.POINTER(_vp), _vp, _i, _i, _i, _i, _i, _d, _d, _d, _d, _d]),
     "qpg_neutral_destroy": (_i, [_vp]),
     "qpg_sim_neutral_wire_count": (_l, [_vp]),
@@ -672,6 +673,7 @@ class Sim:
 
     def laser_advance(self): _chk(self.L.qpg_sim_laser_advance(self.h))
     def set_laser_overlap(self, on): _chk(self.L.qpg_sim_set_laser_overlap(self.h, int(on)))
+    def set_graph_unroll(self, on): _chk(self.L.qpg_sim_set_graph_unroll(self.h, int(on)))
 
     def set_subcyc(self, exp_fac_max, exp_fac_clamped, dt_min, on=True):
         """the sub-cycling variant of the slice loop (proj_subcyc): plain per-slice launches, one host synchronisation per slice"""

@@ -25,6 +25,7 @@ struct qpg_sim_s {
     cudaGraph_t graph;
     cudaGraphExec_t gexec;
     bool graph_ready;
+    bool graph_unroll;    // slice graph without the WHILE node (see build_graph)
     bool use_fused;       // cluster kernels of fused.cu instead of the op-list programs
     bool use_sweep;       // persistent cooperative slab-sweep kernel (sweep.cu)
     int sweep_grid;       // CTAs of the sweep kernel (0 = not yet queried)
@@ -385,6 +386,25 @@ static int build_graph(qpg_sim s)
     size_t ndeps = 0;
     cudaStreamCaptureStatus stat;
     cudaGraphConditionalHandle handle = 0;
+    // unrolled variant (qpg_sim_set_graph_unroll / QPG_GRAPH_UNROLL=1): no WHILE node -- all iter_max predictor-corrector iterations are captured
+    // and the ones behind the converged one skip themselves on the device flag, as on the plain launch path.  cudaGraphLaunch of a graph
+    // with a conditional node costs ~100 us of host time on this driver, of a plain graph ~4 us: a pipeline of many short slabs is paced by the
+    // host with the WHILE node and by the device's kernel dispatch rate (iter_max x 2 mostly skipped kernels more per slice) without it
+    const bool unroll = s->graph_unroll || getenv("QPG_GRAPH_UNROLL") != nullptr;
+    if (unroll) {
+        for (int l = 0; l < s->prm.iter_max && !rc; l++) rc = enqueue_pc_iteration(s);
+        if (!rc) rc = enqueue_slice_tail(s);
+        cudaGraph_t gout = nullptr;
+        e = cudaStreamEndCapture(st, &gout);
+        c->capturing = false;
+        if (e != cudaSuccess && !rc) rc = qpg_cuda_fail(e, "cudaStreamEndCapture");
+        if (rc) { if (gout) cudaGraphDestroy(gout); return rc; }
+        s->graph = gout;
+        e = cudaGraphInstantiate(&s->gexec, s->graph, 0);
+        if (e != cudaSuccess) return qpg_cuda_fail(e, "cudaGraphInstantiate");
+        s->graph_ready = true;
+        return 0;
+    }
     if (!rc) {
         e = cudaStreamGetCaptureInfo(st, &stat, nullptr, &g, &deps, &ndeps);
         if (e != cudaSuccess) rc = qpg_cuda_fail(e, "cudaStreamGetCaptureInfo");
@@ -739,6 +759,13 @@ extern "C" int qpg_sim_set_fused(qpg_sim s, int on)
     return 0;
 }
 extern "C" int qpg_sim_set_graph(qpg_sim s, int use_graph) { ARG_TRY(s, "null sim"); ARG_TRY(!(use_graph && s->subcyc), "sub-cycling needs the plain launch path"); s->prm.use_graph = use_graph != 0; return 0; }
+extern "C" int qpg_sim_set_graph_unroll(qpg_sim s, int on)
+{
+    ARG_TRY(s, "null sim");
+    if ((on != 0) != s->graph_unroll && s->graph_ready) { cudaGraphExecDestroy(s->gexec); cudaGraphDestroy(s->graph); s->gexec = nullptr; s->graph = nullptr; s->graph_ready = false; }
+    s->graph_unroll = on != 0;
+    return 0;
+}
 extern "C" qpg_laser qpg_sim_laser(qpg_sim s) { return s ? s->laser : nullptr; }
 int qpg_laser_advance_overlapped(qpg_laser l, unsigned **progress, unsigned *base);   // laser.cu
 extern "C" int qpg_sim_laser_advance(qpg_sim s)

@@ -269,7 +269,7 @@ def sim_neutral_full_step(api, O, use_graph=0):
     sim.close()
 
 
-def neutral_local_pipeline(api, O, S, nwaves=3):
+def neutral_local_pipeline(api, O, S, nwaves=3, graph_unroll=None):
     """config 5 in small on the xi-pipeline (the deck is `nodes [1,2]`): S stages on one GPU, every stage with the neutral attached to its
     sim; the released electrons, the ions' buffer, rho_ion and the ionisation levels travel forward with the plasma hand-off (neut%psend /
     precv, neutral_class.f03:1025-1101).  `nwaves` 3D steps against the oracle's S-stage run: the wake of a downstream slab is driven by
@@ -285,7 +285,7 @@ def neutral_local_pipeline(api, O, S, nwaves=3):
     orc.set_beam(*bm)
     upd_o = sum(orc.step3d(k + 1) for k in range(nwaves))
     empty = tuple(a[:0] for a in O.inject_uniform(cfg["nr"], cfg["rmax"] / cfg["nr"], 2, 2, 8))
-    lp = LocalPipeline(cfg, empty, bm, S)
+    lp = LocalPipeline(cfg, empty, bm, S, graph_unroll=graph_unroll)       # None: the pipeline's own choice (WHILE node below 6 stages)
     for _ in range(nwaves):
         lp.wave()
     lp.drain()

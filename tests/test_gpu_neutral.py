@@ -60,3 +60,11 @@ def test_neutral_local_pipeline_matches_oracle(mods, S):
     capi, O = mods
     import kernel_cases as K
     K.neutral_local_pipeline(capi, O, S)
+
+
+def test_neutral_pipeline_with_unrolled_slice_graph(mods):
+    """the slice graph without the WHILE node (qpg_sim_set_graph_unroll: all iter_max predictor-corrector iterations captured, the surplus ones
+    skip themselves on the device) -- what a pipeline of >= 6 stages on the per-slice launch path uses -- gives the same run"""
+    capi, O = mods
+    import kernel_cases as K
+    K.neutral_local_pipeline(capi, O, 2, graph_unroll=True)
