@@ -1335,7 +1335,11 @@ def main():
         (run_c4_pipeline if args.stages > 1 else run_c4)(args)
     elif args.config == "C5":
         if args.stages == 0:
-            args.stages = 1 if args.no_graph else 8       # measured on one B200: 1 stage 1.5e8, 4 stages 3.6e8, 8 stages (unrolled slice graph) 4.5e8
+            args.stages = 1 if args.no_graph else 24      # measured on one B200: 1 stage 1.5e8, 4 stages 3.6e8; unrolled slice graph: 8 stages 4.5e8, 16 5.6e8, 24 6.4e8, 32 6.6e8
+        if args.stages > 8:
+            # more than 8 stage streams: the default of 8 hardware queues would serialise them in pairs (8, 12, 16, 24 stages then all run at the pace of 8);
+            # must be set before the CUDA context exists (torch is imported inside the run functions)
+            os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
         (run_c5_pipeline if args.stages > 1 else run_c5)(args)
     else:
         if args.stages == 0:       # auto: as many stages as the field team (one CTA per 32 radial nodes) and the slab length allow, at most 4
