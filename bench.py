@@ -1332,6 +1332,8 @@ def main():
     elif args.config == "C4":
         if args.stages == 0:
             args.stages = 5 if not (args.no_sweep or args.no_graph) else 1      # measured on one B200: 1 stage 2.4e9, 4 stages 5.1e9, 5 stages 5.5e9, 6 stages 4.6e9 updates/s
+        if args.stages > 3:
+            os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")     # S stage streams + S envelope side streams > the default 8 hardware queues (+2 %)
         (run_c4_pipeline if args.stages > 1 else run_c4)(args)
     elif args.config == "C5":
         if args.stages == 0:
