@@ -219,8 +219,9 @@ typedef struct {
     int sp_push_std;          /* 0 = robust pusher (the decks' choice), 1 = std flavour (amjdeposit_std, push_u_std, interp_psi);
                                  std runs on the per-slice launch paths, not in the persistent sweep kernel */
     int sp_push_pgc;          /* 1 = ponderomotive-guiding-centre flavour of the chosen pusher (param.f03 p_push2_std_pgc / p_push2_robust_pgc):
-                                 the sim owns ONE laser envelope (qpg_sim_laser) and runs simulation_class.f03:361-366 / :401 per slice;
-                                 single stage (noff2 = 0, nzp = nz_total), per-slice launch paths (CUDA graph or plain stream) */
+                                 the sim owns ONE laser envelope (qpg_sim_laser: its slab of nzp slices + guards) and runs simulation_class.f03:361-366
+                                 / :401 per slice -- inside the persistent sweep kernel (robust_pgc) or on the per-slice launch paths; on a
+                                 xi-pipeline the stages' envelopes are linked with qpg_laser_set_handoff */
     int laser_iter;           /* laser.iteration: fixed-point passes of the envelope solve per slice (>= 1) */
     double laser_k0;          /* laser.k0 */
     int sp_ppc_r;             /* species ppc(1): the on-axis correction of the susceptibility deposit (part2d_class.f03:2581) */

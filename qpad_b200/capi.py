@@ -588,7 +588,7 @@ class Neutral:
 
 
 class Laser:
-    """field_laser (laser/field_laser_class.f03) on one xi stage: envelope volumes of shape (P, nz+3, nr+2), xi slice j at
+    """field_laser (laser/field_laser_class.f03) of one xi stage (nz = its slab): envelope volumes of shape (P, nz+3, nr+2), xi slice j at
     index j+1; method names follow the type-bound procedures (set_grad + gather = slice, solve = advance)."""
 
     def __init__(self, ctx, nz, k0, ds, iteration=1, handle=None):
@@ -682,7 +682,8 @@ class Sim:
     def subcycles(self): return self.L.qpg_sim_subcycles(self.h)
 
     def attach_neutral(self, element, ion_max, ppc, num_theta, q=-1.0, m=1.0, density=1.0, n0=1.0e17):
-        """a field-ionisation neutral species inside the slice loop (qpg_sim_attach_neutral): per-slice launch paths only"""
+        """a field-ionisation neutral species inside the slice loop (qpg_sim_attach_neutral): per-slice launch paths (not the sweep kernel); on a
+        xi-pipeline its state travels with qpg_sim_neutral_pack / _unpack"""
         self.neutral = Neutral(self.ctx, element, ion_max, ppc, num_theta, q, m, density, n0, self.ctx.dxi)
         _chk(self.L.qpg_sim_attach_neutral(self.h, self.neutral.h, self.neutral.part.h, self.neutral.part_add.h))
         return self.neutral
