@@ -35,8 +35,9 @@ static const double ADK_LI[9] = {3.460272990838495e21, 85.51998980232813, 2.1770
 
 // neutral_class.f03:600-753.  ef = node-interleaved dim-3 image of E.  Keeps the reference's quirks: the imaginary plane of the
 // m > 0 modes is read from the REAL plane (:636-637); the level update is its "2nd order Runge-Kutta" (:661, :688).
-__global__ void k_neutral_ionize(double *__restrict__ lev, double *__restrict__ ion_old, int *__restrict__ cnt, AdkTable adk, const double *__restrict__ ef,
-                                 double wp, double dt, int ppc_tot, int nr, int n_theta, int M, int multi_max)
+// (no __restrict__ on the arrays the steps hand to each other: inside k_neutral_update one step's output is the next one's input)
+__device__ __forceinline__ void neutral_ionize(double *lev, double *ion_old, int *cnt, const AdkTable &adk,
+                                               const double *__restrict__ ef, double wp, double dt, int ppc_tot, int nr, int n_theta, int M, int multi_max)
 {
     const int P = 2 * M + 1, idx_neut = multi_max, idx_ion = multi_max + 1;
     const int n = nr * n_theta;
@@ -87,8 +88,12 @@ __global__ void k_neutral_ionize(double *__restrict__ lev, double *__restrict__ 
     }
 }
 
+__global__ void k_neutral_ionize(double *__restrict__ lev, double *__restrict__ ion_old, int *__restrict__ cnt, AdkTable adk, const double *__restrict__ ef,
+                                 double wp, double dt, int ppc_tot, int nr, int n_theta, int M, int multi_max)
+{ neutral_ionize(lev, ion_old, cnt, adk, ef, wp, dt, ppc_tot, nr, n_theta, M, multi_max); }
+
 // exclusive scan of cnt[0..n) in index order (sector-major, cell-minor = the reference's loop order) by ONE CTA of 1024 threads
-__global__ void __launch_bounds__(1024, 1) k_neutral_scan(const int *__restrict__ cnt, int *__restrict__ off, int *__restrict__ d_nadd, int n)
+__device__ __forceinline__ void neutral_scan(const int *cnt, int *off, int *d_nadd, int n)
 {
     __shared__ int part[1024];
     const int t = threadIdx.x, per = (n + 1023) / 1024, beg = min(t * per, n), end = min(beg + per, n);
@@ -106,11 +111,12 @@ __global__ void __launch_bounds__(1024, 1) k_neutral_scan(const int *__restrict_
     for (int i = beg; i < end; i++) { off[i] = run; run += cnt[i]; }
     if (t == 1023) *d_nadd = part[1023];
 }
+__global__ void __launch_bounds__(1024, 1) k_neutral_scan(const int *__restrict__ cnt, int *__restrict__ off, int *__restrict__ d_nadd, int n) { neutral_scan(cnt, off, d_nadd, n); }
 
 // neutral_class.f03:795-829: the electrons of cell (k, j) at r = (j + (i + 1/2) / cnt) dr, theta = k dtheta, at rest;
 // the ions' buffer gets the same positions with the opposite charge
-__global__ void k_neutral_add(const int *__restrict__ cnt, const int *__restrict__ off, PartView pe, PartView pi, long cap_e, long cap_i, double dr, double density,
-                              double den_min, double coef, int nr, int n_theta)
+__device__ __forceinline__ void neutral_add(const int *cnt, const int *off, const PartView &pe, const PartView &pi, long cap_e, long cap_i,
+                                            double dr, double density, double den_min, double coef, int nr, int n_theta)
 {
     const int n = nr * n_theta, base = *pe.d_npp;
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
@@ -129,14 +135,33 @@ __global__ void k_neutral_add(const int *__restrict__ cnt, const int *__restrict
         }
     }
 }
+__global__ void k_neutral_add(const int *__restrict__ cnt, const int *__restrict__ off, PartView pe, PartView pi, long cap_e, long cap_i, double dr, double density,
+                              double den_min, double coef, int nr, int n_theta)
+{ neutral_add(cnt, off, pe, pi, cap_e, cap_i, dr, density, den_min, coef, nr, n_theta); }
 // flags[7] of the context is latched when released electrons (or ion positions) did not fit the particle sets: the host reports
 // QPG_ERR_STATE at its next synchronisation point instead of silently losing charge (beam.cu does the same for its wire buffer)
-__global__ void k_neutral_counts(int *npp_e, int *npp_i, const int *d_nadd, long cap_e, long cap_i, int *ctx_flags)
+__device__ __forceinline__ void neutral_counts(int *npp_e, int *npp_i, const int *d_nadd, long cap_e, long cap_i, int *ctx_flags)
 {
     const int add = *d_nadd;
     if ((long)*npp_e + add > cap_e || (long)add > cap_i) ctx_flags[7] = 1;
     *npp_e = (int)min((long)*npp_e + add, cap_e);
     *npp_i = (int)min((long)add, cap_i);
+}
+__global__ void k_neutral_counts(int *npp_e, int *npp_i, const int *d_nadd, long cap_e, long cap_i, int *ctx_flags) { neutral_counts(npp_e, npp_i, d_nadd, cap_e, cap_i, ctx_flags); }
+// The whole update as ONE kernel of one CTA (the four steps above with CTA barriers in between): on the per-slice launch path a slice is a chain
+// of ~30 small dependent kernels and a pipeline of many stages is paced by the device's kernel dispatch -- three launches less
+// per slice count; 16 000 (cell, sector) pairs are 16 per thread
+__global__ void __launch_bounds__(1024, 1) k_neutral_update(double *lev, double *ion_old, int *cnt, int *off, int *d_nadd, AdkTable adk, const double *__restrict__ ef, double wp, double dt, int ppc_tot, int nr,
+                                                           int n_theta, int M, int multi_max, PartView pe, PartView pi, long cap_e, long cap_i, double dr, double density,
+                                                           double den_min, double coef, int *npp_e, int *npp_i, int *ctx_flags)
+{
+    neutral_ionize(lev, ion_old, cnt, adk, ef, wp, dt, ppc_tot, nr, n_theta, M, multi_max);
+    __syncthreads();
+    neutral_scan(cnt, off, d_nadd, nr * n_theta);
+    __syncthreads();
+    neutral_add(cnt, off, pe, pi, cap_e, cap_i, dr, density, den_min, coef, nr, n_theta);
+    __syncthreads();
+    if (threadIdx.x == 0) neutral_counts(npp_e, npp_i, d_nadd, cap_e, cap_i, ctx_flags);
 }
 // most electrons one update can release: every (cell, sector) ionises all its ppc particles at once
 long qpg_neutral_max_new_per_update(qpg_neutral ne) { return ne ? (long)ne->ppc1 * ne->ppc2 * ne->ctx->nr * ne->n_theta : 0; }
@@ -201,14 +226,22 @@ extern "C" int qpg_neutral_update(qpg_neutral ne, qpg_field e, qpg_part2d electr
     const int nc = c->nr * ne->n_theta;
     AdkTable tab;
     memcpy(tab.v, ne->adk, sizeof(tab.v));
-    k_neutral_ionize<<<(nc + 127) / 128, 128, 0, c->stream>>>(ne->lev, ne->ion_old, ne->cnt, tab, e->f1, ne->wp, ne->dt, ne->ppc1 * ne->ppc2, c->nr, ne->n_theta, c->M,
-                                                             ne->multi_max);
-    k_neutral_scan<<<1, 1024, 0, c->stream>>>(ne->cnt, ne->off, ne->d_nadd, nc);
     const double coef = (double)ne->multi_max * (ne->qm < 0 ? -1.0 : 1.0) / ((double)(ne->ppc1 * ne->ppc2) * (double)ne->n_theta);
-    k_neutral_add<<<(nc + 127) / 128, 128, 0, c->stream>>>(ne->cnt, ne->off, view_of(electrons), view_of(ions), electrons->npmax, ions->npmax, c->dr, ne->density, ne->den_min,
-                                                         coef, c->nr, ne->n_theta);
-    k_neutral_counts<<<1, 1, 0, c->stream>>>(electrons->d_npp, ions->d_npp, ne->d_nadd, electrons->npmax, ions->npmax, c->flags);
-    count_launch(c, 4);
+    static const bool split = getenv("QPG_NEUTRAL_SPLIT_UPDATE") != nullptr;     // A/B: the four kernels one by one
+    if (!split && nc <= 64 * 1024) {
+        k_neutral_update<<<1, 1024, 0, c->stream>>>(ne->lev, ne->ion_old, ne->cnt, ne->off, ne->d_nadd, tab, e->f1, ne->wp, ne->dt, ne->ppc1 * ne->ppc2, c->nr, ne->n_theta,
+                                                    c->M, ne->multi_max, view_of(electrons), view_of(ions), electrons->npmax, ions->npmax, c->dr, ne->density,
+                                                    ne->den_min, coef, electrons->d_npp, ions->d_npp, c->flags);
+        count_launch(c);
+    } else {
+        k_neutral_ionize<<<(nc + 127) / 128, 128, 0, c->stream>>>(ne->lev, ne->ion_old, ne->cnt, tab, e->f1, ne->wp, ne->dt, ne->ppc1 * ne->ppc2, c->nr, ne->n_theta, c->M,
+                                                                 ne->multi_max);
+        k_neutral_scan<<<1, 1024, 0, c->stream>>>(ne->cnt, ne->off, ne->d_nadd, nc);
+        k_neutral_add<<<(nc + 127) / 128, 128, 0, c->stream>>>(ne->cnt, ne->off, view_of(electrons), view_of(ions), electrons->npmax, ions->npmax, c->dr, ne->density,
+                                                             ne->den_min, coef, c->nr, ne->n_theta);
+        k_neutral_counts<<<1, 1, 0, c->stream>>>(electrons->d_npp, ions->d_npp, ne->d_nadd, electrons->npmax, ions->npmax, c->flags);
+        count_launch(c, 4);
+    }
     CUDA_TRY(cudaGetLastError());
     electrons->npp_hi = electrons->npmax;     // unknown until the next sync; the kernels bound themselves by the device count
     ions->npp_hi = ions->npmax;
