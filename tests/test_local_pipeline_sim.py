@@ -188,6 +188,38 @@ class FakeCtx:
     def launch_count(self): return 0
 
 
+class FakeLaser:
+    """the stage's envelope slab: qpg_laser_set_handoff + the hand-off protocol of qpg_laser_advance (csrc/laser.cu laser_launch_advance): message
+    n = the n-th advance; wait in_ready >= n, copy the guard record in, in_ack = n, solve, wait out_ack >= n - 1, write the own record, out_ready = n"""
+
+    def __init__(self, sim):
+        self.sim, self.links, self.seq = sim, (None,) * 6, 0
+
+    def guard_size(self): return 48
+    def upload_slab(self, ar, ai, noff2): pass
+    def sync(self): pass
+
+    def set_handoff(self, guard_in=None, in_ready=None, in_ack=None, guard_out=None, out_ready=None, out_ack=None):
+        self.links, self.seq = (guard_in, in_ready, in_ack, guard_out, out_ready, out_ack), 0
+
+    def advance(self):
+        s = self.sim
+        gin, in_ready, in_ack, gout, out_ready, out_ack = self.links
+        self.seq += 1
+        n, step = self.seq, s.cur - 1
+        s.kernel(lambda sid, vc: None)                                   # set_rhs
+        if gin is not None:
+            s.stream.push("wait_flag", flag=in_ready, value=n)
+            s.kernel(lambda sid, vc, want=("lasg", s.g - 1, step): do_read(gin, want, sid, vc))
+            s.stream.push("signal", flag=in_ack, value=n)
+        s.kernel(lambda sid, vc: None)                                   # solve
+        if gout is not None:
+            if n > 1:
+                s.stream.push("wait_flag", flag=out_ack, value=n - 1)
+            s.kernel(lambda sid, vc, tag=("lasg", s.g, step): do_write(gout, tag, sid, vc))
+            s.stream.push("signal", flag=out_ready, value=n)
+
+
 class FakeSim:
     G_OF = {}          # (noff2) -> global stage index, filled by the test
 
@@ -197,6 +229,7 @@ class FakeSim:
         self.stream = stream_of(stream)
         self.cur = 0                     # number of slab sweeps started so far = index of the next 3D step of this stage
         self.beam, self.species, self.ctx = FakeBeam(self), FakeSpecies(self), FakeCtx()
+        self.laser = FakeLaser(self) if kw.get("sp_push_pgc") else None
         self.handoff = None
         self.log = []
 
@@ -218,6 +251,20 @@ class FakeSim:
     def renew(self): self.kernel(lambda sid, vc: None)
     def stats(self): return (0, 0, 0)
     def close(self): pass
+
+    # a neutral species attached to the stage (qpg_sim_attach_neutral): its record travels with the forward message
+    def set_laser_overlap(self, on): pass
+    def laser_advance(self): self.laser.advance()
+    def attach_neutral(self, *a, **kw): self.neutral = True
+    def set_graph_unroll(self, on): pass
+    def neutral_wire_count(self): return 96
+
+    def neutral_pack(self, ptr):
+        self.kernel(lambda sid, vc, tag=("neutral", self.g, self.cur - 1): do_write(ptr, tag, sid, vc))
+
+    def neutral_unpack(self, ptr):
+        want = ("neutral", self.g - 1, self.cur)
+        self.kernel(lambda sid, vc: do_read(ptr, want, sid, vc))
 
     def set_back_handoff(self, wire_b, wire_e, flag, seq):
         self.handoff = (wire_b, wire_e, flag, seq)
@@ -343,7 +390,8 @@ def _run_rank(cfg, plasma, beam, S, rank, world, dist, parts, nwaves, upload, ou
     try:
         if dist is not None:
             dist.set_rank(rank)
-        lp = pipeline.LocalPipeline(cfg, plasma, beam, S, rank=rank, world=world, dist=dist, transport="p2p" if world > 1 else None, partition=parts)
+        lp = pipeline.LocalPipeline(cfg, plasma, beam, S, rank=rank, world=world, dist=dist, transport="p2p" if world > 1 else None, partition=parts,
+                                    laser=(np.zeros((1, cfg["nz"] + 3, cfg["nr"] + 2)),) * 2 if cfg.get("laser") else None)
         lp.fill()
         for w in range(nwaves):
             lp.wave(upload=plasma if (upload and w % 2) else None)
@@ -400,3 +448,83 @@ def test_the_checker_catches_a_missing_wait(fake_device, monkeypatch):
     assert not isinstance(out[0], Exception), out[0]
     assert not simulate()
     assert any("does not happen-after its write" in e or "expected ('b'" in e or "expected ('e'" in e for e in fake_device.errors), fake_device.errors[:3]
+
+
+@pytest.mark.parametrize("world,S", [(1, 3), (2, 2), (3, 1)])
+def test_neutral_record_travels_race_free(fake_device, world, S):
+    """a deck with a neutral species: the record of qpg_sim_neutral_pack (released electrons, ion buffer, rho_ion, levels) is written into
+    the next stage's buffer -- a device buffer inside a GPU, the `neu_in` peer buffer between ranks -- under the forward message's events /
+    ready and ack words: every stage reads its upstream neighbour's record of the SAME 3D step, no buffer is overwritten before it was read"""
+    nz, nwaves = 32, 4
+    cfg, plasma, beam = _inputs(nz)
+    cfg.update(neutral=dict(element=3, ion_max=2), ppc1=2, ppc2=2, num_theta=8)
+    G = world * S
+    FakeSim.G_OF = {noff: g for g, (noff, _) in enumerate(pipeline.slab_partition(nz, G))}
+    dist = FakeDist(world) if world > 1 else None
+    out = {}
+    threads = [threading.Thread(target=_run_rank, args=(cfg, plasma, beam, S, r, world, dist, None, nwaves, False, out)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=60)
+    for r in range(world):
+        assert r in out and not isinstance(out[r], Exception), out.get(r)
+    assert not simulate(), "deadlock"
+    assert not fake_device.errors, fake_device.errors[:5]
+    tags = {b.tag for b in fake_device.bufs.values() if b.tag is not None}
+    assert ("neutral", G - 2, G - 2 + nwaves) in tags          # the last record of the last link
+
+
+@pytest.mark.parametrize("world,S", [(1, 4), (2, 2), (3, 1)])
+def test_envelope_guard_handoff_is_deadlock_and_race_free(fake_device, world, S):
+    """a laser deck: LocalPipeline wires every stage's envelope links (buffer and ready word at the consumer, ack word at the producer; device
+    buffers inside a GPU, PeerLinks' las_in / ready_las / ack_las between ranks) and calls the advance after the slab: with the library's
+    hand-off protocol replayed by the stand-in, every advance reads the upstream stage's record of the SAME 3D step and no record is
+    overwritten before it was read, for stages of one GPU and across ranks"""
+    nz, nwaves = 32, 5
+    cfg, plasma, beam = _inputs(nz)
+    cfg.update(max_mode=0, laser=dict(k0=20.0, iteration=3), ppc1=2, ppc2=2, num_theta=8)
+    G = world * S
+    FakeSim.G_OF = {noff: g for g, (noff, _) in enumerate(pipeline.slab_partition(nz, G))}
+    dist = FakeDist(world) if world > 1 else None
+    out = {}
+    threads = [threading.Thread(target=_run_rank, args=(cfg, plasma, beam, S, r, world, dist, None, nwaves, False, out)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=60)
+    for r in range(world):
+        assert r in out and not isinstance(out[r], Exception), out.get(r)
+    assert not simulate(), "deadlock"
+    assert not fake_device.errors, fake_device.errors[:5]
+    tags = {b.tag for b in fake_device.bufs.values() if b.tag is not None}
+    assert ("lasg", G - 2, G - 2 + nwaves) in tags
+    for r in range(world):
+        for sim in out[r].sims:
+            assert sim.laser.seq == G - 1 + nwaves          # one advance per 3D step of the stage
+
+
+def test_the_checker_catches_a_missing_envelope_ack(fake_device, monkeypatch):
+    """sanity of the harness for the envelope link: a producer that does not wait for the consumer's ack before it rewrites the one wire
+    record of the link is reported"""
+    def no_ack_wait(self):
+        s = self.sim
+        gin, in_ready, in_ack, gout, out_ready, out_ack = self.links
+        self.seq += 1
+        n, step = self.seq, s.cur - 1
+        if gin is not None:
+            s.stream.push("wait_flag", flag=in_ready, value=n)
+            s.kernel(lambda sid, vc, want=("lasg", s.g - 1, step): do_read(gin, want, sid, vc))
+            s.stream.push("signal", flag=in_ack, value=n)
+        if gout is not None:
+            s.kernel(lambda sid, vc, tag=("lasg", s.g, step): do_write(gout, tag, sid, vc))
+            s.stream.push("signal", flag=out_ready, value=n)
+    monkeypatch.setattr(FakeLaser, "advance", no_ack_wait)
+    cfg, plasma, beam = _inputs(32)
+    cfg.update(max_mode=0, laser=dict(k0=20.0, iteration=3), ppc1=2, ppc2=2, num_theta=8)
+    FakeSim.G_OF = {noff: g for g, (noff, _) in enumerate(pipeline.slab_partition(32, 3))}
+    out = {}
+    _run_rank(cfg, plasma, beam, 3, 0, 1, None, None, 5, False, out)
+    assert not isinstance(out[0], Exception), out[0]
+    simulate()
+    assert any("lasg" in e and "happen-after" in e for e in fake_device.errors), fake_device.errors[:3]
