@@ -54,3 +54,33 @@ def test_reads_the_reference_deck():
     assert all(cfg[k] == want[k] for k in ("nr", "nz", "max_mode", "rmax", "zmin", "zmax", "dt", "iter_max", "ppc1", "ppc2", "num_theta"))
     b, w = beams[0], want["beam"]
     assert b["density"] == w["density"] and tuple(b["sigma"]) == tuple(w["sigma"]) and tuple(b["center"]) == tuple(w["center"]) and b["ppc"] == w["ppc"]
+
+
+def test_laser_envelope_dumps_in_the_reference_layout(tmp_path):
+    """a laser deck: the envelope dumps ./Lasers1/A_laser/{Re,Im}_<Part>/a_laser_*.h5 (diagnostics_class.f03:662-691, :1005-1019) beside the
+    field dumps; identical data pass, a perturbed envelope is flagged"""
+    from qpad_b200 import decks
+    cfg = dict(nr=48, nz=40, max_mode=0, rmax=12.0, zmin=-3.0, zmax=6.0, dt=2.0, iter_max=4, iter_reltol=1e-3, iter_abstol=1e-6, ppc1=2, ppc2=2, num_theta=8,
+               laser=dict(k0=20.0, a0=1.2, w0=2.5, focal_distance=0.0, lon_center=0.0, t_rise=1.5, t_flat=0.0, t_fall=1.5, iteration=2))
+    plasma = decks.plasma_uniform(cfg["nr"], cfg["rmax"], 2, 2, 8)
+    ours = CR.run_ours_laser(cfg, plasma, 1, "oracle")
+    nr, nz = cfg["nr"], cfg["nz"]
+    assert np.max(np.abs(ours["a_r"])) > 0.5 and np.max(np.abs(ours["psi"])) > 1e-3
+    dump = {"Lasers1/A_laser/Re_Re0": ours["a_r"][0, 2:nz + 2, 1:nr + 1].T.copy(), "Lasers1/A_laser/Im_Re0": ours["a_i"][0, 2:nz + 2, 1:nr + 1].T.copy(),
+            "Fields/Psi/Re0": ours["psi"][0, :, 1:nr + 1, 0].T.copy(), "Fields/Ez/Re0": ours["e"][0, :, 1:nr + 1, 2].T.copy()}
+    f = tmp_path / "lwfa.npz"
+    np.savez(f, **dump)
+    ref = CR.load_reference(str(f), 1)
+    assert set(ref) == {("A_laser_Re", "Re0"), ("A_laser_Im", "Re0"), ("Psi", "Re0"), ("Ez", "Re0")}
+    assert CR.compare(ref, ours, cfg, 1e-6, 1e-5, out=open(os.devnull, "w"))
+    ref[("A_laser_Im", "Re0")] = ref[("A_laser_Im", "Re0")] * (1.0 + 5e-6)
+    assert not CR.compare(ref, ours, cfg, 1e-6, 1e-5, out=open(os.devnull, "w"))
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/input_file/lwfa/qpinput.json"), reason="the reference tree is not on this machine")
+def test_reads_the_reference_lwfa_deck():
+    cfg, beams = CR.deck_from_json("/root/reference/input_file/lwfa/qpinput.json")
+    from qpad_b200 import decks
+    want = decks.CONFIGS["C4"]
+    assert not beams and all(cfg[k] == want[k] for k in ("nr", "nz", "max_mode", "rmax", "zmin", "zmax", "dt", "iter_max", "ppc1", "ppc2", "num_theta"))
+    assert all(cfg["laser"][k] == want["laser"][k] for k in ("k0", "a0", "w0", "focal_distance", "lon_center", "t_rise", "t_flat", "t_fall", "iteration"))

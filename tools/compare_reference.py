@@ -13,6 +13,8 @@ Layout of the reference's field dumps (diagnostics_class.f03:583-601, :947-1044,
     ./Fields/<Name>/<Part>/<name>_%08d.h5      dataset <name>, rank 2 = (r, xi) of one component of one mode part
     <Name>/<name> in Psi/psi, Er/er, Ephi/ephi, Ez/ez, Br/br, Bphi/bphi, Bz/bz;  <Part> = Re0, Re1, Im1, Re2, Im2, ...
     file number = 3D step at which the dump was written.
+Laser decks (nlasers > 0) also dump the envelope (diagnostics_class.f03:662-691, :1005-1019): ./Lasers1/A_laser/<Cplx>_<Part>/a_laser_%08d.h5 with
+    <Cplx> = Re | Im (a_r | a_i of the envelope) and <Part> as above -- compared with the envelope volumes of our run (slices 1..nz, nodes 1..nr).
 Our side: the same deck through the CPU oracle (--impl oracle, default: runs anywhere) or the B200 library (--impl gpu), single
 stage; psi / e / b volumes [plane][slice][node][component] with plane 0 = Re0, 2m-1 = Re m, 2m = Im m and node j <-> r = (j-1) dr.
 
@@ -50,7 +52,8 @@ def part_to_plane(part):
 
 
 def load_reference(path, step):
-    """{(Name, Part): 2-D array} from a QPAD run directory (HDF5, needs h5py) or an .npz export with keys 'Fields/<Name>/<Part>'"""
+    """{(Name, Part): 2-D array} from a QPAD run directory (HDF5, needs h5py) or an .npz export with keys 'Fields/<Name>/<Part>'; envelope dumps of
+    a laser deck come back under the names ("A_laser_Re", Part) / ("A_laser_Im", Part) (npz keys 'Lasers1/A_laser/Re_<Part>' ...)"""
     out = {}
     if os.path.isfile(path) and path.endswith(".npz"):
         z = np.load(path)
@@ -58,6 +61,9 @@ def load_reference(path, step):
             m = re.fullmatch(r"Fields/(\w+)/((?:Re|Im)\d+)", key)
             if m and m.group(1) in FIELDS:
                 out[(m.group(1), m.group(2))] = np.asarray(z[key], dtype=np.float64)
+            m = re.fullmatch(r"Lasers1/A_laser/(Re|Im)_((?:Re|Im)\d+)", key)
+            if m:
+                out[("A_laser_" + m.group(1), m.group(2))] = np.asarray(z[key], dtype=np.float64)
         return out
     try:
         import h5py
@@ -73,6 +79,14 @@ def load_reference(path, step):
             if os.path.exists(f):
                 with h5py.File(f, "r") as h:
                     out[(name, part)] = np.asarray(h[dset], dtype=np.float64)
+    base = os.path.join(path, "Lasers1", "A_laser")
+    if os.path.isdir(base):
+        for sub in sorted(os.listdir(base)):
+            m = re.fullmatch(r"(Re|Im)_((?:Re|Im)\d+)", sub)
+            f = os.path.join(base, sub, f"a_laser_{step:08d}.h5")
+            if m and os.path.exists(f):
+                with h5py.File(f, "r") as h:
+                    out[("A_laser_" + m.group(1), m.group(2))] = np.asarray(h["a_laser"], dtype=np.float64)
     return out
 
 
@@ -90,12 +104,44 @@ def deck_from_json(path):
                iter_max=sim.get("iter_max", 1), iter_reltol=sim.get("iter_reltol", 1e-3), iter_abstol=sim.get("iter_abstol", 1e-3))
     sp = d["species"][0]
     cfg.update(ppc1=sp["ppc"][0], ppc2=sp["ppc"][1], num_theta=sp["num_theta"])
+    if d.get("laser"):
+        l0 = d["laser"][0]
+        cfg["laser"] = {k: l0[k] for k in ("k0", "a0", "w0", "focal_distance", "lon_center", "t_rise", "t_flat", "t_fall", "iteration") if k in l0}
     beams = []
     for b in d.get("beam", []):
         beams.append(dict(ppc=tuple(b["ppc"]), num_theta=b["num_theta"], q=b["q"], m=b["m"], gamma=b["gamma"], density=b["density"], quiet=b.get("quiet_start", True),
                           center=(b["gauss_center"][0], b["gauss_center"][1], b["gauss_center"][2]), sigma=tuple(b["gauss_sigma"]),
                           range1=tuple(b["range1"]), range2=tuple(b["range2"]), range3=tuple(b["range3"]), uth=tuple(b["uth"]), den_min=b.get("den_min", 1e-10)))
     return cfg, beams
+
+
+def run_ours_laser(cfg, plasma, nsteps, impl):
+    """a laser deck (cfg["laser"]: the keys of the deck's laser block; robust_pgc plasma, no beam): fields + envelope volumes after nsteps"""
+    from qpad_b200 import decks
+    keys = ("nr", "nz", "max_mode", "rmax", "zmin", "zmax", "dt", "iter_max", "iter_reltol", "iter_abstol")
+    las = cfg["laser"]
+    a_r, a_i = decks.laser_gaussian(cfg["nr"], cfg["nz"], cfg["rmax"], cfg["zmin"], cfg["zmax"], max_mode=cfg["max_mode"], **las)
+    nz = cfg["nz"]
+    if impl == "oracle":
+        from oracle import oracle as O
+        sim = O.Sim(sp_push_type=5, laser_on=1, laser_iter=las["iteration"], laser_k0=las["k0"], beam_evol=0, **{k: cfg[k] for k in keys + ("ppc1", "ppc2", "num_theta")})
+        sim.set_laser(a_r, a_i)
+        sim.set_beam(np.zeros((0, 3)), np.zeros((0, 3)), np.zeros(0))
+        for k in range(nsteps):
+            sim.step3d(k + 1)
+        out = {n: sim.field(n, 2)[:, :nz] for n in ("psi", "e", "b")}
+        out["a_r"], out["a_i"], _ = sim.laser()
+        return out
+    from qpad_b200 import capi
+    sim = capi.Sim(sp_npmax=2 * len(plasma[4]), beam_npmax=64, beam_evol=0, sp_push_pgc=1, laser_iter=las["iteration"], laser_k0=las["k0"], sp_ppc_r=cfg["ppc1"], use_graph=1,
+                   **{k: cfg[k] for k in keys})
+    sim.init_species(*plasma)
+    sim.laser.upload(a_r, a_i)
+    for _ in range(nsteps):
+        sim.step3d()
+    out = {n: sim.field(n).download_f2()[:, :nz] for n in ("psi", "e", "b")}
+    out["a_r"], out["a_i"] = sim.laser.download()
+    return out
 
 
 def run_ours(cfg, beam_arrays, plasma, nsteps, impl):
@@ -120,11 +166,17 @@ def compare(ref, ours, cfg, tol, vol_tol, out=sys.stdout):
     nr, nz = cfg["nr"], cfg["nz"]
     ok, rows = True, []
     for (name, part), a in sorted(ref.items()):
-        dset, fld, comp = FIELDS[name]
         pl = part_to_plane(part)
-        if pl >= ours[fld].shape[0]:
-            continue
-        mine = ours[fld][pl, :, 1:nr + 1, comp]                 # (xi, r)
+        if name.startswith("A_laser_"):                         # envelope volume (P, nz+3, nr+2): slice j at index j+1
+            vol = ours.get("a_r" if name.endswith("Re") else "a_i")
+            if vol is None or pl >= vol.shape[0]:
+                continue
+            mine = vol[pl, 2:nz + 2, 1:nr + 1]
+        else:
+            dset, fld, comp = FIELDS[name]
+            if pl >= ours[fld].shape[0]:
+                continue
+            mine = ours[fld][pl, :, 1:nr + 1, comp]             # (xi, r)
         a = np.squeeze(a)
         if a.shape == (nr, nz):
             a = a.T
@@ -169,6 +221,11 @@ def main(argv=None):
         cfg, beams = bench.deck_config(args.deck)
         beams = beams if isinstance(beams, list) else [beams]
     plasma = decks.plasma_uniform(cfg["nr"], cfg["rmax"], cfg["ppc1"], cfg["ppc2"], cfg["num_theta"])
+    if cfg.get("laser"):                                        # laser deck: no beam; fields + envelope
+        ref = load_reference(args.ref, args.step)
+        ok = compare(ref, run_ours_laser(cfg, plasma, args.step, args.impl), cfg, args.tol, args.vol_tol)
+        print(json.dumps({"datasets": len(ref), "ok": bool(ok), "tol": args.tol, "vol_tol": args.vol_tol, "impl": args.impl}))
+        return 0 if ok else 1
     if args.beam_npz:
         z = np.load(args.beam_npz)
         bm = (np.ascontiguousarray(z["x"]), np.ascontiguousarray(z["p"]), np.ascontiguousarray(z["q"]))
