@@ -35,20 +35,20 @@ def _run(fn, args):
 
 def test_default_bench_function_runs(bench_mod, monkeypatch):
     from qpad_b200 import decks
-    monkeypatch.setitem(decks.CONFIGS, "C2", dict(decks.CONFIGS["C2"], nr=64, nz=64, ppc1=2, ppc2=2, num_theta=8, iter_max=3))
-    args = types.SimpleNamespace(gpus=1, steps=2, warmup=1, config="C2", balance=1, transport=None, stages=4, no_cpu=True, no_micro=True, roof_slices=16,
-                                 ref_slices=8, no_sweep=False, no_graph=False, legacy_pipeline=False, impl="b200", check=1, fill_steps=[3], rebalance=1)
+    monkeypatch.setitem(decks.CONFIGS, "C2", dict(decks.CONFIGS["C2"], nr=64, nz=48, ppc1=2, ppc2=2, num_theta=8, iter_max=3))
+    args = types.SimpleNamespace(gpus=1, steps=1, warmup=1, config="C2", balance=1, transport=None, stages=4, no_cpu=True, no_micro=True, roof_slices=16,
+                                 ref_slices=8, no_sweep=False, no_graph=False, legacy_pipeline=False, impl="b200", check=1, fill_steps=[2], rebalance=1)
     c0 = emu.lib().emu_coop_launches()
     line = _run(bench_mod.run_b200_local, args)
     assert all(k in line for k in KEYS), [k for k in KEYS if k not in line]
-    assert line["n_gpus"] == 1 and line["steps"] == 2 and line["dtype"] == "f64" and line["gpu_launches"] > 0
+    assert line["n_gpus"] == 1 and line["steps"] == 1 and line["dtype"] == "f64" and line["gpu_launches"] > 0
     assert {"bound", "achieved", "peak", "frac", "traffic"} <= set(line["roofline"]) and {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(line["e2e"])
     assert line["e2e"]["h2d_bytes_per_step"] == 64 * 2048 and line["config"]["pc_iters_per_slice"] > 1.2      # a driven wake, not the quiet plasma
-    assert emu.lib().emu_coop_launches() - c0 >= 4 * 3                                                        # the sweep kernels of the 4 stages ran
+    assert emu.lib().emu_coop_launches() - c0 >= 4 * 2                                                        # the sweep kernels of the 4 stages ran
     # the pipelined run carried its own correctness check: line-outs and beam moments equal to a one-stage run of the same 3D steps
     pc = line["parity_check"]
     assert pc["ok"] and pc["ez_lineout_rel_err"] < 1e-6 and pc["psi_lineout_rel_err"] < 1e-6 and pc["beam_particles"] == pc["beam_particles_single_stage"] > 0, pc
-    assert line["single_step"]["single_step_ms"] > 0 and line["fill_inclusive"]["K=3"]["updates_per_s"] > 0
+    assert line["single_step"]["single_step_ms"] > 0 and line["fill_inclusive"]["K=2"]["updates_per_s"] > 0
 
 
 def test_c5_bench_function_runs(bench_mod, monkeypatch):
