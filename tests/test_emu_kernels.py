@@ -63,3 +63,26 @@ def test_part2d_move_emulated(api):
 
 def test_neutral_overflow_emulated(api):
     K.neutral_overflow(api, O)
+
+
+def test_handoff_entry_points_validate_their_arguments(api):
+    """error behaviour of the round-2 hand-off entry points (no silent acceptance): a link needs its buffer AND both flag words, a stage that
+    hands its last two slices on needs two slices, the neutral's record needs an attached neutral, spin planes must be enabled first"""
+    import numpy as np
+    cfg = dict(nr=32, nz=8, max_mode=0, rmax=4.0, zmin=0.0, zmax=2.0, dt=2.0)
+    sim = api.Sim(sp_npmax=64, beam_npmax=64, sp_push_pgc=1, laser_iter=1, laser_k0=10.0, noff2=0, nzp=1, **cfg)
+    buf = np.zeros(sim.laser.guard_size() + 16)
+    flags = np.zeros(16, dtype=np.uint32)
+    p, f = buf.ctypes.data, flags.ctypes.data
+    with pytest.raises(api.QpadError, match="go together"):
+        sim.laser.set_handoff(guard_in=p, in_ready=f)                                   # ack word missing
+    with pytest.raises(api.QpadError, match="at least two"):
+        sim.laser.set_handoff(guard_out=p, out_ready=f, out_ack=f + 32)                 # a slab of ONE slice cannot hand two on
+    sim.laser.set_handoff(guard_in=p, in_ready=f, in_ack=f + 32)                        # an upstream link alone is fine
+    with pytest.raises(api.QpadError, match="no neutral"):
+        sim.neutral_pack(p)
+    assert sim.neutral_wire_count() == -1
+    with pytest.raises(api.QpadError, match="enable_spin"):
+        sim.beam.upload_spin(np.zeros((0, 3)))
+    assert sim.beam.wire_count() == 7 * sim.beam.wire_cap() + 1
+    sim.close()
