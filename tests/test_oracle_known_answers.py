@@ -282,3 +282,30 @@ def test_spin_precession_in_uniform_b(push):
     x2, p2 = x.copy(), p.copy()
     L.orc_push3d(x2, p2, 1, 0.1, 0.1, nr, nz, 0, 0, qbm, dt, push, ef, bf)
     assert np.array_equal(x2, xs) and np.array_equal(p2, ps)
+
+
+@pytest.mark.parametrize("push", [1, 2])
+def test_betatron_oscillation_in_an_ion_channel(push):
+    """pin of orc_push3d (part3d_class.f03:358-576, interp_emf :691-790): in the focusing field of a blown-out ion channel, E_r = r / 2, a beam
+    electron of energy gamma oscillates at the betatron frequency omega_p / sqrt(2 gamma).  The pushers kick with the field at the old position
+    and then drift with the new momentum -- a leapfrog whose momentum lives half a step behind the position -- so from p_x = 0 the positions
+    follow x0 cos(w (t + dt/2)) / cos(w dt / 2); the bilinear gather of a field linear in r is exact.  Two periods, both pushers: 2e-4 of the
+    amplitude (what is left is the gamma variation of the oscillating electron, (p_x / gamma)^2 / 2 = 8e-5 in the frequency)"""
+    L = O.lib()
+    nr, nz, dr, dz, gamma, dt = 64, 8, 0.05, 0.5, 2000.0, 2.0
+    r = (np.arange(nr + 2) - 1.0) * dr
+    ef = np.zeros((1, nz + 1, nr + 2, 3)); bf = np.zeros((1, nz + 1, nr + 2, 3))
+    ef[0, :, :, 0] = 0.5 * r[None, :]                           # E_r on the m = 0 plane, same in every slice
+    x = np.array([[0.8, 0.0, 1.3]]); p = np.array([[0.0, 0.0, np.sqrt(gamma ** 2 - 1.0)]])
+    w = 1.0 / np.sqrt(2.0 * gamma)
+    nsteps = int(round(2 * 2 * np.pi / w / dt))                 # two betatron periods
+    xs = []
+    for _ in range(nsteps):
+        L.orc_push3d(x, p, 1, dr, dz, nr, nz, 0, 0, -1.0, dt, push, ef, bf)
+        x[0, 2] = 1.3                                           # keep it in the slab (xi slips by dt (1 - v_z) per step)
+        xs.append(x[0, 0])
+    t = dt * np.arange(1, nsteps + 1)
+    want = 0.8 * np.cos(w * (t + 0.5 * dt)) / np.cos(0.5 * w * dt)
+    err = np.max(np.abs(np.array(xs) - want))
+    assert err < 2e-4 * 0.8, err
+    assert min(xs) < -0.79 and abs(x[0, 1]) < 1e-15             # it really oscillates, and stays in its plane
